@@ -1,0 +1,196 @@
+/* phyfoo.h -- C ABI of libphyfoo.so: the B200-native drop-in for PhyFoo's site-scoring /
+ * free-energy hot path.  Plain pointers and sizes only; every pointer is caller-owned HOST memory
+ * unless the name says "device" or it is an opaque handle.  A Java subclass of PhyFoo's models
+ * binds these entry points through JNI or Panama (INTEGRATION.md shows the stubs); the Python
+ * package phyfoo_b200 binds the identical symbols through ctypes.
+ *
+ * Reference interfaces replaced (X.java:N = /root/reference/main/java/src/X.java,
+ * jstacs!/p:N = source inside /root/reference/libs/jstacs.jar):
+ *   Model.getLogProbFor(Sequence,int,int)            jstacs!/de/jstacs/models/Model.java:223
+ *     impl  models/PhyloBayesModel.java:222-267      -> phyfoo_score_windows   (whole sample per call)
+ *     impl  models/PhyloBackground.java:241-305      -> phyfoo_bg_columns
+ *   SingleHiddenMotifMixture.getNewWeights / modify / getProfileOfScoresFor / getStrandProbabilitiesFor
+ *     jstacs!/de/jstacs/models/mixture/motif/SingleHiddenMotifMixture.java:499-566,585-596,643-688,737-754
+ *     StrandModel  jstacs!/de/jstacs/models/mixture/StrandModel.java:561-583,631-640
+ *                                                    -> phyfoo_zoops_estep
+ *   SequenceSpecificDataSelector                     io/SequenceSpecificDataSelector.java:37-99
+ *                                                    -> phyfoo_select
+ *   AbstractFreeEnergyOptimizer.getWeightedLogLikelihoodSum  optimizing/AbstractFreeEnergyOptimizer.java:95-114
+ *   FE_byParameter_ForBayesNodeJstacs.evaluateFunction       optimizing/FE_byParameter_ForBayesNodeJstacs.java:43-53
+ *   MotifParamOptimizer.evaluateFunction                      optimizing/MotifParamOptimizer.java:46-61
+ *   NumericalDifferentiableFunction.evaluateGradientOfFunction
+ *     jstacs!/de/jstacs/algorithms/optimization/NumericalDifferentiableFunction.java:64-84
+ *                                                    -> phyfoo_fe_prepare / phyfoo_fe_eval / phyfoo_fe_grad
+ *   MultiDimensionalDiscreteSequence ctor (column tensor int[pos][species])
+ *     jstacs!/de/jstacs/data/sequences/MultiDimensionalDiscreteSequence.java:46-52
+ *                                                    -> phyfoo_dataset_create (packs on the device)
+ *
+ * Conventions: every function returns 0 on success or a negative PHYFOO_E* code; the message is
+ * available from phyfoo_last_error().  One context belongs to one GPU and to one caller thread at a
+ * time (the reference is single-threaded; this library does not lock).  Calls are synchronous:
+ * results are in the caller's buffers when the call returns.  There is NO CPU fallback: without a
+ * CUDA device phyfoo_init fails with PHYFOO_ENODEVICE.
+ */
+#ifndef PHYFOO_H
+#define PHYFOO_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHYFOO_OK 0
+#define PHYFOO_EINVAL (-1)     /* IllegalArgumentException on the Java side */
+#define PHYFOO_ENODEVICE (-2)  /* no CUDA device / driver */
+#define PHYFOO_ECUDA (-3)      /* a CUDA call failed */
+#define PHYFOO_ENOMEM (-4)
+#define PHYFOO_EUNSUPPORTED (-5)
+
+#define PHYFOO_MODEL_FG 0 /* models/PhyloBayesModel.java (motif, `width` trees) */
+#define PHYFOO_MODEL_BG 1 /* models/PhyloBackground.java (order+1 trees)        */
+
+#define PHYFOO_EVOL_F81ALPHA 0           /* evolution/FS81alpha.java (default, EvolModel.java:7) */
+#define PHYFOO_EVOL_F81BETA 1            /* evolution/FS81beta.java */
+#define PHYFOO_EVOL_HKY_AS_IMPLEMENTED 2 /* evolution/HKY.java with its beta == 0 (ctor bug :32) */
+
+#define PHYFOO_MODE_MEANFIELD 0 /* -calcFreeEnergy() after optimizeByNormalisation (default path) */
+#define PHYFOO_MODE_EXACT 1     /* PhyloBayesModel.CALC_LOGLIKELIHOOD = true (order 0: pruning)     */
+
+typedef struct phyfoo_ctx phyfoo_ctx;
+typedef struct phyfoo_dataset phyfoo_dataset;
+typedef struct phyfoo_model phyfoo_model;
+typedef struct phyfoo_feset phyfoo_feset;
+
+/* Tree and parameters of one model.  Nodes are numbered in DFS pre-order exactly as
+ * io/NewickToBayesNet.java:106-147 numbers them (root = 0, parent[k] < k); leaf_species[k] is the
+ * alignment row observed at leaf k (left-to-right leaf order of the Newick string = species order,
+ * util/Util.java:39-53) and -1 at internal nodes. */
+typedef struct {
+    int32_t kind;                   /* PHYFOO_MODEL_FG / PHYFOO_MODEL_BG */
+    int32_t width;                  /* motif length W (ignored for BG: order+1 trees) */
+    int32_t order;                  /* FG: 0 or 1 (PhyloBayesModel.java:363); BG: Markov order */
+    int32_t n_nodes;                /* N */
+    const int32_t* parent;          /* [N] */
+    const int32_t* leaf_species;    /* [N] */
+    int32_t evol;                   /* PHYFOO_EVOL_* */
+    double hky_ratio;               /* accepted and ignored, like the reference does (HKY.java:32) */
+    const double* branch;           /* [trees][N] distance to parent per position (root entry unused) */
+    const double* pi;               /* per tree t: [ctx_t][4] row-major, concatenated; ctx_t = 4^{#horizontal parents} */
+    int32_t mode;                   /* PHYFOO_MODE_* */
+    int32_t allow_independent_leaf; /* CPF.ALLOW_RETURN_INDEPENDENT_TRANSITION (CPF.java:14); must be 1 */
+    int32_t max_sweeps;             /* 100  (MeanFieldForBayesNet.java:102); 0 = default */
+    int32_t min_sweeps;             /* 2 */
+    double tol;                     /* 1e-5 (:205); 0 = default */
+} phyfoo_model_desc;
+
+typedef struct {
+    int64_t n_windows;      /* window scores produced (per strand) */
+    int64_t n_columns;      /* background columns scored */
+    int64_t sweeps_fg;      /* sum over windows of the mean-field sweep count K_w (integer parity check) */
+    int64_t sweeps_bg;      /* sum over columns of K_c */
+    int32_t kernel_launches;/* kernels launched by the call */
+    float gpu_ms;           /* device time of the call's kernels (CUDA events on the library's stream) */
+} phyfoo_stats;
+
+/* ---- context ---- */
+int phyfoo_init(int device, phyfoo_ctx** out);
+void phyfoo_destroy(phyfoo_ctx* ctx);
+const char* phyfoo_last_error(const phyfoo_ctx* ctx); /* ctx may be NULL: error of a failed phyfoo_init */
+int phyfoo_device_info(phyfoo_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, int64_t* total_mem);
+/* fp64 FMA roofline probe: runs a dependent-chain-free DFMA loop on every SM; returns TFLOP/s */
+int phyfoo_fp64_peak(phyfoo_ctx* ctx, double* tflops_out);
+
+/* ---- dataset: packed columns resident on the device ----
+ * codes[sum cols][n_species], values 0..3 = A,C,G,T and 4 = gap/unobserved
+ * (jstacs!/de/jstacs/data/alphabets/UnobservableDNAAlphabet.java:116); col_offsets[n_aln+1] are the
+ * prefix sums of the alignment lengths.  Packed layout ("packed columns", bit-exact contract):
+ *   base plane k, column c: uint32 at bases[k*n_cols + c], species 16k..16k+15, 2 bits each, species s
+ *   in bits [2(s%16), 2(s%16)+1]; a gap stores base bits 00;
+ *   gap plane k, column c: uint32 at gaps[k*n_cols + c], species 32k..32k+31, bit s%32 set = unobserved. */
+int phyfoo_dataset_create(phyfoo_ctx* ctx, int32_t n_aln, int32_t n_species, const int64_t* col_offsets,
+                          const uint8_t* codes, phyfoo_dataset** out);
+/* same, but `codes` already lives on this context's device (no host->device copy) */
+int phyfoo_dataset_create_device(phyfoo_ctx* ctx, int32_t n_aln, int32_t n_species, const int64_t* col_offsets,
+                                 const uint8_t* codes_device, phyfoo_dataset** out);
+int phyfoo_dataset_packed(phyfoo_ctx* ctx, const phyfoo_dataset* ds, uint32_t* bases_out, uint32_t* gaps_out);
+int64_t phyfoo_dataset_columns(const phyfoo_dataset* ds);
+int64_t phyfoo_dataset_windows(const phyfoo_dataset* ds, int32_t width); /* sum_i max(0, L_i - width + 1) */
+void phyfoo_dataset_free(phyfoo_ctx* ctx, phyfoo_dataset* ds);
+
+/* ---- models ---- */
+int phyfoo_model_create(phyfoo_ctx* ctx, const phyfoo_model_desc* desc, phyfoo_model** out);
+/* PhyloPreparedAbstractModel.setCondProb(double[], position): models/AbstractPhyloModel.java:131-134 */
+int phyfoo_model_set_pi(phyfoo_ctx* ctx, phyfoo_model* m, int32_t position, const double* pi, int32_t n);
+int phyfoo_model_get_pi(phyfoo_ctx* ctx, const phyfoo_model* m, int32_t position, double* pi_out, int32_t n);
+/* VirtualTree.reinitEdglengths (bayesNet/VirtualTree.java:237-255), one branch at a time */
+int phyfoo_model_set_branch(phyfoo_ctx* ctx, phyfoo_model* m, int32_t position, int32_t node, double length);
+int phyfoo_model_set_mode(phyfoo_ctx* ctx, phyfoo_model* m, int32_t mode);
+void phyfoo_model_free(phyfoo_ctx* ctx, phyfoo_model* m);
+
+/* ---- scoring ----
+ * out[w] for every window w of every alignment (alignment-major, offsets ascending; total =
+ * phyfoo_dataset_windows(ds, W)) = PhyloBayesModel.getLogProbFor(seq, j, j+W-1).  strand = 1 scores the
+ * reverse complement of every window (StrandModel.java:636-639).  sweeps_out (nullable) receives K_w. */
+int phyfoo_score_windows(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* fg, int32_t strand,
+                         double* out, int32_t* sweeps_out, phyfoo_stats* stats);
+/* out[c] for every column c = PhyloBackground.getLogProbFor(seq, u, u) (order 0). sweeps_out nullable. */
+int phyfoo_bg_columns(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* bg, double* out,
+                      int32_t* sweeps_out, phyfoo_stats* stats);
+
+/* ZOOPS E-step over the whole (local) sample: SingleHiddenMotifMixture.getNewWeights.
+ *   logw[2]          log component weights (motif, no motif)
+ *   strand_logw      NULL, or log strand weights [2] (motif wrapped in a StrandModel)
+ *   aln_weights      NULL (all 1) or [n_aln]
+ *   gamma_out        NULL or [windows]: seqweights[0] after the call (gamma_j * p_motif * weight)
+ *   profile_out      NULL or [windows]: the unnormalised log profile a_j (getProfileOfScoresFor, UNNORMALIZED_CONDITIONAL)
+ *   w_out[2], ll_out sufficient statistics of the component weights and the log-likelihood (local sums)
+ *   argmax_off       NULL or [n_aln]: first offset of the maximal a_j (util/Util.java:528-538)
+ *   argmax_strand    NULL or [n_aln]: strand call at that offset (0 wins ties) */
+int phyfoo_zoops_estep(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* fg, phyfoo_model* bg,
+                       const double* logw, const double* strand_logw, const double* aln_weights,
+                       double* gamma_out, double* profile_out, double* w_out, double* ll_out,
+                       int32_t* argmax_off, uint8_t* argmax_strand, phyfoo_stats* stats);
+/* Same E-step, but the three local sums [ll, w0, w1] are left in DEVICE memory at `partial_device`
+ * (3 doubles) on `stream` (a cudaStream_t; NULL = the library's stream) so that the caller can
+ * all-reduce them over NCCL without a host round trip.  Asynchronous with respect to the host. */
+int phyfoo_zoops_estep_device(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* fg, phyfoo_model* bg,
+                              const double* logw, const double* strand_logw, const double* aln_weights_device,
+                              double* partial_device, void* stream);
+
+/* ---- M-step data selection (io/SequenceSpecificDataSelector.java:37-99) ----
+ * weights[windows] (e.g. gamma_out), one group per alignment: walk the windows by descending weight,
+ * take those with raw weight >= q, stop after the running sum of normalised weights exceeds t.
+ * sel_aln/sel_off/sel_weight must hold `capacity` entries; *n_selected receives the count
+ * (PHYFOO_ENOMEM if capacity is too small). */
+int phyfoo_select(phyfoo_ctx* ctx, const phyfoo_dataset* ds, int32_t width, const double* weights, double t,
+                  double q, int32_t* sel_aln, int32_t* sel_off, double* sel_weight, int64_t capacity,
+                  int64_t* n_selected);
+
+/* ---- fixed-q free-energy objective (M-step) ----
+ * prepare: runs the mean field to convergence for each listed window (fresh uniform start, like
+ * PhyloBayesModel.train :142-147 / PhyloBackground.train :127-134) and keeps q on the device.
+ * strand may be NULL (all forward). */
+int phyfoo_fe_prepare(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* m, int64_t n_sel,
+                      const int32_t* sel_aln, const int32_t* sel_off, const uint8_t* sel_strand,
+                      const double* sel_weight, phyfoo_feset** out);
+/* every (order+1)-column window of every alignment with per-alignment weights (PhyloBackground.train) */
+int phyfoo_fe_prepare_all(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* m, const double* aln_weights,
+                          phyfoo_feset** out);
+/* f(lambda) = -sum_u w_u F(q_u; theta(lambda)); position >= 0: lambda holds that position's block(s)
+ * (dim = 4*ctx), position < 0: all positions concatenated.  The model is left at lambda. */
+int phyfoo_fe_eval(phyfoo_ctx* ctx, phyfoo_feset* fe, int32_t position, const double* lambda, int32_t dim,
+                   double* f_out);
+/* forward-difference gradient with the reference's perturbation order; g_out[dim] */
+int phyfoo_fe_grad(phyfoo_ctx* ctx, phyfoo_feset* fe, int32_t position, const double* lambda, int32_t dim,
+                   double eps, double* f_out, double* g_out);
+/* device-resident variant for multi-GPU: values[dim+1] = [f(lambda), f(lambda+eps e_0), ...] local sums */
+int phyfoo_fe_values_device(phyfoo_ctx* ctx, phyfoo_feset* fe, int32_t position, const double* lambda,
+                            int32_t dim, double eps, double* values_device, void* stream);
+int64_t phyfoo_fe_size(const phyfoo_feset* fe);
+void phyfoo_fe_free(phyfoo_ctx* ctx, phyfoo_feset* fe);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHYFOO_H */

@@ -1,0 +1,299 @@
+"""ctypes binding of the CPU oracle (oracle/libphyfoo_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  Nothing under phyfoo_b200/ may import this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+F81ALPHA, F81BETA, HKY = 0, 1, 2
+MEANFIELD, EXACT_ELIMINATION, EXACT_PRUNING = 0, 1, 2
+FG, BG = 0, 1
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libphyfoo_oracle.so")
+    src = os.path.join(_HERE, "phyfoo_oracle.cpp")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        dp, u8p, ip = C.POINTER(C.c_double), C.POINTER(C.c_uint8), C.POINTER(C.c_int)
+        L.orc_last_error.restype = C.c_char_p
+        L.orc_model_new.restype = C.c_void_p
+        L.orc_model_new.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_double]
+        L.orc_model_clone.restype = C.c_void_p
+        L.orc_model_clone.argtypes = [C.c_void_p]
+        L.orc_model_free.argtypes = [C.c_void_p]
+        for f in ("orc_model_nodes", "orc_model_species", "orc_model_trees"):
+            getattr(L, f).argtypes = [C.c_void_p]
+        L.orc_model_pi_dim.argtypes = [C.c_void_p, C.c_int]
+        L.orc_model_topology.argtypes = [C.c_void_p, ip, ip, dp]
+        L.orc_model_leaf_label.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
+        L.orc_model_set_pi.argtypes = [C.c_void_p, C.c_int, dp, C.c_int]
+        L.orc_model_get_pi.argtypes = [C.c_void_p, C.c_int, dp]
+        L.orc_model_set_branch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
+        L.orc_model_set_options.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.orc_model_cpf.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, dp]
+        L.orc_model_sweeps_total.restype = C.c_longlong
+        L.orc_model_sweeps_total.argtypes = [C.c_void_p]
+        L.orc_model_reset_stats.argtypes = [C.c_void_p]
+        L.orc_score_window.restype = C.c_double
+        L.orc_score_window.argtypes = [C.c_void_p, u8p, C.c_int, ip]
+        L.orc_score_windows.argtypes = [C.c_void_p, u8p, C.c_int, C.c_int, dp, ip]
+        L.orc_exact_bruteforce.restype = C.c_double
+        L.orc_exact_bruteforce.argtypes = [C.c_void_p, u8p]
+        L.orc_bg_range.restype = C.c_double
+        L.orc_bg_range.argtypes = [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int]
+        L.orc_bg_columns.argtypes = [C.c_void_p, u8p, C.c_int, dp]
+        L.orc_estep.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64), u8p, dp, dp, dp,
+                                C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, C.POINTER(C.c_int32), u8p,
+                                C.POINTER(C.c_longlong)]
+        L.orc_select_group.argtypes = [dp, C.c_int, C.c_double, C.c_double, ip, dp]
+        L.orc_lambda2pi.argtypes = [dp, dp, C.c_int]
+        L.orc_fe_prepare.restype = C.c_void_p
+        L.orc_fe_prepare.argtypes = [C.c_void_p, u8p, C.c_int, dp]
+        L.orc_fe_free.argtypes = [C.c_void_p]
+        L.orc_fe_sum.restype = C.c_double
+        L.orc_fe_sum.argtypes = [C.c_void_p]
+        L.orc_fe_eval.restype = C.c_double
+        L.orc_fe_eval.argtypes = [C.c_void_p, C.c_int, dp, C.c_int]
+        L.orc_fe_grad.argtypes = [C.c_void_p, C.c_int, dp, C.c_int, C.c_double, dp, dp]
+        L.orc_fe_get_q.argtypes = [C.c_void_p, C.c_int, dp]
+        L.orc_encode_alignment.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_int, u8p]
+        L.orc_drop_allgap_columns.argtypes = [u8p, C.c_int, C.c_int]
+        L.orc_pack_columns.argtypes = [u8p, C.c_int64, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        _LIB = L
+    return _LIB
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _u8(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def _err():
+    return lib().orc_last_error().decode()
+
+
+class Model:
+    """One PhyloBayesModel (kind=FG) or PhyloBackground (kind=BG) of the oracle."""
+
+    def __init__(self, kind, W, order, newick, evol=F81ALPHA, hky_ratio=0.0, _h=None):
+        L = lib()
+        self.h = _h or L.orc_model_new(kind, W, order, newick.encode(), evol, hky_ratio)
+        if not self.h:
+            raise ValueError(_err())
+        self.kind, self.order = kind, order
+        self.N = L.orc_model_nodes(self.h)
+        self.S = L.orc_model_species(self.h)
+        self.W = L.orc_model_trees(self.h)
+
+    def clone(self):
+        return Model(self.kind, self.W, self.order, "", _h=lib().orc_model_clone(self.h))
+
+    def __del__(self):
+        try:
+            lib().orc_model_free(self.h)
+        except Exception:
+            pass
+
+    def topology(self):
+        parent = np.zeros(self.N, np.int32)
+        leaf = np.zeros(self.N, np.int32)
+        dist = np.zeros(self.N, np.float64)
+        lib().orc_model_topology(self.h, parent.ctypes.data_as(C.POINTER(C.c_int)),
+                                 leaf.ctypes.data_as(C.POINTER(C.c_int)), _dp(dist))
+        return parent, leaf, dist
+
+    def leaf_labels(self):
+        out = []
+        for s in range(self.S):
+            buf = C.create_string_buffer(256)
+            lib().orc_model_leaf_label(self.h, s, buf, 256)
+            out.append(buf.value.decode())
+        return out
+
+    def pi_dim(self, t):
+        return lib().orc_model_pi_dim(self.h, t)
+
+    def set_pi(self, t, pi):
+        pi = np.ascontiguousarray(pi, np.float64).ravel()
+        if lib().orc_model_set_pi(self.h, t, _dp(pi), pi.size) != 0:
+            raise ValueError(_err())
+
+    def get_pi(self, t):
+        out = np.zeros(self.pi_dim(t))
+        lib().orc_model_get_pi(self.h, t, _dp(out))
+        return out
+
+    def set_branch(self, t, node, length):
+        if lib().orc_model_set_branch(self.h, t, node, float(length)) != 0:
+            raise ValueError(_err())
+
+    def set_options(self, mode=MEANFIELD, allow_indep=True, log_in_loop=False):
+        lib().orc_model_set_options(self.h, mode, int(allow_indep), int(log_in_loop))
+
+    def cpf(self, t, k, indep=False):
+        out = np.zeros(256 * 4)
+        rows = lib().orc_model_cpf(self.h, t, k, int(indep), _dp(out))
+        return out[:rows * 4].reshape(rows, 4).copy()
+
+    def sweeps_total(self):
+        return lib().orc_model_sweeps_total(self.h)
+
+    def reset_stats(self):
+        lib().orc_model_reset_stats(self.h)
+
+    def score_window(self, cols, revcomp=False):
+        cols = np.ascontiguousarray(cols, np.uint8)
+        assert cols.shape == (self.W, self.S)
+        k = C.c_int(0)
+        v = lib().orc_score_window(self.h, _u8(cols), int(revcomp), C.byref(k))
+        if np.isnan(v) and _err():
+            raise RuntimeError(_err())
+        return v, k.value
+
+    def score_windows(self, codes, revcomp=False):
+        codes = np.ascontiguousarray(codes, np.uint8)
+        Lc = codes.shape[0]
+        n = Lc - self.W + 1
+        out = np.zeros(max(n, 0))
+        sw = np.zeros(max(n, 0), np.int32)
+        if n > 0 and lib().orc_score_windows(self.h, _u8(codes), Lc, int(revcomp), _dp(out),
+                                             sw.ctypes.data_as(C.POINTER(C.c_int))) != 0:
+            raise RuntimeError(_err())
+        return out, sw
+
+    def exact_bruteforce(self, cols):
+        cols = np.ascontiguousarray(cols, np.uint8)
+        return lib().orc_exact_bruteforce(self.h, _u8(cols))
+
+    def bg_range(self, codes, start, end):
+        codes = np.ascontiguousarray(codes, np.uint8)
+        return lib().orc_bg_range(self.h, _u8(codes), codes.shape[0], start, end)
+
+    def bg_columns(self, codes):
+        codes = np.ascontiguousarray(codes, np.uint8)
+        out = np.zeros(codes.shape[0])
+        if lib().orc_bg_columns(self.h, _u8(codes), codes.shape[0], _dp(out)) != 0:
+            raise RuntimeError(_err())
+        return out
+
+
+def estep(fg, bg, col_offsets, codes, logw, strand_logw=None, aln_weights=None, faithful_cost=False,
+          threads=1, want=("gamma", "fwd", "rev", "profile")):
+    """SingleHiddenMotifMixture.getNewWeights over a whole sample. Returns a dict."""
+    col_offsets = np.ascontiguousarray(col_offsets, np.int64)
+    codes = np.ascontiguousarray(codes, np.uint8)
+    n_aln = col_offsets.size - 1
+    nwin = int(np.maximum(np.diff(col_offsets) - fg.W + 1, 0).sum())
+    res = {k: (np.zeros(nwin) if k in want else None) for k in ("gamma", "fwd", "rev", "profile")}
+    logw = np.ascontiguousarray(logw, np.float64)
+    sl = None if strand_logw is None else np.ascontiguousarray(strand_logw, np.float64)
+    aw = None if aln_weights is None else np.ascontiguousarray(aln_weights, np.float64)
+    w = np.zeros(2)
+    ll = C.c_double(0)
+    arg_off = np.zeros(n_aln, np.int32)
+    arg_strand = np.zeros(n_aln, np.uint8)
+    sweeps = C.c_longlong(0)
+    rc = lib().orc_estep(fg.h, bg.h, n_aln, col_offsets.ctypes.data_as(C.POINTER(C.c_int64)), _u8(codes),
+                         _dp(logw), _dp(sl), _dp(aw), int(faithful_cost), int(threads), _dp(res["gamma"]),
+                         _dp(res["fwd"]), _dp(res["rev"]), _dp(res["profile"]), _dp(w), C.byref(ll),
+                         arg_off.ctypes.data_as(C.POINTER(C.c_int32)), _u8(arg_strand), C.byref(sweeps))
+    if rc != 0:
+        raise RuntimeError(_err())
+    res.update(w=w, ll=ll.value, argmax_off=arg_off, argmax_strand=arg_strand, sweeps=sweeps.value)
+    return res
+
+
+def select_group(w, t=0.8, q=0.0):
+    w = np.ascontiguousarray(w, np.float64)
+    idx = np.zeros(w.size, np.int32)
+    wo = np.zeros(w.size)
+    n = lib().orc_select_group(_dp(w), w.size, t, q, idx.ctypes.data_as(C.POINTER(C.c_int)), _dp(wo))
+    return idx[:n].copy(), wo[:n].copy()
+
+
+def lambda2pi(lam):
+    lam = np.ascontiguousarray(lam, np.float64)
+    out = np.zeros_like(lam)
+    lib().orc_lambda2pi(_dp(lam), _dp(out), lam.size)
+    return out
+
+
+class FESet:
+    """Fixed-q free-energy objective of the M-step over a list of windows (cols [n][W][S])."""
+
+    def __init__(self, model, cols, weights):
+        cols = np.ascontiguousarray(cols, np.uint8)
+        weights = np.ascontiguousarray(weights, np.float64)
+        self.model, self.n = model, cols.shape[0]
+        self.h = lib().orc_fe_prepare(model.h, _u8(cols), self.n, _dp(weights))
+        if not self.h:
+            raise RuntimeError(_err())
+
+    def __del__(self):
+        try:
+            lib().orc_fe_free(self.h)
+        except Exception:
+            pass
+
+    def sum(self):
+        return lib().orc_fe_sum(self.h)
+
+    def eval(self, pos, lam):
+        lam = np.ascontiguousarray(lam, np.float64)
+        return lib().orc_fe_eval(self.h, pos, _dp(lam), lam.size)
+
+    def grad(self, pos, lam, eps=1e-4):
+        lam = np.array(lam, np.float64)
+        g = np.zeros_like(lam)
+        f0 = C.c_double(0)
+        if lib().orc_fe_grad(self.h, pos, _dp(lam), lam.size, eps, C.byref(f0), _dp(g)) != 0:
+            raise RuntimeError(_err())
+        return f0.value, g
+
+    def q(self, u):
+        out = np.zeros(self.model.W * self.model.N * 4)
+        k = lib().orc_fe_get_q(self.h, u, _dp(out))
+        return out.reshape(self.model.W, self.model.N, 4), k
+
+
+def encode_alignment(rows):
+    S, Lc = len(rows), len(rows[0])
+    arr = (C.c_char_p * S)(*[r.encode() if isinstance(r, str) else r for r in rows])
+    codes = np.zeros((Lc, S), np.uint8)
+    if lib().orc_encode_alignment(arr, S, Lc, _u8(codes)) != 0:
+        raise ValueError(_err())
+    return codes
+
+
+def drop_allgap_columns(codes):
+    codes = np.ascontiguousarray(codes, np.uint8).copy()
+    n = lib().orc_drop_allgap_columns(_u8(codes), codes.shape[0], codes.shape[1])
+    return codes[:n].copy()
+
+
+def pack_columns(codes):
+    codes = np.ascontiguousarray(codes, np.uint8)
+    n, S = codes.shape
+    bases = np.zeros(((S + 15) // 16, n), np.uint32)
+    gaps = np.zeros(((S + 31) // 32, n), np.uint32)
+    lib().orc_pack_columns(_u8(codes), n, S, bases.ctypes.data_as(C.POINTER(C.c_uint32)),
+                           gaps.ctypes.data_as(C.POINTER(C.c_uint32)))
+    return bases, gaps

@@ -1,0 +1,177 @@
+// model_host.hpp -- host-side model state of libphyfoo: flattens the species tree into the
+// "tree program" the kernels walk and turns (evolution model, branch lengths, pi) into the
+// per-position CPF tables and their logs.
+//
+// Reference semantics restated here (it runs once per parameter set, on the host, like the Java):
+//   bayesNet/VirtualTree.java:82-96      CPFs from the evolution model, one tree per position
+//   evolution/FS81alpha.java:76-92       P(b|a) = (a==b)(1-alpha) + alpha*pi_b, alpha = branch "length"
+//   evolution/FS81beta.java:81-103       alpha' = exp(-v/(1-sum pi^2)) clamped to {0,1} within 1e-4
+//   evolution/HKY.java:77-106 (+ :32)    linear HKY whose transversion rate is always 0 as implemented
+//   bayesNet/CPF.java:56-59,238-256      row index l = sum_p 4^p * value(parent p); parent 0 = tree parent
+//   util/MatrixLinearisation.java:15-19  pi = softmax over consecutive blocks of 4 (lambda space)
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/phyfoo.h"
+
+namespace phyfoo {
+
+struct ModelHost {
+    int kind = PHYFOO_MODEL_FG, W = 0, order = 0, N = 0, S = 0, I = 0;
+    int evol = PHYFOO_EVOL_F81ALPHA;
+    int mode = PHYFOO_MODE_MEANFIELD;
+    int max_sweeps = 100, min_sweeps = 2;
+    double tol = 1e-5;
+    std::vector<int> parent, leaf_species;
+    std::vector<double> branch;              // [W][N]
+    std::vector<std::vector<double>> pi;     // per position [ctx][4], ctx = 4^{#horizontal parents of the root}
+    // tree program (see tree_pass.cuh)
+    std::vector<int> par_internal, node_of, leaf_begin, leaf_node, leaf_sp, internal_of;
+    // tables
+    int tbl_stride = 0;                      // doubles per position
+    std::vector<double> logtab, probtab;     // [W][tbl_stride]
+    uint64_t version = 0;                    // bumped on every parameter change (device copy is lazy)
+
+    int ctx_rows(int pos) const {            // PhyloBayesModel.java:338-339 / PhyloBackground.java:367
+        if (kind == PHYFOO_MODEL_FG) return (order >= 1 && pos > 0) ? 4 : 1;
+        int r = 1;
+        for (int j = 0; j < order && j < pos; ++j) r *= 4;
+        return r;
+    }
+
+    void init(const phyfoo_model_desc& d) {
+        kind = d.kind; order = d.order; N = d.n_nodes; evol = d.evol; mode = d.mode;
+        W = (kind == PHYFOO_MODEL_FG) ? d.width : d.order + 1;
+        if (d.max_sweeps > 0) max_sweeps = d.max_sweeps;
+        if (d.min_sweeps > 0) min_sweeps = d.min_sweeps;
+        if (d.tol > 0) tol = d.tol;
+        if (N < 2 || W < 1) throw std::invalid_argument("model: need >= 2 tree nodes and width >= 1");
+        if (kind == PHYFOO_MODEL_FG && order != 0 && order != 1)
+            throw std::invalid_argument("motif order must be 0 or 1 (models/PhyloBayesModel.java:363)");
+        if (d.allow_independent_leaf == 0)
+            throw std::invalid_argument("CPF.ALLOW_RETURN_INDEPENDENT_TRANSITION=false is not supported");
+        parent.assign(d.parent, d.parent + N);
+        leaf_species.assign(d.leaf_species, d.leaf_species + N);
+        if (parent[0] != -1) throw std::invalid_argument("model: node 0 must be the root (DFS pre-order)");
+        std::vector<int> nchild(N, 0);
+        for (int k = 1; k < N; ++k) {
+            if (parent[k] < 0 || parent[k] >= k) throw std::invalid_argument("model: nodes must be in DFS pre-order");
+            nchild[parent[k]]++;
+        }
+        S = 0;
+        for (int k = 0; k < N; ++k) {
+            bool leaf = nchild[k] == 0;
+            if (leaf != (leaf_species[k] >= 0)) throw std::invalid_argument("model: leaf_species must be >= 0 exactly at leaves");
+            if (leaf) S++;
+        }
+        std::vector<char> seen(S, 0);
+        for (int k = 0; k < N; ++k)
+            if (leaf_species[k] >= 0) {
+                if (leaf_species[k] >= S || seen[leaf_species[k]]) throw std::invalid_argument("model: leaf_species must be a permutation of 0..S-1");
+                seen[leaf_species[k]] = 1;
+            }
+        branch.assign(d.branch, d.branch + (size_t)W * N);
+        pi.resize(W);
+        size_t off = 0;
+        for (int t = 0; t < W; ++t) {
+            int n = ctx_rows(t) * 4;
+            pi[t].assign(d.pi + off, d.pi + off + n);
+            off += n;
+        }
+        build_prog();
+        tbl_stride = 4 + 16 * (N - 1);
+        if (order == 0) {
+            logtab.assign((size_t)W * tbl_stride, 0.0);
+            probtab.assign((size_t)W * tbl_stride, 0.0);
+            for (int t = 0; t < W; ++t) build_tables(t);
+        }
+        version++;
+    }
+
+    void build_prog() {
+        internal_of.assign(N, -1);
+        node_of.clear(); par_internal.clear();
+        std::vector<int> nchild(N, 0);
+        for (int k = 1; k < N; ++k) nchild[parent[k]]++;
+        for (int k = 0; k < N; ++k)
+            if (nchild[k] > 0) {
+                internal_of[k] = (int)node_of.size();
+                node_of.push_back(k);
+                par_internal.push_back(k == 0 ? -1 : internal_of[parent[k]]);
+            }
+        I = (int)node_of.size();
+        leaf_begin.assign(I + 1, 0);
+        leaf_node.clear(); leaf_sp.clear();
+        for (int i = 0; i < I; ++i) {
+            leaf_begin[i] = (int)leaf_node.size();
+            for (int k = 1; k < N; ++k)
+                if (parent[k] == node_of[i] && nchild[k] == 0) { leaf_node.push_back(k); leaf_sp.push_back(leaf_species[k]); }
+        }
+        leaf_begin[I] = (int)leaf_node.size();
+    }
+
+    // 4x4 transition for one context row of pi and one branch; out[a*4+b] = P(b | a)
+    void transition(const double* p, double len, double* out) const {
+        if (evol == PHYFOO_EVOL_F81ALPHA) {
+            for (int a = 0; a < 4; ++a)
+                for (int b = 0; b < 4; ++b) out[a * 4 + b] = (a == b) ? (1 - len + p[b] * len) : (p[b] * len);
+        } else if (evol == PHYFOO_EVOL_F81BETA) {
+            double beta = 1. / (1. - p[0] * p[0] - p[1] * p[1] - p[2] * p[2] - p[3] * p[3]);
+            double ta = std::exp(-len * beta);
+            if (ta < 1e-4) ta = 0; else if (ta > 1 - 1e-4) ta = 1;
+            for (int a = 0; a < 4; ++a)
+                for (int b = 0; b < 4; ++b) out[a * 4 + b] = (a == b) ? (ta + p[b] * (1. - ta)) : (p[b] * (1. - ta));
+        } else if (evol == PHYFOO_EVOL_HKY_AS_IMPLEMENTED) {
+            const double al = len, be = len * 0.0;
+            const double aA = al * p[0], aC = al * p[1], aG = al * p[2], aT = al * p[3];
+            const double bA = be * p[0], bC = be * p[1], bG = be * p[2], bT = be * p[3];
+            const double v[16] = {1 - (aG + bT + bC), bC, aG, bT, bA, 1 - (aT + bA + bG), bG, aT,
+                                  aA, bC, 1 - (aA + bT + bC), bT, bA, aC, bG, 1 - (aC + bA + bG)};
+            for (int i = 0; i < 16; ++i) out[i] = v[i];
+        } else throw std::invalid_argument("model: unknown evolution model id");
+    }
+
+    // order-0 tables of position t: [log pi (4)] [node 1 (16)] ... [node N-1 (16)]
+    void build_tables(int t) {
+        double* lt = &logtab[(size_t)t * tbl_stride];
+        double* pt = &probtab[(size_t)t * tbl_stride];
+        const double* p = pi[t].data();
+        for (int a = 0; a < 4; ++a) { pt[a] = p[a]; lt[a] = std::log(p[a]); }
+        for (int k = 1; k < N; ++k) {
+            double tr[16];
+            transition(p, branch[(size_t)t * N + k], tr);
+            for (int i = 0; i < 16; ++i) { pt[4 + 16 * (k - 1) + i] = tr[i]; lt[4 + 16 * (k - 1) + i] = std::log(tr[i]); }
+        }
+    }
+
+    void set_pi(int t, const double* v, int n) {
+        if (t < 0 || t >= W || n != (int)pi[t].size()) throw std::invalid_argument("set_pi: bad position or size");
+        pi[t].assign(v, v + n);
+        if (order == 0) build_tables(t);
+        version++;
+    }
+    void set_branch(int t, int node, double len) {
+        if (t < 0 || t >= W || node <= 0 || node >= N) throw std::invalid_argument("set_branch: bad position or node");
+        branch[(size_t)t * N + node] = len;
+        if (order == 0) build_tables(t);
+        version++;
+    }
+};
+
+// util/MatrixLinearisation.java:15-19 through jstacs Normalisation.logSumNormalisation (:352-375):
+// per block of 4: shift by the max, exp, sum, divide (skipped when the sum is exactly 1).
+inline void lambda_to_pi(const double* lambda, double* pi, int n) {
+    for (int i = 0; i < n; i += 4) {
+        double off = lambda[i];
+        for (int k = 1; k < 4; ++k) off = lambda[i + k] > off ? lambda[i + k] : off;
+        double sum = 0;
+        for (int k = 0; k < 4; ++k) { pi[i + k] = std::exp(lambda[i + k] - off); sum += pi[i + k]; }
+        if (sum != 1.0) for (int k = 0; k < 4; ++k) pi[i + k] /= sum;
+    }
+}
+
+}  // namespace phyfoo
