@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- site log-likelihoods/s of the ZOOPS E-step (BASELINE.json's metric) on 1..8 B200.
+
+A "step" is one pass of the hot path over one batch of synthetic alignments: background column scores, motif
+window scores of every offset, the ZOOPS posterior (gamma, w, log-likelihood, arg-max) and, for N > 1, the
+all-reduce of [ll, w0, w1] over NCCL.  One process per GPU; every rank holds a full-size shard ("weak" scaling:
+alignments are independent).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2|c2star|c3o0] [--impl reference]
+
+Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM; `e2e` goes through the public
+host API with host buffers (pack + copies inside the timed region); `roofline` is for the dominant kernel
+(score_o0_kernel on the motif windows) against the fp64 FMA peak measured on this GPU in the same run;
+`cpu_baseline` is the oracle (C++ restatement of the Java algorithm; no JVM exists here) on the host cores.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "site_loglik_per_sec"
+UNIT = "window scores/s"
+DEFAULT_CONFIG = "c2"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default=DEFAULT_CONFIG)
+    ap.add_argument("--n-aln", type=int, default=None, help="override the number of alignments (debug only)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(cfg):
+    kind = "phylogenetic PWM" if cfg["order"] == 0 else "phylogenetic Bayesian network (order 1)"
+    return (f"{kind}, width {cfg['W']}, {cfg['S']}-species {cfg['tree']} tree, {cfg['n_aln']} synthetic alignments x "
+            f"{cfg['length']} bp, ZOOPS E-step, mean-field scoring (reference default)")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# flop model of SURVEY.md section 8d (order 0, no gaps): per tree and sweep
+# ---------------------------------------------------------------------------------------------------------
+def flops_order0(I, S):
+    update = 8 * (8 * I - 7 + S) + 7 * I
+    fe = 8 * I + 8 + 48 * (I - 1) + 8 * S
+    return update, fe
+
+
+def algorithmic_flops(cfg, I, n_windows, sweeps_total):
+    upd, fe = flops_order0(I, cfg["S"])
+    W = cfg["W"]
+    return W * (sweeps_total * upd + (sweeps_total + n_windows) * fe)
+
+
+def algorithmic_bytes(cfg, n_windows):
+    # ceil(3S/8) bytes per column read once + 8 bytes per window score
+    return n_windows * (-(-3 * cfg["S"] // 8) + 8)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks sampler (NVML) during the timed region
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv, self.err = None, str(e)
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        if self._t:
+            self._stop.set()
+            self._t.join()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (test infrastructure; executed here only as the reported baseline / reference arm)
+# ---------------------------------------------------------------------------------------------------------
+def oracle_models(cfg, newick, pwm):
+    from oracle import oracle as orc
+    fg = orc.Model(orc.FG, cfg["W"], cfg["order"], newick)
+    for t, p in enumerate(pwm):
+        fg.set_pi(t, np.asarray(p).ravel())
+    bg = orc.Model(orc.BG, 0, 0, newick)
+    # the reference's cost model: Math.log inside the inner loops, background ranges recomputed per offset
+    fg.set_options(log_in_loop=True)
+    bg.set_options(log_in_loop=True)
+    return orc, fg, bg
+
+
+def cpu_run(cfg, newick, pwm, sample, n_aln, threads):
+    """E-step of the first n_aln alignments on `threads` host threads; returns (windows/s, seconds, windows)."""
+    orc, fg, bg = oracle_models(cfg, newick, pwm)
+    off = sample.col_offsets[: n_aln + 1]
+    codes = sample.codes[: off[-1]]
+    t0 = time.perf_counter()
+    res = orc.estep(fg, bg, off, codes, np.log([0.9, 0.1]), faithful_cost=True, threads=threads, want=())
+    dt = time.perf_counter() - t0
+    nwin = int(np.maximum(np.diff(off) - cfg["W"] + 1, 0).sum())
+    assert np.isfinite(res["ll"])
+    return nwin / dt, dt, nwin
+
+
+def cpu_sample_size(cfg, newick, pwm, sample, threads, target_s):
+    """Pick how many alignments give about target_s seconds of CPU work (calibrated on a short run)."""
+    n0 = min(sample.n_alignments, max(threads, 2))
+    _, dt, _ = cpu_run(cfg, newick, pwm, sample, n0, threads)
+    n = int(max(n0, min(sample.n_alignments, n0 * target_s / max(dt, 1e-3))))
+    return n
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU algorithm (oracle port; the Java cannot run: no JVM) on all host
+    threads, each step a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from phyfoo_b200 import synth
+    cores = os.cpu_count() or 1
+    full = dict(synth.CONFIGS[args.config])
+    if args.n_aln:
+        full["n_aln"] = args.n_aln
+    # the pool the bounded samples are drawn from: the first alignments of the same seeded workload
+    cfg, newick, pwm, sample, _ = synth.make_config(args.config, n_aln=min(full["n_aln"], 512))
+    steps, warmup = max(args.steps, 1), max(args.warmup, 0)
+    budget = 120.0 / (steps + warmup)            # whole run within a few minutes
+    n = cpu_sample_size(cfg, newick, pwm, sample, cores, min(budget, 10.0))
+    for _ in range(warmup):
+        cpu_run(cfg, newick, pwm, sample, n, cores)
+    t_total, w_total = 0.0, 0
+    for _ in range(steps):
+        _, dt, nw = cpu_run(cfg, newick, pwm, sample, n, cores)
+        t_total += dt
+        w_total += nw
+    value = w_total / t_total
+    samp = f"first {n} of {full['n_aln']} alignments per step ({w_total // steps} windows), oracle E-step with the reference's cost model"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": 1e3 * t_total / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(full), "sample": samp},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": samp},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (phyfoo_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from phyfoo_b200 import core, synth
+    from phyfoo_b200.models import PhyloBackground, PhyloBayesModel, SingleHiddenMotifMixture
+
+    ctx = core.Context(local)
+    cfg, newick, pwm, sample, planted = synth.make_config(args.config, n_aln=args.n_aln)
+    W = cfg["W"]
+    fg = PhyloBayesModel(W, cfg["order"], newick, ctx)
+    fg.setCondProbs(pwm)
+    bg = PhyloBackground(0, newick, ctx)
+    shm = SingleHiddenMotifMixture(fg, bg, zoops=0.9)
+    logw = np.log(shm.weights)
+    ds = sample.device(ctx)
+    n_windows = ds.windows(W)
+    I = fg.tree.n_nodes - fg.tree.n_species
+
+    partial = torch.zeros(3, dtype=torch.float64, device="cuda")
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def step():
+        core.zoops_estep_device(ctx, ds, fg.device_model(), bg.device_model(), logw, None, None, partial.data_ptr(),
+                                stream.cuda_stream)
+        if world > 1:
+            dist.all_reduce(partial)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    launches_per_step = ctx.last_launches()
+    peak_tflops = ctx.fp64_peak()
+
+    sampler = ClockSampler(local)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    dev_ms, fg_ms, bg_ms, zo_ms = 0.0, 0.0, 0.0, 0.0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(args.steps):
+        flush.fill_(1)                      # L2 flush between timed iterations (untimed)
+        e0.record(stream)
+        step()
+        e1.record(stream)
+        e1.synchronize()
+        dev_ms += e0.elapsed_time(e1)
+        km = ctx.estep_kernel_ms()
+        fg_ms += km["fg_ms"]; bg_ms += km["bg_ms"]; zo_ms += km["zoops_ms"]
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    sweeps_fg, sweeps_bg = ctx.estep_sweeps()
+    ll_w = partial.cpu().numpy().copy()
+
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(t.item())
+    total_windows = n_windows * world
+    value = total_windows * args.steps / (dev_ms_max * 1e-3)
+
+    # ---- e2e: public host API, host buffers, pack + copies inside the timed region (per rank, max over ranks)
+    pinned = torch.empty(sample.codes.shape, dtype=torch.uint8).pin_memory()
+    pinned.numpy()[:] = sample.codes
+    from phyfoo_b200.data import PhyloSample
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step():
+        smp = PhyloSample(pinned.numpy(), sample.col_offsets)
+        res = shm.getNewWeights(smp, want_gamma=True)
+        smp.device(ctx).free()
+        return res
+
+    e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res = e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = total_windows * e2e_steps / float(t.item())
+    h2d = int(sample.codes.nbytes + sample.col_offsets.nbytes)
+    d2h = int(res["gamma"].nbytes + res["argmax_off"].nbytes + res["argmax_strand"].nbytes + 24)
+    assert abs(res["ll"] - ll_w[0] / 1.0) <= 1e-9 * abs(res["ll"]) or world > 1
+
+    if rank == 0:
+        flops = algorithmic_flops(cfg, I, n_windows, sweeps_fg)
+        fg_ms_avg = fg_ms / args.steps
+        achieved = flops / (fg_ms_avg * 1e-3) / 1e12
+        abytes = algorithmic_bytes(cfg, n_windows)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(cfg), "name": args.config, "windows_per_gpu": n_windows,
+                       "mean_sweeps_per_window": sweeps_fg / max(n_windows, 1), "seed": hex(cfg["seed"]),
+                       "l2": "flushed between timed iterations (512 MB fill)", "collective": "NCCL all-reduce of 3 fp64" if world > 1 else "none"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "what": "PhyloSample -> pack on device -> E-step -> gamma/arg-max/ll to host"},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "clocks": clocks,
+            "roofline": {"bound": "fp64", "kernel": "score_o0_kernel<meanfield> (motif windows)",
+                         "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
+                         "peak_source": "DFMA microbenchmark in this run (MEASURED_PEAKS.json has no fp64 entry)",
+                         "flops_per_launch": flops, "kernel_ms": fg_ms_avg,
+                         "kernel_share_of_step": fg_ms / max(fg_ms + bg_ms + zo_ms, 1e-9),
+                         "hbm": {"achieved": abytes / (fg_ms_avg * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": abytes / (fg_ms_avg * 1e-3) / 1e9 / hbm_peak, "of": "measured" if peaks else "fallback"},
+                         "traffic": None},
+            "phase_ms": {"bg_columns": bg_ms / args.steps, "fg_windows": fg_ms_avg, "zoops": zo_ms / args.steps},
+            "wall_s": t_wall,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            n = cpu_sample_size(cfg, newick, pwm, sample, cores, args.cpu_seconds)
+            v, dt, nw = cpu_run(cfg, newick, pwm, sample, n, cores)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"first {n} of {cfg['n_aln']} alignments ({nw} windows, {dt:.1f} s), "
+                                              "C++ restatement of the Java algorithm with its cost model (JVM unavailable)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -190,6 +190,16 @@ int phyfoo_fe_values_device(phyfoo_ctx* ctx, phyfoo_feset* fe, int32_t position,
 int64_t phyfoo_fe_size(const phyfoo_feset* fe);
 void phyfoo_fe_free(phyfoo_ctx* ctx, phyfoo_feset* fe);
 
+/* ---- plumbing for callers that overlap the library with their own streams ---- */
+int phyfoo_last_launches(const phyfoo_ctx* ctx); /* kernels launched by the most recent call on this context */
+void* phyfoo_stream(phyfoo_ctx* ctx);            /* the library's cudaStream_t */
+int phyfoo_synchronize(phyfoo_ctx* ctx);
+/* device time (CUDA events on the library's stream) of the phases of the most recent E-step on this context:
+ * background columns, motif windows, ZOOPS posterior + reduction.  Waits for that E-step to finish. */
+int phyfoo_estep_kernel_ms(phyfoo_ctx* ctx, float* bg_ms, float* fg_ms, float* zoops_ms);
+/* sums of mean-field sweep counts of the most recent E-step (integer parity check / roofline flop count) */
+int phyfoo_estep_sweeps(phyfoo_ctx* ctx, int64_t* sweeps_fg, int64_t* sweeps_bg);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,222 @@
+"""Thin object wrappers over the C ABI handles (context, packed dataset, device model, FE set).
+
+numpy arrays in, numpy arrays out; all arithmetic happens in libphyfoo.so on the GPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from .lib import lib, raise_for
+
+_dp = C.POINTER(C.c_double)
+
+
+def _p(a, t):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+class Context:
+    """phyfoo_ctx: one GPU, one caller thread at a time."""
+
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        rc = lib().phyfoo_init(int(device), C.byref(self.h))
+        if rc != _abi.OK:
+            raise_for(rc, None)
+        self.device = int(device)
+
+    def close(self):
+        if self.h:
+            lib().phyfoo_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def device_info(self):
+        sm, ma, mi, mem = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
+        raise_for(lib().phyfoo_device_info(self.h, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(mem)), self.h)
+        return {"sm_count": sm.value, "cc": (ma.value, mi.value), "total_mem": mem.value}
+
+    def fp64_peak(self):
+        v = C.c_double()
+        raise_for(lib().phyfoo_fp64_peak(self.h, C.byref(v)), self.h)
+        return v.value
+
+    def stream(self):
+        return lib().phyfoo_stream(self.h)
+
+    def synchronize(self):
+        raise_for(lib().phyfoo_synchronize(self.h), self.h)
+
+    def last_launches(self):
+        return lib().phyfoo_last_launches(self.h)
+
+    def estep_kernel_ms(self):
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        raise_for(lib().phyfoo_estep_kernel_ms(self.h, C.byref(a), C.byref(b), C.byref(c)), self.h)
+        return {"bg_ms": a.value, "fg_ms": b.value, "zoops_ms": c.value}
+
+    def estep_sweeps(self):
+        a, b = C.c_int64(), C.c_int64()
+        raise_for(lib().phyfoo_estep_sweeps(self.h, C.byref(a), C.byref(b)), self.h)
+        return a.value, b.value
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+class Dataset:
+    """phyfoo_dataset: packed columns resident on the device."""
+
+    def __init__(self, ctx, col_offsets, codes=None, n_species=None, codes_device_ptr=None):
+        self.ctx = ctx
+        self.col_offsets = np.ascontiguousarray(col_offsets, np.int64)
+        self.n_aln = self.col_offsets.size - 1
+        self.h = C.c_void_p()
+        if codes_device_ptr is not None:
+            self.S = int(n_species)
+            rc = lib().phyfoo_dataset_create_device(ctx.h, self.n_aln, self.S, _p(self.col_offsets, C.c_int64),
+                                                    C.c_void_p(codes_device_ptr), C.byref(self.h))
+        else:
+            codes = np.ascontiguousarray(codes, np.uint8)
+            if codes.ndim != 2:
+                raise ValueError("codes must be [columns][species]")
+            self.S = codes.shape[1]
+            if codes.shape[0] != self.col_offsets[-1]:
+                raise ValueError("col_offsets[-1] must equal the number of columns")
+            rc = lib().phyfoo_dataset_create(ctx.h, self.n_aln, self.S, _p(self.col_offsets, C.c_int64),
+                                             _p(codes, C.c_uint8), C.byref(self.h))
+        raise_for(rc, ctx.h)
+        self.n_cols = int(self.col_offsets[-1])
+
+    def free(self):
+        if self.h:
+            lib().phyfoo_dataset_free(self.ctx.h, self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def lengths(self):
+        return np.diff(self.col_offsets)
+
+    def windows(self, width):
+        return int(lib().phyfoo_dataset_windows(self.h, int(width)))
+
+    def window_offsets(self, width):
+        return np.concatenate([[0], np.cumsum(np.maximum(self.lengths() - width + 1, 0))]).astype(np.int64)
+
+    def packed(self):
+        nb, ng = (self.S + 15) // 16, (self.S + 31) // 32
+        bases = np.zeros((nb, self.n_cols), np.uint32)
+        gaps = np.zeros((ng, self.n_cols), np.uint32)
+        raise_for(lib().phyfoo_dataset_packed(self.ctx.h, self.h, _p(bases, C.c_uint32), _p(gaps, C.c_uint32)), self.ctx.h)
+        return bases, gaps
+
+
+class DeviceModel:
+    """phyfoo_model: tree + parameters of one PhyloBayesModel / PhyloBackground."""
+
+    def __init__(self, ctx, kind, width, order, tree, branch, pi_list, evol=_abi.EVOL_F81ALPHA,
+                 mode=_abi.MODE_MEANFIELD, hky_ratio=0.0):
+        self.ctx = ctx
+        desc, keep = _abi.make_desc(kind, width, order, tree, branch, pi_list, evol, mode, hky_ratio)
+        self.h = C.c_void_p()
+        raise_for(lib().phyfoo_model_create(ctx.h, C.byref(desc), C.byref(self.h)), ctx.h)
+        del keep
+        self.kind, self.order = kind, order
+        self.W = width if kind == _abi.MODEL_FG else order + 1
+
+    def free(self):
+        if self.h:
+            lib().phyfoo_model_free(self.ctx.h, self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def set_pi(self, position, pi):
+        pi = np.ascontiguousarray(pi, np.float64).ravel()
+        raise_for(lib().phyfoo_model_set_pi(self.ctx.h, self.h, int(position), _p(pi, C.c_double), pi.size), self.ctx.h)
+
+    def get_pi(self, position, n):
+        out = np.zeros(n)
+        raise_for(lib().phyfoo_model_get_pi(self.ctx.h, self.h, int(position), _p(out, C.c_double), n), self.ctx.h)
+        return out
+
+    def set_branch(self, position, node, length):
+        raise_for(lib().phyfoo_model_set_branch(self.ctx.h, self.h, int(position), int(node), float(length)), self.ctx.h)
+
+    def set_mode(self, mode):
+        raise_for(lib().phyfoo_model_set_mode(self.ctx.h, self.h, int(mode)), self.ctx.h)
+
+
+def _stats_dict(st):
+    return {"n_windows": st.n_windows, "n_columns": st.n_columns, "sweeps_fg": st.sweeps_fg, "sweeps_bg": st.sweeps_bg,
+            "kernel_launches": st.kernel_launches, "gpu_ms": st.gpu_ms}
+
+
+def score_windows(ctx, ds, model, strand=0, want_sweeps=False):
+    n = ds.windows(model.W)
+    out = np.zeros(n)
+    sw = np.zeros(n, np.int32) if want_sweeps else None
+    st = _abi.Stats()
+    raise_for(lib().phyfoo_score_windows(ctx.h, ds.h, model.h, int(strand), _p(out, C.c_double), _p(sw, C.c_int32),
+                                         C.byref(st)), ctx.h)
+    return out, sw, _stats_dict(st)
+
+
+def bg_columns(ctx, ds, model, want_sweeps=False):
+    out = np.zeros(ds.n_cols)
+    sw = np.zeros(ds.n_cols, np.int32) if want_sweeps else None
+    st = _abi.Stats()
+    raise_for(lib().phyfoo_bg_columns(ctx.h, ds.h, model.h, _p(out, C.c_double), _p(sw, C.c_int32), C.byref(st)), ctx.h)
+    return out, sw, _stats_dict(st)
+
+
+def zoops_estep(ctx, ds, fg, bg, logw, strand_logw=None, aln_weights=None, want_gamma=True, want_profile=False,
+                want_argmax=True):
+    n = ds.windows(fg.W)
+    logw = np.ascontiguousarray(logw, np.float64)
+    sl = None if strand_logw is None else np.ascontiguousarray(strand_logw, np.float64)
+    aw = None if aln_weights is None else np.ascontiguousarray(aln_weights, np.float64)
+    gamma = np.zeros(n) if want_gamma else None
+    prof = np.zeros(n) if want_profile else None
+    w = np.zeros(2)
+    ll = C.c_double()
+    ao = np.zeros(ds.n_aln, np.int32) if want_argmax else None
+    astr = np.zeros(ds.n_aln, np.uint8) if want_argmax else None
+    st = _abi.Stats()
+    raise_for(lib().phyfoo_zoops_estep(ctx.h, ds.h, fg.h, bg.h, _p(logw, C.c_double), _p(sl, C.c_double),
+                                       _p(aw, C.c_double), _p(gamma, C.c_double), _p(prof, C.c_double),
+                                       _p(w, C.c_double), C.byref(ll), _p(ao, C.c_int32), _p(astr, C.c_uint8),
+                                       C.byref(st)), ctx.h)
+    return {"gamma": gamma, "profile": prof, "w": w, "ll": ll.value, "argmax_off": ao, "argmax_strand": astr,
+            "stats": _stats_dict(st)}
+
+
+def zoops_estep_device(ctx, ds, fg, bg, logw, strand_logw, aln_weights_ptr, partial_ptr, stream_ptr):
+    """Asynchronous E-step that leaves [ll, w0, w1] (local sums) in device memory for an NCCL all-reduce."""
+    logw = np.ascontiguousarray(logw, np.float64)
+    sl = None if strand_logw is None else np.ascontiguousarray(strand_logw, np.float64)
+    raise_for(lib().phyfoo_zoops_estep_device(ctx.h, ds.h, fg.h, bg.h, _p(logw, C.c_double), _p(sl, C.c_double),
+                                              C.c_void_p(aln_weights_ptr) if aln_weights_ptr else None,
+                                              C.c_void_p(partial_ptr), C.c_void_p(stream_ptr) if stream_ptr else None),
+              ctx.h)

@@ -31,9 +31,10 @@ struct ModelHost {
     std::vector<std::vector<double>> pi;     // per position [ctx][4], ctx = 4^{#horizontal parents of the root}
     // tree program (see tree_pass.cuh)
     std::vector<int> par_internal, node_of, leaf_begin, leaf_node, leaf_sp, internal_of;
-    // tables
-    int tbl_stride = 0;                      // doubles per position
-    std::vector<double> logtab, probtab;     // [W][tbl_stride]
+    // order-0 tables: E entries per position, host layout [W][E]
+    int E = 0;
+    std::vector<double> logtab, probtab;
+    // order >= 1 tables: per position, per node, [4^P][4] (see ctx_rows); host layout described in tables1()
     uint64_t version = 0;                    // bumped on every parameter change (device copy is lazy)
 
     int ctx_rows(int pos) const {            // PhyloBayesModel.java:338-339 / PhyloBackground.java:367
@@ -50,10 +51,14 @@ struct ModelHost {
         if (d.min_sweeps > 0) min_sweeps = d.min_sweeps;
         if (d.tol > 0) tol = d.tol;
         if (N < 2 || W < 1) throw std::invalid_argument("model: need >= 2 tree nodes and width >= 1");
+        if (order < 0) throw std::invalid_argument("model: order must be >= 0");
+        if (kind != PHYFOO_MODEL_FG && kind != PHYFOO_MODEL_BG) throw std::invalid_argument("model: unknown kind");
         if (kind == PHYFOO_MODEL_FG && order != 0 && order != 1)
             throw std::invalid_argument("motif order must be 0 or 1 (models/PhyloBayesModel.java:363)");
+        if (mode != PHYFOO_MODE_MEANFIELD && mode != PHYFOO_MODE_EXACT) throw std::invalid_argument("model: unknown mode");
         if (d.allow_independent_leaf == 0)
             throw std::invalid_argument("CPF.ALLOW_RETURN_INDEPENDENT_TRANSITION=false is not supported");
+        if (!d.parent || !d.leaf_species || !d.branch || !d.pi) throw std::invalid_argument("model: null array in descriptor");
         parent.assign(d.parent, d.parent + N);
         leaf_species.assign(d.leaf_species, d.leaf_species + N);
         if (parent[0] != -1) throw std::invalid_argument("model: node 0 must be the root (DFS pre-order)");
@@ -83,10 +88,10 @@ struct ModelHost {
             off += n;
         }
         build_prog();
-        tbl_stride = 4 + 16 * (N - 1);
+        E = 4 + 16 * (N - 1);
         if (order == 0) {
-            logtab.assign((size_t)W * tbl_stride, 0.0);
-            probtab.assign((size_t)W * tbl_stride, 0.0);
+            logtab.assign((size_t)W * E, 0.0);
+            probtab.assign((size_t)W * E, 0.0);
             for (int t = 0; t < W; ++t) build_tables(t);
         }
         version++;
@@ -114,6 +119,17 @@ struct ModelHost {
         leaf_begin[I] = (int)leaf_node.size();
     }
 
+    // the flattened program as one int array: par_internal[I] node_of[I] leaf_begin[I+1] leaf_node[S] leaf_species[S]
+    std::vector<int> prog_flat() const {
+        std::vector<int> v;
+        v.insert(v.end(), par_internal.begin(), par_internal.end());
+        v.insert(v.end(), node_of.begin(), node_of.end());
+        v.insert(v.end(), leaf_begin.begin(), leaf_begin.end());
+        v.insert(v.end(), leaf_node.begin(), leaf_node.end());
+        v.insert(v.end(), leaf_sp.begin(), leaf_sp.end());
+        return v;
+    }
+
     // 4x4 transition for one context row of pi and one branch; out[a*4+b] = P(b | a)
     void transition(const double* p, double len, double* out) const {
         if (evol == PHYFOO_EVOL_F81ALPHA) {
@@ -137,15 +153,32 @@ struct ModelHost {
 
     // order-0 tables of position t: [log pi (4)] [node 1 (16)] ... [node N-1 (16)]
     void build_tables(int t) {
-        double* lt = &logtab[(size_t)t * tbl_stride];
-        double* pt = &probtab[(size_t)t * tbl_stride];
+        double* lt = &logtab[(size_t)t * E];
+        double* pt = &probtab[(size_t)t * E];
         const double* p = pi[t].data();
         for (int a = 0; a < 4; ++a) { pt[a] = p[a]; lt[a] = std::log(p[a]); }
         for (int k = 1; k < N; ++k) {
             double tr[16];
             transition(p, branch[(size_t)t * N + k], tr);
-            for (int i = 0; i < 16; ++i) { pt[4 + 16 * (k - 1) + i] = tr[i]; lt[4 + 16 * (k - 1) + i] = std::log(tr[i]); }
+            for (int i = 0; i < 16; ++i) { pt[tab_off(k) + i] = tr[i]; lt[tab_off(k) + i] = std::log(tr[i]); }
         }
+    }
+    static int tab_off(int node) { return 4 + 16 * (node - 1); }
+
+    // CPF table of (position t, node k) for ANY order, reference layout [4^P][4], row l = a_treeparent + 4*ctx
+    // (root: rows = ctx).  VirtualTree.java:82-96.
+    std::vector<double> cpf(int t, int k) const {
+        const int ctx = ctx_rows(t);
+        std::vector<double> out;
+        if (k == 0) { out = pi[t]; return out; }
+        out.resize((size_t)ctx * 16);
+        for (int c = 0; c < ctx; ++c) transition(&pi[t][(size_t)c * 4], branch[(size_t)t * N + k], &out[(size_t)c * 16]);
+        return out;
+    }
+
+    bool tables_finite() const {
+        for (double v : logtab) if (!std::isfinite(v)) return false;
+        return true;
     }
 
     void set_pi(int t, const double* v, int n) {

@@ -1,0 +1,1006 @@
+// phyfoo.cu -- libphyfoo.so: the C ABI of include/phyfoo.h on one B200 (sm_100a).
+//
+// Kernels (all fp64, no tensor cores: the contractions are 4x4 per tree edge with data-dependent
+// leaf selection -- SURVEY.md section 2.2):
+//   pack_columns_kernel      K0  codes [cols][S] u8 -> 2-bit base planes + gap planes (bit-exact layout)
+//   score_o0_kernel<MODE>    K1/K2/K4  persistent kernel; W consecutive threads = one window (one
+//                            thread per motif position = one tree); the groups of a block pull windows
+//                            from a global counter, so a window that needs 14 sweeps never holds back
+//                            one that needs 3; tables + tree program + per-thread state in shared memory
+//   zoops_kernel             K3  one block per alignment: a_j, max, log-sum-exp, gamma, w, ll, arg-max
+//   reduce3_kernel           deterministic final sum of the per-alignment partials -> [ll, w0, w1]
+//   select_kernel, fe_*      M-step (data selection, fixed-q free energy sums, forward differences)
+//   dfma_peak_kernel         fp64 FMA roofline probe
+//
+// No CPU fallback anywhere: every entry point needs the CUDA device the context was created on.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "model_host.hpp"
+#include "tree_pass.cuh"
+
+using namespace phyfoo;
+
+// ------------------------------------------------------------------------------------------------
+// handles
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+struct phyfoo_ctx {
+    int device = 0;
+    int sm_count = 0, cc_major = 0, cc_minor = 0;
+    size_t total_mem = 0, smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t kev[4] = {nullptr, nullptr, nullptr, nullptr};   // brackets of the bg / fg / zoops kernels of the last E-step
+    bool kev_valid = false;
+    std::string err;
+    // scratch (grown on demand, reused across calls)
+    DevBuf counters;                 // unsigned long long [8]
+    DevBuf fg_scores, bg_scores;     // window scores (both strands) / column scores
+    DevBuf sweeps_buf;               // int32 per item when the caller wants K
+    DevBuf gamma, profile, part, argoff, argstrand, alnw, out3, gstate, misc;
+    int launches = 0;                // kernels launched by the current call
+};
+
+struct phyfoo_dataset {
+    int n_aln = 0, S = 0, nb = 0, ng = 0;
+    int64_t n_cols = 0;
+    int min_len = 0, max_len = 0;
+    std::vector<int64_t> col_off;
+    int64_t* d_col_off = nullptr;
+    uint32_t* d_bases = nullptr;
+    uint32_t* d_gaps = nullptr;
+    std::map<int, int64_t*> d_win_off;           // per motif width
+    std::map<int, std::vector<int64_t>> win_off;
+};
+
+struct phyfoo_model {
+    ModelHost h;
+    uint64_t uploaded = 0;
+    int* d_prog = nullptr;
+    int prog_len = 0;
+    double* d_logtab = nullptr;   // [E][W]
+    double* d_probtab = nullptr;  // [E][W]
+};
+
+static thread_local std::string g_init_err;
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                         \
+            return PHYFOO_ECUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+static int fail(phyfoo_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg; else g_init_err = msg;
+    return code;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0: packing.  One thread per column; bit-exact contract in include/phyfoo.h.
+// Replaces the int[pos][species] container of jstacs MultiDimensionalDiscreteSequence.java:46-52.
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_columns_kernel(const uint8_t* __restrict__ codes, int64_t n_cols, int S, int nb, int ng,
+                                    uint32_t* __restrict__ bases, uint32_t* __restrict__ gaps, int* __restrict__ bad) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cols) return;
+    const uint8_t* col = codes + c * S;
+    for (int k = 0; k < nb; ++k) {
+        uint32_t w = 0;
+        for (int s = 16 * k; s < min(S, 16 * k + 16); ++s) {
+            uint8_t v = col[s];
+            if (v < 4) w |= (uint32_t)v << (2 * (s & 15));
+            else if (v > 4) *bad = 1;  // WrongAlphabetException territory; caller reports EINVAL
+        }
+        bases[(int64_t)k * n_cols + c] = w;
+    }
+    for (int k = 0; k < ng; ++k) {
+        uint32_t w = 0;
+        for (int s = 32 * k; s < min(S, 32 * k + 32); ++s)
+            if (col[s] >= 4) w |= 1u << (s & 31);
+        gaps[(int64_t)k * n_cols + c] = w;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1/K2/K4: order-0 window scoring
+// ------------------------------------------------------------------------------------------------
+struct ScoreParams {
+    const uint32_t* bases; const uint32_t* gaps; int64_t n_cols; int nb;
+    const int64_t* col_off; const int64_t* win_off; int n_aln;
+    int64_t n_windows; int n_strands; int strand0;
+    int W, I, S, E, prog_len;
+    const double* tab;   // [E][W]
+    const int* prog;
+    double* out;         // [n_strands][n_windows]
+    int32_t* sweeps;     // nullable, same shape
+    unsigned long long* counters;  // [0] next item, [1] sum of sweeps
+    int max_sweeps, min_sweeps; double tol;
+    double* gstate;      // nullable: per-thread state in global memory instead of shared
+    int groups;          // windows in flight per block
+};
+
+__device__ __forceinline__ ColWords load_column(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ gaps,
+                                                int64_t n_cols, int nb, int64_t c) {
+    ColWords cw;
+    cw.b = bases[c];
+    if (nb > 1) cw.b |= (uint64_t)bases[n_cols + c] << 32;
+    cw.g = gaps[c];
+    return cw;
+}
+
+// largest a with off[a] <= w  (off has n+1 entries, off[0] = 0, w < off[n])
+__device__ __forceinline__ int find_alignment(const int64_t* __restrict__ off, int n, int64_t w) {
+    int lo = 0, hi = n;  // invariant: off[lo] <= w < off[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (off[mid] <= w) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 2) score_o0_kernel(ScoreParams p) {
+    extern __shared__ double smem[];
+    const int T = blockDim.x, tid = threadIdx.x;
+    double* s_tab = smem;
+    double* s_F = s_tab + (size_t)p.E * p.W;
+    long long* s_item = (long long*)(s_F + T);
+    double* s_state = (double*)(s_item + p.groups);
+    int* s_prog = (int*)(s_state + (p.gstate ? 0 : (size_t)p.I * 8 * T));
+
+    for (int i = tid; i < p.E * p.W; i += T) s_tab[i] = p.tab[i];
+    for (int i = tid; i < p.prog_len; i += T) s_prog[i] = p.prog[i];
+
+    TreeProg tp;
+    tp.n_internal = p.I; tp.n_leaves = p.S; tp.n_nodes = 0;
+    tp.par_internal = s_prog;
+    tp.node_of = s_prog + p.I;
+    tp.leaf_begin = s_prog + 2 * p.I;
+    tp.leaf_node = s_prog + 3 * p.I + 1;
+    tp.leaf_species = s_prog + 3 * p.I + 1 + p.S;
+
+    const int g = tid / p.W, t = tid - g * p.W;
+    const bool lane_ok = g < p.groups;
+    const Tab tb{s_tab + t, p.W};
+    State st;
+    if (p.gstate) { st.base = p.gstate + ((size_t)blockIdx.x * T + tid); st.stride = gridDim.x * T; }
+    else { st.base = s_state + tid; st.stride = T; }
+
+    const long long n_items = (long long)p.n_windows * p.n_strands;
+    bool need = lane_ok, active = lane_ok, upd = false, conv = false;
+    int k = 0;
+    long long item = -1;
+    double old = 0.0;
+    ColWords cw; cw.b = 0; cw.g = 0;
+
+    for (;;) {
+        if (need && active && t == 0) s_item[g] = (long long)atomicAdd(&p.counters[0], 1ULL);
+        __syncthreads();
+        if (need && active) {
+            item = s_item[g];
+            if (item >= n_items) active = false;
+            else {
+                const int si = (int)(item / p.n_windows);
+                const int64_t w = item - (long long)si * p.n_windows;
+                const int strand = p.n_strands == 2 ? si : p.strand0;
+                const int a = find_alignment(p.win_off, p.n_aln, w);
+                const int64_t c0 = p.col_off[a] + (w - p.win_off[a]);
+                // jstacs StrandModel.java:636-639 / Sequence.java:1321-1333: reverse the columns, complement the symbols
+                const int64_t c = strand ? c0 + (p.W - 1 - t) : c0 + t;
+                cw = load_column(p.bases, p.gaps, p.n_cols, p.nb, c);
+                if (strand) cw = complement(cw);
+                k = 0; conv = false; upd = false; need = false;
+            }
+        }
+        if (!__syncthreads_or(active ? 1 : 0)) break;
+        double F = 0.0;
+        if (active) {
+            if (MODE == PHYFOO_MODE_EXACT) F = -log(pruning_likelihood(tp, tb, st, cw));
+            else F = meanfield_pass(tp, tb, st, cw, upd, nullptr);
+        }
+        s_F[tid] = F;
+        __syncthreads();
+        if (active) {
+            double Fsum = 0.0;
+            const double* fp = s_F + g * p.W;
+            for (int m = 0; m < p.W; ++m) Fsum += fp[m];   // tree-major, like calcFreeEnergy(0, W-1)
+            bool done;
+            if (MODE == PHYFOO_MODE_EXACT) done = true;
+            else if (!upd) { old = Fsum; upd = true; done = false; }          // F_0, MeanFieldForBayesNet.java:105
+            else {
+                if (fabs(old - Fsum) < p.tol) conv = true;                    // :204-207 (sticky)
+                old = Fsum; ++k;
+                done = !((k < p.max_sweeps && !conv) || k < p.min_sweeps);    // :107
+            }
+            if (done) {
+                if (t == 0) {
+                    p.out[item] = -Fsum;                                      // PhyloBayesModel.java:259
+                    if (p.sweeps) p.sweeps[item] = k;
+                    if (MODE != PHYFOO_MODE_EXACT) atomicAdd(&p.counters[1], (unsigned long long)k);
+                }
+                need = true;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: ZOOPS posterior, one block per alignment.
+// jstacs SingleHiddenMotifMixture.java:520-564 (getNewWeights), :585-596 (modify),
+// UniformPositionPrior.java:55-61, StrandModel.java:631-640, Normalisation.java:63-91,352-375.
+// ------------------------------------------------------------------------------------------------
+struct ZoopsParams {
+    const double* fwd; const double* rev;    // [n_windows] each (rev may be null)
+    const double* bgcol;                     // [n_cols] background log-score per column (order 0)
+    const int64_t* col_off; const int64_t* win_off; int n_aln; int W;
+    double logw0, logw1; int has_strand; double slw0, slw1;
+    const double* aln_w;                     // nullable
+    double* gamma; double* profile;          // nullable, [n_windows]
+    double* part;                            // [3][n_aln]: ll, w0, w1 per alignment
+    int32_t* argoff; uint8_t* argstrand;     // nullable
+};
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+    // deterministic: warp shuffles in a fixed pattern, then warp 0 adds the warp sums in order
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) sh[wid] = v;
+    __syncthreads();
+    double r = 0.0;
+    for (int i = 0; i < nw; ++i) r += sh[i];
+    return r;
+}
+
+__device__ __forceinline__ double logsum2(double v0, double v1) {   // Normalisation.getLogSum, :63-91
+    const double off = fmax(v0, v1);
+    if (isinf(off) && off < 0) return off;
+    return off + log(exp(v0 - off) + exp(v1 - off));
+}
+
+__global__ void __launch_bounds__(256) zoops_kernel(ZoopsParams p) {
+    __shared__ double sh[32];
+    __shared__ double sh_v[8];
+    __shared__ int sh_i[8];
+    const int a = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    const int64_t c0 = p.col_off[a];
+    const int L = (int)(p.col_off[a + 1] - c0);
+    const int64_t w0 = p.win_off[a];
+    const int n = (int)(p.win_off[a + 1] - w0);
+    const double weight = p.aln_w ? p.aln_w[a] : 1.0;
+
+    // logPSeq = bg.getLogProbFor(seq, 0, l-1), :526
+    double ps = 0.0;
+    for (int u = tid; u < L; u += T) ps += p.bgcol[c0 + u];
+    const double log_pseq = block_sum(ps, sh);
+
+    // a_j and its maximum (first index wins: util/Util.java:528-538)
+    const double lprior = -log((double)n);
+    double best = -INFINITY;
+    int best_j = 0x7fffffff;
+    for (int j = tid; j < n; j += T) {
+        double motif = p.fwd[w0 + j];
+        if (p.has_strand) motif = logsum2(p.slw0 + motif, p.slw1 + p.rev[w0 + j]);
+        double bgw = 0.0;
+        for (int m = 0; m < p.W; ++m) bgw += p.bgcol[c0 + j + m];   // -bg(s,e), order 0: s=j, e=j+W-1
+        const double aj = lprior + motif - bgw;                       // :536-540
+        if (p.profile) p.profile[w0 + j] = aj;
+        if (p.gamma) p.gamma[w0 + j] = aj;                            // overwritten with gamma_j below
+        if (aj > best) { best = aj; best_j = j; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, best, o);
+        const int oj = __shfl_down_sync(0xffffffffu, best_j, o);
+        if (ov > best || (ov == best && oj < best_j)) { best = ov; best_j = oj; }
+    }
+    if ((tid & 31) == 0) { sh_v[tid >> 5] = best; sh_i[tid >> 5] = best_j; }
+    __syncthreads();
+    best = sh_v[0]; best_j = sh_i[0];
+    for (int i = 1; i < (T + 31) / 32; ++i)
+        if (sh_v[i] > best || (sh_v[i] == best && sh_i[i] < best_j)) { best = sh_v[i]; best_j = sh_i[i]; }
+    if (best_j == 0x7fffffff) best_j = 0;   // every a_j was NaN or -inf
+
+    // sum_j exp(a_j - max)   (Normalisation.logSumNormalisation :352-375)
+    double se = 0.0;
+    for (int j = tid; j < n; j += T) {
+        double aj;
+        if (p.gamma) aj = p.gamma[w0 + j];
+        else {
+            double motif = p.fwd[w0 + j];
+            if (p.has_strand) motif = logsum2(p.slw0 + motif, p.slw1 + p.rev[w0 + j]);
+            double bgw = 0.0;
+            for (int m = 0; m < p.W; ++m) bgw += p.bgcol[c0 + j + m];
+            aj = lprior + motif - bgw;
+        }
+        const double e = exp(aj - best);
+        if (p.gamma) p.gamma[w0 + j] = e;
+        se += e;
+    }
+    const double sum = block_sum(se, sh);
+    const double Z = best + log(sum);
+
+    // modify(): help = {logW0 + Z, logW1} -> logSumNormalisation, :588-590
+    double h0 = p.logw0 + Z, h1 = p.logw1;
+    const double off = fmax(h0, h1);
+    double e0 = exp(h0 - off), e1 = exp(h1 - off);
+    const double hs = e0 + e1;
+    if (hs != 1.0) { e0 /= hs; e1 /= hs; }
+    const double lse = off + log(hs);
+    const double pm = e0 * weight;                                    // :547
+    if (tid == 0) {
+        p.part[a] = weight * (log_pseq + lse);                        // :544
+        p.part[(size_t)p.n_aln + a] = pm;                             // :548
+        p.part[(size_t)2 * p.n_aln + a] = weight * e1;                // :549
+        if (p.argoff) p.argoff[a] = best_j;
+        if (p.argstrand) {
+            int s = 0;
+            if (p.has_strand) s = (p.slw1 + p.rev[w0 + best_j]) > (p.slw0 + p.fwd[w0 + best_j]) ? 1 : 0;  // :737-754
+            p.argstrand[a] = (uint8_t)s;
+        }
+    }
+    if (p.gamma) {
+        for (int j = tid; j < n; j += T) {
+            double e = p.gamma[w0 + j];
+            if (sum != 1.0) e /= sum;
+            p.gamma[w0 + j] = e * pm;                                 // :553-555
+        }
+    }
+}
+
+// [3][n] partials -> out[3]; one block, fixed summation pattern (deterministic for a given n)
+__global__ void __launch_bounds__(1024) reduce3_kernel(const double* __restrict__ part, int n, double* __restrict__ out) {
+    __shared__ double sh[32];
+    for (int r = 0; r < 3; ++r) {
+        double v = 0.0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) v += part[(size_t)r * n + i];
+        const double s = block_sum(v, sh);
+        if (threadIdx.x == 0) out[r] = s;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp64 roofline probe: 8 independent DFMA chains per thread
+// ------------------------------------------------------------------------------------------------
+__global__ void dfma_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+extern "C" int phyfoo_init(int device, phyfoo_ctx** out) {
+    if (!out) return fail(nullptr, PHYFOO_EINVAL, "phyfoo_init: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, PHYFOO_ENODEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                                               " (libphyfoo has no CPU fallback)");
+    if (device < 0 || device >= n) return fail(nullptr, PHYFOO_EINVAL, "phyfoo_init: bad device index");
+    phyfoo_ctx* ctx = new phyfoo_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->kev[0])) != cudaSuccess || (e = cudaEventCreate(&ctx->kev[1])) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->kev[2])) != cudaSuccess || (e = cudaEventCreate(&ctx->kev[3])) != cudaSuccess ||
+        (e = ctx->counters.ensure(8 * sizeof(unsigned long long))) != cudaSuccess) {
+        g_init_err = std::string("phyfoo_init: ") + cudaGetErrorString(e);
+        delete ctx;
+        return PHYFOO_ECUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->cc_major = prop.major; ctx->cc_minor = prop.minor;
+    ctx->total_mem = prop.totalGlobalMem;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    *out = ctx;
+    return PHYFOO_OK;
+}
+
+extern "C" void phyfoo_destroy(phyfoo_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (DevBuf* b : {&ctx->counters, &ctx->fg_scores, &ctx->bg_scores, &ctx->sweeps_buf, &ctx->gamma, &ctx->profile, &ctx->part,
+                      &ctx->argoff, &ctx->argstrand, &ctx->alnw, &ctx->out3, &ctx->gstate, &ctx->misc})
+        b->release();
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+    for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* phyfoo_last_error(const phyfoo_ctx* ctx) { return ctx ? ctx->err.c_str() : g_init_err.c_str(); }
+
+extern "C" int phyfoo_device_info(phyfoo_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, int64_t* total_mem) {
+    if (!ctx) return PHYFOO_EINVAL;
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (cc_major) *cc_major = ctx->cc_major;
+    if (cc_minor) *cc_minor = ctx->cc_minor;
+    if (total_mem) *total_mem = (int64_t)ctx->total_mem;
+    return PHYFOO_OK;
+}
+
+extern "C" int phyfoo_fp64_peak(phyfoo_ctx* ctx, double* tflops_out) {
+    if (!ctx || !tflops_out) return PHYFOO_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    const int blocks = ctx->sm_count * 8, threads = 256, iters = 20000;
+    CU(ctx->misc.ensure((size_t)blocks * threads * sizeof(double)));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        CU(cudaEventRecord(ctx->ev0, ctx->stream));
+        dfma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->misc.as<double>(), iters, 0.999999, 1e-6);
+        CU(cudaEventRecord(ctx->ev1, ctx->stream));
+        CU(cudaEventSynchronize(ctx->ev1));
+        CU(cudaGetLastError());
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        if (rep > 0) best = std::min(best, ms);
+    }
+    *tflops_out = 2.0 * 8.0 * iters * (double)blocks * threads / (best * 1e-3) / 1e12;
+    return PHYFOO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dataset
+// ------------------------------------------------------------------------------------------------
+static int dataset_build(phyfoo_ctx* ctx, int32_t n_aln, int32_t S, const int64_t* col_offsets, const uint8_t* codes,
+                         bool codes_on_device, phyfoo_dataset** out) {
+    if (!ctx) return PHYFOO_EINVAL;
+    if (!out || !col_offsets || (!codes && n_aln > 0)) return fail(ctx, PHYFOO_EINVAL, "dataset_create: NULL argument");
+    *out = nullptr;
+    if (n_aln < 0 || S < 1) return fail(ctx, PHYFOO_EINVAL, "dataset_create: need n_aln >= 0 and n_species >= 1");
+    if (S > 32) return fail(ctx, PHYFOO_EUNSUPPORTED, "dataset_create: more than 32 species are not supported by the packed-column kernels");
+    if (col_offsets[0] != 0) return fail(ctx, PHYFOO_EINVAL, "dataset_create: col_offsets[0] must be 0");
+    for (int i = 0; i < n_aln; ++i)
+        if (col_offsets[i + 1] < col_offsets[i]) return fail(ctx, PHYFOO_EINVAL, "dataset_create: col_offsets must be non-decreasing");
+    CU(cudaSetDevice(ctx->device));
+    phyfoo_dataset* ds = new phyfoo_dataset();
+    ds->n_aln = n_aln; ds->S = S; ds->nb = (S + 15) / 16; ds->ng = (S + 31) / 32;
+    ds->col_off.assign(col_offsets, col_offsets + n_aln + 1);
+    ds->n_cols = col_offsets[n_aln];
+    ds->min_len = n_aln ? INT32_MAX : 0; ds->max_len = 0;
+    for (int i = 0; i < n_aln; ++i) {
+        int64_t L = col_offsets[i + 1] - col_offsets[i];
+        if (L > INT32_MAX / 2) { delete ds; return fail(ctx, PHYFOO_EINVAL, "dataset_create: alignment too long"); }
+        ds->min_len = std::min<int>(ds->min_len, (int)L);
+        ds->max_len = std::max<int>(ds->max_len, (int)L);
+    }
+    const int64_t nc = std::max<int64_t>(ds->n_cols, 1);
+    cudaError_t e;
+    uint8_t* d_codes = nullptr;
+    int* d_bad = nullptr;
+    auto cleanup = [&]() {
+        if (!codes_on_device && d_codes) cudaFree(d_codes);
+        if (d_bad) cudaFree(d_bad);
+    };
+    auto bail = [&](const char* what, cudaError_t err) {
+        ctx->err = std::string(what) + ": " + cudaGetErrorString(err);
+        cleanup();
+        if (ds->d_col_off) cudaFree(ds->d_col_off);
+        if (ds->d_bases) cudaFree(ds->d_bases);
+        if (ds->d_gaps) cudaFree(ds->d_gaps);
+        delete ds;
+        return err == cudaErrorMemoryAllocation ? PHYFOO_ENOMEM : PHYFOO_ECUDA;
+    };
+    if ((e = cudaMalloc(&ds->d_col_off, (size_t)(n_aln + 1) * sizeof(int64_t))) != cudaSuccess) return bail("cudaMalloc col_off", e);
+    if ((e = cudaMalloc(&ds->d_bases, (size_t)ds->nb * nc * 4)) != cudaSuccess) return bail("cudaMalloc bases", e);
+    if ((e = cudaMalloc(&ds->d_gaps, (size_t)ds->ng * nc * 4)) != cudaSuccess) return bail("cudaMalloc gaps", e);
+    if ((e = cudaMalloc(&d_bad, sizeof(int))) != cudaSuccess) return bail("cudaMalloc flag", e);
+    if ((e = cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream)) != cudaSuccess) return bail("memset", e);
+    if ((e = cudaMemcpyAsync(ds->d_col_off, col_offsets, (size_t)(n_aln + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
+        return bail("copy col_off", e);
+    if (ds->n_cols > 0) {
+        if (codes_on_device) d_codes = const_cast<uint8_t*>(codes);
+        else {
+            if ((e = cudaMalloc(&d_codes, (size_t)ds->n_cols * S)) != cudaSuccess) return bail("cudaMalloc codes", e);
+            if ((e = cudaMemcpyAsync(d_codes, codes, (size_t)ds->n_cols * S, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
+                return bail("copy codes", e);
+        }
+        const int threads = 256;
+        const int64_t blocks = (ds->n_cols + threads - 1) / threads;
+        pack_columns_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(d_codes, ds->n_cols, S, ds->nb, ds->ng, ds->d_bases, ds->d_gaps, d_bad);
+        ctx->launches++;
+        if ((e = cudaGetLastError()) != cudaSuccess) return bail("pack_columns_kernel", e);
+    }
+    int bad = 0;
+    if ((e = cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) return bail("copy flag", e);
+    if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bail("pack_columns_kernel", e);
+    cleanup();
+    if (bad) {
+        cudaFree(ds->d_col_off); cudaFree(ds->d_bases); cudaFree(ds->d_gaps);
+        delete ds;
+        return fail(ctx, PHYFOO_EINVAL, "dataset_create: code outside 0..4 (WrongAlphabetException in the reference)");
+    }
+    *out = ds;
+    return PHYFOO_OK;
+}
+
+extern "C" int phyfoo_dataset_create(phyfoo_ctx* ctx, int32_t n_aln, int32_t n_species, const int64_t* col_offsets,
+                                     const uint8_t* codes, phyfoo_dataset** out) {
+    return dataset_build(ctx, n_aln, n_species, col_offsets, codes, false, out);
+}
+extern "C" int phyfoo_dataset_create_device(phyfoo_ctx* ctx, int32_t n_aln, int32_t n_species, const int64_t* col_offsets,
+                                            const uint8_t* codes_device, phyfoo_dataset** out) {
+    return dataset_build(ctx, n_aln, n_species, col_offsets, codes_device, true, out);
+}
+
+extern "C" int phyfoo_dataset_packed(phyfoo_ctx* ctx, const phyfoo_dataset* ds, uint32_t* bases_out, uint32_t* gaps_out) {
+    if (!ctx || !ds) return PHYFOO_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    if (ds->n_cols == 0) return PHYFOO_OK;
+    if (bases_out) CU(cudaMemcpyAsync(bases_out, ds->d_bases, (size_t)ds->nb * ds->n_cols * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (gaps_out) CU(cudaMemcpyAsync(gaps_out, ds->d_gaps, (size_t)ds->ng * ds->n_cols * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PHYFOO_OK;
+}
+
+extern "C" int64_t phyfoo_dataset_columns(const phyfoo_dataset* ds) { return ds ? ds->n_cols : 0; }
+
+extern "C" int64_t phyfoo_dataset_windows(const phyfoo_dataset* ds, int32_t width) {
+    if (!ds || width < 1) return 0;
+    int64_t n = 0;
+    for (int i = 0; i < ds->n_aln; ++i) n += std::max<int64_t>(0, ds->col_off[i + 1] - ds->col_off[i] - width + 1);
+    return n;
+}
+
+extern "C" void phyfoo_dataset_free(phyfoo_ctx* ctx, phyfoo_dataset* ds) {
+    if (!ds) return;
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    cudaFree(ds->d_col_off); cudaFree(ds->d_bases); cudaFree(ds->d_gaps);
+    for (auto& kv : ds->d_win_off) cudaFree(kv.second);
+    delete ds;
+}
+
+// window prefix offsets for motif width W (device + host), cached on the dataset
+static int dataset_win_off(phyfoo_ctx* ctx, const phyfoo_dataset* cds, int W, const int64_t** d_out, const std::vector<int64_t>** h_out) {
+    phyfoo_dataset* ds = const_cast<phyfoo_dataset*>(cds);
+    auto it = ds->d_win_off.find(W);
+    if (it == ds->d_win_off.end()) {
+        std::vector<int64_t> off(ds->n_aln + 1, 0);
+        for (int i = 0; i < ds->n_aln; ++i) off[i + 1] = off[i] + std::max<int64_t>(0, ds->col_off[i + 1] - ds->col_off[i] - W + 1);
+        int64_t* d = nullptr;
+        CU(cudaMalloc(&d, off.size() * sizeof(int64_t)));
+        cudaError_t e = cudaMemcpyAsync(d, off.data(), off.size() * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { cudaFree(d); ctx->err = std::string("win_off copy: ") + cudaGetErrorString(e); return PHYFOO_ECUDA; }
+        ds->d_win_off[W] = d;
+        ds->win_off[W] = std::move(off);
+        it = ds->d_win_off.find(W);
+    }
+    *d_out = it->second;
+    if (h_out) *h_out = &ds->win_off[W];
+    return PHYFOO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// models
+// ------------------------------------------------------------------------------------------------
+extern "C" int phyfoo_model_create(phyfoo_ctx* ctx, const phyfoo_model_desc* desc, phyfoo_model** out) {
+    if (!ctx) return PHYFOO_EINVAL;
+    if (!desc || !out) return fail(ctx, PHYFOO_EINVAL, "model_create: NULL argument");
+    *out = nullptr;
+    phyfoo_model* m = new phyfoo_model();
+    try { m->h.init(*desc); }
+    catch (const std::exception& e) { delete m; return fail(ctx, PHYFOO_EINVAL, e.what()); }
+    if (m->h.S > 32) { delete m; return fail(ctx, PHYFOO_EUNSUPPORTED, "model_create: more than 32 species are not supported"); }
+    *out = m;
+    return PHYFOO_OK;
+}
+
+extern "C" int phyfoo_model_set_pi(phyfoo_ctx* ctx, phyfoo_model* m, int32_t position, const double* pi, int32_t n) {
+    if (!ctx || !m || !pi) return PHYFOO_EINVAL;
+    try { m->h.set_pi(position, pi, n); } catch (const std::exception& e) { return fail(ctx, PHYFOO_EINVAL, e.what()); }
+    return PHYFOO_OK;
+}
+extern "C" int phyfoo_model_get_pi(phyfoo_ctx* ctx, const phyfoo_model* m, int32_t position, double* pi_out, int32_t n) {
+    if (!ctx || !m || !pi_out) return PHYFOO_EINVAL;
+    if (position < 0 || position >= m->h.W || n != (int)m->h.pi[position].size()) return fail(ctx, PHYFOO_EINVAL, "get_pi: bad position or size");
+    std::copy(m->h.pi[position].begin(), m->h.pi[position].end(), pi_out);
+    return PHYFOO_OK;
+}
+extern "C" int phyfoo_model_set_branch(phyfoo_ctx* ctx, phyfoo_model* m, int32_t position, int32_t node, double length) {
+    if (!ctx || !m) return PHYFOO_EINVAL;
+    try { m->h.set_branch(position, node, length); } catch (const std::exception& e) { return fail(ctx, PHYFOO_EINVAL, e.what()); }
+    return PHYFOO_OK;
+}
+extern "C" int phyfoo_model_set_mode(phyfoo_ctx* ctx, phyfoo_model* m, int32_t mode) {
+    if (!ctx || !m) return PHYFOO_EINVAL;
+    if (mode != PHYFOO_MODE_MEANFIELD && mode != PHYFOO_MODE_EXACT) return fail(ctx, PHYFOO_EINVAL, "set_mode: unknown mode");
+    m->h.mode = mode;
+    return PHYFOO_OK;
+}
+extern "C" void phyfoo_model_free(phyfoo_ctx* ctx, phyfoo_model* m) {
+    if (!m) return;
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    cudaFree(m->d_prog); cudaFree(m->d_logtab); cudaFree(m->d_probtab);
+    delete m;
+}
+
+// copy the order-0 tables to the device in [E][W] layout when the parameters changed
+static int model_upload(phyfoo_ctx* ctx, phyfoo_model* m) {
+    ModelHost& h = m->h;
+    if (h.order != 0) return fail(ctx, PHYFOO_EUNSUPPORTED, "order >= 1 networks are not implemented in this build");
+    if (m->uploaded == h.version) return PHYFOO_OK;
+    const size_t n = (size_t)h.E * h.W;
+    if (!m->d_prog) {
+        std::vector<int> prog = h.prog_flat();
+        m->prog_len = (int)prog.size();
+        CU(cudaMalloc(&m->d_prog, prog.size() * sizeof(int)));
+        CU(cudaMemcpyAsync(m->d_prog, prog.data(), prog.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMalloc(&m->d_logtab, n * sizeof(double)));
+        CU(cudaMalloc(&m->d_probtab, n * sizeof(double)));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    std::vector<double> tl(n), tp(n);
+    for (int t = 0; t < h.W; ++t)
+        for (int e = 0; e < h.E; ++e) {
+            tl[(size_t)e * h.W + t] = h.logtab[(size_t)t * h.E + e];
+            tp[(size_t)e * h.W + t] = h.probtab[(size_t)t * h.E + e];
+        }
+    CU(cudaMemcpyAsync(m->d_logtab, tl.data(), n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(m->d_probtab, tp.data(), n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));   // tl/tp are stack-scoped
+    m->uploaded = h.version;
+    return PHYFOO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scoring launches
+// ------------------------------------------------------------------------------------------------
+struct ScorePlan { int threads, groups, blocks; size_t smem; bool gstate; };
+
+static int plan_score(phyfoo_ctx* ctx, const ModelHost& h, int prog_len, long long n_items, int mode, ScorePlan* pl) {
+    const int W = h.W;
+    if (W > 256) return fail(ctx, PHYFOO_EUNSUPPORTED, "motif width > 256 is not supported");
+    const size_t tab_bytes = (size_t)h.E * W * sizeof(double);
+    const size_t per_thread_state = (size_t)h.I * 8 * sizeof(double);
+    const size_t budget = std::min<size_t>(ctx->smem_optin, 227 * 1024);
+    // aim for >= 2 resident blocks per SM when the state allows it
+    int groups = std::max(1, 256 / W);
+    bool gstate = false; (void)gstate;
+    for (;;) {
+        int threads = ((groups * W + 31) / 32) * 32;
+        size_t fixed = tab_bytes + (size_t)threads * 8 + (size_t)groups * 8 + (size_t)prog_len * 4 + 64;
+        size_t target = budget / 2;
+        if (fixed + per_thread_state * threads <= target || (groups * W <= 64 && fixed + per_thread_state * threads <= budget)) {
+            pl->threads = threads; pl->groups = groups; pl->smem = fixed + per_thread_state * threads; pl->gstate = false;
+            break;
+        }
+        if (groups * W <= 64) {   // state does not fit in shared memory even for a small block: keep it in global memory
+            groups = std::max(1, 128 / W);
+            threads = ((groups * W + 31) / 32) * 32;
+            fixed = tab_bytes + (size_t)threads * 8 + (size_t)groups * 8 + (size_t)prog_len * 4 + 64;
+            if (fixed > budget) return fail(ctx, PHYFOO_EUNSUPPORTED, "model tables do not fit in shared memory");
+            pl->threads = threads; pl->groups = groups; pl->smem = fixed; pl->gstate = true; gstate = true;
+            break;
+        }
+        groups = std::max(1, groups / 2);
+    }
+    (void)gstate;
+    const void* fn = mode == PHYFOO_MODE_EXACT ? (const void*)score_o0_kernel<PHYFOO_MODE_EXACT> : (const void*)score_o0_kernel<PHYFOO_MODE_MEANFIELD>;
+    CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, pl->threads, pl->smem));
+    if (per_sm < 1) return fail(ctx, PHYFOO_ECUDA, "score kernel does not fit on an SM");
+    long long want = (n_items + pl->groups - 1) / pl->groups;
+    pl->blocks = (int)std::max<long long>(1, std::min<long long>(want, (long long)per_sm * ctx->sm_count));
+    return PHYFOO_OK;
+}
+
+// scores into d_out[n_strands][n_windows]; strands: 0 = forward only, 1 = reverse only, 2 = both
+static int launch_score(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* m, const int64_t* d_win_off, int64_t n_windows,
+                        int strands, double* d_out, int32_t* d_sweeps, int counter_slot) {
+    int rc = model_upload(ctx, m);
+    if (rc) return rc;
+    ModelHost& h = m->h;
+    if (h.S != ds->S) return fail(ctx, PHYFOO_EINVAL, "model and dataset disagree on the number of species");
+    if (h.evol == PHYFOO_EVOL_HKY_AS_IMPLEMENTED)
+        return fail(ctx, PHYFOO_EUNSUPPORTED, "HKY as implemented in the reference has zero transversion probabilities (HKY.java:32): every score is -inf");
+    if (h.mode == PHYFOO_MODE_MEANFIELD && !h.tables_finite())
+        return fail(ctx, PHYFOO_EUNSUPPORTED, "a CPF entry is 0: the reference's free energy is not finite for this parameter set");
+    const int n_strands = strands == 2 ? 2 : 1;
+    const long long n_items = (long long)n_windows * n_strands;
+    if (n_items == 0) return PHYFOO_OK;
+    ScorePlan pl;
+    rc = plan_score(ctx, h, m->prog_len, n_items, h.mode, &pl);
+    if (rc) return rc;
+    ScoreParams p;
+    p.bases = ds->d_bases; p.gaps = ds->d_gaps; p.n_cols = ds->n_cols; p.nb = ds->nb;
+    p.col_off = ds->d_col_off; p.win_off = d_win_off; p.n_aln = ds->n_aln;
+    p.n_windows = n_windows; p.n_strands = n_strands; p.strand0 = strands == 1 ? 1 : 0;
+    p.W = h.W; p.I = h.I; p.S = h.S; p.E = h.E; p.prog_len = m->prog_len;
+    p.tab = h.mode == PHYFOO_MODE_EXACT ? m->d_probtab : m->d_logtab;
+    p.prog = m->d_prog;
+    p.out = d_out; p.sweeps = d_sweeps;
+    p.counters = ctx->counters.as<unsigned long long>() + 2 * counter_slot;
+    p.max_sweeps = h.max_sweeps; p.min_sweeps = h.min_sweeps; p.tol = h.tol;
+    p.groups = pl.groups;
+    p.gstate = nullptr;
+    if (pl.gstate) {
+        CU(ctx->gstate.ensure((size_t)pl.blocks * pl.threads * h.I * 8 * sizeof(double)));
+        p.gstate = ctx->gstate.as<double>();
+    }
+    CU(cudaMemsetAsync(p.counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    if (h.mode == PHYFOO_MODE_EXACT) score_o0_kernel<PHYFOO_MODE_EXACT><<<pl.blocks, pl.threads, pl.smem, ctx->stream>>>(p);
+    else score_o0_kernel<PHYFOO_MODE_MEANFIELD><<<pl.blocks, pl.threads, pl.smem, ctx->stream>>>(p);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return PHYFOO_OK;
+}
+
+struct CallTimer {
+    phyfoo_ctx* ctx;
+    explicit CallTimer(phyfoo_ctx* c) : ctx(c) { ctx->launches = 0; cudaEventRecord(ctx->ev0, ctx->stream); }
+    float stop() {
+        cudaEventRecord(ctx->ev1, ctx->stream);
+        cudaEventSynchronize(ctx->ev1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        return ms;
+    }
+};
+
+static int read_sweeps(phyfoo_ctx* ctx, int slot, int64_t* out) {
+    unsigned long long v[2];
+    CU(cudaMemcpyAsync(v, ctx->counters.as<unsigned long long>() + 2 * slot, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *out = (int64_t)v[1];
+    return PHYFOO_OK;
+}
+
+extern "C" int phyfoo_score_windows(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* fg, int32_t strand,
+                                    double* out, int32_t* sweeps_out, phyfoo_stats* stats) {
+    if (!ctx) return PHYFOO_EINVAL;
+    if (!ds || !fg || !out) return fail(ctx, PHYFOO_EINVAL, "score_windows: NULL argument");
+    if (strand != 0 && strand != 1) return fail(ctx, PHYFOO_EINVAL, "score_windows: strand must be 0 or 1");
+    CU(cudaSetDevice(ctx->device));
+    const int64_t* d_woff; const std::vector<int64_t>* h_woff;
+    int rc = dataset_win_off(ctx, ds, fg->h.W, &d_woff, &h_woff);
+    if (rc) return rc;
+    const int64_t nw = h_woff->back();
+    CU(ctx->fg_scores.ensure((size_t)std::max<int64_t>(nw, 1) * sizeof(double)));
+    if (sweeps_out) CU(ctx->sweeps_buf.ensure((size_t)std::max<int64_t>(nw, 1) * sizeof(int32_t)));
+    CallTimer tm(ctx);
+    rc = launch_score(ctx, ds, fg, d_woff, nw, strand, ctx->fg_scores.as<double>(), sweeps_out ? ctx->sweeps_buf.as<int32_t>() : nullptr, 0);
+    if (rc) return rc;
+    const float ms = tm.stop();
+    CU(cudaGetLastError());
+    if (nw > 0) {
+        CU(cudaMemcpyAsync(out, ctx->fg_scores.p, (size_t)nw * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (sweeps_out) CU(cudaMemcpyAsync(sweeps_out, ctx->sweeps_buf.p, (size_t)nw * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->n_windows = nw; stats->kernel_launches = ctx->launches; stats->gpu_ms = ms;
+        if (nw > 0 && (rc = read_sweeps(ctx, 0, &stats->sweeps_fg))) return rc;
+    }
+    return PHYFOO_OK;
+}
+
+// per-column background scores (order 0): the same kernel with windows of width 1
+static int launch_bg_columns(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* bg, double* d_out, int32_t* d_sweeps, int slot) {
+    if (bg->h.kind != PHYFOO_MODEL_BG) return fail(ctx, PHYFOO_EINVAL, "bg_columns: model is not a background model");
+    if (bg->h.order != 0) return fail(ctx, PHYFOO_EUNSUPPORTED, "background order >= 1 is not implemented in this build");
+    return launch_score(ctx, ds, bg, ds->d_col_off, ds->n_cols, 0, d_out, d_sweeps, slot);
+}
+
+extern "C" int phyfoo_bg_columns(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* bg, double* out,
+                                 int32_t* sweeps_out, phyfoo_stats* stats) {
+    if (!ctx) return PHYFOO_EINVAL;
+    if (!ds || !bg || !out) return fail(ctx, PHYFOO_EINVAL, "bg_columns: NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    const int64_t nc = ds->n_cols;
+    CU(ctx->bg_scores.ensure((size_t)std::max<int64_t>(nc, 1) * sizeof(double)));
+    if (sweeps_out) CU(ctx->sweeps_buf.ensure((size_t)std::max<int64_t>(nc, 1) * sizeof(int32_t)));
+    CallTimer tm(ctx);
+    int rc = launch_bg_columns(ctx, ds, bg, ctx->bg_scores.as<double>(), sweeps_out ? ctx->sweeps_buf.as<int32_t>() : nullptr, 1);
+    if (rc) return rc;
+    const float ms = tm.stop();
+    CU(cudaGetLastError());
+    if (nc > 0) {
+        CU(cudaMemcpyAsync(out, ctx->bg_scores.p, (size_t)nc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (sweeps_out) CU(cudaMemcpyAsync(sweeps_out, ctx->sweeps_buf.p, (size_t)nc * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->n_columns = nc; stats->kernel_launches = ctx->launches; stats->gpu_ms = ms;
+        if (nc > 0 && (rc = read_sweeps(ctx, 1, &stats->sweeps_bg))) return rc;
+    }
+    return PHYFOO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// E-step
+// ------------------------------------------------------------------------------------------------
+// Enqueues the whole E-step on ctx->stream; leaves [ll, w0, w1] in d_out3.  aln_w_dev nullable (device).
+static int enqueue_estep(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* fg, phyfoo_model* bg, const double* logw,
+                         const double* strand_logw, const double* aln_w_dev, double* d_gamma, double* d_profile,
+                         int32_t* d_argoff, uint8_t* d_argstrand, double* d_out3, int64_t* nw_out) {
+    if (fg->h.kind != PHYFOO_MODEL_FG) return fail(ctx, PHYFOO_EINVAL, "zoops_estep: fg is not a motif model");
+    const int W = fg->h.W;
+    if (ds->n_aln == 0) return fail(ctx, PHYFOO_EINVAL, "zoops_estep: empty sample");
+    if (ds->min_len < W) return fail(ctx, PHYFOO_EINVAL, "zoops_estep: an alignment is shorter than the motif");
+    const int64_t* d_woff; const std::vector<int64_t>* h_woff;
+    int rc = dataset_win_off(ctx, ds, W, &d_woff, &h_woff);
+    if (rc) return rc;
+    const int64_t nw = h_woff->back();
+    *nw_out = nw;
+    const int n_strands = strand_logw ? 2 : 1;
+    CU(ctx->fg_scores.ensure((size_t)nw * n_strands * sizeof(double)));
+    CU(ctx->bg_scores.ensure((size_t)ds->n_cols * sizeof(double)));
+    CU(ctx->part.ensure((size_t)3 * ds->n_aln * sizeof(double)));
+    ctx->kev_valid = false;
+    CU(cudaEventRecord(ctx->kev[0], ctx->stream));
+    rc = launch_bg_columns(ctx, ds, bg, ctx->bg_scores.as<double>(), nullptr, 1);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->kev[1], ctx->stream));
+    rc = launch_score(ctx, ds, fg, d_woff, nw, strand_logw ? 2 : 0, ctx->fg_scores.as<double>(), nullptr, 0);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->kev[2], ctx->stream));
+    ZoopsParams z;
+    z.fwd = ctx->fg_scores.as<double>();
+    z.rev = strand_logw ? ctx->fg_scores.as<double>() + nw : nullptr;
+    z.bgcol = ctx->bg_scores.as<double>();
+    z.col_off = ds->d_col_off; z.win_off = d_woff; z.n_aln = ds->n_aln; z.W = W;
+    z.logw0 = logw[0]; z.logw1 = logw[1];
+    z.has_strand = strand_logw ? 1 : 0;
+    z.slw0 = strand_logw ? strand_logw[0] : 0.0; z.slw1 = strand_logw ? strand_logw[1] : 0.0;
+    z.aln_w = aln_w_dev;
+    z.gamma = d_gamma; z.profile = d_profile;
+    z.part = ctx->part.as<double>();
+    z.argoff = d_argoff; z.argstrand = d_argstrand;
+    zoops_kernel<<<ds->n_aln, 256, 0, ctx->stream>>>(z);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    reduce3_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->part.as<double>(), ds->n_aln, d_out3);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->kev[3], ctx->stream));
+    ctx->kev_valid = true;
+    return PHYFOO_OK;
+}
+
+extern "C" int phyfoo_zoops_estep(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* fg, phyfoo_model* bg,
+                                  const double* logw, const double* strand_logw, const double* aln_weights,
+                                  double* gamma_out, double* profile_out, double* w_out, double* ll_out,
+                                  int32_t* argmax_off, uint8_t* argmax_strand, phyfoo_stats* stats) {
+    if (!ctx) return PHYFOO_EINVAL;
+    if (!ds || !fg || !bg || !logw) return fail(ctx, PHYFOO_EINVAL, "zoops_estep: NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    const int64_t nw_guess = phyfoo_dataset_windows(ds, fg->h.W);
+    if (gamma_out) CU(ctx->gamma.ensure((size_t)std::max<int64_t>(nw_guess, 1) * sizeof(double)));
+    if (profile_out) CU(ctx->profile.ensure((size_t)std::max<int64_t>(nw_guess, 1) * sizeof(double)));
+    if (argmax_off) CU(ctx->argoff.ensure((size_t)std::max(ds->n_aln, 1) * sizeof(int32_t)));
+    if (argmax_strand) CU(ctx->argstrand.ensure((size_t)std::max(ds->n_aln, 1)));
+    CU(ctx->out3.ensure(3 * sizeof(double)));
+    const double* d_alnw = nullptr;
+    if (aln_weights) {
+        CU(ctx->alnw.ensure((size_t)std::max(ds->n_aln, 1) * sizeof(double)));
+        CU(cudaMemcpyAsync(ctx->alnw.p, aln_weights, (size_t)ds->n_aln * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        d_alnw = ctx->alnw.as<double>();
+    }
+    CallTimer tm(ctx);
+    int64_t nw = 0;
+    int rc = enqueue_estep(ctx, ds, fg, bg, logw, strand_logw, d_alnw, gamma_out ? ctx->gamma.as<double>() : nullptr,
+                           profile_out ? ctx->profile.as<double>() : nullptr, argmax_off ? ctx->argoff.as<int32_t>() : nullptr,
+                           argmax_strand ? ctx->argstrand.as<uint8_t>() : nullptr, ctx->out3.as<double>(), &nw);
+    if (rc) return rc;
+    const float ms = tm.stop();
+    CU(cudaGetLastError());
+    double r3[3];
+    CU(cudaMemcpyAsync(r3, ctx->out3.p, sizeof(r3), cudaMemcpyDeviceToHost, ctx->stream));
+    if (gamma_out) CU(cudaMemcpyAsync(gamma_out, ctx->gamma.p, (size_t)nw * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (profile_out) CU(cudaMemcpyAsync(profile_out, ctx->profile.p, (size_t)nw * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (argmax_off) CU(cudaMemcpyAsync(argmax_off, ctx->argoff.p, (size_t)ds->n_aln * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (argmax_strand) CU(cudaMemcpyAsync(argmax_strand, ctx->argstrand.p, (size_t)ds->n_aln, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ll_out) *ll_out = r3[0];
+    if (w_out) { w_out[0] = r3[1]; w_out[1] = r3[2]; }
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->n_windows = nw * (strand_logw ? 2 : 1); stats->n_columns = ds->n_cols;
+        stats->kernel_launches = ctx->launches; stats->gpu_ms = ms;
+        if ((rc = read_sweeps(ctx, 0, &stats->sweeps_fg))) return rc;
+        if ((rc = read_sweeps(ctx, 1, &stats->sweeps_bg))) return rc;
+    }
+    return PHYFOO_OK;
+}
+
+extern "C" int phyfoo_zoops_estep_device(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* fg, phyfoo_model* bg,
+                                         const double* logw, const double* strand_logw, const double* aln_weights_device,
+                                         double* partial_device, void* stream) {
+    if (!ctx) return PHYFOO_EINVAL;
+    if (!ds || !fg || !bg || !logw || !partial_device) return fail(ctx, PHYFOO_EINVAL, "zoops_estep_device: NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    ctx->launches = 0;
+    // The library's kernels run on its own stream; order them after the caller's stream and make the
+    // caller's stream wait for the result, so the call is asynchronous for the host.
+    cudaStream_t user = (cudaStream_t)stream;
+    if (user) {
+        CU(cudaEventRecord(ctx->ev0, user));
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev0, 0));
+    }
+    int64_t nw = 0;
+    int rc = enqueue_estep(ctx, ds, fg, bg, logw, strand_logw, aln_weights_device, nullptr, nullptr, nullptr, nullptr, partial_device, &nw);
+    if (rc) return rc;
+    if (user) {
+        CU(cudaEventRecord(ctx->ev1, ctx->stream));
+        CU(cudaStreamWaitEvent(user, ctx->ev1, 0));
+    }
+    return PHYFOO_OK;
+}
+
+// device time of the three phases of the most recent E-step on this context (waits for it to finish):
+// background columns (incl. its counter memset), motif windows, ZOOPS posterior + final reduction
+extern "C" int phyfoo_estep_kernel_ms(phyfoo_ctx* ctx, float* bg_ms, float* fg_ms, float* zoops_ms) {
+    if (!ctx) return PHYFOO_EINVAL;
+    if (!ctx->kev_valid) return fail(ctx, PHYFOO_EINVAL, "estep_kernel_ms: no E-step has run on this context");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventSynchronize(ctx->kev[3]));
+    float a = 0, b = 0, c = 0;
+    CU(cudaEventElapsedTime(&a, ctx->kev[0], ctx->kev[1]));
+    CU(cudaEventElapsedTime(&b, ctx->kev[1], ctx->kev[2]));
+    CU(cudaEventElapsedTime(&c, ctx->kev[2], ctx->kev[3]));
+    if (bg_ms) *bg_ms = a;
+    if (fg_ms) *fg_ms = b;
+    if (zoops_ms) *zoops_ms = c;
+    return PHYFOO_OK;
+}
+// sums of mean-field sweeps of the most recent E-step (waits for it to finish)
+extern "C" int phyfoo_estep_sweeps(phyfoo_ctx* ctx, int64_t* sweeps_fg, int64_t* sweeps_bg) {
+    if (!ctx) return PHYFOO_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    int64_t a = 0, b = 0;
+    if ((rc = read_sweeps(ctx, 0, &a))) return rc;
+    if ((rc = read_sweeps(ctx, 1, &b))) return rc;
+    if (sweeps_fg) *sweeps_fg = a;
+    if (sweeps_bg) *sweeps_bg = b;
+    return PHYFOO_OK;
+}
+
+extern "C" int phyfoo_last_launches(const phyfoo_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" void* phyfoo_stream(phyfoo_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" int phyfoo_synchronize(phyfoo_ctx* ctx) {
+    if (!ctx) return PHYFOO_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PHYFOO_OK;
+}
+
+#include "mstep.cuh"

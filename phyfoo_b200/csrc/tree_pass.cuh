@@ -16,7 +16,10 @@
 //    the free energy of this sweep and accumulated into the parent's "child sum" for the next one;
 //  * observed leaves never get state: their contribution log T_c(a, x_c) is re-read per sweep;
 //  * an unobserved (gap) leaf is handled inline at its parent (its table is the "independent"
-//    pi row, bayesNet/CPF.java:146-152, so it only needs the parent's q of the same sweep).
+//    pi row, bayesNet/CPF.java:146-152, so it only needs the parent's q of the same sweep);
+//  * "pass 0" (free energy of the uniform start, MeanFieldForBayesNet.java:105) is the same code as
+//    an update pass with the exponent forced to 0 (exp(0)/4 = 0.25 exactly), so threads of one warp
+//    that are in different sweeps of different windows never diverge.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -42,17 +45,28 @@ struct TreeProg {
     const int* leaf_species; // [S]   species (row of the alignment) observed at that leaf
 };
 
-// Per-position log tables: [0..3] = log pi, then for tree node id n >= 1: 16 doubles at
-// 4 + 16*(n-1), row-major [parent value a][own value b] = log P(b | a).
-PHY_HD const double* lt_of(const double* tb, int node) { return tb + 4 + 16 * (node - 1); }
+// Table accessor: entry e of this thread's position.  Entries: [0..3] = log pi (or pi), then for
+// tree node id n >= 1 sixteen entries at 4 + 16*(n-1), row-major [parent value a][own value b].
+// Device layout is [entry][position] (stride = W) so that the W threads of a window group read
+// W consecutive doubles; the host emulation uses stride 1.
+struct Tab {
+    const double* base;
+    int stride;
+    PHY_HD double operator()(int e) const { return base[(size_t)e * stride]; }
+};
+PHY_HD int tab_of(int node) { return 4 + 16 * (node - 1); }
 
-// Observation of species s in a packed column (include/phyfoo.h "packed columns"): 0..3, or 4 = gap.
-PHY_HD int column_obs(const uint32_t* bases, const uint32_t* gaps, int64_t plane_stride, int s, bool revcomp) {
-    uint32_t g = (gaps[(int64_t)(s >> 5) * plane_stride] >> (s & 31)) & 1u;
-    uint32_t b = (bases[(int64_t)(s >> 4) * plane_stride] >> (2 * (s & 15))) & 3u;
-    if (revcomp) b = 3u - b;  // UnobservableDNAAlphabet.java:88-95: complement, gap stays gap
-    return g ? 4 : (int)b;
-}
+// One packed column held in registers (include/phyfoo.h "packed columns", S <= 32): 2 bits per
+// species in b, 1 gap bit per species in g.
+struct ColWords {
+    uint64_t b;
+    uint32_t g;
+    // 0..3, or 4 = unobserved
+    PHY_HD int obs(int s) const { return ((g >> s) & 1u) ? 4 : (int)((b >> (2 * s)) & 3u); }
+};
+// jstacs UnobservableDNAAlphabet.java:88-95: complement = 3 - code, gap stays gap.  Gap species
+// store base bits 00, which complement to 11; obs() looks at the gap bit first, so that is harmless.
+PHY_HD ColWords complement(ColWords c) { c.b = ~c.b; return c; }
 
 // State accessors: q[i][a] and child-sum cs[i][a], strided so that consecutive threads touch
 // consecutive doubles (conflict-free shared memory / coalesced global memory).
@@ -65,59 +79,56 @@ struct State {
 
 // Optional sink for the converged q (M-step "prepare"): internal nodes then leaves.
 struct QSink {
-    double* q_internal;  // [I][4] or nullptr
-    double* q_leaf;      // [S][4] or nullptr (rows of observed leaves are left untouched)
+    double* q_internal;  // [I][4]
+    double* q_leaf;      // [S][4] (rows of observed leaves are left untouched), indexed by CSR leaf slot
+    int stride;
 };
 
-// One pass over the tree.  update == false: q stays as it is (pass 0 evaluates the free energy of the
-// uniform start and primes the child sums).  Returns this tree's free energy F = part1 - part2.
-PHY_HD double meanfield_pass(const TreeProg& tp, const double* tb, const State& st, const uint32_t* bases,
-                             const uint32_t* gaps, int64_t plane_stride, bool revcomp, bool update,
-                             const QSink* sink) {
+// One pass over the tree.  update == false: the exponents are forced to 0, i.e. q is (re)set to
+// uniform; this pass evaluates the free energy of the uniform start and primes the child sums.
+// Returns this tree's free energy F = part1 - part2.
+PHY_HD double meanfield_pass(const TreeProg& tp, const Tab& tb, const State& st, const ColWords& cw,
+                             bool update, const QSink* sink) {
     double F = 0.0;
-    const double* lpi = tb;
+    double lpi[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) lpi[a] = tb(a);
     for (int i = 0; i < tp.n_internal; ++i) {
         const int p = tp.par_internal[i];
-        const double* lt = (i == 0) ? nullptr : lt_of(tb, tp.node_of[i]);
-        double qi[4], lq[4];
-        if (update) {
-            double s[4];
-            if (i == 0) {
+        double lt[16];
+        double s[4], qp[4];
+        if (i == 0) {
 #pragma unroll
-                for (int a = 0; a < 4; ++a) s[a] = lpi[a] + st.cs(0, a);
-            } else {
-                double qp[4];
-#pragma unroll
-                for (int l = 0; l < 4; ++l) qp[l] = st.q(p, l);
-#pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    double acc = 0.0;
-#pragma unroll
-                    for (int l = 0; l < 4; ++l) acc += qp[l] * lt[l * 4 + a];  // own rows, MeanField :117-135
-                    s[a] = acc + st.cs(i, a);                                 // + children, :139-191
-                }
-            }
-            double e[4];
-#pragma unroll
-            for (int a = 0; a < 4; ++a) e[a] = exp(s[a]);                     // :192, no max shift
-            const double z = (e[0] + e[1]) + (e[2] + e[3]);
-            const double lz = log(z);
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                qi[a] = e[a] / z;                                             // :199-201
-                lq[a] = s[a] - lz;
-                st.q(i, a) = qi[a];
-            }
+            for (int a = 0; a < 4; ++a) s[a] = lpi[a] + st.cs(0, a);
         } else {
+            const int e0 = tab_of(tp.node_of[i]);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) lt[k] = tb(e0 + k);
+#pragma unroll
+            for (int l = 0; l < 4; ++l) qp[l] = st.q(p, l);
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
-                qi[a] = st.q(i, a);
-                lq[a] = (qi[a] > 0.0) ? log(qi[a]) : 0.0;
+                double acc = 0.0;
+#pragma unroll
+                for (int l = 0; l < 4; ++l) acc += qp[l] * lt[l * 4 + a];  // own rows, MeanField :117-135
+                s[a] = acc + st.cs(i, a);                                 // + children, :139-191
             }
+        }
+        double e[4], qi[4], lq[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) e[a] = exp(update ? s[a] : 0.0);      // :192, no max shift
+        const double z = ((e[0] + e[1]) + e[2]) + e[3];                   // :195-198
+        const double rz = 1.0 / z;
+        const double lz = log(z);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            qi[a] = e[a] * rz;                                            // :199-201
+            lq[a] = (update ? s[a] : 0.0) - lz;                           // = log q without a second log
+            st.q(i, a) = qi[a];
         }
         // entropy term, :250-267 (q == 0 rows are skipped there; here 0 * finite = 0)
 #pragma unroll
-        for (int a = 0; a < 4; ++a) F += (qi[a] > 0.0) ? qi[a] * lq[a] : 0.0;
+        for (int a = 0; a < 4; ++a) F += qi[a] * lq[a];
 
         // own expectation, :282-291 (root) / :327-358 (hidden non-root), and message to the parent
         if (i == 0) {
@@ -130,7 +141,7 @@ PHY_HD double meanfield_pass(const TreeProg& tp, const double* tb, const State& 
                 double m = 0.0;
 #pragma unroll
                 for (int h = 0; h < 4; ++h) m += qi[h] * lt[l * 4 + h];
-                cross += st.q(p, l) * m;
+                cross += qp[l] * m;
                 st.cs(p, l) += m;
             }
             F -= cross;
@@ -140,36 +151,30 @@ PHY_HD double meanfield_pass(const TreeProg& tp, const double* tb, const State& 
         double c[4] = {0.0, 0.0, 0.0, 0.0};   // observed leaves: sum_c log T_c(a, x_c)   (:147-148,181-182)
         double tsum = 0.0;                     // gap leaves: same value for every a
         for (int k = tp.leaf_begin[i]; k < tp.leaf_begin[i + 1]; ++k) {
-            const int sp = tp.leaf_species[k];
-            const int x = column_obs(bases, gaps, plane_stride, sp, revcomp);
+            const int x = cw.obs(tp.leaf_species[k]);
             if (x < 4) {
-                const double* ltc = lt_of(tb, tp.leaf_node[k]);
+                const int e0 = tab_of(tp.leaf_node[k]);
 #pragma unroll
-                for (int a = 0; a < 4; ++a) c[a] += ltc[a * 4 + x];
+                for (int a = 0; a < 4; ++a) c[a] += tb(e0 + a * 4 + x);
             } else {
                 // unobserved leaf: every table row is log pi ("independent" table); its own update only
                 // needs q of the parent, which is final for this sweep
-                const double qs = (qi[0] + qi[1]) + (qi[2] + qi[3]);
-                double ql[4], lql[4];
-                if (update) {
-                    double e[4];
+                const double qs = ((qi[0] + qi[1]) + qi[2]) + qi[3];
+                double el[4], ql[4], lql[4];
 #pragma unroll
-                    for (int a = 0; a < 4; ++a) e[a] = exp(qs * lpi[a]);
-                    const double z = (e[0] + e[1]) + (e[2] + e[3]);
-                    const double lz = log(z);
+                for (int a = 0; a < 4; ++a) el[a] = exp(update ? qs * lpi[a] : 0.0);
+                const double zl = ((el[0] + el[1]) + el[2]) + el[3];
+                const double rzl = 1.0 / zl;
+                const double lzl = log(zl);
 #pragma unroll
-                    for (int a = 0; a < 4; ++a) { ql[a] = e[a] / z; lql[a] = qs * lpi[a] - lz; }
-                } else {
+                for (int a = 0; a < 4; ++a) { ql[a] = el[a] * rzl; lql[a] = (update ? qs * lpi[a] : 0.0) - lzl; }
+                if (sink) {
 #pragma unroll
-                    for (int a = 0; a < 4; ++a) { ql[a] = 0.25; lql[a] = -1.3862943611198906; }
-                }
-                if (sink && sink->q_leaf) {
-#pragma unroll
-                    for (int a = 0; a < 4; ++a) sink->q_leaf[k * 4 + a] = ql[a];
+                    for (int a = 0; a < 4; ++a) sink->q_leaf[(size_t)(k * 4 + a) * sink->stride] = ql[a];
                 }
                 double t = 0.0, ent = 0.0;
 #pragma unroll
-                for (int a = 0; a < 4; ++a) { t += ql[a] * lpi[a]; ent += (ql[a] > 0.0) ? ql[a] * lql[a] : 0.0; }
+                for (int a = 0; a < 4; ++a) { t += ql[a] * lpi[a]; ent += ql[a] * lql[a]; }
                 F += ent - qs * t;             // entropy (:250-267) and hidden non-root term (:327-358)
                 tsum += t;
             }
@@ -181,64 +186,69 @@ PHY_HD double meanfield_pass(const TreeProg& tp, const double* tb, const State& 
             F -= d;
         }
 #pragma unroll
-        for (int a = 0; a < 4; ++a) c[a] += tsum;
+        for (int a = 0; a < 4; ++a) st.cs(i, a) = c[a] + tsum;
+        if (sink) {
 #pragma unroll
-        for (int a = 0; a < 4; ++a) st.cs(i, a) = c[a];
-        if (sink && sink->q_internal) {
-#pragma unroll
-            for (int a = 0; a < 4; ++a) sink->q_internal[i * 4 + a] = qi[a];
+            for (int a = 0; a < 4; ++a) sink->q_internal[(size_t)(i * 4 + a) * sink->stride] = qi[a];
         }
     }
     return F;
 }
 
-PHY_HD void meanfield_init(const TreeProg& tp, const State& st) {
-    for (int i = 0; i < tp.n_internal; ++i)
-#pragma unroll
-        for (int a = 0; a < 4; ++a) { st.q(i, a) = 0.25; st.cs(i, a) = 0.0; }
-}
+// Before pass 0 of a new window only the child sums need a defined value (q is overwritten by pass 0;
+// cs(i, .) is restarted when node i is visited, before any child adds to it), so nothing to do.
+// The state slots can hold anything finite-or-not: pass 0 never reads them into a result
+// (update == false selects 0.0 instead of s[a]); q(p, .) of the parent is rewritten by pass 0 before
+// the child reads it.
 
 // Free energy of one tree for FIXED q (M-step objective, optimizing/AbstractFreeEnergyOptimizer.java:95-114):
-// q_internal [I][4], q_leaf [S][4] (rows of gap leaves only), tables tb of the parameter set under test.
-PHY_HD double free_energy_fixed_q(const TreeProg& tp, const double* tb, const double* q_internal,
-                                  const double* q_leaf, const uint32_t* bases, const uint32_t* gaps,
-                                  int64_t plane_stride, bool revcomp) {
+// q_internal [I][4], q_leaf [S][4] (rows of gap leaves only; CSR leaf slot order), strided by qstride;
+// tables tb of the parameter set under test.
+PHY_HD double free_energy_fixed_q(const TreeProg& tp, const Tab& tb, const double* q_internal,
+                                  const double* q_leaf, int qstride, const ColWords& cw) {
     double F = 0.0;
-    const double* lpi = tb;
+    double lpi[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) lpi[a] = tb(a);
     for (int i = 0; i < tp.n_internal; ++i) {
-        const double* qi = q_internal + i * 4;
+        double qi[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) qi[a] = q_internal[(size_t)(i * 4 + a) * qstride];
 #pragma unroll
         for (int a = 0; a < 4; ++a) F += (qi[a] > 0.0) ? qi[a] * log(qi[a]) : 0.0;
         if (i == 0) {
 #pragma unroll
             for (int a = 0; a < 4; ++a) F -= qi[a] * lpi[a];
         } else {
-            const double* qp = q_internal + tp.par_internal[i] * 4;
-            const double* lt = lt_of(tb, tp.node_of[i]);
+            const int pi_ = tp.par_internal[i];
+            const int e0 = tab_of(tp.node_of[i]);
             double cross = 0.0;
 #pragma unroll
             for (int l = 0; l < 4; ++l) {
                 double m = 0.0;
 #pragma unroll
-                for (int h = 0; h < 4; ++h) m += qi[h] * lt[l * 4 + h];
-                cross += qp[l] * m;
+                for (int h = 0; h < 4; ++h) m += qi[h] * tb(e0 + l * 4 + h);
+                cross += q_internal[(size_t)(pi_ * 4 + l) * qstride] * m;
             }
             F -= cross;
         }
         for (int k = tp.leaf_begin[i]; k < tp.leaf_begin[i + 1]; ++k) {
-            const int x = column_obs(bases, gaps, plane_stride, tp.leaf_species[k], revcomp);
+            const int x = cw.obs(tp.leaf_species[k]);
             if (x < 4) {
-                const double* ltc = lt_of(tb, tp.leaf_node[k]);
+                const int e0 = tab_of(tp.leaf_node[k]);
                 double d = 0.0;
 #pragma unroll
-                for (int a = 0; a < 4; ++a) d += qi[a] * ltc[a * 4 + x];
+                for (int a = 0; a < 4; ++a) d += qi[a] * tb(e0 + a * 4 + x);
                 F -= d;
             } else {
-                const double* ql = q_leaf + k * 4;
                 double t = 0.0, ent = 0.0;
 #pragma unroll
-                for (int a = 0; a < 4; ++a) { t += ql[a] * lpi[a]; ent += (ql[a] > 0.0) ? ql[a] * log(ql[a]) : 0.0; }
-                F += ent - ((qi[0] + qi[1]) + (qi[2] + qi[3])) * t;
+                for (int a = 0; a < 4; ++a) {
+                    const double ql = q_leaf[(size_t)(k * 4 + a) * qstride];
+                    t += ql * lpi[a];
+                    ent += (ql > 0.0) ? ql * log(ql) : 0.0;
+                }
+                F += ent - (((qi[0] + qi[1]) + qi[2]) + qi[3]) * t;
             }
         }
     }
@@ -246,48 +256,45 @@ PHY_HD double free_energy_fixed_q(const TreeProg& tp, const double* tb, const do
 }
 
 // Felsenstein pruning: P(column) for one tree, gaps as missing data.  Tables here are the
-// PROBABILITIES (not logs): pt[0..3] = pi, node n >= 1 at 4 + 16*(n-1), [a][b] = P(b | a).
-// Scratch: st.q(i, a) holds the partial likelihood of internal node i.
-PHY_HD double pruning_likelihood(const TreeProg& tp, const double* pt, const State& st, const uint32_t* bases,
-                                 const uint32_t* gaps, int64_t plane_stride, bool revcomp) {
+// PROBABILITIES (not logs).  Scratch: st.cs(i, a) holds the running product of the messages of the
+// internal children of internal node i.
+PHY_HD double pruning_likelihood(const TreeProg& tp, const Tab& pt, const State& st, const ColWords& cw) {
+    for (int i = 0; i < tp.n_internal; ++i)
+#pragma unroll
+        for (int a = 0; a < 4; ++a) st.cs(i, a) = 1.0;
     for (int i = tp.n_internal - 1; i >= 0; --i) {
         double part[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) part[a] = 1.0;
-        for (int k = tp.leaf_begin[i]; k < tp.leaf_begin[i + 1]; ++k) {
-            const int x = column_obs(bases, gaps, plane_stride, tp.leaf_species[k], revcomp);
-            const double* t = lt_of(pt, tp.leaf_node[k]);
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-                part[a] *= (x < 4) ? t[a * 4 + x] : ((t[a * 4] + t[a * 4 + 1]) + (t[a * 4 + 2] + t[a * 4 + 3]));
-        }
         // internal children were processed earlier (they have larger pre-order indices) and left
-        // their message in cs(i, .) as a running product
+        // their messages in cs(i, .) as a running product
 #pragma unroll
-        for (int a = 0; a < 4; ++a) part[a] *= st.cs(i, a);
+        for (int a = 0; a < 4; ++a) part[a] = st.cs(i, a);
+        for (int k = tp.leaf_begin[i]; k < tp.leaf_begin[i + 1]; ++k) {
+            const int x = cw.obs(tp.leaf_species[k]);
+            const int e0 = tab_of(tp.leaf_node[k]);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const double v = (x < 4) ? pt(e0 + a * 4 + x)
+                                         : (((pt(e0 + a * 4) + pt(e0 + a * 4 + 1)) + pt(e0 + a * 4 + 2)) + pt(e0 + a * 4 + 3));
+                part[a] *= v;
+            }
+        }
         if (i == 0) {
             double p = 0.0;
 #pragma unroll
-            for (int a = 0; a < 4; ++a) p += pt[a] * part[a];
+            for (int a = 0; a < 4; ++a) p += pt(a) * part[a];
             return p;
         }
-        const double* t = lt_of(pt, tp.node_of[i]);
+        const int e0 = tab_of(tp.node_of[i]);
         const int p = tp.par_internal[i];
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
             double m = 0.0;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) m += t[a * 4 + b] * part[b];
+            for (int b = 0; b < 4; ++b) m += pt(e0 + a * 4 + b) * part[b];
             st.cs(p, a) *= m;
         }
     }
     return 0.0;
-}
-
-PHY_HD void pruning_init(const TreeProg& tp, const State& st) {
-    for (int i = 0; i < tp.n_internal; ++i)
-#pragma unroll
-        for (int a = 0; a < 4; ++a) st.cs(i, a) = 1.0;
 }
 
 }  // namespace phyfoo

@@ -1,0 +1,151 @@
+"""Alignments of orthologous promoters as a column tensor (host side) + the device-resident packed copy.
+
+Mirrors io/PhyloSample.java (reference): FASTA records annotated `>gene=<id>; species=<name>; ...;`
+(io/SampleUtil.java:58-66) are grouped by gene into one alignment each (:75-138), species rows are ordered
+by the leaf order of the Newick string (util/Util.java:39-53), columns that are gaps in every species are
+dropped (:196-223), and symbols are coded A,C,G,T,- -> 0..4 case-insensitively
+(jstacs UnobservableDNAAlphabet.java:116).  The reference iterates genes in Java HashSet order; here genes keep
+the order of their first record.
+"""
+import numpy as np
+
+from . import core
+from .newick import species_order
+
+_CODE = np.full(256, 255, np.uint8)
+for _i, _ch in enumerate("ACGT"):
+    _CODE[ord(_ch)] = _i
+    _CODE[ord(_ch.lower())] = _i
+_CODE[ord("-")] = 4
+
+
+class WrongAlphabetException(ValueError):
+    pass
+
+
+def encode(seq: str) -> np.ndarray:
+    raw = np.frombuffer(seq.encode("ascii"), np.uint8)
+    out = _CODE[raw]
+    if (out == 255).any():
+        bad = chr(int(raw[np.argmax(out == 255)]))
+        raise WrongAlphabetException(f"symbol {bad!r} is not in the alphabet {{A,C,G,T,-}}")
+    return out
+
+
+def parse_annotation(header: str) -> dict:
+    """SplitSequenceAnnotationParser("=", ";"): `key=value; key=value;`"""
+    out = {}
+    for part in header.lstrip(">").split(";"):
+        part = part.strip()
+        if "=" in part:
+            k, v = part.split("=", 1)
+            out[k.strip()] = v.strip()
+    return out
+
+
+def read_fasta(path):
+    records = []
+    header, chunks = None, []
+    with open(path) as fh:
+        for line in fh:
+            line = line.rstrip("\r\n")
+            if line.startswith(">"):
+                if header is not None:
+                    records.append((header, "".join(chunks)))
+                header, chunks = line, []
+            elif line:
+                chunks.append(line)
+    if header is not None:
+        records.append((header, "".join(chunks)))
+    return records
+
+
+class PhyloSample:
+    """A sample of multiple alignments: codes [sum L_i][S] (uint8, 0..4) + col_offsets [n+1]."""
+
+    def __init__(self, codes, col_offsets, species=None, genes=None, annotations=None):
+        self.codes = np.ascontiguousarray(codes, np.uint8)
+        self.col_offsets = np.ascontiguousarray(col_offsets, np.int64)
+        if self.codes.ndim != 2 or self.col_offsets[0] != 0 or self.col_offsets[-1] != self.codes.shape[0]:
+            raise ValueError("codes must be [columns][species] and col_offsets its alignment boundaries")
+        self.species = list(species) if species is not None else None
+        self.genes = list(genes) if genes is not None else None
+        self.annotations = annotations
+        self._device = {}
+
+    # ---- constructors -------------------------------------------------------------------------
+    @classmethod
+    def from_alignments(cls, alignments, **kw):
+        """alignments: list of [L_i][S] code arrays."""
+        lens = [a.shape[0] for a in alignments]
+        codes = np.concatenate(alignments, axis=0) if alignments else np.zeros((0, 1), np.uint8)
+        return cls(codes, np.concatenate([[0], np.cumsum(lens)]), **kw)
+
+    @classmethod
+    def from_fasta(cls, path, newick, species_ident="species", gene_ident="gene", limit=None):
+        order = species_order(newick)
+        index = {name: i for i, name in enumerate(order)}
+        groups, gene_order, annots = {}, [], {}
+        for header, seq in read_fasta(path):
+            ann = parse_annotation(header)
+            gene, sp = ann.get(gene_ident), ann.get(species_ident)
+            if gene is None or sp is None:
+                raise ValueError(f"record without {gene_ident}=/{species_ident}= annotation: {header}")
+            if gene not in groups:
+                groups[gene] = {}
+                gene_order.append(gene)
+                annots[gene] = ann
+            groups[gene][sp] = seq
+        seen = set(sp for g in groups.values() for sp in g)
+        for name in order:
+            if name not in seen:
+                raise IOError(f"A species-name ({name}) exisiting in the tree does not exist in the data-set.")
+        alignments, genes = [], []
+        for gene in gene_order[:limit]:
+            rows = groups[gene]
+            if any(name not in rows for name in order):
+                raise ValueError(f"gene {gene}: missing species")
+            mat = np.stack([encode(rows[name]) for name in order], axis=1)      # [L][S]
+            keep = (mat == 4).sum(axis=1) < mat.shape[1]                          # PhyloSample.java:196-223
+            alignments.append(np.ascontiguousarray(mat[keep]))
+            genes.append(gene)
+        return cls.from_alignments(alignments, species=order, genes=genes, annotations=[annots[g] for g in genes])
+
+    # ---- accessors ----------------------------------------------------------------------------
+    @property
+    def n_alignments(self):
+        return self.col_offsets.size - 1
+
+    def getNumberOfElements(self):
+        return self.n_alignments
+
+    @property
+    def n_species(self):
+        return self.codes.shape[1]
+
+    def lengths(self):
+        return np.diff(self.col_offsets)
+
+    def getElementAt(self, i):
+        return self.codes[self.col_offsets[i]:self.col_offsets[i + 1]]
+
+    def subset(self, idx):
+        idx = list(idx)
+        return PhyloSample.from_alignments([self.getElementAt(i) for i in idx], species=self.species,
+                                           genes=[self.genes[i] for i in idx] if self.genes else None)
+
+    def shard(self, rank, world):
+        """Contiguous block of alignments balanced by column count."""
+        total = int(self.col_offsets[-1])
+        bounds = [int(np.searchsorted(self.col_offsets, total * r / world, side="left")) for r in range(world + 1)]
+        bounds[0], bounds[-1] = 0, self.n_alignments
+        lo, hi = bounds[rank], bounds[rank + 1]
+        return self.subset(range(lo, hi)), (lo, hi)
+
+    def device(self, ctx=None):
+        """The packed, device-resident copy (created once per context)."""
+        ctx = ctx or core.default_context()
+        key = id(ctx)
+        if key not in self._device:
+            self._device[key] = core.Dataset(ctx, self.col_offsets, self.codes)
+        return self._device[key]

@@ -1,0 +1,228 @@
+"""Host-side mirror of the reference's model interface for the hot path, backed by libphyfoo.so.
+
+Same names and argument meaning as the Java classes; the difference is granularity: where the
+reference scores one window per call (`getLogProbFor(Sequence, start, end)`, ~10^7 calls per E-step),
+these classes score the whole sample in one library call and serve per-window queries from the result.
+
+  PhyloBayesModel            models/PhyloBayesModel.java        (motif; order 0 or 1)
+  PhyloBackground            models/PhyloBackground.java        (flanking / background; order k)
+  StrandModel                jstacs de/jstacs/models/mixture/StrandModel.java (forward + reverse complement)
+  SingleHiddenMotifMixture   jstacs de/jstacs/models/mixture/motif/SingleHiddenMotifMixture.java (ZOOPS E-step)
+"""
+import math
+
+import numpy as np
+
+from . import _abi, core
+from .data import PhyloSample
+from .newick import parse_newick
+
+
+class _PhyloModel:
+    """models/AbstractPhyloModel.java + PhyloPreparedAbstractModel.java: parameter access."""
+
+    kind = None
+    # static switches of the reference (models/PhyloBayesModel.java:43-69)
+    CALC_LOGLIKELIHOOD = False
+    EVOL_MODEL = _abi.EVOL_F81ALPHA   # evolution/EvolModel.java:7 MODEL_CLASS
+
+    def __init__(self, length, order, newick, ctx=None):
+        self.ctx = ctx or core.default_context()
+        self.length, self.order, self.newick = int(length), int(order), newick
+        self.tree = parse_newick(newick)
+        self.n_trees = self.length if self.kind == _abi.MODEL_FG else self.order + 1
+        # fillParameter(true): uniform start here; callers set parameters explicitly (the reference draws
+        # them from an unseeded RNG, util/Util.java:35,108-121)
+        self._pi = [np.full((self._ctx_rows(t), 4), 0.25) for t in range(self.n_trees)]
+        self._branch = np.tile(self.tree.branch, (self.n_trees, 1))
+        self._dev = None
+        self._mode = None
+
+    def _ctx_rows(self, t):
+        if self.kind == _abi.MODEL_FG:
+            return 4 if (self.order >= 1 and t > 0) else 1      # PhyloBayesModel.java:338-339
+        return 4 ** min(self.order, t)                           # PhyloBackground.java:386-394
+
+    def getLength(self):
+        return self.length
+
+    def getOrder(self):
+        return self.order
+
+    # ---- parameters (models/AbstractPhyloModel.java:131-134,160-163; util/MatrixLinearisation.java:89-110) ----
+    def getCondProb(self, i):
+        return self._pi[i].ravel().copy()
+
+    def getCondProbs(self):
+        return [self.getCondProb(i) for i in range(self.n_trees)]
+
+    def getLnCondProb(self, i):
+        return np.log(self.getCondProb(i))
+
+    def getLnCondProbs(self):
+        return [self.getLnCondProb(i) for i in range(self.n_trees)]
+
+    def setCondProb(self, condProb, position):
+        cp = np.asarray(condProb, np.float64).reshape(self._pi[position].shape)
+        self._pi[position] = cp.copy()
+        if self._dev is not None:
+            self._dev.set_pi(position, cp)
+
+    def setCondProbs(self, condProbs):
+        for i, cp in enumerate(condProbs):
+            self.setCondProb(cp, i)
+
+    def setLnCondProb(self, lam, position):
+        self.setCondProb(np.exp(np.asarray(lam, np.float64)), position)
+
+    def setLnCondProbs(self, lambdas):
+        for i, lam in enumerate(lambdas):
+            self.setLnCondProb(lam, i)
+
+    def reinitEdgelengths(self, *trees):
+        """models/AbstractPhyloModel.java:77-91: one Newick string for all positions, or one per position."""
+        if len(trees) not in (1, self.n_trees):
+            raise ValueError("The number of given trees must be equal to length of this model")
+        for t in range(self.n_trees):
+            tr = parse_newick(trees[0] if len(trees) == 1 else trees[t])
+            if tr.n_nodes != self.tree.n_nodes or (tr.parent != self.tree.parent).any():
+                raise ValueError("tree topology differs from the model's")
+            self._branch[t] = tr.branch
+            if self._dev is not None:
+                for k in range(1, tr.n_nodes):
+                    self._dev.set_branch(t, k, tr.branch[k])
+
+    def setBranchLength(self, position, node, length):
+        self._branch[position, node] = length
+        if self._dev is not None:
+            self._dev.set_branch(position, node, length)
+
+    # ---- device handle ------------------------------------------------------------------------
+    def mode(self):
+        return _abi.MODE_EXACT if type(self).CALC_LOGLIKELIHOOD or _PhyloModel.CALC_LOGLIKELIHOOD else _abi.MODE_MEANFIELD
+
+    def device_model(self):
+        if self._dev is None:
+            self._dev = core.DeviceModel(self.ctx, self.kind, self.length, self.order, self.tree, self._branch,
+                                         self._pi, evol=type(self).EVOL_MODEL, mode=self.mode())
+            self._mode = self.mode()
+        elif self._mode != self.mode():
+            self._dev.set_mode(self.mode())
+            self._mode = self.mode()
+        return self._dev
+
+    def _check(self, sample):
+        if sample.n_species != self.tree.n_species:
+            raise ValueError("The sample's number of species differs from the tree's number of leaves")
+
+
+class PhyloBayesModel(_PhyloModel):
+    """The phylogenetic motif model (phylogenetic PWM for order 0, phylogenetic Bayesian network for order 1)."""
+
+    kind = _abi.MODEL_FG
+
+    def __init__(self, motifLength, order, newickString, ctx=None):
+        if order not in (0, 1):
+            raise ValueError("motif order must be 0 or 1 (models/PhyloBayesModel.java:363)")
+        super().__init__(motifLength, order, newickString, ctx)
+        self.last_stats = None
+
+    def getMotifLength(self):
+        return self.length
+
+    def getLogProbFor(self, sample: PhyloSample, strand=0, want_sweeps=False):
+        """Scores of every window of every alignment (alignment-major, offsets ascending) =
+        PhyloBayesModel.getLogProbFor(seq, j, j+W-1) for all (seq, j)  (models/PhyloBayesModel.java:222-267)."""
+        self._check(sample)
+        out, sw, st = core.score_windows(self.ctx, sample.device(self.ctx), self.device_model(), strand, want_sweeps)
+        self.last_stats = st
+        return (out, sw) if want_sweeps else out
+
+
+class PhyloBackground(_PhyloModel):
+    """The phylogenetic background / flanking model (order-k Markov chain over trees)."""
+
+    kind = _abi.MODEL_BG
+
+    def __init__(self, order, newickString, ctx=None):
+        super().__init__(0, order, newickString, ctx)
+        self.last_stats = None
+
+    def getColumnLogProbs(self, sample: PhyloSample, want_sweeps=False):
+        """Per-column terms whose sum over [start, end] is getLogProbFor(seq, start, end)
+        (models/PhyloBackground.java:241-305; order 0: independent columns)."""
+        self._check(sample)
+        out, sw, st = core.bg_columns(self.ctx, sample.device(self.ctx), self.device_model(), want_sweeps)
+        self.last_stats = st
+        return (out, sw) if want_sweeps else out
+
+    def getLogProbFor(self, sample: PhyloSample):
+        """double[] getLogProbFor(Sample) (jstacs AbstractModel.java:217-240): one value per alignment."""
+        cols = self.getColumnLogProbs(sample)
+        off = sample.col_offsets
+        return np.array([cols[off[i]:off[i + 1]].sum() for i in range(sample.n_alignments)])
+
+
+class StrandModel:
+    """jstacs StrandModel: mixture of a motif model and its reverse complement; weights {forward, backward}."""
+
+    def __init__(self, model: PhyloBayesModel, forwardProb=0.5):
+        self.model = model
+        self.weights = np.array([forwardProb, 1.0 - forwardProb])
+
+    def getLength(self):
+        return self.model.getLength()
+
+    def logWeights(self):
+        return np.log(self.weights)
+
+
+class SingleHiddenMotifMixture:
+    """ZOOPS mixture of one motif model and a flanking model with a uniform position prior."""
+
+    def __init__(self, motif, flanking: PhyloBackground, zoops=None, componentHyperParams=(1.0, 1.0)):
+        self.strand = motif if isinstance(motif, StrandModel) else None
+        self.motif = motif.model if self.strand else motif
+        self.flanking = flanking
+        if zoops is not None and 0 < zoops <= 1:
+            # estimateComponentProbs = false (jstacs SingleHiddenMotifMixture.java:310-329, models/ModelUtil.java:110-121)
+            self.weights = np.array([zoops, 1.0 - zoops])
+            self.estimateComponentProbs = False
+        else:
+            self.weights = np.array([0.5, 0.5])
+            self.estimateComponentProbs = True
+        self.hyper = np.asarray(componentHyperParams, np.float64)
+        self.last = None
+
+    def getNumberOfMotifs(self):
+        return 1   # jstacs SingleHiddenMotifMixture.java:716-718
+
+    def getNewWeights(self, sample: PhyloSample, seqWeights=None, want_gamma=True, want_profile=False):
+        """One E-step (jstacs SingleHiddenMotifMixture.java:499-566).  Returns a dict with
+        gamma (seqweights[0] per window), w (sufficient statistics of the component weights), ll, argmax_off/strand."""
+        with np.errstate(divide="ignore"):
+            logw = np.log(self.weights)
+        res = core.zoops_estep(self.motif.ctx, sample.device(self.motif.ctx), self.motif.device_model(),
+                               self.flanking.device_model(), logw,
+                               None if self.strand is None else self.strand.logWeights(),
+                               seqWeights, want_gamma, want_profile, True)
+        self.last = res
+        return res
+
+    def setComponentWeights(self, w):
+        """AbstractMixtureModel.getNewComponentProbs (jstacs :1542-1578): (w + hyper) normalised."""
+        if self.estimateComponentProbs:
+            v = np.asarray(w, np.float64) + self.hyper
+            self.weights = v / v.sum()
+
+    def getLogProbFor(self, sample: PhyloSample):
+        """log-likelihood of the sample under the current parameters (sum over alignments)."""
+        return self.getNewWeights(sample, want_gamma=False)["ll"]
+
+    def getProfileOfScoresFor(self, sample: PhyloSample):
+        """Unnormalised conditional profile a_j of every alignment (jstacs :643-688)."""
+        return self.getNewWeights(sample, want_gamma=False, want_profile=True)["profile"]
+
+    def getStrandProbabilitiesFor(self, sample: PhyloSample):
+        res = self.getNewWeights(sample, want_gamma=False)
+        return res["argmax_off"], res["argmax_strand"]

@@ -17,37 +17,40 @@ static TreeProg prog_of(const ModelHost& m) {
     return tp;
 }
 
+static ColWords words_of(const uint8_t* col, int S, bool rc) {
+    ColWords cw; cw.b = 0; cw.g = 0;
+    for (int s = 0; s < S; ++s) {
+        if (col[s] >= 4) cw.g |= 1u << s;
+        else cw.b |= (uint64_t)col[s] << (2 * s);
+    }
+    return rc ? complement(cw) : cw;
+}
+
 extern "C" int emul_score_windows(const phyfoo_model_desc* d, const uint8_t* codes, int L, int strand,
                                   double* out, int* sweeps) {
     try {
         ModelHost m; m.init(*d);
-        const int S = m.S, W = m.W, nb = (S + 15) / 16, ng = (S + 31) / 32;
-        std::vector<uint32_t> bases((size_t)nb * L, 0), gaps((size_t)ng * L, 0);
-        for (int c = 0; c < L; ++c)
-            for (int s = 0; s < S; ++s) {
-                uint8_t v = codes[(size_t)c * S + s];
-                if (v >= 4) gaps[(size_t)(s / 32) * L + c] |= 1u << (s % 32);
-                else bases[(size_t)(s / 16) * L + c] |= (uint32_t)v << (2 * (s % 16));
-            }
+        const int S = m.S, W = m.W;
         TreeProg tp = prog_of(m);
-        std::vector<double> state((size_t)W * m.I * 8);
+        std::vector<double> state((size_t)W * m.I * 8, 1e300);   // poisoned: pass 0 must not depend on it
         for (int j = 0; j + W <= L; ++j) {
-            std::vector<double> F(W);
             auto pass = [&](bool update) {
                 double sum = 0;
                 for (int t = 0; t < W; ++t) {
                     State st{state.data() + (size_t)t * m.I * 8, 1};
                     int col = strand ? j + W - 1 - t : j + t;
+                    ColWords cw = words_of(codes + (size_t)col * S, S, strand != 0);
                     if (m.mode == PHYFOO_MODE_EXACT) {
-                        pruning_init(tp, st);
-                        sum += std::log(pruning_likelihood(tp, &m.probtab[(size_t)t * m.tbl_stride], st, &bases[col], &gaps[col], L, strand != 0));
-                    } else
-                        sum += meanfield_pass(tp, &m.logtab[(size_t)t * m.tbl_stride], st, &bases[col], &gaps[col], L, strand != 0, update, nullptr);
+                        Tab pt{&m.probtab[(size_t)t * m.E], 1};
+                        sum += -std::log(pruning_likelihood(tp, pt, st, cw));
+                    } else {
+                        Tab lt{&m.logtab[(size_t)t * m.E], 1};
+                        sum += meanfield_pass(tp, lt, st, cw, update, nullptr);
+                    }
                 }
                 return sum;
             };
-            if (m.mode == PHYFOO_MODE_EXACT) { out[j] = pass(false); if (sweeps) sweeps[j] = 0; continue; }
-            for (int t = 0; t < W; ++t) { State st{state.data() + (size_t)t * m.I * 8, 1}; meanfield_init(tp, st); }
+            if (m.mode == PHYFOO_MODE_EXACT) { out[j] = -pass(false); if (sweeps) sweeps[j] = 0; continue; }
             double old = pass(false), cur = old;
             int k = 0; bool conv = false;
             while ((k < m.max_sweeps && !conv) || k < m.min_sweeps) {

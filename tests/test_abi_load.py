@@ -1,0 +1,56 @@
+"""The C-ABI library loads, exports every symbol include/phyfoo.h declares, and fails loudly without a GPU."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from util import ROOT
+
+from phyfoo_b200 import _abi
+from phyfoo_b200 import lib as plib
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "phyfoo.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(phyfoo_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_exports_every_declared_symbol():
+    plib.build()
+    L = plib.lib()
+    syms = header_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(L, s), f"libphyfoo.so does not export {s}"
+    assert sorted(plib.SYMBOLS) == syms
+
+
+def test_struct_layouts_match_header():
+    # phyfoo_model_desc: 4 int32, 2 pointers, int32 (+pad), double, 2 pointers, 4 int32, double
+    assert C.sizeof(_abi.ModelDesc) == 16 + 16 + 8 + 8 + 16 + 16 + 8
+    assert C.sizeof(_abi.Stats) == 4 * 8 + 4 + 4
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = C.c_void_p()
+    rc = plib.lib().phyfoo_init(0, C.byref(h))
+    assert rc == _abi.ENODEVICE
+    assert b"no CPU fallback" in plib.lib().phyfoo_last_error(None)
+    from phyfoo_b200 import core
+    with pytest.raises(plib.PhyfooError):
+        core.Context(0)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "phyfoo_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("test infrastructure", "").lower() or f in (), \
+                    f"{f} mentions the oracle: the product path must not depend on it"

@@ -1,0 +1,84 @@
+"""The kernels' per-thread arithmetic (phyfoo_b200/csrc/tree_pass.cuh, __host__ __device__) compiled for the
+host and checked against the oracle: scores within 1e-9 relative, mean-field sweep counts identical.
+This is the CPU-side guard for the GPU parity tests (tests/test_gpu_parity.py does the same through the C ABI)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from util import ROOT, orc, oracle_fg, random_codes, rel_err
+
+from phyfoo_b200 import _abi, synth
+from phyfoo_b200.newick import parse_newick
+
+EMUL_DIR = os.path.join(ROOT, "tests", "emul")
+
+
+@pytest.fixture(scope="module")
+def emul():
+    so = os.path.join(EMUL_DIR, "libemul.so")
+    srcs = [os.path.join(EMUL_DIR, "emul.cpp"), os.path.join(ROOT, "phyfoo_b200", "csrc", "tree_pass.cuh"),
+            os.path.join(ROOT, "phyfoo_b200", "csrc", "model_host.hpp")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", srcs[0], "-o", so])
+    L = C.CDLL(so)
+    L.emul_score_windows.argtypes = [C.POINTER(_abi.ModelDesc), C.POINTER(C.c_uint8), C.c_int, C.c_int,
+                                     C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    return L
+
+
+def run_emul(L, newick, pwm, codes, strand, mode, evol=_abi.EVOL_F81ALPHA):
+    tree = parse_newick(newick)
+    W = len(pwm)
+    desc, keep = _abi.make_desc(_abi.MODEL_FG, W, 0, tree, np.tile(tree.branch, (W, 1)), pwm, evol, mode)
+    n = codes.shape[0] - W + 1
+    out = np.zeros(n)
+    sw = np.zeros(n, np.int32)
+    rc = L.emul_score_windows(C.byref(desc), codes.ctypes.data_as(C.POINTER(C.c_uint8)), codes.shape[0], strand,
+                              out.ctypes.data_as(C.POINTER(C.c_double)), sw.ctypes.data_as(C.POINTER(C.c_int)))
+    assert rc == 0
+    return out, sw
+
+
+TREES = [synth.star_newick(5), synth.caterpillar_newick(5), synth.random_binary_newick(12, 3),
+         "((A:0.1,B:0.3):0.15,(C:0.2,(D:0.05,E:0.4):0.25):0.1,F:0.3)"]
+
+
+@pytest.mark.parametrize("newick", TREES)
+@pytest.mark.parametrize("gap_rate", [0.0, 0.1])
+@pytest.mark.parametrize("strand", [0, 1])
+def test_meanfield_pass_matches_oracle(emul, newick, gap_rate, strand):
+    rng = np.random.default_rng(11)
+    S = parse_newick(newick).n_species
+    W = 6
+    pwm = synth.random_pwm(W, 0, 29)
+    codes = random_codes(rng, 40, S, gap_rate)
+    got, sw = run_emul(emul, newick, pwm, codes, strand, _abi.MODE_MEANFIELD)
+    ref, rsw = oracle_fg(newick, pwm).score_windows(codes, bool(strand))
+    assert np.array_equal(sw, rsw)
+    assert rel_err(got, ref) < 1e-9
+
+
+@pytest.mark.parametrize("newick", TREES)
+def test_pruning_matches_oracle(emul, newick):
+    rng = np.random.default_rng(12)
+    S = parse_newick(newick).n_species
+    W = 5
+    pwm = synth.random_pwm(W, 0, 31)
+    codes = random_codes(rng, 30, S, 0.15)
+    got, _ = run_emul(emul, newick, pwm, codes, 0, _abi.MODE_EXACT)
+    ref, _ = oracle_fg(newick, pwm, mode=orc.EXACT_PRUNING).score_windows(codes)
+    assert rel_err(got, ref) < 1e-12
+
+
+def test_f81beta_tables(emul):
+    rng = np.random.default_rng(13)
+    newick = synth.caterpillar_newick(5, 0.3)
+    pwm = synth.random_pwm(4, 0, 37)
+    codes = random_codes(rng, 20, 5)
+    got, sw = run_emul(emul, newick, pwm, codes, 0, _abi.MODE_MEANFIELD, _abi.EVOL_F81BETA)
+    ref, rsw = oracle_fg(newick, pwm, evol=orc.F81BETA).score_windows(codes)
+    assert np.array_equal(sw, rsw)
+    assert rel_err(got, ref) < 1e-9

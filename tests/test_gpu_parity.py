@@ -1,0 +1,214 @@
+"""GPU parity: libphyfoo.so (through its C ABI, via the host-side mirror classes) against the CPU oracle on the
+same seeded inputs.  Bar: scores/gradients within 1e-9 relative (fp64), mean-field sweep counts, packed column
+words and arg-max site calls bit-exact."""
+import numpy as np
+import pytest
+
+from util import orc, oracle_bg, oracle_fg, random_codes, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from phyfoo_b200 import core
+    return core.default_context()
+
+
+def _sample(rng, lens, S, gap_rate):
+    from phyfoo_b200.data import PhyloSample
+    codes = random_codes(rng, int(sum(lens)), S, gap_rate)
+    return PhyloSample(codes, np.concatenate([[0], np.cumsum(lens)]))
+
+
+def _trees():
+    from phyfoo_b200 import synth
+    return {"star5": synth.star_newick(5), "cat5": synth.caterpillar_newick(5),
+            "rand12": synth.random_binary_newick(12, 3),
+            "mixed6": "((A:0.1,B:0.3):0.15,(C:0.2,(D:0.05,E:0.4):0.25):0.1,F:0.3)",
+            "rand30": synth.random_binary_newick(30, 5), "star20": synth.star_newick(20, 0.3)}
+
+
+def _S(newick):
+    from phyfoo_b200.newick import parse_newick
+    return parse_newick(newick).n_species
+
+
+def test_pack_columns_bit_exact(ctx):
+    rng = np.random.default_rng(0)
+    for S in (1, 5, 12, 16, 17, 30, 32):
+        smp = _sample(rng, [7, 1, 33, 100], S, 0.2)
+        bases, gaps = smp.device(ctx).packed()
+        rb, rg = orc.pack_columns(smp.codes)
+        assert np.array_equal(bases, rb) and np.array_equal(gaps, rg)
+    from phyfoo_b200.lib import IllegalArgumentException
+    from phyfoo_b200.data import PhyloSample
+    bad = PhyloSample(np.full((4, 3), 7, np.uint8), [0, 4])
+    with pytest.raises(IllegalArgumentException):
+        bad.device(ctx)
+
+
+@pytest.mark.parametrize("tree", ["star5", "cat5", "rand12", "mixed6", "rand30", "star20"])
+@pytest.mark.parametrize("gap_rate", [0.0, 0.1])
+def test_meanfield_window_scores(ctx, tree, gap_rate):
+    from phyfoo_b200 import synth
+    from phyfoo_b200.models import PhyloBayesModel
+    newick = _trees()[tree]
+    S = _S(newick)
+    rng = np.random.default_rng(21)
+    W = 7
+    pwm = synth.random_pwm(W, 0, 41)
+    smp = _sample(rng, [30, 7, 64, 19, 8], S, gap_rate)
+    m = PhyloBayesModel(W, 0, newick, ctx)
+    m.setCondProbs(pwm)
+    om = oracle_fg(newick, pwm)
+    for strand in (0, 1):
+        got, sw = m.getLogProbFor(smp, strand, want_sweeps=True)
+        ref = np.concatenate([om.score_windows(smp.getElementAt(i), bool(strand))[0] for i in range(smp.n_alignments)])
+        rsw = np.concatenate([om.score_windows(smp.getElementAt(i), bool(strand))[1] for i in range(smp.n_alignments)])
+        assert got.shape == ref.shape
+        assert np.array_equal(sw, rsw), "mean-field sweep counts differ"
+        assert rel_err(got, ref) < TOL
+        assert m.last_stats["sweeps_fg"] == int(rsw.sum())
+
+
+@pytest.mark.parametrize("tree", ["star5", "cat5", "rand12", "rand30"])
+def test_exact_window_scores(ctx, tree):
+    from phyfoo_b200 import synth, _abi
+    from phyfoo_b200.models import PhyloBayesModel
+    newick = _trees()[tree]
+    S = _S(newick)
+    rng = np.random.default_rng(22)
+    W = 5
+    pwm = synth.random_pwm(W, 0, 43)
+    smp = _sample(rng, [40, 5, 23], S, 0.1)
+    m = PhyloBayesModel(W, 0, newick, ctx)
+    m.setCondProbs(pwm)
+    m.device_model().set_mode(_abi.MODE_EXACT)
+    m._mode = _abi.MODE_EXACT
+    got = core_score(ctx, smp, m)
+    om = oracle_fg(newick, pwm, mode=orc.EXACT_PRUNING)
+    ref = np.concatenate([om.score_windows(smp.getElementAt(i))[0] for i in range(smp.n_alignments)])
+    assert rel_err(got, ref) < 1e-12
+
+
+def core_score(ctx, smp, m, strand=0):
+    from phyfoo_b200 import core
+    return core.score_windows(ctx, smp.device(ctx), m._dev, strand)[0]
+
+
+@pytest.mark.parametrize("tree", ["star5", "cat5", "rand12"])
+def test_background_columns(ctx, tree):
+    from phyfoo_b200.models import PhyloBackground
+    newick = _trees()[tree]
+    S = _S(newick)
+    rng = np.random.default_rng(23)
+    smp = _sample(rng, [50, 3, 17], S, 0.1)
+    bg = PhyloBackground(0, newick, ctx)
+    pi = np.array([[0.1, 0.4, 0.3, 0.2]])
+    bg.setCondProb(pi, 0)
+    got, sw = bg.getColumnLogProbs(smp, want_sweeps=True)
+    ob = oracle_bg(newick, 0, [pi])
+    ref = ob.bg_columns(smp.codes)
+    assert rel_err(got, ref) < TOL
+    per = bg.getLogProbFor(smp)
+    for i in range(smp.n_alignments):
+        L = smp.lengths()[i]
+        r = ob.bg_range(smp.getElementAt(i), 0, L - 1)
+        assert abs(per[i] - r) <= TOL * abs(r)
+
+
+@pytest.mark.parametrize("tree,strand", [("cat5", False), ("cat5", True), ("star5", True), ("rand12", False)])
+def test_zoops_estep(ctx, tree, strand):
+    from phyfoo_b200 import synth
+    from phyfoo_b200.models import PhyloBackground, PhyloBayesModel, SingleHiddenMotifMixture, StrandModel
+    newick = _trees()[tree]
+    S = _S(newick)
+    W = 6
+    pwm = synth.random_pwm(W, 0, 47)
+    smp, planted = synth.make_sample(newick, 12, 60, 99, pwm=pwm, gap_rate=0.05, length_jitter=10)
+    fg = PhyloBayesModel(W, 0, newick, ctx); fg.setCondProbs(pwm)
+    bg = PhyloBackground(0, newick, ctx)
+    motif = StrandModel(fg, 0.6) if strand else fg
+    shm = SingleHiddenMotifMixture(motif, bg, zoops=0.8)
+    wts = np.random.default_rng(5).random(smp.n_alignments) + 0.5
+    res = shm.getNewWeights(smp, seqWeights=wts, want_profile=True)
+    ofg, obg = oracle_fg(newick, pwm), oracle_bg(newick, 0)
+    ref = orc.estep(ofg, obg, smp.col_offsets, smp.codes, np.log([0.8, 0.2]),
+                    np.log([0.6, 0.4]) if strand else None, wts)
+    assert np.array_equal(res["argmax_off"], ref["argmax_off"]), "arg-max site calls must be bit-exact"
+    assert np.array_equal(res["argmax_strand"], ref["argmax_strand"])
+    assert rel_err(res["profile"], ref["profile"]) < TOL
+    assert np.max(np.abs(res["gamma"] - ref["gamma"])) < TOL
+    assert abs(res["ll"] - ref["ll"]) <= TOL * abs(ref["ll"])
+    assert np.max(np.abs(res["w"] - ref["w"])) <= TOL * np.max(np.abs(ref["w"]))
+    assert res["stats"]["sweeps_fg"] + res["stats"]["sweeps_bg"] == ref["sweeps"]
+    # size-independent properties: sum of gamma per alignment = p_motif * weight; w0 + w1 = sum of weights
+    assert abs(res["gamma"].sum() - res["w"][0]) < 1e-9
+    assert abs(res["w"].sum() - wts.sum()) < 1e-9
+    # planted sites are found by the arg-max for most alignments
+    hit = (res["argmax_off"] == planted).mean()
+    assert hit >= 0.5
+
+
+def test_ragged_and_error_behaviour(ctx):
+    from phyfoo_b200 import synth
+    from phyfoo_b200.lib import IllegalArgumentException
+    from phyfoo_b200.data import PhyloSample
+    from phyfoo_b200.models import PhyloBackground, PhyloBayesModel, SingleHiddenMotifMixture
+    newick = synth.caterpillar_newick(5)
+    rng = np.random.default_rng(3)
+    W = 8
+    fg = PhyloBayesModel(W, 0, newick, ctx); fg.setCondProbs(synth.random_pwm(W, 0, 1))
+    # alignments shorter than the motif contribute no windows to the score list
+    smp = _sample(rng, [3, 8, 20, 7], 5, 0.0)
+    got = fg.getLogProbFor(smp)
+    assert got.shape[0] == 1 + 13
+    om = oracle_fg(newick, fg.getCondProbs()[:W] and [p.reshape(1, 4) for p in fg.getCondProbs()])
+    ref = np.concatenate([om.score_windows(smp.getElementAt(i))[0] for i in (1, 2)])
+    assert rel_err(got, ref) < TOL
+    # ... but the ZOOPS E-step refuses them, like the reference's position prior does
+    shm = SingleHiddenMotifMixture(fg, PhyloBackground(0, newick, ctx), zoops=1.0)
+    with pytest.raises(IllegalArgumentException):
+        shm.getNewWeights(smp)
+    # species mismatch
+    with pytest.raises(ValueError):
+        fg.getLogProbFor(_sample(rng, [10], 4, 0.0))
+    # empty sample: no windows, no error
+    empty = PhyloSample(np.zeros((0, 5), np.uint8), [0])
+    assert fg.getLogProbFor(empty).shape == (0,)
+
+
+def test_full_size_properties(ctx):
+    """BASELINE config 2 at full size (2000 x 5 x 500, W=12): properties that need no oracle."""
+    from phyfoo_b200 import synth
+    from phyfoo_b200.models import PhyloBackground, PhyloBayesModel, SingleHiddenMotifMixture
+    cfg, newick, pwm, smp, planted = synth.make_config("c2")
+    fg = PhyloBayesModel(cfg["W"], 0, newick, ctx); fg.setCondProbs(pwm)
+    bg = PhyloBackground(0, newick, ctx)
+    shm = SingleHiddenMotifMixture(fg, bg, zoops=1.0)
+    res = shm.getNewWeights(smp)
+    assert np.isfinite(res["ll"])
+    per_aln = np.add.reduceat(res["gamma"], smp.device(ctx).window_offsets(cfg["W"])[:-1])
+    assert np.max(np.abs(per_aln - 1.0)) < 1e-9                 # ZOOPS = 1: posterior over offsets sums to 1
+    assert abs(res["w"][0] - cfg["n_aln"]) < 1e-6 and abs(res["w"][1]) < 1e-9
+    assert (res["argmax_off"] == planted).mean() > 0.8
+    # idempotence / determinism: the same call returns the same bits
+    res2 = shm.getNewWeights(smp)
+    assert res2["ll"] == res["ll"] and np.array_equal(res2["gamma"], res["gamma"])
+    # mean field is a lower bound of the exact log-likelihood, window by window
+    mf = fg.getLogProbFor(smp)
+    PhyloBayesModel.CALC_LOGLIKELIHOOD = True
+    try:
+        ex = fg.getLogProbFor(smp)
+    finally:
+        PhyloBayesModel.CALC_LOGLIKELIHOOD = False
+    assert (mf <= ex + 1e-9).all()
+    # the first alignments against the oracle
+    om = oracle_fg(newick, pwm)
+    for i in range(3):
+        ref, _ = om.score_windows(smp.getElementAt(i))
+        o = smp.device(ctx).window_offsets(cfg["W"])
+        assert rel_err(mf[o[i]:o[i + 1]], ref) < TOL
