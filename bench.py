@@ -228,7 +228,9 @@ def run_ours(args):
 
     partial = torch.zeros(3, dtype=torch.float64, device="cuda")
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
-    stream = torch.cuda.current_stream()
+    # a non-default torch stream: handle 0 would mean "the library's own stream" to the C ABI
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
 
     def step():
         core.zoops_estep_device(ctx, ds, fg.device_model(), bg.device_model(), logw, None, None, partial.data_ptr(),

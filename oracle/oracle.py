@@ -210,14 +210,15 @@ def estep(fg, bg, col_offsets, codes, logw, strand_logw=None, aln_weights=None, 
     ll = C.c_double(0)
     arg_off = np.zeros(n_aln, np.int32)
     arg_strand = np.zeros(n_aln, np.uint8)
-    sweeps = C.c_longlong(0)
+    sweeps = (C.c_longlong * 2)(0, 0)
     rc = lib().orc_estep(fg.h, bg.h, n_aln, col_offsets.ctypes.data_as(C.POINTER(C.c_int64)), _u8(codes),
                          _dp(logw), _dp(sl), _dp(aw), int(faithful_cost), int(threads), _dp(res["gamma"]),
                          _dp(res["fwd"]), _dp(res["rev"]), _dp(res["profile"]), _dp(w), C.byref(ll),
-                         arg_off.ctypes.data_as(C.POINTER(C.c_int32)), _u8(arg_strand), C.byref(sweeps))
+                         arg_off.ctypes.data_as(C.POINTER(C.c_int32)), _u8(arg_strand), sweeps)
     if rc != 0:
         raise RuntimeError(_err())
-    res.update(w=w, ll=ll.value, argmax_off=arg_off, argmax_strand=arg_strand, sweeps=sweeps.value)
+    res.update(w=w, ll=ll.value, argmax_off=arg_off, argmax_strand=arg_strand, sweeps=sweeps[0] + sweeps[1],
+               sweeps_fg=sweeps[0], sweeps_bg=sweeps[1])
     return res
 
 

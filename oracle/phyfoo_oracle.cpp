@@ -880,7 +880,7 @@ int orc_estep(void* hfg, void* hbg, int n_aln, const int64_t* col_offsets, const
     for (int i = 0; i < n_aln; ++i) woff[i + 1] = woff[i] + std::max<int64_t>(0, (col_offsets[i + 1] - col_offsets[i]) - W + 1);
     std::vector<EStepOut> per(n_aln);
     std::string err;
-    long long sweeps = 0;
+    long long sweeps = 0, sweeps_bg = 0;
     if (threads < 1) threads = 1;
     std::atomic<int> next{0};
     std::mutex mu;
@@ -906,7 +906,8 @@ int orc_estep(void* hfg, void* hbg, int n_aln, const int64_t* col_offsets, const
             }
         }
         std::lock_guard<std::mutex> lk(mu);
-        sweeps += fg.sweeps_total + bg.sweeps_total;
+        sweeps += fg.sweeps_total;
+        sweeps_bg += bg.sweeps_total;
     };
     if (threads == 1) worker();
     else {
@@ -920,7 +921,9 @@ int orc_estep(void* hfg, void* hbg, int n_aln, const int64_t* col_offsets, const
     for (int i = 0; i < n_aln; ++i) { ll += per[i].ll; w0 += per[i].w0; w1 += per[i].w1; }
     if (ll_out) *ll_out = ll;
     if (w_out) { w_out[0] = w0; w_out[1] = w1; }
-    if (sweeps_out) *sweeps_out = sweeps;
+    // [0] motif sweeps, [1] background sweeps.  NB the Java optimises the first window of every background range
+    // twice (PhyloBackground.java:271-273 and :284-287), so a range of one order-0 column costs two optimisations.
+    if (sweeps_out) { sweeps_out[0] = sweeps; sweeps_out[1] = sweeps_bg; }
     return 0;
     ORC_CATCH(-1)
 }
