@@ -220,3 +220,76 @@ def zoops_estep_device(ctx, ds, fg, bg, logw, strand_logw, aln_weights_ptr, part
                                               C.c_void_p(aln_weights_ptr) if aln_weights_ptr else None,
                                               C.c_void_p(partial_ptr), C.c_void_p(stream_ptr) if stream_ptr else None),
               ctx.h)
+
+
+def select(ctx, ds, width, weights=None, t=0.8, q=0.0):
+    """io/SequenceSpecificDataSelector.java:37-99 over all alignments.  weights = None: the gamma of the most
+    recent zoops_estep on this context (still resident on the device).  Returns (aln, off, weight)."""
+    w = None if weights is None else np.ascontiguousarray(weights, np.float64)
+    n = C.c_int64(0)
+    cap = max(4 * ds.n_aln, 1024)
+    while True:
+        sa, so, sw = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap)
+        rc = lib().phyfoo_select(ctx.h, ds.h, int(width), _p(w, C.c_double), float(t), float(q), _p(sa, C.c_int32),
+                                 _p(so, C.c_int32), _p(sw, C.c_double), cap, C.byref(n))
+        if rc == _abi.ENOMEM and n.value > cap:
+            cap = int(n.value)
+            continue
+        raise_for(rc, ctx.h)
+        return sa[:n.value].copy(), so[:n.value].copy(), sw[:n.value].copy()
+
+
+class FESet:
+    """phyfoo_feset: the fixed-q free-energy objective of the M-step over a list of windows
+    (optimizing/AbstractFreeEnergyOptimizer.java:95-114); q lives on the device."""
+
+    def __init__(self, ctx, ds, model, sel_aln=None, sel_off=None, sel_weight=None, sel_strand=None, aln_weights=None):
+        self.ctx, self.ds, self.model = ctx, ds, model
+        self.h = C.c_void_p()
+        if sel_aln is None:
+            aw = None if aln_weights is None else np.ascontiguousarray(aln_weights, np.float64)
+            rc = lib().phyfoo_fe_prepare_all(ctx.h, ds.h, model.h, _p(aw, C.c_double), C.byref(self.h))
+        else:
+            sa = np.ascontiguousarray(sel_aln, np.int32)
+            so = np.ascontiguousarray(sel_off, np.int32)
+            sw = np.ascontiguousarray(sel_weight, np.float64)
+            ss = None if sel_strand is None else np.ascontiguousarray(sel_strand, np.uint8)
+            rc = lib().phyfoo_fe_prepare(ctx.h, ds.h, model.h, sa.size, _p(sa, C.c_int32), _p(so, C.c_int32),
+                                         _p(ss, C.c_uint8), _p(sw, C.c_double), C.byref(self.h))
+        raise_for(rc, ctx.h)
+
+    def free(self):
+        if self.h:
+            lib().phyfoo_fe_free(self.ctx.h, self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return int(lib().phyfoo_fe_size(self.h))
+
+    def eval(self, position, lam):
+        """evaluateFunction(lambda): f = -sum_u w_u F(q_u; theta(lambda)); the model is left at lambda."""
+        lam = np.ascontiguousarray(lam, np.float64)
+        f = C.c_double()
+        raise_for(lib().phyfoo_fe_eval(self.ctx.h, self.h, int(position), _p(lam, C.c_double), lam.size, C.byref(f)), self.ctx.h)
+        return f.value
+
+    def grad(self, position, lam, eps=1e-4):
+        """evaluateGradientOfFunction(lambda): forward differences (jstacs NumericalDifferentiableFunction.java:64-84)."""
+        lam = np.ascontiguousarray(lam, np.float64)
+        f = C.c_double()
+        g = np.zeros(lam.size)
+        raise_for(lib().phyfoo_fe_grad(self.ctx.h, self.h, int(position), _p(lam, C.c_double), lam.size, float(eps),
+                                       C.byref(f), _p(g, C.c_double)), self.ctx.h)
+        return f.value, g
+
+    def values_device(self, position, lam, eps, values_ptr, stream_ptr):
+        lam = np.ascontiguousarray(lam, np.float64)
+        raise_for(lib().phyfoo_fe_values_device(self.ctx.h, self.h, int(position), _p(lam, C.c_double), lam.size, float(eps),
+                                                C.c_void_p(values_ptr), C.c_void_p(stream_ptr) if stream_ptr else None),
+                  self.ctx.h)

@@ -152,15 +152,14 @@ struct ModelHost {
     }
 
     // order-0 tables of position t: [log pi (4)] [node 1 (16)] ... [node N-1 (16)]
-    void build_tables(int t) {
-        double* lt = &logtab[(size_t)t * E];
-        double* pt = &probtab[(size_t)t * E];
-        const double* p = pi[t].data();
-        for (int a = 0; a < 4; ++a) { pt[a] = p[a]; lt[a] = std::log(p[a]); }
+    void build_tables(int t) { build_tables_into(t, pi[t].data(), &logtab[(size_t)t * E], &probtab[(size_t)t * E]); }
+    // same, for an arbitrary stationary distribution p[4] (M-step: parameter sets under test); pt may be null
+    void build_tables_into(int t, const double* p, double* lt, double* pt) const {
+        for (int a = 0; a < 4; ++a) { if (pt) pt[a] = p[a]; lt[a] = std::log(p[a]); }
         for (int k = 1; k < N; ++k) {
             double tr[16];
             transition(p, branch[(size_t)t * N + k], tr);
-            for (int i = 0; i < 16; ++i) { pt[tab_off(k) + i] = tr[i]; lt[tab_off(k) + i] = std::log(tr[i]); }
+            for (int i = 0; i < 16; ++i) { if (pt) pt[tab_off(k) + i] = tr[i]; lt[tab_off(k) + i] = std::log(tr[i]); }
         }
     }
     static int tab_off(int node) { return 4 + 16 * (node - 1); }

@@ -60,6 +60,8 @@ struct phyfoo_ctx {
     DevBuf fg_scores, bg_scores;     // window scores (both strands) / column scores
     DevBuf sweeps_buf;               // int32 per item when the caller wants K
     DevBuf gamma, profile, part, argoff, argstrand, alnw, out3, gstate, misc;
+    DevBuf selw, sel_tmp, sel_out;   // M-step selection scratch
+    int64_t gamma_windows = -1;      // number of windows whose gamma of the last E-step is resident in `gamma`
     int launches = 0;                // kernels launched by the current call
 };
 
@@ -142,6 +144,10 @@ struct ScoreParams {
     int max_sweeps, min_sweeps; double tol;
     double* gstate;      // nullable: per-thread state in global memory instead of shared
     int groups;          // windows in flight per block
+    // M-step "prepare": explicit window list instead of all windows, and a sink for the converged q
+    const int64_t* item_col0;     // nullable: first column of window `item`
+    const uint8_t* item_strand;   // nullable (all forward)
+    double* q_int; double* q_leaf; double* ent;   // nullable; strided by n_windows * W (one slot per tree)
 };
 
 __device__ __forceinline__ ColWords load_column(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ gaps,
@@ -163,7 +169,8 @@ __device__ __forceinline__ int find_alignment(const int64_t* __restrict__ off, i
     return lo;
 }
 
-template <int MODE>
+// ITEMS = true: M-step "prepare" variant (explicit window list, converged q written out)
+template <int MODE, bool ITEMS>
 __global__ void __launch_bounds__(256, 2) score_o0_kernel(ScoreParams p) {
     extern __shared__ double smem[];
     const int T = blockDim.x, tid = threadIdx.x;
@@ -205,11 +212,18 @@ __global__ void __launch_bounds__(256, 2) score_o0_kernel(ScoreParams p) {
             item = s_item[g];
             if (item >= n_items) active = false;
             else {
-                const int si = (int)(item / p.n_windows);
-                const int64_t w = item - (long long)si * p.n_windows;
-                const int strand = p.n_strands == 2 ? si : p.strand0;
-                const int a = find_alignment(p.win_off, p.n_aln, w);
-                const int64_t c0 = p.col_off[a] + (w - p.win_off[a]);
+                int strand;
+                int64_t c0;
+                if (ITEMS) {
+                    c0 = p.item_col0[item];
+                    strand = p.item_strand ? p.item_strand[item] : 0;
+                } else {
+                    const int si = (int)(item / p.n_windows);
+                    const int64_t w = item - (long long)si * p.n_windows;
+                    strand = p.n_strands == 2 ? si : p.strand0;
+                    const int a = find_alignment(p.win_off, p.n_aln, w);
+                    c0 = p.col_off[a] + (w - p.win_off[a]);
+                }
                 // jstacs StrandModel.java:636-639 / Sequence.java:1321-1333: reverse the columns, complement the symbols
                 const int64_t c = strand ? c0 + (p.W - 1 - t) : c0 + t;
                 cw = load_column(p.bases, p.gaps, p.n_cols, p.nb, c);
@@ -221,7 +235,7 @@ __global__ void __launch_bounds__(256, 2) score_o0_kernel(ScoreParams p) {
         double F = 0.0;
         if (active) {
             if (MODE == PHYFOO_MODE_EXACT) F = -log(pruning_likelihood(tp, tb, st, cw));
-            else F = meanfield_pass(tp, tb, st, cw, upd, nullptr);
+            else F = meanfield_pass(tp, tb, st, cw, upd);
         }
         s_F[tid] = F;
         __syncthreads();
@@ -238,6 +252,12 @@ __global__ void __launch_bounds__(256, 2) score_o0_kernel(ScoreParams p) {
                 done = !((k < p.max_sweeps && !conv) || k < p.min_sweeps);    // :107
             }
             if (done) {
+                if (MODE != PHYFOO_MODE_EXACT && ITEMS) {
+                    // FE-set layout: tree slot = position-major (t * n + window) so one position's trees are contiguous
+                    const size_t n_trees = (size_t)p.n_windows * p.W, tree = (size_t)t * p.n_windows + item;
+                    const QSink sink{p.q_int + tree, p.q_leaf + tree, n_trees};
+                    p.ent[tree] = store_q(tp, tb, st, cw, sink);
+                }
                 if (t == 0) {
                     p.out[item] = -Fsum;                                      // PhyloBayesModel.java:259
                     if (p.sweeps) p.sweeps[item] = k;
@@ -434,7 +454,7 @@ extern "C" void phyfoo_destroy(phyfoo_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf* b : {&ctx->counters, &ctx->fg_scores, &ctx->bg_scores, &ctx->sweeps_buf, &ctx->gamma, &ctx->profile, &ctx->part,
-                      &ctx->argoff, &ctx->argstrand, &ctx->alnw, &ctx->out3, &ctx->gstate, &ctx->misc})
+                      &ctx->argoff, &ctx->argstrand, &ctx->alnw, &ctx->out3, &ctx->gstate, &ctx->misc, &ctx->selw, &ctx->sel_tmp, &ctx->sel_out})
         b->release();
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
@@ -682,7 +702,7 @@ static int model_upload(phyfoo_ctx* ctx, phyfoo_model* m) {
 // ------------------------------------------------------------------------------------------------
 struct ScorePlan { int threads, groups, blocks; size_t smem; bool gstate; };
 
-static int plan_score(phyfoo_ctx* ctx, const ModelHost& h, int prog_len, long long n_items, int mode, ScorePlan* pl) {
+static int plan_score(phyfoo_ctx* ctx, const ModelHost& h, int prog_len, long long n_items, int mode, bool items, ScorePlan* pl) {
     const int W = h.W;
     if (W > 256) return fail(ctx, PHYFOO_EUNSUPPORTED, "motif width > 256 is not supported");
     const size_t tab_bytes = (size_t)h.E * W * sizeof(double);
@@ -710,7 +730,8 @@ static int plan_score(phyfoo_ctx* ctx, const ModelHost& h, int prog_len, long lo
         groups = std::max(1, groups / 2);
     }
     (void)gstate;
-    const void* fn = mode == PHYFOO_MODE_EXACT ? (const void*)score_o0_kernel<PHYFOO_MODE_EXACT> : (const void*)score_o0_kernel<PHYFOO_MODE_MEANFIELD>;
+    const void* fn = mode == PHYFOO_MODE_EXACT ? (const void*)score_o0_kernel<PHYFOO_MODE_EXACT, false>
+                   : items ? (const void*)score_o0_kernel<PHYFOO_MODE_MEANFIELD, true> : (const void*)score_o0_kernel<PHYFOO_MODE_MEANFIELD, false>;
     CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, pl->threads, pl->smem));
@@ -720,42 +741,50 @@ static int plan_score(phyfoo_ctx* ctx, const ModelHost& h, int prog_len, long lo
     return PHYFOO_OK;
 }
 
-// scores into d_out[n_strands][n_windows]; strands: 0 = forward only, 1 = reverse only, 2 = both
+struct ScoreItems { const int64_t* col0; const uint8_t* strand; double* q_int; double* q_leaf; double* ent; };
+
+// scores into d_out[n_strands][n_windows]; strands: 0 = forward only, 1 = reverse only, 2 = both.
+// items != NULL: score the listed windows (n_windows of them) instead and store their converged q.
 static int launch_score(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* m, const int64_t* d_win_off, int64_t n_windows,
-                        int strands, double* d_out, int32_t* d_sweeps, int counter_slot) {
+                        int strands, double* d_out, int32_t* d_sweeps, int counter_slot, const ScoreItems* items = nullptr) {
     int rc = model_upload(ctx, m);
     if (rc) return rc;
     ModelHost& h = m->h;
+    // the M-step always runs the mean field, whatever CALC_LOGLIKELIHOOD says (PhyloBayesModel.java:142-147)
+    const int mode = items ? PHYFOO_MODE_MEANFIELD : h.mode;
     if (h.S != ds->S) return fail(ctx, PHYFOO_EINVAL, "model and dataset disagree on the number of species");
     if (h.evol == PHYFOO_EVOL_HKY_AS_IMPLEMENTED)
         return fail(ctx, PHYFOO_EUNSUPPORTED, "HKY as implemented in the reference has zero transversion probabilities (HKY.java:32): every score is -inf");
-    if (h.mode == PHYFOO_MODE_MEANFIELD && !h.tables_finite())
+    if (mode == PHYFOO_MODE_MEANFIELD && !h.tables_finite())
         return fail(ctx, PHYFOO_EUNSUPPORTED, "a CPF entry is 0: the reference's free energy is not finite for this parameter set");
     const int n_strands = strands == 2 ? 2 : 1;
     const long long n_items = (long long)n_windows * n_strands;
     if (n_items == 0) return PHYFOO_OK;
     ScorePlan pl;
-    rc = plan_score(ctx, h, m->prog_len, n_items, h.mode, &pl);
+    rc = plan_score(ctx, h, m->prog_len, n_items, mode, items != nullptr, &pl);
     if (rc) return rc;
     ScoreParams p;
     p.bases = ds->d_bases; p.gaps = ds->d_gaps; p.n_cols = ds->n_cols; p.nb = ds->nb;
     p.col_off = ds->d_col_off; p.win_off = d_win_off; p.n_aln = ds->n_aln;
     p.n_windows = n_windows; p.n_strands = n_strands; p.strand0 = strands == 1 ? 1 : 0;
     p.W = h.W; p.I = h.I; p.S = h.S; p.E = h.E; p.prog_len = m->prog_len;
-    p.tab = h.mode == PHYFOO_MODE_EXACT ? m->d_probtab : m->d_logtab;
+    p.tab = mode == PHYFOO_MODE_EXACT ? m->d_probtab : m->d_logtab;
     p.prog = m->d_prog;
     p.out = d_out; p.sweeps = d_sweeps;
     p.counters = ctx->counters.as<unsigned long long>() + 2 * counter_slot;
     p.max_sweeps = h.max_sweeps; p.min_sweeps = h.min_sweeps; p.tol = h.tol;
     p.groups = pl.groups;
+    p.item_col0 = nullptr; p.item_strand = nullptr; p.q_int = nullptr; p.q_leaf = nullptr; p.ent = nullptr;
+    if (items) { p.item_col0 = items->col0; p.item_strand = items->strand; p.q_int = items->q_int; p.q_leaf = items->q_leaf; p.ent = items->ent; }
     p.gstate = nullptr;
     if (pl.gstate) {
         CU(ctx->gstate.ensure((size_t)pl.blocks * pl.threads * h.I * 8 * sizeof(double)));
         p.gstate = ctx->gstate.as<double>();
     }
     CU(cudaMemsetAsync(p.counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
-    if (h.mode == PHYFOO_MODE_EXACT) score_o0_kernel<PHYFOO_MODE_EXACT><<<pl.blocks, pl.threads, pl.smem, ctx->stream>>>(p);
-    else score_o0_kernel<PHYFOO_MODE_MEANFIELD><<<pl.blocks, pl.threads, pl.smem, ctx->stream>>>(p);
+    if (mode == PHYFOO_MODE_EXACT) score_o0_kernel<PHYFOO_MODE_EXACT, false><<<pl.blocks, pl.threads, pl.smem, ctx->stream>>>(p);
+    else if (items) score_o0_kernel<PHYFOO_MODE_MEANFIELD, true><<<pl.blocks, pl.threads, pl.smem, ctx->stream>>>(p);
+    else score_o0_kernel<PHYFOO_MODE_MEANFIELD, false><<<pl.blocks, pl.threads, pl.smem, ctx->stream>>>(p);
     ctx->launches++;
     CU(cudaGetLastError());
     return PHYFOO_OK;
@@ -920,6 +949,7 @@ extern "C" int phyfoo_zoops_estep(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phy
                            profile_out ? ctx->profile.as<double>() : nullptr, argmax_off ? ctx->argoff.as<int32_t>() : nullptr,
                            argmax_strand ? ctx->argstrand.as<uint8_t>() : nullptr, ctx->out3.as<double>(), &nw);
     if (rc) return rc;
+    ctx->gamma_windows = gamma_out ? nw : -1;
     const float ms = tm.stop();
     CU(cudaGetLastError());
     double r3[3];

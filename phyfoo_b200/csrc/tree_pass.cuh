@@ -77,18 +77,19 @@ struct State {
     PHY_HD double& cs(int i, int a) const { return base[(size_t)(i * 8 + 4 + a) * stride]; }
 };
 
-// Optional sink for the converged q (M-step "prepare"): internal nodes then leaves.
+// Sink for the converged q of one tree (M-step "prepare"): entry (i, a) at q_internal[(i*4+a)*stride],
+// gap-leaf entry (CSR leaf slot k, a) at q_leaf[(k*4+a)*stride]; rows of observed leaves are left untouched.
 struct QSink {
-    double* q_internal;  // [I][4]
-    double* q_leaf;      // [S][4] (rows of observed leaves are left untouched), indexed by CSR leaf slot
-    int stride;
+    double* q_internal;
+    double* q_leaf;
+    size_t stride;
 };
 
 // One pass over the tree.  update == false: the exponents are forced to 0, i.e. q is (re)set to
 // uniform; this pass evaluates the free energy of the uniform start and primes the child sums.
 // Returns this tree's free energy F = part1 - part2.
 PHY_HD double meanfield_pass(const TreeProg& tp, const Tab& tb, const State& st, const ColWords& cw,
-                             bool update, const QSink* sink) {
+                             bool update) {
     double F = 0.0;
     double lpi[4];
 #pragma unroll
@@ -168,10 +169,6 @@ PHY_HD double meanfield_pass(const TreeProg& tp, const Tab& tb, const State& st,
                 const double lzl = log(zl);
 #pragma unroll
                 for (int a = 0; a < 4; ++a) { ql[a] = el[a] * rzl; lql[a] = (update ? qs * lpi[a] : 0.0) - lzl; }
-                if (sink) {
-#pragma unroll
-                    for (int a = 0; a < 4; ++a) sink->q_leaf[(size_t)(k * 4 + a) * sink->stride] = ql[a];
-                }
                 double t = 0.0, ent = 0.0;
 #pragma unroll
                 for (int a = 0; a < 4; ++a) { t += ql[a] * lpi[a]; ent += ql[a] * lql[a]; }
@@ -187,10 +184,6 @@ PHY_HD double meanfield_pass(const TreeProg& tp, const Tab& tb, const State& st,
         }
 #pragma unroll
         for (int a = 0; a < 4; ++a) st.cs(i, a) = c[a] + tsum;
-        if (sink) {
-#pragma unroll
-            for (int a = 0; a < 4; ++a) sink->q_internal[(size_t)(i * 4 + a) * sink->stride] = qi[a];
-        }
     }
     return F;
 }
@@ -201,12 +194,47 @@ PHY_HD double meanfield_pass(const TreeProg& tp, const Tab& tb, const State& st,
 // (update == false selects 0.0 instead of s[a]); q(p, .) of the parent is rewritten by pass 0 before
 // the child reads it.
 
-// Free energy of one tree for FIXED q (M-step objective, optimizing/AbstractFreeEnergyOptimizer.java:95-114):
-// q_internal [I][4], q_leaf [S][4] (rows of gap leaves only; CSR leaf slot order), strided by qstride;
-// tables tb of the parameter set under test.
-PHY_HD double free_energy_fixed_q(const TreeProg& tp, const Tab& tb, const double* q_internal,
-                                  const double* q_leaf, int qstride, const ColWords& cw) {
-    double F = 0.0;
+// After the last sweep of a window: write the converged q of this tree (internal nodes from the state, gap
+// leaves recomputed from their parent's final q with the arithmetic of the pass, so the bits are the same)
+// and the tree's entropy term  sum_hidden sum_h q log q  (MeanFieldForBayesNet.java:250-267), which does not
+// depend on the parameters and is therefore computed once for the whole M-step.
+PHY_HD double store_q(const TreeProg& tp, const Tab& tb, const State& st, const ColWords& cw, const QSink& sink) {
+    double ent = 0.0;
+    double lpi[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) lpi[a] = tb(a);
+    for (int i = 0; i < tp.n_internal; ++i) {
+        double qi[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            qi[a] = st.q(i, a);
+            sink.q_internal[(size_t)(i * 4 + a) * sink.stride] = qi[a];
+            ent += (qi[a] > 0.0) ? qi[a] * log(qi[a]) : 0.0;
+        }
+        for (int k = tp.leaf_begin[i]; k < tp.leaf_begin[i + 1]; ++k) {
+            if (cw.obs(tp.leaf_species[k]) < 4) continue;
+            const double qs = ((qi[0] + qi[1]) + qi[2]) + qi[3];
+            double el[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) el[a] = exp(qs * lpi[a]);
+            const double rzl = 1.0 / (((el[0] + el[1]) + el[2]) + el[3]);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const double ql = el[a] * rzl;
+                sink.q_leaf[(size_t)(k * 4 + a) * sink.stride] = ql;
+                ent += (ql > 0.0) ? ql * log(ql) : 0.0;
+            }
+        }
+    }
+    return ent;
+}
+
+// E_q[ sum_nodes log CPF ] of one tree for FIXED q ("part2" of calcFreeEnergy, MeanFieldForBayesNet.java:269-364)
+// under the tables tb of the parameter set under test; free energy = entropy - this.
+// M-step objective: optimizing/AbstractFreeEnergyOptimizer.java:95-114.
+PHY_HD double expected_log_cpf(const TreeProg& tp, const Tab& tb, const double* q_internal, const double* q_leaf,
+                               size_t qstride, const ColWords& cw) {
+    double acc = 0.0;
     double lpi[4];
 #pragma unroll
     for (int a = 0; a < 4; ++a) lpi[a] = tb(a);
@@ -214,11 +242,9 @@ PHY_HD double free_energy_fixed_q(const TreeProg& tp, const Tab& tb, const doubl
         double qi[4];
 #pragma unroll
         for (int a = 0; a < 4; ++a) qi[a] = q_internal[(size_t)(i * 4 + a) * qstride];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) F += (qi[a] > 0.0) ? qi[a] * log(qi[a]) : 0.0;
         if (i == 0) {
 #pragma unroll
-            for (int a = 0; a < 4; ++a) F -= qi[a] * lpi[a];
+            for (int a = 0; a < 4; ++a) acc += qi[a] * lpi[a];                       // :282-291
         } else {
             const int pi_ = tp.par_internal[i];
             const int e0 = tab_of(tp.node_of[i]);
@@ -228,9 +254,9 @@ PHY_HD double free_energy_fixed_q(const TreeProg& tp, const Tab& tb, const doubl
                 double m = 0.0;
 #pragma unroll
                 for (int h = 0; h < 4; ++h) m += qi[h] * tb(e0 + l * 4 + h);
-                cross += q_internal[(size_t)(pi_ * 4 + l) * qstride] * m;
+                cross += q_internal[(size_t)(pi_ * 4 + l) * qstride] * m;           // :327-358
             }
-            F -= cross;
+            acc += cross;
         }
         for (int k = tp.leaf_begin[i]; k < tp.leaf_begin[i + 1]; ++k) {
             const int x = cw.obs(tp.leaf_species[k]);
@@ -238,21 +264,87 @@ PHY_HD double free_energy_fixed_q(const TreeProg& tp, const Tab& tb, const doubl
                 const int e0 = tab_of(tp.leaf_node[k]);
                 double d = 0.0;
 #pragma unroll
-                for (int a = 0; a < 4; ++a) d += qi[a] * tb(e0 + a * 4 + x);
-                F -= d;
+                for (int a = 0; a < 4; ++a) d += qi[a] * tb(e0 + a * 4 + x);         // :292-326
+                acc += d;
             } else {
-                double t = 0.0, ent = 0.0;
+                double t = 0.0;
 #pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    const double ql = q_leaf[(size_t)(k * 4 + a) * qstride];
-                    t += ql * lpi[a];
-                    ent += (ql > 0.0) ? ql * log(ql) : 0.0;
-                }
-                F += ent - (((qi[0] + qi[1]) + qi[2]) + qi[3]) * t;
+                for (int a = 0; a < 4; ++a) t += q_leaf[(size_t)(k * 4 + a) * qstride] * lpi[a];
+                acc += (((qi[0] + qi[1]) + qi[2]) + qi[3]) * t;                     // independent table: every row is log pi
             }
         }
     }
-    return F;
+    return acc;
+}
+
+// The same expectation under K parameter sets at once (forward-difference gradient: K = dim + 1): the q loads are
+// shared, the per-set arithmetic and its order are those of expected_log_cpf, so acc[k] carries the same bits.
+// tabs: K tables of E entries each, entry e of set k at tabs[k * E + e].
+template <int K>
+PHY_HD void expected_log_cpf_multi(const TreeProg& tp, const double* tabs, int E, const double* q_internal,
+                                   const double* q_leaf, size_t qstride, const ColWords& cw, double* acc) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = 0.0;
+    for (int i = 0; i < tp.n_internal; ++i) {
+        double qi[4], qp[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) qi[a] = q_internal[(size_t)(i * 4 + a) * qstride];
+        if (i == 0) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const double* tb = tabs + (size_t)k * E;
+                double r = 0.0;
+#pragma unroll
+                for (int a = 0; a < 4; ++a) r += qi[a] * tb[a];
+                acc[k] += r;
+            }
+        } else {
+            const int pi_ = tp.par_internal[i];
+            const int e0 = tab_of(tp.node_of[i]);
+#pragma unroll
+            for (int l = 0; l < 4; ++l) qp[l] = q_internal[(size_t)(pi_ * 4 + l) * qstride];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const double* tb = tabs + (size_t)k * E + e0;
+                double cross = 0.0;
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                    double m = 0.0;
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) m += qi[h] * tb[l * 4 + h];
+                    cross += qp[l] * m;
+                }
+                acc[k] += cross;
+            }
+        }
+        for (int c = tp.leaf_begin[i]; c < tp.leaf_begin[i + 1]; ++c) {
+            const int x = cw.obs(tp.leaf_species[c]);
+            if (x < 4) {
+                const int e0 = tab_of(tp.leaf_node[c]);
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const double* tb = tabs + (size_t)k * E + e0;
+                    double d = 0.0;
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) d += qi[a] * tb[a * 4 + x];
+                    acc[k] += d;
+                }
+            } else {
+                double ql[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) ql[a] = q_leaf[(size_t)(c * 4 + a) * qstride];
+                const double qs = ((qi[0] + qi[1]) + qi[2]) + qi[3];
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const double* tb = tabs + (size_t)k * E;
+                    double t = 0.0;
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) t += ql[a] * tb[a];
+                    acc[k] += qs * t;
+                }
+            }
+        }
+    }
 }
 
 // Felsenstein pruning: P(column) for one tree, gaps as missing data.  Tables here are the

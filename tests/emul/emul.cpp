@@ -45,7 +45,7 @@ extern "C" int emul_score_windows(const phyfoo_model_desc* d, const uint8_t* cod
                         sum += -std::log(pruning_likelihood(tp, pt, st, cw));
                     } else {
                         Tab lt{&m.logtab[(size_t)t * m.E], 1};
-                        sum += meanfield_pass(tp, lt, st, cw, update, nullptr);
+                        sum += meanfield_pass(tp, lt, st, cw, update);
                     }
                 }
                 return sum;
@@ -61,6 +61,81 @@ extern "C" int emul_score_windows(const phyfoo_model_desc* d, const uint8_t* cod
             out[j] = -cur;
             if (sweeps) sweeps[j] = k;
         }
+        return 0;
+    } catch (const std::exception& e) { std::fprintf(stderr, "emul: %s\n", e.what()); return -1; }
+}
+
+// Fixed-q objective the way the M-step kernels compute it: mean field to convergence per window (store_q), then
+// values[k] = sum_t G_t - ENT for the parameter sets k = 0 (lambda) and 1..4 (lambda + eps e_i) of position `pos`.
+extern "C" int emul_fe_values(const phyfoo_model_desc* d, const uint8_t* cols /*[n][W][S]*/, int n, const double* weights,
+                              int pos, const double* lambda, double eps, double* values /*[5]*/) {
+    try {
+        ModelHost m; m.init(*d);
+        const int S = m.S, W = m.W, I = m.I, E = m.E;
+        TreeProg tp = prog_of(m);
+        const size_t n_trees = (size_t)n * W;
+        std::vector<double> qint((size_t)4 * I * n_trees), qleaf((size_t)4 * S * n_trees), ent(n_trees);
+        std::vector<double> state((size_t)W * I * 8, 1e300);
+        for (int u = 0; u < n; ++u) {
+            auto words = [&](int t) { return words_of(cols + ((size_t)u * W + t) * S, S, false); };
+            auto pass = [&](bool update) {
+                double sum = 0;
+                for (int t = 0; t < W; ++t) {
+                    State st{state.data() + (size_t)t * I * 8, 1};
+                    Tab lt{&m.logtab[(size_t)t * E], 1};
+                    sum += meanfield_pass(tp, lt, st, words(t), update);
+                }
+                return sum;
+            };
+            double old = pass(false);
+            int k = 0; bool conv = false;
+            while ((k < m.max_sweeps && !conv) || k < m.min_sweeps) {
+                double cur = pass(true);
+                if (std::fabs(old - cur) < m.tol) conv = true;
+                old = cur; ++k;
+            }
+            for (int t = 0; t < W; ++t) {
+                State st{state.data() + (size_t)t * I * 8, 1};
+                Tab lt{&m.logtab[(size_t)t * E], 1};
+                const size_t tree = (size_t)t * n + u;
+                ent[tree] = store_q(tp, lt, st, words(t), QSink{qint.data() + tree, qleaf.data() + tree, n_trees});
+            }
+        }
+        double ENT = 0;
+        for (int u = 0; u < n; ++u) { double e = 0; for (int t = 0; t < W; ++t) e += ent[(size_t)t * n + u]; ENT += weights[u] * e; }
+        std::vector<double> G(W, 0.0);
+        for (int t = 0; t < W; ++t)
+            for (int u = 0; u < n; ++u) {
+                const size_t tree = (size_t)t * n + u;
+                double e1[1];
+                expected_log_cpf_multi<1>(tp, &m.logtab[(size_t)t * E], E, qint.data() + tree, qleaf.data() + tree, n_trees,
+                                          words_of(cols + ((size_t)u * W + t) * S, S, false), e1);
+                G[t] += weights[u] * e1[0];
+                Tab lt{&m.logtab[(size_t)t * E], 1};
+                double single = expected_log_cpf(tp, lt, qint.data() + tree, qleaf.data() + tree, n_trees, words_of(cols + ((size_t)u * W + t) * S, S, false));
+                if (single != e1[0]) throw std::runtime_error("expected_log_cpf_multi<1> differs from expected_log_cpf");
+            }
+        std::vector<double> tabs((size_t)5 * E), x(lambda, lambda + 4);
+        double pi[4];
+        lambda_to_pi(x.data(), pi, 4);
+        m.build_tables_into(pos, pi, &tabs[0], nullptr);
+        for (int i = 0; i < 4; ++i) {
+            double keep = x[i]; x[i] += eps;
+            lambda_to_pi(x.data(), pi, 4);
+            m.build_tables_into(pos, pi, &tabs[(size_t)(1 + i) * E], nullptr);
+            x[i] = keep;
+        }
+        double gk[5] = {0, 0, 0, 0, 0};
+        for (int u = 0; u < n; ++u) {
+            const size_t tree = (size_t)pos * n + u;
+            double e5[5];
+            expected_log_cpf_multi<5>(tp, tabs.data(), E, qint.data() + tree, qleaf.data() + tree, n_trees,
+                                      words_of(cols + ((size_t)u * W + pos) * S, S, false), e5);
+            for (int k = 0; k < 5; ++k) gk[k] += weights[u] * e5[k];
+        }
+        double rest = 0;
+        for (int t = 0; t < W; ++t) if (t != pos) rest += G[t];
+        for (int k = 0; k < 5; ++k) values[k] = (rest + gk[k]) - ENT;
         return 0;
     } catch (const std::exception& e) { std::fprintf(stderr, "emul: %s\n", e.what()); return -1; }
 }

@@ -82,3 +82,30 @@ def test_f81beta_tables(emul):
     ref, rsw = oracle_fg(newick, pwm, evol=orc.F81BETA).score_windows(codes)
     assert np.array_equal(sw, rsw)
     assert rel_err(got, ref) < 1e-9
+
+
+@pytest.mark.parametrize("newick", TREES)
+@pytest.mark.parametrize("gap_rate", [0.0, 0.15])
+def test_fixed_q_objective_matches_oracle(emul, newick, gap_rate):
+    """store_q + expected_log_cpf_multi (the M-step kernels' arithmetic) against the oracle's FESet: f(lambda) within
+    1e-9 relative; the forward-difference gradient within 1e-9 * |g| plus the cancellation noise of f/eps."""
+    emul.emul_fe_values.argtypes = [C.POINTER(_abi.ModelDesc), C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_double), C.c_int,
+                                    C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_double)]
+    rng = np.random.default_rng(17)
+    tree = parse_newick(newick)
+    S, W, n, pos, eps = tree.n_species, 4, 9, 2, 1e-4
+    pwm = synth.random_pwm(W, 0, 41)
+    cols = np.stack([random_codes(rng, W, S, gap_rate) for _ in range(n)])
+    wts = rng.random(n)
+    lam = np.log(rng.dirichlet(np.ones(4))) + 0.3
+    desc, keep = _abi.make_desc(_abi.MODEL_FG, W, 0, tree, np.tile(tree.branch, (W, 1)), pwm)
+    vals = np.zeros(5)
+    rc = emul.emul_fe_values(C.byref(desc), cols.ctypes.data_as(C.POINTER(C.c_uint8)), n, wts.ctypes.data_as(C.POINTER(C.c_double)),
+                             pos, lam.ctypes.data_as(C.POINTER(C.c_double)), eps, vals.ctypes.data_as(C.POINTER(C.c_double)))
+    assert rc == 0
+    fs = orc.FESet(oracle_fg(newick, pwm), cols, wts)
+    f0, g = fs.grad(pos, lam, eps)
+    assert abs(vals[0] - f0) <= 1e-9 * abs(f0)
+    got_g = (vals[1:] - vals[0]) / eps
+    noise = 64 * np.finfo(float).eps * abs(f0) / eps
+    assert np.all(np.abs(got_g - g) <= 1e-9 * np.abs(g) + noise), (got_g, g)
