@@ -192,7 +192,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": samp},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -345,12 +345,25 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"first {n} of {cfg['n_aln']} alignments ({nw} windows, {dt:.1f} s), "
                                               "C++ restatement of the Java algorithm with its cost model (JVM unavailable)"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else a library prints (e.g. NCCL's version banner) was
+    re-routed to stderr by main()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)            # C-level stdout of this process (NCCL, CUDA libraries) -> stderr
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -214,3 +214,21 @@ def test_full_size_properties(ctx):
         ref, _ = om.score_windows(smp.getElementAt(i))
         o = smp.device(ctx).window_offsets(cfg["W"])
         assert rel_err(mf[o[i]:o[i + 1]], ref) < TOL
+
+
+def test_sharded_estep_single_rank(ctx):
+    """The multi-GPU entry (device-resident partials, no host round trip) at world size 1 equals the host API."""
+    from phyfoo_b200 import sharding, synth
+    from phyfoo_b200.models import PhyloBackground, PhyloBayesModel, SingleHiddenMotifMixture, StrandModel
+    newick = synth.caterpillar_newick(5)
+    pwm = synth.random_pwm(7, 0, 11)
+    smp, _ = synth.make_sample(newick, 9, 50, 13, pwm=pwm, gap_rate=0.03)
+    fg = PhyloBayesModel(7, 0, newick, ctx); fg.setCondProbs(pwm)
+    bg = PhyloBackground(0, newick, ctx)
+    for motif in (fg, StrandModel(fg, 0.3)):
+        shm = SingleHiddenMotifMixture(motif, bg, zoops=0.75)
+        ref = shm.getNewWeights(smp)
+        se = sharding.ShardedEStep(shm, smp)
+        se.step()
+        got = se.result()
+        assert got["ll"] == ref["ll"] and np.array_equal(got["w"], ref["w"])
