@@ -31,6 +31,7 @@ struct ModelHost {
     std::vector<std::vector<double>> pi;     // per position [ctx][4], ctx = 4^{#horizontal parents of the root}
     // tree program (see tree_pass.cuh)
     std::vector<int> par_internal, node_of, leaf_begin, leaf_node, leaf_sp, internal_of;
+    std::vector<int> ichild_begin, ichild;   // CSR of the internal tree children of internal node i (order-1 kernel)
     // order-0 tables: E entries per position, host layout [W][E]
     int E = 0;
     std::vector<double> logtab, probtab;
@@ -117,9 +118,18 @@ struct ModelHost {
                 if (parent[k] == node_of[i] && nchild[k] == 0) { leaf_node.push_back(k); leaf_sp.push_back(leaf_species[k]); }
         }
         leaf_begin[I] = (int)leaf_node.size();
+        ichild_begin.assign(I + 1, 0);
+        ichild.clear();
+        for (int i = 0; i < I; ++i) {
+            ichild_begin[i] = (int)ichild.size();
+            for (int k = 1; k < N; ++k)
+                if (parent[k] == node_of[i] && nchild[k] > 0) ichild.push_back(internal_of[k]);
+        }
+        ichild_begin[I] = (int)ichild.size();
     }
 
     // the flattened program as one int array: par_internal[I] node_of[I] leaf_begin[I+1] leaf_node[S] leaf_species[S]
+    // ichild_begin[I+1] ichild[I-1]
     std::vector<int> prog_flat() const {
         std::vector<int> v;
         v.insert(v.end(), par_internal.begin(), par_internal.end());
@@ -127,6 +137,8 @@ struct ModelHost {
         v.insert(v.end(), leaf_begin.begin(), leaf_begin.end());
         v.insert(v.end(), leaf_node.begin(), leaf_node.end());
         v.insert(v.end(), leaf_sp.begin(), leaf_sp.end());
+        v.insert(v.end(), ichild_begin.begin(), ichild_begin.end());
+        v.insert(v.end(), ichild.begin(), ichild.end());
         return v;
     }
 
@@ -176,8 +188,31 @@ struct ModelHost {
     }
 
     bool tables_finite() const {
+        if (order >= 1) {
+            std::vector<double> t1;
+            tables1(t1);
+            for (double v : t1) if (!std::isfinite(v)) return false;
+            return true;
+        }
         for (double v : logtab) if (!std::isfinite(v)) return false;
         return true;
+    }
+
+    // order-1 motif tables (net1.cuh): per position E1 = 16 + 64 (N-1) logs; root [ctx][4] at 0, node k >= 1
+    // [l = a_treeparent + 4 ctx][b] at 16 + 64 (k-1).  Unused rows (t = 0 has a single context) are 0.
+    int E1() const { return 16 + 64 * (N - 1); }
+    void tables1(std::vector<double>& out) const {
+        const int e1 = E1();
+        out.assign((size_t)W * e1, 0.0);
+        for (int t = 0; t < W; ++t) {
+            double* o = &out[(size_t)t * e1];
+            const int ctx = ctx_rows(t);
+            for (int i = 0; i < ctx * 4; ++i) o[i] = std::log(pi[t][i]);
+            for (int k = 1; k < N; ++k) {
+                const std::vector<double> tr = cpf(t, k);
+                for (size_t i = 0; i < tr.size(); ++i) o[16 + 64 * (k - 1) + i] = std::log(tr[i]);
+            }
+        }
     }
 
     void set_pi(int t, const double* v, int n) {

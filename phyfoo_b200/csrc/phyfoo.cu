@@ -84,6 +84,7 @@ struct phyfoo_model {
     int prog_len = 0;
     double* d_logtab = nullptr;   // [E][W]
     double* d_probtab = nullptr;  // [E][W]
+    double* d_tab1 = nullptr;     // order 1: [W][E1] log tables (net1.cuh)
 };
 
 static thread_local std::string g_init_err;
@@ -665,15 +666,32 @@ extern "C" int phyfoo_model_set_mode(phyfoo_ctx* ctx, phyfoo_model* m, int32_t m
 extern "C" void phyfoo_model_free(phyfoo_ctx* ctx, phyfoo_model* m) {
     if (!m) return;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
-    cudaFree(m->d_prog); cudaFree(m->d_logtab); cudaFree(m->d_probtab);
+    cudaFree(m->d_prog); cudaFree(m->d_logtab); cudaFree(m->d_probtab); cudaFree(m->d_tab1);
     delete m;
 }
 
 // copy the order-0 tables to the device in [E][W] layout when the parameters changed
 static int model_upload(phyfoo_ctx* ctx, phyfoo_model* m) {
     ModelHost& h = m->h;
-    if (h.order != 0) return fail(ctx, PHYFOO_EUNSUPPORTED, "order >= 1 networks are not implemented in this build");
+    if (h.order != 0 && !(h.order == 1 && h.kind == PHYFOO_MODEL_FG))
+        return fail(ctx, PHYFOO_EUNSUPPORTED, "background models of order >= 1 are not implemented in this build");
     if (m->uploaded == h.version) return PHYFOO_OK;
+    if (h.order == 1) {
+        std::vector<double> t1;
+        h.tables1(t1);
+        if (!m->d_prog) {
+            std::vector<int> prog = h.prog_flat();
+            m->prog_len = (int)prog.size();
+            CU(cudaMalloc(&m->d_prog, prog.size() * sizeof(int)));
+            CU(cudaMemcpyAsync(m->d_prog, prog.data(), prog.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaMalloc(&m->d_tab1, t1.size() * sizeof(double)));
+            CU(cudaStreamSynchronize(ctx->stream));
+        }
+        CU(cudaMemcpyAsync(m->d_tab1, t1.data(), t1.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        m->uploaded = h.version;
+        return PHYFOO_OK;
+    }
     const size_t n = (size_t)h.E * h.W;
     if (!m->d_prog) {
         std::vector<int> prog = h.prog_flat();
@@ -743,6 +761,57 @@ static int plan_score(phyfoo_ctx* ctx, const ModelHost& h, int prog_len, long lo
 
 struct ScoreItems { const int64_t* col0; const uint8_t* strand; double* q_int; double* q_leaf; double* ent; };
 
+#include "net1.cuh"
+
+// order-1 motif network: quad per window (net1.cuh)
+static int launch_net1(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* m, const int64_t* d_win_off, int64_t n_windows,
+                       int strands, double* d_out, int32_t* d_sweeps, int counter_slot, const ScoreItems* items) {
+    ModelHost& h = m->h;
+    if (h.mode == PHYFOO_MODE_EXACT && !items)
+        return fail(ctx, PHYFOO_EUNSUPPORTED, "exact likelihood of an order-1 network is infeasible in the reference too "
+                                              "(SimpleNodeElimination's 9-node frontier, SimpleNodeElimination.java:33-45)");
+    if (items && items->q_int) return fail(ctx, PHYFOO_EUNSUPPORTED, "fixed-q objective of order-1 networks is not implemented in this build");
+    const int n_strands = strands == 2 ? 2 : 1;
+    const long long n_items = (long long)n_windows * n_strands;
+    // windows per block: as many windows per SM as shared memory holds, in multiples of 8 (whole warps)
+    const size_t per_window = (size_t)h.W * h.I * 4 * sizeof(double) + (size_t)h.W * 12;
+    const size_t fixed = (size_t)m->prog_len * sizeof(int) + 64;
+    const size_t budget = std::min<size_t>(ctx->smem_optin, 227 * 1024);
+    int best_nwb = 0, best_per_sm = 0;
+    for (int nwb = 8; nwb <= 64; nwb += 8) {
+        const size_t need = fixed + per_window * nwb;
+        if (need > budget) break;
+        const int blocks_sm = (int)std::min<size_t>((228 * 1024) / (need + 1024), 2048 / (4 * nwb));
+        if (blocks_sm * nwb > best_per_sm) { best_per_sm = blocks_sm * nwb; best_nwb = nwb; }
+    }
+    if (!best_nwb) return fail(ctx, PHYFOO_EUNSUPPORTED, "order-1 window state does not fit in shared memory (motif too wide or tree too large)");
+    const size_t smem = fixed + per_window * best_nwb;
+    CU(cudaFuncSetAttribute(score_o1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_o1_kernel, 4 * best_nwb, smem));
+    if (per_sm < 1) return fail(ctx, PHYFOO_ECUDA, "order-1 kernel does not fit on an SM");
+    const long long want = (n_items + best_nwb - 1) / best_nwb;
+    const int blocks = (int)std::max<long long>(1, std::min<long long>(want, (long long)per_sm * ctx->sm_count));
+    const int64_t n_slots = (int64_t)blocks * best_nwb;
+    CU(ctx->gstate.ensure((size_t)h.W * h.S * 4 * n_slots * sizeof(double)));
+    Net1Params p;
+    p.bases = ds->d_bases; p.gaps = ds->d_gaps; p.n_cols = ds->n_cols; p.nb = ds->nb;
+    p.col_off = ds->d_col_off; p.win_off = d_win_off; p.n_aln = ds->n_aln;
+    p.n_windows = n_windows; p.n_strands = n_strands; p.strand0 = strands == 1 ? 1 : 0;
+    p.W = h.W; p.I = h.I; p.S = h.S; p.E1 = h.E1(); p.prog_len = m->prog_len; p.prog = m->d_prog;
+    p.tab = m->d_tab1;
+    p.out = d_out; p.sweeps = d_sweeps;
+    p.counters = ctx->counters.as<unsigned long long>() + 2 * counter_slot;
+    p.max_sweeps = h.max_sweeps; p.min_sweeps = h.min_sweeps; p.tol = h.tol;
+    p.gq = ctx->gstate.as<double>(); p.n_slots = n_slots; p.nwb = best_nwb;
+    p.item_col0 = items ? items->col0 : nullptr; p.item_strand = items ? items->strand : nullptr;
+    CU(cudaMemsetAsync(p.counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    score_o1_kernel<<<blocks, 4 * best_nwb, smem, ctx->stream>>>(p);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return PHYFOO_OK;
+}
+
 // scores into d_out[n_strands][n_windows]; strands: 0 = forward only, 1 = reverse only, 2 = both.
 // items != NULL: score the listed windows (n_windows of them) instead and store their converged q.
 static int launch_score(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* m, const int64_t* d_win_off, int64_t n_windows,
@@ -760,6 +829,7 @@ static int launch_score(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model*
     const int n_strands = strands == 2 ? 2 : 1;
     const long long n_items = (long long)n_windows * n_strands;
     if (n_items == 0) return PHYFOO_OK;
+    if (h.order == 1) return launch_net1(ctx, ds, m, d_win_off, n_windows, strands, d_out, d_sweeps, counter_slot, items);
     ScorePlan pl;
     rc = plan_score(ctx, h, m->prog_len, n_items, mode, items != nullptr, &pl);
     if (rc) return rc;

@@ -1,0 +1,89 @@
+"""GPU parity of the order-1 phylogenetic Bayesian network motif (BASELINE config 3's model; reference:
+models/PhyloBayesModel.java:356-370 with model.fg.order = 1) against the CPU oracle: window scores within 1e-9
+relative, mean-field sweep counts and arg-max site calls bit-exact, with and without gaps, both strands."""
+import numpy as np
+import pytest
+
+from util import orc, oracle_bg, oracle_fg, random_codes, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from phyfoo_b200 import core
+    return core.default_context()
+
+
+def _trees():
+    from phyfoo_b200 import synth
+    return {"star5": synth.star_newick(5), "cat5": synth.caterpillar_newick(5),
+            "rand12": synth.random_binary_newick(12, 3),
+            "mixed6": "((A:0.1,B:0.3):0.15,(C:0.2,(D:0.05,E:0.4):0.25):0.1,F:0.3)"}
+
+
+@pytest.mark.parametrize("tree", ["star5", "cat5", "mixed6", "rand12"])
+@pytest.mark.parametrize("gap_rate", [0.0, 0.15])
+def test_order1_window_scores(ctx, tree, gap_rate):
+    from phyfoo_b200 import synth
+    from phyfoo_b200.data import PhyloSample
+    from phyfoo_b200.models import PhyloBayesModel
+    from phyfoo_b200.newick import parse_newick
+    newick = _trees()[tree]
+    S = parse_newick(newick).n_species
+    rng = np.random.default_rng(41)
+    W = 5 if tree == "rand12" else 6
+    pwm = synth.random_pwm(W, 1, 61)
+    lens = [W, 23, 3, 40]
+    smp = PhyloSample(random_codes(rng, sum(lens), S, gap_rate), np.concatenate([[0], np.cumsum(lens)]))
+    fg = PhyloBayesModel(W, 1, newick, ctx)
+    fg.setCondProbs(pwm)
+    om = oracle_fg(newick, pwm, order=1)
+    for strand in (0, 1):
+        got, sw = fg.getLogProbFor(smp, strand=strand, want_sweeps=True)
+        ref, rsw = [], []
+        for i in range(smp.n_alignments):
+            r, k = om.score_windows(smp.getElementAt(i), bool(strand))
+            ref.append(r); rsw.append(k)
+        ref, rsw = np.concatenate(ref), np.concatenate(rsw)
+        assert got.shape == ref.shape
+        assert np.array_equal(sw, rsw), (sw[:10], rsw[:10])
+        assert rel_err(got, ref) < TOL
+        assert fg.last_stats["sweeps_fg"] == int(rsw.sum())
+
+
+def test_order1_zoops_estep(ctx):
+    from phyfoo_b200 import synth
+    from phyfoo_b200.models import PhyloBackground, PhyloBayesModel, SingleHiddenMotifMixture, StrandModel
+    newick = synth.caterpillar_newick(5)
+    W = 6
+    pwm = synth.random_pwm(W, 1, 67)
+    smp, planted = synth.make_sample(newick, 10, 45, 3, pwm=pwm, gap_rate=0.04, length_jitter=6)
+    fg = PhyloBayesModel(W, 1, newick, ctx); fg.setCondProbs(pwm)
+    bg = PhyloBackground(0, newick, ctx)
+    for strand in (False, True):
+        shm = SingleHiddenMotifMixture(StrandModel(fg, 0.5) if strand else fg, bg, zoops=0.85)
+        res = shm.getNewWeights(smp)
+        ref = orc.estep(oracle_fg(newick, pwm, order=1), oracle_bg(newick, 0), smp.col_offsets, smp.codes, np.log([0.85, 0.15]),
+                        np.log([0.5, 0.5]) if strand else None)
+        assert np.array_equal(res["argmax_off"], ref["argmax_off"]) and np.array_equal(res["argmax_strand"], ref["argmax_strand"])
+        assert np.max(np.abs(res["gamma"] - ref["gamma"])) < TOL
+        assert abs(res["ll"] - ref["ll"]) <= TOL * abs(ref["ll"])
+        assert res["stats"]["sweeps_fg"] == ref["sweeps_fg"]
+
+
+def test_order1_unsupported_paths_fail_loudly(ctx):
+    from phyfoo_b200 import synth
+    from phyfoo_b200.lib import PhyfooError
+    from phyfoo_b200.models import PhyloBayesModel
+    newick = synth.star_newick(5)
+    smp, _ = synth.make_sample(newick, 2, 20, 1)
+    fg = PhyloBayesModel(4, 1, newick, ctx)
+    PhyloBayesModel.CALC_LOGLIKELIHOOD = True
+    try:
+        with pytest.raises(PhyfooError):
+            fg.getLogProbFor(smp)
+    finally:
+        PhyloBayesModel.CALC_LOGLIKELIHOOD = False
