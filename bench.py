@@ -58,9 +58,28 @@ def flops_order0(I, S):
     return update, fe
 
 
+def flops_order1(I, S, W):
+    """Order-1 network, no gaps, per WINDOW: (flop of one update sweep, flop of one free-energy evaluation) under the
+    counting rule of SURVEY.md section 8d (an accumulation = 2 flop, a q factor beyond the first = 1 flop, normalisation
+    = 7 flop per hidden node).  tests/test_oracle_pins.py checks these closed forms against the oracle's term counter."""
+    upd = fe = 0
+    for t in range(W):
+        nxt = (32 + 192 * (I - 1)) if t + 1 < W else 0
+        if t == 0:
+            upd += 8 + 32 * (I - 1) + 32 * (I - 1) + 8 * S + nxt + 7 * I
+            fe += 8 * I + 8 + 48 * (I - 1) + 8 * S
+        else:
+            upd += 32 + 192 * (I - 1) + 192 * (I - 1) + 8 * S + nxt + 7 * I
+            fe += 8 * I + 48 + 256 * (I - 1) + 8 * S
+    return upd, fe
+
+
 def algorithmic_flops(cfg, I, n_windows, sweeps_total):
-    upd, fe = flops_order0(I, cfg["S"])
     W = cfg["W"]
+    if cfg["order"] == 1:
+        upd, fe = flops_order1(I, cfg["S"], W)
+        return sweeps_total * upd + (sweeps_total + n_windows) * fe
+    upd, fe = flops_order0(I, cfg["S"])
     return W * (sweeps_total * upd + (sweeps_total + n_windows) * fe)
 
 
@@ -327,7 +346,7 @@ def run_ours(args):
                     "steps": e2e_steps, "what": "PhyloSample -> pack on device -> E-step -> gamma/arg-max/ll to host"},
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
-            "roofline": {"bound": "fp64", "kernel": "score_o0_kernel<meanfield> (motif windows)",
+            "roofline": {"bound": "fp64", "kernel": ("score_o1_kernel" if cfg["order"] == 1 else "score_o0_kernel<meanfield>") + " (motif windows)",
                          "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
                          "peak_source": "DFMA microbenchmark in this run (MEASURED_PEAKS.json has no fp64 entry)",
                          "flops_per_launch": flops, "kernel_ms": fg_ms_avg,

@@ -190,6 +190,15 @@ int phyfoo_fe_values_device(phyfoo_ctx* ctx, phyfoo_feset* fe, int32_t position,
 int64_t phyfoo_fe_size(const phyfoo_feset* fe);
 void phyfoo_fe_free(phyfoo_ctx* ctx, phyfoo_feset* fe);
 
+/* ---- options ----
+ * "pattern_memo": 0 = never, 1 = when it pays off (default), 2 = whenever it applies.  For order-0 models and few
+ * species (3 S <= 18 bits) the library scores each occurring column pattern once per position and parameter set and
+ * gathers per window; results are bit-identical to the direct kernel (the reference's own, disabled, caches had the
+ * same aim: models/AbstractPhyloModel.java:100-119, models/PhyloBackground.java:196). */
+int phyfoo_set_option(phyfoo_ctx* ctx, const char* name, int64_t value);
+/* scoring path of the most recent motif/background launch: 0 direct kernel, 1 pattern table, 2 order-1 network */
+int phyfoo_last_score_path(const phyfoo_ctx* ctx);
+
 /* ---- plumbing for callers that overlap the library with their own streams ---- */
 int phyfoo_last_launches(const phyfoo_ctx* ctx); /* kernels launched by the most recent call on this context */
 void* phyfoo_stream(phyfoo_ctx* ctx);            /* the library's cudaStream_t */

@@ -51,6 +51,7 @@ def lib():
         L.orc_model_reset_stats.argtypes = [C.c_void_p]
         L.orc_score_window.restype = C.c_double
         L.orc_score_window.argtypes = [C.c_void_p, u8p, C.c_int, ip]
+        L.orc_count_terms.argtypes = [C.c_void_p, u8p, C.c_int, dp]
         L.orc_score_windows.argtypes = [C.c_void_p, u8p, C.c_int, C.c_int, dp, ip]
         L.orc_exact_bruteforce.restype = C.c_double
         L.orc_exact_bruteforce.argtypes = [C.c_void_p, u8p]
@@ -167,6 +168,14 @@ class Model:
         if np.isnan(v) and _err():
             raise RuntimeError(_err())
         return v, k.value
+
+    def count_terms(self, cols, revcomp=False):
+        """SURVEY.md section 8d term counter for one window: dict(upd_flops, fe_flops, upd_transc, fe_transc, sweeps)."""
+        cols = np.ascontiguousarray(cols, np.uint8)
+        out = np.zeros(5)
+        if lib().orc_count_terms(self.h, _u8(cols), int(revcomp), _dp(out)) != 0:
+            raise RuntimeError(_err())
+        return dict(upd_flops=out[0], fe_flops=out[1], upd_transc=out[2], fe_transc=out[3], sweeps=int(out[4]))
 
     def score_windows(self, codes, revcomp=False):
         codes = np.ascontiguousarray(codes, np.uint8)

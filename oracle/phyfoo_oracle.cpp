@@ -152,6 +152,11 @@ struct Model {
     bool log_in_loop = false;                // cost model of the Java (Math.log inside the loops); same bits
     // statistics
     long long sweeps_total = 0, calls_total = 0;
+    // instrumented term counter (SURVEY.md section 8d counting rule): every prod*log CPF accumulation = 2 flop,
+    // every q factor beyond the first = 1 flop, normalisation = 7 flop per hidden node, q log q = 2 flop;
+    // exp/log calls are counted separately as transcendentals (logs of CPF entries are per-parameter constants)
+    bool count_terms = false;
+    long long c_upd_flops = 0, c_upd_transc = 0, c_fe_flops = 0, c_fe_transc = 0, c_sweeps = 0, c_fe_calls = 0;
 
     int gid(int t, int k) const { return t * N + k; }
 };
@@ -302,6 +307,20 @@ struct MeanField {
 
     double free_energy(int start, int end) const {  // :232-365
         double part1 = 0, part2 = 0;
+        if (m->count_terms) {   // same loops, counting the structurally non-zero terms
+            long long fl = 0, tr = 0;
+            for (int t = start; t <= end; ++t)
+                for (int i = 0; i < m->N; ++i) {
+                    const Node& nd = m->nodes[m->gid(t, i)];
+                    int nhid = 0, rows = 1;
+                    for (size_t p = 0; p < nd.par.size(); ++p) { if (!m->nodes[nd.par[p]].observed) { ++nhid; rows *= 4; } }
+                    if (!nd.observed) { fl += 4 * 2; tr += 4; }
+                    if (nd.is_root() && !nd.observed) fl += 4 * 2;
+                    else if (nd.observed) fl += (long long)rows * (2 + std::max(nhid - 1, 0));
+                    else fl += 4LL * rows * (2 + nhid);
+                }
+            m->c_fe_flops += fl; m->c_fe_transc += tr; m->c_fe_calls++;
+        }
         for (int t = start; t <= end; ++t)
             for (int i = 0; i < m->N; ++i) {
                 int g = m->gid(t, i);
@@ -375,9 +394,11 @@ struct MeanField {
                     double acc = 0;
                     for (int l = 0; l < nd.size; ++l) {          // own rows, :117-135 (observed parents NOT filtered)
                         double prod = 1;
+                        int nfac = 0;
                         for (int p = 0; p < np; ++p)
-                            if (!m->nodes[nd.par[p]].observed) prod *= q[hmap[nd.par[p]] + digit(l, p)];
+                            if (!m->nodes[nd.par[p]].observed) { prod *= q[hmap[nd.par[p]] + digit(l, p)]; ++nfac; }
                         acc += prod * lg(nd, l, a);
+                        if (m->count_terms) m->c_upd_flops += 2 + std::max(nfac - 1, 0);
                     }
                     for (size_t c = 0; c < nd.chi.size(); ++c) {  // children, :139-191
                         int ci = nd.chi[c];
@@ -395,12 +416,21 @@ struct MeanField {
                                     if (pa.observed && pa.obs != qp) true_obs = false;
                                     if (ch.par[p] != i && !pa.observed) prod *= q[hmap[ch.par[p]] + qp];
                                 }
-                                if (digit(l, idx) == a && true_obs) acc += prod * lg(ch, l, ac);
+                                if (digit(l, idx) == a && true_obs) {
+                                    acc += prod * lg(ch, l, ac);
+                                    if (m->count_terms) {
+                                        int nfac = ch.observed ? 0 : 1;
+                                        for (int p = 0; p < ncp; ++p) if (ch.par[p] != i && !m->nodes[ch.par[p]].observed) ++nfac;
+                                        m->c_upd_flops += 2 + std::max(nfac - 1, 0);
+                                    }
+                                }
                             }
                         }
                     }
                     newq[hi + a] = std::exp(acc);               // :192 (no max shift)
+                    if (m->count_terms) m->c_upd_transc += 1;
                 }
+                if (m->count_terms) m->c_upd_flops += 7;
                 double sum = 0;
                 for (int a = 0; a < 4; ++a) sum += newq[hi + a];
                 for (int a = 0; a < 4; ++a) q[hi + a] = newq[hi + a] / sum;  // Gauss-Seidel, :195-201
@@ -409,6 +439,7 @@ struct MeanField {
             if (std::fabs(old_score - new_score) < 1e-5) converged = true;  // :204-207 (sticky)
             old_score = new_score;
             ++k;
+            if (m->count_terms) m->c_sweeps++;
         }
         sweeps = k;
     }
@@ -837,6 +868,28 @@ void orc_model_reset_stats(void* h) { ((Model*)h)->sweeps_total = 0; ((Model*)h)
 
 double orc_score_window(void* h, const uint8_t* cols, int revcomp, int* sweeps) {
     ORC_TRY return score_window(*(Model*)h, cols, revcomp != 0, sweeps); ORC_CATCH(NAN)
+}
+// Term counter: scores one window with counting on and returns, per unit,
+// out[0] = flop of one update sweep, out[1] = flop of one free-energy evaluation, out[2] / out[3] = their
+// transcendental calls, out[4] = sweeps of this window.  Total work of a window = K*upd + (K+1)*fe.
+int orc_count_terms(void* h, const uint8_t* cols, int revcomp, double* out) {
+    ORC_TRY
+    Model* m = (Model*)h;
+    m->count_terms = true;
+    m->c_upd_flops = m->c_upd_transc = m->c_fe_flops = m->c_fe_transc = m->c_sweeps = m->c_fe_calls = 0;
+    int k = 0;
+    const int mode = m->mode;
+    m->mode = MEANFIELD;
+    score_window(*m, cols, revcomp != 0, &k);
+    m->mode = mode;
+    m->count_terms = false;
+    out[0] = (double)m->c_upd_flops / std::max<long long>(m->c_sweeps, 1);
+    out[1] = (double)m->c_fe_flops / std::max<long long>(m->c_fe_calls, 1);
+    out[2] = (double)m->c_upd_transc / std::max<long long>(m->c_sweeps, 1);
+    out[3] = (double)m->c_fe_transc / std::max<long long>(m->c_fe_calls, 1);
+    out[4] = (double)k;
+    return 0;
+    ORC_CATCH(-1)
 }
 // all offsets of one alignment; out[L-W+1]
 int orc_score_windows(void* h, const uint8_t* codes, int L, int revcomp, double* out, int* sweeps) {

@@ -56,6 +56,13 @@ class Context:
     def last_launches(self):
         return lib().phyfoo_last_launches(self.h)
 
+    def set_option(self, name, value):
+        raise_for(lib().phyfoo_set_option(self.h, name.encode(), int(value)), self.h)
+
+    def last_score_path(self):
+        """0 = direct kernel, 1 = pattern table, 2 = order-1 network."""
+        return lib().phyfoo_last_score_path(self.h)
+
     def estep_kernel_ms(self):
         a, b, c = C.c_float(), C.c_float(), C.c_float()
         raise_for(lib().phyfoo_estep_kernel_ms(self.h, C.byref(a), C.byref(b), C.byref(c)), self.h)

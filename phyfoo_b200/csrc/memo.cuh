@@ -1,0 +1,167 @@
+// memo.cuh -- "pattern table" path of the order-0 scoring kernels for few species (3 S <= 18 bits).
+//
+// For an order-0 model the trees of a window do not interact: the free energy of tree t after k sweeps depends only
+// on (the column's pattern, t, k).  The window-level stop rule (MeanFieldForBayesNet.java:102-107,204-209) couples
+// them only through the SUM over t.  With S = 5 species there are at most 5^5 = 3125 distinct columns, so instead of
+// running ~10 sweeps for each of the n_windows * W trees, this path
+//   1. marks the column patterns that occur in the data set (once per data set),
+//   2. runs the mean field for every (occurring pattern, position) for k = 0..max_sweeps and stores the whole
+//      free-energy trajectory F_k           (memo_traj_kernel: the same meanfield_pass as the direct kernel),
+//   3. scores every window by walking k: F_k(window) = sum_t traj[t][pattern(c0 + t)][k] in tree order, applying the
+//      reference's stop rule to that sum  (memo_window_kernel: pure gathers, no transcendental).
+// The per-tree values and the order of the sum over t are those of score_o0_kernel, so scores, sweep counts and
+// arg-max calls are bit-identical to the direct path (tests/test_gpu_memo.py compares the two paths bit for bit).
+// Exact mode is the same with a one-entry "trajectory" (-log P(column | t)).
+#pragma once
+
+struct MemoSet {                 // per (data set): which patterns occur (forward and reverse-complement use)
+    int code_bits = 0;           // 3 S
+    int n_codes = 0;             // 1 << code_bits
+    int cap = 0;                 // upper bound of the number of occurring patterns (host-side, for allocations)
+    int32_t* d_dense_of = nullptr;   // [n_codes] dense id or -1
+    int32_t* d_code_of = nullptr;    // [cap]
+    int32_t* d_count = nullptr;      // [1] number of occurring patterns D (device-resident; kernels read it)
+};
+
+// canonical pattern code of a packed column: base bits with 00 under gaps | gap bits << 2S
+__device__ __forceinline__ uint32_t memo_code(ColWords cw, int S) {
+    uint32_t b = (uint32_t)cw.b & ((1u << (2 * S)) - 1u);
+    const uint32_t g = cw.g & ((1u << S) - 1u);
+    for (int s = 0; s < S; ++s)
+        if ((g >> s) & 1u) b &= ~(3u << (2 * s));
+    return b | (g << (2 * S));
+}
+__device__ __forceinline__ ColWords memo_words(uint32_t code, int S) {
+    ColWords cw; cw.b = code & ((1u << (2 * S)) - 1u); cw.g = code >> (2 * S); return cw;
+}
+
+__global__ void memo_mark_kernel(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ gaps, int64_t n_cols, int nb, int S,
+                                 int32_t* __restrict__ flags) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cols) return;
+    const ColWords cw = load_column(bases, gaps, n_cols, nb, c);
+    flags[memo_code(cw, S)] = 1;
+    flags[memo_code(complement(cw), S)] = 1;      // reverse-complement windows read the complemented column
+}
+
+// flags -> dense ids (ascending code order), one block; flags array is overwritten with dense_of
+__global__ void __launch_bounds__(1024) memo_compact_kernel(int32_t* __restrict__ flags_dense, int n_codes, int32_t* __restrict__ code_of,
+                                                            int cap, int32_t* __restrict__ count) {
+    __shared__ int s_warp[32];
+    __shared__ int s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < n_codes; c0 += blockDim.x) {
+        const int c = c0 + threadIdx.x;
+        const int f = (c < n_codes && flags_dense[c]) ? 1 : 0;
+        int v = f;
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if ((threadIdx.x & 31) >= o) v += u; }
+        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = v;
+        __syncthreads();
+        int before = s_base;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) before += s_warp[w];
+        const int id = before + v - f;
+        if (c < n_codes) flags_dense[c] = f ? id : -1;
+        if (f && id < cap) code_of[id] = c;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_base = before + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = s_base;
+}
+
+struct MemoTrajParams {
+    const int32_t* code_of; const int32_t* count;
+    int W, I, S, E, prog_len, cap, K1;      // K1 = trajectory length (max_sweeps + 1, or 1 in exact mode)
+    const double* tab;                      // [E][W] (logs for the mean field, probabilities for exact mode)
+    const int* prog;
+    double* traj;                           // [(t * cap + d) * K1 + k]
+};
+
+// one thread per (pattern d, position t): the mean-field trajectory F_0..F_max of that tree
+template <int MODE>
+__global__ void __launch_bounds__(128) memo_traj_kernel(MemoTrajParams p) {
+    extern __shared__ double smem[];
+    const int T = blockDim.x, tid = threadIdx.x;
+    double* s_tab = smem;                                   // [E][W]
+    double* s_state = s_tab + (size_t)p.E * p.W;            // [I*8][T]
+    int* s_prog = (int*)(s_state + (size_t)p.I * 8 * T);
+    for (int i = tid; i < p.E * p.W; i += T) s_tab[i] = p.tab[i];
+    for (int i = tid; i < p.prog_len; i += T) s_prog[i] = p.prog[i];
+    __syncthreads();
+    TreeProg tp;
+    tp.n_internal = p.I; tp.n_leaves = p.S; tp.n_nodes = 0;
+    tp.par_internal = s_prog;
+    tp.node_of = s_prog + p.I;
+    tp.leaf_begin = s_prog + 2 * p.I;
+    tp.leaf_node = s_prog + 3 * p.I + 1;
+    tp.leaf_species = s_prog + 3 * p.I + 1 + p.S;
+    const State st{s_state + tid, T};
+    const int D = *p.count;
+    const long long n = (long long)D * p.W;
+    for (long long it = (long long)blockIdx.x * T + tid; it < n; it += (long long)gridDim.x * T) {
+        const int d = (int)(it / p.W), t = (int)(it - (long long)d * p.W);
+        const ColWords cw = memo_words((uint32_t)p.code_of[d], p.S);
+        const Tab tb{s_tab + t, p.W};
+        double* out = p.traj + ((size_t)t * p.cap + d) * p.K1;
+        if (MODE == PHYFOO_MODE_EXACT) { out[0] = -log(pruning_likelihood(tp, tb, st, cw)); continue; }
+        for (int k = 0; k < p.K1; ++k) out[k] = meanfield_pass(tp, tb, st, cw, k > 0);
+    }
+}
+
+struct MemoWindowParams {
+    const uint32_t* bases; const uint32_t* gaps; int64_t n_cols; int nb;
+    const int64_t* col_off; const int64_t* win_off; int n_aln;
+    int64_t n_windows; int n_strands; int strand0;
+    int W, S, cap, K1;
+    const int32_t* dense_of; const double* traj;
+    double* out; int32_t* sweeps; unsigned long long* counters;
+    int max_sweeps, min_sweeps; double tol; int exact;
+};
+
+// one thread per window: walk k, summing the W trajectories in tree order, until the reference's stop rule fires
+__global__ void __launch_bounds__(256) memo_window_kernel(MemoWindowParams p) {
+    const long long n_items = (long long)p.n_windows * p.n_strands;
+    unsigned long long ksum = 0;
+    for (long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += (long long)gridDim.x * blockDim.x) {
+        const int si = (int)(item / p.n_windows);
+        const int64_t w = item - (long long)si * p.n_windows;
+        const int strand = p.n_strands == 2 ? si : p.strand0;
+        const int a = find_alignment(p.win_off, p.n_aln, w);
+        const int64_t c0 = p.col_off[a] + (w - p.win_off[a]);
+        const double* row[16];
+        // W <= 16 here (the launcher falls back to the direct kernel otherwise): trajectory rows of the W trees
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            if (t < p.W) {
+                const int64_t c = strand ? c0 + (p.W - 1 - t) : c0 + t;       // jstacs StrandModel.java:636-639
+                ColWords cw = load_column(p.bases, p.gaps, p.n_cols, p.nb, c);
+                if (strand) cw = complement(cw);
+                const int d = p.dense_of[memo_code(cw, p.S)];
+                row[t] = p.traj + ((size_t)t * p.cap + d) * p.K1;
+            }
+        }
+        double Fsum = 0.0;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) if (t < p.W) Fsum += row[t][0];           // tree-major, like calcFreeEnergy(0, W-1)
+        int k = 0;
+        if (!p.exact) {
+            double old = Fsum;                                                // F_0, MeanFieldForBayesNet.java:105
+            bool conv = false;
+            while ((k < p.max_sweeps && !conv) || k < p.min_sweeps) {         // :107
+                ++k;
+                Fsum = 0.0;
+#pragma unroll
+                for (int t = 0; t < 16; ++t) if (t < p.W) Fsum += row[t][k];
+                if (fabs(old - Fsum) < p.tol) conv = true;                    // :204-207 (sticky)
+                old = Fsum;
+            }
+        }
+        p.out[item] = -Fsum;                                                  // PhyloBayesModel.java:259
+        if (p.sweeps) p.sweeps[item] = k;
+        ksum += (unsigned long long)k;
+    }
+    // sweep statistics: one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) ksum += __shfl_down_sync(0xffffffffu, ksum, o);
+    if ((threadIdx.x & 31) == 0 && ksum) atomicAdd(&p.counters[1], ksum);
+}

@@ -62,10 +62,15 @@ struct phyfoo_ctx {
     DevBuf gamma, profile, part, argoff, argstrand, alnw, out3, gstate, misc;
     DevBuf selw, sel_tmp, sel_out;   // M-step selection scratch
     int64_t gamma_windows = -1;      // number of windows whose gamma of the last E-step is resident in `gamma`
+    DevBuf memo_traj;                // pattern-table path: free-energy trajectories (memo.cuh)
+    int memo_mode = 1;               // 0 = never, 1 = when it pays off, 2 = whenever it applies
+    int last_path = 0;               // scoring path of the most recent motif/background launch: 0 direct, 1 pattern table, 2 order-1 net
     int launches = 0;                // kernels launched by the current call
 };
 
+struct MemoSet;
 struct phyfoo_dataset {
+    MemoSet* memo = nullptr;                     // pattern set (memo.cuh), built on first use
     int n_aln = 0, S = 0, nb = 0, ng = 0;
     int64_t n_cols = 0;
     int min_len = 0, max_len = 0;
@@ -97,6 +102,8 @@ static thread_local std::string g_init_err;
             return PHYFOO_ECUDA;                                                                   \
         }                                                                                          \
     } while (0)
+
+static void memo_release(MemoSet* ms);
 
 static int fail(phyfoo_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg; else g_init_err = msg;
@@ -455,7 +462,7 @@ extern "C" void phyfoo_destroy(phyfoo_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf* b : {&ctx->counters, &ctx->fg_scores, &ctx->bg_scores, &ctx->sweeps_buf, &ctx->gamma, &ctx->profile, &ctx->part,
-                      &ctx->argoff, &ctx->argstrand, &ctx->alnw, &ctx->out3, &ctx->gstate, &ctx->misc, &ctx->selw, &ctx->sel_tmp, &ctx->sel_out})
+                      &ctx->argoff, &ctx->argstrand, &ctx->alnw, &ctx->out3, &ctx->gstate, &ctx->misc, &ctx->selw, &ctx->sel_tmp, &ctx->sel_out, &ctx->memo_traj})
         b->release();
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
@@ -602,6 +609,7 @@ extern "C" void phyfoo_dataset_free(phyfoo_ctx* ctx, phyfoo_dataset* ds) {
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
     cudaFree(ds->d_col_off); cudaFree(ds->d_bases); cudaFree(ds->d_gaps);
     for (auto& kv : ds->d_win_off) cudaFree(kv.second);
+    memo_release(ds->memo);
     delete ds;
 }
 
@@ -762,6 +770,101 @@ static int plan_score(phyfoo_ctx* ctx, const ModelHost& h, int prog_len, long lo
 struct ScoreItems { const int64_t* col0; const uint8_t* strand; double* q_int; double* q_leaf; double* ent; };
 
 #include "net1.cuh"
+#include "memo.cuh"
+
+static void memo_release(MemoSet* ms) {
+    if (!ms) return;
+    cudaFree(ms->d_dense_of); cudaFree(ms->d_code_of); cudaFree(ms->d_count);
+    delete ms;
+}
+
+// occurring column patterns of the data set (forward and complemented), built once
+static int dataset_memo(phyfoo_ctx* ctx, const phyfoo_dataset* cds, MemoSet** out) {
+    phyfoo_dataset* ds = const_cast<phyfoo_dataset*>(cds);
+    if (!ds->memo) {
+        MemoSet* ms = new MemoSet();
+        ms->code_bits = 3 * ds->S; ms->n_codes = 1 << ms->code_bits;
+        long long valid = 1;
+        for (int s = 0; s < ds->S; ++s) valid *= 5;
+        ms->cap = (int)std::max<long long>(1, std::min<long long>(valid, 2 * ds->n_cols));
+        cudaError_t e;
+        if ((e = cudaMalloc(&ms->d_dense_of, (size_t)ms->n_codes * sizeof(int32_t))) != cudaSuccess ||
+            (e = cudaMalloc(&ms->d_code_of, (size_t)ms->cap * sizeof(int32_t))) != cudaSuccess ||
+            (e = cudaMalloc(&ms->d_count, sizeof(int32_t))) != cudaSuccess ||
+            (e = cudaMemsetAsync(ms->d_dense_of, 0, (size_t)ms->n_codes * sizeof(int32_t), ctx->stream)) != cudaSuccess) {
+            memo_release(ms);
+            ctx->err = std::string("pattern set: ") + cudaGetErrorString(e);
+            return PHYFOO_ECUDA;
+        }
+        if (ds->n_cols > 0) {
+            memo_mark_kernel<<<(unsigned)((ds->n_cols + 255) / 256), 256, 0, ctx->stream>>>(ds->d_bases, ds->d_gaps, ds->n_cols, ds->nb, ds->S, ms->d_dense_of);
+            ctx->launches++;
+        }
+        memo_compact_kernel<<<1, 1024, 0, ctx->stream>>>(ms->d_dense_of, ms->n_codes, ms->d_code_of, ms->cap, ms->d_count);
+        ctx->launches++;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) { memo_release(ms); ctx->err = std::string("pattern set kernels: ") + cudaGetErrorString(e); return PHYFOO_ECUDA; }
+        ds->memo = ms;
+    }
+    *out = ds->memo;
+    return PHYFOO_OK;
+}
+
+static bool memo_applies(const phyfoo_ctx* ctx, const phyfoo_dataset* ds, const ModelHost& h, long long n_items) {
+    if (ctx->memo_mode == 0 || h.order != 0 || 3 * ds->S > 18 || h.W > 16) return false;
+    if (ctx->memo_mode == 2) return true;
+    long long valid = 1;
+    for (int s = 0; s < ds->S; ++s) valid *= 5;
+    const long long cap = std::min<long long>(valid, 2 * ds->n_cols);
+    // trajectories cost cap * W * (max_sweeps + 1) tree passes, the direct kernel about n_items * W * 10
+    return n_items * 10 >= 4 * cap * (h.max_sweeps + 1);
+}
+
+// pattern-table path (memo.cuh): trajectories of the occurring patterns, then one gather pass over the windows
+static int launch_memo(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* m, int mode, const int64_t* d_win_off, int64_t n_windows,
+                       int strands, double* d_out, int32_t* d_sweeps, int counter_slot) {
+    ModelHost& h = m->h;
+    MemoSet* ms = nullptr;
+    int rc = dataset_memo(ctx, ds, &ms);
+    if (rc) return rc;
+    const int K1 = mode == PHYFOO_MODE_EXACT ? 1 : h.max_sweeps + 1;
+    CU(ctx->memo_traj.ensure((size_t)ms->cap * h.W * K1 * sizeof(double)));
+    MemoTrajParams tp;
+    tp.code_of = ms->d_code_of; tp.count = ms->d_count;
+    tp.W = h.W; tp.I = h.I; tp.S = h.S; tp.E = h.E; tp.prog_len = m->prog_len; tp.cap = ms->cap; tp.K1 = K1;
+    tp.tab = mode == PHYFOO_MODE_EXACT ? m->d_probtab : m->d_logtab;
+    tp.prog = m->d_prog; tp.traj = ctx->memo_traj.as<double>();
+    const int threads = 128;
+    const size_t smem = (size_t)h.E * h.W * sizeof(double) + (size_t)h.I * 8 * threads * sizeof(double) + (size_t)m->prog_len * sizeof(int) + 16;
+    const long long trees = (long long)ms->cap * h.W;
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((trees + threads - 1) / threads, 8LL * ctx->sm_count));
+    unsigned long long* counters = ctx->counters.as<unsigned long long>() + 2 * counter_slot;
+    CU(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    if (mode == PHYFOO_MODE_EXACT) {
+        CU(cudaFuncSetAttribute(memo_traj_kernel<PHYFOO_MODE_EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        memo_traj_kernel<PHYFOO_MODE_EXACT><<<blocks, threads, smem, ctx->stream>>>(tp);
+    } else {
+        CU(cudaFuncSetAttribute(memo_traj_kernel<PHYFOO_MODE_MEANFIELD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        memo_traj_kernel<PHYFOO_MODE_MEANFIELD><<<blocks, threads, smem, ctx->stream>>>(tp);
+    }
+    ctx->launches++;
+    CU(cudaGetLastError());
+    MemoWindowParams wp;
+    wp.bases = ds->d_bases; wp.gaps = ds->d_gaps; wp.n_cols = ds->n_cols; wp.nb = ds->nb;
+    wp.col_off = ds->d_col_off; wp.win_off = d_win_off; wp.n_aln = ds->n_aln;
+    wp.n_windows = n_windows; wp.n_strands = strands == 2 ? 2 : 1; wp.strand0 = strands == 1 ? 1 : 0;
+    wp.W = h.W; wp.S = h.S; wp.cap = ms->cap; wp.K1 = K1;
+    wp.dense_of = ms->d_dense_of; wp.traj = ctx->memo_traj.as<double>();
+    wp.out = d_out; wp.sweeps = d_sweeps; wp.counters = counters;
+    wp.max_sweeps = h.max_sweeps; wp.min_sweeps = h.min_sweeps; wp.tol = h.tol; wp.exact = mode == PHYFOO_MODE_EXACT ? 1 : 0;
+    const long long n_items = (long long)n_windows * wp.n_strands;
+    const int wblocks = (int)std::max<long long>(1, std::min<long long>((n_items + 255) / 256, 16LL * ctx->sm_count));
+    memo_window_kernel<<<wblocks, 256, 0, ctx->stream>>>(wp);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    ctx->last_path = 1;
+    return PHYFOO_OK;
+}
 
 // order-1 motif network: quad per window (net1.cuh)
 static int launch_net1(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* m, const int64_t* d_win_off, int64_t n_windows,
@@ -829,7 +932,9 @@ static int launch_score(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model*
     const int n_strands = strands == 2 ? 2 : 1;
     const long long n_items = (long long)n_windows * n_strands;
     if (n_items == 0) return PHYFOO_OK;
-    if (h.order == 1) return launch_net1(ctx, ds, m, d_win_off, n_windows, strands, d_out, d_sweeps, counter_slot, items);
+    if (h.order == 1) { ctx->last_path = 2; return launch_net1(ctx, ds, m, d_win_off, n_windows, strands, d_out, d_sweeps, counter_slot, items); }
+    if (!items && memo_applies(ctx, ds, h, n_items)) return launch_memo(ctx, ds, m, mode, d_win_off, n_windows, strands, d_out, d_sweeps, counter_slot);
+    ctx->last_path = 0;
     ScorePlan pl;
     rc = plan_score(ctx, h, m->prog_len, n_items, mode, items != nullptr, &pl);
     if (rc) return rc;
@@ -1095,6 +1200,16 @@ extern "C" int phyfoo_estep_sweeps(phyfoo_ctx* ctx, int64_t* sweeps_fg, int64_t*
 }
 
 extern "C" int phyfoo_last_launches(const phyfoo_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int phyfoo_last_score_path(const phyfoo_ctx* ctx) { return ctx ? ctx->last_path : -1; }
+extern "C" int phyfoo_set_option(phyfoo_ctx* ctx, const char* name, int64_t value) {
+    if (!ctx || !name) return PHYFOO_EINVAL;
+    if (std::strcmp(name, "pattern_memo") == 0) {
+        if (value < 0 || value > 2) return fail(ctx, PHYFOO_EINVAL, "set_option: pattern_memo must be 0 (off), 1 (auto) or 2 (always)");
+        ctx->memo_mode = (int)value;
+        return PHYFOO_OK;
+    }
+    return fail(ctx, PHYFOO_EINVAL, std::string("set_option: unknown option ") + name);
+}
 extern "C" void* phyfoo_stream(phyfoo_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 extern "C" int phyfoo_synchronize(phyfoo_ctx* ctx) {
     if (!ctx) return PHYFOO_EINVAL;

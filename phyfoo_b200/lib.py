@@ -28,7 +28,7 @@ SYMBOLS = [
     "phyfoo_score_windows", "phyfoo_bg_columns", "phyfoo_zoops_estep", "phyfoo_zoops_estep_device",
     "phyfoo_select", "phyfoo_fe_prepare", "phyfoo_fe_prepare_all", "phyfoo_fe_eval", "phyfoo_fe_grad",
     "phyfoo_fe_values_device", "phyfoo_fe_size", "phyfoo_fe_free",
-    "phyfoo_last_launches", "phyfoo_stream", "phyfoo_synchronize", "phyfoo_estep_kernel_ms", "phyfoo_estep_sweeps",
+    "phyfoo_set_option", "phyfoo_last_score_path", "phyfoo_last_launches", "phyfoo_stream", "phyfoo_synchronize", "phyfoo_estep_kernel_ms", "phyfoo_estep_sweeps",
 ]
 
 
@@ -102,6 +102,8 @@ def lib():
     L.phyfoo_fe_free.argtypes = [vp, vp]
     L.phyfoo_fe_free.restype = None
     L.phyfoo_last_launches.argtypes = [vp]
+    L.phyfoo_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    L.phyfoo_last_score_path.argtypes = [vp]
     L.phyfoo_stream.argtypes = [vp]
     L.phyfoo_stream.restype = vp
     L.phyfoo_synchronize.argtypes = [vp]

@@ -1,0 +1,106 @@
+"""The pattern-table path (csrc/memo.cuh) against the direct kernel: bit-identical scores, sweep counts, gamma and
+arg-max calls (same per-tree arithmetic, same summation order), and both against the oracle."""
+import numpy as np
+import pytest
+
+from util import orc, oracle_bg, oracle_fg, random_codes, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def ctx():
+    from phyfoo_b200 import core
+    c = core.default_context()
+    yield c
+    c.set_option("pattern_memo", 1)
+
+
+def _both(ctx, fn):
+    ctx.set_option("pattern_memo", 0)
+    direct = fn()
+    assert ctx.last_score_path() == 0
+    ctx.set_option("pattern_memo", 2)
+    memo = fn()
+    return direct, memo
+
+
+@pytest.mark.parametrize("newick_name", ["star5", "cat5", "mixed6", "star3"])
+@pytest.mark.parametrize("gap_rate", [0.0, 0.2])
+def test_memo_equals_direct_bit_for_bit(ctx, newick_name, gap_rate):
+    from phyfoo_b200 import synth
+    from phyfoo_b200.data import PhyloSample
+    from phyfoo_b200.models import PhyloBackground, PhyloBayesModel
+    from phyfoo_b200.newick import parse_newick
+    newick = {"star5": synth.star_newick(5), "cat5": synth.caterpillar_newick(5), "star3": synth.star_newick(3, 0.35),
+              "mixed6": "((A:0.1,B:0.3):0.15,(C:0.2,(D:0.05,E:0.4):0.25):0.1,F:0.3)"}[newick_name]
+    S = parse_newick(newick).n_species
+    rng = np.random.default_rng(77)
+    W = 7
+    lens = [W, 60, 5, 131, 33]
+    smp = PhyloSample(random_codes(rng, sum(lens), S, gap_rate), np.concatenate([[0], np.cumsum(lens)]))
+    fg = PhyloBayesModel(W, 0, newick, ctx); fg.setCondProbs(synth.random_pwm(W, 0, 5))
+    bg = PhyloBackground(0, newick, ctx); bg.setCondProb(np.array([[0.3, 0.2, 0.1, 0.4]]), 0)
+    for strand in (0, 1):
+        (d, dk), (m, mk) = _both(ctx, lambda: fg.getLogProbFor(smp, strand=strand, want_sweeps=True))
+        assert ctx.last_score_path() == 1
+        assert np.array_equal(d, m) and np.array_equal(dk, mk)
+    (d, dk), (m, mk) = _both(ctx, lambda: bg.getColumnLogProbs(smp, want_sweeps=True))
+    assert np.array_equal(d, m) and np.array_equal(dk, mk)
+    PhyloBayesModel.CALC_LOGLIKELIHOOD = True
+    try:
+        d, m = _both(ctx, lambda: fg.getLogProbFor(smp))
+        assert np.array_equal(d, m)
+    finally:
+        PhyloBayesModel.CALC_LOGLIKELIHOOD = False
+    # and against the oracle
+    om = oracle_fg(newick, fg.getCondProbs() and [p.reshape(1, 4) for p in fg.getCondProbs()])
+    ref = np.concatenate([om.score_windows(smp.getElementAt(i))[0] for i in range(smp.n_alignments)])
+    ctx.set_option("pattern_memo", 2)
+    assert rel_err(fg.getLogProbFor(smp), ref) < 1e-9
+
+
+def test_memo_estep_and_parameter_updates(ctx):
+    from phyfoo_b200 import synth
+    from phyfoo_b200.models import PhyloBackground, PhyloBayesModel, SingleHiddenMotifMixture, StrandModel
+    newick = synth.caterpillar_newick(5)
+    W = 8
+    pwm = synth.random_pwm(W, 0, 9)
+    smp, planted = synth.make_sample(newick, 30, 90, 4, pwm=pwm, gap_rate=0.02, length_jitter=9)
+    fg = PhyloBayesModel(W, 0, newick, ctx); fg.setCondProbs(pwm)
+    bg = PhyloBackground(0, newick, ctx)
+    for motif in (fg, StrandModel(fg, 0.4)):
+        shm = SingleHiddenMotifMixture(motif, bg, zoops=0.9)
+        d, m = _both(ctx, lambda: shm.getNewWeights(smp))
+        assert d["ll"] == m["ll"] and np.array_equal(d["gamma"], m["gamma"]) and np.array_equal(d["w"], m["w"])
+        assert np.array_equal(d["argmax_off"], m["argmax_off"]) and np.array_equal(d["argmax_strand"], m["argmax_strand"])
+        assert d["stats"]["sweeps_fg"] == m["stats"]["sweeps_fg"] and d["stats"]["sweeps_bg"] == m["stats"]["sweeps_bg"]
+    # new parameters are picked up by the tables (trajectories are rebuilt per call)
+    fg.setCondProb(np.array([[0.7, 0.1, 0.1, 0.1]]), 3)
+    shm = SingleHiddenMotifMixture(fg, bg, zoops=0.9)
+    d, m = _both(ctx, lambda: shm.getNewWeights(smp))
+    assert d["ll"] == m["ll"] and np.array_equal(d["gamma"], m["gamma"])
+    ref = orc.estep(oracle_fg(newick, [p.reshape(1, 4) for p in fg.getCondProbs()]), oracle_bg(newick, 0), smp.col_offsets,
+                    smp.codes, np.log([0.9, 0.1]))
+    assert abs(m["ll"] - ref["ll"]) <= 1e-9 * abs(ref["ll"]) and np.array_equal(m["argmax_off"], ref["argmax_off"])
+
+
+def test_memo_does_not_apply_to_many_species_or_order1(ctx):
+    from phyfoo_b200 import synth
+    from phyfoo_b200.models import PhyloBayesModel
+    ctx.set_option("pattern_memo", 2)
+    newick = synth.random_binary_newick(12, 3)
+    smp, _ = synth.make_sample(newick, 2, 30, 1)
+    fg = PhyloBayesModel(5, 0, newick, ctx)
+    fg.getLogProbFor(smp)
+    assert ctx.last_score_path() == 0
+    n5 = synth.star_newick(5)
+    smp5, _ = synth.make_sample(n5, 2, 30, 1)
+    fg1 = PhyloBayesModel(5, 1, n5, ctx)
+    fg1.getLogProbFor(smp5)
+    assert ctx.last_score_path() == 2
+    from phyfoo_b200.lib import IllegalArgumentException
+    with pytest.raises(IllegalArgumentException):
+        ctx.set_option("pattern_memo", 7)
+    with pytest.raises(IllegalArgumentException):
+        ctx.set_option("no_such_option", 1)

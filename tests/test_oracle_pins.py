@@ -240,3 +240,17 @@ def test_encoding_and_packing():
             assert (4 if g else b) == c[col, s]
             if g:
                 assert b == 0
+
+
+def test_term_counter_matches_closed_forms():
+    """The flop model bench.py uses for the roofline equals the oracle's instrumented counter."""
+    import bench
+    rng = np.random.default_rng(12)
+    for newick, S, I in ((STAR, 5, 1), (CAT, 5, 4), (synth.random_binary_newick(12, 3), 12, 11)):
+        for W in (1, 3, 5):
+            c0 = oracle_fg(newick, synth.random_pwm(W, 0, 1)).count_terms(random_codes(rng, W, S))
+            upd, fe = bench.flops_order0(I, S)
+            assert (c0["upd_flops"], c0["fe_flops"]) == (W * upd, W * fe)
+            assert c0["upd_transc"] == 4 * I * W                      # 4 exp per hidden node and sweep
+            c1 = oracle_fg(newick, synth.random_pwm(W, 1, 1), order=1).count_terms(random_codes(rng, W, S))
+            assert (c1["upd_flops"], c1["fe_flops"]) == bench.flops_order1(I, S, W)
