@@ -40,6 +40,7 @@ def parse_args():
     ap.add_argument("--n-aln", type=int, default=None, help="override the number of alignments (debug only)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-memo", action="store_true", help="switch the pattern-table path off (direct kernel only)")
     return ap.parse_args()
 
 
@@ -231,11 +232,14 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from phyfoo_b200 import core, synth
+    from phyfoo_b200.data import PhyloSample
     from phyfoo_b200.models import PhyloBackground, PhyloBayesModel, SingleHiddenMotifMixture
 
     ctx = core.Context(local)
+    if args.no_memo:
+        ctx.set_option("pattern_memo", 0)
     cfg, newick, pwm, sample, planted = synth.make_config(args.config, n_aln=args.n_aln)
-    W = cfg["W"]
+    W, S = cfg["W"], cfg["S"]
     fg = PhyloBayesModel(W, cfg["order"], newick, ctx)
     fg.setCondProbs(pwm)
     bg = PhyloBackground(0, newick, ctx)
@@ -257,10 +261,28 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(partial)
 
+    def timed(n_steps):
+        """n_steps E-steps, L2 flushed before each (untimed), CUDA events on the launching stream.  Returns the summed
+        device ms and the per-kernel device ms (library events), keyed by launch order."""
+        total, per_kernel = 0.0, {}
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(n_steps):
+            flush.fill_(1)
+            e0.record(stream)
+            step()
+            e1.record(stream)
+            e1.synchronize()
+            total += e0.elapsed_time(e1)
+            for i, (name, ms) in enumerate(ctx.last_kernel_times()):
+                key = (i, name)
+                per_kernel[key] = per_kernel.get(key, 0.0) + ms
+        return total, {k: v / n_steps for k, v in per_kernel.items()}
+
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
     launches_per_step = ctx.last_launches()
+    path = ctx.last_score_path()
     peak_tflops = ctx.fp64_peak()
 
     sampler = ClockSampler(local)
@@ -269,17 +291,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     sampler.start()
     t_wall0 = time.perf_counter()
-    dev_ms, fg_ms, bg_ms, zo_ms = 0.0, 0.0, 0.0, 0.0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for _ in range(args.steps):
-        flush.fill_(1)                      # L2 flush between timed iterations (untimed)
-        e0.record(stream)
-        step()
-        e1.record(stream)
-        e1.synchronize()
-        dev_ms += e0.elapsed_time(e1)
-        km = ctx.estep_kernel_ms()
-        fg_ms += km["fg_ms"]; bg_ms += km["bg_ms"]; zo_ms += km["zoops_ms"]
+    dev_ms, kernels = timed(args.steps)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -295,15 +307,27 @@ def run_ours(args):
     total_windows = n_windows * world
     value = total_windows * args.steps / (dev_ms_max * 1e-3)
 
-    # ---- e2e: public host API, host buffers, pack + copies inside the timed region (per rank, max over ranks)
-    pinned = torch.empty(sample.codes.shape, dtype=torch.uint8).pin_memory()
-    pinned.numpy()[:] = sample.codes
-    from phyfoo_b200.data import PhyloSample
+    # the direct kernel on the same workload (the path every configuration with more than 6 species takes), for the roofline
+    direct = None
+    if path == 1 and rank == 0:
+        ctx.set_option("pattern_memo", 0)
+        step(); torch.cuda.synchronize()
+        d_ms, d_kernels = timed(3)
+        ctx.set_option("pattern_memo", 1)
+        step(); torch.cuda.synchronize()
+        direct = (d_ms / 3, d_kernels)
+
+    # ---- e2e: public host API, host buffers, pack + copies inside the timed region (per rank, max over ranks).
+    # Inputs come from page-locked host memory, results land in page-locked host memory that the caller reuses.
+    pinned = ctx.pinned_empty(sample.codes.shape, np.uint8)
+    pinned[:] = sample.codes
+    out = {"gamma": ctx.pinned_empty(n_windows), "argmax_off": ctx.pinned_empty(sample.n_alignments, np.int32),
+           "argmax_strand": ctx.pinned_empty(sample.n_alignments, np.uint8)}
     e2e_steps = max(3, min(args.steps, 10))
 
     def e2e_step():
-        smp = PhyloSample(pinned.numpy(), sample.col_offsets)
-        res = shm.getNewWeights(smp, want_gamma=True)
+        smp = PhyloSample(pinned, sample.col_offsets)
+        res = shm.getNewWeights(smp, want_gamma=True, out=out)
         smp.device(ctx).free()
         return res
 
@@ -322,41 +346,90 @@ def run_ours(args):
     e2e_value = total_windows * e2e_steps / float(t.item())
     h2d = int(sample.codes.nbytes + sample.col_offsets.nbytes)
     d2h = int(res["gamma"].nbytes + res["argmax_off"].nbytes + res["argmax_strand"].nbytes + 24)
-    assert abs(res["ll"] - ll_w[0] / 1.0) <= 1e-9 * abs(res["ll"]) or world > 1
+    assert world > 1 or abs(res["ll"] - ll_w[0]) <= 1e-9 * abs(res["ll"])
 
     if rank == 0:
-        flops = algorithmic_flops(cfg, I, n_windows, sweeps_fg)
-        fg_ms_avg = fg_ms / args.steps
-        achieved = flops / (fg_ms_avg * 1e-3) / 1e12
-        abytes = algorithmic_bytes(cfg, n_windows)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        hbm_of = "measured" if peaks else "fallback"
+        step_ms = dev_ms_max / args.steps
+        flops = algorithmic_flops(cfg, I, n_windows, sweeps_fg)
+        abytes = algorithmic_bytes(cfg, n_windows)
+        kern_list = [{"kernel": name, "ms": round(ms, 5)} for (_, name), ms in sorted(kernels.items())]
+
+        def fp64_roofline(kernel_name, kernel_ms, note=None):
+            achieved = flops / (kernel_ms * 1e-3) / 1e12
+            r = {"bound": "fp64", "kernel": kernel_name, "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+                 "frac": achieved / peak_tflops,
+                 "peak_source": "DFMA microbenchmark in this run (MEASURED_PEAKS.json has no fp64 entry)",
+                 "flops_per_launch": flops, "kernel_ms": kernel_ms,
+                 "hbm": {"achieved": abytes / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": abytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak, "of": hbm_of},
+                 "traffic": None}
+            if note:
+                r["note"] = note
+            return r
+
+        fg_name = "score_o1_kernel" if cfg["order"] == 1 else "score_o0_kernel"
+        extra = {}
+        if path != 1:
+            fg_ms = max(ms for (_, name), ms in kernels.items() if name == fg_name)     # the motif-window launch
+            roofline = fp64_roofline(fg_name + " (motif windows)", fg_ms)
+            roofline["kernel_share_of_step"] = fg_ms / step_ms
+        else:
+            # pattern-table path: per-pattern trajectories (fp64, a small latency-bound grid) + gathers per window
+            D = ds.patterns()
+            win_ms = max(ms for (_, name), ms in kernels.items() if name == "memo_window_kernel")
+            traj_ms = sum(ms for (_, name), ms in kernels.items() if name == "memo_traj_kernel")
+            upd, fe = flops_order0(I, S)
+            K1 = 101
+            traj_flops = D * (W + 1) * K1 * (upd + fe)            # motif positions + the background tree
+            gather_bytes = W * (sweeps_fg + n_windows) * 8         # trajectory entries the stop rule consumes
+            if win_ms >= traj_ms:
+                roofline = {"bound": "hbm", "kernel": "memo_window_kernel (motif windows; gathers from an L2-resident table)",
+                            "achieved": abytes / (win_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": abytes / (win_ms * 1e-3) / 1e9 / hbm_peak, "of": hbm_of,
+                            "bytes_per_launch": abytes, "kernel_ms": win_ms, "kernel_share_of_step": win_ms / step_ms,
+                            "table_gather": {"bytes": gather_bytes, "GB/s": gather_bytes / (win_ms * 1e-3) / 1e9,
+                                             "what": "8 B x W x (K_w + 1) trajectory entries per window, served by L2"},
+                            "traffic": None}
+            else:
+                achieved = traj_flops / (traj_ms * 1e-3) / 1e12
+                roofline = {"bound": "fp64", "kernel": "memo_traj_kernel (mean-field trajectories of the occurring column patterns)",
+                            "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
+                            "peak_source": "DFMA microbenchmark in this run (MEASURED_PEAKS.json has no fp64 entry)",
+                            "flops_per_launch": traj_flops, "kernel_ms": traj_ms, "kernel_share_of_step": traj_ms / step_ms,
+                            "note": f"{D} patterns x {W + 1} trees x {K1} passes: a {D * (W + 1)}-thread grid, latency-bound by design",
+                            "traffic": None}
+            d_ms, d_kernels = direct
+            d_fg = max(ms for (_, name), ms in d_kernels.items() if name == fg_name)
+            extra["roofline_direct"] = fp64_roofline(
+                fg_name + " (motif windows, direct path: pattern table switched off)", d_fg,
+                "what every configuration with more than 6 species runs; measured in this run, 3 steps, not part of `value`")
+            extra["roofline_direct"]["step_ms"] = d_ms
+            extra["pattern_table"] = {"patterns": D, "trajectory_flops_per_step": traj_flops,
+                                      "direct_flops_per_step": flops, "work_ratio": flops / max(traj_flops, 1)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+            "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(cfg), "name": args.config, "windows_per_gpu": n_windows,
                        "mean_sweeps_per_window": sweeps_fg / max(n_windows, 1), "seed": hex(cfg["seed"]),
+                       "scoring_path": {0: "direct kernel", 1: "pattern table (bit-identical to the direct kernel)", 2: "order-1 network kernel"}[path],
                        "l2": "flushed between timed iterations (512 MB fill)", "collective": "NCCL all-reduce of 3 fp64" if world > 1 else "none"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "what": "PhyloSample -> pack on device -> E-step -> gamma/arg-max/ll to host"},
+                    "steps": e2e_steps, "what": "PhyloSample (page-locked host codes) -> pack on device -> E-step -> gamma/arg-max/ll to page-locked host buffers"},
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
-            "roofline": {"bound": "fp64", "kernel": ("score_o1_kernel" if cfg["order"] == 1 else "score_o0_kernel<meanfield>") + " (motif windows)",
-                         "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
-                         "peak_source": "DFMA microbenchmark in this run (MEASURED_PEAKS.json has no fp64 entry)",
-                         "flops_per_launch": flops, "kernel_ms": fg_ms_avg,
-                         "kernel_share_of_step": fg_ms / max(fg_ms + bg_ms + zo_ms, 1e-9),
-                         "hbm": {"achieved": abytes / (fg_ms_avg * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                 "frac": abytes / (fg_ms_avg * 1e-3) / 1e9 / hbm_peak, "of": "measured" if peaks else "fallback"},
-                         "traffic": None},
-            "phase_ms": {"bg_columns": bg_ms / args.steps, "fg_windows": fg_ms_avg, "zoops": zo_ms / args.steps},
+            "roofline": roofline,
+            "kernels_ms": kern_list,
             "wall_s": t_wall,
         }
+        line.update(extra)
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             n = cpu_sample_size(cfg, newick, pwm, sample, cores, args.cpu_seconds)

@@ -116,6 +116,8 @@ int phyfoo_dataset_create_device(phyfoo_ctx* ctx, int32_t n_aln, int32_t n_speci
 int phyfoo_dataset_packed(phyfoo_ctx* ctx, const phyfoo_dataset* ds, uint32_t* bases_out, uint32_t* gaps_out);
 int64_t phyfoo_dataset_columns(const phyfoo_dataset* ds);
 int64_t phyfoo_dataset_windows(const phyfoo_dataset* ds, int32_t width); /* sum_i max(0, L_i - width + 1) */
+/* distinct column patterns (forward and complemented) of the data set, or -1 when the pattern table does not apply (S > 6) */
+int64_t phyfoo_dataset_patterns(phyfoo_ctx* ctx, const phyfoo_dataset* ds);
 void phyfoo_dataset_free(phyfoo_ctx* ctx, phyfoo_dataset* ds);
 
 /* ---- models ---- */
@@ -196,10 +198,19 @@ void phyfoo_fe_free(phyfoo_ctx* ctx, phyfoo_feset* fe);
  * gathers per window; results are bit-identical to the direct kernel (the reference's own, disabled, caches had the
  * same aim: models/AbstractPhyloModel.java:100-119, models/PhyloBackground.java:196). */
 int phyfoo_set_option(phyfoo_ctx* ctx, const char* name, int64_t value);
+/* "pattern_memo_sweep_cap" (default 100 = every window is served): sweeps stored per pattern; with a smaller cap the
+ * windows that need more go to the direct kernel. */
+/* Device time of every kernel the most recent call launched (CUDA events on the library's stream), in launch order:
+ * returns the number of entries written (<= max_entries) or a negative error; names are static strings. */
+int phyfoo_last_kernel_times(phyfoo_ctx* ctx, int32_t max_entries, const char** names_out, float* ms_out);
 /* scoring path of the most recent motif/background launch: 0 direct kernel, 1 pattern table, 2 order-1 network */
 int phyfoo_last_score_path(const phyfoo_ctx* ctx);
 
 /* ---- plumbing for callers that overlap the library with their own streams ---- */
+/* Page-locked host memory (cudaHostAlloc): buffers handed to the library copy at full PCIe speed when they come from
+ * here (a Java caller wraps the address in a MemorySegment / direct ByteBuffer).  NULL on failure. */
+void* phyfoo_host_alloc(phyfoo_ctx* ctx, int64_t bytes);
+void phyfoo_host_free(phyfoo_ctx* ctx, void* p);
 int phyfoo_last_launches(const phyfoo_ctx* ctx); /* kernels launched by the most recent call on this context */
 void* phyfoo_stream(phyfoo_ctx* ctx);            /* the library's cudaStream_t */
 int phyfoo_synchronize(phyfoo_ctx* ctx);

@@ -59,6 +59,29 @@ class Context:
     def set_option(self, name, value):
         raise_for(lib().phyfoo_set_option(self.h, name.encode(), int(value)), self.h)
 
+    def pinned_empty(self, shape, dtype=np.float64):
+        """numpy array in page-locked host memory (phyfoo_host_alloc); copies to/from it run at full PCIe speed.
+        The memory is released when the array (and every view of it) is garbage collected."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        ptr = lib().phyfoo_host_alloc(self.h, n)
+        if not ptr:
+            raise MemoryError("phyfoo_host_alloc failed")
+        buf = (C.c_char * max(n, 1)).from_address(ptr)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        import weakref
+        weakref.finalize(buf, lib().phyfoo_host_free, None, ptr)
+        return arr
+
+    def last_kernel_times(self):
+        """[(kernel name, device ms)] of the most recent call on this context, in launch order."""
+        names = (C.c_char_p * 64)()
+        ms = (C.c_float * 64)()
+        n = lib().phyfoo_last_kernel_times(self.h, 64, names, ms)
+        if n < 0:
+            raise_for(n, self.h)
+        return [(names[i].decode(), float(ms[i])) for i in range(n)]
+
     def last_score_path(self):
         """0 = direct kernel, 1 = pattern table, 2 = order-1 network."""
         return lib().phyfoo_last_score_path(self.h)
@@ -123,6 +146,10 @@ class Dataset:
 
     def windows(self, width):
         return int(lib().phyfoo_dataset_windows(self.h, int(width)))
+
+    def patterns(self):
+        """Distinct column patterns (forward + complemented), or -1 when the pattern table does not apply."""
+        return int(lib().phyfoo_dataset_patterns(self.ctx.h, self.h))
 
     def window_offsets(self, width):
         return np.concatenate([[0], np.cumsum(np.maximum(self.lengths() - width + 1, 0))]).astype(np.int64)
@@ -199,17 +226,29 @@ def bg_columns(ctx, ds, model, want_sweeps=False):
 
 
 def zoops_estep(ctx, ds, fg, bg, logw, strand_logw=None, aln_weights=None, want_gamma=True, want_profile=False,
-                want_argmax=True):
+                want_argmax=True, out=None):
+    """out: optional dict of preallocated result arrays (gamma / profile [windows] float64, argmax_off [n_aln] int32,
+    argmax_strand [n_aln] uint8), e.g. from Context.pinned_empty, reused across calls."""
     n = ds.windows(fg.W)
+    out = out or {}
     logw = np.ascontiguousarray(logw, np.float64)
     sl = None if strand_logw is None else np.ascontiguousarray(strand_logw, np.float64)
     aw = None if aln_weights is None else np.ascontiguousarray(aln_weights, np.float64)
-    gamma = np.zeros(n) if want_gamma else None
-    prof = np.zeros(n) if want_profile else None
+
+    def buf(key, size, dtype):
+        a = out.get(key)
+        if a is None:
+            return np.zeros(size, dtype)
+        if a.dtype != dtype or a.size < size or not a.flags.c_contiguous:
+            raise ValueError(f"out[{key!r}] must be a contiguous {np.dtype(dtype).name} array of at least {size} elements")
+        return a.ravel()[:size]
+
+    gamma = buf("gamma", n, np.float64) if want_gamma else None
+    prof = buf("profile", n, np.float64) if want_profile else None
     w = np.zeros(2)
     ll = C.c_double()
-    ao = np.zeros(ds.n_aln, np.int32) if want_argmax else None
-    astr = np.zeros(ds.n_aln, np.uint8) if want_argmax else None
+    ao = buf("argmax_off", ds.n_aln, np.int32) if want_argmax else None
+    astr = buf("argmax_strand", ds.n_aln, np.uint8) if want_argmax else None
     st = _abi.Stats()
     raise_for(lib().phyfoo_zoops_estep(ctx.h, ds.h, fg.h, bg.h, _p(logw, C.c_double), _p(sl, C.c_double),
                                        _p(aw, C.c_double), _p(gamma, C.c_double), _p(prof, C.c_double),

@@ -8,7 +8,9 @@
 //   2. runs the mean field for every (occurring pattern, position) for k = 0..max_sweeps and stores the whole
 //      free-energy trajectory F_k           (memo_traj_kernel: the same meanfield_pass as the direct kernel),
 //   3. scores every window by walking k: F_k(window) = sum_t traj[t][pattern(c0 + t)][k] in tree order, applying the
-//      reference's stop rule to that sum  (memo_window_kernel: pure gathers, no transcendental).
+//      reference's stop rule to that sum  (memo_window_kernel: pure gathers, no transcendental);
+//   4. trajectories are stored up to a sweep cap (default: max_sweeps, so every window is served); with a smaller cap
+//      the windows whose stop rule has not fired by then are listed and scored by the direct kernel (score_o0_kernel, ITEMS variant) -- same bits either way.
 // The per-tree values and the order of the sum over t are those of score_o0_kernel, so scores, sweep counts and
 // arg-max calls are bit-identical to the direct path (tests/test_gpu_memo.py compares the two paths bit for bit).
 // Exact mode is the same with a one-entry "trajectory" (-log P(column | t)).
@@ -72,16 +74,18 @@ __global__ void __launch_bounds__(1024) memo_compact_kernel(int32_t* __restrict_
 
 struct MemoTrajParams {
     const int32_t* code_of; const int32_t* count;
-    int W, I, S, E, prog_len, cap, K1;      // K1 = trajectory length (max_sweeps + 1, or 1 in exact mode)
+    int W, I, S, E, prog_len, cap, K1, RS;  // K1 = trajectory length (sweep cap + 1, or 1 in exact mode); RS = row stride
+    int exact;
     const double* tab;                      // [E][W] (logs for the mean field, probabilities for exact mode)
     const int* prog;
-    double* traj;                           // [(t * cap + d) * K1 + k]
+    double* traj;                           // [(t * cap + d) * RS + k], RS a multiple of 4 (32-byte rows)
 };
+struct MemoTrajJobs { MemoTrajParams job[2]; };   // blockIdx.y selects the job (background and motif in one launch)
 
-// one thread per (pattern d, position t): the mean-field trajectory F_0..F_max of that tree
-template <int MODE>
-__global__ void __launch_bounds__(128) memo_traj_kernel(MemoTrajParams p) {
+// one thread per (pattern d, position t): the mean-field trajectory F_0..F_cap of that tree
+__global__ void __launch_bounds__(128) memo_traj_kernel(MemoTrajJobs jobs) {
     extern __shared__ double smem[];
+    const MemoTrajParams& p = jobs.job[blockIdx.y];
     const int T = blockDim.x, tid = threadIdx.x;
     double* s_tab = smem;                                   // [E][W]
     double* s_state = s_tab + (size_t)p.E * p.W;            // [I*8][T]
@@ -103,23 +107,34 @@ __global__ void __launch_bounds__(128) memo_traj_kernel(MemoTrajParams p) {
         const int d = (int)(it / p.W), t = (int)(it - (long long)d * p.W);
         const ColWords cw = memo_words((uint32_t)p.code_of[d], p.S);
         const Tab tb{s_tab + t, p.W};
-        double* out = p.traj + ((size_t)t * p.cap + d) * p.K1;
-        if (MODE == PHYFOO_MODE_EXACT) { out[0] = -log(pruning_likelihood(tp, tb, st, cw)); continue; }
+        double* out = p.traj + ((size_t)t * p.cap + d) * p.RS;
+        if (p.exact) { out[0] = -log(pruning_likelihood(tp, tb, st, cw)); continue; }
         for (int k = 0; k < p.K1; ++k) out[k] = meanfield_pass(tp, tb, st, cw, k > 0);
     }
+}
+
+struct __align__(32) MemoRow4 { double v[4]; };
+// one 32-byte sector in one request (LDG.E.256 on sm_100a), through the read-only path
+__device__ __forceinline__ MemoRow4 memo_load4(const MemoRow4* p) {
+    MemoRow4 r;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p));
+    return r;
 }
 
 struct MemoWindowParams {
     const uint32_t* bases; const uint32_t* gaps; int64_t n_cols; int nb;
     const int64_t* col_off; const int64_t* win_off; int n_aln;
     int64_t n_windows; int n_strands; int strand0;
-    int W, S, cap, K1;
+    int W, S, cap, K1, RS;
     const int32_t* dense_of; const double* traj;
-    double* out; int32_t* sweeps; unsigned long long* counters;
+    double* out; int32_t* sweeps; unsigned long long* counter_sweeps;
     int max_sweeps, min_sweeps; double tol; int exact;
+    // windows whose stop rule has not fired within the stored trajectory go to the direct kernel
+    int* pend_count; int64_t* pend_col0; uint8_t* pend_strand; int64_t* pend_dst;
 };
 
-// one thread per window: walk k, summing the W trajectories in tree order, until the reference's stop rule fires
+// one thread per window: walk k in steps of four (one 32-byte sector per tree and step), summing the W trajectories in
+// tree order, until the reference's stop rule fires
 __global__ void __launch_bounds__(256) memo_window_kernel(MemoWindowParams p) {
     const long long n_items = (long long)p.n_windows * p.n_strands;
     unsigned long long ksum = 0;
@@ -129,7 +144,7 @@ __global__ void __launch_bounds__(256) memo_window_kernel(MemoWindowParams p) {
         const int strand = p.n_strands == 2 ? si : p.strand0;
         const int a = find_alignment(p.win_off, p.n_aln, w);
         const int64_t c0 = p.col_off[a] + (w - p.win_off[a]);
-        const double* row[16];
+        const MemoRow4* row[16];
         // W <= 16 here (the launcher falls back to the direct kernel otherwise): trajectory rows of the W trees
 #pragma unroll
         for (int t = 0; t < 16; ++t) {
@@ -138,30 +153,49 @@ __global__ void __launch_bounds__(256) memo_window_kernel(MemoWindowParams p) {
                 ColWords cw = load_column(p.bases, p.gaps, p.n_cols, p.nb, c);
                 if (strand) cw = complement(cw);
                 const int d = p.dense_of[memo_code(cw, p.S)];
-                row[t] = p.traj + ((size_t)t * p.cap + d) * p.K1;
+                row[t] = (const MemoRow4*)(p.traj + ((size_t)t * p.cap + d) * p.RS);
             }
         }
-        double Fsum = 0.0;
+        double Fsum = 0.0, old = 0.0;
+        int k = 0;                     // sweeps done
+        bool conv = false, done = false, pending = false;
+        for (int kb = 0; !done; kb += 4) {
+            if (kb >= p.K1) { pending = true; break; }                         // trajectory exhausted
+            double f[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-        for (int t = 0; t < 16; ++t) if (t < p.W) Fsum += row[t][0];           // tree-major, like calcFreeEnergy(0, W-1)
-        int k = 0;
-        if (!p.exact) {
-            double old = Fsum;                                                // F_0, MeanFieldForBayesNet.java:105
-            bool conv = false;
-            while ((k < p.max_sweeps && !conv) || k < p.min_sweeps) {         // :107
-                ++k;
-                Fsum = 0.0;
+            for (int t = 0; t < 16; ++t)
+                if (t < p.W) {
+                    const MemoRow4 r = memo_load4(&row[t][kb >> 2]);
 #pragma unroll
-                for (int t = 0; t < 16; ++t) if (t < p.W) Fsum += row[t][k];
-                if (fabs(old - Fsum) < p.tol) conv = true;                    // :204-207 (sticky)
-                old = Fsum;
+                    for (int j = 0; j < 4; ++j) f[j] += r.v[j];                // tree-major, like calcFreeEnergy(0, W-1)
+                }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (done || pending) continue;
+                const int kk = kb + j;                                         // index into the trajectory
+                if (kk >= p.K1) { pending = true; continue; }
+                if (kk == 0) {
+                    Fsum = old = f[0];                                         // F_0, MeanFieldForBayesNet.java:105
+                    if (p.exact) done = true;
+                } else {
+                    Fsum = f[j]; ++k;
+                    if (fabs(old - Fsum) < p.tol) conv = true;                 // :204-207 (sticky)
+                    old = Fsum;
+                }
+                if (!((k < p.max_sweeps && !conv) || k < p.min_sweeps)) done = true;   // :107
             }
+            if (pending) break;
         }
-        p.out[item] = -Fsum;                                                  // PhyloBayesModel.java:259
+        if (pending) {
+            const int idx = atomicAdd(p.pend_count, 1);
+            p.pend_col0[idx] = c0; p.pend_strand[idx] = (uint8_t)strand; p.pend_dst[idx] = item;
+            continue;
+        }
+        p.out[item] = -Fsum;                                                   // PhyloBayesModel.java:259
         if (p.sweeps) p.sweeps[item] = k;
         ksum += (unsigned long long)k;
     }
     // sweep statistics: one atomic per warp
     for (int o = 16; o > 0; o >>= 1) ksum += __shfl_down_sync(0xffffffffu, ksum, o);
-    if ((threadIdx.x & 31) == 0 && ksum) atomicAdd(&p.counters[1], ksum);
+    if ((threadIdx.x & 31) == 0 && ksum) atomicAdd(p.counter_sweeps, ksum);
 }

@@ -109,7 +109,7 @@ extern "C" int phyfoo_select(phyfoo_ctx* ctx, const phyfoo_dataset* ds, int32_t 
     if (!ctx) return PHYFOO_EINVAL;
     if (!ds || !n_selected || width < 1) return fail(ctx, PHYFOO_EINVAL, "select: NULL argument or width < 1");
     CU(cudaSetDevice(ctx->device));
-    ctx->launches = 0;
+    ctx->launches = 0; ctx->n_ktimes = 0;
     *n_selected = 0;
     const int64_t* d_woff; const std::vector<int64_t>* h_woff;
     int rc = dataset_win_off(ctx, ds, width, &d_woff, &h_woff);
@@ -132,8 +132,10 @@ extern "C" int phyfoo_select(phyfoo_ctx* ctx, const phyfoo_dataset* ds, int32_t 
     int64_t* d_out_off = (int64_t*)(tmp_w + nw);
     int32_t* tmp_idx = (int32_t*)(d_out_off + na + 1);
     int32_t* d_count = tmp_idx + nw;
-    select_kernel<<<(unsigned)na, 256, 0, ctx->stream>>>(d_w, d_woff, t, q, tmp_idx, tmp_w, d_count);
-    ctx->launches++;
+    {
+        KernelTimer kt_(ctx, "select_kernel");
+        select_kernel<<<(unsigned)na, 256, 0, ctx->stream>>>(d_w, d_woff, t, q, tmp_idx, tmp_w, d_count);
+    }
     CU(cudaGetLastError());
     std::vector<int32_t> count(na);
     CU(cudaMemcpyAsync(count.data(), d_count, na * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -150,8 +152,10 @@ extern "C" int phyfoo_select(phyfoo_ctx* ctx, const phyfoo_dataset* ds, int32_t 
     int32_t* d_sa = (int32_t*)(d_sw + total);
     int32_t* d_so = d_sa + total;
     CU(cudaMemcpyAsync(d_out_off, out_off.data(), (na + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
-    select_compact_kernel<<<(unsigned)na, 64, 0, ctx->stream>>>(tmp_idx, tmp_w, d_woff, d_out_off, d_sa, d_so, d_sw);
-    ctx->launches++;
+    {
+        KernelTimer kt_(ctx, "select_compact_kernel");
+        select_compact_kernel<<<(unsigned)na, 64, 0, ctx->stream>>>(tmp_idx, tmp_w, d_woff, d_out_off, d_sa, d_so, d_sw);
+    }
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(sel_aln, d_sa, (size_t)total * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(sel_off, d_so, (size_t)total * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -282,15 +286,18 @@ static int fe_launch(phyfoo_ctx* ctx, phyfoo_feset* fe, int pos0, int n_pos, int
     const size_t smem = (size_t)FE_KMAX * fe->E * sizeof(double) + (size_t)fe->m->prog_len * sizeof(int) + 16;
     if (K == 1) {
         CU(cudaFuncSetAttribute(fe_eval_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KernelTimer kt_(ctx, "fe_eval_kernel<1>");
         fe_eval_kernel<1><<<dim3(fe->blocks, n_pos), 256, smem, ctx->stream>>>(p);
     } else {
         CU(cudaFuncSetAttribute(fe_eval_kernel<FE_KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KernelTimer kt_(ctx, "fe_eval_kernel<5>");
         fe_eval_kernel<FE_KMAX><<<dim3(fe->blocks, n_pos), 256, smem, ctx->stream>>>(p);
     }
-    ctx->launches++;
     CU(cudaGetLastError());
-    fe_final_kernel<<<1, 256, (size_t)n_pos * FE_KMAX * sizeof(double), ctx->stream>>>(fe->d_part, fe->blocks, pos0, n_pos, K, fe->W, mode, fe->d_G, fe->d_values);
-    ctx->launches++;
+    {
+        KernelTimer kt_(ctx, "fe_final_kernel");
+        fe_final_kernel<<<1, 256, (size_t)n_pos * FE_KMAX * sizeof(double), ctx->stream>>>(fe->d_part, fe->blocks, pos0, n_pos, K, fe->W, mode, fe->d_G, fe->d_values);
+    }
     CU(cudaGetLastError());
     return PHYFOO_OK;
 }
@@ -345,8 +352,10 @@ static int fe_run_prepare(phyfoo_ctx* ctx, phyfoo_feset* fe) {
     ScoreItems items{fe->d_col0, fe->d_strand, fe->d_qint, fe->d_qleaf, fe->d_ent};
     int rc = launch_score(ctx, fe->ds, fe->m, nullptr, fe->n, 0, ctx->fg_scores.as<double>(), nullptr, 2, &items);
     if (rc) return rc;
-    fe_entropy_kernel<<<1, 1024, 0, ctx->stream>>>(fe->d_ent, fe->d_weight, fe->n, fe->W, fe->d_G + fe->W);
-    ctx->launches++;
+    {
+        KernelTimer kt_(ctx, "fe_entropy_kernel");
+        fe_entropy_kernel<<<1, 1024, 0, ctx->stream>>>(fe->d_ent, fe->d_weight, fe->n, fe->W, fe->d_G + fe->W);
+    }
     CU(cudaGetLastError());
     fe->g_version = 0;
     return fe_refresh(ctx, fe);
@@ -365,7 +374,7 @@ extern "C" int phyfoo_fe_prepare(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyf
         return fail(ctx, PHYFOO_EINVAL, "fe_prepare: NULL argument");
     *out = nullptr;
     CU(cudaSetDevice(ctx->device));
-    ctx->launches = 0;
+    ctx->launches = 0; ctx->n_ktimes = 0;
     int rc = fe_check_model(ctx, ds, m, "fe_prepare");
     if (rc) return rc;
     const int W = m->h.W;
@@ -413,7 +422,7 @@ extern "C" int phyfoo_fe_prepare_all(phyfoo_ctx* ctx, const phyfoo_dataset* ds, 
     if (!ds || !m || !out) return fail(ctx, PHYFOO_EINVAL, "fe_prepare_all: NULL argument");
     *out = nullptr;
     CU(cudaSetDevice(ctx->device));
-    ctx->launches = 0;
+    ctx->launches = 0; ctx->n_ktimes = 0;
     int rc = fe_check_model(ctx, ds, m, "fe_prepare_all");
     if (rc) return rc;
     const int64_t* d_woff; const std::vector<int64_t>* h_woff;
@@ -432,8 +441,10 @@ extern "C" int phyfoo_fe_prepare_all(phyfoo_ctx* ctx, const phyfoo_dataset* ds, 
             d_alnw = ctx->alnw.as<double>();
         }
         if (e == cudaSuccess) {
-            fe_all_items_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_woff, ds->d_col_off, ds->n_aln, n, d_alnw, fe->d_col0, fe->d_weight);
-            ctx->launches++;
+            {
+                KernelTimer kt_(ctx, "fe_all_items_kernel");
+                fe_all_items_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_woff, ds->d_col_off, ds->n_aln, n, d_alnw, fe->d_col0, fe->d_weight);
+            }
             e = cudaGetLastError();
         }
         if (e != cudaSuccess) { fe_release(fe); ctx->err = std::string("fe_prepare_all: ") + cudaGetErrorString(e); return PHYFOO_ECUDA; }
@@ -494,7 +505,7 @@ extern "C" int phyfoo_fe_eval(phyfoo_ctx* ctx, phyfoo_feset* fe, int32_t positio
     if (!ctx) return PHYFOO_EINVAL;
     if (!fe || !f_out) return fail(ctx, PHYFOO_EINVAL, "fe_eval: NULL argument");
     CU(cudaSetDevice(ctx->device));
-    ctx->launches = 0;
+    ctx->launches = 0; ctx->n_ktimes = 0;
     std::vector<double> pi;
     int rc = fe_enqueue(ctx, fe, position, lambda, dim, false, 0.0, &pi);
     if (rc) return rc;
@@ -509,7 +520,7 @@ extern "C" int phyfoo_fe_grad(phyfoo_ctx* ctx, phyfoo_feset* fe, int32_t positio
     if (!fe || !g_out) return fail(ctx, PHYFOO_EINVAL, "fe_grad: NULL argument");
     if (!(eps > 0)) return fail(ctx, PHYFOO_EINVAL, "fe_grad: eps must be > 0");
     CU(cudaSetDevice(ctx->device));
-    ctx->launches = 0;
+    ctx->launches = 0; ctx->n_ktimes = 0;
     std::vector<double> pi;
     int rc = fe_enqueue(ctx, fe, position, lambda, dim, true, eps, &pi);
     if (rc) return rc;
@@ -526,7 +537,7 @@ extern "C" int phyfoo_fe_values_device(phyfoo_ctx* ctx, phyfoo_feset* fe, int32_
     if (!ctx) return PHYFOO_EINVAL;
     if (!fe || !values_device) return fail(ctx, PHYFOO_EINVAL, "fe_values_device: NULL argument");
     CU(cudaSetDevice(ctx->device));
-    ctx->launches = 0;
+    ctx->launches = 0; ctx->n_ktimes = 0;
     std::vector<double> pi;
     int rc = fe_enqueue(ctx, fe, position, lambda, dim, eps > 0, eps, &pi);
     if (rc) return rc;

@@ -30,6 +30,11 @@ using namespace phyfoo;
 // ------------------------------------------------------------------------------------------------
 // handles
 // ------------------------------------------------------------------------------------------------
+// stream-ordered allocations from the device's default memory pool (kept warm: release threshold = unlimited), so that
+// creating and freeing a data set per call costs microseconds instead of synchronous cudaMalloc / cudaFree
+template <class T> static cudaError_t dev_malloc(cudaStream_t st, T** p, size_t bytes) { return cudaMallocAsync((void**)p, bytes ? bytes : 1, st); }
+static void dev_free(cudaStream_t st, void* p) { if (p) cudaFreeAsync(p, st); }
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
@@ -64,6 +69,12 @@ struct phyfoo_ctx {
     int64_t gamma_windows = -1;      // number of windows whose gamma of the last E-step is resident in `gamma`
     DevBuf memo_traj;                // pattern-table path: free-energy trajectories (memo.cuh)
     int memo_mode = 1;               // 0 = never, 1 = when it pays off, 2 = whenever it applies
+    int memo_sweep_cap = 100;         // trajectory length of the pattern-table path; longer windows go to the direct kernel
+    DevBuf memo_pending;             // fallback list of the pattern-table path
+    // per-kernel device times of the most recent call (CUDA events on the library's stream)
+    struct KTime { const char* name; cudaEvent_t e0, e1; };
+    std::vector<KTime> ktimes;
+    int n_ktimes = 0;
     int last_path = 0;               // scoring path of the most recent motif/background launch: 0 direct, 1 pattern table, 2 order-1 net
     int launches = 0;                // kernels launched by the current call
 };
@@ -103,7 +114,27 @@ static thread_local std::string g_init_err;
         }                                                                                          \
     } while (0)
 
-static void memo_release(MemoSet* ms);
+static void memo_release(cudaStream_t st, MemoSet* ms);
+
+// brackets one kernel launch with events so that callers (bench.py) can attribute device time per kernel
+struct KernelTimer {
+    phyfoo_ctx* ctx; int slot;
+    KernelTimer(phyfoo_ctx* c, const char* name) : ctx(c), slot(-1) {
+        if (ctx->n_ktimes >= 64) return;
+        if ((int)ctx->ktimes.size() <= ctx->n_ktimes) {
+            phyfoo_ctx::KTime kt{name, nullptr, nullptr};
+            if (cudaEventCreate(&kt.e0) != cudaSuccess || cudaEventCreate(&kt.e1) != cudaSuccess) return;
+            ctx->ktimes.push_back(kt);
+        }
+        slot = ctx->n_ktimes++;
+        ctx->ktimes[slot].name = name;
+        cudaEventRecord(ctx->ktimes[slot].e0, ctx->stream);
+    }
+    ~KernelTimer() {
+        if (slot >= 0) cudaEventRecord(ctx->ktimes[slot].e1, ctx->stream);
+        ctx->launches++;
+    }
+};
 
 static int fail(phyfoo_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg; else g_init_err = msg;
@@ -148,7 +179,8 @@ struct ScoreParams {
     const int* prog;
     double* out;         // [n_strands][n_windows]
     int32_t* sweeps;     // nullable, same shape
-    unsigned long long* counters;  // [0] next item, [1] sum of sweeps
+    unsigned long long* counter_next;    // work counter (next item)
+    unsigned long long* counter_sweeps;  // running sum of the sweep counts
     int max_sweeps, min_sweeps; double tol;
     double* gstate;      // nullable: per-thread state in global memory instead of shared
     int groups;          // windows in flight per block
@@ -156,6 +188,8 @@ struct ScoreParams {
     const int64_t* item_col0;     // nullable: first column of window `item`
     const uint8_t* item_strand;   // nullable (all forward)
     double* q_int; double* q_leaf; double* ent;   // nullable; strided by n_windows * W (one slot per tree)
+    const int* n_items_dev;       // nullable: number of listed windows lives on the device (pattern-table fallback list)
+    const int64_t* item_dst;      // nullable: out/sweeps index of listed window `item` (default: item)
 };
 
 __device__ __forceinline__ ColWords load_column(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ gaps,
@@ -206,7 +240,7 @@ __global__ void __launch_bounds__(256, 2) score_o0_kernel(ScoreParams p) {
     if (p.gstate) { st.base = p.gstate + ((size_t)blockIdx.x * T + tid); st.stride = gridDim.x * T; }
     else { st.base = s_state + tid; st.stride = T; }
 
-    const long long n_items = (long long)p.n_windows * p.n_strands;
+    const long long n_items = (ITEMS && p.n_items_dev) ? (long long)*p.n_items_dev : (long long)p.n_windows * p.n_strands;
     bool need = lane_ok, active = lane_ok, upd = false, conv = false;
     int k = 0;
     long long item = -1;
@@ -214,7 +248,7 @@ __global__ void __launch_bounds__(256, 2) score_o0_kernel(ScoreParams p) {
     ColWords cw; cw.b = 0; cw.g = 0;
 
     for (;;) {
-        if (need && active && t == 0) s_item[g] = (long long)atomicAdd(&p.counters[0], 1ULL);
+        if (need && active && t == 0) s_item[g] = (long long)atomicAdd(p.counter_next, 1ULL);
         __syncthreads();
         if (need && active) {
             item = s_item[g];
@@ -260,16 +294,17 @@ __global__ void __launch_bounds__(256, 2) score_o0_kernel(ScoreParams p) {
                 done = !((k < p.max_sweeps && !conv) || k < p.min_sweeps);    // :107
             }
             if (done) {
-                if (MODE != PHYFOO_MODE_EXACT && ITEMS) {
+                if (MODE != PHYFOO_MODE_EXACT && ITEMS && p.q_int) {
                     // FE-set layout: tree slot = position-major (t * n + window) so one position's trees are contiguous
                     const size_t n_trees = (size_t)p.n_windows * p.W, tree = (size_t)t * p.n_windows + item;
                     const QSink sink{p.q_int + tree, p.q_leaf + tree, n_trees};
                     p.ent[tree] = store_q(tp, tb, st, cw, sink);
                 }
                 if (t == 0) {
-                    p.out[item] = -Fsum;                                      // PhyloBayesModel.java:259
-                    if (p.sweeps) p.sweeps[item] = k;
-                    if (MODE != PHYFOO_MODE_EXACT) atomicAdd(&p.counters[1], (unsigned long long)k);
+                    const long long dst = (ITEMS && p.item_dst) ? (long long)p.item_dst[item] : item;
+                    p.out[dst] = -Fsum;                                       // PhyloBayesModel.java:259
+                    if (p.sweeps) p.sweeps[dst] = k;
+                    if (MODE != PHYFOO_MODE_EXACT) atomicAdd(p.counter_sweeps, (unsigned long long)k);
                 }
                 need = true;
             }
@@ -444,10 +479,17 @@ extern "C" int phyfoo_init(int device, phyfoo_ctx** out) {
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->kev[0])) != cudaSuccess || (e = cudaEventCreate(&ctx->kev[1])) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->kev[2])) != cudaSuccess || (e = cudaEventCreate(&ctx->kev[3])) != cudaSuccess ||
-        (e = ctx->counters.ensure(8 * sizeof(unsigned long long))) != cudaSuccess) {
+        (e = ctx->counters.ensure(16 * sizeof(unsigned long long))) != cudaSuccess) {
         g_init_err = std::string("phyfoo_init: ") + cudaGetErrorString(e);
         delete ctx;
         return PHYFOO_ECUDA;
+    }
+    {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ULL;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
     }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->cc_major = prop.major; ctx->cc_minor = prop.minor;
@@ -462,10 +504,11 @@ extern "C" void phyfoo_destroy(phyfoo_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf* b : {&ctx->counters, &ctx->fg_scores, &ctx->bg_scores, &ctx->sweeps_buf, &ctx->gamma, &ctx->profile, &ctx->part,
-                      &ctx->argoff, &ctx->argstrand, &ctx->alnw, &ctx->out3, &ctx->gstate, &ctx->misc, &ctx->selw, &ctx->sel_tmp, &ctx->sel_out, &ctx->memo_traj})
+                      &ctx->argoff, &ctx->argstrand, &ctx->alnw, &ctx->out3, &ctx->gstate, &ctx->misc, &ctx->selw, &ctx->sel_tmp, &ctx->sel_out, &ctx->memo_traj, &ctx->memo_pending})
         b->release();
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
+    for (auto& kt : ctx->ktimes) { cudaEventDestroy(kt.e0); cudaEventDestroy(kt.e1); }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -531,36 +574,38 @@ static int dataset_build(phyfoo_ctx* ctx, int32_t n_aln, int32_t S, const int64_
     uint8_t* d_codes = nullptr;
     int* d_bad = nullptr;
     auto cleanup = [&]() {
-        if (!codes_on_device && d_codes) cudaFree(d_codes);
-        if (d_bad) cudaFree(d_bad);
+        if (!codes_on_device && d_codes) dev_free(ctx->stream, d_codes);
+        if (d_bad) dev_free(ctx->stream, d_bad);
     };
     auto bail = [&](const char* what, cudaError_t err) {
         ctx->err = std::string(what) + ": " + cudaGetErrorString(err);
         cleanup();
-        if (ds->d_col_off) cudaFree(ds->d_col_off);
-        if (ds->d_bases) cudaFree(ds->d_bases);
-        if (ds->d_gaps) cudaFree(ds->d_gaps);
+        if (ds->d_col_off) dev_free(ctx->stream, ds->d_col_off);
+        if (ds->d_bases) dev_free(ctx->stream, ds->d_bases);
+        if (ds->d_gaps) dev_free(ctx->stream, ds->d_gaps);
         delete ds;
         return err == cudaErrorMemoryAllocation ? PHYFOO_ENOMEM : PHYFOO_ECUDA;
     };
-    if ((e = cudaMalloc(&ds->d_col_off, (size_t)(n_aln + 1) * sizeof(int64_t))) != cudaSuccess) return bail("cudaMalloc col_off", e);
-    if ((e = cudaMalloc(&ds->d_bases, (size_t)ds->nb * nc * 4)) != cudaSuccess) return bail("cudaMalloc bases", e);
-    if ((e = cudaMalloc(&ds->d_gaps, (size_t)ds->ng * nc * 4)) != cudaSuccess) return bail("cudaMalloc gaps", e);
-    if ((e = cudaMalloc(&d_bad, sizeof(int))) != cudaSuccess) return bail("cudaMalloc flag", e);
+    if ((e = dev_malloc(ctx->stream, &ds->d_col_off, (size_t)(n_aln + 1) * sizeof(int64_t))) != cudaSuccess) return bail("cudaMalloc col_off", e);
+    if ((e = dev_malloc(ctx->stream, &ds->d_bases, (size_t)ds->nb * nc * 4)) != cudaSuccess) return bail("cudaMalloc bases", e);
+    if ((e = dev_malloc(ctx->stream, &ds->d_gaps, (size_t)ds->ng * nc * 4)) != cudaSuccess) return bail("cudaMalloc gaps", e);
+    if ((e = dev_malloc(ctx->stream, &d_bad, sizeof(int))) != cudaSuccess) return bail("cudaMalloc flag", e);
     if ((e = cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream)) != cudaSuccess) return bail("memset", e);
     if ((e = cudaMemcpyAsync(ds->d_col_off, col_offsets, (size_t)(n_aln + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
         return bail("copy col_off", e);
     if (ds->n_cols > 0) {
         if (codes_on_device) d_codes = const_cast<uint8_t*>(codes);
         else {
-            if ((e = cudaMalloc(&d_codes, (size_t)ds->n_cols * S)) != cudaSuccess) return bail("cudaMalloc codes", e);
+            if ((e = dev_malloc(ctx->stream, &d_codes, (size_t)ds->n_cols * S)) != cudaSuccess) return bail("cudaMalloc codes", e);
             if ((e = cudaMemcpyAsync(d_codes, codes, (size_t)ds->n_cols * S, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
                 return bail("copy codes", e);
         }
         const int threads = 256;
         const int64_t blocks = (ds->n_cols + threads - 1) / threads;
-        pack_columns_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(d_codes, ds->n_cols, S, ds->nb, ds->ng, ds->d_bases, ds->d_gaps, d_bad);
-        ctx->launches++;
+        {
+            KernelTimer kt_(ctx, "pack_columns_kernel");
+            pack_columns_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(d_codes, ds->n_cols, S, ds->nb, ds->ng, ds->d_bases, ds->d_gaps, d_bad);
+        }
         if ((e = cudaGetLastError()) != cudaSuccess) return bail("pack_columns_kernel", e);
     }
     int bad = 0;
@@ -568,7 +613,7 @@ static int dataset_build(phyfoo_ctx* ctx, int32_t n_aln, int32_t S, const int64_
     if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bail("pack_columns_kernel", e);
     cleanup();
     if (bad) {
-        cudaFree(ds->d_col_off); cudaFree(ds->d_bases); cudaFree(ds->d_gaps);
+        dev_free(ctx->stream, ds->d_col_off); dev_free(ctx->stream, ds->d_bases); dev_free(ctx->stream, ds->d_gaps);
         delete ds;
         return fail(ctx, PHYFOO_EINVAL, "dataset_create: code outside 0..4 (WrongAlphabetException in the reference)");
     }
@@ -606,10 +651,12 @@ extern "C" int64_t phyfoo_dataset_windows(const phyfoo_dataset* ds, int32_t widt
 
 extern "C" void phyfoo_dataset_free(phyfoo_ctx* ctx, phyfoo_dataset* ds) {
     if (!ds) return;
-    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
-    cudaFree(ds->d_col_off); cudaFree(ds->d_bases); cudaFree(ds->d_gaps);
-    for (auto& kv : ds->d_win_off) cudaFree(kv.second);
-    memo_release(ds->memo);
+    // stream-ordered frees: everything enqueued on the library's stream that still reads the buffers runs first
+    cudaStream_t st = ctx ? ctx->stream : nullptr;
+    if (ctx) cudaSetDevice(ctx->device);
+    dev_free(st, ds->d_col_off); dev_free(st, ds->d_bases); dev_free(st, ds->d_gaps);
+    for (auto& kv : ds->d_win_off) dev_free(st, kv.second);
+    memo_release(st, ds->memo);
     delete ds;
 }
 
@@ -621,10 +668,10 @@ static int dataset_win_off(phyfoo_ctx* ctx, const phyfoo_dataset* cds, int W, co
         std::vector<int64_t> off(ds->n_aln + 1, 0);
         for (int i = 0; i < ds->n_aln; ++i) off[i + 1] = off[i] + std::max<int64_t>(0, ds->col_off[i + 1] - ds->col_off[i] - W + 1);
         int64_t* d = nullptr;
-        CU(cudaMalloc(&d, off.size() * sizeof(int64_t)));
+        CU(dev_malloc(ctx->stream, &d, off.size() * sizeof(int64_t)));
         cudaError_t e = cudaMemcpyAsync(d, off.data(), off.size() * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) { cudaFree(d); ctx->err = std::string("win_off copy: ") + cudaGetErrorString(e); return PHYFOO_ECUDA; }
+        if (e != cudaSuccess) { dev_free(ctx->stream, d); ctx->err = std::string("win_off copy: ") + cudaGetErrorString(e); return PHYFOO_ECUDA; }
         ds->d_win_off[W] = d;
         ds->win_off[W] = std::move(off);
         it = ds->d_win_off.find(W);
@@ -767,14 +814,18 @@ static int plan_score(phyfoo_ctx* ctx, const ModelHost& h, int prog_len, long lo
     return PHYFOO_OK;
 }
 
-struct ScoreItems { const int64_t* col0; const uint8_t* strand; double* q_int; double* q_leaf; double* ent; };
+// explicit window list for the scoring kernels: M-step "prepare" (q sink) or the pattern-table fallback (device-side count)
+struct ScoreItems {
+    const int64_t* col0; const uint8_t* strand; double* q_int; double* q_leaf; double* ent;
+    const int* n_dev = nullptr; const int64_t* dst = nullptr; bool fallback = false;
+};
 
 #include "net1.cuh"
 #include "memo.cuh"
 
-static void memo_release(MemoSet* ms) {
+static void memo_release(cudaStream_t st, MemoSet* ms) {
     if (!ms) return;
-    cudaFree(ms->d_dense_of); cudaFree(ms->d_code_of); cudaFree(ms->d_count);
+    dev_free(st, ms->d_dense_of); dev_free(st, ms->d_code_of); dev_free(st, ms->d_count);
     delete ms;
 }
 
@@ -788,80 +839,145 @@ static int dataset_memo(phyfoo_ctx* ctx, const phyfoo_dataset* cds, MemoSet** ou
         for (int s = 0; s < ds->S; ++s) valid *= 5;
         ms->cap = (int)std::max<long long>(1, std::min<long long>(valid, 2 * ds->n_cols));
         cudaError_t e;
-        if ((e = cudaMalloc(&ms->d_dense_of, (size_t)ms->n_codes * sizeof(int32_t))) != cudaSuccess ||
-            (e = cudaMalloc(&ms->d_code_of, (size_t)ms->cap * sizeof(int32_t))) != cudaSuccess ||
-            (e = cudaMalloc(&ms->d_count, sizeof(int32_t))) != cudaSuccess ||
+        if ((e = dev_malloc(ctx->stream, &ms->d_dense_of, (size_t)ms->n_codes * sizeof(int32_t))) != cudaSuccess ||
+            (e = dev_malloc(ctx->stream, &ms->d_code_of, (size_t)ms->cap * sizeof(int32_t))) != cudaSuccess ||
+            (e = dev_malloc(ctx->stream, &ms->d_count, sizeof(int32_t))) != cudaSuccess ||
             (e = cudaMemsetAsync(ms->d_dense_of, 0, (size_t)ms->n_codes * sizeof(int32_t), ctx->stream)) != cudaSuccess) {
-            memo_release(ms);
+            memo_release(ctx->stream, ms);
             ctx->err = std::string("pattern set: ") + cudaGetErrorString(e);
             return PHYFOO_ECUDA;
         }
         if (ds->n_cols > 0) {
-            memo_mark_kernel<<<(unsigned)((ds->n_cols + 255) / 256), 256, 0, ctx->stream>>>(ds->d_bases, ds->d_gaps, ds->n_cols, ds->nb, ds->S, ms->d_dense_of);
-            ctx->launches++;
+            {
+                KernelTimer kt_(ctx, "memo_mark_kernel");
+                memo_mark_kernel<<<(unsigned)((ds->n_cols + 255) / 256), 256, 0, ctx->stream>>>(ds->d_bases, ds->d_gaps, ds->n_cols, ds->nb, ds->S, ms->d_dense_of);
+            }
         }
-        memo_compact_kernel<<<1, 1024, 0, ctx->stream>>>(ms->d_dense_of, ms->n_codes, ms->d_code_of, ms->cap, ms->d_count);
-        ctx->launches++;
+        {
+            KernelTimer kt_(ctx, "memo_compact_kernel");
+            memo_compact_kernel<<<1, 1024, 0, ctx->stream>>>(ms->d_dense_of, ms->n_codes, ms->d_code_of, ms->cap, ms->d_count);
+        }
         e = cudaGetLastError();
-        if (e != cudaSuccess) { memo_release(ms); ctx->err = std::string("pattern set kernels: ") + cudaGetErrorString(e); return PHYFOO_ECUDA; }
+        if (e != cudaSuccess) { memo_release(ctx->stream, ms); ctx->err = std::string("pattern set kernels: ") + cudaGetErrorString(e); return PHYFOO_ECUDA; }
         ds->memo = ms;
     }
     *out = ds->memo;
     return PHYFOO_OK;
 }
 
-static bool memo_applies(const phyfoo_ctx* ctx, const phyfoo_dataset* ds, const ModelHost& h, long long n_items) {
+// number of distinct column patterns (forward + complemented) of the data set; -1 when the pattern table does not apply
+extern "C" int64_t phyfoo_dataset_patterns(phyfoo_ctx* ctx, const phyfoo_dataset* ds) {
+    if (!ctx || !ds || 3 * ds->S > 18) return -1;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return -1;
+    MemoSet* ms = nullptr;
+    if (dataset_memo(ctx, ds, &ms) != PHYFOO_OK) return -1;
+    int32_t d = 0;
+    if (cudaMemcpyAsync(&d, ms->d_count, sizeof(d), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
+    return d;
+}
+
+static int memo_K1(const phyfoo_ctx* ctx, const ModelHost& h, int mode) {
+    return mode == PHYFOO_MODE_EXACT ? 1 : std::min(ctx->memo_sweep_cap, h.max_sweeps) + 1;
+}
+
+static bool memo_applies(const phyfoo_ctx* ctx, const phyfoo_dataset* ds, const ModelHost& h, int mode, long long n_items) {
     if (ctx->memo_mode == 0 || h.order != 0 || 3 * ds->S > 18 || h.W > 16) return false;
     if (ctx->memo_mode == 2) return true;
     long long valid = 1;
     for (int s = 0; s < ds->S; ++s) valid *= 5;
     const long long cap = std::min<long long>(valid, 2 * ds->n_cols);
-    // trajectories cost cap * W * (max_sweeps + 1) tree passes, the direct kernel about n_items * W * 10
-    return n_items * 10 >= 4 * cap * (h.max_sweeps + 1);
+    // trajectories cost cap * W * K1 tree passes, the direct kernel about n_items * W * 10
+    return n_items * 10 >= 4 * cap * memo_K1(ctx, h, mode);
 }
 
-// pattern-table path (memo.cuh): trajectories of the occurring patterns, then one gather pass over the windows
-static int launch_memo(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* m, int mode, const int64_t* d_win_off, int64_t n_windows,
-                       int strands, double* d_out, int32_t* d_sweeps, int counter_slot) {
-    ModelHost& h = m->h;
+static int launch_score(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* m, const int64_t* d_win_off, int64_t n_windows,
+                        int strands, double* d_out, int32_t* d_sweeps, int counter_slot, const ScoreItems* items = nullptr);
+
+struct MemoJob {
+    phyfoo_model* m; int mode; const int64_t* d_win_off; int64_t n_windows; int strands;
+    double* d_out; int32_t* d_sweeps; int counter_slot;
+};
+
+// pattern-table path (memo.cuh): trajectories of the occurring patterns for up to two models in one launch
+// (background + motif of an E-step), then per model one gather pass over the windows and the fallback list
+static int launch_memo_jobs(phyfoo_ctx* ctx, const phyfoo_dataset* ds, const MemoJob* jobs, int n_jobs) {
     MemoSet* ms = nullptr;
     int rc = dataset_memo(ctx, ds, &ms);
     if (rc) return rc;
-    const int K1 = mode == PHYFOO_MODE_EXACT ? 1 : h.max_sweeps + 1;
-    CU(ctx->memo_traj.ensure((size_t)ms->cap * h.W * K1 * sizeof(double)));
-    MemoTrajParams tp;
-    tp.code_of = ms->d_code_of; tp.count = ms->d_count;
-    tp.W = h.W; tp.I = h.I; tp.S = h.S; tp.E = h.E; tp.prog_len = m->prog_len; tp.cap = ms->cap; tp.K1 = K1;
-    tp.tab = mode == PHYFOO_MODE_EXACT ? m->d_probtab : m->d_logtab;
-    tp.prog = m->d_prog; tp.traj = ctx->memo_traj.as<double>();
-    const int threads = 128;
-    const size_t smem = (size_t)h.E * h.W * sizeof(double) + (size_t)h.I * 8 * threads * sizeof(double) + (size_t)m->prog_len * sizeof(int) + 16;
-    const long long trees = (long long)ms->cap * h.W;
-    const int blocks = (int)std::max<long long>(1, std::min<long long>((trees + threads - 1) / threads, 8LL * ctx->sm_count));
-    unsigned long long* counters = ctx->counters.as<unsigned long long>() + 2 * counter_slot;
-    CU(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
-    if (mode == PHYFOO_MODE_EXACT) {
-        CU(cudaFuncSetAttribute(memo_traj_kernel<PHYFOO_MODE_EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        memo_traj_kernel<PHYFOO_MODE_EXACT><<<blocks, threads, smem, ctx->stream>>>(tp);
-    } else {
-        CU(cudaFuncSetAttribute(memo_traj_kernel<PHYFOO_MODE_MEANFIELD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        memo_traj_kernel<PHYFOO_MODE_MEANFIELD><<<blocks, threads, smem, ctx->stream>>>(tp);
+    for (int j = 0; j < n_jobs; ++j) if ((rc = model_upload(ctx, jobs[j].m))) return rc;
+    size_t traj_off[3] = {0, 0, 0}, pend_off[3] = {0, 0, 0};
+    long long n_items[2] = {0, 0};
+    int K1[2] = {1, 1};
+    for (int j = 0; j < n_jobs; ++j) {
+        const ModelHost& h = jobs[j].m->h;
+        K1[j] = memo_K1(ctx, h, jobs[j].mode);
+        n_items[j] = (long long)jobs[j].n_windows * (jobs[j].strands == 2 ? 2 : 1);
+        traj_off[j + 1] = traj_off[j] + (size_t)ms->cap * h.W * ((K1[j] + 3) / 4 * 4);
+        // per job: [count (8 bytes, int used)] [col0 int64 x n] [dst int64 x n] [strand u8 x n, padded to 8]
+        pend_off[j + 1] = pend_off[j] + 8 + (size_t)n_items[j] * 16 + (((size_t)n_items[j] + 7) / 8) * 8;
     }
-    ctx->launches++;
+    CU(ctx->memo_traj.ensure(traj_off[n_jobs] * sizeof(double)));
+    CU(ctx->memo_pending.ensure(pend_off[n_jobs]));
+    MemoTrajJobs tj;
+    const int threads = 128;
+    size_t smem = 0;
+    long long trees = 0;
+    for (int j = 0; j < n_jobs; ++j) {
+        phyfoo_model* m = jobs[j].m;
+        const ModelHost& h = m->h;
+        MemoTrajParams& tp = tj.job[j];
+        tp.code_of = ms->d_code_of; tp.count = ms->d_count;
+        tp.W = h.W; tp.I = h.I; tp.S = h.S; tp.E = h.E; tp.prog_len = m->prog_len; tp.cap = ms->cap; tp.K1 = K1[j]; tp.RS = (K1[j] + 3) / 4 * 4;
+        tp.exact = jobs[j].mode == PHYFOO_MODE_EXACT ? 1 : 0;
+        tp.tab = tp.exact ? m->d_probtab : m->d_logtab;
+        tp.prog = m->d_prog; tp.traj = ctx->memo_traj.as<double>() + traj_off[j];
+        smem = std::max(smem, (size_t)h.E * h.W * sizeof(double) + (size_t)h.I * 8 * threads * sizeof(double) + (size_t)m->prog_len * sizeof(int) + 16);
+        trees = std::max(trees, (long long)ms->cap * h.W);
+    }
+    if (n_jobs == 1) tj.job[1] = tj.job[0];
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((trees + threads - 1) / threads, 8LL * ctx->sm_count));
+    CU(cudaFuncSetAttribute(memo_traj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        KernelTimer kt_(ctx, "memo_traj_kernel");
+        memo_traj_kernel<<<dim3(blocks, n_jobs), threads, smem, ctx->stream>>>(tj);
+    }
     CU(cudaGetLastError());
-    MemoWindowParams wp;
-    wp.bases = ds->d_bases; wp.gaps = ds->d_gaps; wp.n_cols = ds->n_cols; wp.nb = ds->nb;
-    wp.col_off = ds->d_col_off; wp.win_off = d_win_off; wp.n_aln = ds->n_aln;
-    wp.n_windows = n_windows; wp.n_strands = strands == 2 ? 2 : 1; wp.strand0 = strands == 1 ? 1 : 0;
-    wp.W = h.W; wp.S = h.S; wp.cap = ms->cap; wp.K1 = K1;
-    wp.dense_of = ms->d_dense_of; wp.traj = ctx->memo_traj.as<double>();
-    wp.out = d_out; wp.sweeps = d_sweeps; wp.counters = counters;
-    wp.max_sweeps = h.max_sweeps; wp.min_sweeps = h.min_sweeps; wp.tol = h.tol; wp.exact = mode == PHYFOO_MODE_EXACT ? 1 : 0;
-    const long long n_items = (long long)n_windows * wp.n_strands;
-    const int wblocks = (int)std::max<long long>(1, std::min<long long>((n_items + 255) / 256, 16LL * ctx->sm_count));
-    memo_window_kernel<<<wblocks, 256, 0, ctx->stream>>>(wp);
-    ctx->launches++;
-    CU(cudaGetLastError());
+    for (int j = 0; j < n_jobs; ++j) {
+        phyfoo_model* m = jobs[j].m;
+        const ModelHost& h = m->h;
+        if (n_items[j] == 0) continue;
+        unsigned long long* counters = ctx->counters.as<unsigned long long>();
+        unsigned long long* c_sweeps = counters + 2 * jobs[j].counter_slot + 1;
+        CU(cudaMemsetAsync(c_sweeps, 0, sizeof(unsigned long long), ctx->stream));
+        char* pb = ctx->memo_pending.as<char>() + pend_off[j];
+        int* pend_count = (int*)pb;
+        int64_t* pend_col0 = (int64_t*)(pb + 8);
+        int64_t* pend_dst = pend_col0 + n_items[j];
+        uint8_t* pend_strand = (uint8_t*)(pend_dst + n_items[j]);
+        CU(cudaMemsetAsync(pend_count, 0, 8, ctx->stream));
+        MemoWindowParams wp;
+        wp.bases = ds->d_bases; wp.gaps = ds->d_gaps; wp.n_cols = ds->n_cols; wp.nb = ds->nb;
+        wp.col_off = ds->d_col_off; wp.win_off = jobs[j].d_win_off; wp.n_aln = ds->n_aln;
+        wp.n_windows = jobs[j].n_windows; wp.n_strands = jobs[j].strands == 2 ? 2 : 1; wp.strand0 = jobs[j].strands == 1 ? 1 : 0;
+        wp.W = h.W; wp.S = h.S; wp.cap = ms->cap; wp.K1 = K1[j]; wp.RS = (K1[j] + 3) / 4 * 4;
+        wp.dense_of = ms->d_dense_of; wp.traj = ctx->memo_traj.as<double>() + traj_off[j];
+        wp.out = jobs[j].d_out; wp.sweeps = jobs[j].d_sweeps; wp.counter_sweeps = c_sweeps;
+        wp.max_sweeps = h.max_sweeps; wp.min_sweeps = h.min_sweeps; wp.tol = h.tol; wp.exact = jobs[j].mode == PHYFOO_MODE_EXACT ? 1 : 0;
+        wp.pend_count = pend_count; wp.pend_col0 = pend_col0; wp.pend_strand = pend_strand; wp.pend_dst = pend_dst;
+        const int wblocks = (int)std::max<long long>(1, std::min<long long>((n_items[j] + 255) / 256, 16LL * ctx->sm_count));
+        {
+            KernelTimer kt_(ctx, "memo_window_kernel");
+            memo_window_kernel<<<wblocks, 256, 0, ctx->stream>>>(wp);
+        }
+        CU(cudaGetLastError());
+        if (!wp.exact && K1[j] - 1 < h.max_sweeps) {
+            // windows that need more sweeps than the stored trajectories hold: direct kernel over the (device-side) list
+            ScoreItems items{pend_col0, pend_strand, nullptr, nullptr, nullptr, pend_count, pend_dst, true};
+            rc = launch_score(ctx, ds, m, nullptr, n_items[j], 0, jobs[j].d_out, jobs[j].d_sweeps, jobs[j].counter_slot, &items);
+            if (rc) return rc;
+        }
+    }
     ctx->last_path = 1;
     return PHYFOO_OK;
 }
@@ -909,8 +1025,10 @@ static int launch_net1(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* 
     p.gq = ctx->gstate.as<double>(); p.n_slots = n_slots; p.nwb = best_nwb;
     p.item_col0 = items ? items->col0 : nullptr; p.item_strand = items ? items->strand : nullptr;
     CU(cudaMemsetAsync(p.counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
-    score_o1_kernel<<<blocks, 4 * best_nwb, smem, ctx->stream>>>(p);
-    ctx->launches++;
+    {
+        KernelTimer kt_(ctx, "score_o1_kernel");
+        score_o1_kernel<<<blocks, 4 * best_nwb, smem, ctx->stream>>>(p);
+    }
     CU(cudaGetLastError());
     return PHYFOO_OK;
 }
@@ -918,12 +1036,13 @@ static int launch_net1(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* 
 // scores into d_out[n_strands][n_windows]; strands: 0 = forward only, 1 = reverse only, 2 = both.
 // items != NULL: score the listed windows (n_windows of them) instead and store their converged q.
 static int launch_score(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* m, const int64_t* d_win_off, int64_t n_windows,
-                        int strands, double* d_out, int32_t* d_sweeps, int counter_slot, const ScoreItems* items = nullptr) {
+                        int strands, double* d_out, int32_t* d_sweeps, int counter_slot, const ScoreItems* items) {
     int rc = model_upload(ctx, m);
     if (rc) return rc;
     ModelHost& h = m->h;
     // the M-step always runs the mean field, whatever CALC_LOGLIKELIHOOD says (PhyloBayesModel.java:142-147)
     const int mode = items ? PHYFOO_MODE_MEANFIELD : h.mode;
+    const bool fallback = items && items->fallback;
     if (h.S != ds->S) return fail(ctx, PHYFOO_EINVAL, "model and dataset disagree on the number of species");
     if (h.evol == PHYFOO_EVOL_HKY_AS_IMPLEMENTED)
         return fail(ctx, PHYFOO_EUNSUPPORTED, "HKY as implemented in the reference has zero transversion probabilities (HKY.java:32): every score is -inf");
@@ -933,10 +1052,14 @@ static int launch_score(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model*
     const long long n_items = (long long)n_windows * n_strands;
     if (n_items == 0) return PHYFOO_OK;
     if (h.order == 1) { ctx->last_path = 2; return launch_net1(ctx, ds, m, d_win_off, n_windows, strands, d_out, d_sweeps, counter_slot, items); }
-    if (!items && memo_applies(ctx, ds, h, n_items)) return launch_memo(ctx, ds, m, mode, d_win_off, n_windows, strands, d_out, d_sweeps, counter_slot);
-    ctx->last_path = 0;
+    if (!items && memo_applies(ctx, ds, h, mode, n_items)) {
+        const MemoJob job{m, mode, d_win_off, n_windows, strands, d_out, d_sweeps, counter_slot};
+        return launch_memo_jobs(ctx, ds, &job, 1);
+    }
+    if (!fallback) ctx->last_path = 0;
     ScorePlan pl;
-    rc = plan_score(ctx, h, m->prog_len, n_items, mode, items != nullptr, &pl);
+    // the fallback list of the pattern-table path is short (its length lives on the device): one block per SM
+    rc = plan_score(ctx, h, m->prog_len, fallback ? std::min<long long>(n_items, 64LL * ctx->sm_count) : n_items, mode, items != nullptr, &pl);
     if (rc) return rc;
     ScoreParams p;
     p.bases = ds->d_bases; p.gaps = ds->d_gaps; p.n_cols = ds->n_cols; p.nb = ds->nb;
@@ -946,28 +1069,39 @@ static int launch_score(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model*
     p.tab = mode == PHYFOO_MODE_EXACT ? m->d_probtab : m->d_logtab;
     p.prog = m->d_prog;
     p.out = d_out; p.sweeps = d_sweeps;
-    p.counters = ctx->counters.as<unsigned long long>() + 2 * counter_slot;
+    // counters: [2 slot] work counter, [2 slot + 1] sweep sum; a fallback launch continues the sweep sum of the
+    // pattern-table pass and pulls its work from a counter of its own ([8 + slot])
+    unsigned long long* counters = ctx->counters.as<unsigned long long>();
+    p.counter_next = fallback ? counters + 8 + counter_slot : counters + 2 * counter_slot;
+    p.counter_sweeps = counters + 2 * counter_slot + 1;
     p.max_sweeps = h.max_sweeps; p.min_sweeps = h.min_sweeps; p.tol = h.tol;
     p.groups = pl.groups;
     p.item_col0 = nullptr; p.item_strand = nullptr; p.q_int = nullptr; p.q_leaf = nullptr; p.ent = nullptr;
-    if (items) { p.item_col0 = items->col0; p.item_strand = items->strand; p.q_int = items->q_int; p.q_leaf = items->q_leaf; p.ent = items->ent; }
+    p.n_items_dev = nullptr; p.item_dst = nullptr;
+    if (items) {
+        p.item_col0 = items->col0; p.item_strand = items->strand; p.q_int = items->q_int; p.q_leaf = items->q_leaf; p.ent = items->ent;
+        p.n_items_dev = items->n_dev; p.item_dst = items->dst;
+    }
     p.gstate = nullptr;
     if (pl.gstate) {
         CU(ctx->gstate.ensure((size_t)pl.blocks * pl.threads * h.I * 8 * sizeof(double)));
         p.gstate = ctx->gstate.as<double>();
     }
-    CU(cudaMemsetAsync(p.counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
-    if (mode == PHYFOO_MODE_EXACT) score_o0_kernel<PHYFOO_MODE_EXACT, false><<<pl.blocks, pl.threads, pl.smem, ctx->stream>>>(p);
-    else if (items) score_o0_kernel<PHYFOO_MODE_MEANFIELD, true><<<pl.blocks, pl.threads, pl.smem, ctx->stream>>>(p);
-    else score_o0_kernel<PHYFOO_MODE_MEANFIELD, false><<<pl.blocks, pl.threads, pl.smem, ctx->stream>>>(p);
-    ctx->launches++;
+    CU(cudaMemsetAsync(p.counter_next, 0, sizeof(unsigned long long), ctx->stream));
+    if (!fallback) CU(cudaMemsetAsync(p.counter_sweeps, 0, sizeof(unsigned long long), ctx->stream));
+    {
+        KernelTimer kt_(ctx, fallback ? "score_o0_kernel(fallback list)" : "score_o0_kernel");
+        if (mode == PHYFOO_MODE_EXACT) score_o0_kernel<PHYFOO_MODE_EXACT, false><<<pl.blocks, pl.threads, pl.smem, ctx->stream>>>(p);
+        else if (items) score_o0_kernel<PHYFOO_MODE_MEANFIELD, true><<<pl.blocks, pl.threads, pl.smem, ctx->stream>>>(p);
+        else score_o0_kernel<PHYFOO_MODE_MEANFIELD, false><<<pl.blocks, pl.threads, pl.smem, ctx->stream>>>(p);
+    }
     CU(cudaGetLastError());
     return PHYFOO_OK;
 }
 
 struct CallTimer {
     phyfoo_ctx* ctx;
-    explicit CallTimer(phyfoo_ctx* c) : ctx(c) { ctx->launches = 0; cudaEventRecord(ctx->ev0, ctx->stream); }
+    explicit CallTimer(phyfoo_ctx* c) : ctx(c) { ctx->launches = 0; ctx->n_ktimes = 0; cudaEventRecord(ctx->ev0, ctx->stream); }
     float stop() {
         cudaEventRecord(ctx->ev1, ctx->stream);
         cudaEventSynchronize(ctx->ev1);
@@ -1070,11 +1204,25 @@ static int enqueue_estep(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model
     CU(ctx->part.ensure((size_t)3 * ds->n_aln * sizeof(double)));
     ctx->kev_valid = false;
     CU(cudaEventRecord(ctx->kev[0], ctx->stream));
-    rc = launch_bg_columns(ctx, ds, bg, ctx->bg_scores.as<double>(), nullptr, 1);
-    if (rc) return rc;
-    CU(cudaEventRecord(ctx->kev[1], ctx->stream));
-    rc = launch_score(ctx, ds, fg, d_woff, nw, strand_logw ? 2 : 0, ctx->fg_scores.as<double>(), nullptr, 0);
-    if (rc) return rc;
+    const bool both_memo = bg->h.kind == PHYFOO_MODEL_BG && bg->h.order == 0 && fg->h.S == ds->S && bg->h.S == ds->S &&
+                           fg->h.evol != PHYFOO_EVOL_HKY_AS_IMPLEMENTED && bg->h.evol != PHYFOO_EVOL_HKY_AS_IMPLEMENTED &&
+                           fg->h.order == 0 && fg->h.tables_finite() && bg->h.tables_finite() &&
+                           memo_applies(ctx, ds, fg->h, fg->h.mode, (long long)nw * n_strands) &&
+                           memo_applies(ctx, ds, bg->h, bg->h.mode, (long long)ds->n_cols);
+    if (both_memo) {
+        // background and motif trajectories in ONE launch (both are small, latency-bound grids), then the two gathers
+        const MemoJob jobs[2] = {{bg, bg->h.mode, ds->d_col_off, ds->n_cols, 0, ctx->bg_scores.as<double>(), nullptr, 1},
+                                 {fg, fg->h.mode, d_woff, nw, strand_logw ? 2 : 0, ctx->fg_scores.as<double>(), nullptr, 0}};
+        rc = launch_memo_jobs(ctx, ds, jobs, 2);
+        if (rc) return rc;
+        CU(cudaEventRecord(ctx->kev[1], ctx->stream));   // phases are not separable on this path: see phyfoo_last_kernel_times
+    } else {
+        rc = launch_bg_columns(ctx, ds, bg, ctx->bg_scores.as<double>(), nullptr, 1);
+        if (rc) return rc;
+        CU(cudaEventRecord(ctx->kev[1], ctx->stream));
+        rc = launch_score(ctx, ds, fg, d_woff, nw, strand_logw ? 2 : 0, ctx->fg_scores.as<double>(), nullptr, 0);
+        if (rc) return rc;
+    }
     CU(cudaEventRecord(ctx->kev[2], ctx->stream));
     ZoopsParams z;
     z.fwd = ctx->fg_scores.as<double>();
@@ -1088,11 +1236,15 @@ static int enqueue_estep(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model
     z.gamma = d_gamma; z.profile = d_profile;
     z.part = ctx->part.as<double>();
     z.argoff = d_argoff; z.argstrand = d_argstrand;
-    zoops_kernel<<<ds->n_aln, 256, 0, ctx->stream>>>(z);
-    ctx->launches++;
+    {
+        KernelTimer kt_(ctx, "zoops_kernel");
+        zoops_kernel<<<ds->n_aln, 256, 0, ctx->stream>>>(z);
+    }
     CU(cudaGetLastError());
-    reduce3_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->part.as<double>(), ds->n_aln, d_out3);
-    ctx->launches++;
+    {
+        KernelTimer kt_(ctx, "reduce3_kernel");
+        reduce3_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->part.as<double>(), ds->n_aln, d_out3);
+    }
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->kev[3], ctx->stream));
     ctx->kev_valid = true;
@@ -1152,7 +1304,7 @@ extern "C" int phyfoo_zoops_estep_device(phyfoo_ctx* ctx, const phyfoo_dataset* 
     if (!ctx) return PHYFOO_EINVAL;
     if (!ds || !fg || !bg || !logw || !partial_device) return fail(ctx, PHYFOO_EINVAL, "zoops_estep_device: NULL argument");
     CU(cudaSetDevice(ctx->device));
-    ctx->launches = 0;
+    ctx->launches = 0; ctx->n_ktimes = 0;
     // The library's kernels run on its own stream; order them after the caller's stream and make the
     // caller's stream wait for the result, so the call is asynchronous for the host.
     cudaStream_t user = (cudaStream_t)stream;
@@ -1199,13 +1351,45 @@ extern "C" int phyfoo_estep_sweeps(phyfoo_ctx* ctx, int64_t* sweeps_fg, int64_t*
     return PHYFOO_OK;
 }
 
+// page-locked host memory for callers that want the copies of a call to run at full PCIe speed
+extern "C" void* phyfoo_host_alloc(phyfoo_ctx* ctx, int64_t bytes) {
+    if (!ctx || bytes < 0) return nullptr;
+    void* p = nullptr;
+    if (cudaSetDevice(ctx->device) != cudaSuccess || cudaHostAlloc(&p, bytes ? (size_t)bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        ctx->err = "phyfoo_host_alloc: cudaHostAlloc failed";
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void phyfoo_host_free(phyfoo_ctx* ctx, void* p) { (void)ctx; if (p) cudaFreeHost(p); }
+
 extern "C" int phyfoo_last_launches(const phyfoo_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" int phyfoo_last_score_path(const phyfoo_ctx* ctx) { return ctx ? ctx->last_path : -1; }
+// per-kernel device times of the most recent call on this context (waits for the call's kernels to finish)
+extern "C" int phyfoo_last_kernel_times(phyfoo_ctx* ctx, int32_t max_entries, const char** names_out, float* ms_out) {
+    if (!ctx) return PHYFOO_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    int n = 0;
+    for (int i = 0; i < ctx->n_ktimes && n < max_entries; ++i) {
+        CU(cudaEventSynchronize(ctx->ktimes[i].e1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, ctx->ktimes[i].e0, ctx->ktimes[i].e1));
+        if (names_out) names_out[n] = ctx->ktimes[i].name;
+        if (ms_out) ms_out[n] = ms;
+        ++n;
+    }
+    return n;
+}
 extern "C" int phyfoo_set_option(phyfoo_ctx* ctx, const char* name, int64_t value) {
     if (!ctx || !name) return PHYFOO_EINVAL;
     if (std::strcmp(name, "pattern_memo") == 0) {
         if (value < 0 || value > 2) return fail(ctx, PHYFOO_EINVAL, "set_option: pattern_memo must be 0 (off), 1 (auto) or 2 (always)");
         ctx->memo_mode = (int)value;
+        return PHYFOO_OK;
+    }
+    if (std::strcmp(name, "pattern_memo_sweep_cap") == 0) {
+        if (value < 1 || value > 1000) return fail(ctx, PHYFOO_EINVAL, "set_option: pattern_memo_sweep_cap must be in 1..1000");
+        ctx->memo_sweep_cap = (int)value;
         return PHYFOO_OK;
     }
     return fail(ctx, PHYFOO_EINVAL, std::string("set_option: unknown option ") + name);

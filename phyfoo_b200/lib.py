@@ -22,13 +22,14 @@ _LIB = None
 SYMBOLS = [
     "phyfoo_init", "phyfoo_destroy", "phyfoo_last_error", "phyfoo_device_info", "phyfoo_fp64_peak",
     "phyfoo_dataset_create", "phyfoo_dataset_create_device", "phyfoo_dataset_packed", "phyfoo_dataset_columns",
-    "phyfoo_dataset_windows", "phyfoo_dataset_free",
+    "phyfoo_dataset_windows", "phyfoo_dataset_patterns", "phyfoo_dataset_free",
     "phyfoo_model_create", "phyfoo_model_set_pi", "phyfoo_model_get_pi", "phyfoo_model_set_branch",
     "phyfoo_model_set_mode", "phyfoo_model_free",
     "phyfoo_score_windows", "phyfoo_bg_columns", "phyfoo_zoops_estep", "phyfoo_zoops_estep_device",
     "phyfoo_select", "phyfoo_fe_prepare", "phyfoo_fe_prepare_all", "phyfoo_fe_eval", "phyfoo_fe_grad",
     "phyfoo_fe_values_device", "phyfoo_fe_size", "phyfoo_fe_free",
-    "phyfoo_set_option", "phyfoo_last_score_path", "phyfoo_last_launches", "phyfoo_stream", "phyfoo_synchronize", "phyfoo_estep_kernel_ms", "phyfoo_estep_sweeps",
+    "phyfoo_set_option", "phyfoo_last_score_path", "phyfoo_last_kernel_times", "phyfoo_host_alloc", "phyfoo_host_free",
+    "phyfoo_last_launches", "phyfoo_stream", "phyfoo_synchronize", "phyfoo_estep_kernel_ms", "phyfoo_estep_sweeps",
 ]
 
 
@@ -78,6 +79,8 @@ def lib():
     L.phyfoo_dataset_columns.restype = C.c_int64
     L.phyfoo_dataset_windows.argtypes = [vp, C.c_int32]
     L.phyfoo_dataset_windows.restype = C.c_int64
+    L.phyfoo_dataset_patterns.argtypes = [vp, vp]
+    L.phyfoo_dataset_patterns.restype = C.c_int64
     L.phyfoo_dataset_free.argtypes = [vp, vp]
     L.phyfoo_dataset_free.restype = None
     L.phyfoo_model_create.argtypes = [vp, C.POINTER(_abi.ModelDesc), C.POINTER(vp)]
@@ -102,8 +105,13 @@ def lib():
     L.phyfoo_fe_free.argtypes = [vp, vp]
     L.phyfoo_fe_free.restype = None
     L.phyfoo_last_launches.argtypes = [vp]
+    L.phyfoo_host_alloc.argtypes = [vp, C.c_int64]
+    L.phyfoo_host_alloc.restype = vp
+    L.phyfoo_host_free.argtypes = [vp, vp]
+    L.phyfoo_host_free.restype = None
     L.phyfoo_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.phyfoo_last_score_path.argtypes = [vp]
+    L.phyfoo_last_kernel_times.argtypes = [vp, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]
     L.phyfoo_stream.argtypes = [vp]
     L.phyfoo_stream.restype = vp
     L.phyfoo_synchronize.argtypes = [vp]

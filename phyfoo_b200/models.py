@@ -197,7 +197,7 @@ class SingleHiddenMotifMixture:
     def getNumberOfMotifs(self):
         return 1   # jstacs SingleHiddenMotifMixture.java:716-718
 
-    def getNewWeights(self, sample: PhyloSample, seqWeights=None, want_gamma=True, want_profile=False):
+    def getNewWeights(self, sample: PhyloSample, seqWeights=None, want_gamma=True, want_profile=False, out=None):
         """One E-step (jstacs SingleHiddenMotifMixture.java:499-566).  Returns a dict with
         gamma (seqweights[0] per window), w (sufficient statistics of the component weights), ll, argmax_off/strand."""
         with np.errstate(divide="ignore"):
@@ -205,7 +205,7 @@ class SingleHiddenMotifMixture:
         res = core.zoops_estep(self.motif.ctx, sample.device(self.motif.ctx), self.motif.device_model(),
                                self.flanking.device_model(), logw,
                                None if self.strand is None else self.strand.logWeights(),
-                               seqWeights, want_gamma, want_profile, True)
+                               seqWeights, want_gamma, want_profile, True, out)
         self.last = res
         return res
 

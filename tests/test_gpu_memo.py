@@ -85,6 +85,39 @@ def test_memo_estep_and_parameter_updates(ctx):
     assert abs(m["ll"] - ref["ll"]) <= 1e-9 * abs(ref["ll"]) and np.array_equal(m["argmax_off"], ref["argmax_off"])
 
 
+def test_memo_sweep_cap_fallback_is_bit_identical(ctx):
+    """Windows whose stop rule needs more sweeps than the stored trajectories go to the direct kernel: same bits."""
+    from phyfoo_b200 import synth
+    from phyfoo_b200.models import PhyloBackground, PhyloBayesModel, SingleHiddenMotifMixture, StrandModel
+    newick = synth.caterpillar_newick(5)
+    W = 9
+    pwm = synth.random_pwm(W, 0, 19)
+    smp, _ = synth.make_sample(newick, 25, 120, 8, pwm=pwm, gap_rate=0.03)
+    fg = PhyloBayesModel(W, 0, newick, ctx); fg.setCondProbs(pwm)
+    bg = PhyloBackground(0, newick, ctx)
+    ctx.set_option("pattern_memo", 0)
+    d, dk = fg.getLogProbFor(smp, want_sweeps=True)
+    shm = SingleHiddenMotifMixture(StrandModel(fg, 0.5), bg, zoops=0.9)
+    de = shm.getNewWeights(smp)
+    ctx.set_option("pattern_memo", 2)
+    try:
+        for cap in (1, 3, 6, 100):
+            ctx.set_option("pattern_memo_sweep_cap", cap)
+            m, mk = fg.getLogProbFor(smp, want_sweeps=True)
+            assert ctx.last_score_path() == 1
+            assert np.array_equal(d, m) and np.array_equal(dk, mk), cap
+            assert fg.last_stats["sweeps_fg"] == int(dk.sum())
+            names = [n for n, _ in ctx.last_kernel_times()]
+            assert "memo_traj_kernel" in names and "memo_window_kernel" in names
+            assert ("score_o0_kernel(fallback list)" in names) == (cap < 100)
+            me = shm.getNewWeights(smp)
+            assert me["ll"] == de["ll"] and np.array_equal(me["gamma"], de["gamma"])
+            assert me["stats"]["sweeps_fg"] == de["stats"]["sweeps_fg"] and me["stats"]["sweeps_bg"] == de["stats"]["sweeps_bg"]
+        assert (dk > 6).any() and (dk <= 6).any()      # the cap of 6 really splits the windows between the two kernels
+    finally:
+        ctx.set_option("pattern_memo_sweep_cap", 100)
+
+
 def test_memo_does_not_apply_to_many_species_or_order1(ctx):
     from phyfoo_b200 import synth
     from phyfoo_b200.models import PhyloBayesModel
