@@ -198,9 +198,11 @@ struct ModelHost {
         return true;
     }
 
-    // order-1 motif tables (net1.cuh): per position E1 = 16 + 64 (N-1) logs; root [ctx][4] at 0, node k >= 1
-    // [l = a_treeparent + 4 ctx][b] at 16 + 64 (k-1).  Unused rows (t = 0 has a single context) are 0.
-    int E1() const { return 16 + 64 * (N - 1); }
+    // order-1 motif tables (net1.cuh): per position E1 = 16 + 32 (N-1) logs; root [ctx][4] at 0; node k >= 1: the
+    // reference's table [l = a_treeparent + 4 ctx][b] has F81 structure (one value for every a != b), stored as
+    // off-diagonal Lo[ctx][b] at 16 + 32 (k-1) and diagonal Ld[ctx][b] 16 further.  Unused rows (t = 0 has a single
+    // context) are 0.  Throws if a table does not have that structure bit for bit.
+    int E1() const { return 16 + 32 * (N - 1); }
     void tables1(std::vector<double>& out) const {
         const int e1 = E1();
         out.assign((size_t)W * e1, 0.0);
@@ -209,8 +211,18 @@ struct ModelHost {
             const int ctx = ctx_rows(t);
             for (int i = 0; i < ctx * 4; ++i) o[i] = std::log(pi[t][i]);
             for (int k = 1; k < N; ++k) {
-                const std::vector<double> tr = cpf(t, k);
-                for (size_t i = 0; i < tr.size(); ++i) o[16 + 64 * (k - 1) + i] = std::log(tr[i]);
+                const std::vector<double> tr = cpf(t, k);     // [(a + 4c)][b]
+                double* lo = o + 16 + 32 * (k - 1);
+                double* ld = lo + 16;
+                for (int c = 0; c < ctx; ++c)
+                    for (int b = 0; b < 4; ++b) {
+                        const double off = tr[(size_t)(((b + 1) & 3) + 4 * c) * 4 + b];
+                        for (int a = 0; a < 4; ++a)
+                            if (a != b && tr[(size_t)(a + 4 * c) * 4 + b] != off)
+                                throw std::invalid_argument("order-1 kernel needs F81-structured substitution tables");
+                        lo[c * 4 + b] = std::log(off);
+                        ld[c * 4 + b] = std::log(tr[(size_t)(b + 4 * c) * 4 + b]);
+                    }
             }
         }
     }

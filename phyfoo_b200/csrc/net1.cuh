@@ -18,10 +18,11 @@
 //    interacts with it);
 //  * pass 0 (free energy at the uniform start) is the update pass with the exponent forced to 0.
 //
-// Table layout per position t (E1 = 16 + 64 (N-1) doubles, logs): root [ctx][4] at 0 (ctx = value of the root of
-// position t-1; only row 0 is used at t = 0), node k >= 1 at 16 + 64 (k-1): [l][b], l = a_treeparent + 4 ctx
-// (bayesNet/CPF.java:56-59,238-256: parent 0 is the least significant digit).  The "independent" table of an
-// unobserved leaf (CPF.java:146-152) has pi[ctx][b] in every row = the root table.
+// Table layout per position t (E1 = 16 + 32 (N-1) doubles, logs): root [ctx][4] at 0 (ctx = value of the root of
+// position t-1; only row 0 is used at t = 0); node k >= 1: the reference's table [l][b], l = a_treeparent + 4 ctx
+// (bayesNet/CPF.java:56-59,238-256: parent 0 is the least significant digit) stored as its off-diagonal values
+// Lo[ctx][b] at 16 + 32 (k-1) and its diagonal values Ld[ctx][b] 16 further (see net1_pass).  The "independent" table
+// of an unobserved leaf (CPF.java:146-152) has pi[ctx][b] in every row = the root table.
 #pragma once
 
 struct Net1Params {
@@ -37,6 +38,7 @@ struct Net1Params {
     double* gq;              // gap-leaf q: [(t*S + leaf slot)*4 + a][n_slots]
     int64_t n_slots;
     int nwb;                 // windows per block
+    int tab_in_smem;         // copy the tables into shared memory (when they fit beside the window state)
     const int64_t* item_col0; const uint8_t* item_strand;   // nullable: explicit window list
 };
 
@@ -52,6 +54,8 @@ struct Net1Ctx {
     unsigned qmask; int qb, a;
 };
 
+// table entry: tables live in shared memory when they fit (generic load), else in global memory behind L1
+__device__ __forceinline__ double n1_ld(const double* p) { return *p; }
 __device__ __forceinline__ double& n1_q(const Net1Ctx& c, int t, int i, int a) { return c.q[(size_t)((t * c.I + i) * 4 + a) * c.nwb + c.wq]; }
 __device__ __forceinline__ double& n1_gq(const Net1Ctx& c, int t, int kk, int a) { return c.gq[(size_t)((t * c.S + kk) * 4 + a) * c.n_slots + c.slot]; }
 __device__ __forceinline__ ColWords n1_col(const Net1Ctx& c, int t) {
@@ -65,11 +69,25 @@ __device__ __forceinline__ void n1_normalise(const Net1Ctx& c, double s, bool up
     const double e0 = __shfl_sync(c.qmask, e, c.qb), e1 = __shfl_sync(c.qmask, e, c.qb + 1);
     const double e2 = __shfl_sync(c.qmask, e, c.qb + 2), e3 = __shfl_sync(c.qmask, e, c.qb + 3);
     const double z = ((e0 + e1) + e2) + e3;                                 // :195-198
-    qn = e / z;                                                             // :199-201
+    qn = e * __drcp_rn(z);                                                  // :199-201 (correctly rounded reciprocal, then one product)
     lq = ex - log(z);
 }
 
+// sum of the other three entries of v (index order), i.e. the weight of the off-diagonal rows for own symbol a
+__device__ __forceinline__ double n1_rest(const double* v, int a) {
+    const double x0 = a == 0 ? v[1] : v[0], x1 = a <= 1 ? v[2] : v[1], x2 = a <= 2 ? v[3] : v[2];
+    return (x0 + x1) + x2;
+}
+// v[a] without dynamic register indexing
+__device__ __forceinline__ double n1_pick(const double* v, int a) { return a == 0 ? v[0] : a == 1 ? v[1] : a == 2 ? v[2] : v[3]; }
+
 // One pass over the window's net; returns this lane's share of the free energy F = part1 - part2.
+//
+// The substitution tables have F81 structure (evolution/FS81alpha.java:76-92, FS81beta.java:81-103): for a given
+// context c and target b the entry is the same for every parent symbol a != b, so a table is stored as its
+// off-diagonal values Lo[c][b] and its diagonal values Ld[c][b] (model_host.hpp checks this bit for bit), and a sum
+// over the 16 rows l = a + 4c collapses to  sum_c q_ctx(c) (q_par(b) Ld[c][b] + (sum_{a != b} q_par(a)) Lo[c][b]).
+// Layout per position (E1 = 16 + 32 (N-1) logs): root [ctx][4] at 0; node k >= 1: Lo at 16 + 32 (k-1), Ld 16 further.
 __device__ double net1_pass(const Net1Ctx& c, bool update) {
     const int a = c.a;
     double F = 0.0;
@@ -85,42 +103,58 @@ __device__ double net1_pass(const Net1Ctx& c, bool update) {
         for (int i = 0; i < c.I; ++i) {
             const int k = c.node_of[i];
             const int p = c.par_internal[i];
-            const double* T = tab + 16 + 64 * (k - 1);
+            const double* Lo = tab + 16 + 32 * (k - 1);
+            const double* Ld = Lo + 16;
             // ---- own rows, :117-135 (all parents of an internal node are hidden)
-            double own = 0.0;
+            double own;
             if (i == 0) {
-                if (t == 0) own = __ldg(tab + a);
+                if (t == 0) own = n1_ld(tab + a);
                 else {
+                    own = 0.0;
 #pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) own += n1_q(c, t - 1, 0, cc) * __ldg(tab + cc * 4 + a);
+                    for (int cc = 0; cc < 4; ++cc) own += n1_q(c, t - 1, 0, cc) * n1_ld(tab + cc * 4 + a);
                 }
-            } else if (t == 0) {
-#pragma unroll
-                for (int ap = 0; ap < 4; ++ap) own += n1_q(c, 0, p, ap) * __ldg(T + ap * 4 + a);
             } else {
-                double qp[4], qh[4];
+                double qp[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) { qp[j] = n1_q(c, t, p, j); qh[j] = n1_q(c, t - 1, i, j); }
+                for (int j = 0; j < 4; ++j) qp[j] = n1_q(c, t, p, j);
+                double A, B;
+                if (t == 0) { A = n1_ld(Ld + a); B = n1_ld(Lo + a); }
+                else {
+                    A = 0.0; B = 0.0;
 #pragma unroll
-                for (int l = 0; l < 16; ++l) own += (qp[l & 3] * qh[l >> 2]) * __ldg(T + l * 4 + a);
+                    for (int cc = 0; cc < 4; ++cc) {
+                        const double qh = n1_q(c, t - 1, i, cc);
+                        A += qh * n1_ld(Ld + cc * 4 + a);
+                        B += qh * n1_ld(Lo + cc * 4 + a);
+                    }
+                }
+                own = n1_pick(qp, a) * A + n1_rest(qp, a) * B;
             }
             // ---- children, :139-191: internal tree children, leaf children, then the same node of position t+1
             double ch = 0.0;
             for (int j = c.ichild_begin[i]; j < c.ichild_begin[i + 1]; ++j) {
                 const int ci = c.ichild[j];
-                const double* Tc = tab + 16 + 64 * (c.node_of[ci] - 1);
-                if (t == 0) {
+                const double* Lco = tab + 16 + 32 * (c.node_of[ci] - 1);
+                const double* Lcd = Lco + 16;
+                // this lane handles the child's symbol ac = a: u = sum_cc q_prev(cc) Lo[cc][a], v likewise with Ld
+                double u, v;
+                if (t == 0) { u = n1_ld(Lco + a); v = n1_ld(Lcd + a); }
+                else {
+                    u = 0.0; v = 0.0;
 #pragma unroll
-                    for (int ac = 0; ac < 4; ++ac) ch += n1_q(c, 0, ci, ac) * __ldg(Tc + a * 4 + ac);
-                } else {
-                    double qc[4], qpc[4];
-#pragma unroll
-                    for (int m = 0; m < 4; ++m) { qc[m] = n1_q(c, t, ci, m); qpc[m] = n1_q(c, t - 1, ci, m); }
-#pragma unroll
-                    for (int ac = 0; ac < 4; ++ac)
-#pragma unroll
-                        for (int cc = 0; cc < 4; ++cc) ch += (qc[ac] * qpc[cc]) * __ldg(Tc + (a + 4 * cc) * 4 + ac);
+                    for (int cc = 0; cc < 4; ++cc) {
+                        const double qpc = n1_q(c, t - 1, ci, cc);
+                        u += qpc * n1_ld(Lco + cc * 4 + a);
+                        v += qpc * n1_ld(Lcd + cc * 4 + a);
+                    }
                 }
+                const double qc = n1_q(c, t, ci, a);
+                const double wu = qc * u;                 // contribution of child symbol a to every OTHER own symbol
+                double w[4];
+#pragma unroll
+                for (int m = 0; m < 4; ++m) w[m] = __shfl_sync(c.qmask, wu, c.qb + m);
+                ch += n1_rest(w, a) + qc * v;
             }
             double cobs = 0.0, cgap = 0.0;
             for (int kk = c.leaf_begin[i]; kk < c.leaf_begin[i + 1]; ++kk) {
@@ -128,26 +162,25 @@ __device__ double net1_pass(const Net1Ctx& c, bool update) {
                 const int x = cw.obs(sp);
                 const int y = t > 0 ? cwp.obs(sp) : 0;
                 if (x < 4) {
-                    const double* Tl = tab + 16 + 64 * (c.leaf_node[kk] - 1);
-                    if (t == 0) cobs += __ldg(Tl + a * 4 + x);
-                    else if (y < 4) cobs += __ldg(Tl + (a + 4 * y) * 4 + x);         // observed parents must match the row
+                    const double* Ll = tab + 16 + 32 * (c.leaf_node[kk] - 1) + (a == x ? 16 : 0);
+                    if (t == 0 || y < 4) cobs += n1_ld(Ll + y * 4 + x);                 // observed parents must match the row
                     else {
 #pragma unroll
-                        for (int cc = 0; cc < 4; ++cc) cobs += n1_gq(c, t - 1, kk, cc) * __ldg(Tl + (a + 4 * cc) * 4 + x);
+                        for (int cc = 0; cc < 4; ++cc) cobs += n1_gq(c, t - 1, kk, cc) * n1_ld(Ll + cc * 4 + x);
                     }
                 } else {
                     // unobserved leaf: every row of its table is pi[ctx] (CPF.java:146-152): the same value for every a
                     if (t == 0) {
 #pragma unroll
-                        for (int ac = 0; ac < 4; ++ac) cgap += n1_gq(c, 0, kk, ac) * __ldg(tab + ac);
+                        for (int ac = 0; ac < 4; ++ac) cgap += n1_gq(c, 0, kk, ac) * n1_ld(tab + ac);
                     } else if (y < 4) {
 #pragma unroll
-                        for (int ac = 0; ac < 4; ++ac) cgap += n1_gq(c, t, kk, ac) * __ldg(tab + y * 4 + ac);
+                        for (int ac = 0; ac < 4; ++ac) cgap += n1_gq(c, t, kk, ac) * n1_ld(tab + y * 4 + ac);
                     } else {
 #pragma unroll
                         for (int ac = 0; ac < 4; ++ac)
 #pragma unroll
-                            for (int cc = 0; cc < 4; ++cc) cgap += (n1_gq(c, t, kk, ac) * n1_gq(c, t - 1, kk, cc)) * __ldg(tab + cc * 4 + ac);
+                            for (int cc = 0; cc < 4; ++cc) cgap += (n1_gq(c, t, kk, ac) * n1_gq(c, t - 1, kk, cc)) * n1_ld(tab + cc * 4 + ac);
                     }
                 }
             }
@@ -155,16 +188,20 @@ __device__ double net1_pass(const Net1Ctx& c, bool update) {
             if (has_next) {
                 if (i == 0) {
 #pragma unroll
-                    for (int ac = 0; ac < 4; ++ac) nx += n1_q(c, t + 1, 0, ac) * __ldg(tabn + a * 4 + ac);
+                    for (int ac = 0; ac < 4; ++ac) nx += n1_q(c, t + 1, 0, ac) * n1_ld(tabn + a * 4 + ac);
                 } else {
-                    const double* Tn = tabn + 16 + 64 * (k - 1);
-                    double qx[4], qpn[4];
+                    const double* Lno = tabn + 16 + 32 * (k - 1);
+                    const double* Lnd = Lno + 16;
+                    double qpn[4];
 #pragma unroll
-                    for (int m = 0; m < 4; ++m) { qx[m] = n1_q(c, t + 1, i, m); qpn[m] = n1_q(c, t + 1, p, m); }
+                    for (int m = 0; m < 4; ++m) qpn[m] = n1_q(c, t + 1, p, m);
 #pragma unroll
-                    for (int ac = 0; ac < 4; ++ac)
-#pragma unroll
-                        for (int ap = 0; ap < 4; ++ap) nx += (qx[ac] * qpn[ap]) * __ldg(Tn + (ap + 4 * a) * 4 + ac);
+                    for (int ac = 0; ac < 4; ++ac) {
+                        // rows l = ap + 4a of the next node's table: diagonal for ap == ac, off-diagonal otherwise
+                        const double rest = ac == 0 ? (qpn[1] + qpn[2]) + qpn[3] : ac == 1 ? (qpn[0] + qpn[2]) + qpn[3]
+                                          : ac == 2 ? (qpn[0] + qpn[1]) + qpn[3] : (qpn[0] + qpn[1]) + qpn[2];
+                        nx += n1_q(c, t + 1, i, ac) * (qpn[ac] * n1_ld(Lnd + a * 4 + ac) + rest * n1_ld(Lno + a * 4 + ac));
+                    }
                 }
             }
             const double s = (((own + ch) + cobs) + cgap) + nx;
@@ -183,15 +220,15 @@ __device__ double net1_pass(const Net1Ctx& c, bool update) {
                 const int y = t > 0 ? cwp.obs(sp) : 0;
                 const double qs = ((n1_q(c, t, i, 0) + n1_q(c, t, i, 1)) + n1_q(c, t, i, 2)) + n1_q(c, t, i, 3);
                 double ownl = 0.0, own_fe;
-                if (t == 0) { ownl = qs * __ldg(tab + a); own_fe = ownl; }
+                if (t == 0) { ownl = qs * n1_ld(tab + a); own_fe = ownl; }
                 else if (y < 4) {
                     // update: rows are NOT filtered by the observed parent (:129 TODO); free energy: they are (:327-358)
 #pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) ownl += qs * __ldg(tab + cc * 4 + a);
-                    own_fe = qs * __ldg(tab + y * 4 + a);
+                    for (int cc = 0; cc < 4; ++cc) ownl += qs * n1_ld(tab + cc * 4 + a);
+                    own_fe = qs * n1_ld(tab + y * 4 + a);
                 } else {
 #pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) ownl += (qs * n1_gq(c, t - 1, kk, cc)) * __ldg(tab + cc * 4 + a);
+                    for (int cc = 0; cc < 4; ++cc) ownl += (qs * n1_gq(c, t - 1, kk, cc)) * n1_ld(tab + cc * 4 + a);
                     own_fe = ownl;
                 }
                 double nl = 0.0;
@@ -201,14 +238,13 @@ __device__ double net1_pass(const Net1Ctx& c, bool update) {
 #pragma unroll
                     for (int m = 0; m < 4; ++m) qpn[m] = n1_q(c, t + 1, i, m);
                     if (xn < 4) {
-                        const double* Tln = tabn + 16 + 64 * (c.leaf_node[kk] - 1);
-#pragma unroll
-                        for (int ap = 0; ap < 4; ++ap) nl += qpn[ap] * __ldg(Tln + (ap + 4 * a) * 4 + xn);
+                        const double* Lno = tabn + 16 + 32 * (c.leaf_node[kk] - 1);
+                        nl = n1_pick(qpn, xn) * n1_ld(Lno + 16 + a * 4 + xn) + n1_rest(qpn, xn) * n1_ld(Lno + a * 4 + xn);
                     } else {
 #pragma unroll
                         for (int ac = 0; ac < 4; ++ac)
 #pragma unroll
-                            for (int ap = 0; ap < 4; ++ap) nl += (n1_gq(c, t + 1, kk, ac) * qpn[ap]) * __ldg(tabn + a * 4 + ac);
+                            for (int ap = 0; ap < 4; ++ap) nl += (n1_gq(c, t + 1, kk, ac) * qpn[ap]) * n1_ld(tabn + a * 4 + ac);
                     }
                 }
                 double ql, lql;
@@ -231,7 +267,11 @@ __global__ void __launch_bounds__(256) score_o1_kernel(Net1Params p) {
     uint64_t* s_cb = (uint64_t*)(s_q + (size_t)p.W * p.I * 4 * nwb);     // [W][nwb]
     uint32_t* s_cg = (uint32_t*)(s_cb + (size_t)p.W * nwb);              // [W][nwb]
     int* s_prog = (int*)(s_cg + (size_t)p.W * nwb);
+    // tables behind the program, 8-byte aligned
+    double* s_tab = (double*)(s_prog + ((p.prog_len + 1) & ~1));
     for (int i = tid; i < p.prog_len; i += T) s_prog[i] = p.prog[i];
+    if (p.tab_in_smem)
+        for (int i = tid; i < p.W * p.E1; i += T) s_tab[i] = p.tab[i];
     __syncthreads();
 
     Net1Ctx c;
@@ -245,7 +285,7 @@ __global__ void __launch_bounds__(256) score_o1_kernel(Net1Params p) {
     c.ichild_begin = s_prog + 3 * p.I + 1 + 2 * p.S;
     c.ichild = s_prog + 4 * p.I + 2 + 2 * p.S;
     c.W = p.W; c.I = p.I; c.S = p.S; c.E1 = p.E1;
-    c.tab = p.tab;
+    c.tab = p.tab_in_smem ? s_tab : p.tab;
     c.gq = p.gq; c.n_slots = p.n_slots; c.slot = (int64_t)blockIdx.x * nwb + c.wq;
     const int lane = tid & 31;
     c.qb = lane & ~3; c.a = lane & 3; c.qmask = 0xFu << c.qb;

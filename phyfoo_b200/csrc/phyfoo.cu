@@ -992,16 +992,25 @@ static int launch_net1(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* 
     if (items && items->q_int) return fail(ctx, PHYFOO_EUNSUPPORTED, "fixed-q objective of order-1 networks is not implemented in this build");
     const int n_strands = strands == 2 ? 2 : 1;
     const long long n_items = (long long)n_windows * n_strands;
-    // windows per block: as many windows per SM as shared memory holds, in multiples of 8 (whole warps)
+    // windows per block: as many windows per SM as shared memory holds, in multiples of 8 (whole warps).  The kernel is
+    // latency-bound (one quad per window, ~1.5 warps per scheduler), so windows in flight matter more than where the
+    // tables live: they go to shared memory only when that costs no window (measured on C3: 48 windows/SM with the
+    // tables behind L1/L2 beat 32 windows/SM with the tables in shared memory by 25 %).
     const size_t per_window = (size_t)h.W * h.I * 4 * sizeof(double) + (size_t)h.W * 12;
-    const size_t fixed = (size_t)m->prog_len * sizeof(int) + 64;
+    const size_t tab_bytes = (size_t)h.W * h.E1() * sizeof(double);
     const size_t budget = std::min<size_t>(ctx->smem_optin, 227 * 1024);
-    int best_nwb = 0, best_per_sm = 0;
-    for (int nwb = 8; nwb <= 64; nwb += 8) {
-        const size_t need = fixed + per_window * nwb;
-        if (need > budget) break;
-        const int blocks_sm = (int)std::min<size_t>((228 * 1024) / (need + 1024), 2048 / (4 * nwb));
-        if (blocks_sm * nwb > best_per_sm) { best_per_sm = blocks_sm * nwb; best_nwb = nwb; }
+    int best_nwb = 0, best_per_sm = 0, tab_in_smem = 0;
+    size_t fixed = 0;
+    for (int with_tab = 0; with_tab <= 1; ++with_tab) {
+        const size_t fx = (size_t)((m->prog_len + 1) & ~1) * sizeof(int) + 64 + (with_tab ? tab_bytes : 0);
+        for (int nwb = 8; nwb <= 64; nwb += 8) {
+            const size_t need = fx + per_window * nwb;
+            if (need > budget) break;
+            const int blocks_sm = (int)std::min<size_t>((228 * 1024) / (need + 1024), 2048 / (4 * nwb));
+            if (blocks_sm * nwb > best_per_sm || (with_tab && blocks_sm * nwb == best_per_sm && !tab_in_smem)) {
+                best_per_sm = blocks_sm * nwb; best_nwb = nwb; tab_in_smem = with_tab; fixed = fx;
+            }
+        }
     }
     if (!best_nwb) return fail(ctx, PHYFOO_EUNSUPPORTED, "order-1 window state does not fit in shared memory (motif too wide or tree too large)");
     const size_t smem = fixed + per_window * best_nwb;
@@ -1022,7 +1031,7 @@ static int launch_net1(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* 
     p.out = d_out; p.sweeps = d_sweeps;
     p.counters = ctx->counters.as<unsigned long long>() + 2 * counter_slot;
     p.max_sweeps = h.max_sweeps; p.min_sweeps = h.min_sweeps; p.tol = h.tol;
-    p.gq = ctx->gstate.as<double>(); p.n_slots = n_slots; p.nwb = best_nwb;
+    p.gq = ctx->gstate.as<double>(); p.n_slots = n_slots; p.nwb = best_nwb; p.tab_in_smem = tab_in_smem;
     p.item_col0 = items ? items->col0 : nullptr; p.item_strand = items ? items->strand : nullptr;
     CU(cudaMemsetAsync(p.counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
     {
