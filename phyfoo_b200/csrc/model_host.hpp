@@ -203,28 +203,32 @@ struct ModelHost {
     // off-diagonal Lo[ctx][b] at 16 + 32 (k-1) and diagonal Ld[ctx][b] 16 further.  Unused rows (t = 0 has a single
     // context) are 0.  Throws if a table does not have that structure bit for bit.
     int E1() const { return 16 + 32 * (N - 1); }
+    // tables of position t for an arbitrary parameter set pi_t ([ctx_rows(t)][4]); out[E1]
+    void build_tables1_into(int t, const double* pi_t, double* o) const {
+        const int ctx = ctx_rows(t);
+        for (int i = 0; i < E1(); ++i) o[i] = 0.0;
+        for (int i = 0; i < ctx * 4; ++i) o[i] = std::log(pi_t[i]);
+        for (int k = 1; k < N; ++k) {
+            double* lo = o + 16 + 32 * (k - 1);
+            double* ld = lo + 16;
+            for (int c = 0; c < ctx; ++c) {
+                double tr[16];                                   // [a][b] for context c
+                transition(pi_t + (size_t)c * 4, branch[(size_t)t * N + k], tr);
+                for (int b = 0; b < 4; ++b) {
+                    const double off = tr[((b + 1) & 3) * 4 + b];
+                    for (int a = 0; a < 4; ++a)
+                        if (a != b && tr[a * 4 + b] != off)
+                            throw std::invalid_argument("order-1 kernel needs F81-structured substitution tables");
+                    lo[c * 4 + b] = std::log(off);
+                    ld[c * 4 + b] = std::log(tr[b * 4 + b]);
+                }
+            }
+        }
+    }
     void tables1(std::vector<double>& out) const {
         const int e1 = E1();
         out.assign((size_t)W * e1, 0.0);
-        for (int t = 0; t < W; ++t) {
-            double* o = &out[(size_t)t * e1];
-            const int ctx = ctx_rows(t);
-            for (int i = 0; i < ctx * 4; ++i) o[i] = std::log(pi[t][i]);
-            for (int k = 1; k < N; ++k) {
-                const std::vector<double> tr = cpf(t, k);     // [(a + 4c)][b]
-                double* lo = o + 16 + 32 * (k - 1);
-                double* ld = lo + 16;
-                for (int c = 0; c < ctx; ++c)
-                    for (int b = 0; b < 4; ++b) {
-                        const double off = tr[(size_t)(((b + 1) & 3) + 4 * c) * 4 + b];
-                        for (int a = 0; a < 4; ++a)
-                            if (a != b && tr[(size_t)(a + 4 * c) * 4 + b] != off)
-                                throw std::invalid_argument("order-1 kernel needs F81-structured substitution tables");
-                        lo[c * 4 + b] = std::log(off);
-                        ld[c * 4 + b] = std::log(tr[(size_t)(b + 4 * c) * 4 + b]);
-                    }
-            }
-        }
+        for (int t = 0; t < W; ++t) build_tables1_into(t, pi[t].data(), &out[(size_t)t * e1]);
     }
 
     void set_pi(int t, const double* v, int n) {

@@ -32,9 +32,12 @@ struct phyfoo_feset {
     double* d_values = nullptr;    // [1 + 4W]
     int blocks = 0;
     uint64_t g_version = 0;        // model version d_G belongs to (0 = never)
+    int order = 0, E1 = 0;         // order 1: see mstep1.cuh (q layout [((t*I+i)*4+a)*n + u], one entropy per window)
 };
 
 static const int FE_KMAX = 5;      // order 0: dim = 4 per position -> 5 parameter sets
+
+#include "mstep1.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // selection: one block per alignment
@@ -303,8 +306,116 @@ static int fe_launch(phyfoo_ctx* ctx, phyfoo_feset* fe, int pos0, int n_pos, int
 }
 
 // tables of the model's CURRENT parameters for all positions (set 0), then G_t for all t
+// ---- order 1: one position per launch (mstep1.cuh) ----
+static int fe1_launch(phyfoo_ctx* ctx, phyfoo_feset* fe, int pos, int K, int mode, int value_off, const std::vector<double>& tabs) {
+    CU(cudaMemcpyAsync(fe->d_tabs, tabs.data(), (size_t)K * fe->E1 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const phyfoo_dataset* ds = fe->ds;
+    Fe1EvalParams p;
+    p.bases = ds->d_bases; p.gaps = ds->d_gaps; p.n_cols = ds->n_cols; p.nb = ds->nb;
+    p.col0 = fe->d_col0; p.strand = fe->d_strand; p.weight = fe->d_weight;
+    p.q_int = fe->d_qint; p.q_leaf = fe->d_qleaf; p.n = fe->n;
+    p.W = fe->W; p.I = fe->I; p.S = fe->S; p.E1 = fe->E1; p.prog_len = fe->m->prog_len; p.prog = fe->m->d_prog;
+    p.tabs = fe->d_tabs; p.part = fe->d_part; p.pos = pos;
+    const size_t smem = (size_t)K * fe->E1 * sizeof(double) + (size_t)fe->m->prog_len * sizeof(int) + 16;
+    if (smem > std::min<size_t>(ctx->smem_optin, 227 * 1024))
+        return fail(ctx, PHYFOO_EUNSUPPORTED, "fe_eval: the parameter sets of an order-1 position do not fit in shared memory for this tree");
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((fe->n + 127) / 128, (int64_t)fe->blocks));
+    {
+        KernelTimer kt_(ctx, "fe1_eval_kernel");
+        if (K == 1) { CU(cudaFuncSetAttribute(fe1_eval_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); fe1_eval_kernel<1><<<blocks, 128, smem, ctx->stream>>>(p); }
+        else if (K == 5) { CU(cudaFuncSetAttribute(fe1_eval_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); fe1_eval_kernel<5><<<blocks, 128, smem, ctx->stream>>>(p); }
+        else { CU(cudaFuncSetAttribute(fe1_eval_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); fe1_eval_kernel<17><<<blocks, 128, smem, ctx->stream>>>(p); }
+    }
+    CU(cudaGetLastError());
+    {
+        KernelTimer kt_(ctx, "fe1_final_kernel");
+        fe1_final_kernel<<<1, 256, 0, ctx->stream>>>(fe->d_part, blocks, pos, K, fe->W, mode, value_off, fe->d_G, fe->d_values);
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));   // d_tabs is reused by the next position; `tabs` belongs to the caller
+    return PHYFOO_OK;
+}
+
+static int fe1_refresh(phyfoo_ctx* ctx, phyfoo_feset* fe) {
+    ModelHost& h = fe->m->h;
+    if (fe->g_version == h.version) return PHYFOO_OK;
+    std::vector<double> tabs((size_t)fe->E1);
+    for (int t = 0; t < fe->W; ++t) {
+        h.build_tables1_into(t, h.pi[t].data(), tabs.data());
+        int rc = fe1_launch(ctx, fe, t, 1, 0, 0, tabs);
+        if (rc) return rc;
+    }
+    fe->g_version = h.version;
+    return PHYFOO_OK;
+}
+
+// parameter sets of position t: set 0 = softmax(lambda_t), set 1 + i = softmax(lambda_t + eps e_i); launches the evaluation
+static int fe1_position(phyfoo_ctx* ctx, phyfoo_feset* fe, int t, const double* lambda_t, bool with_grad, double eps, int value_off,
+                        double* pi_out) {
+    ModelHost& h = fe->m->h;
+    const int dim = h.ctx_rows(t) * 4;
+    const int K = with_grad ? dim + 1 : 1;
+    std::vector<double> tabs((size_t)K * fe->E1), x(lambda_t, lambda_t + dim), pi(dim);
+    lambda_to_pi(x.data(), pi_out, dim);
+    h.build_tables1_into(t, pi_out, &tabs[0]);
+    for (int i = 0; with_grad && i < dim; ++i) {
+        const double keep = x[i];
+        x[i] += eps;                               // NumericalDifferentiableFunction.java:73-79: perturb in place, restore
+        lambda_to_pi(x.data(), pi.data(), dim);
+        h.build_tables1_into(t, pi.data(), &tabs[(size_t)(1 + i) * fe->E1]);
+        x[i] = keep;
+    }
+    for (double v : tabs) if (!std::isfinite(v)) return fail(ctx, PHYFOO_EUNSUPPORTED, "a CPF entry is 0 under the parameters under test: the free energy is not finite");
+    return fe1_launch(ctx, fe, t, K, 1, value_off, tabs);
+}
+
+static int fe1_enqueue(phyfoo_ctx* ctx, phyfoo_feset* fe, int position, const double* lambda, int dim, bool with_grad, double eps) {
+    ModelHost& h = fe->m->h;
+    const int W = fe->W;
+    if (position >= W) return fail(ctx, PHYFOO_EINVAL, "fe_eval: position out of range");
+    int want = 0;
+    if (position >= 0) want = h.ctx_rows(position) * 4;
+    else for (int t = 0; t < W; ++t) want += h.ctx_rows(t) * 4;
+    if (!lambda || dim != want) return fail(ctx, PHYFOO_EINVAL, "fe_eval: dim must be 4 x (context rows) per position under test");
+    if (fe->n == 0) {
+        CU(cudaMemsetAsync(fe->d_values, 0, (size_t)(1 + want) * sizeof(double), ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    std::vector<double> pi(16);
+    if (position >= 0) {
+        int rc = fe1_refresh(ctx, fe);
+        if (rc) return rc;
+        if (fe->n > 0 && (rc = fe1_position(ctx, fe, position, lambda, with_grad, eps, 1, pi.data()))) return rc;
+        if (fe->n == 0) lambda_to_pi(lambda, pi.data(), want);
+        h.set_pi(position, pi.data(), want);
+    } else {
+        // all positions (MotifParamOptimizer): move the model to lambda first so that every G_t is at the new base point,
+        // then evaluate the perturbed sets position by position
+        int off = 0;
+        for (int t = 0; t < W; ++t) {
+            const int d = h.ctx_rows(t) * 4;
+            lambda_to_pi(lambda + off, pi.data(), d);
+            h.set_pi(t, pi.data(), d);
+            off += d;
+        }
+        int rc = fe1_refresh(ctx, fe);
+        if (rc) return rc;
+        off = 0;
+        for (int t = 0; t < W && fe->n > 0; ++t) {
+            const int d = h.ctx_rows(t) * 4;
+            if (with_grad || t == W - 1) {
+                if ((rc = fe1_position(ctx, fe, t, lambda + off, with_grad, eps, 1 + off, pi.data()))) return rc;
+            }
+            off += d;
+        }
+    }
+    fe->g_version = h.version;
+    return PHYFOO_OK;
+}
+
 static int fe_refresh(phyfoo_ctx* ctx, phyfoo_feset* fe) {
     ModelHost& h = fe->m->h;
+    if (fe->order == 1) return fe1_refresh(ctx, fe);
     if (fe->g_version == h.version) return PHYFOO_OK;
     std::vector<double> tabs((size_t)fe->W * FE_KMAX * fe->E, 0.0);
     for (int t = 0; t < fe->W; ++t) h.build_tables_into(t, h.pi[t].data(), &tabs[(size_t)t * FE_KMAX * fe->E], nullptr);
@@ -320,7 +431,11 @@ static int fe_create(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* m,
     phyfoo_feset* fe = new phyfoo_feset();
     fe->ds = ds; fe->m = m; fe->n = n;
     fe->W = m->h.W; fe->I = m->h.I; fe->S = m->h.S; fe->E = m->h.E;
+    fe->order = m->h.order; fe->E1 = m->h.E1();
     fe->blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 2LL * ctx->sm_count));
+    const size_t tab_doubles = fe->order == 1 ? (size_t)FE1_KMAX * fe->E1 : (size_t)fe->W * FE_KMAX * fe->E;
+    const size_t part_doubles = fe->order == 1 ? (size_t)fe->blocks * FE1_KMAX : (size_t)fe->W * fe->blocks * FE_KMAX;
+    const size_t value_doubles = fe->order == 1 ? (size_t)(1 + 4 + 16 * (fe->W - 1)) : (size_t)(1 + 4 * fe->W);
     const size_t n_trees = (size_t)std::max<int64_t>(n, 1) * fe->W;
     cudaError_t e;
     if ((e = cudaMalloc(&fe->d_col0, std::max<int64_t>(n, 1) * sizeof(int64_t))) != cudaSuccess ||
@@ -329,9 +444,9 @@ static int fe_create(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* m,
         (e = cudaMalloc(&fe->d_qleaf, n_trees * 4 * fe->S * sizeof(double))) != cudaSuccess ||
         (e = cudaMalloc(&fe->d_ent, n_trees * sizeof(double))) != cudaSuccess ||
         (e = cudaMalloc(&fe->d_G, (fe->W + 1) * sizeof(double))) != cudaSuccess ||
-        (e = cudaMalloc(&fe->d_tabs, (size_t)fe->W * FE_KMAX * fe->E * sizeof(double))) != cudaSuccess ||
-        (e = cudaMalloc(&fe->d_part, (size_t)fe->W * fe->blocks * FE_KMAX * sizeof(double))) != cudaSuccess ||
-        (e = cudaMalloc(&fe->d_values, (size_t)(1 + 4 * fe->W) * sizeof(double))) != cudaSuccess) {
+        (e = cudaMalloc(&fe->d_tabs, tab_doubles * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc(&fe->d_part, part_doubles * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc(&fe->d_values, value_doubles * sizeof(double))) != cudaSuccess) {
         fe_release(fe);
         ctx->err = std::string("fe_prepare: ") + cudaGetErrorString(e);
         return e == cudaErrorMemoryAllocation ? PHYFOO_ENOMEM : PHYFOO_ECUDA;
@@ -354,7 +469,8 @@ static int fe_run_prepare(phyfoo_ctx* ctx, phyfoo_feset* fe) {
     if (rc) return rc;
     {
         KernelTimer kt_(ctx, "fe_entropy_kernel");
-        fe_entropy_kernel<<<1, 1024, 0, ctx->stream>>>(fe->d_ent, fe->d_weight, fe->n, fe->W, fe->d_G + fe->W);
+        // order 0 stores one entropy per tree, order 1 one per window
+        fe_entropy_kernel<<<1, 1024, 0, ctx->stream>>>(fe->d_ent, fe->d_weight, fe->n, fe->order == 1 ? 1 : fe->W, fe->d_G + fe->W);
     }
     CU(cudaGetLastError());
     fe->g_version = 0;
@@ -362,7 +478,8 @@ static int fe_run_prepare(phyfoo_ctx* ctx, phyfoo_feset* fe) {
 }
 
 static int fe_check_model(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* m, const char* who) {
-    if (m->h.order != 0) return fail(ctx, PHYFOO_EUNSUPPORTED, std::string(who) + ": order >= 1 networks are not implemented in this build");
+    if (m->h.order != 0 && !(m->h.order == 1 && m->h.kind == PHYFOO_MODEL_FG))
+        return fail(ctx, PHYFOO_EUNSUPPORTED, std::string(who) + ": background models of order >= 1 are not implemented in this build");
     if (m->h.S != ds->S) return fail(ctx, PHYFOO_EINVAL, std::string(who) + ": model and dataset disagree on the number of species");
     return PHYFOO_OK;
 }
@@ -462,6 +579,7 @@ static int fe_enqueue(phyfoo_ctx* ctx, phyfoo_feset* fe, int position, const dou
                       std::vector<double>* pi_out) {
     ModelHost& h = fe->m->h;
     const int W = fe->W;
+    if (fe->order == 1) return fe1_enqueue(ctx, fe, position, lambda, dim, with_grad, eps);
     const int pos0 = position >= 0 ? position : 0;
     const int n_pos = position >= 0 ? 1 : W;
     if (position >= W) return fail(ctx, PHYFOO_EINVAL, "fe_eval: position out of range");

@@ -40,6 +40,9 @@ struct Net1Params {
     int nwb;                 // windows per block
     int tab_in_smem;         // copy the tables into shared memory (when they fit beside the window state)
     const int64_t* item_col0; const uint8_t* item_strand;   // nullable: explicit window list
+    // M-step "prepare": converged q of every listed window, entry-major across the n_windows listed windows:
+    // sink_qint[((t*I + i)*4 + a) * n + item], sink_qleaf[((t*S + leaf slot)*4 + a) * n + item], sink_ent[item]
+    double* sink_qint; double* sink_qleaf; double* sink_ent;
 };
 
 struct Net1Ctx {
@@ -65,12 +68,12 @@ __device__ __forceinline__ ColWords n1_col(const Net1Ctx& c, int t) {
 // exp of the four exponents of a node -> normalised q of this lane and log q; MeanFieldForBayesNet.java:192-201
 __device__ __forceinline__ void n1_normalise(const Net1Ctx& c, double s, bool update, double& qn, double& lq) {
     const double ex = update ? s : 0.0;
-    const double e = exp(ex);                                               // :192, no max shift
+    const double e = phy_exp(ex);                                               // :192, no max shift
     const double e0 = __shfl_sync(c.qmask, e, c.qb), e1 = __shfl_sync(c.qmask, e, c.qb + 1);
     const double e2 = __shfl_sync(c.qmask, e, c.qb + 2), e3 = __shfl_sync(c.qmask, e, c.qb + 3);
     const double z = ((e0 + e1) + e2) + e3;                                 // :195-198
     qn = e * __drcp_rn(z);                                                  // :199-201 (correctly rounded reciprocal, then one product)
-    lq = ex - log(z);
+    lq = ex - phy_log(z);
 }
 
 // sum of the other three entries of v (index order), i.e. the weight of the off-diagonal rows for own symbol a
@@ -343,6 +346,26 @@ __global__ void __launch_bounds__(256) score_o1_kernel(Net1Params p) {
                 done = !((k < p.max_sweeps && !conv) || k < p.min_sweeps);    // :107
             }
             if (done) {
+                if (p.sink_qint) {
+                    // entropy term sum_hidden sum_h q log q (MeanFieldForBayesNet.java:250-267), parameter independent
+                    double ent = 0.0;
+                    for (int j = a; j < p.W * p.I * 4; j += 4) {
+                        const double v = s_q[(size_t)j * nwb + c.wq];
+                        p.sink_qint[(size_t)j * p.n_windows + item] = v;
+                        ent += v > 0.0 ? v * phy_log(v) : 0.0;
+                    }
+                    for (int t = 0; t < p.W; ++t) {
+                        const ColWords cwt = n1_col(c, t);
+                        for (int kk = 0; kk < p.S; ++kk) {
+                            const double v = n1_gq(c, t, kk, a);
+                            p.sink_qleaf[(size_t)((t * p.S + kk) * 4 + a) * p.n_windows + item] = v;
+                            if (cwt.obs(c.leaf_species[kk]) >= 4) ent += v > 0.0 ? v * phy_log(v) : 0.0;
+                        }
+                    }
+                    const double t0 = __shfl_sync(c.qmask, ent, c.qb), t1 = __shfl_sync(c.qmask, ent, c.qb + 1);
+                    const double t2 = __shfl_sync(c.qmask, ent, c.qb + 2), t3 = __shfl_sync(c.qmask, ent, c.qb + 3);
+                    if (a == 0) p.sink_ent[item] = ((t0 + t1) + t2) + t3;
+                }
                 if (a == 0) {
                     p.out[item] = -Fsum;                                      // PhyloBayesModel.java:259
                     if (p.sweeps) p.sweeps[item] = k;

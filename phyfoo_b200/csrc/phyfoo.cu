@@ -989,7 +989,6 @@ static int launch_net1(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* 
     if (h.mode == PHYFOO_MODE_EXACT && !items)
         return fail(ctx, PHYFOO_EUNSUPPORTED, "exact likelihood of an order-1 network is infeasible in the reference too "
                                               "(SimpleNodeElimination's 9-node frontier, SimpleNodeElimination.java:33-45)");
-    if (items && items->q_int) return fail(ctx, PHYFOO_EUNSUPPORTED, "fixed-q objective of order-1 networks is not implemented in this build");
     const int n_strands = strands == 2 ? 2 : 1;
     const long long n_items = (long long)n_windows * n_strands;
     // windows per block: as many windows per SM as shared memory holds, in multiples of 8 (whole warps).  The kernel is
@@ -1033,6 +1032,7 @@ static int launch_net1(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* 
     p.max_sweeps = h.max_sweeps; p.min_sweeps = h.min_sweeps; p.tol = h.tol;
     p.gq = ctx->gstate.as<double>(); p.n_slots = n_slots; p.nwb = best_nwb; p.tab_in_smem = tab_in_smem;
     p.item_col0 = items ? items->col0 : nullptr; p.item_strand = items ? items->strand : nullptr;
+    p.sink_qint = items ? items->q_int : nullptr; p.sink_qleaf = items ? items->q_leaf : nullptr; p.sink_ent = items ? items->ent : nullptr;
     CU(cudaMemsetAsync(p.counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
     {
         KernelTimer kt_(ctx, "score_o1_kernel");

@@ -24,6 +24,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "fp64_math.cuh"
+
 #if defined(__CUDACC__)
 #define PHY_HD __host__ __device__ __forceinline__
 #else
@@ -117,10 +119,10 @@ PHY_HD double meanfield_pass(const TreeProg& tp, const Tab& tb, const State& st,
         }
         double e[4], qi[4], lq[4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) e[a] = exp(update ? s[a] : 0.0);      // :192, no max shift
+        for (int a = 0; a < 4; ++a) e[a] = phy_exp(update ? s[a] : 0.0);      // :192, no max shift
         const double z = ((e[0] + e[1]) + e[2]) + e[3];                   // :195-198
         const double rz = 1.0 / z;
-        const double lz = log(z);
+        const double lz = phy_log(z);
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
             qi[a] = e[a] * rz;                                            // :199-201
@@ -163,10 +165,10 @@ PHY_HD double meanfield_pass(const TreeProg& tp, const Tab& tb, const State& st,
                 const double qs = ((qi[0] + qi[1]) + qi[2]) + qi[3];
                 double el[4], ql[4], lql[4];
 #pragma unroll
-                for (int a = 0; a < 4; ++a) el[a] = exp(update ? qs * lpi[a] : 0.0);
+                for (int a = 0; a < 4; ++a) el[a] = phy_exp(update ? qs * lpi[a] : 0.0);
                 const double zl = ((el[0] + el[1]) + el[2]) + el[3];
                 const double rzl = 1.0 / zl;
-                const double lzl = log(zl);
+                const double lzl = phy_log(zl);
 #pragma unroll
                 for (int a = 0; a < 4; ++a) { ql[a] = el[a] * rzl; lql[a] = (update ? qs * lpi[a] : 0.0) - lzl; }
                 double t = 0.0, ent = 0.0;
@@ -209,20 +211,20 @@ PHY_HD double store_q(const TreeProg& tp, const Tab& tb, const State& st, const 
         for (int a = 0; a < 4; ++a) {
             qi[a] = st.q(i, a);
             sink.q_internal[(size_t)(i * 4 + a) * sink.stride] = qi[a];
-            ent += (qi[a] > 0.0) ? qi[a] * log(qi[a]) : 0.0;
+            ent += (qi[a] > 0.0) ? qi[a] * phy_log(qi[a]) : 0.0;
         }
         for (int k = tp.leaf_begin[i]; k < tp.leaf_begin[i + 1]; ++k) {
             if (cw.obs(tp.leaf_species[k]) < 4) continue;
             const double qs = ((qi[0] + qi[1]) + qi[2]) + qi[3];
             double el[4];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) el[a] = exp(qs * lpi[a]);
+            for (int a = 0; a < 4; ++a) el[a] = phy_exp(qs * lpi[a]);
             const double rzl = 1.0 / (((el[0] + el[1]) + el[2]) + el[3]);
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
                 const double ql = el[a] * rzl;
                 sink.q_leaf[(size_t)(k * 4 + a) * sink.stride] = ql;
-                ent += (ql > 0.0) ? ql * log(ql) : 0.0;
+                ent += (ql > 0.0) ? ql * phy_log(ql) : 0.0;
             }
         }
     }

@@ -139,3 +139,8 @@ extern "C" int emul_fe_values(const phyfoo_model_desc* d, const uint8_t* cols /*
         return 0;
     } catch (const std::exception& e) { std::fprintf(stderr, "emul: %s\n", e.what()); return -1; }
 }
+
+// phy_exp / phy_log (csrc/fp64_math.cuh) on the host, for the accuracy test
+#include "../../phyfoo_b200/csrc/fp64_math.cuh"
+extern "C" void emul_exp(const double* x, int n, double* out) { for (int i = 0; i < n; ++i) out[i] = phy_exp(x[i]); }
+extern "C" void emul_log(const double* x, int n, double* out) { for (int i = 0; i < n; ++i) out[i] = phy_log(x[i]); }

@@ -20,12 +20,16 @@ EMUL_DIR = os.path.join(ROOT, "tests", "emul")
 def emul():
     so = os.path.join(EMUL_DIR, "libemul.so")
     srcs = [os.path.join(EMUL_DIR, "emul.cpp"), os.path.join(ROOT, "phyfoo_b200", "csrc", "tree_pass.cuh"),
-            os.path.join(ROOT, "phyfoo_b200", "csrc", "model_host.hpp")]
+            os.path.join(ROOT, "phyfoo_b200", "csrc", "model_host.hpp"), os.path.join(ROOT, "phyfoo_b200", "csrc", "fp64_math.cuh"),
+            os.path.join(ROOT, "phyfoo_b200", "csrc", "fp64_math_tables.h")]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", srcs[0], "-o", so])
     L = C.CDLL(so)
     L.emul_score_windows.argtypes = [C.POINTER(_abi.ModelDesc), C.POINTER(C.c_uint8), C.c_int, C.c_int,
                                      C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    for f in (L.emul_exp, L.emul_log):
+        f.argtypes = [C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double)]
+        f.restype = None
     return L
 
 

@@ -87,3 +87,57 @@ def test_order1_unsupported_paths_fail_loudly(ctx):
             fg.getLogProbFor(smp)
     finally:
         PhyloBayesModel.CALC_LOGLIKELIHOOD = False
+
+
+@pytest.mark.parametrize("tree", ["cat5", "mixed6", "rand12"])
+@pytest.mark.parametrize("gap_rate", [0.0, 0.12])
+def test_order1_fixed_q_objective_and_gradient(ctx, tree, gap_rate):
+    """M-step objective of the order-1 motif: f(lambda) and its forward-difference gradient (dim 4 at position 0, 16 = four
+    context rows elsewhere) against the oracle's FESet on the same selected windows, incl. reverse-complement windows."""
+    from phyfoo_b200 import core, synth
+    from phyfoo_b200.models import PhyloBackground, PhyloBayesModel, SingleHiddenMotifMixture
+    from phyfoo_b200.newick import parse_newick
+    EPS = 1e-4
+    newick = _trees()[tree]
+    S = parse_newick(newick).n_species
+    W = 4 if tree == "rand12" else 5
+    pwm = synth.random_pwm(W, 1, 71)
+    smp, _ = synth.make_sample(newick, 14, 40, 9, pwm=pwm, gap_rate=gap_rate, length_jitter=5)
+    fg = PhyloBayesModel(W, 1, newick, ctx); fg.setCondProbs(pwm)
+    bg = PhyloBackground(0, newick, ctx)
+    res = SingleHiddenMotifMixture(fg, bg, zoops=0.9).getNewWeights(smp)
+    ds = smp.device(ctx)
+    sa, so, sw = core.select(ctx, ds, W, res["gamma"])
+    strand = (np.arange(sa.size) % 4 == 1).astype(np.uint8)
+    fe = core.FESet(ctx, ds, fg.device_model(), sa, so, sw, strand)
+    om = oracle_fg(newick, pwm, order=1)
+    cols = np.stack([smp.getElementAt(a)[o:o + W] for a, o in zip(sa, so)])
+    rc = np.where(cols[:, ::-1, :] < 4, 3 - cols[:, ::-1, :], 4).astype(np.uint8)
+    cols = np.where(strand[:, None, None] == 1, rc, cols)
+    ofe = orc.FESet(om, cols, sw)
+    rng = np.random.default_rng(5)
+
+    def tol(g, f0):
+        return TOL * np.abs(g) + 64 * np.finfo(float).eps * abs(f0) / EPS
+
+    for pos in (0, W - 1, 1):
+        rows = 1 if pos == 0 else 4
+        lam = (np.log(rng.dirichlet(np.ones(4), size=rows)) + rng.normal(size=(rows, 1))).ravel()
+        f, rf = fe.eval(pos, lam), ofe.eval(pos, lam)
+        assert abs(f - rf) <= TOL * abs(rf), (pos, f, rf)
+        f0, g = fe.grad(pos, lam, EPS)
+        r0, rg = ofe.grad(pos, lam, EPS)
+        assert abs(f0 - r0) <= TOL * abs(r0)
+        assert np.all(np.abs(g - rg) <= tol(rg, r0)), (pos, g, rg)
+        assert np.allclose(fg.device_model().get_pi(pos, 4 * rows), om.get_pi(pos), rtol=0, atol=1e-15)
+    lam_all = np.concatenate([np.log(rng.dirichlet(np.ones(4), size=(1 if t == 0 else 4))).ravel() for t in range(W)])
+    f0, g = fe.grad(-1, lam_all, EPS)
+    r0, rg = ofe.grad(-1, lam_all, EPS)
+    assert abs(f0 - r0) <= TOL * abs(r0)
+    assert np.all(np.abs(g - rg) <= tol(rg, r0))
+    assert abs(fe.eval(-1, lam_all) - r0) <= TOL * abs(r0)
+    # back at the parameters the q were optimised for: f = sum_u w_u score_u
+    for t in range(W):
+        fe.eval(t, np.log(pwm[t].ravel())); ofe.eval(t, np.log(pwm[t].ravel()))
+    direct = sum(w * om.score_window(c)[0] for w, c in zip(sw, cols))
+    assert abs(fe.eval(0, np.log(pwm[0].ravel())) - direct) <= 1e-9 * abs(direct)
