@@ -13,7 +13,7 @@ import math
 
 import numpy as np
 
-from . import _abi, core
+from . import _abi, core, optimize
 from .data import PhyloSample
 from .newick import parse_newick
 
@@ -139,6 +139,58 @@ class PhyloBayesModel(_PhyloModel):
         return (out, sw) if want_sweeps else out
 
 
+    # ---- M-step (models/PhyloBayesModel.java:122-219) -------------------------------------------------------------
+    SKIP_TRAINING_STEPS = 1            # :57
+    PROB_THRESH_FOR_WEIGHTS = 0.8      # models/PhyloPreparedAbstractModel.java:20
+    MOTIF_QUALITY_THRESHOLD = 0.0      # :21
+    OPTIMIZE_IN_TOTO = False           # :63
+
+    def train(self, sample: PhyloSample, weights, rng=None):
+        """One M-step: select the top-posterior windows per alignment (io/SequenceSpecificDataSelector.java:37-99), fix
+        their mean fields (one GPU pass), then optimise the parameters position by position in random order with BFGS on the
+        forward-difference gradient (optimizing/FE_byParameter_ForBayesNodeJstacs.java:61-83).  weights: gamma per window, or
+        None for the gamma of the most recent E-step still resident on the device.  Returns a dict of statistics."""
+        self._check(sample)
+        self.trainingStep = getattr(self, "trainingStep", 0)
+        if self.trainingStep < self.SKIP_TRAINING_STEPS:
+            self.trainingStep += 1
+            return {"skipped": True}
+        rng = rng or np.random.default_rng()
+        ds = sample.device(self.ctx)
+        sa, so, sw = core.select(self.ctx, ds, self.length, weights, self.PROB_THRESH_FOR_WEIGHTS, self.MOTIF_QUALITY_THRESHOLD)
+        fe = core.FESet(self.ctx, ds, self.device_model(), sa, so, sw)
+        stats = {"skipped": False, "selected": int(sa.size), "evaluations": 0, "f_before": None, "f_after": None}
+        try:
+            if self.OPTIMIZE_IN_TOTO:
+                lam0 = np.concatenate([np.log(p.ravel()) for p in self._pi])
+                stats["f_before"] = fe.eval(-1, lam0)
+                x, f, it, ev = optimize.quasi_newton_bfgs(lambda z: -fe.eval(-1, z), lambda z: _neg(fe.grad(-1, z)), lam0,
+                                                          optimize.TC_MOTIF_ALL_POSITIONS())
+                stats["f_after"] = fe.eval(-1, x)
+                stats["evaluations"] += ev
+            else:
+                for pos in rng.permutation(self.length):            # util/PWMUtil.java:131-144
+                    pos = int(pos)
+                    lam0 = np.log(self._pi[pos].ravel())
+                    f0 = fe.eval(pos, lam0)
+                    if stats["f_before"] is None:
+                        stats["f_before"] = f0
+                    x, f, it, ev = optimize.quasi_newton_bfgs(lambda z: -fe.eval(pos, z), lambda z: _neg(fe.grad(pos, z)), lam0,
+                                                              optimize.TC_MOTIF_SEPARATED_POSITIONS())
+                    stats["f_after"] = fe.eval(pos, x)            # leaves the device model at x
+                    stats["evaluations"] += ev
+            for t in range(self.n_trees):
+                self._pi[t] = self._dev.get_pi(t, self._pi[t].size).reshape(self._pi[t].shape)
+        finally:
+            fe.free()
+        self.trainingStep += 1
+        return stats
+
+
+def _neg(fg):
+    return -fg[0], -fg[1]
+
+
 class PhyloBackground(_PhyloModel):
     """The phylogenetic background / flanking model (order-k Markov chain over trees)."""
 
@@ -161,6 +213,25 @@ class PhyloBackground(_PhyloModel):
         cols = self.getColumnLogProbs(sample)
         off = sample.col_offsets
         return np.array([cols[off[i]:off[i + 1]].sum() for i in range(sample.n_alignments)])
+
+
+    def train(self, sample: PhyloSample, weights=None):
+        """models/PhyloBackground.java:111-176 (order 0): objective over every column of every alignment with per-alignment
+        weights, q fixed after one mean-field pass, BFGS until the objective changes by less than 1e-3."""
+        self._check(sample)
+        if self.order != 0:
+            raise NotImplementedError("background models of order >= 1 are not supported (DESIGN.md)")
+        fe = core.FESet(self.ctx, sample.device(self.ctx), self.device_model(), aln_weights=weights)
+        try:
+            lam0 = np.log(self._pi[0].ravel())
+            before = fe.eval(0, lam0)
+            x, f, it, ev = optimize.quasi_newton_bfgs(lambda z: -fe.eval(0, z), lambda z: _neg(fe.grad(0, z)), lam0,
+                                                      optimize.SMALL_DIFFERENCE_OF_FUNCTIONS())
+            after = fe.eval(0, x)
+            self._pi[0] = self._dev.get_pi(0, 4).reshape(1, 4)
+        finally:
+            fe.free()
+        return {"f_before": before, "f_after": after, "evaluations": ev, "iterations": it}
 
 
 class StrandModel:
@@ -214,6 +285,26 @@ class SingleHiddenMotifMixture:
         if self.estimateComponentProbs:
             v = np.asarray(w, np.float64) + self.hyper
             self.weights = v / v.sum()
+
+    def train(self, sample: PhyloSample, max_iterations=100, eps=1e-6, rng=None, verbose=False):
+        """EM (jstacs AbstractMixtureModel.continueIterations :857-880 with trainOnlyMotifModel = true): E-step on the GPU,
+        M-step of the motif model through PhyloBayesModel.train, component weights from the sufficient statistics.  Stops when
+        the log-likelihood changes by less than eps (SmallDifferenceOfFunctionEvaluationsCondition) or after max_iterations.
+        Returns the list of log-likelihoods, one per E-step."""
+        if self.strand is not None:
+            raise NotImplementedError("EM with a StrandModel motif: the E-step is supported, the strand-split M-step is not yet")
+        history, trained = [], False
+        for it in range(max_iterations):
+            res = self.getNewWeights(sample, want_gamma=True)
+            history.append(res["ll"])
+            if verbose:
+                print(f"{it}\t{res['ll']:.6f}\t{0.0 if it == 0 else res['ll'] - history[-2]:.3e}")
+            if trained and abs(history[-1] - history[-2]) < eps:
+                break
+            st = self.motif.train(sample, None, rng=rng)   # gamma of this E-step is still resident on the device
+            trained = not st["skipped"]                    # the motif ignores its first call (SKIP_TRAINING_STEPS = 1)
+            self.setComponentWeights(res["w"])
+        return history
 
     def getLogProbFor(self, sample: PhyloSample):
         """log-likelihood of the sample under the current parameters (sum over alignments)."""

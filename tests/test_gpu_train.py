@@ -1,0 +1,82 @@
+"""End-to-end use of the path the way the reference's trainer uses it (config 1 in miniature): EM with the GPU E-step and the
+GPU fixed-q objective under a host-side BFGS.  The optimisation trajectory has no reference counterpart to compare with (the
+reference is not reproducible run to run), so these are behavioural checks: the objective and the likelihood improve and the
+planted motif is recovered."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from phyfoo_b200 import core
+    return core.default_context()
+
+
+def _kl(p, q):
+    return float(np.sum(p * np.log(p / q)))
+
+
+@pytest.mark.parametrize("order", [0, 1])
+def test_em_recovers_planted_motif(ctx, order):
+    from phyfoo_b200 import synth
+    from phyfoo_b200.models import PhyloBackground, PhyloBayesModel, SingleHiddenMotifMixture
+    newick = synth.caterpillar_newick(5)
+    W = 8
+    rng = np.random.default_rng(123)
+    truth = [rng.dirichlet(np.full(4, 0.25), size=(4 if (order == 1 and t > 0) else 1)) * 0.94 + 0.015 for t in range(W)]
+    smp, planted = synth.make_sample(newick, 150, 100, 77, pwm=truth, zoops=1.0)
+    # start: the truth blurred towards uniform
+    start = [0.55 * p + 0.45 * 0.25 for p in truth]
+    fg = PhyloBayesModel(W, order, newick, ctx); fg.setCondProbs(start)
+    bg = PhyloBackground(0, newick, ctx)
+    shm = SingleHiddenMotifMixture(fg, bg, zoops=1.0)
+    hist = shm.train(smp, max_iterations=6, eps=1e-4, rng=np.random.default_rng(1))
+    assert len(hist) >= 3
+    assert hist[-1] > hist[0] + 1.0                        # the likelihood improved
+    assert all(b >= a - 1e-3 * abs(a) for a, b in zip(hist[1:], hist[2:]))     # and does not fall apart along the way
+    learned = fg.getCondProbs()
+    kl_start = sum(_kl(np.asarray(t).ravel(), np.asarray(s).ravel()) for t, s in zip(truth, start))
+    kl_end = sum(_kl(np.asarray(t).ravel(), l) for t, l in zip(truth, learned))
+    if order == 0:       # order 1 has four context rows per position; 150 sites cannot pin the rarely visited ones
+        assert kl_end < 0.6 * kl_start
+    calls = shm.getNewWeights(smp)["argmax_off"]
+    assert (calls == planted).mean() > 0.8
+
+
+def test_motif_mstep_increases_its_objective(ctx):
+    from phyfoo_b200 import synth
+    from phyfoo_b200.models import PhyloBackground, PhyloBayesModel, SingleHiddenMotifMixture
+    newick = synth.star_newick(5)
+    W = 6
+    truth = synth.random_pwm(W, 0, 3)
+    smp, _ = synth.make_sample(newick, 80, 60, 5, pwm=truth)
+    fg = PhyloBayesModel(W, 0, newick, ctx); fg.setCondProbs([0.5 * p + 0.125 for p in truth])
+    shm = SingleHiddenMotifMixture(fg, PhyloBackground(0, newick, ctx), zoops=1.0)
+    res = shm.getNewWeights(smp)
+    assert fg.train(smp, res["gamma"])["skipped"]                  # SKIP_TRAINING_STEPS = 1: the first call is ignored
+    st = fg.train(smp, res["gamma"], rng=np.random.default_rng(0))
+    assert not st["skipped"] and st["selected"] >= 80 and st["f_after"] > st["f_before"]
+    fg.OPTIMIZE_IN_TOTO = True
+    try:
+        st2 = fg.train(smp, res["gamma"])
+        assert st2["f_after"] >= st2["f_before"] - 1e-9
+    finally:
+        fg.OPTIMIZE_IN_TOTO = False
+
+
+def test_background_training_moves_pi_towards_composition(ctx):
+    from phyfoo_b200 import synth
+    from phyfoo_b200.data import PhyloSample
+    from phyfoo_b200.models import PhyloBackground
+    from phyfoo_b200.newick import parse_newick
+    newick = synth.caterpillar_newick(5)
+    rng = np.random.default_rng(9)
+    pi_true = np.array([[0.4, 0.1, 0.15, 0.35]])
+    codes, _ = synth.simulate_columns(rng, parse_newick(newick), 6000, pi_true)
+    smp = PhyloSample(codes, [0, 2000, 4500, 6000])
+    bg = PhyloBackground(0, newick, ctx)
+    st = bg.train(smp)
+    assert st["f_after"] > st["f_before"]
+    assert np.abs(bg.getCondProb(0) - pi_true.ravel()).max() < 0.03
