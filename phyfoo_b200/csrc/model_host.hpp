@@ -225,6 +225,30 @@ struct ModelHost {
             }
         }
     }
+    // scoring-kernel layout (net1.cuh): per position E1v = 32 + 64 (N-1): root [Lpi | LpiT], node k >= 1
+    // [Lo | Ld | LoT | LdT] (T = transposed, [b][ctx]); W + 1 positions, the last one all zero
+    int E1v() const { return 32 + 64 * (N - 1); }
+    void tables1v(std::vector<double>& out) const {
+        const int e1 = E1(), ev = E1v();
+        std::vector<double> t1;
+        tables1(t1);
+        out.assign((size_t)(W + 1) * ev, 0.0);
+        for (int t = 0; t < W; ++t) {
+            const double* src = &t1[(size_t)t * e1];
+            double* o = &out[(size_t)t * ev];
+            for (int c = 0; c < 4; ++c)
+                for (int b = 0; b < 4; ++b) { o[c * 4 + b] = src[c * 4 + b]; o[16 + b * 4 + c] = src[c * 4 + b]; }
+            for (int k = 1; k < N; ++k) {
+                const double* lo = src + 16 + 32 * (k - 1);
+                double* d = o + 32 + 64 * (k - 1);
+                for (int c = 0; c < 4; ++c)
+                    for (int b = 0; b < 4; ++b) {
+                        d[c * 4 + b] = lo[c * 4 + b]; d[16 + c * 4 + b] = lo[16 + c * 4 + b];
+                        d[32 + b * 4 + c] = lo[c * 4 + b]; d[48 + b * 4 + c] = lo[16 + c * 4 + b];
+                    }
+            }
+        }
+    }
     void tables1(std::vector<double>& out) const {
         const int e1 = E1();
         out.assign((size_t)W * e1, 0.0);

@@ -18,11 +18,14 @@
 //    interacts with it);
 //  * pass 0 (free energy at the uniform start) is the update pass with the exponent forced to 0.
 //
-// Table layout per position t (E1 = 16 + 32 (N-1) doubles, logs): root [ctx][4] at 0 (ctx = value of the root of
-// position t-1; only row 0 is used at t = 0); node k >= 1: the reference's table [l][b], l = a_treeparent + 4 ctx
-// (bayesNet/CPF.java:56-59,238-256: parent 0 is the least significant digit) stored as its off-diagonal values
-// Lo[ctx][b] at 16 + 32 (k-1) and its diagonal values Ld[ctx][b] 16 further (see net1_pass).  The "independent" table
-// of an unobserved leaf (CPF.java:146-152) has pi[ctx][b] in every row = the root table.
+// Table layout per position t (E1v = 32 + 64 (N-1) doubles, logs; model_host.hpp::tables1v): the reference's table of
+// node k >= 1 is [l][b], l = a_treeparent + 4 ctx (bayesNet/CPF.java:56-59,238-256: parent 0 is the least significant
+// digit).  It has F81 structure (one value for every a != b), so it is stored as off-diagonal values Lo[ctx][b] and
+// diagonal values Ld[ctx][b], each also transposed ([b][ctx]) so that the four values a lane needs are one 32-byte
+// load: root block [Lpi | LpiT] at 0, node block [Lo | Ld | LoT | LdT] at 32 + 64 (k-1).  Rows of contexts that do not
+// exist (t = 0 has one context) are 0 and the "previous position" of t = 0 is a virtual one-hot q = (1,0,0,0); one
+// all-zero position is appended so that the last position's "next node" terms vanish without a branch.  The
+// "independent" table of an unobserved leaf (CPF.java:146-152) has pi[ctx][b] in every row = the root table.
 #pragma once
 
 struct Net1Params {
@@ -31,14 +34,13 @@ struct Net1Params {
     int64_t n_windows; int n_strands; int strand0;
     int W, I, S, E1, prog_len;
     const int* prog;
-    const double* tab;       // [W][E1]
+    const double* tab;       // [W + 1][E1] (last position all zero)
     double* out; int32_t* sweeps;
     unsigned long long* counters;
     int max_sweeps, min_sweeps; double tol;
     double* gq;              // gap-leaf q: [(t*S + leaf slot)*4 + a][n_slots]
     int64_t n_slots;
     int nwb;                 // windows per block
-    int tab_in_smem;         // copy the tables into shared memory (when they fit beside the window state)
     const int64_t* item_col0; const uint8_t* item_strand;   // nullable: explicit window list
     // M-step "prepare": converged q of every listed window, entry-major across the n_windows listed windows:
     // sink_qint[((t*I + i)*4 + a) * n + item], sink_qleaf[((t*S + leaf slot)*4 + a) * n + item], sink_ent[item]
@@ -46,9 +48,10 @@ struct Net1Params {
 };
 
 struct Net1Ctx {
-    // shared-memory views of this block
-    double* q; int nwb; int wq;          // q[((t*I + i)*4 + a) * nwb + wq]
-    const uint64_t* cb; const uint32_t* cg;   // column words [t][nwb]
+    double* q;                // this quad's window: q(t, i, a) at q[(t*I + i) * qs + a], qs = 4 * nwb
+    const double* virt;       // block-shared one-hot (1,0,0,0): the "previous position" of t = 0
+    int qs;
+    const uint64_t* cb; const uint32_t* cg; int nwb; int wq;   // column words [t][nwb]
     const int* par_internal; const int* node_of; const int* leaf_begin; const int* leaf_node; const int* leaf_species;
     const int* ichild_begin; const int* ichild;
     int W, I, S, E1;
@@ -57,107 +60,92 @@ struct Net1Ctx {
     unsigned qmask; int qb, a;
 };
 
-// table entry: tables live in shared memory when they fit (generic load), else in global memory behind L1
-__device__ __forceinline__ double n1_ld(const double* p) { return *p; }
-__device__ __forceinline__ double& n1_q(const Net1Ctx& c, int t, int i, int a) { return c.q[(size_t)((t * c.I + i) * 4 + a) * c.nwb + c.wq]; }
+struct __align__(32) N1Vec4 { double v[4]; };
+// 32 bytes of a table in one request (LDG.E.256 on sm_100a), read-only path
+__device__ __forceinline__ N1Vec4 n1_ld4(const double* p) {
+    N1Vec4 r;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p));
+    return r;
+}
+// the four q of a node from shared memory (two 16-byte loads)
+__device__ __forceinline__ N1Vec4 n1_q4(const double* p) {
+    N1Vec4 r;
+    const double2 x = *reinterpret_cast<const double2*>(p), y = *reinterpret_cast<const double2*>(p + 2);
+    r.v[0] = x.x; r.v[1] = x.y; r.v[2] = y.x; r.v[3] = y.y;
+    return r;
+}
+__device__ __forceinline__ double n1_dot(const N1Vec4& x, const N1Vec4& y) {
+    double r = x.v[0] * y.v[0];
+    r = fma(x.v[1], y.v[1], r); r = fma(x.v[2], y.v[2], r); r = fma(x.v[3], y.v[3], r);
+    return r;
+}
+__device__ __forceinline__ double n1_sum(const N1Vec4& x) { return ((x.v[0] + x.v[1]) + x.v[2]) + x.v[3]; }
 __device__ __forceinline__ double& n1_gq(const Net1Ctx& c, int t, int kk, int a) { return c.gq[(size_t)((t * c.S + kk) * 4 + a) * c.n_slots + c.slot]; }
 __device__ __forceinline__ ColWords n1_col(const Net1Ctx& c, int t) {
-    ColWords w; w.b = c.cb[(size_t)t * c.nwb + c.wq]; w.g = c.cg[(size_t)t * c.nwb + c.wq]; return w;
+    ColWords w; w.b = c.cb[t * c.nwb + c.wq]; w.g = c.cg[t * c.nwb + c.wq]; return w;
 }
 
 // exp of the four exponents of a node -> normalised q of this lane and log q; MeanFieldForBayesNet.java:192-201
-__device__ __forceinline__ void n1_normalise(const Net1Ctx& c, double s, bool update, double& qn, double& lq) {
+__device__ __forceinline__ void n1_normalise(unsigned mask, int qb, double s, bool update, double& qn, double& lq) {
     const double ex = update ? s : 0.0;
-    const double e = phy_exp(ex);                                               // :192, no max shift
-    const double e0 = __shfl_sync(c.qmask, e, c.qb), e1 = __shfl_sync(c.qmask, e, c.qb + 1);
-    const double e2 = __shfl_sync(c.qmask, e, c.qb + 2), e3 = __shfl_sync(c.qmask, e, c.qb + 3);
+    const double e = phy_exp(ex);                                           // :192, no max shift
+    const double e0 = __shfl_sync(mask, e, qb), e1 = __shfl_sync(mask, e, qb + 1);
+    const double e2 = __shfl_sync(mask, e, qb + 2), e3 = __shfl_sync(mask, e, qb + 3);
     const double z = ((e0 + e1) + e2) + e3;                                 // :195-198
     qn = e * __drcp_rn(z);                                                  // :199-201 (correctly rounded reciprocal, then one product)
     lq = ex - phy_log(z);
 }
 
-// sum of the other three entries of v (index order), i.e. the weight of the off-diagonal rows for own symbol a
-__device__ __forceinline__ double n1_rest(const double* v, int a) {
-    const double x0 = a == 0 ? v[1] : v[0], x1 = a <= 1 ? v[2] : v[1], x2 = a <= 2 ? v[3] : v[2];
-    return (x0 + x1) + x2;
-}
-// v[a] without dynamic register indexing
-__device__ __forceinline__ double n1_pick(const double* v, int a) { return a == 0 ? v[0] : a == 1 ? v[1] : a == 2 ? v[2] : v[3]; }
-
 // One pass over the window's net; returns this lane's share of the free energy F = part1 - part2.
-//
-// The substitution tables have F81 structure (evolution/FS81alpha.java:76-92, FS81beta.java:81-103): for a given
-// context c and target b the entry is the same for every parent symbol a != b, so a table is stored as its
-// off-diagonal values Lo[c][b] and its diagonal values Ld[c][b] (model_host.hpp checks this bit for bit), and a sum
-// over the 16 rows l = a + 4c collapses to  sum_c q_ctx(c) (q_par(b) Ld[c][b] + (sum_{a != b} q_par(a)) Lo[c][b]).
-// Layout per position (E1 = 16 + 32 (N-1) logs): root [ctx][4] at 0; node k >= 1: Lo at 16 + 32 (k-1), Ld 16 further.
+// Control flow is warp-uniform except inside the leaf loops (gap leaves), so the node-level shuffles use the full mask.
 __device__ double net1_pass(const Net1Ctx& c, bool update) {
     const int a = c.a;
+    const unsigned full = 0xffffffffu;
     double F = 0.0;
     for (int t = 0; t < c.W; ++t) {
         const double* tab = c.tab + (size_t)t * c.E1;
-        const double* tabn = tab + c.E1;
+        const double* tabn = tab + c.E1;                       // position W is all zero
         const bool has_next = t + 1 < c.W;
+        double* qcur = c.q + t * c.I * c.qs;
+        const double* qprv = t ? qcur - c.I * c.qs : c.virt;   // previous position (virtual one-hot at t = 0)
+        const int sprv = t ? c.qs : 0;
+        const double* qnxt = has_next ? qcur + c.I * c.qs : qcur;   // multiplied by the zero table at the last position
         const ColWords cw = n1_col(c, t);
         ColWords cwp; cwp.b = 0; cwp.g = 0;
         ColWords cwn; cwn.b = 0; cwn.g = 0;
         if (t > 0) cwp = n1_col(c, t - 1);
         if (has_next) cwn = n1_col(c, t + 1);
         for (int i = 0; i < c.I; ++i) {
-            const int k = c.node_of[i];
             const int p = c.par_internal[i];
-            const double* Lo = tab + 16 + 32 * (k - 1);
-            const double* Ld = Lo + 16;
+            const int nb = 32 + 64 * (c.node_of[i] - 1);       // this node's table block
             // ---- own rows, :117-135 (all parents of an internal node are hidden)
             double own;
-            if (i == 0) {
-                if (t == 0) own = n1_ld(tab + a);
-                else {
-                    own = 0.0;
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) own += n1_q(c, t - 1, 0, cc) * n1_ld(tab + cc * 4 + a);
-                }
-            } else {
-                double qp[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) qp[j] = n1_q(c, t, p, j);
-                double A, B;
-                if (t == 0) { A = n1_ld(Ld + a); B = n1_ld(Lo + a); }
-                else {
-                    A = 0.0; B = 0.0;
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) {
-                        const double qh = n1_q(c, t - 1, i, cc);
-                        A += qh * n1_ld(Ld + cc * 4 + a);
-                        B += qh * n1_ld(Lo + cc * 4 + a);
-                    }
-                }
-                own = n1_pick(qp, a) * A + n1_rest(qp, a) * B;
+            const N1Vec4 qh = n1_q4(qprv + i * sprv);
+            if (i == 0) own = n1_dot(qh, n1_ld4(tab + 16 + 4 * a));
+            else {
+                const double A = n1_dot(qh, n1_ld4(tab + nb + 48 + 4 * a));     // diagonal rows
+                const double B = n1_dot(qh, n1_ld4(tab + nb + 32 + 4 * a));     // off-diagonal rows
+                const double tot = n1_sum(n1_q4(qcur + p * c.qs));
+                const double qpa = qcur[p * c.qs + a];
+                own = qpa * A + (tot - qpa) * B;
             }
-            // ---- children, :139-191: internal tree children, leaf children, then the same node of position t+1
-            double ch = 0.0;
+            // ---- children, :139-191: internal tree children (one exchange for all of them), leaves, the next position
+            double ch = 0.0, wu = 0.0;
             for (int j = c.ichild_begin[i]; j < c.ichild_begin[i + 1]; ++j) {
                 const int ci = c.ichild[j];
-                const double* Lco = tab + 16 + 32 * (c.node_of[ci] - 1);
-                const double* Lcd = Lco + 16;
-                // this lane handles the child's symbol ac = a: u = sum_cc q_prev(cc) Lo[cc][a], v likewise with Ld
-                double u, v;
-                if (t == 0) { u = n1_ld(Lco + a); v = n1_ld(Lcd + a); }
-                else {
-                    u = 0.0; v = 0.0;
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) {
-                        const double qpc = n1_q(c, t - 1, ci, cc);
-                        u += qpc * n1_ld(Lco + cc * 4 + a);
-                        v += qpc * n1_ld(Lcd + cc * 4 + a);
-                    }
-                }
-                const double qc = n1_q(c, t, ci, a);
-                const double wu = qc * u;                 // contribution of child symbol a to every OTHER own symbol
-                double w[4];
-#pragma unroll
-                for (int m = 0; m < 4; ++m) w[m] = __shfl_sync(c.qmask, wu, c.qb + m);
-                ch += n1_rest(w, a) + qc * v;
+                const int cb = 32 + 64 * (c.node_of[ci] - 1);
+                const N1Vec4 qpc = n1_q4(qprv + ci * sprv);
+                // this lane handles the child's symbol ac = a
+                const double u = n1_dot(qpc, n1_ld4(tab + cb + 32 + 4 * a));    // parent symbol != a
+                const double v = n1_dot(qpc, n1_ld4(tab + cb + 48 + 4 * a));    // parent symbol == a
+                const double qc = qcur[ci * c.qs + a];
+                wu = fma(qc, u, wu);
+                ch = fma(qc, v, ch);
+            }
+            {
+                const double w0 = __shfl_sync(full, wu, c.qb), w1 = __shfl_sync(full, wu, c.qb + 1);
+                const double w2 = __shfl_sync(full, wu, c.qb + 2), w3 = __shfl_sync(full, wu, c.qb + 3);
+                ch += (((w0 + w1) + w2) + w3) - wu;            // child symbols other than a reach own symbol a off-diagonally
             }
             double cobs = 0.0, cgap = 0.0;
             for (int kk = c.leaf_begin[i]; kk < c.leaf_begin[i + 1]; ++kk) {
@@ -165,54 +153,45 @@ __device__ double net1_pass(const Net1Ctx& c, bool update) {
                 const int x = cw.obs(sp);
                 const int y = t > 0 ? cwp.obs(sp) : 0;
                 if (x < 4) {
-                    const double* Ll = tab + 16 + 32 * (c.leaf_node[kk] - 1) + (a == x ? 16 : 0);
-                    if (t == 0 || y < 4) cobs += n1_ld(Ll + y * 4 + x);                 // observed parents must match the row
+                    const double* Ll = tab + 32 + 64 * (c.leaf_node[kk] - 1) + (a == x ? 16 : 0);
+                    if (y < 4) cobs += __ldg(Ll + y * 4 + x);                   // observed parents must match the row
                     else {
 #pragma unroll
-                        for (int cc = 0; cc < 4; ++cc) cobs += n1_gq(c, t - 1, kk, cc) * n1_ld(Ll + cc * 4 + x);
+                        for (int cc = 0; cc < 4; ++cc) cobs += n1_gq(c, t - 1, kk, cc) * __ldg(Ll + cc * 4 + x);
                     }
                 } else {
                     // unobserved leaf: every row of its table is pi[ctx] (CPF.java:146-152): the same value for every a
-                    if (t == 0) {
+                    if (y < 4) {
 #pragma unroll
-                        for (int ac = 0; ac < 4; ++ac) cgap += n1_gq(c, 0, kk, ac) * n1_ld(tab + ac);
-                    } else if (y < 4) {
-#pragma unroll
-                        for (int ac = 0; ac < 4; ++ac) cgap += n1_gq(c, t, kk, ac) * n1_ld(tab + y * 4 + ac);
+                        for (int ac = 0; ac < 4; ++ac) cgap += n1_gq(c, t, kk, ac) * __ldg(tab + y * 4 + ac);
                     } else {
 #pragma unroll
                         for (int ac = 0; ac < 4; ++ac)
 #pragma unroll
-                            for (int cc = 0; cc < 4; ++cc) cgap += (n1_gq(c, t, kk, ac) * n1_gq(c, t - 1, kk, cc)) * n1_ld(tab + cc * 4 + ac);
+                            for (int cc = 0; cc < 4; ++cc) cgap += (n1_gq(c, t, kk, ac) * n1_gq(c, t - 1, kk, cc)) * __ldg(tab + cc * 4 + ac);
                     }
                 }
             }
-            double nx = 0.0;
-            if (has_next) {
-                if (i == 0) {
+            double nx;
+            {
+                const N1Vec4 qx = n1_q4(qnxt + i * c.qs);
+                if (i == 0) nx = n1_dot(qx, n1_ld4(tabn + 4 * a));
+                else {
+                    const N1Vec4 qpn = n1_q4(qnxt + p * c.qs);
+                    const N1Vec4 Lnd = n1_ld4(tabn + nb + 16 + 4 * a), Lno = n1_ld4(tabn + nb + 4 * a);
+                    const double totn = n1_sum(qpn);
+                    nx = 0.0;
 #pragma unroll
-                    for (int ac = 0; ac < 4; ++ac) nx += n1_q(c, t + 1, 0, ac) * n1_ld(tabn + a * 4 + ac);
-                } else {
-                    const double* Lno = tabn + 16 + 32 * (k - 1);
-                    const double* Lnd = Lno + 16;
-                    double qpn[4];
-#pragma unroll
-                    for (int m = 0; m < 4; ++m) qpn[m] = n1_q(c, t + 1, p, m);
-#pragma unroll
-                    for (int ac = 0; ac < 4; ++ac) {
-                        // rows l = ap + 4a of the next node's table: diagonal for ap == ac, off-diagonal otherwise
-                        const double rest = ac == 0 ? (qpn[1] + qpn[2]) + qpn[3] : ac == 1 ? (qpn[0] + qpn[2]) + qpn[3]
-                                          : ac == 2 ? (qpn[0] + qpn[1]) + qpn[3] : (qpn[0] + qpn[1]) + qpn[2];
-                        nx += n1_q(c, t + 1, i, ac) * (qpn[ac] * n1_ld(Lnd + a * 4 + ac) + rest * n1_ld(Lno + a * 4 + ac));
-                    }
+                    for (int ac = 0; ac < 4; ++ac)   // rows l = ap + 4a of the next node's table: diagonal for ap == ac
+                        nx = fma(qx.v[ac], fma(qpn.v[ac], Lnd.v[ac], (totn - qpn.v[ac]) * Lno.v[ac]), nx);
                 }
             }
             const double s = (((own + ch) + cobs) + cgap) + nx;
             double qn, lq;
-            n1_normalise(c, s, update, qn, lq);
-            __syncwarp(c.qmask);                 // every lane of the quad has read the old q of this node's neighbours
-            n1_q(c, t, i, a) = qn;
-            __syncwarp(c.qmask);
+            n1_normalise(full, c.qb, s, update, qn, lq);
+            __syncwarp();                        // every lane has read the old q of this node's neighbours
+            qcur[i * c.qs + a] = qn;
+            __syncwarp();
             // entropy (:250-267), own expectation (:282-291 / :327-358) and the observed leaves' terms (:292-326)
             F += qn * ((lq - own) - cobs);
 
@@ -221,37 +200,35 @@ __device__ double net1_pass(const Net1Ctx& c, bool update) {
                 const int sp = c.leaf_species[kk];
                 if (cw.obs(sp) < 4) continue;
                 const int y = t > 0 ? cwp.obs(sp) : 0;
-                const double qs = ((n1_q(c, t, i, 0) + n1_q(c, t, i, 1)) + n1_q(c, t, i, 2)) + n1_q(c, t, i, 3);
+                const double qs = n1_sum(n1_q4(qcur + i * c.qs));
                 double ownl = 0.0, own_fe;
-                if (t == 0) { ownl = qs * n1_ld(tab + a); own_fe = ownl; }
+                if (t == 0) { ownl = qs * __ldg(tab + a); own_fe = ownl; }
                 else if (y < 4) {
                     // update: rows are NOT filtered by the observed parent (:129 TODO); free energy: they are (:327-358)
 #pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) ownl += qs * n1_ld(tab + cc * 4 + a);
-                    own_fe = qs * n1_ld(tab + y * 4 + a);
+                    for (int cc = 0; cc < 4; ++cc) ownl += qs * __ldg(tab + cc * 4 + a);
+                    own_fe = qs * __ldg(tab + y * 4 + a);
                 } else {
 #pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) ownl += (qs * n1_gq(c, t - 1, kk, cc)) * n1_ld(tab + cc * 4 + a);
+                    for (int cc = 0; cc < 4; ++cc) ownl += (qs * n1_gq(c, t - 1, kk, cc)) * __ldg(tab + cc * 4 + a);
                     own_fe = ownl;
                 }
                 double nl = 0.0;
                 if (has_next) {
                     const int xn = cwn.obs(sp);
-                    double qpn[4];
-#pragma unroll
-                    for (int m = 0; m < 4; ++m) qpn[m] = n1_q(c, t + 1, i, m);
+                    const N1Vec4 qpn = n1_q4(qnxt + i * c.qs);
                     if (xn < 4) {
-                        const double* Lno = tabn + 16 + 32 * (c.leaf_node[kk] - 1);
-                        nl = n1_pick(qpn, xn) * n1_ld(Lno + 16 + a * 4 + xn) + n1_rest(qpn, xn) * n1_ld(Lno + a * 4 + xn);
+                        const double* Lno = tabn + 32 + 64 * (c.leaf_node[kk] - 1);
+                        const double qd = xn == 0 ? qpn.v[0] : xn == 1 ? qpn.v[1] : xn == 2 ? qpn.v[2] : qpn.v[3];
+                        nl = qd * __ldg(Lno + 16 + a * 4 + xn) + (n1_sum(qpn) - qd) * __ldg(Lno + a * 4 + xn);
                     } else {
+                        const double totn = n1_sum(qpn);
 #pragma unroll
-                        for (int ac = 0; ac < 4; ++ac)
-#pragma unroll
-                            for (int ap = 0; ap < 4; ++ap) nl += (n1_gq(c, t + 1, kk, ac) * qpn[ap]) * n1_ld(tabn + a * 4 + ac);
+                        for (int ac = 0; ac < 4; ++ac) nl += (n1_gq(c, t + 1, kk, ac) * totn) * __ldg(tabn + a * 4 + ac);
                     }
                 }
                 double ql, lql;
-                n1_normalise(c, ownl + nl, update, ql, lql);
+                n1_normalise(c.qmask, c.qb, ownl + nl, update, ql, lql);
                 __syncwarp(c.qmask);
                 n1_gq(c, t, kk, a) = ql;
                 __syncwarp(c.qmask);
@@ -266,19 +243,18 @@ __global__ void __launch_bounds__(256) score_o1_kernel(Net1Params p) {
     extern __shared__ double smem[];
     const int tid = threadIdx.x, T = blockDim.x;
     const int nwb = p.nwb;
-    double* s_q = smem;                                                  // [W*I*4][nwb]
-    uint64_t* s_cb = (uint64_t*)(s_q + (size_t)p.W * p.I * 4 * nwb);     // [W][nwb]
+    double* s_q = smem;                                                  // [W*I][nwb][4]
+    double* s_virt = s_q + (size_t)p.W * p.I * 4 * nwb;                  // [4]
+    uint64_t* s_cb = (uint64_t*)(s_virt + 4);                            // [W][nwb]
     uint32_t* s_cg = (uint32_t*)(s_cb + (size_t)p.W * nwb);              // [W][nwb]
     int* s_prog = (int*)(s_cg + (size_t)p.W * nwb);
-    // tables behind the program, 8-byte aligned
-    double* s_tab = (double*)(s_prog + ((p.prog_len + 1) & ~1));
     for (int i = tid; i < p.prog_len; i += T) s_prog[i] = p.prog[i];
-    if (p.tab_in_smem)
-        for (int i = tid; i < p.W * p.E1; i += T) s_tab[i] = p.tab[i];
+    if (tid < 4) s_virt[tid] = tid == 0 ? 1.0 : 0.0;
     __syncthreads();
 
     Net1Ctx c;
-    c.q = s_q; c.nwb = nwb; c.wq = tid >> 2;
+    c.nwb = nwb; c.wq = tid >> 2; c.qs = 4 * nwb;
+    c.q = s_q + 4 * c.wq; c.virt = s_virt;
     c.cb = s_cb; c.cg = s_cg;
     c.par_internal = s_prog;
     c.node_of = s_prog + p.I;
@@ -288,7 +264,7 @@ __global__ void __launch_bounds__(256) score_o1_kernel(Net1Params p) {
     c.ichild_begin = s_prog + 3 * p.I + 1 + 2 * p.S;
     c.ichild = s_prog + 4 * p.I + 2 + 2 * p.S;
     c.W = p.W; c.I = p.I; c.S = p.S; c.E1 = p.E1;
-    c.tab = p.tab_in_smem ? s_tab : p.tab;
+    c.tab = p.tab;
     c.gq = p.gq; c.n_slots = p.n_slots; c.slot = (int64_t)blockIdx.x * nwb + c.wq;
     const int lane = tid & 31;
     c.qb = lane & ~3; c.a = lane & 3; c.qmask = 0xFu << c.qb;
@@ -300,7 +276,7 @@ __global__ void __launch_bounds__(256) score_o1_kernel(Net1Params p) {
     long long item = -1;
     double old = 0.0;
     // a quad that never receives a window still walks the net (warp-uniform control flow): give it defined inputs
-    for (int t = a; t < p.W; t += 4) { s_cb[(size_t)t * nwb + c.wq] = 0; s_cg[(size_t)t * nwb + c.wq] = 0; }
+    for (int t = a; t < p.W; t += 4) { s_cb[t * nwb + c.wq] = 0; s_cg[t * nwb + c.wq] = 0; }
 
     for (;;) {
         if (need && active) {
@@ -322,20 +298,19 @@ __global__ void __launch_bounds__(256) score_o1_kernel(Net1Params p) {
                     const int64_t col = strand ? c0 + (p.W - 1 - t) : c0 + t;     // jstacs StrandModel.java:636-639
                     ColWords cw = load_column(p.bases, p.gaps, p.n_cols, p.nb, col);
                     if (strand) cw = complement(cw);
-                    cw.b &= p.S >= 32 ? ~0ULL : ((1ULL << (2 * p.S)) - 1);
-                    s_cb[(size_t)t * nwb + c.wq] = cw.b; s_cg[(size_t)t * nwb + c.wq] = cw.g;
+                    s_cb[t * nwb + c.wq] = cw.b; s_cg[t * nwb + c.wq] = cw.g;
                 }
                 k = 0; conv = false; upd = false; need = false;
             }
             // uniform start, MeanFieldForBayesNet.java:52-69 (pass 0 rewrites it; neighbours are read before that)
-            for (int j = a; j < p.W * p.I * 4; j += 4) s_q[(size_t)j * nwb + c.wq] = 0.25;
+            for (int j = 0; j < p.W * p.I; ++j) c.q[j * c.qs + a] = 0.25;
             for (int j = a; j < p.W * p.S * 4; j += 4) p.gq[(size_t)j * p.n_slots + c.slot] = 0.25;
             __syncwarp(c.qmask);
         }
         if (!__any_sync(0xffffffffu, active)) break;
         const double Fl = net1_pass(c, upd);
-        const double f0 = __shfl_sync(c.qmask, Fl, c.qb), f1 = __shfl_sync(c.qmask, Fl, c.qb + 1);
-        const double f2 = __shfl_sync(c.qmask, Fl, c.qb + 2), f3 = __shfl_sync(c.qmask, Fl, c.qb + 3);
+        const double f0 = __shfl_sync(0xffffffffu, Fl, c.qb), f1 = __shfl_sync(0xffffffffu, Fl, c.qb + 1);
+        const double f2 = __shfl_sync(0xffffffffu, Fl, c.qb + 2), f3 = __shfl_sync(0xffffffffu, Fl, c.qb + 3);
         const double Fsum = ((f0 + f1) + f2) + f3;
         if (active) {
             bool done;
@@ -349,9 +324,9 @@ __global__ void __launch_bounds__(256) score_o1_kernel(Net1Params p) {
                 if (p.sink_qint) {
                     // entropy term sum_hidden sum_h q log q (MeanFieldForBayesNet.java:250-267), parameter independent
                     double ent = 0.0;
-                    for (int j = a; j < p.W * p.I * 4; j += 4) {
-                        const double v = s_q[(size_t)j * nwb + c.wq];
-                        p.sink_qint[(size_t)j * p.n_windows + item] = v;
+                    for (int j = 0; j < p.W * p.I; ++j) {
+                        const double v = c.q[j * c.qs + a];
+                        p.sink_qint[(size_t)(j * 4 + a) * p.n_windows + item] = v;
                         ent += v > 0.0 ? v * phy_log(v) : 0.0;
                     }
                     for (int t = 0; t < p.W; ++t) {

@@ -733,7 +733,7 @@ static int model_upload(phyfoo_ctx* ctx, phyfoo_model* m) {
     if (m->uploaded == h.version) return PHYFOO_OK;
     if (h.order == 1) {
         std::vector<double> t1;
-        h.tables1(t1);
+        h.tables1v(t1);
         if (!m->d_prog) {
             std::vector<int> prog = h.prog_flat();
             m->prog_len = (int)prog.size();
@@ -992,24 +992,18 @@ static int launch_net1(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* 
     const int n_strands = strands == 2 ? 2 : 1;
     const long long n_items = (long long)n_windows * n_strands;
     // windows per block: as many windows per SM as shared memory holds, in multiples of 8 (whole warps).  The kernel is
-    // latency-bound (one quad per window, ~1.5 warps per scheduler), so windows in flight matter more than where the
-    // tables live: they go to shared memory only when that costs no window (measured on C3: 48 windows/SM with the
-    // tables behind L1/L2 beat 32 windows/SM with the tables in shared memory by 25 %).
+    // latency-bound (one quad per window), so windows in flight are what matters; the tables stay in global memory
+    // behind L1/L2 (measured on C3: 48 windows/SM with the tables in L2 beat 32 windows/SM with the tables in shared
+    // memory by 25 %).
     const size_t per_window = (size_t)h.W * h.I * 4 * sizeof(double) + (size_t)h.W * 12;
-    const size_t tab_bytes = (size_t)h.W * h.E1() * sizeof(double);
+    const size_t fixed = (size_t)((m->prog_len + 1) & ~1) * sizeof(int) + 32 + 64;
     const size_t budget = std::min<size_t>(ctx->smem_optin, 227 * 1024);
-    int best_nwb = 0, best_per_sm = 0, tab_in_smem = 0;
-    size_t fixed = 0;
-    for (int with_tab = 0; with_tab <= 1; ++with_tab) {
-        const size_t fx = (size_t)((m->prog_len + 1) & ~1) * sizeof(int) + 64 + (with_tab ? tab_bytes : 0);
-        for (int nwb = 8; nwb <= 64; nwb += 8) {
-            const size_t need = fx + per_window * nwb;
-            if (need > budget) break;
-            const int blocks_sm = (int)std::min<size_t>((228 * 1024) / (need + 1024), 2048 / (4 * nwb));
-            if (blocks_sm * nwb > best_per_sm || (with_tab && blocks_sm * nwb == best_per_sm && !tab_in_smem)) {
-                best_per_sm = blocks_sm * nwb; best_nwb = nwb; tab_in_smem = with_tab; fixed = fx;
-            }
-        }
+    int best_nwb = 0, best_per_sm = 0;
+    for (int nwb = 8; nwb <= 64; nwb += 8) {
+        const size_t need = fixed + per_window * nwb;
+        if (need > budget) break;
+        const int blocks_sm = (int)std::min<size_t>((228 * 1024) / (need + 1024), 2048 / (4 * nwb));
+        if (blocks_sm * nwb > best_per_sm) { best_per_sm = blocks_sm * nwb; best_nwb = nwb; }
     }
     if (!best_nwb) return fail(ctx, PHYFOO_EUNSUPPORTED, "order-1 window state does not fit in shared memory (motif too wide or tree too large)");
     const size_t smem = fixed + per_window * best_nwb;
@@ -1025,12 +1019,12 @@ static int launch_net1(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* 
     p.bases = ds->d_bases; p.gaps = ds->d_gaps; p.n_cols = ds->n_cols; p.nb = ds->nb;
     p.col_off = ds->d_col_off; p.win_off = d_win_off; p.n_aln = ds->n_aln;
     p.n_windows = n_windows; p.n_strands = n_strands; p.strand0 = strands == 1 ? 1 : 0;
-    p.W = h.W; p.I = h.I; p.S = h.S; p.E1 = h.E1(); p.prog_len = m->prog_len; p.prog = m->d_prog;
+    p.W = h.W; p.I = h.I; p.S = h.S; p.E1 = h.E1v(); p.prog_len = m->prog_len; p.prog = m->d_prog;
     p.tab = m->d_tab1;
     p.out = d_out; p.sweeps = d_sweeps;
     p.counters = ctx->counters.as<unsigned long long>() + 2 * counter_slot;
     p.max_sweeps = h.max_sweeps; p.min_sweeps = h.min_sweeps; p.tol = h.tol;
-    p.gq = ctx->gstate.as<double>(); p.n_slots = n_slots; p.nwb = best_nwb; p.tab_in_smem = tab_in_smem;
+    p.gq = ctx->gstate.as<double>(); p.n_slots = n_slots; p.nwb = best_nwb;
     p.item_col0 = items ? items->col0 : nullptr; p.item_strand = items ? items->strand : nullptr;
     p.sink_qint = items ? items->q_int : nullptr; p.sink_qleaf = items ? items->q_leaf : nullptr; p.sink_ent = items ? items->ent : nullptr;
     CU(cudaMemsetAsync(p.counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
