@@ -82,14 +82,18 @@ struct MemoTrajParams {
 };
 struct MemoTrajJobs { MemoTrajParams job[2]; };   // blockIdx.y selects the job (background and motif in one launch)
 
-// one thread per (pattern d, position t): the mean-field trajectory F_0..F_cap of that tree
+// four lanes per (pattern d, position t) -- lane a owns symbol a, meanfield_pass_quad -- : the mean-field trajectory
+// F_0..F_cap of that tree.  The grid is small (patterns x positions trees) and every tree is a chain of cap + 1
+// dependent passes, so the kernel is latency-bound: four lanes per tree shorten the chain per lane (one exp instead of
+// four) and quadruple the warps in flight.  Same bits as the one-thread-per-tree pass of the direct kernel.
 __global__ void __launch_bounds__(128) memo_traj_kernel(MemoTrajJobs jobs) {
     extern __shared__ double smem[];
     const MemoTrajParams& p = jobs.job[blockIdx.y];
     const int T = blockDim.x, tid = threadIdx.x;
+    const int TPB = T >> 2;                                 // trees per block
     double* s_tab = smem;                                   // [E][W]
-    double* s_state = s_tab + (size_t)p.E * p.W;            // [I*8][T]
-    int* s_prog = (int*)(s_state + (size_t)p.I * 8 * T);
+    double* s_state = s_tab + (size_t)p.E * p.W;            // [I*8][TPB]
+    int* s_prog = (int*)(s_state + (size_t)p.I * 8 * TPB);
     for (int i = tid; i < p.E * p.W; i += T) s_tab[i] = p.tab[i];
     for (int i = tid; i < p.prog_len; i += T) s_prog[i] = p.prog[i];
     __syncthreads();
@@ -100,16 +104,30 @@ __global__ void __launch_bounds__(128) memo_traj_kernel(MemoTrajJobs jobs) {
     tp.leaf_begin = s_prog + 2 * p.I;
     tp.leaf_node = s_prog + 3 * p.I + 1;
     tp.leaf_species = s_prog + 3 * p.I + 1 + p.S;
-    const State st{s_state + tid, T};
+    const int slot = tid >> 2, a = tid & 3;
+    const int qb = (tid & 31) & ~3;
+    const unsigned mask = 0xFu << qb;
+    const State st{s_state + slot, TPB};
     const int D = *p.count;
     const long long n = (long long)D * p.W;
-    for (long long it = (long long)blockIdx.x * T + tid; it < n; it += (long long)gridDim.x * T) {
+    // warp-uniform trip count: quads past the end recompute the last tree and do not store
+    const long long first = (long long)blockIdx.x * TPB + ((tid >> 5) << 3);     // first tree of this warp
+    for (long long it0 = first; it0 < n; it0 += (long long)gridDim.x * TPB) {
+        const long long it_raw = it0 + ((tid & 31) >> 2);
+        const bool live = it_raw < n;
+        const long long it = live ? it_raw : n - 1;
         const int d = (int)(it / p.W), t = (int)(it - (long long)d * p.W);
         const ColWords cw = memo_words((uint32_t)p.code_of[d], p.S);
         const Tab tb{s_tab + t, p.W};
         double* out = p.traj + ((size_t)t * p.cap + d) * p.RS;
-        if (p.exact) { out[0] = -log(pruning_likelihood(tp, tb, st, cw)); continue; }
-        for (int k = 0; k < p.K1; ++k) out[k] = meanfield_pass(tp, tb, st, cw, k > 0);
+        if (p.exact) {
+            if (a == 0 && live) out[0] = -log(pruning_likelihood(tp, tb, st, cw));
+            continue;
+        }
+        for (int k = 0; k < p.K1; ++k) {
+            const double F = meanfield_pass_quad<true>(tp, tb, st, cw, k > 0, a, qb, mask);
+            if (a == 0 && live) out[k] = F;
+        }
     }
 }
 
@@ -142,7 +160,7 @@ __global__ void __launch_bounds__(256) memo_window_kernel(MemoWindowParams p) {
         const int si = (int)(item / p.n_windows);
         const int64_t w = item - (long long)si * p.n_windows;
         const int strand = p.n_strands == 2 ? si : p.strand0;
-        const int a = find_alignment(p.win_off, p.n_aln, w);
+        const int a = find_alignment_hint(p.win_off, p.n_aln, w, p.n_windows);
         const int64_t c0 = p.col_off[a] + (w - p.win_off[a]);
         const MemoRow4* row[16];
         // W <= 16 here (the launcher falls back to the direct kernel otherwise): trajectory rows of the W trees

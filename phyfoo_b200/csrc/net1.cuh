@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(256) score_o1_kernel(Net1Params p) {
                     const int si = (int)(item / p.n_windows);
                     const int64_t w = item - (long long)si * p.n_windows;
                     strand = p.n_strands == 2 ? si : p.strand0;
-                    const int al = find_alignment(p.win_off, p.n_aln, w);
+                    const int al = find_alignment_hint(p.win_off, p.n_aln, w, p.n_windows);
                     c0 = p.col_off[al] + (w - p.win_off[al]);
                 }
                 for (int t = a; t < p.W; t += 4) {

@@ -211,6 +211,27 @@ __device__ __forceinline__ int find_alignment(const int64_t* __restrict__ off, i
     return lo;
 }
 
+// the same with a first guess from the average alignment length (equal-length alignments: no search at all)
+__device__ __forceinline__ int find_alignment_hint(const int64_t* __restrict__ off, int n, int64_t w, int64_t n_windows) {
+    int a = (int)(((double)w * (double)n) / (double)n_windows);
+    a = min(max(a, 0), n - 1);
+    if (off[a] > w) {                              // guess too far right: gallop left, then bisect
+        int step = 1, hi = a;
+        while (a > 0 && off[a] > w) { hi = a; a = max(0, a - step); step <<= 1; }
+        while (hi - a > 1) { const int mid = (a + hi) >> 1; if (off[mid] <= w) a = mid; else hi = mid; }
+    } else if (off[a + 1] <= w) {                  // too far left
+        int step = 1, lo = a + 1;
+        a = lo;
+        while (a < n - 1 && off[a + 1] <= w) { lo = a + 1; a = min(n - 1, a + step); step <<= 1; }
+        int hi = a + 1;                            // off[lo] <= w < off[hi]
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (off[mid] <= w) lo = mid; else hi = mid; }
+        a = lo;
+    }
+    return a;
+}
+
+static const int SCORE_CHUNK = 4;   // windows a group takes from the global counter at a time
+
 // ITEMS = true: M-step "prepare" variant (explicit window list, converged q written out)
 template <int MODE, bool ITEMS>
 __global__ void __launch_bounds__(256, 2) score_o0_kernel(ScoreParams p) {
@@ -243,15 +264,17 @@ __global__ void __launch_bounds__(256, 2) score_o0_kernel(ScoreParams p) {
     const long long n_items = (ITEMS && p.n_items_dev) ? (long long)*p.n_items_dev : (long long)p.n_windows * p.n_strands;
     bool need = lane_ok, active = lane_ok, upd = false, conv = false;
     int k = 0;
-    long long item = -1;
+    long long item = -1, chunk_end = 0;     // the group owns items [item + 1, chunk_end) of its current chunk
     double old = 0.0;
     ColWords cw; cw.b = 0; cw.g = 0;
 
     for (;;) {
-        if (need && active && t == 0) s_item[g] = (long long)atomicAdd(p.counter_next, 1ULL);
+        const bool refill = need && active && item + 1 >= chunk_end;      // uniform within a group
+        if (refill && t == 0) s_item[g] = (long long)atomicAdd(p.counter_next, (unsigned long long)SCORE_CHUNK);
         __syncthreads();
         if (need && active) {
-            item = s_item[g];
+            if (refill) { item = s_item[g]; chunk_end = item + SCORE_CHUNK; }
+            else ++item;
             if (item >= n_items) active = false;
             else {
                 int strand;
@@ -263,7 +286,7 @@ __global__ void __launch_bounds__(256, 2) score_o0_kernel(ScoreParams p) {
                     const int si = (int)(item / p.n_windows);
                     const int64_t w = item - (long long)si * p.n_windows;
                     strand = p.n_strands == 2 ? si : p.strand0;
-                    const int a = find_alignment(p.win_off, p.n_aln, w);
+                    const int a = find_alignment_hint(p.win_off, p.n_aln, w, p.n_windows);
                     c0 = p.col_off[a] + (w - p.win_off[a]);
                 }
                 // jstacs StrandModel.java:636-639 / Sequence.java:1321-1333: reverse the columns, complement the symbols
@@ -932,11 +955,12 @@ static int launch_memo_jobs(phyfoo_ctx* ctx, const phyfoo_dataset* ds, const Mem
         tp.exact = jobs[j].mode == PHYFOO_MODE_EXACT ? 1 : 0;
         tp.tab = tp.exact ? m->d_probtab : m->d_logtab;
         tp.prog = m->d_prog; tp.traj = ctx->memo_traj.as<double>() + traj_off[j];
-        smem = std::max(smem, (size_t)h.E * h.W * sizeof(double) + (size_t)h.I * 8 * threads * sizeof(double) + (size_t)m->prog_len * sizeof(int) + 16);
+        smem = std::max(smem, (size_t)h.E * h.W * sizeof(double) + (size_t)h.I * 8 * (threads / 4) * sizeof(double) + (size_t)m->prog_len * sizeof(int) + 16);
         trees = std::max(trees, (long long)ms->cap * h.W);
     }
     if (n_jobs == 1) tj.job[1] = tj.job[0];
-    const int blocks = (int)std::max<long long>(1, std::min<long long>((trees + threads - 1) / threads, 8LL * ctx->sm_count));
+    const int tpb = threads / 4;   // four lanes per tree
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((trees + tpb - 1) / tpb, 16LL * ctx->sm_count));
     CU(cudaFuncSetAttribute(memo_traj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         KernelTimer kt_(ctx, "memo_traj_kernel");
