@@ -160,6 +160,19 @@ int phyfoo_zoops_estep_device(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_
                               const double* logw, const double* strand_logw, const double* aln_weights_device,
                               double* partial_device, void* stream);
 
+/* ---- genome scan / classification front-end (classification/ClassificationUtil.java) ----
+ * Consumers of the per-offset motif scores that keep them on the device (config 5: 2*10^9 window scores).
+ * scan_hits, per alignment: the number of offsets with score > threshold (determineSensitivityPerSeq :266-278 counts the
+ * alignments where this is > 0; determinePositionSet :287-298 lists them), the first such offset (-1 if none), the
+ * maximal score and its first offset (util/Util.java:528-538).  Any output pointer may be NULL. */
+int phyfoo_scan_hits(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* fg, int32_t strand, double threshold,
+                     int32_t* n_hits, int32_t* first_hit, double* max_score, int32_t* arg_max);
+/* order statistics of all window scores of the sample: values_out[i] = sorted scores[ranks[i]] (ascending).
+ * determineThresholdsForSpecifitiesPerPos :244-264 asks for rank (int)((n - 1) * specificity), determineThresholdForSpecifity
+ * :161-180 for (int)(n * specificity); n is returned in n_scores_out (call with n_ranks = 0 to learn it). */
+int phyfoo_score_order_stats(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* fg, int32_t strand, int32_t n_ranks,
+                             const int64_t* ranks, double* values_out, int64_t* n_scores_out);
+
 /* ---- M-step data selection (io/SequenceSpecificDataSelector.java:37-99) ----
  * weights[windows] (e.g. gamma_out), one group per alignment: walk the windows by descending weight,
  * take those with raw weight >= q, stop after the running sum of normalised weights exceeds t.

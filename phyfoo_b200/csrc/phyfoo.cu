@@ -1430,3 +1430,79 @@ extern "C" int phyfoo_synchronize(phyfoo_ctx* ctx) {
 }
 
 #include "mstep.cuh"
+#include "scan.cuh"
+
+// scores every window of the sample into ctx->fg_scores (device) without copying them out
+static int scan_scores(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* fg, int strand, const int64_t** d_woff, int64_t* nw) {
+    if (strand != 0 && strand != 1) return fail(ctx, PHYFOO_EINVAL, "scan: strand must be 0 or 1");
+    const std::vector<int64_t>* h_woff;
+    int rc = dataset_win_off(ctx, ds, fg->h.W, d_woff, &h_woff);
+    if (rc) return rc;
+    *nw = h_woff->back();
+    CU(ctx->fg_scores.ensure((size_t)std::max<int64_t>(*nw, 1) * sizeof(double)));
+    return launch_score(ctx, ds, fg, *d_woff, *nw, strand, ctx->fg_scores.as<double>(), nullptr, 0);
+}
+
+extern "C" int phyfoo_scan_hits(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* fg, int32_t strand, double threshold,
+                                int32_t* n_hits, int32_t* first_hit, double* max_score, int32_t* arg_max) {
+    if (!ctx) return PHYFOO_EINVAL;
+    if (!ds || !fg) return fail(ctx, PHYFOO_EINVAL, "scan_hits: NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    ctx->launches = 0; ctx->n_ktimes = 0;
+    const int64_t* d_woff; int64_t nw = 0;
+    int rc = scan_scores(ctx, ds, fg, strand, &d_woff, &nw);
+    if (rc) return rc;
+    const size_t na = (size_t)ds->n_aln;
+    if (na == 0) return PHYFOO_OK;
+    CU(ctx->misc.ensure(na * (3 * sizeof(int32_t) + sizeof(double)) + 64));
+    double* d_max = ctx->misc.as<double>();
+    int32_t* d_hits = (int32_t*)(d_max + na);
+    int32_t* d_first = d_hits + na;
+    int32_t* d_arg = d_first + na;
+    {
+        KernelTimer kt_(ctx, "scan_hits_kernel");
+        scan_hits_kernel<<<(unsigned)na, 256, 0, ctx->stream>>>(ctx->fg_scores.as<double>(), d_woff, threshold, d_hits, d_first, d_max, d_arg);
+    }
+    CU(cudaGetLastError());
+    if (n_hits) CU(cudaMemcpyAsync(n_hits, d_hits, na * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (first_hit) CU(cudaMemcpyAsync(first_hit, d_first, na * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (max_score) CU(cudaMemcpyAsync(max_score, d_max, na * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (arg_max) CU(cudaMemcpyAsync(arg_max, d_arg, na * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PHYFOO_OK;
+}
+
+extern "C" int phyfoo_score_order_stats(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* fg, int32_t strand, int32_t n_ranks,
+                                        const int64_t* ranks, double* values_out, int64_t* n_scores_out) {
+    if (!ctx) return PHYFOO_EINVAL;
+    if (!ds || !fg || n_ranks < 0 || (n_ranks > 0 && (!ranks || !values_out))) return fail(ctx, PHYFOO_EINVAL, "score_order_stats: NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    ctx->launches = 0; ctx->n_ktimes = 0;
+    const int64_t* d_woff; int64_t nw = 0;
+    int rc = scan_scores(ctx, ds, fg, strand, &d_woff, &nw);
+    if (rc) return rc;
+    if (n_scores_out) *n_scores_out = nw;
+    if (n_ranks == 0) return PHYFOO_OK;
+    if (nw == 0) return fail(ctx, PHYFOO_EINVAL, "score_order_stats: the sample has no windows");
+    if (nw > INT32_MAX) return fail(ctx, PHYFOO_EUNSUPPORTED, "score_order_stats: more than 2^31 scores in one call");
+    for (int i = 0; i < n_ranks; ++i)
+        if (ranks[i] < 0 || ranks[i] >= nw) return fail(ctx, PHYFOO_EINVAL, "score_order_stats: rank out of range");
+    size_t tmp_bytes = 0;
+    CU(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, (const double*)nullptr, (double*)nullptr, (int)nw, 0, 64, ctx->stream));
+    CU(ctx->sel_tmp.ensure(tmp_bytes + 256));
+    CU(ctx->selw.ensure((size_t)nw * sizeof(double)));
+    CU(cub::DeviceRadixSort::SortKeys(ctx->sel_tmp.p, tmp_bytes, ctx->fg_scores.as<double>(), ctx->selw.as<double>(), (int)nw, 0, 64, ctx->stream));
+    ctx->launches += 1;
+    CU(ctx->misc.ensure((size_t)n_ranks * (sizeof(int64_t) + sizeof(double))));
+    double* d_out = ctx->misc.as<double>();
+    int64_t* d_idx = (int64_t*)(d_out + n_ranks);
+    CU(cudaMemcpyAsync(d_idx, ranks, (size_t)n_ranks * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    {
+        KernelTimer kt_(ctx, "scan_pick_kernel");
+        scan_pick_kernel<<<(n_ranks + 127) / 128, 128, 0, ctx->stream>>>(ctx->selw.as<double>(), d_idx, n_ranks, d_out);
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(values_out, d_out, (size_t)n_ranks * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PHYFOO_OK;
+}
