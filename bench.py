@@ -229,7 +229,9 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (phyfoo_b200 has no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        # a short collective timeout: a rank-asymmetric bug must abort the run in minutes, not hold 8 GPUs for the default 10
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
 
     from phyfoo_b200 import core, synth
     from phyfoo_b200.data import PhyloSample
@@ -308,8 +310,9 @@ def run_ours(args):
     value = total_windows * args.steps / (dev_ms_max * 1e-3)
 
     # the direct kernel on the same workload (the path every configuration with more than 6 species takes), for the roofline
+    # (every rank runs it: step() contains the all-reduce, so a rank-0-only run would leave rank 0 alone in a collective)
     direct = None
-    if path == 1 and rank == 0:
+    if path == 1:
         ctx.set_option("pattern_memo", 0)
         step(); torch.cuda.synchronize()
         d_ms, d_kernels = timed(3)

@@ -202,6 +202,11 @@ int phyfoo_fe_grad(phyfoo_ctx* ctx, phyfoo_feset* fe, int32_t position, const do
 /* device-resident variant for multi-GPU: values[dim+1] = [f(lambda), f(lambda+eps e_0), ...] local sums */
 int phyfoo_fe_values_device(phyfoo_ctx* ctx, phyfoo_feset* fe, int32_t position, const double* lambda,
                             int32_t dim, double eps, double* values_device, void* stream);
+/* Sufficient statistics of the objective (order 0): counts_out[W][E], E = 4 + 16 (N - 1): expected counts of the log-table
+ * entries of each position (4 root entries, then [parent symbol][own symbol] per non-root node in tree node order),
+ * entropy_out: the parameter-independent term.  Then f(theta) = sum_t sum_e counts[t][e] * log table_theta,t[e] - entropy
+ * for ANY parameters (pi or branch lengths) of any position: the optimizer needs no further device pass. */
+int phyfoo_fe_suffstats(phyfoo_ctx* ctx, phyfoo_feset* fe, double* counts_out, double* entropy_out);
 int64_t phyfoo_fe_size(const phyfoo_feset* fe);
 void phyfoo_fe_free(phyfoo_ctx* ctx, phyfoo_feset* fe);
 

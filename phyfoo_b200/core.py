@@ -334,6 +334,14 @@ class FESet:
                                        C.byref(f), _p(g, C.c_double)), self.ctx.h)
         return f.value, g
 
+    def suffstats(self, W, E):
+        """(counts [W][E], entropy): expected counts of the log-table entries per position, from one device pass
+        (phyfoo_fe_suffstats; order 0).  f(theta) = sum(counts * log tables_theta) - entropy for any parameters."""
+        counts = np.zeros((W, E))
+        ent = C.c_double()
+        raise_for(lib().phyfoo_fe_suffstats(self.ctx.h, self.h, _p(counts, C.c_double), C.byref(ent)), self.ctx.h)
+        return counts, ent.value
+
     def values_device(self, position, lam, eps, values_ptr, stream_ptr):
         lam = np.ascontiguousarray(lam, np.float64)
         raise_for(lib().phyfoo_fe_values_device(self.ctx.h, self.h, int(position), _p(lam, C.c_double), lam.size, float(eps),

@@ -667,6 +667,136 @@ extern "C" int phyfoo_fe_values_device(phyfoo_ctx* ctx, phyfoo_feset* fe, int32_
     return PHYFOO_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// sufficient statistics of the fixed-q objective (order 0): with q fixed,
+//   f(theta) = sum_t sum_e C[t][e] * logtab_theta,t[e] - ENT,
+// where C[t][e] are the expected counts of table entry e of position t (entry layout of model_host.hpp: 4 root
+// entries, then 16 per non-root node [parent symbol][own symbol]) summed over the selected windows with their weights.
+// One pass over the windows, then every later evaluation -- any parameter of any position, pi or branch length -- is
+// a host-side dot product of W*E terms (SURVEY.md section 7 hard part 3; the reference re-sweeps all windows per evaluation).
+// Accumulation uses shared-memory atomics per block (summation order within a block is not fixed: results agree
+// to fp64 re-association run to run), block partials are reduced in a fixed order.
+// ------------------------------------------------------------------------------------------------
+struct FeCountParams {
+    const uint32_t* bases; const uint32_t* gaps; int64_t n_cols; int nb;
+    const int64_t* col0; const uint8_t* strand; const double* weight;
+    const double* q_int; const double* q_leaf;
+    int64_t n;
+    int W, I, S, E, prog_len;
+    const int* prog;
+    double* part;               // [W][gridDim.x][E]
+};
+
+__global__ void __launch_bounds__(256) fe_count_kernel(FeCountParams p) {
+    extern __shared__ double smem[];
+    const int T = blockDim.x, tid = threadIdx.x;
+    const int t = blockIdx.y;
+    double* s_c = smem;                                     // [E]
+    int* s_prog = (int*)(s_c + p.E);
+    for (int i = tid; i < p.E; i += T) s_c[i] = 0.0;
+    for (int i = tid; i < p.prog_len; i += T) s_prog[i] = p.prog[i];
+    __syncthreads();
+    const int* par_internal = s_prog;
+    const int* node_of = s_prog + p.I;
+    const int* leaf_begin = s_prog + 2 * p.I;
+    const int* leaf_node = s_prog + 3 * p.I + 1;
+    const int* leaf_species = s_prog + 3 * p.I + 1 + p.S;
+    const size_t n_trees = (size_t)p.n * p.W;
+    for (int64_t u = (int64_t)blockIdx.x * T + tid; u < p.n; u += (int64_t)gridDim.x * T) {
+        const int strand = p.strand ? p.strand[u] : 0;
+        const int64_t c = strand ? p.col0[u] + (p.W - 1 - t) : p.col0[u] + t;
+        ColWords cw = load_column(p.bases, p.gaps, p.n_cols, p.nb, c);
+        if (strand) cw = complement(cw);
+        const size_t tree = (size_t)t * p.n + u;
+        const double w = p.weight[u];
+        for (int i = 0; i < p.I; ++i) {
+            double qi[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) qi[a] = p.q_int[(size_t)(i * 4 + a) * n_trees + tree];
+            if (i == 0) {
+#pragma unroll
+                for (int a = 0; a < 4; ++a) atomicAdd(&s_c[a], w * qi[a]);                       // :282-291
+            } else {
+                const int e0 = tab_of(node_of[i]);
+                const int pi_ = par_internal[i];
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                    const double wl = w * p.q_int[(size_t)(pi_ * 4 + l) * n_trees + tree];
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) atomicAdd(&s_c[e0 + l * 4 + h], wl * qi[h]);     // :327-358
+                }
+            }
+            const double qs = ((qi[0] + qi[1]) + qi[2]) + qi[3];
+            for (int k = leaf_begin[i]; k < leaf_begin[i + 1]; ++k) {
+                const int x = cw.obs(leaf_species[k]);
+                if (x < 4) {
+                    const int e0 = tab_of(leaf_node[k]);
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) atomicAdd(&s_c[e0 + a * 4 + x], w * qi[a]);      // :292-326
+                } else {
+                    // "independent" table: every row is log pi -> counts go to the root entries
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) atomicAdd(&s_c[a], (w * qs) * p.q_leaf[(size_t)(k * 4 + a) * n_trees + tree]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    double* out = p.part + ((size_t)t * gridDim.x + blockIdx.x) * p.E;
+    for (int i = tid; i < p.E; i += T) out[i] = s_c[i];
+}
+
+// C[t][e] = sum over blocks of part (fixed order): one thread per (t, e)
+__global__ void fe_count_reduce_kernel(const double* __restrict__ part, int blocks, int WE, int E, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= WE) return;
+    const int t = i / E, e = i - t * E;
+    double v = 0.0;
+    for (int b = 0; b < blocks; ++b) v += part[((size_t)t * blocks + b) * E + e];
+    out[i] = v;
+}
+
+extern "C" int phyfoo_fe_suffstats(phyfoo_ctx* ctx, phyfoo_feset* fe, double* counts_out, double* entropy_out) {
+    if (!ctx) return PHYFOO_EINVAL;
+    if (!fe || !counts_out) return fail(ctx, PHYFOO_EINVAL, "fe_suffstats: NULL argument");
+    if (fe->order != 0) return fail(ctx, PHYFOO_EUNSUPPORTED, "fe_suffstats: order-1 networks are not supported (use fe_eval / fe_grad)");
+    CU(cudaSetDevice(ctx->device));
+    ctx->launches = 0; ctx->n_ktimes = 0;
+    const int W = fe->W, E = fe->E;
+    const size_t WE = (size_t)W * E;
+    if (fe->n == 0) {
+        for (size_t i = 0; i < WE; ++i) counts_out[i] = 0.0;
+        if (entropy_out) *entropy_out = 0.0;
+        return PHYFOO_OK;
+    }
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((fe->n + 255) / 256, (int64_t)ctx->sm_count));
+    CU(ctx->misc.ensure(((size_t)blocks + 1) * WE * sizeof(double)));
+    double* d_part = ctx->misc.as<double>();
+    double* d_c = d_part + (size_t)blocks * WE;
+    const phyfoo_dataset* ds = fe->ds;
+    FeCountParams p;
+    p.bases = ds->d_bases; p.gaps = ds->d_gaps; p.n_cols = ds->n_cols; p.nb = ds->nb;
+    p.col0 = fe->d_col0; p.strand = fe->d_strand; p.weight = fe->d_weight;
+    p.q_int = fe->d_qint; p.q_leaf = fe->d_qleaf; p.n = fe->n;
+    p.W = W; p.I = fe->I; p.S = fe->S; p.E = E; p.prog_len = fe->m->prog_len; p.prog = fe->m->d_prog;
+    p.part = d_part;
+    const size_t smem = (size_t)E * sizeof(double) + (size_t)fe->m->prog_len * sizeof(int) + 16;
+    {
+        KernelTimer kt_(ctx, "fe_count_kernel");
+        fe_count_kernel<<<dim3(blocks, W), 256, smem, ctx->stream>>>(p);
+    }
+    CU(cudaGetLastError());
+    {
+        KernelTimer kt_(ctx, "fe_count_reduce_kernel");
+        fe_count_reduce_kernel<<<(unsigned)((WE + 127) / 128), 128, 0, ctx->stream>>>(d_part, blocks, (int)WE, E, d_c);
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(counts_out, d_c, WE * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (entropy_out) CU(cudaMemcpyAsync(entropy_out, fe->d_G + W, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PHYFOO_OK;
+}
+
 extern "C" int64_t phyfoo_fe_size(const phyfoo_feset* fe) { return fe ? fe->n : 0; }
 
 extern "C" void phyfoo_fe_free(phyfoo_ctx* ctx, phyfoo_feset* fe) {

@@ -1,0 +1,56 @@
+"""Per-branch substitution tables on the host (numpy mirror of evolution/FS81alpha.java:76-92 and FS81beta.java:81-103, the
+same formulas csrc/model_host.hpp uses), in the entry layout of the device tables: 4 root entries (pi), then 16 per
+non-root node k at 4 + 16 (k - 1), row-major [parent symbol a][own symbol b].
+
+Used by the sufficient-statistics form of the M-step objective (SuffStatObjective): with the expected counts C from ONE
+device pass, f(theta) = sum_t sum_e C[t][e] log table_theta,t[e] - ENT is a host-side dot product for any pi or branch
+lengths."""
+import numpy as np
+
+from . import _abi
+
+
+def transition(pi, length, evol=_abi.EVOL_F81ALPHA):
+    """4x4 P(b | a) for one branch."""
+    pi = np.asarray(pi, np.float64)
+    if evol == _abi.EVOL_F81ALPHA:
+        keep = 1.0 - length
+        mix = length
+    elif evol == _abi.EVOL_F81BETA:
+        beta = 1.0 / (1.0 - np.sum(pi * pi))
+        ta = float(np.exp(-length * beta))
+        if ta < 1e-4:
+            ta = 0.0
+        elif ta > 1 - 1e-4:
+            ta = 1.0
+        keep, mix = ta, 1.0 - ta
+    else:
+        raise ValueError("HKY as implemented in the reference has zero transversion probabilities (HKY.java:32)")
+    T = np.tile(pi * mix, (4, 1))
+    T[np.arange(4), np.arange(4)] = keep + pi * mix
+    return T
+
+
+def tables(pi, branch, evol=_abi.EVOL_F81ALPHA):
+    """Probability table of one position: entries [pi(4), node 1 (16), ..., node N-1 (16)]; branch[N] (entry 0 unused)."""
+    N = len(branch)
+    out = np.empty(4 + 16 * (N - 1))
+    out[:4] = pi
+    for k in range(1, N):
+        out[4 + 16 * (k - 1): 4 + 16 * k] = transition(pi, branch[k], evol).ravel()
+    return out
+
+
+def branch_from_logit(x, minimum=0.0005):
+    """optimizing/branchlengths/EdgeOptimizer.java:44-51: alpha = (e^x + 0.0005) / (1 + e^x), NaN -> 1."""
+    with np.errstate(over="ignore", invalid="ignore"):
+        e = np.exp(np.asarray(x, np.float64))
+        a = (e + minimum) / (1.0 + e)
+    return np.where(np.isnan(a), 1.0, a)
+
+
+def logit_from_branch(alpha):
+    """EdgeOptimizer.java:103-109: x = log(alpha / (1 - alpha)), alpha == 1 is nudged to 1 - 1e-6."""
+    a = np.asarray(alpha, np.float64).copy()
+    a[a == 1.0] -= 1e-6
+    return np.log(a / (1.0 - a))

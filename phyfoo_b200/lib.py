@@ -27,7 +27,7 @@ SYMBOLS = [
     "phyfoo_model_set_mode", "phyfoo_model_free",
     "phyfoo_score_windows", "phyfoo_bg_columns", "phyfoo_zoops_estep", "phyfoo_zoops_estep_device",
     "phyfoo_scan_hits", "phyfoo_score_order_stats", "phyfoo_select", "phyfoo_fe_prepare", "phyfoo_fe_prepare_all", "phyfoo_fe_eval", "phyfoo_fe_grad",
-    "phyfoo_fe_values_device", "phyfoo_fe_size", "phyfoo_fe_free",
+    "phyfoo_fe_values_device", "phyfoo_fe_suffstats", "phyfoo_fe_size", "phyfoo_fe_free",
     "phyfoo_set_option", "phyfoo_last_score_path", "phyfoo_last_kernel_times", "phyfoo_host_alloc", "phyfoo_host_free",
     "phyfoo_last_launches", "phyfoo_stream", "phyfoo_synchronize", "phyfoo_estep_kernel_ms", "phyfoo_estep_sweeps",
 ]
@@ -102,6 +102,7 @@ def lib():
     L.phyfoo_fe_eval.argtypes = [vp, vp, C.c_int32, dp, C.c_int32, dp]
     L.phyfoo_fe_grad.argtypes = [vp, vp, C.c_int32, dp, C.c_int32, C.c_double, dp, dp]
     L.phyfoo_fe_values_device.argtypes = [vp, vp, C.c_int32, dp, C.c_int32, C.c_double, vp, vp]
+    L.phyfoo_fe_suffstats.argtypes = [vp, vp, dp, dp]
     L.phyfoo_fe_size.argtypes = [vp]
     L.phyfoo_fe_size.restype = C.c_int64
     L.phyfoo_fe_free.argtypes = [vp, vp]

@@ -187,6 +187,41 @@ class PhyloBayesModel(_PhyloModel):
         return stats
 
 
+    EDGE_LEARNING = 0                  # models/PhyloBayesModel.java:47: 0 off, 1 per position, 2 one set for all positions
+    EDGE_LEARNING_ONE_LENGTH = False
+
+    def trainEdges(self, sample: PhyloSample, weights, globally=None, equal=None):
+        """Branch-length learning on the fixed-q objective (optimizing/branchlengths/EdgeOptimizer.java:44-125,
+        GlobalEdgeOptimizer.java): logit-parametrised branch lengths, BFGS until the objective changes by less than 1e-3.
+        One device pass collects the sufficient statistics; the optimisation itself runs on the host.  Order-0 models."""
+        if self.order != 0:
+            raise NotImplementedError("branch-length learning is implemented for order-0 models")
+        from . import evolution
+        globally = (self.EDGE_LEARNING == 2) if globally is None else globally
+        equal = self.EDGE_LEARNING_ONE_LENGTH if equal is None else equal
+        ds = sample.device(self.ctx)
+        sa, so, sw = core.select(self.ctx, ds, self.length, weights, self.PROB_THRESH_FOR_WEIGHTS, self.MOTIF_QUALITY_THRESHOLD)
+        fe = core.FESet(self.ctx, ds, self.device_model(), sa, so, sw)
+        try:
+            obj = optimize.SuffStatObjective(fe, self._pi, self._branch, type(self).EVOL_MODEL)
+        finally:
+            fe.free()
+        before = obj.value()
+        evals = 0
+        for t in ([0] if globally else range(self.length)):
+            b = self._branch[t, 1:]
+            x0 = evolution.logit_from_branch(np.array([b.mean()]) if equal else b)
+            fun = lambda z: -obj.eval_edges(t, z, equal, globally)          # noqa: E731
+            x, f, it, ev = optimize.quasi_newton_bfgs(fun, lambda z: obj.grad(fun, z), x0,
+                                                      optimize.SMALL_DIFFERENCE_OF_FUNCTIONS())
+            obj.eval_edges(t, x, equal, globally)
+            evals += ev
+        for t in range(self.length):
+            for k in range(1, self.tree.n_nodes):
+                self.setBranchLength(t, k, float(obj.branch[t, k]))
+        return {"f_before": before, "f_after": obj.value(), "evaluations": evals, "selected": int(sa.size)}
+
+
 def _neg(fg):
     return -fg[0], -fg[1]
 

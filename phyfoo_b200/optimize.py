@@ -128,3 +128,70 @@ def quasi_newton_bfgs(fun, grad, x0, condition, lin_eps=1e-3, start_distance=0.1
         if not go_on or alpha == 0.0:
             break
     return x, f, it, evals
+
+
+class SuffStatObjective:
+    """The fixed-q objective in sufficient-statistics form (SURVEY.md section 7 hard part 3): after ONE device pass
+    (core.FESet.suffstats) every evaluation is a dot product on the host,
+        f(theta) = sum_t sum_e C[t][e] * log table_theta,t[e] - ENT,
+    for the stationary distributions (FE_byParameter_ForBayesNodeJstacs / MotifParamOptimizer) and for the branch
+    lengths (optimizing/branchlengths/EdgeOptimizer.java, GlobalEdgeOptimizer.java) alike.  Order-0 models."""
+
+    def __init__(self, fe, pi, branch, evol):
+        from . import evolution
+        self._ev = evolution
+        self.pi = [np.asarray(p, np.float64).ravel().copy() for p in pi]
+        self.branch = np.array(branch, np.float64)                   # [W][N]
+        self.evol = evol
+        self.W, self.N = self.branch.shape
+        self.E = 4 + 16 * (self.N - 1)
+        self.counts, self.entropy = fe.suffstats(self.W, self.E)
+        self._G = np.array([self.position_term(t, self.pi[t], self.branch[t]) for t in range(self.W)])
+
+    def position_term(self, t, pi, branch):
+        with np.errstate(divide="ignore"):
+            lt = np.log(self._ev.tables(pi, branch, self.evol))
+        c = self.counts[t]
+        nz = c != 0.0
+        return float(np.dot(c[nz], lt[nz]))
+
+    def value(self):
+        return float(self._G.sum() - self.entropy)
+
+    def set_position(self, t, pi=None, branch=None):
+        if pi is not None:
+            self.pi[t] = np.asarray(pi, np.float64).ravel().copy()
+        if branch is not None:
+            self.branch[t] = branch
+        self._G[t] = self.position_term(t, self.pi[t], self.branch[t])
+
+    # ---- evaluateFunction / evaluateGradientOfFunction in the reference's parametrisations ----
+    def eval_lambda(self, t, lam):
+        """FE_byParameter_ForBayesNodeJstacs.evaluateFunction: pi_t = softmax(lambda); the model is left at lambda."""
+        lam = np.asarray(lam, np.float64)
+        e = np.exp(lam - lam.max())
+        s = e.sum()
+        self.set_position(t, pi=e / s if s != 1.0 else e)
+        return self.value()
+
+    def eval_edges(self, t, x, equal=False, globally=False):
+        """EdgeOptimizer.evaluateFunction: branch lengths of position t (or of all positions) from logits x."""
+        alpha = self._ev.branch_from_logit(x)
+        b = np.zeros(self.N)
+        b[1:] = alpha[0] if equal else alpha
+        for pos in (range(self.W) if globally else [t]):
+            self.set_position(pos, branch=b)
+        return self.value()
+
+    def grad(self, fun, x, eps=1e-4):
+        """jstacs NumericalDifferentiableFunction.java:64-84: forward differences, x[i] perturbed in place and restored."""
+        x = np.array(x, np.float64)
+        f0 = fun(x)
+        g = np.zeros_like(x)
+        for i in range(x.size):
+            keep = x[i]
+            x[i] += eps
+            g[i] = (fun(x) - f0) / eps
+            x[i] = keep
+        fun(x)
+        return f0, g

@@ -162,3 +162,55 @@ def test_fe_errors_and_empty(ctx):
         fe2.eval(0, np.zeros(3))
     with pytest.raises(IllegalArgumentException):
         fe2.eval(7, np.zeros(4))
+
+
+@pytest.mark.parametrize("tree", ["cat5", "rand12", "mixed6"])
+@pytest.mark.parametrize("evol", ["alpha", "beta"])
+def test_sufficient_statistics_objective(ctx, tree, evol):
+    """One device pass -> expected counts; then f(theta) for ANY pi or branch lengths is a host-side dot product.  Checked
+    against the faithful device evaluation (fe.eval) and against the oracle with changed pi and changed branch lengths."""
+    from phyfoo_b200 import _abi, core, optimize, synth
+    from phyfoo_b200.models import PhyloBackground, PhyloBayesModel, SingleHiddenMotifMixture
+    from test_gpu_parity import _trees
+    newick = _trees()[tree]
+    W = 5
+    pwm = synth.random_pwm(W, 0, 83)
+    smp, _ = synth.make_sample(newick, 30, 60, 17, pwm=pwm, gap_rate=0.08, length_jitter=6)
+    ev_id, ev_orc = (_abi.EVOL_F81ALPHA, orc.F81ALPHA) if evol == "alpha" else (_abi.EVOL_F81BETA, orc.F81BETA)
+    old = PhyloBayesModel.EVOL_MODEL
+    PhyloBayesModel.EVOL_MODEL = ev_id
+    try:
+        fg = PhyloBayesModel(W, 0, newick, ctx); fg.setCondProbs(pwm)
+        bg = PhyloBackground(0, newick, ctx)
+        res = SingleHiddenMotifMixture(fg, bg, zoops=0.9).getNewWeights(smp)
+        ds = smp.device(ctx)
+        sa, so, sw = core.select(ctx, ds, W, None)
+        fe = core.FESet(ctx, ds, fg.device_model(), sa, so, sw)
+        obj = optimize.SuffStatObjective(fe, fg._pi, fg._branch, ev_id)
+    finally:
+        PhyloBayesModel.EVOL_MODEL = old
+    om = oracle_fg(newick, pwm, evol=ev_orc)
+    cols = np.stack([smp.getElementAt(a)[o:o + W] for a, o in zip(sa, so)])
+    ofe = orc.FESet(om, cols, sw)
+    assert abs(obj.value() - ofe.sum()) <= TOL * abs(ofe.sum())
+    rng = np.random.default_rng(7)
+    # a new stationary distribution at one position: host dot product == device evaluation == oracle
+    lam = np.log(rng.dirichlet(np.ones(4))) + 0.7
+    f_host = obj.eval_lambda(2, lam)
+    f_dev, f_orc = fe.eval(2, lam), ofe.eval(2, lam)
+    assert abs(f_host - f_orc) <= TOL * abs(f_orc) and abs(f_dev - f_orc) <= TOL * abs(f_orc)
+    f0, g = obj.grad(lambda z: obj.eval_lambda(2, z), lam, EPS)
+    r0, rg = ofe.grad(2, lam, EPS)
+    assert np.all(np.abs(g - rg) <= _grad_tol(rg, r0))
+    # new branch lengths at one position (EdgeOptimizer's parameters): oracle with the same branch lengths set
+    N = fg.tree.n_nodes
+    x = rng.normal(-1.0, 0.7, N - 1)
+    f_edges = obj.eval_edges(3, x)
+    from phyfoo_b200 import evolution
+    alpha = evolution.branch_from_logit(x)
+    for k in range(1, N):
+        om.set_branch(3, k, alpha[k - 1])
+    assert abs(f_edges - ofe.sum()) <= TOL * abs(ofe.sum())
+    assert abs(evolution.logit_from_branch(alpha) - x).max() < 1e-9
+    # counts are non-negative and each position's root counts sum to the total weight (plus the gap-leaf share)
+    assert (obj.counts >= 0).all() and (obj.counts[:, :4].sum(axis=1) >= sw.sum() - 1e-9).all()
