@@ -83,3 +83,54 @@ class ShardedEStep:
         self.stream.synchronize()
         v = self.partial.cpu().numpy()
         return {"ll": float(v[0]), "w": v[1:].copy()}
+
+
+class ShardedObjective:
+    """The M-step objective over this rank's shard of the selected windows with ONE all-reduce per evaluation:
+    [f(lambda), f(lambda + eps e_0), ...] (dim + 1 doubles) per gradient, left on the device by phyfoo_fe_values_device and
+    summed over the ranks on the same stream.  Every rank ends up with the same f and g."""
+
+    def __init__(self, fe, device):
+        import torch
+        self.fe = fe
+        self.values = torch.zeros(64, dtype=torch.float64, device=f"cuda:{device}")
+        self.stream = torch.cuda.Stream(device=device)
+
+    def grad(self, position, lam, eps=1e-4):
+        import torch
+        lam = np.ascontiguousarray(lam, np.float64)
+        n = lam.size + 1
+        if n > self.values.numel():
+            self.values = torch.zeros(n, dtype=torch.float64, device=self.values.device)
+        with torch.cuda.stream(self.stream):
+            self.fe.values_device(position, lam, eps, self.values.data_ptr(), self.stream.cuda_stream)
+            v = self.values[:n]
+            allreduce_sum_(v)
+        self.stream.synchronize()
+        v = v.cpu().numpy()
+        return float(v[0]), (v[1:] - v[0]) / eps
+
+    def eval(self, position, lam):
+        import torch
+        lam = np.ascontiguousarray(lam, np.float64)
+        with torch.cuda.stream(self.stream):
+            self.fe.values_device(position, lam, 0.0, self.values.data_ptr(), self.stream.cuda_stream)
+            v = self.values[:1]
+            allreduce_sum_(v)
+        self.stream.synchronize()
+        return float(v.cpu().numpy()[0])
+
+
+def allreduce_counts_(counts, entropy):
+    """Sufficient statistics of the M-step objective summed over the ranks: one all-reduce of W*E + 1 doubles, after which
+    every rank optimises on the host without further communication.  counts: numpy [W][E]; returns (counts, entropy)."""
+    d = _dist()
+    if not d or d.get_world_size() == 1:
+        return counts, entropy
+    import torch
+    t = torch.from_numpy(np.concatenate([np.asarray(counts, np.float64).ravel(), [entropy]]))
+    if d.get_backend() == "nccl":
+        t = t.cuda()
+    d.all_reduce(t, op=d.ReduceOp.SUM)
+    t = t.cpu().numpy()
+    return t[:-1].reshape(np.asarray(counts).shape), float(t[-1])

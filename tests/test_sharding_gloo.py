@@ -54,6 +54,53 @@ def _worker(rank, world, port, out_dir):
         dist.destroy_process_group()
 
 
+def _mstep_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        newick = synth.caterpillar_newick(5)
+        W = 5
+        pwm = synth.random_pwm(W, 0, 3)
+        rng = np.random.default_rng(4)
+        cols = rng.integers(0, 4, size=(21, W, 5)).astype(np.uint8)
+        wts = rng.random(21)
+        # selected windows are sharded like alignments: contiguous blocks
+        lo, hi = sharding.shard_bounds(np.arange(22) * W, world)[rank]
+        fg, _ = _models(newick, pwm)
+        fe = orc.FESet(fg, cols[lo:hi], wts[lo:hi])
+        lam = np.log([0.1, 0.2, 0.3, 0.4])
+        f0, g = fe.grad(2, lam, 1e-4)
+        vals = torch.tensor(np.concatenate([[f0], f0 + g * 1e-4]), dtype=torch.float64)      # [f, f_1..f_dim] of this shard
+        sharding.allreduce_sum_(vals)
+        counts = np.full((W, 3), float(rank + 1))
+        c, e = sharding.allreduce_counts_(counts, 0.5 * (rank + 1))
+        np.savez(os.path.join(out_dir, f"m{rank}.npz"), vals=vals.numpy(), c=c, e=e)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_mstep_values_allreduce(tmp_path):
+    """[f, f_1..f_dim] per shard summed over ranks gives the full-sample forward-difference gradient."""
+    world = 2
+    mp.spawn(_mstep_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    newick = synth.caterpillar_newick(5)
+    W = 5
+    pwm = synth.random_pwm(W, 0, 3)
+    rng = np.random.default_rng(4)
+    cols = rng.integers(0, 4, size=(21, W, 5)).astype(np.uint8)
+    wts = rng.random(21)
+    fg, _ = _models(newick, pwm)
+    f0, g = orc.FESet(fg, cols, wts).grad(2, np.log([0.1, 0.2, 0.3, 0.4]), 1e-4)
+    for r in range(world):
+        z = np.load(tmp_path / f"m{r}.npz")
+        v = z["vals"]
+        assert abs(v[0] - f0) <= 1e-12 * abs(f0)
+        assert np.max(np.abs((v[1:] - v[0]) / 1e-4 - g)) <= 1e-9 * np.max(np.abs(g)) + 64 * np.finfo(float).eps * abs(f0) / 1e-4
+        assert np.array_equal(z["c"], np.full((W, 3), 3.0)) and float(z["e"]) == 1.5
+
+
 def test_shard_bounds_cover_and_balance():
     rng = np.random.default_rng(0)
     lens = rng.integers(300, 401, 750)
