@@ -173,6 +173,18 @@ int phyfoo_scan_hits(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* fg
 int phyfoo_score_order_stats(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* fg, int32_t strand, int32_t n_ranks,
                              const int64_t* ranks, double* values_out, int64_t* n_scores_out);
 
+/* ---- non-phylogenetic alignment models, order 0 (the reference's `model.evolution=false` branch) ----
+ * models/AlignmentBasedModel.java:188-248: window score = sum over species rows of sum over motif positions of
+ * log condprob[i][base], a gap scoring log(0.25); condprob[width][4].  out[windows], alignment-major. */
+int phyfoo_ab_score_windows(phyfoo_ctx* ctx, const phyfoo_dataset* ds, int32_t width, const double* condprob, int32_t strand, double* out);
+/* models/AlignmentBasedBGModel.java:173-246: out[c] = sum over rows of log condprob4[base] (gap: log 0.25) for every column;
+ * getLogProbFor(seq, s, e) is the sum of out over [s, e]. */
+int phyfoo_ab_bg_columns(phyfoo_ctx* ctx, const phyfoo_dataset* ds, const double* condprob4, double* out);
+/* models/AlignmentBasedModel.java:82-168 (count M-step over the selected windows, PSEUDO_COUNT = 1e-8 there): condprob_out[width][4] */
+int phyfoo_ab_train(phyfoo_ctx* ctx, const phyfoo_dataset* ds, int32_t width, int64_t n_sel, const int32_t* sel_aln,
+                    const int32_t* sel_off, const uint8_t* sel_strand, const double* sel_weight, double pseudo_count,
+                    double* condprob_out);
+
 /* ---- M-step data selection (io/SequenceSpecificDataSelector.java:37-99) ----
  * weights[windows] (e.g. gamma_out), one group per alignment: walk the windows by descending weight,
  * take those with raw weight >= q, stop after the running sum of normalised weights exceeds t.

@@ -61,6 +61,9 @@ def lib():
         L.orc_estep.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64), u8p, dp, dp, dp,
                                 C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, C.POINTER(C.c_int32), u8p,
                                 C.POINTER(C.c_longlong)]
+        L.orc_ab_score_windows.argtypes = [dp, C.c_int, u8p, C.c_int, C.c_int, C.c_int, dp]
+        L.orc_ab_bg_range.argtypes = [dp, u8p, C.c_int, C.c_int, C.c_int, C.c_int, dp]
+        L.orc_ab_train.argtypes = [u8p, C.c_int, C.c_int, C.c_int, dp, C.c_double, dp]
         L.orc_select_group.argtypes = [dp, C.c_int, C.c_double, C.c_double, ip, dp]
         L.orc_lambda2pi.argtypes = [dp, dp, C.c_int]
         L.orc_fe_prepare.restype = C.c_void_p
@@ -307,3 +310,30 @@ def pack_columns(codes):
     lib().orc_pack_columns(_u8(codes), n, S, bases.ctypes.data_as(C.POINTER(C.c_uint32)),
                            gaps.ctypes.data_as(C.POINTER(C.c_uint32)))
     return bases, gaps
+
+
+# ---- non-phylogenetic alignment models, order 0 (models/AlignmentBasedModel.java, AlignmentBasedBGModel.java) ----
+def ab_score_windows(condprob, codes, revcomp=False):
+    condprob = np.ascontiguousarray(condprob, np.float64)
+    codes = np.ascontiguousarray(codes, np.uint8)
+    W = condprob.shape[0]
+    out = np.zeros(max(codes.shape[0] - W + 1, 0))
+    lib().orc_ab_score_windows(_dp(condprob), W, _u8(codes), codes.shape[0], codes.shape[1], int(revcomp), _dp(out))
+    return out
+
+
+def ab_bg_range(condprob4, codes, start, end):
+    condprob4 = np.ascontiguousarray(condprob4, np.float64)
+    codes = np.ascontiguousarray(codes, np.uint8)
+    out = C.c_double()
+    lib().orc_ab_bg_range(_dp(condprob4), _u8(codes), codes.shape[0], codes.shape[1], start, end, C.byref(out))
+    return out.value
+
+
+def ab_train(cols, weights, pseudo=1e-8):
+    cols = np.ascontiguousarray(cols, np.uint8)
+    weights = np.ascontiguousarray(weights, np.float64)
+    n, W, S = cols.shape
+    out = np.zeros((W, 4))
+    lib().orc_ab_train(_u8(cols), n, W, S, _dp(weights), pseudo, _dp(out))
+    return out

@@ -981,6 +981,60 @@ int orc_estep(void* hfg, void* hbg, int n_aln, const int64_t* col_offsets, const
     ORC_CATCH(-1)
 }
 
+// ------------------------------------------------------------------------------------------
+// Non-phylogenetic alignment models, order 0 (the `model.evolution=false` branch, models/ModelUtil.java:84-90).
+// models/AlignmentBasedModel.java:188-248: score of a window = sum over species rows o of (sum over motif positions
+// i of log(condProb[i][x] / 1)), a gap scoring log(0.25) (:189-191 isCompletylUnObserved for a single position);
+// the inner sum starts at 0 for every row (:170-175) and is then added to the running total (:241-243).
+// models/AlignmentBasedBGModel.java:173-246: per position, per row, one running total (:236-240).
+// Orders >= 1 use the ACCESS_TABLE expansion with its acknowledged bug (:128-141) and are not restated.
+// ------------------------------------------------------------------------------------------
+int orc_ab_score_windows(const double* condprob /*[W][4]*/, int W, const uint8_t* codes, int L, int S, int revcomp, double* out) {
+    for (int j = 0; j + W <= L; ++j) {
+        double log_sum = 0;
+        for (int o = 0; o < S; ++o) {
+            double sum = 0;
+            for (int i = 0; i < W; ++i) {
+                int c = revcomp ? codes[(size_t)(j + W - 1 - i) * S + o] : codes[(size_t)(j + i) * S + o];
+                if (revcomp && c < 4) c = 3 - c;
+                sum += (c >= 4) ? std::log(0.25) : std::log(condprob[i * 4 + c] / 1);
+            }
+            log_sum += sum;
+        }
+        out[j] = log_sum;
+    }
+    return 0;
+}
+int orc_ab_bg_range(const double* condprob /*[4]*/, const uint8_t* codes, int L, int S, int start, int end, double* out) {
+    double log_sum = 0;
+    for (int l = start; l <= end; ++l)
+        for (int o = 0; o < S; ++o) {
+            const int c = codes[(size_t)l * S + o];
+            log_sum += (c >= 4) ? std::log(0.25) : std::log(condprob[c] / 1);
+        }
+    *out = (end < start) ? 0.0 : log_sum;
+    return 0;
+}
+// AlignmentBasedModel.train :97-168 for order 0: counts[i][b] = PSEUDO_COUNT + sum over selected windows, rows:
+// weight for the observed base, weight / 4 for each base under a gap; then each block of 4 is normalised by its sum
+// (Normalisation.sumNormalisation, jstacs :410-418).  cols [n][W][S].
+int orc_ab_train(const uint8_t* cols, int n, int W, int S, const double* weights, double pseudo, double* condprob_out) {
+    std::vector<double> counts((size_t)W * 4, pseudo);
+    for (int w = 0; w < n; ++w)
+        for (int o = 0; o < S; ++o)
+            for (int l = 0; l < W; ++l) {
+                const int c = cols[((size_t)w * W + l) * S + o];
+                if (c >= 4) for (int a = 0; a < 4; ++a) counts[l * 4 + a] += weights[w] / 4;
+                else counts[l * 4 + c] += weights[w] / 1;
+            }
+    for (int i = 0; i < W; ++i) {
+        double sum = counts[i * 4];
+        for (int k = 1; k < 4; ++k) sum += counts[i * 4 + k];
+        for (int k = 0; k < 4; ++k) condprob_out[i * 4 + k] = counts[i * 4 + k] / sum;
+    }
+    return 0;
+}
+
 int orc_select_group(const double* w, int n, double t, double q, int* idx_out, double* w_out) {
     ORC_TRY return select_group(w, n, t, q, idx_out, w_out); ORC_CATCH(-1)
 }

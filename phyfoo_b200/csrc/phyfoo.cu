@@ -1431,6 +1431,7 @@ extern "C" int phyfoo_synchronize(phyfoo_ctx* ctx) {
 
 #include "mstep.cuh"
 #include "scan.cuh"
+#include "ab.cuh"
 
 // scores every window of the sample into ctx->fg_scores (device) without copying them out
 static int scan_scores(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* fg, int strand, const int64_t** d_woff, int64_t* nw) {

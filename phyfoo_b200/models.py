@@ -352,3 +352,78 @@ class SingleHiddenMotifMixture:
     def getStrandProbabilitiesFor(self, sample: PhyloSample):
         res = self.getNewWeights(sample, want_gamma=False)
         return res["argmax_off"], res["argmax_strand"]
+
+
+class AlignmentBasedModel:
+    """models/AlignmentBasedModel.java, order 0: the non-phylogenetic motif model (`model.evolution=false`): one PWM applied
+    to every species row, gaps scoring log(0.25), count-based M-step."""
+
+    PSEUDO_COUNT = 1e-8                  # :32
+    SKIP_TRAINING_STEPS = 1              # :31
+    PROB_THRESH_FOR_WEIGHTS = 0.8
+    MOTIF_QUALITY_THRESHOLD = 0.0
+
+    def __init__(self, length, order=0, ctx=None):
+        if order != 0:
+            raise NotImplementedError("alignment-based models of order >= 1 are not implemented (DESIGN.md)")
+        self.ctx = ctx or core.default_context()
+        self.length, self.order = int(length), 0
+        self.condProb = np.full((self.length, 4), 0.25)
+        self.trainingStep = 0
+
+    def getLength(self):
+        return self.length
+
+    def setCondProbs(self, condProbs):
+        self.condProb = np.asarray(condProbs, np.float64).reshape(self.length, 4).copy()
+
+    def getCondProbs(self):
+        return self.condProb.copy()
+
+    def getLogProbFor(self, sample: PhyloSample, strand=0):
+        ds = sample.device(self.ctx)
+        out = np.zeros(ds.windows(self.length))
+        cp = np.ascontiguousarray(self.condProb)
+        core.raise_for(core.lib().phyfoo_ab_score_windows(self.ctx.h, ds.h, self.length, core._p(cp, core.C.c_double), int(strand),
+                                                          core._p(out, core.C.c_double)), self.ctx.h)
+        return out
+
+    def train(self, sample: PhyloSample, weights):
+        if self.trainingStep < self.SKIP_TRAINING_STEPS:
+            self.trainingStep += 1
+            return {"skipped": True}
+        ds = sample.device(self.ctx)
+        sa, so, sw = core.select(self.ctx, ds, self.length, weights, self.PROB_THRESH_FOR_WEIGHTS, self.MOTIF_QUALITY_THRESHOLD)
+        out = np.zeros((self.length, 4))
+        core.raise_for(core.lib().phyfoo_ab_train(self.ctx.h, ds.h, self.length, sa.size, core._p(sa, core.C.c_int32),
+                                                  core._p(so, core.C.c_int32), None, core._p(sw, core.C.c_double),
+                                                  float(self.PSEUDO_COUNT), core._p(out, core.C.c_double)), self.ctx.h)
+        self.condProb = out
+        self.trainingStep += 1
+        return {"skipped": False, "selected": int(sa.size)}
+
+
+class AlignmentBasedBGModel:
+    """models/AlignmentBasedBGModel.java, order 0: the non-phylogenetic background."""
+
+    def __init__(self, order=0, ctx=None):
+        if order != 0:
+            raise NotImplementedError("alignment-based models of order >= 1 are not implemented (DESIGN.md)")
+        self.ctx = ctx or core.default_context()
+        self.condProb = np.full(4, 0.25)
+
+    def setCondProbs(self, condProb):
+        self.condProb = np.asarray(condProb, np.float64).reshape(4).copy()
+
+    def getColumnLogProbs(self, sample: PhyloSample):
+        ds = sample.device(self.ctx)
+        out = np.zeros(ds.n_cols)
+        cp = np.ascontiguousarray(self.condProb)
+        core.raise_for(core.lib().phyfoo_ab_bg_columns(self.ctx.h, ds.h, core._p(cp, core.C.c_double), core._p(out, core.C.c_double)),
+                       self.ctx.h)
+        return out
+
+    def getLogProbFor(self, sample: PhyloSample):
+        cols = self.getColumnLogProbs(sample)
+        off = sample.col_offsets
+        return np.array([cols[off[i]:off[i + 1]].sum() for i in range(sample.n_alignments)])
