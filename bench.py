@@ -377,7 +377,8 @@ def run_ours(args):
                 r["note"] = note
             return r
 
-        fg_name = "score_o1_kernel" if cfg["order"] == 1 else "score_o0_kernel"
+        names = {name for (_, name) in kernels}
+        fg_name = ("score_o1w_kernel" if "score_o1w_kernel" in names else "score_o1_kernel") if cfg["order"] == 1 else "score_o0_kernel"
         extra = {}
         if path != 1:
             fg_ms = max(ms for (_, name), ms in kernels.items() if name == fg_name)     # the motif-window launch

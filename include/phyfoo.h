@@ -230,6 +230,8 @@ void phyfoo_fe_free(phyfoo_ctx* ctx, phyfoo_feset* fe);
 int phyfoo_set_option(phyfoo_ctx* ctx, const char* name, int64_t value);
 /* "pattern_memo_sweep_cap" (default 100 = every window is served): sweeps stored per pattern; with a smaller cap the
  * windows that need more go to the direct kernel. */
+/* "order1_kernel": 1 (default) = wavefront kernel (16 lanes per window, list-scheduled node updates), 0 = one quad of
+ * lanes per window walking the nodes one by one.  Same fixed-point iteration; free energies agree to re-association. */
 /* Device time of every kernel the most recent call launched (CUDA events on the library's stream), in launch order:
  * returns the number of entries written (<= max_entries) or a negative error; names are static strings. */
 int phyfoo_last_kernel_times(phyfoo_ctx* ctx, int32_t max_entries, const char** names_out, float* ms_out);

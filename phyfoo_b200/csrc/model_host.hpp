@@ -11,9 +11,11 @@
 //   util/MatrixLinearisation.java:15-19  pi = softmax over consecutive blocks of 4 (lambda space)
 #pragma once
 #include <cmath>
+#include <algorithm>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/phyfoo.h"
@@ -253,6 +255,86 @@ struct ModelHost {
         const int e1 = E1();
         out.assign((size_t)W * e1, 0.0);
         for (int t = 0; t < W; ++t) build_tables1_into(t, pi[t].data(), &out[(size_t)t * e1]);
+    }
+
+    // ---- wavefront kernel (net1w.cuh) ----
+    // tables: per position 64 N logs, node k block [Lo | Ld | LoT | LdT] at 64 k, root block [Lpi | Lpi | LpiT | LpiT];
+    // W + 1 positions (the last all zero) followed by one zero block of 64 for null list entries
+    int E1w() const { return 64 * N; }
+    void tables1w(std::vector<double>& out) const {
+        const int e1 = E1(), ew = E1w();
+        std::vector<double> t1;
+        tables1(t1);
+        out.assign((size_t)(W + 1) * ew + 64, 0.0);
+        for (int t = 0; t < W; ++t) {
+            const double* src = &t1[(size_t)t * e1];
+            double* o = &out[(size_t)t * ew];
+            for (int c = 0; c < 4; ++c)
+                for (int b = 0; b < 4; ++b) {
+                    o[c * 4 + b] = o[16 + c * 4 + b] = src[c * 4 + b];
+                    o[32 + b * 4 + c] = o[48 + b * 4 + c] = src[c * 4 + b];
+                }
+            for (int k = 1; k < N; ++k) {
+                const double* lo = src + 16 + 32 * (k - 1);
+                double* d = o + 64 * k;
+                for (int c = 0; c < 4; ++c)
+                    for (int b = 0; b < 4; ++b) {
+                        d[c * 4 + b] = lo[c * 4 + b]; d[16 + c * 4 + b] = lo[16 + c * 4 + b];
+                        d[32 + b * 4 + c] = lo[c * 4 + b]; d[48 + b * 4 + c] = lo[16 + c * 4 + b];
+                    }
+            }
+        }
+    }
+    // program: par_internal[I] node_of[I] leaf_node[S] leaf_species[S] ich[I][MC] lf[I][ML] sched[n_steps][4]
+    // (padded child / leaf lists, -1 = null) and the list schedule of the W*I node updates into steps of <= 4:
+    // node (t, i) may run once (t, parent), (t-1, i) and (t-1, child) for every internal child are in EARLIER steps.
+    void wave_program(std::vector<int>& prog, int& MC, int& ML, int& n_steps) const {
+        MC = 1; ML = 1;
+        for (int i = 0; i < I; ++i) {
+            MC = std::max(MC, ichild_begin[i + 1] - ichild_begin[i]);
+            ML = std::max(ML, leaf_begin[i + 1] - leaf_begin[i]);
+        }
+        std::vector<int> depth(I, 0);
+        for (int i = 1; i < I; ++i) depth[i] = depth[par_internal[i]] + 1;
+        const int n = W * I;
+        std::vector<int> done(n, -1);                       // step in which the node runs
+        std::vector<int> sched;
+        int left = n, step = 0;
+        while (left > 0) {
+            std::vector<std::pair<int, int>> ready;         // (priority, node id)
+            for (int id = 0; id < n; ++id) {
+                if (done[id] >= 0) continue;
+                const int t = id / I, i = id % I;
+                auto ok = [&](int tt, int ii) { const int d = done[tt * I + ii]; return d >= 0 && d < step; };
+                bool r = true;
+                if (i > 0 && !ok(t, par_internal[i])) r = false;
+                if (r && t > 0) {
+                    if (!ok(t - 1, i)) r = false;
+                    for (int j = ichild_begin[i]; r && j < ichild_begin[i + 1]; ++j) if (!ok(t - 1, ichild[j])) r = false;
+                }
+                if (r) ready.push_back({depth[i] + 2 * t, id});
+            }
+            std::sort(ready.begin(), ready.end());
+            for (int sl = 0; sl < 4; ++sl) {
+                if (sl < (int)ready.size()) {
+                    const int id = ready[sl].second;
+                    done[id] = step; --left;
+                    sched.push_back(((id / I) << 16) | (id % I));
+                } else sched.push_back(-1);
+            }
+            ++step;
+        }
+        n_steps = step;
+        prog.clear();
+        prog.insert(prog.end(), par_internal.begin(), par_internal.end());
+        prog.insert(prog.end(), node_of.begin(), node_of.end());
+        prog.insert(prog.end(), leaf_node.begin(), leaf_node.end());
+        prog.insert(prog.end(), leaf_sp.begin(), leaf_sp.end());
+        for (int i = 0; i < I; ++i)
+            for (int j = 0; j < MC; ++j) prog.push_back(ichild_begin[i] + j < ichild_begin[i + 1] ? ichild[ichild_begin[i] + j] : -1);
+        for (int i = 0; i < I; ++i)
+            for (int j = 0; j < ML; ++j) prog.push_back(leaf_begin[i] + j < leaf_begin[i + 1] ? leaf_begin[i] + j : -1);
+        prog.insert(prog.end(), sched.begin(), sched.end());
     }
 
     void set_pi(int t, const double* v, int n) {

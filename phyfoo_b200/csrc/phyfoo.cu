@@ -69,7 +69,8 @@ struct phyfoo_ctx {
     int64_t gamma_windows = -1;      // number of windows whose gamma of the last E-step is resident in `gamma`
     DevBuf memo_traj;                // pattern-table path: free-energy trajectories (memo.cuh)
     int memo_mode = 1;               // 0 = never, 1 = when it pays off, 2 = whenever it applies
-    int memo_sweep_cap = 100;         // trajectory length of the pattern-table path; longer windows go to the direct kernel
+    int memo_sweep_cap = 100;
+    int order1_kernel = 1;           // 0 = one quad per window (net1.cuh), 1 = wavefront, 16 lanes per window (net1w.cuh)         // trajectory length of the pattern-table path; longer windows go to the direct kernel
     DevBuf memo_pending;             // fallback list of the pattern-table path
     // per-kernel device times of the most recent call (CUDA events on the library's stream)
     struct KTime { const char* name; cudaEvent_t e0, e1; };
@@ -101,6 +102,9 @@ struct phyfoo_model {
     double* d_logtab = nullptr;   // [E][W]
     double* d_probtab = nullptr;  // [E][W]
     double* d_tab1 = nullptr;     // order 1: [W][E1] log tables (net1.cuh)
+    double* d_tab1w = nullptr;    // order 1, wavefront kernel (net1w.cuh)
+    int* d_prog1w = nullptr;
+    int prog1w_len = 0, MC = 1, ML = 1, n_steps = 0;
 };
 
 static thread_local std::string g_init_err;
@@ -744,7 +748,7 @@ extern "C" int phyfoo_model_set_mode(phyfoo_ctx* ctx, phyfoo_model* m, int32_t m
 extern "C" void phyfoo_model_free(phyfoo_ctx* ctx, phyfoo_model* m) {
     if (!m) return;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
-    cudaFree(m->d_prog); cudaFree(m->d_logtab); cudaFree(m->d_probtab); cudaFree(m->d_tab1);
+    cudaFree(m->d_prog); cudaFree(m->d_logtab); cudaFree(m->d_probtab); cudaFree(m->d_tab1); cudaFree(m->d_tab1w); cudaFree(m->d_prog1w);
     delete m;
 }
 
@@ -755,9 +759,16 @@ static int model_upload(phyfoo_ctx* ctx, phyfoo_model* m) {
         return fail(ctx, PHYFOO_EUNSUPPORTED, "background models of order >= 1 are not implemented in this build");
     if (m->uploaded == h.version) return PHYFOO_OK;
     if (h.order == 1) {
-        std::vector<double> t1;
+        std::vector<double> t1, t1w;
         h.tables1v(t1);
+        h.tables1w(t1w);
         if (!m->d_prog) {
+            std::vector<int> pw;
+            h.wave_program(pw, m->MC, m->ML, m->n_steps);
+            m->prog1w_len = (int)pw.size();
+            CU(cudaMalloc(&m->d_prog1w, pw.size() * sizeof(int)));
+            CU(cudaMemcpyAsync(m->d_prog1w, pw.data(), pw.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaMalloc(&m->d_tab1w, t1w.size() * sizeof(double)));
             std::vector<int> prog = h.prog_flat();
             m->prog_len = (int)prog.size();
             CU(cudaMalloc(&m->d_prog, prog.size() * sizeof(int)));
@@ -766,6 +777,7 @@ static int model_upload(phyfoo_ctx* ctx, phyfoo_model* m) {
             CU(cudaStreamSynchronize(ctx->stream));
         }
         CU(cudaMemcpyAsync(m->d_tab1, t1.data(), t1.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(m->d_tab1w, t1w.data(), t1w.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         m->uploaded = h.version;
         return PHYFOO_OK;
@@ -844,6 +856,7 @@ struct ScoreItems {
 };
 
 #include "net1.cuh"
+#include "net1w.cuh"
 #include "memo.cuh"
 
 static void memo_release(cudaStream_t st, MemoSet* ms) {
@@ -1006,6 +1019,50 @@ static int launch_memo_jobs(phyfoo_ctx* ctx, const phyfoo_dataset* ds, const Mem
     return PHYFOO_OK;
 }
 
+// order-1 motif network, wavefront kernel (net1w.cuh): 16 lanes per window, two windows per warp
+static int launch_net1w(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* m, const int64_t* d_win_off, int64_t n_windows,
+                        int strands, double* d_out, int32_t* d_sweeps, int counter_slot, const ScoreItems* items) {
+    ModelHost& h = m->h;
+    const int n_strands = strands == 2 ? 2 : 1;
+    const long long n_items = (long long)n_windows * n_strands;
+    const size_t per_window = (size_t)h.W * h.I * 4 * sizeof(double) + (size_t)h.W * 12;
+    const size_t fixed = (size_t)((m->prog1w_len + 1) & ~1) * sizeof(int) + 32 + 64;
+    const size_t budget = std::min<size_t>(ctx->smem_optin, 227 * 1024);
+    int nwb = 16;
+    while (nwb > 2 && fixed + per_window * nwb > budget / 3) nwb >>= 1;     // three blocks per SM when possible
+    while (nwb > 2 && fixed + per_window * nwb > budget) nwb >>= 1;
+    if (fixed + per_window * nwb > budget) return fail(ctx, PHYFOO_EUNSUPPORTED, "order-1 window state does not fit in shared memory (motif too wide or tree too large)");
+    const size_t smem = fixed + per_window * nwb;
+    CU(cudaFuncSetAttribute(score_o1w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_o1w_kernel, 16 * nwb, smem));
+    if (per_sm < 1) return fail(ctx, PHYFOO_ECUDA, "order-1 wavefront kernel does not fit on an SM");
+    const long long want = (n_items + nwb - 1) / nwb;
+    const int blocks = (int)std::max<long long>(1, std::min<long long>(want, (long long)per_sm * ctx->sm_count));
+    const int64_t n_slots = (int64_t)blocks * nwb;
+    CU(ctx->gstate.ensure((size_t)h.W * h.S * 4 * n_slots * sizeof(double)));
+    Net1wParams p;
+    p.bases = ds->d_bases; p.gaps = ds->d_gaps; p.n_cols = ds->n_cols; p.nb = ds->nb;
+    p.col_off = ds->d_col_off; p.win_off = d_win_off; p.n_aln = ds->n_aln;
+    p.n_windows = n_windows; p.n_strands = n_strands; p.strand0 = strands == 1 ? 1 : 0;
+    p.W = h.W; p.I = h.I; p.S = h.S; p.E1 = h.E1w(); p.prog_len = m->prog1w_len; p.prog = m->d_prog1w;
+    p.MC = m->MC; p.ML = m->ML; p.n_steps = m->n_steps;
+    p.tab = m->d_tab1w;
+    p.out = d_out; p.sweeps = d_sweeps;
+    p.counters = ctx->counters.as<unsigned long long>() + 2 * counter_slot;
+    p.max_sweeps = h.max_sweeps; p.min_sweeps = h.min_sweeps; p.tol = h.tol;
+    p.gq = ctx->gstate.as<double>(); p.n_slots = n_slots; p.nwb = nwb;
+    p.item_col0 = items ? items->col0 : nullptr; p.item_strand = items ? items->strand : nullptr;
+    p.sink_qint = items ? items->q_int : nullptr; p.sink_qleaf = items ? items->q_leaf : nullptr; p.sink_ent = items ? items->ent : nullptr;
+    CU(cudaMemsetAsync(p.counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    {
+        KernelTimer kt_(ctx, "score_o1w_kernel");
+        score_o1w_kernel<<<blocks, 16 * nwb, smem, ctx->stream>>>(p);
+    }
+    CU(cudaGetLastError());
+    return PHYFOO_OK;
+}
+
 // order-1 motif network: quad per window (net1.cuh)
 static int launch_net1(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* m, const int64_t* d_win_off, int64_t n_windows,
                        int strands, double* d_out, int32_t* d_sweeps, int counter_slot, const ScoreItems* items) {
@@ -1013,6 +1070,7 @@ static int launch_net1(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* 
     if (h.mode == PHYFOO_MODE_EXACT && !items)
         return fail(ctx, PHYFOO_EUNSUPPORTED, "exact likelihood of an order-1 network is infeasible in the reference too "
                                               "(SimpleNodeElimination's 9-node frontier, SimpleNodeElimination.java:33-45)");
+    if (ctx->order1_kernel == 1) return launch_net1w(ctx, ds, m, d_win_off, n_windows, strands, d_out, d_sweeps, counter_slot, items);
     const int n_strands = strands == 2 ? 2 : 1;
     const long long n_items = (long long)n_windows * n_strands;
     // windows per block: as many windows per SM as shared memory holds, in multiples of 8 (whole warps).  The kernel is
@@ -1412,6 +1470,11 @@ extern "C" int phyfoo_set_option(phyfoo_ctx* ctx, const char* name, int64_t valu
     if (std::strcmp(name, "pattern_memo") == 0) {
         if (value < 0 || value > 2) return fail(ctx, PHYFOO_EINVAL, "set_option: pattern_memo must be 0 (off), 1 (auto) or 2 (always)");
         ctx->memo_mode = (int)value;
+        return PHYFOO_OK;
+    }
+    if (std::strcmp(name, "order1_kernel") == 0) {
+        if (value != 0 && value != 1) return fail(ctx, PHYFOO_EINVAL, "set_option: order1_kernel must be 0 (quad per window) or 1 (wavefront)");
+        ctx->order1_kernel = (int)value;
         return PHYFOO_OK;
     }
     if (std::strcmp(name, "pattern_memo_sweep_cap") == 0) {

@@ -141,3 +141,42 @@ def test_order1_fixed_q_objective_and_gradient(ctx, tree, gap_rate):
         fe.eval(t, np.log(pwm[t].ravel())); ofe.eval(t, np.log(pwm[t].ravel()))
     direct = sum(w * om.score_window(c)[0] for w, c in zip(sw, cols))
     assert abs(fe.eval(0, np.log(pwm[0].ravel())) - direct) <= 1e-9 * abs(direct)
+
+
+@pytest.mark.parametrize("tree", ["star5", "cat5", "mixed6", "rand12"])
+def test_order1_wavefront_equals_node_by_node_kernel(ctx, tree):
+    """The wavefront kernel (list-scheduled node updates, 16 lanes per window) against the quad kernel that walks the nodes
+    one by one: identical sweep counts, free energies equal to re-association, both strands, gaps, the M-step objective."""
+    from phyfoo_b200 import core, synth
+    from phyfoo_b200.data import PhyloSample
+    from phyfoo_b200.models import PhyloBayesModel
+    from phyfoo_b200.newick import parse_newick
+    newick = _trees()[tree]
+    S = parse_newick(newick).n_species
+    rng = np.random.default_rng(43)
+    W = 7
+    pwm = synth.random_pwm(W, 1, 91)
+    lens = [W, 61, 2, 95, W + 1]
+    smp = PhyloSample(random_codes(rng, sum(lens), S, 0.1), np.concatenate([[0], np.cumsum(lens)]))
+    fg = PhyloBayesModel(W, 1, newick, ctx); fg.setCondProbs(pwm)
+    try:
+        res = {}
+        for kern in (0, 1):
+            ctx.set_option("order1_kernel", kern)
+            res[kern] = [fg.getLogProbFor(smp, strand=s, want_sweeps=True) for s in (0, 1)]
+            names = [n for n, _ in ctx.last_kernel_times()]
+            assert names == ["score_o1w_kernel" if kern else "score_o1_kernel"]
+            n = res[kern][0][0].size
+            sa, so = np.repeat(np.arange(smp.n_alignments), np.maximum(smp.lengths() - W + 1, 0))[: min(n, 40)], None
+            off = smp.device(ctx).window_offsets(W)
+            so = (np.arange(n)[: sa.size] - off[sa]).astype(np.int32)
+            fe = core.FESet(ctx, smp.device(ctx), fg.device_model(), sa.astype(np.int32), so, np.linspace(0.5, 1.5, sa.size))
+            res[kern].append(fe.grad(2, np.log(pwm[2].ravel()) + 0.05, 1e-4))
+            fe.eval(2, np.log(pwm[2].ravel()))
+        for s in (0, 1):
+            assert np.array_equal(res[0][s][1], res[1][s][1])
+            assert rel_err(res[1][s][0], res[0][s][0]) < 1e-12
+        (f0, g0), (f1, g1) = res[0][2], res[1][2]
+        assert abs(f0 - f1) <= 1e-12 * abs(f0) and np.max(np.abs(g0 - g1)) <= 1e-9 * np.max(np.abs(g0)) + 64 * np.finfo(float).eps * abs(f0) / 1e-4
+    finally:
+        ctx.set_option("order1_kernel", 1)
