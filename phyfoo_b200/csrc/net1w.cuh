@@ -38,11 +38,15 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
     extern __shared__ double smem[];
     const int tid = threadIdx.x, T = blockDim.x;
     const int nwb = p.nwb;
-    double* s_q = smem;                                                  // [W*I][nwb][4]
-    double* s_virt = s_q + (size_t)p.W * p.I * 4 * nwb;                  // [4] one-hot
-    uint64_t* s_cb = (uint64_t*)(s_virt + 4);                            // [W][nwb]
-    uint32_t* s_cg = (uint32_t*)(s_cb + (size_t)p.W * nwb);              // [W][nwb]
-    int* s_prog = (int*)(s_cg + (size_t)p.W * nwb);
+    // q rows are padded by one 32-byte slot: the four node slots of a window read four different rows at once, and with a
+    // row stride of a multiple of 128 bytes they would all hit the same banks
+    const int qs = 4 * nwb + 4;
+    double* s_q = smem;                                                  // [W*I][nwb (+1)][4]
+    double* s_virt = s_q + (size_t)p.W * p.I * qs;                       // [4] one-hot
+    int* s_prog = (int*)(s_virt + 4);
+    // leaf codes of the window: observation of (position t, leaf slot kk) in the low nibble, of (t-1, kk) in the high
+    // nibble (0 at t = 0), 4 = unobserved; [W*S][nwb] bytes behind the program
+    uint8_t* s_lc = (uint8_t*)(s_prog + p.prog_len);
     for (int i = tid; i < p.prog_len; i += T) s_prog[i] = p.prog[i];
     if (tid < 4) s_virt[tid] = tid == 0 ? 1.0 : 0.0;
     __syncthreads();
@@ -62,7 +66,6 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
     const int wb = lane & ~15;               // first lane of this window
     const unsigned qmask = 0xFu << qb;
     const unsigned full = 0xffffffffu;
-    const int qs = 4 * nwb;
     double* qbase = s_q + 4 * wq;
     const double* zero_blk = p.tab + (size_t)(p.W + 1) * p.E1;
     const int64_t gslot = (int64_t)blockIdx.x * nwb + wq;
@@ -73,7 +76,7 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
     int k = 0;
     long long item = -1;
     double old = 0.0;
-    for (int t = l16; t < p.W; t += 16) { s_cb[t * nwb + wq] = 0; s_cg[t * nwb + wq] = 0; }
+    for (int j = l16; j < p.W * p.S; j += 16) s_lc[j * nwb + wq] = 0;
 
     for (;;) {
         if (need && active) {
@@ -94,8 +97,13 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
                 for (int t = l16; t < p.W; t += 16) {
                     const int64_t col = strand ? c0 + (p.W - 1 - t) : c0 + t;     // jstacs StrandModel.java:636-639
                     ColWords cw = load_column(p.bases, p.gaps, p.n_cols, p.nb, col);
-                    if (strand) cw = complement(cw);
-                    s_cb[t * nwb + wq] = cw.b; s_cg[t * nwb + wq] = cw.g;
+                    ColWords cwp; cwp.b = 0; cwp.g = 0;
+                    if (t > 0) cwp = load_column(p.bases, p.gaps, p.n_cols, p.nb, strand ? col + 1 : col - 1);
+                    if (strand) { cw = complement(cw); cwp = complement(cwp); }
+                    for (int kk = 0; kk < p.S; ++kk) {
+                        const int sp = leaf_species[kk];
+                        s_lc[(t * p.S + kk) * nwb + wq] = (uint8_t)(cw.obs(sp) | ((t > 0 ? cwp.obs(sp) : 0) << 4));
+                    }
                 }
                 k = 0; conv = false; upd = false; need = false;
             }
@@ -119,10 +127,7 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
             const double* qprv = t ? qcur - p.I * qs : s_virt;
             const int sprv = t ? qs : 0;
             const double* qnxt = has_next ? qcur + p.I * qs : qcur;
-            ColWords cw, cwp, cwn;
-            cw.b = s_cb[t * nwb + wq]; cw.g = s_cg[t * nwb + wq];
-            cwp.b = t ? s_cb[(t - 1) * nwb + wq] : 0; cwp.g = t ? s_cg[(t - 1) * nwb + wq] : 0;
-            cwn.b = has_next ? s_cb[(t + 1) * nwb + wq] : 0; cwn.g = has_next ? s_cg[(t + 1) * nwb + wq] : 0;
+            const uint8_t* lct = s_lc + (size_t)t * p.S * nwb + wq;          // leaf codes of this position
 
             const int par = par_internal[i];
             const int nb = 64 * node_of[i];
@@ -157,9 +162,8 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
             for (int j = 0; j < p.ML; ++j) {
                 const int kk = lf[i * p.ML + j];
                 if (kk < 0 || !live) continue;
-                const int sp = leaf_species[kk];
-                const int x = cw.obs(sp);
-                const int y = t > 0 ? cwp.obs(sp) : 0;
+                const int lc = lct[kk * nwb];
+                const int x = lc & 15, y = lc >> 4;
                 if (x < 4) {
                     const double* Ll = tab + 64 * leaf_node[kk] + (a == x ? 16 : 0);
                     if (y < 4) cobs += __ldg(Ll + y * 4 + x);
@@ -204,9 +208,9 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
                 for (int j = 0; j < p.ML; ++j) {
                     const int kk = lf[i * p.ML + j];
                     if (kk < 0) continue;
-                    const int sp = leaf_species[kk];
-                    if (cw.obs(sp) < 4) continue;
-                    const int y = t > 0 ? cwp.obs(sp) : 0;
+                    const int lc = lct[kk * nwb];
+                    if ((lc & 15) < 4) continue;
+                    const int y = lc >> 4;
                     const double qsum = n1_sum(n1_q4(qcur + i * qs));
                     double ownl = 0.0, own_fe;
                     if (t == 0) { ownl = qsum * __ldg(tab + a); own_fe = ownl; }
@@ -221,7 +225,7 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
                     }
                     double nl = 0.0;
                     if (has_next) {
-                        const int xn = cwn.obs(sp);
+                        const int xn = lct[(p.S + kk) * nwb] & 15;
                         const N1Vec4 qpn = n1_q4(qnxt + i * qs);
                         if (xn < 4) {
                             const double* Lno = tabn + 64 * leaf_node[kk];
@@ -268,8 +272,7 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
                         const int t = j / (p.S * 4), kk = (j >> 2) % p.S;
                         const double v = p.gq[(size_t)j * p.n_slots + gslot];
                         p.sink_qleaf[(size_t)j * p.n_windows + item] = v;
-                        ColWords cwt; cwt.b = s_cb[t * nwb + wq]; cwt.g = s_cg[t * nwb + wq];
-                        if (cwt.obs(leaf_species[kk]) >= 4) ent += v > 0.0 ? v * phy_log(v) : 0.0;
+                        if ((s_lc[(t * p.S + kk) * nwb + wq] & 15) >= 4) ent += v > 0.0 ? v * phy_log(v) : 0.0;
                     }
                     const unsigned wm = 0xFFFFu << wb;
                     ent += __shfl_xor_sync(wm, ent, 1); ent += __shfl_xor_sync(wm, ent, 2);
