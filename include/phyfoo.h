@@ -140,6 +140,15 @@ int phyfoo_score_windows(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model
 int phyfoo_bg_columns(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* bg, double* out,
                       int32_t* sweeps_out, phyfoo_stats* stats);
 
+/* Order-1 background (models/PhyloBackground.java:241-305).  For a range [s, e] with e > s the reference returns
+ *   -F(0,0) of the window (s, s+1)  +  sum_{u = s+1..e} -F(1,1) of the window (u-1, u)
+ * (each window's mean field optimised on its own).  cond_out[c] = the conditional term of column c (0 at the first column
+ * of an alignment), first_out[c] (nullable) = the start term of a range beginning at column c (0 at the last column of an
+ * alignment); getLogProbFor(seq, s, e) = first[s] + sum cond[s+1..e].  Ranges of a single column have no defined value in
+ * the reference (stale observations, MeanFieldForBayesNet.java:84) -- which is why the ZOOPS E-step is not offered with
+ * an order-1 background -- and alignments shorter than 2 columns are refused. */
+int phyfoo_bg_columns_order1(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* bg, double* cond_out, double* first_out);
+
 /* ZOOPS E-step over the whole (local) sample: SingleHiddenMotifMixture.getNewWeights.
  *   logw[2]          log component weights (motif, no motif)
  *   strand_logw      NULL, or log strand weights [2] (motif wrapped in a StrandModel)

@@ -26,6 +26,7 @@ struct Net1wParams {
     int MC, ML, n_steps;
     const double* tab;       // [W + 1][E1] + 64 zeros
     double* out; int32_t* sweeps;
+    double* out_last;        // nullable: free energy of the LAST tree alone (background ranges: calcFreeEnergy(order, order))
     unsigned long long* counters;
     int max_sweeps, min_sweeps; double tol;
     double* gq; int64_t n_slots;
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
         if (!__any_sync(full, active)) break;
 
         // ---- one sweep (or the pass at the uniform start), in wavefront steps
-        double F = 0.0;
+        double F = 0.0, Flast = 0.0;          // Flast: terms of the last tree only
         for (int step = 0; step < p.n_steps; ++step) {
             const int code = sched[step * 4 + slot];
             const bool live = code >= 0;
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
             __syncwarp();
             if (live) qcur[i * qs + a] = qn;
             __syncwarp();
-            if (live) F += qn * ((lq - own) - cobs);
+            if (live) { const double f = qn * ((lq - own) - cobs); F += f; if (!has_next) Flast += f; }
 
             // unobserved leaf children: update + free-energy terms (the only divergent part)
             if (live) {
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
                     __syncwarp(qmask);
                     GQ(t, kk, a) = ql;
                     __syncwarp(qmask);
-                    F += ql * (lql - own_fe);
+                    { const double f = ql * (lql - own_fe); F += f; if (!has_next) Flast += f; }
                 }
             }
         }
@@ -252,6 +253,12 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
         F += __shfl_xor_sync(full, F, 4);
         F += __shfl_xor_sync(full, F, 8);
         const double Fsum = F;
+        if (p.out_last) {
+            Flast += __shfl_xor_sync(full, Flast, 1);
+            Flast += __shfl_xor_sync(full, Flast, 2);
+            Flast += __shfl_xor_sync(full, Flast, 4);
+            Flast += __shfl_xor_sync(full, Flast, 8);
+        }
         if (active) {
             bool done;
             if (!upd) { old = Fsum; upd = true; done = false; }               // F_0, MeanFieldForBayesNet.java:105
@@ -280,6 +287,7 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
                     if (l16 == 0) p.sink_ent[item] = ent;
                 }
                 if (l16 == 0) {
+                    if (p.out_last) p.out_last[item] = -Flast;
                     p.out[item] = -Fsum;                                      // PhyloBayesModel.java:259
                     if (p.sweeps) p.sweeps[item] = k;
                     atomicAdd(&p.counters[1], (unsigned long long)k);

@@ -755,8 +755,8 @@ extern "C" void phyfoo_model_free(phyfoo_ctx* ctx, phyfoo_model* m) {
 // copy the order-0 tables to the device in [E][W] layout when the parameters changed
 static int model_upload(phyfoo_ctx* ctx, phyfoo_model* m) {
     ModelHost& h = m->h;
-    if (h.order != 0 && !(h.order == 1 && h.kind == PHYFOO_MODEL_FG))
-        return fail(ctx, PHYFOO_EUNSUPPORTED, "background models of order >= 1 are not implemented in this build");
+    if (h.order != 0 && h.order != 1)
+        return fail(ctx, PHYFOO_EUNSUPPORTED, "background models of order >= 2 are not implemented in this build");
     if (m->uploaded == h.version) return PHYFOO_OK;
     if (h.order == 1) {
         std::vector<double> t1, t1w;
@@ -853,6 +853,7 @@ static int plan_score(phyfoo_ctx* ctx, const ModelHost& h, int prog_len, long lo
 struct ScoreItems {
     const int64_t* col0; const uint8_t* strand; double* q_int; double* q_leaf; double* ent;
     const int* n_dev = nullptr; const int64_t* dst = nullptr; bool fallback = false;
+    double* out_last = nullptr;     // order-1 kernels: free energy of the last tree alone (background ranges)
 };
 
 #include "net1.cuh"
@@ -1049,7 +1050,7 @@ static int launch_net1w(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model*
     p.W = h.W; p.I = h.I; p.S = h.S; p.E1 = h.E1w(); p.prog_len = m->prog1w_len; p.prog = m->d_prog1w;
     p.MC = m->MC; p.ML = m->ML; p.n_steps = m->n_steps;
     p.tab = m->d_tab1w;
-    p.out = d_out; p.sweeps = d_sweeps;
+    p.out = d_out; p.sweeps = d_sweeps; p.out_last = items ? items->out_last : nullptr;
     p.counters = ctx->counters.as<unsigned long long>() + 2 * counter_slot;
     p.max_sweeps = h.max_sweeps; p.min_sweeps = h.min_sweeps; p.tol = h.tol;
     p.gq = ctx->gstate.as<double>(); p.n_slots = n_slots; p.nwb = nwb;
@@ -1240,6 +1241,74 @@ static int launch_bg_columns(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_m
     if (bg->h.kind != PHYFOO_MODEL_BG) return fail(ctx, PHYFOO_EINVAL, "bg_columns: model is not a background model");
     if (bg->h.order != 0) return fail(ctx, PHYFOO_EUNSUPPORTED, "background order >= 1 is not implemented in this build");
     return launch_score(ctx, ds, bg, ds->d_col_off, ds->n_cols, 0, d_out, d_sweeps, slot);
+}
+
+// order-1 background (models/PhyloBackground.java:241-305): every 2-column window (u-1, u) of every alignment through the
+// order-1 network kernel (W = 2); its free energy restricted to the last tree is the conditional term of column u
+// (:284-297 calcFreeEnergy(order, order)), restricted to the first tree the start term of a range beginning at u-1
+// (:273-283 calcFreeEnergy(0, 0)).
+__global__ void bg1_items_kernel(const int64_t* __restrict__ win_off, const int64_t* __restrict__ col_off, int n_aln, int64_t n,
+                                 int64_t* __restrict__ col0) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n) return;
+    const int a = find_alignment(win_off, n_aln, u);
+    col0[u] = col_off[a] + (u - win_off[a]);
+}
+// cond[c0 + 1] = last-tree term of window c0; first[c0] = whole-window term minus the last-tree term
+__global__ void bg1_scatter_kernel(const int64_t* __restrict__ col0, const double* __restrict__ total, const double* __restrict__ last,
+                                   int64_t n, double* __restrict__ cond, double* __restrict__ first) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n) return;
+    cond[col0[u] + 1] = last[u];
+    if (first) first[col0[u]] = total[u] - last[u];
+}
+
+extern "C" int phyfoo_bg_columns_order1(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* bg, double* cond_out, double* first_out) {
+    if (!ctx) return PHYFOO_EINVAL;
+    if (!ds || !bg || !cond_out) return fail(ctx, PHYFOO_EINVAL, "bg_columns_order1: NULL argument");
+    if (bg->h.kind != PHYFOO_MODEL_BG || bg->h.order != 1) return fail(ctx, PHYFOO_EINVAL, "bg_columns_order1: needs a background model of order 1");
+    if (bg->h.mode != PHYFOO_MODE_MEANFIELD) return fail(ctx, PHYFOO_EUNSUPPORTED, "bg_columns_order1: exact mode is not defined for order-1 networks");
+    if (bg->h.S != ds->S) return fail(ctx, PHYFOO_EINVAL, "model and dataset disagree on the number of species");
+    CU(cudaSetDevice(ctx->device));
+    ctx->launches = 0; ctx->n_ktimes = 0;
+    if (ds->n_aln > 0 && ds->min_len < 2) return fail(ctx, PHYFOO_EINVAL, "bg_columns_order1: an alignment is shorter than order + 1 columns (the reference's score of such a range is not a function of the inputs, MeanFieldForBayesNet.java:84)");
+    int rc = model_upload(ctx, bg);
+    if (rc) return rc;
+    if (!bg->h.tables_finite()) return fail(ctx, PHYFOO_EUNSUPPORTED, "a CPF entry is 0: the reference's free energy is not finite for this parameter set");
+    const int64_t* d_woff; const std::vector<int64_t>* h_woff;
+    rc = dataset_win_off(ctx, ds, 2, &d_woff, &h_woff);
+    if (rc) return rc;
+    const int64_t n = h_woff->back(), nc = ds->n_cols;
+    if (n == 0) return PHYFOO_OK;
+    CU(ctx->bg_scores.ensure((size_t)(2 * n + 2 * nc) * sizeof(double)));
+    CU(ctx->misc.ensure((size_t)n * sizeof(int64_t)));
+    double* d_total = ctx->bg_scores.as<double>();
+    double* d_last = d_total + n;
+    double* d_cond = d_last + n;
+    double* d_first = d_cond + nc;
+    int64_t* d_col0 = ctx->misc.as<int64_t>();
+    CU(cudaMemsetAsync(d_cond, 0, (size_t)2 * nc * sizeof(double), ctx->stream));
+    {
+        KernelTimer kt_(ctx, "bg1_items_kernel");
+        bg1_items_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_woff, ds->d_col_off, ds->n_aln, n, d_col0);
+    }
+    CU(cudaGetLastError());
+    ScoreItems items{d_col0, nullptr, nullptr, nullptr, nullptr};
+    items.out_last = d_last;
+    const int keep = ctx->order1_kernel;
+    ctx->order1_kernel = 1;                       // the per-tree output lives in the wavefront kernel
+    rc = launch_net1(ctx, ds, bg, nullptr, n, 0, d_total, nullptr, 1, &items);
+    ctx->order1_kernel = keep;
+    if (rc) return rc;
+    {
+        KernelTimer kt_(ctx, "bg1_scatter_kernel");
+        bg1_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_col0, d_total, d_last, n, d_cond, first_out ? d_first : nullptr);
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(cond_out, d_cond, (size_t)nc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (first_out) CU(cudaMemcpyAsync(first_out, d_first, (size_t)nc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PHYFOO_OK;
 }
 
 extern "C" int phyfoo_bg_columns(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* bg, double* out,

@@ -25,7 +25,7 @@ SYMBOLS = [
     "phyfoo_dataset_windows", "phyfoo_dataset_patterns", "phyfoo_dataset_free",
     "phyfoo_model_create", "phyfoo_model_set_pi", "phyfoo_model_get_pi", "phyfoo_model_set_branch",
     "phyfoo_model_set_mode", "phyfoo_model_free",
-    "phyfoo_score_windows", "phyfoo_bg_columns", "phyfoo_zoops_estep", "phyfoo_zoops_estep_device",
+    "phyfoo_score_windows", "phyfoo_bg_columns", "phyfoo_bg_columns_order1", "phyfoo_zoops_estep", "phyfoo_zoops_estep_device",
     "phyfoo_ab_score_windows", "phyfoo_ab_bg_columns", "phyfoo_ab_train", "phyfoo_scan_hits", "phyfoo_score_order_stats", "phyfoo_select", "phyfoo_fe_prepare", "phyfoo_fe_prepare_all", "phyfoo_fe_eval", "phyfoo_fe_grad",
     "phyfoo_fe_values_device", "phyfoo_fe_suffstats", "phyfoo_fe_size", "phyfoo_fe_free",
     "phyfoo_set_option", "phyfoo_last_score_path", "phyfoo_last_kernel_times", "phyfoo_host_alloc", "phyfoo_host_free",
@@ -92,6 +92,7 @@ def lib():
     L.phyfoo_model_free.restype = None
     L.phyfoo_score_windows.argtypes = [vp, vp, vp, C.c_int32, dp, ip32, sp]
     L.phyfoo_bg_columns.argtypes = [vp, vp, vp, dp, ip32, sp]
+    L.phyfoo_bg_columns_order1.argtypes = [vp, vp, vp, dp, dp]
     L.phyfoo_zoops_estep.argtypes = [vp, vp, vp, vp, dp, dp, dp, dp, dp, dp, dp, ip32, u8p, sp]
     L.phyfoo_zoops_estep_device.argtypes = [vp, vp, vp, vp, dp, dp, vp, vp, vp]
     L.phyfoo_ab_score_windows.argtypes = [vp, vp, C.c_int32, dp, C.c_int32, dp]

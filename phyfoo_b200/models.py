@@ -243,10 +243,37 @@ class PhyloBackground(_PhyloModel):
         self.last_stats = st
         return (out, sw) if want_sweeps else out
 
+    def getRangeTerms(self, sample: PhyloSample):
+        """Order-1 background: (cond, first) per column with getLogProbFor(seq, s, e) = first[s] + sum(cond[s+1..e]) for e > s
+        (models/PhyloBackground.java:273-297); see phyfoo_bg_columns_order1."""
+        if self.order != 1:
+            raise ValueError("getRangeTerms is for order-1 backgrounds; order 0 uses getColumnLogProbs")
+        self._check(sample)
+        ds = sample.device(self.ctx)
+        cond, first = np.zeros(ds.n_cols), np.zeros(ds.n_cols)
+        core.raise_for(core.lib().phyfoo_bg_columns_order1(self.ctx.h, ds.h, self.device_model().h, core._p(cond, core.C.c_double),
+                                                           core._p(first, core.C.c_double)), self.ctx.h)
+        return cond, first
+
+    def getLogProbForRange(self, sample: PhyloSample, aln, start, end):
+        """getLogProbFor(seq, start, end) for one alignment (end inclusive)."""
+        if end < start:
+            return 0.0
+        off = int(sample.col_offsets[aln])
+        if self.order == 0:
+            return float(self.getColumnLogProbs(sample)[off + start: off + end + 1].sum())
+        if end == start:
+            raise ValueError("a single-column range has no defined value under an order-1 background in the reference")
+        cond, first = self.getRangeTerms(sample)
+        return float(first[off + start] + cond[off + start + 1: off + end + 1].sum())
+
     def getLogProbFor(self, sample: PhyloSample):
         """double[] getLogProbFor(Sample) (jstacs AbstractModel.java:217-240): one value per alignment."""
-        cols = self.getColumnLogProbs(sample)
         off = sample.col_offsets
+        if self.order == 1:
+            cond, first = self.getRangeTerms(sample)
+            return np.array([first[off[i]] + cond[off[i] + 1:off[i + 1]].sum() for i in range(sample.n_alignments)])
+        cols = self.getColumnLogProbs(sample)
         return np.array([cols[off[i]:off[i + 1]].sum() for i in range(sample.n_alignments)])
 
 

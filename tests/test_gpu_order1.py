@@ -180,3 +180,36 @@ def test_order1_wavefront_equals_node_by_node_kernel(ctx, tree):
         assert abs(f0 - f1) <= 1e-12 * abs(f0) and np.max(np.abs(g0 - g1)) <= 1e-9 * np.max(np.abs(g0)) + 64 * np.finfo(float).eps * abs(f0) / 1e-4
     finally:
         ctx.set_option("order1_kernel", 1)
+
+
+@pytest.mark.parametrize("tree", ["cat5", "rand12"])
+@pytest.mark.parametrize("gap_rate", [0.0, 0.1])
+def test_order1_background_ranges(ctx, tree, gap_rate):
+    """PhyloBackground of order 1 (models/PhyloBackground.java:241-305): whole-alignment scores and sub-ranges of at least two
+    columns against the oracle's bg_range; single-column ranges and too short alignments are refused."""
+    from phyfoo_b200.data import PhyloSample
+    from phyfoo_b200.lib import IllegalArgumentException
+    from phyfoo_b200.models import PhyloBackground
+    from phyfoo_b200.newick import parse_newick
+    newick = _trees()[tree]
+    S = parse_newick(newick).n_species
+    rng = np.random.default_rng(47)
+    lens = [2, 31, 9, 50]
+    smp = PhyloSample(random_codes(rng, sum(lens), S, gap_rate), np.concatenate([[0], np.cumsum(lens)]))
+    pi = [rng.dirichlet(np.ones(4), size=1), rng.dirichlet(np.ones(4), size=4)]
+    bg = PhyloBackground(1, newick, ctx)
+    bg.setCondProbs(pi)
+    ob = oracle_bg(newick, 1, pi)
+    per = bg.getLogProbFor(smp)
+    for i, L in enumerate(lens):
+        r = ob.bg_range(smp.getElementAt(i), 0, L - 1)
+        assert abs(per[i] - r) <= TOL * abs(r), (i, per[i], r)
+    for (i, s, e) in ((1, 3, 20), (3, 0, 1), (3, 17, 49), (2, 7, 8)):
+        r = ob.bg_range(smp.getElementAt(i), s, e)
+        assert abs(bg.getLogProbForRange(smp, i, s, e) - r) <= TOL * abs(r)
+    assert bg.getLogProbForRange(smp, 1, 5, 4) == 0.0
+    with pytest.raises(ValueError):
+        bg.getLogProbForRange(smp, 1, 5, 5)
+    short = PhyloSample(random_codes(rng, 4, S), [0, 1, 4])
+    with pytest.raises(IllegalArgumentException):
+        bg.getLogProbFor(short)
