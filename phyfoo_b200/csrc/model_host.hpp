@@ -260,12 +260,12 @@ struct ModelHost {
     // ---- wavefront kernel (net1w.cuh) ----
     // tables: per position 64 N logs, node k block [Lo | Ld | LoT | LdT] at 64 k, root block [Lpi | Lpi | LpiT | LpiT];
     // W + 1 positions (the last all zero) followed by one zero block of 64 for null list entries
-    int E1w() const { return 64 * N; }
+    int E1w() const { return 64 * (N + 1); }   // block N of every position is all zero (null leaf entries)
     void tables1w(std::vector<double>& out) const {
         const int e1 = E1(), ew = E1w();
         std::vector<double> t1;
         tables1(t1);
-        out.assign((size_t)(W + 1) * ew + 64, 0.0);
+        out.assign((size_t)(W + 1) * ew, 0.0);
         for (int t = 0; t < W; ++t) {
             const double* src = &t1[(size_t)t * e1];
             double* o = &out[(size_t)t * ew];
@@ -335,6 +335,22 @@ struct ModelHost {
         for (int i = 0; i < I; ++i)
             for (int j = 0; j < ML; ++j) prog.push_back(leaf_begin[i] + j < leaf_begin[i + 1] ? leaf_begin[i] + j : -1);
         prog.insert(prog.end(), sched.begin(), sched.end());
+        // node records [I][2 + 3 MC + 2 ML]: par, 64 node | per child: internal index (self if null), 64 node(child), live flag
+        // | per leaf: CSR slot (S if null), 64 node(leaf) (64 N = the zero block if null)
+        for (int i = 0; i < I; ++i) {
+            prog.push_back(par_internal[i]);
+            prog.push_back(64 * node_of[i]);
+            for (int j = 0; j < MC; ++j) {
+                const bool has = ichild_begin[i] + j < ichild_begin[i + 1];
+                const int ci = has ? ichild[ichild_begin[i] + j] : i;
+                prog.push_back(ci); prog.push_back(64 * node_of[ci]); prog.push_back(has ? 1 : 0);
+            }
+            for (int j = 0; j < ML; ++j) {
+                const bool has = leaf_begin[i] + j < leaf_begin[i + 1];
+                prog.push_back(has ? leaf_begin[i] + j : S);
+                prog.push_back(has ? 64 * leaf_node[leaf_begin[i] + j] : 64 * N);
+            }
+        }
     }
 
     void set_pi(int t, const double* v, int n) {

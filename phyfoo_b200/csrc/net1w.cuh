@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
     int* s_prog = (int*)(s_virt + 4);
     // leaf codes of the window: observation of (position t, leaf slot kk) in the low nibble, of (t-1, kk) in the high
     // nibble (0 at t = 0), 4 = unobserved; [W*S][nwb] bytes behind the program
-    uint8_t* s_lc = (uint8_t*)(s_prog + p.prog_len);
+    uint8_t* s_lc = (uint8_t*)(s_prog + p.prog_len);                     // [W][S + 1][nwb], row S stays 0
     for (int i = tid; i < p.prog_len; i += T) s_prog[i] = p.prog[i];
     if (tid < 4) s_virt[tid] = tid == 0 ? 1.0 : 0.0;
     __syncthreads();
@@ -58,6 +58,10 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
     const int* ich = s_prog + 2 * p.I + 2 * p.S;
     const int* lf = ich + p.I * p.MC;
     const int* sched = lf + p.I * p.ML;
+    // node records: everything a node update needs besides t, as table / row offsets with null entries already resolved
+    // (null child: the node itself with weight 0; null leaf: leaf row S (code 0) and the zero table block N)
+    const int R = 2 + 3 * p.MC + 2 * p.ML;
+    const int* rec = sched + 4 * p.n_steps;
 
     const int lane = tid & 31;
     const int wq = tid >> 4;                 // window slot in the block
@@ -68,7 +72,6 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
     const unsigned qmask = 0xFu << qb;
     const unsigned full = 0xffffffffu;
     double* qbase = s_q + 4 * wq;
-    const double* zero_blk = p.tab + (size_t)(p.W + 1) * p.E1;
     const int64_t gslot = (int64_t)blockIdx.x * nwb + wq;
     auto GQ = [&](int t, int kk, int s) -> double& { return p.gq[(size_t)((t * p.S + kk) * 4 + s) * p.n_slots + gslot]; };
 
@@ -77,7 +80,7 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
     int k = 0;
     long long item = -1;
     double old = 0.0;
-    for (int j = l16; j < p.W * p.S; j += 16) s_lc[j * nwb + wq] = 0;
+    for (int j = l16; j < p.W * (p.S + 1); j += 16) s_lc[j * nwb + wq] = 0;
 
     for (;;) {
         if (need && active) {
@@ -103,7 +106,7 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
                     if (strand) { cw = complement(cw); cwp = complement(cwp); }
                     for (int kk = 0; kk < p.S; ++kk) {
                         const int sp = leaf_species[kk];
-                        s_lc[(t * p.S + kk) * nwb + wq] = (uint8_t)(cw.obs(sp) | ((t > 0 ? cwp.obs(sp) : 0) << 4));
+                        s_lc[(t * (p.S + 1) + kk) * nwb + wq] = (uint8_t)(cw.obs(sp) | ((t > 0 ? cwp.obs(sp) : 0) << 4));
                     }
                 }
                 k = 0; conv = false; upd = false; need = false;
@@ -128,10 +131,9 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
             const double* qprv = t ? qcur - p.I * qs : s_virt;
             const int sprv = t ? qs : 0;
             const double* qnxt = has_next ? qcur + p.I * qs : qcur;
-            const uint8_t* lct = s_lc + (size_t)t * p.S * nwb + wq;          // leaf codes of this position
-
-            const int par = par_internal[i];
-            const int nb = 64 * node_of[i];
+            const uint8_t* lct = s_lc + t * (p.S + 1) * nwb + wq;             // leaf codes of this position
+            const int* r = rec + i * R;
+            const int par = r[0], nb = r[1];
             // own rows (root: virtual one-hot parent, duplicated tables)
             const N1Vec4 qh = n1_q4(qprv + i * sprv);
             const double A = n1_dot(qh, n1_ld4(tab + nb + 48 + 4 * a));
@@ -140,16 +142,14 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
             const double tot = n1_sum(n1_q4(qpp));
             const double qpa = qpp[a];
             const double own = qpa * A + (tot - qpa) * B;
-            // internal children (padded with null entries), one exchange for all of them
+            // internal children (null entries: the node itself with weight 0), one exchange for all of them
             double ch = 0.0, wu = 0.0;
             for (int j = 0; j < p.MC; ++j) {
-                const int ci = ich[i * p.MC + j];
-                const bool has = ci >= 0;
-                const double* tb = has ? tab + 64 * node_of[ci] : zero_blk;
-                const N1Vec4 qpc = n1_q4(has ? qprv + ci * sprv : s_virt);
-                const double u = n1_dot(qpc, n1_ld4(tb + 32 + 4 * a));
-                const double v = n1_dot(qpc, n1_ld4(tb + 48 + 4 * a));
-                const double qc = has ? qcur[ci * qs + a] : 0.0;
+                const int ci = r[2 + 3 * j], cnb = r[3 + 3 * j];
+                const N1Vec4 qpc = n1_q4(qprv + ci * sprv);
+                const double u = n1_dot(qpc, n1_ld4(tab + cnb + 32 + 4 * a));
+                const double v = n1_dot(qpc, n1_ld4(tab + cnb + 48 + 4 * a));
+                const double qc = r[4 + 3 * j] ? qcur[ci * qs + a] : 0.0;
                 wu = fma(qc, u, wu);
                 ch = fma(qc, v, ch);
             }
@@ -158,15 +158,14 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
                 const double w2 = __shfl_sync(full, wu, qb + 2), w3 = __shfl_sync(full, wu, qb + 3);
                 ch += (((w0 + w1) + w2) + w3) - wu;
             }
-            // leaf children (padded)
+            // leaf children (null entries: code 0 and the zero table block)
             double cobs = 0.0, cgap = 0.0;
             for (int j = 0; j < p.ML; ++j) {
-                const int kk = lf[i * p.ML + j];
-                if (kk < 0 || !live) continue;
+                const int kk = r[2 + 3 * p.MC + 2 * j], lnb = r[3 + 3 * p.MC + 2 * j];
                 const int lc = lct[kk * nwb];
                 const int x = lc & 15, y = lc >> 4;
                 if (x < 4) {
-                    const double* Ll = tab + 64 * leaf_node[kk] + (a == x ? 16 : 0);
+                    const double* Ll = tab + lnb + (a == x ? 16 : 0);
                     if (y < 4) cobs += __ldg(Ll + y * 4 + x);
                     else {
 #pragma unroll
@@ -207,10 +206,9 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
             // unobserved leaf children: update + free-energy terms (the only divergent part)
             if (live) {
                 for (int j = 0; j < p.ML; ++j) {
-                    const int kk = lf[i * p.ML + j];
-                    if (kk < 0) continue;
+                    const int kk = r[2 + 3 * p.MC + 2 * j], lnb = r[3 + 3 * p.MC + 2 * j];
                     const int lc = lct[kk * nwb];
-                    if ((lc & 15) < 4) continue;
+                    if ((lc & 15) < 4) continue;                  // observed (null entries carry code 0)
                     const int y = lc >> 4;
                     const double qsum = n1_sum(n1_q4(qcur + i * qs));
                     double ownl = 0.0, own_fe;
@@ -226,10 +224,10 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
                     }
                     double nl = 0.0;
                     if (has_next) {
-                        const int xn = lct[(p.S + kk) * nwb] & 15;
+                        const int xn = lct[(p.S + 1 + kk) * nwb] & 15;
                         const N1Vec4 qpn = n1_q4(qnxt + i * qs);
                         if (xn < 4) {
-                            const double* Lno = tabn + 64 * leaf_node[kk];
+                            const double* Lno = tabn + lnb;
                             const double qd = xn == 0 ? qpn.v[0] : xn == 1 ? qpn.v[1] : xn == 2 ? qpn.v[2] : qpn.v[3];
                             nl = qd * __ldg(Lno + 16 + a * 4 + xn) + (n1_sum(qpn) - qd) * __ldg(Lno + a * 4 + xn);
                         } else {
@@ -279,7 +277,7 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
                         const int t = j / (p.S * 4), kk = (j >> 2) % p.S;
                         const double v = p.gq[(size_t)j * p.n_slots + gslot];
                         p.sink_qleaf[(size_t)j * p.n_windows + item] = v;
-                        if ((s_lc[(t * p.S + kk) * nwb + wq] & 15) >= 4) ent += v > 0.0 ? v * phy_log(v) : 0.0;
+                        if ((s_lc[(t * (p.S + 1) + kk) * nwb + wq] & 15) >= 4) ent += v > 0.0 ? v * phy_log(v) : 0.0;
                     }
                     const unsigned wm = 0xFFFFu << wb;
                     ent += __shfl_xor_sync(wm, ent, 1); ent += __shfl_xor_sync(wm, ent, 2);

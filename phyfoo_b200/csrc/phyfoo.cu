@@ -1027,7 +1027,7 @@ static int launch_net1w(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model*
     const int n_strands = strands == 2 ? 2 : 1;
     const long long n_items = (long long)n_windows * n_strands;
     // per window: q of the hidden internal nodes + leaf codes; fixed: one padding slot per q row, one-hot, program
-    const size_t per_window = (size_t)h.W * h.I * 4 * sizeof(double) + (size_t)h.W * h.S;
+    const size_t per_window = (size_t)h.W * h.I * 4 * sizeof(double) + (size_t)h.W * (h.S + 1);
     const size_t fixed = (size_t)h.W * h.I * 32 + (size_t)m->prog1w_len * sizeof(int) + 32 + 64;
     const size_t budget = std::min<size_t>(ctx->smem_optin, 227 * 1024);
     int nwb = 16;
