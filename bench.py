@@ -378,12 +378,24 @@ def run_ours(args):
             return r
 
         names = {name for (_, name) in kernels}
+        # DRAM bytes per launch of the same kernel on the same workload from the committed ncu --set full captures
+        # (scripts/summarize_ncu.py -> profiles/traffic.json); only the C2 captures were taken at bench size
+        try:
+            traffic_db = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        except Exception:
+            traffic_db = {}
+
+        def traffic_of(key):
+            return traffic_db.get(key) if args.config == "c2" and not args.n_aln else None
+
         fg_name = ("score_o1w_kernel" if "score_o1w_kernel" in names else "score_o1_kernel") if cfg["order"] == 1 else "score_o0_kernel"
         extra = {}
         if path != 1:
             fg_ms = max(ms for (_, name), ms in kernels.items() if name == fg_name)     # the motif-window launch
             roofline = fp64_roofline(fg_name + " (motif windows)", fg_ms)
             roofline["kernel_share_of_step"] = fg_ms / step_ms
+            if fg_name == "score_o0_kernel":
+                roofline["traffic"] = traffic_of("r01_c2_direct_kernel:score_o0_kernel<0, 0>")
         else:
             # pattern-table path: per-pattern trajectories (fp64, a small latency-bound grid) + gathers per window
             D = ds.patterns()
@@ -400,21 +412,22 @@ def run_ours(args):
                             "bytes_per_launch": abytes, "kernel_ms": win_ms, "kernel_share_of_step": win_ms / step_ms,
                             "table_gather": {"bytes": gather_bytes, "GB/s": gather_bytes / (win_ms * 1e-3) / 1e9,
                                              "what": "8 B x W x (K_w + 1) trajectory entries per window, served by L2"},
-                            "traffic": None}
+                            "traffic": traffic_of("r01_c2_pattern_table:memo_window_kernel")}
             else:
                 achieved = traj_flops / (traj_ms * 1e-3) / 1e12
                 roofline = {"bound": "fp64", "kernel": "memo_traj_kernel (mean-field trajectories of the occurring column patterns)",
                             "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
                             "peak_source": "DFMA microbenchmark in this run (MEASURED_PEAKS.json has no fp64 entry)",
                             "flops_per_launch": traj_flops, "kernel_ms": traj_ms, "kernel_share_of_step": traj_ms / step_ms,
-                            "note": f"{D} patterns x {W + 1} trees x {K1} passes: a {D * (W + 1)}-thread grid, latency-bound by design",
-                            "traffic": None}
+                            "note": f"{D} patterns x {W + 1} trees x {K1} passes: {4 * D * (W + 1)} threads (four lanes per tree), latency-bound by design",
+                            "traffic": traffic_of("r01_c2_pattern_table:memo_traj_kernel")}
             d_ms, d_kernels = direct
             d_fg = max(ms for (_, name), ms in d_kernels.items() if name == fg_name)
             extra["roofline_direct"] = fp64_roofline(
                 fg_name + " (motif windows, direct path: pattern table switched off)", d_fg,
                 "what every configuration with more than 6 species runs; measured in this run, 3 steps, not part of `value`")
             extra["roofline_direct"]["step_ms"] = d_ms
+            extra["roofline_direct"]["traffic"] = traffic_of("r01_c2_direct_kernel:score_o0_kernel<0, 0>")
             extra["pattern_table"] = {"patterns": D, "trajectory_flops_per_step": traj_flops,
                                       "direct_flops_per_step": flops, "work_ratio": flops / max(traj_flops, 1)}
         line = {

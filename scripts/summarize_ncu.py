@@ -73,6 +73,20 @@ if os.path.exists(rep):
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     lines += ["## `ncu --set full --clock-control none --import-source on` (per captured launch)", ""]
+    # DRAM traffic per launch of every captured kernel -> profiles/traffic.json (bench.py reports it as roofline.traffic)
+    tpath = os.path.join(out_dir, "traffic.json")
+    traffic = json.load(open(tpath)) if os.path.exists(tpath) else {}
+    unit_scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for r in rows[2:]:
+        try:
+            ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            b = float(r[ir]) * unit_scale.get(units[ir], 1.0) + float(r[iw]) * unit_scale.get(units[iw], 1.0)
+            name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "")
+            key = f"{label}:{name}"
+            traffic[key] = max(traffic.get(key, 0.0), b)      # several captured launches of one kernel: the largest (the motif launch)
+        except (ValueError, IndexError):
+            pass
+    json.dump(traffic, open(tpath, "w"), indent=1, sort_keys=True)
     for r in rows[2:]:
         lines += [f"### {r[hdr.index('Kernel Name')]}  grid {r[hdr.index('launch__grid_size')]} x block {r[hdr.index('launch__block_size')]}", "",
                   "| metric | value | unit |", "|---|---|---|"]
