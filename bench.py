@@ -402,7 +402,7 @@ def run_ours(args):
             win_ms = max(ms for (_, name), ms in kernels.items() if name == "memo_window_kernel")
             traj_ms = sum(ms for (_, name), ms in kernels.items() if name == "memo_traj_kernel")
             upd, fe = flops_order0(I, S)
-            K1 = 101
+            K1 = 65              # pattern_memo_sweep_cap (64) + 1 passes per tree
             traj_flops = D * (W + 1) * K1 * (upd + fe)            # motif positions + the background tree
             gather_bytes = W * (sweeps_fg + n_windows) * 8         # trajectory entries the stop rule consumes
             if win_ms >= traj_ms:

@@ -237,8 +237,9 @@ void phyfoo_fe_free(phyfoo_ctx* ctx, phyfoo_feset* fe);
  * gathers per window; results are bit-identical to the direct kernel (the reference's own, disabled, caches had the
  * same aim: models/AbstractPhyloModel.java:100-119, models/PhyloBackground.java:196). */
 int phyfoo_set_option(phyfoo_ctx* ctx, const char* name, int64_t value);
-/* "pattern_memo_sweep_cap" (default 100 = every window is served): sweeps stored per pattern; with a smaller cap the
- * windows that need more go to the direct kernel. */
+/* "pattern_memo_sweep_cap" (default 64): sweeps stored per pattern; the (rare) windows whose stop rule needs more are
+ * listed on the device and scored by the direct kernel -- same bits either way; 100 = max_sweeps serves every window
+ * from the table. */
 /* "order1_kernel": 1 (default) = wavefront kernel (16 lanes per window, list-scheduled node updates), 0 = one quad of
  * lanes per window walking the nodes one by one.  Same fixed-point iteration; free energies agree to re-association. */
 /* Device time of every kernel the most recent call launched (CUDA events on the library's stream), in launch order:

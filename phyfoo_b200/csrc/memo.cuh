@@ -9,8 +9,9 @@
 //      free-energy trajectory F_k           (memo_traj_kernel: the same meanfield_pass as the direct kernel),
 //   3. scores every window by walking k: F_k(window) = sum_t traj[t][pattern(c0 + t)][k] in tree order, applying the
 //      reference's stop rule to that sum  (memo_window_kernel: pure gathers, no transcendental);
-//   4. trajectories are stored up to a sweep cap (default: max_sweeps, so every window is served); with a smaller cap
-//      the windows whose stop rule has not fired by then are listed and scored by the direct kernel (score_o0_kernel, ITEMS variant) -- same bits either way.
+//   4. trajectories are stored up to a sweep cap (default 64 of max_sweeps = 100: the trajectory kernel is a chain of
+//      dependent passes, so its time is proportional to the cap); the rare windows whose stop rule has not fired by then
+//      are listed on the device and scored by the direct kernel (score_o0_kernel, ITEMS variant) -- same bits either way.
 // The per-tree values and the order of the sum over t are those of score_o0_kernel, so scores, sweep counts and
 // arg-max calls are bit-identical to the direct path (tests/test_gpu_memo.py compares the two paths bit for bit).
 // Exact mode is the same with a one-entry "trajectory" (-log P(column | t)).

@@ -69,7 +69,7 @@ struct phyfoo_ctx {
     int64_t gamma_windows = -1;      // number of windows whose gamma of the last E-step is resident in `gamma`
     DevBuf memo_traj;                // pattern-table path: free-energy trajectories (memo.cuh)
     int memo_mode = 1;               // 0 = never, 1 = when it pays off, 2 = whenever it applies
-    int memo_sweep_cap = 100;
+    int memo_sweep_cap = 64;
     int order1_kernel = 1;           // 0 = one quad per window (net1.cuh), 1 = wavefront, 16 lanes per window (net1w.cuh)         // trajectory length of the pattern-table path; longer windows go to the direct kernel
     DevBuf memo_pending;             // fallback list of the pattern-table path
     // per-kernel device times of the most recent call (CUDA events on the library's stream)

@@ -115,7 +115,7 @@ def test_memo_sweep_cap_fallback_is_bit_identical(ctx):
             assert me["stats"]["sweeps_fg"] == de["stats"]["sweeps_fg"] and me["stats"]["sweeps_bg"] == de["stats"]["sweeps_bg"]
         assert (dk > 6).any() and (dk <= 6).any()      # the cap of 6 really splits the windows between the two kernels
     finally:
-        ctx.set_option("pattern_memo_sweep_cap", 100)
+        ctx.set_option("pattern_memo_sweep_cap", 64)
 
 
 def test_memo_does_not_apply_to_many_species_or_order1(ctx):
