@@ -240,6 +240,15 @@ int phyfoo_set_option(phyfoo_ctx* ctx, const char* name, int64_t value);
 /* "pattern_memo_sweep_cap" (default 64): sweeps stored per pattern; the (rare) windows whose stop rule needs more are
  * listed on the device and scored by the direct kernel -- same bits either way; 100 = max_sweeps serves every window
  * from the table. */
+/* "pattern_memo_split" (default 0 = off; otherwise a multiple of 4): the trajectories are computed in two phases -- the
+ * first `split` passes, then the rest on a second stream while the first gather pass over the windows runs (most windows
+ * stop within a few sweeps); windows the first pass could not finish are gathered again once the second phase is done.
+ * Results do not depend on the setting.  (Measured on C2: the two kernels compete for the same issue slots, so the
+ * overlap gains 7 % with the four-lane trajectory kernel and nothing with the wavefront kernel; kept as a tuning knob.) */
+/* "pattern_memo_wave" (default 1): the trajectory kernel runs the nodes of a tree as a wavefront over (node, sweep) --
+ * node i of sweep k at step 2 k + depth(i), so nodes of alternating depth of consecutive sweeps run side by side on their
+ * own lanes -- when the tree has 2..8 internal nodes and at most four per depth parity; 0 = four lanes per tree walking
+ * the nodes one by one.  Same bits either way. */
 /* "order1_kernel": 1 (default) = wavefront kernel (16 lanes per window, list-scheduled node updates), 0 = one quad of
  * lanes per window walking the nodes one by one.  Same fixed-point iteration; free energies agree to re-association. */
 /* Device time of every kernel the most recent call launched (CUDA events on the library's stream), in launch order:

@@ -25,7 +25,8 @@ class Stats(C.Structure):
                 ("sweeps_bg", C.c_int64), ("kernel_launches", C.c_int32), ("gpu_ms", C.c_float)]
 
 
-def make_desc(kind, width, order, tree, branch, pi_list, evol=EVOL_F81ALPHA, mode=MODE_MEANFIELD, hky_ratio=0.0):
+def make_desc(kind, width, order, tree, branch, pi_list, evol=EVOL_F81ALPHA, mode=MODE_MEANFIELD, hky_ratio=0.0,
+              max_sweeps=0, min_sweeps=0, tol=0.0):
     """Returns (desc, keepalive): keepalive holds the numpy arrays the struct points into."""
     parent = np.ascontiguousarray(tree.parent, np.int32)
     leaf = np.ascontiguousarray(tree.leaf_species, np.int32)
@@ -34,5 +35,5 @@ def make_desc(kind, width, order, tree, branch, pi_list, evol=EVOL_F81ALPHA, mod
     d = ModelDesc(kind, width, order, parent.size, parent.ctypes.data_as(C.POINTER(C.c_int32)),
                   leaf.ctypes.data_as(C.POINTER(C.c_int32)), evol, hky_ratio,
                   branch.ctypes.data_as(C.POINTER(C.c_double)), pi.ctypes.data_as(C.POINTER(C.c_double)),
-                  mode, 1, 0, 0, 0.0)
+                  mode, 1, int(max_sweeps), int(min_sweeps), float(tol))
     return d, (parent, leaf, branch, pi)

@@ -166,9 +166,9 @@ class DeviceModel:
     """phyfoo_model: tree + parameters of one PhyloBayesModel / PhyloBackground."""
 
     def __init__(self, ctx, kind, width, order, tree, branch, pi_list, evol=_abi.EVOL_F81ALPHA,
-                 mode=_abi.MODE_MEANFIELD, hky_ratio=0.0):
+                 mode=_abi.MODE_MEANFIELD, hky_ratio=0.0, max_sweeps=0, min_sweeps=0, tol=0.0):
         self.ctx = ctx
-        desc, keep = _abi.make_desc(kind, width, order, tree, branch, pi_list, evol, mode, hky_ratio)
+        desc, keep = _abi.make_desc(kind, width, order, tree, branch, pi_list, evol, mode, hky_ratio, max_sweeps, min_sweeps, tol)
         self.h = C.c_void_p()
         raise_for(lib().phyfoo_model_create(ctx.h, C.byref(desc), C.byref(self.h)), ctx.h)
         del keep

@@ -80,6 +80,15 @@ struct MemoTrajParams {
     const double* tab;                      // [E][W] (logs for the mean field, probabilities for exact mode)
     const int* prog;
     double* traj;                           // [(t * cap + d) * RS + k], RS a multiple of 4 (32-byte rows)
+    // passes k0 .. k1-1 of the trajectory in this launch; a launch with k0 > 0 resumes from the state a previous launch
+    // saved (state: [I * 8][D * W] doubles), a launch with k1 < K1 saves it
+    int k0, k1;
+    double* state;
+    // wavefront variant (memo_traj_wave_kernel): node i of sweep k runs at step 2 k + depth(i); sched[parity][slot] = the
+    // internal node a node slot works on at steps of that parity (-1: none)
+    int dmax, ML, MCH;                      // deepest internal node, most leaf / internal children of one node
+    signed char sched[2][4];
+    signed char depth[8];
 };
 struct MemoTrajJobs { MemoTrajParams job[2]; };   // blockIdx.y selects the job (background and motif in one launch)
 
@@ -90,6 +99,7 @@ struct MemoTrajJobs { MemoTrajParams job[2]; };   // blockIdx.y selects the job 
 __global__ void __launch_bounds__(128) memo_traj_kernel(MemoTrajJobs jobs) {
     extern __shared__ double smem[];
     const MemoTrajParams& p = jobs.job[blockIdx.y];
+    if (p.k0 >= p.k1) return;                               // this job has no passes in this phase
     const int T = blockDim.x, tid = threadIdx.x;
     const int TPB = T >> 2;                                 // trees per block
     double* s_tab = smem;                                   // [E][W]
@@ -125,10 +135,227 @@ __global__ void __launch_bounds__(128) memo_traj_kernel(MemoTrajJobs jobs) {
             if (a == 0 && live) out[0] = -log(pruning_likelihood(tp, tb, st, cw));
             continue;
         }
-        for (int k = 0; k < p.K1; ++k) {
+        if (p.k0 > 0) {
+            for (int e = a; e < p.I * 8; e += 4) s_state[(size_t)e * TPB + slot] = p.state[(size_t)e * n + it];
+            __syncwarp();
+        }
+        for (int k = p.k0; k < p.k1; ++k) {
             const double F = meanfield_pass_quad<true>(tp, tb, st, cw, k > 0, a, qb, mask);
             if (a == 0 && live) out[k] = F;
         }
+        if (p.k1 < p.K1 && live)
+            for (int e = a; e < p.I * 8; e += 4) p.state[(size_t)e * n + it] = s_state[(size_t)e * TPB + slot];
+    }
+}
+
+// The same trajectories as a WAVEFRONT over (node, sweep): in the reference's sweep order a node needs its parent of the
+// same sweep and its children of the previous sweep, so node i of sweep k can run at step tau = 2 k + depth(i) and nodes
+// of alternating depth -- belonging to consecutive sweeps -- run side by side.  LPT lanes per tree = node slots x four
+// symbols; the chain of dependent node updates shrinks from I per sweep to 2 per sweep.  Per node the arithmetic is that
+// of meanfield_pass_quad (CANONICAL ARITHMETIC in tree_pass.cuh): children leave their message in a slot of their own
+// and the parent adds the slots in child order to its base, which is the order `cs(p) += m` produces in the sequential
+// pass; the per-node free-energy terms of a sweep are kept until its deepest node is done and then summed in node order.
+// Same bits as memo_traj_kernel and as the direct kernel (tests/test_gpu_memo.py).
+// EARLY STOP (launches that cover the whole trajectory): the sweep map is deterministic, so once the q of every node
+// equals, bit for bit, the q of the previous sweep (fixed point) or of the sweep before that (two-cycle in the last
+// bits), the rest of the trajectory repeats the last two values; a warp stops when its trees all got there and fills
+// the rows.  (C2: 31 of 65 passes per warp on average.)
+// Per-tree shared-memory block: q[I][4] base[I][4] msg[I][4] q2[I][4] ring[4 sweeps][I][2] flags, padded to 4 (mod 16)
+// doubles so that the quads of the trees of a warp fall into different banks.
+template <int LPT>
+__global__ void __launch_bounds__(128, 6) memo_traj_wave_kernel(MemoTrajJobs jobs) {
+    extern __shared__ double smem[];
+    const MemoTrajParams& p = jobs.job[blockIdx.y];
+    if (p.k0 >= p.k1) return;
+    const int T = blockDim.x, tid = threadIdx.x, I = p.I;
+    constexpr int TPW = 32 / LPT;
+    const int TPB = T / LPT;
+    int ST = 26 * I + 2; ST += (4 - (ST & 15) + 16) & 15;
+    double* s_tab = smem;                                   // [W][E]: entry offsets become immediates of the loads
+    double* s_tree = s_tab + (size_t)p.E * p.W;             // [TPB][ST]
+    int* s_prog = (int*)(s_tree + (size_t)TPB * ST);
+    for (int i = tid; i < p.E * p.W; i += T) s_tab[(i % p.W) * p.E + i / p.W] = p.tab[i];
+    for (int i = tid; i < p.prog_len; i += T) s_prog[i] = p.prog[i];
+    for (int i = tid; i < TPB; i += T) s_tree[(size_t)i * ST + 26 * I] = 0.0;     // the message of an absent child
+    __syncthreads();
+    const int* par_internal = s_prog;
+    const int* node_of = s_prog + I;
+    const int* leaf_begin = s_prog + 2 * I;
+    const int* leaf_node = s_prog + 3 * I + 1;
+    const int* leaf_species = leaf_node + p.S;
+    const int* ichild_begin = leaf_species + p.S;
+    const int* ichild = ichild_begin + I + 1;
+    const int lane = tid & 31, sub = lane % LPT, slot = sub >> 2, a = sub & 3;
+    const int qb = lane & ~3;
+    const unsigned mask = 0xFu << qb;
+    double* tr = s_tree + (size_t)(tid / LPT) * ST;
+    double* Q = tr; double* BASE = tr + 4 * I; double* MSG = tr + 8 * I; double* Q2 = tr + 12 * I; double* RING = tr + 16 * I;
+    int* FLAG = (int*)(tr + 24 * I);                        // [4 sweeps][I]
+    const double* ZERO = tr + 26 * I;
+    const bool early = p.k0 == 0 && p.k1 == p.K1;
+    constexpr unsigned LANE0 = LPT == 8 ? 0x01010101u : 0x00010001u;
+    const int D = *p.count;
+    const long long n = (long long)D * p.W;
+    const long long first = (long long)blockIdx.x * TPB + (long long)(tid >> 5) * TPW;
+    for (long long it0 = first; it0 < n; it0 += (long long)gridDim.x * TPB) {
+        const long long it_raw = it0 + lane / LPT;
+        const bool live = it_raw < n;
+        const long long it = live ? it_raw : n - 1;
+        const int d = (int)(it / p.W), t = (int)(it - (long long)d * p.W);
+        const ColWords cw = memo_words((uint32_t)p.code_of[d], p.S);
+        const Tab tb{s_tab + t * p.E, 1};
+        double* out = p.traj + ((size_t)t * p.cap + d) * p.RS;
+        unsigned gm = 0;                                    // internal nodes with an unobserved leaf child
+        for (int i = 0; i < I; ++i)
+            for (int k = leaf_begin[i]; k < leaf_begin[i + 1]; ++k)
+                if (cw.obs(leaf_species[k]) == 4) gm |= 1u << i;
+        __syncwarp();                                       // the previous tree of this lane group is completely done
+        if (p.k0 > 0) {
+            for (int e = sub; e < 12 * I; e += LPT) tr[e] = p.state[(size_t)it * (12 * I) + e];
+            __syncwarp();
+        }
+        const double lpia = tb(a);
+        // this lane's node at even and at odd steps, with everything that does not change from sweep to sweep: table
+        // offset, parent, children, and c[a] = sum over the observed leaf children of log T(a, x) (the sequential pass
+        // re-reads it every sweep; the value is the same)
+        int nd_i[2], nd_cb[2], nd_ce[2], nd_dep[2];
+        int nd_to[2], nd_tm[2], nd_qp[2], nd_m1[2], nd_m2[2];      // offsets into smem (32-bit, shared address space)
+        double nd_c[2];
+#pragma unroll
+        for (int par = 0; par < 2; ++par) {
+            const int i_s = p.sched[par][slot];
+            const int i = i_s < 0 ? 0 : i_s;
+            nd_i[par] = i_s; nd_dep[par] = p.depth[i];
+            const int e0 = i ? tab_of(node_of[i]) : 0;
+            nd_to[par] = t * p.E + e0 + a;                  // own rows: + 4 l
+            nd_tm[par] = t * p.E + e0 + a * 4;              // message row: + h
+            nd_qp[par] = (int)(Q - smem) + (i ? par_internal[i] * 4 : 0);
+            const int cb = ichild_begin[i], ce = ichild_begin[i + 1];
+            nd_m1[par] = cb < ce ? (int)(MSG - smem) + ichild[cb] * 4 + a : (int)(ZERO - smem);
+            nd_m2[par] = cb + 1 < ce ? (int)(MSG - smem) + ichild[cb + 1] * 4 + a : (int)(ZERO - smem);
+            nd_cb[par] = cb + 2; nd_ce[par] = ce;           // further internal children (multifurcating trees)
+            double c = 0.0;
+            for (int k = leaf_begin[i]; k < leaf_begin[i + 1]; ++k) {
+                const int x = cw.obs(leaf_species[k]);
+                if (x < 4) c += tb(tab_of(leaf_node[k]) + a * 4 + x);
+            }
+            nd_c[par] = c;
+        }
+        const int tau_end = 2 * (p.k1 - 1) + p.dmax;
+        double Fcur = 0.0, Fprev = 0.0;
+        bool tree_done = false;
+        int fa_last = 0;
+        int kc_stop = -1;                                   // >= 0: the warp stopped after completing this sweep
+        for (int tau0 = 2 * p.k0; tau0 <= tau_end && kc_stop < 0; tau0 += 2) {
+#pragma unroll
+            for (int par = 0; par < 2; ++par) {
+                const int tau = tau0 + par;
+                if (tau > tau_end || kc_stop >= 0) break;
+                const int i_s = nd_i[par];
+                const int i = i_s < 0 ? 0 : i_s;
+                const int k = (tau - nd_dep[par]) >> 1;
+                const bool act = i_s >= 0 && k >= p.k0 && k < p.k1;
+                const bool update = act && k > 0;
+                const double* to = smem + nd_to[par];
+                const double* tm = smem + nd_tm[par];
+                double own;
+                {
+                    // (the root runs the chain on its own q and drops the result; so does its message below)
+                    const double2 p01 = *(const double2*)(smem + nd_qp[par]), p23 = *(const double2*)(smem + nd_qp[par] + 2);
+                    double acc = fma(p01.x, to[0], 0.0);
+                    acc = fma(p01.y, to[4], acc);
+                    acc = fma(p23.x, to[8], acc);
+                    acc = fma(p23.y, to[12], acc);
+                    own = i == 0 ? lpia : acc;
+                }
+                // base + the children's messages in child order; an absent child adds +0.0, which leaves every value but
+                // -0.0 unchanged, and the base (a sum starting from +0.0) is never -0.0
+                double cs = (BASE[i * 4 + a] + smem[nd_m1[par]]) + smem[nd_m2[par]];
+                for (int cc = nd_cb[par]; cc < nd_ce[par]; ++cc) cs += MSG[ichild[cc] * 4 + a];
+                const long long q_old1 = __double_as_longlong(Q[i * 4 + a]), q_old2 = __double_as_longlong(Q2[i * 4 + a]);
+                const double s = own + cs;
+                const double ex = update ? s : 0.0;
+                const double e = phy_exp(ex);
+                const double ev0 = __shfl_sync(0xffffffffu, e, qb), ev1 = __shfl_sync(0xffffffffu, e, qb + 1);
+                const double ev2 = __shfl_sync(0xffffffffu, e, qb + 2), ev3 = __shfl_sync(0xffffffffu, e, qb + 3);
+                const double z = ((ev0 + ev1) + ev2) + ev3;
+                const double rz = phy_rcp(z);
+                const double lz = phy_log(z);
+                const double q0 = phy_mul(ev0, rz), q1 = phy_mul(ev1, rz), q2 = phy_mul(ev2, rz), q3 = phy_mul(ev3, rz);
+                const double qa = phy_mul(e, rz);
+                const double lq = ex - lz;
+                double m = fma(q0, tm[0], 0.0);
+                m = fma(q1, tm[1], m);
+                m = fma(q2, tm[2], m);
+                m = fma(q3, tm[3], m);
+                const double c = nd_c[par];
+                const double ft = quad_sum4(0xffffffffu, qb, phy_mul(qa, (lq - own) - c));
+                // bit 0: this node's q equals that of the previous sweep, bit 1: that of the sweep before (all four symbols)
+                int fl = (__double_as_longlong(qa) == q_old1 ? 1 : 0) | (__double_as_longlong(qa) == q_old2 ? 2 : 0);
+                fl &= __shfl_xor_sync(0xffffffffu, fl, 1);
+                fl &= __shfl_xor_sync(0xffffffffu, fl, 2);
+                double tsum = 0.0, Fgap = 0.0;
+                if ((gm >> i) & 1u) {
+                    const double qs = ((q0 + q1) + q2) + q3;
+                    const double lp0 = tb(0), lp1 = tb(1), lp2 = tb(2), lp3 = tb(3);
+                    for (int k2 = leaf_begin[i]; k2 < leaf_begin[i + 1]; ++k2) {
+                        if (cw.obs(leaf_species[k2]) < 4) continue;
+                        const double xl = phy_mul(qs, lpia);
+                        const double exl = update ? xl : 0.0;
+                        const double el = phy_exp(exl);
+                        const double l0 = __shfl_sync(mask, el, qb), l1 = __shfl_sync(mask, el, qb + 1);
+                        const double l2 = __shfl_sync(mask, el, qb + 2), l3 = __shfl_sync(mask, el, qb + 3);
+                        const double zl = ((l0 + l1) + l2) + l3;
+                        const double rzl = phy_rcp(zl);
+                        const double lzl = phy_log(zl);
+                        double tt = fma(phy_mul(l0, rzl), lp0, 0.0);
+                        tt = fma(phy_mul(l1, rzl), lp1, tt);
+                        tt = fma(phy_mul(l2, rzl), lp2, tt);
+                        tt = fma(phy_mul(l3, rzl), lp3, tt);
+                        const double ql = phy_mul(el, rzl);
+                        Fgap += quad_sum4(mask, qb, phy_mul(ql, (exl - lzl) - xl));
+                        tsum += tt;
+                    }
+                }
+                if (act) {
+                    Q2[i * 4 + a] = __longlong_as_double(q_old1);
+                    Q[i * 4 + a] = qa;
+                    MSG[i * 4 + a] = m;
+                    BASE[i * 4 + a] = c + tsum;
+                    if (a == 0) { RING[((k & 3) * I + i) * 2] = ft; RING[((k & 3) * I + i) * 2 + 1] = Fgap; FLAG[(k & 3) * I + i] = fl; }
+                }
+                __syncwarp();
+                // the sweep whose deepest node ran in this step is complete: its free energy, terms in node order
+                const int kc2 = tau - p.dmax;
+                if (kc2 >= 2 * p.k0 && !(kc2 & 1)) {
+                    const int kc = kc2 >> 1;
+                    if (sub == 0) {
+                        double F = 0.0;
+                        int fa = kc >= 2 ? 3 : kc;                             // sweep 1 has one predecessor, sweep 0 none
+                        for (int j = 0; j < I; ++j) {
+                            F += RING[((kc & 3) * I + j) * 2];
+                            if ((gm >> j) & 1u) F += RING[((kc & 3) * I + j) * 2 + 1];
+                            fa &= FLAG[(kc & 3) * I + j];
+                        }
+                        if (live) out[kc] = F;
+                        Fprev = Fcur; Fcur = F; fa_last = fa;
+                        tree_done = tree_done || fa != 0;
+                    }
+                    if (early && __ballot_sync(0xffffffffu, sub == 0 && tree_done) == LANE0) kc_stop = kc;
+                }
+            }
+        }
+        if (kc_stop >= 0) {
+            // every tree of the warp is periodic from here on.  F of a sweep depends on the q of that sweep and of the one
+            // before: at a fixed point (bit 0 at the last sweep) every later value equals the last one, in a two-cycle the
+            // last two values alternate
+            const double Fc = __shfl_sync(0xffffffffu, Fcur, lane - sub);
+            const double Fp = __shfl_sync(0xffffffffu, (fa_last & 1) ? Fcur : Fprev, lane - sub);
+            if (live)
+                for (int j = kc_stop + 1 + sub; j < p.K1; j += LPT) out[j] = ((j - kc_stop) & 1) ? Fp : Fc;
+        }
+        if (p.k1 < p.K1 && live)       // (the step loop ended with a __syncwarp: every lane's stores are visible)
+            for (int e = sub; e < 12 * I; e += LPT) p.state[(size_t)it * (12 * I) + e] = tr[e];
     }
 }
 
@@ -148,22 +375,34 @@ struct MemoWindowParams {
     const int32_t* dense_of; const double* traj;
     double* out; int32_t* sweeps; unsigned long long* counter_sweeps;
     int max_sweeps, min_sweeps; double tol; int exact;
-    // windows whose stop rule has not fired within the stored trajectory go to the direct kernel
+    // windows whose stop rule has not fired within the K1 stored passes are listed: for the second gather pass (when the
+    // trajectories are computed in two phases) or for the direct kernel
     int* pend_count; int64_t* pend_col0; uint8_t* pend_strand; int64_t* pend_dst;
+    // LIST variant: the windows to score (the list a previous pass left)
+    const int* in_count; const int64_t* in_col0; const uint8_t* in_strand; const int64_t* in_dst;
 };
 
 // one thread per window: walk k in steps of four (one 32-byte sector per tree and step), summing the W trajectories in
 // tree order, until the reference's stop rule fires
-__global__ void __launch_bounds__(256) memo_window_kernel(MemoWindowParams p) {
-    const long long n_items = (long long)p.n_windows * p.n_strands;
+template <bool LIST>
+__global__ void __launch_bounds__(256, 4) memo_window_kernel(MemoWindowParams p) {
+    const long long n_items = LIST ? (long long)*p.in_count : (long long)p.n_windows * p.n_strands;
     unsigned long long ksum = 0;
-    for (long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += (long long)gridDim.x * blockDim.x) {
-        const int si = (int)(item / p.n_windows);
-        const int64_t w = item - (long long)si * p.n_windows;
-        const int strand = p.n_strands == 2 ? si : p.strand0;
-        const int a = find_alignment_hint(p.win_off, p.n_aln, w, p.n_windows);
-        const int64_t c0 = p.col_off[a] + (w - p.win_off[a]);
-        const MemoRow4* row[16];
+    for (long long idx0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx0 < n_items; idx0 += (long long)gridDim.x * blockDim.x) {
+        long long item; int strand; int64_t c0;
+        if (LIST) {
+            item = p.in_dst[idx0]; strand = p.in_strand[idx0]; c0 = p.in_col0[idx0];
+        } else {
+            item = idx0;
+            const int si = (int)(item / p.n_windows);
+            const int64_t w = item - (long long)si * p.n_windows;
+            strand = p.n_strands == 2 ? si : p.strand0;
+            const int a = find_alignment_hint(p.win_off, p.n_aln, w, p.n_windows);
+            c0 = p.col_off[a] + (w - p.win_off[a]);
+        }
+        uint32_t row[16];              // in 32-byte units: a 32-bit offset per tree keeps the kernel at 64 registers
+        const MemoRow4* const base = (const MemoRow4*)p.traj;
+        const uint32_t RS4 = (uint32_t)p.RS >> 2;
         // W <= 16 here (the launcher falls back to the direct kernel otherwise): trajectory rows of the W trees
 #pragma unroll
         for (int t = 0; t < 16; ++t) {
@@ -172,7 +411,7 @@ __global__ void __launch_bounds__(256) memo_window_kernel(MemoWindowParams p) {
                 ColWords cw = load_column(p.bases, p.gaps, p.n_cols, p.nb, c);
                 if (strand) cw = complement(cw);
                 const int d = p.dense_of[memo_code(cw, p.S)];
-                row[t] = (const MemoRow4*)(p.traj + ((size_t)t * p.cap + d) * p.RS);
+                row[t] = ((uint32_t)t * (uint32_t)p.cap + (uint32_t)d) * RS4;
             }
         }
         double Fsum = 0.0, old = 0.0;
@@ -184,7 +423,7 @@ __global__ void __launch_bounds__(256) memo_window_kernel(MemoWindowParams p) {
 #pragma unroll
             for (int t = 0; t < 16; ++t)
                 if (t < p.W) {
-                    const MemoRow4 r = memo_load4(&row[t][kb >> 2]);
+                    const MemoRow4 r = memo_load4(base + (row[t] + (uint32_t)(kb >> 2)));
 #pragma unroll
                     for (int j = 0; j < 4; ++j) f[j] += r.v[j];                // tree-major, like calcFreeEnergy(0, W-1)
                 }

@@ -70,6 +70,11 @@ struct phyfoo_ctx {
     DevBuf memo_traj;                // pattern-table path: free-energy trajectories (memo.cuh)
     int memo_mode = 1;               // 0 = never, 1 = when it pays off, 2 = whenever it applies
     int memo_sweep_cap = 64;
+    int memo_wave = 1;               // trajectories by the wavefront kernel when the tree allows it (0: one quad per tree)
+    int memo_split = 0;              // > 0: first trajectory phase (passes); the rest runs on `aux` under the first window pass
+    cudaStream_t aux = nullptr;      // second trajectory phase of the pattern-table path
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    DevBuf memo_state;               // mean-field state of every (pattern, position) tree between the two phases
     int order1_kernel = 1;           // 0 = one quad per window (net1.cuh), 1 = wavefront, 16 lanes per window (net1w.cuh)         // trajectory length of the pattern-table path; longer windows go to the direct kernel
     DevBuf memo_pending;             // fallback list of the pattern-table path
     // per-kernel device times of the most recent call (CUDA events on the library's stream)
@@ -123,7 +128,8 @@ static void memo_release(cudaStream_t st, MemoSet* ms);
 // brackets one kernel launch with events so that callers (bench.py) can attribute device time per kernel
 struct KernelTimer {
     phyfoo_ctx* ctx; int slot;
-    KernelTimer(phyfoo_ctx* c, const char* name) : ctx(c), slot(-1) {
+    cudaStream_t stream;
+    KernelTimer(phyfoo_ctx* c, const char* name, cudaStream_t on = nullptr) : ctx(c), slot(-1), stream(on ? on : c->stream) {
         if (ctx->n_ktimes >= 64) return;
         if ((int)ctx->ktimes.size() <= ctx->n_ktimes) {
             phyfoo_ctx::KTime kt{name, nullptr, nullptr};
@@ -132,10 +138,10 @@ struct KernelTimer {
         }
         slot = ctx->n_ktimes++;
         ctx->ktimes[slot].name = name;
-        cudaEventRecord(ctx->ktimes[slot].e0, ctx->stream);
+        cudaEventRecord(ctx->ktimes[slot].e0, stream);
     }
     ~KernelTimer() {
-        if (slot >= 0) cudaEventRecord(ctx->ktimes[slot].e1, ctx->stream);
+        if (slot >= 0) cudaEventRecord(ctx->ktimes[slot].e1, stream);
         ctx->launches++;
     }
 };
@@ -503,6 +509,9 @@ extern "C" int phyfoo_init(int device, phyfoo_ctx** out) {
     cudaDeviceProp prop;
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->kev[0])) != cudaSuccess || (e = cudaEventCreate(&ctx->kev[1])) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->kev[2])) != cudaSuccess || (e = cudaEventCreate(&ctx->kev[3])) != cudaSuccess ||
@@ -530,12 +539,17 @@ extern "C" void phyfoo_destroy(phyfoo_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->aux) cudaStreamSynchronize(ctx->aux);
+    ctx->memo_state.release();
     for (DevBuf* b : {&ctx->counters, &ctx->fg_scores, &ctx->bg_scores, &ctx->sweeps_buf, &ctx->gamma, &ctx->profile, &ctx->part,
                       &ctx->argoff, &ctx->argstrand, &ctx->alnw, &ctx->out3, &ctx->gstate, &ctx->misc, &ctx->selw, &ctx->sel_tmp, &ctx->sel_out, &ctx->memo_traj, &ctx->memo_pending})
         b->release();
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
     for (auto& kt : ctx->ktimes) { cudaEventDestroy(kt.e0); cudaEventDestroy(kt.e1); }
+    if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+    if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+    if (ctx->aux) cudaStreamDestroy(ctx->aux);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -943,23 +957,54 @@ static int launch_memo_jobs(phyfoo_ctx* ctx, const phyfoo_dataset* ds, const Mem
     int rc = dataset_memo(ctx, ds, &ms);
     if (rc) return rc;
     for (int j = 0; j < n_jobs; ++j) if ((rc = model_upload(ctx, jobs[j].m))) return rc;
-    size_t traj_off[3] = {0, 0, 0}, pend_off[3] = {0, 0, 0};
+    size_t traj_off[3] = {0, 0, 0}, pend_off[3] = {0, 0, 0}, state_off[3] = {0, 0, 0};
     long long n_items[2] = {0, 0};
-    int K1[2] = {1, 1};
+    int K1[2] = {1, 1}, KA[2] = {1, 1};
+    bool split = false;
     for (int j = 0; j < n_jobs; ++j) {
         const ModelHost& h = jobs[j].m->h;
         K1[j] = memo_K1(ctx, h, jobs[j].mode);
+        // two phases: passes 0..KA-1 first, the rest on the second stream while the first gather pass runs (most windows stop
+        // within the first few sweeps); KA a multiple of 4 so that the two never touch the same 32-byte sector of a row
+        KA[j] = (ctx->memo_split > 0 && ctx->memo_split + 4 <= K1[j]) ? ctx->memo_split : K1[j];
+        split = split || KA[j] < K1[j];
         n_items[j] = (long long)jobs[j].n_windows * (jobs[j].strands == 2 ? 2 : 1);
         traj_off[j + 1] = traj_off[j] + (size_t)ms->cap * h.W * ((K1[j] + 3) / 4 * 4);
-        // per job: [count (8 bytes, int used)] [col0 int64 x n] [dst int64 x n] [strand u8 x n, padded to 8]
-        pend_off[j + 1] = pend_off[j] + 8 + (size_t)n_items[j] * 16 + (((size_t)n_items[j] + 7) / 8) * 8;
+        state_off[j + 1] = state_off[j] + (KA[j] < K1[j] ? (size_t)ms->cap * h.W * h.I * 12 : 0);   // wavefront: q, base, msg
+        // per job, twice (list of the first gather pass, list for the direct kernel):
+        // [count (8 bytes, int used)] [col0 int64 x n] [dst int64 x n] [strand u8 x n, padded to 8]
+        pend_off[j + 1] = pend_off[j] + 2 * (8 + (size_t)n_items[j] * 16 + (((size_t)n_items[j] + 7) / 8) * 8);
     }
     CU(ctx->memo_traj.ensure(traj_off[n_jobs] * sizeof(double)));
     CU(ctx->memo_pending.ensure(pend_off[n_jobs]));
+    if (split) CU(ctx->memo_state.ensure(state_off[n_jobs] * sizeof(double)));
     MemoTrajJobs tj;
     const int threads = 128;
     size_t smem = 0;
     long long trees = 0;
+    // wavefront schedule (memo_traj_wave_kernel): node slots = the larger of the even-depth and odd-depth internal nodes
+    int lpt = 4;
+    bool wave = ctx->memo_wave != 0;
+    for (int j = 0; j < n_jobs && wave; ++j) {
+        const ModelHost& h = jobs[j].m->h;
+        MemoTrajParams& tp = tj.job[j];
+        if (h.I < 2 || h.I > 8 || jobs[j].mode == PHYFOO_MODE_EXACT) { wave = false; break; }
+        int cnt[2] = {0, 0};
+        memset(tp.sched, -1, sizeof(tp.sched));
+        tp.dmax = 0; tp.ML = 0; tp.MCH = 0;
+        for (int i = 0; i < h.I && wave; ++i) {
+            const int dep = i == 0 ? 0 : tp.depth[h.par_internal[i]] + 1;
+            tp.depth[i] = (signed char)dep;
+            tp.dmax = std::max(tp.dmax, dep);
+            tp.ML = std::max(tp.ML, h.leaf_begin[i + 1] - h.leaf_begin[i]);
+            tp.MCH = std::max(tp.MCH, h.ichild_begin[i + 1] - h.ichild_begin[i]);
+            if (cnt[dep & 1] >= 4) { wave = false; break; }
+            tp.sched[dep & 1][cnt[dep & 1]++] = (signed char)i;
+        }
+        if (tp.dmax > 6) wave = false;          // the ring keeps the terms of four sweeps
+        lpt = std::max(lpt, std::max(cnt[0], cnt[1]) <= 2 ? 8 : 16);
+    }
+    if (!wave) lpt = 4;
     for (int j = 0; j < n_jobs; ++j) {
         phyfoo_model* m = jobs[j].m;
         const ModelHost& h = m->h;
@@ -969,18 +1014,43 @@ static int launch_memo_jobs(phyfoo_ctx* ctx, const phyfoo_dataset* ds, const Mem
         tp.exact = jobs[j].mode == PHYFOO_MODE_EXACT ? 1 : 0;
         tp.tab = tp.exact ? m->d_probtab : m->d_logtab;
         tp.prog = m->d_prog; tp.traj = ctx->memo_traj.as<double>() + traj_off[j];
-        smem = std::max(smem, (size_t)h.E * h.W * sizeof(double) + (size_t)h.I * 8 * (threads / 4) * sizeof(double) + (size_t)m->prog_len * sizeof(int) + 16);
+        tp.k0 = 0; tp.k1 = KA[j]; tp.state = split ? ctx->memo_state.as<double>() + state_off[j] : nullptr;
+        const size_t per_tree = wave ? (size_t)(26 * h.I + 16) : (size_t)h.I * 8;
+        smem = std::max(smem, (size_t)h.E * h.W * sizeof(double) + per_tree * (threads / lpt) * sizeof(double) + (size_t)m->prog_len * sizeof(int) + 16);
         trees = std::max(trees, (long long)ms->cap * h.W);
     }
     if (n_jobs == 1) tj.job[1] = tj.job[0];
-    const int tpb = threads / 4;   // four lanes per tree
+    const int tpb = threads / lpt;   // lanes per tree: four symbols x node slots
     const int blocks = (int)std::max<long long>(1, std::min<long long>((trees + tpb - 1) / tpb, 16LL * ctx->sm_count));
-    CU(cudaFuncSetAttribute(memo_traj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    {
-        KernelTimer kt_(ctx, "memo_traj_kernel");
-        memo_traj_kernel<<<dim3(blocks, n_jobs), threads, smem, ctx->stream>>>(tj);
+    auto launch_traj = [&](cudaStream_t st, const char* name) -> cudaError_t {
+        KernelTimer kt_(ctx, name, st);
+        if (!wave) {
+            cudaError_t e = cudaFuncSetAttribute(memo_traj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            memo_traj_kernel<<<dim3(blocks, n_jobs), threads, smem, st>>>(tj);
+        } else if (lpt == 8) {
+            cudaError_t e = cudaFuncSetAttribute(memo_traj_wave_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            memo_traj_wave_kernel<8><<<dim3(blocks, n_jobs), threads, smem, st>>>(tj);
+        } else {
+            cudaError_t e = cudaFuncSetAttribute(memo_traj_wave_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            memo_traj_wave_kernel<16><<<dim3(blocks, n_jobs), threads, smem, st>>>(tj);
+        }
+        return cudaGetLastError();
+    };
+    CU(launch_traj(ctx->stream, "memo_traj_kernel"));
+    if (split) {
+        CU(cudaEventRecord(ctx->ev_a, ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->aux, ctx->ev_a, 0));
+        for (int j = 0; j < n_jobs; ++j) {
+            tj.job[j].k0 = KA[j]; tj.job[j].k1 = K1[j];      // a job without a second phase gets an empty pass range
+        }
+        if (n_jobs == 1) tj.job[1] = tj.job[0];
+        CU(launch_traj(ctx->aux, "memo_traj_kernel(second phase, concurrent)"));
+        CU(cudaEventRecord(ctx->ev_b, ctx->aux));
     }
-    CU(cudaGetLastError());
+    MemoWindowParams wps[2];
     for (int j = 0; j < n_jobs; ++j) {
         phyfoo_model* m = jobs[j].m;
         const ModelHost& h = m->h;
@@ -988,30 +1058,57 @@ static int launch_memo_jobs(phyfoo_ctx* ctx, const phyfoo_dataset* ds, const Mem
         unsigned long long* counters = ctx->counters.as<unsigned long long>();
         unsigned long long* c_sweeps = counters + 2 * jobs[j].counter_slot + 1;
         CU(cudaMemsetAsync(c_sweeps, 0, sizeof(unsigned long long), ctx->stream));
-        char* pb = ctx->memo_pending.as<char>() + pend_off[j];
-        int* pend_count = (int*)pb;
-        int64_t* pend_col0 = (int64_t*)(pb + 8);
-        int64_t* pend_dst = pend_col0 + n_items[j];
-        uint8_t* pend_strand = (uint8_t*)(pend_dst + n_items[j]);
-        CU(cudaMemsetAsync(pend_count, 0, 8, ctx->stream));
-        MemoWindowParams wp;
+        MemoWindowParams& wp = wps[j];
         wp.bases = ds->d_bases; wp.gaps = ds->d_gaps; wp.n_cols = ds->n_cols; wp.nb = ds->nb;
         wp.col_off = ds->d_col_off; wp.win_off = jobs[j].d_win_off; wp.n_aln = ds->n_aln;
         wp.n_windows = jobs[j].n_windows; wp.n_strands = jobs[j].strands == 2 ? 2 : 1; wp.strand0 = jobs[j].strands == 1 ? 1 : 0;
-        wp.W = h.W; wp.S = h.S; wp.cap = ms->cap; wp.K1 = K1[j]; wp.RS = (K1[j] + 3) / 4 * 4;
+        wp.W = h.W; wp.S = h.S; wp.cap = ms->cap; wp.K1 = KA[j]; wp.RS = (K1[j] + 3) / 4 * 4;
         wp.dense_of = ms->d_dense_of; wp.traj = ctx->memo_traj.as<double>() + traj_off[j];
         wp.out = jobs[j].d_out; wp.sweeps = jobs[j].d_sweeps; wp.counter_sweeps = c_sweeps;
         wp.max_sweeps = h.max_sweeps; wp.min_sweeps = h.min_sweeps; wp.tol = h.tol; wp.exact = jobs[j].mode == PHYFOO_MODE_EXACT ? 1 : 0;
-        wp.pend_count = pend_count; wp.pend_col0 = pend_col0; wp.pend_strand = pend_strand; wp.pend_dst = pend_dst;
+        // list 0: left by the first gather pass when the trajectories come in two phases; list 1: for the direct kernel
+        const size_t list_bytes = (pend_off[j + 1] - pend_off[j]) / 2;
+        char* pb = ctx->memo_pending.as<char>() + pend_off[j] + (KA[j] < K1[j] ? 0 : list_bytes);
+        wp.pend_count = (int*)pb;
+        wp.pend_col0 = (int64_t*)(pb + 8);
+        wp.pend_dst = wp.pend_col0 + n_items[j];
+        wp.pend_strand = (uint8_t*)(wp.pend_dst + n_items[j]);
+        wp.in_count = nullptr; wp.in_col0 = nullptr; wp.in_strand = nullptr; wp.in_dst = nullptr;
+        CU(cudaMemsetAsync(ctx->memo_pending.as<char>() + pend_off[j], 0, 8, ctx->stream));
+        CU(cudaMemsetAsync(ctx->memo_pending.as<char>() + pend_off[j] + list_bytes, 0, 8, ctx->stream));
         const int wblocks = (int)std::max<long long>(1, std::min<long long>((n_items[j] + 255) / 256, 16LL * ctx->sm_count));
         {
             KernelTimer kt_(ctx, "memo_window_kernel");
-            memo_window_kernel<<<wblocks, 256, 0, ctx->stream>>>(wp);
+            memo_window_kernel<false><<<wblocks, 256, 0, ctx->stream>>>(wp);
         }
         CU(cudaGetLastError());
+    }
+    if (split) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_b, 0));
+    for (int j = 0; j < n_jobs; ++j) {
+        phyfoo_model* m = jobs[j].m;
+        const ModelHost& h = m->h;
+        if (n_items[j] == 0) continue;
+        MemoWindowParams& wp = wps[j];
+        if (KA[j] < K1[j]) {
+            // second gather pass over the windows the first one left, now with the whole trajectories
+            const size_t list_bytes = (pend_off[j + 1] - pend_off[j]) / 2;
+            wp.in_count = wp.pend_count; wp.in_col0 = wp.pend_col0; wp.in_strand = wp.pend_strand; wp.in_dst = wp.pend_dst;
+            char* pb = ctx->memo_pending.as<char>() + pend_off[j] + list_bytes;
+            wp.pend_count = (int*)pb;
+            wp.pend_col0 = (int64_t*)(pb + 8);
+            wp.pend_dst = wp.pend_col0 + n_items[j];
+            wp.pend_strand = (uint8_t*)(wp.pend_dst + n_items[j]);
+            wp.K1 = K1[j];
+            const int wblocks = (int)std::max<long long>(1, std::min<long long>((n_items[j] + 255) / 256, 2LL * ctx->sm_count));
+            {
+                KernelTimer kt_(ctx, "memo_window_kernel(second pass)");
+                memo_window_kernel<true><<<wblocks, 256, 0, ctx->stream>>>(wp);
+            }
+            CU(cudaGetLastError());
+        }
         if (!wp.exact && K1[j] - 1 < h.max_sweeps) {
             // windows that need more sweeps than the stored trajectories hold: direct kernel over the (device-side) list
-            ScoreItems items{pend_col0, pend_strand, nullptr, nullptr, nullptr, pend_count, pend_dst, true};
+            ScoreItems items{wp.pend_col0, wp.pend_strand, nullptr, nullptr, nullptr, wp.pend_count, wp.pend_dst, true};
             rc = launch_score(ctx, ds, m, nullptr, n_items[j], 0, jobs[j].d_out, jobs[j].d_sweeps, jobs[j].counter_slot, &items);
             if (rc) return rc;
         }
@@ -1551,6 +1648,16 @@ extern "C" int phyfoo_set_option(phyfoo_ctx* ctx, const char* name, int64_t valu
     if (std::strcmp(name, "pattern_memo_sweep_cap") == 0) {
         if (value < 1 || value > 1000) return fail(ctx, PHYFOO_EINVAL, "set_option: pattern_memo_sweep_cap must be in 1..1000");
         ctx->memo_sweep_cap = (int)value;
+        return PHYFOO_OK;
+    }
+    if (std::strcmp(name, "pattern_memo_wave") == 0) {
+        if (value != 0 && value != 1) return fail(ctx, PHYFOO_EINVAL, "set_option: pattern_memo_wave must be 0 or 1");
+        ctx->memo_wave = (int)value;
+        return PHYFOO_OK;
+    }
+    if (std::strcmp(name, "pattern_memo_split") == 0) {
+        if (value < 0 || value > 1000 || value % 4) return fail(ctx, PHYFOO_EINVAL, "set_option: pattern_memo_split must be 0 (one phase) or a multiple of 4");
+        ctx->memo_split = (int)value;
         return PHYFOO_OK;
     }
     return fail(ctx, PHYFOO_EINVAL, std::string("set_option: unknown option ") + name);

@@ -25,6 +25,11 @@ class _PhyloModel:
     # static switches of the reference (models/PhyloBayesModel.java:43-69)
     CALC_LOGLIKELIHOOD = False
     EVOL_MODEL = _abi.EVOL_F81ALPHA   # evolution/EvolModel.java:7 MODEL_CLASS
+    # mean-field sweep limits and stop tolerance (algorithm/MeanFieldForBayesNet.java:102-107,205); 0 = the reference's
+    # constants (100, 2, 1e-5).  Read when the device model is created.
+    MAX_SWEEPS = 0
+    MIN_SWEEPS = 0
+    TOL = 0.0
 
     def __init__(self, length, order, newick, ctx=None):
         self.ctx = ctx or core.default_context()
@@ -104,7 +109,8 @@ class _PhyloModel:
     def device_model(self):
         if self._dev is None:
             self._dev = core.DeviceModel(self.ctx, self.kind, self.length, self.order, self.tree, self._branch,
-                                         self._pi, evol=type(self).EVOL_MODEL, mode=self.mode())
+                                         self._pi, evol=type(self).EVOL_MODEL, mode=self.mode(),
+                                         max_sweeps=self.MAX_SWEEPS, min_sweeps=self.MIN_SWEEPS, tol=self.TOL)
             self._mode = self.mode()
         elif self._mode != self.mode():
             self._dev.set_mode(self.mode())
@@ -145,11 +151,14 @@ class PhyloBayesModel(_PhyloModel):
     MOTIF_QUALITY_THRESHOLD = 0.0      # :21
     OPTIMIZE_IN_TOTO = False           # :63
 
-    def train(self, sample: PhyloSample, weights, rng=None):
+    def train(self, sample: PhyloSample, weights, rng=None, rev_weights=None):
         """One M-step: select the top-posterior windows per alignment (io/SequenceSpecificDataSelector.java:37-99), fix
         their mean fields (one GPU pass), then optimise the parameters position by position in random order with BFGS on the
         forward-difference gradient (optimizing/FE_byParameter_ForBayesNodeJstacs.java:61-83).  weights: gamma per window, or
-        None for the gamma of the most recent E-step still resident on the device.  Returns a dict of statistics."""
+        None for the gamma of the most recent E-step still resident on the device.  rev_weights: when the caller is a
+        StrandModel, the weights of the reverse-complement copies of the windows; the selector then thresholds the two strands
+        of an alignment independently, as the reference does because it groups windows by their parent object
+        (io/SequenceSpecificDataSelector.java:45-49).  Returns a dict of statistics."""
         self._check(sample)
         self.trainingStep = getattr(self, "trainingStep", 0)
         if self.trainingStep < self.SKIP_TRAINING_STEPS:
@@ -158,7 +167,13 @@ class PhyloBayesModel(_PhyloModel):
         rng = rng or np.random.default_rng()
         ds = sample.device(self.ctx)
         sa, so, sw = core.select(self.ctx, ds, self.length, weights, self.PROB_THRESH_FOR_WEIGHTS, self.MOTIF_QUALITY_THRESHOLD)
-        fe = core.FESet(self.ctx, ds, self.device_model(), sa, so, sw)
+        ss = None
+        if rev_weights is not None:
+            ra, ro, rw = core.select(self.ctx, ds, self.length, rev_weights, self.PROB_THRESH_FOR_WEIGHTS,
+                                     self.MOTIF_QUALITY_THRESHOLD)
+            ss = np.concatenate([np.zeros(sa.size, np.uint8), np.ones(ra.size, np.uint8)])
+            sa, so, sw = np.concatenate([sa, ra]), np.concatenate([so, ro]), np.concatenate([sw, rw])
+        fe = core.FESet(self.ctx, ds, self.device_model(), sa, so, sw, ss)
         stats = {"skipped": False, "selected": int(sa.size), "evaluations": 0, "f_before": None, "f_after": None}
         try:
             if self.OPTIMIZE_IN_TOTO:
@@ -297,17 +312,68 @@ class PhyloBackground(_PhyloModel):
 
 
 class StrandModel:
-    """jstacs StrandModel: mixture of a motif model and its reverse complement; weights {forward, backward}."""
+    """jstacs StrandModel as PhyFoo builds it (models/ModelUtil.java:98-108): a mixture of a motif model and its reverse
+    complement with estimated strand weights {forward, backward}, hyper-parameters {1, 1} and Dirichlet(1) initialisation."""
 
-    def __init__(self, model: PhyloBayesModel, forwardProb=0.5):
+    def __init__(self, model: PhyloBayesModel, forwardProb=0.5, componentHyperParams=(1.0, 1.0), estimateComponentProbs=True,
+                 alpha=1.0):
         self.model = model
         self.weights = np.array([forwardProb, 1.0 - forwardProb])
+        self.hyper = np.asarray(componentHyperParams, np.float64)
+        self.estimateComponentProbs = bool(estimateComponentProbs)
+        self.alpha = float(alpha)
 
     def getLength(self):
         return self.model.getLength()
 
     def logWeights(self):
-        return np.log(self.weights)
+        with np.errstate(divide="ignore"):
+            return np.log(self.weights)
+
+    def getLogProbFor(self, sample: PhyloSample):
+        """logsumexp over the two strands per window (jstacs StrandModel.java:631-640)."""
+        lw = self.logWeights()
+        return np.logaddexp(lw[0] + self.model.getLogProbFor(sample, 0), lw[1] + self.model.getLogProbFor(sample, 1))
+
+    def getNewWeights(self, sample: PhyloSample, dataWeights):
+        """Strand E-step over every window (jstacs StrandModel.java:561-583): both strands scored on the GPU, the strand
+        posterior times the window's data weight on the host (two multiplies per window).  Returns (forward weights, reverse
+        weights, w[2] without the prior, L)."""
+        lw = self.logWeights()
+        a = lw[0] + self.model.getLogProbFor(sample, 0)
+        b = lw[1] + self.model.getLogProbFor(sample, 1)
+        tot = np.logaddexp(a, b)
+        dw = np.ones_like(tot) if dataWeights is None else np.asarray(dataWeights, np.float64)
+        with np.errstate(invalid="ignore"):
+            pf = np.where(np.isfinite(tot), np.exp(a - tot), 0.5)
+        f, r = pf * dw, (1.0 - pf) * dw
+        return f, r, np.array([f.sum(), r.sum()]), float(np.sum(tot * dw))
+
+    def _new_parameters(self, sample, f, r, w, rng):
+        st = self.model.train(sample, f, rng=rng, rev_weights=r)
+        if self.estimateComponentProbs:                        # AbstractMixtureModel.getNewComponentProbs :1542-1578
+            v = np.asarray(w, np.float64) + self.hyper
+            self.weights = v / v.sum()
+        return st
+
+    def doFirstIteration(self, sample: PhyloSample, dataWeights, rng=None):
+        """jstacs StrandModel.java:530-557: each window's weight is split between the strands by a Dirichlet(alpha) draw, then
+        one M-step.  This is what the enclosing mixture calls in its first M-step (AbstractMixtureModel.java:1024-1026)."""
+        rng = rng or np.random.default_rng()
+        dw = np.asarray(dataWeights, np.float64)
+        split = rng.dirichlet(np.full(2, self.alpha), size=dw.size)
+        f, r = dw * split[:, 0], dw * split[:, 1]
+        return self._new_parameters(sample, f, r, np.array([f.sum(), r.sum()]), rng)
+
+    def continueIterations(self, sample: PhyloSample, dataWeights, iterations=1, rng=None):
+        """jstacs AbstractMixtureModel.java:946-977 as the enclosing mixture calls it from the second M-step on (:1028-1030):
+        strand E-step, M-step, repeated `iterations` times, and a closing E-step whose likelihood is returned."""
+        f, r, w, L = self.getNewWeights(sample, dataWeights)
+        st = None
+        for _ in range(iterations):
+            st = self._new_parameters(sample, f, r, w, rng)
+            f, r, w, L = self.getNewWeights(sample, dataWeights)
+        return st, L
 
 
 class SingleHiddenMotifMixture:
@@ -353,8 +419,6 @@ class SingleHiddenMotifMixture:
         M-step of the motif model through PhyloBayesModel.train, component weights from the sufficient statistics.  Stops when
         the log-likelihood changes by less than eps (SmallDifferenceOfFunctionEvaluationsCondition) or after max_iterations.
         Returns the list of log-likelihoods, one per E-step."""
-        if self.strand is not None:
-            raise NotImplementedError("EM with a StrandModel motif: the E-step is supported, the strand-split M-step is not yet")
         history, trained = [], False
         for it in range(max_iterations):
             res = self.getNewWeights(sample, want_gamma=True)
@@ -363,7 +427,12 @@ class SingleHiddenMotifMixture:
                 print(f"{it}\t{res['ll']:.6f}\t{0.0 if it == 0 else res['ll'] - history[-2]:.3e}")
             if trained and abs(history[-1] - history[-2]) < eps:
                 break
-            st = self.motif.train(sample, None, rng=rng)   # gamma of this E-step is still resident on the device
+            if self.strand is None:
+                st = self.motif.train(sample, None, rng=rng)   # gamma of this E-step is still resident on the device
+            elif it == 0:                                      # jstacs AbstractMixtureModel.java:1017-1033
+                st = self.strand.doFirstIteration(sample, res["gamma"], rng)
+            else:
+                st, _ = self.strand.continueIterations(sample, res["gamma"], 1, rng)
             trained = not st["skipped"]                    # the motif ignores its first call (SKIP_TRAINING_STEPS = 1)
             self.setComponentWeights(res["w"])
         return history

@@ -144,3 +144,29 @@ extern "C" int emul_fe_values(const phyfoo_model_desc* d, const uint8_t* cols /*
 #include "../../phyfoo_b200/csrc/fp64_math.cuh"
 extern "C" void emul_exp(const double* x, int n, double* out) { for (int i = 0; i < n; ++i) out[i] = phy_exp(x[i]); }
 extern "C" void emul_log(const double* x, int n, double* out) { for (int i = 0; i < n; ++i) out[i] = phy_log(x[i]); }
+
+// For every (column, position) tree: the first pass k >= 1 whose state (q and child sums) equals the state after pass k-1
+// bit for bit -- from there on the trajectory is constant -- or -1 when that does not happen within max_passes.
+extern "C" int emul_fixed_point(const phyfoo_model_desc* d, const uint8_t* cols /*[n][S]*/, int n, int max_passes, int* out /*[n][W]*/) {
+    try {
+        ModelHost m; m.init(*d);
+        TreeProg tp = prog_of(m);
+        std::vector<double> state((size_t)m.I * 8), prev, prev2;
+        for (int c = 0; c < n; ++c)
+            for (int t = 0; t < m.W; ++t) {
+                State st{state.data(), 1};
+                ColWords cw = words_of(cols + (size_t)c * m.S, m.S, false);
+                Tab lt{&m.logtab[(size_t)t * m.E], 1};
+                std::fill(state.begin(), state.end(), 0.0);
+                int found = -1;
+                for (int k = 0; k < (max_passes < 0 ? -max_passes : max_passes); ++k) {
+                    prev2 = prev; prev = state;
+                    meanfield_pass(tp, lt, st, cw, k > 0);
+                    if (k > 0 && std::memcmp(prev.data(), state.data(), state.size() * sizeof(double)) == 0) { found = k; break; }
+                    if (max_passes < 0 && k > 1 && std::memcmp(prev2.data(), state.data(), state.size() * sizeof(double)) == 0) { found = k; break; }
+                }
+                out[(size_t)c * m.W + t] = found;
+            }
+        return 0;
+    } catch (const std::exception& e) { std::fprintf(stderr, "emul: %s\n", e.what()); return -1; }
+}

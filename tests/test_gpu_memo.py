@@ -25,7 +25,7 @@ def _both(ctx, fn):
     return direct, memo
 
 
-@pytest.mark.parametrize("newick_name", ["star5", "cat5", "mixed6", "star3"])
+@pytest.mark.parametrize("newick_name", ["star5", "cat5", "mixed6", "bal6", "star3"])
 @pytest.mark.parametrize("gap_rate", [0.0, 0.2])
 def test_memo_equals_direct_bit_for_bit(ctx, newick_name, gap_rate):
     from phyfoo_b200 import synth
@@ -33,7 +33,9 @@ def test_memo_equals_direct_bit_for_bit(ctx, newick_name, gap_rate):
     from phyfoo_b200.models import PhyloBackground, PhyloBayesModel
     from phyfoo_b200.newick import parse_newick
     newick = {"star5": synth.star_newick(5), "cat5": synth.caterpillar_newick(5), "star3": synth.star_newick(3, 0.35),
-              "mixed6": "((A:0.1,B:0.3):0.15,(C:0.2,(D:0.05,E:0.4):0.25):0.1,F:0.3)"}[newick_name]
+              "mixed6": "((A:0.1,B:0.3):0.15,(C:0.2,(D:0.05,E:0.4):0.25):0.1,F:0.3)",
+              # three internal nodes at depth 1: three node slots (16 lanes per tree) in the wavefront trajectory kernel
+              "bal6": "((A:0.1,B:0.2):0.1,(C:0.3,D:0.1):0.2,(E:0.2,F:0.25):0.15)"}[newick_name]
     S = parse_newick(newick).n_species
     rng = np.random.default_rng(77)
     W = 7
@@ -116,6 +118,98 @@ def test_memo_sweep_cap_fallback_is_bit_identical(ctx):
         assert (dk > 6).any() and (dk <= 6).any()      # the cap of 6 really splits the windows between the two kernels
     finally:
         ctx.set_option("pattern_memo_sweep_cap", 64)
+
+
+def test_memo_two_phase_trajectories_are_bit_identical(ctx):
+    """"pattern_memo_split": the second trajectory phase runs on its own stream under the first gather pass; windows the first
+    pass leaves are gathered again (and, past the sweep cap, go to the direct kernel).  Same bits for every setting."""
+    from phyfoo_b200 import synth
+    from phyfoo_b200.models import PhyloBackground, PhyloBayesModel, SingleHiddenMotifMixture, StrandModel
+    newick = synth.caterpillar_newick(5)
+    W = 10
+    pwm = synth.random_pwm(W, 0, 23)
+    smp, _ = synth.make_sample(newick, 40, 150, 9, pwm=pwm, gap_rate=0.02, length_jitter=20)
+    fg = PhyloBayesModel(W, 0, newick, ctx); fg.setCondProbs(pwm)
+    bg = PhyloBackground(0, newick, ctx)
+    shm = SingleHiddenMotifMixture(StrandModel(fg, 0.4), bg, zoops=0.8)
+    ctx.set_option("pattern_memo", 0)
+    d, dk = fg.getLogProbFor(smp, want_sweeps=True)
+    de = shm.getNewWeights(smp)
+    ctx.set_option("pattern_memo", 2)
+    try:
+        for cap, split, wave in ((64, 0, 1), (64, 4, 1), (64, 8, 0), (64, 16, 1), (23, 16, 1), (23, 20, 0), (11, 8, 1), (100, 32, 1),
+                                 (64, 0, 0)):
+            ctx.set_option("pattern_memo_sweep_cap", cap)
+            ctx.set_option("pattern_memo_split", split)
+            ctx.set_option("pattern_memo_wave", wave)
+            m, mk = fg.getLogProbFor(smp, want_sweeps=True)
+            assert ctx.last_score_path() == 1
+            assert np.array_equal(d, m) and np.array_equal(dk, mk), (cap, split, wave)
+            assert fg.last_stats["sweeps_fg"] == int(dk.sum())
+            names = [n for n, _ in ctx.last_kernel_times()]
+            two = split > 0 and split + 4 <= cap + 1
+            assert ("memo_window_kernel(second pass)" in names) == two, (cap, split, names)
+            assert ("memo_traj_kernel(second phase, concurrent)" in names) == two
+            me = shm.getNewWeights(smp)
+            assert me["ll"] == de["ll"] and np.array_equal(me["gamma"], de["gamma"]), (cap, split)
+            assert np.array_equal(me["argmax_off"], de["argmax_off"]) and np.array_equal(me["argmax_strand"], de["argmax_strand"])
+            assert me["stats"]["sweeps_fg"] == de["stats"]["sweeps_fg"] and me["stats"]["sweeps_bg"] == de["stats"]["sweeps_bg"]
+        assert (dk > 8).any() and (dk < 8).any()
+    finally:
+        ctx.set_option("pattern_memo_sweep_cap", 64)
+        ctx.set_option("pattern_memo_split", 0)
+        ctx.set_option("pattern_memo_wave", 1)
+    with pytest.raises(Exception):
+        ctx.set_option("pattern_memo_split", 6)
+
+
+@pytest.mark.parametrize("newick_name", ["cat5", "bal6"])
+@pytest.mark.parametrize("gap_rate", [0.0, 0.15])
+def test_memo_trajectories_past_their_fixed_point(ctx, newick_name, gap_rate):
+    """The wavefront trajectory kernel stops a tree once its q repeats bit for bit (fixed point or two-cycle) and fills the
+    rest of the row.  With a stop tolerance of 1e-300 a window only stops when its summed free energy repeats exactly, so
+    the windows read the rows far past that point -- up to sweep 99 and 100 (both parities of the two-cycle fill)."""
+    from phyfoo_b200 import synth
+    from phyfoo_b200.data import PhyloSample
+    from phyfoo_b200.models import PhyloBayesModel
+    from phyfoo_b200.newick import parse_newick
+    newick = {"cat5": synth.caterpillar_newick(5),
+              "bal6": "((A:0.1,B:0.2):0.1,(C:0.3,D:0.1):0.2,(E:0.2,F:0.25):0.15)"}[newick_name]
+    S = parse_newick(newick).n_species
+    rng = np.random.default_rng(5)
+    W = 6
+    lens = [80, 47, 122]
+    smp = PhyloSample(random_codes(rng, sum(lens), S, gap_rate), np.concatenate([[0], np.cumsum(lens)]))
+
+    class Tight(PhyloBayesModel):
+        TOL = 1e-300
+
+    class Tight99(Tight):
+        MAX_SWEEPS = 99
+
+    try:
+        seen = []
+        for cls in (Tight, Tight99):
+            fg = cls(W, 0, newick, ctx); fg.setCondProbs(synth.random_pwm(W, 0, 12))
+            ctx.set_option("pattern_memo_sweep_cap", 100)
+            ctx.set_option("pattern_memo_split", 0)
+            ctx.set_option("pattern_memo", 0)
+            d, dk = fg.getLogProbFor(smp, want_sweeps=True)
+            ctx.set_option("pattern_memo", 2)
+            for wave in (1, 0):
+                ctx.set_option("pattern_memo_wave", wave)
+                m, mk = fg.getLogProbFor(smp, want_sweeps=True)
+                assert ctx.last_score_path() == 1
+                assert np.array_equal(dk, mk) and np.array_equal(d, m), (cls.__name__, wave)
+            seen.append(dk)
+        assert seen[0].max() > 30                                        # rows are read far past the default stop rule
+        if newick_name == "cat5" and gap_rate == 0.0:
+            assert (seen[0] == 100).any() and (seen[1] == 99).any()      # windows in a two-cycle run to the limit
+            assert (seen[0] < 60).any()                                  # and others stop at an exact fixed point
+    finally:
+        ctx.set_option("pattern_memo_sweep_cap", 64)
+        ctx.set_option("pattern_memo_split", 0)
+        ctx.set_option("pattern_memo_wave", 1)
 
 
 def test_memo_does_not_apply_to_many_species_or_order1(ctx):

@@ -100,3 +100,44 @@ def test_edge_learning_improves_the_objective_and_recovers_branch_scale(ctx):
     assert 0.2 < learned[0, 0] < 0.5
     st2 = fg.trainEdges(smp, res["gamma"], globally=False, equal=False)
     assert st2["f_after"] >= st2["f_before"] - 1e-9
+
+
+def test_strand_model_em_recovers_sites_on_both_strands(ctx):
+    """model.strandmodel = true: half of the planted sites are reverse-complemented.  The strand E-step agrees with the oracle's
+    two-strand scores, the strand-split M-step (selector run per strand group, quirk 11) improves the likelihood, and the site
+    and strand calls match the planting."""
+    from phyfoo_b200 import synth
+    from phyfoo_b200.data import PhyloSample
+    from phyfoo_b200.models import PhyloBackground, PhyloBayesModel, SingleHiddenMotifMixture, StrandModel
+    from util import oracle_fg
+    newick = synth.caterpillar_newick(5)
+    W = 8
+    rng = np.random.default_rng(5)
+    truth = [rng.dirichlet(np.full(4, 0.2), size=1) * 0.94 + 0.015 for _ in range(W)]
+    smp, planted = synth.make_sample(newick, 160, 90, 21, pwm=truth, zoops=1.0)
+    codes = smp.codes.copy()
+    rev = np.arange(160) % 2 == 1
+    for i in np.nonzero(rev)[0]:
+        lo = smp.col_offsets[i] + planted[i]
+        win = codes[lo:lo + W][::-1]
+        codes[lo:lo + W] = np.where(win < 4, 3 - win, win)
+    smp = PhyloSample(codes, smp.col_offsets)
+    start = [0.6 * p + 0.4 * 0.25 for p in truth]
+    fg = PhyloBayesModel(W, 0, newick, ctx); fg.setCondProbs(start)
+    sm = StrandModel(fg)
+    # strand E-step against the oracle's scores
+    om = oracle_fg(newick, start)
+    f, r, w, L = sm.getNewWeights(smp, None)
+    a = np.concatenate([om.score_windows(smp.getElementAt(i), False)[0] for i in range(8)]) + np.log(0.5)
+    b = np.concatenate([om.score_windows(smp.getElementAt(i), True)[0] for i in range(8)]) + np.log(0.5)
+    n8 = a.size
+    assert np.allclose(f[:n8], np.exp(a - np.logaddexp(a, b)), rtol=1e-9, atol=1e-12)
+    assert np.allclose(f + r, 1.0) and np.isclose(w.sum(), f.size)
+    shm = SingleHiddenMotifMixture(sm, PhyloBackground(0, newick, ctx), zoops=1.0)
+    hist = shm.train(smp, max_iterations=6, eps=1e-4, rng=np.random.default_rng(2))
+    assert len(hist) >= 3 and hist[-1] > hist[0] + 1.0
+    res = shm.getNewWeights(smp)
+    assert (res["argmax_off"] == planted).mean() > 0.8
+    ok = res["argmax_off"] == planted
+    assert (res["argmax_strand"][ok] == rev[ok]).mean() > 0.8
+    assert 0.3 < sm.weights[0] < 0.7 and np.isclose(sm.weights.sum(), 1.0)
