@@ -391,8 +391,13 @@ def run_ours(args):
         except Exception:
             traffic_db = {}
 
-        def traffic_of(key):
-            return traffic_db.get(key) if args.config == "c2" and not args.n_aln else None
+        def traffic_of(*keys):
+            if args.config != "c2" or args.n_aln:
+                return None
+            for key in keys:
+                if key in traffic_db:
+                    return traffic_db[key]
+            return None
 
         fg_name = ("score_o1w_kernel" if "score_o1w_kernel" in names else "score_o1_kernel") if cfg["order"] == 1 else "score_o0_kernel"
         extra = {}
@@ -418,16 +423,18 @@ def run_ours(args):
                             "bytes_per_launch": abytes, "kernel_ms": win_ms, "kernel_share_of_step": win_ms / step_ms,
                             "table_gather": {"bytes": gather_bytes, "GB/s": gather_bytes / (win_ms * 1e-3) / 1e9,
                                              "what": "8 B x W x (K_w + 1) trajectory entries per window, served by L2"},
-                            "traffic": traffic_of("r01_c2_pattern_table:memo_window_kernel")}
+                            "traffic": traffic_of("r01_c2_pattern_table:memo_window_kernel<0, 4>", "r01_c2_pattern_table:memo_window_kernel")}
             else:
                 achieved = traj_flops / (traj_ms * 1e-3) / 1e12
                 roofline = {"bound": "fp64", "kernel": "memo_traj_kernel (mean-field trajectories of the occurring column patterns)",
                             "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
                             "peak_source": "DFMA microbenchmark in this run (MEASURED_PEAKS.json has no fp64 entry)",
                             "flops_per_launch": traj_flops, "kernel_ms": traj_ms, "kernel_share_of_step": traj_ms / step_ms,
-                            "note": f"{D} patterns x {W + 1} trees x {K1} passes: {4 * D * (W + 1)} threads (four lanes per tree), latency-bound by design; "
-                                    "kernel_ms sums the two phases; the second one runs on its own stream under the gather kernels",
-                            "traffic": traffic_of("r01_c2_pattern_table:memo_traj_kernel")}
+                            "note": f"{D} patterns x {W + 1} trees x {K1} trajectory entries each; flops count every entry although a "
+                                    "tree stops once its q repeats bit for bit (the rest of its row is filled); wavefront over "
+                                    "(node, sweep), node slots x four symbols lanes per tree: a small grid of dependent steps, "
+                                    "bound by issue slots and instruction latency, not by the fp64 pipe",
+                            "traffic": traffic_of("r01_c2_pattern_table:memo_traj_wave_kernel<8>", "r01_c2_pattern_table:memo_traj_kernel")}
             d_ms, d_kernels = direct
             d_fg = max(ms for (_, name), ms in d_kernels.items() if name == fg_name)
             extra["roofline_direct"] = fp64_roofline(
