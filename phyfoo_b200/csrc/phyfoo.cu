@@ -710,8 +710,9 @@ static int dataset_win_off(phyfoo_ctx* ctx, const phyfoo_dataset* cds, int W, co
         for (int i = 0; i < ds->n_aln; ++i) off[i + 1] = off[i] + std::max<int64_t>(0, ds->col_off[i + 1] - ds->col_off[i] - W + 1);
         int64_t* d = nullptr;
         CU(dev_malloc(ctx->stream, &d, off.size() * sizeof(int64_t)));
+        // (no synchronisation: the source is pageable memory, which the runtime stages before the call returns, and the
+        // vector's buffer lives on in ds->win_off)
         cudaError_t e = cudaMemcpyAsync(d, off.data(), off.size() * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { dev_free(ctx->stream, d); ctx->err = std::string("win_off copy: ") + cudaGetErrorString(e); return PHYFOO_ECUDA; }
         ds->d_win_off[W] = d;
         ds->win_off[W] = std::move(off);
@@ -1530,23 +1531,27 @@ extern "C" int phyfoo_zoops_estep(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phy
                            argmax_strand ? ctx->argstrand.as<uint8_t>() : nullptr, ctx->out3.as<double>(), &nw);
     if (rc) return rc;
     ctx->gamma_windows = gamma_out ? nw : -1;
-    const float ms = tm.stop();
+    // one synchronisation for the whole call: end-of-kernels event, then every copy (results, sweep counters), then wait
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
     CU(cudaGetLastError());
     double r3[3];
+    unsigned long long cnt[4] = {0, 0, 0, 0};
     CU(cudaMemcpyAsync(r3, ctx->out3.p, sizeof(r3), cudaMemcpyDeviceToHost, ctx->stream));
-    if (gamma_out) CU(cudaMemcpyAsync(gamma_out, ctx->gamma.p, (size_t)nw * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    if (profile_out) CU(cudaMemcpyAsync(profile_out, ctx->profile.p, (size_t)nw * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (stats) CU(cudaMemcpyAsync(cnt, ctx->counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
     if (argmax_off) CU(cudaMemcpyAsync(argmax_off, ctx->argoff.p, (size_t)ds->n_aln * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     if (argmax_strand) CU(cudaMemcpyAsync(argmax_strand, ctx->argstrand.p, (size_t)ds->n_aln, cudaMemcpyDeviceToHost, ctx->stream));
+    if (gamma_out) CU(cudaMemcpyAsync(gamma_out, ctx->gamma.p, (size_t)nw * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (profile_out) CU(cudaMemcpyAsync(profile_out, ctx->profile.p, (size_t)nw * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     if (ll_out) *ll_out = r3[0];
     if (w_out) { w_out[0] = r3[1]; w_out[1] = r3[2]; }
     if (stats) {
         memset(stats, 0, sizeof(*stats));
         stats->n_windows = nw * (strand_logw ? 2 : 1); stats->n_columns = ds->n_cols;
         stats->kernel_launches = ctx->launches; stats->gpu_ms = ms;
-        if ((rc = read_sweeps(ctx, 0, &stats->sweeps_fg))) return rc;
-        if ((rc = read_sweeps(ctx, 1, &stats->sweeps_bg))) return rc;
+        stats->sweeps_fg = (int64_t)cnt[1]; stats->sweeps_bg = (int64_t)cnt[3];      // counters: [2 slot + 1] = sweep sum
     }
     return PHYFOO_OK;
 }

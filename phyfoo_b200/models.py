@@ -32,7 +32,7 @@ class _PhyloModel:
     TOL = 0.0
 
     def __init__(self, length, order, newick, ctx=None):
-        self.ctx = ctx or core.default_context()
+        self._ctx = ctx                     # resolved on first use: parameters can be set and files read without a device
         self.length, self.order, self.newick = int(length), int(order), newick
         self.tree = parse_newick(newick)
         self.n_trees = self.length if self.kind == _abi.MODEL_FG else self.order + 1
@@ -42,6 +42,12 @@ class _PhyloModel:
         self._branch = np.tile(self.tree.branch, (self.n_trees, 1))
         self._dev = None
         self._mode = None
+
+    @property
+    def ctx(self):
+        if self._ctx is None:
+            self._ctx = core.default_context()
+        return self._ctx
 
     def _ctx_rows(self, t):
         if self.kind == _abi.MODEL_FG:
@@ -135,6 +141,17 @@ class PhyloBayesModel(_PhyloModel):
 
     def getMotifLength(self):
         return self.length
+
+    def toXML(self):
+        """models/PhyloBayesModel.java:291-299 (branch lengths are written with three decimals, like the reference)."""
+        from . import xmlio
+        return xmlio.phylo_bayes_model_to_xml(self)
+
+    @classmethod
+    def fromXML(cls, xml, ctx=None):
+        """PhyloBayesModel(StringBuffer) (models/PhyloBayesModel.java:300-309)."""
+        from . import xmlio
+        return xmlio.read_phylo_bayes_model(xml, ctx)
 
     def getLogProbFor(self, sample: PhyloSample, strand=0, want_sweeps=False):
         """Scores of every window of every alignment (alignment-major, offsets ascending) =
@@ -249,6 +266,16 @@ class PhyloBackground(_PhyloModel):
     def __init__(self, order, newickString, ctx=None):
         super().__init__(0, order, newickString, ctx)
         self.last_stats = None
+
+    def toXML(self):
+        """models/PhyloBackground.java:330-336."""
+        from . import xmlio
+        return xmlio.phylo_background_to_xml(self)
+
+    @classmethod
+    def fromXML(cls, xml, ctx=None):
+        from . import xmlio
+        return xmlio.read_phylo_background(xml, ctx)
 
     def getColumnLogProbs(self, sample: PhyloSample, want_sweeps=False):
         """Per-column terms whose sum over [start, end] is getLogProbFor(seq, start, end)
