@@ -40,6 +40,7 @@ def parse_args():
     ap.add_argument("--n-aln", type=int, default=None, help="override the number of alignments (debug only)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mstep", action="store_true", help="skip the secondary optimizer-iteration timings")
     ap.add_argument("--no-memo", action="store_true", help="switch the pattern-table path off (direct kernel only)")
     ap.add_argument("--memo-split", type=int, default=None, help="pattern_memo_split of the library (tuning only)")
     ap.add_argument("--memo-wave", type=int, default=None, help="pattern_memo_wave of the library (tuning only)")
@@ -357,6 +358,61 @@ def run_ours(args):
     d2h = int(res["gamma"].nbytes + res["argmax_off"].nbytes + res["argmax_strand"].nbytes + 24)
     assert world > 1 or abs(res["ll"] - ll_w[0]) <= 1e-9 * abs(res["ll"])
 
+    # ---- one forward-difference gradient of the M-step objective (dim + 1 objective sums in one
+    # pass, plus the all-reduce at N > 1) and one whole EM iteration (the E-step above + the M-step of the motif model:
+    # selection, fixing q, position-wise BFGS).  Secondary numbers; they change the model, so they come last.
+    from phyfoo_b200 import sharding
+    optimizer = None
+    if cfg["order"] == 0 and not args.no_mstep:
+        core.zoops_estep(ctx, ds, fg.device_model(), bg.device_model(), logw, None, None, True, False, False)   # gamma stays resident
+        t0 = time.perf_counter()
+        sa, so, sw = core.select(ctx, ds, W, None, fg.PROB_THRESH_FOR_WEIGHTS, fg.MOTIF_QUALITY_THRESHOLD)
+        fe = core.FESet(ctx, ds, fg.device_model(), sa, so, sw)
+        ctx.synchronize()
+        prepare_ms = (time.perf_counter() - t0) * 1e3
+        obj = sharding.ShardedObjective(fe, local) if world > 1 else fe
+        lam = np.log(np.asarray(fg.getCondProb(0), np.float64).ravel())
+        for _ in range(3):
+            obj.grad(0, lam)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        n_grad = 20
+        for _ in range(n_grad):
+            obj.grad(0, lam)
+        grad_ms = (time.perf_counter() - t0) * 1e3 / n_grad
+        fe.free()
+
+        def mstep(suffstats):
+            fg.setCondProbs(pwm)
+            core.zoops_estep(ctx, ds, fg.device_model(), bg.device_model(), logw, None, None, True, False, False)
+            fg.trainingStep = fg.SKIP_TRAINING_STEPS          # the reference ignores the first call; time a real M-step
+            fg.MSTEP_SUFFICIENT_STATISTICS = suffstats
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            st = fg.train(sample, None, rng=np.random.default_rng(1))
+            return (time.perf_counter() - t0) * 1e3, st
+
+        mstep_ms, st = mstep(False)
+        mstep_ss_ms, st_ss = mstep(True)
+        fg.MSTEP_SUFFICIENT_STATISTICS = False
+        t = torch.tensor([grad_ms, mstep_ms, prepare_ms, mstep_ss_ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        grad_ms, mstep_ms, prepare_ms, mstep_ss_ms = (float(x) for x in t.tolist())
+        optimizer = {"gradient_ms": grad_ms, "dim": int(lam.size), "selected_windows_per_gpu": int(sa.size),
+                     "select_and_fix_q_ms": prepare_ms, "mstep_ms": mstep_ms, "mstep_evaluations": int(st["evaluations"]),
+                     "em_iteration_ms": dev_ms_max / args.steps + mstep_ms,
+                     "mstep_sufficient_statistics_ms": mstep_ss_ms, "mstep_sufficient_statistics_evaluations": int(st_ss["evaluations"]),
+                     "em_iteration_sufficient_statistics_ms": dev_ms_max / args.steps + mstep_ss_ms,
+                     "what": "wall clock, max over ranks: evaluateGradientOfFunction of one motif position (forward differences, "
+                             "dim + 1 objective sums over the selected windows in one pass" + (", one all-reduce" if world > 1 else "") +
+                             "); M-step = selection + mean fields of the selected windows + BFGS position by position "
+                             "(host optimiser, device objective); EM iteration = E-step (ms_per_step) + M-step; sufficient statistics: "
+                             "PhyloBayesModel.MSTEP_SUFFICIENT_STATISTICS = True (one device pass for the expected counts, evaluations "
+                             "are host dot products; same objective, opt-in)"}
+
     if rank == 0:
         peaks = {}
         try:
@@ -460,6 +516,8 @@ def run_ours(args):
             "kernels_ms": kern_list,
             "wall_s": t_wall,
         }
+        if optimizer:
+            line["optimizer"] = optimizer
         line.update(extra)
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1

@@ -167,6 +167,10 @@ class PhyloBayesModel(_PhyloModel):
     PROB_THRESH_FOR_WEIGHTS = 0.8      # models/PhyloPreparedAbstractModel.java:20
     MOTIF_QUALITY_THRESHOLD = 0.0      # :21
     OPTIMIZE_IN_TOTO = False           # :63
+    # False (default): every evaluation of the objective is a pass over the selected windows on the device, the reference's
+    # own evaluation order.  True (order 0): one device pass collects the expected counts of the table entries, every
+    # evaluation is then a dot product on the host (same function, sums re-associated).
+    MSTEP_SUFFICIENT_STATISTICS = False
 
     def train(self, sample: PhyloSample, weights, rng=None, rev_weights=None):
         """One M-step: select the top-posterior windows per alignment (io/SequenceSpecificDataSelector.java:37-99), fix
@@ -192,7 +196,34 @@ class PhyloBayesModel(_PhyloModel):
             sa, so, sw = np.concatenate([sa, ra]), np.concatenate([so, ro]), np.concatenate([sw, rw])
         fe = core.FESet(self.ctx, ds, self.device_model(), sa, so, sw, ss)
         stats = {"skipped": False, "selected": int(sa.size), "evaluations": 0, "f_before": None, "f_after": None}
+        local = fe
+        import sys
+        from . import sharding
+        if "torch" in sys.modules and sharding.world()[1] > 1:
+            # every rank holds a shard of the alignments: one all-reduce of [f, f_1..f_dim] per evaluation, after which all
+            # ranks see the same objective and take the same optimiser steps; rng must be seeded alike
+            fe = sharding.ShardedObjective(local, self.ctx.device)
         try:
+            if self.MSTEP_SUFFICIENT_STATISTICS and self.order == 0 and not self.OPTIMIZE_IN_TOTO:
+                # one device pass for the expected counts, then the same position-wise BFGS on host dot products
+                obj = optimize.SuffStatObjective(local, self._pi, self._branch, type(self).EVOL_MODEL)
+                if fe is not local:
+                    obj.counts, obj.entropy = sharding.allreduce_counts_(obj.counts, obj.entropy)
+                    for t in range(self.length):
+                        obj.set_position(t)
+                stats["f_before"] = obj.value()
+                for pos in rng.permutation(self.length):
+                    pos = int(pos)
+                    fun = lambda z: -obj.eval_lambda(pos, z)          # noqa: E731
+                    x, f, it, ev = optimize.quasi_newton_bfgs(fun, lambda z: obj.grad(fun, z), np.log(self._pi[pos].ravel()),
+                                                              optimize.TC_MOTIF_SEPARATED_POSITIONS())
+                    obj.eval_lambda(pos, x)
+                    stats["evaluations"] += ev
+                stats["f_after"] = obj.value()
+                for t in range(self.length):
+                    self.setCondProb(obj.pi[t].reshape(self._pi[t].shape), t)
+                self.trainingStep += 1
+                return stats
             if self.OPTIMIZE_IN_TOTO:
                 lam0 = np.concatenate([np.log(p.ravel()) for p in self._pi])
                 stats["f_before"] = fe.eval(-1, lam0)
@@ -214,7 +245,7 @@ class PhyloBayesModel(_PhyloModel):
             for t in range(self.n_trees):
                 self._pi[t] = self._dev.get_pi(t, self._pi[t].size).reshape(self._pi[t].shape)
         finally:
-            fe.free()
+            local.free()
         self.trainingStep += 1
         return stats
 

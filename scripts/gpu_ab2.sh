@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 i=0
 for extra in "$@"; do
   i=$((i+1))
-  timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline $extra > gpurun_out/ab2_$i.json 2> gpurun_out/ab2_$i.err
+  timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-mstep $extra > gpurun_out/ab2_$i.json 2> gpurun_out/ab2_$i.err
   python - <<PY
 import json
 d=json.load(open("gpurun_out/ab2_$i.json"))

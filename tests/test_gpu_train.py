@@ -141,3 +141,30 @@ def test_strand_model_em_recovers_sites_on_both_strands(ctx):
     ok = res["argmax_off"] == planted
     assert (res["argmax_strand"][ok] == rev[ok]).mean() > 0.8
     assert 0.3 < sm.weights[0] < 0.7 and np.isclose(sm.weights.sum(), 1.0)
+
+
+def test_mstep_on_sufficient_statistics_reaches_the_same_optimum(ctx):
+    """MSTEP_SUFFICIENT_STATISTICS: the same objective evaluated as a dot product of expected counts with the log tables; the
+    position-wise BFGS ends at the optimum of the per-window evaluation (the reference's evaluation order)."""
+    from phyfoo_b200 import synth
+    from phyfoo_b200.models import PhyloBackground, PhyloBayesModel, SingleHiddenMotifMixture
+    newick = synth.caterpillar_newick(5)
+    W = 6
+    truth = synth.random_pwm(W, 0, 17)
+    smp, _ = synth.make_sample(newick, 120, 70, 6, pwm=truth, gap_rate=0.03)
+    start = [0.5 * p + 0.125 for p in truth]
+    out = []
+    for ss in (False, True):
+        fg = PhyloBayesModel(W, 0, newick, ctx); fg.setCondProbs(start)
+        fg.MSTEP_SUFFICIENT_STATISTICS = ss
+        shm = SingleHiddenMotifMixture(fg, PhyloBackground(0, newick, ctx), zoops=1.0)
+        res = shm.getNewWeights(smp)
+        fg.trainingStep = fg.SKIP_TRAINING_STEPS
+        st = fg.train(smp, res["gamma"], rng=np.random.default_rng(4))
+        assert st["f_after"] > st["f_before"]
+        out.append((st, np.concatenate([np.asarray(p).ravel() for p in fg.getCondProbs()])))
+    (a, pa), (b, pb) = out
+    assert a["selected"] == b["selected"]
+    assert abs(a["f_before"] - b["f_before"]) <= 1e-9 * abs(a["f_before"])
+    assert abs(a["f_after"] - b["f_after"]) <= 1e-6 * abs(a["f_after"])
+    assert np.abs(pa - pb).max() < 2e-3
