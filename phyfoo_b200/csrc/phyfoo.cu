@@ -281,7 +281,9 @@ __global__ void __launch_bounds__(256, 2) score_o0_kernel(ScoreParams p) {
     for (;;) {
         const bool refill = need && active && item + 1 >= chunk_end;      // uniform within a group
         if (refill && t == 0) s_item[g] = (long long)atomicAdd(p.counter_next, (unsigned long long)SCORE_CHUNK);
-        __syncthreads();
+        // one barrier publishes the fetched chunk AND votes on the exit; a thread that runs out of items in this iteration
+        // is counted as active once more, which costs the block one idle pass at the very end
+        const int any_active = __syncthreads_or(active ? 1 : 0);
         if (need && active) {
             if (refill) { item = s_item[g]; chunk_end = item + SCORE_CHUNK; }
             else ++item;
@@ -306,7 +308,7 @@ __global__ void __launch_bounds__(256, 2) score_o0_kernel(ScoreParams p) {
                 k = 0; conv = false; upd = false; need = false;
             }
         }
-        if (!__syncthreads_or(active ? 1 : 0)) break;
+        if (!any_active) break;
         double F = 0.0;
         if (active) {
             if (MODE == PHYFOO_MODE_EXACT) F = -log(pruning_likelihood(tp, tb, st, cw));

@@ -32,12 +32,27 @@ def transition(pi, length, evol=_abi.EVOL_F81ALPHA):
 
 
 def tables(pi, branch, evol=_abi.EVOL_F81ALPHA):
-    """Probability table of one position: entries [pi(4), node 1 (16), ..., node N-1 (16)]; branch[N] (entry 0 unused)."""
-    N = len(branch)
-    out = np.empty(4 + 16 * (N - 1))
+    """Probability table of one position: entries [pi(4), node 1 (16), ..., node N-1 (16)]; branch[N] (entry 0 unused).
+    All nodes at once (this sits in the inner loop of the sufficient-statistics objective); entry for entry the values of
+    transition()."""
+    pi = np.asarray(pi, np.float64)
+    b = np.asarray(branch, np.float64)[1:]
+    if evol == _abi.EVOL_F81ALPHA:
+        keep, mix = 1.0 - b, b
+    elif evol == _abi.EVOL_F81BETA:
+        beta = 1.0 / (1.0 - np.sum(pi * pi))
+        ta = np.exp(-b * beta)
+        ta = np.where(ta < 1e-4, 0.0, np.where(ta > 1 - 1e-4, 1.0, ta))
+        keep, mix = ta, 1.0 - ta
+    else:
+        raise ValueError("HKY as implemented in the reference has zero transversion probabilities (HKY.java:32)")
+    off = pi[None, :] * mix[:, None]                                  # [N-1][4]: P(b | a != b)
+    T = np.repeat(off[:, None, :], 4, axis=1)                         # [N-1][4][4]
+    d = np.arange(4)
+    T[:, d, d] = keep[:, None] + off
+    out = np.empty(4 + 16 * b.size)
     out[:4] = pi
-    for k in range(1, N):
-        out[4 + 16 * (k - 1): 4 + 16 * k] = transition(pi, branch[k], evol).ravel()
+    out[4:] = T.ravel()
     return out
 
 

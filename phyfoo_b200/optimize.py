@@ -145,15 +145,28 @@ class SuffStatObjective:
         self.evol = evol
         self.W, self.N = self.branch.shape
         self.E = 4 + 16 * (self.N - 1)
-        self.counts, self.entropy = fe.suffstats(self.W, self.E)
+        self._counts, self.entropy = fe.suffstats(self.W, self.E)
+        self._index()
         self._G = np.array([self.position_term(t, self.pi[t], self.branch[t]) for t in range(self.W)])
+
+    @property
+    def counts(self):
+        return self._counts
+
+    @counts.setter
+    def counts(self, c):
+        self._counts = c
+        self._index()
+
+    def _index(self):
+        # entries with a zero count never enter the sum (their log table may be -inf)
+        self._nz = [np.nonzero(self._counts[t] != 0.0)[0] for t in range(self.W)]
+        self._cnz = [self._counts[t][self._nz[t]] for t in range(self.W)]
 
     def position_term(self, t, pi, branch):
         with np.errstate(divide="ignore"):
-            lt = np.log(self._ev.tables(pi, branch, self.evol))
-        c = self.counts[t]
-        nz = c != 0.0
-        return float(np.dot(c[nz], lt[nz]))
+            lt = np.log(self._ev.tables(pi, branch, self.evol)[self._nz[t]])
+        return float(np.dot(self._cnz[t], lt))
 
     def value(self):
         return float(self._G.sum() - self.entropy)
