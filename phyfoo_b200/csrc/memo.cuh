@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(128, 6) memo_traj_wave_kernel(MemoTrajJobs job
     const int T = blockDim.x, tid = threadIdx.x, I = p.I;
     constexpr int TPW = 32 / LPT;
     const int TPB = T / LPT;
-    int ST = 26 * I + 2; ST += (4 - (ST & 15) + 16) & 15;
+    int ST = 26 * I + 5; ST += (4 - (ST & 15) + 16) & 15;
     double* s_tab = smem;                                   // [W][E]: entry offsets become immediates of the loads
     double* s_tree = s_tab + (size_t)p.E * p.W;             // [TPB][ST]
     int* s_prog = (int*)(s_tree + (size_t)TPB * ST);
@@ -192,6 +192,8 @@ __global__ void __launch_bounds__(128, 6) memo_traj_wave_kernel(MemoTrajJobs job
     double* Q = tr; double* BASE = tr + 4 * I; double* MSG = tr + 8 * I; double* Q2 = tr + 12 * I; double* RING = tr + 16 * I;
     int* FLAG = (int*)(tr + 24 * I);                        // [4 sweeps][I]
     const double* ZERO = tr + 26 * I;
+    double* FLAST = tr + 26 * I + 1;                        // [0] F of the sweep before the last completed one, [1] of the last,
+                                                            // [2] (as int) the last sweep's periodicity flags
     const bool early = p.k0 == 0 && p.k1 == p.K1;
     constexpr unsigned LANE0 = LPT == 8 ? 0x01010101u : 0x00010001u;
     const int D = *p.count;
@@ -218,22 +220,25 @@ __global__ void __launch_bounds__(128, 6) memo_traj_wave_kernel(MemoTrajJobs job
         // this lane's node at even and at odd steps, with everything that does not change from sweep to sweep: table
         // offset, parent, children, and c[a] = sum over the observed leaf children of log T(a, x) (the sequential pass
         // re-reads it every sweep; the value is the same)
-        int nd_i[2], nd_cb[2], nd_ce[2], nd_dep[2];
+        int nd_i[2];                                               // node (or -1) | depth << 8
         int nd_to[2], nd_tm[2], nd_qp[2], nd_m1[2], nd_m2[2];      // offsets into smem (32-bit, shared address space)
+        int nd_own[2];                                             // this lane's q entry; base / msg / q2 follow at 4 I steps
+        const int I4 = 4 * I, tro = (int)(tr - smem);
         double nd_c[2];
 #pragma unroll
         for (int par = 0; par < 2; ++par) {
             const int i_s = p.sched[par][slot];
             const int i = i_s < 0 ? 0 : i_s;
-            nd_i[par] = i_s; nd_dep[par] = p.depth[i];
+            nd_i[par] = (i_s & 0xff) | ((int)p.depth[i] << 8);
             const int e0 = i ? tab_of(node_of[i]) : 0;
+            nd_own[par] = tro + i * 4 + a;
             nd_to[par] = t * p.E + e0 + a;                  // own rows: + 4 l
             nd_tm[par] = t * p.E + e0 + a * 4;              // message row: + h
             nd_qp[par] = (int)(Q - smem) + (i ? par_internal[i] * 4 : 0);
             const int cb = ichild_begin[i], ce = ichild_begin[i + 1];
             nd_m1[par] = cb < ce ? (int)(MSG - smem) + ichild[cb] * 4 + a : (int)(ZERO - smem);
             nd_m2[par] = cb + 1 < ce ? (int)(MSG - smem) + ichild[cb + 1] * 4 + a : (int)(ZERO - smem);
-            nd_cb[par] = cb + 2; nd_ce[par] = ce;           // further internal children (multifurcating trees)
+
             double c = 0.0;
             for (int k = leaf_begin[i]; k < leaf_begin[i + 1]; ++k) {
                 const int x = cw.obs(leaf_species[k]);
@@ -242,18 +247,16 @@ __global__ void __launch_bounds__(128, 6) memo_traj_wave_kernel(MemoTrajJobs job
             nd_c[par] = c;
         }
         const int tau_end = 2 * (p.k1 - 1) + p.dmax;
-        double Fcur = 0.0, Fprev = 0.0;
         bool tree_done = false;
-        int fa_last = 0;
         int kc_stop = -1;                                   // >= 0: the warp stopped after completing this sweep
         for (int tau0 = 2 * p.k0; tau0 <= tau_end && kc_stop < 0; tau0 += 2) {
 #pragma unroll
             for (int par = 0; par < 2; ++par) {
                 const int tau = tau0 + par;
                 if (tau > tau_end || kc_stop >= 0) break;
-                const int i_s = nd_i[par];
+                const int i_s = (int)(signed char)(nd_i[par] & 0xff);
                 const int i = i_s < 0 ? 0 : i_s;
-                const int k = (tau - nd_dep[par]) >> 1;
+                const int k = (tau - (nd_i[par] >> 8)) >> 1;
                 const bool act = i_s >= 0 && k >= p.k0 && k < p.k1;
                 const bool update = act && k > 0;
                 const double* to = smem + nd_to[par];
@@ -270,9 +273,11 @@ __global__ void __launch_bounds__(128, 6) memo_traj_wave_kernel(MemoTrajJobs job
                 }
                 // base + the children's messages in child order; an absent child adds +0.0, which leaves every value but
                 // -0.0 unchanged, and the base (a sum starting from +0.0) is never -0.0
-                double cs = (BASE[i * 4 + a] + smem[nd_m1[par]]) + smem[nd_m2[par]];
-                for (int cc = nd_cb[par]; cc < nd_ce[par]; ++cc) cs += MSG[ichild[cc] * 4 + a];
-                const long long q_old1 = __double_as_longlong(Q[i * 4 + a]), q_old2 = __double_as_longlong(Q2[i * 4 + a]);
+                double* const mine = smem + nd_own[par];               // q; + I4 base, + 2 I4 msg, + 3 I4 q of the sweep before
+                double cs = (mine[I4] + smem[nd_m1[par]]) + smem[nd_m2[par]];
+                if (p.MCH > 2)                                         // further internal children (multifurcating trees)
+                    for (int cc = ichild_begin[i] + 2; cc < ichild_begin[i + 1]; ++cc) cs += MSG[ichild[cc] * 4 + a];
+                const long long q_old1 = __double_as_longlong(mine[0]), q_old2 = __double_as_longlong(mine[3 * I4]);
                 const double s = own + cs;
                 const double ex = update ? s : 0.0;
                 const double e = phy_exp(ex);
@@ -318,10 +323,10 @@ __global__ void __launch_bounds__(128, 6) memo_traj_wave_kernel(MemoTrajJobs job
                     }
                 }
                 if (act) {
-                    Q2[i * 4 + a] = __longlong_as_double(q_old1);
-                    Q[i * 4 + a] = qa;
-                    MSG[i * 4 + a] = m;
-                    BASE[i * 4 + a] = c + tsum;
+                    mine[3 * I4] = __longlong_as_double(q_old1);
+                    mine[0] = qa;
+                    mine[2 * I4] = m;
+                    mine[I4] = c + tsum;
                     if (a == 0) { RING[((k & 3) * I + i) * 2] = ft; RING[((k & 3) * I + i) * 2 + 1] = Fgap; FLAG[(k & 3) * I + i] = fl; }
                 }
                 __syncwarp();
@@ -338,7 +343,7 @@ __global__ void __launch_bounds__(128, 6) memo_traj_wave_kernel(MemoTrajJobs job
                             fa &= FLAG[(kc & 3) * I + j];
                         }
                         if (live) out[kc] = F;
-                        Fprev = Fcur; Fcur = F; fa_last = fa;
+                        FLAST[0] = FLAST[1]; FLAST[1] = F; *(int*)(FLAST + 2) = fa;
                         tree_done = tree_done || fa != 0;
                     }
                     if (early && __ballot_sync(0xffffffffu, sub == 0 && tree_done) == LANE0) kc_stop = kc;
@@ -349,8 +354,9 @@ __global__ void __launch_bounds__(128, 6) memo_traj_wave_kernel(MemoTrajJobs job
             // every tree of the warp is periodic from here on.  F of a sweep depends on the q of that sweep and of the one
             // before: at a fixed point (bit 0 at the last sweep) every later value equals the last one, in a two-cycle the
             // last two values alternate
-            const double Fc = __shfl_sync(0xffffffffu, Fcur, lane - sub);
-            const double Fp = __shfl_sync(0xffffffffu, (fa_last & 1) ? Fcur : Fprev, lane - sub);
+            __syncwarp();
+            const double Fc = FLAST[1];
+            const double Fp = (*(const int*)(FLAST + 2) & 1) ? Fc : FLAST[0];
             if (live)
                 for (int j = kc_stop + 1 + sub; j < p.K1; j += LPT) out[j] = ((j - kc_stop) & 1) ? Fp : Fc;
         }

@@ -1018,7 +1018,7 @@ static int launch_memo_jobs(phyfoo_ctx* ctx, const phyfoo_dataset* ds, const Mem
         tp.tab = tp.exact ? m->d_probtab : m->d_logtab;
         tp.prog = m->d_prog; tp.traj = ctx->memo_traj.as<double>() + traj_off[j];
         tp.k0 = 0; tp.k1 = KA[j]; tp.state = split ? ctx->memo_state.as<double>() + state_off[j] : nullptr;
-        const size_t per_tree = wave ? (size_t)(26 * h.I + 16) : (size_t)h.I * 8;
+        const size_t per_tree = wave ? (size_t)(26 * h.I + 21) : (size_t)h.I * 8;
         smem = std::max(smem, (size_t)h.E * h.W * sizeof(double) + per_tree * (threads / lpt) * sizeof(double) + (size_t)m->prog_len * sizeof(int) + 16);
         trees = std::max(trees, (long long)ms->cap * h.W);
     }
