@@ -8,7 +8,7 @@
 //                            from a global counter, so a window that needs 14 sweeps never holds back
 //                            one that needs 3; tables + tree program + per-thread state in shared memory
 //   zoops_kernel             K3  one block per alignment: a_j, max, log-sum-exp, gamma, w, ll, arg-max
-//   reduce3_kernel           deterministic final sum of the per-alignment partials -> [ll, w0, w1]
+//                            (the block that finishes last sums the per-alignment partials -> [ll, w0, w1])
 //   select_kernel, fe_*      M-step (data selection, fixed-q free energy sums, forward differences)
 //   dfma_peak_kernel         fp64 FMA roofline probe
 //
@@ -361,6 +361,8 @@ struct ZoopsParams {
     double* gamma; double* profile;          // nullable, [n_windows]
     double* part;                            // [3][n_aln]: ll, w0, w1 per alignment
     int32_t* argoff; uint8_t* argstrand;     // nullable
+    double* out3;                            // [ll, w0, w1] summed over the alignments by the block that finishes last
+    unsigned int* ticket;                    // zero between launches
 };
 
 __device__ __forceinline__ double block_sum(double v, double* sh) {
@@ -468,17 +470,28 @@ __global__ void __launch_bounds__(256) zoops_kernel(ZoopsParams p) {
             p.gamma[w0 + j] = e * pm;                                 // :553-555
         }
     }
-}
-
-// [3][n] partials -> out[3]; one block, fixed summation pattern (deterministic for a given n)
-__global__ void __launch_bounds__(1024) reduce3_kernel(const double* __restrict__ part, int n, double* __restrict__ out) {
-    __shared__ double sh[32];
-    for (int r = 0; r < 3; ++r) {
-        double v = 0.0;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) v += part[(size_t)r * n + i];
-        const double s = block_sum(v, sh);
-        if (threadIdx.x == 0) out[r] = s;
-        __syncthreads();
+    // the block that finishes last adds the per-alignment partials in a fixed pattern (deterministic for a given n_aln):
+    // no second launch for three numbers
+    __shared__ int s_last;
+    if (tid == 0) {
+        __threadfence();
+        s_last = atomicAdd(p.ticket, 1u) == gridDim.x - 1 ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        double v[3] = {0.0, 0.0, 0.0};
+        for (int i = tid; i < p.n_aln; i += T) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) v[r] += __ldcg(p.part + (size_t)r * p.n_aln + i);
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const double s3 = block_sum(v[r], sh);
+            if (tid == 0) p.out3[r] = s3;
+            __syncthreads();
+        }
+        if (tid == 0) *p.ticket = 0u;
     }
 }
 
@@ -517,7 +530,8 @@ extern "C" int phyfoo_init(int device, phyfoo_ctx** out) {
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->kev[0])) != cudaSuccess || (e = cudaEventCreate(&ctx->kev[1])) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->kev[2])) != cudaSuccess || (e = cudaEventCreate(&ctx->kev[3])) != cudaSuccess ||
-        (e = ctx->counters.ensure(16 * sizeof(unsigned long long))) != cudaSuccess) {
+        (e = ctx->counters.ensure(16 * sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMemset(ctx->counters.p, 0, 16 * sizeof(unsigned long long))) != cudaSuccess) {
         g_init_err = std::string("phyfoo_init: ") + cudaGetErrorString(e);
         delete ctx;
         return PHYFOO_ECUDA;
@@ -1492,14 +1506,13 @@ static int enqueue_estep(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model
     z.gamma = d_gamma; z.profile = d_profile;
     z.part = ctx->part.as<double>();
     z.argoff = d_argoff; z.argstrand = d_argstrand;
-    {
+    z.out3 = d_out3;
+    z.ticket = (unsigned int*)(ctx->counters.as<unsigned long long>() + 12);
+    if (ds->n_aln > 0) {
         KernelTimer kt_(ctx, "zoops_kernel");
         zoops_kernel<<<ds->n_aln, 256, 0, ctx->stream>>>(z);
-    }
-    CU(cudaGetLastError());
-    {
-        KernelTimer kt_(ctx, "reduce3_kernel");
-        reduce3_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->part.as<double>(), ds->n_aln, d_out3);
+    } else {
+        CU(cudaMemsetAsync(d_out3, 0, 3 * sizeof(double), ctx->stream));
     }
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->kev[3], ctx->stream));
