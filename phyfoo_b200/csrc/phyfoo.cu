@@ -992,6 +992,9 @@ static int launch_memo_jobs(phyfoo_ctx* ctx, const phyfoo_dataset* ds, const Mem
         // [count (8 bytes, int used)] [col0 int64 x n] [dst int64 x n] [strand u8 x n, padded to 8]
         pend_off[j + 1] = pend_off[j] + 2 * (8 + (size_t)n_items[j] * 16 + (((size_t)n_items[j] + 7) / 8) * 8);
     }
+    // every counter of this call in one memset: [2 slot] work, [2 slot + 1] sweep sums, [4 + 2 j + l] lengths of the pending
+    // lists, [8 + slot] work counters of the fallback launches ([12] is the posterior kernel's ticket, zero between launches)
+    CU(cudaMemsetAsync(ctx->counters.p, 0, 12 * sizeof(unsigned long long), ctx->stream));
     CU(ctx->memo_traj.ensure(traj_off[n_jobs] * sizeof(double)));
     CU(ctx->memo_pending.ensure(pend_off[n_jobs]));
     if (split) CU(ctx->memo_state.ensure(state_off[n_jobs] * sizeof(double)));
@@ -1074,7 +1077,6 @@ static int launch_memo_jobs(phyfoo_ctx* ctx, const phyfoo_dataset* ds, const Mem
         if (n_items[j] == 0) continue;
         unsigned long long* counters = ctx->counters.as<unsigned long long>();
         unsigned long long* c_sweeps = counters + 2 * jobs[j].counter_slot + 1;
-        CU(cudaMemsetAsync(c_sweeps, 0, sizeof(unsigned long long), ctx->stream));
         MemoWindowParams& wp = wps[j];
         wp.bases = ds->d_bases; wp.gaps = ds->d_gaps; wp.n_cols = ds->n_cols; wp.nb = ds->nb;
         wp.col_off = ds->d_col_off; wp.win_off = jobs[j].d_win_off; wp.n_aln = ds->n_aln;
@@ -1085,14 +1087,13 @@ static int launch_memo_jobs(phyfoo_ctx* ctx, const phyfoo_dataset* ds, const Mem
         wp.max_sweeps = h.max_sweeps; wp.min_sweeps = h.min_sweeps; wp.tol = h.tol; wp.exact = jobs[j].mode == PHYFOO_MODE_EXACT ? 1 : 0;
         // list 0: left by the first gather pass when the trajectories come in two phases; list 1: for the direct kernel
         const size_t list_bytes = (pend_off[j + 1] - pend_off[j]) / 2;
-        char* pb = ctx->memo_pending.as<char>() + pend_off[j] + (KA[j] < K1[j] ? 0 : list_bytes);
-        wp.pend_count = (int*)pb;
+        const int first_list = KA[j] < K1[j] ? 0 : 1;
+        char* pb = ctx->memo_pending.as<char>() + pend_off[j] + first_list * list_bytes;
+        wp.pend_count = (int*)(counters + 4 + 2 * j + first_list);
         wp.pend_col0 = (int64_t*)(pb + 8);
         wp.pend_dst = wp.pend_col0 + n_items[j];
         wp.pend_strand = (uint8_t*)(wp.pend_dst + n_items[j]);
         wp.in_count = nullptr; wp.in_col0 = nullptr; wp.in_strand = nullptr; wp.in_dst = nullptr;
-        CU(cudaMemsetAsync(ctx->memo_pending.as<char>() + pend_off[j], 0, 8, ctx->stream));
-        CU(cudaMemsetAsync(ctx->memo_pending.as<char>() + pend_off[j] + list_bytes, 0, 8, ctx->stream));
         const int wblocks = (int)std::max<long long>(1, std::min<long long>((n_items[j] + 255) / 256, 16LL * ctx->sm_count));
         {
             KernelTimer kt_(ctx, "memo_window_kernel");
@@ -1111,7 +1112,7 @@ static int launch_memo_jobs(phyfoo_ctx* ctx, const phyfoo_dataset* ds, const Mem
             const size_t list_bytes = (pend_off[j + 1] - pend_off[j]) / 2;
             wp.in_count = wp.pend_count; wp.in_col0 = wp.pend_col0; wp.in_strand = wp.pend_strand; wp.in_dst = wp.pend_dst;
             char* pb = ctx->memo_pending.as<char>() + pend_off[j] + list_bytes;
-            wp.pend_count = (int*)pb;
+            wp.pend_count = (int*)(ctx->counters.as<unsigned long long>() + 4 + 2 * j + 1);
             wp.pend_col0 = (int64_t*)(pb + 8);
             wp.pend_dst = wp.pend_col0 + n_items[j];
             wp.pend_strand = (uint8_t*)(wp.pend_dst + n_items[j]);
@@ -1289,8 +1290,10 @@ static int launch_score(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model*
         CU(ctx->gstate.ensure((size_t)pl.blocks * pl.threads * h.I * 8 * sizeof(double)));
         p.gstate = ctx->gstate.as<double>();
     }
-    CU(cudaMemsetAsync(p.counter_next, 0, sizeof(unsigned long long), ctx->stream));
-    if (!fallback) CU(cudaMemsetAsync(p.counter_sweeps, 0, sizeof(unsigned long long), ctx->stream));
+    if (!fallback) {            // (a fallback launch finds its counters cleared by the pattern-table pass)
+        CU(cudaMemsetAsync(p.counter_next, 0, sizeof(unsigned long long), ctx->stream));
+        CU(cudaMemsetAsync(p.counter_sweeps, 0, sizeof(unsigned long long), ctx->stream));
+    }
     {
         KernelTimer kt_(ctx, fallback ? "score_o0_kernel(fallback list)" : "score_o0_kernel");
         if (mode == PHYFOO_MODE_EXACT) score_o0_kernel<PHYFOO_MODE_EXACT, false><<<pl.blocks, pl.threads, pl.smem, ctx->stream>>>(p);
