@@ -21,6 +21,7 @@ struct MemoSet {                 // per (data set): which patterns occur (forwar
     int code_bits = 0;           // 3 S
     int n_codes = 0;             // 1 << code_bits
     int cap = 0;                 // upper bound of the number of occurring patterns (host-side, for allocations)
+    int32_t* d_flags = nullptr;      // [n_codes] 1 where a column of the data set has this code (forward strand only)
     int32_t* d_dense_of = nullptr;   // [n_codes] dense id or -1
     int32_t* d_code_of = nullptr;    // [cap]
     int32_t* d_count = nullptr;      // [1] number of occurring patterns D (device-resident; kernels read it)
@@ -42,35 +43,63 @@ __global__ void memo_mark_kernel(const uint32_t* __restrict__ bases, const uint3
                                  int32_t* __restrict__ flags) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_cols) return;
-    const ColWords cw = load_column(bases, gaps, n_cols, nb, c);
-    flags[memo_code(cw, S)] = 1;
-    flags[memo_code(complement(cw), S)] = 1;      // reverse-complement windows read the complemented column
+    flags[memo_code(load_column(bases, gaps, n_cols, nb, c), S)] = 1;     // the complemented column: memo_compact_kernel
 }
 
-// flags -> dense ids (ascending code order), one block; flags array is overwritten with dense_of
-__global__ void __launch_bounds__(1024) memo_compact_kernel(int32_t* __restrict__ flags_dense, int n_codes, int32_t* __restrict__ code_of,
+// code of the complemented column (reverse-complement windows read it): complement is an involution on the canonical
+// codes (base bits 00 under gaps)
+__device__ __forceinline__ uint32_t memo_comp_code(uint32_t code, int S) {
+    return memo_code(complement(memo_words(code, S)), S);
+}
+__device__ __forceinline__ bool memo_occurs(const int32_t* __restrict__ flags, uint32_t c, int S) {
+    const uint32_t mask = (1u << (2 * S)) - 1u, b = c & mask, g = c >> (2 * S);
+    uint32_t under = 0;                                                   // base bits that sit under a gap
+    for (int s = 0; s < S; ++s) under |= ((g >> s) & 1u) ? 3u << (2 * s) : 0u;
+    if (b & under) return false;                                          // not a canonical code: no column has it
+    const uint32_t comp = ((~b) & mask & ~under) | (g << (2 * S));        // = memo_comp_code(c, S)
+    return (flags[c] | flags[comp]) != 0;
+}
+
+// flags -> dense ids in ascending code order; a code occurs if it or its complement was marked.  One block: every warp
+// owns a segment of the codes (coalesced reads, ballots instead of block-wide scans); two block barriers in total.
+__global__ void __launch_bounds__(1024) memo_compact_kernel(const int32_t* __restrict__ flags, int n_codes, int S,
+                                                            int32_t* __restrict__ dense_of, int32_t* __restrict__ code_of,
                                                             int cap, int32_t* __restrict__ count) {
-    __shared__ int s_warp[32];
-    __shared__ int s_base;
-    if (threadIdx.x == 0) s_base = 0;
-    __syncthreads();
-    for (int c0 = 0; c0 < n_codes; c0 += blockDim.x) {
-        const int c = c0 + threadIdx.x;
-        const int f = (c < n_codes && flags_dense[c]) ? 1 : 0;
-        int v = f;
-        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if ((threadIdx.x & 31) >= o) v += u; }
-        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = v;
-        __syncthreads();
-        int before = s_base;
-        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) before += s_warp[w];
-        const int id = before + v - f;
-        if (c < n_codes) flags_dense[c] = f ? id : -1;
-        if (f && id < cap) code_of[id] = c;
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) s_base = before + v;
-        __syncthreads();
+    __shared__ int s_tot[32];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, n_warps = blockDim.x >> 5;
+    const int seg = (((n_codes + n_warps - 1) / n_warps) + 31) & ~31;
+    const int lo = min(w * seg, n_codes), hi = min(lo + seg, n_codes);
+    // (a segment of up to 1024 codes is 32 rounds: the lane keeps its 32 answers in a register for the second pass)
+    const bool keep = hi - lo <= 1024;
+    unsigned mine_bits = 0;
+    int total = 0, round = 0;
+    for (int base = lo; base < hi; base += 32, ++round) {
+        const int c = base + lane;
+        const bool f = c < hi && memo_occurs(flags, (uint32_t)c, S);
+        if (keep && f) mine_bits |= 1u << round;
+        total += __popc(__ballot_sync(0xffffffffu, f));
     }
-    if (threadIdx.x == 0) *count = s_base;
+    if (lane == 0) s_tot[w] = total;
+    __syncthreads();
+    if (w == 0) {
+        const int mine = lane < n_warps ? s_tot[lane] : 0;
+        int v = mine;
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+        s_tot[lane] = v - mine;                 // exclusive
+        if (lane == 31) *count = v;
+    }
+    __syncthreads();
+    int running = s_tot[w];
+    round = 0;
+    for (int base = lo; base < hi; base += 32, ++round) {
+        const int c = base + lane;
+        const bool f = keep ? ((mine_bits >> round) & 1u) != 0 : (c < hi && memo_occurs(flags, (uint32_t)c, S));
+        const unsigned m = __ballot_sync(0xffffffffu, f);
+        const int id = running + __popc(m & ((1u << lane) - 1u));
+        if (c < hi) dense_of[c] = f ? id : -1;
+        if (f && id < cap) code_of[id] = c;
+        running += __popc(m);
+    }
 }
 
 struct MemoTrajParams {

@@ -893,7 +893,7 @@ struct ScoreItems {
 
 static void memo_release(cudaStream_t st, MemoSet* ms) {
     if (!ms) return;
-    dev_free(st, ms->d_dense_of); dev_free(st, ms->d_code_of); dev_free(st, ms->d_count);
+    dev_free(st, ms->d_flags); dev_free(st, ms->d_dense_of); dev_free(st, ms->d_code_of); dev_free(st, ms->d_count);
     delete ms;
 }
 
@@ -907,10 +907,11 @@ static int dataset_memo(phyfoo_ctx* ctx, const phyfoo_dataset* cds, MemoSet** ou
         for (int s = 0; s < ds->S; ++s) valid *= 5;
         ms->cap = (int)std::max<long long>(1, std::min<long long>(valid, 2 * ds->n_cols));
         cudaError_t e;
-        if ((e = dev_malloc(ctx->stream, &ms->d_dense_of, (size_t)ms->n_codes * sizeof(int32_t))) != cudaSuccess ||
+        if ((e = dev_malloc(ctx->stream, &ms->d_flags, (size_t)ms->n_codes * sizeof(int32_t))) != cudaSuccess ||
+            (e = dev_malloc(ctx->stream, &ms->d_dense_of, (size_t)ms->n_codes * sizeof(int32_t))) != cudaSuccess ||
             (e = dev_malloc(ctx->stream, &ms->d_code_of, (size_t)ms->cap * sizeof(int32_t))) != cudaSuccess ||
             (e = dev_malloc(ctx->stream, &ms->d_count, sizeof(int32_t))) != cudaSuccess ||
-            (e = cudaMemsetAsync(ms->d_dense_of, 0, (size_t)ms->n_codes * sizeof(int32_t), ctx->stream)) != cudaSuccess) {
+            (e = cudaMemsetAsync(ms->d_flags, 0, (size_t)ms->n_codes * sizeof(int32_t), ctx->stream)) != cudaSuccess) {
             memo_release(ctx->stream, ms);
             ctx->err = std::string("pattern set: ") + cudaGetErrorString(e);
             return PHYFOO_ECUDA;
@@ -918,12 +919,12 @@ static int dataset_memo(phyfoo_ctx* ctx, const phyfoo_dataset* cds, MemoSet** ou
         if (ds->n_cols > 0) {
             {
                 KernelTimer kt_(ctx, "memo_mark_kernel");
-                memo_mark_kernel<<<(unsigned)((ds->n_cols + 255) / 256), 256, 0, ctx->stream>>>(ds->d_bases, ds->d_gaps, ds->n_cols, ds->nb, ds->S, ms->d_dense_of);
+                memo_mark_kernel<<<(unsigned)((ds->n_cols + 255) / 256), 256, 0, ctx->stream>>>(ds->d_bases, ds->d_gaps, ds->n_cols, ds->nb, ds->S, ms->d_flags);
             }
         }
         {
             KernelTimer kt_(ctx, "memo_compact_kernel");
-            memo_compact_kernel<<<1, 1024, 0, ctx->stream>>>(ms->d_dense_of, ms->n_codes, ms->d_code_of, ms->cap, ms->d_count);
+            memo_compact_kernel<<<1, 1024, 0, ctx->stream>>>(ms->d_flags, ms->n_codes, ds->S, ms->d_dense_of, ms->d_code_of, ms->cap, ms->d_count);
         }
         e = cudaGetLastError();
         if (e != cudaSuccess) { memo_release(ctx->stream, ms); ctx->err = std::string("pattern set kernels: ") + cudaGetErrorString(e); return PHYFOO_ECUDA; }
