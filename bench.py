@@ -394,8 +394,9 @@ def run_ours(args):
             st = fg.train(sample, None, rng=np.random.default_rng(1))
             return (time.perf_counter() - t0) * 1e3, st
 
-        mstep_ms, st = mstep(False)
-        mstep_ss_ms, st_ss = mstep(True)
+        # host-side wall clock: best of two runs each (same start, same seed)
+        mstep_ms, st = min(mstep(False), mstep(False), key=lambda r: r[0])
+        mstep_ss_ms, st_ss = min(mstep(True), mstep(True), key=lambda r: r[0])
         fg.MSTEP_SUFFICIENT_STATISTICS = False
         t = torch.tensor([grad_ms, mstep_ms, prepare_ms, mstep_ss_ms], dtype=torch.float64, device="cuda")
         if world > 1:
