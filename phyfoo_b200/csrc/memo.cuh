@@ -275,10 +275,13 @@ __global__ void __launch_bounds__(128, 6) memo_traj_wave_kernel(MemoTrajJobs job
             }
             nd_c[par] = c;
         }
-        const int tau_end = 2 * (p.k1 - 1) + p.dmax;
+        // (the fields of p sit behind a run-time index into the kernel parameters: copies for the loop)
+        const int k0 = p.k0, k1 = p.k1, dmax = p.dmax;
+        const bool many_children = p.MCH > 2;
+        const int tau_end = 2 * (k1 - 1) + dmax;
         bool tree_done = false;
         int kc_stop = -1;                                   // >= 0: the warp stopped after completing this sweep
-        for (int tau0 = 2 * p.k0; tau0 <= tau_end && kc_stop < 0; tau0 += 2) {
+        for (int tau0 = 2 * k0; tau0 <= tau_end && kc_stop < 0; tau0 += 2) {
 #pragma unroll
             for (int par = 0; par < 2; ++par) {
                 const int tau = tau0 + par;
@@ -286,7 +289,7 @@ __global__ void __launch_bounds__(128, 6) memo_traj_wave_kernel(MemoTrajJobs job
                 const int i_s = (int)(signed char)(nd_i[par] & 0xff);
                 const int i = i_s < 0 ? 0 : i_s;
                 const int k = (tau - (nd_i[par] >> 8)) >> 1;
-                const bool act = i_s >= 0 && k >= p.k0 && k < p.k1;
+                const bool act = i_s >= 0 && k >= k0 && k < k1;
                 const bool update = act && k > 0;
                 const double* to = smem + nd_to[par];
                 const double* tm = smem + nd_tm[par];
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__(128, 6) memo_traj_wave_kernel(MemoTrajJobs job
                 // -0.0 unchanged, and the base (a sum starting from +0.0) is never -0.0
                 double* const mine = smem + nd_own[par];               // q; + I4 base, + 2 I4 msg, + 3 I4 q of the sweep before
                 double cs = (mine[I4] + smem[nd_m1[par]]) + smem[nd_m2[par]];
-                if (p.MCH > 2)                                         // further internal children (multifurcating trees)
+                if (many_children)                                     // further internal children (multifurcating trees)
                     for (int cc = ichild_begin[i] + 2; cc < ichild_begin[i + 1]; ++cc) cs += MSG[ichild[cc] * 4 + a];
                 const long long q_old1 = __double_as_longlong(mine[0]), q_old2 = __double_as_longlong(mine[3 * I4]);
                 const double s = own + cs;
@@ -360,8 +363,8 @@ __global__ void __launch_bounds__(128, 6) memo_traj_wave_kernel(MemoTrajJobs job
                 }
                 __syncwarp();
                 // the sweep whose deepest node ran in this step is complete: its free energy, terms in node order
-                const int kc2 = tau - p.dmax;
-                if (kc2 >= 2 * p.k0 && !(kc2 & 1)) {
+                const int kc2 = tau - dmax;
+                if (kc2 >= 2 * k0 && !(kc2 & 1)) {
                     const int kc = kc2 >> 1;
                     if (sub == 0) {
                         double F = 0.0;

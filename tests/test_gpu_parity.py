@@ -214,6 +214,24 @@ def test_full_size_properties(ctx):
         ref, _ = om.score_windows(smp.getElementAt(i))
         o = smp.device(ctx).window_offsets(cfg["W"])
         assert rel_err(mf[o[i]:o[i + 1]], ref) < TOL
+    # the two scoring paths at full size: same bits, same sweep counts
+    assert ctx.last_score_path() == 1                           # the default for five species is the pattern table
+    ctx.set_option("pattern_memo", 0)
+    try:
+        d, dk = fg.getLogProbFor(smp, want_sweeps=True)
+        assert ctx.last_score_path() == 0
+    finally:
+        ctx.set_option("pattern_memo", 1)
+    m, mk = fg.getLogProbFor(smp, want_sweeps=True)
+    assert np.array_equal(d, m) and np.array_equal(dk, mk) and np.array_equal(m, mf)
+    # strand symmetry: the reverse strand of the reverse-complemented alignments is the forward strand read backwards
+    from phyfoo_b200.data import PhyloSample
+    L = cfg["length"]
+    rc = smp.codes.reshape(cfg["n_aln"], L, -1)[:, ::-1, :]
+    rc = np.where(rc < 4, 3 - rc, rc).reshape(-1, smp.codes.shape[1])
+    back = fg.getLogProbFor(PhyloSample(rc, smp.col_offsets), strand=1)
+    nwin = L - cfg["W"] + 1
+    assert np.array_equal(back.reshape(cfg["n_aln"], nwin)[:, ::-1], m.reshape(cfg["n_aln"], nwin))
 
 
 def test_sharded_estep_single_rank(ctx):
