@@ -191,12 +191,14 @@ __global__ void __launch_bounds__(128) memo_traj_kernel(MemoTrajJobs jobs) {
 // the rows.  (C2: 31 of 65 passes per warp on average.)
 // Per-tree shared-memory block: q[I][4] base[I][4] msg[I][4] q2[I][4] ring[4 sweeps][I][2] flags, padded to 4 (mod 16)
 // doubles so that the quads of the trees of a warp fall into different banks.
-template <int LPT>
+// IT: the number of internal nodes when it is known at compile time (0: read from the parameters) -- with it the strides
+// of the per-tree block are immediates instead of multiplications that the register cap makes the compiler redo per step
+template <int LPT, int IT>
 __global__ void __launch_bounds__(128, 6) memo_traj_wave_kernel(MemoTrajJobs jobs) {
     extern __shared__ double smem[];
     const MemoTrajParams& p = jobs.job[blockIdx.y];
     if (p.k0 >= p.k1) return;
-    const int T = blockDim.x, tid = threadIdx.x, I = p.I;
+    const int T = blockDim.x, tid = threadIdx.x, I = IT ? IT : p.I;
     constexpr int TPW = 32 / LPT;
     const int TPB = T / LPT;
     int ST = 26 * I + 5; ST += (4 - (ST & 15) + 16) & 15;

@@ -1049,14 +1049,29 @@ static int launch_memo_jobs(phyfoo_ctx* ctx, const phyfoo_dataset* ds, const Mem
             cudaError_t e = cudaFuncSetAttribute(memo_traj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             memo_traj_kernel<<<dim3(blocks, n_jobs), threads, smem, st>>>(tj);
-        } else if (lpt == 8) {
-            cudaError_t e = cudaFuncSetAttribute(memo_traj_wave_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            memo_traj_wave_kernel<8><<<dim3(blocks, n_jobs), threads, smem, st>>>(tj);
         } else {
-            cudaError_t e = cudaFuncSetAttribute(memo_traj_wave_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            // the number of internal nodes as a template argument when both jobs agree on it (binary trees of <= 6 species)
+            int it = tj.job[0].I;
+            for (int j = 1; j < n_jobs; ++j) if (tj.job[j].I != it) it = 0;
+            void (*fn)(MemoTrajJobs) = nullptr;
+            if (lpt == 8) {
+                switch (it) {
+                    case 2: fn = memo_traj_wave_kernel<8, 2>; break;
+                    case 3: fn = memo_traj_wave_kernel<8, 3>; break;
+                    case 4: fn = memo_traj_wave_kernel<8, 4>; break;
+                    case 5: fn = memo_traj_wave_kernel<8, 5>; break;
+                    default: fn = memo_traj_wave_kernel<8, 0>;
+                }
+            } else {
+                switch (it) {
+                    case 4: fn = memo_traj_wave_kernel<16, 4>; break;
+                    case 5: fn = memo_traj_wave_kernel<16, 5>; break;
+                    default: fn = memo_traj_wave_kernel<16, 0>;
+                }
+            }
+            cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
-            memo_traj_wave_kernel<16><<<dim3(blocks, n_jobs), threads, smem, st>>>(tj);
+            fn<<<dim3(blocks, n_jobs), threads, smem, st>>>(tj);
         }
         return cudaGetLastError();
     };
