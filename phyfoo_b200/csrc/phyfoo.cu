@@ -363,6 +363,7 @@ struct ZoopsParams {
     int32_t* argoff; uint8_t* argstrand;     // nullable
     double* out3;                            // [ll, w0, w1] summed over the alignments by the block that finishes last
     unsigned int* ticket;                    // zero between launches
+    int stage;                               // 1: dynamic shared memory holds [max_len] background terms + [max_len] a_j
 };
 
 __device__ __forceinline__ double block_sum(double v, double* sh) {
@@ -394,9 +395,19 @@ __global__ void __launch_bounds__(256) zoops_kernel(ZoopsParams p) {
     const int n = (int)(p.win_off[a + 1] - w0);
     const double weight = p.aln_w ? p.aln_w[a] : 1.0;
 
+    // the alignment's background terms (each is read W times) and its a_j (read twice more) staged in shared memory
+    extern __shared__ double s_stage[];
+    double* s_bg = s_stage;
+    double* s_aj = s_stage + L;
+    const double* bgc = p.bgcol + c0;
+    if (p.stage) {
+        for (int u = tid; u < L; u += T) s_bg[u] = p.bgcol[c0 + u];
+        __syncthreads();
+        bgc = s_bg;
+    }
     // logPSeq = bg.getLogProbFor(seq, 0, l-1), :526
     double ps = 0.0;
-    for (int u = tid; u < L; u += T) ps += p.bgcol[c0 + u];
+    for (int u = tid; u < L; u += T) ps += bgc[u];
     const double log_pseq = block_sum(ps, sh);
 
     // a_j and its maximum (first index wins: util/Util.java:528-538)
@@ -407,10 +418,11 @@ __global__ void __launch_bounds__(256) zoops_kernel(ZoopsParams p) {
         double motif = p.fwd[w0 + j];
         if (p.has_strand) motif = logsum2(p.slw0 + motif, p.slw1 + p.rev[w0 + j]);
         double bgw = 0.0;
-        for (int m = 0; m < p.W; ++m) bgw += p.bgcol[c0 + j + m];   // -bg(s,e), order 0: s=j, e=j+W-1
+        for (int m = 0; m < p.W; ++m) bgw += bgc[j + m];             // -bg(s,e), order 0: s=j, e=j+W-1
         const double aj = lprior + motif - bgw;                       // :536-540
         if (p.profile) p.profile[w0 + j] = aj;
-        if (p.gamma) p.gamma[w0 + j] = aj;                            // overwritten with gamma_j below
+        if (p.stage) s_aj[j] = aj;
+        else if (p.gamma) p.gamma[w0 + j] = aj;                       // overwritten with gamma_j below
         if (aj > best) { best = aj; best_j = j; }
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -429,7 +441,8 @@ __global__ void __launch_bounds__(256) zoops_kernel(ZoopsParams p) {
     double se = 0.0;
     for (int j = tid; j < n; j += T) {
         double aj;
-        if (p.gamma) aj = p.gamma[w0 + j];
+        if (p.stage) aj = s_aj[j];                                    // (written by this thread in the first pass)
+        else if (p.gamma) aj = p.gamma[w0 + j];
         else {
             double motif = p.fwd[w0 + j];
             if (p.has_strand) motif = logsum2(p.slw0 + motif, p.slw1 + p.rev[w0 + j]);
@@ -1527,9 +1540,13 @@ static int enqueue_estep(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model
     z.argoff = d_argoff; z.argstrand = d_argstrand;
     z.out3 = d_out3;
     z.ticket = (unsigned int*)(ctx->counters.as<unsigned long long>() + 12);
+    size_t zs = (size_t)2 * ds->max_len * sizeof(double);
+    z.stage = zs <= 96 * 1024 ? 1 : 0;
+    if (!z.stage) zs = 0;
+    if (zs > 48 * 1024) CU(cudaFuncSetAttribute(zoops_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zs));
     if (ds->n_aln > 0) {
         KernelTimer kt_(ctx, "zoops_kernel");
-        zoops_kernel<<<ds->n_aln, 256, 0, ctx->stream>>>(z);
+        zoops_kernel<<<ds->n_aln, 256, zs, ctx->stream>>>(z);
     } else {
         CU(cudaMemsetAsync(d_out3, 0, 3 * sizeof(double), ctx->stream));
     }
