@@ -220,7 +220,8 @@ __global__ void __launch_bounds__(128, 6) memo_traj_wave_kernel(MemoTrajJobs job
     const int qb = lane & ~3;
     const unsigned mask = 0xFu << qb;
     double* tr = s_tree + (size_t)(tid / LPT) * ST;
-    double* Q = tr; double* BASE = tr + 4 * I; double* MSG = tr + 8 * I; double* Q2 = tr + 12 * I; double* RING = tr + 16 * I;
+    // per-tree block: q at 0, base at 4 I, msg at 8 I, the q of the sweep before at 12 I (reached through nd_own below)
+    double* Q = tr; double* MSG = tr + 8 * I; double* RING = tr + 16 * I;
     int* FLAG = (int*)(tr + 24 * I);                        // [4 sweeps][I]
     const double* ZERO = tr + 26 * I;
     double* FLAST = tr + 26 * I + 1;                        // [0] F of the sweep before the last completed one, [1] of the last,

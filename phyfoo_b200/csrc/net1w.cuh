@@ -51,9 +51,6 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
     for (int i = tid; i < p.prog_len; i += T) s_prog[i] = p.prog[i];
     if (tid < 4) s_virt[tid] = tid == 0 ? 1.0 : 0.0;
     __syncthreads();
-    const int* par_internal = s_prog;
-    const int* node_of = s_prog + p.I;
-    const int* leaf_node = s_prog + 2 * p.I;
     const int* leaf_species = s_prog + 2 * p.I + p.S;
     const int* ich = s_prog + 2 * p.I + 2 * p.S;
     const int* lf = ich + p.I * p.MC;

@@ -862,7 +862,6 @@ static int plan_score(phyfoo_ctx* ctx, const ModelHost& h, int prog_len, long lo
     const size_t budget = std::min<size_t>(ctx->smem_optin, 227 * 1024);
     // aim for >= 2 resident blocks per SM when the state allows it
     int groups = std::max(1, 256 / W);
-    bool gstate = false; (void)gstate;
     for (;;) {
         int threads = ((groups * W + 31) / 32) * 32;
         size_t fixed = tab_bytes + (size_t)threads * 8 + (size_t)groups * 8 + (size_t)prog_len * 4 + 64;
@@ -876,12 +875,11 @@ static int plan_score(phyfoo_ctx* ctx, const ModelHost& h, int prog_len, long lo
             threads = ((groups * W + 31) / 32) * 32;
             fixed = tab_bytes + (size_t)threads * 8 + (size_t)groups * 8 + (size_t)prog_len * 4 + 64;
             if (fixed > budget) return fail(ctx, PHYFOO_EUNSUPPORTED, "model tables do not fit in shared memory");
-            pl->threads = threads; pl->groups = groups; pl->smem = fixed; pl->gstate = true; gstate = true;
+            pl->threads = threads; pl->groups = groups; pl->smem = fixed; pl->gstate = true;
             break;
         }
         groups = std::max(1, groups / 2);
     }
-    (void)gstate;
     const void* fn = mode == PHYFOO_MODE_EXACT ? (const void*)score_o0_kernel<PHYFOO_MODE_EXACT, false>
                    : items ? (const void*)score_o0_kernel<PHYFOO_MODE_MEANFIELD, true> : (const void*)score_o0_kernel<PHYFOO_MODE_MEANFIELD, false>;
     CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));

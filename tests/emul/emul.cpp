@@ -170,3 +170,159 @@ extern "C" int emul_fixed_point(const phyfoo_model_desc* d, const uint8_t* cols 
         return 0;
     } catch (const std::exception& e) { std::fprintf(stderr, "emul: %s\n", e.what()); return -1; }
 }
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Host model of the wavefront trajectory kernel (csrc/memo.cuh::memo_traj_wave_kernel): node i of sweep k at step
+// 2 k + depth(i), children's messages in slots of their own added in child order, per-node free-energy terms summed in node
+// order when the sweep's deepest node is done, early stop at a bitwise fixed point or two-cycle of q with the periodic
+// fill.  Not the CUDA code, but the same algorithm step for step, so the schedule and the fill logic can be checked against
+// the sequential pass (meanfield_pass) without a GPU: traj[c][t][k] for k < K1 and the pass at which each tree stopped.
+// ---------------------------------------------------------------------------------------------------------------------------
+namespace {
+struct WaveTree {
+    int I; std::vector<int> depth, par; std::vector<std::vector<int>> kids;
+    std::vector<double> Q, Q2, BASE, MSG;       // [I][4]
+};
+
+// one node update with the canonical arithmetic of tree_pass.cuh; returns the node's free-energy term(s)
+void wave_node(const TreeProg& tp, const Tab& tb, const ColWords& cw, WaveTree& w, int i, bool update, double& ft, double& fgap,
+               bool& any_gap, int& flags) {
+    double lpi[4], own[4], s[4], e[4], q[4], lq[4];
+    for (int a = 0; a < 4; ++a) lpi[a] = tb(a);
+    const int e0 = i ? tab_of(tp.node_of[i]) : 0;
+    for (int a = 0; a < 4; ++a) {
+        if (i == 0) own[a] = lpi[a];
+        else {
+            double acc = 0.0;
+            for (int l = 0; l < 4; ++l) acc = fma(w.Q[w.par[i] * 4 + l], tb(e0 + l * 4 + a), acc);
+            own[a] = acc;
+        }
+        double cs = w.BASE[i * 4 + a];
+        for (int c : w.kids[i]) cs += w.MSG[c * 4 + a];
+        s[a] = own[a] + cs;
+        e[a] = phy_exp(update ? s[a] : 0.0);
+    }
+    const double z = ((e[0] + e[1]) + e[2]) + e[3];
+    const double rz = phy_rcp(z), lz = phy_log(z);
+    flags = 3;
+    for (int a = 0; a < 4; ++a) {
+        q[a] = phy_mul(e[a], rz);
+        lq[a] = (update ? s[a] : 0.0) - lz;
+        if (std::memcmp(&q[a], &w.Q[i * 4 + a], 8) != 0) flags &= ~1;
+        if (std::memcmp(&q[a], &w.Q2[i * 4 + a], 8) != 0) flags &= ~2;
+    }
+    double c[4] = {0, 0, 0, 0};
+    any_gap = false;
+    for (int k = tp.leaf_begin[i]; k < tp.leaf_begin[i + 1]; ++k) {
+        const int x = cw.obs(tp.leaf_species[k]);
+        if (x < 4) { for (int a = 0; a < 4; ++a) c[a] += tb(tab_of(tp.leaf_node[k]) + a * 4 + x); }
+        else any_gap = true;
+    }
+    double f[4];
+    for (int a = 0; a < 4; ++a) f[a] = phy_mul(q[a], (lq[a] - own[a]) - c[a]);
+    ft = ((f[0] + f[1]) + f[2]) + f[3];
+    double tsum = 0.0; fgap = 0.0;
+    if (any_gap) {
+        const double qs = ((q[0] + q[1]) + q[2]) + q[3];
+        for (int k = tp.leaf_begin[i]; k < tp.leaf_begin[i + 1]; ++k) {
+            if (cw.obs(tp.leaf_species[k]) < 4) continue;
+            double xl[4], el[4], fl[4];
+            for (int a = 0; a < 4; ++a) { xl[a] = phy_mul(qs, lpi[a]); el[a] = phy_exp(update ? xl[a] : 0.0); }
+            const double zl = ((el[0] + el[1]) + el[2]) + el[3];
+            const double rzl = phy_rcp(zl), lzl = phy_log(zl);
+            double t = 0.0;
+            for (int a = 0; a < 4; ++a) {
+                const double ql = phy_mul(el[a], rzl);
+                t = fma(ql, lpi[a], t);
+                fl[a] = phy_mul(ql, ((update ? xl[a] : 0.0) - lzl) - xl[a]);
+            }
+            fgap += ((fl[0] + fl[1]) + fl[2]) + fl[3];
+            tsum += t;
+        }
+    }
+    double m[4] = {0, 0, 0, 0};
+    if (i != 0)
+        for (int l = 0; l < 4; ++l) { double acc = 0.0; for (int h = 0; h < 4; ++h) acc = fma(q[h], tb(e0 + l * 4 + h), acc); m[l] = acc; }
+    for (int a = 0; a < 4; ++a) {
+        w.Q2[i * 4 + a] = w.Q[i * 4 + a];
+        w.Q[i * 4 + a] = q[a];
+        w.MSG[i * 4 + a] = m[a];
+        w.BASE[i * 4 + a] = c[a] + tsum;
+    }
+}
+}  // namespace
+
+extern "C" int emul_wave_traj(const phyfoo_model_desc* d, const uint8_t* cols /*[n][S]*/, int n, int K1, int early,
+                              double* traj /*[n][W][K1]*/, int* stopped /*[n][W]: last computed sweep*/) {
+    try {
+        ModelHost m; m.init(*d);
+        TreeProg tp = prog_of(m);
+        WaveTree w; w.I = m.I; w.depth.assign(m.I, 0); w.par = m.par_internal; w.kids.assign(m.I, {});
+        int dmax = 0;
+        for (int i = 1; i < m.I; ++i) { w.depth[i] = w.depth[w.par[i]] + 1; dmax = std::max(dmax, w.depth[i]); w.kids[w.par[i]].push_back(i); }
+        for (int c = 0; c < n; ++c)
+            for (int t = 0; t < m.W; ++t) {
+                const ColWords cw = words_of(cols + (size_t)c * m.S, m.S, false);
+                Tab lt{&m.logtab[(size_t)t * m.E], 1};
+                double* out = traj + ((size_t)c * m.W + t) * K1;
+                w.Q.assign(m.I * 4, 1e300); w.Q2 = w.BASE = w.MSG = w.Q;          // poisoned: nothing may depend on it
+                std::vector<double> ring_ft(4 * m.I), ring_fg(4 * m.I);
+                std::vector<int> ring_fl(4 * m.I), ring_gap(4 * m.I);
+                double Fcur = 0, Fprev = 0; int fa_last = 0, kc_stop = -1;
+                const int tau_end = 2 * (K1 - 1) + dmax;
+                for (int tau = 0; tau <= tau_end && kc_stop < 0; ++tau) {
+                    // all nodes of this step read the state the previous steps left (no node of a step reads another one's output)
+                    WaveTree before = w;
+                    for (int i = 0; i < m.I; ++i) {
+                        if ((tau - w.depth[i]) & 1 || tau < w.depth[i]) continue;
+                        const int k = (tau - w.depth[i]) >> 1;
+                        if (k >= K1) continue;
+                        WaveTree scratch = before;
+                        double ft, fg; bool gap; int fl;
+                        wave_node(tp, lt, cw, scratch, i, k > 0, ft, fg, gap, fl);
+                        for (int a = 0; a < 4; ++a) {
+                            w.Q[i * 4 + a] = scratch.Q[i * 4 + a]; w.Q2[i * 4 + a] = scratch.Q2[i * 4 + a];
+                            w.MSG[i * 4 + a] = scratch.MSG[i * 4 + a]; w.BASE[i * 4 + a] = scratch.BASE[i * 4 + a];
+                        }
+                        const int r = (k & 3) * m.I + i;
+                        ring_ft[r] = ft; ring_fg[r] = fg; ring_fl[r] = fl; ring_gap[r] = gap;
+                    }
+                    const int kc2 = tau - dmax;
+                    if (kc2 >= 0 && !(kc2 & 1)) {
+                        const int kc = kc2 >> 1;
+                        double F = 0.0; int fa = kc >= 2 ? 3 : kc;
+                        for (int j = 0; j < m.I; ++j) {
+                            const int r = (kc & 3) * m.I + j;
+                            F += ring_ft[r];
+                            if (ring_gap[r]) F += ring_fg[r];
+                            fa &= ring_fl[r];
+                        }
+                        out[kc] = F; Fprev = Fcur; Fcur = F; fa_last = fa;
+                        if (early && fa != 0) kc_stop = kc;
+                    }
+                }
+                stopped[(size_t)c * m.W + t] = kc_stop < 0 ? K1 - 1 : kc_stop;
+                if (kc_stop >= 0)
+                    for (int j = kc_stop + 1; j < K1; ++j) out[j] = ((j - kc_stop) & 1) ? ((fa_last & 1) ? Fcur : Fprev) : Fcur;
+            }
+        return 0;
+    } catch (const std::exception& e) { std::fprintf(stderr, "emul: %s\n", e.what()); return -1; }
+}
+
+// the same trajectories from the sequential pass (what the direct kernel runs per tree)
+extern "C" int emul_seq_traj(const phyfoo_model_desc* d, const uint8_t* cols, int n, int K1, double* traj) {
+    try {
+        ModelHost m; m.init(*d);
+        TreeProg tp = prog_of(m);
+        std::vector<double> state((size_t)m.I * 8);
+        for (int c = 0; c < n; ++c)
+            for (int t = 0; t < m.W; ++t) {
+                State st{state.data(), 1};
+                const ColWords cw = words_of(cols + (size_t)c * m.S, m.S, false);
+                Tab lt{&m.logtab[(size_t)t * m.E], 1};
+                std::fill(state.begin(), state.end(), 1e300);
+                for (int k = 0; k < K1; ++k) traj[((size_t)c * m.W + t) * K1 + k] = meanfield_pass(tp, lt, st, cw, k > 0);
+            }
+        return 0;
+    } catch (const std::exception& e) { std::fprintf(stderr, "emul: %s\n", e.what()); return -1; }
+}

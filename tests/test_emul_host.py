@@ -113,3 +113,35 @@ def test_fixed_q_objective_matches_oracle(emul, newick, gap_rate):
     got_g = (vals[1:] - vals[0]) / eps
     noise = 64 * np.finfo(float).eps * abs(f0) / eps
     assert np.all(np.abs(got_g - g) <= 1e-9 * np.abs(g) + noise), (got_g, g)
+
+
+WAVE_TREES = [synth.caterpillar_newick(5), "((A:0.1,B:0.3):0.15,(C:0.2,(D:0.05,E:0.4):0.25):0.1,F:0.3)",
+              "((A:0.1,B:0.2):0.1,(C:0.3,D:0.1):0.2,(E:0.2,F:0.25):0.15)", synth.star_newick(4), synth.random_binary_newick(9, 2)]
+
+
+@pytest.mark.parametrize("newick", WAVE_TREES)
+@pytest.mark.parametrize("gap_rate", [0.0, 0.2])
+def test_wavefront_trajectories_equal_the_sequential_pass(emul, newick, gap_rate):
+    """The algorithm of the wavefront trajectory kernel (csrc/memo.cuh) modelled on the host: node i of sweep k at step
+    2 k + depth(i), message slots per child, terms summed per sweep in node order, early stop at a bitwise fixed point or
+    two-cycle with the periodic fill -- every trajectory entry equals the sequential pass bit for bit."""
+    tree = parse_newick(newick)
+    rng = np.random.default_rng(11)
+    W, n, K1 = 3, 60, 101
+    pwm = synth.random_pwm(W, 0, 9)
+    cols = random_codes(rng, n, tree.n_species, gap_rate)
+    desc, keep = _abi.make_desc(_abi.MODEL_FG, W, 0, tree, np.tile(tree.branch, (W, 1)), pwm, _abi.EVOL_F81ALPHA, _abi.MODE_MEANFIELD)
+    dp = C.POINTER(C.c_double)
+    seq = np.zeros((n, W, K1))
+    assert emul.emul_seq_traj(C.byref(desc), cols.ctypes.data_as(C.POINTER(C.c_uint8)), n, K1, seq.ctypes.data_as(dp)) == 0
+    for early in (0, 1):
+        wave = np.zeros((n, W, K1))
+        stopped = np.zeros((n, W), np.int32)
+        rc = emul.emul_wave_traj(C.byref(desc), cols.ctypes.data_as(C.POINTER(C.c_uint8)), n, K1, early, wave.ctypes.data_as(dp),
+                                 stopped.ctypes.data_as(C.POINTER(C.c_int)))
+        assert rc == 0
+        assert np.array_equal(wave.view(np.uint64), seq.view(np.uint64)), early
+        if early:
+            assert (stopped < K1 - 1).mean() > 0.5            # most trees become periodic long before the last sweep
+        else:
+            assert (stopped == K1 - 1).all()
