@@ -30,6 +30,8 @@ struct Net1wParams {
     unsigned long long* counters;
     int max_sweeps, min_sweeps; double tol;
     double* gq; int64_t n_slots;
+    double* gc;              // [n_slots][W * I * 4]: the observed-leaf sums of a window without gaps (they do not change from
+                             // sweep to sweep; computed in the pass at the uniform start, read back afterwards)
     int nwb;
     const int64_t* item_col0; const uint8_t* item_strand;
     double* sink_qint; double* sink_qleaf; double* sink_ent;
@@ -73,10 +75,11 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
     auto GQ = [&](int t, int kk, int s) -> double& { return p.gq[(size_t)((t * p.S + kk) * 4 + s) * p.n_slots + gslot]; };
 
     const long long n_items = (long long)p.n_windows * p.n_strands;
-    bool need = true, active = true, upd = false, conv = false;
+    bool need = true, active = true, upd = false, conv = false, nogap = false;
     int k = 0;
     long long item = -1;
     double old = 0.0;
+    double* const gcw = p.gc + (size_t)gslot * (p.W * p.I * 4);
     for (int j = l16; j < p.W * (p.S + 1); j += 16) s_lc[j * nwb + wq] = 0;
 
     for (;;) {
@@ -95,17 +98,20 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
                     const int al = find_alignment_hint(p.win_off, p.n_aln, w, p.n_windows);
                     c0 = p.col_off[al] + (w - p.win_off[al]);
                 }
+                unsigned any_gap_bits = 0;
                 for (int t = l16; t < p.W; t += 16) {
                     const int64_t col = strand ? c0 + (p.W - 1 - t) : c0 + t;     // jstacs StrandModel.java:636-639
                     ColWords cw = load_column(p.bases, p.gaps, p.n_cols, p.nb, col);
                     ColWords cwp; cwp.b = 0; cwp.g = 0;
                     if (t > 0) cwp = load_column(p.bases, p.gaps, p.n_cols, p.nb, strand ? col + 1 : col - 1);
                     if (strand) { cw = complement(cw); cwp = complement(cwp); }
+                    any_gap_bits |= cw.g;
                     for (int kk = 0; kk < p.S; ++kk) {
                         const int sp = leaf_species[kk];
                         s_lc[(t * (p.S + 1) + kk) * nwb + wq] = (uint8_t)(cw.obs(sp) | ((t > 0 ? cwp.obs(sp) : 0) << 4));
                     }
                 }
+                nogap = !__any_sync(0xFFFFu << wb, (any_gap_bits & (p.S >= 32 ? 0xffffffffu : (1u << p.S) - 1u)) != 0);
                 k = 0; conv = false; upd = false; need = false;
             }
             // uniform start, MeanFieldForBayesNet.java:52-69
@@ -155,9 +161,12 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
                 const double w2 = __shfl_sync(full, wu, qb + 2), w3 = __shfl_sync(full, wu, qb + 3);
                 ch += (((w0 + w1) + w2) + w3) - wu;
             }
-            // leaf children (null entries: code 0 and the zero table block)
+            // leaf children (null entries: code 0 and the zero table block).  In a window without gaps the sum over the
+            // observed leaves is the same in every sweep: kept from the pass at the uniform start
             double cobs = 0.0, cgap = 0.0;
-            for (int j = 0; j < p.ML; ++j) {
+            const bool cached = nogap && upd;
+            if (cached) cobs = gcw[(t * p.I + i) * 4 + a];
+            else for (int j = 0; j < p.ML; ++j) {
                 const int kk = r[2 + 3 * p.MC + 2 * j], lnb = r[3 + 3 * p.MC + 2 * j];
                 const int lc = lct[kk * nwb];
                 const int x = lc & 15, y = lc >> 4;
@@ -180,6 +189,7 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
                     }
                 }
             }
+            if (nogap && !upd && live) gcw[(t * p.I + i) * 4 + a] = cobs;
             // the same node at the next position (all-zero tables behind the last position)
             double nx = 0.0;
             {
@@ -201,7 +211,7 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
             if (live) { const double f = qn * ((lq - own) - cobs); F += f; if (!has_next) Flast += f; }
 
             // unobserved leaf children: update + free-energy terms (the only divergent part)
-            if (live) {
+            if (live && !nogap) {
                 for (int j = 0; j < p.ML; ++j) {
                     const int kk = r[2 + 3 * p.MC + 2 * j], lnb = r[3 + 3 * p.MC + 2 * j];
                     const int lc = lct[kk * nwb];

@@ -1185,7 +1185,7 @@ static int launch_net1w(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model*
     const long long want = (n_items + nwb - 1) / nwb;
     const int blocks = (int)std::max<long long>(1, std::min<long long>(want, (long long)per_sm * ctx->sm_count));
     const int64_t n_slots = (int64_t)blocks * nwb;
-    CU(ctx->gstate.ensure((size_t)h.W * h.S * 4 * n_slots * sizeof(double)));
+    CU(ctx->gstate.ensure(((size_t)h.W * h.S * 4 + (size_t)h.W * h.I * 4) * n_slots * sizeof(double)));
     Net1wParams p;
     p.bases = ds->d_bases; p.gaps = ds->d_gaps; p.n_cols = ds->n_cols; p.nb = ds->nb;
     p.col_off = ds->d_col_off; p.win_off = d_win_off; p.n_aln = ds->n_aln;
@@ -1197,6 +1197,7 @@ static int launch_net1w(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model*
     p.counters = ctx->counters.as<unsigned long long>() + 2 * counter_slot;
     p.max_sweeps = h.max_sweeps; p.min_sweeps = h.min_sweeps; p.tol = h.tol;
     p.gq = ctx->gstate.as<double>(); p.n_slots = n_slots; p.nwb = nwb;
+    p.gc = p.gq + (size_t)h.W * h.S * 4 * n_slots;
     p.item_col0 = items ? items->col0 : nullptr; p.item_strand = items ? items->strand : nullptr;
     p.sink_qint = items ? items->q_int : nullptr; p.sink_qleaf = items ? items->q_leaf : nullptr; p.sink_ent = items ? items->ent : nullptr;
     CU(cudaMemsetAsync(p.counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
