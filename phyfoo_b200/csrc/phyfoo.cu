@@ -1177,6 +1177,7 @@ static int launch_net1w(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model*
     while (nwb > 2 && fixed + per_window * nwb > budget) nwb >>= 1;
     if (fixed + per_window * nwb > budget) return fail(ctx, PHYFOO_EUNSUPPORTED, "order-1 window state does not fit in shared memory (motif too wide or tree too large)");
     // (measured on C3: 3 blocks per SM 2.89, 2 blocks 2.41, 1 block 1.42 M windows/s -- warps in flight beat a larger L1)
+    // (again after the observed-leaf cache: 3 blocks per SM 3.54, 2 blocks 2.90 M windows/s)
     const size_t smem = fixed + per_window * nwb;
     CU(cudaFuncSetAttribute(score_o1w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
