@@ -877,13 +877,28 @@ static int plan_score(phyfoo_ctx* ctx, const ModelHost& h, int prog_len, long lo
             if (resident > best_resident) { best_resident = resident; best_groups = groups; }
         }
     }
+    // state in global memory (coalesced, behind L2) when that at least doubles the windows in flight per SM: the state of a
+    // 12-species tree (704 B) leaves room for one block of 21 windows, that of a 30-species tree (1.9 KB) for 5 windows,
+    // while the tables alone allow two blocks of 256 threads.  Measured: 12 species 13.5 -> 18.4 M windows/s
+    // (--config c3o0), 30 species 0.97 -> 3.30 M windows/s (--config c5 --n-aln 3000)
+    long long g_resident = 0; int g_groups = 0;
+    {
+        const int groups = max_groups, threads = ((groups * W + 31) / 32) * 32;
+        const size_t fixed = tab_bytes + (size_t)threads * 8 + (size_t)groups * 8 + (size_t)prog_len * 4 + 64;
+        if (fixed <= budget) {
+            const long long by_smem = (long long)((228 * 1024) / (fixed + 1024));
+            const long long by_regs = 65536 / (128LL * threads);
+            g_resident = std::min(by_smem, std::max(1LL, by_regs)) * groups; g_groups = groups;
+        }
+    }
+    if (g_groups && g_resident >= 2 * best_resident) best_groups = 0;
     if (best_groups) {
         const int threads = ((best_groups * W + 31) / 32) * 32;
         pl->threads = threads; pl->groups = best_groups; pl->gstate = false;
         pl->smem = tab_bytes + (size_t)threads * 8 + (size_t)best_groups * 8 + (size_t)prog_len * 4 + 64 + per_thread_state * threads;
     } else {
-        // state does not fit in shared memory even for one window per block: keep it in global memory
-        const int groups = std::max(1, 128 / W);
+        // state in global memory
+        const int groups = g_groups ? g_groups : std::max(1, 128 / W);
         const int threads = ((groups * W + 31) / 32) * 32;
         const size_t fixed = tab_bytes + (size_t)threads * 8 + (size_t)groups * 8 + (size_t)prog_len * 4 + 64;
         if (fixed > budget) return fail(ctx, PHYFOO_EUNSUPPORTED, "model tables do not fit in shared memory");
