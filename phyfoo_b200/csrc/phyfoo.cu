@@ -243,10 +243,8 @@ __device__ __forceinline__ int find_alignment_hint(const int64_t* __restrict__ o
 static const int SCORE_CHUNK = 4;   // windows a group takes from the global counter at a time
 
 // ITEMS = true: M-step "prepare" variant (explicit window list, converged q written out)
-// MINB: resident blocks per SM the kernel is compiled for (1 when the shared-memory state of a large tree leaves room for
-// one block only: the compiler may then use more than 128 registers)
-template <int MODE, bool ITEMS, int MINB = 2>
-__global__ void __launch_bounds__(256, MINB) score_o0_kernel(ScoreParams p) {
+template <int MODE, bool ITEMS>
+__global__ void __launch_bounds__(256, 2) score_o0_kernel(ScoreParams p) {
     extern __shared__ double smem[];
     const int T = blockDim.x, tid = threadIdx.x;
     double* s_tab = smem;
@@ -854,7 +852,7 @@ static int model_upload(phyfoo_ctx* ctx, phyfoo_model* m) {
 // ------------------------------------------------------------------------------------------------
 // scoring launches
 // ------------------------------------------------------------------------------------------------
-struct ScorePlan { int threads, groups, blocks; size_t smem; bool gstate; bool one_block; };
+struct ScorePlan { int threads, groups, blocks; size_t smem; bool gstate; };
 
 static int plan_score(phyfoo_ctx* ctx, const ModelHost& h, int prog_len, long long n_items, int mode, bool items, ScorePlan* pl) {
     const int W = h.W;
@@ -904,12 +902,8 @@ static int plan_score(phyfoo_ctx* ctx, const ModelHost& h, int prog_len, long lo
         if (fixed > budget) return fail(ctx, PHYFOO_EUNSUPPORTED, "model tables do not fit in shared memory");
         pl->threads = threads; pl->groups = groups; pl->smem = fixed; pl->gstate = true;
     }
-    // one block per SM by shared memory and a plain mean-field pass over all windows: the variant compiled for one block
-    pl->one_block = mode != PHYFOO_MODE_EXACT && !items && !pl->gstate && 2 * (pl->smem + 1024) > 228 * 1024;
     const void* fn = mode == PHYFOO_MODE_EXACT ? (const void*)score_o0_kernel<PHYFOO_MODE_EXACT, false>
-                   : items ? (const void*)score_o0_kernel<PHYFOO_MODE_MEANFIELD, true>
-                   : pl->one_block ? (const void*)score_o0_kernel<PHYFOO_MODE_MEANFIELD, false, 1>
-                                   : (const void*)score_o0_kernel<PHYFOO_MODE_MEANFIELD, false>;
+                   : items ? (const void*)score_o0_kernel<PHYFOO_MODE_MEANFIELD, true> : (const void*)score_o0_kernel<PHYFOO_MODE_MEANFIELD, false>;
     CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, pl->threads, pl->smem));
@@ -1355,7 +1349,6 @@ static int launch_score(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model*
         KernelTimer kt_(ctx, fallback ? "score_o0_kernel(fallback list)" : "score_o0_kernel");
         if (mode == PHYFOO_MODE_EXACT) score_o0_kernel<PHYFOO_MODE_EXACT, false><<<pl.blocks, pl.threads, pl.smem, ctx->stream>>>(p);
         else if (items) score_o0_kernel<PHYFOO_MODE_MEANFIELD, true><<<pl.blocks, pl.threads, pl.smem, ctx->stream>>>(p);
-        else if (pl.one_block) score_o0_kernel<PHYFOO_MODE_MEANFIELD, false, 1><<<pl.blocks, pl.threads, pl.smem, ctx->stream>>>(p);
         else score_o0_kernel<PHYFOO_MODE_MEANFIELD, false><<<pl.blocks, pl.threads, pl.smem, ctx->stream>>>(p);
     }
     CU(cudaGetLastError());
