@@ -326,3 +326,19 @@ extern "C" int emul_seq_traj(const phyfoo_model_desc* d, const uint8_t* cols, in
         return 0;
     } catch (const std::exception& e) { std::fprintf(stderr, "emul: %s\n", e.what()); return -1; }
 }
+
+// the list schedule of the order-1 wavefront kernel (model_host.hpp::wave_program): sched[n_steps][4] entries (t << 16 | i, -1 = idle)
+extern "C" int emul_wave_schedule(const phyfoo_model_desc* d, int* sched_out, int max_entries, int* n_steps, int* n_internal,
+                                  int* par_internal_out /*[I]*/) {
+    try {
+        ModelHost m; m.init(*d);
+        std::vector<int> prog; int MC, ML, ns;
+        m.wave_program(prog, MC, ML, ns);
+        const int off = 2 * m.I + 2 * m.S + m.I * MC + m.I * ML;
+        if (4 * ns > max_entries) return -2;
+        for (int k = 0; k < 4 * ns; ++k) sched_out[k] = prog[off + k];
+        for (int i = 0; i < m.I; ++i) par_internal_out[i] = m.par_internal[i];
+        *n_steps = ns; *n_internal = m.I;
+        return 0;
+    } catch (const std::exception& e) { std::fprintf(stderr, "emul: %s\n", e.what()); return -1; }
+}

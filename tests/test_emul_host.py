@@ -145,3 +145,43 @@ def test_wavefront_trajectories_equal_the_sequential_pass(emul, newick, gap_rate
             assert (stopped < K1 - 1).mean() > 0.5            # most trees become periodic long before the last sweep
         else:
             assert (stopped == K1 - 1).all()
+
+
+@pytest.mark.parametrize("newick", [synth.caterpillar_newick(5), synth.random_binary_newick(12, 3), synth.random_binary_newick(30, 5),
+                                    synth.star_newick(6), "((A:0.1,B:0.3):0.15,(C:0.2,(D:0.05,E:0.4):0.25):0.1,F:0.3)"])
+@pytest.mark.parametrize("W", [1, 2, 12])
+def test_order1_wavefront_schedule_respects_the_reference_sweep(emul, newick, W):
+    """The list schedule of the order-1 wavefront kernel (csrc/model_host.hpp::wave_program): every node update (t, i) runs
+    exactly once per sweep, at most four per step, AFTER the nodes whose new values the reference's Gauss-Seidel order gives
+    it -- (t, parent), (t-1, i), (t-1, children) -- and BEFORE the nodes whose old values it reads -- (t, children), (t+1, i),
+    (t+1, parent).  Any such schedule reproduces the reference's sweep bit for bit (csrc/net1w.cuh)."""
+    tree = parse_newick(newick)
+    pwm = synth.random_pwm(W, 1, 3)
+    desc, keep = _abi.make_desc(_abi.MODEL_FG, W, 1, tree, np.tile(tree.branch, (W, 1)), pwm, _abi.EVOL_F81ALPHA, _abi.MODE_MEANFIELD)
+    cap = 4 * W * tree.n_nodes + 64
+    sched = np.zeros(cap, np.int32)
+    par = np.zeros(tree.n_nodes, np.int32)
+    ns, ni = C.c_int(), C.c_int()
+    ip = C.POINTER(C.c_int)
+    assert emul.emul_wave_schedule(C.byref(desc), sched.ctypes.data_as(ip), cap, C.byref(ns), C.byref(ni), par.ctypes.data_as(ip)) == 0
+    I, n_steps = ni.value, ns.value
+    par = par[:I]
+    sched = sched[:4 * n_steps].reshape(n_steps, 4)
+    step_of = {}
+    for s in range(n_steps):
+        live = [int(c) for c in sched[s] if c >= 0]
+        assert 1 <= len(live) <= 4
+        for c in live:
+            key = (c >> 16, c & 0xffff)
+            assert key not in step_of and key[0] < W and key[1] < I
+            step_of[key] = s
+    assert len(step_of) == W * I                                       # every node update once per sweep
+    kids = {i: [c for c in range(1, I) if par[c] == i] for i in range(I)}
+    for (t, i), s in step_of.items():
+        new = ([(t, int(par[i]))] if i > 0 else []) + ([(t - 1, i)] + [(t - 1, c) for c in kids[i]] if t > 0 else [])
+        old = [(t, c) for c in kids[i]] + ([(t + 1, i)] + ([(t + 1, int(par[i]))] if i > 0 else []) if t + 1 < W else [])
+        assert all(step_of[k] < s for k in new), (t, i)
+        assert all(step_of[k] > s for k in old), (t, i)
+    # the chain is much shorter than the W * I sequential updates once the tree is not a path
+    if I >= 4 and W == 12:
+        assert n_steps <= 0.6 * W * I
