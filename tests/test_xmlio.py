@@ -116,3 +116,23 @@ def test_temperature_other_than_one_is_rejected():
                                                        "<TEMPERATURE><className>java.lang.Double</className>0.5", 1)
     with pytest.raises(NotImplementedError):
         xmlio.read_phylo_bayes_model(text)
+
+
+def test_newick_writer_and_parser_round_trip_random_trees():
+    """bayesNet/VirtualTree.java:208-234 writes what io/NewickToBayesNet.java:106-147 reads: topology, leaf order and the
+    three-decimal branch lengths survive; a second round trip is the identity."""
+    from phyfoo_b200 import synth
+    from phyfoo_b200.newick import parse_newick
+    rng = np.random.default_rng(3)
+    for trial in range(40):
+        S = int(rng.integers(2, 24))
+        text = synth.random_binary_newick(S, int(rng.integers(1, 10 ** 6)), 0.0004, 1.3)
+        if trial % 3 == 0:                                   # a multifurcating root as in the star data sets
+            text = "(" + ",".join(f"L{k}:{rng.uniform(0.001, 0.9):.4f}" for k in range(S)) + ")"
+        t1 = parse_newick(text)
+        s1 = xmlio.newick_string(t1, t1.branch)
+        t2 = parse_newick(s1)
+        assert (t2.parent == t1.parent).all() and t2.labels == t1.labels and (t2.leaf_species == t1.leaf_species).all()
+        assert np.array_equal(t2.branch, np.round(t1.branch * 1000.0) / 1000.0)
+        assert xmlio.newick_string(t2, t2.branch) == s1
+        assert s1.endswith(";") and s1.count("(") == s1.count(")")
