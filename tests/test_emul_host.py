@@ -185,3 +185,41 @@ def test_order1_wavefront_schedule_respects_the_reference_sweep(emul, newick, W)
     # the chain is much shorter than the W * I sequential updates once the tree is not a path
     if I >= 4 and W == 12:
         assert n_steps <= 0.6 * W * I
+
+
+@pytest.mark.parametrize("newick", [synth.caterpillar_newick(5), "((A:0.1,B:0.3):0.15,(C:0.2,(D:0.05,E:0.4):0.25):0.1,F:0.3)"])
+@pytest.mark.parametrize("gap_rate", [0.0, 0.15])
+def test_pattern_table_decomposition(emul, newick, gap_rate):
+    """What the pattern-table path rests on (csrc/memo.cuh): for an order-0 model the free energy of a window after k sweeps is
+    the tree-order sum of per-(column, position) trajectories, and the reference's stop rule applied to that sum gives the
+    window's score and sweep count -- bit for bit what the window-by-window pass computes.  Also with a sweep cap: windows whose
+    rule has not fired within the cap are exactly the ones the direct kernel has to take."""
+    tree = parse_newick(newick)
+    S = tree.n_species
+    rng = np.random.default_rng(17)
+    W, L, K1 = 4, 120, 101
+    pwm = synth.random_pwm(W, 0, 21)
+    codes = random_codes(rng, L, S, gap_rate)
+    ref, ref_k = run_emul(emul, newick, pwm, codes, 0, _abi.MODE_MEANFIELD)
+    desc, keep = _abi.make_desc(_abi.MODEL_FG, W, 0, tree, np.tile(tree.branch, (W, 1)), pwm, _abi.EVOL_F81ALPHA, _abi.MODE_MEANFIELD)
+    traj = np.zeros((L, W, K1))
+    assert emul.emul_seq_traj(C.byref(desc), codes.ctypes.data_as(C.POINTER(C.c_uint8)), L, K1, traj.ctypes.data_as(C.POINTER(C.c_double))) == 0
+    cap = 12
+    pending = 0
+    for j in range(L - W + 1):
+        def F(k):
+            s = 0.0
+            for t in range(W):
+                s = s + traj[j + t, t, k]                   # tree-major, like calcFreeEnergy(0, W-1)
+            return s
+        old, k, conv = F(0), 0, False
+        cur = old
+        while (k < 100 and not conv) or k < 2:              # MeanFieldForBayesNet.java:107, :204-207
+            cur = F(k + 1)
+            if abs(old - cur) < 1e-5:
+                conv = True
+            old = cur
+            k += 1
+        assert k == ref_k[j] and -cur == ref[j], j
+        pending += k > cap
+    assert pending == int((ref_k > cap).sum())
