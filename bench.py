@@ -3,10 +3,14 @@
 
 A "step" is one pass of the hot path over one batch of synthetic alignments: background column scores, motif
 window scores of every offset, the ZOOPS posterior (gamma, w, log-likelihood, arg-max) and, for N > 1, the
-all-reduce of [ll, w0, w1] over NCCL.  One process per GPU; every rank holds a full-size shard ("weak" scaling:
-alignments are independent).
+all-reduce of [ll, w0, w1] over NCCL.  Default workload: BASELINE.json configs[2] = north_star's target shape
+(C3: order-1 phylogenetic Bayesian network, W = 12, 12-species tree, 10 000 alignments x 1 kb).  One process per
+GPU; at N > 1 the SAME 10 000 alignments are split into contiguous blocks balanced by column count
+(sharding.shard_bounds, the partition PhyloSample.shard makes): "strong" scaling, every rank scores different
+alignments.  Before the timed region rank 0 scores the first alignments of its shard with the oracle and asserts
+parity (scores 1e-9 relative, sweep counts and arg-max calls exact); the line carries `parity_checked`.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2|c2star|c3o0] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config c3|c2|c2star|c3o0|c5] [--impl reference]
 
 Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM; `e2e` goes through the public
 host API with host buffers (pack + copies inside the timed region); `roofline` is for the dominant kernel
@@ -27,7 +31,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "site_loglik_per_sec"
 UNIT = "window scores/s"
-DEFAULT_CONFIG = "c2"
+DEFAULT_CONFIG = "c3"
 
 
 def parse_args():
@@ -44,6 +48,9 @@ def parse_args():
     ap.add_argument("--no-memo", action="store_true", help="switch the pattern-table path off (direct kernel only)")
     ap.add_argument("--memo-split", type=int, default=None, help="pattern_memo_split of the library (tuning only)")
     ap.add_argument("--memo-wave", type=int, default=None, help="pattern_memo_wave of the library (tuning only)")
+    ap.add_argument("--order1-kernel", type=int, default=None, help="order1_kernel of the library (tuning only)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity check before the timed region")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary configurations (c2, c3o0)")
     return ap.parse_args()
 
 
@@ -221,6 +228,242 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------
+PARITY_ALIGNMENTS = {0: 16, 1: 3}      # alignments of the parity check, by motif order (the order-1 oracle is ~30x slower)
+
+
+def parity_check(cfg, newick, pwm, sample, shm, k):
+    """The first k alignments of this rank's shard through the public API against the oracle: gamma / ll at 1e-9 relative,
+    mean-field sweep counts and arg-max site calls exact (the bars of tests/test_gpu_parity.py).  Raises on a mismatch."""
+    from oracle import oracle as orc
+    sub = sample.slice(0, k)
+    res = shm.getNewWeights(sub, want_gamma=True)
+    ofg = orc.Model(orc.FG, cfg["W"], cfg["order"], newick)
+    for t, p in enumerate(pwm):
+        ofg.set_pi(t, np.asarray(p).ravel())
+    obg = orc.Model(orc.BG, 0, 0, newick)
+    ref = orc.estep(ofg, obg, sub.col_offsets, sub.codes, np.log(shm.weights), threads=os.cpu_count() or 1, want=("gamma",))
+    err_ll = abs(res["ll"] - ref["ll"]) / abs(ref["ll"])
+    err_g = float(np.max(np.abs(res["gamma"] - ref["gamma"])))
+    ok = (err_ll <= 1e-9 and err_g <= 1e-9 and np.array_equal(res["argmax_off"], ref["argmax_off"])
+          and res["stats"]["sweeps_fg"] == ref["sweeps_fg"] and 2 * res["stats"]["sweeps_bg"] == ref["sweeps_bg"])
+    if not ok:
+        raise SystemExit(f"bench.py: parity check against the oracle FAILED on {cfg}: ll rel err {err_ll:.3e}, gamma abs err "
+                         f"{err_g:.3e}, sweeps {res['stats']['sweeps_fg']} vs {ref['sweeps_fg']}, arg-max equal: "
+                         f"{np.array_equal(res['argmax_off'], ref['argmax_off'])}")
+    sub.device(shm.motif.ctx).free()
+    return {"alignments": int(k), "windows": int(res["gamma"].size), "ll_rel_err": err_ll, "gamma_abs_err": err_g,
+            "sweep_counts": "identical", "argmax_calls": "identical"}
+
+
+class EStepRunner:
+    """One configuration resident on this rank's GPU: models, packed shard, the device-side E-step."""
+
+    def __init__(self, ctx, torch, dist, world, rank, name, n_aln=None, stream=None, flush=None):
+        from phyfoo_b200 import sharding, synth
+        from phyfoo_b200.models import PhyloBackground, PhyloBayesModel, SingleHiddenMotifMixture
+        self.ctx, self.torch, self.dist, self.world, self.rank, self.name = ctx, torch, dist, world, rank, name
+        self.cfg, self.newick, self.pwm, full, self.planted = synth.make_config(name, n_aln=n_aln)
+        W = self.cfg["W"]
+        self.total_windows = int(np.maximum(full.lengths() - W + 1, 0).sum())
+        self.total_alignments = full.n_alignments
+        if world > 1:
+            self.bounds = sharding.shard_bounds(full.col_offsets, world)
+            lo, hi = self.bounds[rank]
+            self.sample = full.slice(lo, hi)
+        else:
+            self.bounds = [(0, full.n_alignments)]
+            self.sample = full
+        del full
+        self.fg = PhyloBayesModel(W, self.cfg["order"], self.newick, ctx)
+        self.fg.setCondProbs(self.pwm)
+        self.bg = PhyloBackground(0, self.newick, ctx)
+        self.shm = SingleHiddenMotifMixture(self.fg, self.bg, zoops=0.9)
+        self.logw = np.log(self.shm.weights)
+        self.ds = self.sample.device(ctx)
+        self.n_windows = self.ds.windows(W)
+        self.I = self.fg.tree.n_nodes - self.fg.tree.n_species
+        self.partial = torch.zeros(3, dtype=torch.float64, device="cuda")
+        self.stream, self.flush = stream, flush
+
+    def step(self):
+        from phyfoo_b200 import core
+        core.zoops_estep_device(self.ctx, self.ds, self.fg.device_model(), self.bg.device_model(), self.logw, None, None,
+                                self.partial.data_ptr(), self.stream.cuda_stream)
+        if self.world > 1:
+            self.dist.all_reduce(self.partial)
+
+    def timed(self, n_steps):
+        """n_steps E-steps, L2 flushed before each (untimed), CUDA events on the launching stream.  Returns the summed
+        device ms and the per-kernel device ms (library events), keyed by launch order."""
+        torch = self.torch
+        total, per_kernel = 0.0, {}
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(n_steps):
+            self.flush.fill_(1)
+            e0.record(self.stream)
+            self.step()
+            e1.record(self.stream)
+            e1.synchronize()
+            total += e0.elapsed_time(e1)
+            for i, (name, ms) in enumerate(self.ctx.last_kernel_times()):
+                key = (i, name)
+                per_kernel[key] = per_kernel.get(key, 0.0) + ms
+        return total, {k: v / n_steps for k, v in per_kernel.items()}
+
+    def max_over_ranks(self, values):
+        t = self.torch.tensor(list(values), dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
+    def free(self):
+        self.ds.free()
+
+
+def fp64_roofline(flops, abytes, kernel_name, kernel_ms, peak_tflops, hbm_peak, hbm_of, note=None):
+    achieved = flops / (kernel_ms * 1e-3) / 1e12
+    r = {"bound": "fp64", "kernel": kernel_name, "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+         "frac": achieved / peak_tflops,
+         "peak_source": "DFMA microbenchmark in this run (MEASURED_PEAKS.json has no fp64 entry)",
+         "flops_per_launch": flops, "kernel_ms": kernel_ms,
+         "hbm": {"achieved": abytes / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                 "frac": abytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak, "of": hbm_of},
+         "traffic": None}
+    if note:
+        r["note"] = note
+    return r
+
+
+def roofline_of(run, kernels, step_ms, sweeps_fg, peak_tflops, hbm_peak, hbm_of, traffic_db, direct=None):
+    """roofline of the kernel(s) with the largest share of the step + extra sub-objects (pattern-table path)."""
+    cfg, I, S, W, n_windows = run.cfg, run.I, run.cfg["S"], run.cfg["W"], run.n_windows
+    flops = algorithmic_flops(cfg, I, n_windows, sweeps_fg)
+    abytes = algorithmic_bytes(cfg, n_windows)
+    names = {name for (_, name) in kernels}
+    path = run.ctx.last_score_path()
+    extra = {}
+
+    def traffic_of(*keys):
+        for key in keys:
+            if key in traffic_db:
+                return traffic_db[key]
+        return None
+
+    o1 = [n for n in ("score_o1n_kernel", "score_o1w_kernel", "score_o1_kernel") if n in names]
+    fg_name = o1[0] if cfg["order"] == 1 and o1 else "score_o0_kernel"
+    if path != 1:
+        # the motif-window launches of the scoring kernel (an order-1 step may add a fallback launch for windows with gaps)
+        fg_ms = max(ms for (_, name), ms in kernels.items() if name == fg_name)
+        roofline = fp64_roofline(flops, abytes, fg_name + " (motif windows)", fg_ms, peak_tflops, hbm_peak, hbm_of)
+        roofline["kernel_share_of_step"] = fg_ms / step_ms
+        roofline["traffic"] = traffic_of(f"r02_{run.name}:{fg_name}", f"r01_{run.name}_direct_kernel:score_o0_kernel<0, 0>")
+        if cfg["order"] == 1:
+            roofline["note"] = ("flops_per_launch is the ALGORITHMIC count of SURVEY.md section 8d (the reference's generic 16-row "
+                                "contractions, measured sweep counts); the kernel executes fewer fp64 operations than that (F81 "
+                                "structure of the tables, shared context sums, no logarithm per node), so frac can exceed the share "
+                                "of the fp64 pipe ncu reports")
+    else:
+        # pattern-table path: per-pattern trajectories (fp64, a small latency-bound grid) + gathers per window
+        D = run.ds.patterns()
+        win_ms = sum(ms for (_, name), ms in kernels.items() if name == "memo_window_kernel")     # background + motif launches
+        traj_ms = sum(ms for (_, name), ms in kernels.items() if name.startswith("memo_traj"))    # both phases
+        upd, fe = flops_order0(I, S)
+        K1 = 65              # pattern_memo_sweep_cap (64) + 1 passes per tree
+        traj_flops = D * (W + 1) * K1 * (upd + fe)            # motif positions + the background tree
+        gather_bytes = W * (sweeps_fg + n_windows) * 8         # trajectory entries the stop rule consumes
+        if win_ms >= traj_ms:
+            roofline = {"bound": "hbm", "kernel": "memo_window_kernel (background + motif launches; gathers from an L2-resident table)",
+                        "achieved": abytes / (win_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": abytes / (win_ms * 1e-3) / 1e9 / hbm_peak, "of": hbm_of,
+                        "bytes_per_launch": abytes, "kernel_ms": win_ms, "kernel_share_of_step": win_ms / step_ms,
+                        "table_gather": {"bytes": gather_bytes, "GB/s": gather_bytes / (win_ms * 1e-3) / 1e9,
+                                         "what": "8 B x W x (K_w + 1) trajectory entries per window, served by L2"},
+                        "traffic": traffic_of("r01_c2_pattern_table:memo_window_kernel<0, 4>", "r01_c2_pattern_table:memo_window_kernel")}
+        else:
+            achieved = traj_flops / (traj_ms * 1e-3) / 1e12
+            roofline = {"bound": "fp64", "kernel": "memo_traj_kernel (mean-field trajectories of the occurring column patterns)",
+                        "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
+                        "peak_source": "DFMA microbenchmark in this run (MEASURED_PEAKS.json has no fp64 entry)",
+                        "flops_per_launch": traj_flops, "kernel_ms": traj_ms, "kernel_share_of_step": traj_ms / step_ms,
+                        "note": f"{D} patterns x {W + 1} trees x {K1} trajectory entries each; flops count every entry although a "
+                                "tree stops once its q repeats bit for bit (the rest of its row is filled: about half of the "
+                                "entries are executed); a small grid of dependent steps, bound by issue slots and instruction "
+                                "latency, not by the fp64 pipe",
+                        "traffic": traffic_of("r01_c2_pattern_table:memo_traj_wave_kernel<8>", "r01_c2_pattern_table:memo_traj_kernel")}
+        extra["pattern_table"] = {"patterns": D, "trajectory_flops_per_step": traj_flops, "direct_flops_per_step": flops,
+                                  "work_ratio": flops / max(traj_flops, 1), "trajectory_ms": traj_ms, "gather_ms": win_ms}
+        if direct:
+            d_ms, d_kernels = direct
+            d_fg = max(ms for (_, name), ms in d_kernels.items() if name == "score_o0_kernel")
+            extra["roofline_direct"] = fp64_roofline(
+                flops, abytes, "score_o0_kernel (motif windows, direct path: pattern table switched off)", d_fg, peak_tflops,
+                hbm_peak, hbm_of, "what every configuration with more than 6 species runs; measured in this run, 3 steps, not part of `value`")
+            extra["roofline_direct"]["step_ms"] = d_ms
+    return roofline, extra
+
+
+def optimizer_timings(run, args, step_ms):
+    """one forward-difference gradient of the M-step objective (dim + 1 objective sums in one pass,
+    plus the all-reduce at N > 1) and one whole EM iteration (E-step + M-step of the motif model: selection, fixing q,
+    position-wise BFGS).  Wall clock, max over ranks.  They change the model, so they come last."""
+    from phyfoo_b200 import core, sharding
+    ctx, fg, bg, ds, cfg, world = run.ctx, run.fg, run.bg, run.ds, run.cfg, run.world
+    W = cfg["W"]
+    core.zoops_estep(ctx, ds, fg.device_model(), bg.device_model(), run.logw, None, None, True, False, False)   # gamma stays resident
+    t0 = time.perf_counter()
+    sa, so, sw = core.select(ctx, ds, W, None, fg.PROB_THRESH_FOR_WEIGHTS, fg.MOTIF_QUALITY_THRESHOLD)
+    fe = core.FESet(ctx, ds, fg.device_model(), sa, so, sw)
+    ctx.synchronize()
+    prepare_ms = (time.perf_counter() - t0) * 1e3
+    obj = sharding.ShardedObjective(fe, ctx.device) if world > 1 else fe
+    pos = 1 if cfg["order"] == 1 else 0                 # an order-1 motif: a position with four context rows (dim 16)
+    lam = np.log(np.asarray(fg.getCondProb(pos), np.float64).ravel())
+    for _ in range(3):
+        obj.grad(pos, lam)
+    if world > 1:
+        run.dist.barrier()
+    t0 = time.perf_counter()
+    n_grad = 20
+    for _ in range(n_grad):
+        obj.grad(pos, lam)
+    grad_ms = (time.perf_counter() - t0) * 1e3 / n_grad
+    fe.free()
+
+    def mstep(suffstats):
+        fg.setCondProbs(run.pwm)
+        core.zoops_estep(ctx, ds, fg.device_model(), bg.device_model(), run.logw, None, None, True, False, False)
+        fg.trainingStep = fg.SKIP_TRAINING_STEPS          # the reference ignores the first call; time a real M-step
+        fg.MSTEP_SUFFICIENT_STATISTICS = suffstats
+        if world > 1:
+            run.dist.barrier()
+        t0 = time.perf_counter()
+        st = fg.train(run.sample, None, rng=np.random.default_rng(1), sharded=world > 1)
+        return (time.perf_counter() - t0) * 1e3, st
+
+    repeats = 2 if cfg["order"] == 0 else 1
+    mstep_ms, st = min((mstep(False) for _ in range(repeats)), key=lambda r: r[0])
+    out = {"gradient_ms": grad_ms, "dim": int(lam.size), "position": pos, "selected_windows_per_gpu": int(sa.size),
+           "select_and_fix_q_ms": prepare_ms}
+    if cfg["order"] == 0:
+        mstep_ss_ms, st_ss = min((mstep(True) for _ in range(repeats)), key=lambda r: r[0])
+        fg.MSTEP_SUFFICIENT_STATISTICS = False
+        grad_ms, mstep_ms, prepare_ms, mstep_ss_ms = run.max_over_ranks([grad_ms, mstep_ms, prepare_ms, mstep_ss_ms])
+        out.update({"mstep_sufficient_statistics_ms": mstep_ss_ms,
+                    "mstep_sufficient_statistics_evaluations": int(st_ss["evaluations"]),
+                    "em_iteration_sufficient_statistics_ms": step_ms + mstep_ss_ms})
+    else:
+        grad_ms, mstep_ms, prepare_ms = run.max_over_ranks([grad_ms, mstep_ms, prepare_ms])
+    fg.setCondProbs(run.pwm)
+    out.update({"gradient_ms": grad_ms, "select_and_fix_q_ms": prepare_ms, "mstep_ms": mstep_ms,
+                "mstep_evaluations": int(st["evaluations"]), "em_iteration_ms": step_ms + mstep_ms,
+                "what": "wall clock, max over ranks: evaluateGradientOfFunction of one motif position (forward differences, "
+                        "dim + 1 objective sums over the selected windows in one pass" + (", one all-reduce" if world > 1 else "") +
+                        "); M-step = selection + mean fields of the selected windows + BFGS position by position "
+                        "(host optimiser, device objective); EM iteration = E-step (ms_per_step) + M-step; sufficient statistics "
+                        "(order 0): one device pass for the expected counts, evaluations are dot products inside libphyfoo.so"})
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -234,11 +477,10 @@ def run_ours(args):
     if world > 1:
         import datetime
         # a short collective timeout: a rank-asymmetric bug must abort the run in minutes, not hold 8 GPUs for the default 10
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=300))
 
-    from phyfoo_b200 import core, synth
+    from phyfoo_b200 import core
     from phyfoo_b200.data import PhyloSample
-    from phyfoo_b200.models import PhyloBackground, PhyloBayesModel, SingleHiddenMotifMixture
 
     ctx = core.Context(local)
     if args.memo_split is not None:
@@ -247,48 +489,23 @@ def run_ours(args):
         ctx.set_option("pattern_memo_wave", args.memo_wave)
     if args.no_memo:
         ctx.set_option("pattern_memo", 0)
-    cfg, newick, pwm, sample, planted = synth.make_config(args.config, n_aln=args.n_aln)
-    W, S = cfg["W"], cfg["S"]
-    fg = PhyloBayesModel(W, cfg["order"], newick, ctx)
-    fg.setCondProbs(pwm)
-    bg = PhyloBackground(0, newick, ctx)
-    shm = SingleHiddenMotifMixture(fg, bg, zoops=0.9)
-    logw = np.log(shm.weights)
-    ds = sample.device(ctx)
-    n_windows = ds.windows(W)
-    I = fg.tree.n_nodes - fg.tree.n_species
-
-    partial = torch.zeros(3, dtype=torch.float64, device="cuda")
+    if args.order1_kernel is not None:
+        ctx.set_option("order1_kernel", args.order1_kernel)
+    warmup = max(args.warmup, 3)                 # timing rule: at least three untimed steps; the line reports what ran
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
     # a non-default torch stream: handle 0 would mean "the library's own stream" to the C ABI
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
 
-    def step():
-        core.zoops_estep_device(ctx, ds, fg.device_model(), bg.device_model(), logw, None, None, partial.data_ptr(),
-                                stream.cuda_stream)
-        if world > 1:
-            dist.all_reduce(partial)
+    run = EStepRunner(ctx, torch, dist, world, rank, args.config, args.n_aln, stream, flush)
+    cfg, sample, W, S = run.cfg, run.sample, run.cfg["W"], run.cfg["S"]
 
-    def timed(n_steps):
-        """n_steps E-steps, L2 flushed before each (untimed), CUDA events on the launching stream.  Returns the summed
-        device ms and the per-kernel device ms (library events), keyed by launch order."""
-        total, per_kernel = 0.0, {}
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        for _ in range(n_steps):
-            flush.fill_(1)
-            e0.record(stream)
-            step()
-            e1.record(stream)
-            e1.synchronize()
-            total += e0.elapsed_time(e1)
-            for i, (name, ms) in enumerate(ctx.last_kernel_times()):
-                key = (i, name)
-                per_kernel[key] = per_kernel.get(key, 0.0) + ms
-        return total, {k: v / n_steps for k, v in per_kernel.items()}
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = parity_check(cfg, run.newick, run.pwm, sample, run.shm, min(PARITY_ALIGNMENTS[cfg["order"]], sample.n_alignments))
 
-    for _ in range(max(args.warmup, 3)):
-        step()
+    for _ in range(warmup):
+        run.step()
     torch.cuda.synchronize()
     launches_per_step = ctx.last_launches()
     path = ctx.last_score_path()
@@ -300,44 +517,43 @@ def run_ours(args):
     torch.cuda.synchronize()
     sampler.start()
     t_wall0 = time.perf_counter()
-    dev_ms, kernels = timed(args.steps)
+    dev_ms, kernels = run.timed(args.steps)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
     sweeps_fg, sweeps_bg = ctx.estep_sweeps()
-    ll_w = partial.cpu().numpy().copy()
+    ll_w = run.partial.cpu().numpy().copy()
 
-    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms_max = float(t.item())
-    total_windows = n_windows * world
+    dev_ms_max, = run.max_over_ranks([dev_ms])
+    total_windows = run.total_windows                  # strong scaling: the ranks' shards add up to the one data set
     value = total_windows * args.steps / (dev_ms_max * 1e-3)
+    step_ms = dev_ms_max / args.steps
 
     # the direct kernel on the same workload (the path every configuration with more than 6 species takes), for the roofline
     # (every rank runs it: step() contains the all-reduce, so a rank-0-only run would leave rank 0 alone in a collective)
     direct = None
     if path == 1:
         ctx.set_option("pattern_memo", 0)
-        step(); torch.cuda.synchronize()
-        d_ms, d_kernels = timed(3)
+        run.step(); torch.cuda.synchronize()
+        d_ms, d_kernels = run.timed(3)
         ctx.set_option("pattern_memo", 1)
-        step(); torch.cuda.synchronize()
+        run.step(); torch.cuda.synchronize()
         direct = (d_ms / 3, d_kernels)
 
     # ---- e2e: public host API, host buffers, pack + copies inside the timed region (per rank, max over ranks).
     # Inputs come from page-locked host memory, results land in page-locked host memory that the caller reuses.
     pinned = ctx.pinned_empty(sample.codes.shape, np.uint8)
     pinned[:] = sample.codes
+    n_windows = run.n_windows
     out = {"gamma": ctx.pinned_empty(n_windows), "argmax_off": ctx.pinned_empty(sample.n_alignments, np.int32),
            "argmax_strand": ctx.pinned_empty(sample.n_alignments, np.uint8)}
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(args.steps, 10 if step_ms < 100 else 5))
 
     def e2e_step():
         smp = PhyloSample(pinned, sample.col_offsets)
-        res = shm.getNewWeights(smp, want_gamma=True, out=out)
+        res = run.shm.getNewWeights(smp, want_gamma=True, out=out)
         smp.device(ctx).free()
         return res
 
@@ -349,166 +565,64 @@ def run_ours(args):
     for _ in range(e2e_steps):
         res = e2e_step()
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = total_windows * e2e_steps / float(t.item())
+    e2e_s, = run.max_over_ranks([time.perf_counter() - t0])
+    e2e_value = total_windows * e2e_steps / e2e_s
     h2d = int(sample.codes.nbytes + sample.col_offsets.nbytes)
     d2h = int(res["gamma"].nbytes + res["argmax_off"].nbytes + res["argmax_strand"].nbytes + 24)
     assert world > 1 or abs(res["ll"] - ll_w[0]) <= 1e-9 * abs(res["ll"])
 
-    # ---- one forward-difference gradient of the M-step objective (dim + 1 objective sums in one
-    # pass, plus the all-reduce at N > 1) and one whole EM iteration (the E-step above + the M-step of the motif model:
-    # selection, fixing q, position-wise BFGS).  Secondary numbers; they change the model, so they come last.
-    from phyfoo_b200 import sharding
     optimizer = None
-    if cfg["order"] == 0 and not args.no_mstep:
-        core.zoops_estep(ctx, ds, fg.device_model(), bg.device_model(), logw, None, None, True, False, False)   # gamma stays resident
-        t0 = time.perf_counter()
-        sa, so, sw = core.select(ctx, ds, W, None, fg.PROB_THRESH_FOR_WEIGHTS, fg.MOTIF_QUALITY_THRESHOLD)
-        fe = core.FESet(ctx, ds, fg.device_model(), sa, so, sw)
-        ctx.synchronize()
-        prepare_ms = (time.perf_counter() - t0) * 1e3
-        obj = sharding.ShardedObjective(fe, local) if world > 1 else fe
-        lam = np.log(np.asarray(fg.getCondProb(0), np.float64).ravel())
-        for _ in range(3):
-            obj.grad(0, lam)
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        n_grad = 20
-        for _ in range(n_grad):
-            obj.grad(0, lam)
-        grad_ms = (time.perf_counter() - t0) * 1e3 / n_grad
-        fe.free()
+    if not args.no_mstep:
+        optimizer = optimizer_timings(run, args, step_ms)
 
-        def mstep(suffstats):
-            fg.setCondProbs(pwm)
-            core.zoops_estep(ctx, ds, fg.device_model(), bg.device_model(), logw, None, None, True, False, False)
-            fg.trainingStep = fg.SKIP_TRAINING_STEPS          # the reference ignores the first call; time a real M-step
-            fg.MSTEP_SUFFICIENT_STATISTICS = suffstats
-            if world > 1:
-                dist.barrier()
-            t0 = time.perf_counter()
-            st = fg.train(sample, None, rng=np.random.default_rng(1))
-            return (time.perf_counter() - t0) * 1e3, st
-
-        # host-side wall clock: best of two runs each (same start, same seed)
-        mstep_ms, st = min(mstep(False), mstep(False), key=lambda r: r[0])
-        mstep_ss_ms, st_ss = min(mstep(True), mstep(True), key=lambda r: r[0])
-        fg.MSTEP_SUFFICIENT_STATISTICS = False
-        t = torch.tensor([grad_ms, mstep_ms, prepare_ms, mstep_ss_ms], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        grad_ms, mstep_ms, prepare_ms, mstep_ss_ms = (float(x) for x in t.tolist())
-        optimizer = {"gradient_ms": grad_ms, "dim": int(lam.size), "selected_windows_per_gpu": int(sa.size),
-                     "select_and_fix_q_ms": prepare_ms, "mstep_ms": mstep_ms, "mstep_evaluations": int(st["evaluations"]),
-                     "em_iteration_ms": dev_ms_max / args.steps + mstep_ms,
-                     "mstep_sufficient_statistics_ms": mstep_ss_ms, "mstep_sufficient_statistics_evaluations": int(st_ss["evaluations"]),
-                     "em_iteration_sufficient_statistics_ms": dev_ms_max / args.steps + mstep_ss_ms,
-                     "what": "wall clock, max over ranks: evaluateGradientOfFunction of one motif position (forward differences, "
-                             "dim + 1 objective sums over the selected windows in one pass" + (", one all-reduce" if world > 1 else "") +
-                             "); M-step = selection + mean fields of the selected windows + BFGS position by position "
-                             "(host optimiser, device objective); EM iteration = E-step (ms_per_step) + M-step; sufficient statistics: "
-                             "PhyloBayesModel.MSTEP_SUFFICIENT_STATISTICS = True (one device pass for the expected counts, evaluations "
-                             "are host dot products; same objective, opt-in)"}
+    # ---- secondary configurations (N = 1 only, short): C2 (BASELINE.json configs[1]) and C3's data with an order-0 motif
+    extras = {}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_of = "measured (MEASURED_PEAKS.json)" if peaks else "fallback"
+    try:
+        traffic_db = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        traffic_db = {}
+    if world == 1 and not args.no_extra and args.config == DEFAULT_CONFIG and not args.n_aln:
+        run.free()
+        for name in ("c2", "c3o0"):
+            ex = EStepRunner(ctx, torch, dist, 1, 0, name, None, stream, flush)
+            pc = parity_check(ex.cfg, ex.newick, ex.pwm, ex.sample, ex.shm, PARITY_ALIGNMENTS[0]) if not args.no_parity else None
+            for _ in range(3):
+                ex.step()
+            torch.cuda.synchronize()
+            n_ex = 20 if name == "c2" else 5
+            ms, kern = ex.timed(n_ex)
+            sw_fg, _ = ctx.estep_sweeps()
+            rl, ex_extra = roofline_of(ex, kern, ms / n_ex, sw_fg, peak_tflops, hbm_peak, hbm_of, traffic_db)
+            extras[name] = {"workload": workload_name(ex.cfg), "value": ex.n_windows * n_ex / (ms * 1e-3), "unit": UNIT,
+                            "ms_per_step": ms / n_ex, "steps": n_ex, "warmup": 3, "parity_checked": pc,
+                            "scoring_path": PATHS[ctx.last_score_path()], "roofline": rl,
+                            "kernels_ms": [{"kernel": nm, "ms": round(v, 5)} for (_, nm), v in sorted(kern.items())]}
+            extras[name].update(ex_extra)
+            ex.free()
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        hbm_of = "measured" if peaks else "fallback"
-        step_ms = dev_ms_max / args.steps
-        flops = algorithmic_flops(cfg, I, n_windows, sweeps_fg)
-        abytes = algorithmic_bytes(cfg, n_windows)
         kern_list = [{"kernel": name, "ms": round(ms, 5)} for (_, name), ms in sorted(kernels.items())]
-
-        def fp64_roofline(kernel_name, kernel_ms, note=None):
-            achieved = flops / (kernel_ms * 1e-3) / 1e12
-            r = {"bound": "fp64", "kernel": kernel_name, "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-                 "frac": achieved / peak_tflops,
-                 "peak_source": "DFMA microbenchmark in this run (MEASURED_PEAKS.json has no fp64 entry)",
-                 "flops_per_launch": flops, "kernel_ms": kernel_ms,
-                 "hbm": {"achieved": abytes / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": abytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak, "of": hbm_of},
-                 "traffic": None}
-            if note:
-                r["note"] = note
-            return r
-
-        names = {name for (_, name) in kernels}
-        # DRAM bytes per launch of the same kernel on the same workload from the committed ncu --set full captures
-        # (scripts/summarize_ncu.py -> profiles/traffic.json); only the C2 captures were taken at bench size
-        try:
-            traffic_db = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        except Exception:
-            traffic_db = {}
-
-        def traffic_of(*keys):
-            if args.config != "c2" or args.n_aln:
-                return None
-            for key in keys:
-                if key in traffic_db:
-                    return traffic_db[key]
-            return None
-
-        fg_name = ("score_o1w_kernel" if "score_o1w_kernel" in names else "score_o1_kernel") if cfg["order"] == 1 else "score_o0_kernel"
-        extra = {}
-        if path != 1:
-            fg_ms = max(ms for (_, name), ms in kernels.items() if name == fg_name)     # the motif-window launch
-            roofline = fp64_roofline(fg_name + " (motif windows)", fg_ms)
-            roofline["kernel_share_of_step"] = fg_ms / step_ms
-            if fg_name == "score_o0_kernel":
-                roofline["traffic"] = traffic_of("r01_c2_direct_kernel:score_o0_kernel<0, 0>")
-        else:
-            # pattern-table path: per-pattern trajectories (fp64, a small latency-bound grid) + gathers per window
-            D = ds.patterns()
-            win_ms = max(ms for (_, name), ms in kernels.items() if name == "memo_window_kernel")
-            traj_ms = sum(ms for (_, name), ms in kernels.items() if name.startswith("memo_traj_kernel"))   # both phases
-            upd, fe = flops_order0(I, S)
-            K1 = 65              # pattern_memo_sweep_cap (64) + 1 passes per tree
-            traj_flops = D * (W + 1) * K1 * (upd + fe)            # motif positions + the background tree
-            gather_bytes = W * (sweeps_fg + n_windows) * 8         # trajectory entries the stop rule consumes
-            if win_ms >= traj_ms:
-                roofline = {"bound": "hbm", "kernel": "memo_window_kernel (motif windows; gathers from an L2-resident table)",
-                            "achieved": abytes / (win_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                            "frac": abytes / (win_ms * 1e-3) / 1e9 / hbm_peak, "of": hbm_of,
-                            "bytes_per_launch": abytes, "kernel_ms": win_ms, "kernel_share_of_step": win_ms / step_ms,
-                            "table_gather": {"bytes": gather_bytes, "GB/s": gather_bytes / (win_ms * 1e-3) / 1e9,
-                                             "what": "8 B x W x (K_w + 1) trajectory entries per window, served by L2"},
-                            "traffic": traffic_of("r01_c2_pattern_table:memo_window_kernel<0, 4>", "r01_c2_pattern_table:memo_window_kernel")}
-            else:
-                achieved = traj_flops / (traj_ms * 1e-3) / 1e12
-                roofline = {"bound": "fp64", "kernel": "memo_traj_kernel (mean-field trajectories of the occurring column patterns)",
-                            "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
-                            "peak_source": "DFMA microbenchmark in this run (MEASURED_PEAKS.json has no fp64 entry)",
-                            "flops_per_launch": traj_flops, "kernel_ms": traj_ms, "kernel_share_of_step": traj_ms / step_ms,
-                            "note": f"{D} patterns x {W + 1} trees x {K1} trajectory entries each; flops count every entry although a "
-                                    "tree stops once its q repeats bit for bit (the rest of its row is filled); wavefront over "
-                                    "(node, sweep), node slots x four symbols lanes per tree: a small grid of dependent steps, "
-                                    "bound by issue slots and instruction latency, not by the fp64 pipe",
-                            "traffic": traffic_of("r01_c2_pattern_table:memo_traj_wave_kernel<8>", "r01_c2_pattern_table:memo_traj_kernel")}
-            d_ms, d_kernels = direct
-            d_fg = max(ms for (_, name), ms in d_kernels.items() if name == fg_name)
-            extra["roofline_direct"] = fp64_roofline(
-                fg_name + " (motif windows, direct path: pattern table switched off)", d_fg,
-                "what every configuration with more than 6 species runs; measured in this run, 3 steps, not part of `value`")
-            extra["roofline_direct"]["step_ms"] = d_ms
-            extra["roofline_direct"]["traffic"] = traffic_of("r01_c2_direct_kernel:score_o0_kernel<0, 0>")
-            extra["pattern_table"] = {"patterns": D, "trajectory_flops_per_step": traj_flops,
-                                      "direct_flops_per_step": flops, "work_ratio": flops / max(traj_flops, 1)}
+        roofline, extra = roofline_of(run, kernels, step_ms, sweeps_fg, peak_tflops, hbm_peak, hbm_of, traffic_db, direct)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(cfg), "name": args.config, "windows_per_gpu": n_windows,
+            "warmup": warmup, "ms_per_step": step_ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(cfg), "name": args.config, "windows_total": total_windows,
+                       "windows_per_gpu": n_windows, "alignments_per_gpu": [hi - lo for lo, hi in run.bounds],
+                       "sharding": "contiguous alignment blocks balanced by column count (PhyloSample.shard); every rank "
+                                   "scores different alignments of the one data set" if world > 1 else "none (one GPU)",
                        "mean_sweeps_per_window": sweeps_fg / max(n_windows, 1), "seed": hex(cfg["seed"]),
-                       "scoring_path": {0: "direct kernel", 1: "pattern table (bit-identical to the direct kernel)", 2: "order-1 network kernel"}[path],
-                       "l2": "flushed between timed iterations (512 MB fill)", "collective": "NCCL all-reduce of 3 fp64" if world > 1 else "none"},
+                       "scoring_path": PATHS[path],
+                       "l2": "flushed between timed iterations (512 MB fill)",
+                       "collective": "NCCL all-reduce of 3 fp64 per step" if world > 1 else "none"},
+            "parity_checked": parity,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "what": "PhyloSample (page-locked host codes) -> pack on device -> E-step -> gamma/arg-max/ll to page-locked host buffers"},
             "gpu_launches": int(launches_per_step * args.steps),
@@ -517,19 +631,27 @@ def run_ours(args):
             "kernels_ms": kern_list,
             "wall_s": t_wall,
         }
+        if args.warmup != warmup:
+            line["warmup_requested"] = args.warmup
         if optimizer:
             line["optimizer"] = optimizer
         line.update(extra)
+        if extras:
+            line["extra"] = extras
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            n = cpu_sample_size(cfg, newick, pwm, sample, cores, args.cpu_seconds)
-            v, dt, nw = cpu_run(cfg, newick, pwm, sample, n, cores)
+            n = cpu_sample_size(cfg, run.newick, run.pwm, sample, cores, args.cpu_seconds)
+            v, dt, nw = cpu_run(cfg, run.newick, run.pwm, sample, n, cores)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"first {n} of {cfg['n_aln']} alignments ({nw} windows, {dt:.1f} s), "
                                               "C++ restatement of the Java algorithm with its cost model (JVM unavailable)"}
         emit(line)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+PATHS = {0: "direct kernel", 1: "pattern table (bit-identical to the direct kernel)", 2: "order-1 network kernel"}
 
 
 def emit(line):

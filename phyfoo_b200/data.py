@@ -131,16 +131,27 @@ class PhyloSample:
 
     def subset(self, idx):
         idx = list(idx)
+        if not idx:
+            return PhyloSample(np.zeros((0, self.n_species), np.uint8), np.zeros(1, np.int64), species=self.species,
+                               genes=[] if self.genes else None)
         return PhyloSample.from_alignments([self.getElementAt(i) for i in idx], species=self.species,
                                            genes=[self.genes[i] for i in idx] if self.genes else None)
 
+    def slice(self, lo, hi):
+        """Alignments lo..hi-1 as a sample of their own (one contiguous copy of the column block).  An empty range keeps
+        the number of species."""
+        lo, hi = int(lo), int(hi)
+        c0, c1 = int(self.col_offsets[lo]), int(self.col_offsets[hi])
+        return PhyloSample(self.codes[c0:c1], self.col_offsets[lo:hi + 1] - c0, species=self.species,
+                           genes=self.genes[lo:hi] if self.genes else None,
+                           annotations=self.annotations[lo:hi] if self.annotations else None)
+
     def shard(self, rank, world):
-        """Contiguous block of alignments balanced by column count."""
-        total = int(self.col_offsets[-1])
-        bounds = [int(np.searchsorted(self.col_offsets, total * r / world, side="left")) for r in range(world + 1)]
-        bounds[0], bounds[-1] = 0, self.n_alignments
-        lo, hi = bounds[rank], bounds[rank + 1]
-        return self.subset(range(lo, hi)), (lo, hi)
+        """Contiguous block of alignments balanced by column count; every rank gets at least one
+        alignment when there are at least `world` of them (sharding.shard_bounds)."""
+        from .sharding import shard_bounds
+        lo, hi = shard_bounds(self.col_offsets, world)[rank]
+        return self.slice(lo, hi), (lo, hi)
 
     def device(self, ctx=None):
         """The packed, device-resident copy (created once per context)."""

@@ -172,14 +172,16 @@ class PhyloBayesModel(_PhyloModel):
     # evaluation is then a dot product on the host (same function, sums re-associated).
     MSTEP_SUFFICIENT_STATISTICS = False
 
-    def train(self, sample: PhyloSample, weights, rng=None, rev_weights=None):
+    def train(self, sample: PhyloSample, weights, rng=None, rev_weights=None, sharded=False):
         """One M-step: select the top-posterior windows per alignment (io/SequenceSpecificDataSelector.java:37-99), fix
         their mean fields (one GPU pass), then optimise the parameters position by position in random order with BFGS on the
         forward-difference gradient (optimizing/FE_byParameter_ForBayesNodeJstacs.java:61-83).  weights: gamma per window, or
         None for the gamma of the most recent E-step still resident on the device.  rev_weights: when the caller is a
         StrandModel, the weights of the reverse-complement copies of the windows; the selector then thresholds the two strands
         of an alignment independently, as the reference does because it groups windows by their parent object
-        (io/SequenceSpecificDataSelector.java:45-49).  Returns a dict of statistics."""
+        (io/SequenceSpecificDataSelector.java:45-49).  sharded=True: `sample` is this rank's
+        shard of the alignments (torch.distributed is initialised): every objective evaluation is all-reduced, and the random
+        order of the positions comes from rank 0, so all ranks take the same optimiser steps.  Returns a dict of statistics."""
         self._check(sample)
         self.trainingStep = getattr(self, "trainingStep", 0)
         if self.trainingStep < self.SKIP_TRAINING_STEPS:
@@ -197,12 +199,13 @@ class PhyloBayesModel(_PhyloModel):
         fe = core.FESet(self.ctx, ds, self.device_model(), sa, so, sw, ss)
         stats = {"skipped": False, "selected": int(sa.size), "evaluations": 0, "f_before": None, "f_after": None}
         local = fe
-        import sys
         from . import sharding
-        if "torch" in sys.modules and sharding.world()[1] > 1:
+        order = rng.permutation(self.length).astype(np.int64)    # util/PWMUtil.java:131-144
+        if sharded:
             # every rank holds a shard of the alignments: one all-reduce of [f, f_1..f_dim] per evaluation, after which all
-            # ranks see the same objective and take the same optimiser steps; rng must be seeded alike
+            # ranks see the same objective and take the same optimiser steps
             fe = sharding.ShardedObjective(local, self.ctx.device)
+            sharding.broadcast_host_(order)
         try:
             if self.MSTEP_SUFFICIENT_STATISTICS and self.order == 0 and not self.OPTIMIZE_IN_TOTO:
                 # one device pass for the expected counts, then the same position-wise BFGS on host dot products
@@ -212,7 +215,7 @@ class PhyloBayesModel(_PhyloModel):
                     for t in range(self.length):
                         obj.set_position(t)
                 stats["f_before"] = obj.value()
-                for pos in rng.permutation(self.length):
+                for pos in order:
                     pos = int(pos)
                     fun = lambda z: -obj.eval_lambda(pos, z)          # noqa: E731
                     x, f, it, ev = optimize.quasi_newton_bfgs(fun, lambda z: obj.grad(fun, z), np.log(self._pi[pos].ravel()),
@@ -232,7 +235,7 @@ class PhyloBayesModel(_PhyloModel):
                 stats["f_after"] = fe.eval(-1, x)
                 stats["evaluations"] += ev
             else:
-                for pos in rng.permutation(self.length):            # util/PWMUtil.java:131-144
+                for pos in order:
                     pos = int(pos)
                     lam0 = np.log(self._pi[pos].ravel())
                     f0 = fe.eval(pos, lam0)
@@ -380,6 +383,7 @@ class StrandModel:
         self.hyper = np.asarray(componentHyperParams, np.float64)
         self.estimateComponentProbs = bool(estimateComponentProbs)
         self.alpha = float(alpha)
+        self.sharded = False          # set by SingleHiddenMotifMixture.train(sharded=True)
 
     def getLength(self):
         return self.model.getLength()
@@ -408,7 +412,10 @@ class StrandModel:
         return f, r, np.array([f.sum(), r.sum()]), float(np.sum(tot * dw))
 
     def _new_parameters(self, sample, f, r, w, rng):
-        st = self.model.train(sample, f, rng=rng, rev_weights=r)
+        st = self.model.train(sample, f, rng=rng, rev_weights=r, sharded=self.sharded)
+        if self.sharded:
+            from . import sharding
+            w = sharding.allreduce_host_(np.array(w, np.float64))
         if self.estimateComponentProbs:                        # AbstractMixtureModel.getNewComponentProbs :1542-1578
             v = np.asarray(w, np.float64) + self.hyper
             self.weights = v / v.sum()
@@ -472,21 +479,29 @@ class SingleHiddenMotifMixture:
             v = np.asarray(w, np.float64) + self.hyper
             self.weights = v / v.sum()
 
-    def train(self, sample: PhyloSample, max_iterations=100, eps=1e-6, rng=None, verbose=False):
+    def train(self, sample: PhyloSample, max_iterations=100, eps=1e-6, rng=None, verbose=False, sharded=False):
         """EM (jstacs AbstractMixtureModel.continueIterations :857-880 with trainOnlyMotifModel = true): E-step on the GPU,
         M-step of the motif model through PhyloBayesModel.train, component weights from the sufficient statistics.  Stops when
         the log-likelihood changes by less than eps (SmallDifferenceOfFunctionEvaluationsCondition) or after max_iterations.
-        Returns the list of log-likelihoods, one per E-step."""
+        sharded=True: `sample` is this rank's shard (one process per GPU, torch.distributed initialised): [ll, w0, w1] of
+        every E-step and every M-step objective value are all-reduced, so all ranks see the same numbers, leave the loop in
+        the same iteration and set the same component weights.  Returns the list of log-likelihoods, one per E-step."""
         history, trained = [], False
+        if self.strand is not None:
+            self.strand.sharded = bool(sharded)
         for it in range(max_iterations):
             res = self.getNewWeights(sample, want_gamma=True)
+            if sharded:
+                from . import sharding
+                v = sharding.allreduce_host_(np.array([res["ll"], res["w"][0], res["w"][1]]))
+                res["ll"], res["w"] = float(v[0]), v[1:].copy()
             history.append(res["ll"])
             if verbose:
                 print(f"{it}\t{res['ll']:.6f}\t{0.0 if it == 0 else res['ll'] - history[-2]:.3e}")
             if trained and abs(history[-1] - history[-2]) < eps:
                 break
             if self.strand is None:
-                st = self.motif.train(sample, None, rng=rng)   # gamma of this E-step is still resident on the device
+                st = self.motif.train(sample, None, rng=rng, sharded=sharded)   # gamma of this E-step is still resident
             elif it == 0:                                      # jstacs AbstractMixtureModel.java:1017-1033
                 st = self.strand.doFirstIteration(sample, res["gamma"], rng)
             else:

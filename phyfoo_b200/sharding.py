@@ -9,14 +9,18 @@ import numpy as np
 
 
 def shard_bounds(col_offsets, world):
-    """[(lo, hi)] per rank: contiguous alignment blocks whose column counts are as equal as the boundaries allow."""
+    """[(lo, hi)] per rank: contiguous alignment blocks whose column counts are as equal as the boundaries allow.  With
+    at least `world` alignments every rank gets at least one (very unequal lengths would otherwise leave a rank without
+    work); with fewer, the last ranks get empty blocks and must contribute zeros to the all-reduce (ShardedEStep does)."""
     col_offsets = np.asarray(col_offsets, np.int64)
     n = col_offsets.size - 1
     total = int(col_offsets[-1])
     cuts = [int(np.searchsorted(col_offsets, total * r / world, side="left")) for r in range(world + 1)]
     cuts[0], cuts[-1] = 0, n
-    for r in range(1, world + 1):
-        cuts[r] = max(cuts[r], cuts[r - 1])
+    for r in range(1, world):
+        lo = r if n >= world else min(r, n)                # rank r-1 keeps at least one alignment ...
+        hi = n - (world - r) if n >= world else n          # ... and so do the ranks behind this cut
+        cuts[r] = min(max(cuts[r], cuts[r - 1], lo), hi)
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
@@ -37,6 +41,35 @@ def allreduce_sum_(tensor):
     if d and d.get_world_size() > 1:
         d.all_reduce(tensor, op=d.ReduceOp.SUM)
     return tensor
+
+
+def allreduce_host_(values):
+    """Sum of a small host vector over the ranks (numpy float64 in, the same array out, identical on every rank)."""
+    d = _dist()
+    if not d or d.get_world_size() == 1:
+        return values
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(values, np.float64).copy())
+    if d.get_backend() == "nccl":
+        t = t.cuda()
+    d.all_reduce(t, op=d.ReduceOp.SUM)
+    values[...] = t.cpu().numpy().reshape(np.shape(values))
+    return values
+
+
+def broadcast_host_(values, src=0):
+    """Rank `src`'s copy of a small host array (int64 or float64) on every rank -- e.g. the random order of the motif
+    positions in the M-step, which every rank must walk alike (util/PWMUtil.java:131-144 draws it from an unseeded RNG)."""
+    d = _dist()
+    if not d or d.get_world_size() == 1:
+        return values
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(values).copy())
+    if d.get_backend() == "nccl":
+        t = t.cuda()
+    d.broadcast(t, src=src)
+    values[...] = t.cpu().numpy().reshape(np.shape(values))
+    return values
 
 
 def gather_in_rank_order(array):
@@ -61,7 +94,7 @@ class ShardedEStep:
         self.shm = shm
         self.bounds = shard_bounds(sample.col_offsets, self.world)
         lo, hi = self.bounds[self.rank]
-        self.local = sample.subset(range(lo, hi)) if self.world > 1 else sample
+        self.local = sample.slice(lo, hi) if self.world > 1 else sample
         self.ctx = shm.motif.ctx
         self.partial = torch.zeros(3, dtype=torch.float64, device=f"cuda:{self.ctx.device}")
         self.stream = torch.cuda.Stream(device=self.ctx.device)
@@ -74,9 +107,13 @@ class ShardedEStep:
         with np.errstate(divide="ignore"):
             logw = np.log(shm.weights)
         with torch.cuda.stream(self.stream):
-            core.zoops_estep_device(self.ctx, self.local.device(self.ctx), shm.motif.device_model(), shm.flanking.device_model(),
-                                    logw, None if shm.strand is None else shm.strand.logWeights(), None,
-                                    self.partial.data_ptr(), self.stream.cuda_stream)
+            if self.local.n_alignments == 0:
+                self.partial.zero_()                   # an empty shard (fewer alignments than ranks) contributes zeros
+            else:
+                core.zoops_estep_device(self.ctx, self.local.device(self.ctx), shm.motif.device_model(),
+                                        shm.flanking.device_model(), logw,
+                                        None if shm.strand is None else shm.strand.logWeights(), None,
+                                        self.partial.data_ptr(), self.stream.cuda_stream)
             allreduce_sum_(self.partial)
 
     def result(self):
