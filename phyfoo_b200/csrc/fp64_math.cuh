@@ -45,7 +45,8 @@ PHY_MATH_HD double phy_from_bits(uint64_t u) {
 #endif
 }
 
-PHY_MATH_HD double phy_exp(double x) {
+// exp with the 64-entry table 2^(j/64) passed in (a kernel's copy in shared memory); phy_exp below uses the global one
+PHY_MATH_HD double phy_exp_tab(double x, const double* tab64) {
     if (!(fabs(x) < 690.0)) {                                   // rare: huge, tiny, inf, NaN
         if (x != x) return x;
         if (x > 709.782712893384) return INFINITY;
@@ -61,11 +62,7 @@ PHY_MATH_HD double phy_exp(double x) {
     kd -= 0x1.8p52;
     double r = fma(kd, -PHY_LN2_64_HI, x);
     r = fma(kd, -PHY_LN2_64_LO, r);
-#if defined(__CUDA_ARCH__)
-    const double T = d_phy_exp_tab[ki & 63];
-#else
-    const double T = h_phy_exp_tab[ki & 63];
-#endif
+    const double T = tab64[ki & 63];
     double q = fma(r, 0x1.6c16c16c16c17p-10, 0x1.1111111111111p-7);   // 1/720, 1/120
     q = fma(q, r, 0x1.5555555555555p-5);                               // 1/24
     q = fma(q, r, 0x1.5555555555555p-3);                               // 1/6
@@ -83,6 +80,14 @@ PHY_MATH_HD double phy_exp(double x) {
         return s * 0x1p-1000;
     }
     return phy_from_bits(phy_bits(res) + ((uint64_t)(int64_t)k << 52));
+#endif
+}
+
+PHY_MATH_HD double phy_exp(double x) {
+#if defined(__CUDA_ARCH__)
+    return phy_exp_tab(x, d_phy_exp_tab);
+#else
+    return phy_exp_tab(x, h_phy_exp_tab);
 #endif
 }
 

@@ -353,6 +353,128 @@ struct ModelHost {
         }
     }
 
+    // ---- node-per-thread kernel (net1n.cuh) ----
+    // One thread updates one hidden node (all four symbols); a window is worked on by 4 node slots, a warp holds 8 windows
+    // (lane = 8 slot + window).  Everything a node update touches is addressed through a precomputed record of offsets, in
+    // doubles, into the warp's region of shared memory (rows of 32 doubles = the 4 q of a node for 8 windows, AB rows of 64):
+    //   region: q rows [W*I] | zero row | one-hot row | trash row | AB rows [2*I] | trash AB row
+    // Record layout (n1n_rec_len(MC) ints): qself, qpar, qnself, qnpar, abself, abnext, tabnext, flags (1 live, 2 last
+    // position), then per child (qchild, abchild).  AB rows: the context sums a node update at position t needs of the
+    // SAME node at t-1, A(a) = sum_c q_prev(c) Ld[c][a] and B(a) = sum_c q_prev(c) Lo[c][a]; they are produced by the
+    // update of (t-1, i) and read by (t, i) and by (t, parent(i)); two rows per node (position parity) suffice because both
+    // readers precede (t+1, i) ... and the update of the last position produces the rows of position 0 (virtual one-hot
+    // predecessor) for the next sweep.
+    static int n1n_rec_len(int MC) { return (8 + 2 * MC + 3) & ~3; }
+    struct N1nLayout { int q0, zero_row, onehot_row, trash_row, ab0, trash_ab, region; };
+    N1nLayout n1n_layout() const {
+        N1nLayout L;
+        L.q0 = 0; L.zero_row = W * I * 32; L.onehot_row = L.zero_row + 32; L.trash_row = L.onehot_row + 32;
+        L.ab0 = L.trash_row + 32; L.trash_ab = L.ab0 + 2 * I * 64; L.region = L.trash_ab + 64;
+        return L;
+    }
+    // tables of the internal nodes for the kernel's shared memory: [W][I][32] = Lo[ctx][b] | Ld[ctx][b] (root: log pi twice)
+    void tables1n(std::vector<double>& out) const {
+        const int e1 = E1();
+        std::vector<double> t1;
+        tables1(t1);
+        out.assign((size_t)W * I * 32, 0.0);
+        for (int t = 0; t < W; ++t)
+            for (int i = 0; i < I; ++i) {
+                const int k = node_of[i];
+                double* o = &out[((size_t)t * I + i) * 32];
+                const double* src = &t1[(size_t)t * e1];
+                if (k == 0) for (int j = 0; j < 16; ++j) o[j] = o[16 + j] = src[j];
+                else for (int j = 0; j < 32; ++j) o[j] = src[16 + 32 * (k - 1) + j];
+            }
+    }
+    // tables of the leaves (window set-up only, read from global memory): [W][S (CSR leaf slot)][32] = Lo | Ld
+    void leaf_tables1n(std::vector<double>& out) const {
+        const int e1 = E1();
+        std::vector<double> t1;
+        tables1(t1);
+        out.assign((size_t)W * S * 32, 0.0);
+        for (int t = 0; t < W; ++t)
+            for (int kk = 0; kk < S; ++kk)
+                for (int j = 0; j < 32; ++j) out[((size_t)t * S + kk) * 32 + j] = t1[(size_t)t * e1 + 16 + 32 * (leaf_node[kk] - 1) + j];
+    }
+    // program: header [n_steps, MC, rec_len, I] | leaf_begin[I+1] | leaf_species[S] | records [n_steps][4][rec_len].
+    // List schedule of the W*I node updates into steps of <= 4, longest remaining dependency chain first: node (t, i) may run
+    // once (t, parent), (t-1, i) and (t-1, child) for every internal child are in EARLIER steps (see net1w.cuh for why any
+    // such schedule reproduces the reference's sweep).
+    void node_program(std::vector<int>& prog, int& MC, int& n_steps) const {
+        MC = 1;
+        for (int i = 0; i < I; ++i) MC = std::max(MC, ichild_begin[i + 1] - ichild_begin[i]);
+        const int n = W * I, RL = n1n_rec_len(MC);
+        const N1nLayout L = n1n_layout();
+        auto deps = [&](int id, std::vector<int>& d) {
+            d.clear();
+            const int t = id / I, i = id % I;
+            if (i > 0) d.push_back(t * I + par_internal[i]);
+            if (t > 0) {
+                d.push_back((t - 1) * I + i);
+                for (int j = ichild_begin[i]; j < ichild_begin[i + 1]; ++j) d.push_back((t - 1) * I + ichild[j]);
+            }
+        };
+        std::vector<int> height(n, 1), d;
+        for (int id = n - 1; id >= 0; --id) {               // ids are in a topological order
+            deps(id, d);
+            for (int p : d) height[p] = std::max(height[p], height[id] + 1);
+        }
+        std::vector<int> done(n, -1), sched;
+        int left = n, step = 0;
+        while (left > 0) {
+            std::vector<std::pair<int, int>> ready;
+            for (int id = 0; id < n; ++id) {
+                if (done[id] >= 0) continue;
+                deps(id, d);
+                bool r = true;
+                for (int p : d) if (done[p] < 0 || done[p] >= step) { r = false; break; }
+                if (r) ready.push_back({-height[id], id});
+            }
+            std::sort(ready.begin(), ready.end());
+            for (int sl = 0; sl < 4; ++sl) {
+                if (sl < (int)ready.size()) { done[ready[sl].second] = step; --left; sched.push_back(ready[sl].second); }
+                else sched.push_back(-1);
+            }
+            ++step;
+        }
+        n_steps = step;
+        prog.clear();
+        prog.push_back(n_steps); prog.push_back(MC); prog.push_back(RL); prog.push_back(I);
+        prog.insert(prog.end(), leaf_begin.begin(), leaf_begin.end());
+        prog.insert(prog.end(), leaf_sp.begin(), leaf_sp.end());
+        auto qrow = [&](int t, int i) { return L.q0 + (t * I + i) * 32; };
+        auto abrow = [&](int t, int i) { return L.ab0 + ((t & 1) * I + i) * 64; };     // position 0 lives in parity 0
+        for (int s = 0; s < n_steps; ++s)
+            for (int sl = 0; sl < 4; ++sl) {
+                std::vector<int> r(RL, 0);
+                const int id = sched[s * 4 + sl];
+                if (id < 0) {
+                    r[0] = L.trash_row; r[1] = L.onehot_row; r[2] = L.trash_row; r[3] = L.onehot_row;
+                    r[4] = L.trash_ab; r[5] = L.trash_ab; r[6] = 0; r[7] = 0;
+                    for (int j = 0; j < MC; ++j) { r[8 + 2 * j] = L.zero_row; r[9 + 2 * j] = L.trash_ab; }
+                } else {
+                    const int t = id / I, i = id % I, p = par_internal[i];
+                    const bool last = t + 1 == W;
+                    r[0] = qrow(t, i);
+                    r[1] = p >= 0 ? qrow(t, p) : L.onehot_row;
+                    r[2] = last ? r[0] : qrow(t + 1, i);
+                    r[3] = (last || p < 0) ? r[1] : qrow(t + 1, p);
+                    r[4] = abrow(t, i);
+                    r[5] = abrow(last ? 0 : t + 1, i);
+                    r[6] = (((last ? 0 : t + 1) * I) + i) * 32;
+                    r[7] = 1 | (last ? 2 : 0);
+                    for (int j = 0; j < MC; ++j) {
+                        const bool has = ichild_begin[i] + j < ichild_begin[i + 1];
+                        const int ci = has ? ichild[ichild_begin[i] + j] : i;
+                        r[8 + 2 * j] = has ? qrow(t, ci) : L.zero_row;
+                        r[9 + 2 * j] = abrow(t, ci);
+                    }
+                }
+                prog.insert(prog.end(), r.begin(), r.end());
+            }
+    }
+
     void set_pi(int t, const double* v, int n) {
         if (t < 0 || t >= W || n != (int)pi[t].size()) throw std::invalid_argument("set_pi: bad position or size");
         pi[t].assign(v, v + n);

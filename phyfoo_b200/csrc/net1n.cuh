@@ -1,0 +1,354 @@
+// net1n.cuh -- order-1 phylogenetic Bayesian network, node-per-thread kernel (net1.cuh has the model, net1w.cuh the
+// argument why a list schedule of the node updates reproduces the reference's Gauss-Seidel sweep).
+//
+// Mapping: ONE THREAD updates one hidden node with all four symbols in registers; a window is worked on by 4 node slots
+// (the list schedule of model_host.hpp::node_program runs <= 4 independent nodes per step), a warp holds 8 windows
+// (lane = 8 slot + window), a block a few warps that share the tables.  Compared with the 16-lanes-per-window kernel of
+// net1w.cuh this removes every shuffle of the node update, loads each q vector once instead of once per symbol lane, and
+// amortises the address arithmetic over four symbols -- the old kernel issued ~550 instructions per step of which a fifth
+// were fp64.  What bounds this one is shared-memory bandwidth and the fp64 pipe (profiles/r02_c3_*).
+//
+// Per node update (t, i), reference loops algorithm/MeanFieldForBayesNet.java:108-202 (update) and :232-365 (free energy):
+//   own(a)  = q_par(a) A(a) + (tot_par - q_par(a)) B(a)      A(a) = sum_c q_{t-1,i}(c) Ld[c][a], B(a) likewise with Lo
+//   ch(a)   = sum_j [ q_j(a) A_j(a) + sum_{a' != a} q_j(a') B_j(a') ]      internal children j (old q, new context sums)
+//   nx(a)   = sum_a' q_{t+1,i}(a') [ q_{t+1,par}(a') Ld'[a][a'] + (tot - q_{t+1,par}(a')) Lo'[a][a'] ]   (old values)
+//   cobs(a) = sum over observed leaf children of log T_leaf[a, y][x]       (constant per window: kept from the set-up)
+//   s = own + ch + cobs + nx;  q = exp(s) / z,  z = sum exp(s)             (no max shift, :192-201)
+// The context sums A, B of a node are needed twice (by the node and by its tree parent), so the update of (t-1, i)
+// produces them ("AB rows", two per node by position parity) right after it has the new q in registers; the tables of
+// (t+1, i) it needs for that are the ones the nx term reads anyway.
+// Free energy without a logarithm per node: the node's terms are sum_a q(a) (log q(a) - own(a) - cobs(a)), and
+// log q(a) = s(a) - log z, so they equal sum_a q(a) (ch(a) + nx(a)) - log z (pass at the uniform start: -(own + cobs) and
+// z = 4).  The log z of a thread's nodes are summed as ONE logarithm of the product of their mantissas plus ln 2 times the
+// sum of their exponents (integer adds), one phy_log per thread and sweep instead of one per node.
+// Windows with an unobserved leaf go to a device-side list and are scored by the net1w.cuh kernel afterwards (the bundled
+// data and the headline configurations have no gaps).
+//
+// PHY_HD parts (n1n_update) compile for the host as well: tests/emul runs them against the oracle without a GPU.
+#pragma once
+#include "fp64_math.cuh"
+
+#if defined(__CUDACC__)
+#define N1N_HD __host__ __device__ __forceinline__
+#else
+#define N1N_HD inline
+#endif
+
+namespace phyfoo {
+
+struct N1nAcc {
+    double Fq;      // sum over this thread's nodes of sum_a q(a) g(a)
+    double M;       // product of the mantissas of z
+    int E;          // sum of the exponents of z
+    double Fslow;   // sum of log z of nodes whose z is not a normal number (zero, denormal, inf, NaN)
+};
+
+// rows: a q row is 32 doubles = [half 0: 8 windows x (q0, q1)] [half 1: 8 windows x (q2, q3)]; `reg` already points at this
+// thread's window (2 * w doubles in), so its four values sit at +0, +1, +16, +17.  An AB row is 64 doubles = four such halves
+// (A0 A1 | A2 A3 | B0 B1 | B2 B3).  16-byte accesses: LDS.128 / STS.128, 8 windows x 16 B = all 32 banks once.
+struct alignas(16) N1nD2 { double x, y; };
+N1N_HD void n1n_ld4(const double* p, double (&v)[4]) {
+    const N1nD2 a = *reinterpret_cast<const N1nD2*>(p), b = *reinterpret_cast<const N1nD2*>(p + 16);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+N1N_HD void n1n_st4(double* p, const double (&v)[4]) {
+    N1nD2 a, b; a.x = v[0]; a.y = v[1]; b.x = v[2]; b.y = v[3];
+    *reinterpret_cast<N1nD2*>(p) = a; *reinterpret_cast<N1nD2*>(p + 16) = b;
+}
+N1N_HD double n1n_sum4(const double (&v)[4]) { return ((v[0] + v[1]) + v[2]) + v[3]; }
+
+N1N_HD int n1n_hi(double z) {
+#if defined(__CUDA_ARCH__)
+    return __double2hiint(z);
+#else
+    return (int)(phy_bits(z) >> 32);
+#endif
+}
+N1N_HD double n1n_with_hi(double z, int hi) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(hi, __double2loint(z));
+#else
+    return phy_from_bits(((uint64_t)(uint32_t)hi << 32) | (phy_bits(z) & 0xffffffffULL));
+#endif
+}
+N1N_HD double n1n_rcp(double z) {
+#if defined(__CUDA_ARCH__)
+    return __drcp_rn(z);
+#else
+    return 1.0 / z;
+#endif
+}
+// log z accumulated as (mantissa product, exponent sum)
+N1N_HD void n1n_acc_logz(N1nAcc& acc, double z) {
+    const int hi = n1n_hi(z);
+    const unsigned ef = ((unsigned)hi >> 20);                    // sign + exponent field: a positive normal number has 1..0x7fe
+    if (ef - 1u < 0x7feu) {
+        acc.E += (int)ef - 1023;
+        acc.M *= n1n_with_hi(z, (hi & 0x000fffff) | 0x3ff00000);
+    } else acc.Fslow += phy_log(z);
+}
+// fold the exponent of the running mantissa product into E (every 64 nodes at the latest: 2^64 is far from overflow)
+N1N_HD void n1n_fold(N1nAcc& acc) {
+    const int hi = n1n_hi(acc.M);
+    acc.E += (hi >> 20) - 1023;
+    acc.M = n1n_with_hi(acc.M, (hi & 0x000fffff) | 0x3ff00000);
+}
+N1N_HD double n1n_free_energy(const N1nAcc& acc) {
+    const double lz = fma((double)acc.E, PHY_LN2_HI, fma((double)acc.E, PHY_LN2_LO, phy_log(acc.M)));
+    return (acc.Fq - acc.Fslow) - lz;
+}
+
+// One node update.  reg: this thread's window in the warp's region; tab: tables [W][I][32] (Lo | Ld); exptab: 2^(j/64);
+// r: the record (model_host.hpp::node_program); cobs: observed-leaf sums of this node; upd == false: the pass at the uniform
+// start (exponents forced to 0).  All reads come before the two row stores; the caller synchronises the warp afterwards.
+template <int MC>
+N1N_HD void n1n_update(double* reg, const double* tab, const double* exptab, const int* r, const double (&cobs)[4],
+                       bool upd, N1nAcc& acc) {
+    const int flags = r[7];
+    const bool live = (flags & 1) != 0, last = (flags & 2) != 0;
+    double qp[4], A[4], B[4], own[4], ch[4], nx[4];
+    n1n_ld4(reg + r[1], qp);
+    n1n_ld4(reg + r[4], A);
+    n1n_ld4(reg + r[4] + 32, B);
+    const double totp = n1n_sum4(qp);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) own[a] = fma(qp[a], A[a], (totp - qp[a]) * B[a]);
+    // internal children: null entries read the all-zero q row
+    {
+        double chv[4] = {0.0, 0.0, 0.0, 0.0}, wu[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int j = 0; j < MC; ++j) {
+            double qc[4], Aj[4], Bj[4];
+            n1n_ld4(reg + r[8 + 2 * j], qc);
+            n1n_ld4(reg + r[9 + 2 * j], Aj);
+            n1n_ld4(reg + r[9 + 2 * j] + 32, Bj);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) { wu[a] = fma(qc[a], Bj[a], wu[a]); chv[a] = fma(qc[a], Aj[a], chv[a]); }
+        }
+        const double sw = n1n_sum4(wu);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) ch[a] = chv[a] + (sw - wu[a]);
+    }
+    // the same node at the next position (old values); its tables also serve the context sums produced below
+    double T[32];
+    {
+        const double* tp = tab + r[6];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { const N1nD2 v = *reinterpret_cast<const N1nD2*>(tp + 2 * j); T[2 * j] = v.x; T[2 * j + 1] = v.y; }
+    }
+    {
+        double qx[4], qpn[4], m[4];
+        n1n_ld4(reg + r[2], qx);
+        n1n_ld4(reg + r[3], qpn);
+        const double totn = n1n_sum4(qpn);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) m[c] = totn - qpn[c];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            double v = 0.0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v = fma(qx[c], fma(qpn[c], T[16 + a * 4 + c], m[c] * T[a * 4 + c]), v);
+            nx[a] = last ? 0.0 : v;
+        }
+    }
+    double e[4], g[4], qn[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const double s = ((own[a] + ch[a]) + cobs[a]) + nx[a];
+        e[a] = phy_exp_tab(upd ? s : 0.0, exptab);                                 // MeanFieldForBayesNet.java:192, no max shift
+        g[a] = upd ? ch[a] + nx[a] : -(own[a] + cobs[a]);
+    }
+    const double z = n1n_sum4(e);                                                   // :195-198
+    const double rz = n1n_rcp(z);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) qn[a] = e[a] * rz;                                  // :199-201
+    if (live) {
+        double f = qn[0] * g[0];
+        f = fma(qn[1], g[1], f); f = fma(qn[2], g[2], f); f = fma(qn[3], g[3], f);
+        acc.Fq += f;
+        n1n_acc_logz(acc, z);
+    }
+    // context sums of the same node at the next position (the last position produces those of position 0: one-hot)
+    double An[4], Bn[4];
+    {
+        double qa[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) qa[c] = last ? (c == 0 ? 1.0 : 0.0) : qn[c];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            double u = qa[0] * T[a], v = qa[0] * T[16 + a];
+#pragma unroll
+            for (int c = 1; c < 4; ++c) { u = fma(qa[c], T[c * 4 + a], u); v = fma(qa[c], T[16 + c * 4 + a], v); }
+            Bn[a] = u; An[a] = v;
+        }
+    }
+    n1n_st4(reg + r[0], qn);
+    n1n_st4(reg + r[5], An);
+    n1n_st4(reg + r[5] + 32, Bn);
+}
+
+}  // namespace phyfoo
+
+#if defined(__CUDACC__)
+// ----------------------------------------------------------------------------------------------------------------------
+// device side
+// ----------------------------------------------------------------------------------------------------------------------
+struct Net1nParams {
+    const uint32_t* bases; const uint32_t* gaps; int64_t n_cols; int nb;
+    const int64_t* col_off; const int64_t* win_off; int n_aln;
+    int64_t n_windows; int n_strands; int strand0;
+    int W, I, S;
+    const int* prog; int prog_len;       // model_host.hpp::node_program
+    const double* tab;                   // [W][I][32]
+    const double* leaf_tab;              // [W][S][32]
+    double* out; int32_t* sweeps;
+    unsigned long long* counters;        // [0] work counter, [1] sweep sum
+    int max_sweeps, min_sweeps; double tol;
+    double* gc;                          // observed-leaf sums: one region of `gc_region` doubles per warp of the grid
+    int region, gc_region, ab0, zero_row, onehot_row;
+    int check_gaps;                      // 0: the data set has no unobserved symbol at all
+    int* fb_count; int64_t* fb_col0; uint8_t* fb_strand; int64_t* fb_dst;   // windows with gaps, for the net1w.cuh kernel
+};
+
+template <int MC>
+__global__ void __launch_bounds__(256, 1) score_o1n_kernel(Net1nParams p) {
+    extern __shared__ double smem[];
+    const int tid = threadIdx.x, T = blockDim.x, NW = T >> 5;
+    const int W = p.W, I = p.I, S = p.S;
+    double* s_tab = smem;                                   // [W][I][32]
+    double* s_exp = s_tab + (size_t)W * I * 32;             // [64]
+    double* s_reg = s_exp + 64;                             // [NW][region]
+    int* s_prog = (int*)(s_reg + (size_t)NW * p.region);
+    for (int i = tid; i < W * I * 32; i += T) s_tab[i] = p.tab[i];
+    for (int i = tid; i < 64; i += T) s_exp[i] = phyfoo::d_phy_exp_tab[i];
+    for (int i = tid; i < NW * p.region; i += T) s_reg[i] = 0.0;
+    for (int i = tid; i < p.prog_len; i += T) s_prog[i] = p.prog[i];
+    __syncthreads();
+    for (int i = tid; i < NW * 8; i += T) s_reg[(size_t)(i >> 3) * p.region + p.onehot_row + 2 * (i & 7)] = 1.0;
+    __syncthreads();
+    const int n_steps = s_prog[0], RL = s_prog[2];
+    const int* leaf_begin = s_prog + 4;
+    const int* leaf_species = leaf_begin + I + 1;
+    const int* s_rec = leaf_species + S;
+
+    const int lane = tid & 31, warp = tid >> 5;
+    const int w = lane & 7, slot = lane >> 3;
+    const unsigned full = 0xffffffffu;
+    double* regw = s_reg + (size_t)warp * p.region;         // the warp's region
+    double* reg = regw + 2 * w;                             // this thread's window
+    double* gcw = p.gc + (size_t)(blockIdx.x * NW + warp) * p.gc_region;
+    const double* gct = gcw + 2 * w;
+    const long long n_items = (long long)p.n_windows * p.n_strands;
+    const unsigned gap_mask = S >= 32 ? 0xffffffffu : (1u << S) - 1u;
+
+    bool need = true, active = true, upd = false, conv = false;
+    int k = 0;
+    long long item = -1;
+    double old = 0.0;
+
+    for (;;) {
+        // ---- windows that finished pull the next one; the whole warp sets a new window up
+        unsigned nm = __ballot_sync(full, need && active) & 0xffu;
+        while (nm) {
+            const int wi = __ffs(nm) - 1;
+            nm &= nm - 1;
+            long long it = -1; int64_t c0 = 0; int strand = 0;
+            for (;;) {
+                long long v = 0;
+                if (lane == 0) v = (long long)atomicAdd(&p.counters[0], 1ULL);
+                it = __shfl_sync(full, v, 0);
+                if (it >= n_items) { it = -1; break; }
+                const int si = (int)(it / p.n_windows);
+                const int64_t wdx = it - (long long)si * p.n_windows;
+                strand = p.n_strands == 2 ? si : p.strand0;
+                const int al = find_alignment_hint(p.win_off, p.n_aln, wdx, p.n_windows);
+                c0 = p.col_off[al] + (wdx - p.win_off[al]);
+                if (!p.check_gaps) break;
+                unsigned any = 0;
+                for (int t = lane; t < W; t += 32) {
+                    const int64_t col = c0 + t;
+                    for (int gpl = 0; gpl < (S + 31) / 32; ++gpl) any |= p.gaps[(size_t)gpl * p.n_cols + col] & gap_mask;
+                }
+                if (!__any_sync(full, any != 0)) break;
+                if (lane == 0) {
+                    const int idx = atomicAdd(p.fb_count, 1);
+                    p.fb_col0[idx] = c0; p.fb_strand[idx] = (uint8_t)strand; p.fb_dst[idx] = it;
+                }
+            }
+            if (it >= 0) {
+                // observed-leaf sums of every node (constant over the sweeps), uniform start (MeanFieldForBayesNet.java:52-69)
+                for (int idx = lane; idx < W * I * 4; idx += 32) {
+                    const int t = idx / (4 * I), rem = idx - t * 4 * I, i = rem >> 2, a = rem & 3;
+                    const int64_t col = strand ? c0 + (W - 1 - t) : c0 + t;       // jstacs StrandModel.java:636-639
+                    ColWords cw = load_column(p.bases, p.gaps, p.n_cols, p.nb, col);
+                    ColWords cwp; cwp.b = 0; cwp.g = 0;
+                    if (t > 0) cwp = load_column(p.bases, p.gaps, p.n_cols, p.nb, strand ? col + 1 : col - 1);
+                    if (strand) { cw = complement(cw); cwp = complement(cwp); }
+                    double c = 0.0;
+                    for (int kk = leaf_begin[i]; kk < leaf_begin[i + 1]; ++kk) {
+                        const int sp = leaf_species[kk];
+                        const int x = cw.obs(sp) & 3, y = t > 0 ? (cwp.obs(sp) & 3) : 0;
+                        c += __ldg(p.leaf_tab + ((size_t)(t * S + kk) * 32 + (a == x ? 16 : 0) + y * 4 + x));
+                    }
+                    const int o = (t * I + i) * 32 + (a >> 1) * 16 + 2 * wi + (a & 1);
+                    gcw[o] = c;
+                    regw[o] = 0.25;
+                }
+                // context sums of position 0: the virtual predecessor is the one-hot (1, 0, 0, 0)
+                for (int idx = lane; idx < I * 8; idx += 32) {
+                    const int i = idx >> 3, e = idx & 7;
+                    regw[p.ab0 + i * 64 + (e >> 1) * 16 + 2 * wi + (e & 1)] = s_tab[i * 32 + (e < 4 ? 16 + e : e - 4)];
+                }
+            }
+            if (w == wi) {
+                if (it >= 0) { item = it; k = 0; conv = false; upd = false; need = false; }
+                else active = false;
+            }
+        }
+        __syncwarp();
+        if (!__any_sync(full, active)) break;
+
+        // ---- one sweep (or the pass at the uniform start)
+        phyfoo::N1nAcc acc; acc.Fq = 0.0; acc.M = 1.0; acc.E = 0; acc.Fslow = 0.0;
+        const int* r = s_rec + slot * RL;
+        double cn[4];
+        {
+            const double2 c01 = __ldcg(reinterpret_cast<const double2*>(gct + r[0]));
+            const double2 c23 = __ldcg(reinterpret_cast<const double2*>(gct + r[0] + 16));
+            cn[0] = c01.x; cn[1] = c01.y; cn[2] = c23.x; cn[3] = c23.y;
+        }
+        for (int step = 0; step < n_steps; ++step, r += 4 * RL) {
+            const double cobs[4] = {cn[0], cn[1], cn[2], cn[3]};
+            if (step + 1 < n_steps) {
+                const int o = r[4 * RL];
+                const double2 c01 = __ldcg(reinterpret_cast<const double2*>(gct + o));
+                const double2 c23 = __ldcg(reinterpret_cast<const double2*>(gct + o + 16));
+                cn[0] = c01.x; cn[1] = c01.y; cn[2] = c23.x; cn[3] = c23.y;
+            }
+            phyfoo::n1n_update<MC>(reg, s_tab, s_exp, r, cobs, upd, acc);
+            if ((step & 63) == 63) phyfoo::n1n_fold(acc);
+            __syncwarp();
+        }
+        double F = phyfoo::n1n_free_energy(acc);
+        F += __shfl_xor_sync(full, F, 8);
+        F += __shfl_xor_sync(full, F, 16);
+        if (active) {
+            bool done;
+            if (!upd) { old = F; upd = true; done = false; }                      // F_0, MeanFieldForBayesNet.java:105
+            else {
+                if (fabs(old - F) < p.tol) conv = true;                           // :204-207 (sticky)
+                old = F; ++k;
+                done = !((k < p.max_sweeps && !conv) || k < p.min_sweeps);        // :107
+            }
+            if (done) {
+                if (slot == 0) {
+                    p.out[item] = -F;                                             // PhyloBayesModel.java:259
+                    if (p.sweeps) p.sweeps[item] = k;
+                    atomicAdd(&p.counters[1], (unsigned long long)k);
+                }
+                need = true;
+            }
+        }
+    }
+}
+#endif  // __CUDACC__

@@ -35,6 +35,9 @@ struct Net1wParams {
     int nwb;
     const int64_t* item_col0; const uint8_t* item_strand;
     double* sink_qint; double* sink_qleaf; double* sink_ent;
+    const int* n_items_dev;           // nullable: length of the item list lives on the device (windows with gaps listed by net1n.cuh)
+    const int64_t* item_dst;          // nullable: out / sweeps index of listed item (default: the item's own index)
+    unsigned long long* counter_next; // work counter (counters[0] unless the launch continues another kernel's sweep sum)
 };
 
 __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
@@ -74,7 +77,7 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
     const int64_t gslot = (int64_t)blockIdx.x * nwb + wq;
     auto GQ = [&](int t, int kk, int s) -> double& { return p.gq[(size_t)((t * p.S + kk) * 4 + s) * p.n_slots + gslot]; };
 
-    const long long n_items = (long long)p.n_windows * p.n_strands;
+    const long long n_items = p.n_items_dev ? (long long)*p.n_items_dev : (long long)p.n_windows * p.n_strands;
     bool need = true, active = true, upd = false, conv = false, nogap = false;
     int k = 0;
     long long item = -1;
@@ -85,7 +88,7 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
     for (;;) {
         if (need && active) {
             long long it = 0;
-            if (l16 == 0) it = (long long)atomicAdd(&p.counters[0], 1ULL);
+            if (l16 == 0) it = (long long)atomicAdd(p.counter_next, 1ULL);
             item = __shfl_sync(0xFFFFu << wb, it, wb);
             if (item >= n_items) active = false;
             else {
@@ -292,9 +295,10 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
                     if (l16 == 0) p.sink_ent[item] = ent;
                 }
                 if (l16 == 0) {
-                    if (p.out_last) p.out_last[item] = -Flast;
-                    p.out[item] = -Fsum;                                      // PhyloBayesModel.java:259
-                    if (p.sweeps) p.sweeps[item] = k;
+                    const long long oi = p.item_dst ? p.item_dst[item] : item;
+                    if (p.out_last) p.out_last[oi] = -Flast;
+                    p.out[oi] = -Fsum;                                        // PhyloBayesModel.java:259
+                    if (p.sweeps) p.sweeps[oi] = k;
                     atomicAdd(&p.counters[1], (unsigned long long)k);
                 }
                 need = true;

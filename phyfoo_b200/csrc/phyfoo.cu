@@ -75,8 +75,10 @@ struct phyfoo_ctx {
     cudaStream_t aux = nullptr;      // second trajectory phase of the pattern-table path
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     DevBuf memo_state;               // mean-field state of every (pattern, position) tree between the two phases
-    int order1_kernel = 1;           // 0 = one quad per window (net1.cuh), 1 = wavefront, 16 lanes per window (net1w.cuh)         // trajectory length of the pattern-table path; longer windows go to the direct kernel
+    int order1_kernel = 2;           // 0 = one quad per window (net1.cuh), 1 = wavefront, 16 lanes per window (net1w.cuh),
+                                     // 2 = one thread per node (net1n.cuh; windows with gaps through the wavefront kernel)
     DevBuf memo_pending;             // fallback list of the pattern-table path
+    DevBuf o1n_cache, o1n_fb;        // node-per-thread order-1 kernel: observed-leaf sums per warp; list of windows with gaps
     // per-kernel device times of the most recent call (CUDA events on the library's stream)
     struct KTime { const char* name; cudaEvent_t e0, e1; };
     std::vector<KTime> ktimes;
@@ -90,6 +92,7 @@ struct phyfoo_dataset {
     MemoSet* memo = nullptr;                     // pattern set (memo.cuh), built on first use
     int n_aln = 0, S = 0, nb = 0, ng = 0;
     int64_t n_cols = 0;
+    int64_t n_gap_cols = 0;                      // columns with at least one unobserved symbol
     int min_len = 0, max_len = 0;
     std::vector<int64_t> col_off;
     int64_t* d_col_off = nullptr;
@@ -110,6 +113,10 @@ struct phyfoo_model {
     double* d_tab1w = nullptr;    // order 1, wavefront kernel (net1w.cuh)
     int* d_prog1w = nullptr;
     int prog1w_len = 0, MC = 1, ML = 1, n_steps = 0;
+    double* d_tab1n = nullptr;    // order 1, node-per-thread kernel (net1n.cuh): internal-node tables [W][I][32]
+    double* d_leaftab1n = nullptr;//                                              leaf tables [W][S][32]
+    int* d_prog1n = nullptr;
+    int prog1n_len = 0, MC1n = 1, n_steps1n = 0;
 };
 
 static thread_local std::string g_init_err;
@@ -169,12 +176,18 @@ __global__ void pack_columns_kernel(const uint8_t* __restrict__ codes, int64_t n
         }
         bases[(int64_t)k * n_cols + c] = w;
     }
+    uint32_t any = 0;
     for (int k = 0; k < ng; ++k) {
         uint32_t w = 0;
         for (int s = 32 * k; s < min(S, 32 * k + 32); ++s)
             if (col[s] >= 4) w |= 1u << (s & 31);
         gaps[(int64_t)k * n_cols + c] = w;
+        any |= w;
     }
+    // bad[1]: number of columns with an unobserved symbol (one atomic per warp); the order-1 kernels choose their path by it
+    const unsigned act = __activemask();
+    const unsigned m = __ballot_sync(act, any != 0);
+    if (m && (threadIdx.x & 31) == __ffs(act) - 1) atomicAdd(bad + 1, __popc(m));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -659,8 +672,8 @@ static int dataset_build(phyfoo_ctx* ctx, int32_t n_aln, int32_t S, const int64_
     if ((e = dev_malloc(ctx->stream, &ds->d_col_off, (size_t)(n_aln + 1) * sizeof(int64_t))) != cudaSuccess) return bail("cudaMalloc col_off", e);
     if ((e = dev_malloc(ctx->stream, &ds->d_bases, (size_t)ds->nb * nc * 4)) != cudaSuccess) return bail("cudaMalloc bases", e);
     if ((e = dev_malloc(ctx->stream, &ds->d_gaps, (size_t)ds->ng * nc * 4)) != cudaSuccess) return bail("cudaMalloc gaps", e);
-    if ((e = dev_malloc(ctx->stream, &d_bad, sizeof(int))) != cudaSuccess) return bail("cudaMalloc flag", e);
-    if ((e = cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream)) != cudaSuccess) return bail("memset", e);
+    if ((e = dev_malloc(ctx->stream, &d_bad, 2 * sizeof(int))) != cudaSuccess) return bail("cudaMalloc flag", e);
+    if ((e = cudaMemsetAsync(d_bad, 0, 2 * sizeof(int), ctx->stream)) != cudaSuccess) return bail("memset", e);
     if ((e = cudaMemcpyAsync(ds->d_col_off, col_offsets, (size_t)(n_aln + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
         return bail("copy col_off", e);
     if (ds->n_cols > 0) {
@@ -678,10 +691,12 @@ static int dataset_build(phyfoo_ctx* ctx, int32_t n_aln, int32_t S, const int64_
         }
         if ((e = cudaGetLastError()) != cudaSuccess) return bail("pack_columns_kernel", e);
     }
-    int bad = 0;
-    if ((e = cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) return bail("copy flag", e);
+    int bad2[2] = {0, 0};
+    if ((e = cudaMemcpyAsync(bad2, d_bad, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) return bail("copy flag", e);
     if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bail("pack_columns_kernel", e);
     cleanup();
+    const int bad = bad2[0];
+    ds->n_gap_cols = bad2[1];
     if (bad) {
         dev_free(ctx->stream, ds->d_col_off); dev_free(ctx->stream, ds->d_bases); dev_free(ctx->stream, ds->d_gaps);
         delete ds;
@@ -793,6 +808,7 @@ extern "C" void phyfoo_model_free(phyfoo_ctx* ctx, phyfoo_model* m) {
     if (!m) return;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
     cudaFree(m->d_prog); cudaFree(m->d_logtab); cudaFree(m->d_probtab); cudaFree(m->d_tab1); cudaFree(m->d_tab1w); cudaFree(m->d_prog1w);
+    cudaFree(m->d_tab1n); cudaFree(m->d_leaftab1n); cudaFree(m->d_prog1n);
     delete m;
 }
 
@@ -803,10 +819,19 @@ static int model_upload(phyfoo_ctx* ctx, phyfoo_model* m) {
         return fail(ctx, PHYFOO_EUNSUPPORTED, "background models of order >= 2 are not implemented in this build");
     if (m->uploaded == h.version) return PHYFOO_OK;
     if (h.order == 1) {
-        std::vector<double> t1, t1w;
+        std::vector<double> t1, t1w, t1n, tl1n;
         h.tables1v(t1);
         h.tables1w(t1w);
+        h.tables1n(t1n);
+        h.leaf_tables1n(tl1n);
         if (!m->d_prog) {
+            std::vector<int> pn;
+            h.node_program(pn, m->MC1n, m->n_steps1n);
+            m->prog1n_len = (int)pn.size();
+            CU(cudaMalloc(&m->d_prog1n, pn.size() * sizeof(int)));
+            CU(cudaMemcpyAsync(m->d_prog1n, pn.data(), pn.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaMalloc(&m->d_tab1n, t1n.size() * sizeof(double)));
+            CU(cudaMalloc(&m->d_leaftab1n, tl1n.size() * sizeof(double)));
             std::vector<int> pw;
             h.wave_program(pw, m->MC, m->ML, m->n_steps);
             m->prog1w_len = (int)pw.size();
@@ -822,6 +847,8 @@ static int model_upload(phyfoo_ctx* ctx, phyfoo_model* m) {
         }
         CU(cudaMemcpyAsync(m->d_tab1, t1.data(), t1.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(m->d_tab1w, t1w.data(), t1w.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(m->d_tab1n, t1n.data(), t1n.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(m->d_leaftab1n, tl1n.data(), tl1n.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         m->uploaded = h.version;
         return PHYFOO_OK;
@@ -922,6 +949,7 @@ struct ScoreItems {
 
 #include "net1.cuh"
 #include "net1w.cuh"
+#include "net1n.cuh"
 #include "memo.cuh"
 
 static void memo_release(cudaStream_t st, MemoSet* ms) {
@@ -1223,9 +1251,15 @@ static int launch_net1w(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model*
     p.gc = p.gq + (size_t)h.W * h.S * 4 * n_slots;
     p.item_col0 = items ? items->col0 : nullptr; p.item_strand = items ? items->strand : nullptr;
     p.sink_qint = items ? items->q_int : nullptr; p.sink_qleaf = items ? items->q_leaf : nullptr; p.sink_ent = items ? items->ent : nullptr;
-    CU(cudaMemsetAsync(p.counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    p.n_items_dev = items ? items->n_dev : nullptr; p.item_dst = items ? items->dst : nullptr;
+    const bool fallback = items && items->fallback;
+    // a fallback launch (windows with gaps listed by the node-per-thread kernel) pulls its work from a counter of its own
+    // ([8 + slot]) and continues the sweep sum of that kernel
+    p.counter_next = fallback ? ctx->counters.as<unsigned long long>() + 8 + counter_slot : p.counters;
+    if (fallback) CU(cudaMemsetAsync(p.counter_next, 0, sizeof(unsigned long long), ctx->stream));
+    else CU(cudaMemsetAsync(p.counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
     {
-        KernelTimer kt_(ctx, "score_o1w_kernel");
+        KernelTimer kt_(ctx, fallback ? "score_o1w_kernel(windows with gaps)" : "score_o1w_kernel");
         score_o1w_kernel<<<blocks, 16 * nwb, smem, ctx->stream>>>(p);
     }
     CU(cudaGetLastError());
@@ -1233,13 +1267,84 @@ static int launch_net1w(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model*
 }
 
 // order-1 motif network: quad per window (net1.cuh)
+// order-1 motif network, node-per-thread kernel (net1n.cuh): 4 threads per window, 8 windows per warp; returns 1 when the
+// configuration is not one it takes (the caller then runs the wavefront kernel), 0 when launched
+static int launch_net1n(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* m, const int64_t* d_win_off, int64_t n_windows,
+                        int strands, double* d_out, int32_t* d_sweeps, int counter_slot) {
+    ModelHost& h = m->h;
+    if (m->MC1n > 3 || !m->d_prog1n) return 1;
+    // mostly gapped data: nearly every window would go through the list anyway
+    if ((double)ds->n_gap_cols * h.W >= 0.5 * (double)std::max<int64_t>(ds->n_cols, 1)) return 1;
+    const int n_strands = strands == 2 ? 2 : 1;
+    const long long n_items = (long long)n_windows * n_strands;
+    const ModelHost::N1nLayout L = h.n1n_layout();
+    const size_t fixed = ((size_t)h.W * h.I * 32 + 64) * sizeof(double) + (size_t)m->prog1n_len * sizeof(int) + 16;
+    const size_t per_warp = (size_t)L.region * sizeof(double);
+    const size_t budget = std::min<size_t>(ctx->smem_optin, 227 * 1024);
+    if (fixed + per_warp > budget) return 1;
+    int nw = (int)std::min<size_t>(8, (budget - fixed) / per_warp);
+    const long long want_warps = (n_items + 7) / 8;
+    const void* fn = m->MC1n <= 1 ? (const void*)score_o1n_kernel<1> : m->MC1n == 2 ? (const void*)score_o1n_kernel<2> : (const void*)score_o1n_kernel<3>;
+    const size_t smem = fixed + per_warp * nw;
+    CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((want_warps + nw - 1) / nw, ctx->sm_count));
+    const size_t cache_bytes = (size_t)blocks * nw * L.region * sizeof(double);
+    const bool fresh = cache_bytes > ctx->o1n_cache.cap;
+    CU(ctx->o1n_cache.ensure(cache_bytes));
+    if (fresh) CU(cudaMemsetAsync(ctx->o1n_cache.p, 0, ctx->o1n_cache.cap, ctx->stream));   // idle slots read their (unused) rows
+    const bool check = ds->n_gap_cols > 0;
+    int* fb_count = nullptr;
+    if (check) {
+        // list of windows with gaps: [count (16 bytes)] [col0: int64 x n] [dst: int64 x n] [strand: uint8 x n]
+        CU(ctx->o1n_fb.ensure(16 + (size_t)n_items * 17));
+        fb_count = ctx->o1n_fb.as<int>();
+        CU(cudaMemsetAsync(fb_count, 0, 16, ctx->stream));
+    }
+    Net1nParams p;
+    p.bases = ds->d_bases; p.gaps = ds->d_gaps; p.n_cols = ds->n_cols; p.nb = ds->nb;
+    p.col_off = ds->d_col_off; p.win_off = d_win_off; p.n_aln = ds->n_aln;
+    p.n_windows = n_windows; p.n_strands = n_strands; p.strand0 = strands == 1 ? 1 : 0;
+    p.W = h.W; p.I = h.I; p.S = h.S;
+    p.prog = m->d_prog1n; p.prog_len = m->prog1n_len; p.tab = m->d_tab1n; p.leaf_tab = m->d_leaftab1n;
+    p.out = d_out; p.sweeps = d_sweeps;
+    p.counters = ctx->counters.as<unsigned long long>() + 2 * counter_slot;
+    p.max_sweeps = h.max_sweeps; p.min_sweeps = h.min_sweeps; p.tol = h.tol;
+    p.gc = ctx->o1n_cache.as<double>();
+    p.region = L.region; p.gc_region = L.region; p.ab0 = L.ab0; p.zero_row = L.zero_row; p.onehot_row = L.onehot_row;
+    p.check_gaps = check ? 1 : 0;
+    p.fb_count = fb_count;
+    p.fb_col0 = check ? (int64_t*)((char*)ctx->o1n_fb.p + 16) : nullptr;
+    p.fb_dst = check ? p.fb_col0 + n_items : nullptr;
+    p.fb_strand = check ? (uint8_t*)(p.fb_dst + n_items) : nullptr;
+    CU(cudaMemsetAsync(p.counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    {
+        KernelTimer kt_(ctx, "score_o1n_kernel");
+        if (m->MC1n <= 1) score_o1n_kernel<1><<<blocks, 32 * nw, smem, ctx->stream>>>(p);
+        else if (m->MC1n == 2) score_o1n_kernel<2><<<blocks, 32 * nw, smem, ctx->stream>>>(p);
+        else score_o1n_kernel<3><<<blocks, 32 * nw, smem, ctx->stream>>>(p);
+    }
+    CU(cudaGetLastError());
+    if (check) {
+        ScoreItems it{p.fb_col0, p.fb_strand, nullptr, nullptr, nullptr};
+        it.n_dev = fb_count; it.dst = p.fb_dst; it.fallback = true;
+        // (n_windows of the launch: the list's capacity bound for the grid; the kernel reads the real length on the device)
+        int rc = launch_net1w(ctx, ds, m, d_win_off, std::min<long long>(n_items, 64LL * ctx->sm_count), 0, d_out, d_sweeps, counter_slot, &it);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
 static int launch_net1(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* m, const int64_t* d_win_off, int64_t n_windows,
                        int strands, double* d_out, int32_t* d_sweeps, int counter_slot, const ScoreItems* items) {
     ModelHost& h = m->h;
     if (h.mode == PHYFOO_MODE_EXACT && !items)
         return fail(ctx, PHYFOO_EUNSUPPORTED, "exact likelihood of an order-1 network is infeasible in the reference too "
                                               "(SimpleNodeElimination's 9-node frontier, SimpleNodeElimination.java:33-45)");
-    if (ctx->order1_kernel == 1) return launch_net1w(ctx, ds, m, d_win_off, n_windows, strands, d_out, d_sweeps, counter_slot, items);
+    if (ctx->order1_kernel == 2 && !items) {
+        const int rc = launch_net1n(ctx, ds, m, d_win_off, n_windows, strands, d_out, d_sweeps, counter_slot);
+        if (rc <= 0) return rc;
+    }
+    if (ctx->order1_kernel >= 1) return launch_net1w(ctx, ds, m, d_win_off, n_windows, strands, d_out, d_sweeps, counter_slot, items);
     const int n_strands = strands == 2 ? 2 : 1;
     const long long n_items = (long long)n_windows * n_strands;
     // windows per block: as many windows per SM as shared memory holds, in multiples of 8 (whole warps).  The kernel is
@@ -1719,7 +1824,7 @@ extern "C" int phyfoo_set_option(phyfoo_ctx* ctx, const char* name, int64_t valu
         return PHYFOO_OK;
     }
     if (std::strcmp(name, "order1_kernel") == 0) {
-        if (value != 0 && value != 1) return fail(ctx, PHYFOO_EINVAL, "set_option: order1_kernel must be 0 (quad per window) or 1 (wavefront)");
+        if (value < 0 || value > 2) return fail(ctx, PHYFOO_EINVAL, "set_option: order1_kernel must be 0 (quad per window), 1 (wavefront) or 2 (thread per node)");
         ctx->order1_kernel = (int)value;
         return PHYFOO_OK;
     }

@@ -342,3 +342,99 @@ extern "C" int emul_wave_schedule(const phyfoo_model_desc* d, int* sched_out, in
         return 0;
     } catch (const std::exception& e) { std::fprintf(stderr, "emul: %s\n", e.what()); return -1; }
 }
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Host run of the node-per-thread order-1 kernel's arithmetic (csrc/net1n.cuh::n1n_update, the very code the kernel inlines)
+// under the kernel's program (model_host.hpp::node_program): one window at a time in window slot `wslot` of a warp region,
+// the four node slots of a step run one after the other -- in both orders, which must agree bit for bit because no node of
+// a step may read what another node of the same step writes.  Windows must be free of gaps (the kernel sends the others to
+// the net1w.cuh kernel).
+// ---------------------------------------------------------------------------------------------------------------------------
+#include "../../phyfoo_b200/csrc/net1n.cuh"
+
+namespace {
+template <int MC>
+int run_o1n(const ModelHost& m, const std::vector<int>& prog, const uint8_t* codes, int L, int strand, int wslot, double* out, int* sweeps) {
+    const int W = m.W, I = m.I, S = m.S;
+    const int n_steps = prog[0], RL = prog[2];
+    const int* leaf_begin = prog.data() + 4;
+    const int* leaf_species = leaf_begin + I + 1;
+    const int* rec = leaf_species + S;
+    const ModelHost::N1nLayout Lt = m.n1n_layout();
+    std::vector<double> tab, leaf_tab;
+    m.tables1n(tab);
+    m.leaf_tables1n(leaf_tab);
+    std::vector<double> region(Lt.region, 0.0), gc(Lt.region, 0.0);
+    for (int w = 0; w < 8; ++w) region[Lt.onehot_row + 2 * w] = 1.0;
+    for (int j = 0; j + W <= L; ++j) {
+        // set-up: observed-leaf sums, uniform start, context sums of position 0
+        for (int t = 0; t < W; ++t) {
+            const int col = strand ? j + W - 1 - t : j + t;
+            ColWords cw = words_of(codes + (size_t)col * S, S, strand != 0);
+            ColWords cwp; cwp.b = 0; cwp.g = 0;
+            if (t > 0) cwp = words_of(codes + (size_t)(strand ? col + 1 : col - 1) * S, S, strand != 0);
+            if (cw.g) return -3;
+            for (int i = 0; i < I; ++i)
+                for (int a = 0; a < 4; ++a) {
+                    double c = 0.0;
+                    for (int kk = leaf_begin[i]; kk < leaf_begin[i + 1]; ++kk) {
+                        const int sp = leaf_species[kk];
+                        const int x = cw.obs(sp), y = t > 0 ? cwp.obs(sp) : 0;
+                        c += leaf_tab[(size_t)(t * S + kk) * 32 + (a == x ? 16 : 0) + y * 4 + x];
+                    }
+                    const int o = (t * I + i) * 32 + (a >> 1) * 16 + 2 * wslot + (a & 1);
+                    gc[o] = c; region[o] = 0.25;
+                }
+        }
+        for (int i = 0; i < I; ++i)
+            for (int e = 0; e < 8; ++e)
+                region[Lt.ab0 + i * 64 + (e >> 1) * 16 + 2 * wslot + (e & 1)] = tab[(size_t)i * 32 + (e < 4 ? 16 + e : e - 4)];
+        bool upd = false, conv = false; int k = 0; double old = 0.0;
+        for (;;) {
+            N1nAcc acc[4];
+            for (auto& a : acc) { a.Fq = 0.0; a.M = 1.0; a.E = 0; a.Fslow = 0.0; }
+            for (int step = 0; step < n_steps; ++step) {
+                std::vector<double> alt = region;
+                N1nAcc acc_alt[4] = {acc[0], acc[1], acc[2], acc[3]};
+                for (int order = 0; order < 2; ++order)
+                    for (int q = 0; q < 4; ++q) {
+                        const int slot = order ? 3 - q : q;
+                        const int* r = rec + (size_t)(step * 4 + slot) * RL;
+                        double* reg = (order ? alt.data() : region.data()) + 2 * wslot;
+                        const double* g = gc.data() + 2 * wslot + r[0];
+                        const double cobs[4] = {g[0], g[1], g[16], g[17]};
+                        n1n_update<MC>(reg, tab.data(), h_phy_exp_tab, r, cobs, upd, order ? acc_alt[slot] : acc[slot]);
+                    }
+                // the trash rows are written by every idle slot: exclude them from the comparison
+                for (int o = 0; o < Lt.region; ++o) {
+                    const bool trash = (o >= Lt.trash_row && o < Lt.trash_row + 32) || o >= Lt.trash_ab;
+                    if (!trash && std::memcmp(&alt[o], &region[o], 8) != 0) return -4;
+                }
+                if ((step & 63) == 63) for (auto& a : acc) n1n_fold(a);
+            }
+            const double f0 = n1n_free_energy(acc[0]), f1 = n1n_free_energy(acc[1]), f2 = n1n_free_energy(acc[2]), f3 = n1n_free_energy(acc[3]);
+            const double F = (f0 + f1) + (f2 + f3);            // the kernel's butterfly over lanes w, w+8, w+16, w+24
+            if (!upd) { old = F; upd = true; continue; }
+            if (std::fabs(old - F) < m.tol) conv = true;
+            old = F; ++k;
+            if (!((k < m.max_sweeps && !conv) || k < m.min_sweeps)) { out[j] = -F; if (sweeps) sweeps[j] = k; break; }
+        }
+    }
+    return 0;
+}
+}  // namespace
+
+extern "C" int emul_score_o1n(const phyfoo_model_desc* d, const uint8_t* codes, int L, int strand, int wslot, double* out, int* sweeps,
+                              int* n_steps_out) {
+    try {
+        ModelHost m; m.init(*d);
+        if (m.order != 1) return -2;
+        std::vector<int> prog; int MC, ns;
+        m.node_program(prog, MC, ns);
+        if (n_steps_out) *n_steps_out = ns;
+        if (MC == 1) return run_o1n<1>(m, prog, codes, L, strand, wslot, out, sweeps);
+        if (MC == 2) return run_o1n<2>(m, prog, codes, L, strand, wslot, out, sweeps);
+        if (MC == 3) return run_o1n<3>(m, prog, codes, L, strand, wslot, out, sweeps);
+        return -5;
+    } catch (const std::exception& e) { std::fprintf(stderr, "emul: %s\n", e.what()); return -1; }
+}

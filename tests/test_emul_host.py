@@ -21,7 +21,8 @@ def emul():
     so = os.path.join(EMUL_DIR, "libemul.so")
     srcs = [os.path.join(EMUL_DIR, "emul.cpp"), os.path.join(ROOT, "phyfoo_b200", "csrc", "tree_pass.cuh"),
             os.path.join(ROOT, "phyfoo_b200", "csrc", "model_host.hpp"), os.path.join(ROOT, "phyfoo_b200", "csrc", "fp64_math.cuh"),
-            os.path.join(ROOT, "phyfoo_b200", "csrc", "fp64_math_tables.h")]
+            os.path.join(ROOT, "phyfoo_b200", "csrc", "fp64_math_tables.h"),
+            os.path.join(ROOT, "phyfoo_b200", "csrc", "net1n.cuh")]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", srcs[0], "-o", so])
     L = C.CDLL(so)
@@ -223,3 +224,42 @@ def test_pattern_table_decomposition(emul, newick, gap_rate):
         assert k == ref_k[j] and -cur == ref[j], j
         pending += k > cap
     assert pending == int((ref_k > cap).sum())
+
+
+# ---- order-1 network, node-per-thread kernel (csrc/net1n.cuh): its update function under its own program, on the host ----
+@pytest.fixture(scope="module")
+def emul_o1n(emul):
+    emul.emul_score_o1n.argtypes = [C.POINTER(_abi.ModelDesc), C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int,
+                                    C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    return emul
+
+
+O1N_TREES = {"star5": synth.star_newick(5), "cat5": synth.caterpillar_newick(5), "rand12": synth.random_binary_newick(12, 3),
+             "mixed6": "((A:0.1,B:0.3):0.15,(C:0.2,(D:0.05,E:0.4):0.25):0.1,F:0.3)",
+             "c3": synth.config_newick(synth.CONFIGS["c3"])}
+
+
+@pytest.mark.parametrize("tree,W", [("star5", 1), ("star5", 6), ("cat5", 2), ("cat5", 7), ("mixed6", 5), ("rand12", 3), ("c3", 12)])
+def test_order1_node_update_matches_oracle(emul_o1n, tree, W):
+    """n1n_update under node_program's schedule and records = the reference's sweep: scores within 1e-9 relative and the
+    same sweep counts as the oracle; the emulation also runs the node slots of every step in both orders and requires
+    identical state (no node of a step reads what another node of the step writes)."""
+    from util import oracle_fg
+    newick = O1N_TREES[tree]
+    tr = parse_newick(newick)
+    rng = np.random.default_rng(5 + W)
+    pwm = synth.random_pwm(W, 1, 61 + W)
+    codes = random_codes(rng, W + 9, tr.n_species)
+    desc, keep = _abi.make_desc(_abi.MODEL_FG, W, 1, tr, np.tile(tr.branch, (W, 1)), pwm, _abi.EVOL_F81ALPHA, _abi.MODE_MEANFIELD)
+    om = oracle_fg(newick, pwm, order=1)
+    n = codes.shape[0] - W + 1
+    for strand in (0, 1):
+        out, sw, ns = np.zeros(n), np.zeros(n, np.int32), C.c_int()
+        rc = emul_o1n.emul_score_o1n(C.byref(desc), codes.ctypes.data_as(C.POINTER(C.c_uint8)), codes.shape[0], strand, (W + strand) % 8,
+                                     out.ctypes.data_as(C.POINTER(C.c_double)), sw.ctypes.data_as(C.POINTER(C.c_int)), C.byref(ns))
+        assert rc == 0
+        ref, rsw = om.score_windows(codes, bool(strand))
+        assert np.array_equal(sw, rsw)
+        assert rel_err(out, ref) < 1e-9
+        n_int = int((np.bincount(tr.parent[1:], minlength=tr.n_nodes) > 0).sum())
+        assert ns.value >= -(-W * n_int // 4)            # at most four nodes per step

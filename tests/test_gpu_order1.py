@@ -179,7 +179,50 @@ def test_order1_wavefront_equals_node_by_node_kernel(ctx, tree):
         (f0, g0), (f1, g1) = res[0][2], res[1][2]
         assert abs(f0 - f1) <= 1e-12 * abs(f0) and np.max(np.abs(g0 - g1)) <= 1e-9 * np.max(np.abs(g0)) + 64 * np.finfo(float).eps * abs(f0) / 1e-4
     finally:
-        ctx.set_option("order1_kernel", 1)
+        ctx.set_option("order1_kernel", 2)
+
+
+@pytest.mark.parametrize("tree,W", [("star5", 4), ("cat5", 7), ("mixed6", 1), ("mixed6", 6), ("rand12", 12)])
+def test_order1_node_per_thread_kernel(ctx, tree, W):
+    """The node-per-thread kernel (net1n.cuh, default): windows without gaps on it, the few windows with an unobserved leaf
+    through its device-side list to the wavefront kernel.  Against the oracle (scores 1e-9 relative, sweep counts exact) and
+    against the wavefront kernel alone (same sweep counts, scores equal to re-association); both strands, ragged lengths."""
+    from phyfoo_b200 import synth
+    from phyfoo_b200.data import PhyloSample
+    from phyfoo_b200.models import PhyloBayesModel
+    from phyfoo_b200.newick import parse_newick
+    newick = _trees()[tree]
+    S = parse_newick(newick).n_species
+    rng = np.random.default_rng(53 + W)
+    pwm = synth.random_pwm(W, 1, 97)
+    lens = [W, 150, max(W - 1, 1), 333, W + 1, 77]
+    codes = random_codes(rng, sum(lens), S)
+    gap_cols = rng.choice(codes.shape[0], 6, replace=False)          # a handful of columns with one unobserved leaf
+    codes[gap_cols, rng.integers(0, S, gap_cols.size)] = 4
+    smp = PhyloSample(codes, np.concatenate([[0], np.cumsum(lens)]))
+    fg = PhyloBayesModel(W, 1, newick, ctx); fg.setCondProbs(pwm)
+    om = oracle_fg(newick, pwm, order=1)
+    try:
+        res = {}
+        for kern in (2, 1):
+            ctx.set_option("order1_kernel", kern)
+            res[kern] = [fg.getLogProbFor(smp, strand=s, want_sweeps=True) for s in (0, 1)]
+            names = [n for n, _ in ctx.last_kernel_times()]
+            assert names == (["score_o1n_kernel", "score_o1w_kernel(windows with gaps)"] if kern == 2 else ["score_o1w_kernel"])
+            if kern == 2:
+                assert fg.last_stats["sweeps_fg"] == int(res[2][1][1].sum())
+        for s in (0, 1):
+            ref, rsw = [], []
+            for i in range(smp.n_alignments):
+                r, k = om.score_windows(smp.getElementAt(i), bool(s))
+                ref.append(r); rsw.append(k)
+            ref, rsw = np.concatenate(ref), np.concatenate(rsw)
+            assert np.array_equal(res[2][s][1], rsw)
+            assert rel_err(res[2][s][0], ref) < TOL
+            assert np.array_equal(res[2][s][1], res[1][s][1])
+            assert rel_err(res[2][s][0], res[1][s][0]) < 1e-12
+    finally:
+        ctx.set_option("order1_kernel", 2)
 
 
 @pytest.mark.parametrize("tree", ["cat5", "rand12"])
