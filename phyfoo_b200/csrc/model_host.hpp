@@ -365,6 +365,9 @@ struct ModelHost {
     // readers precede (t+1, i) ... and the update of the last position produces the rows of position 0 (virtual one-hot
     // predecessor) for the next sweep.
     static int n1n_rec_len(int MC) { return (8 + 2 * MC + 3) & ~3; }
+    // a node's 32 table entries are padded to 34 doubles: the four node slots of a warp read the same entry of four
+    // different nodes at once, and with a row of 256 bytes these would all sit in the same banks
+    static const int N1N_TAB_STRIDE = 34;
     struct N1nLayout { int q0, zero_row, onehot_row, trash_row, ab0, trash_ab, region; };
     N1nLayout n1n_layout() const {
         N1nLayout L;
@@ -372,16 +375,17 @@ struct ModelHost {
         L.ab0 = L.trash_row + 32; L.trash_ab = L.ab0 + 2 * I * 64; L.region = L.trash_ab + 64;
         return L;
     }
-    // tables of the internal nodes for the kernel's shared memory: [W][I][32] = Lo[ctx][b] | Ld[ctx][b] (root: log pi twice)
+    // tables of the internal nodes for the kernel's shared memory: [W][I][34] = Lo[ctx][b] | Ld[ctx][b] | 2 pad (root: log
+    // pi twice)
     void tables1n(std::vector<double>& out) const {
         const int e1 = E1();
         std::vector<double> t1;
         tables1(t1);
-        out.assign((size_t)W * I * 32, 0.0);
+        out.assign((size_t)W * I * N1N_TAB_STRIDE, 0.0);
         for (int t = 0; t < W; ++t)
             for (int i = 0; i < I; ++i) {
                 const int k = node_of[i];
-                double* o = &out[((size_t)t * I + i) * 32];
+                double* o = &out[((size_t)t * I + i) * N1N_TAB_STRIDE];
                 const double* src = &t1[(size_t)t * e1];
                 if (k == 0) for (int j = 0; j < 16; ++j) o[j] = o[16 + j] = src[j];
                 else for (int j = 0; j < 32; ++j) o[j] = src[16 + 32 * (k - 1) + j];
@@ -397,7 +401,8 @@ struct ModelHost {
             for (int kk = 0; kk < S; ++kk)
                 for (int j = 0; j < 32; ++j) out[((size_t)t * S + kk) * 32 + j] = t1[(size_t)t * e1 + 16 + 32 * (leaf_node[kk] - 1) + j];
     }
-    // program: header [n_steps, MC, rec_len, I] | leaf_begin[I+1] | leaf_species[S] | records [n_steps][4][rec_len].
+    // program: header [n_steps, MC, rec_len, records offset] | leaf_begin[I+1] | leaf_species[S] | pad to a multiple of 4 |
+    // records [n_steps][4][rec_len] (16-byte aligned: the kernel loads them as int4).
     // List schedule of the W*I node updates into steps of <= 4, longest remaining dependency chain first: node (t, i) may run
     // once (t, parent), (t-1, i) and (t-1, child) for every internal child are in EARLIER steps (see net1w.cuh for why any
     // such schedule reproduces the reference's sweep).
@@ -440,9 +445,11 @@ struct ModelHost {
         }
         n_steps = step;
         prog.clear();
-        prog.push_back(n_steps); prog.push_back(MC); prog.push_back(RL); prog.push_back(I);
+        prog.push_back(n_steps); prog.push_back(MC); prog.push_back(RL); prog.push_back(0);
         prog.insert(prog.end(), leaf_begin.begin(), leaf_begin.end());
         prog.insert(prog.end(), leaf_sp.begin(), leaf_sp.end());
+        while (prog.size() & 3) prog.push_back(0);
+        prog[3] = (int)prog.size();
         auto qrow = [&](int t, int i) { return L.q0 + (t * I + i) * 32; };
         auto abrow = [&](int t, int i) { return L.ab0 + ((t & 1) * I + i) * 64; };     // position 0 lives in parity 0
         for (int s = 0; s < n_steps; ++s)
@@ -462,7 +469,7 @@ struct ModelHost {
                     r[3] = (last || p < 0) ? r[1] : qrow(t + 1, p);
                     r[4] = abrow(t, i);
                     r[5] = abrow(last ? 0 : t + 1, i);
-                    r[6] = (((last ? 0 : t + 1) * I) + i) * 32;
+                    r[6] = (((last ? 0 : t + 1) * I) + i) * N1N_TAB_STRIDE;
                     r[7] = 1 | (last ? 2 : 0);
                     for (int j = 0; j < MC; ++j) {
                         const bool has = ichild_begin[i] + j < ichild_begin[i + 1];

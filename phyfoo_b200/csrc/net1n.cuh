@@ -30,8 +30,10 @@
 
 #if defined(__CUDACC__)
 #define N1N_HD __host__ __device__ __forceinline__
+#define N1N_RARE __host__ __device__ __noinline__      // rare paths stay out of the step loop's instruction stream
 #else
 #define N1N_HD inline
+#define N1N_RARE inline
 #endif
 
 namespace phyfoo {
@@ -78,6 +80,64 @@ N1N_HD double n1n_rcp(double z) {
     return 1.0 / z;
 #endif
 }
+// reciprocal of a normal number away from the ends of the exponent range: the seed and the two Newton steps of the
+// library's __drcp_rn without its special-case tests (the caller has looked at the exponent already)
+N1N_HD double n1n_rcp_normal(double z) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(z));
+    double e = fma(-z, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-z, r, 1.0);
+    return fma(r, e, r);
+#else
+    return 1.0 / z;
+#endif
+}
+struct N1nD4 { double v0, v1, v2, v3; };
+N1N_RARE N1nD4 n1n_exp4_rare(double x0, double x1, double x2, double x3, const double* tab64) {
+    N1nD4 r;
+    r.v0 = phy_exp_tab(x0, tab64); r.v1 = phy_exp_tab(x1, tab64); r.v2 = phy_exp_tab(x2, tab64); r.v3 = phy_exp_tab(x3, tab64);
+    return r;
+}
+// z = sum of the exponentials is zero, denormal, huge, inf or NaN: library reciprocal, log z taken directly
+struct N1nZR { double rz, lz; };
+N1N_RARE N1nZR n1n_z_rare(double z) {
+    N1nZR r;
+    r.rz = n1n_rcp(z); r.lz = phy_log(z);
+    return r;
+}
+// four exponentials at once: the common case (every |x| < 690) is straight-line code, so that the four polynomial chains
+// interleave; bit for bit phy_exp_tab
+N1N_HD void n1n_exp4(const double (&x)[4], const double* tab64, double (&e)[4]) {
+    const bool common = fabs(x[0]) < 690.0 && fabs(x[1]) < 690.0 && fabs(x[2]) < 690.0 && fabs(x[3]) < 690.0;
+    if (common) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const double t = x[a] * PHY_64_OVER_LN2;
+            double kd = t + 0x1.8p52;
+#if defined(__CUDA_ARCH__)
+            const int32_t ki = __double2loint(kd);
+#else
+            const int32_t ki = (int32_t)(uint32_t)phy_bits(kd);
+#endif
+            kd -= 0x1.8p52;
+            double r = fma(kd, -PHY_LN2_64_HI, x[a]);
+            r = fma(kd, -PHY_LN2_64_LO, r);
+            const double T = tab64[ki & 63];
+            double q = fma(r, 0x1.6c16c16c16c17p-10, 0x1.1111111111111p-7);
+            q = fma(q, r, 0x1.5555555555555p-5);
+            q = fma(q, r, 0x1.5555555555555p-3);
+            q = fma(q, r, 0.5);
+            const double pm = fma(r * r, q, r);
+            const double res = fma(T, pm, T);
+            e[a] = n1n_with_hi(res, n1n_hi(res) + ((ki >> 6) << 20));       // |x| < 690: the result is a normal number
+        }
+    } else {
+        const N1nD4 r = n1n_exp4_rare(x[0], x[1], x[2], x[3], tab64);
+        e[0] = r.v0; e[1] = r.v1; e[2] = r.v2; e[3] = r.v3;
+    }
+}
 // log z accumulated as (mantissa product, exponent sum)
 N1N_HD void n1n_acc_logz(N1nAcc& acc, double z) {
     const int hi = n1n_hi(z);
@@ -98,7 +158,7 @@ N1N_HD double n1n_free_energy(const N1nAcc& acc) {
     return (acc.Fq - acc.Fslow) - lz;
 }
 
-// One node update.  reg: this thread's window in the warp's region; tab: tables [W][I][32] (Lo | Ld); exptab: 2^(j/64);
+// One node update.  reg: this thread's window in the warp's region; tab: tables [W][I][34] (Lo | Ld | pad); exptab: 2^(j/64);
 // r: the record (model_host.hpp::node_program); cobs: observed-leaf sums of this node; upd == false: the pass at the uniform
 // start (exponents forced to 0).  All reads come before the two row stores; the caller synchronises the warp afterwards.
 template <int MC>
@@ -151,22 +211,35 @@ N1N_HD void n1n_update(double* reg, const double* tab, const double* exptab, con
             nx[a] = last ? 0.0 : v;
         }
     }
-    double e[4], g[4], qn[4];
+    double e[4], g[4], qn[4], ex[4];
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         const double s = ((own[a] + ch[a]) + cobs[a]) + nx[a];
-        e[a] = phy_exp_tab(upd ? s : 0.0, exptab);                                 // MeanFieldForBayesNet.java:192, no max shift
+        ex[a] = upd ? s : 0.0;
         g[a] = upd ? ch[a] + nx[a] : -(own[a] + cobs[a]);
     }
+    n1n_exp4(ex, exptab, e);                                                        // MeanFieldForBayesNet.java:192, no max shift
     const double z = n1n_sum4(e);                                                   // :195-198
-    const double rz = n1n_rcp(z);
+    // z is a normal number well inside the exponent range unless the exponents were extreme: one test for the reciprocal
+    // and for the (mantissa, exponent) accumulation of log z
+    const int zhi = n1n_hi(z);
+    const unsigned zef = (unsigned)zhi >> 20;
+    const bool znormal = zef - 24u < 2000u;
+    double rz;
+    if (znormal) {
+        rz = n1n_rcp_normal(z);
+        if (live) { acc.E += (int)zef - 1023; acc.M *= n1n_with_hi(z, (zhi & 0x000fffff) | 0x3ff00000); }
+    } else {
+        const N1nZR r = n1n_z_rare(z);
+        rz = r.rz;
+        if (live) acc.Fslow += r.lz;
+    }
 #pragma unroll
     for (int a = 0; a < 4; ++a) qn[a] = e[a] * rz;                                  // :199-201
-    if (live) {
+    {
         double f = qn[0] * g[0];
         f = fma(qn[1], g[1], f); f = fma(qn[2], g[2], f); f = fma(qn[3], g[3], f);
-        acc.Fq += f;
-        n1n_acc_logz(acc, z);
+        acc.Fq += live ? f : 0.0;
     }
     // context sums of the same node at the next position (the last position produces those of position 0: one-hot)
     double An[4], Bn[4];
@@ -199,7 +272,7 @@ struct Net1nParams {
     int64_t n_windows; int n_strands; int strand0;
     int W, I, S;
     const int* prog; int prog_len;       // model_host.hpp::node_program
-    const double* tab;                   // [W][I][32]
+    const double* tab;                   // [W][I][34]
     const double* leaf_tab;              // [W][S][32]
     double* out; int32_t* sweeps;
     unsigned long long* counters;        // [0] work counter, [1] sweep sum
@@ -215,11 +288,12 @@ __global__ void __launch_bounds__(256, 1) score_o1n_kernel(Net1nParams p) {
     extern __shared__ double smem[];
     const int tid = threadIdx.x, T = blockDim.x, NW = T >> 5;
     const int W = p.W, I = p.I, S = p.S;
-    double* s_tab = smem;                                   // [W][I][32]
-    double* s_exp = s_tab + (size_t)W * I * 32;             // [64]
+    const int TS = phyfoo::ModelHost::N1N_TAB_STRIDE;
+    double* s_tab = smem;                                   // [W][I][34]
+    double* s_exp = s_tab + (size_t)W * I * TS;             // [64]
     double* s_reg = s_exp + 64;                             // [NW][region]
     int* s_prog = (int*)(s_reg + (size_t)NW * p.region);
-    for (int i = tid; i < W * I * 32; i += T) s_tab[i] = p.tab[i];
+    for (int i = tid; i < W * I * TS; i += T) s_tab[i] = p.tab[i];
     for (int i = tid; i < 64; i += T) s_exp[i] = phyfoo::d_phy_exp_tab[i];
     for (int i = tid; i < NW * p.region; i += T) s_reg[i] = 0.0;
     for (int i = tid; i < p.prog_len; i += T) s_prog[i] = p.prog[i];
@@ -229,7 +303,7 @@ __global__ void __launch_bounds__(256, 1) score_o1n_kernel(Net1nParams p) {
     const int n_steps = s_prog[0], RL = s_prog[2];
     const int* leaf_begin = s_prog + 4;
     const int* leaf_species = leaf_begin + I + 1;
-    const int* s_rec = leaf_species + S;
+    const int* s_rec = s_prog + s_prog[3];
 
     const int lane = tid & 31, warp = tid >> 5;
     const int w = lane & 7, slot = lane >> 3;
@@ -276,28 +350,32 @@ __global__ void __launch_bounds__(256, 1) score_o1n_kernel(Net1nParams p) {
                 }
             }
             if (it >= 0) {
-                // observed-leaf sums of every node (constant over the sweeps), uniform start (MeanFieldForBayesNet.java:52-69)
-                for (int idx = lane; idx < W * I * 4; idx += 32) {
-                    const int t = idx / (4 * I), rem = idx - t * 4 * I, i = rem >> 2, a = rem & 3;
+                // observed-leaf sums of every node (constant over the sweeps), uniform start (MeanFieldForBayesNet.java:52-69):
+                // one lane per (position, node), all four symbols
+                for (int idx = lane; idx < W * I; idx += 32) {
+                    const int t = idx / I, i = idx - t * I;
                     const int64_t col = strand ? c0 + (W - 1 - t) : c0 + t;       // jstacs StrandModel.java:636-639
                     ColWords cw = load_column(p.bases, p.gaps, p.n_cols, p.nb, col);
                     ColWords cwp; cwp.b = 0; cwp.g = 0;
                     if (t > 0) cwp = load_column(p.bases, p.gaps, p.n_cols, p.nb, strand ? col + 1 : col - 1);
                     if (strand) { cw = complement(cw); cwp = complement(cwp); }
-                    double c = 0.0;
+                    double c[4] = {0.0, 0.0, 0.0, 0.0};
                     for (int kk = leaf_begin[i]; kk < leaf_begin[i + 1]; ++kk) {
                         const int sp = leaf_species[kk];
                         const int x = cw.obs(sp) & 3, y = t > 0 ? (cwp.obs(sp) & 3) : 0;
-                        c += __ldg(p.leaf_tab + ((size_t)(t * S + kk) * 32 + (a == x ? 16 : 0) + y * 4 + x));
+                        const double* lt = p.leaf_tab + ((size_t)(t * S + kk) * 32 + y * 4 + x);
+                        const double off = __ldg(lt), diag = __ldg(lt + 16);
+#pragma unroll
+                        for (int a = 0; a < 4; ++a) c[a] += a == x ? diag : off;
                     }
-                    const int o = (t * I + i) * 32 + (a >> 1) * 16 + 2 * wi + (a & 1);
-                    gcw[o] = c;
-                    regw[o] = 0.25;
+                    const int o = idx * 32 + 2 * wi;
+                    gcw[o] = c[0]; gcw[o + 1] = c[1]; gcw[o + 16] = c[2]; gcw[o + 17] = c[3];
+                    regw[o] = 0.25; regw[o + 1] = 0.25; regw[o + 16] = 0.25; regw[o + 17] = 0.25;
                 }
                 // context sums of position 0: the virtual predecessor is the one-hot (1, 0, 0, 0)
                 for (int idx = lane; idx < I * 8; idx += 32) {
                     const int i = idx >> 3, e = idx & 7;
-                    regw[p.ab0 + i * 64 + (e >> 1) * 16 + 2 * wi + (e & 1)] = s_tab[i * 32 + (e < 4 ? 16 + e : e - 4)];
+                    regw[p.ab0 + i * 64 + (e >> 1) * 16 + 2 * wi + (e & 1)] = s_tab[i * TS + (e < 4 ? 16 + e : e - 4)];
                 }
             }
             if (w == wi) {
@@ -325,7 +403,14 @@ __global__ void __launch_bounds__(256, 1) score_o1n_kernel(Net1nParams p) {
                 const double2 c23 = __ldcg(reinterpret_cast<const double2*>(gct + o + 16));
                 cn[0] = c01.x; cn[1] = c01.y; cn[2] = c23.x; cn[3] = c23.y;
             }
-            phyfoo::n1n_update<MC>(reg, s_tab, s_exp, r, cobs, upd, acc);
+            constexpr int RLC = (8 + 2 * MC + 3) & ~3;
+            int rr[RLC];
+#pragma unroll
+            for (int j = 0; j < RLC / 4; ++j) {
+                const int4 v = reinterpret_cast<const int4*>(r)[j];
+                rr[4 * j] = v.x; rr[4 * j + 1] = v.y; rr[4 * j + 2] = v.z; rr[4 * j + 3] = v.w;
+            }
+            phyfoo::n1n_update<MC>(reg, s_tab, s_exp, rr, cobs, upd, acc);
             if ((step & 63) == 63) phyfoo::n1n_fold(acc);
             __syncwarp();
         }

@@ -1278,7 +1278,7 @@ static int launch_net1n(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model*
     const int n_strands = strands == 2 ? 2 : 1;
     const long long n_items = (long long)n_windows * n_strands;
     const ModelHost::N1nLayout L = h.n1n_layout();
-    const size_t fixed = ((size_t)h.W * h.I * 32 + 64) * sizeof(double) + (size_t)m->prog1n_len * sizeof(int) + 16;
+    const size_t fixed = ((size_t)h.W * h.I * ModelHost::N1N_TAB_STRIDE + 64) * sizeof(double) + (size_t)m->prog1n_len * sizeof(int) + 16;
     const size_t per_warp = (size_t)L.region * sizeof(double);
     const size_t budget = std::min<size_t>(ctx->smem_optin, 227 * 1024);
     if (fixed + per_warp > budget) return 1;

@@ -359,7 +359,7 @@ int run_o1n(const ModelHost& m, const std::vector<int>& prog, const uint8_t* cod
     const int n_steps = prog[0], RL = prog[2];
     const int* leaf_begin = prog.data() + 4;
     const int* leaf_species = leaf_begin + I + 1;
-    const int* rec = leaf_species + S;
+    const int* rec = prog.data() + prog[3];
     const ModelHost::N1nLayout Lt = m.n1n_layout();
     std::vector<double> tab, leaf_tab;
     m.tables1n(tab);
@@ -388,7 +388,7 @@ int run_o1n(const ModelHost& m, const std::vector<int>& prog, const uint8_t* cod
         }
         for (int i = 0; i < I; ++i)
             for (int e = 0; e < 8; ++e)
-                region[Lt.ab0 + i * 64 + (e >> 1) * 16 + 2 * wslot + (e & 1)] = tab[(size_t)i * 32 + (e < 4 ? 16 + e : e - 4)];
+                region[Lt.ab0 + i * 64 + (e >> 1) * 16 + 2 * wslot + (e & 1)] = tab[(size_t)i * ModelHost::N1N_TAB_STRIDE + (e < 4 ? 16 + e : e - 4)];
         bool upd = false, conv = false; int k = 0; double old = 0.0;
         for (;;) {
             N1nAcc acc[4];
