@@ -356,23 +356,25 @@ struct ModelHost {
     // ---- node-per-thread kernel (net1n.cuh) ----
     // One thread updates one hidden node (all four symbols); a window is worked on by 4 node slots, a warp holds 8 windows
     // (lane = 8 slot + window).  Everything a node update touches is addressed through a precomputed record of offsets, in
-    // doubles, into the warp's region of shared memory (rows of 32 doubles = the 4 q of a node for 8 windows, AB rows of 64):
-    //   region: q rows [W*I] | zero row | one-hot row | trash row | AB rows [2*I] | trash AB row
-    // Record layout (n1n_rec_len(MC) ints): qself, qpar, qnself, qnpar, abself, abnext, tabnext, flags (1 live, 2 last
-    // position), then per child (qchild, abchild).  AB rows: the context sums a node update at position t needs of the
-    // SAME node at t-1, A(a) = sum_c q_prev(c) Ld[c][a] and B(a) = sum_c q_prev(c) Lo[c][a]; they are produced by the
-    // update of (t-1, i) and read by (t, i) and by (t, parent(i)); two rows per node (position parity) suffice because both
-    // readers precede (t+1, i) ... and the update of the last position produces the rows of position 0 (virtual one-hot
-    // predecessor) for the next sweep.
-    static int n1n_rec_len(int MC) { return (8 + 2 * MC + 3) & ~3; }
+    // doubles, into the warp's region of shared memory (rows of 32 doubles = four values of a node for 8 windows):
+    //   region: q rows [W*I] | zero row | one-hot row | AB rows [I] (64 doubles each) | message rows [I]
+    // Record layout (n1n_rec_len(MC) ints): qself, qpar, qnself, qnpar, ab, msg, tabnext, flags (1 live, 2 last position,
+    // 4 message from the node's own new q: W = 1), then one message row per child (the zero row for a null entry).
+    // AB row of node i: the context sums the update of (t, i) needs of the SAME node at t-1, A(a) = sum_c q_prev(c) Ld[c][a]
+    // and B(a) = sum_c q_prev(c) Lo[c][a]; produced by the update of (t-1, i) -- in place, the row's only reader is (t, i)
+    // itself -- and by the update of the last position for position 0 of the next sweep (virtual one-hot predecessor).
+    // Message row of node j: what j contributes to the exponents of its tree parent at the NEXT position,
+    // msg(a) = q_j(a) A_j(a) + sum_{a' != a} q_j(a') B_j(a') with the old q of (t+1, j) and the new context sums; produced by
+    // the update of (t, j), read by (t+1, parent(j)), which runs before (t+1, j) overwrites it.
+    static int n1n_rec_len(int MC) { return (8 + MC + 3) & ~3; }
     // a node's 32 table entries are padded to 34 doubles: the four node slots of a warp read the same entry of four
     // different nodes at once, and with a row of 256 bytes these would all sit in the same banks
     static const int N1N_TAB_STRIDE = 34;
-    struct N1nLayout { int q0, zero_row, onehot_row, trash_row, ab0, trash_ab, region; };
+    struct N1nLayout { int q0, zero_row, onehot_row, ab0, msg0, region; };
     N1nLayout n1n_layout() const {
         N1nLayout L;
-        L.q0 = 0; L.zero_row = W * I * 32; L.onehot_row = L.zero_row + 32; L.trash_row = L.onehot_row + 32;
-        L.ab0 = L.trash_row + 32; L.trash_ab = L.ab0 + 2 * I * 64; L.region = L.trash_ab + 64;
+        L.q0 = 0; L.zero_row = W * I * 32; L.onehot_row = L.zero_row + 32;
+        L.ab0 = L.onehot_row + 32; L.msg0 = L.ab0 + I * 64; L.region = L.msg0 + I * 32;
         return L;
     }
     // tables of the internal nodes for the kernel's shared memory: [W][I][34] = Lo[ctx][b] | Ld[ctx][b] | 2 pad (root: log
@@ -451,31 +453,24 @@ struct ModelHost {
         while (prog.size() & 3) prog.push_back(0);
         prog[3] = (int)prog.size();
         auto qrow = [&](int t, int i) { return L.q0 + (t * I + i) * 32; };
-        auto abrow = [&](int t, int i) { return L.ab0 + ((t & 1) * I + i) * 64; };     // position 0 lives in parity 0
         for (int s = 0; s < n_steps; ++s)
             for (int sl = 0; sl < 4; ++sl) {
                 std::vector<int> r(RL, 0);
                 const int id = sched[s * 4 + sl];
-                if (id < 0) {
-                    r[0] = L.trash_row; r[1] = L.onehot_row; r[2] = L.trash_row; r[3] = L.onehot_row;
-                    r[4] = L.trash_ab; r[5] = L.trash_ab; r[6] = 0; r[7] = 0;
-                    for (int j = 0; j < MC; ++j) { r[8 + 2 * j] = L.zero_row; r[9 + 2 * j] = L.trash_ab; }
-                } else {
+                if (id >= 0) {
                     const int t = id / I, i = id % I, p = par_internal[i];
                     const bool last = t + 1 == W;
                     r[0] = qrow(t, i);
                     r[1] = p >= 0 ? qrow(t, p) : L.onehot_row;
-                    r[2] = last ? r[0] : qrow(t + 1, i);
+                    r[2] = qrow(last ? 0 : t + 1, i);          // the last position: the message for position 0 needs q(0, i)
                     r[3] = (last || p < 0) ? r[1] : qrow(t + 1, p);
-                    r[4] = abrow(t, i);
-                    r[5] = abrow(last ? 0 : t + 1, i);
+                    r[4] = L.ab0 + i * 64;
+                    r[5] = L.msg0 + i * 32;
                     r[6] = (((last ? 0 : t + 1) * I) + i) * N1N_TAB_STRIDE;
-                    r[7] = 1 | (last ? 2 : 0);
+                    r[7] = 1 | (last ? 2 : 0) | (W == 1 ? 4 : 0);
                     for (int j = 0; j < MC; ++j) {
                         const bool has = ichild_begin[i] + j < ichild_begin[i + 1];
-                        const int ci = has ? ichild[ichild_begin[i] + j] : i;
-                        r[8 + 2 * j] = has ? qrow(t, ci) : L.zero_row;
-                        r[9 + 2 * j] = abrow(t, ci);
+                        r[8 + j] = has ? L.msg0 + ichild[ichild_begin[i] + j] * 32 : L.zero_row;
                     }
                 }
                 prog.insert(prog.end(), r.begin(), r.end());

@@ -158,14 +158,26 @@ N1N_HD double n1n_free_energy(const N1nAcc& acc) {
     return (acc.Fq - acc.Fslow) - lz;
 }
 
+// message of a node to its tree parent: msg(a) = q(a) A(a) + sum_{a' != a} q(a') B(a')
+N1N_HD void n1n_message(const double (&q)[4], const double (&A)[4], const double (&B)[4], double (&msg)[4]) {
+    double w[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) w[a] = q[a] * B[a];
+    const double sw = n1n_sum4(w);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) msg[a] = fma(q[a], A[a], sw - w[a]);
+}
+
 // One node update.  reg: this thread's window in the warp's region; tab: tables [W][I][34] (Lo | Ld | pad); exptab: 2^(j/64);
 // r: the record (model_host.hpp::node_program); cobs: observed-leaf sums of this node; upd == false: the pass at the uniform
-// start (exponents forced to 0).  All reads come before the two row stores; the caller synchronises the warp afterwards.
+// start (exponents forced to 0).  All reads come before the row stores; the caller synchronises the warp afterwards.  A slot
+// without a node in this step (record flags 0) does nothing.
 template <int MC>
 N1N_HD void n1n_update(double* reg, const double* tab, const double* exptab, const int* r, const double (&cobs)[4],
                        bool upd, N1nAcc& acc) {
     const int flags = r[7];
-    const bool live = (flags & 1) != 0, last = (flags & 2) != 0;
+    if (!(flags & 1)) return;
+    const bool last = (flags & 2) != 0;
     double qp[4], A[4], B[4], own[4], ch[4], nx[4];
     n1n_ld4(reg + r[1], qp);
     n1n_ld4(reg + r[4], A);
@@ -173,21 +185,14 @@ N1N_HD void n1n_update(double* reg, const double* tab, const double* exptab, con
     const double totp = n1n_sum4(qp);
 #pragma unroll
     for (int a = 0; a < 4; ++a) own[a] = fma(qp[a], A[a], (totp - qp[a]) * B[a]);
-    // internal children: null entries read the all-zero q row
-    {
-        double chv[4] = {0.0, 0.0, 0.0, 0.0}, wu[4] = {0.0, 0.0, 0.0, 0.0};
+    // internal children: their messages (null entries read the all-zero row)
+    n1n_ld4(reg + r[8], ch);
 #pragma unroll
-        for (int j = 0; j < MC; ++j) {
-            double qc[4], Aj[4], Bj[4];
-            n1n_ld4(reg + r[8 + 2 * j], qc);
-            n1n_ld4(reg + r[9 + 2 * j], Aj);
-            n1n_ld4(reg + r[9 + 2 * j] + 32, Bj);
+    for (int j = 1; j < MC; ++j) {
+        double mj[4];
+        n1n_ld4(reg + r[8 + j], mj);
 #pragma unroll
-            for (int a = 0; a < 4; ++a) { wu[a] = fma(qc[a], Bj[a], wu[a]); chv[a] = fma(qc[a], Aj[a], chv[a]); }
-        }
-        const double sw = n1n_sum4(wu);
-#pragma unroll
-        for (int a = 0; a < 4; ++a) ch[a] = chv[a] + (sw - wu[a]);
+        for (int a = 0; a < 4; ++a) ch[a] += mj[a];
     }
     // the same node at the next position (old values); its tables also serve the context sums produced below
     double T[32];
@@ -196,9 +201,10 @@ N1N_HD void n1n_update(double* reg, const double* tab, const double* exptab, con
 #pragma unroll
         for (int j = 0; j < 16; ++j) { const N1nD2 v = *reinterpret_cast<const N1nD2*>(tp + 2 * j); T[2 * j] = v.x; T[2 * j + 1] = v.y; }
     }
+    double qx[4];
+    n1n_ld4(reg + r[2], qx);
     {
-        double qx[4], qpn[4], m[4];
-        n1n_ld4(reg + r[2], qx);
+        double qpn[4], m[4];
         n1n_ld4(reg + r[3], qpn);
         const double totn = n1n_sum4(qpn);
 #pragma unroll
@@ -220,44 +226,62 @@ N1N_HD void n1n_update(double* reg, const double* tab, const double* exptab, con
     }
     n1n_exp4(ex, exptab, e);                                                        // MeanFieldForBayesNet.java:192, no max shift
     const double z = n1n_sum4(e);                                                   // :195-198
+    // The reciprocal of z is a chain of dependent operations; what is linear in q is computed on the unnormalised
+    // exponentials next to it and scaled afterwards: the node's free-energy terms and the context sums of the same node
+    // at the next position (the last position produces those of position 0: one-hot, scale 1).
+    double fu = e[0] * g[0];
+    fu = fma(e[1], g[1], fu); fu = fma(e[2], g[2], fu); fu = fma(e[3], g[3], fu);
+    double An[4], Bn[4];
+    {
+        double ea[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) ea[c] = last ? (c == 0 ? 1.0 : 0.0) : e[c];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            double u = ea[0] * T[a], v = ea[0] * T[16 + a];
+#pragma unroll
+            for (int c = 1; c < 4; ++c) { u = fma(ea[c], T[c * 4 + a], u); v = fma(ea[c], T[16 + c * 4 + a], v); }
+            Bn[a] = u; An[a] = v;
+        }
+    }
+    // message to the tree parent at the next position, with the old q of (t+1, i) -- of (0, i) at the last position --
+    // and the new context sums; unnormalised like them
+    double msg[4];
+    n1n_message(qx, An, Bn, msg);
     // z is a normal number well inside the exponent range unless the exponents were extreme: one test for the reciprocal
     // and for the (mantissa, exponent) accumulation of log z
     const int zhi = n1n_hi(z);
     const unsigned zef = (unsigned)zhi >> 20;
     const bool znormal = zef - 24u < 2000u;
-    double rz;
-    if (znormal) {
-        rz = n1n_rcp_normal(z);
-        if (live) { acc.E += (int)zef - 1023; acc.M *= n1n_with_hi(z, (zhi & 0x000fffff) | 0x3ff00000); }
-    } else {
-        const N1nZR r = n1n_z_rare(z);
-        rz = r.rz;
-        if (live) acc.Fslow += r.lz;
+    double rz = n1n_rcp_normal(z);
+    if (znormal) { acc.E += (int)zef - 1023; acc.M *= n1n_with_hi(z, (zhi & 0x000fffff) | 0x3ff00000); }
+    else {
+        const N1nZR rr = n1n_z_rare(z);
+        rz = rr.rz;
+        acc.Fslow += rr.lz;
     }
+    const double sc = last ? 1.0 : rz;
 #pragma unroll
-    for (int a = 0; a < 4; ++a) qn[a] = e[a] * rz;                                  // :199-201
-    {
-        double f = qn[0] * g[0];
-        f = fma(qn[1], g[1], f); f = fma(qn[2], g[2], f); f = fma(qn[3], g[3], f);
-        acc.Fq += live ? f : 0.0;
-    }
-    // context sums of the same node at the next position (the last position produces those of position 0: one-hot)
-    double An[4], Bn[4];
-    {
-        double qa[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) qa[c] = last ? (c == 0 ? 1.0 : 0.0) : qn[c];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            double u = qa[0] * T[a], v = qa[0] * T[16 + a];
-#pragma unroll
-            for (int c = 1; c < 4; ++c) { u = fma(qa[c], T[c * 4 + a], u); v = fma(qa[c], T[16 + c * 4 + a], v); }
-            Bn[a] = u; An[a] = v;
-        }
-    }
+    for (int a = 0; a < 4; ++a) { qn[a] = e[a] * rz; An[a] *= sc; Bn[a] *= sc; msg[a] *= sc; }   // :199-201
+    acc.Fq = fma(fu, rz, acc.Fq);
+    if (flags & 4) n1n_message(qn, An, Bn, msg);        // a motif of a single position: the message carries the node's own new q
     n1n_st4(reg + r[0], qn);
-    n1n_st4(reg + r[5], An);
-    n1n_st4(reg + r[5] + 32, Bn);
+    n1n_st4(reg + r[4], An);
+    n1n_st4(reg + r[4] + 32, Bn);
+    n1n_st4(reg + r[5], msg);
+}
+
+// window set-up of the rows that do not come out of a node update: context sums of position 0 (the virtual predecessor is
+// the one-hot (1, 0, 0, 0): row 0 of the tables) and the message of the uniform start to the parent at position 0
+N1N_HD void n1n_setup_node(double* reg, const double* tab, int ab_row, int msg_row, int tab_row) {
+    double A[4], B[4], msg[4];
+    const double q0[4] = {0.25, 0.25, 0.25, 0.25};
+#pragma unroll
+    for (int a = 0; a < 4; ++a) { B[a] = tab[tab_row + a]; A[a] = tab[tab_row + 16 + a]; }
+    n1n_message(q0, A, B, msg);
+    n1n_st4(reg + ab_row, A);
+    n1n_st4(reg + ab_row + 32, B);
+    n1n_st4(reg + msg_row, msg);
 }
 
 }  // namespace phyfoo
@@ -278,7 +302,7 @@ struct Net1nParams {
     unsigned long long* counters;        // [0] work counter, [1] sweep sum
     int max_sweeps, min_sweeps; double tol;
     double* gc;                          // observed-leaf sums: one region of `gc_region` doubles per warp of the grid
-    int region, gc_region, ab0, zero_row, onehot_row;
+    int region, gc_region, ab0, msg0, zero_row, onehot_row;
     int check_gaps;                      // 0: the data set has no unobserved symbol at all
     int* fb_count; int64_t* fb_col0; uint8_t* fb_strand; int64_t* fb_dst;   // windows with gaps, for the net1w.cuh kernel
 };
@@ -372,11 +396,9 @@ __global__ void __launch_bounds__(256, 1) score_o1n_kernel(Net1nParams p) {
                     gcw[o] = c[0]; gcw[o + 1] = c[1]; gcw[o + 16] = c[2]; gcw[o + 17] = c[3];
                     regw[o] = 0.25; regw[o + 1] = 0.25; regw[o + 16] = 0.25; regw[o + 17] = 0.25;
                 }
-                // context sums of position 0: the virtual predecessor is the one-hot (1, 0, 0, 0)
-                for (int idx = lane; idx < I * 8; idx += 32) {
-                    const int i = idx >> 3, e = idx & 7;
-                    regw[p.ab0 + i * 64 + (e >> 1) * 16 + 2 * wi + (e & 1)] = s_tab[i * TS + (e < 4 ? 16 + e : e - 4)];
-                }
+                // context sums and messages of position 0
+                for (int i = lane; i < I; i += 32)
+                    phyfoo::n1n_setup_node(regw + 2 * wi, s_tab, p.ab0 + i * 64, p.msg0 + i * 32, i * TS);
             }
             if (w == wi) {
                 if (it >= 0) { item = it; k = 0; conv = false; upd = false; need = false; }
@@ -388,31 +410,41 @@ __global__ void __launch_bounds__(256, 1) score_o1n_kernel(Net1nParams p) {
 
         // ---- one sweep (or the pass at the uniform start)
         phyfoo::N1nAcc acc; acc.Fq = 0.0; acc.M = 1.0; acc.E = 0; acc.Fslow = 0.0;
+        // the record of the next step and its observed-leaf sums (L2) are fetched a step ahead
+        constexpr int RLC = (8 + MC + 3) & ~3;
         const int* r = s_rec + slot * RL;
+        int rr[RLC];
+#pragma unroll
+        for (int j = 0; j < RLC / 4; ++j) {
+            const int4 v = reinterpret_cast<const int4*>(r)[j];
+            rr[4 * j] = v.x; rr[4 * j + 1] = v.y; rr[4 * j + 2] = v.z; rr[4 * j + 3] = v.w;
+        }
         double cn[4];
         {
-            const double2 c01 = __ldcg(reinterpret_cast<const double2*>(gct + r[0]));
-            const double2 c23 = __ldcg(reinterpret_cast<const double2*>(gct + r[0] + 16));
+            const double2 c01 = __ldcg(reinterpret_cast<const double2*>(gct + rr[0]));
+            const double2 c23 = __ldcg(reinterpret_cast<const double2*>(gct + rr[0] + 16));
             cn[0] = c01.x; cn[1] = c01.y; cn[2] = c23.x; cn[3] = c23.y;
         }
-        for (int step = 0; step < n_steps; ++step, r += 4 * RL) {
+        for (int step = 0; step < n_steps; ++step) {
             const double cobs[4] = {cn[0], cn[1], cn[2], cn[3]};
-            if (step + 1 < n_steps) {
-                const int o = r[4 * RL];
-                const double2 c01 = __ldcg(reinterpret_cast<const double2*>(gct + o));
-                const double2 c23 = __ldcg(reinterpret_cast<const double2*>(gct + o + 16));
-                cn[0] = c01.x; cn[1] = c01.y; cn[2] = c23.x; cn[3] = c23.y;
-            }
-            constexpr int RLC = (8 + 2 * MC + 3) & ~3;
-            int rr[RLC];
+            r += 4 * RL;
+            int rn[RLC];
+            const int4* rp = reinterpret_cast<const int4*>(step + 1 < n_steps ? r : r - 4 * RL);
 #pragma unroll
             for (int j = 0; j < RLC / 4; ++j) {
-                const int4 v = reinterpret_cast<const int4*>(r)[j];
-                rr[4 * j] = v.x; rr[4 * j + 1] = v.y; rr[4 * j + 2] = v.z; rr[4 * j + 3] = v.w;
+                const int4 v = rp[j];
+                rn[4 * j] = v.x; rn[4 * j + 1] = v.y; rn[4 * j + 2] = v.z; rn[4 * j + 3] = v.w;
+            }
+            {
+                const double2 c01 = __ldcg(reinterpret_cast<const double2*>(gct + rn[0]));
+                const double2 c23 = __ldcg(reinterpret_cast<const double2*>(gct + rn[0] + 16));
+                cn[0] = c01.x; cn[1] = c01.y; cn[2] = c23.x; cn[3] = c23.y;
             }
             phyfoo::n1n_update<MC>(reg, s_tab, s_exp, rr, cobs, upd, acc);
             if ((step & 63) == 63) phyfoo::n1n_fold(acc);
             __syncwarp();
+#pragma unroll
+            for (int j = 0; j < RLC; ++j) rr[j] = rn[j];
         }
         double F = phyfoo::n1n_free_energy(acc);
         F += __shfl_xor_sync(full, F, 8);

@@ -1310,7 +1310,7 @@ static int launch_net1n(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model*
     p.counters = ctx->counters.as<unsigned long long>() + 2 * counter_slot;
     p.max_sweeps = h.max_sweeps; p.min_sweeps = h.min_sweeps; p.tol = h.tol;
     p.gc = ctx->o1n_cache.as<double>();
-    p.region = L.region; p.gc_region = L.region; p.ab0 = L.ab0; p.zero_row = L.zero_row; p.onehot_row = L.onehot_row;
+    p.region = L.region; p.gc_region = L.region; p.ab0 = L.ab0; p.msg0 = L.msg0; p.zero_row = L.zero_row; p.onehot_row = L.onehot_row;
     p.check_gaps = check ? 1 : 0;
     p.fb_count = fb_count;
     p.fb_col0 = check ? (int64_t*)((char*)ctx->o1n_fb.p + 16) : nullptr;
