@@ -249,8 +249,12 @@ int phyfoo_set_option(phyfoo_ctx* ctx, const char* name, int64_t value);
  * node i of sweep k at step 2 k + depth(i), so nodes of alternating depth of consecutive sweeps run side by side on their
  * own lanes -- when the tree has 2..8 internal nodes and at most four per depth parity; 0 = four lanes per tree walking
  * the nodes one by one.  Same bits either way. */
-/* "order1_kernel": 1 (default) = wavefront kernel (16 lanes per window, list-scheduled node updates), 0 = one quad of
- * lanes per window walking the nodes one by one.  Same fixed-point iteration; free energies agree to re-association. */
+/* "order1_kernel": 2 (default) = one thread per hidden node (all four symbols), 4 node slots x 8 windows per warp, windows
+ * with an unobserved leaf through a device-side list to kernel 1; 1 = wavefront kernel (16 lanes per window, list-scheduled
+ * node updates); 0 = one quad of lanes per window walking the nodes one by one.  Same fixed-point iteration; free energies
+ * agree to re-association.
+ * "order1_qglobal": kernel 2 keeps the q of a window's hidden nodes in shared memory (0) or in global memory behind L1 with
+ * n warps per SM (1..8), which doubles the windows in flight for trees like C3's; -1 (default) chooses. */
 /* Device time of every kernel the most recent call launched (CUDA events on the library's stream), in launch order:
  * returns the number of entries written (<= max_entries) or a negative error; names are static strings. */
 int phyfoo_last_kernel_times(phyfoo_ctx* ctx, int32_t max_entries, const char** names_out, float* ms_out);

@@ -357,7 +357,9 @@ struct ModelHost {
     // One thread updates one hidden node (all four symbols); a window is worked on by 4 node slots, a warp holds 8 windows
     // (lane = 8 slot + window).  Everything a node update touches is addressed through a precomputed record of offsets, in
     // doubles, into the warp's region of shared memory (rows of 32 doubles = four values of a node for 8 windows):
-    //   region: q rows [W*I] | zero row | one-hot row | AB rows [I] (64 doubles each) | message rows [I]
+    //   region: zero row | AB rows [I] (64 doubles each) | message rows [I] || one-hot row | q rows [W*I]
+    // (the part behind || may live in global memory instead -- behind L1 -- which leaves room for twice the warps per SM;
+    // offsets are the same in both placements)
     // Record layout (n1n_rec_len(MC) ints): qself, qpar, qnself, qnpar, ab, msg, tabnext, flags (1 live, 2 last position,
     // 4 message from the node's own new q: W = 1), then one message row per child (the zero row for a null entry).
     // AB row of node i: the context sums the update of (t, i) needs of the SAME node at t-1, A(a) = sum_c q_prev(c) Ld[c][a]
@@ -370,11 +372,11 @@ struct ModelHost {
     // a node's 32 table entries are padded to 34 doubles: the four node slots of a warp read the same entry of four
     // different nodes at once, and with a row of 256 bytes these would all sit in the same banks
     static const int N1N_TAB_STRIDE = 34;
-    struct N1nLayout { int q0, zero_row, onehot_row, ab0, msg0, region; };
+    struct N1nLayout { int q0, zero_row, onehot_row, ab0, msg0, sregion, region; };
     N1nLayout n1n_layout() const {
         N1nLayout L;
-        L.q0 = 0; L.zero_row = W * I * 32; L.onehot_row = L.zero_row + 32;
-        L.ab0 = L.onehot_row + 32; L.msg0 = L.ab0 + I * 64; L.region = L.msg0 + I * 32;
+        L.zero_row = 0; L.ab0 = 32; L.msg0 = L.ab0 + I * 64; L.sregion = L.msg0 + I * 32;
+        L.onehot_row = L.sregion; L.q0 = L.onehot_row + 32; L.region = L.q0 + W * I * 32;
         return L;
     }
     // tables of the internal nodes for the kernel's shared memory: [W][I][34] = Lo[ctx][b] | Ld[ctx][b] | 2 pad (root: log

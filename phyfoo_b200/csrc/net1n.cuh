@@ -168,18 +168,21 @@ N1N_HD void n1n_message(const double (&q)[4], const double (&A)[4], const double
     for (int a = 0; a < 4; ++a) msg[a] = fma(q[a], A[a], sw - w[a]);
 }
 
-// One node update.  reg: this thread's window in the warp's region; tab: tables [W][I][34] (Lo | Ld | pad); exptab: 2^(j/64);
+// One node update.  reg: this thread's window in the warp's region (AB and message rows), qreg: the same for the q rows
+// (the same pointer when the whole region is in shared memory); tab: tables [W][I][34] (Lo | Ld | pad); exptab: 2^(j/64);
 // r: the record (model_host.hpp::node_program); cobs: observed-leaf sums of this node; upd == false: the pass at the uniform
 // start (exponents forced to 0).  All reads come before the row stores; the caller synchronises the warp afterwards.  A slot
 // without a node in this step (record flags 0) does nothing.
+// qx, qpn: the (old) q of the same node and of its parent at the next position, rows r[2] and r[3] -- no update of the
+// previous step can have written them, so the caller loads them a step ahead.
 template <int MC>
-N1N_HD void n1n_update(double* reg, const double* tab, const double* exptab, const int* r, const double (&cobs)[4],
-                       bool upd, N1nAcc& acc) {
+N1N_HD void n1n_update(double* qreg, double* reg, const double* tab, const double* exptab, const int* r, const double (&cobs)[4],
+                       const double (&qx)[4], const double (&qpn)[4], bool upd, N1nAcc& acc) {
     const int flags = r[7];
     if (!(flags & 1)) return;
     const bool last = (flags & 2) != 0;
     double qp[4], A[4], B[4], own[4], ch[4], nx[4];
-    n1n_ld4(reg + r[1], qp);
+    n1n_ld4(qreg + r[1], qp);
     n1n_ld4(reg + r[4], A);
     n1n_ld4(reg + r[4] + 32, B);
     const double totp = n1n_sum4(qp);
@@ -201,11 +204,8 @@ N1N_HD void n1n_update(double* reg, const double* tab, const double* exptab, con
 #pragma unroll
         for (int j = 0; j < 16; ++j) { const N1nD2 v = *reinterpret_cast<const N1nD2*>(tp + 2 * j); T[2 * j] = v.x; T[2 * j + 1] = v.y; }
     }
-    double qx[4];
-    n1n_ld4(reg + r[2], qx);
     {
-        double qpn[4], m[4];
-        n1n_ld4(reg + r[3], qpn);
+        double m[4];
         const double totn = n1n_sum4(qpn);
 #pragma unroll
         for (int c = 0; c < 4; ++c) m[c] = totn - qpn[c];
@@ -265,7 +265,7 @@ N1N_HD void n1n_update(double* reg, const double* tab, const double* exptab, con
     for (int a = 0; a < 4; ++a) { qn[a] = e[a] * rz; An[a] *= sc; Bn[a] *= sc; msg[a] *= sc; }   // :199-201
     acc.Fq = fma(fu, rz, acc.Fq);
     if (flags & 4) n1n_message(qn, An, Bn, msg);        // a motif of a single position: the message carries the node's own new q
-    n1n_st4(reg + r[0], qn);
+    n1n_st4(qreg + r[0], qn);
     n1n_st4(reg + r[4], An);
     n1n_st4(reg + r[4] + 32, Bn);
     n1n_st4(reg + r[5], msg);
@@ -301,13 +301,16 @@ struct Net1nParams {
     double* out; int32_t* sweeps;
     unsigned long long* counters;        // [0] work counter, [1] sweep sum
     int max_sweeps, min_sweeps; double tol;
-    double* gc;                          // observed-leaf sums: one region of `gc_region` doubles per warp of the grid
-    int region, gc_region, ab0, msg0, zero_row, onehot_row;
+    double* gc;                          // observed-leaf sums: one region of `region` doubles per warp of the grid
+    double* gq;                          // q rows in global memory (QG variant): one region per warp of the grid
+    int region, sregion, ab0, msg0, q0, onehot_row;
     int check_gaps;                      // 0: the data set has no unobserved symbol at all
     int* fb_count; int64_t* fb_col0; uint8_t* fb_strand; int64_t* fb_dst;   // windows with gaps, for the net1w.cuh kernel
 };
 
-template <int MC>
+// QG: the q rows live in global memory (read through L1, written through to L2) and shared memory holds the AB and
+// message rows only -- twice the warps per SM, i.e. two per scheduler
+template <int MC, bool QG>
 __global__ void __launch_bounds__(256, 1) score_o1n_kernel(Net1nParams p) {
     extern __shared__ double smem[];
     const int tid = threadIdx.x, T = blockDim.x, NW = T >> 5;
@@ -315,14 +318,17 @@ __global__ void __launch_bounds__(256, 1) score_o1n_kernel(Net1nParams p) {
     const int TS = phyfoo::ModelHost::N1N_TAB_STRIDE;
     double* s_tab = smem;                                   // [W][I][34]
     double* s_exp = s_tab + (size_t)W * I * TS;             // [64]
-    double* s_reg = s_exp + 64;                             // [NW][region]
-    int* s_prog = (int*)(s_reg + (size_t)NW * p.region);
+    double* s_reg = s_exp + 64;                             // [NW][region] (QG: [NW][sregion])
+    const int sreg = QG ? p.sregion : p.region;
+    int* s_prog = (int*)(s_reg + (size_t)NW * sreg);
     for (int i = tid; i < W * I * TS; i += T) s_tab[i] = p.tab[i];
     for (int i = tid; i < 64; i += T) s_exp[i] = phyfoo::d_phy_exp_tab[i];
-    for (int i = tid; i < NW * p.region; i += T) s_reg[i] = 0.0;
+    for (int i = tid; i < NW * sreg; i += T) s_reg[i] = 0.0;
     for (int i = tid; i < p.prog_len; i += T) s_prog[i] = p.prog[i];
+    double* const q_all = QG ? p.gq + (size_t)blockIdx.x * NW * p.region : s_reg;      // q rows of the block's warps
+    if (QG) for (int i = tid; i < NW * p.region; i += T) q_all[i] = 0.0;
     __syncthreads();
-    for (int i = tid; i < NW * 8; i += T) s_reg[(size_t)(i >> 3) * p.region + p.onehot_row + 2 * (i & 7)] = 1.0;
+    for (int i = tid; i < NW * 8; i += T) q_all[(size_t)(i >> 3) * (QG ? p.region : sreg) + p.onehot_row + 2 * (i & 7)] = 1.0;
     __syncthreads();
     const int n_steps = s_prog[0], RL = s_prog[2];
     const int* leaf_begin = s_prog + 4;
@@ -332,9 +338,11 @@ __global__ void __launch_bounds__(256, 1) score_o1n_kernel(Net1nParams p) {
     const int lane = tid & 31, warp = tid >> 5;
     const int w = lane & 7, slot = lane >> 3;
     const unsigned full = 0xffffffffu;
-    double* regw = s_reg + (size_t)warp * p.region;         // the warp's region
+    double* regw = s_reg + (size_t)warp * sreg;             // the warp's region
     double* reg = regw + 2 * w;                             // this thread's window
-    double* gcw = p.gc + (size_t)(blockIdx.x * NW + warp) * p.gc_region;
+    double* qregw = q_all + (size_t)warp * (QG ? p.region : sreg);
+    double* qreg = qregw + 2 * w;
+    double* gcw = p.gc + (size_t)(blockIdx.x * NW + warp) * p.region;
     const double* gct = gcw + 2 * w;
     const long long n_items = (long long)p.n_windows * p.n_strands;
     const unsigned gap_mask = S >= 32 ? 0xffffffffu : (1u << S) - 1u;
@@ -392,9 +400,9 @@ __global__ void __launch_bounds__(256, 1) score_o1n_kernel(Net1nParams p) {
 #pragma unroll
                         for (int a = 0; a < 4; ++a) c[a] += a == x ? diag : off;
                     }
-                    const int o = idx * 32 + 2 * wi;
+                    const int o = p.q0 + idx * 32 + 2 * wi;
                     gcw[o] = c[0]; gcw[o + 1] = c[1]; gcw[o + 16] = c[2]; gcw[o + 17] = c[3];
-                    regw[o] = 0.25; regw[o + 1] = 0.25; regw[o + 16] = 0.25; regw[o + 17] = 0.25;
+                    qregw[o] = 0.25; qregw[o + 1] = 0.25; qregw[o + 16] = 0.25; qregw[o + 17] = 0.25;
                 }
                 // context sums and messages of position 0
                 for (int i = lane; i < I; i += 32)
@@ -425,8 +433,12 @@ __global__ void __launch_bounds__(256, 1) score_o1n_kernel(Net1nParams p) {
             const double2 c23 = __ldcg(reinterpret_cast<const double2*>(gct + rr[0] + 16));
             cn[0] = c01.x; cn[1] = c01.y; cn[2] = c23.x; cn[3] = c23.y;
         }
+        double qxn[4], qpnn[4];
+        phyfoo::n1n_ld4(qreg + rr[2], qxn);
+        phyfoo::n1n_ld4(qreg + rr[3], qpnn);
         for (int step = 0; step < n_steps; ++step) {
             const double cobs[4] = {cn[0], cn[1], cn[2], cn[3]};
+            const double qx[4] = {qxn[0], qxn[1], qxn[2], qxn[3]}, qpn[4] = {qpnn[0], qpnn[1], qpnn[2], qpnn[3]};
             r += 4 * RL;
             int rn[RLC];
             const int4* rp = reinterpret_cast<const int4*>(step + 1 < n_steps ? r : r - 4 * RL);
@@ -440,7 +452,9 @@ __global__ void __launch_bounds__(256, 1) score_o1n_kernel(Net1nParams p) {
                 const double2 c23 = __ldcg(reinterpret_cast<const double2*>(gct + rn[0] + 16));
                 cn[0] = c01.x; cn[1] = c01.y; cn[2] = c23.x; cn[3] = c23.y;
             }
-            phyfoo::n1n_update<MC>(reg, s_tab, s_exp, rr, cobs, upd, acc);
+            phyfoo::n1n_ld4(qreg + rn[2], qxn);
+            phyfoo::n1n_ld4(qreg + rn[3], qpnn);
+            phyfoo::n1n_update<MC>(qreg, reg, s_tab, s_exp, rr, cobs, qx, qpn, upd, acc);
             if ((step & 63) == 63) phyfoo::n1n_fold(acc);
             __syncwarp();
 #pragma unroll

@@ -78,6 +78,8 @@ struct phyfoo_ctx {
     int order1_kernel = 2;           // 0 = one quad per window (net1.cuh), 1 = wavefront, 16 lanes per window (net1w.cuh),
                                      // 2 = one thread per node (net1n.cuh; windows with gaps through the wavefront kernel)
     DevBuf memo_pending;             // fallback list of the pattern-table path
+    int order1_qglobal = -1;         // node-per-thread kernel: -1 = choose, 0 = q rows in shared memory, n > 0 = q rows in global memory
+                                     // behind L1 with n warps per SM (<= 8)
     DevBuf o1n_cache, o1n_fb;        // node-per-thread order-1 kernel: observed-leaf sums per warp; list of windows with gaps
     // per-kernel device times of the most recent call (CUDA events on the library's stream)
     struct KTime { const char* name; cudaEvent_t e0, e1; };
@@ -1279,16 +1281,26 @@ static int launch_net1n(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model*
     const long long n_items = (long long)n_windows * n_strands;
     const ModelHost::N1nLayout L = h.n1n_layout();
     const size_t fixed = ((size_t)h.W * h.I * ModelHost::N1N_TAB_STRIDE + 64) * sizeof(double) + (size_t)m->prog1n_len * sizeof(int) + 16;
-    const size_t per_warp = (size_t)L.region * sizeof(double);
     const size_t budget = std::min<size_t>(ctx->smem_optin, 227 * 1024);
+    // q rows in shared memory: as many warps per SM as fit (4 at C3).  q rows in global memory behind L1 (order1_qglobal):
+    // shared memory holds the AB and message rows only, 8 warps per SM (registers: ~200 x 256 threads)
+    // (measured on C3, 2000 alignments: shared memory, 4 warps 192 ms; global memory, 4 / 6 / 7 / 8 warps 263 / 198 / 164 / 153 ms:
+    // a lone warp per scheduler cannot hide its own latencies, two keep the fp64 pipe ~88 % busy)
+    int want_qg = ctx->order1_qglobal;
+    if (want_qg < 0) want_qg = (fixed + 8 * (size_t)L.region * sizeof(double) <= budget) ? 0 : 8;
+    const bool qg = want_qg != 0;
+    const size_t per_warp = (size_t)(qg ? L.sregion : L.region) * sizeof(double);
     if (fixed + per_warp > budget) return 1;
-    int nw = (int)std::min<size_t>(8, (budget - fixed) / per_warp);
+    int nw = (int)std::min<size_t>(qg ? want_qg : 8, (budget - fixed) / per_warp);
+    nw = std::max(1, std::min(nw, 8));
     const long long want_warps = (n_items + 7) / 8;
-    const void* fn = m->MC1n <= 1 ? (const void*)score_o1n_kernel<1> : m->MC1n == 2 ? (const void*)score_o1n_kernel<2> : (const void*)score_o1n_kernel<3>;
+    const void* fn = nullptr;
+    if (qg) fn = m->MC1n <= 1 ? (const void*)score_o1n_kernel<1, true> : m->MC1n == 2 ? (const void*)score_o1n_kernel<2, true> : (const void*)score_o1n_kernel<3, true>;
+    else fn = m->MC1n <= 1 ? (const void*)score_o1n_kernel<1, false> : m->MC1n == 2 ? (const void*)score_o1n_kernel<2, false> : (const void*)score_o1n_kernel<3, false>;
     const size_t smem = fixed + per_warp * nw;
     CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int blocks = (int)std::max<long long>(1, std::min<long long>((want_warps + nw - 1) / nw, ctx->sm_count));
-    const size_t cache_bytes = (size_t)blocks * nw * L.region * sizeof(double);
+    const size_t cache_bytes = (size_t)blocks * nw * L.region * sizeof(double) * (qg ? 2 : 1);
     const bool fresh = cache_bytes > ctx->o1n_cache.cap;
     CU(ctx->o1n_cache.ensure(cache_bytes));
     if (fresh) CU(cudaMemsetAsync(ctx->o1n_cache.p, 0, ctx->o1n_cache.cap, ctx->stream));   // idle slots read their (unused) rows
@@ -1310,7 +1322,8 @@ static int launch_net1n(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model*
     p.counters = ctx->counters.as<unsigned long long>() + 2 * counter_slot;
     p.max_sweeps = h.max_sweeps; p.min_sweeps = h.min_sweeps; p.tol = h.tol;
     p.gc = ctx->o1n_cache.as<double>();
-    p.region = L.region; p.gc_region = L.region; p.ab0 = L.ab0; p.msg0 = L.msg0; p.zero_row = L.zero_row; p.onehot_row = L.onehot_row;
+    p.gq = qg ? p.gc + (size_t)blocks * nw * L.region : nullptr;
+    p.region = L.region; p.sregion = L.sregion; p.ab0 = L.ab0; p.msg0 = L.msg0; p.q0 = L.q0; p.onehot_row = L.onehot_row;
     p.check_gaps = check ? 1 : 0;
     p.fb_count = fb_count;
     p.fb_col0 = check ? (int64_t*)((char*)ctx->o1n_fb.p + 16) : nullptr;
@@ -1319,9 +1332,8 @@ static int launch_net1n(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model*
     CU(cudaMemsetAsync(p.counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
     {
         KernelTimer kt_(ctx, "score_o1n_kernel");
-        if (m->MC1n <= 1) score_o1n_kernel<1><<<blocks, 32 * nw, smem, ctx->stream>>>(p);
-        else if (m->MC1n == 2) score_o1n_kernel<2><<<blocks, 32 * nw, smem, ctx->stream>>>(p);
-        else score_o1n_kernel<3><<<blocks, 32 * nw, smem, ctx->stream>>>(p);
+        void* args[] = {&p};
+        CU(cudaLaunchKernel(fn, dim3(blocks), dim3(32 * nw), args, smem, ctx->stream));
     }
     CU(cudaGetLastError());
     if (check) {
@@ -1821,6 +1833,11 @@ extern "C" int phyfoo_set_option(phyfoo_ctx* ctx, const char* name, int64_t valu
     if (std::strcmp(name, "pattern_memo") == 0) {
         if (value < 0 || value > 2) return fail(ctx, PHYFOO_EINVAL, "set_option: pattern_memo must be 0 (off), 1 (auto) or 2 (always)");
         ctx->memo_mode = (int)value;
+        return PHYFOO_OK;
+    }
+    if (std::strcmp(name, "order1_qglobal") == 0) {
+        if (value < -1 || value > 8) return fail(ctx, PHYFOO_EINVAL, "set_option: order1_qglobal must be -1 (choose), 0 (q rows in shared memory) or 1..8 warps per SM");
+        ctx->order1_qglobal = (int)value;
         return PHYFOO_OK;
     }
     if (std::strcmp(name, "order1_kernel") == 0) {

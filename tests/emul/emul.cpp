@@ -382,7 +382,7 @@ int run_o1n(const ModelHost& m, const std::vector<int>& prog, const uint8_t* cod
                         const int x = cw.obs(sp), y = t > 0 ? cwp.obs(sp) : 0;
                         c += leaf_tab[(size_t)(t * S + kk) * 32 + (a == x ? 16 : 0) + y * 4 + x];
                     }
-                    const int o = (t * I + i) * 32 + (a >> 1) * 16 + 2 * wslot + (a & 1);
+                    const int o = Lt.q0 + (t * I + i) * 32 + (a >> 1) * 16 + 2 * wslot + (a & 1);
                     gc[o] = c; region[o] = 0.25;
                 }
         }
@@ -402,7 +402,10 @@ int run_o1n(const ModelHost& m, const std::vector<int>& prog, const uint8_t* cod
                         double* reg = (order ? alt.data() : region.data()) + 2 * wslot;
                         const double* g = gc.data() + 2 * wslot + r[0];
                         const double cobs[4] = {g[0], g[1], g[16], g[17]};
-                        n1n_update<MC>(reg, tab.data(), h_phy_exp_tab, r, cobs, upd, order ? acc_alt[slot] : acc[slot]);
+                        double qx[4], qpn[4];
+                        n1n_ld4(reg + r[2], qx);
+                        n1n_ld4(reg + r[3], qpn);
+                        n1n_update<MC>(reg, reg, tab.data(), h_phy_exp_tab, r, cobs, qx, qpn, upd, order ? acc_alt[slot] : acc[slot]);
                     }
                 for (int o = 0; o < Lt.region; ++o)
                     if (std::memcmp(&alt[o], &region[o], 8) != 0) return -4;

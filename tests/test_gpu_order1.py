@@ -182,10 +182,12 @@ def test_order1_wavefront_equals_node_by_node_kernel(ctx, tree):
         ctx.set_option("order1_kernel", 2)
 
 
+@pytest.mark.parametrize("qglobal", [0, 8, 3])
 @pytest.mark.parametrize("tree,W", [("star5", 4), ("cat5", 7), ("mixed6", 1), ("mixed6", 6), ("rand12", 12)])
-def test_order1_node_per_thread_kernel(ctx, tree, W):
+def test_order1_node_per_thread_kernel(ctx, tree, W, qglobal):
     """The node-per-thread kernel (net1n.cuh, default): windows without gaps on it, the few windows with an unobserved leaf
-    through its device-side list to the wavefront kernel.  Against the oracle (scores 1e-9 relative, sweep counts exact) and
+    through its device-side list to the wavefront kernel; q rows in shared memory (qglobal = 0) or in global memory behind
+    L1 with 8 or 3 warps per SM.  Against the oracle (scores 1e-9 relative, sweep counts exact) and
     against the wavefront kernel alone (same sweep counts, scores equal to re-association); both strands, ragged lengths."""
     from phyfoo_b200 import synth
     from phyfoo_b200.data import PhyloSample
@@ -204,6 +206,7 @@ def test_order1_node_per_thread_kernel(ctx, tree, W):
     om = oracle_fg(newick, pwm, order=1)
     try:
         res = {}
+        ctx.set_option("order1_qglobal", qglobal)
         for kern in (2, 1):
             ctx.set_option("order1_kernel", kern)
             res[kern] = [fg.getLogProbFor(smp, strand=s, want_sweeps=True) for s in (0, 1)]
@@ -223,6 +226,7 @@ def test_order1_node_per_thread_kernel(ctx, tree, W):
             assert rel_err(res[2][s][0], res[1][s][0]) < 1e-12
     finally:
         ctx.set_option("order1_kernel", 2)
+        ctx.set_option("order1_qglobal", -1)
 
 
 @pytest.mark.parametrize("tree", ["cat5", "rand12"])
