@@ -107,15 +107,14 @@ N1N_RARE N1nZR n1n_z_rare(double z) {
     r.rz = n1n_rcp(z); r.lz = phy_log(z);
     return r;
 }
+N1N_HD bool n1n_exp_common(const double (&x)[4]);
 // four exponentials at once: the common case (every |x| < 690) is straight-line code, so that the four polynomial chains
-// interleave; bit for bit phy_exp_tab
+// interleave; phy_exp_tab's arithmetic
 N1N_HD void n1n_exp4(const double (&x)[4], const double* tab64, double (&e)[4]) {
-    const bool common = fabs(x[0]) < 690.0 && fabs(x[1]) < 690.0 && fabs(x[2]) < 690.0 && fabs(x[3]) < 690.0;
-    if (common) {
+    if (n1n_exp_common(x)) {
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
-            const double t = x[a] * PHY_64_OVER_LN2;
-            double kd = t + 0x1.8p52;
+            double kd = fma(x[a], PHY_64_OVER_LN2, 0x1.8p52);       // (phy_exp_tab rounds the product first: same k except at ties)
 #if defined(__CUDA_ARCH__)
             const int32_t ki = __double2loint(kd);
 #else
@@ -158,44 +157,52 @@ N1N_HD double n1n_free_energy(const N1nAcc& acc) {
     return (acc.Fq - acc.Fslow) - lz;
 }
 
-// message of a node to its tree parent: msg(a) = q(a) A(a) + sum_{a' != a} q(a') B(a')
-N1N_HD void n1n_message(const double (&q)[4], const double (&A)[4], const double (&B)[4], double (&msg)[4]) {
-    double w[4];
+// message of a node to its tree parent: msg(a) = q(a) A(a) + sum_{a' != a} q(a') B(a') = q(a) D(a) + sum_a' q(a') B(a')
+N1N_HD void n1n_message(const double (&q)[4], const double (&D)[4], const double (&B)[4], double (&msg)[4]) {
+    double sw = q[0] * B[0];
+    sw = fma(q[1], B[1], sw); sw = fma(q[2], B[2], sw); sw = fma(q[3], B[3], sw);
 #pragma unroll
-    for (int a = 0; a < 4; ++a) w[a] = q[a] * B[a];
-    const double sw = n1n_sum4(w);
-#pragma unroll
-    for (int a = 0; a < 4; ++a) msg[a] = fma(q[a], A[a], sw - w[a]);
+    for (int a = 0; a < 4; ++a) msg[a] = fma(q[a], D[a], sw);
+}
+
+// |x| < 690 for all four: integer compares on the high words (690.0 = 0x4085900000000000)
+N1N_HD bool n1n_exp_common(const double (&x)[4]) {
+    return ((n1n_hi(x[0]) & 0x7fffffff) < 0x40859000) & ((n1n_hi(x[1]) & 0x7fffffff) < 0x40859000) &
+           ((n1n_hi(x[2]) & 0x7fffffff) < 0x40859000) & ((n1n_hi(x[3]) & 0x7fffffff) < 0x40859000);
 }
 
 // One node update.  reg: this thread's window in the warp's region (AB and message rows), qreg: the same for the q rows
-// (the same pointer when the whole region is in shared memory); tab: tables [W][I][34] (Lo | Ld | pad); exptab: 2^(j/64);
-// r: the record (model_host.hpp::node_program); cobs: observed-leaf sums of this node; upd == false: the pass at the uniform
-// start (exponents forced to 0).  All reads come before the row stores; the caller synchronises the warp afterwards.  A slot
-// without a node in this step (record flags 0) does nothing.
+// (the same pointer when the whole region is in shared memory); tab: tables [W][I][34] (Lo | D = Ld - Lo | pad); exptab:
+// 2^(j/64); r: the record (model_host.hpp::node_program); cobs: observed-leaf sums of this node; upd == false: the pass at the
+// uniform start (exponents forced to 0).  All reads come before the row stores; the caller synchronises the warp afterwards.
+// A slot without a node in this step (record flags 0) does nothing.
 // qx, qpn: the (old) q of the same node and of its parent at the next position, rows r[2] and r[3] -- no update of the
 // previous step can have written them, so the caller loads them a step ahead.
+// Arithmetic (D rows and tables hold diagonal minus off-diagonal):
+//   own(a) = q_par(a) Dm(a) + tot_par B(a)                                  [= q_par(a) A(a) + (tot_par - q_par(a)) B(a)]
+//   nx(a)  = sum_c (qx(c) qpn(c)) D'[a][c] + tot_next sum_c qx(c) Lo'[a][c]
+//   s = (own + cobs) + (ch + nx);  the node's free-energy terms use g = ch + nx (pass at the uniform start: -(own + cobs))
 template <int MC>
 N1N_HD void n1n_update(double* qreg, double* reg, const double* tab, const double* exptab, const int* r, const double (&cobs)[4],
                        const double (&qx)[4], const double (&qpn)[4], bool upd, N1nAcc& acc) {
     const int flags = r[7];
     if (!(flags & 1)) return;
     const bool last = (flags & 2) != 0;
-    double qp[4], A[4], B[4], own[4], ch[4], nx[4];
+    double qp[4], Dm[4], B[4], oc[4], cn[4];
     n1n_ld4(qreg + r[1], qp);
-    n1n_ld4(reg + r[4], A);
+    n1n_ld4(reg + r[4], Dm);
     n1n_ld4(reg + r[4] + 32, B);
     const double totp = n1n_sum4(qp);
 #pragma unroll
-    for (int a = 0; a < 4; ++a) own[a] = fma(qp[a], A[a], (totp - qp[a]) * B[a]);
+    for (int a = 0; a < 4; ++a) oc[a] = fma(qp[a], Dm[a], totp * B[a]) + cobs[a];
     // internal children: their messages (null entries read the all-zero row)
-    n1n_ld4(reg + r[8], ch);
+    n1n_ld4(reg + r[8], cn);
 #pragma unroll
     for (int j = 1; j < MC; ++j) {
         double mj[4];
         n1n_ld4(reg + r[8 + j], mj);
 #pragma unroll
-        for (int a = 0; a < 4; ++a) ch[a] += mj[a];
+        for (int a = 0; a < 4; ++a) cn[a] += mj[a];
     }
     // the same node at the next position (old values); its tables also serve the context sums produced below
     double T[32];
@@ -204,34 +211,33 @@ N1N_HD void n1n_update(double* qreg, double* reg, const double* tab, const doubl
 #pragma unroll
         for (int j = 0; j < 16; ++j) { const N1nD2 v = *reinterpret_cast<const N1nD2*>(tp + 2 * j); T[2 * j] = v.x; T[2 * j + 1] = v.y; }
     }
-    {
-        double m[4];
+    if (!last) {
+        double rr[4];
         const double totn = n1n_sum4(qpn);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) m[c] = totn - qpn[c];
+        for (int c = 0; c < 4; ++c) rr[c] = qx[c] * qpn[c];
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
-            double v = 0.0;
+            double u = qx[0] * T[a * 4], v = rr[0] * T[16 + a * 4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) v = fma(qx[c], fma(qpn[c], T[16 + a * 4 + c], m[c] * T[a * 4 + c]), v);
-            nx[a] = last ? 0.0 : v;
+            for (int c = 1; c < 4; ++c) { u = fma(qx[c], T[a * 4 + c], u); v = fma(rr[c], T[16 + a * 4 + c], v); }
+            cn[a] += fma(totn, u, v);
         }
     }
     double e[4], g[4], qn[4], ex[4];
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
-        const double s = ((own[a] + ch[a]) + cobs[a]) + nx[a];
-        ex[a] = upd ? s : 0.0;
-        g[a] = upd ? ch[a] + nx[a] : -(own[a] + cobs[a]);
+        ex[a] = upd ? oc[a] + cn[a] : 0.0;
+        g[a] = upd ? cn[a] : -oc[a];
     }
     n1n_exp4(ex, exptab, e);                                                        // MeanFieldForBayesNet.java:192, no max shift
     const double z = n1n_sum4(e);                                                   // :195-198
     // The reciprocal of z is a chain of dependent operations; what is linear in q is computed on the unnormalised
-    // exponentials next to it and scaled afterwards: the node's free-energy terms and the context sums of the same node
-    // at the next position (the last position produces those of position 0: one-hot, scale 1).
+    // exponentials next to it and scaled afterwards: the node's free-energy terms, the context sums of the same node at
+    // the next position (the last position produces those of position 0: one-hot, scale 1) and the message to the parent.
     double fu = e[0] * g[0];
     fu = fma(e[1], g[1], fu); fu = fma(e[2], g[2], fu); fu = fma(e[3], g[3], fu);
-    double An[4], Bn[4];
+    double Dn[4], Bn[4], msg[4];
     {
         double ea[4];
 #pragma unroll
@@ -241,13 +247,11 @@ N1N_HD void n1n_update(double* qreg, double* reg, const double* tab, const doubl
             double u = ea[0] * T[a], v = ea[0] * T[16 + a];
 #pragma unroll
             for (int c = 1; c < 4; ++c) { u = fma(ea[c], T[c * 4 + a], u); v = fma(ea[c], T[16 + c * 4 + a], v); }
-            Bn[a] = u; An[a] = v;
+            Bn[a] = u; Dn[a] = v;
         }
     }
-    // message to the tree parent at the next position, with the old q of (t+1, i) -- of (0, i) at the last position --
-    // and the new context sums; unnormalised like them
-    double msg[4];
-    n1n_message(qx, An, Bn, msg);
+    // message to the tree parent at the next position, with the old q of (t+1, i) -- of (0, i) at the last position
+    n1n_message(qx, Dn, Bn, msg);
     // z is a normal number well inside the exponent range unless the exponents were extreme: one test for the reciprocal
     // and for the (mantissa, exponent) accumulation of log z
     const int zhi = n1n_hi(z);
@@ -256,17 +260,17 @@ N1N_HD void n1n_update(double* qreg, double* reg, const double* tab, const doubl
     double rz = n1n_rcp_normal(z);
     if (znormal) { acc.E += (int)zef - 1023; acc.M *= n1n_with_hi(z, (zhi & 0x000fffff) | 0x3ff00000); }
     else {
-        const N1nZR rr = n1n_z_rare(z);
-        rz = rr.rz;
-        acc.Fslow += rr.lz;
+        const N1nZR zr = n1n_z_rare(z);
+        rz = zr.rz;
+        acc.Fslow += zr.lz;
     }
     const double sc = last ? 1.0 : rz;
 #pragma unroll
-    for (int a = 0; a < 4; ++a) { qn[a] = e[a] * rz; An[a] *= sc; Bn[a] *= sc; msg[a] *= sc; }   // :199-201
+    for (int a = 0; a < 4; ++a) { qn[a] = e[a] * rz; Dn[a] *= sc; Bn[a] *= sc; msg[a] *= sc; }   // :199-201
     acc.Fq = fma(fu, rz, acc.Fq);
-    if (flags & 4) n1n_message(qn, An, Bn, msg);        // a motif of a single position: the message carries the node's own new q
+    if (flags & 4) n1n_message(qn, Dn, Bn, msg);        // a motif of a single position: the message carries the node's own new q
     n1n_st4(qreg + r[0], qn);
-    n1n_st4(reg + r[4], An);
+    n1n_st4(reg + r[4], Dn);
     n1n_st4(reg + r[4] + 32, Bn);
     n1n_st4(reg + r[5], msg);
 }
@@ -274,12 +278,12 @@ N1N_HD void n1n_update(double* qreg, double* reg, const double* tab, const doubl
 // window set-up of the rows that do not come out of a node update: context sums of position 0 (the virtual predecessor is
 // the one-hot (1, 0, 0, 0): row 0 of the tables) and the message of the uniform start to the parent at position 0
 N1N_HD void n1n_setup_node(double* reg, const double* tab, int ab_row, int msg_row, int tab_row) {
-    double A[4], B[4], msg[4];
+    double D[4], B[4], msg[4];
     const double q0[4] = {0.25, 0.25, 0.25, 0.25};
 #pragma unroll
-    for (int a = 0; a < 4; ++a) { B[a] = tab[tab_row + a]; A[a] = tab[tab_row + 16 + a]; }
-    n1n_message(q0, A, B, msg);
-    n1n_st4(reg + ab_row, A);
+    for (int a = 0; a < 4; ++a) { B[a] = tab[tab_row + a]; D[a] = tab[tab_row + 16 + a]; }
+    n1n_message(q0, D, B, msg);
+    n1n_st4(reg + ab_row, D);
     n1n_st4(reg + ab_row + 32, B);
     n1n_st4(reg + msg_row, msg);
 }
@@ -304,6 +308,7 @@ struct Net1nParams {
     double* gc;                          // observed-leaf sums: one region of `region` doubles per warp of the grid
     double* gq;                          // q rows in global memory (QG variant): one region per warp of the grid
     int region, sregion, ab0, msg0, q0, onehot_row;
+    double f0_const;                     // model_host.hpp::n1n_f0_const(): free energy of the uniform start minus the window's part
     int check_gaps;                      // 0: the data set has no unobserved symbol at all
     int* fb_count; int64_t* fb_col0; uint8_t* fb_strand; int64_t* fb_dst;   // windows with gaps, for the net1w.cuh kernel
 };
@@ -359,6 +364,7 @@ __global__ void __launch_bounds__(256, 1) score_o1n_kernel(Net1nParams p) {
             const int wi = __ffs(nm) - 1;
             nm &= nm - 1;
             long long it = -1; int64_t c0 = 0; int strand = 0;
+            double f0 = 0.0;
             for (;;) {
                 long long v = 0;
                 if (lane == 0) v = (long long)atomicAdd(&p.counters[0], 1ULL);
@@ -383,7 +389,9 @@ __global__ void __launch_bounds__(256, 1) score_o1n_kernel(Net1nParams p) {
             }
             if (it >= 0) {
                 // observed-leaf sums of every node (constant over the sweeps), uniform start (MeanFieldForBayesNet.java:52-69):
-                // one lane per (position, node), all four symbols
+                // one lane per (position, node), all four symbols.  Their total gives the free energy of the uniform start
+                // (F_0, :105) in closed form, so the first pass over the net is already the first sweep.
+                double csum = 0.0;
                 for (int idx = lane; idx < W * I; idx += 32) {
                     const int t = idx / I, i = idx - t * I;
                     const int64_t col = strand ? c0 + (W - 1 - t) : c0 + t;       // jstacs StrandModel.java:636-639
@@ -403,13 +411,17 @@ __global__ void __launch_bounds__(256, 1) score_o1n_kernel(Net1nParams p) {
                     const int o = p.q0 + idx * 32 + 2 * wi;
                     gcw[o] = c[0]; gcw[o + 1] = c[1]; gcw[o + 16] = c[2]; gcw[o + 17] = c[3];
                     qregw[o] = 0.25; qregw[o + 1] = 0.25; qregw[o + 16] = 0.25; qregw[o + 17] = 0.25;
+                    csum += (c[0] + c[1]) + (c[2] + c[3]);
                 }
+#pragma unroll
+                for (int sh = 16; sh >= 1; sh >>= 1) csum += __shfl_xor_sync(full, csum, sh);
+                f0 = fma(-0.25, csum, p.f0_const);
                 // context sums and messages of position 0
                 for (int i = lane; i < I; i += 32)
                     phyfoo::n1n_setup_node(regw + 2 * wi, s_tab, p.ab0 + i * 64, p.msg0 + i * 32, i * TS);
             }
             if (w == wi) {
-                if (it >= 0) { item = it; k = 0; conv = false; upd = false; need = false; }
+                if (it >= 0) { item = it; k = 0; conv = false; upd = true; old = f0; need = false; }     // F_0, :105
                 else active = false;
             }
         }
@@ -464,13 +476,9 @@ __global__ void __launch_bounds__(256, 1) score_o1n_kernel(Net1nParams p) {
         F += __shfl_xor_sync(full, F, 8);
         F += __shfl_xor_sync(full, F, 16);
         if (active) {
-            bool done;
-            if (!upd) { old = F; upd = true; done = false; }                      // F_0, MeanFieldForBayesNet.java:105
-            else {
-                if (fabs(old - F) < p.tol) conv = true;                           // :204-207 (sticky)
-                old = F; ++k;
-                done = !((k < p.max_sweeps && !conv) || k < p.min_sweeps);        // :107
-            }
+            if (fabs(old - F) < p.tol) conv = true;                               // MeanFieldForBayesNet.java:204-207 (sticky)
+            old = F; ++k;
+            bool done = !((k < p.max_sweeps && !conv) || k < p.min_sweeps);       // :107
             if (done) {
                 if (slot == 0) {
                     p.out[item] = -F;                                             // PhyloBayesModel.java:259

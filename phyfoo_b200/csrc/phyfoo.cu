@@ -119,6 +119,7 @@ struct phyfoo_model {
     double* d_leaftab1n = nullptr;//                                              leaf tables [W][S][32]
     int* d_prog1n = nullptr;
     int prog1n_len = 0, MC1n = 1, n_steps1n = 0;
+    double f0_const1n = 0.0;
 };
 
 static thread_local std::string g_init_err;
@@ -826,6 +827,7 @@ static int model_upload(phyfoo_ctx* ctx, phyfoo_model* m) {
         h.tables1w(t1w);
         h.tables1n(t1n);
         h.leaf_tables1n(tl1n);
+        m->f0_const1n = h.n1n_f0_const();
         if (!m->d_prog) {
             std::vector<int> pn;
             h.node_program(pn, m->MC1n, m->n_steps1n);
@@ -1324,6 +1326,7 @@ static int launch_net1n(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model*
     p.gc = ctx->o1n_cache.as<double>();
     p.gq = qg ? p.gc + (size_t)blocks * nw * L.region : nullptr;
     p.region = L.region; p.sregion = L.sregion; p.ab0 = L.ab0; p.msg0 = L.msg0; p.q0 = L.q0; p.onehot_row = L.onehot_row;
+    p.f0_const = m->f0_const1n;
     p.check_gaps = check ? 1 : 0;
     p.fb_count = fb_count;
     p.fb_col0 = check ? (int64_t*)((char*)ctx->o1n_fb.p + 16) : nullptr;

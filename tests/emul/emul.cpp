@@ -388,7 +388,32 @@ int run_o1n(const ModelHost& m, const std::vector<int>& prog, const uint8_t* cod
         }
         for (int i = 0; i < I; ++i)
             n1n_setup_node(region.data() + 2 * wslot, tab.data(), Lt.ab0 + i * 64, Lt.msg0 + i * 32, i * ModelHost::N1N_TAB_STRIDE);
-        bool upd = false, conv = false; int k = 0; double old = 0.0;
+        // F_0 in closed form (the kernel's set-up does the same), the first pass is the first sweep
+        double csum = 0.0;
+        for (int n = 0; n < W * I; ++n) {
+            const double* g = gc.data() + Lt.q0 + n * 32 + 2 * wslot;
+            csum += (g[0] + g[1]) + (g[16] + g[17]);
+        }
+        bool upd = true, conv = false; int k = 0; double old = fma(-0.25, csum, m.n1n_f0_const());
+        {   // the closed form against an actual pass at the uniform start (on a copy of the state)
+            std::vector<double> tmp = region;
+            N1nAcc a0[4];
+            for (auto& a : a0) { a.Fq = 0.0; a.M = 1.0; a.E = 0; a.Fslow = 0.0; }
+            for (int step = 0; step < n_steps; ++step)
+                for (int slot = 0; slot < 4; ++slot) {
+                    const int* r = rec + (size_t)(step * 4 + slot) * RL;
+                    double* reg = tmp.data() + 2 * wslot;
+                    const double* g = gc.data() + 2 * wslot + r[0];
+                    const double cobs[4] = {g[0], g[1], g[16], g[17]};
+                    double qx[4], qpn[4];
+                    n1n_ld4(reg + r[2], qx);
+                    n1n_ld4(reg + r[3], qpn);
+                    n1n_update<MC>(reg, reg, tab.data(), h_phy_exp_tab, r, cobs, qx, qpn, false, a0[slot]);
+                }
+            const double F0 = (n1n_free_energy(a0[0]) + n1n_free_energy(a0[1])) + (n1n_free_energy(a0[2]) + n1n_free_energy(a0[3]));
+            if (std::fabs(F0 - old) > 1e-12 * std::fabs(F0)) return -6;
+            for (int o = 0; o < Lt.region; ++o) if (std::fabs(tmp[o] - region[o]) > 1e-13 * std::fabs(region[o])) return -7;   // ... and leaves the state alone
+        }
         for (;;) {
             N1nAcc acc[4];
             for (auto& a : acc) { a.Fq = 0.0; a.M = 1.0; a.E = 0; a.Fslow = 0.0; }
@@ -413,7 +438,6 @@ int run_o1n(const ModelHost& m, const std::vector<int>& prog, const uint8_t* cod
             }
             const double f0 = n1n_free_energy(acc[0]), f1 = n1n_free_energy(acc[1]), f2 = n1n_free_energy(acc[2]), f3 = n1n_free_energy(acc[3]);
             const double F = (f0 + f1) + (f2 + f3);            // the kernel's butterfly over lanes w, w+8, w+16, w+24
-            if (!upd) { old = F; upd = true; continue; }
             if (std::fabs(old - F) < m.tol) conv = true;
             old = F; ++k;
             if (!((k < m.max_sweeps && !conv) || k < m.min_sweeps)) { out[j] = -F; if (sweeps) sweeps[j] = k; break; }
