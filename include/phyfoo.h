@@ -27,7 +27,8 @@
  *
  * Conventions: every function returns 0 on success or a negative PHYFOO_E* code; the message is
  * available from phyfoo_last_error().  One context belongs to one GPU and to one caller thread at a
- * time (the reference is single-threaded; this library does not lock).  Calls are synchronous:
+ * time (the reference is single-threaded; this library does not lock); several GPUs behind one caller:
+ * the phyfoo_multi_* entry points at the end of this file.  Calls are synchronous:
  * results are in the caller's buffers when the call returns.  There is NO CPU fallback: without a
  * CUDA device phyfoo_init fails with PHYFOO_ENODEVICE.
  */
@@ -274,6 +275,55 @@ int phyfoo_synchronize(phyfoo_ctx* ctx);
 int phyfoo_estep_kernel_ms(phyfoo_ctx* ctx, float* bg_ms, float* fg_ms, float* zoops_ms);
 /* sums of mean-field sweep counts of the most recent E-step (integer parity check / roofline flop count) */
 int phyfoo_estep_sweeps(phyfoo_ctx* ctx, int64_t* sweeps_fg, int64_t* sweeps_bg);
+
+/* ---- several GPUs behind ONE caller (a JVM is one process) ----
+ * the library takes a list of devices, shards the data set itself (contiguous blocks of alignments
+ * balanced by column count; alignments are independent), replicates the models and owns the NCCL communicator
+ * (ncclCommInitAll; libnccl.so.2 is bound at run time, PHYFOO_NCCL_LIB overrides the name).  The only exchange per consumer
+ * is a sum all-reduce of a few doubles -- [ll, w0, w1] per E-step, [f, f_1..f_dim] per gradient -- issued with ncclAllReduce
+ * on every device's stream right behind the kernel that produces them, before the one device-to-host copy.  One worker
+ * thread per device runs the per-device part of each call; the calls themselves are synchronous like the single-GPU ones
+ * and take the same arguments, with per-window / per-alignment arrays in the order of the WHOLE sample.  Results equal the
+ * single-GPU ones up to the re-association of the all-reduced sums (1e-12 relative; scores, gamma, arg-max calls and
+ * selected windows are bit-identical). */
+typedef struct phyfoo_mctx phyfoo_mctx;
+typedef struct phyfoo_mdataset phyfoo_mdataset;
+typedef struct phyfoo_mmodel phyfoo_mmodel;
+typedef struct phyfoo_mfeset phyfoo_mfeset;
+
+int phyfoo_init_multi(const int* device_ids, int n_devices, phyfoo_mctx** out);
+void phyfoo_destroy_multi(phyfoo_mctx* mctx);
+const char* phyfoo_multi_last_error(const phyfoo_mctx* mctx); /* mctx may be NULL: error of a failed phyfoo_init_multi */
+int phyfoo_multi_size(const phyfoo_mctx* mctx);
+phyfoo_ctx* phyfoo_multi_ctx(phyfoo_mctx* mctx, int rank);    /* the device's own context (borrowed; e.g. for phyfoo_host_alloc) */
+int phyfoo_multi_set_option(phyfoo_mctx* mctx, const char* name, int64_t value);
+/* packs and shards: device r holds alignments bounds[r] .. bounds[r+1]-1 (bounds_out[n_devices + 1]) */
+int phyfoo_multi_dataset_create(phyfoo_mctx* mctx, int32_t n_aln, int32_t n_species, const int64_t* col_offsets,
+                                const uint8_t* codes, phyfoo_mdataset** out);
+int phyfoo_multi_dataset_bounds(const phyfoo_mdataset* ds, int32_t* bounds_out);
+void phyfoo_multi_dataset_free(phyfoo_mctx* mctx, phyfoo_mdataset* ds);
+int phyfoo_multi_model_create(phyfoo_mctx* mctx, const phyfoo_model_desc* desc, phyfoo_mmodel** out);
+int phyfoo_multi_model_set_pi(phyfoo_mctx* mctx, phyfoo_mmodel* m, int32_t position, const double* pi, int32_t n);
+int phyfoo_multi_model_get_pi(phyfoo_mctx* mctx, const phyfoo_mmodel* m, int32_t position, double* pi_out, int32_t n);
+int phyfoo_multi_model_set_branch(phyfoo_mctx* mctx, phyfoo_mmodel* m, int32_t position, int32_t node, double length);
+int phyfoo_multi_model_set_mode(phyfoo_mctx* mctx, phyfoo_mmodel* m, int32_t mode);
+void phyfoo_multi_model_free(phyfoo_mctx* mctx, phyfoo_mmodel* m);
+/* SingleHiddenMotifMixture.getNewWeights over the whole sample: arguments as phyfoo_zoops_estep; w_out / ll_out are the sums
+ * over all devices; stats: sums (gpu_ms: the slowest device) */
+int phyfoo_multi_zoops_estep(phyfoo_mctx* mctx, const phyfoo_mdataset* ds, phyfoo_mmodel* fg, phyfoo_mmodel* bg,
+                             const double* logw, const double* strand_logw, const double* aln_weights,
+                             double* gamma_out, double* profile_out, double* w_out, double* ll_out,
+                             int32_t* argmax_off, uint8_t* argmax_strand, phyfoo_stats* stats);
+/* M-step: phyfoo_select + phyfoo_fe_prepare on every device.  weights: NULL = the gamma of the last phyfoo_multi_zoops_estep
+ * (still resident on each device), or [windows of the whole sample].  n_selected (nullable): total number of selected windows. */
+int phyfoo_multi_fe_prepare_selected(phyfoo_mctx* mctx, const phyfoo_mdataset* ds, phyfoo_mmodel* m, const double* weights,
+                                     double t, double q, phyfoo_mfeset** out, int64_t* n_selected);
+/* evaluateFunction / evaluateGradientOfFunction over all devices: [f, f_1..f_dim] all-reduced before the copy-out */
+int phyfoo_multi_fe_eval(phyfoo_mctx* mctx, phyfoo_mfeset* fe, int32_t position, const double* lambda, int32_t dim, double* f_out);
+int phyfoo_multi_fe_grad(phyfoo_mctx* mctx, phyfoo_mfeset* fe, int32_t position, const double* lambda, int32_t dim, double eps,
+                         double* f_out, double* g_out);
+int64_t phyfoo_multi_fe_size(const phyfoo_mfeset* fe);
+void phyfoo_multi_fe_free(phyfoo_mctx* mctx, phyfoo_mfeset* fe);
 
 #ifdef __cplusplus
 }

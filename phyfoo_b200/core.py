@@ -347,3 +347,171 @@ class FESet:
         raise_for(lib().phyfoo_fe_values_device(self.ctx.h, self.h, int(position), _p(lam, C.c_double), lam.size, float(eps),
                                                 C.c_void_p(values_ptr), C.c_void_p(stream_ptr) if stream_ptr else None),
                   self.ctx.h)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# several GPUs behind one caller (include/phyfoo.h "phyfoo_multi_*", csrc/multi.cuh): the library shards the sample over the
+# listed devices and all-reduces the few doubles each consumer needs over NCCL; the arguments and results are those of the
+# single-GPU calls, with per-window / per-alignment arrays in the order of the whole sample
+# ---------------------------------------------------------------------------------------------------------------------------
+def _mraise(code, mh):
+    if code == _abi.OK:
+        return
+    msg = lib().phyfoo_multi_last_error(mh)
+    from .lib import IllegalArgumentException, PhyfooError
+    msg = msg.decode() if msg else ""
+    raise (IllegalArgumentException if code == _abi.EINVAL else PhyfooError)(code, msg)
+
+
+class MultiContext:
+    """phyfoo_mctx: one caller, several GPUs (one worker thread and one NCCL rank per device inside the library)."""
+
+    def __init__(self, devices):
+        import os
+        if "PHYFOO_NCCL_LIB" not in os.environ:
+            try:                                     # the NCCL that ships with the torch wheel, if there is one
+                import nvidia.nccl as _n
+                cand = os.path.join(os.path.dirname(_n.__file__ or list(_n.__path__)[0]), "lib", "libnccl.so.2")
+                if os.path.exists(cand):
+                    os.environ["PHYFOO_NCCL_LIB"] = cand
+            except Exception:
+                pass
+        devices = [int(d) for d in devices]
+        arr = (C.c_int * len(devices))(*devices)
+        self.h = C.c_void_p()
+        rc = lib().phyfoo_init_multi(arr, len(devices), C.byref(self.h))
+        if rc != _abi.OK:
+            _mraise(rc, None)
+        self.devices = devices
+
+    def close(self):
+        if self.h:
+            lib().phyfoo_destroy_multi(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return lib().phyfoo_multi_size(self.h)
+
+    def set_option(self, name, value):
+        _mraise(lib().phyfoo_multi_set_option(self.h, name.encode(), int(value)), self.h)
+
+
+class MultiDataset:
+    def __init__(self, mctx, col_offsets, codes):
+        self.mctx = mctx
+        self.col_offsets = np.ascontiguousarray(col_offsets, np.int64)
+        codes = np.ascontiguousarray(codes, np.uint8)
+        self.n_aln, self.S = self.col_offsets.size - 1, codes.shape[1]
+        self.h = C.c_void_p()
+        _mraise(lib().phyfoo_multi_dataset_create(mctx.h, self.n_aln, self.S, _p(self.col_offsets, C.c_int64), _p(codes, C.c_uint8),
+                                                  C.byref(self.h)), mctx.h)
+        b = np.zeros(len(mctx) + 1, np.int32)
+        lib().phyfoo_multi_dataset_bounds(self.h, _p(b, C.c_int32))
+        self.bounds = b
+
+    def windows(self, width):
+        return int(np.maximum(np.diff(self.col_offsets) - width + 1, 0).sum())
+
+    def free(self):
+        if self.h:
+            lib().phyfoo_multi_dataset_free(self.mctx.h, self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class MultiModel:
+    def __init__(self, mctx, kind, width, order, tree, branch, pi_list, evol=_abi.EVOL_F81ALPHA, mode=_abi.MODE_MEANFIELD):
+        self.mctx = mctx
+        desc, keep = _abi.make_desc(kind, width, order, tree, branch, pi_list, evol, mode)
+        self.h = C.c_void_p()
+        _mraise(lib().phyfoo_multi_model_create(mctx.h, C.byref(desc), C.byref(self.h)), mctx.h)
+        del keep
+        self.W = width if kind == _abi.MODEL_FG else order + 1
+
+    def set_pi(self, position, pi):
+        pi = np.ascontiguousarray(pi, np.float64).ravel()
+        _mraise(lib().phyfoo_multi_model_set_pi(self.mctx.h, self.h, int(position), _p(pi, C.c_double), pi.size), self.mctx.h)
+
+    def get_pi(self, position, n):
+        out = np.zeros(n)
+        _mraise(lib().phyfoo_multi_model_get_pi(self.mctx.h, self.h, int(position), _p(out, C.c_double), n), self.mctx.h)
+        return out
+
+    def free(self):
+        if self.h:
+            lib().phyfoo_multi_model_free(self.mctx.h, self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def multi_zoops_estep(mctx, mds, fg, bg, logw, strand_logw=None, aln_weights=None, want_gamma=True, want_argmax=True):
+    n = mds.windows(fg.W)
+    logw = np.ascontiguousarray(logw, np.float64)
+    sl = None if strand_logw is None else np.ascontiguousarray(strand_logw, np.float64)
+    aw = None if aln_weights is None else np.ascontiguousarray(aln_weights, np.float64)
+    gamma = np.zeros(n) if want_gamma else None
+    w, ll = np.zeros(2), C.c_double()
+    ao = np.zeros(mds.n_aln, np.int32) if want_argmax else None
+    astr = np.zeros(mds.n_aln, np.uint8) if want_argmax else None
+    st = _abi.Stats()
+    _mraise(lib().phyfoo_multi_zoops_estep(mctx.h, mds.h, fg.h, bg.h, _p(logw, C.c_double), _p(sl, C.c_double), _p(aw, C.c_double),
+                                           _p(gamma, C.c_double), None, _p(w, C.c_double), C.byref(ll), _p(ao, C.c_int32),
+                                           _p(astr, C.c_uint8), C.byref(st)), mctx.h)
+    return {"gamma": gamma, "w": w, "ll": ll.value, "argmax_off": ao, "argmax_strand": astr, "stats": _stats_dict(st)}
+
+
+class MultiFESet:
+    """The M-step objective over all devices: select (on the resident gamma, or on `weights`) + fix q, then
+    evaluateFunction / evaluateGradientOfFunction with one all-reduce each."""
+
+    def __init__(self, mctx, mds, model, weights=None, t=0.8, q=0.0):
+        self.mctx = mctx
+        w = None if weights is None else np.ascontiguousarray(weights, np.float64)
+        self.h = C.c_void_p()
+        n = C.c_int64()
+        _mraise(lib().phyfoo_multi_fe_prepare_selected(mctx.h, mds.h, model.h, _p(w, C.c_double), float(t), float(q), C.byref(self.h),
+                                                       C.byref(n)), mctx.h)
+        self.n_selected = n.value
+
+    def __len__(self):
+        return int(lib().phyfoo_multi_fe_size(self.h))
+
+    def eval(self, position, lam):
+        lam = np.ascontiguousarray(lam, np.float64)
+        f = C.c_double()
+        _mraise(lib().phyfoo_multi_fe_eval(self.mctx.h, self.h, int(position), _p(lam, C.c_double), lam.size, C.byref(f)), self.mctx.h)
+        return f.value
+
+    def grad(self, position, lam, eps=1e-4):
+        lam = np.ascontiguousarray(lam, np.float64)
+        f, g = C.c_double(), np.zeros(lam.size)
+        _mraise(lib().phyfoo_multi_fe_grad(self.mctx.h, self.h, int(position), _p(lam, C.c_double), lam.size, float(eps), C.byref(f),
+                                           _p(g, C.c_double)), self.mctx.h)
+        return f.value, g
+
+    def free(self):
+        if self.h:
+            lib().phyfoo_multi_fe_free(self.mctx.h, self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

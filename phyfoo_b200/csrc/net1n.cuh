@@ -24,7 +24,7 @@
 // Windows with an unobserved leaf go to a device-side list and are scored by the net1w.cuh kernel afterwards (the bundled
 // data and the headline configurations have no gaps).
 //
-// PHY_HD parts (n1n_update) compile for the host as well: tests/emul runs them against the oracle without a GPU.
+// The N1N_HD parts (n1n_update) compile for the host as well: tests/emul runs them on the CPU without a GPU.
 #pragma once
 #include "fp64_math.cuh"
 

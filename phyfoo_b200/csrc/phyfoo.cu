@@ -16,7 +16,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <array>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -1951,3 +1953,5 @@ extern "C" int phyfoo_score_order_stats(phyfoo_ctx* ctx, const phyfoo_dataset* d
     CU(cudaStreamSynchronize(ctx->stream));
     return PHYFOO_OK;
 }
+
+#include "multi.cuh"

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(_HERE, "libphyfoo.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC"]
+              "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-ldl"]
 
 _LIB = None
 
@@ -30,6 +30,11 @@ SYMBOLS = [
     "phyfoo_fe_values_device", "phyfoo_fe_suffstats", "phyfoo_fe_size", "phyfoo_fe_free",
     "phyfoo_set_option", "phyfoo_last_score_path", "phyfoo_last_kernel_times", "phyfoo_host_alloc", "phyfoo_host_free",
     "phyfoo_last_launches", "phyfoo_stream", "phyfoo_synchronize", "phyfoo_estep_kernel_ms", "phyfoo_estep_sweeps",
+    "phyfoo_init_multi", "phyfoo_destroy_multi", "phyfoo_multi_last_error", "phyfoo_multi_size", "phyfoo_multi_ctx",
+    "phyfoo_multi_set_option", "phyfoo_multi_dataset_create", "phyfoo_multi_dataset_bounds", "phyfoo_multi_dataset_free",
+    "phyfoo_multi_model_create", "phyfoo_multi_model_set_pi", "phyfoo_multi_model_get_pi", "phyfoo_multi_model_set_branch",
+    "phyfoo_multi_model_set_mode", "phyfoo_multi_model_free", "phyfoo_multi_zoops_estep", "phyfoo_multi_fe_prepare_selected",
+    "phyfoo_multi_fe_eval", "phyfoo_multi_fe_grad", "phyfoo_multi_fe_size", "phyfoo_multi_fe_free",
 ]
 
 
@@ -125,6 +130,35 @@ def lib():
     fp = C.POINTER(C.c_float)
     L.phyfoo_estep_kernel_ms.argtypes = [vp, fp, fp, fp]
     L.phyfoo_estep_sweeps.argtypes = [vp, i64p, i64p]
+    # ---- several GPUs behind one caller (csrc/multi.cuh)
+    L.phyfoo_init_multi.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    L.phyfoo_destroy_multi.argtypes = [vp]
+    L.phyfoo_destroy_multi.restype = None
+    L.phyfoo_multi_last_error.argtypes = [vp]
+    L.phyfoo_multi_last_error.restype = C.c_char_p
+    L.phyfoo_multi_size.argtypes = [vp]
+    L.phyfoo_multi_ctx.argtypes = [vp, C.c_int]
+    L.phyfoo_multi_ctx.restype = vp
+    L.phyfoo_multi_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    L.phyfoo_multi_dataset_create.argtypes = [vp, C.c_int32, C.c_int32, i64p, u8p, C.POINTER(vp)]
+    L.phyfoo_multi_dataset_bounds.argtypes = [vp, ip32]
+    L.phyfoo_multi_dataset_free.argtypes = [vp, vp]
+    L.phyfoo_multi_dataset_free.restype = None
+    L.phyfoo_multi_model_create.argtypes = [vp, C.POINTER(_abi.ModelDesc), C.POINTER(vp)]
+    L.phyfoo_multi_model_set_pi.argtypes = [vp, vp, C.c_int32, dp, C.c_int32]
+    L.phyfoo_multi_model_get_pi.argtypes = [vp, vp, C.c_int32, dp, C.c_int32]
+    L.phyfoo_multi_model_set_branch.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_double]
+    L.phyfoo_multi_model_set_mode.argtypes = [vp, vp, C.c_int32]
+    L.phyfoo_multi_model_free.argtypes = [vp, vp]
+    L.phyfoo_multi_model_free.restype = None
+    L.phyfoo_multi_zoops_estep.argtypes = [vp, vp, vp, vp, dp, dp, dp, dp, dp, dp, dp, ip32, u8p, sp]
+    L.phyfoo_multi_fe_prepare_selected.argtypes = [vp, vp, vp, dp, C.c_double, C.c_double, C.POINTER(vp), i64p]
+    L.phyfoo_multi_fe_eval.argtypes = [vp, vp, C.c_int32, dp, C.c_int32, dp]
+    L.phyfoo_multi_fe_grad.argtypes = [vp, vp, C.c_int32, dp, C.c_int32, C.c_double, dp, dp]
+    L.phyfoo_multi_fe_size.argtypes = [vp]
+    L.phyfoo_multi_fe_size.restype = C.c_int64
+    L.phyfoo_multi_fe_free.argtypes = [vp, vp]
+    L.phyfoo_multi_fe_free.restype = None
     _LIB = L
     return L
 
