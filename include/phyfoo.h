@@ -164,8 +164,10 @@ int phyfoo_zoops_estep(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* 
                        double* gamma_out, double* profile_out, double* w_out, double* ll_out,
                        int32_t* argmax_off, uint8_t* argmax_strand, phyfoo_stats* stats);
 /* Same E-step, but the three local sums [ll, w0, w1] are left in DEVICE memory at `partial_device`
- * (3 doubles) on `stream` (a cudaStream_t; NULL = the library's stream) so that the caller can
- * all-reduce them over NCCL without a host round trip.  Asynchronous with respect to the host. */
+ * (3 doubles) on `stream` (a cudaStream_t) so that the caller can all-reduce them over NCCL without a host round trip:
+ * the library's work is ordered after what `stream` holds and `stream` waits for the result; asynchronous with respect to
+ * the host.  stream == NULL (no caller stream; the legacy default stream does not order against the library's non-blocking
+ * stream): the call returns when the three doubles are complete. */
 int phyfoo_zoops_estep_device(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* fg, phyfoo_model* bg,
                               const double* logw, const double* strand_logw, const double* aln_weights_device,
                               double* partial_device, void* stream);

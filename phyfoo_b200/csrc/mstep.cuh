@@ -126,7 +126,8 @@ extern "C" int phyfoo_select(phyfoo_ctx* ctx, const phyfoo_dataset* ds, int32_t 
         d_w = ctx->selw.as<double>();
     } else {
         // weights == NULL: gamma of the most recent phyfoo_zoops_estep on this context, still on the device
-        if (ctx->gamma_windows != nw) return fail(ctx, PHYFOO_EINVAL, "select: weights is NULL but no gamma of matching size is resident (run phyfoo_zoops_estep with gamma_out first)");
+        if (ctx->gamma_windows != nw || ctx->gamma_ds != ds || ctx->gamma_width != width)
+            return fail(ctx, PHYFOO_EINVAL, "select: weights is NULL but no gamma of this data set and motif width is resident (run phyfoo_zoops_estep with gamma_out first)");
         d_w = ctx->gamma.as<double>();
     }
     const size_t na = (size_t)ds->n_aln;

@@ -342,6 +342,7 @@ extern "C" int phyfoo_multi_zoops_estep(phyfoo_mctx* mc, const phyfoo_mdataset* 
                                     argmax_strand ? ctx->argstrand.as<uint8_t>() : nullptr, mc->d_red[r], &nw[r]);
         if (e) return e;
         ctx->gamma_windows = gamma_out ? nw[r] : -1;
+        ctx->gamma_ds = gamma_out ? ds : nullptr; ctx->gamma_width = W;
         return PHYFOO_OK;
     });
     if (rc) return mcollect(mc, rc, "multi_zoops_estep");

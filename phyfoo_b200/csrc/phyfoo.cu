@@ -68,7 +68,8 @@ struct phyfoo_ctx {
     DevBuf sweeps_buf;               // int32 per item when the caller wants K
     DevBuf gamma, profile, part, argoff, argstrand, alnw, out3, gstate, misc;
     DevBuf selw, sel_tmp, sel_out;   // M-step selection scratch
-    int64_t gamma_windows = -1;      // number of windows whose gamma of the last E-step is resident in `gamma`
+    int64_t gamma_windows = -1;      // number of windows whose gamma of the last E-step is resident in `gamma` ...
+    const phyfoo_dataset* gamma_ds = nullptr; int gamma_width = 0;   // ... and the data set and motif width it belongs to
     DevBuf memo_traj;                // pattern-table path: free-energy trajectories (memo.cuh)
     int memo_mode = 1;               // 0 = never, 1 = when it pays off, 2 = whenever it applies
     int memo_sweep_cap = 64;
@@ -744,6 +745,7 @@ extern "C" void phyfoo_dataset_free(phyfoo_ctx* ctx, phyfoo_dataset* ds) {
     // stream-ordered frees: everything enqueued on the library's stream that still reads the buffers runs first
     cudaStream_t st = ctx ? ctx->stream : nullptr;
     if (ctx) cudaSetDevice(ctx->device);
+    if (ctx && ctx->gamma_ds == ds) { ctx->gamma_ds = nullptr; ctx->gamma_windows = -1; }   // the resident gamma dies with its data set
     dev_free(st, ds->d_col_off); dev_free(st, ds->d_bases); dev_free(st, ds->d_gaps);
     for (auto& kv : ds->d_win_off) dev_free(st, kv.second);
     memo_release(st, ds->memo);
@@ -1060,9 +1062,18 @@ static int launch_memo_jobs(phyfoo_ctx* ctx, const phyfoo_dataset* ds, const Mem
         // [count (8 bytes, int used)] [col0 int64 x n] [dst int64 x n] [strand u8 x n, padded to 8]
         pend_off[j + 1] = pend_off[j] + 2 * (8 + (size_t)n_items[j] * 16 + (((size_t)n_items[j] + 7) / 8) * 8);
     }
-    // every counter of this call in one memset: [2 slot] work, [2 slot + 1] sweep sums, [4 + 2 j + l] lengths of the pending
-    // lists, [8 + slot] work counters of the fallback launches ([12] is the posterior kernel's ticket, zero between launches)
-    CU(cudaMemsetAsync(ctx->counters.p, 0, 12 * sizeof(unsigned long long), ctx->stream));
+    // the counters of this call's jobs: [2 slot] work, [2 slot + 1] sweep sums, [4 + 2 j + l] lengths of the pending lists,
+    // [8 + slot] work counters of the fallback launches ([12] is the posterior kernel's ticket, zero between launches).
+    // Two jobs use every slot: one memset; a single job leaves the other model's sweep sum alone (e.g. the background's,
+    // scored by the direct kernel just before, which phyfoo_estep_sweeps reports)
+    if (n_jobs == 2) CU(cudaMemsetAsync(ctx->counters.p, 0, 12 * sizeof(unsigned long long), ctx->stream));
+    else {
+        unsigned long long* cnt = ctx->counters.as<unsigned long long>();
+        const int sl = jobs[0].counter_slot;
+        CU(cudaMemsetAsync(cnt + 2 * sl, 0, 2 * sizeof(unsigned long long), ctx->stream));
+        CU(cudaMemsetAsync(cnt + 4, 0, 2 * sizeof(unsigned long long), ctx->stream));
+        CU(cudaMemsetAsync(cnt + 8 + sl, 0, sizeof(unsigned long long), ctx->stream));
+    }
     CU(ctx->memo_traj.ensure(traj_off[n_jobs] * sizeof(double)));
     CU(ctx->memo_pending.ensure(pend_off[n_jobs]));
     if (split) CU(ctx->memo_state.ensure(state_off[n_jobs] * sizeof(double)));
@@ -1726,6 +1737,7 @@ extern "C" int phyfoo_zoops_estep(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phy
                            argmax_strand ? ctx->argstrand.as<uint8_t>() : nullptr, ctx->out3.as<double>(), &nw);
     if (rc) return rc;
     ctx->gamma_windows = gamma_out ? nw : -1;
+    ctx->gamma_ds = gamma_out ? ds : nullptr; ctx->gamma_width = fg->h.W;
     // one synchronisation for the whole call: end-of-kernels event, then every copy (results, sweep counters), then wait
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
     CU(cudaGetLastError());
@@ -1771,6 +1783,10 @@ extern "C" int phyfoo_zoops_estep_device(phyfoo_ctx* ctx, const phyfoo_dataset* 
     if (user) {
         CU(cudaEventRecord(ctx->ev1, ctx->stream));
         CU(cudaStreamWaitEvent(user, ctx->ev1, 0));
+    } else {
+        // no caller stream to order against (the legacy default stream does not synchronise with the library's non-blocking
+        // stream): finish before returning, so that whatever the caller does next sees the three doubles
+        CU(cudaStreamSynchronize(ctx->stream));
     }
     return PHYFOO_OK;
 }
