@@ -234,6 +234,32 @@ int phyfoo_fe_suffstats(phyfoo_ctx* ctx, phyfoo_feset* fe, double* counts_out, d
 int64_t phyfoo_fe_size(const phyfoo_feset* fe);
 void phyfoo_fe_free(phyfoo_ctx* ctx, phyfoo_feset* fe);
 
+/* ---- the same objective on sufficient statistics, evaluated on the host INSIDE the library (order 0) ----
+ * phyfoo_ss_create: one device pass (phyfoo_fe_suffstats) and a private copy of the model's parameters.  After that
+ * evaluateFunction / evaluateGradientOfFunction cost a dot product of 4 + 16 (N - 1) terms and need neither the device nor a
+ * collective: the sequential, data-dependent line search of the Jstacs optimizer (jstacs!/.../Optimizer.java:122-330) is no
+ * longer a chain of kernel launches.  Same function as phyfoo_fe_eval (sums re-associated: 1e-12 relative,
+ * tests/test_gpu_mstep.py follows a whole optimisation with both).  The object is left at the last lambda, like the model of
+ * phyfoo_fe_eval; read the result with phyfoo_ss_get_pi and write it back with phyfoo_model_set_pi. */
+typedef struct phyfoo_ssobj phyfoo_ssobj;
+int phyfoo_ss_create(phyfoo_ctx* ctx, phyfoo_feset* fe, phyfoo_ssobj** out);
+/* from counts the caller holds ([W][E], phyfoo_fe_suffstats layout); no device involved */
+int phyfoo_ss_create_host(const phyfoo_model_desc* desc, const double* counts, double entropy, phyfoo_ssobj** out);
+int phyfoo_ss_eval(phyfoo_ssobj* ss, int32_t position, const double* lambda, int32_t dim, double* f_out);
+int phyfoo_ss_grad(phyfoo_ssobj* ss, int32_t position, const double* lambda, int32_t dim, double eps, double* f_out, double* g_out);
+/* branch lengths of one position (position < 0: of all positions) set to branch[N] (entry 0 unused): EdgeOptimizer /
+ * GlobalEdgeOptimizer.evaluateFunction (optimizing/branchlengths/EdgeOptimizer.java:44-74) after the logit map */
+int phyfoo_ss_eval_branches(phyfoo_ssobj* ss, int32_t position, const double* branch, double* f_out);
+int phyfoo_ss_get_pi(const phyfoo_ssobj* ss, int32_t position, double* pi_out, int32_t n);
+double phyfoo_ss_value(const phyfoo_ssobj* ss);
+int64_t phyfoo_ss_evaluations(const phyfoo_ssobj* ss);
+/* A whole M-step of the motif model in one call: the positions order[0..n_pos-1] one after the other (the caller draws the
+ * order, util/PWMUtil.java:131-144), each by a BFGS on the forward-difference gradient with the termination rule of
+ * optimizing/PreparedConditions.java:20-27.  The library's stand-in for the Jstacs optimizer (whose own trajectory is not
+ * reproducible); a Java caller can keep its Optimizer and bind phyfoo_ss_eval / phyfoo_ss_grad instead. */
+int phyfoo_ss_optimize(phyfoo_ssobj* ss, const int32_t* order, int32_t n_pos, double* f_before, double* f_after, int64_t* evaluations);
+void phyfoo_ss_free(phyfoo_ssobj* ss);
+
 /* ---- options ----
  * "pattern_memo": 0 = never, 1 = when it pays off (default), 2 = whenever it applies.  For order-0 models and few
  * species (3 S <= 18 bits) the library scores each occurring column pattern once per position and parameter set and
@@ -324,6 +350,8 @@ int phyfoo_multi_fe_prepare_selected(phyfoo_mctx* mctx, const phyfoo_mdataset* d
 int phyfoo_multi_fe_eval(phyfoo_mctx* mctx, phyfoo_mfeset* fe, int32_t position, const double* lambda, int32_t dim, double* f_out);
 int phyfoo_multi_fe_grad(phyfoo_mctx* mctx, phyfoo_mfeset* fe, int32_t position, const double* lambda, int32_t dim, double eps,
                          double* f_out, double* g_out);
+/* sufficient statistics of all devices: counts and entropy all-reduced once (W * E + 1 doubles), then phyfoo_ss_* as above */
+int phyfoo_multi_ss_create(phyfoo_mctx* mctx, phyfoo_mfeset* fe, phyfoo_ssobj** out);
 int64_t phyfoo_multi_fe_size(const phyfoo_mfeset* fe);
 void phyfoo_multi_fe_free(phyfoo_mctx* mctx, phyfoo_mfeset* fe);
 

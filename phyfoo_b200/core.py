@@ -515,3 +515,72 @@ class MultiFESet:
             self.free()
         except Exception:
             pass
+
+
+class SSObjective:
+    """phyfoo_ssobj: the fixed-q objective on sufficient statistics, evaluated on the host inside the library (order 0).
+    From an FESet (one device pass), a MultiFESet (counts all-reduced over the devices) or given counts."""
+
+    def __init__(self, fe=None, desc=None, counts=None, entropy=0.0):
+        self.h = C.c_void_p()
+        if isinstance(fe, MultiFESet):
+            _mraise(lib().phyfoo_multi_ss_create(fe.mctx.h, fe.h, C.byref(self.h)), fe.mctx.h)
+        elif fe is not None:
+            raise_for(lib().phyfoo_ss_create(fe.ctx.h, fe.h, C.byref(self.h)), fe.ctx.h)
+        else:
+            c = np.ascontiguousarray(counts, np.float64)
+            rc = lib().phyfoo_ss_create_host(C.byref(desc), _p(c, C.c_double), float(entropy), C.byref(self.h))
+            if rc != _abi.OK:
+                raise ValueError(f"phyfoo_ss_create_host failed ({rc})")
+
+    def free(self):
+        if self.h:
+            lib().phyfoo_ss_free(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def value(self):
+        return lib().phyfoo_ss_value(self.h)
+
+    def evaluations(self):
+        return int(lib().phyfoo_ss_evaluations(self.h))
+
+    def eval(self, position, lam):
+        lam = np.ascontiguousarray(lam, np.float64)
+        f = C.c_double()
+        if lib().phyfoo_ss_eval(self.h, int(position), _p(lam, C.c_double), lam.size, C.byref(f)) != _abi.OK:
+            raise ValueError("phyfoo_ss_eval: bad argument")
+        return f.value
+
+    def grad(self, position, lam, eps=1e-4):
+        lam = np.ascontiguousarray(lam, np.float64)
+        f, g = C.c_double(), np.zeros(lam.size)
+        if lib().phyfoo_ss_grad(self.h, int(position), _p(lam, C.c_double), lam.size, float(eps), C.byref(f), _p(g, C.c_double)) != _abi.OK:
+            raise ValueError("phyfoo_ss_grad: bad argument")
+        return f.value, g
+
+    def eval_branches(self, position, branch):
+        b = np.ascontiguousarray(branch, np.float64)
+        f = C.c_double()
+        if lib().phyfoo_ss_eval_branches(self.h, int(position), _p(b, C.c_double), C.byref(f)) != _abi.OK:
+            raise ValueError("phyfoo_ss_eval_branches: bad argument")
+        return f.value
+
+    def get_pi(self, position):
+        out = np.zeros(4)
+        lib().phyfoo_ss_get_pi(self.h, int(position), _p(out, C.c_double), 4)
+        return out
+
+    def optimize(self, order):
+        """One M-step of the motif model: the positions in `order`, each by the library's BFGS.  Returns (f_before, f_after,
+        evaluations)."""
+        o = np.ascontiguousarray(order, np.int32)
+        fb, fa, ev = C.c_double(), C.c_double(), C.c_int64()
+        if lib().phyfoo_ss_optimize(self.h, _p(o, C.c_int32), o.size, C.byref(fb), C.byref(fa), C.byref(ev)) != _abi.OK:
+            raise ValueError("phyfoo_ss_optimize: bad argument")
+        return fb.value, fa.value, ev.value

@@ -475,3 +475,44 @@ extern "C" void phyfoo_multi_fe_free(phyfoo_mctx* mc, phyfoo_mfeset* mf) {
     for (size_t r = 0; r < mf->fe.size(); ++r) phyfoo_fe_free(mc ? mc->ctx[r] : nullptr, mf->fe[r]);
     delete mf;
 }
+
+// sufficient statistics over all devices: the expected counts (W * E doubles) and the entropy are all-reduced once; every
+// later evaluation is a host-side dot product inside the library (suffstat_host.hpp), without any device call or collective
+extern "C" int phyfoo_multi_ss_create(phyfoo_mctx* mc, phyfoo_mfeset* mf, phyfoo_ssobj** out) {
+    if (!mc) return PHYFOO_EINVAL;
+    if (!mf || !out) return mfail(mc, PHYFOO_EINVAL, "multi_ss_create: NULL argument");
+    *out = nullptr;
+    const int world = (int)mc->ctx.size();
+    const ModelHost& h0 = mf->fe[0]->m->h;
+    const size_t WE = (size_t)h0.W * h0.E;
+    std::vector<std::vector<double>> part(world, std::vector<double>(WE + 1, 0.0));
+    int rc = mc->workers.run([&](int r) { mc->ctx[r]->err.clear(); return phyfoo_fe_suffstats(mc->ctx[r], mf->fe[r], part[r].data(), &part[r][WE]); });
+    if (rc) return mcollect(mc, rc, "multi_ss_create");
+    if (world > 1) {
+        // through the devices and NCCL like every other exchange of this library (W * E + 1 doubles, once per M-step)
+        std::vector<double*> d_buf(world, nullptr);
+        rc = mc->workers.run([&](int r) {
+            phyfoo_ctx* ctx = mc->ctx[r];
+            CU(cudaSetDevice(ctx->device));
+            CU(ctx->misc.ensure((WE + 1) * sizeof(double)));
+            d_buf[r] = ctx->misc.as<double>();
+            CU(cudaMemcpyAsync(d_buf[r], part[r].data(), (WE + 1) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            return PHYFOO_OK;
+        });
+        if (rc) return mcollect(mc, rc, "multi_ss_create");
+        rc = mc->workers.run([&](int r) {
+            phyfoo_ctx* ctx = mc->ctx[r];
+            CU(cudaSetDevice(ctx->device));
+            const int e = mreduce(mc, r, d_buf[r], WE + 1);
+            if (e) return e;
+            if (r == 0) CU(cudaMemcpyAsync(part[0].data(), d_buf[0], (WE + 1) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            return PHYFOO_OK;
+        });
+        if (rc) return mcollect(mc, rc, "multi_ss_create");
+    }
+    phyfoo_ssobj* ss = new phyfoo_ssobj();
+    ss->o.init(h0, part[0].data(), part[0][WE]);
+    *out = ss;
+    return PHYFOO_OK;
+}

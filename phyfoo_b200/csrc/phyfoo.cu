@@ -1970,4 +1970,90 @@ extern "C" int phyfoo_score_order_stats(phyfoo_ctx* ctx, const phyfoo_dataset* d
     return PHYFOO_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// sufficient-statistics objective on the host inside the library (suffstat_host.hpp)
+// ------------------------------------------------------------------------------------------------
+#include "suffstat_host.hpp"
+
+struct phyfoo_ssobj { SuffStatObjective o; };
+
+extern "C" int phyfoo_ss_create(phyfoo_ctx* ctx, phyfoo_feset* fe, phyfoo_ssobj** out) {
+    if (!ctx) return PHYFOO_EINVAL;
+    if (!fe || !out) return fail(ctx, PHYFOO_EINVAL, "ss_create: NULL argument");
+    *out = nullptr;
+    const ModelHost& h = fe->m->h;
+    std::vector<double> c((size_t)h.W * h.E);
+    double ent = 0.0;
+    const int rc = phyfoo_fe_suffstats(ctx, fe, c.data(), &ent);
+    if (rc) return rc;
+    phyfoo_ssobj* ss = new phyfoo_ssobj();
+    ss->o.init(h, c.data(), ent);
+    *out = ss;
+    return PHYFOO_OK;
+}
+// from given counts (e.g. counts a caller reduced itself); no device involved
+extern "C" int phyfoo_ss_create_host(const phyfoo_model_desc* desc, const double* counts, double entropy, phyfoo_ssobj** out) {
+    if (!desc || !counts || !out) return PHYFOO_EINVAL;
+    *out = nullptr;
+    try {
+        ModelHost h;
+        h.init(*desc);
+        if (h.order != 0) return PHYFOO_EUNSUPPORTED;
+        phyfoo_ssobj* ss = new phyfoo_ssobj();
+        ss->o.init(h, counts, entropy);
+        *out = ss;
+    } catch (const std::exception&) { return PHYFOO_EINVAL; }
+    return PHYFOO_OK;
+}
+extern "C" void phyfoo_ss_free(phyfoo_ssobj* ss) { delete ss; }
+extern "C" double phyfoo_ss_value(const phyfoo_ssobj* ss) { return ss ? ss->o.value() : NAN; }
+extern "C" int64_t phyfoo_ss_evaluations(const phyfoo_ssobj* ss) { return ss ? ss->o.evaluations : 0; }
+extern "C" int phyfoo_ss_eval(phyfoo_ssobj* ss, int32_t position, const double* lambda, int32_t dim, double* f_out) {
+    if (!ss || !lambda || !f_out || position < 0 || position >= ss->o.h.W || dim != 4) return PHYFOO_EINVAL;
+    *f_out = ss->o.eval_lambda(position, lambda);
+    return PHYFOO_OK;
+}
+extern "C" int phyfoo_ss_grad(phyfoo_ssobj* ss, int32_t position, const double* lambda, int32_t dim, double eps, double* f_out, double* g_out) {
+    if (!ss || !lambda || !g_out || position < 0 || position >= ss->o.h.W || dim != 4 || !(eps > 0)) return PHYFOO_EINVAL;
+    double x[4] = {lambda[0], lambda[1], lambda[2], lambda[3]};
+    const double f0 = ss->o.eval_lambda(position, x);
+    for (int i = 0; i < 4; ++i) {                       // jstacs NumericalDifferentiableFunction.java:64-84
+        const double keep = x[i];
+        x[i] += eps;
+        g_out[i] = (ss->o.eval_lambda(position, x) - f0) / eps;
+        x[i] = keep;
+    }
+    ss->o.eval_lambda(position, x);
+    if (f_out) *f_out = f0;
+    return PHYFOO_OK;
+}
+extern "C" int phyfoo_ss_eval_branches(phyfoo_ssobj* ss, int32_t position, const double* branch, double* f_out) {
+    if (!ss || !branch || !f_out || position >= ss->o.h.W) return PHYFOO_EINVAL;
+    *f_out = ss->o.eval_branches(position, branch);
+    return PHYFOO_OK;
+}
+extern "C" int phyfoo_ss_get_pi(const phyfoo_ssobj* ss, int32_t position, double* pi_out, int32_t n) {
+    if (!ss || !pi_out || position < 0 || position >= ss->o.h.W || n != 4) return PHYFOO_EINVAL;
+    for (int i = 0; i < 4; ++i) pi_out[i] = ss->o.h.pi[position][i];
+    return PHYFOO_OK;
+}
+// the M-step of PhyloBayesModel.train on this objective: the listed positions one after the other (the caller draws the
+// order, util/PWMUtil.java:131-144), each from its current parameters, termination TC_MOTIF_SEPARATED_POSITIONS
+extern "C" int phyfoo_ss_optimize(phyfoo_ssobj* ss, const int32_t* order, int32_t n_pos, double* f_before, double* f_after, int64_t* evaluations) {
+    if (!ss || !order || n_pos < 0) return PHYFOO_EINVAL;
+    if (f_before) *f_before = ss->o.value();
+    const long long e0 = ss->o.evaluations;
+    for (int j = 0; j < n_pos; ++j) {
+        const int t = order[j];
+        if (t < 0 || t >= ss->o.h.W) return PHYFOO_EINVAL;
+        std::vector<double> x(4);
+        for (int i = 0; i < 4; ++i) x[i] = std::log(ss->o.h.pi[t][i]);
+        bfgs_minimise([&](const double* z) { return -ss->o.eval_lambda(t, z); }, x, tc_motif_separated_positions());
+        ss->o.eval_lambda(t, x.data());
+    }
+    if (f_after) *f_after = ss->o.value();
+    if (evaluations) *evaluations = ss->o.evaluations - e0;
+    return PHYFOO_OK;
+}
+
 #include "multi.cuh"

@@ -35,6 +35,8 @@ SYMBOLS = [
     "phyfoo_multi_model_create", "phyfoo_multi_model_set_pi", "phyfoo_multi_model_get_pi", "phyfoo_multi_model_set_branch",
     "phyfoo_multi_model_set_mode", "phyfoo_multi_model_free", "phyfoo_multi_zoops_estep", "phyfoo_multi_fe_prepare_selected",
     "phyfoo_multi_fe_eval", "phyfoo_multi_fe_grad", "phyfoo_multi_fe_size", "phyfoo_multi_fe_free",
+    "phyfoo_ss_create", "phyfoo_ss_create_host", "phyfoo_ss_eval", "phyfoo_ss_grad", "phyfoo_ss_eval_branches", "phyfoo_ss_get_pi",
+    "phyfoo_ss_value", "phyfoo_ss_evaluations", "phyfoo_ss_optimize", "phyfoo_ss_free", "phyfoo_multi_ss_create",
 ]
 
 
@@ -130,6 +132,21 @@ def lib():
     fp = C.POINTER(C.c_float)
     L.phyfoo_estep_kernel_ms.argtypes = [vp, fp, fp, fp]
     L.phyfoo_estep_sweeps.argtypes = [vp, i64p, i64p]
+    # ---- sufficient-statistics objective on the host inside the library (csrc/suffstat_host.hpp)
+    L.phyfoo_ss_create.argtypes = [vp, vp, C.POINTER(vp)]
+    L.phyfoo_ss_create_host.argtypes = [C.POINTER(_abi.ModelDesc), dp, C.c_double, C.POINTER(vp)]
+    L.phyfoo_ss_eval.argtypes = [vp, C.c_int32, dp, C.c_int32, dp]
+    L.phyfoo_ss_grad.argtypes = [vp, C.c_int32, dp, C.c_int32, C.c_double, dp, dp]
+    L.phyfoo_ss_eval_branches.argtypes = [vp, C.c_int32, dp, dp]
+    L.phyfoo_ss_get_pi.argtypes = [vp, C.c_int32, dp, C.c_int32]
+    L.phyfoo_ss_value.argtypes = [vp]
+    L.phyfoo_ss_value.restype = C.c_double
+    L.phyfoo_ss_evaluations.argtypes = [vp]
+    L.phyfoo_ss_evaluations.restype = C.c_int64
+    L.phyfoo_ss_optimize.argtypes = [vp, ip32, C.c_int32, dp, dp, i64p]
+    L.phyfoo_ss_free.argtypes = [vp]
+    L.phyfoo_ss_free.restype = None
+    L.phyfoo_multi_ss_create.argtypes = [vp, vp, C.POINTER(vp)]
     # ---- several GPUs behind one caller (csrc/multi.cuh)
     L.phyfoo_init_multi.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
     L.phyfoo_destroy_multi.argtypes = [vp]

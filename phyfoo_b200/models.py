@@ -167,10 +167,12 @@ class PhyloBayesModel(_PhyloModel):
     PROB_THRESH_FOR_WEIGHTS = 0.8      # models/PhyloPreparedAbstractModel.java:20
     MOTIF_QUALITY_THRESHOLD = 0.0      # :21
     OPTIMIZE_IN_TOTO = False           # :63
-    # False (default): every evaluation of the objective is a pass over the selected windows on the device, the reference's
-    # own evaluation order.  True (order 0): one device pass collects the expected counts of the table entries, every
-    # evaluation is then a dot product on the host (same function, sums re-associated).
-    MSTEP_SUFFICIENT_STATISTICS = False
+    # True (default; applies to order 0): one device pass collects the expected counts of the table entries, every evaluation
+    # of the objective is then a dot product on the host inside libphyfoo.so and a whole M-step is one library call
+    # (phyfoo_ss_optimize).  False: every evaluation is a pass over the selected windows on the device, the reference's own
+    # evaluation order.  Same function, sums re-associated (1e-12 relative along a whole optimisation:
+    # tests/test_gpu_mstep.py); order-1 motifs always take the device evaluation.
+    MSTEP_SUFFICIENT_STATISTICS = True
 
     def train(self, sample: PhyloSample, weights, rng=None, rev_weights=None, sharded=False):
         """One M-step: select the top-posterior windows per alignment (io/SequenceSpecificDataSelector.java:37-99), fix
@@ -208,23 +210,21 @@ class PhyloBayesModel(_PhyloModel):
             sharding.broadcast_host_(order)
         try:
             if self.MSTEP_SUFFICIENT_STATISTICS and self.order == 0 and not self.OPTIMIZE_IN_TOTO:
-                # one device pass for the expected counts, then the same position-wise BFGS on host dot products
-                obj = optimize.SuffStatObjective(local, self._pi, self._branch, type(self).EVOL_MODEL)
-                if fe is not local:
-                    obj.counts, obj.entropy = sharding.allreduce_counts_(obj.counts, obj.entropy)
-                    for t in range(self.length):
-                        obj.set_position(t)
-                stats["f_before"] = obj.value()
-                for pos in order:
-                    pos = int(pos)
-                    fun = lambda z: -obj.eval_lambda(pos, z)          # noqa: E731
-                    x, f, it, ev = optimize.quasi_newton_bfgs(fun, lambda z: obj.grad(fun, z), np.log(self._pi[pos].ravel()),
-                                                              optimize.TC_MOTIF_SEPARATED_POSITIONS())
-                    obj.eval_lambda(pos, x)
-                    stats["evaluations"] += ev
-                stats["f_after"] = obj.value()
+                # one device pass for the expected counts (all-reduced when sharded), then the position-wise BFGS on host dot
+                # products inside the library
+                if sharded:
+                    counts, entropy = local.suffstats(self.length, 4 + 16 * (self.tree.n_nodes - 1))
+                    counts, entropy = sharding.allreduce_counts_(counts, entropy)
+                    desc, keep = _abi.make_desc(self.kind, self.length, 0, self.tree, self._branch, self._pi, type(self).EVOL_MODEL,
+                                                _abi.MODE_MEANFIELD)
+                    obj = core.SSObjective(desc=desc, counts=counts, entropy=entropy)
+                    del keep
+                else:
+                    obj = core.SSObjective(local)
+                stats["f_before"], stats["f_after"], stats["evaluations"] = obj.optimize(order)
                 for t in range(self.length):
-                    self.setCondProb(obj.pi[t].reshape(self._pi[t].shape), t)
+                    self.setCondProb(obj.get_pi(t).reshape(self._pi[t].shape), t)
+                obj.free()
                 self.trainingStep += 1
                 return stats
             if self.OPTIMIZE_IN_TOTO:

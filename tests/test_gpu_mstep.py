@@ -215,3 +215,51 @@ def test_sufficient_statistics_objective(ctx, tree, evol):
     assert abs(evolution.logit_from_branch(alpha) - x).max() < 0.05
     # counts are non-negative and each position's root counts sum to the total weight (plus the gap-leaf share)
     assert (obj.counts >= 0).all() and (obj.counts[:, :4].sum(axis=1) >= sw.sum() - 1e-9).all()
+
+
+def test_library_suffstat_objective_follows_the_device_objective_along_an_optimisation(ctx):
+    """phyfoo_ss_* (expected counts from one device pass, evaluations on the host inside the library) against phyfoo_fe_eval
+    (a device pass over the selected windows per evaluation): every point a whole position-wise BFGS visits, 1e-12 relative;
+    then the one-call M-step (phyfoo_ss_optimize) against the same optimiser driven through phyfoo_fe_eval / phyfoo_fe_grad."""
+    from phyfoo_b200 import core, optimize, synth
+    from phyfoo_b200.models import PhyloBackground, PhyloBayesModel, SingleHiddenMotifMixture
+    newick = synth.random_binary_newick(7, 4)
+    W = 6
+    pwm = synth.random_pwm(W, 0, 5)
+    smp, _ = synth.make_sample(newick, 60, 80, 6, pwm=pwm, gap_rate=0.03, length_jitter=10)
+    fg = PhyloBayesModel(W, 0, newick, ctx); fg.setCondProbs(synth.random_pwm(W, 0, 77))     # start away from the optimum
+    bg = PhyloBackground(0, newick, ctx)
+    res = SingleHiddenMotifMixture(fg, bg, zoops=0.9).getNewWeights(smp)
+    ds = smp.device(ctx)
+    sa, so, sw = core.select(ctx, ds, W, res["gamma"])
+    fe = core.FESet(ctx, ds, fg.device_model(), sa, so, sw)
+    ss = core.SSObjective(fe)
+    visited = []
+    for pos in (3, 0, 5):
+        def fun(z, pos=pos):
+            visited.append((pos, np.array(z)))
+            return -ss.eval(pos, z)
+        x, f, it, ev = optimize.quasi_newton_bfgs(fun, lambda z: tuple(-v for v in ss.grad(pos, z)), np.log(ss.get_pi(pos)),
+                                                  optimize.TC_MOTIF_SEPARATED_POSITIONS())
+        ss.eval(pos, x)
+        fe.eval(pos, x)                                   # the device model follows
+    assert len(visited) > 30
+    ss2 = core.SSObjective(fe)                            # counts do not depend on the parameters: same object, fresh copy of the model
+    for pos, z in visited[-40:]:
+        a, b = ss2.eval(pos, z), fe.eval(pos, z)
+        assert abs(a - b) <= 1e-12 * abs(b), (pos, a, b)
+    # one-call M-step vs the same optimiser on the device objective
+    fg.setCondProbs(synth.random_pwm(W, 0, 77))
+    fe2 = core.FESet(ctx, ds, fg.device_model(), sa, so, sw)
+    ss3 = core.SSObjective(fe2)
+    order = np.arange(W, dtype=np.int32)[::-1].copy()
+    fb, fa, ev = ss3.optimize(order)
+    for pos in order:
+        pos = int(pos)
+        lam0 = np.log(fg.getCondProb(pos))
+        x, f, it, n = optimize.quasi_newton_bfgs(lambda z: -fe2.eval(pos, z), lambda z: tuple(-v for v in fe2.grad(pos, z)), lam0,
+                                                 optimize.TC_MOTIF_SEPARATED_POSITIONS())
+        f_dev = fe2.eval(pos, x)
+    assert fa > fb and abs(fa - f_dev) <= 1e-7 * abs(fa)
+    for f_ in (fe, fe2):
+        f_.free()

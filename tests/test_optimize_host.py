@@ -75,3 +75,70 @@ def test_bfgs_on_sufficient_statistics_finds_the_closed_form_optimum():
     obj.eval_lambda(0, x)
     assert np.abs(obj.pi[0] - want).max() < 2e-3 and it >= 1 and ev > 5
     assert obj.value() > -fun(np.log(np.full(4, 0.25))) - 1e-12        # the objective did not get worse
+
+
+# ---- the sufficient-statistics objective and its optimiser inside libphyfoo.so (csrc/suffstat_host.hpp): host code ----
+def _ss_case(seed=3, W=5):
+    from phyfoo_b200 import _abi, synth
+    from phyfoo_b200.newick import parse_newick
+    tree = parse_newick(synth.random_binary_newick(6, 9))
+    rng = np.random.default_rng(seed)
+    pwm = [rng.dirichlet(np.ones(4), size=1) for _ in range(W)]
+    branch = np.tile(tree.branch, (W, 1))
+    E = 4 + 16 * (tree.n_nodes - 1)
+    counts = rng.gamma(2.0, 3.0, size=(W, E)) * (rng.random((W, E)) > 0.1)
+    desc, keep = _abi.make_desc(_abi.MODEL_FG, W, 0, tree, branch, pwm, _abi.EVOL_F81ALPHA, _abi.MODE_MEANFIELD)
+    return tree, pwm, branch, counts, desc, keep
+
+
+class _FakeFE:
+    def __init__(self, counts, entropy):
+        self.c, self.e = counts, entropy
+
+    def suffstats(self, W, E):
+        return self.c.copy(), self.e
+
+
+def test_library_suffstat_objective_matches_numpy_objective():
+    from phyfoo_b200 import _abi, core, optimize
+    tree, pwm, branch, counts, desc, keep = _ss_case()
+    ss = core.SSObjective(desc=desc, counts=counts, entropy=1.25)
+    ref = optimize.SuffStatObjective(_FakeFE(counts, 1.25), pwm, branch, _abi.EVOL_F81ALPHA)
+    assert abs(ss.value() - ref.value()) <= 1e-13 * abs(ref.value())
+    rng = np.random.default_rng(1)
+    for t in (0, 3, 4):
+        lam = rng.normal(size=4)
+        f, g = ss.grad(t, lam)
+        f_ref, g_ref = ref.grad(lambda z: ref.eval_lambda(t, z), lam)
+        assert abs(f - f_ref) <= 1e-13 * abs(f_ref)
+        assert np.max(np.abs(g - g_ref)) <= 1e-7 * np.max(np.abs(g_ref))      # both subtract sums of size |f| and divide by 1e-4
+        assert np.allclose(ss.get_pi(t), ref.pi[t], rtol=1e-15, atol=0)
+    b = np.concatenate([[0.0], rng.uniform(0.05, 0.4, tree.n_nodes - 1)])
+    f = ss.eval_branches(2, b)
+    ref.set_position(2, branch=b)
+    assert abs(f - ref.value()) <= 1e-13 * abs(f)
+
+
+def test_library_bfgs_matches_python_stand_in():
+    """phyfoo_ss_optimize (C++) against optimize.quasi_newton_bfgs (numpy) on the same objective: the same algorithm, so
+    the same optimum to rounding."""
+    from phyfoo_b200 import _abi, core, optimize
+    tree, pwm, branch, counts, desc, keep = _ss_case(seed=11)
+    W = len(pwm)
+    ss = core.SSObjective(desc=desc, counts=counts, entropy=0.0)
+    ref = optimize.SuffStatObjective(_FakeFE(counts, 0.0), pwm, branch, _abi.EVOL_F81ALPHA)
+    order = np.array([2, 0, 4, 1, 3], np.int32)
+    fb, fa, ev = ss.optimize(order)
+    assert abs(fb - ref.value()) <= 1e-13 * abs(fb)
+    for pos in order:
+        pos = int(pos)
+        fun = lambda z: -ref.eval_lambda(pos, z)          # noqa: E731
+        x, f, it, n = optimize.quasi_newton_bfgs(fun, lambda z: ref.grad(fun, z), np.log(ref.pi[pos]), optimize.TC_MOTIF_SEPARATED_POSITIONS())
+        ref.eval_lambda(pos, x)
+    assert fa >= fb
+    assert abs(fa - ref.value()) <= 1e-9 * abs(fa)
+    for t in range(W):
+        assert np.allclose(ss.get_pi(t), ref.pi[t], rtol=0, atol=1e-6)
+    # the closed-form optimum of one position: f is sum_e C log table; for the root entries alone (a star of zero-length
+    # branches would be degenerate) check monotone improvement instead
+    assert ev > 5 * W
