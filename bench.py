@@ -334,13 +334,12 @@ def fp64_roofline(flops, abytes, kernel_name, kernel_ms, peak_tflops, hbm_peak, 
     return r
 
 
-def roofline_of(run, kernels, step_ms, sweeps_fg, peak_tflops, hbm_peak, hbm_of, traffic_db, direct=None):
+def roofline_of(run, path, kernels, step_ms, sweeps_fg, peak_tflops, hbm_peak, hbm_of, traffic_db, direct=None):
     """roofline of the kernel(s) with the largest share of the step + extra sub-objects (pattern-table path)."""
     cfg, I, S, W, n_windows = run.cfg, run.I, run.cfg["S"], run.cfg["W"], run.n_windows
     flops = algorithmic_flops(cfg, I, n_windows, sweeps_fg)
     abytes = algorithmic_bytes(cfg, n_windows)
     names = {name for (_, name) in kernels}
-    path = run.ctx.last_score_path()
     extra = {}
 
     def traffic_of(*keys):
@@ -603,7 +602,7 @@ def run_ours(args):
             n_ex = 20 if name == "c2" else 5
             ms, kern = ex.timed(n_ex)
             sw_fg, _ = ctx.estep_sweeps()
-            rl, ex_extra = roofline_of(ex, kern, ms / n_ex, sw_fg, peak_tflops, hbm_peak, hbm_of, traffic_db)
+            rl, ex_extra = roofline_of(ex, ctx.last_score_path(), kern, ms / n_ex, sw_fg, peak_tflops, hbm_peak, hbm_of, traffic_db)
             extras[name] = {"workload": workload_name(ex.cfg), "value": ex.n_windows * n_ex / (ms * 1e-3), "unit": UNIT,
                             "ms_per_step": ms / n_ex, "steps": n_ex, "warmup": 3, "parity_checked": pc,
                             "scoring_path": PATHS[ctx.last_score_path()], "roofline": rl,
@@ -613,7 +612,7 @@ def run_ours(args):
 
     if rank == 0:
         kern_list = [{"kernel": name, "ms": round(ms, 5)} for (_, name), ms in sorted(kernels.items())]
-        roofline, extra = roofline_of(run, kernels, step_ms, sweeps_fg, peak_tflops, hbm_peak, hbm_of, traffic_db, direct)
+        roofline, extra = roofline_of(run, path, kernels, step_ms, sweeps_fg, peak_tflops, hbm_peak, hbm_of, traffic_db, direct)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": step_ms, "higher_is_better": True,
