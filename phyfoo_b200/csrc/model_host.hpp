@@ -178,6 +178,32 @@ struct ModelHost {
     }
     static int tab_off(int node) { return 4 + 16 * (node - 1); }
 
+    // compact order-0 log tables for substitution tables with F81 structure (tree_pass_f81.cuh): per position
+    // Ef = 4 + 8 (N - 1) entries: log pi, then per node Lo[b] (log off-diagonal, the same for every a != b) | D[b] = log
+    // diagonal - Lo[b].  Returns false when a table does not have that structure bit for bit or an entry is not finite.
+    int Ef() const { return 4 + 8 * (N - 1); }
+    bool tables0f(std::vector<double>& out) const {
+        const int ef = Ef();
+        out.assign((size_t)W * ef, 0.0);
+        for (int t = 0; t < W; ++t) {
+            const double* pt = &probtab[(size_t)t * E];
+            const double* lt = &logtab[(size_t)t * E];
+            double* o = &out[(size_t)t * ef];
+            for (int a = 0; a < 4; ++a) { o[a] = lt[a]; if (!std::isfinite(o[a])) return false; }
+            for (int k = 1; k < N; ++k)
+                for (int b = 0; b < 4; ++b) {
+                    const int off_row = (b + 1) & 3;
+                    for (int a = 0; a < 4; ++a)
+                        if (a != b && pt[tab_off(k) + a * 4 + b] != pt[tab_off(k) + off_row * 4 + b]) return false;
+                    const double lo = lt[tab_off(k) + off_row * 4 + b], ld = lt[tab_off(k) + b * 4 + b];
+                    if (!std::isfinite(lo) || !std::isfinite(ld)) return false;
+                    o[4 + 8 * (k - 1) + b] = lo;
+                    o[4 + 8 * (k - 1) + 4 + b] = ld - lo;
+                }
+        }
+        return true;
+    }
+
     // CPF table of (position t, node k) for ANY order, reference layout [4^P][4], row l = a_treeparent + 4*ctx
     // (root: rows = ctx).  VirtualTree.java:82-96.
     std::vector<double> cpf(int t, int k) const {

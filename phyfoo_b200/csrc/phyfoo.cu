@@ -81,6 +81,8 @@ struct phyfoo_ctx {
     int order1_kernel = 2;           // 0 = one quad per window (net1.cuh), 1 = wavefront, 16 lanes per window (net1w.cuh),
                                      // 2 = one thread per node (net1n.cuh; windows with gaps through the wavefront kernel)
     DevBuf memo_pending;             // fallback list of the pattern-table path
+    int order0_kernel = -1;          // order-0 mean-field scoring: -1 = choose (F81-structured kernel for more than 6 species, where the
+                                     // pattern table does not apply), 0 = generic kernel (tree_pass.cuh), 1 = F81-structured kernel
     int order1_qglobal = -1;         // node-per-thread kernel: -1 = choose, 0 = q rows in shared memory, n > 0 = q rows in global memory
                                      // behind L1 with n warps per SM (<= 8)
     DevBuf o1n_cache, o1n_fb;        // node-per-thread order-1 kernel: observed-leaf sums per warp; list of windows with gaps
@@ -118,6 +120,8 @@ struct phyfoo_model {
     double* d_tab1w = nullptr;    // order 1, wavefront kernel (net1w.cuh)
     int* d_prog1w = nullptr;
     int prog1w_len = 0, MC = 1, ML = 1, n_steps = 0;
+    double* d_tabf = nullptr;     // order 0, compact tables of the F81-structured kernel (tree_pass_f81.cuh): [Ef][W]
+    bool f81_ok = false;          // the tables have F81 structure and are finite (else the generic kernel scores)
     double* d_tab1n = nullptr;    // order 1, node-per-thread kernel (net1n.cuh): internal-node tables [W][I][32]
     double* d_leaftab1n = nullptr;//                                              leaf tables [W][S][32]
     int* d_prog1n = nullptr;
@@ -815,7 +819,7 @@ extern "C" void phyfoo_model_free(phyfoo_ctx* ctx, phyfoo_model* m) {
     if (!m) return;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
     cudaFree(m->d_prog); cudaFree(m->d_logtab); cudaFree(m->d_probtab); cudaFree(m->d_tab1); cudaFree(m->d_tab1w); cudaFree(m->d_prog1w);
-    cudaFree(m->d_tab1n); cudaFree(m->d_leaftab1n); cudaFree(m->d_prog1n);
+    cudaFree(m->d_tab1n); cudaFree(m->d_leaftab1n); cudaFree(m->d_prog1n); cudaFree(m->d_tabf);
     delete m;
 }
 
@@ -869,7 +873,15 @@ static int model_upload(phyfoo_ctx* ctx, phyfoo_model* m) {
         CU(cudaMemcpyAsync(m->d_prog, prog.data(), prog.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMalloc(&m->d_logtab, n * sizeof(double)));
         CU(cudaMalloc(&m->d_probtab, n * sizeof(double)));
+        CU(cudaMalloc(&m->d_tabf, (size_t)h.Ef() * h.W * sizeof(double)));
         CU(cudaStreamSynchronize(ctx->stream));
+    }
+    std::vector<double> tf, tft((size_t)h.Ef() * h.W);
+    m->f81_ok = h.tables0f(tf);
+    if (m->f81_ok) {
+        for (int t = 0; t < h.W; ++t)
+            for (int e = 0; e < h.Ef(); ++e) tft[(size_t)e * h.W + t] = tf[(size_t)t * h.Ef() + e];
+        CU(cudaMemcpyAsync(m->d_tabf, tft.data(), tft.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     }
     std::vector<double> tl(n), tp(n);
     for (int t = 0; t < h.W; ++t)
@@ -958,6 +970,7 @@ struct ScoreItems {
 #include "net1.cuh"
 #include "net1w.cuh"
 #include "net1n.cuh"
+#include "tree_pass_f81.cuh"
 #include "memo.cuh"
 
 static void memo_release(cudaStream_t st, MemoSet* ms) {
@@ -1420,6 +1433,60 @@ static int launch_net1(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* 
     return PHYFOO_OK;
 }
 
+// order-0 mean field with F81-structured tables (tree_pass_f81.cuh): groups of a few warps whose lane count is a multiple of
+// the motif width exchange the trees' free energies; returns 1 when the configuration does not fit (generic kernel then)
+static int launch_score_f81(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* m, const int64_t* d_win_off, int64_t n_windows,
+                            int strands, double* d_out, int32_t* d_sweeps, int counter_slot) {
+    ModelHost& h = m->h;
+    const int W = h.W;
+    const int n_strands = strands == 2 ? 2 : 1;
+    const long long n_items = (long long)n_windows * n_strands;
+    // group: the fewest warps whose lanes the windows fill best (W = 12: 3 warps = 8 windows, no idle lane)
+    int best_nwg = 0; double best_use = 0.0;
+    for (int nwg = 1; nwg <= 8; ++nwg) {
+        if (32 * nwg < W) continue;
+        const double use = (double)((32 * nwg) / W * W) / (32 * nwg);
+        if (use > best_use + 1e-9) { best_use = use; best_nwg = nwg; }
+    }
+    if (!best_nwg) return 1;
+    const int GL = 32 * best_nwg;
+    const int n_groups = std::max(1, std::min(15, 512 / GL));
+    const int T = n_groups * GL;
+    const size_t budget = std::min<size_t>(ctx->smem_optin, 227 * 1024);
+    const size_t fixed = ((size_t)h.Ef() * W + 64 + 2 * (size_t)T) * sizeof(double) + (size_t)n_groups * (GL / W) * sizeof(long long) +
+                         (size_t)m->prog_len * sizeof(int) + 64;
+    if (fixed > budget) return 1;
+    const size_t state = (size_t)h.I * 8 * T * sizeof(double);
+    const bool gstate = fixed + state > budget;
+    const size_t smem = fixed + (gstate ? 0 : state);
+    CU(cudaFuncSetAttribute(score_o0f_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long per_block = (long long)n_groups * (GL / W);
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((n_items + per_block - 1) / per_block, ctx->sm_count));
+    ScoreFParams p;
+    p.bases = ds->d_bases; p.gaps = ds->d_gaps; p.n_cols = ds->n_cols; p.nb = ds->nb;
+    p.col_off = ds->d_col_off; p.win_off = d_win_off; p.n_aln = ds->n_aln;
+    p.n_windows = n_windows; p.n_strands = n_strands; p.strand0 = strands == 1 ? 1 : 0;
+    p.W = W; p.I = h.I; p.S = h.S; p.Ef = h.Ef(); p.prog_len = m->prog_len;
+    p.tab = m->d_tabf; p.prog = m->d_prog;
+    p.out = d_out; p.sweeps = d_sweeps;
+    unsigned long long* counters = ctx->counters.as<unsigned long long>();
+    p.counter_next = counters + 2 * counter_slot; p.counter_sweeps = counters + 2 * counter_slot + 1;
+    p.max_sweeps = h.max_sweeps; p.min_sweeps = h.min_sweeps; p.tol = h.tol;
+    p.group_lanes = GL; p.n_groups = n_groups;
+    p.gstate = nullptr;
+    if (gstate) {
+        CU(ctx->gstate.ensure((size_t)blocks * T * h.I * 8 * sizeof(double)));
+        p.gstate = ctx->gstate.as<double>();
+    }
+    CU(cudaMemsetAsync(p.counter_next, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    {
+        KernelTimer kt_(ctx, "score_o0f_kernel");
+        score_o0f_kernel<<<blocks, T, smem, ctx->stream>>>(p);
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
 // scores into d_out[n_strands][n_windows]; strands: 0 = forward only, 1 = reverse only, 2 = both.
 // items != NULL: score the listed windows (n_windows of them) instead and store their converged q.
 static int launch_score(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* m, const int64_t* d_win_off, int64_t n_windows,
@@ -1444,6 +1511,11 @@ static int launch_score(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model*
         return launch_memo_jobs(ctx, ds, &job, 1);
     }
     if (!fallback) ctx->last_path = 0;
+    if (!items && mode == PHYFOO_MODE_MEANFIELD && m->f81_ok && h.W <= 256 &&
+        (ctx->order0_kernel == 1 || (ctx->order0_kernel < 0 && 3 * h.S > 18))) {
+        rc = launch_score_f81(ctx, ds, m, d_win_off, n_windows, strands, d_out, d_sweeps, counter_slot);
+        if (rc <= 0) return rc;
+    }
     ScorePlan pl;
     // the fallback list of the pattern-table path is short (its length lives on the device): one block per SM
     rc = plan_score(ctx, h, m->prog_len, fallback ? std::min<long long>(n_items, 64LL * ctx->sm_count) : n_items, mode, items != nullptr, &pl);
@@ -1854,6 +1926,11 @@ extern "C" int phyfoo_set_option(phyfoo_ctx* ctx, const char* name, int64_t valu
     if (std::strcmp(name, "pattern_memo") == 0) {
         if (value < 0 || value > 2) return fail(ctx, PHYFOO_EINVAL, "set_option: pattern_memo must be 0 (off), 1 (auto) or 2 (always)");
         ctx->memo_mode = (int)value;
+        return PHYFOO_OK;
+    }
+    if (std::strcmp(name, "order0_kernel") == 0) {
+        if (value < -1 || value > 1) return fail(ctx, PHYFOO_EINVAL, "set_option: order0_kernel must be -1 (choose), 0 (generic) or 1 (F81-structured)");
+        ctx->order0_kernel = (int)value;
         return PHYFOO_OK;
     }
     if (std::strcmp(name, "order1_qglobal") == 0) {

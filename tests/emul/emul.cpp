@@ -461,3 +461,47 @@ extern "C" int emul_score_o1n(const phyfoo_model_desc* d, const uint8_t* codes, 
         return -5;
     } catch (const std::exception& e) { std::fprintf(stderr, "emul: %s\n", e.what()); return -1; }
 }
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Host run of the F81-structured order-0 pass (csrc/tree_pass_f81.cuh::meanfield_pass_f81) with the window-level stop rule of
+// score_o0f_kernel: per pass every tree contributes (terms, log z accumulator) -> n1n_free_energy, the window's free energy
+// is their tree-major sum.
+// ---------------------------------------------------------------------------------------------------------------------------
+#include "../../phyfoo_b200/csrc/tree_pass_f81.cuh"
+
+extern "C" int emul_score_o0f(const phyfoo_model_desc* d, const uint8_t* codes, int L, int strand, double* out, int* sweeps) {
+    try {
+        ModelHost m; m.init(*d);
+        if (m.order != 0) return -2;
+        std::vector<double> tabf;
+        if (!m.tables0f(tabf)) return -3;
+        const int S = m.S, W = m.W, ef = m.Ef();
+        TreeProg tp = prog_of(m);
+        std::vector<double> state((size_t)W * m.I * 8, std::nan(""));     // poisoned: the pass at the uniform start must not use it
+        for (int j = 0; j + W <= L; ++j) {
+            auto pass = [&](bool update) {
+                double sum = 0;
+                for (int t = 0; t < W; ++t) {
+                    State st{state.data() + (size_t)t * m.I * 8, 1};
+                    const int col = strand ? j + W - 1 - t : j + t;
+                    const ColWords cw = words_of(codes + (size_t)col * S, S, strand != 0);
+                    Tab lt{&tabf[(size_t)t * ef], 1};
+                    N1nAcc acc; acc.Fq = 0.0; acc.M = 1.0; acc.E = 0; acc.Fslow = 0.0;
+                    meanfield_pass_f81(tp, lt, st, cw, update, h_phy_exp_tab, acc);
+                    sum += n1n_free_energy(acc);
+                }
+                return sum;
+            };
+            double old = pass(false), cur = old;
+            int k = 0; bool conv = false;
+            while ((k < m.max_sweeps && !conv) || k < m.min_sweeps) {
+                cur = pass(true);
+                if (std::fabs(old - cur) < m.tol) conv = true;
+                old = cur; ++k;
+            }
+            out[j] = -cur;
+            if (sweeps) sweeps[j] = k;
+        }
+        return 0;
+    } catch (const std::exception& e) { std::fprintf(stderr, "emul: %s\n", e.what()); return -1; }
+}

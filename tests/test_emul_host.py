@@ -22,7 +22,7 @@ def emul():
     srcs = [os.path.join(EMUL_DIR, "emul.cpp"), os.path.join(ROOT, "phyfoo_b200", "csrc", "tree_pass.cuh"),
             os.path.join(ROOT, "phyfoo_b200", "csrc", "model_host.hpp"), os.path.join(ROOT, "phyfoo_b200", "csrc", "fp64_math.cuh"),
             os.path.join(ROOT, "phyfoo_b200", "csrc", "fp64_math_tables.h"),
-            os.path.join(ROOT, "phyfoo_b200", "csrc", "net1n.cuh")]
+            os.path.join(ROOT, "phyfoo_b200", "csrc", "net1n.cuh"), os.path.join(ROOT, "phyfoo_b200", "csrc", "tree_pass_f81.cuh")]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", srcs[0], "-o", so])
     L = C.CDLL(so)
@@ -263,3 +263,30 @@ def test_order1_node_update_matches_oracle(emul_o1n, tree, W):
         assert rel_err(out, ref) < 1e-9
         n_int = int((np.bincount(tr.parent[1:], minlength=tr.n_nodes) > 0).sum())
         assert ns.value >= -(-W * n_int // 4)            # at most four nodes per step
+
+
+# ---- order 0, F81-structured pass (csrc/tree_pass_f81.cuh): compact tables, free energy without a logarithm per node ----
+@pytest.mark.parametrize("tree", ["star5", "cat5", "mixed6", "rand12", "c3"])
+@pytest.mark.parametrize("evol", [_abi.EVOL_F81ALPHA, _abi.EVOL_F81BETA])
+@pytest.mark.parametrize("gap_rate", [0.0, 0.1])
+def test_order0_f81_pass_matches_oracle(emul, tree, evol, gap_rate):
+    from util import oracle_fg, orc
+    emul.emul_score_o0f.argtypes = [C.POINTER(_abi.ModelDesc), C.POINTER(C.c_uint8), C.c_int, C.c_int, C.POINTER(C.c_double),
+                                    C.POINTER(C.c_int)]
+    newick = O1N_TREES[tree]
+    tr = parse_newick(newick)
+    rng = np.random.default_rng(17)
+    W = 5
+    pwm = synth.random_pwm(W, 0, 63)
+    codes = random_codes(rng, W + 12, tr.n_species, gap_rate)
+    desc, keep = _abi.make_desc(_abi.MODEL_FG, W, 0, tr, np.tile(tr.branch, (W, 1)), pwm, evol, _abi.MODE_MEANFIELD)
+    om = oracle_fg(newick, pwm, order=0, evol=orc.F81ALPHA if evol == _abi.EVOL_F81ALPHA else orc.F81BETA)
+    n = codes.shape[0] - W + 1
+    for strand in (0, 1):
+        out, sw = np.zeros(n), np.zeros(n, np.int32)
+        rc = emul.emul_score_o0f(C.byref(desc), codes.ctypes.data_as(C.POINTER(C.c_uint8)), codes.shape[0], strand,
+                                 out.ctypes.data_as(C.POINTER(C.c_double)), sw.ctypes.data_as(C.POINTER(C.c_int)))
+        assert rc == 0
+        ref, rsw = om.score_windows(codes, bool(strand))
+        assert np.array_equal(sw, rsw)
+        assert rel_err(out, ref) < 1e-9

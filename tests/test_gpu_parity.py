@@ -250,3 +250,43 @@ def test_sharded_estep_single_rank(ctx):
         se.step()
         got = se.result()
         assert got["ll"] == ref["ll"] and np.array_equal(got["w"], ref["w"])
+
+
+@pytest.mark.parametrize("tree", ["star5", "cat5", "mixed6", "rand12", "rand30"])
+@pytest.mark.parametrize("W", [1, 5, 12, 20, 40])
+def test_f81_structured_kernel_equals_generic_kernel(ctx, tree, W):
+    """score_o0f_kernel (compact F81 tables, free energy without a logarithm per node, groups of warps with a named barrier)
+    against the generic kernel and the oracle: same sweep counts, scores equal to re-association; motif widths that give
+    groups of 1, 5, 3, 5 and 5 warps, both strands, ragged lengths, gaps, F81alpha and F81beta."""
+    from phyfoo_b200 import _abi, synth
+    from phyfoo_b200.data import PhyloSample
+    from phyfoo_b200.models import PhyloBayesModel
+    from phyfoo_b200.newick import parse_newick
+    newick = _trees()[tree]
+    S = parse_newick(newick).n_species
+    rng = np.random.default_rng(71 + W)
+    pwm = synth.random_pwm(W, 0, 5)
+    lens = [W, 3 * W + 7, max(W - 1, 1), 260, W + 1]
+    smp = PhyloSample(random_codes(rng, sum(lens), S, 0.03), np.concatenate([[0], np.cumsum(lens)]))
+    for evol in (_abi.EVOL_F81ALPHA, _abi.EVOL_F81BETA):
+        PhyloBayesModel.EVOL_MODEL = evol
+        try:
+            fg = PhyloBayesModel(W, 0, newick, ctx); fg.setCondProbs(pwm)
+            res = {}
+            for kern in (0, 1):
+                ctx.set_option("order0_kernel", kern)
+                ctx.set_option("pattern_memo", 0)
+                res[kern] = [fg.getLogProbFor(smp, strand=s, want_sweeps=True) for s in (0, 1)]
+                assert [n for n, _ in ctx.last_kernel_times()] == ["score_o0f_kernel" if kern else "score_o0_kernel"]
+                assert fg.last_stats["sweeps_fg"] == int(res[kern][1][1].sum())
+            for s in (0, 1):
+                assert np.array_equal(res[0][s][1], res[1][s][1])
+                assert rel_err(res[1][s][0], res[0][s][0]) < 1e-12
+            if evol == _abi.EVOL_F81ALPHA and W <= 12:
+                om = oracle_fg(newick, pwm)
+                ref = np.concatenate([om.score_windows(smp.getElementAt(i), False)[0] for i in range(smp.n_alignments)])
+                assert rel_err(res[1][0][0], ref) < TOL
+        finally:
+            PhyloBayesModel.EVOL_MODEL = _abi.EVOL_F81ALPHA
+            ctx.set_option("order0_kernel", -1)
+            ctx.set_option("pattern_memo", 1)
