@@ -353,7 +353,7 @@ def roofline_of(run, path, kernels, step_ms, sweeps_fg, peak_tflops, hbm_peak, h
         return None
 
     o1 = [n for n in ("score_o1n_kernel", "score_o1w_kernel", "score_o1_kernel") if n in names]
-    fg_name = o1[0] if cfg["order"] == 1 and o1 else "score_o0_kernel"
+    fg_name = o1[0] if cfg["order"] == 1 and o1 else ("score_o0f_kernel" if "score_o0f_kernel" in names else "score_o0_kernel")
     if path != 1:
         # the motif-window launches of the scoring kernel (an order-1 step may add a fallback launch for windows with gaps)
         fg_ms = max(ms for (_, name), ms in kernels.items() if name == fg_name)

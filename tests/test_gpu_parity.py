@@ -262,6 +262,8 @@ def test_f81_structured_kernel_equals_generic_kernel(ctx, tree, W):
     from phyfoo_b200.data import PhyloSample
     from phyfoo_b200.models import PhyloBayesModel
     from phyfoo_b200.newick import parse_newick
+    if tree == "rand30" and W > 20:
+        pytest.skip("the generic kernel's tables of a 30-species motif of width 40 do not fit in shared memory")
     newick = _trees()[tree]
     S = parse_newick(newick).n_species
     rng = np.random.default_rng(71 + W)
