@@ -1450,15 +1450,29 @@ static int launch_score_f81(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_mo
     }
     if (!best_nwg) return 1;
     const int GL = 32 * best_nwg;
-    const int n_groups = std::max(1, std::min(15, 512 / GL));
-    const int T = n_groups * GL;
+    int n_slots = 0;
+    for (int i = 0; i < h.I; ++i) n_slots += h.ichild_begin[i + 1] > h.ichild_begin[i];
+    const size_t state_per_thread = (size_t)(n_slots * 8 + h.I) * sizeof(double);
     const size_t budget = std::min<size_t>(ctx->smem_optin, 227 * 1024);
-    const size_t fixed = ((size_t)h.Ef() * W + 64 + 2 * (size_t)T) * sizeof(double) + (size_t)n_groups * (GL / W) * sizeof(long long) +
-                         (size_t)m->prog_len * sizeof(int) + 64;
+    auto fixed_for = [&](int T, int ng) {
+        return ((size_t)h.Ef() * W + 64 + 2 * (size_t)T) * sizeof(double) + (size_t)ng * (GL / W) * sizeof(long long) +
+               (size_t)(m->prog_len + h.I) * sizeof(int) + 64;
+    };
+    // state in shared memory when at least 8 warps per SM fit that way (a 12-species tree: 472 bytes per thread, 12 warps);
+    // otherwise in global memory (coalesced, behind L1/L2) with as many groups as the register file allows
+    int n_groups = std::max(1, std::min(15, 512 / GL));
+    bool gstate = true;
+    for (int ng = n_groups; ng >= 1; --ng) {
+        const int T = ng * GL;
+        if (fixed_for(T, ng) + state_per_thread * T <= budget) {
+            if (T >= 256 || ng == n_groups) { n_groups = ng; gstate = false; }
+            break;
+        }
+    }
+    const int T = n_groups * GL;
+    const size_t fixed = fixed_for(T, n_groups);
     if (fixed > budget) return 1;
-    const size_t state = (size_t)h.I * 8 * T * sizeof(double);
-    const bool gstate = fixed + state > budget;
-    const size_t smem = fixed + (gstate ? 0 : state);
+    const size_t smem = fixed + (gstate ? 0 : state_per_thread * T);
     CU(cudaFuncSetAttribute(score_o0f_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long per_block = (long long)n_groups * (GL / W);
     const int blocks = (int)std::max<long long>(1, std::min<long long>((n_items + per_block - 1) / per_block, ctx->sm_count));
@@ -1472,10 +1486,10 @@ static int launch_score_f81(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_mo
     unsigned long long* counters = ctx->counters.as<unsigned long long>();
     p.counter_next = counters + 2 * counter_slot; p.counter_sweeps = counters + 2 * counter_slot + 1;
     p.max_sweeps = h.max_sweeps; p.min_sweeps = h.min_sweeps; p.tol = h.tol;
-    p.group_lanes = GL; p.n_groups = n_groups;
+    p.group_lanes = GL; p.n_groups = n_groups; p.n_slots = n_slots;
     p.gstate = nullptr;
     if (gstate) {
-        CU(ctx->gstate.ensure((size_t)blocks * T * h.I * 8 * sizeof(double)));
+        CU(ctx->gstate.ensure((size_t)blocks * T * state_per_thread));
         p.gstate = ctx->gstate.as<double>();
     }
     CU(cudaMemsetAsync(p.counter_next, 0, 2 * sizeof(unsigned long long), ctx->stream));

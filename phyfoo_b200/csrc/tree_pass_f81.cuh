@@ -25,16 +25,31 @@ namespace phyfoo {
 // compact table accessor: entries [0..3] log pi, then per tree node n >= 1 eight entries at 4 + 8 (n - 1): Lo[4] | D[4]
 PHY_HD int tabf_of(int node) { return 4 + 8 * (node - 1); }
 
-// One pass over the tree; returns the part of the tree's free energy that is not log z (acc collects those).
-// State: q(i, a) as in tree_pass.cuh; cs(i, a) holds ONLY what the children contribute beyond the observed leaves
-// (messages of the internal children, sums of the gap leaves), restarted when node i is visited.
-PHY_HD void meanfield_pass_f81(const TreeProg& tp, const Tab& tb, const State& st, const ColWords& cw, bool update,
+// Per-thread state of the pass, strided so that consecutive threads touch consecutive doubles.  Only what a later node
+// update reads is kept: q(s, .) and the message sums cs(s, .) of the internal nodes that HAVE internal children (slot s; the
+// q of the others is read by nobody during scoring), and one scalar per node for the sums of its gap leaves (touched only
+// when the column has an unobserved symbol).  A 12-species binary tree: 6 slots + 11 scalars = 472 bytes instead of 704.
+struct StateF {
+    double* base;
+    int stride;
+    int n_slots;
+    PHY_HD double& q(int s, int a) const { return base[(s * 8 + a) * stride]; }
+    PHY_HD double& cs(int s, int a) const { return base[(s * 8 + 4 + a) * stride]; }
+    PHY_HD double& ts(int i) const { return base[(n_slots * 8 + i) * stride]; }
+};
+PHY_HD int statef_doubles(int n_slots, int n_internal) { return n_slots * 8 + n_internal; }
+
+// One pass over the tree; acc collects the tree's free energy (terms and the log z accumulator).
+// slot[i]: state slot of internal node i, -1 when it has no internal child.
+PHY_HD void meanfield_pass_f81(const TreeProg& tp, const int* slot, const Tab& tb, const StateF& st, const ColWords& cw, bool update,
                                const double* exptab, N1nAcc& acc) {
     double lpi[4];
 #pragma unroll
     for (int a = 0; a < 4; ++a) lpi[a] = tb(a);
+    const bool col_gap = cw.g != 0;
     for (int i = 0; i < tp.n_internal; ++i) {
         const int p = tp.par_internal[i];
+        const int sl = slot[i], sp = i ? slot[p] : -1;
         double Lo[4], D[4], oc[4];
         if (i == 0) {
 #pragma unroll
@@ -43,7 +58,7 @@ PHY_HD void meanfield_pass_f81(const TreeProg& tp, const Tab& tb, const State& s
             const int e0 = tabf_of(tp.node_of[i]);
             double qp[4];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) { Lo[a] = tb(e0 + a); D[a] = tb(e0 + 4 + a); qp[a] = st.q(p, a); }
+            for (int a = 0; a < 4; ++a) { Lo[a] = tb(e0 + a); D[a] = tb(e0 + 4 + a); qp[a] = st.q(sp, a); }
             const double tot = ((qp[0] + qp[1]) + qp[2]) + qp[3];
 #pragma unroll
             for (int a = 0; a < 4; ++a) oc[a] = fma(qp[a], D[a], tot * Lo[a]);      // own rows, MeanField :117-135
@@ -59,10 +74,19 @@ PHY_HD void meanfield_pass_f81(const TreeProg& tp, const Tab& tb, const State& s
                 for (int a = 0; a < 4; ++a) oc[a] += a == x ? lo + d : lo;
             } else any_gap = true;
         }
-        double m[4], ex[4], g[4], e[4], qi[4];
+        // children's part from the previous pass (:139-191): messages of the internal children, sums of the gap leaves
+        double m[4] = {0.0, 0.0, 0.0, 0.0}, ex[4], g[4], e[4], qi[4];
+        if (sl >= 0) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) m[a] = st.cs(sl, a);
+        }
+        if (col_gap) {
+            const double tsv = st.ts(i);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) m[a] += tsv;
+        }
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
-            m[a] = st.cs(i, a);                                   // children's part from the previous pass (:139-191)
             ex[a] = update ? oc[a] + m[a] : 0.0;
             g[a] = update ? m[a] : -oc[a];
         }
@@ -82,43 +106,55 @@ PHY_HD void meanfield_pass_f81(const TreeProg& tp, const Tab& tb, const State& s
         }
         acc.Fq = fma(fu, rz, acc.Fq);
 #pragma unroll
-        for (int a = 0; a < 4; ++a) { qi[a] = e[a] * rz; st.q(i, a) = qi[a]; }       // :199-201
+        for (int a = 0; a < 4; ++a) qi[a] = e[a] * rz;                              // :199-201
+        if (sl >= 0) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) { st.q(sl, a) = qi[a]; st.cs(sl, a) = 0.0; }   // the children add their messages below
+        }
         if (i != 0) {
             // message to the parent: expectation of the log table over this node's new q
             double sw = qi[0] * Lo[0];
             sw = fma(qi[1], Lo[1], sw); sw = fma(qi[2], Lo[2], sw); sw = fma(qi[3], Lo[3], sw);
 #pragma unroll
-            for (int l = 0; l < 4; ++l) st.cs(p, l) += fma(qi[l], D[l], sw);
+            for (int l = 0; l < 4; ++l) st.cs(sp, l) += fma(qi[l], D[l], sw);
         }
-        double tsum = 0.0;
-        if (any_gap) {
-            // unobserved leaves: every table row is log pi ("independent" table, bayesNet/CPF.java:146-152); their own update
-            // only needs q of the parent, which is final for this sweep.  Free-energy terms: entropy (:250-267) and the hidden
-            // non-root term (:327-358) sum to -log z_l (pass at the uniform start: -sum_a q_l(a) x_l(a) - log 4)
-            const double qs = ((qi[0] + qi[1]) + qi[2]) + qi[3];
-            for (int k = tp.leaf_begin[i]; k < tp.leaf_begin[i + 1]; ++k) {
-                if (cw.obs(tp.leaf_species[k]) < 4) continue;
-                double xl[4], xe[4], el[4];
+        if (col_gap) {
+            double tsum = 0.0;
+            if (any_gap) {
+                // unobserved leaves: every table row is log pi ("independent" table, bayesNet/CPF.java:146-152); their own
+                // update only needs q of the parent, which is final for this sweep.  Free-energy terms: entropy (:250-267) and
+                // the hidden non-root term (:327-358) sum to -log z_l (pass at the uniform start: -sum_a q_l(a) x_l(a) - log 4)
+                const double qs = ((qi[0] + qi[1]) + qi[2]) + qi[3];
+                for (int k = tp.leaf_begin[i]; k < tp.leaf_begin[i + 1]; ++k) {
+                    if (cw.obs(tp.leaf_species[k]) < 4) continue;
+                    double xl[4], xe[4], el[4];
 #pragma unroll
-                for (int a = 0; a < 4; ++a) { xl[a] = qs * lpi[a]; xe[a] = update ? xl[a] : 0.0; }
-                n1n_exp4(xe, exptab, el);
-                const double zl = ((el[0] + el[1]) + el[2]) + el[3];
-                const N1nZR zr = n1n_z_rare(zl);                                    // (rare path: gaps) library reciprocal, log z directly
-                double t = 0.0, fl = 0.0;
+                    for (int a = 0; a < 4; ++a) { xl[a] = qs * lpi[a]; xe[a] = update ? xl[a] : 0.0; }
+                    n1n_exp4(xe, exptab, el);
+                    const double zl = ((el[0] + el[1]) + el[2]) + el[3];
+                    const N1nZR zr = n1n_z_rare(zl);                                // (rare path: gaps) library reciprocal, log z directly
+                    double t = 0.0, fl = 0.0;
 #pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    const double ql = el[a] * zr.rz;
-                    t = fma(ql, lpi[a], t);
-                    fl = fma(ql, update ? 0.0 : -xl[a], fl);
+                    for (int a = 0; a < 4; ++a) {
+                        const double ql = el[a] * zr.rz;
+                        t = fma(ql, lpi[a], t);
+                        fl = fma(ql, update ? 0.0 : -xl[a], fl);
+                    }
+                    acc.Fq += fl;
+                    acc.Fslow += zr.lz;
+                    tsum += t;
                 }
-                acc.Fq += fl;
-                acc.Fslow += zr.lz;
-                tsum += t;
             }
+            st.ts(i) = tsum;
         }
-#pragma unroll
-        for (int a = 0; a < 4; ++a) st.cs(i, a) = tsum;
     }
+}
+
+// slot[i] for every internal node from the CSR of internal children; returns the number of slots
+PHY_HD int f81_slots(int n_internal, const int* ichild_begin, int* slot) {
+    int n = 0;
+    for (int i = 0; i < n_internal; ++i) slot[i] = ichild_begin[i + 1] > ichild_begin[i] ? n++ : -1;
+    return n;
 }
 
 }  // namespace phyfoo
@@ -135,6 +171,7 @@ struct ScoreFParams {
     unsigned long long* counter_next; unsigned long long* counter_sweeps;
     int max_sweeps, min_sweeps; double tol;
     double* gstate;          // nullable: per-thread state in global memory instead of shared
+    int n_slots;             // internal nodes with internal children (StateF)
     int group_lanes;         // lanes of a group (a multiple of 32); windows per group = group_lanes / W
     int n_groups;            // groups per block
 };
@@ -155,7 +192,9 @@ __global__ void __launch_bounds__(512, 1) score_o0f_kernel(ScoreFParams p) {
     double* s_F = s_exp + 64;                                        // [2][T]
     long long* s_next = (long long*)(s_F + 2 * T);                   // [n_groups][wpg] item fetched ahead for the window slot
     double* s_state = (double*)(s_next + (size_t)p.n_groups * wpg);
-    int* s_prog = (int*)(s_state + (p.gstate ? 0 : (size_t)p.I * 8 * T));
+    const int state_doubles = phyfoo::statef_doubles(p.n_slots, p.I);
+    int* s_prog = (int*)(s_state + (p.gstate ? 0 : (size_t)state_doubles * T));
+    int* s_slot = s_prog + p.prog_len;                               // [I]
     for (int i = tid; i < p.Ef * W; i += T) s_tab[i] = p.tab[i];
     for (int i = tid; i < 64; i += T) s_exp[i] = phyfoo::d_phy_exp_tab[i];
     for (int i = tid; i < p.prog_len; i += T) s_prog[i] = p.prog[i];
@@ -167,6 +206,8 @@ __global__ void __launch_bounds__(512, 1) score_o0f_kernel(ScoreFParams p) {
     tp.leaf_begin = s_prog + 2 * p.I;
     tp.leaf_node = s_prog + 3 * p.I + 1;
     tp.leaf_species = s_prog + 3 * p.I + 1 + p.S;
+    __syncthreads();
+    if (tid == 0) phyfoo::f81_slots(p.I, s_prog + 3 * p.I + 1 + 2 * p.S, s_slot);
 
     const int grp = tid / GL, gl = tid - grp * GL;                   // group and lane within it
     const int ws = gl / W, t = gl - ws * W;                          // window slot within the group, tree (motif position)
@@ -174,7 +215,8 @@ __global__ void __launch_bounds__(512, 1) score_o0f_kernel(ScoreFParams p) {
     const int bar_id = 1 + grp;
     long long* my_next = s_next + (size_t)grp * wpg + ws;
     const phyfoo::Tab tb{s_tab + t, W};
-    phyfoo::State st;
+    phyfoo::StateF st;
+    st.n_slots = p.n_slots;
     if (p.gstate) { st.base = p.gstate + ((size_t)blockIdx.x * T + tid); st.stride = gridDim.x * T; }
     else { st.base = s_state + tid; st.stride = T; }
     const long long n_items = (long long)p.n_windows * p.n_strands;
@@ -216,7 +258,7 @@ __global__ void __launch_bounds__(512, 1) score_o0f_kernel(ScoreFParams p) {
         double F = 0.0;
         if (active) {
             phyfoo::N1nAcc acc; acc.Fq = 0.0; acc.M = 1.0; acc.E = 0; acc.Fslow = 0.0;
-            phyfoo::meanfield_pass_f81(tp, tb, st, cw, upd, s_exp, acc);
+            phyfoo::meanfield_pass_f81(tp, s_slot, tb, st, cw, upd, s_exp, acc);
             F = phyfoo::n1n_free_energy(acc);
         }
         s_F[buf * T + tid] = F;

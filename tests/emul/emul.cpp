@@ -477,17 +477,20 @@ extern "C" int emul_score_o0f(const phyfoo_model_desc* d, const uint8_t* codes, 
         if (!m.tables0f(tabf)) return -3;
         const int S = m.S, W = m.W, ef = m.Ef();
         TreeProg tp = prog_of(m);
-        std::vector<double> state((size_t)W * m.I * 8, std::nan(""));     // poisoned: the pass at the uniform start must not use it
+        std::vector<int> slot(m.I);
+        const int n_slots = f81_slots(m.I, m.ichild_begin.data(), slot.data());
+        const int sd = statef_doubles(n_slots, m.I);
+        std::vector<double> state((size_t)W * sd, std::nan(""));          // poisoned: the pass at the uniform start must not use it
         for (int j = 0; j + W <= L; ++j) {
             auto pass = [&](bool update) {
                 double sum = 0;
                 for (int t = 0; t < W; ++t) {
-                    State st{state.data() + (size_t)t * m.I * 8, 1};
+                    StateF st{state.data() + (size_t)t * sd, 1, n_slots};
                     const int col = strand ? j + W - 1 - t : j + t;
                     const ColWords cw = words_of(codes + (size_t)col * S, S, strand != 0);
                     Tab lt{&tabf[(size_t)t * ef], 1};
                     N1nAcc acc; acc.Fq = 0.0; acc.M = 1.0; acc.E = 0; acc.Fslow = 0.0;
-                    meanfield_pass_f81(tp, lt, st, cw, update, h_phy_exp_tab, acc);
+                    meanfield_pass_f81(tp, slot.data(), lt, st, cw, update, h_phy_exp_tab, acc);
                     sum += n1n_free_energy(acc);
                 }
                 return sum;
