@@ -873,16 +873,14 @@ static int model_upload(phyfoo_ctx* ctx, phyfoo_model* m) {
         CU(cudaMemcpyAsync(m->d_prog, prog.data(), prog.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMalloc(&m->d_logtab, n * sizeof(double)));
         CU(cudaMalloc(&m->d_probtab, n * sizeof(double)));
-        CU(cudaMalloc(&m->d_tabf, (size_t)(h.Ef() | 1) * h.W * sizeof(double)));
+        CU(cudaMalloc(&m->d_tabf, (size_t)h.Ef() * h.W * sizeof(double)));
         CU(cudaStreamSynchronize(ctx->stream));
     }
-    // compact tables of the F81-structured kernel: one row per position, padded so that the rows start in different banks
-    const int efp = h.Ef() | 1;
-    std::vector<double> tf, tft((size_t)efp * h.W, 0.0);
+    std::vector<double> tf, tft((size_t)h.Ef() * h.W);
     m->f81_ok = h.tables0f(tf);
     if (m->f81_ok) {
         for (int t = 0; t < h.W; ++t)
-            for (int e = 0; e < h.Ef(); ++e) tft[(size_t)t * efp + e] = tf[(size_t)t * h.Ef() + e];
+            for (int e = 0; e < h.Ef(); ++e) tft[(size_t)e * h.W + t] = tf[(size_t)t * h.Ef() + e];
         CU(cudaMemcpyAsync(m->d_tabf, tft.data(), tft.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     }
     std::vector<double> tl(n), tp(n);
@@ -1454,11 +1452,10 @@ static int launch_score_f81(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_mo
     const int GL = 32 * best_nwg;
     int n_slots = 0;
     for (int i = 0; i < h.I; ++i) n_slots += h.ichild_begin[i + 1] > h.ichild_begin[i];
-    const size_t state_per_thread = (size_t)statef_doubles(n_slots, h.I) * sizeof(double);
-    const int efp = h.Ef() | 1;
+    const size_t state_per_thread = (size_t)(n_slots * 8 + h.I) * sizeof(double);
     const size_t budget = std::min<size_t>(ctx->smem_optin, 227 * 1024);
     auto fixed_for = [&](int T, int ng) {
-        return ((size_t)efp * W + 64 + 2 * (size_t)T) * sizeof(double) + (size_t)ng * (GL / W) * sizeof(long long) +
+        return ((size_t)h.Ef() * W + 64 + 2 * (size_t)T) * sizeof(double) + (size_t)ng * (GL / W) * sizeof(long long) +
                (size_t)(m->prog_len + h.I) * sizeof(int) + 64;
     };
     // state in shared memory when at least 8 warps per SM fit that way (a 12-species tree: 472 bytes per thread, 12 warps);
@@ -1476,14 +1473,14 @@ static int launch_score_f81(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_mo
     const size_t fixed = fixed_for(T, n_groups);
     if (fixed > budget) return 1;
     const size_t smem = fixed + (gstate ? 0 : state_per_thread * T);
-    CU(cudaFuncSetAttribute(gstate ? score_o0f_kernel<true> : score_o0f_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(score_o0f_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long per_block = (long long)n_groups * (GL / W);
     const int blocks = (int)std::max<long long>(1, std::min<long long>((n_items + per_block - 1) / per_block, ctx->sm_count));
     ScoreFParams p;
     p.bases = ds->d_bases; p.gaps = ds->d_gaps; p.n_cols = ds->n_cols; p.nb = ds->nb;
     p.col_off = ds->d_col_off; p.win_off = d_win_off; p.n_aln = ds->n_aln;
     p.n_windows = n_windows; p.n_strands = n_strands; p.strand0 = strands == 1 ? 1 : 0;
-    p.W = W; p.I = h.I; p.S = h.S; p.Ef = h.Ef(); p.Ef_pad = efp; p.prog_len = m->prog_len;
+    p.W = W; p.I = h.I; p.S = h.S; p.Ef = h.Ef(); p.prog_len = m->prog_len;
     p.tab = m->d_tabf; p.prog = m->d_prog;
     p.out = d_out; p.sweeps = d_sweeps;
     unsigned long long* counters = ctx->counters.as<unsigned long long>();
@@ -1498,8 +1495,7 @@ static int launch_score_f81(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_mo
     CU(cudaMemsetAsync(p.counter_next, 0, 2 * sizeof(unsigned long long), ctx->stream));
     {
         KernelTimer kt_(ctx, "score_o0f_kernel");
-        if (gstate) score_o0f_kernel<true><<<blocks, T, smem, ctx->stream>>>(p);
-        else score_o0f_kernel<false><<<blocks, T, smem, ctx->stream>>>(p);
+        score_o0f_kernel<<<blocks, T, smem, ctx->stream>>>(p);
     }
     CU(cudaGetLastError());
     return 0;

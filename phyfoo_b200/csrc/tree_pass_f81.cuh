@@ -25,47 +25,27 @@ namespace phyfoo {
 // compact table accessor: entries [0..3] log pi, then per tree node n >= 1 eight entries at 4 + 8 (n - 1): Lo[4] | D[4]
 PHY_HD int tabf_of(int node) { return 4 + 8 * (node - 1); }
 
-// Per-thread state of the pass: ONE contiguous record per thread (16-byte aligned, an odd number of 16-byte units long, so
-// that the 128-bit accesses of the lanes of a warp spread over all banks of shared memory; in global memory a q or cs vector
-// is one 32-byte sector).  Only what a later node update reads is kept: q(s, .) and the message sums cs(s, .) of the internal
-// nodes that HAVE internal children (slot s; the q of the others is read by nobody during scoring), and one scalar per node
-// for the sums of its gap leaves (touched only when the column has an unobserved symbol).  A 12-species binary tree:
-// 6 slots + 11 scalars = 59 -> 62 doubles = 496 bytes instead of 704.
+// Per-thread state of the pass, strided so that consecutive threads touch consecutive doubles.  Only what a later node
+// update reads is kept: q(s, .) and the message sums cs(s, .) of the internal nodes that HAVE internal children (slot s; the
+// q of the others is read by nobody during scoring), and one scalar per node for the sums of its gap leaves (touched only
+// when the column has an unobserved symbol).  A 12-species binary tree: 6 slots + 11 scalars = 472 bytes instead of 704.
 struct StateF {
-    double* base;          // this thread's record
+    double* base;
+    int stride;
     int n_slots;
-    PHY_HD void ld_q(int s, double (&v)[4]) const { ld4(base + s * 8, v); }
-    PHY_HD void ld_cs(int s, double (&v)[4]) const { ld4(base + s * 8 + 4, v); }
-    PHY_HD void st_q_zero_cs(int s, const double (&v)[4]) const {
-        const double z[4] = {0.0, 0.0, 0.0, 0.0};
-        st4(base + s * 8, v); st4(base + s * 8 + 4, z);
-    }
-    PHY_HD void st_cs(int s, const double (&v)[4]) const { st4(base + s * 8 + 4, v); }
-    PHY_HD double& ts(int i) const { return base[n_slots * 8 + i]; }
-    static PHY_HD void ld4(const double* p, double (&v)[4]) {
-        const N1nD2 a = *reinterpret_cast<const N1nD2*>(p), b = *reinterpret_cast<const N1nD2*>(p + 2);
-        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
-    }
-    static PHY_HD void st4(double* p, const double (&v)[4]) {
-        N1nD2 a, b; a.x = v[0]; a.y = v[1]; b.x = v[2]; b.y = v[3];
-        *reinterpret_cast<N1nD2*>(p) = a; *reinterpret_cast<N1nD2*>(p + 2) = b;
-    }
+    PHY_HD double& q(int s, int a) const { return base[(s * 8 + a) * stride]; }
+    PHY_HD double& cs(int s, int a) const { return base[(s * 8 + 4 + a) * stride]; }
+    PHY_HD double& ts(int i) const { return base[(n_slots * 8 + i) * stride]; }
 };
-// record length in doubles: n_slots * 8 + n_internal rounded up to an odd number of 16-byte units
-PHY_HD int statef_doubles(int n_slots, int n_internal) {
-    int units = (n_slots * 8 + n_internal + 1) / 2;
-    if (!(units & 1)) ++units;
-    return 2 * units;
-}
+PHY_HD int statef_doubles(int n_slots, int n_internal) { return n_slots * 8 + n_internal; }
 
 // One pass over the tree; acc collects the tree's free energy (terms and the log z accumulator).
 // slot[i]: state slot of internal node i, -1 when it has no internal child.
-// tb: this position's compact table (Ef entries, contiguous).
-PHY_HD void meanfield_pass_f81(const TreeProg& tp, const int* slot, const double* tb, const StateF& st, const ColWords& cw, bool update,
+PHY_HD void meanfield_pass_f81(const TreeProg& tp, const int* slot, const Tab& tb, const StateF& st, const ColWords& cw, bool update,
                                const double* exptab, N1nAcc& acc) {
     double lpi[4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) lpi[a] = tb[a];
+    for (int a = 0; a < 4; ++a) lpi[a] = tb(a);
     const bool col_gap = cw.g != 0;
     for (int i = 0; i < tp.n_internal; ++i) {
         const int p = tp.par_internal[i];
@@ -75,11 +55,10 @@ PHY_HD void meanfield_pass_f81(const TreeProg& tp, const int* slot, const double
 #pragma unroll
             for (int a = 0; a < 4; ++a) oc[a] = lpi[a];
         } else {
-            const double* te = tb + tabf_of(tp.node_of[i]);
+            const int e0 = tabf_of(tp.node_of[i]);
             double qp[4];
-            st.ld_q(sp, qp);
 #pragma unroll
-            for (int a = 0; a < 4; ++a) { Lo[a] = te[a]; D[a] = te[4 + a]; }
+            for (int a = 0; a < 4; ++a) { Lo[a] = tb(e0 + a); D[a] = tb(e0 + 4 + a); qp[a] = st.q(sp, a); }
             const double tot = ((qp[0] + qp[1]) + qp[2]) + qp[3];
 #pragma unroll
             for (int a = 0; a < 4; ++a) oc[a] = fma(qp[a], D[a], tot * Lo[a]);      // own rows, MeanField :117-135
@@ -89,15 +68,18 @@ PHY_HD void meanfield_pass_f81(const TreeProg& tp, const int* slot, const double
         for (int k = tp.leaf_begin[i]; k < tp.leaf_begin[i + 1]; ++k) {
             const int x = cw.obs(tp.leaf_species[k]);
             if (x < 4) {
-                const double* te = tb + tabf_of(tp.leaf_node[k]);
-                const double lo = te[x], d = te[4 + x];
+                const int e0 = tabf_of(tp.leaf_node[k]);
+                const double lo = tb(e0 + x), d = tb(e0 + 4 + x);
 #pragma unroll
                 for (int a = 0; a < 4; ++a) oc[a] += a == x ? lo + d : lo;
             } else any_gap = true;
         }
         // children's part from the previous pass (:139-191): messages of the internal children, sums of the gap leaves
         double m[4] = {0.0, 0.0, 0.0, 0.0}, ex[4], g[4], e[4], qi[4];
-        if (sl >= 0) st.ld_cs(sl, m);
+        if (sl >= 0) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) m[a] = st.cs(sl, a);
+        }
         if (col_gap) {
             const double tsv = st.ts(i);
 #pragma unroll
@@ -125,16 +107,16 @@ PHY_HD void meanfield_pass_f81(const TreeProg& tp, const int* slot, const double
         acc.Fq = fma(fu, rz, acc.Fq);
 #pragma unroll
         for (int a = 0; a < 4; ++a) qi[a] = e[a] * rz;                              // :199-201
-        if (sl >= 0) st.st_q_zero_cs(sl, qi);                                       // the children add their messages below
+        if (sl >= 0) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) { st.q(sl, a) = qi[a]; st.cs(sl, a) = 0.0; }   // the children add their messages below
+        }
         if (i != 0) {
             // message to the parent: expectation of the log table over this node's new q
             double sw = qi[0] * Lo[0];
             sw = fma(qi[1], Lo[1], sw); sw = fma(qi[2], Lo[2], sw); sw = fma(qi[3], Lo[3], sw);
-            double pc[4];
-            st.ld_cs(sp, pc);
 #pragma unroll
-            for (int l = 0; l < 4; ++l) pc[l] += fma(qi[l], D[l], sw);
-            st.st_cs(sp, pc);
+            for (int l = 0; l < 4; ++l) st.cs(sp, l) += fma(qi[l], D[l], sw);
         }
         if (col_gap) {
             double tsum = 0.0;
@@ -183,8 +165,7 @@ struct ScoreFParams {
     const int64_t* col_off; const int64_t* win_off; int n_aln;
     int64_t n_windows; int n_strands; int strand0;
     int W, I, S, Ef, prog_len;
-    const double* tab;       // compact tables [W][Ef_pad] (Ef_pad: Ef or Ef + 1, so that the rows of the positions start in different banks)
-    int Ef_pad;
+    const double* tab;       // compact tables [Ef][W]
     const int* prog;
     double* out; int32_t* sweeps;
     unsigned long long* counter_next; unsigned long long* counter_sweeps;
@@ -202,20 +183,19 @@ __device__ __forceinline__ int named_bar_or(int id, int n_threads, bool pred) {
     return r;
 }
 
-template <bool GSTATE>
 __global__ void __launch_bounds__(512, 1) score_o0f_kernel(ScoreFParams p) {
     extern __shared__ double smem[];
     const int T = blockDim.x, tid = threadIdx.x;
     const int W = p.W, GL = p.group_lanes, wpg = GL / W;           // windows per group
-    double* s_tab = smem;                                            // [W][Ef_pad]
-    double* s_exp = s_tab + (size_t)p.Ef_pad * W;                    // [64]
+    double* s_tab = smem;                                            // [Ef][W]
+    double* s_exp = s_tab + (size_t)p.Ef * W;                        // [64]
     double* s_F = s_exp + 64;                                        // [2][T]
     long long* s_next = (long long*)(s_F + 2 * T);                   // [n_groups][wpg] item fetched ahead for the window slot
-    double* s_state = (double*)(((size_t)(s_next + (size_t)p.n_groups * wpg) + 15) & ~(size_t)15);     // 16-byte aligned records
+    double* s_state = (double*)(s_next + (size_t)p.n_groups * wpg);
     const int state_doubles = phyfoo::statef_doubles(p.n_slots, p.I);
-    int* s_prog = (int*)(s_state + (GSTATE ? 0 : (size_t)state_doubles * T));
+    int* s_prog = (int*)(s_state + (p.gstate ? 0 : (size_t)state_doubles * T));
     int* s_slot = s_prog + p.prog_len;                               // [I]
-    for (int i = tid; i < p.Ef_pad * W; i += T) s_tab[i] = p.tab[i];
+    for (int i = tid; i < p.Ef * W; i += T) s_tab[i] = p.tab[i];
     for (int i = tid; i < 64; i += T) s_exp[i] = phyfoo::d_phy_exp_tab[i];
     for (int i = tid; i < p.prog_len; i += T) s_prog[i] = p.prog[i];
 
@@ -234,11 +214,11 @@ __global__ void __launch_bounds__(512, 1) score_o0f_kernel(ScoreFParams p) {
     const bool lane_ok = ws < wpg;
     const int bar_id = 1 + grp;
     long long* my_next = s_next + (size_t)grp * wpg + ws;
-    const double* tb = s_tab + (lane_ok ? t : 0) * p.Ef_pad;
+    const phyfoo::Tab tb{s_tab + t, W};
     phyfoo::StateF st;
     st.n_slots = p.n_slots;
-    if (GSTATE) st.base = p.gstate + ((size_t)blockIdx.x * T + tid) * state_doubles;
-    else st.base = s_state + (size_t)tid * state_doubles;
+    if (p.gstate) { st.base = p.gstate + ((size_t)blockIdx.x * T + tid); st.stride = gridDim.x * T; }
+    else { st.base = s_state + tid; st.stride = T; }
     const long long n_items = (long long)p.n_windows * p.n_strands;
 
     // Every window slot holds one item fetched ahead.  Protocol: when a window takes its item (a register copy, `pre`, that

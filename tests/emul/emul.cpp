@@ -485,11 +485,12 @@ extern "C" int emul_score_o0f(const phyfoo_model_desc* d, const uint8_t* codes, 
             auto pass = [&](bool update) {
                 double sum = 0;
                 for (int t = 0; t < W; ++t) {
-                    StateF st{state.data() + (size_t)t * sd, n_slots};
+                    StateF st{state.data() + (size_t)t * sd, 1, n_slots};
                     const int col = strand ? j + W - 1 - t : j + t;
                     const ColWords cw = words_of(codes + (size_t)col * S, S, strand != 0);
+                    Tab lt{&tabf[(size_t)t * ef], 1};
                     N1nAcc acc; acc.Fq = 0.0; acc.M = 1.0; acc.E = 0; acc.Fslow = 0.0;
-                    meanfield_pass_f81(tp, slot.data(), &tabf[(size_t)t * ef], st, cw, update, h_phy_exp_tab, acc);
+                    meanfield_pass_f81(tp, slot.data(), lt, st, cw, update, h_phy_exp_tab, acc);
                     sum += n1n_free_energy(acc);
                 }
                 return sum;
