@@ -38,6 +38,11 @@ struct Net1wParams {
     const int* n_items_dev;           // nullable: length of the item list lives on the device (windows with gaps listed by net1n.cuh)
     const int64_t* item_dst;          // nullable: out / sweeps index of listed item (default: the item's own index)
     unsigned long long* counter_next; // work counter (counters[0] unless the launch continues another kernel's sweep sum)
+    // background ranges of a single column (order 1, W = 2; models/PhyloBackground.java:260-283 with a range shorter than
+    // order + 1): the second tree of the net keeps the observation of an EARLIER call (MeanFieldForBayesNet.java:84), i.e. an
+    // arbitrary column item_col1[item], and the stop rule spans the first tree only (the sequence has one position)
+    const int64_t* item_col1;         // nullable: column observed by tree 1 of listed item (default: the column after col0)
+    int stop_first;                   // 1: stop rule on the free energy of the first tree alone (needs W = 2)
 };
 
 __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
@@ -103,10 +108,12 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
                 }
                 unsigned any_gap_bits = 0;
                 for (int t = l16; t < p.W; t += 16) {
-                    const int64_t col = strand ? c0 + (p.W - 1 - t) : c0 + t;     // jstacs StrandModel.java:636-639
+                    int64_t col = strand ? c0 + (p.W - 1 - t) : c0 + t;           // jstacs StrandModel.java:636-639
+                    int64_t colp = strand ? col + 1 : col - 1;
+                    if (p.item_col1 && t == 1) { col = p.item_col1[item]; colp = c0; }
                     ColWords cw = load_column(p.bases, p.gaps, p.n_cols, p.nb, col);
                     ColWords cwp; cwp.b = 0; cwp.g = 0;
-                    if (t > 0) cwp = load_column(p.bases, p.gaps, p.n_cols, p.nb, strand ? col + 1 : col - 1);
+                    if (t > 0) cwp = load_column(p.bases, p.gaps, p.n_cols, p.nb, colp);
                     if (strand) { cw = complement(cw); cwp = complement(cwp); }
                     any_gap_bits |= cw.g;
                     for (int kk = 0; kk < p.S; ++kk) {
@@ -261,7 +268,7 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
         F += __shfl_xor_sync(full, F, 4);
         F += __shfl_xor_sync(full, F, 8);
         const double Fsum = F;
-        if (p.out_last) {
+        if (p.out_last || p.stop_first) {
             Flast += __shfl_xor_sync(full, Flast, 1);
             Flast += __shfl_xor_sync(full, Flast, 2);
             Flast += __shfl_xor_sync(full, Flast, 4);
@@ -269,10 +276,11 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
         }
         if (active) {
             bool done;
-            if (!upd) { old = Fsum; upd = true; done = false; }               // F_0, MeanFieldForBayesNet.java:105
+            const double Fstop = p.stop_first ? Fsum - Flast : Fsum;          // calcFreeEnergy() spans the sequence's positions
+            if (!upd) { old = Fstop; upd = true; done = false; }              // F_0, MeanFieldForBayesNet.java:105
             else {
-                if (fabs(old - Fsum) < p.tol) conv = true;                    // :204-207 (sticky)
-                old = Fsum; ++k;
+                if (fabs(old - Fstop) < p.tol) conv = true;                   // :204-207 (sticky)
+                old = Fstop; ++k;
                 done = !((k < p.max_sweeps && !conv) || k < p.min_sweeps);    // :107
             }
             if (done) {

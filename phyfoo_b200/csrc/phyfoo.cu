@@ -377,7 +377,10 @@ __global__ void __launch_bounds__(256, 2) score_o0_kernel(ScoreParams p) {
 // ------------------------------------------------------------------------------------------------
 struct ZoopsParams {
     const double* fwd; const double* rev;    // [n_windows] each (rev may be null)
-    const double* bgcol;                     // [n_cols] background log-score per column (order 0)
+    const double* bgcol;                     // [n_cols] background log-score per column (order 0); order 1: the conditional terms
+    // order-1 background (nullable): start terms per column, single-column ranges bg(j + W, e) per column and bg(s, j - 1) per
+    // window (bg1_terms_device); a_j = prior + motif - bg(s, e) + bg(s, j - 1) + bg(j + W, e), s = max(j - 1, 0), e = min(j + W, L - 1)
+    const double* bg1_first; const double* bg1_single; const double* bg1_left;
     const int64_t* col_off; const int64_t* win_off; int n_aln; int W;
     double logw0, logw1; int has_strand; double slw0, slw1;
     const double* aln_w;                     // nullable
@@ -428,9 +431,10 @@ __global__ void __launch_bounds__(256) zoops_kernel(ZoopsParams p) {
         __syncthreads();
         bgc = s_bg;
     }
-    // logPSeq = bg.getLogProbFor(seq, 0, l-1), :526
+    // logPSeq = bg.getLogProbFor(seq, 0, l-1), :526 (order 1: start term of column 0 + the conditional terms of the others)
+    const bool o1 = p.bg1_first != nullptr;
     double ps = 0.0;
-    for (int u = tid; u < L; u += T) ps += bgc[u];
+    for (int u = tid; u < L; u += T) ps += (o1 && u == 0) ? p.bg1_first[c0] : bgc[u];
     const double log_pseq = block_sum(ps, sh);
 
     // a_j and its maximum (first index wins: util/Util.java:528-538)
@@ -441,7 +445,14 @@ __global__ void __launch_bounds__(256) zoops_kernel(ZoopsParams p) {
         double motif = p.fwd[w0 + j];
         if (p.has_strand) motif = logsum2(p.slw0 + motif, p.slw1 + p.rev[w0 + j]);
         double bgw = 0.0;
-        for (int m = 0; m < p.W; ++m) bgw += bgc[j + m];             // -bg(s,e), order 0: s=j, e=j+W-1
+        if (!o1) for (int m = 0; m < p.W; ++m) bgw += bgc[j + m];    // bg(s,e), order 0: s=j, e=j+W-1
+        else {
+            const int s = j > 0 ? j - 1 : 0, e = j + p.W < L - 1 ? j + p.W : L - 1;
+            bgw = p.bg1_first[c0 + s];
+            for (int u = s + 1; u <= e; ++u) bgw += bgc[u];
+            if (j > 0) bgw -= p.bg1_left[w0 + j];                     // + bg(s, j-1)
+            if (j + p.W <= L - 1) bgw -= p.bg1_single[c0 + j + p.W];  // + bg(j+W, e)
+        }
         const double aj = lprior + motif - bgw;                       // :536-540
         if (p.profile) p.profile[w0 + j] = aj;
         if (p.stage) s_aj[j] = aj;
@@ -470,7 +481,14 @@ __global__ void __launch_bounds__(256) zoops_kernel(ZoopsParams p) {
             double motif = p.fwd[w0 + j];
             if (p.has_strand) motif = logsum2(p.slw0 + motif, p.slw1 + p.rev[w0 + j]);
             double bgw = 0.0;
-            for (int m = 0; m < p.W; ++m) bgw += p.bgcol[c0 + j + m];
+            if (!o1) for (int m = 0; m < p.W; ++m) bgw += p.bgcol[c0 + j + m];
+            else {
+                const int s = j > 0 ? j - 1 : 0, e = j + p.W < L - 1 ? j + p.W : L - 1;
+                bgw = p.bg1_first[c0 + s];
+                for (int u = s + 1; u <= e; ++u) bgw += p.bgcol[c0 + u];
+                if (j > 0) bgw -= p.bg1_left[w0 + j];
+                if (j + p.W <= L - 1) bgw -= p.bg1_single[c0 + j + p.W];
+            }
             aj = lprior + motif - bgw;
         }
         const double e = exp(aj - best);
@@ -965,6 +983,8 @@ struct ScoreItems {
     const int64_t* col0; const uint8_t* strand; double* q_int; double* q_leaf; double* ent;
     const int* n_dev = nullptr; const int64_t* dst = nullptr; bool fallback = false;
     double* out_last = nullptr;     // order-1 kernels: free energy of the last tree alone (background ranges)
+    const int64_t* col1 = nullptr;  // order-1 wavefront kernel, W = 2: column of the second tree (single-column background ranges)
+    bool stop_first = false;        //   ... and the stop rule on the first tree alone
 };
 
 #include "net1.cuh"
@@ -1282,6 +1302,7 @@ static int launch_net1w(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model*
     p.item_col0 = items ? items->col0 : nullptr; p.item_strand = items ? items->strand : nullptr;
     p.sink_qint = items ? items->q_int : nullptr; p.sink_qleaf = items ? items->q_leaf : nullptr; p.sink_ent = items ? items->ent : nullptr;
     p.n_items_dev = items ? items->n_dev : nullptr; p.item_dst = items ? items->dst : nullptr;
+    p.item_col1 = items ? items->col1 : nullptr; p.stop_first = items && items->stop_first ? 1 : 0;
     const bool fallback = items && items->fallback;
     // a fallback launch (windows with gaps listed by the node-per-thread kernel) pulls its work from a counter of its own
     // ([8 + slot]) and continues the sweep sum of that kernel
@@ -1651,15 +1672,40 @@ __global__ void bg1_scatter_kernel(const int64_t* __restrict__ col0, const doubl
     if (first) first[col0[u]] = total[u] - last[u];
 }
 
-extern "C" int phyfoo_bg_columns_order1(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* bg, double* cond_out, double* first_out) {
-    if (!ctx) return PHYFOO_EINVAL;
-    if (!ds || !bg || !cond_out) return fail(ctx, PHYFOO_EINVAL, "bg_columns_order1: NULL argument");
-    if (bg->h.kind != PHYFOO_MODEL_BG || bg->h.order != 1) return fail(ctx, PHYFOO_EINVAL, "bg_columns_order1: needs a background model of order 1");
-    if (bg->h.mode != PHYFOO_MODE_MEANFIELD) return fail(ctx, PHYFOO_EUNSUPPORTED, "bg_columns_order1: exact mode is not defined for order-1 networks");
+// pairs of columns for the single-column ranges: (c, c) for every column
+__global__ void bg1_pairs_same_kernel(int64_t n, int64_t* __restrict__ colA, int64_t* __restrict__ colB) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n) return;
+    colA[u] = u; colB[u] = u;
+}
+// ... and (j - 1, min(j + W, L - 1)) for offset j of every alignment (the range left of the motif, whose second tree still
+// holds the last column of the range bg(s, e) scored just before it; j = 0 has no such range: a dummy pair)
+__global__ void bg1_pairs_left_kernel(const int64_t* __restrict__ win_off, const int64_t* __restrict__ col_off, int n_aln, int64_t n, int W,
+                                      int64_t* __restrict__ colA, int64_t* __restrict__ colB) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n) return;
+    const int a = find_alignment(win_off, n_aln, u);
+    const int64_t c0 = col_off[a], L = col_off[a + 1] - c0, j = u - win_off[a];
+    colA[u] = c0 + (j > 0 ? j - 1 : 0);
+    colB[u] = c0 + (j + W < L - 1 ? j + W : L - 1);
+}
+__global__ void bg1_first_term_kernel(const double* __restrict__ total, const double* __restrict__ last, int64_t n, double* __restrict__ out) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < n) out[u] = total[u] - last[u];
+}
+
+// Order-1 background terms on the device, in ctx->bg_scores: cond[nc], first[nc] (every 2-column window of every alignment
+// through the order-1 network kernel, W = 2) and, for the ZOOPS E-step (W_motif > 0), single[nc] and left[windows]: the
+// single-column ranges bg(j + W, e) and bg(s, j - 1) of jstacs SingleHiddenMotifMixture.java:536-540, whose second tree the
+// reference leaves at the observation of the previous call (MeanFieldForBayesNet.java:84) -- column e = min(j + W, L - 1) in
+// both cases, because bg(s, e) is scored just before them.
+struct Bg1Terms { double* cond; double* first; double* single; double* left; };
+static int bg1_terms_device(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* bg, int W_motif, const int64_t* d_woff_motif,
+                            int64_t nw_motif, Bg1Terms* out) {
+    if (bg->h.kind != PHYFOO_MODEL_BG || bg->h.order != 1) return fail(ctx, PHYFOO_EINVAL, "needs a background model of order 1");
+    if (bg->h.mode != PHYFOO_MODE_MEANFIELD) return fail(ctx, PHYFOO_EUNSUPPORTED, "exact mode is not defined for order-1 networks");
     if (bg->h.S != ds->S) return fail(ctx, PHYFOO_EINVAL, "model and dataset disagree on the number of species");
-    CU(cudaSetDevice(ctx->device));
-    ctx->launches = 0; ctx->n_ktimes = 0;
-    if (ds->n_aln > 0 && ds->min_len < 2) return fail(ctx, PHYFOO_EINVAL, "bg_columns_order1: an alignment is shorter than order + 1 columns (the reference's score of such a range is not a function of the inputs, MeanFieldForBayesNet.java:84)");
+    if (ds->n_aln > 0 && ds->min_len < 2) return fail(ctx, PHYFOO_EINVAL, "order-1 background: an alignment is shorter than order + 1 columns (the reference's score of such a range is not a function of the inputs, MeanFieldForBayesNet.java:84)");
     int rc = model_upload(ctx, bg);
     if (rc) return rc;
     if (!bg->h.tables_finite()) return fail(ctx, PHYFOO_EUNSUPPORTED, "a CPF entry is 0: the reference's free energy is not finite for this parameter set");
@@ -1667,34 +1713,68 @@ extern "C" int phyfoo_bg_columns_order1(phyfoo_ctx* ctx, const phyfoo_dataset* d
     rc = dataset_win_off(ctx, ds, 2, &d_woff, &h_woff);
     if (rc) return rc;
     const int64_t n = h_woff->back(), nc = ds->n_cols;
-    if (n == 0) return PHYFOO_OK;
-    CU(ctx->bg_scores.ensure((size_t)(2 * n + 2 * nc) * sizeof(double)));
-    CU(ctx->misc.ensure((size_t)n * sizeof(int64_t)));
+    const int64_t n_extra = W_motif > 0 ? std::max(nc, nw_motif) : 0;
+    const int64_t n_items = std::max(n, n_extra);
+    // [total | last] (scratch of the current launch) | cond | first | single | left
+    CU(ctx->bg_scores.ensure((size_t)(2 * n_items + 3 * nc + (W_motif > 0 ? nw_motif : 0) + 4) * sizeof(double)));
+    CU(ctx->misc.ensure((size_t)2 * std::max<int64_t>(n_items, 1) * sizeof(int64_t)));
     double* d_total = ctx->bg_scores.as<double>();
-    double* d_last = d_total + n;
-    double* d_cond = d_last + n;
-    double* d_first = d_cond + nc;
-    int64_t* d_col0 = ctx->misc.as<int64_t>();
-    CU(cudaMemsetAsync(d_cond, 0, (size_t)2 * nc * sizeof(double), ctx->stream));
-    {
-        KernelTimer kt_(ctx, "bg1_items_kernel");
-        bg1_items_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_woff, ds->d_col_off, ds->n_aln, n, d_col0);
-    }
-    CU(cudaGetLastError());
-    ScoreItems items{d_col0, nullptr, nullptr, nullptr, nullptr};
-    items.out_last = d_last;
+    double* d_last = d_total + n_items;
+    out->cond = d_last + n_items; out->first = out->cond + nc; out->single = out->first + nc; out->left = out->single + nc;
+    int64_t* d_colA = ctx->misc.as<int64_t>();
+    int64_t* d_colB = d_colA + std::max<int64_t>(n_items, 1);
+    CU(cudaMemsetAsync(out->cond, 0, (size_t)2 * nc * sizeof(double), ctx->stream));
     const int keep = ctx->order1_kernel;
-    ctx->order1_kernel = 1;                       // the per-tree output lives in the wavefront kernel
-    rc = launch_net1(ctx, ds, bg, nullptr, n, 0, d_total, nullptr, 1, &items);
-    ctx->order1_kernel = keep;
-    if (rc) return rc;
-    {
-        KernelTimer kt_(ctx, "bg1_scatter_kernel");
-        bg1_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_col0, d_total, d_last, n, d_cond, first_out ? d_first : nullptr);
+    auto run = [&](int64_t cnt, const int64_t* colB, bool stop_first) {
+        ScoreItems items{d_colA, nullptr, nullptr, nullptr, nullptr};
+        items.out_last = d_last; items.col1 = colB; items.stop_first = stop_first;
+        ctx->order1_kernel = 1;                   // the per-tree output lives in the wavefront kernel
+        const int r = launch_net1(ctx, ds, bg, nullptr, cnt, 0, d_total, nullptr, 1, &items);
+        ctx->order1_kernel = keep;
+        return r;
+    };
+    if (n > 0) {
+        {
+            KernelTimer kt_(ctx, "bg1_items_kernel");
+            bg1_items_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_woff, ds->d_col_off, ds->n_aln, n, d_colA);
+        }
+        CU(cudaGetLastError());
+        if ((rc = run(n, nullptr, false))) return rc;
+        {
+            KernelTimer kt_(ctx, "bg1_scatter_kernel");
+            bg1_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_colA, d_total, d_last, n, out->cond, out->first);
+        }
+        CU(cudaGetLastError());
     }
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(cond_out, d_cond, (size_t)nc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    if (first_out) CU(cudaMemcpyAsync(first_out, d_first, (size_t)nc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (W_motif > 0 && nc > 0) {
+        bg1_pairs_same_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, ctx->stream>>>(nc, d_colA, d_colB);
+        CU(cudaGetLastError());
+        if ((rc = run(nc, d_colB, true))) return rc;
+        bg1_first_term_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, ctx->stream>>>(d_total, d_last, nc, out->single);
+        CU(cudaGetLastError());
+        if (nw_motif > 0) {
+            bg1_pairs_left_kernel<<<(unsigned)((nw_motif + 255) / 256), 256, 0, ctx->stream>>>(d_woff_motif, ds->d_col_off, ds->n_aln, nw_motif, W_motif, d_colA, d_colB);
+            CU(cudaGetLastError());
+            if ((rc = run(nw_motif, d_colB, true))) return rc;
+            bg1_first_term_kernel<<<(unsigned)((nw_motif + 255) / 256), 256, 0, ctx->stream>>>(d_total, d_last, nw_motif, out->left);
+            CU(cudaGetLastError());
+        }
+    }
+    return PHYFOO_OK;
+}
+
+extern "C" int phyfoo_bg_columns_order1(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* bg, double* cond_out, double* first_out) {
+    if (!ctx) return PHYFOO_EINVAL;
+    if (!ds || !bg || !cond_out) return fail(ctx, PHYFOO_EINVAL, "bg_columns_order1: NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    ctx->launches = 0; ctx->n_ktimes = 0;
+    Bg1Terms t;
+    const int rc = bg1_terms_device(ctx, ds, bg, 0, nullptr, 0, &t);
+    if (rc) return rc;
+    const int64_t nc = ds->n_cols;
+    if (nc == 0) return PHYFOO_OK;
+    CU(cudaMemcpyAsync(cond_out, t.cond, (size_t)nc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (first_out) CU(cudaMemcpyAsync(first_out, t.first, (size_t)nc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return PHYFOO_OK;
 }
@@ -1747,6 +1827,8 @@ static int enqueue_estep(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model
     CU(ctx->part.ensure((size_t)3 * ds->n_aln * sizeof(double)));
     ctx->kev_valid = false;
     CU(cudaEventRecord(ctx->kev[0], ctx->stream));
+    Bg1Terms bg1{nullptr, nullptr, nullptr, nullptr};
+    bool have_bg1 = false;
     const bool both_memo = bg->h.kind == PHYFOO_MODEL_BG && bg->h.order == 0 && fg->h.S == ds->S && bg->h.S == ds->S &&
                            fg->h.evol != PHYFOO_EVOL_HKY_AS_IMPLEMENTED && bg->h.evol != PHYFOO_EVOL_HKY_AS_IMPLEMENTED &&
                            fg->h.order == 0 && fg->h.tables_finite() && bg->h.tables_finite() &&
@@ -1760,7 +1842,10 @@ static int enqueue_estep(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model
         if (rc) return rc;
         CU(cudaEventRecord(ctx->kev[1], ctx->stream));   // phases are not separable on this path: see phyfoo_last_kernel_times
     } else {
-        rc = launch_bg_columns(ctx, ds, bg, ctx->bg_scores.as<double>(), nullptr, 1);
+        if (bg->h.kind == PHYFOO_MODEL_BG && bg->h.order == 1) {
+            rc = bg1_terms_device(ctx, ds, bg, W, d_woff, nw, &bg1);
+            have_bg1 = true;
+        } else rc = launch_bg_columns(ctx, ds, bg, ctx->bg_scores.as<double>(), nullptr, 1);
         if (rc) return rc;
         CU(cudaEventRecord(ctx->kev[1], ctx->stream));
         rc = launch_score(ctx, ds, fg, d_woff, nw, strand_logw ? 2 : 0, ctx->fg_scores.as<double>(), nullptr, 0);
@@ -1770,7 +1855,8 @@ static int enqueue_estep(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model
     ZoopsParams z;
     z.fwd = ctx->fg_scores.as<double>();
     z.rev = strand_logw ? ctx->fg_scores.as<double>() + nw : nullptr;
-    z.bgcol = ctx->bg_scores.as<double>();
+    z.bgcol = have_bg1 ? bg1.cond : ctx->bg_scores.as<double>();
+    z.bg1_first = have_bg1 ? bg1.first : nullptr; z.bg1_single = bg1.single; z.bg1_left = bg1.left;
     z.col_off = ds->d_col_off; z.win_off = d_woff; z.n_aln = ds->n_aln; z.W = W;
     z.logw0 = logw[0]; z.logw1 = logw[1];
     z.has_strand = strand_logw ? 1 : 0;

@@ -260,3 +260,38 @@ def test_order1_background_ranges(ctx, tree, gap_rate):
     short = PhyloSample(random_codes(rng, 4, S), [0, 1, 4])
     with pytest.raises(IllegalArgumentException):
         bg.getLogProbFor(short)
+
+
+@pytest.mark.parametrize("tree", ["cat5", "rand12"])
+@pytest.mark.parametrize("fg_order", [0, 1])
+@pytest.mark.parametrize("gap_rate", [0.0, 0.06])
+def test_zoops_estep_with_order1_background(ctx, tree, fg_order, gap_rate):
+    """SingleHiddenMotifMixture.getNewWeights with a PhyloBackground of order 1 (jstacs SingleHiddenMotifMixture.java:536-540
+    with models/PhyloBackground.java:241-305): per offset bg(s, e), bg(s, j-1) and bg(j+W, e) with s = j-1, e = j+W.  The two
+    flank ranges are single columns, for which the reference's two-tree net keeps the observation of the previous call in its
+    second tree (MeanFieldForBayesNet.java:84) -- always column e here, because bg(s, e) is scored just before; the oracle
+    keeps that state like the Java object graph does.  gamma / ll at 1e-9, arg-max calls exact, ragged lengths incl. L = W."""
+    from phyfoo_b200 import synth
+    from phyfoo_b200.data import PhyloSample
+    from phyfoo_b200.models import PhyloBackground, PhyloBayesModel, SingleHiddenMotifMixture, StrandModel
+    from phyfoo_b200.newick import parse_newick
+    newick = _trees()[tree]
+    S = parse_newick(newick).n_species
+    rng = np.random.default_rng(59)
+    W = 5
+    pwm = synth.random_pwm(W, fg_order, 3)
+    lens = [W, W + 1, W + 2, 31, 64]
+    smp = PhyloSample(random_codes(rng, sum(lens), S, gap_rate), np.concatenate([[0], np.cumsum(lens)]))
+    pi = [rng.dirichlet(np.ones(4), size=1), rng.dirichlet(np.ones(4), size=4)]
+    fg = PhyloBayesModel(W, fg_order, newick, ctx); fg.setCondProbs(pwm)
+    bg = PhyloBackground(1, newick, ctx); bg.setCondProbs(pi)
+    aw = rng.uniform(0.5, 2.0, len(lens))
+    for strand in (False, True):
+        shm = SingleHiddenMotifMixture(StrandModel(fg, 0.4) if strand else fg, bg, zoops=0.8)
+        res = shm.getNewWeights(smp, seqWeights=aw, want_profile=True)
+        ref = orc.estep(oracle_fg(newick, pwm, order=fg_order), oracle_bg(newick, 1, pi), smp.col_offsets, smp.codes, np.log([0.8, 0.2]),
+                        np.log([0.4, 0.6]) if strand else None, aw)
+        assert rel_err(res["profile"], ref["profile"]) < TOL
+        assert np.array_equal(res["argmax_off"], ref["argmax_off"]) and np.array_equal(res["argmax_strand"], ref["argmax_strand"])
+        assert np.max(np.abs(res["gamma"] - ref["gamma"])) < TOL
+        assert abs(res["ll"] - ref["ll"]) <= TOL * abs(ref["ll"]) and np.allclose(res["w"], ref["w"], rtol=1e-9, atol=0)
