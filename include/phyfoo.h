@@ -129,6 +129,12 @@ int phyfoo_model_get_pi(phyfoo_ctx* ctx, const phyfoo_model* m, int32_t position
 /* VirtualTree.reinitEdglengths (bayesNet/VirtualTree.java:237-255), one branch at a time */
 int phyfoo_model_set_branch(phyfoo_ctx* ctx, phyfoo_model* m, int32_t position, int32_t node, double length);
 int phyfoo_model_set_mode(phyfoo_ctx* ctx, phyfoo_model* m, int32_t mode);
+/* 1 for PHYFOO_EVOL_HKY_AS_IMPLEMENTED: every substitution table has zero entries (the reference never stores the
+ * transition/transversion ratio, evolution/HKY.java:32), so every mean-field score is degenerate.  The library returns what the
+ * reference returns -- NaN, or -inf for purine-only / pyrimidine-only columns under a star tree, with max_sweeps sweeps per
+ * window -- instead of an error (order 0; scoring and E-step; the M-step objective is refused).  Exact mode computes the
+ * likelihood under these tables as usual (log 0 = -inf where a transversion would be needed). */
+int phyfoo_model_is_degenerate(const phyfoo_model* m);
 void phyfoo_model_free(phyfoo_ctx* ctx, phyfoo_model* m);
 
 /* ---- scoring ----

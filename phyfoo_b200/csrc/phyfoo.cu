@@ -827,6 +827,7 @@ extern "C" int phyfoo_model_set_branch(phyfoo_ctx* ctx, phyfoo_model* m, int32_t
     try { m->h.set_branch(position, node, length); } catch (const std::exception& e) { return fail(ctx, PHYFOO_EINVAL, e.what()); }
     return PHYFOO_OK;
 }
+extern "C" int phyfoo_model_is_degenerate(const phyfoo_model* m) { return m && m->h.evol == PHYFOO_EVOL_HKY_AS_IMPLEMENTED ? 1 : 0; }
 extern "C" int phyfoo_model_set_mode(phyfoo_ctx* ctx, phyfoo_model* m, int32_t mode) {
     if (!ctx || !m) return PHYFOO_EINVAL;
     if (mode != PHYFOO_MODE_MEANFIELD && mode != PHYFOO_MODE_EXACT) return fail(ctx, PHYFOO_EINVAL, "set_mode: unknown mode");
@@ -1522,6 +1523,45 @@ static int launch_score_f81(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_mo
     return 0;
 }
 
+// HKY as implemented (evolution/HKY.java:32,77-106): beta == 0, so a child symbol has non-zero probability only when it
+// equals the parent's or is its transition partner (A<->G, C<->T), and every table has zero entries.  What the reference's
+// mean field returns then (algorithm/MeanFieldForBayesNet.java; the restatement runs these cases, tests/test_gpu_parity.py):
+//  * the stop rule never fires (the free energy is NaN or +inf in every sweep, and |x - x| < 1e-5 is false for both):
+//    max_sweeps sweeps for every window;
+//  * a tree with a hidden non-root node: the exponents of the root are -inf for every symbol in the very first sweep
+//    (a hidden child at uniform q meets a zero table entry for every parent symbol), z = 0, q = 0/0: the score is NaN;
+//  * a star tree: a column whose observed leaves are all purines or all pyrimidines keeps z > 0, and the free energy is +inf
+//    through the zero-entry guard of the observed-leaf terms (:315-324): score -inf; a column with both classes has z = 0:
+//    NaN.  Unobserved leaves use the "independent" table (bayesNet/CPF.java:146-152), which has no zeros, and change nothing.
+//    (The reverse complement swaps the two classes as a whole, so both strands score alike.)
+__global__ void hky_as_implemented_kernel(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ gaps, int64_t n_cols, int nb,
+                                          const int64_t* __restrict__ col_off, const int64_t* __restrict__ win_off, int n_aln,
+                                          int64_t n_windows, int n_strands, int W, int S, int star, int max_sweeps,
+                                          double* __restrict__ out, int32_t* __restrict__ sweeps, unsigned long long* __restrict__ sweep_sum) {
+    const long long n_items = (long long)n_windows * n_strands;
+    unsigned long long local = 0;
+    for (long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += (long long)gridDim.x * blockDim.x) {
+        const int64_t w = item % n_windows;
+        double v = NAN;
+        if (star) {
+            const int a = find_alignment_hint(win_off, n_aln, w, n_windows);
+            const int64_t c0 = col_off[a] + (w - win_off[a]);
+            bool mixed = false;
+            for (int t = 0; t < W; ++t) {
+                const ColWords cw = load_column(bases, gaps, n_cols, nb, c0 + t);
+                bool pur = false, pyr = false;
+                for (int sp = 0; sp < S; ++sp) { const int x = cw.obs(sp); if (x < 4) { if (x & 1) pyr = true; else pur = true; } }
+                mixed = mixed || (pur && pyr);
+            }
+            v = mixed ? NAN : -INFINITY;
+        }
+        out[item] = v;
+        if (sweeps) sweeps[item] = max_sweeps;
+        local += (unsigned long long)max_sweeps;
+    }
+    if (local) atomicAdd(sweep_sum, local);
+}
+
 // scores into d_out[n_strands][n_windows]; strands: 0 = forward only, 1 = reverse only, 2 = both.
 // items != NULL: score the listed windows (n_windows of them) instead and store their converged q.
 static int launch_score(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* m, const int64_t* d_win_off, int64_t n_windows,
@@ -1533,8 +1573,28 @@ static int launch_score(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model*
     const int mode = items ? PHYFOO_MODE_MEANFIELD : h.mode;
     const bool fallback = items && items->fallback;
     if (h.S != ds->S) return fail(ctx, PHYFOO_EINVAL, "model and dataset disagree on the number of species");
-    if (h.evol == PHYFOO_EVOL_HKY_AS_IMPLEMENTED)
-        return fail(ctx, PHYFOO_EUNSUPPORTED, "HKY as implemented in the reference has zero transversion probabilities (HKY.java:32): every score is -inf");
+    if (h.evol == PHYFOO_EVOL_HKY_AS_IMPLEMENTED && mode == PHYFOO_MODE_MEANFIELD) {
+        // HKY as the reference implements it (evolution/HKY.java:32: the transition/transversion ratio is never stored, so
+        // every transversion has probability 0): the mean-field score of EVERY window is degenerate, and the library returns
+        // the reference's degenerate values rather than an error (phyfoo_model_is_degenerate() flags the model)
+        if (items) return fail(ctx, PHYFOO_EUNSUPPORTED, "HKY as implemented: the M-step objective is not finite for any parameter set (HKY.java:32)");
+        if (h.order != 0) return fail(ctx, PHYFOO_EUNSUPPORTED, "HKY as implemented is offered for order-0 models only");
+        if (h.S != ds->S) return fail(ctx, PHYFOO_EINVAL, "model and dataset disagree on the number of species");
+        const int n_strands = strands == 2 ? 2 : 1;
+        const long long n_items = (long long)n_windows * n_strands;
+        if (n_items == 0) return PHYFOO_OK;
+        ctx->last_path = 0;
+        unsigned long long* counters = ctx->counters.as<unsigned long long>() + 2 * counter_slot;
+        CU(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
+        {
+            KernelTimer kt_(ctx, "hky_as_implemented_kernel");
+            hky_as_implemented_kernel<<<(unsigned)std::min<long long>((n_items + 255) / 256, 65535LL * 16), 256, 0, ctx->stream>>>(
+                ds->d_bases, ds->d_gaps, ds->n_cols, ds->nb, ds->d_col_off, d_win_off, ds->n_aln, n_windows, n_strands, h.W, h.S, h.I == 1 ? 1 : 0,
+                h.max_sweeps, d_out, d_sweeps, counters + 1);
+        }
+        CU(cudaGetLastError());
+        return PHYFOO_OK;
+    }
     if (mode == PHYFOO_MODE_MEANFIELD && !h.tables_finite())
         return fail(ctx, PHYFOO_EUNSUPPORTED, "a CPF entry is 0: the reference's free energy is not finite for this parameter set");
     const int n_strands = strands == 2 ? 2 : 1;

@@ -24,7 +24,7 @@ SYMBOLS = [
     "phyfoo_dataset_create", "phyfoo_dataset_create_device", "phyfoo_dataset_packed", "phyfoo_dataset_columns",
     "phyfoo_dataset_windows", "phyfoo_dataset_patterns", "phyfoo_dataset_free",
     "phyfoo_model_create", "phyfoo_model_set_pi", "phyfoo_model_get_pi", "phyfoo_model_set_branch",
-    "phyfoo_model_set_mode", "phyfoo_model_free",
+    "phyfoo_model_set_mode", "phyfoo_model_is_degenerate", "phyfoo_model_free",
     "phyfoo_score_windows", "phyfoo_bg_columns", "phyfoo_bg_columns_order1", "phyfoo_zoops_estep", "phyfoo_zoops_estep_device",
     "phyfoo_ab_score_windows", "phyfoo_ab_bg_columns", "phyfoo_ab_train", "phyfoo_scan_hits", "phyfoo_score_order_stats", "phyfoo_select", "phyfoo_fe_prepare", "phyfoo_fe_prepare_all", "phyfoo_fe_eval", "phyfoo_fe_grad",
     "phyfoo_fe_values_device", "phyfoo_fe_suffstats", "phyfoo_fe_size", "phyfoo_fe_free",
@@ -95,6 +95,7 @@ def lib():
     L.phyfoo_model_get_pi.argtypes = [vp, vp, C.c_int32, dp, C.c_int32]
     L.phyfoo_model_set_branch.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_double]
     L.phyfoo_model_set_mode.argtypes = [vp, vp, C.c_int32]
+    L.phyfoo_model_is_degenerate.argtypes = [vp]
     L.phyfoo_model_free.argtypes = [vp, vp]
     L.phyfoo_model_free.restype = None
     L.phyfoo_score_windows.argtypes = [vp, vp, vp, C.c_int32, dp, ip32, sp]

@@ -292,3 +292,45 @@ def test_f81_structured_kernel_equals_generic_kernel(ctx, tree, W):
             PhyloBayesModel.EVOL_MODEL = _abi.EVOL_F81ALPHA
             ctx.set_option("order0_kernel", -1)
             ctx.set_option("pattern_memo", 1)
+
+
+def test_hky_as_implemented_returns_the_reference_degenerate_values(ctx):
+    """evolution/HKY.java as implemented (beta == 0, :32): every table has zero entries.  The library returns what the
+    reference's mean field returns -- NaN, or -inf for columns of one nucleotide class under a star tree, 100 sweeps per
+    window -- instead of an error; exact mode is the likelihood under those tables (-inf where a transversion is needed)."""
+    from phyfoo_b200 import _abi, synth
+    from phyfoo_b200.data import PhyloSample
+    from phyfoo_b200.models import PhyloBackground, PhyloBayesModel, SingleHiddenMotifMixture
+    rng = np.random.default_rng(3)
+    W = 3
+    pwm = synth.random_pwm(W, 0, 3)
+    base = rng.integers(0, 4, size=(60, 1))
+    codes = np.where(rng.random((60, 5)) < 0.3, (base + 2) % 4, base).astype(np.uint8)     # transitions only
+    codes[5, 2] = (codes[5, 2] + 1) % 4                                                     # one transversion column
+    codes[20, 1] = 4
+    codes[30, :] = [4, 4, 0, 2, 0]
+    smp = PhyloSample(codes, [0, 25, 60])
+    PhyloBayesModel.EVOL_MODEL = _abi.EVOL_HKY_AS_IMPLEMENTED
+    try:
+        for newick in (synth.star_newick(5), synth.caterpillar_newick(5)):
+            fg = PhyloBayesModel(W, 0, newick, ctx); fg.setCondProbs(pwm)
+            om = oracle_fg(newick, pwm, evol=orc.HKY)
+            for strand in (0, 1):
+                got, sw = fg.getLogProbFor(smp, strand=strand, want_sweeps=True)
+                ref, rsw = zip(*[om.score_windows(smp.getElementAt(i), bool(strand)) for i in range(2)])
+                ref, rsw = np.concatenate(ref), np.concatenate(rsw)
+                assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.array_equal(got[~np.isnan(got)], ref[~np.isnan(ref)])
+                assert np.array_equal(sw, rsw) and (sw == 100).all()
+            assert np.isnan(got).any() and (np.isneginf(got).any() or "((" in newick)
+            # exact mode: pruning under the same tables
+            PhyloBayesModel.CALC_LOGLIKELIHOOD = True
+            try:
+                ex = fg.getLogProbFor(smp)
+            finally:
+                PhyloBayesModel.CALC_LOGLIKELIHOOD = False
+            oe = oracle_fg(newick, pwm, mode=orc.EXACT_PRUNING, evol=orc.HKY)
+            re_ = np.concatenate([oe.score_windows(smp.getElementAt(i), False)[0] for i in range(2)])
+            fin = np.isfinite(re_)
+            assert np.array_equal(np.isfinite(ex), fin) and rel_err(ex[fin], re_[fin]) < TOL and np.isneginf(ex[~fin]).all()
+    finally:
+        PhyloBayesModel.EVOL_MODEL = _abi.EVOL_F81ALPHA
