@@ -178,6 +178,24 @@ int phyfoo_zoops_estep_device(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_
                               const double* logw, const double* strand_logw, const double* aln_weights_device,
                               double* partial_device, void* stream);
 
+/* ---- ZOOPS mixture of several motif models (BASELINE.json configs[3]: 3 motifs + homogeneous background) ----
+ * The reference's mixture has exactly one motif component (jstacs!/.../SingleHiddenMotifMixture.java:716-718
+ * getNumberOfMotifs() == 1); this is its direct generalisation (DESIGN.md "multi-motif mixture"): an alignment holds at most
+ * one site of at most one of K <= 8 motifs,
+ *   a_{k,j} = -log n_k + motif_k(j) - bg(j, j + W_k - 1),   Z_k = logsumexp_j a_{k,j},
+ *   (p_1..p_K, p_0) = logSumNormalisation(logw_1 + Z_1, ..., logw_K + Z_K, logw_0),   ll += weight (logPSeq + lse),
+ *   gamma_{k,j} = exp(a_{k,j} - Z_k) p_k weight,   w_k += p_k weight,
+ * with the one-motif E-step's arithmetic per component (K = 1 gives phyfoo_zoops_estep's numbers).  logw[K + 1]: the motifs,
+ * then "no motif"; gamma_out: NULL or K pointers (each NULL or [windows of that width]); w_out[K + 1]; argmax_motif / argmax_off
+ * [n_aln]: first maximum of logw_k + a_{k,j} in (k, j) order.  Order-0 PhyloBackground.  The gamma of every component stays
+ * on the device for phyfoo_select_multi (the M-step of component k: phyfoo_select_multi -> phyfoo_fe_prepare -> phyfoo_ss_* /
+ * phyfoo_fe_*, exactly the one-motif M-step with gamma_k as weights). */
+int phyfoo_zoops_estep_multi(phyfoo_ctx* ctx, const phyfoo_dataset* ds, int32_t n_motifs, phyfoo_model* const* fgs, phyfoo_model* bg,
+                             const double* logw, const double* aln_weights, double* const* gamma_out, double* w_out, double* ll_out,
+                             int32_t* argmax_motif, int32_t* argmax_off, phyfoo_stats* stats);
+int phyfoo_select_multi(phyfoo_ctx* ctx, const phyfoo_dataset* ds, int32_t motif, double t, double q, int32_t* sel_aln,
+                        int32_t* sel_off, double* sel_weight, int64_t capacity, int64_t* n_selected);
+
 /* ---- genome scan / classification front-end (classification/ClassificationUtil.java) ----
  * Consumers of the per-offset motif scores that keep them on the device (config 5: 2*10^9 window scores).
  * scan_hits, per alignment: the number of offsets with score > threshold (determineSensitivityPerSeq :266-278 counts the

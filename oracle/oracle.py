@@ -337,3 +337,64 @@ def ab_train(cols, weights, pseudo=1e-8):
     out = np.zeros((W, 4))
     lib().orc_ab_train(_u8(cols), n, W, S, _dp(weights), pseudo, _dp(out))
     return out
+
+
+# ---- ZOOPS mixture of K motif models (BASELINE.json configs[3]; no reference counterpart: jstacs SingleHiddenMotifMixture
+# has one motif component, :716-718).  Specification = DESIGN.md "multi-motif mixture": the one-motif E-step
+# (SingleHiddenMotifMixture.java:520-564, modify :585-596) per component, then ONE logSumNormalisation over the K + 1
+# components.  Plain loops over the oracle's own window and column scores; K = 1 must reproduce estep() above.
+def estep_multi(fgs, bg, col_offsets, codes, logw, aln_weights=None):
+    col_offsets = np.ascontiguousarray(col_offsets, np.int64)
+    codes = np.ascontiguousarray(codes, np.uint8)
+    K, n_aln = len(fgs), col_offsets.size - 1
+    logw = np.asarray(logw, np.float64)
+    gam = [[] for _ in range(K)]
+    w = np.zeros(K + 1)
+    ll = 0.0
+    arg_m, arg_o = np.zeros(n_aln, np.int32), np.zeros(n_aln, np.int32)
+    for a in range(n_aln):
+        aln = codes[col_offsets[a]:col_offsets[a + 1]]
+        L = aln.shape[0]
+        weight = 1.0 if aln_weights is None else float(aln_weights[a])
+        bgc = bg.bg_columns(aln)                     # order 0: per-column log-scores; ranges are their sums in column order
+        log_pseq = 0.0
+        for u in range(L):
+            log_pseq += bgc[u]
+        Z, e_all, best_all = [], [], []
+        for k, fg in enumerate(fgs):
+            W = fg.W
+            n = L - W + 1
+            sc, _ = fg.score_windows(aln, False)
+            aj = np.zeros(n)
+            for j in range(n):
+                bgw = 0.0
+                for m in range(W):
+                    bgw += bgc[j + m]
+                aj[j] = -np.log(float(n)) + sc[j] - bgw
+            off = aj.max()                                       # Normalisation.logSumNormalisation :352-375
+            e = np.exp(aj - off)
+            s = 0.0
+            for v in e:
+                s += v
+            if s != 1.0:
+                e = e / s
+            Z.append(off + np.log(s)); e_all.append(e); best_all.append((off, int(np.argmax(aj))))
+        help_ = np.array([logw[k] + Z[k] for k in range(K)] + [logw[K]])
+        off = help_.max()
+        h = np.exp(help_ - off)
+        hs = 0.0
+        for v in h:
+            hs += v
+        if hs != 1.0:
+            h = h / hs
+        ll += weight * (log_pseq + (off + np.log(hs)))
+        best_v, best_k = -np.inf, 0
+        for k in range(K):
+            w[k] += weight * h[k]
+            gam[k].append(e_all[k] * (h[k] * weight))
+            v = logw[k] + best_all[k][0]
+            if v > best_v:
+                best_v, best_k = v, k
+        w[K] += weight * h[K]
+        arg_m[a], arg_o[a] = best_k, best_all[best_k][1]
+    return {"gamma": [np.concatenate(g) for g in gam], "w": w, "ll": ll, "argmax_motif": arg_m, "argmax_off": arg_o}

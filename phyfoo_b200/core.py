@@ -584,3 +584,39 @@ class SSObjective:
         if lib().phyfoo_ss_optimize(self.h, _p(o, C.c_int32), o.size, C.byref(fb), C.byref(fa), C.byref(ev)) != _abi.OK:
             raise ValueError("phyfoo_ss_optimize: bad argument")
         return fb.value, fa.value, ev.value
+
+
+# ---- ZOOPS mixture of several motif models (phyfoo_zoops_estep_multi) ----
+def zoops_estep_multi(ctx, ds, fgs, bg, logw, aln_weights=None, want_gamma=True, want_argmax=True):
+    """fgs: list of K DeviceModels; logw[K + 1] (motifs, then "no motif").  Returns gamma (list of K arrays), w[K + 1], ll,
+    argmax_motif / argmax_off per alignment."""
+    K = len(fgs)
+    logw = np.ascontiguousarray(logw, np.float64)
+    if logw.size != K + 1:
+        raise ValueError("logw must hold one entry per motif plus one for 'no motif'")
+    aw = None if aln_weights is None else np.ascontiguousarray(aln_weights, np.float64)
+    handles = (C.c_void_p * K)(*[m.h for m in fgs])
+    gam = [np.zeros(ds.windows(m.W)) for m in fgs] if want_gamma else None
+    gptr = (C.POINTER(C.c_double) * K)(*[_p(g, C.c_double) for g in gam]) if want_gamma else None
+    w, ll = np.zeros(K + 1), C.c_double()
+    am = np.zeros(ds.n_aln, np.int32) if want_argmax else None
+    ao = np.zeros(ds.n_aln, np.int32) if want_argmax else None
+    st = _abi.Stats()
+    raise_for(lib().phyfoo_zoops_estep_multi(ctx.h, ds.h, K, handles, bg.h, _p(logw, C.c_double), _p(aw, C.c_double), gptr, _p(w, C.c_double),
+                                             C.byref(ll), _p(am, C.c_int32), _p(ao, C.c_int32), C.byref(st)), ctx.h)
+    return {"gamma": gam, "w": w, "ll": ll.value, "argmax_motif": am, "argmax_off": ao, "stats": _stats_dict(st)}
+
+
+def select_multi(ctx, ds, motif, t=0.8, q=0.0):
+    """SequenceSpecificDataSelector on the gamma of component `motif` of the last zoops_estep_multi (resident on the device)."""
+    n = C.c_int64(0)
+    cap = max(4 * ds.n_aln, 1024)
+    while True:
+        sa, so, sw = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap)
+        rc = lib().phyfoo_select_multi(ctx.h, ds.h, int(motif), float(t), float(q), _p(sa, C.c_int32), _p(so, C.c_int32), _p(sw, C.c_double),
+                                       cap, C.byref(n))
+        if rc == _abi.ENOMEM and n.value > cap:
+            cap = int(n.value)
+            continue
+        raise_for(rc, ctx.h)
+        return sa[:n.value].copy(), so[:n.value].copy(), sw[:n.value].copy()

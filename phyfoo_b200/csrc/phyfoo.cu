@@ -85,7 +85,9 @@ struct phyfoo_ctx {
                                      // pattern table does not apply), 0 = generic kernel (tree_pass.cuh), 1 = F81-structured kernel
     int order1_qglobal = -1;         // node-per-thread kernel: -1 = choose, 0 = q rows in shared memory, n > 0 = q rows in global memory
                                      // behind L1 with n warps per SM (<= 8)
-    DevBuf o1n_cache, o1n_fb;        // node-per-thread order-1 kernel: observed-leaf sums per warp; list of windows with gaps
+    DevBuf o1n_cache, o1n_fb;
+    DevBuf multi_scores[8], multi_gamma[8];   // K-motif mixture: window scores and gamma per component (resident between E- and M-step)
+    int64_t multi_windows[8] = {0}; int multi_width[8] = {0}; int multi_k = 0; const phyfoo_dataset* multi_ds = nullptr;        // node-per-thread order-1 kernel: observed-leaf sums per warp; list of windows with gaps
     // per-kernel device times of the most recent call (CUDA events on the library's stream)
     struct KTime { const char* name; cudaEvent_t e0, e1; };
     std::vector<KTime> ktimes;
@@ -612,8 +614,10 @@ extern "C" void phyfoo_destroy(phyfoo_ctx* ctx) {
     if (ctx->aux) cudaStreamSynchronize(ctx->aux);
     ctx->memo_state.release();
     for (DevBuf* b : {&ctx->counters, &ctx->fg_scores, &ctx->bg_scores, &ctx->sweeps_buf, &ctx->gamma, &ctx->profile, &ctx->part,
-                      &ctx->argoff, &ctx->argstrand, &ctx->alnw, &ctx->out3, &ctx->gstate, &ctx->misc, &ctx->selw, &ctx->sel_tmp, &ctx->sel_out, &ctx->memo_traj, &ctx->memo_pending})
+                      &ctx->argoff, &ctx->argstrand, &ctx->alnw, &ctx->out3, &ctx->gstate, &ctx->misc, &ctx->selw, &ctx->sel_tmp, &ctx->sel_out, &ctx->memo_traj, &ctx->memo_pending,
+                      &ctx->memo_state, &ctx->o1n_cache, &ctx->o1n_fb})
         b->release();
+    for (int k = 0; k < 8; ++k) { ctx->multi_scores[k].release(); ctx->multi_gamma[k].release(); }
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
     for (auto& kt : ctx->ktimes) { cudaEventDestroy(kt.e0); cudaEventDestroy(kt.e1); }
@@ -768,6 +772,7 @@ extern "C" void phyfoo_dataset_free(phyfoo_ctx* ctx, phyfoo_dataset* ds) {
     cudaStream_t st = ctx ? ctx->stream : nullptr;
     if (ctx) cudaSetDevice(ctx->device);
     if (ctx && ctx->gamma_ds == ds) { ctx->gamma_ds = nullptr; ctx->gamma_windows = -1; }   // the resident gamma dies with its data set
+    if (ctx && ctx->multi_ds == ds) { ctx->multi_ds = nullptr; ctx->multi_k = 0; }
     dev_free(st, ds->d_col_off); dev_free(st, ds->d_bases); dev_free(st, ds->d_gaps);
     for (auto& kv : ds->d_win_off) dev_free(st, kv.second);
     memo_release(st, ds->memo);
@@ -2205,6 +2210,225 @@ extern "C" int phyfoo_score_order_stats(phyfoo_ctx* ctx, const phyfoo_dataset* d
     CU(cudaMemcpyAsync(values_out, d_out, (size_t)n_ranks * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return PHYFOO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ZOOPS mixture of SEVERAL motif models + "no motif" (BASELINE.json configs[3]; DESIGN.md section "multi-motif mixture").
+// The reference's SingleHiddenMotifMixture has exactly one motif component (jstacs SingleHiddenMotifMixture.java:716-718);
+// this is its direct generalisation: an alignment holds at most one site of at most one of K motifs,
+//   a_{k,j} = -log n_k + motif_k(j) - bg(j, j + W_k - 1),  Z_k = logsumexp_j a_{k,j},
+//   help = (logw_1 + Z_1, ..., logw_K + Z_K, logw_0) -> logSumNormalisation -> p_1..p_K, p_0,
+//   ll += weight (logPSeq + lse),  gamma_{k,j} = exp(a_{k,j} - Z_k) p_k weight,  w_k += p_k weight,
+// with the arithmetic of the one-motif kernel per component (K = 1 reproduces it bit for bit); order-0 background.
+// ------------------------------------------------------------------------------------------------
+static const int ZOOPS_KMAX = 8;
+struct ZoopsMultiParams {
+    int K;
+    const double* score[ZOOPS_KMAX];         // [n_windows_k] window scores of motif k
+    const int64_t* win_off[ZOOPS_KMAX];      // window offsets for its width
+    int W[ZOOPS_KMAX];
+    double logw[ZOOPS_KMAX + 1];             // motifs 0..K-1, then "no motif"
+    const double* bgcol; const int64_t* col_off; int n_aln;
+    const double* aln_w;
+    double* gamma[ZOOPS_KMAX];               // nullable
+    double* part;                            // [K + 2][n_aln]: ll, w_1..w_K, w_0
+    int32_t* arg_motif; int32_t* arg_off;    // nullable: first maximum of logw_k + a_{k,j} in (k, j) order
+    double* out;                             // [K + 2]
+    unsigned int* ticket;
+};
+
+__global__ void __launch_bounds__(256) zoops_multi_kernel(ZoopsMultiParams p) {
+    __shared__ double sh[32];
+    __shared__ double sh_v[8];
+    __shared__ int sh_i[8];
+    __shared__ double s_Z[ZOOPS_KMAX], s_best[ZOOPS_KMAX];
+    __shared__ int s_bestj[ZOOPS_KMAX];
+    const int a = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    const int64_t c0 = p.col_off[a];
+    const int L = (int)(p.col_off[a + 1] - c0);
+    const double weight = p.aln_w ? p.aln_w[a] : 1.0;
+    const double* bgc = p.bgcol + c0;
+    double ps = 0.0;
+    for (int u = tid; u < L; u += T) ps += bgc[u];
+    const double log_pseq = block_sum(ps, sh);                            // bg.getLogProbFor(seq, 0, l-1)
+    for (int k = 0; k < p.K; ++k) {
+        const int64_t w0 = p.win_off[k][a];
+        const int n = (int)(p.win_off[k][a + 1] - w0), W = p.W[k];
+        const double lprior = -log((double)n);
+        double best = -INFINITY;
+        int best_j = 0x7fffffff;
+        for (int j = tid; j < n; j += T) {
+            double bgw = 0.0;
+            for (int m = 0; m < W; ++m) bgw += bgc[j + m];
+            const double aj = lprior + p.score[k][w0 + j] - bgw;
+            if (p.gamma[k]) p.gamma[k][w0 + j] = aj;
+            if (aj > best) { best = aj; best_j = j; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_down_sync(0xffffffffu, best, o);
+            const int oj = __shfl_down_sync(0xffffffffu, best_j, o);
+            if (ov > best || (ov == best && oj < best_j)) { best = ov; best_j = oj; }
+        }
+        __syncthreads();
+        if ((tid & 31) == 0) { sh_v[tid >> 5] = best; sh_i[tid >> 5] = best_j; }
+        __syncthreads();
+        best = sh_v[0]; best_j = sh_i[0];
+        for (int i = 1; i < (T + 31) / 32; ++i)
+            if (sh_v[i] > best || (sh_v[i] == best && sh_i[i] < best_j)) { best = sh_v[i]; best_j = sh_i[i]; }
+        if (best_j == 0x7fffffff) best_j = 0;
+        double se = 0.0;
+        for (int j = tid; j < n; j += T) {
+            double aj;
+            if (p.gamma[k]) aj = p.gamma[k][w0 + j];
+            else {
+                double bgw = 0.0;
+                for (int m = 0; m < W; ++m) bgw += bgc[j + m];
+                aj = lprior + p.score[k][w0 + j] - bgw;
+            }
+            const double e = exp(aj - best);
+            if (p.gamma[k]) p.gamma[k][w0 + j] = e;
+            se += e;
+        }
+        const double sum = block_sum(se, sh);
+        if (tid == 0) { s_Z[k] = best + log(sum); s_best[k] = best; s_bestj[k] = best_j; sh[31] = sum; }
+        __syncthreads();
+        const double sumk = sh[31];
+        if (p.gamma[k] && sumk != 1.0)
+            for (int j = tid; j < n; j += T) p.gamma[k][w0 + j] /= sumk;  // normalised over j; scaled by p_k below
+        __syncthreads();
+    }
+    // component posterior: logSumNormalisation over (logw_k + Z_k, logw_0)
+    double help[ZOOPS_KMAX + 1];
+    double off = p.logw[p.K];
+    for (int k = 0; k < p.K; ++k) { help[k] = p.logw[k] + s_Z[k]; off = fmax(off, help[k]); }
+    help[p.K] = p.logw[p.K];
+    double hs = 0.0;
+    for (int k = 0; k <= p.K; ++k) { help[k] = exp(help[k] - off); hs += help[k]; }
+    if (hs != 1.0) for (int k = 0; k <= p.K; ++k) help[k] /= hs;
+    const double lse = off + log(hs);
+    if (tid == 0) {
+        p.part[a] = weight * (log_pseq + lse);
+        for (int k = 0; k <= p.K; ++k) p.part[(size_t)(1 + k) * p.n_aln + a] = weight * help[k];
+        if (p.arg_off) {
+            double bv = -INFINITY; int bk = 0;
+            for (int k = 0; k < p.K; ++k) { const double v = p.logw[k] + s_best[k]; if (v > bv) { bv = v; bk = k; } }
+            p.arg_motif[a] = bk; p.arg_off[a] = s_bestj[bk];
+        }
+    }
+    for (int k = 0; k < p.K; ++k) {
+        if (!p.gamma[k]) continue;
+        const int64_t w0 = p.win_off[k][a];
+        const int n = (int)(p.win_off[k][a + 1] - w0);
+        const double pk = help[k] * weight;
+        for (int j = tid; j < n; j += T) p.gamma[k][w0 + j] *= pk;
+    }
+    __shared__ int s_last;
+    if (tid == 0) {
+        __threadfence();
+        s_last = atomicAdd(p.ticket, 1u) == gridDim.x - 1 ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        for (int r = 0; r < p.K + 2; ++r) {
+            double v = 0.0;
+            for (int i = tid; i < p.n_aln; i += T) v += __ldcg(p.part + (size_t)r * p.n_aln + i);
+            const double s3 = block_sum(v, sh);
+            if (tid == 0) p.out[r] = s3;
+            __syncthreads();
+        }
+        if (tid == 0) *p.ticket = 0u;
+    }
+}
+
+// One E-step of the K-motif mixture.  Window scores of motif k stay resident in ctx->multi_scores[k] / gamma in
+// ctx->multi_gamma[k] (phyfoo_select_multi reads them for the M-step of component k).
+extern "C" int phyfoo_zoops_estep_multi(phyfoo_ctx* ctx, const phyfoo_dataset* ds, int32_t n_motifs, phyfoo_model* const* fgs, phyfoo_model* bg,
+                                        const double* logw, const double* aln_weights, double* const* gamma_out, double* w_out, double* ll_out,
+                                        int32_t* argmax_motif, int32_t* argmax_off, phyfoo_stats* stats) {
+    if (!ctx) return PHYFOO_EINVAL;
+    if (!ds || !fgs || !bg || !logw || n_motifs < 1 || n_motifs > ZOOPS_KMAX) return fail(ctx, PHYFOO_EINVAL, "zoops_estep_multi: NULL argument or more than 8 motifs");
+    if (bg->h.kind != PHYFOO_MODEL_BG || bg->h.order != 0) return fail(ctx, PHYFOO_EUNSUPPORTED, "zoops_estep_multi: the background must be a PhyloBackground of order 0");
+    if (ds->n_aln == 0) return fail(ctx, PHYFOO_EINVAL, "zoops_estep_multi: empty sample");
+    CU(cudaSetDevice(ctx->device));
+    CallTimer tm(ctx);
+    ZoopsMultiParams z;
+    z.K = n_motifs;
+    int64_t nw[ZOOPS_KMAX];
+    int64_t sweeps_fg = 0, n_windows = 0;
+    const double* d_alnw = nullptr;
+    if (aln_weights) {
+        CU(ctx->alnw.ensure((size_t)ds->n_aln * sizeof(double)));
+        CU(cudaMemcpyAsync(ctx->alnw.p, aln_weights, (size_t)ds->n_aln * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        d_alnw = ctx->alnw.as<double>();
+    }
+    CU(ctx->bg_scores.ensure((size_t)std::max<int64_t>(ds->n_cols, 1) * sizeof(double)));
+    int rc = launch_bg_columns(ctx, ds, bg, ctx->bg_scores.as<double>(), nullptr, 1);
+    if (rc) return rc;
+    for (int k = 0; k < n_motifs; ++k) {
+        phyfoo_model* fg = fgs[k];
+        if (!fg || fg->h.kind != PHYFOO_MODEL_FG) return fail(ctx, PHYFOO_EINVAL, "zoops_estep_multi: a motif model is missing or not a motif");
+        if (ds->min_len < fg->h.W) return fail(ctx, PHYFOO_EINVAL, "zoops_estep_multi: an alignment is shorter than a motif");
+        const int64_t* d_woff; const std::vector<int64_t>* h_woff;
+        if ((rc = dataset_win_off(ctx, ds, fg->h.W, &d_woff, &h_woff))) return rc;
+        nw[k] = h_woff->back();
+        n_windows += nw[k];
+        CU(ctx->multi_scores[k].ensure((size_t)nw[k] * sizeof(double)));
+        CU(ctx->multi_gamma[k].ensure((size_t)nw[k] * sizeof(double)));
+        if ((rc = launch_score(ctx, ds, fg, d_woff, nw[k], 0, ctx->multi_scores[k].as<double>(), nullptr, 0))) return rc;
+        int64_t sk = 0;
+        if (stats && (rc = read_sweeps(ctx, 0, &sk))) return rc;
+        sweeps_fg += sk;
+        z.score[k] = ctx->multi_scores[k].as<double>(); z.win_off[k] = d_woff; z.W[k] = fg->h.W; z.logw[k] = logw[k];
+        z.gamma[k] = ctx->multi_gamma[k].as<double>();
+        ctx->multi_windows[k] = nw[k]; ctx->multi_width[k] = fg->h.W;
+    }
+    ctx->multi_ds = ds; ctx->multi_k = n_motifs;
+    z.logw[n_motifs] = logw[n_motifs];
+    z.bgcol = ctx->bg_scores.as<double>(); z.col_off = ds->d_col_off; z.n_aln = ds->n_aln; z.aln_w = d_alnw;
+    CU(ctx->part.ensure((size_t)(n_motifs + 2) * ds->n_aln * sizeof(double)));
+    CU(ctx->out3.ensure((ZOOPS_KMAX + 2) * sizeof(double)));
+    CU(ctx->argoff.ensure((size_t)2 * ds->n_aln * sizeof(int32_t)));
+    z.part = ctx->part.as<double>(); z.out = ctx->out3.as<double>();
+    z.arg_off = argmax_off ? ctx->argoff.as<int32_t>() : nullptr;
+    z.arg_motif = argmax_off ? ctx->argoff.as<int32_t>() + ds->n_aln : nullptr;
+    z.ticket = (unsigned int*)(ctx->counters.as<unsigned long long>() + 12);
+    {
+        KernelTimer kt_(ctx, "zoops_multi_kernel");
+        zoops_multi_kernel<<<ds->n_aln, 256, 0, ctx->stream>>>(z);
+    }
+    CU(cudaGetLastError());
+    const float ms = tm.stop();
+    double r[ZOOPS_KMAX + 2];
+    CU(cudaMemcpyAsync(r, ctx->out3.p, (size_t)(n_motifs + 2) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (argmax_off) CU(cudaMemcpyAsync(argmax_off, z.arg_off, (size_t)ds->n_aln * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (argmax_off && argmax_motif) CU(cudaMemcpyAsync(argmax_motif, z.arg_motif, (size_t)ds->n_aln * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (gamma_out)
+        for (int k = 0; k < n_motifs; ++k)
+            if (gamma_out[k]) CU(cudaMemcpyAsync(gamma_out[k], z.gamma[k], (size_t)nw[k] * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ll_out) *ll_out = r[0];
+    if (w_out) for (int k = 0; k <= n_motifs; ++k) w_out[k] = r[1 + k];
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->n_windows = n_windows; stats->n_columns = ds->n_cols; stats->kernel_launches = ctx->launches; stats->gpu_ms = ms;
+        stats->sweeps_fg = sweeps_fg;
+    }
+    return PHYFOO_OK;
+}
+// io/SequenceSpecificDataSelector.java:37-99 on the gamma of component k of the last phyfoo_zoops_estep_multi (still resident)
+extern "C" int phyfoo_select_multi(phyfoo_ctx* ctx, const phyfoo_dataset* ds, int32_t motif, double t, double q, int32_t* sel_aln,
+                                   int32_t* sel_off, double* sel_weight, int64_t capacity, int64_t* n_selected) {
+    if (!ctx) return PHYFOO_EINVAL;
+    if (!ds || motif < 0 || motif >= ctx->multi_k || ctx->multi_ds != ds) return fail(ctx, PHYFOO_EINVAL, "select_multi: no gamma of this data set and component is resident (run phyfoo_zoops_estep_multi first)");
+    // hand the component's gamma to phyfoo_select as the resident one
+    std::swap(ctx->gamma, ctx->multi_gamma[motif]);
+    const int64_t kw = ctx->gamma_windows; const phyfoo_dataset* kd = ctx->gamma_ds; const int kwd = ctx->gamma_width;
+    ctx->gamma_windows = ctx->multi_windows[motif]; ctx->gamma_ds = ds; ctx->gamma_width = ctx->multi_width[motif];
+    const int rc = phyfoo_select(ctx, ds, ctx->multi_width[motif], nullptr, t, q, sel_aln, sel_off, sel_weight, capacity, n_selected);
+    std::swap(ctx->gamma, ctx->multi_gamma[motif]);
+    ctx->gamma_windows = kw; ctx->gamma_ds = kd; ctx->gamma_width = kwd;
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -198,6 +198,13 @@ class PhyloBayesModel(_PhyloModel):
                                      self.MOTIF_QUALITY_THRESHOLD)
             ss = np.concatenate([np.zeros(sa.size, np.uint8), np.ones(ra.size, np.uint8)])
             sa, so, sw = np.concatenate([sa, ra]), np.concatenate([so, ro]), np.concatenate([sw, rw])
+        return self.train_selected(sample, sa, so, sw, ss, rng, sharded)
+
+    def train_selected(self, sample: PhyloSample, sa, so, sw, ss=None, rng=None, sharded=False):
+        """The M-step proper on an explicit selection (alignment, offset, weight[, strand]) -- what train() does after the
+        selector; a mixture of several motifs (MultiMotifMixture) calls it with the selection of each component."""
+        rng = rng or np.random.default_rng()
+        ds = sample.device(self.ctx)
         fe = core.FESet(self.ctx, ds, self.device_model(), sa, so, sw, ss)
         stats = {"skipped": False, "selected": int(sa.size), "evaluations": 0, "f_before": None, "f_after": None}
         local = fe
@@ -521,6 +528,61 @@ class SingleHiddenMotifMixture:
     def getStrandProbabilitiesFor(self, sample: PhyloSample):
         res = self.getNewWeights(sample, want_gamma=False)
         return res["argmax_off"], res["argmax_strand"]
+
+
+class MultiMotifMixture:
+    """ZOOPS mixture of K motif models and a flanking model ("no motif"): BASELINE.json configs[3].  The reference's
+    SingleHiddenMotifMixture has one motif component (getNumberOfMotifs() == 1); this is its generalisation with the same
+    E-step arithmetic per component (include/phyfoo.h phyfoo_zoops_estep_multi, DESIGN.md "multi-motif mixture"): one site of
+    at most one motif per alignment.  M-step: every motif is trained like the single one, with its own gamma_k as weights
+    (PhyloBayesModel.train); component weights from the sufficient statistics w[K + 1] with hyper-parameters 1
+    (jstacs AbstractMixtureModel.getNewComponentProbs :1542-1578)."""
+
+    def __init__(self, motifs, flanking, weights=None, estimateComponentProbs=True):
+        self.motifs, self.flanking = list(motifs), flanking
+        K = len(self.motifs)
+        self.weights = np.full(K + 1, 1.0 / (K + 1)) if weights is None else np.asarray(weights, np.float64)
+        self.estimateComponentProbs = bool(estimateComponentProbs)
+        self.hyper = np.ones(K + 1)
+        self.ctx = self.motifs[0].ctx
+
+    def getNumberOfMotifs(self):
+        return len(self.motifs)
+
+    def getNewWeights(self, sample: PhyloSample, seqWeights=None, want_gamma=True):
+        with np.errstate(divide="ignore"):
+            logw = np.log(self.weights)
+        return core.zoops_estep_multi(self.ctx, sample.device(self.ctx), [m.device_model() for m in self.motifs],
+                                      self.flanking.device_model(), logw, seqWeights, want_gamma)
+
+    def train(self, sample: PhyloSample, max_iterations=20, eps=1e-6, rng=None, sharded=False):
+        """EM; returns the log-likelihoods, one per E-step.  sharded: `sample` is this rank's shard (see
+        SingleHiddenMotifMixture.train)."""
+        rng = rng or np.random.default_rng(0)
+        history, trained = [], False
+        for it in range(max_iterations):
+            res = self.getNewWeights(sample, want_gamma=False)
+            ll, w = res["ll"], res["w"]
+            if sharded:
+                from . import sharding
+                v = sharding.allreduce_host_(np.concatenate([[ll], w]))
+                ll, w = float(v[0]), v[1:].copy()
+            history.append(ll)
+            if trained and abs(history[-1] - history[-2]) < eps:
+                break
+            ds = sample.device(self.ctx)
+            for k, m in enumerate(self.motifs):
+                m.trainingStep = getattr(m, "trainingStep", 0)
+                if m.trainingStep < m.SKIP_TRAINING_STEPS:
+                    m.trainingStep += 1
+                    continue
+                sa, so, sw = core.select_multi(self.ctx, ds, k, m.PROB_THRESH_FOR_WEIGHTS, m.MOTIF_QUALITY_THRESHOLD)
+                m.train_selected(sample, sa, so, sw, rng=rng, sharded=sharded)
+                trained = True
+            if self.estimateComponentProbs:
+                v = w + self.hyper
+                self.weights = v / v.sum()
+        return history
 
 
 class AlignmentBasedModel:
