@@ -10,7 +10,7 @@ GPU; at N > 1 the SAME 10 000 alignments are split into contiguous blocks balanc
 alignments.  Before the timed region rank 0 scores the first alignments of its shard with the oracle and asserts
 parity (scores 1e-9 relative, sweep counts and arg-max calls exact); the line carries `parity_checked`.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--config c3|c2|c2star|c3o0|c5] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config c3|c1|c2|c2star|c3o0|c4|c5] [--impl reference]
 
 Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM; `e2e` goes through the public
 host API with host buffers (pack + copies inside the timed region); `roofline` is for the dominant kernel
@@ -60,7 +60,10 @@ def parse_args():
 
 def workload_name(cfg):
     kind = "phylogenetic PWM" if cfg["order"] == 0 else "phylogenetic Bayesian network (order 1)"
-    return (f"{kind}, width {cfg['W']}, {cfg['S']}-species {cfg['tree']} tree, {cfg['n_aln']} synthetic alignments x "
+    if cfg.get("motifs"):
+        kind = f"{cfg['motifs']} phylogenetic PWMs + homogeneous background (ZOOPS mixture of several motifs)"
+    src = "bundled (reference data/synthetic_data/trees/data_tree1_1.0.fg, first 200)" if cfg.get("bundled") else "synthetic"
+    return (f"{kind}, width {cfg['W']}, {cfg['S']}-species {cfg['tree']} tree, {cfg['n_aln']} {src} alignments x "
             f"{cfg['length']} bp, ZOOPS E-step, mean-field scoring (reference default)")
 
 
@@ -578,6 +581,16 @@ def run_ours(args):
     d2h = int(res["gamma"].nbytes + res["argmax_off"].nbytes + res["argmax_strand"].nbytes + 24)
     assert world > 1 or abs(res["ll"] - ll_w[0]) <= 1e-9 * abs(res["ll"])
 
+    # arg-max site calls against the planted sites of this rank's alignments (c1: the MOTIF_POS annotations of the bundled data)
+    planted_hits = None
+    pl = np.asarray(run.planted)[run.bounds[rank][0]:run.bounds[rank][1]]
+    has = pl >= 0
+    if has.any():
+        d = np.abs(res["argmax_off"][has].astype(np.int64) - pl[has])
+        planted_hits = {"alignments_with_a_site": int(has.sum()), "of": f"rank 0's {sample.n_alignments} alignments",
+                        "argmax_exact": float(np.mean(d == 0)), "argmax_within_half_width": float(np.mean(d <= W // 2)),
+                        "model": "the generating PWM and tree"}
+
     optimizer = None
     if not args.no_mstep:
         optimizer = optimizer_timings(run, args, step_ms)
@@ -620,7 +633,8 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": step_ms, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "bundled with the reference (synthetic, its own generator)" if cfg.get("bundled") else "synthetic",
             "config": {"workload": workload_name(cfg), "name": args.config, "windows_total": total_windows,
                        "windows_per_gpu": n_windows, "alignments_per_gpu": [hi - lo for lo, hi in run.bounds],
                        "sharding": "contiguous alignment blocks balanced by column count (PhyloSample.shard); every rank "
@@ -640,6 +654,8 @@ def run_ours(args):
         }
         if args.warmup != warmup:
             line["warmup_requested"] = args.warmup
+        if planted_hits:
+            line["planted_sites"] = planted_hits
         if optimizer:
             line["optimizer"] = optimizer
         line.update(extra)
@@ -652,6 +668,176 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"first {n} of {cfg['n_aln']} alignments ({nw} windows, {dt:.1f} s), "
                                               "C++ restatement of the Java algorithm with its cost model (JVM unavailable)"}
+        emit(line)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[3]: ZOOPS mixture of several motifs (c4), alignments sharded over the ranks
+# ---------------------------------------------------------------------------------------------------------
+def run_multi_motif(args):
+    """--config c4: 3 phylogenetic PWMs + homogeneous background, 100 000 alignments x 1 kb over the ranks (every rank
+    generates and scores its own block of n_aln / N alignments; weak in memory, strong in the problem: the blocks add up to
+    the one data set).  A step = background columns + K motif scoring launches + the K-component posterior
+    (phyfoo_zoops_estep_multi) and, at N > 1, the all-reduce of [ll, w_0..w_K]."""
+    import torch
+    import torch.distributed as dist
+    from phyfoo_b200 import core, sharding, synth
+    from phyfoo_b200.data import PhyloSample
+    from phyfoo_b200.models import MultiMotifMixture, PhyloBackground, PhyloBayesModel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (phyfoo_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=600))
+    ctx = core.Context(local)
+    warmup = max(args.warmup, 3)
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    cfg, newick, pwms, sample, planted, kind = synth.make_config_multi(args.config, n_aln=args.n_aln, shard=(rank, world))
+    W, K = cfg["W"], cfg["motifs"]
+    fgs = []
+    for p in pwms:
+        m = PhyloBayesModel(W, cfg["order"], newick, ctx)
+        m.setCondProbs(p)
+        fgs.append(m)
+    bg = PhyloBackground(0, newick, ctx)
+    wts = np.concatenate([np.full(K, cfg["zoops"] / K), [1.0 - cfg["zoops"]]])
+    mix = MultiMotifMixture(fgs, bg, weights=wts)
+    logw = np.log(wts)
+    I = fgs[0].tree.n_nodes - fgs[0].tree.n_species
+
+    parity = None
+    if rank == 0 and not args.no_parity:
+        from oracle import oracle as orc
+        sub = sample.slice(0, min(8, sample.n_alignments))
+        res = mix.getNewWeights(sub)
+        ofgs = []
+        for p in pwms:
+            o = orc.Model(orc.FG, W, cfg["order"], newick)
+            for t, row in enumerate(p):
+                o.set_pi(t, np.asarray(row).ravel())
+            ofgs.append(o)
+        ref = orc.estep_multi(ofgs, orc.Model(orc.BG, 0, 0, newick), sub.col_offsets, sub.codes, logw)
+        err_ll = abs(res["ll"] - ref["ll"]) / abs(ref["ll"])
+        err_g = max(float(np.max(np.abs(g - r))) for g, r in zip(res["gamma"], ref["gamma"]))
+        same = np.array_equal(res["argmax_off"], ref["argmax_off"]) and np.array_equal(res["argmax_motif"], ref["argmax_motif"])
+        if not (err_ll <= 1e-9 and err_g <= 1e-9 and same):
+            raise SystemExit(f"bench.py: c4 parity check against the specification FAILED: ll {err_ll:.3e}, gamma {err_g:.3e}, arg-max equal {same}")
+        sub.device(ctx).free()
+        parity = {"alignments": sub.n_alignments, "windows": int(sum(g.size for g in res["gamma"])), "ll_rel_err": err_ll,
+                  "gamma_abs_err": err_g, "argmax_calls": "identical",
+                  "against": "oracle/oracle.py::estep_multi (the specification of DESIGN.md on the oracle's window and column scores)"}
+
+    ds = sample.device(ctx)
+    handles = [m.device_model() for m in fgs]
+
+    def step():
+        r = core.zoops_estep_multi(ctx, ds, handles, bg.device_model(), logw, None, want_gamma=False, want_argmax=False)
+        v = np.concatenate([[r["ll"]], r["w"]])
+        if world > 1:
+            sharding.allreduce_host_(v)
+        return r, v
+
+    for _ in range(warmup):
+        step()
+    peak_tflops = ctx.fp64_peak()
+    sampler = ClockSampler(local)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    dev_ms, per_kernel, sweeps = 0.0, {}, 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        r, v = step()
+        dev_ms += r["stats"]["gpu_ms"]
+        sweeps = r["stats"]["sweeps_fg"]
+        for i, (name, ms) in enumerate(ctx.last_kernel_times()):
+            per_kernel[(i, name)] = per_kernel.get((i, name), 0.0) + ms / args.steps
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    n_win_local = K * ds.windows(W)
+    tot = np.array([float(n_win_local), float(sample.n_alignments)])
+    mx = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        sharding.allreduce_host_(tot)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(mx.item())
+    step_ms = dev_ms_max / args.steps
+    value = tot[0] * args.steps / (dev_ms_max * 1e-3)
+
+    # e2e: host codes -> pack -> E-step -> gamma of every component / arg-max / ll to the host
+    pinned = ctx.pinned_empty(sample.codes.shape, np.uint8)
+    pinned[:] = sample.codes
+    e2e_steps = 3
+
+    def e2e_step():
+        smp = PhyloSample(pinned, sample.col_offsets)
+        r = mix.getNewWeights(smp, want_gamma=True)
+        smp.device(ctx).free()
+        return r
+
+    res = e2e_step()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res = e2e_step()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = tot[0] * e2e_steps / float(e2e_s.item())
+    hit = None
+    has = planted >= 0
+    if has.any():
+        hit = {"alignments_with_a_site": int(has.sum()), "of": f"rank 0's {sample.n_alignments} alignments",
+               "argmax_motif_and_offset_exact": float(np.mean((res["argmax_off"][has] == planted[has]) & (res["argmax_motif"][has] == kind[has])))}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        fg_ms = sum(ms for (_, name), ms in per_kernel.items() if name.startswith("score_o0") and ms > 0) \
+            - min(ms for (_, name), ms in per_kernel.items() if name.startswith("score_o0"))       # minus the background launch
+        one = dict(cfg)
+        flops = algorithmic_flops(one, I, ds.windows(W), sweeps // K) * K
+        roofline = fp64_roofline(flops, K * algorithmic_bytes(one, ds.windows(W)), f"score_o0f_kernel ({K} motif launches per step)",
+                                 fg_ms, peak_tflops, peaks.get("hbm_gbs", 6650.0),
+                                 "measured (MEASURED_PEAKS.json)" if peaks else "fallback")
+        roofline["kernel_share_of_step"] = fg_ms / (dev_ms / args.steps)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+                "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": workload_name(cfg), "name": args.config, "windows_total": int(tot[0]),
+                           "alignments_total": int(tot[1]), "windows_per_gpu": int(n_win_local),
+                           "what_counts": "one window score per motif component and offset",
+                           "sharding": "every rank generates and scores its own block of n_aln / N alignments" if world > 1 else "none (one GPU)",
+                           "mean_sweeps_per_window": sweeps / max(n_win_local, 1),
+                           "l2": "flushed between timed iterations (512 MB fill)",
+                           "collective": f"NCCL all-reduce of {K + 2} fp64 per step" if world > 1 else "none"},
+                "parity_checked": parity,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(sample.codes.nbytes + sample.col_offsets.nbytes),
+                        "d2h_bytes_per_step": int(sum(g.nbytes for g in res["gamma"]) + 8 * sample.n_alignments + 8 * (K + 2)),
+                        "steps": e2e_steps, "what": "host codes -> pack on device -> K-motif E-step -> gamma of every component / arg-max / ll on the host"},
+                "gpu_launches": int(ctx.last_launches() * args.steps), "clocks": clocks, "roofline": roofline,
+                "kernels_ms": [{"kernel": nm, "ms": round(v, 5)} for (_, nm), v in sorted(per_kernel.items())],
+                "wall_s": wall, "ll": float(v[0]), "component_weights": [float(x) for x in v[1:]]}
+        if hit:
+            line["planted_sites"] = hit
         emit(line)
     if world > 1:
         dist.barrier()
@@ -676,8 +862,11 @@ def main():
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)            # C-level stdout of this process (NCCL, CUDA libraries) -> stderr
     args = parse_args()
+    from phyfoo_b200 import synth
     if args.impl == "reference":
         run_reference(args)
+    elif synth.CONFIGS.get(args.config, {}).get("motifs"):
+        run_multi_motif(args)
     else:
         run_ours(args)
 

@@ -116,6 +116,12 @@ CONFIGS = {
     "c3": dict(n_aln=10000, S=12, length=1000, W=12, order=1, tree="random", seed=0x5EED0003),
     "c3o0": dict(n_aln=10000, S=12, length=1000, W=12, order=0, tree="random", seed=0x5EED0003),
     "c5": dict(n_aln=1000000, S=30, length=2000, W=12, order=0, tree="random", seed=0x5EED0005),
+    # configs[3]: 3 motifs + homogeneous background, 100k alignments x 1 kb (sharded over 8 GPUs); one site of one of the
+    # motifs in 80 % of the alignments
+    "c4": dict(n_aln=100000, S=12, length=1000, W=12, order=0, tree="random", seed=0x5EED0004, motifs=3, zoops=0.8),
+    # configs[0]: the reference's own bundled data (first 200 alignments of trees/data_tree1_1.0.fg, W = 10, generating
+    # caterpillar tree); inputs from tests/golden/c1_tree1_first200.npz (scripts/make_c1_fixture.py)
+    "c1": dict(n_aln=200, S=5, length=350, W=10, order=0, tree="caterpillar", seed=0, bundled=True),
 }
 
 
@@ -127,7 +133,51 @@ def config_newick(cfg):
     return random_binary_newick(cfg["S"], cfg["seed"])
 
 
+def make_config_c1(n_aln=None):
+    """BASELINE configs[0]: the bundled alignments with their planted MOTIF_POS and the generating PWM / tree."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "c1_tree1_first200.npz"))
+    cfg = dict(CONFIGS["c1"])
+    smp = PhyloSample(z["codes"], z["col_offsets"])
+    planted = z["motif_pos"].astype(np.int64)
+    if n_aln is not None and n_aln < smp.n_alignments:
+        smp, planted = smp.slice(0, n_aln), planted[:n_aln]
+    cfg["n_aln"] = smp.n_alignments
+    return cfg, str(z["newick_cat"]), [p[None, :] for p in z["pwm"]], smp, planted
+
+
+def make_config_multi(name, n_aln=None, shard=None):
+    """A configuration with several motifs (c4).  shard = (rank, world): only this rank's block of n_aln / world alignments
+    is generated, from a seed of its own (the whole set would be 1.2 GB of codes per process).  Returns
+    (cfg, newick, [pwm_k], sample, planted offsets, planted motif index [-1 where none])."""
+    cfg = dict(CONFIGS[name])
+    if n_aln is not None:
+        cfg["n_aln"] = int(n_aln)
+    newick = config_newick(cfg)
+    K = cfg["motifs"]
+    pwms = [random_pwm(cfg["W"], cfg["order"], cfg["seed"] + 1 + k) for k in range(K)]
+    rank, world = shard or (0, 1)
+    lo, hi = cfg["n_aln"] * rank // world, cfg["n_aln"] * (rank + 1) // world
+    rng = np.random.default_rng(cfg["seed"] + 1000 + rank)
+    sample, _ = make_sample(newick, hi - lo, cfg["length"], cfg["seed"] + 2000 + rank)
+    tree = parse_newick(newick)
+    W = cfg["W"]
+    n = hi - lo
+    kind = np.where(rng.random(n) < cfg["zoops"], rng.integers(0, K, n), -1)
+    pos = (rng.random(n) * (cfg["length"] - W + 1)).astype(np.int64)
+    codes = sample.codes
+    for k in range(K):
+        idx = np.nonzero(kind == k)[0]
+        for t in range(W):
+            cols, _ = simulate_columns(rng, tree, idx.size, np.asarray(pwms[k][t]))
+            codes[sample.col_offsets[idx] + pos[idx] + t] = cols
+    planted = np.where(kind >= 0, pos, -1)
+    return cfg, newick, pwms, PhyloSample(codes, sample.col_offsets), planted, kind
+
+
 def make_config(name, n_aln=None, gap_rate=0.0):
+    if name == "c1":
+        return make_config_c1(n_aln)
     cfg = dict(CONFIGS[name])
     if n_aln is not None:
         cfg["n_aln"] = int(n_aln)

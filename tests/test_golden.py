@@ -112,3 +112,33 @@ def test_gpu_matches_golden(key):
     r0, rg = float(GOLD[f"fe_f0_{key}"]), GOLD[f"fe_grad_{key}"]
     assert abs(f0 - r0) <= 1e-9 * abs(r0)
     assert np.all(np.abs(g - rg) <= 1e-9 * np.abs(rg) + 64 * np.finfo(float).eps * abs(r0) / 1e-4)
+
+
+def test_c1_fixture_is_the_first_200_bundled_alignments_and_the_oracle_finds_the_planted_sites():
+    """BASELINE configs[0] (bench.py --config c1): tests/golden/c1_tree1_first200.npz (scripts/make_c1_fixture.py) extends
+    the 8-alignment fixture; under the generating PWM and tree the oracle's arg-max site is the annotated MOTIF_POS in most
+    alignments (the number bench.py reports for the CUDA path as `planted_sites`)."""
+    from phyfoo_b200 import synth
+    cfg, newick, pwm, smp, planted = synth.make_config("c1")
+    assert smp.n_alignments == 200 and cfg["W"] == 10 and len(pwm) == 10 and newick == _newick("cat")
+    off8 = GOLD["col_offsets"]
+    assert np.array_equal(smp.col_offsets[:N_ALN + 1], off8) and np.array_equal(smp.codes[:off8[-1]], GOLD["codes"])
+    assert np.array_equal(planted[:N_ALN], GOLD["motif_pos"])
+    lens = smp.lengths()
+    assert lens.min() >= 300 and lens.max() <= 400 and np.all(planted + 10 <= lens)
+    fg = orc.Model(orc.FG, 10, 0, newick)
+    for t, p in enumerate(pwm):
+        fg.set_pi(t, np.asarray(p).ravel())
+    sub = smp.slice(0, 40)
+    ref = orc.estep(fg, orc.Model(orc.BG, 0, 0, newick), sub.col_offsets, sub.codes, np.log([0.9, 0.1]))
+    assert np.mean(ref["argmax_off"] == planted[:40]) >= 0.6
+
+
+def test_c4_shards_are_distinct_blocks_with_one_planted_site_of_one_motif():
+    from phyfoo_b200 import synth
+    a = synth.make_config_multi("c4", n_aln=64, shard=(0, 2))
+    b = synth.make_config_multi("c4", n_aln=64, shard=(1, 2))
+    assert a[3].n_alignments == b[3].n_alignments == 32 and not np.array_equal(a[3].codes, b[3].codes)
+    assert len(a[2]) == 3 and all(np.allclose(x, y) for x, y in zip(a[2], b[2]))          # the same three PWMs on every rank
+    planted, kind = a[4], a[5]
+    assert np.array_equal(planted >= 0, kind >= 0) and set(np.unique(kind)) <= {-1, 0, 1, 2}
