@@ -350,9 +350,11 @@ def roofline_of(run, path, kernels, step_ms, sweeps_fg, peak_tflops, hbm_peak, h
     extra = {}
 
     def traffic_of(*keys):
+        # profiles/traffic.json: "<profile label>:<kernel name as ncu prints it>" -> dram bytes read + written per launch
         for key in keys:
-            if key in traffic_db:
-                return traffic_db[key]
+            for have, v in traffic_db.items():
+                if have == key or have.startswith(key + "<"):
+                    return v
         return None
 
     o1 = [n for n in ("score_o1n_kernel", "score_o1w_kernel", "score_o1_kernel") if n in names]

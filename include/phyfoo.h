@@ -220,6 +220,25 @@ int phyfoo_ab_bg_columns(phyfoo_ctx* ctx, const phyfoo_dataset* ds, const double
 int phyfoo_ab_train(phyfoo_ctx* ctx, const phyfoo_dataset* ds, int32_t width, int64_t n_sel, const int32_t* sel_aln,
                     const int32_t* sel_off, const uint8_t* sel_strand, const double* sel_weight, double pseudo_count,
                     double* condprob_out);
+/* Orders 0..2 of the same models (AlignmentBasedModel.java:97-228, AlignmentBasedBGModel.java:40-222): per species row a Markov
+ * chain over the columns, entry of position p = condprob[p][sum_k 4^k x(l - k)] (k = 0 the column itself, k <= min(order, p) its
+ * predecessors: inside the window for the motif, back to the start of the alignment for the background).  Tables are
+ * concatenated: position p holds 4^(min(p, order) + 1) doubles, the current symbol fastest; the background has order + 1 tables
+ * (column l of an alignment uses table min(l, order)).  phyfoo_ab_table_size(width, order) = doubles of a motif table set,
+ * phyfoo_ab_table_size(0, order) = of a background's; -1 for an unsupported order.  Gaps follow the reference's expansion of an
+ * unobserved symbol into the four bases, including the stale entries its background likelihood averages over when two
+ * predecessors of a column are gaps (AlignmentBasedBGModel.java:185-191). */
+int phyfoo_ab_table_size(int32_t width, int32_t order);
+int phyfoo_ab_score_windows_order(phyfoo_ctx* ctx, const phyfoo_dataset* ds, int32_t width, int32_t order, const double* condprob,
+                                  int32_t strand, double* out);
+int phyfoo_ab_bg_columns_order(phyfoo_ctx* ctx, const phyfoo_dataset* ds, int32_t order, const double* condprob, double* out);
+int phyfoo_ab_train_order(phyfoo_ctx* ctx, const phyfoo_dataset* ds, int32_t width, int32_t order, int64_t n_sel, const int32_t* sel_aln,
+                          const int32_t* sel_off, const uint8_t* sel_strand, const double* sel_weight, double pseudo_count,
+                          double* condprob_out);
+/* AlignmentBasedBGModel.train (:40-137, PSEUDO_COUNT = 1e-2 there): counts over every column of every alignment weighted with
+ * aln_weights[n_aln] (NULL = 1), a gap's weight split over its expansions; condprob_out as above */
+int phyfoo_ab_bg_train_order(phyfoo_ctx* ctx, const phyfoo_dataset* ds, int32_t order, const double* aln_weights, double pseudo_count,
+                             double* condprob_out);
 
 /* ---- M-step data selection (io/SequenceSpecificDataSelector.java:37-99) ----
  * weights[windows] (e.g. gamma_out), one group per alignment: walk the windows by descending weight,

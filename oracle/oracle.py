@@ -339,6 +339,204 @@ def ab_train(cols, weights, pseudo=1e-8):
     return out
 
 
+# ---- the same models for any order (test-sized inputs: plain loops that follow the Java statement by statement) ----
+def _ab_pows(order):
+    return [4 ** k for k in range(order + 2)]
+
+
+def ab_motif_ln_cond_prob(cond, order, row, pos_seq, pos_mot):
+    """AlignmentBasedModel.getLnCondProb(sequence, posSeq, posMot), models/AlignmentBasedModel.java:187-228.  cond[posMot] is the
+    table of that motif position, row the codes of one species row (4 = unobserved)."""
+    import math
+    pows = _ab_pows(order)
+    if all(row[i] == 4 for i in range(pos_seq - min(order, pos_mot), pos_seq + 1)):        # :189-191 isCompletylUnObserved
+        return math.log(0.25)
+    table = [0] * sum(pows[i] * 4 for i in range(order + 1))                                # ACCESS_TABLE, :33,65-69
+    head = pre = 0
+    k = 0
+    while k <= order and k <= pos_mot:                                                      # :196
+        if row[pos_seq - k] == 4:                                                           # :199-207
+            old_pre = pre
+            pre = head
+            i = old_pre
+            while i < pre or (pre == 0 and i == 0):
+                for a in range(4):
+                    table[head] = table[i] + a * pows[k]
+                    head += 1
+                i += 1
+        else:                                                                               # :208-213
+            head = 1 if head == 0 else head
+            for i in range(pre, head):
+                table[i] += int(row[pos_seq - k]) * pows[k]
+        k += 1
+    sum_prob = 0.0
+    for i in range(pre, head):                                                              # :216-219
+        sum_prob += cond[pos_mot][table[i]]
+    return math.log(sum_prob / (head - pre))
+
+
+def ab_score_windows_order(cond, order, codes, revcomp=False):
+    """AlignmentBasedModel.getLogProbFor (:232-248) for every offset of one alignment; revcomp: the reverse complement of the
+    window as jstacs StrandModel presents it (columns reversed, symbols complemented)."""
+    codes = np.asarray(codes)
+    W, (L, S) = len(cond), codes.shape
+    out = np.zeros(max(L - W + 1, 0))
+    for j in range(out.size):
+        win = codes[j:j + W]
+        if revcomp:
+            win = np.where(win[::-1] == 4, 4, 3 - win[::-1])
+        log_sum = 0.0
+        for o in range(S):                                                                  # :241-243
+            s = 0.0
+            for i in range(W):                                                              # :170-175
+                s += ab_motif_ln_cond_prob(cond, order, win[:, o], i, i)
+            log_sum += s
+        out[j] = log_sum
+    return out
+
+
+def ab_bg_ln_cond_prob(cond, order, row, pos_seq):
+    """AlignmentBasedBGModel.getLnCondProb(sequence, posSeq), models/AlignmentBasedBGModel.java:172-222."""
+    import math
+    pows = _ab_pows(order)
+    if all(row[i] == 4 for i in range(max(0, pos_seq - order), pos_seq + 1)):               # :174-176
+        return math.log(0.25)
+    observations = []
+    pre_size = 0
+    k = 0
+    while k <= order and k <= pos_seq:                                                      # :180
+        if row[pos_seq - k] == 4:                                                           # :183-199
+            pre_size = len(observations)
+            if len(observations) == 0:
+                for a in range(4):
+                    tmp = [0] * (order + 1)
+                    tmp[k] = a
+                    observations.append(tmp)
+            else:
+                for i in range(pre_size):                                                   # every earlier entry, :191
+                    for a in range(4):
+                        tmp = list(observations[i])
+                        tmp[k] = a
+                        observations.append(tmp)
+        else:                                                                               # :200-208
+            if len(observations) == 0:
+                observations.append([0] * (order + 1))
+            for obs in observations:
+                obs[k] = int(row[pos_seq - k])
+        k += 1
+    sum_prob = 0.0
+    size = len(observations) - pre_size
+    for obs in observations[pre_size:]:                                                     # :211-219
+        access = 0
+        k = 0
+        while k <= order and k <= pos_seq:
+            access += pows[k] * obs[k]
+            k += 1
+        sum_prob += cond[min(pos_seq, order)][access] / size
+    return math.log(sum_prob)
+
+
+def ab_bg_range_order(cond, order, codes, start, end):
+    """AlignmentBasedBGModel.getLogProbFor(sequence, start, end), :227-243."""
+    codes = np.asarray(codes)
+    if end < start:
+        return 0.0
+    log_sum = 0.0
+    for l in range(start, end + 1):
+        for o in range(codes.shape[1]):
+            log_sum += ab_bg_ln_cond_prob(cond, order, codes[:, o], l)
+    return log_sum
+
+
+def _ab_normalise(counts):
+    out = []
+    for c in counts:                                                                        # :150-158 / :124-136
+        c = np.asarray(c, np.float64).copy()
+        for k in range(0, c.size, 4):
+            c[k:k + 4] = c[k:k + 4] / (((c[k] + c[k + 1]) + c[k + 2]) + c[k + 3])
+        out.append(c)
+    return out
+
+
+def ab_train_order(cols, weights, order, pseudo=1e-8):
+    """AlignmentBasedModel.train, :82-168, on the selected windows cols[n][W][S] with their weights."""
+    cols = np.asarray(cols)
+    n, W, S = cols.shape
+    pows = _ab_pows(order)
+    counts = [np.full(pows[min(i, order)] * 4, pseudo) for i in range(W)]
+    table = [0] * sum(pows[i] * 4 for i in range(order + 1))
+    for w in range(n):
+        for o in range(S):                                                                  # :120
+            for l in range(W):
+                for i in range(len(table)):
+                    table[i] = 0
+                head = pre = 0
+                k = 0
+                while k <= order and k <= l:                                                # :127
+                    x = int(cols[w, l - k, o])
+                    if x == 4:                                                              # :132-141
+                        old_pre = pre
+                        pre = head
+                        i = old_pre
+                        while i < pre or (pre == 0 and i == 0):
+                            for a in range(4):
+                                table[head] = table[i] + a * pows[k]
+                                head += 1
+                            i += 1
+                    else:
+                        head = 1 if head == 0 else head
+                        for i in range(pre, head):
+                            table[i] += x * pows[k]
+                    k += 1
+                for i in range(pre, head):                                                  # :149-151
+                    counts[l][table[i]] += weights[w] / (head - pre)
+    return _ab_normalise(counts)
+
+
+def ab_bg_train_order(alignments, weights, order, pseudo=1e-2):
+    """AlignmentBasedBGModel.train, :40-137; alignments: list of codes[L][S]."""
+    pows = _ab_pows(order)
+    counts = [np.full(pows[i] * 4, pseudo) for i in range(order + 1)]
+    for w, codes in enumerate(alignments):
+        codes = np.asarray(codes)
+        for o in range(codes.shape[1]):
+            for l in range(codes.shape[0]):
+                observations = []
+                pre_size = 0
+                k = 0
+                while k <= order and k <= l:
+                    x = int(codes[l - k, o])
+                    if x == 4:
+                        old_pre = pre_size
+                        pre_size = len(observations)
+                        if len(observations) == 0:
+                            for a in range(4):
+                                tmp = [0] * (order + 1)
+                                tmp[k] = a
+                                observations.append(tmp)
+                        else:
+                            for i in range(old_pre, pre_size):                              # :91
+                                for a in range(4):
+                                    tmp = list(observations[i])
+                                    tmp[k] = a
+                                    observations.append(tmp)
+                    else:
+                        if len(observations) == 0:
+                            observations.append([0] * (order + 1))
+                        for obs in observations:
+                            obs[k] = x
+                    k += 1
+                size = len(observations) - pre_size
+                for obs in observations[pre_size:]:
+                    h = 0
+                    k = 0
+                    while k <= order and k <= l:
+                        h += pows[k] * obs[k]
+                        k += 1
+                    counts[min(l, order)][h] += (1.0 if weights is None else weights[w]) / size
+    return _ab_normalise(counts)
+
+
 # ---- ZOOPS mixture of K motif models (BASELINE.json configs[3]; no reference counterpart: jstacs SingleHiddenMotifMixture
 # has one motif component, :716-718).  Specification = DESIGN.md "multi-motif mixture": the one-motif E-step
 # (SingleHiddenMotifMixture.java:520-564, modify :585-596) per component, then ONE logSumNormalisation over the K + 1

@@ -83,6 +83,8 @@ struct phyfoo_ctx {
     DevBuf memo_pending;             // fallback list of the pattern-table path
     int order0_kernel = -1;          // order-0 mean-field scoring: -1 = choose (F81-structured kernel for more than 6 species, where the
                                      // pattern table does not apply), 0 = generic kernel (tree_pass.cuh), 1 = F81-structured kernel
+    int l2_persist = 1;              // per-window state kept in global memory (order-1 q rows, large-tree state): L2 access-policy window
+    size_t l2_persist_max = 0, l2_window_max = 0;
     int order1_qglobal = -1;         // node-per-thread kernel: -1 = choose, 0 = q rows in shared memory, n > 0 = q rows in global memory
                                      // behind L1 with n warps per SM (<= 8)
     DevBuf o1n_cache, o1n_fb;
@@ -603,6 +605,11 @@ extern "C" int phyfoo_init(int device, phyfoo_ctx** out) {
     ctx->cc_major = prop.major; ctx->cc_minor = prop.minor;
     ctx->total_mem = prop.totalGlobalMem;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    // L2 set-aside for the kernels that keep per-window state in global memory: without it their ~40-80 MB of rows, rewritten
+    // every sweep, keep falling out of L2 (ncu on C3: 350 GB written to DRAM per E-step against 128 MB of algorithmic bytes)
+    ctx->l2_persist_max = (size_t)std::max(prop.persistingL2CacheMaxSize, 0);
+    ctx->l2_window_max = (size_t)std::max(prop.accessPolicyMaxWindowSize, 0);
+    if (ctx->l2_persist_max) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, ctx->l2_persist_max);
     *out = ctx;
     return PHYFOO_OK;
 }
@@ -1323,6 +1330,19 @@ static int launch_net1w(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model*
     return PHYFOO_OK;
 }
 
+// L2 access-policy window over a scratch region for the launches that follow on the library's stream (bytes = 0: off)
+static void l2_window(phyfoo_ctx* ctx, void* base, size_t bytes) {
+    if (!ctx->l2_persist || !ctx->l2_persist_max || !ctx->l2_window_max) return;
+    cudaStreamAttrValue a;
+    memset(&a, 0, sizeof(a));
+    a.accessPolicyWindow.base_ptr = base;
+    a.accessPolicyWindow.num_bytes = std::min(bytes, ctx->l2_window_max);
+    a.accessPolicyWindow.hitRatio = bytes ? (float)std::min(1.0, (double)ctx->l2_persist_max / (double)std::max<size_t>(a.accessPolicyWindow.num_bytes, 1)) : 0.f;
+    a.accessPolicyWindow.hitProp = bytes ? cudaAccessPropertyPersisting : cudaAccessPropertyNormal;
+    a.accessPolicyWindow.missProp = bytes ? cudaAccessPropertyStreaming : cudaAccessPropertyNormal;
+    cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &a);
+}
+
 // order-1 motif network: quad per window (net1.cuh)
 // order-1 motif network, node-per-thread kernel (net1n.cuh): 4 threads per window, 8 windows per warp; returns 1 when the
 // configuration is not one it takes (the caller then runs the wavefront kernel), 0 when launched
@@ -1386,11 +1406,13 @@ static int launch_net1n(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model*
     p.fb_dst = check ? p.fb_col0 + n_items : nullptr;
     p.fb_strand = check ? (uint8_t*)(p.fb_dst + n_items) : nullptr;
     CU(cudaMemsetAsync(p.counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    if (qg) l2_window(ctx, ctx->o1n_cache.p, cache_bytes);
     {
         KernelTimer kt_(ctx, "score_o1n_kernel");
         void* args[] = {&p};
         CU(cudaLaunchKernel(fn, dim3(blocks), dim3(32 * nw), args, smem, ctx->stream));
     }
+    if (qg) l2_window(ctx, nullptr, 0);
     CU(cudaGetLastError());
     if (check) {
         ScoreItems it{p.fb_col0, p.fb_strand, nullptr, nullptr, nullptr};
@@ -1520,10 +1542,12 @@ static int launch_score_f81(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_mo
         p.gstate = ctx->gstate.as<double>();
     }
     CU(cudaMemsetAsync(p.counter_next, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    if (gstate) l2_window(ctx, ctx->gstate.p, (size_t)blocks * T * state_per_thread);
     {
         KernelTimer kt_(ctx, "score_o0f_kernel");
         score_o0f_kernel<<<blocks, T, smem, ctx->stream>>>(p);
     }
+    if (gstate) l2_window(ctx, nullptr, 0);
     CU(cudaGetLastError());
     return 0;
 }
@@ -2096,6 +2120,10 @@ extern "C" int phyfoo_set_option(phyfoo_ctx* ctx, const char* name, int64_t valu
     if (std::strcmp(name, "order0_kernel") == 0) {
         if (value < -1 || value > 1) return fail(ctx, PHYFOO_EINVAL, "set_option: order0_kernel must be -1 (choose), 0 (generic) or 1 (F81-structured)");
         ctx->order0_kernel = (int)value;
+        return PHYFOO_OK;
+    }
+    if (std::strcmp(name, "l2_persist") == 0) {
+        ctx->l2_persist = value != 0;
         return PHYFOO_OK;
     }
     if (std::strcmp(name, "order1_qglobal") == 0) {

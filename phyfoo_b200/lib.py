@@ -27,7 +27,7 @@ SYMBOLS = [
     "phyfoo_model_set_mode", "phyfoo_model_is_degenerate", "phyfoo_model_free",
     "phyfoo_score_windows", "phyfoo_bg_columns", "phyfoo_bg_columns_order1", "phyfoo_zoops_estep", "phyfoo_zoops_estep_device",
     "phyfoo_zoops_estep_multi", "phyfoo_select_multi",
-    "phyfoo_ab_score_windows", "phyfoo_ab_bg_columns", "phyfoo_ab_train", "phyfoo_scan_hits", "phyfoo_score_order_stats", "phyfoo_select", "phyfoo_fe_prepare", "phyfoo_fe_prepare_all", "phyfoo_fe_eval", "phyfoo_fe_grad",
+    "phyfoo_ab_score_windows", "phyfoo_ab_bg_columns", "phyfoo_ab_train", "phyfoo_ab_table_size", "phyfoo_ab_score_windows_order", "phyfoo_ab_bg_columns_order", "phyfoo_ab_train_order", "phyfoo_ab_bg_train_order", "phyfoo_scan_hits", "phyfoo_score_order_stats", "phyfoo_select", "phyfoo_fe_prepare", "phyfoo_fe_prepare_all", "phyfoo_fe_eval", "phyfoo_fe_grad",
     "phyfoo_fe_values_device", "phyfoo_fe_suffstats", "phyfoo_fe_size", "phyfoo_fe_free",
     "phyfoo_set_option", "phyfoo_last_score_path", "phyfoo_last_kernel_times", "phyfoo_host_alloc", "phyfoo_host_free",
     "phyfoo_last_launches", "phyfoo_stream", "phyfoo_synchronize", "phyfoo_estep_kernel_ms", "phyfoo_estep_sweeps",
@@ -109,6 +109,11 @@ def lib():
     L.phyfoo_ab_score_windows.argtypes = [vp, vp, C.c_int32, dp, C.c_int32, dp]
     L.phyfoo_ab_bg_columns.argtypes = [vp, vp, dp, dp]
     L.phyfoo_ab_train.argtypes = [vp, vp, C.c_int32, C.c_int64, ip32, ip32, u8p, dp, C.c_double, dp]
+    L.phyfoo_ab_table_size.argtypes = [C.c_int32, C.c_int32]
+    L.phyfoo_ab_score_windows_order.argtypes = [vp, vp, C.c_int32, C.c_int32, dp, C.c_int32, dp]
+    L.phyfoo_ab_bg_columns_order.argtypes = [vp, vp, C.c_int32, dp, dp]
+    L.phyfoo_ab_train_order.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int64, ip32, ip32, u8p, dp, C.c_double, dp]
+    L.phyfoo_ab_bg_train_order.argtypes = [vp, vp, C.c_int32, dp, C.c_double, dp]
     L.phyfoo_scan_hits.argtypes = [vp, vp, vp, C.c_int32, C.c_double, ip32, ip32, dp, ip32]
     L.phyfoo_score_order_stats.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, i64p, dp, i64p]
     L.phyfoo_select.argtypes = [vp, vp, C.c_int32, dp, C.c_double, C.c_double, ip32, ip32, dp, C.c_int64, i64p]

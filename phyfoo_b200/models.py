@@ -585,9 +585,30 @@ class MultiMotifMixture:
         return history
 
 
+def _ab_sizes(n_tables, order):
+    return [4 ** (min(p, order) + 1) for p in range(n_tables)]
+
+
+def _ab_pack(tables, sizes):
+    flat = np.concatenate([np.asarray(t, np.float64).ravel() for t in tables])
+    if flat.size != sum(sizes):
+        raise ValueError(f"expected tables of sizes {sizes}")
+    return np.ascontiguousarray(flat)
+
+
+def _ab_unpack(flat, sizes):
+    out, o = [], 0
+    for n in sizes:
+        out.append(flat[o:o + n].copy())
+        o += n
+    return out
+
+
 class AlignmentBasedModel:
-    """models/AlignmentBasedModel.java, order 0: the non-phylogenetic motif model (`model.evolution=false`): one PWM applied
-    to every species row, gaps scoring log(0.25), count-based M-step."""
+    """models/AlignmentBasedModel.java: the non-phylogenetic motif model (`model.evolution=false`): per species row a Markov
+    chain of the given order over the window's columns (order 0: one PWM applied to every row), a column whose context is
+    unobserved scoring log(0.25), count-based M-step.  condProb[p] has 4^(min(p, order) + 1) entries indexed
+    sum_k 4^k x(l - k) (the current symbol fastest, :127-147); orders 0..2."""
 
     PSEUDO_COUNT = 1e-8                  # :32
     SKIP_TRAINING_STEPS = 1              # :31
@@ -595,28 +616,37 @@ class AlignmentBasedModel:
     MOTIF_QUALITY_THRESHOLD = 0.0
 
     def __init__(self, length, order=0, ctx=None):
-        if order != 0:
-            raise NotImplementedError("alignment-based models of order >= 1 are not implemented (DESIGN.md)")
+        if not 0 <= order <= 2:
+            raise NotImplementedError("alignment-based models: orders 0..2")
         self.ctx = ctx or core.default_context()
-        self.length, self.order = int(length), 0
-        self.condProb = np.full((self.length, 4), 0.25)
+        self.length, self.order = int(length), int(order)
+        self.sizes = _ab_sizes(self.length, self.order)
+        self.condProb = [np.full(n, 0.25) for n in self.sizes]
         self.trainingStep = 0
 
     def getLength(self):
         return self.length
 
+    def getOrder(self):
+        return self.order
+
     def setCondProbs(self, condProbs):
-        self.condProb = np.asarray(condProbs, np.float64).reshape(self.length, 4).copy()
+        self.condProb = _ab_unpack(_ab_pack(condProbs, self.sizes), self.sizes)
 
     def getCondProbs(self):
-        return self.condProb.copy()
+        return np.stack(self.condProb) if self.order == 0 else [c.copy() for c in self.condProb]
 
     def getLogProbFor(self, sample: PhyloSample, strand=0):
         ds = sample.device(self.ctx)
         out = np.zeros(ds.windows(self.length))
-        cp = np.ascontiguousarray(self.condProb)
-        core.raise_for(core.lib().phyfoo_ab_score_windows(self.ctx.h, ds.h, self.length, core._p(cp, core.C.c_double), int(strand),
-                                                          core._p(out, core.C.c_double)), self.ctx.h)
+        cp = _ab_pack(self.condProb, self.sizes)
+        if self.order == 0:
+            rc = core.lib().phyfoo_ab_score_windows(self.ctx.h, ds.h, self.length, core._p(cp, core.C.c_double), int(strand),
+                                                    core._p(out, core.C.c_double))
+        else:
+            rc = core.lib().phyfoo_ab_score_windows_order(self.ctx.h, ds.h, self.length, self.order, core._p(cp, core.C.c_double),
+                                                          int(strand), core._p(out, core.C.c_double))
+        core.raise_for(rc, self.ctx.h)
         return out
 
     def train(self, sample: PhyloSample, weights):
@@ -625,36 +655,67 @@ class AlignmentBasedModel:
             return {"skipped": True}
         ds = sample.device(self.ctx)
         sa, so, sw = core.select(self.ctx, ds, self.length, weights, self.PROB_THRESH_FOR_WEIGHTS, self.MOTIF_QUALITY_THRESHOLD)
-        out = np.zeros((self.length, 4))
-        core.raise_for(core.lib().phyfoo_ab_train(self.ctx.h, ds.h, self.length, sa.size, core._p(sa, core.C.c_int32),
+        out = np.zeros(sum(self.sizes))
+        if self.order == 0:
+            rc = core.lib().phyfoo_ab_train(self.ctx.h, ds.h, self.length, sa.size, core._p(sa, core.C.c_int32),
+                                            core._p(so, core.C.c_int32), None, core._p(sw, core.C.c_double),
+                                            float(self.PSEUDO_COUNT), core._p(out, core.C.c_double))
+        else:
+            rc = core.lib().phyfoo_ab_train_order(self.ctx.h, ds.h, self.length, self.order, sa.size, core._p(sa, core.C.c_int32),
                                                   core._p(so, core.C.c_int32), None, core._p(sw, core.C.c_double),
-                                                  float(self.PSEUDO_COUNT), core._p(out, core.C.c_double)), self.ctx.h)
-        self.condProb = out
+                                                  float(self.PSEUDO_COUNT), core._p(out, core.C.c_double))
+        core.raise_for(rc, self.ctx.h)
+        self.condProb = _ab_unpack(out, self.sizes)
         self.trainingStep += 1
         return {"skipped": False, "selected": int(sa.size)}
 
 
 class AlignmentBasedBGModel:
-    """models/AlignmentBasedBGModel.java, order 0: the non-phylogenetic background."""
+    """models/AlignmentBasedBGModel.java: the non-phylogenetic background, orders 0..2 (order + 1 tables; column l of an
+    alignment uses table min(l, order) and looks back to the start of the alignment whatever range is asked for, so
+    getLogProbFor(seq, s, e) is the sum of the per-column terms over [s, e])."""
+
+    PSEUDO_COUNT = 1e-2                  # :31
 
     def __init__(self, order=0, ctx=None):
-        if order != 0:
-            raise NotImplementedError("alignment-based models of order >= 1 are not implemented (DESIGN.md)")
+        if not 0 <= order <= 2:
+            raise NotImplementedError("alignment-based models: orders 0..2")
         self.ctx = ctx or core.default_context()
-        self.condProb = np.full(4, 0.25)
+        self.order = int(order)
+        self.sizes = _ab_sizes(self.order + 1, self.order)
+        self.condProb = [np.full(n, 0.25) for n in self.sizes]
 
     def setCondProbs(self, condProb):
-        self.condProb = np.asarray(condProb, np.float64).reshape(4).copy()
+        if self.order == 0:
+            condProb = [np.asarray(condProb, np.float64).reshape(4)]
+        self.condProb = _ab_unpack(_ab_pack(condProb, self.sizes), self.sizes)
+
+    def getCondProbs(self):
+        return self.condProb[0].copy() if self.order == 0 else [c.copy() for c in self.condProb]
 
     def getColumnLogProbs(self, sample: PhyloSample):
         ds = sample.device(self.ctx)
         out = np.zeros(ds.n_cols)
-        cp = np.ascontiguousarray(self.condProb)
-        core.raise_for(core.lib().phyfoo_ab_bg_columns(self.ctx.h, ds.h, core._p(cp, core.C.c_double), core._p(out, core.C.c_double)),
-                       self.ctx.h)
+        cp = _ab_pack(self.condProb, self.sizes)
+        if self.order == 0:
+            rc = core.lib().phyfoo_ab_bg_columns(self.ctx.h, ds.h, core._p(cp, core.C.c_double), core._p(out, core.C.c_double))
+        else:
+            rc = core.lib().phyfoo_ab_bg_columns_order(self.ctx.h, ds.h, self.order, core._p(cp, core.C.c_double), core._p(out, core.C.c_double))
+        core.raise_for(rc, self.ctx.h)
         return out
 
     def getLogProbFor(self, sample: PhyloSample):
         cols = self.getColumnLogProbs(sample)
         off = sample.col_offsets
         return np.array([cols[off[i]:off[i + 1]].sum() for i in range(sample.n_alignments)])
+
+    def train(self, sample: PhyloSample, weights=None):
+        """:40-137: counts over every column of every alignment, weighted per alignment."""
+        ds = sample.device(self.ctx)
+        out = np.zeros(sum(self.sizes))
+        w = None if weights is None else np.ascontiguousarray(weights, np.float64)
+        if w is not None and w.size != sample.n_alignments:
+            raise ValueError("one weight per alignment")
+        core.raise_for(core.lib().phyfoo_ab_bg_train_order(self.ctx.h, ds.h, self.order, core._p(w, core.C.c_double),
+                                                           float(self.PSEUDO_COUNT), core._p(out, core.C.c_double)), self.ctx.h)
+        self.condProb = _ab_unpack(out, self.sizes)

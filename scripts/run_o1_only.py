@@ -12,6 +12,8 @@ reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 qglobal = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 cfg, newick, pwm, sample, planted = synth.make_config("c3", n_aln=n_aln)
 ctx = core.default_context()
+if len(sys.argv) > 5:
+    ctx.set_option("l2_persist", int(sys.argv[5]))
 ctx.set_option("order1_kernel", kernel)
 ctx.set_option("order1_qglobal", qglobal)
 fg = PhyloBayesModel(cfg["W"], 1, newick, ctx)

@@ -508,3 +508,35 @@ extern "C" int emul_score_o0f(const phyfoo_model_desc* d, const uint8_t* codes, 
         return 0;
     } catch (const std::exception& e) { std::fprintf(stderr, "emul: %s\n", e.what()); return -1; }
 }
+
+// ---- alignment-based models of order >= 1: the kernels' term (ab.cuh::ab_term) on the host, through the shared expansion ----
+#include "../../phyfoo_b200/csrc/ab_expand.hpp"
+// row[L]: codes of one species row; variant 0 = motif (context inside [l - min(order, pos_mot), l]), 1 = background (pos_mot = l)
+extern "C" double emul_ab_term(const double* cond /* table of this position */, int order, const uint8_t* row, int l, int pos_mot, int variant) {
+    const int kmax = pos_mot < order ? pos_mot : order;
+    int sym[AB_MAX_ORDER + 1];
+    bool any_gap = false, any_obs = false;
+    int h = 0, pw = 1;
+    for (int k = 0; k <= kmax; ++k, pw *= 4) {
+        sym[k] = row[l - k];
+        if (sym[k] == 4) any_gap = true; else { any_obs = true; h += sym[k] * pw; }
+    }
+    if (!any_obs) return std::log(0.25);
+    if (!any_gap) return std::log(cond[h] / 1);
+    int idx[AB_MAX_EXPAND], pre, n;
+    ab_expand(sym, kmax, variant, idx, pre, n);
+    const int size = n - pre;
+    double sum = 0.0;
+    if (variant) { for (int i = pre; i < n; ++i) sum += cond[idx[i]] / size; }
+    else { for (int i = pre; i < n; ++i) sum += cond[idx[i]]; sum /= size; }
+    return std::log(sum);
+}
+// the training loops' expansion: hashes and their common divisor
+extern "C" int emul_ab_expand(const uint8_t* row, int l, int kmax, int variant, int* idx_out) {
+    int sym[AB_MAX_ORDER + 1];
+    for (int k = 0; k <= kmax; ++k) sym[k] = row[l - k];
+    int idx[AB_MAX_EXPAND], pre, n;
+    ab_expand(sym, kmax, variant, idx, pre, n);
+    for (int i = pre; i < n; ++i) idx_out[i - pre] = idx[i];
+    return n - pre;
+}

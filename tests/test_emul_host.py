@@ -22,7 +22,8 @@ def emul():
     srcs = [os.path.join(EMUL_DIR, "emul.cpp"), os.path.join(ROOT, "phyfoo_b200", "csrc", "tree_pass.cuh"),
             os.path.join(ROOT, "phyfoo_b200", "csrc", "model_host.hpp"), os.path.join(ROOT, "phyfoo_b200", "csrc", "fp64_math.cuh"),
             os.path.join(ROOT, "phyfoo_b200", "csrc", "fp64_math_tables.h"),
-            os.path.join(ROOT, "phyfoo_b200", "csrc", "net1n.cuh"), os.path.join(ROOT, "phyfoo_b200", "csrc", "tree_pass_f81.cuh")]
+            os.path.join(ROOT, "phyfoo_b200", "csrc", "net1n.cuh"), os.path.join(ROOT, "phyfoo_b200", "csrc", "tree_pass_f81.cuh"),
+            os.path.join(ROOT, "phyfoo_b200", "csrc", "ab_expand.hpp")]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", srcs[0], "-o", so])
     L = C.CDLL(so)
@@ -31,6 +32,9 @@ def emul():
     for f in (L.emul_exp, L.emul_log):
         f.argtypes = [C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double)]
         f.restype = None
+    L.emul_ab_term.argtypes = [C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int]
+    L.emul_ab_term.restype = C.c_double
+    L.emul_ab_expand.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
     return L
 
 
@@ -290,3 +294,32 @@ def test_order0_f81_pass_matches_oracle(emul, tree, evol, gap_rate):
         ref, rsw = om.score_windows(codes, bool(strand))
         assert np.array_equal(sw, rsw)
         assert rel_err(out, ref) < 1e-9
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_alignment_based_expansion_matches_the_java_statement_by_statement(emul, order):
+    """csrc/ab_expand.hpp (what ab_windows_order_kernel / ab_columns_order_kernel / the count kernels run per row and column)
+    against oracle.ab_motif_ln_cond_prob / ab_bg_ln_cond_prob, the literal restatements of AlignmentBasedModel.java:187-228 and
+    AlignmentBasedBGModel.java:172-222 -- every gap pattern of a context, including the background's stale list entries when
+    two predecessors are gaps."""
+    import itertools
+    rng = np.random.default_rng(order)
+    W = order + 2
+    cond = [rng.dirichlet(np.ones(4), size=4 ** min(p, order)).ravel() for p in range(W)]
+    bg = cond[:order + 1]
+    for pattern in itertools.product([0, 1, 2, 3, 4], repeat=order + 1):
+        row = np.array(list(pattern[::-1]) + [1], np.uint8)          # row[l - k] = pattern[k] at l = order
+        l = order
+        rp = row.ctypes.data_as(C.POINTER(C.c_uint8))
+        for pos_mot in range(order + 1):                              # motif position: context length min(order, pos_mot)
+            got = emul.emul_ab_term(cond[pos_mot].ctypes.data_as(C.POINTER(C.c_double)), order, rp, l, pos_mot, 0)
+            ref = orc.ab_motif_ln_cond_prob(cond, order, row, l, pos_mot)
+            assert got == ref or abs(got - ref) <= 1e-15 * abs(ref), (pattern, pos_mot, got, ref)
+        got = emul.emul_ab_term(bg[order].ctypes.data_as(C.POINTER(C.c_double)), order, rp, l, l, 1)
+        ref = orc.ab_bg_ln_cond_prob(bg, order, row, l)
+        assert got == ref or abs(got - ref) <= 1e-15 * abs(ref), (pattern, got, ref)
+    # the background at the start of an alignment (l < order): shorter contexts, table min(l, order)
+    row = np.array([4, 2, 4, 1], np.uint8)
+    for l in range(order):
+        got = emul.emul_ab_term(bg[l].ctypes.data_as(C.POINTER(C.c_double)), order, row.ctypes.data_as(C.POINTER(C.c_uint8)), l, l, 1)
+        assert abs(got - orc.ab_bg_ln_cond_prob(bg, order, row, l)) <= 1e-15
