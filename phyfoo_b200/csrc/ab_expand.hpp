@@ -1,5 +1,5 @@
 // ab_expand.hpp -- table layout and gap expansion of the alignment-based models of order >= 1 (see ab.cuh); host and device,
-// so that tests/emul can run the same lines on the CPU against the oracle's statement-by-statement restatement of the Java.
+// so that tests/emul can run the same lines on the CPU against a statement-by-statement restatement of the Java.
 #pragma once
 #if defined(__CUDACC__)
 #define AB_HD __host__ __device__ inline

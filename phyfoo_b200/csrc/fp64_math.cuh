@@ -9,9 +9,17 @@
 // Special cases follow IEEE / java.lang.Math: exp(-inf) = 0, exp(x < -745.2) = 0 through denormals, exp(NaN) = NaN,
 // log(0) = -inf, log(z < 0) = NaN, log(inf) = inf, denormal arguments are handled.
 #pragma once
+#if defined(__CUDACC_RTC__)
+// run-time compilation (jit_o0.hpp): no host headers; the fixed-width types and the two macros the device paths use
+typedef signed char int8_t; typedef unsigned char uint8_t; typedef int int32_t; typedef unsigned int uint32_t;
+typedef long long int64_t; typedef unsigned long long uint64_t; typedef unsigned long size_t;
+#define INFINITY __longlong_as_double(0x7FF0000000000000LL)
+#define NAN __longlong_as_double(0x7FF8000000000000LL)
+#else
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
+#endif
 
 #include "fp64_math_tables.h"
 

@@ -229,43 +229,7 @@ struct ScoreParams {
     const int64_t* item_dst;      // nullable: out/sweeps index of listed window `item` (default: item)
 };
 
-__device__ __forceinline__ ColWords load_column(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ gaps,
-                                                int64_t n_cols, int nb, int64_t c) {
-    ColWords cw;
-    cw.b = bases[c];
-    if (nb > 1) cw.b |= (uint64_t)bases[n_cols + c] << 32;
-    cw.g = gaps[c];
-    return cw;
-}
-
-// largest a with off[a] <= w  (off has n+1 entries, off[0] = 0, w < off[n])
-__device__ __forceinline__ int find_alignment(const int64_t* __restrict__ off, int n, int64_t w) {
-    int lo = 0, hi = n;  // invariant: off[lo] <= w < off[hi]
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (off[mid] <= w) lo = mid; else hi = mid;
-    }
-    return lo;
-}
-
-// the same with a first guess from the average alignment length (equal-length alignments: no search at all)
-__device__ __forceinline__ int find_alignment_hint(const int64_t* __restrict__ off, int n, int64_t w, int64_t n_windows) {
-    int a = (int)(((double)w * (double)n) / (double)n_windows);
-    a = min(max(a, 0), n - 1);
-    if (off[a] > w) {                              // guess too far right: gallop left, then bisect
-        int step = 1, hi = a;
-        while (a > 0 && off[a] > w) { hi = a; a = max(0, a - step); step <<= 1; }
-        while (hi - a > 1) { const int mid = (a + hi) >> 1; if (off[mid] <= w) a = mid; else hi = mid; }
-    } else if (off[a + 1] <= w) {                  // too far left
-        int step = 1, lo = a + 1;
-        a = lo;
-        while (a < n - 1 && off[a + 1] <= w) { lo = a + 1; a = min(n - 1, a + step); step <<= 1; }
-        int hi = a + 1;                            // off[lo] <= w < off[hi]
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (off[mid] <= w) lo = mid; else hi = mid; }
-        a = lo;
-    }
-    return a;
-}
+#include "score_common.cuh"
 
 static const int SCORE_CHUNK = 4;   // windows a group takes from the global counter at a time
 

@@ -21,10 +21,7 @@
 //    an update pass with the exponent forced to 0 (exp(0)/4 = 0.25 exactly), so threads of one warp
 //    that are in different sweeps of different windows never diverge.
 #pragma once
-#include <math.h>
-#include <stdint.h>
-
-#include "fp64_math.cuh"
+#include "fp64_math.cuh"      // brings <math.h> / <stdint.h> (or their stand-ins under NVRTC)
 
 #if defined(__CUDACC__)
 #define PHY_HD __host__ __device__ __forceinline__

@@ -160,29 +160,6 @@ PHY_HD int f81_slots(int n_internal, const int* ichild_begin, int* slot) {
 }  // namespace phyfoo
 
 #if defined(__CUDACC__)
-struct ScoreFParams {
-    const uint32_t* bases; const uint32_t* gaps; int64_t n_cols; int nb;
-    const int64_t* col_off; const int64_t* win_off; int n_aln;
-    int64_t n_windows; int n_strands; int strand0;
-    int W, I, S, Ef, prog_len;
-    const double* tab;       // compact tables [Ef][W]
-    const int* prog;
-    double* out; int32_t* sweeps;
-    unsigned long long* counter_next; unsigned long long* counter_sweeps;
-    int max_sweeps, min_sweeps; double tol;
-    double* gstate;          // nullable: per-thread state in global memory instead of shared
-    int n_slots;             // internal nodes with internal children (StateF)
-    int group_lanes;         // lanes of a group (a multiple of 32); windows per group = group_lanes / W
-    int n_groups;            // groups per block
-};
-
-__device__ __forceinline__ int named_bar_or(int id, int n_threads, bool pred) {
-    int r;
-    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %3, 0;\n\tbar.red.or.pred q, %1, %2, p;\n\tselp.u32 %0, 1, 0, q;\n\t}"
-                 : "=r"(r) : "r"(id), "r"(n_threads), "r"((int)pred) : "memory");
-    return r;
-}
-
 __global__ void __launch_bounds__(512, 1) score_o0f_kernel(ScoreFParams p) {
     extern __shared__ double smem[];
     const int T = blockDim.x, tid = threadIdx.x;
