@@ -333,6 +333,17 @@ int phyfoo_last_kernel_times(phyfoo_ctx* ctx, int32_t max_entries, const char** 
 /* scoring path of the most recent motif/background launch: 0 direct kernel, 1 pattern table, 2 order-1 network */
 int phyfoo_last_score_path(const phyfoo_ctx* ctx);
 
+/* ---- order-0 scoring kernel compiled at run time for a model's tree (csrc/jit_o0.hpp; option "order0_kernel" = 2, and the
+ * default choice for more than 6 species) ----
+ * The tree of a model is fixed, so its mean-field pass (algorithm/MeanFieldForBayesNet.java:108-202, :232-365) is generated as
+ * straight-line CUDA for that tree and compiled with NVRTC for sm_100a on first use (libnvrtc.so.12 and libcuda.so.1 are opened
+ * with dlopen; without them, or when a compilation fails, scoring runs the precompiled F81-structured kernel and
+ * phyfoo_jit_note says why).  phyfoo_jit_check generates and compiles without a device: source_out / log_out (nullable,
+ * NUL-terminated, truncated) receive the generated source and the compiler log, *cubin_bytes the size of the image. */
+int phyfoo_jit_check(const phyfoo_model_desc* desc, int32_t gaps, char* source_out, int64_t source_cap, char* log_out, int64_t log_cap,
+                     int64_t* cubin_bytes);
+const char* phyfoo_jit_note(const phyfoo_ctx* ctx);
+
 /* ---- plumbing for callers that overlap the library with their own streams ---- */
 /* Page-locked host memory (cudaHostAlloc): buffers handed to the library copy at full PCIe speed when they come from
  * here (a Java caller wraps the address in a MemorySegment / direct ByteBuffer).  NULL on failure. */

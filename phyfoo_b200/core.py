@@ -59,6 +59,10 @@ class Context:
     def set_option(self, name, value):
         raise_for(lib().phyfoo_set_option(self.h, name.encode(), int(value)), self.h)
 
+    def jit_note(self):
+        """Why the last request for a run-time compiled order-0 kernel fell back to the precompiled one ('' if it did not)."""
+        return lib().phyfoo_jit_note(self.h).decode()
+
     def pinned_empty(self, shape, dtype=np.float64):
         """numpy array in page-locked host memory (phyfoo_host_alloc); copies to/from it run at full PCIe speed.
         The memory is released when the array (and every view of it) is garbage collected."""

@@ -12,7 +12,7 @@
 #if defined(__CUDACC_RTC__)
 // run-time compilation (jit_o0.hpp): no host headers; the fixed-width types and the two macros the device paths use
 typedef signed char int8_t; typedef unsigned char uint8_t; typedef int int32_t; typedef unsigned int uint32_t;
-typedef long long int64_t; typedef unsigned long long uint64_t; typedef unsigned long size_t;
+typedef long long int64_t; typedef unsigned long long uint64_t;
 #define INFINITY __longlong_as_double(0x7FF0000000000000LL)
 #define NAN __longlong_as_double(0x7FF8000000000000LL)
 #else

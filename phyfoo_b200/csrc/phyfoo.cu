@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -53,6 +54,8 @@ struct DevBuf {
     template <class T> T* as() const { return (T*)p; }
 };
 
+struct JitKernel;      // jit_o0.hpp
+
 struct phyfoo_ctx {
     int device = 0;
     int sm_count = 0, cc_major = 0, cc_minor = 0;
@@ -83,6 +86,8 @@ struct phyfoo_ctx {
     DevBuf memo_pending;             // fallback list of the pattern-table path
     int order0_kernel = -1;          // order-0 mean-field scoring: -1 = choose (F81-structured kernel for more than 6 species, where the
                                      // pattern table does not apply), 0 = generic kernel (tree_pass.cuh), 1 = F81-structured kernel
+    std::map<std::string, std::shared_ptr<JitKernel>> jit_cache;   // generated source -> loaded kernel (jit_o0.hpp)
+    std::string jit_note;            // why the last request for a run-time compiled kernel was not served
     int l2_persist = 1;              // per-window state kept in global memory (order-1 q rows, large-tree state): L2 access-policy window
     size_t l2_persist_max = 0, l2_window_max = 0;
     int order1_qglobal = -1;         // node-per-thread kernel: -1 = choose, 0 = q rows in shared memory, n > 0 = q rows in global memory
@@ -968,6 +973,7 @@ struct ScoreItems {
 #include "net1w.cuh"
 #include "net1n.cuh"
 #include "tree_pass_f81.cuh"
+#include "jit_o0.hpp"
 #include "memo.cuh"
 
 static void memo_release(cudaStream_t st, MemoSet* ms) {
@@ -1516,6 +1522,80 @@ static int launch_score_f81(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_mo
     return 0;
 }
 
+// The kernel compiled for this model's tree (jit_o0.hpp).  Returns 0 when launched, 1 when the caller should take the next
+// kernel (no NVRTC / driver library, compilation failed -- ctx->jit_note says why), < 0... never: errors are PHYFOO_* > 1.
+static int jit_get(phyfoo_ctx* ctx, const ModelHost& h, bool gaps, int nb, std::shared_ptr<JitKernel>* out) {
+    JitApi& api = jit_api();
+    if (!api.ok || !api.have_driver) { ctx->jit_note = api.why; return 1; }
+    JitShape sh;
+    // 1024 threads of 64 registers or 512 of 128: the generated pass needs ~100+ registers, so at most 512 threads
+    if (!jit_o0_shape(h, gaps, std::min<size_t>(ctx->smem_optin, 227 * 1024), 512, &sh)) { ctx->jit_note = "no block shape fits"; return 1; }
+    const std::string src = jit_o0_source(h, sh, gaps, nb);
+    auto it = ctx->jit_cache.find(src);
+    if (it != ctx->jit_cache.end()) {
+        if (!it->second) { return 1; }          // failed before: do not try again
+        *out = it->second;
+        return 0;
+    }
+    ctx->jit_cache[src] = nullptr;
+    std::string log;
+    std::vector<char> cubin;
+    if (jit_compile(src, log, &cubin)) { ctx->jit_note = log; return 1; }
+    auto k = std::make_shared<JitKernel>();
+    int rc = api.ModuleLoadData(&k->module, cubin.data());
+    if (rc) { ctx->jit_note = "cuModuleLoadData failed: " + std::to_string(rc); return 1; }
+    rc = api.ModuleGetFunction(&k->fn, k->module, "score_o0j_kernel");
+    if (rc) { ctx->jit_note = "cuModuleGetFunction failed: " + std::to_string(rc); return 1; }
+    rc = api.FuncSetAttribute(k->fn, 8 /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES */, (int)sh.smem);
+    if (rc) { ctx->jit_note = "cuFuncSetAttribute(shared memory) failed: " + std::to_string(rc); return 1; }
+    api.FuncGetAttribute(&k->regs, 4 /* CU_FUNC_ATTRIBUTE_NUM_REGS */, k->fn);
+    k->shape = sh;
+    ctx->jit_cache[src] = k;
+    *out = k;
+    return 0;
+}
+
+static int launch_score_jit(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* m, const int64_t* d_win_off, int64_t n_windows,
+                            int strands, double* d_out, int32_t* d_sweeps, int counter_slot) {
+    ModelHost& h = m->h;
+    std::shared_ptr<JitKernel> k;
+    const int got = jit_get(ctx, h, ds->n_gap_cols > 0, ds->nb, &k);
+    if (got) return got;
+    const JitShape& sh = k->shape;
+    const int n_strands = strands == 2 ? 2 : 1;
+    const long long n_items = (long long)n_windows * n_strands;
+    const long long per_block = (long long)sh.NG * (sh.GL / h.W);
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((n_items + per_block - 1) / per_block, ctx->sm_count));
+    ScoreFParams p;
+    p.bases = ds->d_bases; p.gaps = ds->d_gaps; p.n_cols = ds->n_cols; p.nb = ds->nb;
+    p.col_off = ds->d_col_off; p.win_off = d_win_off; p.n_aln = ds->n_aln;
+    p.n_windows = n_windows; p.n_strands = n_strands; p.strand0 = strands == 1 ? 1 : 0;
+    p.W = h.W; p.I = h.I; p.S = h.S; p.Ef = h.Ef(); p.prog_len = m->prog_len;
+    p.tab = m->d_tabf; p.prog = m->d_prog;
+    p.out = d_out; p.sweeps = d_sweeps;
+    unsigned long long* counters = ctx->counters.as<unsigned long long>();
+    p.counter_next = counters + 2 * counter_slot; p.counter_sweeps = counters + 2 * counter_slot + 1;
+    p.max_sweeps = h.max_sweeps; p.min_sweeps = h.min_sweeps; p.tol = h.tol;
+    p.group_lanes = sh.GL; p.n_groups = sh.NG; p.n_slots = 0;
+    p.gstate = nullptr;
+    if (sh.gstate) {
+        CU(ctx->gstate.ensure((size_t)blocks * sh.T * sh.state_doubles * sizeof(double)));
+        p.gstate = ctx->gstate.as<double>();
+    }
+    CU(cudaMemsetAsync(p.counter_next, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    if (sh.gstate) l2_window(ctx, ctx->gstate.p, (size_t)blocks * sh.T * sh.state_doubles * sizeof(double));
+    int rc;
+    {
+        KernelTimer kt_(ctx, "score_o0j_kernel");
+        void* args[] = {&p};
+        rc = jit_api().LaunchKernel(k->fn, blocks, 1, 1, sh.T, 1, 1, (unsigned)sh.smem, ctx->stream, args, nullptr);
+    }
+    if (sh.gstate) l2_window(ctx, nullptr, 0);
+    if (rc) return fail(ctx, PHYFOO_ECUDA, "cuLaunchKernel(score_o0j_kernel) failed: " + std::to_string(rc));
+    CU(cudaGetLastError());
+    return 0;
+}
+
 // HKY as implemented (evolution/HKY.java:32,77-106): beta == 0, so a child symbol has non-zero probability only when it
 // equals the parent's or is its transition partner (A<->G, C<->T), and every table has zero entries.  What the reference's
 // mean field returns then (algorithm/MeanFieldForBayesNet.java; the restatement runs these cases, tests/test_gpu_parity.py):
@@ -1600,7 +1680,12 @@ static int launch_score(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model*
     }
     if (!fallback) ctx->last_path = 0;
     if (!items && mode == PHYFOO_MODE_MEANFIELD && m->f81_ok && h.W <= 256 &&
-        (ctx->order0_kernel == 1 || (ctx->order0_kernel < 0 && 3 * h.S > 18))) {
+        (ctx->order0_kernel >= 1 || (ctx->order0_kernel < 0 && 3 * h.S > 18))) {
+        if (ctx->order0_kernel != 1) {
+            // the kernel compiled for this tree; a window group needs the state of its trees in shared memory to be worth it
+            rc = launch_score_jit(ctx, ds, m, d_win_off, n_windows, strands, d_out, d_sweeps, counter_slot);
+            if (rc != 1) return rc;
+        }
         rc = launch_score_f81(ctx, ds, m, d_win_off, n_windows, strands, d_out, d_sweeps, counter_slot);
         if (rc <= 0) return rc;
     }
@@ -2082,7 +2167,7 @@ extern "C" int phyfoo_set_option(phyfoo_ctx* ctx, const char* name, int64_t valu
         return PHYFOO_OK;
     }
     if (std::strcmp(name, "order0_kernel") == 0) {
-        if (value < -1 || value > 1) return fail(ctx, PHYFOO_EINVAL, "set_option: order0_kernel must be -1 (choose), 0 (generic) or 1 (F81-structured)");
+        if (value < -1 || value > 2) return fail(ctx, PHYFOO_EINVAL, "set_option: order0_kernel must be -1 (choose), 0 (generic), 1 (F81-structured) or 2 (compiled for the tree at run time)");
         ctx->order0_kernel = (int)value;
         return PHYFOO_OK;
     }
@@ -2422,6 +2507,40 @@ extern "C" int phyfoo_select_multi(phyfoo_ctx* ctx, const phyfoo_dataset* ds, in
     ctx->gamma_windows = kw; ctx->gamma_ds = kd; ctx->gamma_width = kwd;
     return rc;
 }
+
+// ---- the run-time compiled order-0 kernel (jit_o0.hpp): inspection without a device ----
+// Generates the kernel of this model's tree (gaps: with the code for unobserved symbols) and compiles it for sm_100a.
+// source_out / log_out (nullable, NUL-terminated, truncated to their capacities) receive the generated source and the
+// compiler's log; *cubin_bytes the size of the image.  PHYFOO_EUNSUPPORTED: no NVRTC library, order != 0, or no block shape.
+extern "C" int phyfoo_jit_check(const phyfoo_model_desc* desc, int32_t gaps, char* source_out, int64_t source_cap, char* log_out, int64_t log_cap,
+                                int64_t* cubin_bytes) {
+    if (!desc) return PHYFOO_EINVAL;
+    auto put = [](char* dst, int64_t cap, const std::string& text) {
+        if (!dst || cap <= 0) return;
+        const size_t n = std::min<size_t>(text.size(), (size_t)cap - 1);
+        memcpy(dst, text.data(), n);
+        dst[n] = 0;
+    };
+    if (cubin_bytes) *cubin_bytes = 0;
+    try {
+        ModelHost h;
+        h.init(*desc);
+        if (h.order != 0) return PHYFOO_EUNSUPPORTED;
+        JitShape sh;
+        if (!jit_o0_shape(h, gaps != 0, 227 * 1024, 512, &sh)) { put(log_out, log_cap, "no block shape fits"); return PHYFOO_EUNSUPPORTED; }
+        const std::string src = jit_o0_source(h, sh, gaps != 0, (h.S + 15) / 16);
+        put(source_out, source_cap, src);
+        std::string log;
+        std::vector<char> cubin;
+        if (!jit_api().ok) { put(log_out, log_cap, jit_api().why); return PHYFOO_EUNSUPPORTED; }
+        if (jit_compile(src, log, &cubin)) { put(log_out, log_cap, log); return PHYFOO_ECUDA; }
+        put(log_out, log_cap, log);
+        if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
+    } catch (const std::exception& e) { put(log_out, log_cap, e.what()); return PHYFOO_EINVAL; }
+    return PHYFOO_OK;
+}
+// why the last request for a run-time compiled kernel fell back to score_o0f_kernel ("" when it did not)
+extern "C" const char* phyfoo_jit_note(const phyfoo_ctx* ctx) { return ctx ? ctx->jit_note.c_str() : ""; }
 
 // ------------------------------------------------------------------------------------------------
 // sufficient-statistics objective on the host inside the library (suffstat_host.hpp)
