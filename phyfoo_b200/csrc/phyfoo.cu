@@ -1680,14 +1680,17 @@ static int launch_score(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model*
     }
     if (!fallback) ctx->last_path = 0;
     if (!items && mode == PHYFOO_MODE_MEANFIELD && m->f81_ok && h.W <= 256 &&
-        (ctx->order0_kernel >= 1 || (ctx->order0_kernel < 0 && 3 * h.S > 18))) {
+        ctx->order0_kernel != 0) {
         if (ctx->order0_kernel != 1) {
-            // the kernel compiled for this tree; a window group needs the state of its trees in shared memory to be worth it
+            // the kernel compiled for this model's tree (any number of species)
             rc = launch_score_jit(ctx, ds, m, d_win_off, n_windows, strands, d_out, d_sweeps, counter_slot);
             if (rc != 1) return rc;
         }
-        rc = launch_score_f81(ctx, ds, m, d_win_off, n_windows, strands, d_out, d_sweeps, counter_slot);
-        if (rc <= 0) return rc;
+        // precompiled kernels: F81-structured for more than 6 species (or on request), the generic one below otherwise
+        if (ctx->order0_kernel >= 1 || 3 * h.S > 18) {
+            rc = launch_score_f81(ctx, ds, m, d_win_off, n_windows, strands, d_out, d_sweeps, counter_slot);
+            if (rc <= 0) return rc;
+        }
     }
     ScorePlan pl;
     // the fallback list of the pattern-table path is short (its length lives on the device): one block per SM

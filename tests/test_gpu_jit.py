@@ -80,3 +80,38 @@ def test_compiled_kernel_is_the_default_for_large_trees_and_is_cached(ctx):
     t0 = time.perf_counter()
     fg2.getLogProbFor(smp)
     assert time.perf_counter() - t0 < 0.5
+
+
+@pytest.mark.parametrize("tree", ["cat5", "rand12"])
+@pytest.mark.parametrize("W", [1, 20, 40])
+def test_compiled_kernel_other_widths_and_f81beta(ctx, tree, W):
+    """Group shapes of 1, 5 and 5 warps (W = 1 is the background model's shape), F81beta tables, ragged lengths with alignments
+    shorter than the motif."""
+    from phyfoo_b200 import _abi, synth
+    from phyfoo_b200.data import PhyloSample
+    from phyfoo_b200.models import PhyloBayesModel
+    from phyfoo_b200.newick import parse_newick
+    from util import random_codes
+    newick = _trees()[tree]
+    S = parse_newick(newick).n_species
+    rng = np.random.default_rng(5 + W)
+    pwm = synth.random_pwm(W, 0, 6)
+    lens = [W, 3 * W + 7, max(W - 1, 1), 150, W + 1]
+    smp = PhyloSample(random_codes(rng, sum(lens), S, 0.03), np.concatenate([[0], np.cumsum(lens)]))
+    ctx.set_option("pattern_memo", 0)
+    try:
+        for evol in (_abi.EVOL_F81ALPHA, _abi.EVOL_F81BETA):
+            PhyloBayesModel.EVOL_MODEL = evol
+            fg = PhyloBayesModel(W, 0, newick, ctx)
+            fg.setCondProbs(pwm)
+            res = {}
+            for kern in (1, 2):
+                ctx.set_option("order0_kernel", kern)
+                res[kern] = [fg.getLogProbFor(smp, strand=s, want_sweeps=True) for s in (0, 1)]
+                assert [n for n, _ in ctx.last_kernel_times()] == ["score_o0j_kernel" if kern == 2 else "score_o0f_kernel"], ctx.jit_note()
+            for s in (0, 1):
+                assert np.array_equal(res[1][s][1], res[2][s][1]) and np.array_equal(res[1][s][0], res[2][s][0])
+    finally:
+        PhyloBayesModel.EVOL_MODEL = _abi.EVOL_F81ALPHA
+        ctx.set_option("order0_kernel", -1)
+        ctx.set_option("pattern_memo", 1)

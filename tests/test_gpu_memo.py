@@ -1,4 +1,5 @@
-"""The pattern-table path (csrc/memo.cuh) against the direct kernel: bit-identical scores, sweep counts, gamma and
+"""The pattern-table path (csrc/memo.cuh) against the generic direct kernel (order0_kernel = 0; the F81-structured and the
+run-time compiled kernels re-associate the sums and agree with it to rounding, tests/test_gpu_jit.py): bit-identical scores, sweep counts, gamma and
 arg-max calls (same per-tree arithmetic, same summation order), and both against the oracle."""
 import numpy as np
 import pytest
@@ -12,8 +13,10 @@ pytestmark = pytest.mark.gpu
 def ctx():
     from phyfoo_b200 import core
     c = core.default_context()
+    c.set_option("order0_kernel", 0)      # "direct" here = the generic kernel, whose per-tree arithmetic the pattern table shares
     yield c
     c.set_option("pattern_memo", 1)
+    c.set_option("order0_kernel", -1)
 
 
 def _both(ctx, fn):

@@ -217,11 +217,13 @@ def test_full_size_properties(ctx):
     # the two scoring paths at full size: same bits, same sweep counts
     assert ctx.last_score_path() == 1                           # the default for five species is the pattern table
     ctx.set_option("pattern_memo", 0)
+    ctx.set_option("order0_kernel", 0)                          # the generic kernel: the pattern table's own per-tree arithmetic
     try:
         d, dk = fg.getLogProbFor(smp, want_sweeps=True)
         assert ctx.last_score_path() == 0
     finally:
         ctx.set_option("pattern_memo", 1)
+        ctx.set_option("order0_kernel", -1)
     m, mk = fg.getLogProbFor(smp, want_sweeps=True)
     assert np.array_equal(d, m) and np.array_equal(dk, mk) and np.array_equal(m, mf)
     # strand symmetry: the reverse strand of the reverse-complemented alignments is the forward strand read backwards
