@@ -352,8 +352,10 @@ def roofline_of(run, path, kernels, step_ms, sweeps_fg, peak_tflops, hbm_peak, h
     def traffic_of(*keys):
         # profiles/traffic.json: "<profile label>:<kernel name as ncu prints it>" -> dram bytes read + written per launch
         for key in keys:
-            for have, v in traffic_db.items():
-                if have == key or have.startswith(key + "<"):
+            label, _, kernel = key.partition(":")
+            for have, v in sorted(traffic_db.items(), reverse=True):          # the latest capture of a configuration first
+                hl, _, hk = have.partition(":")
+                if (hl == label or hl.startswith(label + "_")) and (hk == kernel or hk.startswith(kernel + "<")):
                     return v
         return None
 

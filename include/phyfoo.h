@@ -151,9 +151,10 @@ int phyfoo_bg_columns(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* b
  *   -F(0,0) of the window (s, s+1)  +  sum_{u = s+1..e} -F(1,1) of the window (u-1, u)
  * (each window's mean field optimised on its own).  cond_out[c] = the conditional term of column c (0 at the first column
  * of an alignment), first_out[c] (nullable) = the start term of a range beginning at column c (0 at the last column of an
- * alignment); getLogProbFor(seq, s, e) = first[s] + sum cond[s+1..e].  Ranges of a single column have no defined value in
- * the reference (stale observations, MeanFieldForBayesNet.java:84) -- which is why the ZOOPS E-step is not offered with
- * an order-1 background -- and alignments shorter than 2 columns are refused. */
+ * alignment); getLogProbFor(seq, s, e) = first[s] + sum cond[s+1..e].  A range of a single column has no value of its own in
+ * the reference: its second tree keeps the observation of an earlier call (MeanFieldForBayesNet.java:84); this entry point
+ * therefore covers ranges of >= 2 columns, and phyfoo_zoops_estep with an order-1 background reproduces the two single-column
+ * flank ranges of every offset as the reference's call order produces them.  Alignments shorter than 2 columns are refused. */
 int phyfoo_bg_columns_order1(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* bg, double* cond_out, double* first_out);
 
 /* ZOOPS E-step over the whole (local) sample: SingleHiddenMotifMixture.getNewWeights.
@@ -326,7 +327,12 @@ int phyfoo_set_option(phyfoo_ctx* ctx, const char* name, int64_t value);
  * node updates); 0 = one quad of lanes per window walking the nodes one by one.  Same fixed-point iteration; free energies
  * agree to re-association.
  * "order1_qglobal": kernel 2 keeps the q of a window's hidden nodes in shared memory (0) or in global memory behind L1 with
- * n warps per SM (1..8), which doubles the windows in flight for trees like C3's; -1 (default) chooses. */
+ * n warps per SM (1..8), which doubles the windows in flight for trees like C3's; -1 (default) chooses.
+ * "order0_kernel": order-0 mean-field scoring outside the pattern table: 2 = the kernel compiled at run time for the model's
+ * tree (below), 1 = its precompiled form for tables with F81 structure, 0 = the generic kernel; -1 (default) = 2, then 1 for
+ * more than 6 species, else 0.  Kernels 1 and 2 are bit-identical; kernel 0 agrees with them to re-association.
+ * "l2_persist" (default 1): per-window state kept in global memory (the q rows of the order-1 kernel, the state of very large
+ * trees) is covered by an L2 access-policy window on the library's stream for the duration of the launch. */
 /* Device time of every kernel the most recent call launched (CUDA events on the library's stream), in launch order:
  * returns the number of entries written (<= max_entries) or a negative error; names are static strings. */
 int phyfoo_last_kernel_times(phyfoo_ctx* ctx, int32_t max_entries, const char** names_out, float* ms_out);
