@@ -468,6 +468,17 @@ class SingleHiddenMotifMixture:
     def getNumberOfMotifs(self):
         return 1   # jstacs SingleHiddenMotifMixture.java:716-718
 
+    def toXML(self, **kw):
+        """The reference's model file (jstacs AbstractMixtureModel.toXML :1628-1678; tools/Classification and
+        models/ModelUtil.java:228-237 load it)."""
+        from . import xmlio
+        return xmlio.shm_to_xml(self, **kw)
+
+    @classmethod
+    def fromXML(cls, xml, ctx=None):
+        from . import xmlio
+        return xmlio.read_shm(xml, ctx)
+
     def getNewWeights(self, sample: PhyloSample, seqWeights=None, want_gamma=True, want_profile=False, out=None):
         """One E-step (jstacs SingleHiddenMotifMixture.java:499-566).  Returns a dict with
         gamma (seqweights[0] per window), w (sufficient statistics of the component weights), ll, argmax_off/strand."""

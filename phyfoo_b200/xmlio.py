@@ -16,7 +16,8 @@ where the elements of an array of primitives / strings carry no class name.  Wha
 Reading follows the reference's reload semantics: a reloaded model is always F81-alpha (BayesNetHandler.java:325,337, SURVEY.md
 appendix B-4) and its branch lengths are the three-decimal values of the file.  No model file ships with the reference and there
 is no JVM here, so the format is restated from the serialisation code and checked by round trips and hand-assembled files
-(tests/test_xmlio.py); files written here have not been loaded by the Java side.
+(tests/test_xmlio.py); files written here have not been loaded by the Java side.  Mixture files (SingleHiddenMotifMixture,
+StrandModel) are written as well (shm_to_xml), with the termination condition in the loader's legacy <epsilon> form.
 """
 import re
 from decimal import Decimal
@@ -277,6 +278,72 @@ def phylo_background_to_xml(model):
     xml = add_tags(_bnh_xml(model), "_bnh")
     xml += append_object(JValue("java.lang.Byte", model.order), "order")
     return xml + _alphabets_xml()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# mixture writers (jstacs AbstractMixtureModel.toXML, :1628-1678)
+_ENUM_ALGORITHM = "de.jstacs.models.mixture.AbstractMixtureModel$Algorithm"
+_ENUM_PARAMETERIZATION = "de.jstacs.models.mixture.AbstractMixtureModel$Parameterization"
+
+
+def _enum_xml(cls, name, tag):
+    """XMLParser.java:190-191: an enum is its class name and <name>CONSTANT</name>."""
+    return "<" + tag + "><className>" + _escape(cls) + "</className><name>" + name + "</name></" + tag + ">"
+
+
+def _mixture_to_xml(simple_name, length, models, optimize, estimate, hyper, weights, trained, best, epsilon, alpha=1.0, further=""):
+    """The field order of AbstractMixtureModel.toXML.  The termination condition is written in the form the loader still accepts
+    from older files -- <epsilon> for a SmallDifferenceOfFunctionEvaluationsCondition (AbstractMixtureModel.java:1713-1714) --
+    instead of the nested ParameterSet of a CombinedCondition: PhyFoo's pipelines replace the loaded model's condition before
+    they train on (training/TrainingUtil.java:56-68, PostTrainModel.java:90), and scoring does not use it."""
+    x = append_object(JValue("java.lang.Integer", length), "length")
+    x += append_object(JValue("java.lang.Integer", 2), "dimension")
+    x += append_object(JValue("java.lang.Integer", 1), "starts")                          # models/ModelUtil.java:101,114
+    x += append_object(JValue("java.lang.Boolean", estimate), "estimateComponentProbs")
+    x += append_object(JValue("[D", list(np.asarray(hyper, np.float64))), "componentHyperParams")
+    x += append_object(JValue("[Lde.jstacs.models.Model;", models), "models")
+    x += append_object(JValue("[Z", optimize), "optimizeModel")
+    x += append_object(JValue("java.lang.Boolean", trained), "algorithmHasBeenRun")
+    x += append_object(JValue("[D", list(np.asarray(weights, np.float64))), "weights")
+    x += _enum_xml(_ENUM_ALGORITHM, "EM", "algorithm")
+    x += append_object(JValue("java.lang.Double", alpha), "alpha")
+    x += append_object(JValue("java.lang.Double", epsilon), "epsilon")
+    x += _enum_xml(_ENUM_PARAMETERIZATION, "LAMBDA", "parametrization")
+    x += append_object(JValue("java.lang.Double", float("-inf") if best is None else best), "best")
+    return add_tags(x + further, simple_name)
+
+
+def _component_jvalue(model):
+    from .models import PhyloBackground, PhyloBayesModel, StrandModel
+    if isinstance(model, StrandModel):
+        return JValue("de.jstacs.models.mixture.StrandModel", strand_model_to_xml(model))
+    if isinstance(model, PhyloBayesModel):
+        return JValue("models.PhyloBayesModel", phylo_bayes_model_to_xml(model))
+    if isinstance(model, PhyloBackground):
+        return JValue("models.PhyloBackground", phylo_background_to_xml(model))
+    raise NotImplementedError(f"{type(model).__name__} in a mixture file")
+
+
+def strand_model_to_xml(sm, trained=True, best=None):
+    """jstacs StrandModel as models/ModelUtil.java:98-108 builds it: one inner model, two components (forward, backward)."""
+    return _mixture_to_xml("StrandModel", sm.getLength(), [_component_jvalue(sm.model)], [True], sm.estimateComponentProbs, sm.hyper,
+                           sm.weights, trained, best, 1e-4, sm.alpha)
+
+
+def shm_to_xml(shm, trained=True, best=None, epsilon=1e-4):
+    """SingleHiddenMotifMixture.toXML: AbstractMixtureModel's fields, then the position prior of HiddenMotifMixture.java:208-213
+    (a UniformPositionPrior, PositionPrior.java:121-127), framed by the class's simple name.  models = {motif (possibly inside a
+    StrandModel), flanking}; only the motif is optimised (trainOnlyMotifModel = true, models/ModelUtil.java:112)."""
+    motif = shm.strand if shm.strand is not None else shm.motif
+    prior = add_tags(append_object(JValue("java.lang.Integer", shm.motif.getLength()), "motifLength"), "UniformPositionPrior")
+    further = append_object(JValue("de.jstacs.models.mixture.motif.positionprior.UniformPositionPrior", prior), "posPrior")
+    return _mixture_to_xml("SingleHiddenMotifMixture", 0, [_component_jvalue(motif), _component_jvalue(shm.flanking)], [True, False],
+                           shm.estimateComponentProbs, shm.hyper, shm.weights, trained, best, epsilon, 1.0, further)
+
+
+def save_shm(path, shm, **kw):
+    with open(path, "w") as f:
+        f.write(shm_to_xml(shm, **kw))
 
 
 # ---------------------------------------------------------------------------------------------------------------------------

@@ -136,3 +136,37 @@ def test_newick_writer_and_parser_round_trip_random_trees():
         assert np.array_equal(t2.branch, np.round(t1.branch * 1000.0) / 1000.0)
         assert xmlio.newick_string(t2, t2.branch) == s1
         assert s1.endswith(";") and s1.count("(") == s1.count(")")
+
+
+def test_mixture_writer_round_trip_and_layout():
+    """SingleHiddenMotifMixture / StrandModel files as the library writes them (xmlio.shm_to_xml): the field order of jstacs
+    AbstractMixtureModel.toXML (:1628-1678) with the loader's legacy <epsilon> termination condition (:1713-1714), the position
+    prior of HiddenMotifMixture.java:208-213; reading them back gives the same models and weights, writing again the same text."""
+    from phyfoo_b200.models import SingleHiddenMotifMixture, StrandModel
+    newick, fg0, fg1, bg = _models()
+    for motif in (fg0, StrandModel(fg0, 0.55), fg1):
+        shm = SingleHiddenMotifMixture(motif, bg, zoops=0.9)
+        text = shm.toXML(best=-1234.5)
+        back = SingleHiddenMotifMixture.fromXML(text)
+        assert np.allclose(back.weights, [0.9, 0.1]) and back.estimateComponentProbs is False
+        assert (back.strand is None) == (shm.strand is None)
+        if shm.strand is not None:
+            assert np.allclose(back.strand.weights, [0.55, 0.45]) and back.strand.estimateComponentProbs
+        assert xmlio.phylo_bayes_model_to_xml(back.motif) == xmlio.phylo_bayes_model_to_xml(xmlio.read_phylo_bayes_model(xmlio.phylo_bayes_model_to_xml(shm.motif)))
+        assert back.toXML(best=-1234.5) == xmlio.shm_to_xml(xmlio.read_shm(back.toXML(best=-1234.5)), best=-1234.5)
+        root = xmlio.parse(text).child("SingleHiddenMotifMixture")
+        tags = [c.tag for c in root.children if c.tag != "className"]
+        assert tags == ["length", "dimension", "starts", "estimateComponentProbs", "componentHyperParams", "models", "optimizeModel",
+                        "algorithmHasBeenRun", "weights", "algorithm", "alpha", "epsilon", "parametrization", "best", "posPrior"]
+        assert root.child("algorithm").child("className").text == "de.jstacs.models.mixture.AbstractMixtureModel$Algorithm"
+        assert root.child("algorithm").child("name").text == "EM" and root.child("parametrization").child("name").text == "LAMBDA"
+        assert xmlio.value(root.child("optimizeModel")) == [True, False] and xmlio.value(root.child("best")) == -1234.5
+        prior = root.child("posPrior")
+        assert prior.child("className").text.endswith("positionprior.UniformPositionPrior")
+        assert xmlio.value(prior.child("UniformPositionPrior").child("motifLength")) == shm.motif.getLength()
+        assert text.startswith("<SingleHiddenMotifMixture>\n<length><className>java.lang.Integer</className>0</length>")
+    # estimated component weights (algorithm.zoops outside (0, 1], models/ModelUtil.java:122-133)
+    shm = SingleHiddenMotifMixture(fg0, bg)
+    shm.weights = np.array([0.25, 0.75])
+    back = xmlio.read_shm(shm.toXML())
+    assert back.estimateComponentProbs and np.allclose(back.weights, [0.25, 0.75])
