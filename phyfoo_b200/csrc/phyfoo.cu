@@ -88,6 +88,7 @@ struct phyfoo_ctx {
                                      // pattern table does not apply), 0 = generic kernel (tree_pass.cuh), 1 = F81-structured kernel
     std::map<std::string, std::shared_ptr<JitKernel>> jit_cache;   // generated source -> loaded kernel (jit_o0.hpp)
     std::string jit_note;            // why the last request for a run-time compiled kernel was not served
+    int jit_max_threads = 512;       // block size cap of the run-time compiled kernel (tuning)
     int l2_persist = 1;              // per-window state kept in global memory (order-1 q rows, large-tree state): L2 access-policy window
     size_t l2_persist_max = 0, l2_window_max = 0;
     int order1_qglobal = -1;         // node-per-thread kernel: -1 = choose, 0 = q rows in shared memory, n > 0 = q rows in global memory
@@ -578,6 +579,7 @@ extern "C" int phyfoo_init(int device, phyfoo_ctx** out) {
     // every sweep, keep falling out of L2 (ncu on C3: 350 GB written to DRAM per E-step against 128 MB of algorithmic bytes)
     ctx->l2_persist_max = (size_t)std::max(prop.persistingL2CacheMaxSize, 0);
     ctx->l2_window_max = (size_t)std::max(prop.accessPolicyMaxWindowSize, 0);
+    if (getenv("PHYFOO_VERBOSE")) fprintf(stderr, "phyfoo: L2 %d bytes, persisting max %d, window max %d\n", prop.l2CacheSize, prop.persistingL2CacheMaxSize, prop.accessPolicyMaxWindowSize);
     if (ctx->l2_persist_max) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, ctx->l2_persist_max);
     *out = ctx;
     return PHYFOO_OK;
@@ -1337,6 +1339,8 @@ static int launch_net1n(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model*
     const size_t per_warp = (size_t)(qg ? L.sregion : L.region) * sizeof(double);
     if (fixed + per_warp > budget) return 1;
     int nw = (int)std::min<size_t>(qg ? want_qg : 8, (budget - fixed) / per_warp);
+    // (12 / 16 warps per SM with launch bounds of 384 / 512 threads, i.e. 168 / 128 registers and a few spills: 174 / 286 ms
+    // against 133 ms at 8 warps on 2000 alignments of C3)
     nw = std::max(1, std::min(nw, 8));
     const long long want_warps = (n_items + 7) / 8;
     const void* fn = nullptr;
@@ -1376,6 +1380,8 @@ static int launch_net1n(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model*
     p.fb_dst = check ? p.fb_col0 + n_items : nullptr;
     p.fb_strand = check ? (uint8_t*)(p.fb_dst + n_items) : nullptr;
     CU(cudaMemsetAsync(p.counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    // (window over the q rows alone, leaving the observed-leaf sums to the normal policy: measured worse -- 31 instead of 18 GB of
+    // DRAM traffic per 2 M windows)
     if (qg) l2_window(ctx, ctx->o1n_cache.p, cache_bytes);
     {
         KernelTimer kt_(ctx, "score_o1n_kernel");
@@ -1529,7 +1535,7 @@ static int jit_get(phyfoo_ctx* ctx, const ModelHost& h, bool gaps, int nb, std::
     if (!api.ok || !api.have_driver) { ctx->jit_note = api.why; return 1; }
     JitShape sh;
     // 1024 threads of 64 registers or 512 of 128: the generated pass needs ~100+ registers, so at most 512 threads
-    if (!jit_o0_shape(h, gaps, std::min<size_t>(ctx->smem_optin, 227 * 1024), 512, &sh)) { ctx->jit_note = "no block shape fits"; return 1; }
+    if (!jit_o0_shape(h, gaps, std::min<size_t>(ctx->smem_optin, 227 * 1024), ctx->jit_max_threads, &sh)) { ctx->jit_note = "no block shape fits"; return 1; }
     const std::string src = jit_o0_source(h, sh, gaps, nb);
     auto it = ctx->jit_cache.find(src);
     if (it != ctx->jit_cache.end()) {
@@ -2172,6 +2178,11 @@ extern "C" int phyfoo_set_option(phyfoo_ctx* ctx, const char* name, int64_t valu
     if (std::strcmp(name, "order0_kernel") == 0) {
         if (value < -1 || value > 2) return fail(ctx, PHYFOO_EINVAL, "set_option: order0_kernel must be -1 (choose), 0 (generic), 1 (F81-structured) or 2 (compiled for the tree at run time)");
         ctx->order0_kernel = (int)value;
+        return PHYFOO_OK;
+    }
+    if (std::strcmp(name, "jit_max_threads") == 0) {
+        if (value < 32 || value > 1024) return fail(ctx, PHYFOO_EINVAL, "set_option: jit_max_threads must be 32..1024");
+        ctx->jit_max_threads = (int)value;
         return PHYFOO_OK;
     }
     if (std::strcmp(name, "l2_persist") == 0) {

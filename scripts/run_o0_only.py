@@ -10,6 +10,8 @@ n_aln = int(sys.argv[2]) if len(sys.argv) > 2 else 600
 kernel = int(sys.argv[3]) if len(sys.argv) > 3 else -1
 cfg, newick, pwm, sample, planted = synth.make_config(name, n_aln=n_aln)
 ctx = core.default_context()
+if len(sys.argv) > 5:
+    ctx.set_option("jit_max_threads", int(sys.argv[5]))
 if len(sys.argv) > 4:
     ctx.set_option("l2_persist", int(sys.argv[4]))
 ctx.set_option("order0_kernel", kernel)
