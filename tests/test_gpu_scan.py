@@ -1,6 +1,8 @@
 """Genome-scan / classification front-end (classification/ClassificationUtil.java semantics): the device-side consumers of
 the per-offset scores against the same computations in numpy on the host copy of the scores (bit-exact: thresholds are order
-statistics, hits are comparisons), and the host mirrors against hand-checked cases."""
+statistics, hits are comparisons), and the host mirrors against hand-checked cases.  The first test is about the scan LOGIC: its
+scores are the GPU's own on both sides (self-referential for the scores by design); test_scan_on_oracle_scores closes that loop
+with thresholds, hit counts and arg-max offsets computed from the oracle's window scores."""
 import numpy as np
 import pytest
 
@@ -59,3 +61,27 @@ def test_host_mirrors_hand_checked():
     assert cl.getDynamicClassificationRate([1.0, 2.0, 3.0], [0.0, 0.5, 2.5]) == 5 / 6
     with pytest.raises(ValueError):
         cl.calculateAUC([1.0], [1.0, 2.0])
+
+
+@pytest.mark.gpu
+def test_scan_on_oracle_scores(setup):
+    """The same consumers with the ORACLE's window scores as the reference: hit counts / first hits / arg-max offsets of the
+    device scan equal those of numpy on the oracle's scores wherever no oracle score lies within 1e-9 relative of the
+    threshold, and the device threshold for a specificity equals the oracle's order statistic to 1e-9."""
+    from phyfoo_b200 import classification as cl
+    from util import oracle_fg
+    ctx, fg, pos, neg, planted = setup
+    om = oracle_fg(fg.newick, fg.getCondProbs())
+    ops = [om.score_windows(pos.getElementAt(i), False)[0] for i in range(pos.n_alignments)]
+    ons = [om.score_windows(neg.getElementAt(i), False)[0] for i in range(neg.n_alignments)]
+    spec = [0.5, 0.9, 0.99]
+    thr_ref = cl.determineThresholdsForSpecifitiesPerPos(ons, spec)
+    thr_dev = cl.determineThresholdsForSpecifitiesPerPos_device(fg, neg, spec)
+    assert np.max(np.abs(thr_dev - thr_ref) / np.abs(thr_ref)) < 1e-9
+    for t in thr_ref:
+        h = cl.scan_hits_device(fg, pos, t)
+        for i, x in enumerate(ops):
+            assert h["arg_max"][i] == int(np.argmax(x)) and abs(h["max_score"][i] - x.max()) <= 1e-9 * abs(x.max())
+            if np.min(np.abs(x - t)) > 1e-9 * abs(t):              # no score on the knife's edge of the threshold
+                assert h["n_hits"][i] == int((x > t).sum())
+                assert h["first_hit"][i] == (int(np.argmax(x > t)) if (x > t).any() else -1)
