@@ -54,7 +54,7 @@ def parse_args():
     ap.add_argument("--memo-wave", type=int, default=None, help="pattern_memo_wave of the library (tuning only)")
     ap.add_argument("--order1-kernel", type=int, default=None, help="order1_kernel of the library (tuning only)")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity check before the timed region")
-    ap.add_argument("--no-extra", action="store_true", help="skip the secondary configurations (c2, c3o0)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary configurations (c2, c3o0, c5 on 3000 alignments, c1)")
     return ap.parse_args()
 
 
@@ -615,14 +615,17 @@ def run_ours(args):
     except Exception:
         traffic_db = {}
     if world == 1 and not args.no_extra and args.config == DEFAULT_CONFIG and not args.n_aln:
+        from phyfoo_b200.synth import CONFIGS as synth_configs
         run.free()
-        for name in ("c2", "c3o0"):
-            ex = EStepRunner(ctx, torch, dist, 1, 0, name, None, stream, flush)
+        # C2 (configs[1], pattern table), C3's data with an order-0 motif, the 30-species tree of C5 (configs[4]) on 3000 of its
+        # alignments, and C1 (configs[0]: the reference's bundled alignments)
+        for name, n_ex_aln in (("c2", None), ("c3o0", None), ("c5", 3000), ("c1", None)):
+            ex = EStepRunner(ctx, torch, dist, 1, 0, name, n_ex_aln, stream, flush)
             pc = parity_check(ex.cfg, ex.newick, ex.pwm, ex.sample, ex.shm, PARITY_ALIGNMENTS[0]) if not args.no_parity else None
             for _ in range(3):
                 ex.step()
             torch.cuda.synchronize()
-            n_ex = 20 if name == "c2" else 5
+            n_ex = 20 if name in ("c2", "c1") else 5 if name == "c3o0" else 3
             ms, kern = ex.timed(n_ex)
             sw_fg, _ = ctx.estep_sweeps()
             rl, ex_extra = roofline_of(ex, ctx.last_score_path(), kern, ms / n_ex, sw_fg, peak_tflops, hbm_peak, hbm_of, traffic_db)
@@ -631,6 +634,14 @@ def run_ours(args):
                             "scoring_path": PATHS[ctx.last_score_path()], "roofline": rl,
                             "kernels_ms": [{"kernel": nm, "ms": round(v, 5)} for (_, nm), v in sorted(kern.items())]}
             extras[name].update(ex_extra)
+            am = ex.shm.getNewWeights(ex.sample, want_gamma=False)["argmax_off"]
+            pl = np.asarray(ex.planted)
+            if (pl >= 0).any():
+                d = np.abs(am[pl >= 0].astype(np.int64) - pl[pl >= 0])
+                extras[name]["planted_sites"] = {"alignments_with_a_site": int((pl >= 0).sum()), "argmax_exact": float(np.mean(d == 0)),
+                                                 "argmax_within_half_width": float(np.mean(d <= ex.cfg["W"] // 2))}
+            if n_ex_aln:
+                extras[name]["alignments"] = f"{n_ex_aln} of the configuration's {synth_configs[name]['n_aln']}"
             ex.free()
 
     if rank == 0:
