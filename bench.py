@@ -361,8 +361,8 @@ def roofline_of(run, path, kernels, step_ms, sweeps_fg, peak_tflops, hbm_peak, h
 
     o1 = [n for n in ("score_o1n_kernel", "score_o1w_kernel", "score_o1_kernel") if n in names]
     o0 = [n for n in ("score_o0j_kernel", "score_o0f_kernel", "score_o0_kernel") if n in names]
-    fg_name = o1[0] if cfg["order"] == 1 and o1 else o0[0]
     if path != 1:
+        fg_name = o1[0] if cfg["order"] == 1 and o1 else o0[0]
         # the motif-window launches of the scoring kernel (an order-1 step may add a fallback launch for windows with gaps)
         fg_ms = max(ms for (_, name), ms in kernels.items() if name == fg_name)
         roofline = fp64_roofline(flops, abytes, fg_name + " (motif windows)", fg_ms, peak_tflops, hbm_peak, hbm_of)
@@ -455,28 +455,24 @@ def optimizer_timings(run, args, step_ms):
     repeats = 2 if cfg["order"] == 0 else 1
     out = {"gradient_ms": grad_ms, "dim": int(lam.size), "position": pos, "selected_windows_per_gpu": int(sa.size),
            "select_and_fix_q_ms": prepare_ms}
-    if cfg["order"] == 0:
-        # default M-step of an order-0 motif: sufficient statistics, one library call (phyfoo_ss_optimize); beside it the
-        # per-window evaluation on the device under the same optimiser (the reference's own evaluation order)
-        mstep_ms, st = min((mstep(True) for _ in range(repeats)), key=lambda r: r[0])
-        mstep_dev_ms, st_dev = min((mstep(False) for _ in range(repeats)), key=lambda r: r[0])
-        fg.MSTEP_SUFFICIENT_STATISTICS = True
-        grad_ms, mstep_ms, prepare_ms, mstep_dev_ms = run.max_over_ranks([grad_ms, mstep_ms, prepare_ms, mstep_dev_ms])
-        out.update({"mstep_device_evaluation_ms": mstep_dev_ms, "mstep_device_evaluation_evaluations": int(st_dev["evaluations"]),
-                    "em_iteration_device_evaluation_ms": step_ms + mstep_dev_ms})
-    else:
-        mstep_ms, st = min((mstep(False) for _ in range(repeats)), key=lambda r: r[0])
-        grad_ms, mstep_ms, prepare_ms = run.max_over_ranks([grad_ms, mstep_ms, prepare_ms])
+    # default M-step: sufficient statistics, one library call (phyfoo_ss_optimize); beside it the per-window evaluation on the
+    # device under the same optimiser (the reference's own evaluation order)
+    mstep_ms, st = min((mstep(True) for _ in range(repeats)), key=lambda r: r[0])
+    mstep_dev_ms, st_dev = min((mstep(False) for _ in range(repeats)), key=lambda r: r[0])
+    fg.MSTEP_SUFFICIENT_STATISTICS = True
+    grad_ms, mstep_ms, prepare_ms, mstep_dev_ms = run.max_over_ranks([grad_ms, mstep_ms, prepare_ms, mstep_dev_ms])
+    out.update({"mstep_device_evaluation_ms": mstep_dev_ms, "mstep_device_evaluation_evaluations": int(st_dev["evaluations"]),
+                "em_iteration_device_evaluation_ms": step_ms + mstep_dev_ms})
     fg.setCondProbs(run.pwm)
     out.update({"gradient_ms": grad_ms, "select_and_fix_q_ms": prepare_ms, "mstep_ms": mstep_ms,
                 "mstep_evaluations": int(st["evaluations"]), "em_iteration_ms": step_ms + mstep_ms,
                 "what": "wall clock, max over ranks: evaluateGradientOfFunction of one motif position on the device (forward "
                         "differences, dim + 1 objective sums over the selected windows in one pass" + (", one all-reduce" if world > 1 else "") +
                         "); M-step = selection + mean fields of the selected windows + BFGS position by position; EM iteration = "
-                        "E-step (ms_per_step) + M-step.  Order 0: the M-step runs on sufficient statistics (one device pass for the "
+                        "E-step (ms_per_step) + M-step.  The M-step runs on sufficient statistics (one device pass for the "
                         "expected counts" + (", one all-reduce of them" if world > 1 else "") + ", then the optimiser and its "
                         "evaluations on the host inside libphyfoo.so: phyfoo_ss_optimize); mstep_device_evaluation_ms is the same "
-                        "optimiser with a device pass per evaluation.  Order 1: device pass per evaluation under the host optimiser"})
+                        "optimiser with a device pass per evaluation"})
     return out
 
 

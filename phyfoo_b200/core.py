@@ -575,9 +575,10 @@ class SSObjective:
             raise ValueError("phyfoo_ss_eval_branches: bad argument")
         return f.value
 
-    def get_pi(self, position):
-        out = np.zeros(4)
-        lib().phyfoo_ss_get_pi(self.h, int(position), _p(out, C.c_double), 4)
+    def get_pi(self, position, n=4):
+        out = np.zeros(int(n))
+        if lib().phyfoo_ss_get_pi(self.h, int(position), _p(out, C.c_double), int(n)) != _abi.OK:
+            raise ValueError("phyfoo_ss_get_pi: bad argument (n must be 4 x the context rows of the position)")
         return out
 
     def optimize(self, order):

@@ -760,10 +760,9 @@ __global__ void fe_count_reduce_kernel(const double* __restrict__ part, int bloc
 extern "C" int phyfoo_fe_suffstats(phyfoo_ctx* ctx, phyfoo_feset* fe, double* counts_out, double* entropy_out) {
     if (!ctx) return PHYFOO_EINVAL;
     if (!fe || !counts_out) return fail(ctx, PHYFOO_EINVAL, "fe_suffstats: NULL argument");
-    if (fe->order != 0) return fail(ctx, PHYFOO_EUNSUPPORTED, "fe_suffstats: order-1 networks are not supported (use fe_eval / fe_grad)");
     CU(cudaSetDevice(ctx->device));
     ctx->launches = 0; ctx->n_ktimes = 0;
-    const int W = fe->W, E = fe->E;
+    const int W = fe->W, E = fe->order == 1 ? fe->E1 : fe->E;          // order 1: the entries of build_tables1_into (mstep1.cuh)
     const size_t WE = (size_t)W * E;
     if (fe->n == 0) {
         for (size_t i = 0; i < WE; ++i) counts_out[i] = 0.0;
@@ -782,7 +781,14 @@ extern "C" int phyfoo_fe_suffstats(phyfoo_ctx* ctx, phyfoo_feset* fe, double* co
     p.W = W; p.I = fe->I; p.S = fe->S; p.E = E; p.prog_len = fe->m->prog_len; p.prog = fe->m->d_prog;
     p.part = d_part;
     const size_t smem = (size_t)E * sizeof(double) + (size_t)fe->m->prog_len * sizeof(int) + 16;
-    {
+    if (fe->order == 1) {
+        Fe1CountParams p1;
+        p1.bases = p.bases; p1.gaps = p.gaps; p1.n_cols = p.n_cols; p1.nb = p.nb; p1.col0 = p.col0; p1.strand = p.strand; p1.weight = p.weight;
+        p1.q_int = p.q_int; p1.q_leaf = p.q_leaf; p1.n = p.n; p1.W = W; p1.I = fe->I; p1.S = fe->S; p1.E1 = E; p1.prog_len = p.prog_len;
+        p1.prog = p.prog; p1.part = d_part;
+        KernelTimer kt_(ctx, "fe1_count_kernel");
+        fe1_count_kernel<<<dim3(blocks, W), 128, smem, ctx->stream>>>(p1);
+    } else {
         KernelTimer kt_(ctx, "fe_count_kernel");
         fe_count_kernel<<<dim3(blocks, W), 256, smem, ctx->stream>>>(p);
     }

@@ -484,7 +484,7 @@ extern "C" int phyfoo_multi_ss_create(phyfoo_mctx* mc, phyfoo_mfeset* mf, phyfoo
     *out = nullptr;
     const int world = (int)mc->ctx.size();
     const ModelHost& h0 = mf->fe[0]->m->h;
-    const size_t WE = (size_t)h0.W * h0.E;
+    const size_t WE = (size_t)h0.W * (h0.order == 1 ? h0.E1() : h0.E);
     std::vector<std::vector<double>> part(world, std::vector<double>(WE + 1, 0.0));
     int rc = mc->workers.run([&](int r) { mc->ctx[r]->err.clear(); return phyfoo_fe_suffstats(mc->ctx[r], mf->fe[r], part[r].data(), &part[r][WE]); });
     if (rc) return mcollect(mc, rc, "multi_ss_create");

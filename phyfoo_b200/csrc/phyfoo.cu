@@ -2568,7 +2568,7 @@ extern "C" int phyfoo_ss_create(phyfoo_ctx* ctx, phyfoo_feset* fe, phyfoo_ssobj*
     if (!fe || !out) return fail(ctx, PHYFOO_EINVAL, "ss_create: NULL argument");
     *out = nullptr;
     const ModelHost& h = fe->m->h;
-    std::vector<double> c((size_t)h.W * h.E);
+    std::vector<double> c((size_t)h.W * (h.order == 1 ? h.E1() : h.E));
     double ent = 0.0;
     const int rc = phyfoo_fe_suffstats(ctx, fe, c.data(), &ent);
     if (rc) return rc;
@@ -2584,7 +2584,7 @@ extern "C" int phyfoo_ss_create_host(const phyfoo_model_desc* desc, const double
     try {
         ModelHost h;
         h.init(*desc);
-        if (h.order != 0) return PHYFOO_EUNSUPPORTED;
+        if (h.order > 1) return PHYFOO_EUNSUPPORTED;
         phyfoo_ssobj* ss = new phyfoo_ssobj();
         ss->o.init(h, counts, entropy);
         *out = ss;
@@ -2595,15 +2595,16 @@ extern "C" void phyfoo_ss_free(phyfoo_ssobj* ss) { delete ss; }
 extern "C" double phyfoo_ss_value(const phyfoo_ssobj* ss) { return ss ? ss->o.value() : NAN; }
 extern "C" int64_t phyfoo_ss_evaluations(const phyfoo_ssobj* ss) { return ss ? ss->o.evaluations : 0; }
 extern "C" int phyfoo_ss_eval(phyfoo_ssobj* ss, int32_t position, const double* lambda, int32_t dim, double* f_out) {
-    if (!ss || !lambda || !f_out || position < 0 || position >= ss->o.h.W || dim != 4) return PHYFOO_EINVAL;
+    if (!ss || !lambda || !f_out || position < 0 || position >= ss->o.h.W || dim != ss->o.dim(position)) return PHYFOO_EINVAL;
     *f_out = ss->o.eval_lambda(position, lambda);
     return PHYFOO_OK;
 }
 extern "C" int phyfoo_ss_grad(phyfoo_ssobj* ss, int32_t position, const double* lambda, int32_t dim, double eps, double* f_out, double* g_out) {
-    if (!ss || !lambda || !g_out || position < 0 || position >= ss->o.h.W || dim != 4 || !(eps > 0)) return PHYFOO_EINVAL;
-    double x[4] = {lambda[0], lambda[1], lambda[2], lambda[3]};
+    if (!ss || !lambda || !g_out || position < 0 || position >= ss->o.h.W || dim != ss->o.dim(position) || !(eps > 0)) return PHYFOO_EINVAL;
+    double x[16];
+    for (int i = 0; i < dim; ++i) x[i] = lambda[i];
     const double f0 = ss->o.eval_lambda(position, x);
-    for (int i = 0; i < 4; ++i) {                       // jstacs NumericalDifferentiableFunction.java:64-84
+    for (int i = 0; i < dim; ++i) {                     // jstacs NumericalDifferentiableFunction.java:64-84
         const double keep = x[i];
         x[i] += eps;
         g_out[i] = (ss->o.eval_lambda(position, x) - f0) / eps;
@@ -2619,8 +2620,8 @@ extern "C" int phyfoo_ss_eval_branches(phyfoo_ssobj* ss, int32_t position, const
     return PHYFOO_OK;
 }
 extern "C" int phyfoo_ss_get_pi(const phyfoo_ssobj* ss, int32_t position, double* pi_out, int32_t n) {
-    if (!ss || !pi_out || position < 0 || position >= ss->o.h.W || n != 4) return PHYFOO_EINVAL;
-    for (int i = 0; i < 4; ++i) pi_out[i] = ss->o.h.pi[position][i];
+    if (!ss || !pi_out || position < 0 || position >= ss->o.h.W || n != ss->o.dim(position)) return PHYFOO_EINVAL;
+    for (int i = 0; i < n; ++i) pi_out[i] = ss->o.h.pi[position][i];
     return PHYFOO_OK;
 }
 // the M-step of PhyloBayesModel.train on this objective: the listed positions one after the other (the caller draws the
@@ -2632,8 +2633,9 @@ extern "C" int phyfoo_ss_optimize(phyfoo_ssobj* ss, const int32_t* order, int32_
     for (int j = 0; j < n_pos; ++j) {
         const int t = order[j];
         if (t < 0 || t >= ss->o.h.W) return PHYFOO_EINVAL;
-        std::vector<double> x(4);
-        for (int i = 0; i < 4; ++i) x[i] = std::log(ss->o.h.pi[t][i]);
+        const int d = ss->o.dim(t);
+        std::vector<double> x(d);
+        for (int i = 0; i < d; ++i) x[i] = std::log(ss->o.h.pi[t][i]);
         bfgs_minimise([&](const double* z) { return -ss->o.eval_lambda(t, z); }, x, tc_motif_separated_positions());
         ss->o.eval_lambda(t, x.data());
     }

@@ -27,9 +27,11 @@ struct SuffStatObjective {
     std::vector<double> G;             // [W] per-position terms under the current parameters
     long long evaluations = 0;
 
+    int EE = 0;                        // entries per position: E (order 0) or E1 (order-1 network, build_tables1_into)
     void init(const ModelHost& model, const double* c, double ent) {
         h = model;
-        counts.assign(c, c + (size_t)h.W * h.E);
+        EE = h.order == 1 ? h.E1() : h.E;
+        counts.assign(c, c + (size_t)h.W * EE);
         entropy = ent;
         G.assign(h.W, 0.0);
         for (int t = 0; t < h.W; ++t) G[t] = term(t, h.pi[t].data());
@@ -37,11 +39,12 @@ struct SuffStatObjective {
     // sum_e C[t][e] log table[e] for position t under the stationary distribution p (entries with a zero count never enter
     // the sum: their log may be -inf)
     double term(int t, const double* p) const {
-        std::vector<double> lt(h.E);
-        h.build_tables_into(t, p, lt.data(), nullptr);
-        const double* c = &counts[(size_t)t * h.E];
+        std::vector<double> lt(EE);
+        if (h.order == 1) h.build_tables1_into(t, p, lt.data());
+        else h.build_tables_into(t, p, lt.data(), nullptr);
+        const double* c = &counts[(size_t)t * EE];
         double s = 0.0;
-        for (int e = 0; e < h.E; ++e) if (c[e] != 0.0) s += c[e] * lt[e];
+        for (int e = 0; e < EE; ++e) if (c[e] != 0.0) s += c[e] * lt[e];
         return s;
     }
     double value() const {
@@ -50,10 +53,12 @@ struct SuffStatObjective {
         return s - entropy;
     }
     // evaluateFunction(lambda) of one position: pi_t = softmax(lambda); the object (like the reference's model) is left there
+    int dim(int t) const { return h.order == 1 ? h.ctx_rows(t) * 4 : 4; }
     double eval_lambda(int t, const double* lambda) {
-        double p[4];
-        lambda_to_pi(lambda, p, 4);
-        h.pi[t].assign(p, p + 4);
+        double p[16];
+        const int d = dim(t);                                  // an order-1 position t >= 1: four context rows, a softmax per row
+        lambda_to_pi(lambda, p, d);
+        h.pi[t].assign(p, p + d);
         G[t] = term(t, p);
         ++evaluations;
         return value();

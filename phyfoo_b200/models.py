@@ -216,13 +216,14 @@ class PhyloBayesModel(_PhyloModel):
             fe = sharding.ShardedObjective(local, self.ctx.device)
             sharding.broadcast_host_(order)
         try:
-            if self.MSTEP_SUFFICIENT_STATISTICS and self.order == 0 and not self.OPTIMIZE_IN_TOTO:
+            if self.MSTEP_SUFFICIENT_STATISTICS and self.order <= 1 and not self.OPTIMIZE_IN_TOTO:
                 # one device pass for the expected counts (all-reduced when sharded), then the position-wise BFGS on host dot
                 # products inside the library
                 if sharded:
-                    counts, entropy = local.suffstats(self.length, 4 + 16 * (self.tree.n_nodes - 1))
+                    n_entries = (16 + 32 * (self.tree.n_nodes - 1)) if self.order == 1 else (4 + 16 * (self.tree.n_nodes - 1))
+                    counts, entropy = local.suffstats(self.length, n_entries)
                     counts, entropy = sharding.allreduce_counts_(counts, entropy)
-                    desc, keep = _abi.make_desc(self.kind, self.length, 0, self.tree, self._branch, self._pi, type(self).EVOL_MODEL,
+                    desc, keep = _abi.make_desc(self.kind, self.length, self.order, self.tree, self._branch, self._pi, type(self).EVOL_MODEL,
                                                 _abi.MODE_MEANFIELD)
                     obj = core.SSObjective(desc=desc, counts=counts, entropy=entropy)
                     del keep
@@ -230,7 +231,7 @@ class PhyloBayesModel(_PhyloModel):
                     obj = core.SSObjective(local)
                 stats["f_before"], stats["f_after"], stats["evaluations"] = obj.optimize(order)
                 for t in range(self.length):
-                    self.setCondProb(obj.get_pi(t).reshape(self._pi[t].shape), t)
+                    self.setCondProb(obj.get_pi(t, self._pi[t].size).reshape(self._pi[t].shape), t)
                 obj.free()
                 self.trainingStep += 1
                 return stats
@@ -266,9 +267,9 @@ class PhyloBayesModel(_PhyloModel):
     def trainEdges(self, sample: PhyloSample, weights, globally=None, equal=None):
         """Branch-length learning on the fixed-q objective (optimizing/branchlengths/EdgeOptimizer.java:44-125,
         GlobalEdgeOptimizer.java): logit-parametrised branch lengths, BFGS until the objective changes by less than 1e-3.
-        One device pass collects the sufficient statistics; the optimisation itself runs on the host.  Order-0 models."""
-        if self.order != 0:
-            raise NotImplementedError("branch-length learning is implemented for order-0 models")
+        One device pass collects the sufficient statistics; the optimisation itself runs on the host.  Orders 0 and 1."""
+        if self.order == 1:
+            return self._trainEdges_order1(sample, weights, globally, equal)
         from . import evolution
         globally = (self.EDGE_LEARNING == 2) if globally is None else globally
         equal = self.EDGE_LEARNING_ONE_LENGTH if equal is None else equal
@@ -297,6 +298,59 @@ class PhyloBayesModel(_PhyloModel):
 
 def _neg(fg):
     return -fg[0], -fg[1]
+
+
+def _train_edges_order1(self, sample, weights, globally=None, equal=None):
+    """trainEdges for the order-1 network: the same optimisation on the library's sufficient-statistics objective
+    (phyfoo_ss_eval_branches over the expected counts of fe1_count_kernel)."""
+    from . import evolution
+    globally = (self.EDGE_LEARNING == 2) if globally is None else globally
+    equal = self.EDGE_LEARNING_ONE_LENGTH if equal is None else equal
+    ds = sample.device(self.ctx)
+    sa, so, sw = core.select(self.ctx, ds, self.length, weights, self.PROB_THRESH_FOR_WEIGHTS, self.MOTIF_QUALITY_THRESHOLD)
+    fe = core.FESet(self.ctx, ds, self.device_model(), sa, so, sw)
+    try:
+        obj = core.SSObjective(fe)
+    finally:
+        fe.free()
+    N = self.tree.n_nodes
+    before, evals, learned = obj.value(), 0, {}
+
+    def eval_edges(t, z):
+        alpha = evolution.branch_from_logit(z)
+        b = np.zeros(N)
+        b[1:] = alpha[0] if equal else alpha
+        learned[t] = b
+        return obj.eval_branches(-1 if globally else t, b)
+
+    def fd(fun, x, eps=1e-4):                  # jstacs NumericalDifferentiableFunction.java:64-84
+        x = np.array(x, np.float64)
+        f0, g = fun(x), np.zeros(x.size)
+        for i in range(x.size):
+            keep = x[i]
+            x[i] += eps
+            g[i] = (fun(x) - f0) / eps
+            x[i] = keep
+        fun(x)
+        return f0, g
+
+    for t in ([0] if globally else range(self.length)):
+        b = self._branch[t, 1:]
+        x0 = evolution.logit_from_branch(np.array([b.mean()]) if equal else b)
+        fun = lambda z: -eval_edges(t, z)                                   # noqa: E731
+        x, f, it, ev = optimize.quasi_newton_bfgs(fun, lambda z: fd(fun, z), x0, optimize.SMALL_DIFFERENCE_OF_FUNCTIONS())
+        eval_edges(t, x)
+        evals += ev
+    after = obj.value()
+    obj.free()
+    for t in range(self.length):
+        b = learned[0] if globally else learned[t]
+        for k in range(1, N):
+            self.setBranchLength(t, k, float(b[k]))
+    return {"f_before": before, "f_after": after, "evaluations": evals, "selected": int(sa.size)}
+
+
+PhyloBayesModel._trainEdges_order1 = _train_edges_order1
 
 
 class PhyloBackground(_PhyloModel):

@@ -141,6 +141,22 @@ def test_order1_fixed_q_objective_and_gradient(ctx, tree, gap_rate):
         fe.eval(t, np.log(pwm[t].ravel())); ofe.eval(t, np.log(pwm[t].ravel()))
     direct = sum(w * om.score_window(c)[0] for w, c in zip(sw, cols))
     assert abs(fe.eval(0, np.log(pwm[0].ravel())) - direct) <= 1e-9 * abs(direct)
+    # the same objective from sufficient statistics (fe1_count_kernel + host dot products inside the library): value and
+    # forward-difference gradient equal the per-window evaluation along a walk over the positions, also after branch changes
+    ss = core.SSObjective(fe)
+    assert abs(ss.value() - direct) <= 1e-10 * abs(direct)
+    for pos in (1, 0, W - 1, 1):
+        rows = 1 if pos == 0 else 4
+        lam = (np.log(rng.dirichlet(np.ones(4), size=rows)) + rng.normal(size=(rows, 1))).ravel()
+        f, rf = ss.eval(pos, lam), fe.eval(pos, lam)
+        assert abs(f - rf) <= 1e-11 * abs(rf), (pos, f, rf)
+        f0, g = ss.grad(pos, lam, EPS)
+        r0, rg = fe.grad(pos, lam, EPS)
+        assert abs(f0 - r0) <= 1e-11 * abs(r0) and np.all(np.abs(g - rg) <= tol(rg, r0))
+        assert np.allclose(ss.get_pi(pos, 4 * rows), fg.device_model().get_pi(pos, 4 * rows), rtol=0, atol=1e-15)
+    with pytest.raises(ValueError):
+        ss.eval(1, np.zeros(4))                                    # an order-1 position t >= 1 has 16 parameters
+    ss.free()
 
 
 @pytest.mark.parametrize("tree", ["star5", "cat5", "mixed6", "rand12"])
