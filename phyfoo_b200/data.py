@@ -7,6 +7,8 @@ dropped (:196-223), and symbols are coded A,C,G,T,- -> 0..4 case-insensitively
 (jstacs UnobservableDNAAlphabet.java:116).  The reference iterates genes in Java HashSet order; here genes keep
 the order of their first record.
 """
+import re
+
 import numpy as np
 
 from . import core
@@ -60,8 +62,33 @@ def read_fasta(path):
     return records
 
 
+_BRANCH = re.compile(r":([0-9]*\.[0-9]*)")          # the pattern of io/PhyloSample.java:283 and bayesNet/VirtualTree.java:240
+
+
+def combineBranchLengths(newick1: str, newick2: str, weight: float) -> str:
+    """io/PhyloSample.java:272-310: newick1 with every branch length replaced by weight * its own + (1 - weight) * the
+    length at the same place of newick2 (lengths are matched by their order of appearance), printed like
+    String.valueOf(double)."""
+    from .xmlio import jdouble
+    d1 = [float(m.group(1)) for m in _BRANCH.finditer(newick1)]
+    d2 = [float(m.group(1)) for m in _BRANCH.finditer(newick2)]
+    if len(d2) < len(d1):
+        raise IndexError("the second tree has fewer branch lengths than the first")       # DoubleList.get out of range
+    out, last = [], 0
+    for s, m in enumerate(_BRANCH.finditer(newick1)):
+        out.append(newick1[last:m.start(1)])
+        out.append(jdouble(d1[s] * weight + d2[s] * (1 - weight)))
+        last = m.end(1)
+    out.append(newick1[last:])
+    return "".join(out)
+
+
 class PhyloSample:
-    """A sample of multiple alignments: codes [sum L_i][S] (uint8, 0..4) + col_offsets [n+1]."""
+    """A sample of multiple alignments: codes [sum L_i][S] (uint8, 0..4) + col_offsets [n+1].  `learnedTopology` (None, or one
+    Newick string or None per alignment; set by training.learnTopologies = PhyloSample.train of the reference,
+    io/PhyloSample.java:243-270) makes the models score an alignment under its own branch lengths."""
+
+    combineBranchLengths = staticmethod(combineBranchLengths)
 
     def __init__(self, codes, col_offsets, species=None, genes=None, annotations=None):
         self.codes = np.ascontiguousarray(codes, np.uint8)
@@ -71,6 +98,7 @@ class PhyloSample:
         self.species = list(species) if species is not None else None
         self.genes = list(genes) if genes is not None else None
         self.annotations = annotations
+        self.learnedTopology = None
         self._device = {}
 
     # ---- constructors -------------------------------------------------------------------------
@@ -142,9 +170,11 @@ class PhyloSample:
         the number of species."""
         lo, hi = int(lo), int(hi)
         c0, c1 = int(self.col_offsets[lo]), int(self.col_offsets[hi])
-        return PhyloSample(self.codes[c0:c1], self.col_offsets[lo:hi + 1] - c0, species=self.species,
-                           genes=self.genes[lo:hi] if self.genes else None,
-                           annotations=self.annotations[lo:hi] if self.annotations else None)
+        out = PhyloSample(self.codes[c0:c1], self.col_offsets[lo:hi + 1] - c0, species=self.species,
+                          genes=self.genes[lo:hi] if self.genes else None,
+                          annotations=self.annotations[lo:hi] if self.annotations else None)
+        out.learnedTopology = self.learnedTopology[lo:hi] if self.learnedTopology else None
+        return out
 
     def shard(self, rank, world):
         """Contiguous block of alignments balanced by column count; every rank gets at least one

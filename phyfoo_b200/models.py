@@ -9,12 +9,13 @@ these classes score the whole sample in one library call and serve per-window qu
   StrandModel                jstacs de/jstacs/models/mixture/StrandModel.java (forward + reverse complement)
   SingleHiddenMotifMixture   jstacs de/jstacs/models/mixture/motif/SingleHiddenMotifMixture.java (ZOOPS E-step)
 """
+import contextlib
 import math
 
 import numpy as np
 
 from . import _abi, core, optimize
-from .data import PhyloSample
+from .data import PhyloSample, combineBranchLengths
 from .newick import parse_newick
 
 
@@ -103,6 +104,12 @@ class _PhyloModel:
                 for k in range(1, tr.n_nodes):
                     self._dev.set_branch(t, k, tr.branch[k])
 
+    def getNewickString(self, position=0):
+        """getBNH().getVirtualTree(position).getNewickString() (bayesNet/VirtualTree.java:63-66,208-234): branch lengths
+        rounded to three decimals."""
+        from . import xmlio
+        return xmlio.newick_string(self.tree, self._branch[position])
+
     def setBranchLength(self, position, node, length):
         self._branch[position, node] = length
         if self._dev is not None:
@@ -126,6 +133,58 @@ class _PhyloModel:
     def _check(self, sample):
         if sample.n_species != self.tree.n_species:
             raise ValueError("The sample's number of species differs from the tree's number of leaves")
+
+    # ---- per-alignment learned topologies (models/PhyloBackground.java:250-253,301-303; PhyloBayesModel.java:233-247,263-265) ----
+    @contextlib.contextmanager
+    def _under_topology(self, topology):
+        """The model with the branch lengths of `topology` (an alignment's learnedTopology) for the duration of a call, as the
+        reference's getLogProbFor does per sequence.  Afterwards the branch lengths are those of the Newick strings taken
+        before, i.e. ROUNDED to three decimals (getNewickString) -- the reference's side effect, kept; a background model
+        resets every position to the string of position 0.  topology = None: nothing happens."""
+        if topology is None:
+            yield
+            return
+        old = [self.getNewickString(t) for t in range(self.n_trees)]
+        if self.kind == _abi.MODEL_FG:
+            self.reinitEdgelengths(*[combineBranchLengths(topology, o, 1.0) for o in old])
+        else:
+            self.reinitEdgelengths(topology)
+        try:
+            yield
+        finally:
+            if self.kind == _abi.MODEL_FG:
+                self.reinitEdgelengths(*old)
+            else:
+                self.reinitEdgelengths(old[0])
+
+    def _per_topology(self, sample, fn):
+        """fn(sample) for a sample without learned topologies; otherwise fn over every run of consecutive alignments with the
+        same learnedTopology (each under that topology, in alignment order -- one batch call per run) and the list of the
+        results.  Returns (results, split) with split = False when fn ran once on the whole sample."""
+        runs = topology_runs(sample)
+        if runs is None:
+            return [fn(sample)], False
+        out = []
+        for lo, hi, topo in runs:
+            with self._under_topology(topo):
+                out.append(fn(sample.slice(lo, hi)))
+        return out, True
+
+
+def topology_runs(sample):
+    """None when no alignment of the sample carries a learnedTopology, else [(lo, hi, topology or None)] over runs of
+    consecutive alignments with the same one."""
+    topo = getattr(sample, "learnedTopology", None)
+    if not topo or all(t is None for t in topo):
+        return None
+    runs, i, n = [], 0, sample.n_alignments
+    while i < n:
+        j = i + 1
+        while j < n and topo[j] == topo[i]:
+            j += 1
+        runs.append((i, j, topo[i]))
+        i = j
+    return runs
 
 
 class PhyloBayesModel(_PhyloModel):
@@ -157,8 +216,14 @@ class PhyloBayesModel(_PhyloModel):
         """Scores of every window of every alignment (alignment-major, offsets ascending) =
         PhyloBayesModel.getLogProbFor(seq, j, j+W-1) for all (seq, j)  (models/PhyloBayesModel.java:222-267)."""
         self._check(sample)
-        out, sw, st = core.score_windows(self.ctx, sample.device(self.ctx), self.device_model(), strand, want_sweeps)
-        self.last_stats = st
+
+        def score(smp):
+            out, sw, st = core.score_windows(self.ctx, smp.device(self.ctx), self.device_model(), strand, want_sweeps)
+            self.last_stats = st
+            return out, sw
+        parts, split = self._per_topology(sample, score)          # alignments with a learnedTopology: under their own branch lengths
+        out = np.concatenate([p[0] for p in parts]) if split else parts[0][0]
+        sw = (np.concatenate([p[1] for p in parts]) if split else parts[0][1]) if want_sweeps else None
         return (out, sw) if want_sweeps else out
 
 
@@ -300,20 +365,14 @@ def _neg(fg):
     return -fg[0], -fg[1]
 
 
-def _train_edges_order1(self, sample, weights, globally=None, equal=None):
-    """trainEdges for the order-1 network: the same optimisation on the library's sufficient-statistics objective
-    (phyfoo_ss_eval_branches over the expected counts of fe1_count_kernel)."""
+def _learn_edges(model, obj, globally, equal):
+    """EdgeOptimizer.startOptimizing for every position (one run for all positions when `globally`) on the library's
+    sufficient-statistics objective `obj` (phyfoo_ss_eval_branches): logit-parametrised branch lengths from the model's current
+    ones (their mean when `equal`), BFGS on the forward-difference gradient until the objective changes by less than 1e-3
+    (optimizing/branchlengths/EdgeOptimizer.java:44-125, GlobalEdgeOptimizer.java:33-103).  Writes the learned lengths into
+    the model; returns (f_before, f_after, evaluations)."""
     from . import evolution
-    globally = (self.EDGE_LEARNING == 2) if globally is None else globally
-    equal = self.EDGE_LEARNING_ONE_LENGTH if equal is None else equal
-    ds = sample.device(self.ctx)
-    sa, so, sw = core.select(self.ctx, ds, self.length, weights, self.PROB_THRESH_FOR_WEIGHTS, self.MOTIF_QUALITY_THRESHOLD)
-    fe = core.FESet(self.ctx, ds, self.device_model(), sa, so, sw)
-    try:
-        obj = core.SSObjective(fe)
-    finally:
-        fe.free()
-    N = self.tree.n_nodes
+    N = model.tree.n_nodes
     before, evals, learned = obj.value(), 0, {}
 
     def eval_edges(t, z):
@@ -334,19 +393,37 @@ def _train_edges_order1(self, sample, weights, globally=None, equal=None):
         fun(x)
         return f0, g
 
-    for t in ([0] if globally else range(self.length)):
-        b = self._branch[t, 1:]
+    for t in ([0] if globally else range(model.n_trees)):
+        b = model._branch[t, 1:]
         x0 = evolution.logit_from_branch(np.array([b.mean()]) if equal else b)
         fun = lambda z: -eval_edges(t, z)                                   # noqa: E731
         x, f, it, ev = optimize.quasi_newton_bfgs(fun, lambda z: fd(fun, z), x0, optimize.SMALL_DIFFERENCE_OF_FUNCTIONS())
         eval_edges(t, x)
         evals += ev
     after = obj.value()
-    obj.free()
-    for t in range(self.length):
+    for t in range(model.n_trees):
         b = learned[0] if globally else learned[t]
         for k in range(1, N):
-            self.setBranchLength(t, k, float(b[k]))
+            model.setBranchLength(t, k, float(b[k]))
+    return before, after, evals
+
+
+def _train_edges_order1(self, sample, weights, globally=None, equal=None):
+    """trainEdges for the order-1 network: the same optimisation on the library's sufficient-statistics objective
+    (phyfoo_ss_eval_branches over the expected counts of fe1_count_kernel)."""
+    globally = (self.EDGE_LEARNING == 2) if globally is None else globally
+    equal = self.EDGE_LEARNING_ONE_LENGTH if equal is None else equal
+    ds = sample.device(self.ctx)
+    sa, so, sw = core.select(self.ctx, ds, self.length, weights, self.PROB_THRESH_FOR_WEIGHTS, self.MOTIF_QUALITY_THRESHOLD)
+    fe = core.FESet(self.ctx, ds, self.device_model(), sa, so, sw)
+    try:
+        obj = core.SSObjective(fe)
+    finally:
+        fe.free()
+    try:
+        before, after, evals = _learn_edges(self, obj, globally, equal)
+    finally:
+        obj.free()
     return {"f_before": before, "f_after": after, "evaluations": evals, "selected": int(sa.size)}
 
 
@@ -376,8 +453,14 @@ class PhyloBackground(_PhyloModel):
         """Per-column terms whose sum over [start, end] is getLogProbFor(seq, start, end)
         (models/PhyloBackground.java:241-305; order 0: independent columns)."""
         self._check(sample)
-        out, sw, st = core.bg_columns(self.ctx, sample.device(self.ctx), self.device_model(), want_sweeps)
-        self.last_stats = st
+
+        def score(smp):
+            out, sw, st = core.bg_columns(self.ctx, smp.device(self.ctx), self.device_model(), want_sweeps)
+            self.last_stats = st
+            return out, sw
+        parts, split = self._per_topology(sample, score)
+        out = np.concatenate([p[0] for p in parts]) if split else parts[0][0]
+        sw = (np.concatenate([p[1] for p in parts]) if split else parts[0][1]) if want_sweeps else None
         return (out, sw) if want_sweeps else out
 
     def getRangeTerms(self, sample: PhyloSample):
@@ -386,11 +469,15 @@ class PhyloBackground(_PhyloModel):
         if self.order != 1:
             raise ValueError("getRangeTerms is for order-1 backgrounds; order 0 uses getColumnLogProbs")
         self._check(sample)
-        ds = sample.device(self.ctx)
-        cond, first = np.zeros(ds.n_cols), np.zeros(ds.n_cols)
-        core.raise_for(core.lib().phyfoo_bg_columns_order1(self.ctx.h, ds.h, self.device_model().h, core._p(cond, core.C.c_double),
-                                                           core._p(first, core.C.c_double)), self.ctx.h)
-        return cond, first
+
+        def terms(smp):
+            ds = smp.device(self.ctx)
+            cond, first = np.zeros(ds.n_cols), np.zeros(ds.n_cols)
+            core.raise_for(core.lib().phyfoo_bg_columns_order1(self.ctx.h, ds.h, self.device_model().h, core._p(cond, core.C.c_double),
+                                                               core._p(first, core.C.c_double)), self.ctx.h)
+            return cond, first
+        parts, split = self._per_topology(sample, terms)
+        return (np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])) if split else parts[0]
 
     def getLogProbForRange(self, sample: PhyloSample, aln, start, end):
         """getLogProbFor(seq, start, end) for one alignment (end inclusive)."""
@@ -414,23 +501,54 @@ class PhyloBackground(_PhyloModel):
         return np.array([cols[off[i]:off[i + 1]].sum() for i in range(sample.n_alignments)])
 
 
+    TRAIN_MOTIF = True                 # models/PhyloBackground.java:41
+    EDGE_LEARNING = False              # :43
+    EDGE_LEARNING_ONE_LENGTH = False   # models/AbstractPhyloModel.java:25
+    # True: the evaluations of the optimisers are host dot products over the expected counts of ONE device pass
+    # (phyfoo_ss_*); False: a device pass over every column per evaluation of the pi objective (the reference's order of work)
+    MSTEP_SUFFICIENT_STATISTICS = True
+
     def train(self, sample: PhyloSample, weights=None):
         """models/PhyloBackground.java:111-176 (order 0): objective over every column of every alignment with per-alignment
-        weights, q fixed after one mean-field pass, BFGS until the objective changes by less than 1e-3."""
+        weights (extendWeights :178-186 reads one weight per alignment of `sample`, so a longer vector is cut), q fixed after
+        one mean-field pass; TRAIN_MOTIF: BFGS on pi until the objective changes by less than 1e-3; EDGE_LEARNING: then the
+        branch lengths (EdgeOptimizer, per position, EDGE_LEARNING_ONE_LENGTH = one length for all branches) on the same
+        fixed q."""
         self._check(sample)
         if self.order != 0:
             raise NotImplementedError("background models of order >= 1 are not supported (DESIGN.md)")
+        if weights is not None:
+            weights = np.ascontiguousarray(np.asarray(weights, np.float64)[:sample.n_alignments])
+        stats = {"f_before": None, "f_after": None, "evaluations": 0, "iterations": 0}
         fe = core.FESet(self.ctx, sample.device(self.ctx), self.device_model(), aln_weights=weights)
+        obj = None
         try:
             lam0 = np.log(self._pi[0].ravel())
-            before = fe.eval(0, lam0)
-            x, f, it, ev = optimize.quasi_newton_bfgs(lambda z: -fe.eval(0, z), lambda z: _neg(fe.grad(0, z)), lam0,
-                                                      optimize.SMALL_DIFFERENCE_OF_FUNCTIONS())
-            after = fe.eval(0, x)
-            self._pi[0] = self._dev.get_pi(0, 4).reshape(1, 4)
+            if type(self).MSTEP_SUFFICIENT_STATISTICS or type(self).EDGE_LEARNING:
+                obj = core.SSObjective(fe)
+            if type(self).TRAIN_MOTIF:
+                ev_obj = obj if type(self).MSTEP_SUFFICIENT_STATISTICS else fe
+                stats["f_before"] = ev_obj.eval(0, lam0)
+                x, f, it, ev = optimize.quasi_newton_bfgs(lambda z: -ev_obj.eval(0, z), lambda z: _neg(ev_obj.grad(0, z)), lam0,
+                                                          optimize.SMALL_DIFFERENCE_OF_FUNCTIONS())
+                stats["f_after"] = ev_obj.eval(0, x)
+                stats["evaluations"], stats["iterations"] = ev, it
+                pi = ev_obj.get_pi(0, 4) if ev_obj is obj else self._dev.get_pi(0, 4)
+                self.setCondProb(pi.reshape(1, 4), 0)
+                if obj is not None and ev_obj is not obj:
+                    obj.eval(0, np.log(pi))                      # the edge objective continues from the new pi
+            if type(self).EDGE_LEARNING:
+                before, after, evals = _learn_edges(self, obj, False, type(self).EDGE_LEARNING_ONE_LENGTH)
+                stats["edges_f_before"], stats["edges_f_after"] = before, after
+                stats["evaluations"] += evals
+                if stats["f_before"] is None:
+                    stats["f_before"] = before
+                stats["f_after"] = after
         finally:
+            if obj is not None:
+                obj.free()
             fe.free()
-        return {"f_before": before, "f_after": after, "evaluations": ev, "iterations": it}
+        return stats
 
 
 class StrandModel:
@@ -538,12 +656,38 @@ class SingleHiddenMotifMixture:
         gamma (seqweights[0] per window), w (sufficient statistics of the component weights), ll, argmax_off/strand."""
         with np.errstate(divide="ignore"):
             logw = np.log(self.weights)
-        res = core.zoops_estep(self.motif.ctx, sample.device(self.motif.ctx), self.motif.device_model(),
-                               self.flanking.device_model(), logw,
-                               None if self.strand is None else self.strand.logWeights(),
-                               seqWeights, want_gamma, want_profile, True, out)
+        runs = topology_runs(sample)
+        if runs is not None:
+            res = self._estep_per_topology(sample, runs, logw, seqWeights, want_gamma, want_profile)
+        else:
+            res = core.zoops_estep(self.motif.ctx, sample.device(self.motif.ctx), self.motif.device_model(),
+                                   self.flanking.device_model(), logw,
+                                   None if self.strand is None else self.strand.logWeights(),
+                                   seqWeights, want_gamma, want_profile, True, out)
         self.last = res
         return res
+
+    def _estep_per_topology(self, sample, runs, logw, seqWeights, want_gamma, want_profile):
+        """The E-step over a sample whose alignments carry learned topologies: one batch call per run of alignments with the
+        same topology, motif and flanking model both under that run's branch lengths (the reference re-initialises them inside
+        every getLogProbFor call); ll and w add up over the runs, the per-window and per-alignment results are concatenated.
+        (The posteriors of such an E-step do not stay resident on the device for a following train(sample, None).)"""
+        sl = None if self.strand is None else self.strand.logWeights()
+        parts = []
+        for lo, hi, topo in runs:
+            with self.motif._under_topology(topo), self.flanking._under_topology(topo):
+                sub = sample.slice(lo, hi)
+                parts.append(core.zoops_estep(self.motif.ctx, sub.device(self.motif.ctx), self.motif.device_model(),
+                                              self.flanking.device_model(), logw, sl,
+                                              None if seqWeights is None else np.asarray(seqWeights, np.float64)[lo:hi],
+                                              want_gamma, want_profile, True, None))
+        cat = lambda k: None if parts[0][k] is None else np.concatenate([p[k] for p in parts])      # noqa: E731
+        stats = dict(parts[-1]["stats"])
+        for k in stats:
+            if isinstance(stats[k], (int, float)):
+                stats[k] = sum(p["stats"][k] for p in parts)
+        return {"gamma": cat("gamma"), "profile": cat("profile"), "w": sum(p["w"] for p in parts), "ll": math.fsum(p["ll"] for p in parts),
+                "argmax_off": cat("argmax_off"), "argmax_strand": cat("argmax_strand"), "stats": stats}
 
     def setComponentWeights(self, w):
         """AbstractMixtureModel.getNewComponentProbs (jstacs :1542-1578): (w + hyper) normalised."""
