@@ -157,6 +157,19 @@ int phyfoo_bg_columns(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* b
  * flank ranges of every offset as the reference's call order produces them.  Alignments shorter than 2 columns are refused. */
 int phyfoo_bg_columns_order1(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* bg, double* cond_out, double* first_out);
 
+/* Background of ANY order k >= 1 (models/PhyloBackground.java:241-305, structure :381-398) through the generic net kernel
+ * (csrc/netg.cuh: parent / child lists and full CPF tables of up to 4^(k+1) rows, one thread per (k+1)-column window):
+ *   first_out[c] = - sum of the free energies of the single trees 0 .. k-1 of the window starting at column c   (:273-283)
+ *   cond_out[c]  = - free energy of the last tree of the window ending at column c                               (:284-297)
+ * (0 where the window would leave its alignment), so that for a range of at least k + 1 columns
+ *   getLogProbFor(seq, s, e) = first[s] + sum cond[s+k .. e].
+ * Shorter ranges have no value of their own in the reference (their trailing trees keep the observation of an earlier call,
+ * MeanFieldForBayesNet.java:84); phyfoo_zoops_estep with such a background reproduces the flank ranges of every offset as the
+ * reference's call order produces them.  sweeps_out (nullable): mean-field sweeps per (k+1)-column window, alignment-major.
+ * k = 1 gives the values of phyfoo_bg_columns_order1.  Alignments shorter than k + 1 columns are refused; k <= 7. */
+int phyfoo_bg_range_terms(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* bg, double* cond_out, double* first_out,
+                          int32_t* sweeps_out);
+
 /* ZOOPS E-step over the whole (local) sample: SingleHiddenMotifMixture.getNewWeights.
  *   logw[2]          log component weights (motif, no motif)
  *   strand_logw      NULL, or log strand weights [2] (motif wrapped in a StrandModel)
@@ -332,7 +345,10 @@ int phyfoo_set_option(phyfoo_ctx* ctx, const char* name, int64_t value);
  * tree (below), 1 = its precompiled form for tables with F81 structure, 0 = the generic kernel; -1 (default) = 2, then 1 for
  * more than 6 species, else 0.  Kernels 1 and 2 are bit-identical; kernel 0 agrees with them to re-association.
  * "l2_persist" (default 1): per-window state kept in global memory (the q rows of the order-1 kernel, the state of very large
- * trees) is covered by an L2 access-policy window on the library's stream for the duration of the launch. */
+ * trees) is covered by an L2 access-policy window on the library's stream for the duration of the launch.
+ * "bg_generic" (default 0): 1 = an order-1 background inside phyfoo_zoops_estep goes through the generic net kernel
+ * (csrc/netg.cuh) that backgrounds of order >= 2 always use, instead of the order-1 wavefront kernel; same values to
+ * re-association (a cross-check of the two statements of the mean field). */
 /* Device time of every kernel the most recent call launched (CUDA events on the library's stream), in launch order:
  * returns the number of entries written (<= max_entries) or a negative error; names are static strings. */
 int phyfoo_last_kernel_times(phyfoo_ctx* ctx, int32_t max_entries, const char** names_out, float* ms_out);

@@ -215,6 +215,58 @@ struct ModelHost {
         return out;
     }
 
+    // ---- generic net (netg.cuh): any order, the reference's parent / child lists and full CPF tables ----------------------
+    // horizontal parents of tree t, nearest first (PhyloBackground.java:389-393; PhyloBayesModel.java:363-365)
+    std::vector<int> horizontal_parents(int t) const {
+        std::vector<int> v;
+        if (kind == PHYFOO_MODEL_FG) { if (order == 1 && t > 0) v.push_back(t - 1); }
+        else for (int j = 0; j < order; ++j) if (t - j > 0) v.push_back(t - j - 1);
+        return v;
+    }
+    // rec [W * N][9], lists (parent ids; (child id, index among the child's parents) pairs), tab (log CPF, log independent table)
+    void netg_build(std::vector<int>& rec, std::vector<int>& lists, std::vector<double>& tab) const {
+        const int G = W * N;
+        rec.assign((size_t)G * 9, 0); lists.clear(); tab.clear();
+        std::vector<std::vector<int>> par(G), chi(G);
+        for (int t = 0; t < W; ++t)
+            for (int k = 0; k < N; ++k) {
+                if (k > 0) par[t * N + k].push_back(t * N + parent[k]);
+                for (int k2 = k + 1; k2 < N; ++k2) if (parent[k2] == k) chi[t * N + k].push_back(t * N + k2);
+            }
+        for (int t = 0; t < W; ++t)                                   // BayesNetHandler.connectVirtualTrees :230-256, in call order
+            for (int hp : horizontal_parents(t))
+                for (int k = 0; k < N; ++k) { chi[hp * N + k].push_back(t * N + k); par[t * N + k].push_back(hp * N + k); }
+        for (int t = 0; t < W; ++t) {
+            const int ctx = ctx_rows(t);
+            for (int k = 0; k < N; ++k) {
+                const int g = t * N + k;
+                int* r = &rec[(size_t)g * 9];
+                r[0] = (int)par[g].size(); r[1] = (int)lists.size();
+                lists.insert(lists.end(), par[g].begin(), par[g].end());
+                r[2] = (int)chi[g].size(); r[3] = (int)lists.size();
+                for (int c : chi[g]) {
+                    int idx = -1;
+                    for (size_t q = 0; q < par[c].size(); ++q) if (par[c][q] == g) idx = (int)q;
+                    lists.push_back(c); lists.push_back(idx);
+                }
+                int rows = 1;
+                for (int q = 0; q < r[0]; ++q) rows *= 4;
+                r[6] = rows; r[7] = leaf_species[k]; r[8] = t;
+                const std::vector<double> cp = cpf(t, k);
+                if ((int)cp.size() != rows * 4) throw std::invalid_argument("netg: table shape");
+                r[4] = (int)tab.size();
+                for (double x : cp) tab.push_back(std::log(x));
+                r[5] = r[4];
+                if (leaf_species[k] >= 0) {                            // independent table: pi of the row's context, FS81alpha.java:52-64
+                    r[5] = (int)tab.size();
+                    for (int c = 0; c < ctx; ++c)
+                        for (int a = 0; a < 4; ++a)
+                            for (int b = 0; b < 4; ++b) tab.push_back(std::log(pi[t][(size_t)c * 4 + b]));
+                }
+            }
+        }
+    }
+
     bool tables_finite() const {
         if (order >= 1) {
             std::vector<double> t1;

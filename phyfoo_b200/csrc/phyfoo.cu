@@ -81,6 +81,7 @@ struct phyfoo_ctx {
     cudaStream_t aux = nullptr;      // second trajectory phase of the pattern-table path
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     DevBuf memo_state;               // mean-field state of every (pattern, position) tree between the two phases
+    int bg_generic = 0;              // 1: an order-1 background goes through the generic net kernel too (netg.cuh; cross-checks)
     int order1_kernel = 2;           // 0 = one quad per window (net1.cuh), 1 = wavefront, 16 lanes per window (net1w.cuh),
                                      // 2 = one thread per node (net1n.cuh; windows with gaps through the wavefront kernel)
     DevBuf memo_pending;             // fallback list of the pattern-table path
@@ -137,6 +138,10 @@ struct phyfoo_model {
     int* d_prog1n = nullptr;
     int prog1n_len = 0, MC1n = 1, n_steps1n = 0;
     double f0_const1n = 0.0;
+    // generic net (netg.cuh): background models of order >= 2
+    int* d_netg_rec = nullptr; int* d_netg_lists = nullptr; double* d_netg_tab = nullptr;
+    size_t netg_lists_len = 0, netg_tab_len = 0;
+    uint64_t netg_uploaded = 0;
 };
 
 static thread_local std::string g_init_err;
@@ -355,6 +360,7 @@ struct ZoopsParams {
     // order-1 background (nullable): start terms per column, single-column ranges bg(j + W, e) per column and bg(s, j - 1) per
     // window (bg1_terms_device); a_j = prior + motif - bg(s, e) + bg(s, j - 1) + bg(j + W, e), s = max(j - 1, 0), e = min(j + W, L - 1)
     const double* bg1_first; const double* bg1_single; const double* bg1_left;
+    const double* bgk_right; int bg_order;   // generic path (any order k): the right flank per offset; s = max(j-k, 0), e = min(j+W+k-1, L-1)
     const int64_t* col_off; const int64_t* win_off; int n_aln; int W;
     double logw0, logw1; int has_strand; double slw0, slw1;
     const double* aln_w;                     // nullable
@@ -421,11 +427,12 @@ __global__ void __launch_bounds__(256) zoops_kernel(ZoopsParams p) {
         double bgw = 0.0;
         if (!o1) for (int m = 0; m < p.W; ++m) bgw += bgc[j + m];    // bg(s,e), order 0: s=j, e=j+W-1
         else {
-            const int s = j > 0 ? j - 1 : 0, e = j + p.W < L - 1 ? j + p.W : L - 1;
+            const int ko = p.bg_order;
+            const int s = j > ko ? j - ko : 0, e = j + p.W + ko - 1 < L - 1 ? j + p.W + ko - 1 : L - 1;
             bgw = p.bg1_first[c0 + s];
-            for (int u = s + 1; u <= e; ++u) bgw += bgc[u];
+            for (int u = s + ko; u <= e; ++u) bgw += bgc[u];
             if (j > 0) bgw -= p.bg1_left[w0 + j];                     // + bg(s, j-1)
-            if (j + p.W <= L - 1) bgw -= p.bg1_single[c0 + j + p.W];  // + bg(j+W, e)
+            if (j + p.W <= L - 1) bgw -= p.bgk_right ? p.bgk_right[w0 + j] : p.bg1_single[c0 + j + p.W];  // + bg(j+W, e)
         }
         const double aj = lprior + motif - bgw;                       // :536-540
         if (p.profile) p.profile[w0 + j] = aj;
@@ -457,11 +464,12 @@ __global__ void __launch_bounds__(256) zoops_kernel(ZoopsParams p) {
             double bgw = 0.0;
             if (!o1) for (int m = 0; m < p.W; ++m) bgw += p.bgcol[c0 + j + m];
             else {
-                const int s = j > 0 ? j - 1 : 0, e = j + p.W < L - 1 ? j + p.W : L - 1;
+                const int ko = p.bg_order;
+                const int s = j > ko ? j - ko : 0, e = j + p.W + ko - 1 < L - 1 ? j + p.W + ko - 1 : L - 1;
                 bgw = p.bg1_first[c0 + s];
-                for (int u = s + 1; u <= e; ++u) bgw += p.bgcol[c0 + u];
+                for (int u = s + ko; u <= e; ++u) bgw += p.bgcol[c0 + u];
                 if (j > 0) bgw -= p.bg1_left[w0 + j];
-                if (j + p.W <= L - 1) bgw -= p.bg1_single[c0 + j + p.W];
+                if (j + p.W <= L - 1) bgw -= p.bgk_right ? p.bgk_right[w0 + j] : p.bg1_single[c0 + j + p.W];
             }
             aj = lprior + motif - bgw;
         }
@@ -822,6 +830,7 @@ extern "C" void phyfoo_model_free(phyfoo_ctx* ctx, phyfoo_model* m) {
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
     cudaFree(m->d_prog); cudaFree(m->d_logtab); cudaFree(m->d_probtab); cudaFree(m->d_tab1); cudaFree(m->d_tab1w); cudaFree(m->d_prog1w);
     cudaFree(m->d_tab1n); cudaFree(m->d_leaftab1n); cudaFree(m->d_prog1n); cudaFree(m->d_tabf);
+    cudaFree(m->d_netg_rec); cudaFree(m->d_netg_lists); cudaFree(m->d_netg_tab);
     delete m;
 }
 
@@ -829,7 +838,7 @@ extern "C" void phyfoo_model_free(phyfoo_ctx* ctx, phyfoo_model* m) {
 static int model_upload(phyfoo_ctx* ctx, phyfoo_model* m) {
     ModelHost& h = m->h;
     if (h.order != 0 && h.order != 1)
-        return fail(ctx, PHYFOO_EUNSUPPORTED, "background models of order >= 2 are not implemented in this build");
+        return fail(ctx, PHYFOO_EUNSUPPORTED, "a background model of order >= 2 is scored through phyfoo_bg_range_terms / phyfoo_zoops_estep (generic net kernel) only");
     if (m->uploaded == h.version) return PHYFOO_OK;
     if (h.order == 1) {
         std::vector<double> t1, t1w, t1n, tl1n;
@@ -974,6 +983,7 @@ struct ScoreItems {
 #include "net1.cuh"
 #include "net1w.cuh"
 #include "net1n.cuh"
+#include "netg.cuh"
 #include "tree_pass_f81.cuh"
 #include "jit_o0.hpp"
 #include "memo.cuh"
@@ -1795,7 +1805,7 @@ extern "C" int phyfoo_score_windows(phyfoo_ctx* ctx, const phyfoo_dataset* ds, p
 // per-column background scores (order 0): the same kernel with windows of width 1
 static int launch_bg_columns(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* bg, double* d_out, int32_t* d_sweeps, int slot) {
     if (bg->h.kind != PHYFOO_MODEL_BG) return fail(ctx, PHYFOO_EINVAL, "bg_columns: model is not a background model");
-    if (bg->h.order != 0) return fail(ctx, PHYFOO_EUNSUPPORTED, "background order >= 1 is not implemented in this build");
+    if (bg->h.order != 0) return fail(ctx, PHYFOO_EUNSUPPORTED, "bg_columns is for order 0: a background of order >= 1 has range terms (phyfoo_bg_range_terms)");
     return launch_score(ctx, ds, bg, ds->d_col_off, ds->n_cols, 0, d_out, d_sweeps, slot);
 }
 
@@ -1910,6 +1920,175 @@ static int bg1_terms_device(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_mo
     return PHYFOO_OK;
 }
 
+// ---- background models of any order >= 1 through the generic net kernel (netg.cuh) ------------------------------------------
+// Items name the column of every tree.  Full windows (order + 1 consecutive columns of an alignment) give, per column c,
+//   first[c] = - sum of the free energies of the single trees 0 .. order-1 of the window starting at c   (PhyloBackground.java:273-283)
+//   cond[c]  = - free energy of the last tree of the window ending at c                                    (:284-297)
+// so that getLogProbFor(seq, s, e) = first[s] + sum cond[s+order .. e] for ranges of at least order + 1 columns.  The ZOOPS E-step
+// (jstacs SingleHiddenMotifMixture.java:536-540) also asks, per offset j, for the flanks bg(s, j-1) and bg(j+W, e) with
+// s = max(j - order, 0), e = min(j + W + order - 1, L - 1): both shorter than order + 1 columns, so their trailing trees hold what
+// the call before them left there (MeanFieldForBayesNet.java:84): bg(s, e) ends on the window (e-order .. e); the left flank
+// then observes its n1 = j - s columns in the trees 0 .. n1-1, the right flank its n2 = e - j - W + 1 columns in 0 .. n2-1.
+static int netg_upload(phyfoo_ctx* ctx, phyfoo_model* m) {
+    if (m->netg_uploaded == m->h.version) return PHYFOO_OK;
+    std::vector<int> rec, lists; std::vector<double> tab;
+    try { m->h.netg_build(rec, lists, tab); } catch (const std::exception& e) { return fail(ctx, PHYFOO_EINVAL, std::string("generic net: ") + e.what()); }
+    for (double v : tab) if (!std::isfinite(v)) return fail(ctx, PHYFOO_EUNSUPPORTED, "a CPF entry is 0: the reference's free energy is not finite for this parameter set");
+    if (!m->d_netg_rec || lists.size() > m->netg_lists_len || tab.size() > m->netg_tab_len) {
+        cudaFree(m->d_netg_rec); cudaFree(m->d_netg_lists); cudaFree(m->d_netg_tab);
+        m->d_netg_rec = nullptr; m->d_netg_lists = nullptr; m->d_netg_tab = nullptr;
+        CU(cudaMalloc(&m->d_netg_rec, rec.size() * sizeof(int)));
+        CU(cudaMalloc(&m->d_netg_lists, std::max<size_t>(lists.size(), 1) * sizeof(int)));
+        CU(cudaMalloc(&m->d_netg_tab, tab.size() * sizeof(double)));
+        m->netg_lists_len = lists.size(); m->netg_tab_len = tab.size();
+    }
+    CU(cudaMemcpyAsync(m->d_netg_rec, rec.data(), rec.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(m->d_netg_lists, lists.data(), lists.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(m->d_netg_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));      // the vectors are stack-scoped
+    m->netg_uploaded = m->h.version;
+    return PHYFOO_OK;
+}
+
+// full windows: item u = window u of width T (alignment-major); cols[t][u] = first column + t
+__global__ void bgk_items_full_kernel(const int64_t* __restrict__ win_off, const int64_t* __restrict__ col_off, int n_aln, int64_t n, int T,
+                                      int64_t* __restrict__ cols) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n) return;
+    const int a = find_alignment(win_off, n_aln, u);
+    const int64_t c = col_off[a] + (u - win_off[a]);
+    for (int t = 0; t < T; ++t) cols[(size_t)t * n + u] = c + t;
+}
+__global__ void bgk_scatter_full_kernel(const int64_t* __restrict__ cols, const double* __restrict__ ofirst, const double* __restrict__ olast,
+                                        int64_t n, int k, double* __restrict__ cond, double* __restrict__ first) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n) return;
+    cond[cols[u] + k] = -olast[u];
+    first[cols[u]] = -ofirst[u];
+}
+// the two flank ranges of offset j (item u = motif window u): right == 0: bg(s, j-1); right == 1: bg(j+W, e).  A flank without
+// columns is a dummy item (len 1, its value is not used).
+__global__ void bgk_items_flank_kernel(const int64_t* __restrict__ win_off, const int64_t* __restrict__ col_off, int n_aln, int64_t n, int W, int k,
+                                       int right, int64_t* __restrict__ cols, int32_t* __restrict__ len) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n) return;
+    const int a = find_alignment(win_off, n_aln, u);
+    const int64_t c0 = col_off[a], L = col_off[a + 1] - c0, j = u - win_off[a];
+    const int64_t s = j > k ? j - k : 0, e = j + W + k - 1 < L - 1 ? j + W + k - 1 : L - 1;
+    const int64_t n1 = j - s, n2 = e - (j + W) + 1;
+    for (int t = 0; t <= k; ++t) {
+        const int64_t after_full = e - k + t;                              // what bg(s, e) left in tree t
+        const int64_t after_left = (n1 > 0 && t < n1) ? s + t : after_full;
+        int64_t c;
+        if (!right) c = after_left;
+        else c = t < n2 ? j + W + t : after_left;
+        cols[(size_t)t * n + u] = c0 + c;
+    }
+    const int64_t ln = right ? n2 : n1;
+    len[u] = (int32_t)(ln > 0 ? ln : 1);
+}
+__global__ void bgk_negate_kernel(const double* __restrict__ in, int64_t n, double* __restrict__ out) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < n) out[u] = -in[u];
+}
+
+struct BgkTerms { double* cond; double* first; double* left; double* right; };
+static int bgk_terms_device(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* bg, int W_motif, const int64_t* d_woff_motif,
+                            int64_t nw_motif, BgkTerms* out, int32_t* d_sweeps_full = nullptr) {
+    ModelHost& h = bg->h;
+    const int k = h.order, T = k + 1;
+    if (h.kind != PHYFOO_MODEL_BG || k < 1) return fail(ctx, PHYFOO_EINVAL, "needs a background model of order >= 1");
+    if (T > phyfoo::NETG_MAX_TREES) return fail(ctx, PHYFOO_EUNSUPPORTED, "background order above 7");
+    if (h.mode != PHYFOO_MODE_MEANFIELD) return fail(ctx, PHYFOO_EUNSUPPORTED, "exact mode is not defined for networks of order >= 1");
+    if (h.evol == PHYFOO_EVOL_HKY_AS_IMPLEMENTED) return fail(ctx, PHYFOO_EUNSUPPORTED, "HKY as implemented: background orders >= 1 are not supported");
+    if (h.S != ds->S) return fail(ctx, PHYFOO_EINVAL, "model and dataset disagree on the number of species");
+    if (ds->n_aln > 0 && ds->min_len < T) return fail(ctx, PHYFOO_EINVAL, "background of order k: an alignment is shorter than k + 1 columns (the reference's score of such a range is not a function of the inputs, MeanFieldForBayesNet.java:84)");
+    int rc = netg_upload(ctx, bg);
+    if (rc) return rc;
+    const int64_t* d_woff; const std::vector<int64_t>* h_woff;
+    rc = dataset_win_off(ctx, ds, T, &d_woff, &h_woff);
+    if (rc) return rc;
+    const int64_t n = h_woff->back(), nc = ds->n_cols;
+    const int64_t n_items = std::max<int64_t>(std::max(n, W_motif > 0 ? nw_motif : 0), 1);
+    // [ofirst | olast] (scratch of the current launch) | cond | first | left | right
+    CU(ctx->bg_scores.ensure((size_t)(2 * n_items + 2 * nc + 2 * (W_motif > 0 ? nw_motif : 0) + 4) * sizeof(double)));
+    CU(ctx->misc.ensure((size_t)T * n_items * sizeof(int64_t) + (size_t)n_items * sizeof(int32_t)));
+    double* d_ofirst = ctx->bg_scores.as<double>();
+    double* d_olast = d_ofirst + n_items;
+    out->cond = d_olast + n_items; out->first = out->cond + nc; out->left = out->first + nc; out->right = out->left + (W_motif > 0 ? nw_motif : 0);
+    int64_t* d_cols = ctx->misc.as<int64_t>();
+    int32_t* d_len = (int32_t*)(d_cols + (size_t)T * n_items);
+    CU(cudaMemsetAsync(out->cond, 0, (size_t)2 * nc * sizeof(double), ctx->stream));
+    const int G = h.W * h.N;
+    unsigned long long* sweep_sum = ctx->counters.as<unsigned long long>() + 2 * 1 + 1;          // slot 1 = background
+    CU(cudaMemsetAsync(ctx->counters.as<unsigned long long>() + 2, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    auto run = [&](int64_t cnt, const int32_t* len, int32_t* sweeps, const char* name) -> int {
+        // q in global memory, one slot per thread of the grid: at most ~512 MB
+        const size_t per_thread = (size_t)G * 4 * sizeof(double);
+        long long blocks = std::min<long long>((cnt + 127) / 128, 8LL * ctx->sm_count);
+        blocks = std::max<long long>(1, std::min<long long>(blocks, (long long)((512ull << 20) / (per_thread * 128))));
+        const size_t stride = (size_t)blocks * 128;
+        CU(ctx->gstate.ensure(per_thread * stride));
+        NetgParams p;
+        p.bases = ds->d_bases; p.gaps = ds->d_gaps; p.n_cols = ds->n_cols; p.nb = ds->nb;
+        p.view.n_nodes = G; p.view.n_trees = h.W; p.view.nodes_per_tree = h.N;
+        p.view.rec = bg->d_netg_rec; p.view.lists = bg->d_netg_lists; p.view.tab = bg->d_netg_tab;
+        p.item_cols = d_cols; p.item_len = len; p.n_items = cnt;
+        p.q = ctx->gstate.as<double>(); p.q_stride = stride;
+        p.out_first = d_ofirst; p.out_last = d_olast; p.sweeps = sweeps; p.sweep_sum = sweep_sum;
+        p.max_sweeps = h.max_sweeps; p.min_sweeps = h.min_sweeps; p.tol = h.tol;
+        {
+            KernelTimer kt_(ctx, name);
+            score_netg_kernel<<<(unsigned)blocks, 128, 0, ctx->stream>>>(p);
+        }
+        CU(cudaGetLastError());
+        return PHYFOO_OK;
+    };
+    if (n > 0) {
+        bgk_items_full_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_woff, ds->d_col_off, ds->n_aln, n, T, d_cols);
+        CU(cudaGetLastError());
+        if ((rc = run(n, nullptr, d_sweeps_full, "score_netg_kernel"))) return rc;
+        bgk_scatter_full_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_cols, d_ofirst, d_olast, n, k, out->cond, out->first);
+        CU(cudaGetLastError());
+    }
+    if (W_motif > 0 && nw_motif > 0) {
+        for (int right = 0; right < 2; ++right) {
+            bgk_items_flank_kernel<<<(unsigned)((nw_motif + 255) / 256), 256, 0, ctx->stream>>>(d_woff_motif, ds->d_col_off, ds->n_aln, nw_motif, W_motif, k,
+                                                                                                right, d_cols, d_len);
+            CU(cudaGetLastError());
+            if ((rc = run(nw_motif, d_len, nullptr, right ? "score_netg_kernel(right flanks)" : "score_netg_kernel(left flanks)"))) return rc;
+            bgk_negate_kernel<<<(unsigned)((nw_motif + 255) / 256), 256, 0, ctx->stream>>>(d_ofirst, nw_motif, right ? out->right : out->left);
+            CU(cudaGetLastError());
+        }
+    }
+    return PHYFOO_OK;
+}
+
+extern "C" int phyfoo_bg_range_terms(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* bg, double* cond_out, double* first_out,
+                                     int32_t* sweeps_out) {
+    if (!ctx) return PHYFOO_EINVAL;
+    if (!ds || !bg || !cond_out) return fail(ctx, PHYFOO_EINVAL, "bg_range_terms: NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    ctx->launches = 0; ctx->n_ktimes = 0;
+    const int64_t nc = ds->n_cols;
+    if (bg->h.kind != PHYFOO_MODEL_BG || bg->h.order < 1) return fail(ctx, PHYFOO_EINVAL, "bg_range_terms: needs a background model of order >= 1 (order 0: phyfoo_bg_columns)");
+    const int T = bg->h.order + 1;
+    const int64_t* d_woff; const std::vector<int64_t>* h_woff;
+    int rc = dataset_win_off(ctx, ds, T, &d_woff, &h_woff);
+    if (rc) return rc;
+    const int64_t n = h_woff->back();
+    if (sweeps_out) CU(ctx->sweeps_buf.ensure((size_t)std::max<int64_t>(n, 1) * sizeof(int32_t)));
+    BgkTerms t;
+    rc = bgk_terms_device(ctx, ds, bg, 0, nullptr, 0, &t, sweeps_out ? ctx->sweeps_buf.as<int32_t>() : nullptr);
+    if (rc) return rc;
+    if (nc == 0) return PHYFOO_OK;
+    CU(cudaMemcpyAsync(cond_out, t.cond, (size_t)nc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (first_out) CU(cudaMemcpyAsync(first_out, t.first, (size_t)nc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (sweeps_out && n > 0) CU(cudaMemcpyAsync(sweeps_out, ctx->sweeps_buf.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PHYFOO_OK;
+}
+
 extern "C" int phyfoo_bg_columns_order1(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* bg, double* cond_out, double* first_out) {
     if (!ctx) return PHYFOO_EINVAL;
     if (!ds || !bg || !cond_out) return fail(ctx, PHYFOO_EINVAL, "bg_columns_order1: NULL argument");
@@ -1975,7 +2154,8 @@ static int enqueue_estep(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model
     ctx->kev_valid = false;
     CU(cudaEventRecord(ctx->kev[0], ctx->stream));
     Bg1Terms bg1{nullptr, nullptr, nullptr, nullptr};
-    bool have_bg1 = false;
+    BgkTerms bgk{nullptr, nullptr, nullptr, nullptr};
+    bool have_bg1 = false, have_bgk = false;
     const bool both_memo = bg->h.kind == PHYFOO_MODEL_BG && bg->h.order == 0 && fg->h.S == ds->S && bg->h.S == ds->S &&
                            fg->h.evol != PHYFOO_EVOL_HKY_AS_IMPLEMENTED && bg->h.evol != PHYFOO_EVOL_HKY_AS_IMPLEMENTED &&
                            fg->h.order == 0 && fg->h.tables_finite() && bg->h.tables_finite() &&
@@ -1989,7 +2169,11 @@ static int enqueue_estep(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model
         if (rc) return rc;
         CU(cudaEventRecord(ctx->kev[1], ctx->stream));   // phases are not separable on this path: see phyfoo_last_kernel_times
     } else {
-        if (bg->h.kind == PHYFOO_MODEL_BG && bg->h.order == 1) {
+        if (bg->h.kind == PHYFOO_MODEL_BG && bg->h.order >= 1 && (bg->h.order >= 2 || ctx->bg_generic)) {
+            rc = bgk_terms_device(ctx, ds, bg, W, d_woff, nw, &bgk);
+            bg1.cond = bgk.cond; bg1.first = bgk.first; bg1.left = bgk.left; bg1.single = nullptr;
+            have_bg1 = true; have_bgk = true;
+        } else if (bg->h.kind == PHYFOO_MODEL_BG && bg->h.order == 1) {
             rc = bg1_terms_device(ctx, ds, bg, W, d_woff, nw, &bg1);
             have_bg1 = true;
         } else rc = launch_bg_columns(ctx, ds, bg, ctx->bg_scores.as<double>(), nullptr, 1);
@@ -2004,6 +2188,7 @@ static int enqueue_estep(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model
     z.rev = strand_logw ? ctx->fg_scores.as<double>() + nw : nullptr;
     z.bgcol = have_bg1 ? bg1.cond : ctx->bg_scores.as<double>();
     z.bg1_first = have_bg1 ? bg1.first : nullptr; z.bg1_single = bg1.single; z.bg1_left = bg1.left;
+    z.bgk_right = have_bgk ? bgk.right : nullptr; z.bg_order = have_bg1 ? bg->h.order : 0;
     z.col_off = ds->d_col_off; z.win_off = d_woff; z.n_aln = ds->n_aln; z.W = W;
     z.logw0 = logw[0]; z.logw1 = logw[1];
     z.has_strand = strand_logw ? 1 : 0;
@@ -2192,6 +2377,11 @@ extern "C" int phyfoo_set_option(phyfoo_ctx* ctx, const char* name, int64_t valu
     if (std::strcmp(name, "order1_qglobal") == 0) {
         if (value < -1 || value > 8) return fail(ctx, PHYFOO_EINVAL, "set_option: order1_qglobal must be -1 (choose), 0 (q rows in shared memory) or 1..8 warps per SM");
         ctx->order1_qglobal = (int)value;
+        return PHYFOO_OK;
+    }
+    if (std::strcmp(name, "bg_generic") == 0) {
+        if (value != 0 && value != 1) return fail(ctx, PHYFOO_EINVAL, "set_option: bg_generic must be 0 or 1");
+        ctx->bg_generic = (int)value;
         return PHYFOO_OK;
     }
     if (std::strcmp(name, "order1_kernel") == 0) {

@@ -463,21 +463,35 @@ class PhyloBackground(_PhyloModel):
         sw = (np.concatenate([p[1] for p in parts]) if split else parts[0][1]) if want_sweeps else None
         return (out, sw) if want_sweeps else out
 
-    def getRangeTerms(self, sample: PhyloSample):
-        """Order-1 background: (cond, first) per column with getLogProbFor(seq, s, e) = first[s] + sum(cond[s+1..e]) for e > s
-        (models/PhyloBackground.java:273-297); see phyfoo_bg_columns_order1."""
-        if self.order != 1:
-            raise ValueError("getRangeTerms is for order-1 backgrounds; order 0 uses getColumnLogProbs")
+    def getRangeTerms(self, sample: PhyloSample, want_sweeps=False):
+        """Background of order k >= 1: (cond, first) per column with getLogProbFor(seq, s, e) = first[s] + sum(cond[s+k..e])
+        for ranges of at least k + 1 columns (models/PhyloBackground.java:273-297); see phyfoo_bg_range_terms.  Order 1 runs
+        the order-1 network kernel (phyfoo_bg_columns_order1), higher orders the generic net kernel."""
+        if self.order < 1:
+            raise ValueError("getRangeTerms is for backgrounds of order >= 1; order 0 uses getColumnLogProbs")
         self._check(sample)
 
         def terms(smp):
             ds = smp.device(self.ctx)
             cond, first = np.zeros(ds.n_cols), np.zeros(ds.n_cols)
-            core.raise_for(core.lib().phyfoo_bg_columns_order1(self.ctx.h, ds.h, self.device_model().h, core._p(cond, core.C.c_double),
-                                                               core._p(first, core.C.c_double)), self.ctx.h)
-            return cond, first
+            if self.order == 1 and not want_sweeps and not type(self).GENERIC_NET:
+                rc = core.lib().phyfoo_bg_columns_order1(self.ctx.h, ds.h, self.device_model().h, core._p(cond, core.C.c_double),
+                                                         core._p(first, core.C.c_double))
+                sw = None
+            else:
+                sw = np.zeros(max(int(ds.windows(self.order + 1)), 1), np.int32) if want_sweeps else None
+                rc = core.lib().phyfoo_bg_range_terms(self.ctx.h, ds.h, self.device_model().h, core._p(cond, core.C.c_double),
+                                                      core._p(first, core.C.c_double), core._p(sw, core.C.c_int32))
+                if sw is not None:
+                    sw = sw[:int(ds.windows(self.order + 1))]
+            core.raise_for(rc, self.ctx.h)
+            return (cond, first, sw) if want_sweeps else (cond, first)
         parts, split = self._per_topology(sample, terms)
-        return (np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])) if split else parts[0]
+        if not split:
+            return parts[0]
+        return tuple(np.concatenate([p[i] for p in parts]) for i in range(len(parts[0])))
+
+    GENERIC_NET = False                # True: order 1 through the generic net kernel as well (cross-check)
 
     def getLogProbForRange(self, sample: PhyloSample, aln, start, end):
         """getLogProbFor(seq, start, end) for one alignment (end inclusive)."""
@@ -486,17 +500,20 @@ class PhyloBackground(_PhyloModel):
         off = int(sample.col_offsets[aln])
         if self.order == 0:
             return float(self.getColumnLogProbs(sample)[off + start: off + end + 1].sum())
-        if end == start:
-            raise ValueError("a single-column range has no defined value under an order-1 background in the reference")
+        k = self.order
+        if end - start < k:
+            raise ValueError("a range shorter than order + 1 columns has no defined value in the reference (its trailing trees "
+                             "keep the observation of an earlier call)")
         cond, first = self.getRangeTerms(sample)
-        return float(first[off + start] + cond[off + start + 1: off + end + 1].sum())
+        return float(first[off + start] + cond[off + start + k: off + end + 1].sum())
 
     def getLogProbFor(self, sample: PhyloSample):
         """double[] getLogProbFor(Sample) (jstacs AbstractModel.java:217-240): one value per alignment."""
         off = sample.col_offsets
-        if self.order == 1:
+        if self.order >= 1:
+            k = self.order
             cond, first = self.getRangeTerms(sample)
-            return np.array([first[off[i]] + cond[off[i] + 1:off[i + 1]].sum() for i in range(sample.n_alignments)])
+            return np.array([first[off[i]] + cond[off[i] + k:off[i + 1]].sum() for i in range(sample.n_alignments)])
         cols = self.getColumnLogProbs(sample)
         return np.array([cols[off[i]:off[i + 1]].sum() for i in range(sample.n_alignments)])
 

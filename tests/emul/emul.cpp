@@ -540,3 +540,23 @@ extern "C" int emul_ab_expand(const uint8_t* row, int l, int kmax, int variant, 
     for (int i = pre; i < n; ++i) idx_out[i - pre] = idx[i];
     return n - pre;
 }
+
+// ---- generic net (netg.cuh): the per-item mean field on explicit (tree -> column) items ---------------------------------
+#include "../../phyfoo_b200/csrc/netg.cuh"
+extern "C" int emul_netg_items(const phyfoo_model_desc* d, const uint8_t* codes /*[L][S]*/, int n_items, const int* cols /*[n_items][T]*/,
+                               const int* len, double* out_first, double* out_last, int* sweeps) {
+    try {
+        ModelHost m; m.init(*d);
+        std::vector<int> rec, lists; std::vector<double> tab;
+        m.netg_build(rec, lists, tab);
+        NetgView v{m.W * m.N, m.W, m.N, rec.data(), lists.data(), tab.data()};
+        std::vector<double> q((size_t)v.n_nodes * 4, 1e300);
+        NetgState st{q.data(), 1};
+        for (int u = 0; u < n_items; ++u) {
+            NetgObs ob;
+            for (int t = 0; t < m.W; ++t) ob.cw[t] = words_of(codes + (size_t)cols[(size_t)u * m.W + t] * m.S, m.S, false);
+            sweeps[u] = netg_item(v, ob, st, len[u], m.max_sweeps, m.min_sweeps, m.tol, &out_first[u], &out_last[u]);
+        }
+        return 0;
+    } catch (const std::exception& e) { std::fprintf(stderr, "emul: %s\n", e.what()); return -1; }
+}

@@ -23,7 +23,7 @@ def emul():
             os.path.join(ROOT, "phyfoo_b200", "csrc", "model_host.hpp"), os.path.join(ROOT, "phyfoo_b200", "csrc", "fp64_math.cuh"),
             os.path.join(ROOT, "phyfoo_b200", "csrc", "fp64_math_tables.h"),
             os.path.join(ROOT, "phyfoo_b200", "csrc", "net1n.cuh"), os.path.join(ROOT, "phyfoo_b200", "csrc", "tree_pass_f81.cuh"),
-            os.path.join(ROOT, "phyfoo_b200", "csrc", "ab_expand.hpp")]
+            os.path.join(ROOT, "phyfoo_b200", "csrc", "ab_expand.hpp"), os.path.join(ROOT, "phyfoo_b200", "csrc", "netg.cuh")]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", srcs[0], "-o", so])
     L = C.CDLL(so)
@@ -323,3 +323,68 @@ def test_alignment_based_expansion_matches_the_java_statement_by_statement(emul,
     for l in range(order):
         got = emul.emul_ab_term(bg[l].ctypes.data_as(C.POINTER(C.c_double)), order, row.ctypes.data_as(C.POINTER(C.c_uint8)), l, l, 1)
         assert abs(got - orc.ab_bg_ln_cond_prob(bg, order, row, l)) <= 1e-15
+
+
+# ---- generic net (csrc/netg.cuh): backgrounds of any order, incl. the stale trees of the short flank ranges ----------------
+def _netg_items(emul, desc, codes, cols, lens):
+    emul.emul_netg_items.argtypes = [C.POINTER(_abi.ModelDesc), C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                     C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    cols = np.ascontiguousarray(cols, np.int32); lens = np.ascontiguousarray(lens, np.int32)
+    n = cols.shape[0]
+    f, l, sw = np.zeros(n), np.zeros(n), np.zeros(n, np.int32)
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    assert emul.emul_netg_items(C.byref(desc), codes.ctypes.data_as(C.POINTER(C.c_uint8)), n, cols.ctypes.data_as(ip),
+                                lens.ctypes.data_as(ip), f.ctypes.data_as(dp), l.ctypes.data_as(dp), sw.ctypes.data_as(ip)) == 0
+    return f, l, sw
+
+
+def flank_items(L, W, k):
+    """(left, right) items of every offset j: the column each of the k + 1 trees observes and the number of leading trees the
+    range itself covers -- the host statement of bgk_items_flank_kernel (csrc/phyfoo.cu)."""
+    left, right = [], []
+    for j in range(L - W + 1):
+        s, e = max(j - k, 0), min(j + W + k - 1, L - 1)
+        n1, n2 = j - s, e - (j + W) + 1
+        after_full = [e - k + t for t in range(k + 1)]
+        after_left = [s + t if (n1 > 0 and t < n1) else after_full[t] for t in range(k + 1)]
+        left.append((after_left, max(n1, 1)))
+        right.append(([j + W + t if t < n2 else after_left[t] for t in range(k + 1)], max(n2, 1)))
+    return left, right
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+@pytest.mark.parametrize("gap_rate", [0.0, 0.12])
+def test_generic_net_background_of_any_order_matches_oracle(emul, order, gap_rate):
+    from util import oracle_bg
+    rng = np.random.default_rng(40 + order)
+    newick = TREES[3]
+    tree = parse_newick(newick)
+    T = order + 1
+    pis = [rng.dirichlet(np.ones(4), size=4 ** min(order, t)) for t in range(T)]
+    desc, keep = _abi.make_desc(_abi.MODEL_BG, 0, order, tree, np.tile(tree.branch, (T, 1)), pis)
+    ob = oracle_bg(newick, order, pis)
+    L, W = 13, 4
+    codes = random_codes(rng, L, tree.n_species, gap_rate)
+    first, last, sw = _netg_items(emul, desc, codes, [[u + t for t in range(T)] for u in range(L - order)], [T] * (L - order))
+    full = lambda s, e: -(first[s] + last[s:e - order + 1].sum())                            # noqa: E731
+    for s, e in [(0, L - 1), (2, 9), (3, 3 + order), (5, L - 1)]:
+        ref = ob.bg_range(codes, s, e)
+        assert abs(full(s, e) - ref) <= 1e-12 * abs(ref)
+    # the three calls of every offset in the reference's order on ONE model object (SingleHiddenMotifMixture.java:536-540): the
+    # short flank ranges see the trees the calls before them left behind
+    left, right = flank_items(L, W, order)
+    lf, _, _ = _netg_items(emul, desc, codes, [c for c, _ in left], [n for _, n in left])
+    rf, _, _ = _netg_items(emul, desc, codes, [c for c, _ in right], [n for _, n in right])
+    ob.bg_range(codes, 0, L - 1)                                                             # logPSeq, :526
+    for j in range(L - W + 1):
+        s, e = max(j - order, 0), min(j + W + order - 1, L - 1)
+        r_full, r_left, r_right = ob.bg_range(codes, s, e), ob.bg_range(codes, s, j - 1), ob.bg_range(codes, j + W, e)
+        assert abs(full(s, e) - r_full) <= 1e-12 * abs(r_full)
+        if j > 0:
+            assert abs(-lf[j] - r_left) <= 1e-12 * abs(r_left), (j, -lf[j], r_left)
+        else:
+            assert r_left == 0.0
+        if j + W <= L - 1:
+            assert abs(-rf[j] - r_right) <= 1e-12 * abs(r_right), (j, -rf[j], r_right)
+        else:
+            assert r_right == 0.0
