@@ -313,7 +313,10 @@ int64_t phyfoo_ss_evaluations(const phyfoo_ssobj* ss);
 /* A whole M-step of the motif model in one call: the positions order[0..n_pos-1] one after the other (the caller draws the
  * order, util/PWMUtil.java:131-144), each by a BFGS on the forward-difference gradient with the termination rule of
  * optimizing/PreparedConditions.java:20-27.  The library's stand-in for the Jstacs optimizer (whose own trajectory is not
- * reproducible); a Java caller can keep its Optimizer and bind phyfoo_ss_eval / phyfoo_ss_grad instead. */
+ * reproducible); a Java caller can keep its Optimizer and bind phyfoo_ss_eval / phyfoo_ss_grad instead.
+ * With q fixed the objective is separable (f = sum_t G_t(theta_t) - ENT), so distinct positions are optimised side by side on up
+ * to 16 host threads, each against the other positions' terms as they were on entry -- the result does not depend on the number
+ * of threads; the environment variable PHYFOO_SS_THREADS=1 runs them strictly one after the other. */
 int phyfoo_ss_optimize(phyfoo_ssobj* ss, const int32_t* order, int32_t n_pos, double* f_before, double* f_after, int64_t* evaluations);
 void phyfoo_ss_free(phyfoo_ssobj* ss);
 

@@ -113,6 +113,43 @@ N1N_HD void n1n_exp4(const double (&x)[4], const double* tab64, double (&e)[4]) 
         e[0] = r.v0; e[1] = r.v1; e[2] = r.v2; e[3] = r.v3;
     }
 }
+// The same with a 16-entry table 2^(j/16) (every fourth entry of the 64-entry one) and one more term of the polynomial
+// (|r| <= ln 2 / 32: the first neglected term r^8 / 8! is below 2e-18): 16 doubles are 128 bytes, one bank pair per entry, so a
+// warp's look-up is one shared-memory wavefront whatever the 32 indices are (64 entries: 4.6 wavefronts on average in the
+// order-1 node kernel, whose busiest unit is the shared-memory data path -- profiles/r02_c3_l2window_summary.md).
+N1N_RARE N1nD4 n1n_exp4_rare_g(double x0, double x1, double x2, double x3) {
+    N1nD4 r;
+    r.v0 = phy_exp(x0); r.v1 = phy_exp(x1); r.v2 = phy_exp(x2); r.v3 = phy_exp(x3);
+    return r;
+}
+N1N_HD void n1n_exp4_t16(const double (&x)[4], const double* tab16, double (&e)[4]) {
+    if (n1n_exp_common(x)) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            double kd = fma(x[a], 0.25 * PHY_64_OVER_LN2, 0x1.8p52);
+#if defined(__CUDA_ARCH__)
+            const int32_t ki = __double2loint(kd);
+#else
+            const int32_t ki = (int32_t)(uint32_t)phy_bits(kd);
+#endif
+            kd -= 0x1.8p52;
+            double r = fma(kd, -4.0 * PHY_LN2_64_HI, x[a]);
+            r = fma(kd, -4.0 * PHY_LN2_64_LO, r);
+            const double T = tab16[ki & 15];
+            double q = fma(r, 0x1.a01a01a01a01ap-13, 0x1.6c16c16c16c17p-10);      // 1/5040, 1/720
+            q = fma(q, r, 0x1.1111111111111p-7);
+            q = fma(q, r, 0x1.5555555555555p-5);
+            q = fma(q, r, 0x1.5555555555555p-3);
+            q = fma(q, r, 0.5);
+            const double pm = fma(r * r, q, r);
+            const double res = fma(T, pm, T);
+            e[a] = n1n_with_hi(res, n1n_hi(res) + ((ki >> 4) << 20));       // |x| < 690: the result is a normal number
+        }
+    } else {
+        const N1nD4 r = n1n_exp4_rare_g(x[0], x[1], x[2], x[3]);
+        e[0] = r.v0; e[1] = r.v1; e[2] = r.v2; e[3] = r.v3;
+    }
+}
 // log z accumulated as (mantissa product, exponent sum)
 N1N_HD void n1n_acc_logz(N1nAcc& acc, double z) {
     const int hi = n1n_hi(z);

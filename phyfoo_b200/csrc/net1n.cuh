@@ -34,7 +34,7 @@ namespace phyfoo {
 
 // One node update.  reg: this thread's window in the warp's region (AB and message rows), qreg: the same for the q rows
 // (the same pointer when the whole region is in shared memory); tab: tables [W][I][34] (Lo | D = Ld - Lo | pad); exptab:
-// 2^(j/64); r: the record (model_host.hpp::node_program); cobs: observed-leaf sums of this node; upd == false: the pass at the
+// 2^(j/16), 16 entries; r: the record (model_host.hpp::node_program); cobs: observed-leaf sums of this node; upd == false: the pass at the
 // uniform start (exponents forced to 0).  All reads come before the row stores; the caller synchronises the warp afterwards.
 // A slot without a node in this step (record flags 0) does nothing.
 // qx, qpn: the (old) q of the same node and of its parent at the next position, rows r[2] and r[3] -- no update of the
@@ -91,7 +91,7 @@ N1N_HD void n1n_update(double* qreg, double* reg, const double* tab, const doubl
         ex[a] = upd ? oc[a] + cn[a] : 0.0;
         g[a] = upd ? cn[a] : -oc[a];
     }
-    n1n_exp4(ex, exptab, e);                                                        // MeanFieldForBayesNet.java:192, no max shift
+    n1n_exp4_t16(ex, exptab, e);                                                    // MeanFieldForBayesNet.java:192, no max shift
     const double z = n1n_sum4(e);                                                   // :195-198
     // The reciprocal of z is a chain of dependent operations; what is linear in q is computed on the unnormalised
     // exponentials next to it and scaled afterwards: the node's free-energy terms, the context sums of the same node at
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(256, 1) score_o1n_kernel(Net1nParams p) {
     const int sreg = QG ? p.sregion : p.region;
     int* s_prog = (int*)(s_reg + (size_t)NW * sreg);
     for (int i = tid; i < W * I * TS; i += T) s_tab[i] = p.tab[i];
-    for (int i = tid; i < 64; i += T) s_exp[i] = phyfoo::d_phy_exp_tab[i];
+    for (int i = tid; i < 64; i += T) s_exp[i] = phyfoo::d_phy_exp_tab[i < 16 ? 4 * i : i];     // [0..15] = 2^(j/16) (n1n_exp4_t16)
     for (int i = tid; i < NW * sreg; i += T) s_reg[i] = 0.0;
     for (int i = tid; i < p.prog_len; i += T) s_prog[i] = p.prog[i];
     double* const q_all = QG ? p.gq + (size_t)blockIdx.x * NW * p.region : s_reg;      // q rows of the block's warps

@@ -23,6 +23,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "model_host.hpp"
@@ -2818,16 +2819,52 @@ extern "C" int phyfoo_ss_get_pi(const phyfoo_ssobj* ss, int32_t position, double
 // order, util/PWMUtil.java:131-144), each from its current parameters, termination TC_MOTIF_SEPARATED_POSITIONS
 extern "C" int phyfoo_ss_optimize(phyfoo_ssobj* ss, const int32_t* order, int32_t n_pos, double* f_before, double* f_after, int64_t* evaluations) {
     if (!ss || !order || n_pos < 0) return PHYFOO_EINVAL;
+    const int W = ss->o.h.W;
+    std::vector<char> seen(W, 0);
+    bool distinct = true;
+    for (int j = 0; j < n_pos; ++j) {
+        if (order[j] < 0 || order[j] >= W) return PHYFOO_EINVAL;
+        if (seen[order[j]]) distinct = false;
+        seen[order[j]] = 1;
+    }
     if (f_before) *f_before = ss->o.value();
     const long long e0 = ss->o.evaluations;
-    for (int j = 0; j < n_pos; ++j) {
-        const int t = order[j];
-        if (t < 0 || t >= ss->o.h.W) return PHYFOO_EINVAL;
-        const int d = ss->o.dim(t);
+    auto one = [](SuffStatObjective& o, int t) {
+        const int d = o.dim(t);
         std::vector<double> x(d);
-        for (int i = 0; i < d; ++i) x[i] = std::log(ss->o.h.pi[t][i]);
-        bfgs_minimise([&](const double* z) { return -ss->o.eval_lambda(t, z); }, x, tc_motif_separated_positions());
-        ss->o.eval_lambda(t, x.data());
+        for (int i = 0; i < d; ++i) x[i] = std::log(o.h.pi[t][i]);
+        bfgs_minimise([&](const double* z) { return -o.eval_lambda(t, z); }, x, tc_motif_separated_positions());
+        o.eval_lambda(t, x.data());
+    };
+    // With q fixed the objective is separable, f = sum_t G_t(theta_t) - ENT: the optimisation of a position neither reads nor
+    // changes the parameters of another one, only the constant the other terms add to f.  Distinct positions therefore run side by
+    // side on host threads, each against the other terms as they were on entry (so the result does not depend on the number of
+    // threads); PHYFOO_SS_THREADS=1 runs them one after the other, each seeing the terms the earlier ones left.
+    int nt = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+    if (const char* e = std::getenv("PHYFOO_SS_THREADS")) nt = std::max(1, std::atoi(e));
+    nt = std::min(nt, (int)n_pos);
+    if (nt > 1 && distinct) {
+        const std::vector<double> G0 = ss->o.G;
+        std::vector<SuffStatObjective> copy(nt, ss->o);
+        std::vector<std::thread> th;
+        for (int k = 0; k < nt; ++k)
+            th.emplace_back([&, k]() {
+                for (int j = k; j < n_pos; j += nt) {
+                    copy[k].G = G0;                      // the other terms as they were on entry
+                    one(copy[k], order[j]);
+                }
+            });
+        for (auto& x : th) x.join();
+        for (int k = 0; k < nt; ++k) {
+            ss->o.evaluations += copy[k].evaluations - e0;
+            for (int j = k; j < n_pos; j += nt) {
+                const int t = order[j];
+                ss->o.h.pi[t] = copy[k].h.pi[t];
+                ss->o.G[t] = ss->o.term(t, ss->o.h.pi[t].data());
+            }
+        }
+    } else {
+        for (int j = 0; j < n_pos; ++j) one(ss->o, order[j]);
     }
     if (f_after) *f_after = ss->o.value();
     if (evaluations) *evaluations = ss->o.evaluations - e0;

@@ -365,6 +365,8 @@ int run_o1n(const ModelHost& m, const std::vector<int>& prog, const uint8_t* cod
     m.tables1n(tab);
     m.leaf_tables1n(leaf_tab);
     std::vector<double> region(Lt.region, 0.0), gc(Lt.region, 0.0);
+    double exp16[16];                                            // 2^(j/16): the table of n1n_exp4_t16
+    for (int j = 0; j < 16; ++j) exp16[j] = h_phy_exp_tab[4 * j];
     for (int w = 0; w < 8; ++w) region[Lt.onehot_row + 2 * w] = 1.0;
     for (int j = 0; j + W <= L; ++j) {
         // set-up: observed-leaf sums, uniform start, context sums of position 0
@@ -408,7 +410,7 @@ int run_o1n(const ModelHost& m, const std::vector<int>& prog, const uint8_t* cod
                     double qx[4], qpn[4];
                     n1n_ld4(reg + r[2], qx);
                     n1n_ld4(reg + r[3], qpn);
-                    n1n_update<MC>(reg, reg, tab.data(), h_phy_exp_tab, r, cobs, qx, qpn, false, a0[slot]);
+                    n1n_update<MC>(reg, reg, tab.data(), exp16, r, cobs, qx, qpn, false, a0[slot]);
                 }
             const double F0 = (n1n_free_energy(a0[0]) + n1n_free_energy(a0[1])) + (n1n_free_energy(a0[2]) + n1n_free_energy(a0[3]));
             if (std::fabs(F0 - old) > 1e-12 * std::fabs(F0)) return -6;
@@ -430,7 +432,7 @@ int run_o1n(const ModelHost& m, const std::vector<int>& prog, const uint8_t* cod
                         double qx[4], qpn[4];
                         n1n_ld4(reg + r[2], qx);
                         n1n_ld4(reg + r[3], qpn);
-                        n1n_update<MC>(reg, reg, tab.data(), h_phy_exp_tab, r, cobs, qx, qpn, upd, order ? acc_alt[slot] : acc[slot]);
+                        n1n_update<MC>(reg, reg, tab.data(), exp16, r, cobs, qx, qpn, upd, order ? acc_alt[slot] : acc[slot]);
                     }
                 for (int o = 0; o < Lt.region; ++o)
                     if (std::memcmp(&alt[o], &region[o], 8) != 0) return -4;

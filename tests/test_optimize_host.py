@@ -142,3 +142,30 @@ def test_library_bfgs_matches_python_stand_in():
     # the closed-form optimum of one position: f is sum_e C log table; for the root entries alone (a star of zero-length
     # branches would be degenerate) check monotone improvement instead
     assert ev > 5 * W
+
+
+def test_library_mstep_on_host_threads_does_not_depend_on_their_number(monkeypatch):
+    """phyfoo_ss_optimize runs distinct positions side by side (the objective is separable); every position is optimised against
+    the other terms as they were on entry, so 2, 3 or 16 threads give the same bits, and the strictly sequential run
+    (PHYFOO_SS_THREADS=1, each position seeing what the earlier ones left) the same optimum to rounding."""
+    from phyfoo_b200 import core
+    tree, pwm, branch, counts, desc, keep = _ss_case(seed=5)
+    W = len(pwm)
+    order = np.array([3, 1, 4, 0, 2], np.int32)
+    res = {}
+    for nt in ("1", "2", "3", "16"):
+        monkeypatch.setenv("PHYFOO_SS_THREADS", nt)
+        ss = core.SSObjective(desc=desc, counts=counts, entropy=0.5)
+        fb, fa, ev = ss.optimize(order)
+        res[nt] = (fb, fa, ev, np.stack([ss.get_pi(t) for t in range(W)]))
+        ss.free()
+    for nt in ("3", "16"):
+        assert res[nt][1] == res["2"][1] and res[nt][2] == res["2"][2] and np.array_equal(res[nt][3], res["2"][3])
+    assert res["1"][0] == res["2"][0] and res["2"][1] > res["2"][0]
+    assert abs(res["1"][1] - res["2"][1]) <= 1e-9 * abs(res["1"][1])
+    assert np.allclose(res["1"][3], res["2"][3], rtol=0, atol=1e-6)
+    monkeypatch.delenv("PHYFOO_SS_THREADS")
+    # a repeated position: one after the other
+    ss = core.SSObjective(desc=desc, counts=counts, entropy=0.5)
+    fb, fa, ev = ss.optimize(np.array([1, 1, 2], np.int32))
+    assert fa > fb
