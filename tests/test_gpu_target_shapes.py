@@ -85,3 +85,56 @@ def test_c5_shape_30_species_width12(ctx):
 
 def test_c5_shape_with_gaps(ctx):
     _check(ctx, "c5", 8, 300, 0.05)
+
+
+def _reverse_complement(smp):
+    """Every alignment read from its other end with complemented bases (gaps stay gaps)."""
+    from phyfoo_b200.data import PhyloSample
+    parts = []
+    for i in range(smp.n_alignments):
+        a = smp.getElementAt(i)[::-1]
+        parts.append(np.where(a < 4, 3 - a, a).astype(np.uint8))
+    return PhyloSample(np.concatenate(parts), smp.col_offsets)
+
+
+@pytest.mark.parametrize("name,n_aln", [("c3", None), ("c3o0", None), ("c5", 1500)])
+def test_full_size_properties_of_the_benched_configurations(ctx, name, n_aln):
+    """The configurations bench.py times, at their full size (C5: 1500 of its 10^6 alignments, 3 * 10^6 windows), through
+    properties that need no oracle:
+      * ZOOPS weight 1: the posterior over the offsets of an alignment sums to 1, w = (number of alignments, 0);
+      * the reverse strand of the reverse-complemented data is the forward strand of the data, window for window and bit for bit
+        (the kernels read the same columns with the same symbols), and the sweep counts agree;
+      * an E-step over two halves of the sample adds up to the E-step over the whole (ll to rounding, gamma bit for bit);
+      * the same call twice returns the same bits;
+      * the arg-max calls land on the planted sites."""
+    from phyfoo_b200 import synth
+    from phyfoo_b200.models import PhyloBackground, PhyloBayesModel, SingleHiddenMotifMixture
+    cfg, newick, pwm, smp, planted = synth.make_config(name, n_aln=n_aln)
+    W = cfg["W"]
+    fg = PhyloBayesModel(W, cfg["order"], newick, ctx); fg.setCondProbs(pwm)
+    bg = PhyloBackground(0, newick, ctx)
+    shm = SingleHiddenMotifMixture(fg, bg, zoops=1.0)
+    res = shm.getNewWeights(smp)
+    off = smp.device(ctx).window_offsets(W)
+    per_aln = np.add.reduceat(res["gamma"], off[:-1])
+    assert np.isfinite(res["ll"]) and np.max(np.abs(per_aln - 1.0)) < 1e-9
+    assert abs(res["w"][0] - smp.n_alignments) < 1e-6 * smp.n_alignments and abs(res["w"][1]) < 1e-9
+    assert (res["argmax_off"] == planted).mean() > (0.6 if cfg["order"] == 1 else 0.9)
+    res2 = shm.getNewWeights(smp)
+    assert res2["ll"] == res["ll"] and np.array_equal(res2["gamma"], res["gamma"]) and np.array_equal(res2["argmax_off"], res["argmax_off"])
+    # halves
+    h = smp.n_alignments // 2
+    a, b = shm.getNewWeights(smp.slice(0, h)), shm.getNewWeights(smp.slice(h, smp.n_alignments))
+    assert abs((a["ll"] + b["ll"]) - res["ll"]) <= 1e-12 * abs(res["ll"])
+    assert np.array_equal(np.concatenate([a["gamma"], b["gamma"]]), res["gamma"])
+    assert np.array_equal(np.concatenate([a["argmax_off"], b["argmax_off"]]), res["argmax_off"])
+    # strands
+    fwd, sw_f = fg.getLogProbFor(smp, strand=0, want_sweeps=True)
+    rc = _reverse_complement(smp)
+    rev, sw_r = fg.getLogProbFor(rc, strand=1, want_sweeps=True)
+    for i in (0, 1, smp.n_alignments // 3, smp.n_alignments - 1):
+        assert np.array_equal(rev[off[i]:off[i + 1]][::-1], fwd[off[i]:off[i + 1]])
+    mirrored = np.concatenate([rev[off[i]:off[i + 1]][::-1] for i in range(smp.n_alignments)])
+    assert np.array_equal(mirrored, fwd)
+    assert int(sw_f.sum()) == int(sw_r.sum())
+    del rc
