@@ -22,6 +22,8 @@ struct phyfoo_feset {
     int W = 0, I = 0, S = 0, E = 0;
     int64_t* d_col0 = nullptr;     // [n] first column of window u
     uint8_t* d_strand = nullptr;   // [n] or null
+    cudaStream_t stream = nullptr; // the context's stream: buffers come from its stream-ordered pool (cudaMalloc / cudaFree of
+                                   // ~150 MB per M-step took 1..400 ms each on the B200 boxes; the pool keeps what was freed)
     double* d_weight = nullptr;    // [n]
     double* d_qint = nullptr;      // [4I][W*n]  entry (i,a) of tree (t,u) at ((i*4+a) * W*n + t*n + u)
     double* d_qleaf = nullptr;     // [4S][W*n]  gap leaves only
@@ -273,8 +275,8 @@ __global__ void __launch_bounds__(256) fe_final_kernel(const double* __restrict_
 }
 
 static void fe_release(phyfoo_feset* fe) {
-    cudaFree(fe->d_col0); cudaFree(fe->d_strand); cudaFree(fe->d_weight); cudaFree(fe->d_qint); cudaFree(fe->d_qleaf);
-    cudaFree(fe->d_ent); cudaFree(fe->d_G); cudaFree(fe->d_tabs); cudaFree(fe->d_part); cudaFree(fe->d_values);
+    void* bufs[] = {fe->d_col0, fe->d_strand, fe->d_weight, fe->d_qint, fe->d_qleaf, fe->d_ent, fe->d_G, fe->d_tabs, fe->d_part, fe->d_values};
+    for (void* b : bufs) dev_free(fe->stream, b);
     delete fe;
 }
 
@@ -439,15 +441,17 @@ static int fe_create(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* m,
     const size_t value_doubles = fe->order == 1 ? (size_t)(1 + 4 + 16 * (fe->W - 1)) : (size_t)(1 + 4 * fe->W);
     const size_t n_trees = (size_t)std::max<int64_t>(n, 1) * fe->W;
     cudaError_t e;
-    if ((e = cudaMalloc(&fe->d_col0, std::max<int64_t>(n, 1) * sizeof(int64_t))) != cudaSuccess ||
-        (e = cudaMalloc(&fe->d_weight, std::max<int64_t>(n, 1) * sizeof(double))) != cudaSuccess ||
-        (e = cudaMalloc(&fe->d_qint, n_trees * 4 * fe->I * sizeof(double))) != cudaSuccess ||
-        (e = cudaMalloc(&fe->d_qleaf, n_trees * 4 * fe->S * sizeof(double))) != cudaSuccess ||
-        (e = cudaMalloc(&fe->d_ent, n_trees * sizeof(double))) != cudaSuccess ||
-        (e = cudaMalloc(&fe->d_G, (fe->W + 1) * sizeof(double))) != cudaSuccess ||
-        (e = cudaMalloc(&fe->d_tabs, tab_doubles * sizeof(double))) != cudaSuccess ||
-        (e = cudaMalloc(&fe->d_part, part_doubles * sizeof(double))) != cudaSuccess ||
-        (e = cudaMalloc(&fe->d_values, value_doubles * sizeof(double))) != cudaSuccess) {
+    fe->stream = ctx->stream;
+    const cudaStream_t st = ctx->stream;
+    if ((e = dev_malloc(st, &fe->d_col0, std::max<int64_t>(n, 1) * sizeof(int64_t))) != cudaSuccess ||
+        (e = dev_malloc(st, &fe->d_weight, std::max<int64_t>(n, 1) * sizeof(double))) != cudaSuccess ||
+        (e = dev_malloc(st, &fe->d_qint, n_trees * 4 * fe->I * sizeof(double))) != cudaSuccess ||
+        (e = dev_malloc(st, &fe->d_qleaf, n_trees * 4 * fe->S * sizeof(double))) != cudaSuccess ||
+        (e = dev_malloc(st, &fe->d_ent, n_trees * sizeof(double))) != cudaSuccess ||
+        (e = dev_malloc(st, &fe->d_G, (fe->W + 1) * sizeof(double))) != cudaSuccess ||
+        (e = dev_malloc(st, &fe->d_tabs, tab_doubles * sizeof(double))) != cudaSuccess ||
+        (e = dev_malloc(st, &fe->d_part, part_doubles * sizeof(double))) != cudaSuccess ||
+        (e = dev_malloc(st, &fe->d_values, value_doubles * sizeof(double))) != cudaSuccess) {
         fe_release(fe);
         ctx->err = std::string("fe_prepare: ") + cudaGetErrorString(e);
         return e == cudaErrorMemoryAllocation ? PHYFOO_ENOMEM : PHYFOO_ECUDA;
@@ -513,7 +517,7 @@ extern "C" int phyfoo_fe_prepare(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyf
         e = cudaMemcpyAsync(fe->d_col0, col0.data(), (size_t)n_sel * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(fe->d_weight, sel_weight, (size_t)n_sel * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess && sel_strand) {
-            e = cudaMalloc(&fe->d_strand, (size_t)n_sel);
+            e = dev_malloc(ctx->stream, &fe->d_strand, (size_t)n_sel);
             if (e == cudaSuccess) e = cudaMemcpyAsync(fe->d_strand, sel_strand, (size_t)n_sel, cudaMemcpyHostToDevice, ctx->stream);
         }
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // col0 is stack-scoped

@@ -2833,8 +2833,10 @@ extern "C" int phyfoo_ss_optimize(phyfoo_ssobj* ss, const int32_t* order, int32_
         const int d = o.dim(t);
         std::vector<double> x(d);
         for (int i = 0; i < d; ++i) x[i] = std::log(o.h.pi[t][i]);
-        bfgs_minimise([&](const double* z) { return -o.eval_lambda(t, z); }, x, tc_motif_separated_positions());
-        o.eval_lambda(t, x.data());
+        // (an exception of the optimizer is caught and the run goes on from the last iterate, as in
+        // optimizing/FE_byParameter_ForBayesNodeJstacs.java:61-83)
+        try { bfgs_minimise([&](const double* z) { return -o.eval_lambda(t, z); }, x, tc_motif_separated_positions()); } catch (const std::exception&) {}
+        o.eval_lambda(t, x.data());                               // initParameters(lambda), :78
     };
     // With q fixed the objective is separable, f = sum_t G_t(theta_t) - ENT: the optimisation of a position neither reads nor
     // changes the parameters of another one, only the constant the other terms add to f.  Distinct positions therefore run side by

@@ -353,7 +353,8 @@ class PhyloBayesModel(_PhyloModel):
             fun = lambda z: -obj.eval_edges(t, z, equal, globally)          # noqa: E731
             x, f, it, ev = optimize.quasi_newton_bfgs(fun, lambda z: obj.grad(fun, z), x0,
                                                       optimize.SMALL_DIFFERENCE_OF_FUNCTIONS())
-            obj.eval_edges(t, x, equal, globally)
+            # (EdgeOptimizer.startOptimizing does not write the optimizer's result back, :104-121: the branch lengths stay at
+            # the last point the optimizer evaluated -- the last perturbation of its last gradient, x + 1e-4 e_last)
             evals += ev
         for t in range(self.length):
             for k in range(1, self.tree.n_nodes):
@@ -369,8 +370,8 @@ def _learn_edges(model, obj, globally, equal):
     """EdgeOptimizer.startOptimizing for every position (one run for all positions when `globally`) on the library's
     sufficient-statistics objective `obj` (phyfoo_ss_eval_branches): logit-parametrised branch lengths from the model's current
     ones (their mean when `equal`), BFGS on the forward-difference gradient until the objective changes by less than 1e-3
-    (optimizing/branchlengths/EdgeOptimizer.java:44-125, GlobalEdgeOptimizer.java:33-103).  Writes the learned lengths into
-    the model; returns (f_before, f_after, evaluations)."""
+    (optimizing/branchlengths/EdgeOptimizer.java:44-125, GlobalEdgeOptimizer.java:33-103).  Writes the learned lengths -- those
+    of the optimizer's last evaluation, as the reference leaves them -- into the model; returns (f_before, f_after, evaluations)."""
     from . import evolution
     N = model.tree.n_nodes
     before, evals, learned = obj.value(), 0, {}
@@ -382,7 +383,7 @@ def _learn_edges(model, obj, globally, equal):
         learned[t] = b
         return obj.eval_branches(-1 if globally else t, b)
 
-    def fd(fun, x, eps=1e-4):                  # jstacs NumericalDifferentiableFunction.java:64-84
+    def fd(fun, x, eps=1e-4):                  # jstacs NumericalDifferentiableFunction.java:64-84 (no closing evaluation)
         x = np.array(x, np.float64)
         f0, g = fun(x), np.zeros(x.size)
         for i in range(x.size):
@@ -390,7 +391,6 @@ def _learn_edges(model, obj, globally, equal):
             x[i] += eps
             g[i] = (fun(x) - f0) / eps
             x[i] = keep
-        fun(x)
         return f0, g
 
     for t in ([0] if globally else range(model.n_trees)):
@@ -398,7 +398,8 @@ def _learn_edges(model, obj, globally, equal):
         x0 = evolution.logit_from_branch(np.array([b.mean()]) if equal else b)
         fun = lambda z: -eval_edges(t, z)                                   # noqa: E731
         x, f, it, ev = optimize.quasi_newton_bfgs(fun, lambda z: fd(fun, z), x0, optimize.SMALL_DIFFERENCE_OF_FUNCTIONS())
-        eval_edges(t, x)
+        # EdgeOptimizer.startOptimizing does not write the optimizer's result back (:104-121): the branch lengths stay at the
+        # last point the optimizer evaluated -- the last perturbation of its last gradient, x + 1e-4 e_last in logit space
         evals += ev
     after = obj.value()
     for t in range(model.n_trees):

@@ -23,6 +23,6 @@ for rep in range(3):
     ss = core.SSObjective(fe); t.append(time.perf_counter())
     fb, fa, ev = ss.optimize(np.arange(W, dtype=np.int32)); t.append(time.perf_counter())
     pis = [ss.get_pi(p, fg._pi[p].size) for p in range(W)]; t.append(time.perf_counter())
-    ss.free(); fe.free(); t.append(time.perf_counter())
-    names = ["estep+gamma", "select", "fix q (FESet)", "expected counts (ss_create)", "optimise (ss_optimize)", "get_pi", "free"]
+    ss.free(); t.append(time.perf_counter()); fe.free(); t.append(time.perf_counter()); ctx.synchronize(); t.append(time.perf_counter())
+    names = ["estep+gamma", "select", "fix q (FESet)", "expected counts (ss_create)", "optimise (ss_optimize)", "get_pi", "ss.free", "fe.free", "sync"]
     print(rep, {n: round((b - a) * 1e3, 3) for n, a, b in zip(names, t, t[1:])}, "evals", ev, "selected", sa.size, "select kernels", k_sel, "fix-q kernels", k_fix)

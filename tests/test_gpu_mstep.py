@@ -200,6 +200,7 @@ def test_sufficient_statistics_objective(ctx, tree, evol):
     f_dev, f_orc = fe.eval(2, lam), ofe.eval(2, lam)
     assert abs(f_host - f_orc) <= TOL * abs(f_orc) and abs(f_dev - f_orc) <= TOL * abs(f_orc)
     f0, g = obj.grad(lambda z: obj.eval_lambda(2, z), lam, EPS)
+    obj.eval_lambda(2, lam)                          # (the gradient leaves the object at its last perturbed point, like the Java)
     r0, rg = ofe.grad(2, lam, EPS)
     assert np.all(np.abs(g - rg) <= _grad_tol(rg, r0))
     # new branch lengths at one position (EdgeOptimizer's parameters): oracle with the same branch lengths set

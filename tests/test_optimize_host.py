@@ -110,6 +110,7 @@ def test_library_suffstat_objective_matches_numpy_objective():
         lam = rng.normal(size=4)
         f, g = ss.grad(t, lam)
         f_ref, g_ref = ref.grad(lambda z: ref.eval_lambda(t, z), lam)
+        ref.eval_lambda(t, lam)                          # (the numpy gradient leaves the object at its last perturbed point)
         assert abs(f - f_ref) <= 1e-13 * abs(f_ref)
         assert np.max(np.abs(g - g_ref)) <= 1e-7 * np.max(np.abs(g_ref))      # both subtract sums of size |f| and divide by 1e-4
         assert np.allclose(ss.get_pi(t), ref.pi[t], rtol=1e-15, atol=0)
@@ -119,10 +120,12 @@ def test_library_suffstat_objective_matches_numpy_objective():
     assert abs(f - ref.value()) <= 1e-13 * abs(f)
 
 
-def test_library_bfgs_matches_python_stand_in():
-    """phyfoo_ss_optimize (C++) against optimize.quasi_newton_bfgs (numpy) on the same objective: the same algorithm, so
-    the same optimum to rounding."""
+def test_library_bfgs_matches_python_restatement(monkeypatch):
+    """phyfoo_ss_optimize (C++, csrc/suffstat_host.hpp) against optimize.quasi_newton_bfgs (numpy) on the same objective: both
+    restate jstacs Optimizer.quasiNewtonBFGS / findBracket / brentsMethod statement by statement, so they take the same
+    iterates -- the same number of function evaluations and the same optimum to rounding."""
     from phyfoo_b200 import _abi, core, optimize
+    monkeypatch.setenv("PHYFOO_SS_THREADS", "1")           # one position after the other, like the loop below
     tree, pwm, branch, counts, desc, keep = _ss_case(seed=11)
     W = len(pwm)
     ss = core.SSObjective(desc=desc, counts=counts, entropy=0.0)
@@ -130,18 +133,46 @@ def test_library_bfgs_matches_python_stand_in():
     order = np.array([2, 0, 4, 1, 3], np.int32)
     fb, fa, ev = ss.optimize(order)
     assert abs(fb - ref.value()) <= 1e-13 * abs(fb)
+    n_ref = 0
     for pos in order:
         pos = int(pos)
         fun = lambda z: -ref.eval_lambda(pos, z)          # noqa: E731
         x, f, it, n = optimize.quasi_newton_bfgs(fun, lambda z: ref.grad(fun, z), np.log(ref.pi[pos]), optimize.TC_MOTIF_SEPARATED_POSITIONS())
         ref.eval_lambda(pos, x)
+        n_ref += n + 1
     assert fa >= fb
-    assert abs(fa - ref.value()) <= 1e-9 * abs(fa)
-    for t in range(W):
-        assert np.allclose(ss.get_pi(t), ref.pi[t], rtol=0, atol=1e-6)
-    # the closed-form optimum of one position: f is sum_e C log table; for the root entries alone (a star of zero-length
-    # branches would be degenerate) check monotone improvement instead
+    assert abs(fa - ref.value()) <= 1e-12 * abs(fa)
+    assert ev == n_ref                                     # the same line searches, evaluation for evaluation
+    for t in range(W):                                     # (the two objectives differ in the last bits, which the forward
+        assert np.allclose(ss.get_pi(t), ref.pi[t], rtol=0, atol=1e-6)     # differences magnify by |f| / 1e-4)
     assert ev > 5 * W
+
+
+def test_jstacs_line_search_pieces():
+    """findBracket / brentsMethod / LimitedMedianStartDistance on functions with known answers."""
+    from phyfoo_b200 import optimize
+    f = lambda a: (a - 0.3) ** 2 + 1.0                     # noqa: E731
+    br = optimize.find_bracket(f, 0.0, f(0.0), 0.1)       # downhill at the start: expand by the golden ratio
+    assert br[0] < br[2] < br[4] and br[3] <= br[1] and br[3] <= br[5] and br[0] <= 0.3 <= br[4]
+    x, fx = optimize.brents_method(f, br[0], br[2], br[3], br[4], 1e-3)
+    assert abs(x - 0.3) < 1e-3 and abs(fx - 1.0) < 1e-6
+    br = optimize.find_bracket(f, 0.0, f(0.0), 5.0)       # overshoots: shrink towards the lower end
+    assert br[0] == 0.0 and br[2] < 5.0 and br[3] <= br[1] and br[0] <= 0.3 <= br[4]
+    sdf = optimize.LimitedMedianStartDistance(10, 0.1)
+    assert abs(sdf.get_new_start_distance() - 0.0667) < 1e-15
+    for v in (1.0, 2.0, 3.0, 4.0, 5.0, 6.0):
+        sdf.set_last_distance(v)
+    assert abs(sdf.get_new_start_distance() - 0.667 * 0.5 * (1.0 + 2.0)) < 1e-15       # memory: 1..6 and four times 0.1
+    # SmallStepCondition compares the SQUARED step length
+    tc = optimize.CombinedCondition(1, small_step=1e-4)
+    d = np.array([3.0, 4.0])
+    assert tc.do_next_iteration(1, 0.0, 0.0, d, d, 0.0021) and not tc.do_next_iteration(1, 0.0, 0.0, d, d, 0.0019)
+    # a quadratic bowl: BFGS finds the minimum
+    A = np.array([[3.0, 1.0], [1.0, 2.0]]); b = np.array([1.0, -1.0])
+    fun = lambda z: 0.5 * z @ A @ z - b @ z               # noqa: E731
+    grad = lambda z: (fun(z), A @ z - b)                  # noqa: E731
+    x, fmin, it, ev = optimize.quasi_newton_bfgs(fun, grad, np.zeros(2), optimize.CombinedCondition(1, small_gradient=1e-8))
+    assert np.allclose(x, np.linalg.solve(A, b), atol=1e-5) and it >= 2
 
 
 def test_library_mstep_on_host_threads_does_not_depend_on_their_number(monkeypatch):
