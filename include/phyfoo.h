@@ -301,6 +301,14 @@ void phyfoo_fe_free(phyfoo_ctx* ctx, phyfoo_feset* fe);
 typedef struct phyfoo_ssobj phyfoo_ssobj;
 int phyfoo_ss_create(phyfoo_ctx* ctx, phyfoo_feset* fe, phyfoo_ssobj** out);
 /* from counts the caller holds ([W][E], phyfoo_fe_suffstats layout); no device involved */
+/* The same objective for a BACKGROUND of order k >= 1 (models/PhyloBackground.java:111-176: the mean fields of every
+ * (k+1)-column window of every alignment, fixed once; f(theta) = - sum_p w_p F_p(theta) over the whole net of each window): one
+ * pass of the generic net kernel (csrc/netg.cuh) collects the expected counts of the net's table entries.  aln_weights (nullable,
+ * [n_aln]): window number p carries the weight of the alignment that holds COLUMN number p -- the reference indexes its per-column
+ * weight vector with the window number (PhyloBackground.java:114,178-186; AbstractFreeEnergyOptimizer.java:104-108), kept.
+ * Position t of the returned object has 4^min(t, k) x 4 parameters (phyfoo_ss_eval / _grad), phyfoo_ss_eval_branches works as
+ * for the motif models.  (Order 0: phyfoo_fe_prepare_all + phyfoo_ss_create.) */
+int phyfoo_ss_create_bg(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* bg, const double* aln_weights, phyfoo_ssobj** out);
 int phyfoo_ss_create_host(const phyfoo_model_desc* desc, const double* counts, double entropy, phyfoo_ssobj** out);
 int phyfoo_ss_eval(phyfoo_ssobj* ss, int32_t position, const double* lambda, int32_t dim, double* f_out);
 int phyfoo_ss_grad(phyfoo_ssobj* ss, int32_t position, const double* lambda, int32_t dim, double eps, double* f_out, double* g_out);

@@ -525,9 +525,15 @@ class SSObjective:
     """phyfoo_ssobj: the fixed-q objective on sufficient statistics, evaluated on the host inside the library (order 0).
     From an FESet (one device pass), a MultiFESet (counts all-reduced over the devices) or given counts."""
 
-    def __init__(self, fe=None, desc=None, counts=None, entropy=0.0):
+    def __init__(self, fe=None, desc=None, counts=None, entropy=0.0, background=None):
+        """background = (ctx, dataset, device model of a background of order >= 1, per-alignment weights or None):
+        phyfoo_ss_create_bg -- the mean fields of every (order + 1)-column window, fixed in one pass of the generic net kernel."""
         self.h = C.c_void_p()
-        if isinstance(fe, MultiFESet):
+        if background is not None:
+            ctx, ds, model, w = background
+            w = None if w is None else np.ascontiguousarray(w, np.float64)
+            raise_for(lib().phyfoo_ss_create_bg(ctx.h, ds.h, model.h, _p(w, C.c_double), C.byref(self.h)), ctx.h)
+        elif isinstance(fe, MultiFESet):
             _mraise(lib().phyfoo_multi_ss_create(fe.mctx.h, fe.h, C.byref(self.h)), fe.mctx.h)
         elif fe is not None:
             raise_for(lib().phyfoo_ss_create(fe.ctx.h, fe.h, C.byref(self.h)), fe.ctx.h)

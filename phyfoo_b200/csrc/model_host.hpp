@@ -252,19 +252,27 @@ struct ModelHost {
                 int rows = 1;
                 for (int q = 0; q < r[0]; ++q) rows *= 4;
                 r[6] = rows; r[7] = leaf_species[k]; r[8] = t;
-                const std::vector<double> cp = cpf(t, k);
-                if ((int)cp.size() != rows * 4) throw std::invalid_argument("netg: table shape");
-                r[4] = (int)tab.size();
-                for (double x : cp) tab.push_back(std::log(x));
-                r[5] = r[4];
-                if (leaf_species[k] >= 0) {                            // independent table: pi of the row's context, FS81alpha.java:52-64
-                    r[5] = (int)tab.size();
-                    for (int c = 0; c < ctx; ++c)
-                        for (int a = 0; a < 4; ++a)
-                            for (int b = 0; b < 4; ++b) tab.push_back(std::log(pi[t][(size_t)c * 4 + b]));
-                }
+                const size_t before = tab.size();
+                netg_node_logtab(t, k, tab);
+                r[4] = (int)before;
+                r[5] = leaf_species[k] >= 0 ? (int)before + rows * 4 : (int)before;
+                if ((int)(tab.size() - before) != rows * 4 * (leaf_species[k] >= 0 ? 2 : 1)) throw std::invalid_argument("netg: table shape");
             }
         }
+    }
+    // log CPF of node (t, k) [rows][4], followed for a leaf by the log of its independent table (pi of the row's context,
+    // FS81alpha.java:52-64) -- appended to out
+    void netg_node_logtab(int t, int k, std::vector<double>& out) const {
+        for (double x : cpf(t, k)) out.push_back(std::log(x));
+        if (leaf_species[k] >= 0)
+            for (int c = 0; c < ctx_rows(t); ++c)
+                for (int a = 0; a < 4; ++a)
+                    for (int b = 0; b < 4; ++b) out.push_back(std::log(pi[t][(size_t)c * 4 + b]));
+    }
+    // the tables of tree t alone, in netg_build's order (its slice of the table array)
+    void netg_tree_logtab(int t, std::vector<double>& out) const {
+        out.clear();
+        for (int k = 0; k < N; ++k) netg_node_logtab(t, k, out);
     }
 
     bool tables_finite() const {

@@ -181,6 +181,39 @@ NETG_HD int netg_item(const NetgView& v, const NetgObs& ob, const NetgState& st,
     return k;
 }
 
+// Expected counts of the table entries under the fixed q of one item: the coefficients netg_free_energy multiplies the log table
+// entries with (over ALL trees), times w, handed to add(entry index into the table array, value); returns w * sum q log q (the
+// entropy part).  With them the fixed-q objective of optimizing/AbstractFreeEnergyOptimizer.java:95-114 is
+// f(theta) = sum_e C[e] log table_theta[e] - ENT for any parameter set.
+template <class Add>
+NETG_HD double netg_counts(const NetgView& v, const NetgObs& ob, const NetgState& st, double w, Add&& add) {
+    double part1 = 0.0;
+    for (int g = 0; g < v.n_nodes; ++g) {
+        const int* r = v.rec + (size_t)g * NETG_REC;
+        const int o = ob.of(r);
+        const int base = o == 4 ? r[5] : r[4];
+        if (o == 4)
+            for (int h = 0; h < 4; ++h) { const double qh = st.at(g, h); if (qh > 0) part1 += qh * phy_log(qh); }
+        if (r[0] == 0 && o == 4) {
+            for (int h = 0; h < 4; ++h) add(base + h, w * st.at(g, h));
+        } else if (o != 4) {
+            for (int l = 0; l < r[6]; ++l) {
+                bool agrees;
+                const double prod = netg_parent_product(v, ob, st, r, l, -1, 1.0, agrees);
+                if (agrees && prod != 0.0) add(base + l * 4 + o, w * prod);
+            }
+        } else {
+            for (int l = 0; l < r[6]; ++l) {
+                bool agrees;
+                const double prod = netg_parent_product(v, ob, st, r, l, -1, 1.0, agrees);
+                if (!agrees || prod == 0.0) continue;
+                for (int h2 = 0; h2 < 4; ++h2) add(base + l * 4 + h2, w * (prod * st.at(g, h2)));
+            }
+        }
+    }
+    return w * part1;
+}
+
 }  // namespace phyfoo
 
 #if defined(__CUDACC__)
@@ -211,5 +244,31 @@ __global__ void __launch_bounds__(128) score_netg_kernel(NetgParams p) {
         sw += (unsigned long long)k;
     }
     if (p.sweep_sum && sw) atomicAdd(p.sweep_sum, sw);
+}
+#endif
+
+#if defined(__CUDACC__)
+// M-step of a background of order >= 1: mean field of every window, then its expected counts into counts[] (one slot per table
+// entry, global atomics) and its entropy part into *entropy.  item u = window u; its weight is weight_of_column[u] when given --
+// the reference indexes the per-COLUMN weight vector with the WINDOW number (models/PhyloBackground.java:114,178-186 against
+// optimizing/AbstractFreeEnergyOptimizer.java:104-108), kept.
+struct NetgCountParams {
+    NetgParams s;
+    const double* aln_w; const int64_t* col_off; int n_aln;   // aln_w NULL: every weight 1
+    double* counts; double* entropy;
+};
+__global__ void __launch_bounds__(128) netg_count_kernel(NetgCountParams p) {
+    const size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    phyfoo::NetgState st{p.s.q + slot, p.s.q_stride};
+    double ent = 0.0;
+    for (int64_t u = (int64_t)slot; u < p.s.n_items; u += (int64_t)gridDim.x * blockDim.x) {
+        phyfoo::NetgObs ob;
+        for (int t = 0; t < p.s.view.n_trees; ++t) ob.cw[t] = load_column(p.s.bases, p.s.gaps, p.s.n_cols, p.s.nb, p.s.item_cols[(size_t)t * p.s.n_items + u]);
+        double f = 0.0, l = 0.0;
+        phyfoo::netg_item(p.s.view, ob, st, p.s.view.n_trees, p.s.max_sweeps, p.s.min_sweeps, p.s.tol, &f, &l);
+        const double w = p.aln_w ? p.aln_w[find_alignment(p.col_off, p.n_aln, u)] : 1.0;
+        ent += phyfoo::netg_counts(p.s.view, ob, st, w, [&](int e, double val) { atomicAdd(p.counts + e, val); });
+    }
+    if (ent != 0.0) atomicAdd(p.entropy, ent);
 }
 #endif

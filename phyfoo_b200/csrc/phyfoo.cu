@@ -141,7 +141,7 @@ struct phyfoo_model {
     double f0_const1n = 0.0;
     // generic net (netg.cuh): background models of order >= 2
     int* d_netg_rec = nullptr; int* d_netg_lists = nullptr; double* d_netg_tab = nullptr;
-    size_t netg_lists_len = 0, netg_tab_len = 0;
+    size_t netg_lists_len = 0, netg_tab_len = 0, netg_tab_used = 0;
     uint64_t netg_uploaded = 0;
 };
 
@@ -1947,6 +1947,7 @@ static int netg_upload(phyfoo_ctx* ctx, phyfoo_model* m) {
     CU(cudaMemcpyAsync(m->d_netg_lists, lists.data(), lists.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(m->d_netg_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));      // the vectors are stack-scoped
+    m->netg_tab_used = tab.size();
     m->netg_uploaded = m->h.version;
     return PHYFOO_OK;
 }
@@ -2769,6 +2770,77 @@ extern "C" int phyfoo_ss_create(phyfoo_ctx* ctx, phyfoo_feset* fe, phyfoo_ssobj*
     return PHYFOO_OK;
 }
 // from given counts (e.g. counts a caller reduced itself); no device involved
+// The M-step objective of a BACKGROUND of order k >= 1 (models/PhyloBackground.java:111-176): every (k+1)-column window of every
+// alignment is a mean field over the whole net; with q fixed, f(theta) = - sum_p w_p F_p(theta).  One pass of the generic net
+// kernel (netg.cuh) fixes q and collects the expected counts of the net's table entries; everything after that is host work on
+// the returned object (phyfoo_ss_eval / _grad / _eval_branches: position t has 4^min(t, k) x 4 parameters).
+extern "C" int phyfoo_ss_create_bg(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* bg, const double* aln_weights, phyfoo_ssobj** out) {
+    if (!ctx) return PHYFOO_EINVAL;
+    if (!ds || !bg || !out) return fail(ctx, PHYFOO_EINVAL, "ss_create_bg: NULL argument");
+    *out = nullptr;
+    CU(cudaSetDevice(ctx->device));
+    ctx->launches = 0; ctx->n_ktimes = 0;
+    ModelHost& h = bg->h;
+    const int k = h.order, T = k + 1;
+    if (h.kind != PHYFOO_MODEL_BG || k < 1) return fail(ctx, PHYFOO_EINVAL, "ss_create_bg: needs a background model of order >= 1 (order 0: phyfoo_fe_prepare_all + phyfoo_ss_create)");
+    if (T > phyfoo::NETG_MAX_TREES) return fail(ctx, PHYFOO_EUNSUPPORTED, "background order above 7");
+    if (h.evol == PHYFOO_EVOL_HKY_AS_IMPLEMENTED) return fail(ctx, PHYFOO_EUNSUPPORTED, "HKY as implemented: the M-step objective is not finite for any parameter set (HKY.java:32)");
+    if (h.S != ds->S) return fail(ctx, PHYFOO_EINVAL, "model and dataset disagree on the number of species");
+    if (ds->n_aln > 0 && ds->min_len < T) return fail(ctx, PHYFOO_EINVAL, "background of order k: an alignment is shorter than k + 1 columns");
+    int rc = netg_upload(ctx, bg);
+    if (rc) return rc;
+    const int64_t* d_woff; const std::vector<int64_t>* h_woff;
+    rc = dataset_win_off(ctx, ds, T, &d_woff, &h_woff);
+    if (rc) return rc;
+    const int64_t n = h_woff->back();
+    const size_t n_entries = bg->netg_tab_used;
+    std::vector<double> c(n_entries + 1, 0.0);
+    if (n > 0) {
+        CU(ctx->misc.ensure((size_t)T * n * sizeof(int64_t)));
+        CU(ctx->bg_scores.ensure((size_t)(2 * n + n_entries + 1) * sizeof(double)));
+        int64_t* d_cols = ctx->misc.as<int64_t>();
+        double* d_ofirst = ctx->bg_scores.as<double>();
+        double* d_counts = d_ofirst + 2 * n;
+        CU(cudaMemsetAsync(d_counts, 0, (n_entries + 1) * sizeof(double), ctx->stream));
+        const double* d_alnw = nullptr;
+        if (aln_weights) {
+            CU(ctx->alnw.ensure((size_t)ds->n_aln * sizeof(double)));
+            CU(cudaMemcpyAsync(ctx->alnw.p, aln_weights, (size_t)ds->n_aln * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            d_alnw = ctx->alnw.as<double>();
+        }
+        bgk_items_full_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_woff, ds->d_col_off, ds->n_aln, n, T, d_cols);
+        CU(cudaGetLastError());
+        const int G = h.W * h.N;
+        const size_t per_thread = (size_t)G * 4 * sizeof(double);
+        long long blocks = std::min<long long>((n + 127) / 128, 8LL * ctx->sm_count);
+        blocks = std::max<long long>(1, std::min<long long>(blocks, (long long)((512ull << 20) / (per_thread * 128))));
+        CU(ctx->gstate.ensure(per_thread * (size_t)blocks * 128));
+        NetgCountParams p;
+        p.s.bases = ds->d_bases; p.s.gaps = ds->d_gaps; p.s.n_cols = ds->n_cols; p.s.nb = ds->nb;
+        p.s.view.n_nodes = G; p.s.view.n_trees = h.W; p.s.view.nodes_per_tree = h.N;
+        p.s.view.rec = bg->d_netg_rec; p.s.view.lists = bg->d_netg_lists; p.s.view.tab = bg->d_netg_tab;
+        p.s.item_cols = d_cols; p.s.item_len = nullptr; p.s.n_items = n;
+        p.s.q = ctx->gstate.as<double>(); p.s.q_stride = (size_t)blocks * 128;
+        p.s.out_first = d_ofirst; p.s.out_last = d_ofirst + n; p.s.sweeps = nullptr; p.s.sweep_sum = nullptr;
+        p.s.max_sweeps = h.max_sweeps; p.s.min_sweeps = h.min_sweeps; p.s.tol = h.tol;
+        p.aln_w = d_alnw; p.col_off = ds->d_col_off; p.n_aln = ds->n_aln;
+        p.counts = d_counts; p.entropy = d_counts + n_entries;
+        {
+            KernelTimer kt_(ctx, "netg_count_kernel");
+            netg_count_kernel<<<(unsigned)blocks, 128, 0, ctx->stream>>>(p);
+        }
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(c.data(), d_counts, (n_entries + 1) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    try {
+        phyfoo_ssobj* ss = new phyfoo_ssobj();
+        ss->o.init_generic(h, c.data(), n_entries, c[n_entries]);
+        *out = ss;
+    } catch (const std::exception& e) { return fail(ctx, PHYFOO_EINVAL, std::string("ss_create_bg: ") + e.what()); }
+    return PHYFOO_OK;
+}
+
 extern "C" int phyfoo_ss_create_host(const phyfoo_model_desc* desc, const double* counts, double entropy, phyfoo_ssobj** out) {
     if (!desc || !counts || !out) return PHYFOO_EINVAL;
     *out = nullptr;
@@ -2792,8 +2864,8 @@ extern "C" int phyfoo_ss_eval(phyfoo_ssobj* ss, int32_t position, const double* 
 }
 extern "C" int phyfoo_ss_grad(phyfoo_ssobj* ss, int32_t position, const double* lambda, int32_t dim, double eps, double* f_out, double* g_out) {
     if (!ss || !lambda || !g_out || position < 0 || position >= ss->o.h.W || dim != ss->o.dim(position) || !(eps > 0)) return PHYFOO_EINVAL;
-    double x[16];
-    for (int i = 0; i < dim; ++i) x[i] = lambda[i];
+    std::vector<double> xv(lambda, lambda + dim);
+    double* x = xv.data();
     const double f0 = ss->o.eval_lambda(position, x);
     for (int i = 0; i < dim; ++i) {                     // jstacs NumericalDifferentiableFunction.java:64-84
         const double keep = x[i];

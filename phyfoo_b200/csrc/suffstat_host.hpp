@@ -30,17 +30,42 @@ struct SuffStatObjective {
     long long evaluations = 0;
 
     int EE = 0;                        // entries per position: E (order 0) or E1 (order-1 network, build_tables1_into)
+    // generic mode (backgrounds of order >= 1, netg.cuh): counts over the generic net's table array, tree t owns the slice
+    // [g_off[t], g_off[t + 1])
+    bool generic = false;
+    std::vector<size_t> g_off;
     void init(const ModelHost& model, const double* c, double ent) {
         h = model;
+        generic = false;
         EE = h.order == 1 ? h.E1() : h.E;
         counts.assign(c, c + (size_t)h.W * EE);
         entropy = ent;
         G.assign(h.W, 0.0);
         for (int t = 0; t < h.W; ++t) G[t] = term(t, h.pi[t].data());
     }
+    void init_generic(const ModelHost& model, const double* c, size_t n_entries, double ent) {
+        h = model;
+        generic = true;
+        g_off.assign(h.W + 1, 0);
+        std::vector<double> lt;
+        for (int t = 0; t < h.W; ++t) { h.netg_tree_logtab(t, lt); g_off[t + 1] = g_off[t] + lt.size(); }
+        if (g_off[h.W] != n_entries) throw std::invalid_argument("suffstat: counts do not match the net's table array");
+        counts.assign(c, c + n_entries);
+        entropy = ent;
+        G.assign(h.W, 0.0);
+        for (int t = 0; t < h.W; ++t) G[t] = term(t, h.pi[t].data());
+    }
     // sum_e C[t][e] log table[e] for position t under the stationary distribution p (entries with a zero count never enter
-    // the sum: their log may be -inf)
+    // the sum: their log may be -inf).  Generic mode: p is h.pi[t] (every caller has stored it there already).
     double term(int t, const double* p) const {
+        if (generic) {
+            std::vector<double> lt;
+            h.netg_tree_logtab(t, lt);
+            const double* c = &counts[g_off[t]];
+            double s = 0.0;
+            for (size_t e = 0; e < lt.size(); ++e) if (c[e] != 0.0) s += c[e] * lt[e];
+            return s;
+        }
         std::vector<double> lt(EE);
         if (h.order == 1) h.build_tables1_into(t, p, lt.data());
         else h.build_tables_into(t, p, lt.data(), nullptr);
@@ -55,13 +80,13 @@ struct SuffStatObjective {
         return s - entropy;
     }
     // evaluateFunction(lambda) of one position: pi_t = softmax(lambda); the object (like the reference's model) is left there
-    int dim(int t) const { return h.order == 1 ? h.ctx_rows(t) * 4 : 4; }
+    int dim(int t) const { return generic ? h.ctx_rows(t) * 4 : (h.order == 1 ? h.ctx_rows(t) * 4 : 4); }
     double eval_lambda(int t, const double* lambda) {
-        double p[16];
-        const int d = dim(t);                                  // an order-1 position t >= 1: four context rows, a softmax per row
-        lambda_to_pi(lambda, p, d);
-        h.pi[t].assign(p, p + d);
-        G[t] = term(t, p);
+        const int d = dim(t);                                  // four parameters per context row, a softmax per row
+        std::vector<double> p(d);
+        lambda_to_pi(lambda, p.data(), d);
+        h.pi[t].assign(p.begin(), p.end());
+        G[t] = term(t, p.data());
         ++evaluations;
         return value();
     }

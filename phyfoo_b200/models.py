@@ -527,17 +527,18 @@ class PhyloBackground(_PhyloModel):
     MSTEP_SUFFICIENT_STATISTICS = True
 
     def train(self, sample: PhyloSample, weights=None):
-        """models/PhyloBackground.java:111-176 (order 0): objective over every column of every alignment with per-alignment
+        """models/PhyloBackground.java:111-176 (order 0; order >= 1: _train_background_order_k below): objective over every
+        column of every alignment with per-alignment
         weights (extendWeights :178-186 reads one weight per alignment of `sample`, so a longer vector is cut), q fixed after
         one mean-field pass; TRAIN_MOTIF: BFGS on pi until the objective changes by less than 1e-3; EDGE_LEARNING: then the
         branch lengths (EdgeOptimizer, per position, EDGE_LEARNING_ONE_LENGTH = one length for all branches) on the same
         fixed q."""
         self._check(sample)
-        if self.order != 0:
-            raise NotImplementedError("background models of order >= 1 are not supported (DESIGN.md)")
         if weights is not None:
             weights = np.ascontiguousarray(np.asarray(weights, np.float64)[:sample.n_alignments])
         stats = {"f_before": None, "f_after": None, "evaluations": 0, "iterations": 0}
+        if self.order >= 1:
+            return self._train_order_k(sample, weights, stats)
         fe = core.FESet(self.ctx, sample.device(self.ctx), self.device_model(), aln_weights=weights)
         obj = None
         try:
@@ -567,6 +568,41 @@ class PhyloBackground(_PhyloModel):
                 obj.free()
             fe.free()
         return stats
+
+
+def _train_background_order_k(self, sample, weights, stats):
+    """PhyloBackground.train for order k >= 1 (models/PhyloBackground.java:111-176): the mean fields of every (k + 1)-column
+    window, fixed in one pass of the generic net kernel, and their expected counts (phyfoo_ss_create_bg); TRAIN_MOTIF: the
+    stationary distributions position by position (position t: 4^min(t, k) context rows of four parameters,
+    FE_byParameter_ForBayesNodeJstacs :61-83); EDGE_LEARNING: the branch lengths position by position.  All evaluations are
+    host dot products inside the library.  `weights` keeps the reference's indexing: window number p carries the weight of the
+    alignment that holds column number p."""
+    obj = core.SSObjective(background=(self.ctx, sample.device(self.ctx), self.device_model(), weights))
+    try:
+        stats["f_before"] = obj.value()
+        if type(self).TRAIN_MOTIF:
+            for t in range(self.n_trees):
+                lam0 = np.log(self._pi[t].ravel())
+                x, f, it, ev = optimize.quasi_newton_bfgs(lambda z: -obj.eval(t, z), lambda z: _neg(obj.grad(t, z)), lam0,
+                                                          optimize.SMALL_DIFFERENCE_OF_FUNCTIONS())
+                obj.eval(t, x)                                   # initParameters(lambda), :78
+                stats["evaluations"] += ev
+                stats["iterations"] += it
+                self.setCondProb(obj.get_pi(t, self._pi[t].size).reshape(self._pi[t].shape), t)
+            stats["f_after"] = obj.value()
+        if type(self).EDGE_LEARNING:
+            before, after, evals = _learn_edges(self, obj, False, type(self).EDGE_LEARNING_ONE_LENGTH)
+            stats["edges_f_before"], stats["edges_f_after"] = before, after
+            stats["evaluations"] += evals
+            stats["f_after"] = after
+        if stats["f_after"] is None:
+            stats["f_after"] = stats["f_before"]
+    finally:
+        obj.free()
+    return stats
+
+
+PhyloBackground._train_order_k = _train_background_order_k
 
 
 class StrandModel:

@@ -562,3 +562,36 @@ extern "C" int emul_netg_items(const phyfoo_model_desc* d, const uint8_t* codes 
         return 0;
     } catch (const std::exception& e) { std::fprintf(stderr, "emul: %s\n", e.what()); return -1; }
 }
+
+// expected counts of the generic net's table entries over a list of full windows (netg_counts), and the table array itself
+extern "C" int emul_netg_tab(const phyfoo_model_desc* d, double* tab_out, int cap) {
+    try {
+        ModelHost m; m.init(*d);
+        std::vector<int> rec, lists; std::vector<double> tab;
+        m.netg_build(rec, lists, tab);
+        if (tab_out) for (int i = 0; i < (int)tab.size() && i < cap; ++i) tab_out[i] = tab[i];
+        return (int)tab.size();
+    } catch (const std::exception& e) { std::fprintf(stderr, "emul: %s\n", e.what()); return -1; }
+}
+extern "C" int emul_netg_counts(const phyfoo_model_desc* d, const uint8_t* codes, int n_items, const int* cols, const double* weights,
+                                double* counts_out, double* entropy_out) {
+    try {
+        ModelHost m; m.init(*d);
+        std::vector<int> rec, lists; std::vector<double> tab;
+        m.netg_build(rec, lists, tab);
+        NetgView v{m.W * m.N, m.W, m.N, rec.data(), lists.data(), tab.data()};
+        std::vector<double> q((size_t)v.n_nodes * 4, 1e300);
+        NetgState st{q.data(), 1};
+        for (size_t i = 0; i < tab.size(); ++i) counts_out[i] = 0.0;
+        double ent = 0.0;
+        for (int u = 0; u < n_items; ++u) {
+            NetgObs ob;
+            for (int t = 0; t < m.W; ++t) ob.cw[t] = words_of(codes + (size_t)cols[(size_t)u * m.W + t] * m.S, m.S, false);
+            double f, l;
+            netg_item(v, ob, st, m.W, m.max_sweeps, m.min_sweeps, m.tol, &f, &l);
+            ent += netg_counts(v, ob, st, weights[u], [&](int e, double val) { counts_out[e] += val; });
+        }
+        *entropy_out = ent;
+        return 0;
+    } catch (const std::exception& e) { std::fprintf(stderr, "emul: %s\n", e.what()); return -1; }
+}

@@ -388,3 +388,53 @@ def test_generic_net_background_of_any_order_matches_oracle(emul, order, gap_rat
             assert abs(-rf[j] - r_right) <= 1e-12 * abs(r_right), (j, -rf[j], r_right)
         else:
             assert r_right == 0.0
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_generic_net_expected_counts_give_the_fixed_q_objective(emul, order):
+    """netg_counts: with q fixed, sum_e C[e] log table_theta[e] - ENT is the oracle's fixed-q objective for ANY parameter set
+    (new stationary distributions at a position with 4^min(t, k) context rows, new branch lengths)."""
+    from util import oracle_bg
+    rng = np.random.default_rng(70 + order)
+    newick = TREES[3]
+    tree = parse_newick(newick)
+    T = order + 1
+    pis = [rng.dirichlet(np.ones(4), size=4 ** min(order, t)) for t in range(T)]
+    branch = np.tile(tree.branch, (T, 1))
+    desc, keep = _abi.make_desc(_abi.MODEL_BG, 0, order, tree, branch, pis)
+    L = 20
+    codes = random_codes(rng, L, tree.n_species, 0.1)
+    n = L - order
+    cols = np.ascontiguousarray([[u + t for t in range(T)] for u in range(n)], np.int32)
+    w = rng.uniform(0.5, 2.0, n)
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    emul.emul_netg_tab.argtypes = [C.POINTER(_abi.ModelDesc), dp, C.c_int]
+    emul.emul_netg_counts.argtypes = [C.POINTER(_abi.ModelDesc), C.POINTER(C.c_uint8), C.c_int, ip, dp, dp, dp]
+    ne = emul.emul_netg_tab(C.byref(desc), None, 0)
+    counts, ent = np.zeros(ne), C.c_double()
+    assert emul.emul_netg_counts(C.byref(desc), codes.ctypes.data_as(C.POINTER(C.c_uint8)), n, cols.ctypes.data_as(ip),
+                                 w.ctypes.data_as(dp), counts.ctypes.data_as(dp), C.byref(ent)) == 0
+
+    def objective(pis_, branch_):
+        d2, k2 = _abi.make_desc(_abi.MODEL_BG, 0, order, tree, branch_, pis_)
+        tab = np.zeros(ne)
+        assert emul.emul_netg_tab(C.byref(d2), tab.ctypes.data_as(dp), ne) == ne
+        nz = counts != 0
+        return float((counts[nz] * tab[nz]).sum() - ent.value)
+
+    ob = oracle_bg(newick, order, pis)
+    ofe = orc.FESet(ob, np.stack([codes[u:u + T] for u in range(n)]), w)
+    ref = ofe.sum()
+    assert abs(objective(pis, branch) - ref) <= 1e-12 * abs(ref)
+    for t in range(T):                                         # new parameters at one position after the other
+        lam = rng.normal(size=pis[t].shape)
+        new = np.exp(lam) / np.exp(lam).sum(axis=1, keepdims=True)
+        pis = [new if i == t else p for i, p in enumerate(pis)]
+        ref = ofe.eval(t, lam.ravel())
+        assert abs(objective(pis, branch) - ref) <= 1e-12 * abs(ref), (t, objective(pis, branch), ref)
+    b2 = branch.copy()
+    b2[T - 1, 1:] = rng.uniform(0.05, 0.5, tree.n_nodes - 1)
+    for k in range(1, tree.n_nodes):
+        ob.set_branch(T - 1, k, b2[T - 1, k])
+    ref = ofe.sum()
+    assert abs(objective(pis, b2) - ref) <= 1e-12 * abs(ref)

@@ -107,3 +107,73 @@ def test_zoops_estep_with_background_of_any_order(ctx, tree, order, fg_order, ga
             assert abs(res["ll"] - ref["ll"]) <= TOL * abs(ref["ll"]) and np.allclose(res["w"], ref["w"], rtol=1e-9, atol=0)
     finally:
         ctx.set_option("bg_generic", 0)
+
+
+@pytest.mark.parametrize("tree,order", [("cat5", 1), ("mixed6", 2)])
+def test_background_training_of_any_order(ctx, tree, order):
+    """PhyloBackground.train for order k >= 1 (models/PhyloBackground.java:111-176) on the expected counts of the generic net
+    (phyfoo_ss_create_bg): the objective values the optimisers report equal the oracle's fixed-q objective under the same
+    parameters -- q fixed under the starting model, window p weighted with the alignment that holds COLUMN p (the reference's
+    indexing) --, training raises the objective and the log-probability of the data, and the device model follows."""
+    from phyfoo_b200 import core
+    from phyfoo_b200.data import PhyloSample
+    from phyfoo_b200.models import PhyloBackground
+    from phyfoo_b200.newick import parse_newick
+    newick = _trees()[tree]
+    tr = parse_newick(newick)
+    rng = np.random.default_rng(83 + order)
+    T = order + 1
+    lens = [25, 40, T, 31]
+    smp = PhyloSample(random_codes(rng, sum(lens), tr.n_species, 0.05), np.concatenate([[0], np.cumsum(lens)]))
+    wts = rng.uniform(0.5, 2.0, len(lens))
+    pi0 = _pis(rng, order)
+    bg = PhyloBackground(order, newick, ctx); bg.setCondProbs(pi0)
+    ll0 = bg.getLogProbFor(smp).sum()
+    # the oracle's objective: every (k+1)-column window of every alignment, weights by the reference's (mis)indexing
+    wins, ww = [], []
+    col_w = np.repeat(wts, lens)
+    for i, L in enumerate(lens):
+        a = smp.getElementAt(i)
+        for u in range(L - order):
+            wins.append(a[u:u + T]); ww.append(col_w[len(ww)])
+    ob = oracle_bg(newick, order, pi0)
+    ofe = orc.FESet(ob, np.stack(wins), np.array(ww))
+    # 1. the objective and its gradient through the C ABI
+    obj = core.SSObjective(background=(ctx, smp.device(ctx), bg.device_model(), wts))
+    assert [n for n, _ in ctx.last_kernel_times()] == ["netg_count_kernel"]
+    assert abs(obj.value() - ofe.sum()) <= TOL * abs(ofe.sum())
+    t = order                                                           # the position with all 4^k context rows
+    lam = rng.normal(size=4 ** order * 4)
+    f, g = obj.grad(t, lam, 1e-4)
+    r0, rg = ofe.grad(t, lam, 1e-4)
+    assert abs(f - r0) <= TOL * abs(r0)
+    assert np.all(np.abs(g - rg) <= TOL * np.abs(rg) + 64 * np.finfo(float).eps * abs(r0) / 1e-4)
+    with pytest.raises(ValueError):
+        obj.eval(t, np.zeros(4)) if order else None
+    obj.free()
+    ofe.eval(t, np.log(pi0[t]).ravel())
+    # 2. training: pi position by position, then the branch lengths
+    PhyloBackground.EDGE_LEARNING = True
+    try:
+        st = bg.train(smp, wts)
+    finally:
+        PhyloBackground.EDGE_LEARNING = False
+    assert st["edges_f_after"] >= st["edges_f_before"] >= st["f_before"] and st["edges_f_after"] > st["f_before"]
+    assert abs(st["f_before"] - ofe.sum()) <= TOL * abs(ofe.sum())
+    for tt in range(T):
+        ofe.eval(tt, np.log(bg.getCondProb(tt)))
+    assert abs(ofe.sum() - st["edges_f_before"]) <= TOL * abs(st["edges_f_before"])
+    for tt in range(T):
+        for k in range(1, tr.n_nodes):
+            ob.set_branch(tt, k, bg._branch[tt, k])
+    assert abs(ofe.sum() - st["edges_f_after"]) <= TOL * abs(st["edges_f_after"])
+    # 3. the device model scores with the trained parameters (a fresh oracle under them agrees) and the data became likelier
+    ob2 = oracle_bg(newick, order, [bg.getCondProb(tt) for tt in range(T)])
+    for tt in range(T):
+        for k in range(1, tr.n_nodes):
+            ob2.set_branch(tt, k, bg._branch[tt, k])
+    per = bg.getLogProbFor(smp)
+    for i, L in enumerate(lens):
+        r = ob2.bg_range(smp.getElementAt(i), 0, L - 1)
+        assert abs(per[i] - r) <= TOL * abs(r)
+    assert per.sum() > ll0
