@@ -142,3 +142,45 @@ def test_c4_shards_are_distinct_blocks_with_one_planted_site_of_one_motif():
     assert len(a[2]) == 3 and all(np.allclose(x, y) for x, y in zip(a[2], b[2]))          # the same three PWMs on every rank
     planted, kind = a[4], a[5]
     assert np.array_equal(planted >= 0, kind >= 0) and set(np.unique(kind)) <= {-1, 0, 1, 2}
+
+
+# ---- backgrounds of orders 1 and 2 (tests/golden/c1_tree1_first8_bgorders.npz, scripts/make_golden_bgorders.py) ----------
+GOLD_BG = np.load(os.path.join(ROOT, "tests", "golden", "c1_tree1_first8_bgorders.npz"))
+N_ESTEP = 3
+
+
+def _bg_pis(order):
+    return [GOLD_BG[f"pi_o{order}_t{t}"] for t in range(order + 1)]
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_oracle_reproduces_golden_background_orders(order):
+    from util import oracle_bg
+    codes, off = GOLD["codes_gapped"], GOLD["col_offsets"]
+    bg = oracle_bg(_newick("cat"), order, _bg_pis(order))
+    for i in (0, 5):                                               # (the E-step vectors are checked on the GPU side)
+        a = codes[off[i]:off[i + 1]]
+        assert abs(bg.bg_range(a, 0, a.shape[0] - 1) - GOLD_BG[f"logprob_o{order}"][i]) <= 1e-12 * abs(GOLD_BG[f"logprob_o{order}"][i])
+        assert abs(bg.bg_range(a, 7, 7 + order + 11) - GOLD_BG[f"range_o{order}"][i]) <= 1e-12 * abs(GOLD_BG[f"range_o{order}"][i])
+    assert np.all(GOLD_BG[f"logprob_o{order}"] < 0) and np.isfinite(GOLD_BG[f"estep_llw_o{order}"]).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("order", [1, 2])
+def test_gpu_matches_golden_background_orders(order):
+    from phyfoo_b200 import core
+    from phyfoo_b200.data import PhyloSample
+    from phyfoo_b200.models import PhyloBackground, PhyloBayesModel, SingleHiddenMotifMixture
+    ctx = core.default_context()
+    newick, codes, off = _newick("cat"), GOLD["codes_gapped"], GOLD["col_offsets"]
+    smp = PhyloSample(codes, off)
+    bg = PhyloBackground(order, newick, ctx); bg.setCondProbs(_bg_pis(order))
+    assert rel_err(bg.getLogProbFor(smp), GOLD_BG[f"logprob_o{order}"]) < 1e-9
+    got = [bg.getLogProbForRange(smp, i, 7, 7 + order + 11) for i in range(N_ALN)]
+    assert rel_err(got, GOLD_BG[f"range_o{order}"]) < 1e-9
+    fg = PhyloBayesModel(W, 0, newick, ctx)
+    fg.setCondProbs([p.reshape(1, 4) for p in GOLD["pwm"]])
+    res = SingleHiddenMotifMixture(fg, bg, zoops=0.9).getNewWeights(smp.slice(0, N_ESTEP))
+    assert np.array_equal(res["argmax_off"], GOLD_BG[f"estep_argmax_off_o{order}"])
+    assert np.max(np.abs(res["gamma"] - GOLD_BG[f"estep_gamma_o{order}"])) < 1e-9
+    assert rel_err([res["ll"], *res["w"]], GOLD_BG[f"estep_llw_o{order}"]) < 1e-9
