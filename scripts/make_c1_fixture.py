@@ -25,6 +25,12 @@ def main():
     path = os.path.join(ROOT, "tests", "golden", "c1_tree1_first200.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {os.path.getsize(path)} bytes, {smp.n_alignments} alignments, lengths {smp.lengths().min()}..{smp.lengths().max()}")
+    # the negatives of the same data set (no planted site): the first 200 alignments of data_tree1_1.0.bg, for the classification
+    # front-end (classification/ClassificationUtil.java: thresholds from the negatives, sensitivity on the positives)
+    neg = PhyloSample.from_fasta(FASTA.replace(".fg", ".bg"), CAT, limit=200)
+    path = os.path.join(ROOT, "tests", "golden", "c1_tree1_bg_first200.npz")
+    np.savez_compressed(path, codes=neg.codes, col_offsets=neg.col_offsets)
+    print(f"wrote {path}: {os.path.getsize(path)} bytes, {neg.n_alignments} alignments")
 
 
 if __name__ == "__main__":

@@ -85,3 +85,67 @@ def test_scan_on_oracle_scores(setup):
             if np.min(np.abs(x - t)) > 1e-9 * abs(t):              # no score on the knife's edge of the threshold
                 assert h["n_hits"][i] == int((x > t).sum())
                 assert h["first_hit"][i] == (int(np.argmax(x > t)) if (x > t).any() else -1)
+
+
+@pytest.mark.gpu
+def test_classification_on_the_references_bundled_positives_and_negatives():
+    """BASELINE configs[0] end to end through the classification front-end: the first 200 alignments of the reference's
+    data/synthetic_data/trees/data_tree1_1.0.fg (one planted site each) against the first 200 of data_tree1_1.0.bg (none), scored
+    under the generating PWM and tree (tests/golden/c1_tree1_first200.npz, c1_tree1_bg_first200.npz; scripts/make_c1_fixture.py).
+    Thresholds from the negatives, sensitivity on the positives (classification/ClassificationUtil.java:231-278), the per-alignment
+    classification by log-likelihood differences (:82-159); device flavours equal the host flavours on the same scores, and the
+    scores of a few alignments are the oracle's."""
+    import os
+    from util import ROOT, oracle_fg, rel_err
+    from phyfoo_b200 import classification as cl, core, synth
+    from phyfoo_b200.data import PhyloSample
+    from phyfoo_b200.models import PhyloBackground, PhyloBayesModel, SingleHiddenMotifMixture
+    ctx = core.default_context()
+    cfg, newick, pwm, pos, planted = synth.make_config("c1")
+    z = np.load(os.path.join(ROOT, "tests", "golden", "c1_tree1_bg_first200.npz"))
+    neg = PhyloSample(z["codes"], z["col_offsets"])
+    W = cfg["W"]
+    fg = PhyloBayesModel(W, 0, newick, ctx); fg.setCondProbs(pwm)
+    bg = PhyloBackground(0, newick, ctx)
+    ps, ns = cl.getScores(fg, pos), cl.getScores(fg, neg)
+    om = oracle_fg(newick, pwm)
+    for i in (0, 117):
+        assert rel_err(ps[i], om.score_windows(pos.getElementAt(i))[0]) < 1e-9
+        assert rel_err(ns[i], om.score_windows(neg.getElementAt(i))[0]) < 1e-9
+    spec = [0.9, 0.99, 0.999, 0.9999]
+    thr = cl.determineThresholdsForSpecifitiesPerPos(ns, spec)
+    assert np.array_equal(thr, cl.determineThresholdsForSpecifitiesPerPos_device(fg, neg, spec))
+    sens = cl.getSensitivitiesPerSeqForSpecifitiesPerPos(ps, ns, spec)
+    assert np.all(np.diff(sens) <= 0) and sens[1] > 0.8             # at 99 % per-position specificity most planted sites are found
+    for t, s in zip(thr, sens):
+        assert cl.determineSensitivityPerSeq_device(t, fg, pos) == s
+    hits = cl.scan_hits_device(fg, pos, thr[2])
+    assert np.array_equal(hits["n_hits"], [int((x > thr[2]).sum()) for x in ps])
+    assert np.array_equal(hits["arg_max"], [int(np.argmax(x)) for x in ps])
+    # (the raw motif score -- not the ratio to the background the E-step uses -- peaks at the planted site in a minority of the
+    # alignments only: conserved columns score high under any phylogenetic model)
+    # false-positive rate per negative alignment at the same threshold stays near (1 - specificity) x windows per alignment
+    fp = cl.determineSensitivityPerSeq_device(thr[2], fg, neg)
+    assert fp < 0.5
+    # ROC over the per-position thresholds and the per-alignment classification under the ZOOPS mixture
+    grid = np.linspace(0.0, 1.0, 101)
+    tg = cl.determineThresholdsForSpecifitiesPerPos(ns, grid)
+    tpr = np.array([cl.determineSensitivityPerSeq(t, ps) for t in tg])
+    fpr = np.array([cl.determineSensitivityPerSeq(t, ns) for t in tg])
+    o = np.argsort(fpr, kind="stable")
+    auc = cl.calculateAUC(np.append(fpr[o], 1.0), np.append(tpr[o], 1.0))
+    assert 0.5 < auc <= 1.0                                       # (0.535: per-alignment ROC of the RAW motif score, see above)
+    shm = SingleHiddenMotifMixture(fg, bg, zoops=0.9)
+
+    def per_alignment_loglik(smp):
+        # getLogProbFor(seq) of the mixture (jstacs SingleHiddenMotifMixture.java:520-550) from the E-step's profile a_j
+        res = shm.getNewWeights(smp, want_gamma=False, want_profile=True)
+        off = smp.device(ctx).window_offsets(W)
+        z = np.array([np.logaddexp.reduce(res["profile"][off[i]:off[i + 1]]) for i in range(smp.n_alignments)])
+        ll = bg.getLogProbFor(smp) + np.logaddexp(np.log(0.9) + z, np.log(0.1))
+        assert abs(ll.sum() - res["ll"]) <= 1e-9 * abs(res["ll"])
+        return ll
+    d_pos = cl.getDifferences(per_alignment_loglik(pos), bg.getLogProbFor(pos))
+    d_neg = cl.getDifferences(per_alignment_loglik(neg), bg.getLogProbFor(neg))
+    rate = cl.getDynamicClassificationRate(d_pos, d_neg)
+    assert rate > 0.75                                            # 0.8325: the mixture's likelihood ratio separates the two sets
