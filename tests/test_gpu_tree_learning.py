@@ -121,3 +121,34 @@ def test_per_alignment_topologies_and_scoring_under_them(ctx):
     res2 = shm.getNewWeights(smp)
     assert res2["gamma"].size == res["gamma"].size and np.isfinite(res2["ll"])
     assert np.allclose(res2["gamma"][nwin[0]:nwin[1]], res["gamma"][nwin[0]:nwin[1]], rtol=0, atol=1e-12)
+
+
+def test_tree_learning_on_the_references_heterogeneity_data(ctx):
+    """The reference's bundled data/synthetic_data/heterogeneity (tests/golden/heterogeneity_bg_first60.npz,
+    scripts/make_heterogeneity_fixture.py): data_1.0.bg was simulated on a star tree with every branch 0.2, data_rBG_1.0.bg with
+    every branch of every alignment drawn from beta(3, 7) (mean 0.3).  TrainingUtil.learnTree recovers the two scales from a
+    common start, and PhyloSample.train gives the divergent alignments of the heterogeneous set the longer trees."""
+    import os
+    from util import ROOT
+    from phyfoo_b200 import training
+    from phyfoo_b200.data import PhyloSample
+    from phyfoo_b200.newick import parse_newick
+    z = np.load(os.path.join(ROOT, "tests", "golden", "heterogeneity_bg_first60.npz"))
+    start = str(z["newick_star"]).replace("0.2", "0.1")
+    homo = PhyloSample(z["codes_homogeneous"], z["col_offsets_homogeneous"])
+    hetero = PhyloSample(z["codes_heterogeneous"], z["col_offsets_heterogeneous"])
+    b_homo = parse_newick(training.learnTree(homo, start, ctx)).branch[1:]
+    b_hetero = parse_newick(training.learnTree(hetero, start, ctx)).branch[1:]
+    assert np.all(np.abs(b_homo - 0.2) < 0.06), b_homo
+    assert b_hetero.mean() > b_homo.mean() + 0.04 and np.all(np.abs(b_hetero - 0.3) < 0.1), (b_homo, b_hetero)
+    # per-alignment trees: the mean branch length of an alignment follows how often its species disagree
+    sub = hetero.slice(0, 16)
+    learned = training.learnTopologies(sub, 0.9, start, ctx)
+    means = np.array([parse_newick(t).branch[1:].mean() for t in learned])
+    disagree = []
+    for i in range(sub.n_alignments):
+        a = sub.getElementAt(i)
+        disagree.append(np.mean([(a[:, s] != a[:, r]).mean() for s in range(5) for r in range(s)]))
+    r = np.corrcoef(means, np.array(disagree))[0, 1]
+    assert r > 0.6, (r, means, disagree)
+    assert means.std() > 0.01
