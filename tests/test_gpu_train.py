@@ -168,3 +168,26 @@ def test_mstep_on_sufficient_statistics_reaches_the_same_optimum(ctx):
     assert abs(a["f_before"] - b["f_before"]) <= 1e-9 * abs(a["f_before"])
     assert abs(a["f_after"] - b["f_after"]) <= 1e-6 * abs(a["f_after"])
     assert np.abs(pa - pb).max() < 2e-3
+
+
+def test_em_on_the_references_bundled_alignments(ctx):
+    """BASELINE configs[0] as a training run: EM (E-step, selector, M-step on sufficient statistics under the restated Jstacs
+    optimizer) on the first 200 alignments of the reference's trees/data_tree1_1.0.fg from the generating PWM blurred half-way to
+    uniform.  The likelihood rises, the learned PWM moves back towards the generating one, and the arg-max site calls reach the
+    annotated MOTIF_POS about as often as under the generating model (84 %)."""
+    from phyfoo_b200 import synth
+    from phyfoo_b200.models import PhyloBackground, PhyloBayesModel, SingleHiddenMotifMixture
+    cfg, newick, pwm, smp, planted = synth.make_config("c1")
+    W = cfg["W"]
+    start = [0.5 * np.asarray(p) + 0.125 for p in pwm]
+    fg = PhyloBayesModel(W, 0, newick, ctx); fg.setCondProbs(start)
+    shm = SingleHiddenMotifMixture(fg, PhyloBackground(0, newick, ctx), zoops=1.0)
+    before = (shm.getNewWeights(smp)["argmax_off"] == planted).mean()
+    hist = shm.train(smp, max_iterations=8, eps=1e-4, rng=np.random.default_rng(2))
+    assert len(hist) >= 3 and hist[-1] > hist[0] + 1.0
+    learned = fg.getCondProbs()
+    kl_start = sum(_kl(np.asarray(t).ravel(), np.asarray(s).ravel()) for t, s in zip(pwm, start))
+    kl_end = sum(_kl(np.asarray(t).ravel(), np.asarray(l).ravel()) for t, l in zip(pwm, learned))
+    assert kl_end < 0.7 * kl_start, (kl_start, kl_end)
+    after = (shm.getNewWeights(smp)["argmax_off"] == planted).mean()
+    assert after >= max(before, 0.75), (before, after)
