@@ -283,17 +283,20 @@ int phyfoo_fe_grad(phyfoo_ctx* ctx, phyfoo_feset* fe, int32_t position, const do
 /* device-resident variant for multi-GPU: values[dim+1] = [f(lambda), f(lambda+eps e_0), ...] local sums */
 int phyfoo_fe_values_device(phyfoo_ctx* ctx, phyfoo_feset* fe, int32_t position, const double* lambda,
                             int32_t dim, double eps, double* values_device, void* stream);
-/* Sufficient statistics of the objective (order 0): counts_out[W][E], E = 4 + 16 (N - 1): expected counts of the log-table
- * entries of each position (4 root entries, then [parent symbol][own symbol] per non-root node in tree node order),
+/* Sufficient statistics of the objective: counts_out[W][E]: expected counts of the log-table entries of each position.  Order 0:
+ * E = 4 + 16 (N - 1) (4 root entries, then [parent symbol][own symbol] per non-root node in tree node order); order-1 motif
+ * network: E = 16 + 32 (N - 1) (root [context][symbol]; per non-root node the off-diagonal entries [context][symbol], then the
+ * diagonal ones -- the F81-structured tables of csrc/model_host.hpp::build_tables1_into);
  * entropy_out: the parameter-independent term.  Then f(theta) = sum_t sum_e counts[t][e] * log table_theta,t[e] - entropy
  * for ANY parameters (pi or branch lengths) of any position: the optimizer needs no further device pass. */
 int phyfoo_fe_suffstats(phyfoo_ctx* ctx, phyfoo_feset* fe, double* counts_out, double* entropy_out);
 int64_t phyfoo_fe_size(const phyfoo_feset* fe);
 void phyfoo_fe_free(phyfoo_ctx* ctx, phyfoo_feset* fe);
 
-/* ---- the same objective on sufficient statistics, evaluated on the host INSIDE the library (order 0) ----
+/* ---- the same objective on sufficient statistics, evaluated on the host INSIDE the library (motif orders 0 and 1; backgrounds of
+ * any order through phyfoo_ss_create_bg below) ----
  * phyfoo_ss_create: one device pass (phyfoo_fe_suffstats) and a private copy of the model's parameters.  After that
- * evaluateFunction / evaluateGradientOfFunction cost a dot product of 4 + 16 (N - 1) terms and need neither the device nor a
+ * evaluateFunction / evaluateGradientOfFunction cost a dot product of E terms and need neither the device nor a
  * collective: the sequential, data-dependent line search of the Jstacs optimizer (jstacs!/.../Optimizer.java:122-330) is no
  * longer a chain of kernel launches.  Same function as phyfoo_fe_eval (sums re-associated: 1e-12 relative,
  * tests/test_gpu_mstep.py follows a whole optimisation with both).  The object is left at the last lambda, like the model of
@@ -320,8 +323,9 @@ double phyfoo_ss_value(const phyfoo_ssobj* ss);
 int64_t phyfoo_ss_evaluations(const phyfoo_ssobj* ss);
 /* A whole M-step of the motif model in one call: the positions order[0..n_pos-1] one after the other (the caller draws the
  * order, util/PWMUtil.java:131-144), each by a BFGS on the forward-difference gradient with the termination rule of
- * optimizing/PreparedConditions.java:20-27.  The library's stand-in for the Jstacs optimizer (whose own trajectory is not
- * reproducible); a Java caller can keep its Optimizer and bind phyfoo_ss_eval / phyfoo_ss_grad instead.
+ * optimizing/PreparedConditions.java:20-27.  The optimizer is Jstacs' quasiNewtonBFGS with its bracketing and Brent line search
+ * restated statement by statement (csrc/suffstat_host.hpp; jstacs Optimizer.java:122-148,202-303,1000-1080); a Java caller can
+ * just as well keep its own Optimizer and bind phyfoo_ss_eval / phyfoo_ss_grad instead.
  * With q fixed the objective is separable (f = sum_t G_t(theta_t) - ENT), so distinct positions are optimised side by side on up
  * to 16 host threads, each against the other positions' terms as they were on entry -- the result does not depend on the number
  * of threads; the environment variable PHYFOO_SS_THREADS=1 runs them strictly one after the other. */

@@ -232,11 +232,11 @@ class PhyloBayesModel(_PhyloModel):
     PROB_THRESH_FOR_WEIGHTS = 0.8      # models/PhyloPreparedAbstractModel.java:20
     MOTIF_QUALITY_THRESHOLD = 0.0      # :21
     OPTIMIZE_IN_TOTO = False           # :63
-    # True (default; applies to order 0): one device pass collects the expected counts of the table entries, every evaluation
+    # True (default; orders 0 and 1): one device pass collects the expected counts of the table entries, every evaluation
     # of the objective is then a dot product on the host inside libphyfoo.so and a whole M-step is one library call
     # (phyfoo_ss_optimize).  False: every evaluation is a pass over the selected windows on the device, the reference's own
     # evaluation order.  Same function, sums re-associated (1e-12 relative along a whole optimisation:
-    # tests/test_gpu_mstep.py); order-1 motifs always take the device evaluation.
+    # tests/test_gpu_mstep.py, tests/test_gpu_order1.py).
     MSTEP_SUFFICIENT_STATISTICS = True
 
     def train(self, sample: PhyloSample, weights, rng=None, rev_weights=None, sharded=False):
