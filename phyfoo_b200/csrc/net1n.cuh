@@ -172,11 +172,15 @@ struct Net1nParams {
     double f0_const;                     // model_host.hpp::n1n_f0_const(): free energy of the uniform start minus the window's part
     int check_gaps;                      // 0: the data set has no unobserved symbol at all
     int* fb_count; int64_t* fb_col0; uint8_t* fb_strand; int64_t* fb_dst;   // windows with gaps, for the net1w.cuh kernel
+    // M-step "prepare" (SINK instantiation): the windows are listed (first column, strand) and the converged q of the hidden
+    // nodes goes to sink_qint[((t I + i) 4 + a) n_windows + item], sum q log q to sink_ent[item] (mstep1.cuh reads them)
+    const int64_t* item_col0; const uint8_t* item_strand;
+    double* sink_qint; double* sink_ent;
 };
 
 // QG: the q rows live in global memory (read through L1, written through to L2) and shared memory holds the AB and
 // message rows only -- twice the warps per SM, i.e. two per scheduler
-template <int MC, bool QG>
+template <int MC, bool QG, bool SINK = false>
 __global__ void __launch_bounds__(256, 1) score_o1n_kernel(Net1nParams p) {
     extern __shared__ double smem[];
     const int tid = threadIdx.x, T = blockDim.x, NW = T >> 5;
@@ -231,11 +235,14 @@ __global__ void __launch_bounds__(256, 1) score_o1n_kernel(Net1nParams p) {
                 if (lane == 0) v = (long long)atomicAdd(&p.counters[0], 1ULL);
                 it = __shfl_sync(full, v, 0);
                 if (it >= n_items) { it = -1; break; }
-                const int si = (int)(it / p.n_windows);
-                const int64_t wdx = it - (long long)si * p.n_windows;
-                strand = p.n_strands == 2 ? si : p.strand0;
-                const int al = find_alignment_hint(p.win_off, p.n_aln, wdx, p.n_windows);
-                c0 = p.col_off[al] + (wdx - p.win_off[al]);
+                if (SINK) { c0 = p.item_col0[it]; strand = p.item_strand ? p.item_strand[it] : 0; }
+                else {
+                    const int si = (int)(it / p.n_windows);
+                    const int64_t wdx = it - (long long)si * p.n_windows;
+                    strand = p.n_strands == 2 ? si : p.strand0;
+                    const int al = find_alignment_hint(p.win_off, p.n_aln, wdx, p.n_windows);
+                    c0 = p.col_off[al] + (wdx - p.win_off[al]);
+                }
                 if (!p.check_gaps) break;
                 unsigned any = 0;
                 for (int t = lane; t < W; t += 32) {
@@ -336,6 +343,7 @@ __global__ void __launch_bounds__(256, 1) score_o1n_kernel(Net1nParams p) {
         double F = phyfoo::n1n_free_energy(acc);
         F += __shfl_xor_sync(full, F, 8);
         F += __shfl_xor_sync(full, F, 16);
+        bool fin = false;
         if (active) {
             if (fabs(old - F) < p.tol) conv = true;                               // MeanFieldForBayesNet.java:204-207 (sticky)
             old = F; ++k;
@@ -347,7 +355,27 @@ __global__ void __launch_bounds__(256, 1) score_o1n_kernel(Net1nParams p) {
                     atomicAdd(&p.counters[1], (unsigned long long)k);
                 }
                 need = true;
+                fin = true;
             }
+        }
+        if (SINK && __any_sync(full, fin)) {
+            // the four slot lanes of a finished window copy its q rows out (node idx = t I + i by lane slot) and add up q log q
+            double ent = 0.0;
+            if (fin) {
+                const size_t n = (size_t)p.n_windows;
+                for (int idx = slot; idx < W * I; idx += 4) {
+                    double qv[4];
+                    phyfoo::n1n_ld4(qreg + p.q0 + idx * 32, qv);
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        p.sink_qint[(size_t)(idx * 4 + a) * n + (size_t)item] = qv[a];
+                        ent += qv[a] > 0.0 ? qv[a] * phyfoo::phy_log(qv[a]) : 0.0;
+                    }
+                }
+            }
+            ent += __shfl_xor_sync(full, ent, 8);
+            ent += __shfl_xor_sync(full, ent, 16);
+            if (fin && slot == 0) p.sink_ent[item] = ent;
         }
     }
 }

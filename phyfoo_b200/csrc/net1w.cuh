@@ -36,7 +36,8 @@ struct Net1wParams {
     const int64_t* item_col0; const uint8_t* item_strand;
     double* sink_qint; double* sink_qleaf; double* sink_ent;
     const int* n_items_dev;           // nullable: length of the item list lives on the device (windows with gaps listed by net1n.cuh)
-    const int64_t* item_dst;          // nullable: out / sweeps index of listed item (default: the item's own index)
+    const int64_t* item_dst;          // nullable: out / sweeps / sink index of listed item (default: the item's own index)
+    int64_t sink_stride;              // windows of the FE set the sinks belong to (0: n_windows)
     unsigned long long* counter_next; // work counter (counters[0] unless the launch continues another kernel's sweep sum)
     // background ranges of a single column (order 1, W = 2; models/PhyloBackground.java:260-283 with a range shorter than
     // order + 1): the second tree of the net keeps the observation of an EARLIER call (MeanFieldForBayesNet.java:84), i.e. an
@@ -286,21 +287,23 @@ __global__ void __launch_bounds__(256, 3) score_o1w_kernel(Net1wParams p) {
             if (done) {
                 if (p.sink_qint) {
                     double ent = 0.0;
+                    const size_t sn = p.sink_stride ? (size_t)p.sink_stride : (size_t)p.n_windows;
+                    const size_t su = p.item_dst ? (size_t)p.item_dst[item] : (size_t)item;
                     for (int j = l16; j < p.W * p.I * 4; j += 16) {
                         const double v = qbase[(j >> 2) * qs + (j & 3)];
-                        p.sink_qint[(size_t)j * p.n_windows + item] = v;
+                        p.sink_qint[(size_t)j * sn + su] = v;
                         ent += v > 0.0 ? v * phy_log(v) : 0.0;
                     }
                     for (int j = l16; j < p.W * p.S * 4; j += 16) {
                         const int t = j / (p.S * 4), kk = (j >> 2) % p.S;
                         const double v = p.gq[(size_t)j * p.n_slots + gslot];
-                        p.sink_qleaf[(size_t)j * p.n_windows + item] = v;
+                        p.sink_qleaf[(size_t)j * sn + su] = v;
                         if ((s_lc[(t * (p.S + 1) + kk) * nwb + wq] & 15) >= 4) ent += v > 0.0 ? v * phy_log(v) : 0.0;
                     }
                     const unsigned wm = 0xFFFFu << wb;
                     ent += __shfl_xor_sync(wm, ent, 1); ent += __shfl_xor_sync(wm, ent, 2);
                     ent += __shfl_xor_sync(wm, ent, 4); ent += __shfl_xor_sync(wm, ent, 8);
-                    if (l16 == 0) p.sink_ent[item] = ent;
+                    if (l16 == 0) p.sink_ent[su] = ent;
                 }
                 if (l16 == 0) {
                     const long long oi = p.item_dst ? p.item_dst[item] : item;

@@ -979,6 +979,7 @@ struct ScoreItems {
     double* out_last = nullptr;     // order-1 kernels: free energy of the last tree alone (background ranges)
     const int64_t* col1 = nullptr;  // order-1 wavefront kernel, W = 2: column of the second tree (single-column background ranges)
     bool stop_first = false;        //   ... and the stop rule on the first tree alone
+    int64_t sink_stride = 0;        // listed fallback items of a "prepare" pass: windows of the FE set (the q sinks' stride)
 };
 
 #include "net1.cuh"
@@ -1299,6 +1300,7 @@ static int launch_net1w(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model*
     p.sink_qint = items ? items->q_int : nullptr; p.sink_qleaf = items ? items->q_leaf : nullptr; p.sink_ent = items ? items->ent : nullptr;
     p.n_items_dev = items ? items->n_dev : nullptr; p.item_dst = items ? items->dst : nullptr;
     p.item_col1 = items ? items->col1 : nullptr; p.stop_first = items && items->stop_first ? 1 : 0;
+    p.sink_stride = items ? items->sink_stride : 0;
     const bool fallback = items && items->fallback;
     // a fallback launch (windows with gaps listed by the node-per-thread kernel) pulls its work from a counter of its own
     // ([8 + slot]) and continues the sweep sum of that kernel
@@ -1330,7 +1332,7 @@ static void l2_window(phyfoo_ctx* ctx, void* base, size_t bytes) {
 // order-1 motif network, node-per-thread kernel (net1n.cuh): 4 threads per window, 8 windows per warp; returns 1 when the
 // configuration is not one it takes (the caller then runs the wavefront kernel), 0 when launched
 static int launch_net1n(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* m, const int64_t* d_win_off, int64_t n_windows,
-                        int strands, double* d_out, int32_t* d_sweeps, int counter_slot) {
+                        int strands, double* d_out, int32_t* d_sweeps, int counter_slot, const ScoreItems* items = nullptr) {
     ModelHost& h = m->h;
     if (m->MC1n > 3 || !m->d_prog1n) return 1;
     // mostly gapped data: nearly every window would go through the list anyway
@@ -1355,7 +1357,11 @@ static int launch_net1n(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model*
     nw = std::max(1, std::min(nw, 8));
     const long long want_warps = (n_items + 7) / 8;
     const void* fn = nullptr;
-    if (qg) fn = m->MC1n <= 1 ? (const void*)score_o1n_kernel<1, true> : m->MC1n == 2 ? (const void*)score_o1n_kernel<2, true> : (const void*)score_o1n_kernel<3, true>;
+    const bool sink = items != nullptr;          // M-step "prepare": listed windows, converged q and entropy stored
+    if (sink) {
+        if (qg) fn = m->MC1n <= 1 ? (const void*)score_o1n_kernel<1, true, true> : m->MC1n == 2 ? (const void*)score_o1n_kernel<2, true, true> : (const void*)score_o1n_kernel<3, true, true>;
+        else fn = m->MC1n <= 1 ? (const void*)score_o1n_kernel<1, false, true> : m->MC1n == 2 ? (const void*)score_o1n_kernel<2, false, true> : (const void*)score_o1n_kernel<3, false, true>;
+    } else if (qg) fn = m->MC1n <= 1 ? (const void*)score_o1n_kernel<1, true> : m->MC1n == 2 ? (const void*)score_o1n_kernel<2, true> : (const void*)score_o1n_kernel<3, true>;
     else fn = m->MC1n <= 1 ? (const void*)score_o1n_kernel<1, false> : m->MC1n == 2 ? (const void*)score_o1n_kernel<2, false> : (const void*)score_o1n_kernel<3, false>;
     const size_t smem = fixed + per_warp * nw;
     CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1390,6 +1396,8 @@ static int launch_net1n(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model*
     p.fb_col0 = check ? (int64_t*)((char*)ctx->o1n_fb.p + 16) : nullptr;
     p.fb_dst = check ? p.fb_col0 + n_items : nullptr;
     p.fb_strand = check ? (uint8_t*)(p.fb_dst + n_items) : nullptr;
+    p.item_col0 = sink ? items->col0 : nullptr; p.item_strand = sink ? items->strand : nullptr;
+    p.sink_qint = sink ? items->q_int : nullptr; p.sink_ent = sink ? items->ent : nullptr;
     CU(cudaMemsetAsync(p.counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
     // (window over the q rows alone, leaving the observed-leaf sums to the normal policy: measured worse -- 31 instead of 18 GB of
     // DRAM traffic per 2 M windows)
@@ -1404,6 +1412,7 @@ static int launch_net1n(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model*
     if (check) {
         ScoreItems it{p.fb_col0, p.fb_strand, nullptr, nullptr, nullptr};
         it.n_dev = fb_count; it.dst = p.fb_dst; it.fallback = true;
+        if (sink) { it.q_int = items->q_int; it.q_leaf = items->q_leaf; it.ent = items->ent; it.sink_stride = n_items; }
         // (n_windows of the launch: the list's capacity bound for the grid; the kernel reads the real length on the device)
         int rc = launch_net1w(ctx, ds, m, d_win_off, std::min<long long>(n_items, 64LL * ctx->sm_count), 0, d_out, d_sweeps, counter_slot, &it);
         if (rc) return rc;
@@ -1417,8 +1426,11 @@ static int launch_net1(phyfoo_ctx* ctx, const phyfoo_dataset* ds, phyfoo_model* 
     if (h.mode == PHYFOO_MODE_EXACT && !items)
         return fail(ctx, PHYFOO_EUNSUPPORTED, "exact likelihood of an order-1 network is infeasible in the reference too "
                                               "(SimpleNodeElimination's 9-node frontier, SimpleNodeElimination.java:33-45)");
-    if (ctx->order1_kernel == 2 && !items) {
-        const int rc = launch_net1n(ctx, ds, m, d_win_off, n_windows, strands, d_out, d_sweeps, counter_slot);
+    // the M-step "prepare" pass of a motif model (listed windows, q sinks, nothing background-specific) runs on the
+    // node-per-thread kernel too
+    const bool prepare = items && items->q_int && !items->col1 && !items->out_last && !items->stop_first && !items->fallback && strands == 0;
+    if (ctx->order1_kernel == 2 && (!items || prepare)) {
+        const int rc = launch_net1n(ctx, ds, m, d_win_off, n_windows, strands, d_out, d_sweeps, counter_slot, prepare ? items : nullptr);
         if (rc <= 0) return rc;
     }
     if (ctx->order1_kernel >= 1) return launch_net1w(ctx, ds, m, d_win_off, n_windows, strands, d_out, d_sweeps, counter_slot, items);
