@@ -200,3 +200,48 @@ def test_library_mstep_on_host_threads_does_not_depend_on_their_number(monkeypat
     ss = core.SSObjective(desc=desc, counts=counts, entropy=0.5)
     fb, fa, ev = ss.optimize(np.array([1, 1, 2], np.int32))
     assert fa > fb
+
+
+def test_library_suffstat_objective_of_an_order1_network_on_the_host():
+    """phyfoo_ss_create_host for an order-1 motif: per position 16 + 32 (N - 1) entries -- root [context][symbol], then per
+    non-root node the off-diagonal log entries [context][symbol] and the diagonal ones (F81 alpha: log(alpha pi_c[b]) and
+    log(1 - alpha + alpha pi_c[b])); the objective is the dot product with the counts, position t >= 1 has 16 parameters."""
+    from phyfoo_b200 import _abi, core, synth
+    from phyfoo_b200.newick import parse_newick
+    tree = parse_newick("((A:0.1,B:0.3):0.15,(C:0.2,D:0.25):0.1)")
+    N, W = tree.n_nodes, 3
+    rng = np.random.default_rng(3)
+    pwm = synth.random_pwm(W, 1, 5)
+    branch = np.tile(tree.branch, (W, 1))
+    E1 = 16 + 32 * (N - 1)
+    counts = rng.uniform(0.0, 3.0, (W, E1))
+    counts[0, 4:16] = 0.0                                           # position 0 has a single context row
+    counts[0, 16:] = counts[0, 16:] * (np.arange(E1 - 16) % 16 < 4)
+    desc, keep = _abi.make_desc(_abi.MODEL_FG, W, 1, tree, branch, pwm, _abi.EVOL_F81ALPHA, _abi.MODE_MEANFIELD)
+    ss = core.SSObjective(desc=desc, counts=counts, entropy=2.5)
+
+    def tab(t, pi):
+        pi = np.asarray(pi).reshape(-1, 4)
+        out = np.zeros(E1)
+        out[:pi.size] = np.log(pi).ravel()
+        for k in range(1, N):
+            a = branch[t, k]
+            for c in range(pi.shape[0]):
+                out[16 + 32 * (k - 1) + 4 * c:16 + 32 * (k - 1) + 4 * c + 4] = np.log(a * pi[c])
+                out[32 + 32 * (k - 1) + 4 * c:32 + 32 * (k - 1) + 4 * c + 4] = np.log(1 - a + a * pi[c])
+        return out
+
+    def objective(pis):
+        return sum(float(counts[t] @ tab(t, pis[t])) for t in range(W)) - 2.5
+    assert abs(ss.value() - objective(pwm)) <= 1e-12 * abs(ss.value())
+    lam = rng.normal(size=16)
+    new = np.exp(lam.reshape(4, 4)); new /= new.sum(axis=1, keepdims=True)
+    f = ss.eval(2, lam)
+    assert abs(f - objective([pwm[0], pwm[1], new])) <= 1e-12 * abs(f)
+    assert np.allclose(ss.get_pi(2, 16), new.ravel(), rtol=1e-14, atol=0)
+    with pytest.raises(ValueError):
+        ss.eval(2, np.zeros(4))
+    f0, g = ss.grad(0, np.log(np.asarray(pwm[0]).ravel()), 1e-4)
+    assert g.size == 4 and np.isfinite(g).all()
+    fb, fa, ev = ss.optimize(np.array([1, 0, 2], np.int32))
+    assert fa >= fb and ev > 0

@@ -63,3 +63,27 @@ def test_train_model_loop_stops_like_the_reference():
     assert training.trainModel(m, None, 1e-1)[0] == 2
     m = _FakeModel(0.0)
     assert training.trainModel(m, None, 1e-1, minSteps=7, weights=[1.0])[0] == 7 and m.seen_weights[0] == [1.0]
+
+
+def test_scoring_under_a_learned_topology_swaps_and_restores_branch_lengths():
+    """models/PhyloBackground.java:250-253,301-303 and PhyloBayesModel.java:233-265 without a device: inside the call the model
+    carries the alignment's branch lengths, afterwards those of the Newick strings taken before -- i.e. rounded to three
+    decimals (bayesNet/VirtualTree.java:208-234), the reference's side effect."""
+    from phyfoo_b200.models import PhyloBackground, PhyloBayesModel
+    base = "((A:0.12345,B:0.2):0.30049,C:0.4)"
+    topo = "((A:0.5,B:0.25):0.125,C:0.0625);"
+    bg = PhyloBackground(0, base)
+    with bg._under_topology(None):
+        assert np.allclose(bg._branch[0, 1:], [0.30049, 0.12345, 0.2, 0.4], rtol=0, atol=0)
+    with bg._under_topology(topo):
+        assert np.allclose(bg._branch[0, 1:], [0.125, 0.5, 0.25, 0.0625], rtol=0, atol=0)
+    assert np.allclose(bg._branch[0, 1:], [0.3, 0.123, 0.2, 0.4], rtol=0, atol=1e-15)
+    fg = PhyloBayesModel(3, 0, base)
+    fg.setBranchLength(1, 2, 0.77777)
+    with fg._under_topology(topo):
+        assert np.allclose(fg._branch[:, 1:], np.tile([0.125, 0.5, 0.25, 0.0625], (3, 1)), rtol=0, atol=0)
+    assert np.allclose(fg._branch[0, 1:], [0.3, 0.123, 0.2, 0.4], rtol=0, atol=1e-15)
+    assert abs(fg._branch[1, 2] - 0.778) < 1e-15                  # per-position lengths come back too, rounded
+    with pytest.raises(ValueError):
+        with bg._under_topology("(A:0.1,B:0.2,C:0.3)"):            # another topology
+            pass
