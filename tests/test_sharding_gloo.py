@@ -54,6 +54,34 @@ def _worker(rank, world, port, out_dir):
         dist.destroy_process_group()
 
 
+def _order1_case(rank):
+    """Expected counts of an order-1 motif's table entries as a rank would hold them (rank < 0: both ranks' sum)."""
+    from phyfoo_b200.newick import parse_newick
+    tree = parse_newick(synth.caterpillar_newick(4))
+    W, E1 = 3, 16 + 32 * (tree.n_nodes - 1)
+    pwm = synth.random_pwm(W, 1, 9)
+
+    def part(r):
+        c = np.random.default_rng(20 + r).uniform(0.0, 2.0, (W, E1))
+        c[0, 4:16] = 0.0
+        c[0, 16:] *= (np.arange(E1 - 16) % 16 < 4)
+        return c
+    if rank < 0:
+        return pwm, part(0) + part(1), 0.25 * 3, np.array([2, 0, 1], np.int32)
+    return pwm, part(rank), 0.25 * (rank + 1), np.array([2, 0, 1], np.int32)
+
+
+def _order1_mstep(pwm, counts, entropy, order):
+    from phyfoo_b200 import _abi, core
+    from phyfoo_b200.newick import parse_newick
+    tree = parse_newick(synth.caterpillar_newick(4))
+    W = len(pwm)
+    desc, keep = _abi.make_desc(_abi.MODEL_FG, W, 1, tree, np.tile(tree.branch, (W, 1)), pwm, _abi.EVOL_F81ALPHA, _abi.MODE_MEANFIELD)
+    ss = core.SSObjective(desc=desc, counts=counts, entropy=float(entropy))
+    ss.optimize(order)
+    return np.concatenate([ss.get_pi(t, 4 if t == 0 else 16) for t in range(W)])
+
+
 def _mstep_worker(rank, world, port, out_dir):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -76,7 +104,11 @@ def _mstep_worker(rank, world, port, out_dir):
         sharding.allreduce_sum_(vals)
         counts = np.full((W, 3), float(rank + 1))
         c, e = sharding.allreduce_counts_(counts, 0.5 * (rank + 1))
-        np.savez(os.path.join(out_dir, f"m{rank}.npz"), vals=vals.numpy(), c=c, e=e)
+        # the sharded M-step of an order-1 motif (models.PhyloBayesModel.train_selected, sharded=True): every rank's expected
+        # counts summed, then the same host optimisation on every rank -- no further collective, identical parameters
+        pi1, c1, e1, order1 = _order1_case(rank)
+        c1, e1 = sharding.allreduce_counts_(c1, e1)
+        np.savez(os.path.join(out_dir, f"m{rank}.npz"), vals=vals.numpy(), c=c, e=e, pi1=_order1_mstep(pi1, c1, e1, order1))
     finally:
         dist.destroy_process_group()
 
@@ -99,6 +131,10 @@ def test_two_rank_mstep_values_allreduce(tmp_path):
         assert abs(v[0] - f0) <= 1e-12 * abs(f0)
         assert np.max(np.abs((v[1:] - v[0]) / 1e-4 - g)) <= 1e-9 * np.max(np.abs(g)) + 64 * np.finfo(float).eps * abs(f0) / 1e-4
         assert np.array_equal(z["c"], np.full((W, 3), 3.0)) and float(z["e"]) == 1.5
+    pi1, c1, e1, order1 = _order1_case(-1)
+    ref = _order1_mstep(pi1, c1, e1, order1)
+    a, b = np.load(tmp_path / "m0.npz")["pi1"], np.load(tmp_path / "m1.npz")["pi1"]
+    assert np.array_equal(a, b) and np.array_equal(a, ref)       # same counts on every rank, same optimiser: same bits
 
 
 def test_shard_bounds_cover_and_balance():
