@@ -254,3 +254,32 @@ def test_term_counter_matches_closed_forms():
             assert c0["upd_transc"] == 4 * I * W                      # 4 exp per hidden node and sweep
             c1 = oracle_fg(newick, synth.random_pwm(W, 1, 1), order=1).count_terms(random_codes(rng, W, S))
             assert (c1["upd_flops"], c1["fe_flops"]) == bench.flops_order1(I, S, W)
+
+
+@pytest.mark.parametrize("order", [2, 3])
+@pytest.mark.parametrize("gap_rate", [0.0, 0.1])
+def test_background_of_higher_order_matches_numpy_restatement(order, gap_rate):
+    """PhyloBackground of order k >= 2 (models/PhyloBackground.java:241-305, structure :381-398): the oracle's range value
+    against the independently written numpy restatement -- the first k positions from the first (k+1)-tree window, every further
+    position the last tree of its own window, each window's mean field optimised from the uniform start."""
+    rng = np.random.default_rng(30 + order)
+    codes = random_codes(rng, 11, 5, gap_rate)
+    pis = [rng.dirichlet(np.ones(4), size=4 ** min(order, t)) for t in range(order + 1)]
+    bg = oracle_bg(CAT, order, pis)
+    net = npr.Net.background(CAT, order)
+    for t, p in enumerate(pis):
+        net.set_pi(t, p)
+    net.build_tables()
+    T = order + 1
+    for start, end in ((0, 10), (2, 2 + order), (3, 9)):
+        total = 0.0
+        net.observe(codes[start:start + T])
+        mf = npr.MeanField(net, T); mf.optimize()
+        for i in range(order):
+            total += mf.free_energy(i, i)
+        for u in range(start, end - order + 1):
+            net.observe(codes[u:u + T])
+            mf = npr.MeanField(net, T); mf.optimize()
+            total += mf.free_energy(order, order)
+        v = bg.bg_range(codes, start, end)
+        assert abs(v + total) <= 1e-12 * abs(total), (start, end, v, -total)
