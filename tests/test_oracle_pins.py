@@ -283,3 +283,64 @@ def test_background_of_higher_order_matches_numpy_restatement(order, gap_rate):
             total += mf.free_energy(order, order)
         v = bg.bg_range(codes, start, end)
         assert abs(v + total) <= 1e-12 * abs(total), (start, end, v, -total)
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_short_background_ranges_keep_the_previous_observation(order):
+    """A range shorter than order + 1 columns observes only its own columns; the trailing trees of the shared net keep what the
+    call before left there (algorithm/MeanFieldForBayesNet.java:84), while the update still sweeps every
+    hidden node and the stop rule and the returned free energy span the range's trees only (models/PhyloBackground.java:
+    260-283).  The oracle keeps that state in its model object; here the same sequence of calls -- the three calls of one motif
+    offset of the ZOOPS E-step (jstacs SingleHiddenMotifMixture.java:536-540) -- on the numpy restatement with an explicit
+    observation map."""
+    rng = np.random.default_rng(50 + order)
+    L, W, j = 14, 4, 5
+    codes = random_codes(rng, L, 5, 0.08)
+    pis = [rng.dirichlet(np.ones(4), size=4 ** min(order, t)) for t in range(order + 1)]
+    bg = oracle_bg(CAT, order, pis)
+    net = npr.Net.background(CAT, order)
+    for t, p in enumerate(pis):
+        net.set_pi(t, p)
+    net.build_tables()
+    T = order + 1
+    leaves = net.leaves
+
+    def observe_trees(first_col, n_trees):                  # VirtualTree.setObservation for the first n_trees trees only
+        for t in range(n_trees):
+            for s, k in enumerate(leaves):
+                c = int(codes[first_col + t][s])
+                if c < 4:
+                    net.obs[(t, k)] = c
+                else:
+                    net.obs.pop((t, k), None)
+
+    def np_range(start, end):
+        if end < start:
+            return 0.0
+        n = end - start + 1
+        first_len = min(T, n)
+        total = 0.0
+        observe_trees(start, first_len)
+        mf = npr.MeanField(net, first_len); mf.optimize()
+        pos = start
+        for i in range(order):
+            if pos > end:
+                break
+            total += mf.free_energy(i, i); pos += 1
+        u = start
+        while pos <= end:
+            wl = first_len if u == start else T
+            observe_trees(u, wl)
+            mf = npr.MeanField(net, wl); mf.optimize()
+            total += mf.free_energy(order, order); pos += 1; u += 1
+        return -total
+
+    net.obs = {}
+    s, e = max(j - order, 0), min(j + W + order - 1, L - 1)
+    for (a, b) in ((0, L - 1), (s, e), (s, j - 1), (j + W, e)):           # logPSeq, then the three ranges of offset j
+        v, ref = np_range(a, b), bg.bg_range(codes, a, b)
+        assert abs(v - ref) <= 1e-12 * abs(ref), ((a, b), v, ref)
+    # the value of the short range does depend on what came before: the same range after a different call differs
+    fresh = oracle_bg(CAT, order, pis)
+    fresh.bg_range(codes, 0, order)                                       # leaves the columns 0 .. order in the trees
+    assert abs(fresh.bg_range(codes, s, j - 1) - bg.bg_range(codes, s, j - 1)) > 1e-9 or order == 0
