@@ -27,6 +27,14 @@ def test_exports_every_declared_symbol():
     assert sorted(plib.SYMBOLS) == syms
 
 
+def test_integration_table_names_every_symbol():
+    """INTEGRATION.md's appendix says, entry point by entry point, which reference code each one stands in for."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    appendix = text[text.index("## Appendix"):]
+    missing = [s for s in header_symbols() if not re.search(r"`" + s + r"`", appendix)]
+    assert not missing, f"INTEGRATION.md appendix does not name {missing}"
+
+
 def test_struct_layouts_match_header():
     # phyfoo_model_desc: 4 int32, 2 pointers, int32 (+pad), double, 2 pointers, 4 int32, double
     assert C.sizeof(_abi.ModelDesc) == 16 + 16 + 8 + 8 + 16 + 16 + 8
