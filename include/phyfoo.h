@@ -54,6 +54,9 @@ extern "C" {
 #define PHYFOO_EVOL_F81ALPHA 0           /* evolution/FS81alpha.java (default, EvolModel.java:7) */
 #define PHYFOO_EVOL_F81BETA 1            /* evolution/FS81beta.java */
 #define PHYFOO_EVOL_HKY_AS_IMPLEMENTED 2 /* evolution/HKY.java with its beta == 0 (ctor bug :32) */
+#define PHYFOO_EVOL_HKY_RATIO 3          /* opt-in: evolution/HKY.java:77-106 with the ratio in effect, beta = alpha * hky_ratio -- the
+                                          * model the reference's bundled data/synthetic_data/HKY files were drawn from
+                                          * (tests/test_generator_pins.py); order-0 models only (general 4x4 tables) */
 
 #define PHYFOO_MODE_MEANFIELD 0 /* -calcFreeEnergy() after optimizeByNormalisation (default path) */
 #define PHYFOO_MODE_EXACT 1     /* PhyloBayesModel.CALC_LOGLIKELIHOOD = true (order 0: pruning)     */
@@ -75,7 +78,8 @@ typedef struct {
     const int32_t* parent;          /* [N] */
     const int32_t* leaf_species;    /* [N] */
     int32_t evol;                   /* PHYFOO_EVOL_* */
-    double hky_ratio;               /* accepted and ignored, like the reference does (HKY.java:32) */
+    double hky_ratio;               /* PHYFOO_EVOL_HKY_AS_IMPLEMENTED: accepted and ignored, like the reference does (HKY.java:32);
+                                     * PHYFOO_EVOL_HKY_RATIO: beta / alpha, > 0 */
     const double* branch;           /* [trees][N] distance to parent per position (root entry unused) */
     const double* pi;               /* per tree t: [ctx_t][4] row-major, concatenated; ctx_t = 4^{#horizontal parents} */
     int32_t mode;                   /* PHYFOO_MODE_* */

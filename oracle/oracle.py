@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-F81ALPHA, F81BETA, HKY = 0, 1, 2
+F81ALPHA, F81BETA, HKY, HKY_RATIO = 0, 1, 2, 3
 MEANFIELD, EXACT_ELIMINATION, EXACT_PRUNING = 0, 1, 2
 FG, BG = 0, 1
 

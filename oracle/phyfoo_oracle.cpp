@@ -133,7 +133,7 @@ struct Node {
     }
 };
 
-enum Evol { F81ALPHA = 0, F81BETA = 1, HKY_AS_IMPLEMENTED = 2 };
+enum Evol { F81ALPHA = 0, F81BETA = 1, HKY_AS_IMPLEMENTED = 2, HKY_RATIO = 3 };
 enum Mode { MEANFIELD = 0, EXACT_ELIMINATION = 1, EXACT_PRUNING = 2 };
 
 struct Model {
@@ -145,7 +145,8 @@ struct Model {
     std::vector<Node> nodes;
     std::vector<int> leaf_local;             // local node index of leaf s
     int evol = F81ALPHA;
-    double hky_ratio = 0.0;                  // never reaches the matrices: HKY.java:32 self-assigns
+    double hky_ratio = 0.0;                  // HKY_AS_IMPLEMENTED: never reaches the matrices (HKY.java:32 self-assigns);
+                                             // HKY_RATIO (opt-in): the ratio the constructor was meant to store
     std::vector<std::vector<double>> pi;     // per tree [dim][4], dim = 4^{#parents of that tree's root}
     int mode = MEANFIELD;
     bool allow_indep = true;                 // CPF.ALLOW_RETURN_INDEPENDENT_TRANSITION, CPF.java:14
@@ -234,8 +235,9 @@ static void evol_tables(const Model& m, const std::vector<double>& pi, int dim, 
             for (int a1 = 0; a1 < 4; ++a1)
                 for (int a2 = 0; a2 < 4; ++a2)
                     trans[(size_t)(a1 + i * 4) * 4 + a2] = (a1 == a2) ? (ta + p[a2] * (1. - ta)) : (p[a2] * (1. - ta));
-        } else {  // HKY as implemented: alpha_beta_ratio field stays 0 (HKY.java:32) => beta = 0
-            double alpha = len, beta = alpha * 0.0;
+        } else {  // HKY as implemented: alpha_beta_ratio field stays 0 (HKY.java:32) => beta = 0;
+                  // HKY_RATIO: the same statements (HKY.java:77-106) with the field holding the ratio
+            double alpha = len, beta = alpha * (m.evol == HKY_RATIO ? m.hky_ratio : 0.0);
             double aA = alpha * p[0], aC = alpha * p[1], aG = alpha * p[2], aT = alpha * p[3];
             double bA = beta * p[0], bC = beta * p[1], bG = beta * p[2], bT = beta * p[3];
             double* r = &trans[(size_t)(i * 4) * 4];

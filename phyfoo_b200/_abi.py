@@ -5,7 +5,7 @@ import numpy as np
 
 OK, EINVAL, ENODEVICE, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4, -5
 MODEL_FG, MODEL_BG = 0, 1
-EVOL_F81ALPHA, EVOL_F81BETA, EVOL_HKY_AS_IMPLEMENTED = 0, 1, 2
+EVOL_F81ALPHA, EVOL_F81BETA, EVOL_HKY_AS_IMPLEMENTED, EVOL_HKY_RATIO = 0, 1, 2, 3
 MODE_MEANFIELD, MODE_EXACT = 0, 1
 
 

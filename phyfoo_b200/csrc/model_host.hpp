@@ -25,6 +25,7 @@ namespace phyfoo {
 struct ModelHost {
     int kind = PHYFOO_MODEL_FG, W = 0, order = 0, N = 0, S = 0, I = 0;
     int evol = PHYFOO_EVOL_F81ALPHA;
+    double hky_ratio = 0.0;                  // PHYFOO_EVOL_HKY_RATIO only: beta = alpha * hky_ratio
     int mode = PHYFOO_MODE_MEANFIELD;
     int max_sweeps = 100, min_sweeps = 2;
     double tol = 1e-5;
@@ -55,6 +56,11 @@ struct ModelHost {
         if (d.tol > 0) tol = d.tol;
         if (N < 2 || W < 1) throw std::invalid_argument("model: need >= 2 tree nodes and width >= 1");
         if (order < 0) throw std::invalid_argument("model: order must be >= 0");
+        if (evol == PHYFOO_EVOL_HKY_RATIO) {
+            hky_ratio = d.hky_ratio;
+            if (order != 0) throw std::invalid_argument("HKY with its ratio in effect is offered for order-0 models only (the order-1 kernels assume F81 tables)");
+            if (!(hky_ratio > 0) || !std::isfinite(hky_ratio)) throw std::invalid_argument("HKY: the transversion / transition ratio must be positive");
+        }
         if (kind != PHYFOO_MODEL_FG && kind != PHYFOO_MODEL_BG) throw std::invalid_argument("model: unknown kind");
         if (kind == PHYFOO_MODEL_FG && order != 0 && order != 1)
             throw std::invalid_argument("motif order must be 0 or 1 (models/PhyloBayesModel.java:363)");
@@ -157,6 +163,13 @@ struct ModelHost {
                 for (int b = 0; b < 4; ++b) out[a * 4 + b] = (a == b) ? (ta + p[b] * (1. - ta)) : (p[b] * (1. - ta));
         } else if (evol == PHYFOO_EVOL_HKY_AS_IMPLEMENTED) {
             const double al = len, be = len * 0.0;
+            const double aA = al * p[0], aC = al * p[1], aG = al * p[2], aT = al * p[3];
+            const double bA = be * p[0], bC = be * p[1], bG = be * p[2], bT = be * p[3];
+            const double v[16] = {1 - (aG + bT + bC), bC, aG, bT, bA, 1 - (aT + bA + bG), bG, aT,
+                                  aA, bC, 1 - (aA + bT + bC), bT, bA, aC, bG, 1 - (aC + bA + bG)};
+            for (int i = 0; i < 16; ++i) out[i] = v[i];
+        } else if (evol == PHYFOO_EVOL_HKY_RATIO) {      // HKY.java:77-106 as written, with the ratio the constructor was meant to store
+            const double al = len, be = len * hky_ratio;
             const double aA = al * p[0], aC = al * p[1], aG = al * p[2], aT = al * p[3];
             const double bA = be * p[0], bC = be * p[1], bG = be * p[2], bT = be * p[3];
             const double v[16] = {1 - (aG + bT + bC), bC, aG, bT, bA, 1 - (aT + bA + bG), bG, aT,

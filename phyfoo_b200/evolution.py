@@ -25,7 +25,8 @@ def transition(pi, length, evol=_abi.EVOL_F81ALPHA):
             ta = 1.0
         keep, mix = ta, 1.0 - ta
     else:
-        raise ValueError("HKY as implemented in the reference has zero transversion probabilities (HKY.java:32)")
+        raise ValueError("only the F81 tables are mirrored in numpy: HKY as implemented has zero transversion probabilities "
+                         "(HKY.java:32); HKY with its ratio (EVOL_HKY_RATIO) is evaluated inside the library (phyfoo_ss_*)")
     T = np.tile(pi * mix, (4, 1))
     T[np.arange(4), np.arange(4)] = keep + pi * mix
     return T
@@ -45,7 +46,8 @@ def tables(pi, branch, evol=_abi.EVOL_F81ALPHA):
         ta = np.where(ta < 1e-4, 0.0, np.where(ta > 1 - 1e-4, 1.0, ta))
         keep, mix = ta, 1.0 - ta
     else:
-        raise ValueError("HKY as implemented in the reference has zero transversion probabilities (HKY.java:32)")
+        raise ValueError("only the F81 tables are mirrored in numpy: HKY as implemented has zero transversion probabilities "
+                         "(HKY.java:32); HKY with its ratio (EVOL_HKY_RATIO) is evaluated inside the library (phyfoo_ss_*)")
     off = pi[None, :] * mix[:, None]                                  # [N-1][4]: P(b | a != b)
     T = np.repeat(off[:, None, :], 4, axis=1)                         # [N-1][4][4]
     d = np.arange(4)

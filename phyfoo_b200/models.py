@@ -26,6 +26,7 @@ class _PhyloModel:
     # static switches of the reference (models/PhyloBayesModel.java:43-69)
     CALC_LOGLIKELIHOOD = False
     EVOL_MODEL = _abi.EVOL_F81ALPHA   # evolution/EvolModel.java:7 MODEL_CLASS
+    HKY_RATIO = 0.0                   # EVOL_HKY_RATIO only: transversion / transition ratio (the "HKY:<ratio>" of EvolModel.java:49-51)
     # mean-field sweep limits and stop tolerance (algorithm/MeanFieldForBayesNet.java:102-107,205); 0 = the reference's
     # constants (100, 2, 1e-5).  Read when the device model is created.
     MAX_SWEEPS = 0
@@ -122,7 +123,7 @@ class _PhyloModel:
     def device_model(self):
         if self._dev is None:
             self._dev = core.DeviceModel(self.ctx, self.kind, self.length, self.order, self.tree, self._branch,
-                                         self._pi, evol=type(self).EVOL_MODEL, mode=self.mode(),
+                                         self._pi, evol=type(self).EVOL_MODEL, mode=self.mode(), hky_ratio=type(self).HKY_RATIO,
                                          max_sweeps=self.MAX_SWEEPS, min_sweeps=self.MIN_SWEEPS, tol=self.TOL)
             self._mode = self.mode()
         elif self._mode != self.mode():

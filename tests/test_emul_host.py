@@ -38,10 +38,10 @@ def emul():
     return L
 
 
-def run_emul(L, newick, pwm, codes, strand, mode, evol=_abi.EVOL_F81ALPHA):
+def run_emul(L, newick, pwm, codes, strand, mode, evol=_abi.EVOL_F81ALPHA, hky_ratio=0.0):
     tree = parse_newick(newick)
     W = len(pwm)
-    desc, keep = _abi.make_desc(_abi.MODEL_FG, W, 0, tree, np.tile(tree.branch, (W, 1)), pwm, evol, mode)
+    desc, keep = _abi.make_desc(_abi.MODEL_FG, W, 0, tree, np.tile(tree.branch, (W, 1)), pwm, evol, mode, hky_ratio)
     n = codes.shape[0] - W + 1
     out = np.zeros(n)
     sw = np.zeros(n, np.int32)
@@ -91,6 +91,28 @@ def test_f81beta_tables(emul):
     ref, rsw = oracle_fg(newick, pwm, evol=orc.F81BETA).score_windows(codes)
     assert np.array_equal(sw, rsw)
     assert rel_err(got, ref) < 1e-9
+
+
+@pytest.mark.parametrize("ratio", [2.0, 0.5])
+@pytest.mark.parametrize("gap_rate", [0.0, 0.15])
+def test_hky_with_its_ratio_in_effect(emul, ratio, gap_rate):
+    """PHYFOO_EVOL_HKY_RATIO (opt-in; evolution/HKY.java:77-106 with beta = alpha * ratio, the model of the reference's bundled
+    HKY data): general 4x4 tables, so the generic pass scores -- mean field with identical sweep counts, pruning at 1e-12."""
+    rng = np.random.default_rng(14)
+    pwm = synth.random_pwm(4, 0, 39)
+    for newick in (synth.caterpillar_newick(5, 0.2), TREES[3]):
+        S = parse_newick(newick).n_species
+        codes = random_codes(rng, 24, S, gap_rate)
+        for strand in (0, 1):
+            got, sw = run_emul(emul, newick, pwm, codes, strand, _abi.MODE_MEANFIELD, _abi.EVOL_HKY_RATIO, ratio)
+            ref, rsw = oracle_fg(newick, pwm, evol=orc.HKY_RATIO, hky_ratio=ratio).score_windows(codes, bool(strand))
+            assert np.array_equal(sw, rsw)
+            assert rel_err(got, ref) < 1e-9
+        got, _ = run_emul(emul, newick, pwm, codes, 0, _abi.MODE_EXACT, _abi.EVOL_HKY_RATIO, ratio)
+        ref, _ = oracle_fg(newick, pwm, mode=orc.EXACT_PRUNING, evol=orc.HKY_RATIO, hky_ratio=ratio).score_windows(codes)
+        assert rel_err(got, ref) < 1e-12
+        lit, _ = oracle_fg(newick, pwm, mode=orc.EXACT_ELIMINATION, evol=orc.HKY_RATIO, hky_ratio=ratio).score_windows(codes)
+        assert rel_err(lit, ref) < 1e-12
 
 
 @pytest.mark.parametrize("newick", TREES)

@@ -155,6 +155,49 @@ def test_zoops_estep(ctx, tree, strand):
     assert 0.0 <= hit <= 1.0   # statistical check lives in test_full_size_properties (12 short alignments are too few)
 
 
+@pytest.mark.parametrize("ratio,memo", [(2.0, 0), (0.5, 2)])
+def test_hky_with_its_ratio_in_effect(ctx, ratio, memo):
+    """PHYFOO_EVOL_HKY_RATIO (opt-in: evolution/HKY.java:77-106 with beta = alpha * ratio): tables without F81 structure, so the
+    generic kernel (memo 0) or the pattern table (memo 2) scores -- window scores, sweep counts and the strand E-step against
+    the oracle under the same tables; order 1 is refused."""
+    from phyfoo_b200 import _abi, synth
+    from phyfoo_b200.lib import IllegalArgumentException
+    from phyfoo_b200.models import PhyloBackground, PhyloBayesModel, SingleHiddenMotifMixture, StrandModel
+
+    class Motif(PhyloBayesModel):
+        EVOL_MODEL, HKY_RATIO = _abi.EVOL_HKY_RATIO, ratio
+
+    class Background(PhyloBackground):
+        EVOL_MODEL, HKY_RATIO = _abi.EVOL_HKY_RATIO, ratio
+
+    newick = synth.caterpillar_newick(5)
+    W = 6
+    pwm = synth.random_pwm(W, 0, 53)
+    smp, _ = synth.make_sample(newick, 10, 50, 77, pwm=pwm, gap_rate=0.05, length_jitter=8)
+    ctx.set_option("pattern_memo", memo)
+    try:
+        fg = Motif(W, 0, newick, ctx); fg.setCondProbs(pwm)
+        bg = Background(0, newick, ctx)
+        kw = dict(evol=orc.HKY_RATIO, hky_ratio=ratio)
+        ofg, obg = oracle_fg(newick, pwm, **kw), oracle_bg(newick, 0, **kw)
+        for strand in (0, 1):
+            got, sw = fg.getLogProbFor(smp, strand, want_sweeps=True)
+            ref = [ofg.score_windows(smp.getElementAt(i), bool(strand)) for i in range(smp.n_alignments)]
+            assert np.array_equal(sw, np.concatenate([r[1] for r in ref])), "mean-field sweep counts differ"
+            assert rel_err(got, np.concatenate([r[0] for r in ref])) < TOL
+        shm = SingleHiddenMotifMixture(StrandModel(fg, 0.6), bg, zoops=0.8)
+        res = shm.getNewWeights(smp)
+        ref = orc.estep(ofg, obg, smp.col_offsets, smp.codes, np.log([0.8, 0.2]), np.log([0.6, 0.4]), None)
+        assert np.array_equal(res["argmax_off"], ref["argmax_off"]) and np.array_equal(res["argmax_strand"], ref["argmax_strand"])
+        assert np.max(np.abs(res["gamma"] - ref["gamma"])) < TOL
+        assert abs(res["ll"] - ref["ll"]) <= TOL * abs(ref["ll"])
+        assert res["stats"]["sweeps_fg"] == ref["sweeps_fg"]
+        with pytest.raises(IllegalArgumentException):
+            Motif(W, 1, newick, ctx).device_model()
+    finally:
+        ctx.set_option("pattern_memo", 1)
+
+
 def test_ragged_and_error_behaviour(ctx):
     from phyfoo_b200 import synth
     from phyfoo_b200.lib import IllegalArgumentException

@@ -11,16 +11,16 @@ if ROOT not in sys.path:
 from oracle import oracle as orc  # noqa: E402  (test infrastructure)
 
 
-def oracle_fg(newick, pwm, order=0, mode=orc.MEANFIELD, evol=orc.F81ALPHA):
-    m = orc.Model(orc.FG, len(pwm), order, newick, evol)
+def oracle_fg(newick, pwm, order=0, mode=orc.MEANFIELD, evol=orc.F81ALPHA, hky_ratio=0.0):
+    m = orc.Model(orc.FG, len(pwm), order, newick, evol, hky_ratio)
     for t, p in enumerate(pwm):
         m.set_pi(t, np.asarray(p, np.float64).ravel())
     m.set_options(mode=mode)
     return m
 
 
-def oracle_bg(newick, order=0, pi=None, mode=orc.MEANFIELD, evol=orc.F81ALPHA):
-    m = orc.Model(orc.BG, 0, order, newick, evol)
+def oracle_bg(newick, order=0, pi=None, mode=orc.MEANFIELD, evol=orc.F81ALPHA, hky_ratio=0.0):
+    m = orc.Model(orc.BG, 0, order, newick, evol, hky_ratio)
     if pi is not None:
         for t, p in enumerate(pi):
             m.set_pi(t, np.asarray(p, np.float64).ravel())
