@@ -197,9 +197,8 @@ def test_device_scores_against_the_bundled_backgrounds(data, tree, ratio):
     mean_field = core.score_windows(ctx, smp.device(ctx), m.device_model(), 0)[0]
     ref = log_table(newick, mode=orc.MEANFIELD, **evol)
     assert np.max(np.abs(mean_field - ref) / np.abs(ref)) < 1e-9
-    m.device_model().set_mode(_abi.MODE_EXACT)
-    m._mode = _abi.MODE_EXACT
-    exact = core.score_windows(ctx, smp.device(ctx), m.device_model(), 0)[0]
+    Model.CALC_LOGLIKELIHOOD = True                   # the reference's static switch (models/PhyloBayesModel.java:54); device_model()
+    exact = core.score_windows(ctx, smp.device(ctx), m.device_model(), 0)[0]      # follows it with phyfoo_model_set_mode
     assert exact.shape == (1024,)
     assert np.max(np.abs(exact - log_table(newick, **evol)) / np.abs(log_table(newick, **evol))) < 1e-12
     assert abs(np.exp(exact).sum() - 1) < 1e-12
