@@ -11,6 +11,10 @@
 // pinned instead by (tests/test_oracle_*.py): closed forms (star tree under F81alpha),
 // brute-force enumeration of the joint for exact mode, the invariant -F <= log P, and an
 // independently written numpy restatement (oracle/np_restatement.py) agreeing to 1e-12.
+// The only outputs of reference code in the image -- its bundled synthetic data, written by its own
+// sampler -- pin the MODEL statistically (tests/test_generator_pins.py: column-pattern histograms
+// against the exact likelihood under the described trees, chi-square over 1024 patterns), not the
+// mean-field numbers bit for bit.
 //
 // Every function cites the reference lines it follows.  "X.java:N" is
 // /root/reference/main/java/src/X.java; "jstacs!/p:N" is a source file inside
