@@ -245,3 +245,45 @@ def test_library_suffstat_objective_of_an_order1_network_on_the_host():
     assert g.size == 4 and np.isfinite(g).all()
     fb, fa, ev = ss.optimize(np.array([1, 0, 2], np.int32))
     assert fa >= fb and ev > 0
+
+
+def test_library_suffstat_objective_under_hky_with_its_ratio():
+    """phyfoo_ss_create_host for an order-0 motif under PHYFOO_EVOL_HKY_RATIO: the objective is the dot product of the counts with
+    the logs of the general 4x4 tables of evolution/HKY.java:77-106 (beta = alpha * ratio), entry layout [pi (4)] then 16 per
+    non-root node row-major [parent][own]; a new lambda re-builds the tables of that position; branch lengths likewise."""
+    from phyfoo_b200 import _abi, core, synth
+    from phyfoo_b200.newick import parse_newick
+    tree = parse_newick("((A:0.1,B:0.3):0.15,(C:0.2,D:0.25):0.1)")
+    N, W, ratio = tree.n_nodes, 2, 2.0
+    rng = np.random.default_rng(4)
+    pwm = synth.random_pwm(W, 0, 6)
+    branch = np.tile(tree.branch, (W, 1))
+    E = 4 + 16 * (N - 1)
+    counts = rng.uniform(0.0, 3.0, (W, E))
+    desc, keep = _abi.make_desc(_abi.MODEL_FG, W, 0, tree, branch, pwm, _abi.EVOL_HKY_RATIO, _abi.MODE_MEANFIELD, ratio)
+    ss = core.SSObjective(desc=desc, counts=counts, entropy=1.5)
+
+    def hky(pi, alpha):
+        a, b = alpha * pi, alpha * ratio * pi
+        return np.array([[1 - (a[2] + b[3] + b[1]), b[1], a[2], b[3]], [b[0], 1 - (a[3] + b[0] + b[2]), b[2], a[3]],
+                         [a[0], b[1], 1 - (a[0] + b[3] + b[1]), b[3]], [b[0], a[1], b[2], 1 - (a[1] + b[0] + b[2])]])
+
+    def tab(pi, br):
+        pi = np.asarray(pi, np.float64).ravel()
+        return np.log(np.concatenate([pi] + [hky(pi, br[k]).ravel() for k in range(1, N)]))
+
+    def objective(pis, brs):
+        return sum(float(counts[t] @ tab(pis[t], brs[t])) for t in range(W)) - 1.5
+    assert abs(ss.value() - objective(pwm, branch)) <= 1e-12 * abs(ss.value())
+    lam = rng.normal(size=4)
+    new = np.exp(lam) / np.exp(lam).sum()
+    f = ss.eval(1, lam)
+    assert abs(f - objective([pwm[0], new], branch)) <= 1e-12 * abs(f)
+    b2 = branch.copy()
+    b2[1, 1:] = rng.uniform(0.05, 0.3, N - 1)
+    f = ss.eval_branches(1, b2[1])
+    assert abs(f - objective([pwm[0], new], b2)) <= 1e-12 * abs(f)
+    # order 1 is refused for this evolution model (the order-1 kernels and their table layout assume F81 structure)
+    d1, k1 = _abi.make_desc(_abi.MODEL_FG, W, 1, tree, branch, synth.random_pwm(W, 1, 6), _abi.EVOL_HKY_RATIO, _abi.MODE_MEANFIELD, ratio)
+    with pytest.raises(Exception):
+        core.SSObjective(desc=d1, counts=np.zeros((W, 16 + 32 * (N - 1))), entropy=0.0)
