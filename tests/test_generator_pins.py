@@ -204,3 +204,73 @@ def test_device_scores_against_the_bundled_backgrounds(data, tree, ratio):
     assert abs(np.exp(exact).sum() - 1) < 1e-12
     assert chi_square(G[data], exact) < ACCEPT
     assert (mean_field <= exact + 1e-9).all()
+
+
+# ---- the ZOOPS posterior on reference-generated positives ----------------------------------------------------------------
+R = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ratio_star_first400.npz"))
+
+
+def _calibration(gamma, argmax_off, W=15):
+    """Two identities of an exact posterior over the planted position J of an alignment, in expectation over data drawn from
+    the model: E[gamma_J] = E[sum_j gamma_j^2] and P(arg-max = J) = E[max_j gamma_j].  Returns their z statistics over the
+    alignments, the hit rate and the mean posterior of the annotated position."""
+    lengths = np.diff(R["col_offsets"])
+    off = np.concatenate([[0], np.cumsum(lengths - W + 1)])
+    pos, n = R["motif_pos"], lengths.size
+    g_true = np.array([gamma[off[i] + pos[i]] for i in range(n)])
+    g_sq = np.array([(gamma[off[i]:off[i + 1]] ** 2).sum() for i in range(n)])
+    g_max = np.array([gamma[off[i]:off[i + 1]].max() for i in range(n)])
+    hit = (argmax_off == pos).astype(np.float64)
+    z = lambda d: float(d.mean() / (d.std(ddof=1) / np.sqrt(n)))
+    return z(g_true - g_sq), z(hit - g_max), float(hit.mean()), float(g_true.mean())
+
+
+def _oracle_estep(newick, pwm):
+    from util import oracle_bg
+    fg, bg = oracle_fg(newick, pwm[:, None, :]), oracle_bg(newick, 0)
+    with np.errstate(divide="ignore"):
+        return orc.estep(fg, bg, R["col_offsets"], R["codes"], np.log([1.0, 0.0]), None, None, threads=4)
+
+
+def test_zoops_posterior_is_calibrated_on_the_reference_generated_positives():
+    """ratio_positive_negative_testing/data_1.0.fg (first 400 alignments, ZOOPS 1.0, one site each at MOTIF_POS, star tree, where
+    the mean field is exact): the E-step under the generating parameters (SingleHiddenMotifMixture.getNewWeights,
+    jstacs!/.../SingleHiddenMotifMixture.java:499-566, uniform position prior) is the exact posterior of the planted position,
+    so both calibration identities hold within 4 standard errors -- and fail under a slower tree or a sharpened / flattened
+    PWM.  This holds the motif and background scores, their difference per offset, the position prior and the normalisation
+    against positions the reference's sampler planted."""
+    pwm = G["pwm_ratio"] / G["pwm_ratio"].sum(axis=1, keepdims=True)
+    star = str(G["star"])
+    res = _oracle_estep(star, pwm)
+    z1, z2, hit, g_true = _calibration(res["gamma"], res["argmax_off"])
+    assert abs(z1) < 4 and abs(z2) < 4
+    assert hit > 0.8 and g_true > 0.75
+    assert abs(res["gamma"].sum() - 400) < 1e-9
+    sharp = pwm ** 2 / (pwm ** 2).sum(axis=1, keepdims=True)
+    flat = np.sqrt(pwm) / np.sqrt(pwm).sum(axis=1, keepdims=True)
+    for newick, p in ((star.replace("0.2", "0.5"), pwm), (star, sharp), (star, flat)):
+        r = _oracle_estep(newick, p)
+        w1, w2, _, _ = _calibration(r["gamma"], r["argmax_off"])
+        assert abs(w1) > 4 and abs(w2) > 4
+
+
+@pytest.mark.gpu
+def test_device_zoops_posterior_on_the_reference_generated_positives():
+    """The same E-step through libphyfoo.so: the oracle's posterior (1e-9), its arg-max calls bit for bit, calibrated."""
+    from phyfoo_b200 import core
+    from phyfoo_b200.data import PhyloSample
+    from phyfoo_b200.models import PhyloBackground, PhyloBayesModel, SingleHiddenMotifMixture
+    ctx = core.default_context()
+    pwm = G["pwm_ratio"] / G["pwm_ratio"].sum(axis=1, keepdims=True)
+    star = str(G["star"])
+    smp = PhyloSample(R["codes"], R["col_offsets"])
+    fg = PhyloBayesModel(15, 0, star, ctx)
+    fg.setCondProbs(pwm[:, None, :])
+    shm = SingleHiddenMotifMixture(fg, PhyloBackground(0, star, ctx), zoops=1.0)
+    res = shm.getNewWeights(smp)
+    ref = _oracle_estep(star, pwm)
+    assert np.array_equal(res["argmax_off"], ref["argmax_off"])
+    assert np.max(np.abs(res["gamma"] - ref["gamma"])) < 1e-9
+    assert abs(res["ll"] - ref["ll"]) <= 1e-9 * abs(ref["ll"])
+    z1, z2, hit, _ = _calibration(res["gamma"], res["argmax_off"])
+    assert abs(z1) < 4 and abs(z2) < 4 and hit > 0.8
