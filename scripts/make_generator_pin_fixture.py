@@ -73,6 +73,10 @@ def main():
     # 6000 alignments each in the files; the first 750 give the same resolution as the other files
     out["bg_hky2"] = column_hist(load("HKY/data_HKY2_1.0.bg", limit=750))
     out["bg_hky05"] = column_hist(load("HKY/data_HKY0.5_1.0.bg", limit=750))
+    # HKY on the three trees (HKY+trees/description_tree*.txt: branches 0.2 with HKY(2), 0.4 with HKY(0.5))
+    for key, rel in (("bg_tree1_hky2", "HKY+trees/data_tree1_HKY2_1.0.bg"), ("bg_tree1_hky05", "HKY+trees/data_tree1_HKY0.5_1.0.bg"),
+                     ("bg_tree3_hky2", "HKY+trees/data_tree3_HKY2_1.0.bg"), ("bg_tree2_hky05", "HKY+trees/data_tree2_HKY0.5_1.0.bg")):
+        out[key] = column_hist(load(rel))
     out["sites_ratio"], out["flanks_ratio"] = site_and_flank_hist(load("ratio_positive_negative_testing/data_1.0.fg"), 15)
     out["sites_tree1"], out["flanks_tree1"] = site_and_flank_hist(load("trees/data_tree1_1.0.fg"), 10)
     path = os.path.join(ROOT, "tests", "golden", "generator_pin.npz")

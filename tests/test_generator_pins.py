@@ -167,6 +167,12 @@ def test_hky_as_implemented_gives_the_bundled_hky_data_probability_zero():
         opt_in = log_table(tree, evol=orc.HKY_RATIO, hky_ratio=ratio)
         assert np.max(np.abs(opt_in - np.log(p)) / np.abs(np.log(p))) < 1e-12
         assert chi_square(G[data], log_table(tree, evol=orc.HKY_RATIO, hky_ratio=1.0)) > 20 * ACCEPT     # ratio 1 = F81
+    # ... and on the three trees of HKY+trees/ (internal nodes: tables of every level)
+    for data, tree, ratio in (("bg_tree1_hky2", "tree1", 2.0), ("bg_tree1_hky05", "tree1", 0.5), ("bg_tree3_hky2", "tree3", 2.0),
+                              ("bg_tree2_hky05", "tree2", 0.5)):
+        newick = str(G[tree]) if ratio == 2.0 else str(G[tree]).replace("0.2", "0.4")      # description_tree*.txt:5,50
+        assert chi_square(G[data], log_table(newick, evol=orc.HKY_RATIO, hky_ratio=ratio)) < ACCEPT
+        assert chi_square(G[data], log_table(newick, evol=orc.HKY_RATIO, hky_ratio=1.0)) > 20 * ACCEPT
     as_implemented = log_table(str(G["star"]), evol=orc.HKY)
     zero = ~np.isfinite(as_implemented)
     assert zero.sum() == 960 and abs(np.exp(as_implemented[~zero]).sum() - 1) < 1e-12
