@@ -35,6 +35,38 @@ def test_integration_table_names_every_symbol():
     assert not missing, f"INTEGRATION.md appendix does not name {missing}"
 
 
+def _java_type(c_decl):
+    c = c_decl.strip()
+    if "*" in c:
+        return "ADDRESS"
+    for prefix, j in (("double", "JAVA_DOUBLE"), ("int64_t", "JAVA_LONG"), ("float", "JAVA_FLOAT"), ("int32_t", "JAVA_INT"), ("int", "JAVA_INT")):
+        if c.startswith(prefix):
+            return j
+    raise AssertionError(f"no Java layout for {c_decl!r}")
+
+
+def test_panama_stubs_match_header():
+    """Every downcall handle INTEGRATION.md shows has the argument and return layouts of its prototype in include/phyfoo.h."""
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "phyfoo.h")).read(), flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b([a-z_0-9\* ]+?)\b(phyfoo_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        args = [a.strip() for a in m.group(3).split(",") if a.strip() and a.strip() != "void"]
+        protos[m.group(2)] = (m.group(1).strip(), args)
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    stubs = list(re.finditer(r'h\("(phyfoo_[a-z0-9_]+)",\s*FunctionDescriptor\.(ofVoid|of)\(([^;]*?)\)\)\s*;', doc, flags=re.S))
+    assert len(stubs) >= 40
+    for m in stubs:
+        name, kind = m.group(1), m.group(2)
+        got = [a.strip() for a in re.sub(r"\s+", " ", m.group(3)).split(",") if a.strip()]
+        ret, args = protos[name]
+        want = [_java_type(a) for a in args]
+        if kind == "of":
+            want = [_java_type(ret + " ")] + want
+        else:
+            assert ret == "void", name
+        assert got == want, f"{name}: stub {got} != header {want}"
+
+
 def test_struct_layouts_match_header():
     # phyfoo_model_desc: 4 int32, 2 pointers, int32 (+pad), double, 2 pointers, 4 int32, double
     assert C.sizeof(_abi.ModelDesc) == 16 + 16 + 8 + 8 + 16 + 16 + 8
