@@ -67,6 +67,33 @@ def test_panama_stubs_match_header():
         assert got == want, f"{name}: stub {got} != header {want}"
 
 
+def test_java_model_desc_layout_follows_the_header_struct():
+    """INTEGRATION.md's MODEL_DESC StructLayout: the header's fields in order with their Java layouts, and padding exactly
+    where natural C alignment puts it (an int before an 8-byte member at an offset that is not a multiple of 8)."""
+    text = open(os.path.join(ROOT, "include", "phyfoo.h")).read()
+    body = text[text.index("typedef struct {"):text.index("} phyfoo_model_desc;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = [(m.group(1).strip(), m.group(2)) for m in re.finditer(r"\n\s*([a-z_0-9 ]+\*?)\s*\b([a-z_]+);", body)]
+    assert [f for _, f in fields][:4] == ["kind", "width", "order", "n_nodes"] and len(fields) == 15
+    want, off = [], 0
+    for decl, name in fields:
+        j = _java_type(decl + " ")
+        size = 4 if j == "JAVA_INT" else 8
+        if off % size:
+            want.append(("pad", size - off % size))
+            off += size - off % size
+        want.append((j, name))
+        off += size
+    assert off == C.sizeof(_abi.ModelDesc)
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = doc[doc.index("static final StructLayout MODEL_DESC"):]
+    block = block[:block.index(";")]
+    got = []
+    for m in re.finditer(r'(JAVA_INT|JAVA_DOUBLE|JAVA_LONG|ADDRESS)\.withName\("([a-z_]+)"\)|MemoryLayout\.paddingLayout\((\d+)\)', block):
+        got.append(("pad", int(m.group(3))) if m.group(3) else (m.group(1), m.group(2)))
+    assert got == want
+
+
 def test_struct_layouts_match_header():
     # phyfoo_model_desc: 4 int32, 2 pointers, int32 (+pad), double, 2 pointers, 4 int32, double
     assert C.sizeof(_abi.ModelDesc) == 16 + 16 + 8 + 8 + 16 + 16 + 8
