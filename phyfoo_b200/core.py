@@ -435,9 +435,10 @@ class MultiDataset:
 
 
 class MultiModel:
-    def __init__(self, mctx, kind, width, order, tree, branch, pi_list, evol=_abi.EVOL_F81ALPHA, mode=_abi.MODE_MEANFIELD):
+    def __init__(self, mctx, kind, width, order, tree, branch, pi_list, evol=_abi.EVOL_F81ALPHA, mode=_abi.MODE_MEANFIELD,
+                 hky_ratio=0.0):
         self.mctx = mctx
-        desc, keep = _abi.make_desc(kind, width, order, tree, branch, pi_list, evol, mode)
+        desc, keep = _abi.make_desc(kind, width, order, tree, branch, pi_list, evol, mode, hky_ratio)
         self.h = C.c_void_p()
         _mraise(lib().phyfoo_multi_model_create(mctx.h, C.byref(desc), C.byref(self.h)), mctx.h)
         del keep

@@ -10,9 +10,20 @@ import numpy as np
 from . import _abi
 
 
-def transition(pi, length, evol=_abi.EVOL_F81ALPHA):
+def hky_transition(pi, alpha, beta):
+    """evolution/HKY.java:77-106 as written: transitions a<->g, c<->t at rate alpha, transversions at rate beta."""
+    a, b = alpha * np.asarray(pi, np.float64), beta * np.asarray(pi, np.float64)
+    return np.array([[1 - (a[2] + b[3] + b[1]), b[1], a[2], b[3]],
+                     [b[0], 1 - (a[3] + b[0] + b[2]), b[2], a[3]],
+                     [a[0], b[1], 1 - (a[0] + b[3] + b[1]), b[3]],
+                     [b[0], a[1], b[2], 1 - (a[1] + b[0] + b[2])]])
+
+
+def transition(pi, length, evol=_abi.EVOL_F81ALPHA, hky_ratio=0.0):
     """4x4 P(b | a) for one branch."""
     pi = np.asarray(pi, np.float64)
+    if evol == _abi.EVOL_HKY_RATIO:
+        return hky_transition(pi, length, length * hky_ratio)
     if evol == _abi.EVOL_F81ALPHA:
         keep = 1.0 - length
         mix = length
@@ -25,19 +36,21 @@ def transition(pi, length, evol=_abi.EVOL_F81ALPHA):
             ta = 1.0
         keep, mix = ta, 1.0 - ta
     else:
-        raise ValueError("only the F81 tables are mirrored in numpy: HKY as implemented has zero transversion probabilities "
-                         "(HKY.java:32); HKY with its ratio (EVOL_HKY_RATIO) is evaluated inside the library (phyfoo_ss_*)")
+        raise ValueError("HKY as implemented has zero transversion probabilities "
+                         "(HKY.java:32) and no finite objective")
     T = np.tile(pi * mix, (4, 1))
     T[np.arange(4), np.arange(4)] = keep + pi * mix
     return T
 
 
-def tables(pi, branch, evol=_abi.EVOL_F81ALPHA):
+def tables(pi, branch, evol=_abi.EVOL_F81ALPHA, hky_ratio=0.0):
     """Probability table of one position: entries [pi(4), node 1 (16), ..., node N-1 (16)]; branch[N] (entry 0 unused).
     All nodes at once (this sits in the inner loop of the sufficient-statistics objective); entry for entry the values of
     transition()."""
     pi = np.asarray(pi, np.float64)
     b = np.asarray(branch, np.float64)[1:]
+    if evol == _abi.EVOL_HKY_RATIO:
+        return np.concatenate([pi] + [hky_transition(pi, x, x * hky_ratio).ravel() for x in b])
     if evol == _abi.EVOL_F81ALPHA:
         keep, mix = 1.0 - b, b
     elif evol == _abi.EVOL_F81BETA:
@@ -46,8 +59,8 @@ def tables(pi, branch, evol=_abi.EVOL_F81ALPHA):
         ta = np.where(ta < 1e-4, 0.0, np.where(ta > 1 - 1e-4, 1.0, ta))
         keep, mix = ta, 1.0 - ta
     else:
-        raise ValueError("only the F81 tables are mirrored in numpy: HKY as implemented has zero transversion probabilities "
-                         "(HKY.java:32); HKY with its ratio (EVOL_HKY_RATIO) is evaluated inside the library (phyfoo_ss_*)")
+        raise ValueError("HKY as implemented has zero transversion probabilities "
+                         "(HKY.java:32) and no finite objective")
     off = pi[None, :] * mix[:, None]                                  # [N-1][4]: P(b | a != b)
     T = np.repeat(off[:, None, :], 4, axis=1)                         # [N-1][4][4]
     d = np.arange(4)

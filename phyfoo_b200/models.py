@@ -290,7 +290,7 @@ class PhyloBayesModel(_PhyloModel):
                     counts, entropy = local.suffstats(self.length, n_entries)
                     counts, entropy = sharding.allreduce_counts_(counts, entropy)
                     desc, keep = _abi.make_desc(self.kind, self.length, self.order, self.tree, self._branch, self._pi, type(self).EVOL_MODEL,
-                                                _abi.MODE_MEANFIELD)
+                                                _abi.MODE_MEANFIELD, type(self).HKY_RATIO)
                     obj = core.SSObjective(desc=desc, counts=counts, entropy=entropy)
                     del keep
                 else:
@@ -343,7 +343,7 @@ class PhyloBayesModel(_PhyloModel):
         sa, so, sw = core.select(self.ctx, ds, self.length, weights, self.PROB_THRESH_FOR_WEIGHTS, self.MOTIF_QUALITY_THRESHOLD)
         fe = core.FESet(self.ctx, ds, self.device_model(), sa, so, sw)
         try:
-            obj = optimize.SuffStatObjective(fe, self._pi, self._branch, type(self).EVOL_MODEL)
+            obj = optimize.SuffStatObjective(fe, self._pi, self._branch, type(self).EVOL_MODEL, type(self).HKY_RATIO)
         finally:
             fe.free()
         before = obj.value()

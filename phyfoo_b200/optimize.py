@@ -233,8 +233,9 @@ class SuffStatObjective:
     for the stationary distributions (FE_byParameter_ForBayesNodeJstacs / MotifParamOptimizer) and for the branch
     lengths (optimizing/branchlengths/EdgeOptimizer.java, GlobalEdgeOptimizer.java) alike.  Order-0 models."""
 
-    def __init__(self, fe, pi, branch, evol):
+    def __init__(self, fe, pi, branch, evol, hky_ratio=0.0):
         from . import evolution
+        self.hky_ratio = float(hky_ratio)
         self._ev = evolution
         self.pi = [np.asarray(p, np.float64).ravel().copy() for p in pi]
         self.branch = np.array(branch, np.float64)                   # [W][N]
@@ -261,7 +262,7 @@ class SuffStatObjective:
 
     def position_term(self, t, pi, branch):
         with np.errstate(divide="ignore"):
-            lt = np.log(self._ev.tables(pi, branch, self.evol)[self._nz[t]])
+            lt = np.log(self._ev.tables(pi, branch, self.evol, self.hky_ratio)[self._nz[t]])
         return float(np.dot(self._cnz[t], lt))
 
     def value(self):

@@ -287,3 +287,40 @@ def test_library_suffstat_objective_under_hky_with_its_ratio():
     d1, k1 = _abi.make_desc(_abi.MODEL_FG, W, 1, tree, branch, synth.random_pwm(W, 1, 6), _abi.EVOL_HKY_RATIO, _abi.MODE_MEANFIELD, ratio)
     with pytest.raises(Exception):
         core.SSObjective(desc=d1, counts=np.zeros((W, 16 + 32 * (N - 1))), entropy=0.0)
+
+
+def test_numpy_tables_under_hky_with_its_ratio_equal_the_library():
+    """evolution.tables / SuffStatObjective (numpy mirror used by trainEdges) under EVOL_HKY_RATIO against phyfoo_ss_* on the
+    same counts: the objective at the start, after a new stationary distribution and after new branch lengths."""
+    from phyfoo_b200 import _abi, core, evolution, optimize, synth
+    from phyfoo_b200.newick import parse_newick
+    tree = parse_newick("((A:0.1,B:0.3):0.15,(C:0.2,(D:0.05,E:0.2):0.25):0.1)")
+    N, W, ratio = tree.n_nodes, 3, 0.5
+    rng = np.random.default_rng(8)
+    pwm = synth.random_pwm(W, 0, 9)
+    branch = np.tile(tree.branch, (W, 1))
+    E = 4 + 16 * (N - 1)
+    counts = rng.uniform(0.0, 2.0, (W, E))
+    T = evolution.transition(np.ravel(pwm[0]), 0.2, _abi.EVOL_HKY_RATIO, ratio)
+    assert np.allclose(T.sum(axis=1), 1) and abs(T[0, 1] / T[0, 2] - ratio * np.ravel(pwm[0])[1] / np.ravel(pwm[0])[2]) < 1e-15
+
+    class Counts:                                    # what core.FESet.suffstats hands over after the device pass
+        def suffstats(self, w, e):
+            return counts.copy(), 0.75
+
+    obj = optimize.SuffStatObjective(Counts(), pwm, branch, _abi.EVOL_HKY_RATIO, ratio)
+    desc, keep = _abi.make_desc(_abi.MODEL_FG, W, 0, tree, branch, pwm, _abi.EVOL_HKY_RATIO, _abi.MODE_MEANFIELD, ratio)
+    ss = core.SSObjective(desc=desc, counts=counts, entropy=0.75)
+    assert abs(obj.value() - ss.value()) <= 1e-12 * abs(ss.value())
+    lam = rng.normal(size=4)
+    new = np.exp(lam) / np.exp(lam).sum()
+    f_lib = ss.eval(2, lam)
+    obj.set_position(2, pi=new)
+    f_np = sum(obj.position_term(t, obj.pi[t], obj.branch[t]) for t in range(W)) - 0.75
+    assert abs(f_np - f_lib) <= 1e-12 * abs(f_lib)
+    b = branch[1].copy()
+    b[1:] = rng.uniform(0.05, 0.3, N - 1)
+    f_lib = ss.eval_branches(1, b)
+    obj.set_position(1, branch=b)
+    f_np = sum(obj.position_term(t, obj.pi[t], obj.branch[t]) for t in range(W)) - 0.75
+    assert abs(f_np - f_lib) <= 1e-12 * abs(f_lib)
