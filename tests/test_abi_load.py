@@ -121,3 +121,38 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("test infrastructure", "").lower() or f in (), \
                     f"{f} mentions the oracle: the product path must not depend on it"
+
+
+def test_header_is_plain_c_and_a_c_caller_links(tmp_path):
+    """include/phyfoo.h compiles as pedantic C99 (what cgo / JNI / Panama's jextract read), a C caller links against
+    libphyfoo.so with nothing else on the link line, and without a device both init calls fail loudly with PHYFOO_ENODEVICE."""
+    import subprocess
+    plib.build()
+    src = tmp_path / "caller.c"
+    src.write_text(r'''
+#include "phyfoo.h"
+#include <stdio.h>
+int main(void) {
+    phyfoo_ctx* ctx = 0;
+    phyfoo_mctx* mctx = 0;
+    int dev[1] = {0};
+    int rc = phyfoo_init(0, &ctx);
+    int rcm = phyfoo_init_multi(dev, 1, &mctx);
+    printf("%d %d %d|%s\n", rc, rcm, (int)sizeof(phyfoo_model_desc), rc ? phyfoo_last_error(ctx) : "");
+    if (mctx) phyfoo_destroy_multi(mctx);
+    if (ctx) phyfoo_destroy(ctx);
+    return 0;
+}
+''')
+    exe = tmp_path / "caller"
+    libdir = os.path.join(ROOT, "phyfoo_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                           "-o", str(exe), "-L", libdir, "-l:libphyfoo.so", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    head, _, err = out.stdout.strip().partition("|")
+    rc, rcm, size = (int(x) for x in head.split())
+    assert size == C.sizeof(_abi.ModelDesc)
+    assert (rc, rcm) in ((_abi.OK, _abi.OK), (_abi.ENODEVICE, _abi.ENODEVICE))
+    if rc:
+        assert "no CPU fallback" in err
