@@ -1,0 +1,107 @@
+#!/usr/bin/env python
+"""Generates tests/golden/refexec_meanfield.npz: window scores and sweep counts produced by the REFERENCE'S OWN STATEMENTS --
+MeanFieldForBayesNet.init / optimizeByNormalisation / calcFreeEnergy of /root/reference/main/java/src/algorithm/
+MeanFieldForBayesNet.java, translated token by token and executed by tests/refexec.py (no JVM exists in this image) -- on
+seeded inputs: motif windows of orders 0 and 1 on four trees (both strands, with and without gaps) and background ranges of
+orders 0..2.  The .npz holds the inputs next to the outputs, so it can be checked anywhere: tests/test_reference_statements.py
+holds the oracle against it (bit for bit) and tests/test_zz_gpu_reference_statements.py the CUDA path.
+
+Runs only where /root/reference exists (the build container):    python scripts/make_refexec_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import refexec                                        # noqa: E402
+from oracle import np_restatement as npr              # noqa: E402
+from phyfoo_b200 import synth                         # noqa: E402
+
+TREES = {"star5": synth.star_newick(5, 0.2), "cat5": synth.caterpillar_newick(5, 0.2),
+         "mixed6": "((A:0.1,B:0.3):0.15,(C:0.2,(D:0.05,E:0.4):0.25):0.1,F:0.3)", "rand12": synth.random_binary_newick(12, 3)}
+
+
+def codes(rng, L, S, gap_rate):
+    c = rng.integers(0, 4, size=(L, S)).astype(np.uint8)
+    if gap_rate > 0:
+        c[rng.random((L, S)) < gap_rate] = 4
+        c[(c == 4).all(axis=1), 0] = 0                 # the reference drops all-gap columns when it reads a file
+    return c
+
+
+def motif_cases(rng):
+    for name, newick in TREES.items():
+        S = len(npr.parse_newick(newick)[3])
+        for order, W in ((0, 5), (1, 4)):         # widths the GPU tests of both orders also use
+            pwm = synth.random_pwm(W, order, 100 + 7 * order + S)
+            net = npr.Net.motif(newick, W, order)
+            for t, p in enumerate(pwm):
+                net.set_pi(t, p)
+            net.build_tables()
+            ref = refexec.ReferenceMeanField(net)
+            for gap_rate in (0.0, 0.15):
+                aln = codes(rng, W + (3 if name == "rand12" else 5), S, gap_rate)
+                n = aln.shape[0] - W + 1
+                score, sweeps = np.zeros((2, n)), np.zeros((2, n), np.int32)
+                for strand in (0, 1):
+                    for j in range(n):
+                        score[strand, j], sweeps[strand, j] = ref.score(aln[j:j + W], bool(strand))
+                yield dict(kind="motif", tree=name, newick=newick, order=order, W=W, gap_rate=gap_rate,
+                           pwm=np.concatenate([np.ravel(p) for p in pwm]), codes=aln, score=score, sweeps=sweeps)
+
+
+def background_cases(rng):
+    """PhyloBackground.getLogProbFor on ranges of exactly order + 1 columns (models/PhyloBackground.java:241-305): the net
+    of order + 1 trees is observed, optimised, the first `order` terms calcFreeEnergy(i, i) are taken, then it is re-initialised,
+    optimised again and calcFreeEnergy(order, order) is added; the value is minus the sum.  (The driver loop is restated in
+    these few lines; every free-energy number comes from the reference's statements.)"""
+    for name in ("cat5", "mixed6"):
+        newick = TREES[name]
+        S = len(npr.parse_newick(newick)[3])
+        for order in (0, 1, 2):
+            net = npr.Net.background(newick, order)
+            r = np.random.default_rng(200 + order)
+            for t in range(order + 1):
+                p = r.dirichlet(np.ones(4), size=4 ** t)
+                net.set_pi(t, p)
+            net.build_tables()
+            ref = refexec.ReferenceMeanField(net)
+            for gap_rate in (0.0, 0.15):
+                aln = codes(rng, order + 5, S, gap_rate)
+                n = aln.shape[0] - order
+                value, sweeps = np.zeros(n), np.zeros(n, np.int32)
+                for j in range(n):
+                    cols = aln[j:j + order + 1]
+                    ref.initObservation(cols)
+                    ref.init()
+                    ref.free_energy_calls = 0
+                    ref.optimizeByNormalisation()
+                    s = sum(ref.calcFreeEnergy(i, i) for i in range(order))
+                    ref.initObservation(cols)
+                    ref.init()
+                    ref.optimizeByNormalisation()
+                    s += ref.calcFreeEnergy(order, order)
+                    value[j], sweeps[j] = -s, ref.free_energy_calls - 2
+                yield dict(kind="background", tree=name, newick=newick, order=order, W=order + 1, gap_rate=gap_rate,
+                           pwm=np.concatenate([np.ravel(p) for p in net.pi]), codes=aln, score=value[None, :], sweeps=sweeps[None, :])
+
+
+def main():
+    rng = np.random.default_rng(20261020)
+    out, n = {}, 0
+    for case in list(motif_cases(rng)) + list(background_cases(rng)):
+        for k, v in case.items():
+            out[f"c{n}_{k}"] = np.array(v)
+        n += 1
+    out["n_cases"] = np.array(n)
+    path = os.path.join(ROOT, "tests", "golden", "refexec_meanfield.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: {os.path.getsize(path)} bytes, {n} cases, "
+          f"{sum(out[f'c{i}_score'].size for i in range(n))} scores from the reference's statements")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,455 @@
+"""Executes the reference's OWN statements for the mean-field sweep and the free energy.
+
+TEST INFRASTRUCTURE ONLY.  No JVM exists in this image, so the Java cannot run as Java.  But the two methods that carry the
+path's arithmetic -- MeanFieldForBayesNet.optimizeByNormalisation (algorithm/MeanFieldForBayesNet.java:92-211) and
+calcFreeEnergy(int, int) (:232-365), plus init() (:52-69) -- are written in a C-like subset of Java (declarations, for / while /
+if, array indexing, field access, Math.log / exp / abs).  This module reads that file from /root/reference AT TEST TIME,
+translates those method bodies token by token into Python (same statements, same order, same operands; nothing is re-derived)
+and runs them against a small object graph with the field and method names the Java uses (nodes, parents, children, CPF tables
+with their look-up rows).  No reference source is copied into the repository: without /root/reference the functions here
+raise, and the tests that need them are skipped (the golden vectors they produced are committed and are what travels).
+
+What is mechanical: every statement of the three methods.  What is NOT: the object graph the statements walk (tree structure,
+parent / child order, table rows), which is built from oracle/np_restatement.py; that substrate is pinned separately against
+the reference's own sampler output (tests/test_generator_pins.py).
+"""
+import math
+import os
+import re
+
+REFERENCE_FILE = "/root/reference/main/java/src/algorithm/MeanFieldForBayesNet.java"
+
+_TOKEN = re.compile(r"""
+    (?P<bc>/\*.*?\*/) | (?P<lc>//[^\n]*) | (?P<str>"(?:\\.|[^"\\])*") |
+    (?P<num>(?:\d+\.\d*|\.\d+|\d+)(?:[eE][+-]?\d+)?[dDfFlL]?) |
+    (?P<id>[A-Za-z_$][A-Za-z_0-9$]*) |
+    (?P<op>\+\+|--|\+=|-=|\*=|/=|==|!=|<=|>=|&&|\|\||[{}()\[\];,.<>=+\-*/%!?:]) |
+    (?P<ws>\s+)
+""", re.S | re.X)
+
+TYPES = {"int", "double", "boolean", "long", "float"}
+
+
+def tokenize(src):
+    out, pos = [], 0
+    while pos < len(src):
+        m = _TOKEN.match(src, pos)
+        if not m:
+            if ord(src[pos]) > 127:                # a stray non-ASCII byte outside comments: skip
+                pos += 1
+                continue
+            raise SyntaxError(f"cannot tokenize at {src[pos:pos + 30]!r}")
+        pos = m.end()
+        kind = m.lastgroup
+        if kind in ("bc", "lc", "ws"):
+            continue
+        out.append((kind, m.group(kind)))
+    return out
+
+
+def _match(tokens, i, open_, close):
+    """index of the token closing the bracket opened at tokens[i]"""
+    depth = 0
+    for j in range(i, len(tokens)):
+        if tokens[j][1] == open_:
+            depth += 1
+        elif tokens[j][1] == close:
+            depth -= 1
+            if depth == 0:
+                return j
+    raise SyntaxError("unbalanced " + open_)
+
+
+def find_method(tokens, name, n_params):
+    """(parameter names, body tokens without the outer braces) of the method `name` with n_params parameters"""
+    for i in range(len(tokens) - 2):
+        if tokens[i] == ("id", name) and tokens[i + 1][1] == "(" and i > 0 and tokens[i - 1][0] == "id":
+            j = _match(tokens, i + 1, "(", ")")
+            if j + 1 >= len(tokens) or tokens[j + 1][1] != "{":
+                continue                                        # a call, not a declaration
+            params = [t[1] for k, t in enumerate(tokens[i + 2:j]) if t[0] == "id" and tokens[i + 2 + k + 1][1] in (",", ")")]
+            if len(params) != n_params:
+                continue
+            end = _match(tokens, j + 1, "{", "}")
+            return params, tokens[j + 2:end]
+    raise LookupError(name)
+
+
+class Translator:
+    """Java-subset statements -> Python source.  Every construct outside the subset raises."""
+
+    def __init__(self, fields, methods, params):
+        self.fields, self.methods = set(fields), set(methods)
+        self.locals = set(params)
+        self.lines = []
+
+    # ---- expressions ---------------------------------------------------------------------------------------------------
+    def expr(self, toks):
+        out, i = [], 0
+        while i < len(toks):
+            kind, t = toks[i]
+            prev = toks[i - 1][1] if i else None
+            nxt = toks[i + 1][1] if i + 1 < len(toks) else None
+            if t == "new":                                      # new double[expr] / new int[expr]
+                ty = toks[i + 1][1]
+                j = _match(toks, i + 2, "[", "]")
+                if j + 1 < len(toks) and toks[j + 1][1] == "[":
+                    raise NotImplementedError("multi-dimensional new")
+                zero = {"double": "0.0", "int": "0", "boolean": "False"}[ty]
+                out.append(f"_JArray([{zero}] * ({self.expr(toks[i + 3:j])}))")
+                i = j + 1
+                continue
+            if kind == "id":
+                if prev == ".":
+                    out.append(t)
+                elif t in ("true", "false"):
+                    out.append(t.capitalize())
+                elif t == "null":
+                    out.append("None")
+                elif t == "this":
+                    out.append("self")
+                elif t in self.locals:
+                    out.append(t)
+                elif t in self.methods and nxt == "(":
+                    out.append("self." + t)
+                elif t in self.fields:
+                    out.append("self." + t)
+                elif t in ("Math", "Double", "Alphabet", "MeanFieldForBayesNet", "Arrays", "System"):
+                    out.append(t)
+                else:
+                    raise NameError(f"unknown identifier {t!r} in the reference statement")
+            elif kind == "num":
+                out.append(t.rstrip("dDfFlL"))
+            elif t == "&&":
+                out.append("and")
+            elif t == "||":
+                out.append("or")
+            elif t == "!":
+                out.append("not")
+            elif t in ("++", "--", "?", "instanceof"):
+                raise NotImplementedError(t + " inside an expression")
+            elif kind == "str":
+                out.append(t)
+            else:
+                out.append(t)
+            i += 1
+        s = " ".join(out)
+        for a, b in (("Math . log", "_jlog"), ("Math . exp", "_jexp"), ("Math . abs", "abs"), ("Math . min", "min"),
+                     ("Double . NEGATIVE_INFINITY", "_NEG_INF"), ("Alphabet . size", "4"),
+                     ("MeanFieldForBayesNet . CALC_LIKELIHOOD", "self.CALC_LIKELIHOOD")):
+            s = s.replace(a, b)
+        return s
+
+    # ---- statements ----------------------------------------------------------------------------------------------------
+    def emit(self, ind, text):
+        self.lines.append("    " * ind + text)
+
+    def split_top(self, toks, sep):
+        parts, depth, cur = [], 0, []
+        for t in toks:
+            if t[1] in "([{":
+                depth += 1
+            elif t[1] in ")]}":
+                depth -= 1
+            if t[1] == sep and depth == 0:
+                parts.append(cur)
+                cur = []
+            else:
+                cur.append(t)
+        parts.append(cur)
+        return parts
+
+    def simple(self, toks, ind):
+        """one statement without its terminating semicolon"""
+        if not toks:
+            return
+        v = [t[1] for t in toks]
+        if v[0] == "continue":
+            self.emit(ind, "continue")                          # (labels are checked in stmt())
+            return
+        if v[0] == "break":
+            self.emit(ind, "break")
+            return
+        if v[0] == "return":
+            self.emit(ind, "return " + self.expr(toks[1:]) if len(toks) > 1 else "return")
+            return
+        if v[:3] == ["System", ".", "out"]:
+            self.emit(ind, "pass")
+            return
+        if v[:3] == ["Arrays", ".", "fill"]:
+            a, b = self.split_top(toks[4:-1], ",")
+            self.emit(ind, f"_fill({self.expr(a)}, {self.expr(b)})")
+            return
+        # declaration:  type [ [] ]* name [= expr] {, name [= expr]}
+        if toks[0][0] == "id" and (v[0] in TYPES or (v[0][0].isupper() and len(toks) > 1 and (toks[1][0] == "id" or v[1] == "["))) \
+                and v[0] not in ("Math", "System", "Arrays"):
+            j = 1
+            while j + 1 < len(toks) and v[j] == "[" and v[j + 1] == "]":
+                j += 2
+            if j < len(toks) and toks[j][0] == "id":
+                for d in self.split_top(toks[j:], ","):
+                    name = d[0][1]
+                    self.locals.add(name)
+                    if len(d) > 1:
+                        assert d[1][1] == "=", d
+                        self.emit(ind, f"{name} = {self.expr(d[2:])}")
+                    else:
+                        self.emit(ind, f"{name} = None")
+                return
+        if v[-1] in ("++", "--"):
+            self.emit(ind, f"{self.expr(toks[:-1])} {'+' if v[-1] == '++' else '-'}= 1")
+            return
+        self.emit(ind, self.expr(toks))                         # assignment or call
+
+    def stmt(self, toks, i, ind, loop_labels):
+        """translates the statement starting at toks[i]; returns the index behind it"""
+        t = toks[i][1]
+        if t == "{":
+            j = _match(toks, i, "{", "}")
+            n = len(self.lines)
+            k = i + 1
+            while k < j:
+                k = self.stmt(toks, k, ind, loop_labels)
+            if len(self.lines) == n:
+                self.emit(ind, "pass")
+            return j + 1
+        if toks[i][0] == "id" and i + 1 < len(toks) and toks[i + 1][1] == ":" and t not in ("default", "case"):
+            return self._labelled(toks, i, ind, loop_labels)
+        if t in ("for", "while"):
+            return self._loop(toks, i, ind, loop_labels, None)
+        if t == "if":
+            j = _match(toks, i + 1, "(", ")")
+            self.emit(ind, f"if {self.expr(toks[i + 2:j])}:")
+            k = self.stmt(toks, j + 1, ind + 1, loop_labels)
+            if k < len(toks) and toks[k][1] == "else":
+                self.emit(ind, "else:")
+                k = self.stmt(toks, k + 1, ind + 1, loop_labels)
+            return k
+        if t == ";":
+            return i + 1
+        j = i
+        depth = 0
+        while toks[j][1] != ";" or depth:
+            depth += toks[j][1] in "([{"
+            depth -= toks[j][1] in ")]}"
+            j += 1
+        if t == "continue" and j - i == 2:
+            if not loop_labels or loop_labels[-1] != toks[i + 1][1]:
+                raise NotImplementedError("continue to an outer label")
+            self.simple(toks[i:i + 1], ind)
+        else:
+            self.simple(toks[i:j], ind)
+        return j + 1
+
+    def _labelled(self, toks, i, ind, loop_labels):
+        if toks[i + 2][1] not in ("for", "while"):
+            raise NotImplementedError("label on a non-loop")
+        return self._loop(toks, i + 2, ind, loop_labels, toks[i][1])
+
+    def _loop(self, toks, i, ind, loop_labels, label):
+        j = _match(toks, i + 1, "(", ")")
+        head = toks[i + 2:j]
+        labels = loop_labels + [label]
+        if toks[i][1] == "while":
+            self.emit(ind, f"while {self.expr(head)}:")
+            return self.stmt(toks, j + 1, ind + 1, labels)
+        init, cond, upd = self.split_top(head, ";")
+        iv = [t[1] for t in init]
+        cv = [t[1] for t in cond]
+        uv = [t[1] for t in upd]
+        # for (int v = A; v < B; v++)  /  v <= B   -- the only shape the three methods use
+        if len(iv) >= 4 and iv[0] == "int" and iv[2] == "=" and cv[0] == iv[1] and cv[1] in ("<", "<=") and uv == [iv[1], "++"]:
+            var = iv[1]
+            self.locals.add(var)
+            lo, hi = self.expr(init[3:]), self.expr(cond[2:])
+            self.emit(ind, f"for {var} in range({lo}, ({hi}){' + 1' if cv[1] == '<=' else ''}):")
+            return self.stmt(toks, j + 1, ind + 1, labels)
+        raise NotImplementedError("for-loop shape " + " ".join(iv + [";"] + cv + [";"] + uv))
+
+
+def _jlog(x):
+    """java.lang.Math.log: -Infinity at 0, NaN below"""
+    if x > 0:
+        return math.log(x)
+    return -math.inf if x == 0 else math.nan
+
+
+def _jexp(x):
+    try:
+        return math.exp(x)
+    except OverflowError:
+        return math.inf
+
+
+class _JArray(list):
+    """a Java array: a list with a .length"""
+    length = property(len)
+
+
+def _fill(a, v):
+    for i in range(len(a)):
+        a[i] = v
+
+
+FIELDS = ["bnh", "q", "seq", "parent", "node2hiddenNodeMap", "hiddenNodes", "ns", "CALC_LIKELIHOOD"]
+METHODS = ["init", "optimizeByNormalisation", "calcFreeEnergy", "calcLogLikelihood"]
+
+
+def translate(path=REFERENCE_FILE):
+    """{method name: python source} for init(), optimizeByNormalisation(), calcFreeEnergy(start, end), calcFreeEnergy()."""
+    if not os.path.exists(path):
+        raise FileNotFoundError(path)
+    with open(path, encoding="latin-1") as f:
+        toks = tokenize(f.read())
+    out = {}
+    for py_name, java_name, n in (("init", "init", 0), ("optimizeByNormalisation", "optimizeByNormalisation", 0),
+                                  ("calcFreeEnergy2", "calcFreeEnergy", 2), ("calcFreeEnergy0", "calcFreeEnergy", 0)):
+        params, body = find_method(toks, java_name, n)
+        tr = Translator(FIELDS, METHODS, params)
+        tr.emit(0, f"def {py_name}(self{''.join(', ' + p for p in params)}):")
+        k = 0
+        while k < len(body):
+            k = tr.stmt(body, k, 1, [])
+        out[py_name] = "\n".join(tr.lines) + "\n"
+    return out
+
+
+# ---- the object graph the statements walk (names as in bayesNet/*.java) ---------------------------------------------------
+class _Props:
+    def __init__(self, leaf):
+        self._isObserved, self._observedIndex, self._leaf = False, 0, leaf
+
+    def isPhyloLeaf(self):
+        return self._leaf
+
+    def setObservation(self, idx):                              # bayesNet/BayesNetNodeProperties.java:88-99
+        if idx >= 4:
+            self._isObserved = False
+        else:
+            self._observedIndex, self._isObserved = idx, True
+
+
+class _CPF:
+    def __init__(self, node, table, independent):
+        self._node = node
+        self._condProb = [list(map(float, r)) for r in table]
+        self._indepedentCondProb = [list(map(float, r)) for r in independent]
+        self._size = len(self._condProb)
+        npar = node.numberOfParents
+        self._lookup = [[(l // 4 ** p) % 4 for p in range(npar)] for l in range(self._size)]       # CPF.java:238-256
+
+    def _independent(self):                                     # CPF.java:146-152,218-224 (ALLOW_RETURN_INDEPENDENT_TRANSITION)
+        return self._node.props.isPhyloLeaf() and not self._node.props._isObserved
+
+    def get(self, l, obs):
+        return (self._indepedentCondProb if self._independent() else self._condProb)[l][obs]
+
+    def getCondProb(self):
+        return self._indepedentCondProb if self._independent() else self._condProb
+
+    def getLookUpPointer(self):
+        return self._lookup
+
+
+class _Node:
+    def __init__(self, number, leaf):
+        self.nodeNumber, self.props = number, _Props(leaf)
+        self.Aparents, self.Achildren = [], []
+
+    numberOfParents = property(lambda self: len(self.Aparents))
+    numberOfChilds = property(lambda self: len(self.Achildren))
+
+    def isRoot(self):                                           # bayesNet/BayesNetNode.java:144-146
+        return len(self.Aparents) == 0
+
+    def getParentIndex(self, parent):                           # :154-156
+        return self.Aparents.index(parent)
+
+
+class _NodeList:
+    def __init__(self, nodes):
+        self.nodes, self.numberOfNodes = nodes, len(nodes)
+
+    def getNode(self, i):
+        return self.nodes[i]
+
+
+class _Handler:
+    def __init__(self, net, trees):
+        self._net, self._myTreesArray, self.motifLength = net, trees, len(trees)
+
+    def getNet(self):
+        return self._net
+
+
+class _Seq:
+    def __init__(self, length):
+        self._length = length
+
+    def getLength(self):
+        return self._length
+
+
+class ReferenceMeanField:
+    """MeanFieldForBayesNet with the reference's own method bodies (translated on construction) over the nodes of an
+    oracle.np_restatement.Net (tables built).  score(cols) = what PhyloBayesModel.getLogProbFor does with it
+    (models/PhyloBayesModel.java:250-260): initObservation, init, optimizeByNormalisation, -calcFreeEnergy(0, W-1)."""
+    CALC_LIKELIHOOD = False
+    _code = None
+
+    def __init__(self, net):
+        if ReferenceMeanField._code is None:
+            ns = {"_jlog": _jlog, "_jexp": _jexp, "_NEG_INF": -math.inf, "_fill": _fill, "_JArray": _JArray}
+            src = translate()
+            for s in src.values():
+                exec(compile(s, REFERENCE_FILE + " (translated)", "exec"), ns)
+            ReferenceMeanField._code, ReferenceMeanField.source = ns, src
+        self.net = net
+        index = {n: i for i, n in enumerate(net.order_nodes)}
+        leaves = set(net.leaves)
+        nodes = [_Node(i, k in leaves) for i, (t, k) in enumerate(net.order_nodes)]
+        for n, i in index.items():
+            nodes[i].Aparents = [nodes[index[p]] for p in net.par[n]]
+            nodes[i].Achildren = [nodes[index[c]] for c in net.chi[n]]
+        for n, i in index.items():
+            nodes[i].CPF = _CPF(nodes[i], net.tab[n].reshape(-1, 4), net.ind[n].reshape(-1, 4))
+        self.nodes = nodes
+        trees = [_NodeList([nodes[index[(t, k)]] for k in range(net.N)]) for t in range(net.W)]
+        self.leaf_nodes = [[nodes[index[(t, k)]] for k in net.leaves] for t in range(net.W)]
+        self.bnh = _Handler(_NodeList(nodes), trees)
+        self.seq = _Seq(net.W)
+        self.q = self.node2hiddenNodeMap = self.parent = self.ns = None
+        self.hiddenNodes = 0
+        self.free_energy_calls = 0
+
+    # the three translated methods
+    def init(self):
+        return self._code["init"](self)
+
+    def optimizeByNormalisation(self):
+        return self._code["optimizeByNormalisation"](self)
+
+    def calcFreeEnergy(self, *a):
+        if a:
+            return self._code["calcFreeEnergy2"](self, *a)
+        self.free_energy_calls += 1                             # the sweep loop calls the no-argument form: once before, once per sweep
+        return self._code["calcFreeEnergy0"](self)
+
+    def initObservation(self, cols, revcomp=False):
+        """MeanFieldForBayesNet.initObservation :78-89 -> VirtualTree.setObservation :183-198 (leaves in leaf order); the
+        reverse strand reads the complemented columns in reverse order (what the reference's reverse-complement Sequence holds)"""
+        W = self.net.W
+        for t in range(W):
+            col = cols[W - 1 - t] if revcomp else cols[t]
+            for s, node in enumerate(self.leaf_nodes[t]):
+                c = int(col[s])
+                node.props.setObservation(3 - c if (revcomp and c < 4) else c)
+
+    def score(self, cols, revcomp=False):
+        """(-F, sweeps)"""
+        self.initObservation(cols, revcomp)
+        self.init()
+        self.free_energy_calls = 0
+        self.optimizeByNormalisation()
+        sweeps = self.free_energy_calls - 1                     # one call before the loop, one per sweep
+        return -self.calcFreeEnergy(0, self.net.W - 1), sweeps

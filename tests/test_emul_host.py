@@ -460,3 +460,42 @@ def test_generic_net_expected_counts_give_the_fixed_q_objective(emul, order):
         ob.set_branch(T - 1, k, b2[T - 1, k])
     ref = ofe.sum()
     assert abs(objective(pis, b2) - ref) <= 1e-12 * abs(ref)
+
+
+# ---- the kernels' arithmetic against outputs of the reference's own statements (tests/golden/refexec_meanfield.npz) ----------
+def test_kernel_arithmetic_reproduces_the_reference_statements(emul_o1n):
+    """The per-thread code of the order-0 kernels (generic pass and F81-structured pass) and of the order-1 node kernel,
+    compiled for the host, on the golden inputs of tests/test_reference_statements.py: scores within 1e-9 relative of what the
+    reference's translated statements produced, sweep counts identical (what tests/test_zz_gpu_reference_statements.py asks of
+    the library on the device)."""
+    from test_reference_statements import cases, motif_pwm
+    emul = emul_o1n
+    emul.emul_score_o0f.argtypes = [C.POINTER(_abi.ModelDesc), C.POINTER(C.c_uint8), C.c_int, C.c_int, C.POINTER(C.c_double),
+                                    C.POINTER(C.c_int)]
+    checked = 0
+    for c in cases("motif"):
+        W, order, newick = int(c["W"]), int(c["order"]), str(c["newick"])
+        tr = parse_newick(newick)
+        pwm = motif_pwm(c)
+        codes = np.ascontiguousarray(c["codes"], np.uint8)
+        n = codes.shape[0] - W + 1
+        desc, keep = _abi.make_desc(_abi.MODEL_FG, W, order, tr, np.tile(tr.branch, (W, 1)), pwm, _abi.EVOL_F81ALPHA, _abi.MODE_MEANFIELD)
+        for strand in (0, 1):
+            ref, rsw = c["score"][strand], c["sweeps"][strand]
+            results = []
+            if order == 0:
+                results.append(run_emul(emul, newick, pwm, codes, strand, _abi.MODE_MEANFIELD))
+                out, sw = np.zeros(n), np.zeros(n, np.int32)
+                assert emul.emul_score_o0f(C.byref(desc), codes.ctypes.data_as(C.POINTER(C.c_uint8)), codes.shape[0], strand,
+                                           out.ctypes.data_as(C.POINTER(C.c_double)), sw.ctypes.data_as(C.POINTER(C.c_int))) == 0
+                results.append((out, sw))
+            elif not (codes == 4).any():                       # the node kernel takes gap-free windows (the rest go to net1w.cuh)
+                out, sw, ns = np.zeros(n), np.zeros(n, np.int32), C.c_int()
+                assert emul.emul_score_o1n(C.byref(desc), codes.ctypes.data_as(C.POINTER(C.c_uint8)), codes.shape[0], strand, 3,
+                                           out.ctypes.data_as(C.POINTER(C.c_double)), sw.ctypes.data_as(C.POINTER(C.c_int)), C.byref(ns)) == 0
+                results.append((out, sw))
+            for out, sw in results:
+                assert np.array_equal(sw, rsw), (str(c["tree"]), order, strand)
+                assert rel_err(out, ref) < 1e-9
+                checked += out.size
+    assert checked >= 2 * 88 + 40

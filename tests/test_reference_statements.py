@@ -1,0 +1,127 @@
+"""The mean-field sweep and the free energy pinned by the reference's own statements.
+
+tests/refexec.py reads algorithm/MeanFieldForBayesNet.java from /root/reference, translates init(), optimizeByNormalisation()
+and calcFreeEnergy(int, int) statement by statement and executes them (there is no JVM here; nothing of the file is copied
+into the repository).  scripts/make_refexec_golden.py ran them on seeded inputs and committed inputs and outputs as
+tests/golden/refexec_meanfield.npz.  Here:
+  * anywhere: the C++ oracle and the independent numpy restatement against those golden vectors -- scores to the last bits,
+    mean-field sweep counts exactly (SURVEY.md section 8 rows a5, a6, a7, and a10 for ranges of order + 1 columns);
+  * where /root/reference exists: the translation is redone and re-executed, and must reproduce the committed vectors.
+The CUDA path is held against the same vectors in tests/test_zz_gpu_reference_statements.py.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from util import oracle_bg, oracle_fg
+
+from oracle import np_restatement as npr
+
+import refexec
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refexec_meanfield.npz"))
+HAVE_REFERENCE = os.path.exists(refexec.REFERENCE_FILE)
+needs_reference = pytest.mark.skipif(not HAVE_REFERENCE, reason="/root/reference is not on this machine")
+
+
+def cases(kind):
+    for i in range(int(G["n_cases"])):
+        if str(G[f"c{i}_kind"]) == kind:
+            yield {k: G[f"c{i}_{k}"] for k in ("newick", "order", "W", "pwm", "codes", "score", "sweeps", "tree", "gap_rate")}
+
+
+def motif_pwm(c):
+    """per position [contexts][4]: one context row at position 0 and for order 0, four behind an order-1 edge"""
+    W, order, flat = int(c["W"]), int(c["order"]), np.asarray(c["pwm"])
+    rows = [1 if (order == 0 or t == 0) else 4 for t in range(W)]
+    off = np.concatenate([[0], np.cumsum(rows)]) * 4
+    return [flat[off[t]:off[t + 1]].reshape(rows[t], 4) for t in range(W)]
+
+
+def background_pi(c):
+    order, flat = int(c["order"]), np.asarray(c["pwm"])
+    rows = [4 ** t for t in range(order + 1)]
+    off = np.concatenate([[0], np.cumsum(rows)]) * 4
+    return [flat[off[t]:off[t + 1]].reshape(rows[t], 4) for t in range(order + 1)]
+
+
+def test_golden_vectors_cover_the_path():
+    motif, bg = list(cases("motif")), list(cases("background"))
+    assert len(motif) == 16 and len(bg) == 12
+    assert {int(c["order"]) for c in motif} == {0, 1} and {int(c["order"]) for c in bg} == {0, 1, 2}
+    assert any((c["codes"] == 4).any() for c in motif) and any(not (c["codes"] == 4).any() for c in motif)
+    sweeps = np.concatenate([c["sweeps"].ravel() for c in motif])
+    assert sweeps.min() >= 2 and sweeps.max() > 20 and len(set(sweeps.tolist())) > 10      # the stop rule is exercised
+
+
+def test_oracle_reproduces_the_reference_statements_on_motif_windows():
+    worst, identical, total = 0.0, 0, 0
+    for c in cases("motif"):
+        W, pwm = int(c["W"]), motif_pwm(c)
+        om = oracle_fg(str(c["newick"]), pwm, order=int(c["order"]))
+        for strand in (0, 1):
+            got, sw = om.score_windows(c["codes"], bool(strand))
+            assert np.array_equal(sw, c["sweeps"][strand]), (str(c["tree"]), int(c["order"]), strand)
+            worst = max(worst, float(np.max(np.abs(got - c["score"][strand]) / np.abs(c["score"][strand]))))
+            identical += int((got == c["score"][strand]).sum())
+            total += got.size
+    assert worst < 1e-13
+    assert identical >= 0.9 * total            # same statements in the same order: nearly every score is the same double
+
+
+def test_oracle_reproduces_the_reference_statements_on_background_ranges():
+    for c in cases("background"):
+        order = int(c["order"])
+        ob = oracle_bg(str(c["newick"]), order, background_pi(c))
+        for j in range(c["score"].shape[1]):
+            ob.reset_stats()
+            got = ob.bg_range(c["codes"], j, j + order)
+            ref = c["score"][0, j]
+            assert abs(got - ref) <= 1e-13 * abs(ref)
+            assert ob.sweeps_total() == c["sweeps"][0, j]            # both optimisations of the range's net
+
+
+def test_numpy_restatement_reproduces_the_reference_statements():
+    for c in cases("motif"):
+        W, order = int(c["W"]), int(c["order"])
+        net = npr.Net.motif(str(c["newick"]), W, order)
+        for t, p in enumerate(motif_pwm(c)):
+            net.set_pi(t, p)
+        net.build_tables()
+        for strand in (0, 1):
+            for j in range(c["score"].shape[1]):
+                v, k = npr.score_window(net, c["codes"][j:j + W], bool(strand))
+                assert k == c["sweeps"][strand, j]
+                assert abs(v - c["score"][strand, j]) <= 1e-12 * abs(v)
+
+
+@needs_reference
+def test_translation_is_of_the_three_methods_and_nothing_is_rewritten():
+    src = refexec.translate()
+    assert set(src) == {"init", "optimizeByNormalisation", "calcFreeEnergy2", "calcFreeEnergy0"}
+    opt, fe = src["optimizeByNormalisation"], src["calcFreeEnergy2"]
+    # landmarks of the reference's text (MeanFieldForBayesNet.java:100-107,192-201,204-209,351-357)
+    assert "maxSteps = 100" in opt and "minsteps = 2" in opt and "< 1e-5" in opt
+    assert "while k < maxSteps and not converged or k < minsteps:" in opt
+    assert opt.count("_jlog") == 2 and opt.count("_jexp") == 1 and "/ sum" in opt
+    assert fe.count("_jlog") == 4 and fe.count("_NEG_INF") == 2 and "return part1 - part2" in fe
+    for s in src.values():
+        compile(s, "translated", "exec")
+
+
+@needs_reference
+def test_reexecuting_the_reference_statements_reproduces_the_committed_vectors():
+    for c in cases("motif"):
+        if str(c["tree"]) == "rand12" and int(c["order"]) == 1:
+            continue                                                   # (seconds of pure Python; covered by the generator run)
+        W, order = int(c["W"]), int(c["order"])
+        net = npr.Net.motif(str(c["newick"]), W, order)
+        for t, p in enumerate(motif_pwm(c)):
+            net.set_pi(t, p)
+        net.build_tables()
+        ref = refexec.ReferenceMeanField(net)
+        for strand in (0, 1):
+            for j in range(0, c["score"].shape[1], 2):
+                v, k = ref.score(c["codes"][j:j + W], bool(strand))
+                assert k == c["sweeps"][strand, j] and v == c["score"][strand, j]

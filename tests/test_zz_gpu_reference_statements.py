@@ -1,0 +1,53 @@
+"""libphyfoo.so against outputs of the reference's own statements (tests/golden/refexec_meanfield.npz: produced by executing
+MeanFieldForBayesNet.init / optimizeByNormalisation / calcFreeEnergy of the reference, translated token by token by
+tests/refexec.py -- see tests/test_reference_statements.py and scripts/make_refexec_golden.py).  Bars of north_star: window
+scores within 1e-9 relative, mean-field sweep counts exact; motif windows of orders 0 and 1 on four trees, both strands, with
+and without gaps, and background ranges of order + 1 columns for orders 0..2."""
+import numpy as np
+import pytest
+
+from test_reference_statements import background_pi, cases, motif_pwm
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from phyfoo_b200 import core
+    return core.default_context()
+
+
+def test_motif_window_scores_equal_the_reference_statements(ctx):
+    from phyfoo_b200.data import PhyloSample
+    from phyfoo_b200.models import PhyloBayesModel
+    n = 0
+    for c in cases("motif"):
+        W, order = int(c["W"]), int(c["order"])
+        fg = PhyloBayesModel(W, order, str(c["newick"]), ctx)
+        fg.setCondProbs(motif_pwm(c))
+        smp = PhyloSample(np.ascontiguousarray(c["codes"], np.uint8), [0, c["codes"].shape[0]])
+        for strand in (0, 1):
+            got, sw = fg.getLogProbFor(smp, strand=strand, want_sweeps=True)
+            ref, rsw = c["score"][strand], c["sweeps"][strand]
+            assert got.shape == ref.shape
+            assert np.array_equal(sw, rsw), (str(c["tree"]), order, strand, sw, rsw)
+            assert float(np.max(np.abs(got - ref) / np.abs(ref))) < TOL, (str(c["tree"]), order, strand)
+            n += got.size
+    assert n == 176
+
+
+def test_background_ranges_equal_the_reference_statements(ctx):
+    from phyfoo_b200.data import PhyloSample
+    from phyfoo_b200.models import PhyloBackground
+    n = 0
+    for c in cases("background"):
+        order = int(c["order"])
+        bg = PhyloBackground(order, str(c["newick"]), ctx)
+        bg.setCondProbs(background_pi(c))
+        smp = PhyloSample(np.ascontiguousarray(c["codes"], np.uint8), [0, c["codes"].shape[0]])
+        for j in range(c["score"].shape[1]):
+            got, ref = bg.getLogProbForRange(smp, 0, j, j + order), c["score"][0, j]
+            assert abs(got - ref) <= TOL * abs(ref), (str(c["tree"]), order, j)
+            n += 1
+    assert n == 60
