@@ -3,7 +3,8 @@
 MeanFieldForBayesNet.init / optimizeByNormalisation / calcFreeEnergy of /root/reference/main/java/src/algorithm/
 MeanFieldForBayesNet.java, translated token by token and executed by tests/refexec.py (no JVM exists in this image) -- on
 seeded inputs: motif windows of orders 0 and 1 on four trees (both strands, with and without gaps) and background ranges of
-orders 0..2.  The .npz holds the inputs next to the outputs, so it can be checked anywhere: tests/test_reference_statements.py
+orders 0..2, and one ZOOPS E-step (SingleHiddenMotifMixture.getNewWeights / modify and Normalisation.logSumNormalisation from
+libs/jstacs.jar, fed with those scores).  The .npz holds the inputs next to the outputs, so it can be checked anywhere: tests/test_reference_statements.py
 holds the oracle against it (bit for bit) and tests/test_zz_gpu_reference_statements.py the CUDA path.
 
 Runs only where /root/reference exists (the build container):    python scripts/make_refexec_golden.py
@@ -89,6 +90,41 @@ def background_cases(rng):
                            pwm=np.concatenate([np.ravel(p) for p in net.pi]), codes=aln, score=value[None, :], sweeps=sweeps[None, :])
 
 
+def estep_case(rng):
+    """One ZOOPS E-step in which EVERY number comes from reference statements: the motif window scores and the background's
+    per-column terms from MeanFieldForBayesNet (above), the posterior from SingleHiddenMotifMixture.getNewWeights / modify and
+    Normalisation.logSumNormalisation of libs/jstacs.jar (refexec.ReferenceEStep).  Background of order 0: a range is the sum of
+    its columns' terms in column order (models/PhyloBackground.java:262-294 with order = 0: one mean field per column)."""
+    newick, W, zoops = TREES["cat5"], 5, 0.8
+    lengths = [W, 14, 9]
+    aln = codes(rng, sum(lengths), 5, 0.05)
+    off = np.concatenate([[0], np.cumsum(lengths)])
+    pwm = synth.random_pwm(W, 0, 311)
+    net = npr.Net.motif(newick, W, 0)
+    for t, p in enumerate(pwm):
+        net.set_pi(t, p)
+    net.build_tables()
+    fg = refexec.ReferenceMeanField(net)
+    bnet = npr.Net.background(newick, 0)
+    bnet.build_tables()
+    bg = refexec.ReferenceMeanField(bnet)
+    scores = [fg.score(aln[off[i] + j:off[i] + j + W])[0] for i in range(len(lengths)) for j in range(lengths[i] - W + 1)]
+    minus_fe = [bg.score(aln[c:c + 1])[0] for c in range(aln.shape[0])]
+
+    def background(i, s, e):
+        log_sum = 0.0
+        for c in range(s, e + 1):                       # logSum += calcFreeEnergy(0, 0) column by column; the value is -logSum
+            log_sum += -minus_fe[off[i] + c]
+        return -log_sum if e >= s else 0.0
+
+    weights = rng.random(len(lengths)) + 0.5
+    es = refexec.ReferenceEStep(lengths, W, lambda w: scores[w], background, zoops, 0)
+    ll, w, gamma = es.getNewWeights(weights)
+    return dict(estep_newick=newick, estep_W=W, estep_zoops=zoops, estep_pwm=np.concatenate([np.ravel(p) for p in pwm]),
+                estep_codes=aln, estep_col_offsets=off, estep_weights=weights, estep_scores=np.array(scores),
+                estep_bg_columns=np.array(minus_fe), estep_ll=ll, estep_w=np.array(w), estep_gamma=np.array(gamma))
+
+
 def main():
     rng = np.random.default_rng(20261020)
     out, n = {}, 0
@@ -97,6 +133,7 @@ def main():
             out[f"c{n}_{k}"] = np.array(v)
         n += 1
     out["n_cases"] = np.array(n)
+    out.update({k: np.array(v) for k, v in estep_case(rng).items()})
     path = os.path.join(ROOT, "tests", "golden", "refexec_meanfield.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {os.path.getsize(path)} bytes, {n} cases, "

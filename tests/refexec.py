@@ -20,10 +20,10 @@ import re
 REFERENCE_FILE = "/root/reference/main/java/src/algorithm/MeanFieldForBayesNet.java"
 
 _TOKEN = re.compile(r"""
-    (?P<bc>/\*.*?\*/) | (?P<lc>//[^\n]*) | (?P<str>"(?:\\.|[^"\\])*") |
+    (?P<bc>/\*.*?\*/) | (?P<lc>//[^\n]*) | (?P<str>"(?:\\.|[^"\\])*"|'(?:\\.|[^'\\])+') |
     (?P<num>(?:\d+\.\d*|\.\d+|\d+)(?:[eE][+-]?\d+)?[dDfFlL]?) |
     (?P<id>[A-Za-z_$][A-Za-z_0-9$]*) |
-    (?P<op>\+\+|--|\+=|-=|\*=|/=|==|!=|<=|>=|&&|\|\||[{}()\[\];,.<>=+\-*/%!?:]) |
+    (?P<op>\+\+|--|\+=|-=|\*=|/=|==|!=|<=|>=|&&|\|\||[{}()\[\];,.<>=+\-*/%!?:@&|^~]) |
     (?P<ws>\s+)
 """, re.S | re.X)
 
@@ -60,18 +60,26 @@ def _match(tokens, i, open_, close):
     raise SyntaxError("unbalanced " + open_)
 
 
-def find_method(tokens, name, n_params):
-    """(parameter names, body tokens without the outer braces) of the method `name` with n_params parameters"""
+def find_method(tokens, name, n_params, signature=None):
+    """(parameter names, body tokens without the outer braces) of the method `name` with n_params parameters (and, when
+    overloads share the count, with the parameter list `signature`, e.g. "double[] d, double v, int start, int end")"""
     for i in range(len(tokens) - 2):
-        if tokens[i] == ("id", name) and tokens[i + 1][1] == "(" and i > 0 and tokens[i - 1][0] == "id":
+        if tokens[i] == ("id", name) and tokens[i + 1][1] == "(" and i > 0 and (tokens[i - 1][0] == "id" or tokens[i - 1][1] == "]"):
             j = _match(tokens, i + 1, "(", ")")
-            if j + 1 >= len(tokens) or tokens[j + 1][1] != "{":
+            b = j + 1
+            if b < len(tokens) and tokens[b][1] == "throws":
+                while tokens[b][1] != "{":
+                    b += 1
+            if b >= len(tokens) or tokens[b][1] != "{":
                 continue                                        # a call, not a declaration
-            params = [t[1] for k, t in enumerate(tokens[i + 2:j]) if t[0] == "id" and tokens[i + 2 + k + 1][1] in (",", ")")]
+            inner = tokens[i + 2:j]
+            params = [t[1] for k, t in enumerate(inner) if t[0] == "id" and (k + 1 == len(inner) or inner[k + 1][1] == ",")]
             if len(params) != n_params:
                 continue
-            end = _match(tokens, j + 1, "{", "}")
-            return params, tokens[j + 2:end]
+            if signature is not None and "".join(t[1] for t in inner) != signature.replace(" ", ""):
+                continue
+            end = _match(tokens, b, "{", "}")
+            return params, tokens[b + 1:end]
     raise LookupError(name)
 
 
@@ -114,7 +122,7 @@ class Translator:
                     out.append("self." + t)
                 elif t in self.fields:
                     out.append("self." + t)
-                elif t in ("Math", "Double", "Alphabet", "MeanFieldForBayesNet", "Arrays", "System"):
+                elif t in ("Math", "Double", "Alphabet", "MeanFieldForBayesNet", "Arrays", "System", "Normalisation"):
                     out.append(t)
                 else:
                     raise NameError(f"unknown identifier {t!r} in the reference statement")
@@ -135,6 +143,7 @@ class Translator:
             i += 1
         s = " ".join(out)
         for a, b in (("Math . log", "_jlog"), ("Math . exp", "_jexp"), ("Math . abs", "abs"), ("Math . min", "min"),
+                     ("Math . max", "max"), ("Double . isInfinite", "_isinf"), ("Normalisation .", "_Normalisation ."),
                      ("Double . NEGATIVE_INFINITY", "_NEG_INF"), ("Alphabet . size", "4"),
                      ("MeanFieldForBayesNet . CALC_LIKELIHOOD", "self.CALC_LIKELIHOOD")):
             s = s.replace(a, b)
@@ -175,6 +184,12 @@ class Translator:
             return
         if v[:3] == ["System", ".", "out"]:
             self.emit(ind, "pass")
+            return
+        if v[0] == "throw":
+            self.emit(ind, "raise RuntimeError('the reference throws here')")
+            return
+        if any(x in ("++", "--") for x in v[:-1]):              # e.g. a[i++] = ...: outside the subset; fails only if reached
+            self.emit(ind, "raise NotImplementedError('statement outside the translated subset of Java')")
             return
         if v[:3] == ["Arrays", ".", "fill"]:
             a, b = self.split_top(toks[4:-1], ",")
@@ -264,7 +279,17 @@ class Translator:
             lo, hi = self.expr(init[3:]), self.expr(cond[2:])
             self.emit(ind, f"for {var} in range({lo}, ({hi}){' + 1' if cv[1] == '<=' else ''}):")
             return self.stmt(toks, j + 1, ind + 1, labels)
-        raise NotImplementedError("for-loop shape " + " ".join(iv + [";"] + cv + [";"] + uv))
+        # general shape: init statements; while (cond) { body; updates }  -- only for bodies without `continue`
+        end = _match(toks, j + 1, "{", "}") if toks[j + 1][1] == "{" else None
+        if end is None or any(t[1] == "continue" for t in toks[j + 1:end]):
+            raise NotImplementedError("for-loop shape " + " ".join(iv + [";"] + cv + [";"] + uv))
+        for part in self.split_top(init, ","):
+            self.simple(part, ind)
+        self.emit(ind, f"while {self.expr(cond) if cond else 'True'}:")
+        k = self.stmt(toks, j + 1, ind + 1, labels)
+        for part in self.split_top(upd, ","):
+            self.simple(part, ind + 1)
+        return k
 
 
 def _jlog(x):
@@ -453,3 +478,155 @@ class ReferenceMeanField:
         self.optimizeByNormalisation()
         sweeps = self.free_energy_calls - 1                     # one call before the loop, one per sweep
         return -self.calcFreeEnergy(0, self.net.W - 1), sweeps
+
+
+# ---- the ZOOPS E-step: Jstacs statements from libs/jstacs.jar ----------------------------------------------------------------
+JSTACS_JAR = "/root/reference/libs/jstacs.jar"
+SHM_JAVA = "de/jstacs/models/mixture/motif/SingleHiddenMotifMixture.java"
+NORMALISATION_JAVA = "de/jstacs/utils/Normalisation.java"
+PRIOR_JAVA = "de/jstacs/models/mixture/motif/positionprior/UniformPositionPrior.java"
+
+
+def _jar_tokens(member):
+    import zipfile
+    with zipfile.ZipFile(JSTACS_JAR) as z:
+        return tokenize(z.read(member).decode("latin-1"))
+
+
+def _translate_method(tokens, py_name, java_name, n, fields, methods, signature=None, case=None):
+    params, body = find_method(tokens, java_name, n, signature)
+    if case is not None:                                        # the body of one `case X:` of the method's switch
+        v = [t[1] for t in body]
+        a = next(i for i in range(len(v) - 2) if v[i] == "case" and v[i + 1] == case and v[i + 2] == ":") + 3
+        b = next(i for i in range(a, len(v)) if v[i] in ("case", "default"))
+        body = body[a:b]
+    tr = Translator(fields, methods, params)
+    tr.emit(0, f"def {py_name}(self{''.join(', ' + p for p in params)}):")
+    k = 0
+    while k < len(body):
+        k = tr.stmt(body, k, 1, [])
+    return "\n".join(tr.lines) + "\n"
+
+
+def translate_estep():
+    """{name: python source}: SingleHiddenMotifMixture.getNewWeights and modify (EM branch)
+    (jstacs!/de/jstacs/models/mixture/motif/SingleHiddenMotifMixture.java:499-566,585-596), UniformPositionPrior.
+    getLogPriorForPositions (:55-61) and the Normalisation methods they reach (jstacs!/de/jstacs/utils/Normalisation.java:
+    199-201,241-253,352-376,472-476)."""
+    if not os.path.exists(JSTACS_JAR):
+        raise FileNotFoundError(JSTACS_JAR)
+    shm, nrm, pri = _jar_tokens(SHM_JAVA), _jar_tokens(NORMALISATION_JAVA), _jar_tokens(PRIOR_JAVA)
+    shm_fields = ["sample", "refBgSample", "model", "posPrior", "logWeights", "trainOnlyMotifModel", "bgMaxMarkovOrder", "algorithm"]
+    shm_methods = ["getMotifLength", "initWithPrior", "modify"]
+    nrm_methods = ["logSumNormalisation", "normalisation", "getLogSum"]
+    return {
+        "getNewWeights": _translate_method(shm, "getNewWeights", "getNewWeights", 3, shm_fields, shm_methods),
+        "modify": _translate_method(shm, "modify", "modify", 4, shm_fields, shm_methods, case="EM"),
+        "getLogPriorForPositions": _translate_method(pri, "getLogPriorForPositions", "getLogPriorForPositions", 2, ["motifLength"], []),
+        "lsn5": _translate_method(nrm, "lsn5", "logSumNormalisation", 5, [], nrm_methods),
+        "lsn6": _translate_method(nrm, "lsn6", "logSumNormalisation", 6, [], nrm_methods,
+                                  "double[] d, int startD, int endD, double[] secondValues, double[] dest, int startDest"),
+        "lsn7": _translate_method(nrm, "lsn7", "logSumNormalisation", 7, [], nrm_methods),
+        "norm4": _translate_method(nrm, "norm4", "normalisation", 4, [], nrm_methods, "double[] d, double v, int start, int end"),
+    }
+
+
+class _Normalisation:
+    """static methods of de.jstacs.utils.Normalisation, overloads picked by the number of arguments like javac does here"""
+
+    def __init__(self, ns):
+        self._ns = ns
+
+    def logSumNormalisation(self, *a):
+        return self._ns[{5: "lsn5", 6: "lsn6", 7: "lsn7"}[len(a)]](self, *a)
+
+    def normalisation(self, d, v, start, end):
+        assert isinstance(start, int) and isinstance(end, int)
+        return self._ns["norm4"](self, d, v, start, end)
+
+
+class _Windows:
+    def __init__(self, n):
+        self.n = n
+
+    def getNumberOfElements(self):
+        return self.n
+
+    def getElementAt(self, i):
+        return i
+
+
+class _Alignments:
+    def __init__(self, lengths):
+        self.seqs = [_AlignedSeq(i, L) for i, L in enumerate(lengths)]
+
+    def getElementAt(self, i):
+        return self.seqs[i]
+
+
+class _AlignedSeq:
+    def __init__(self, index, length):
+        self.index, self.length = index, length
+
+    def getLength(self):
+        return self.length
+
+
+class _Scores:
+    """a component model as getNewWeights sees it: getLogProbFor(sequence-or-window, start, end)"""
+
+    def __init__(self, fn):
+        self.fn = fn
+
+    def getLogProbFor(self, what, start, end):
+        return self.fn(what, start, end)
+
+
+class _Prior:
+    def __init__(self, ns, motif_length):
+        self._ns, self.motifLength = ns, motif_length
+
+    def getLogPriorForPositions(self, seq_length, *starts):
+        return self._ns["getLogPriorForPositions"](self, seq_length, starts)
+
+
+class ReferenceEStep:
+    """SingleHiddenMotifMixture.getNewWeights with the reference's own statements.  The two component models are callables:
+    motif(window index) -> log-score of that window, background(alignment index, start, end) -> log-score of the column range
+    (end inclusive; 0 for an empty range like models/PhyloBackground.java:242-244)."""
+    _ns = None
+
+    def __init__(self, lengths, W, motif, background, zoops, bg_order=0, hyper=(0.0, 0.0)):
+        if ReferenceEStep._ns is None:
+            ns = {"_jlog": _jlog, "_jexp": _jexp, "_NEG_INF": -math.inf, "_fill": _fill, "_JArray": _JArray, "_isinf": math.isinf}
+            src = translate_estep()
+            for s in src.values():
+                exec(compile(s, JSTACS_JAR + " (translated)", "exec"), ns)
+            ns["_Normalisation"] = _Normalisation(ns)
+            ReferenceEStep._ns, ReferenceEStep.source = ns, src
+        self.W, self.lengths, self.hyper = W, [int(x) for x in lengths], hyper
+        self.n_windows = sum(L - W + 1 for L in self.lengths)
+        self.sample = [_Windows(self.n_windows), _Alignments(self.lengths)]
+        self.refBgSample = list(range(len(self.lengths) + 1))
+        self.model = [_Scores(lambda w, s, e: motif(w)), _Scores(lambda seq, s, e: background(seq.index, s, e))]
+        self.posPrior = _Prior(self._ns, W)
+        with_log = lambda x: math.log(x) if x > 0 else -math.inf
+        self.logWeights = _JArray([with_log(zoops), with_log(1.0 - zoops)])
+        self.trainOnlyMotifModel, self.bgMaxMarkovOrder, self.algorithm = True, bg_order, "EM"
+
+    def getMotifLength(self, component):
+        return self.W
+
+    def initWithPrior(self, w):                                 # jstacs AbstractMixtureModel.java:1098-1100 (System.arraycopy)
+        w[0], w[1] = self.hyper
+
+    def modify(self, *a):
+        return self._ns["modify"](self, *a)
+
+    def getNewWeights(self, data_weights=None):
+        """-> (ll, w[2], seqweights[0])"""
+        w = _JArray([0.0, 0.0])
+        seqweights = _JArray([_JArray([0.0] * self.n_windows), _JArray([])])
+        dw = None if data_weights is None else _JArray([float(x) for x in data_weights])
+        ll = self._ns["getNewWeights"](self, dw, w, seqweights)
+        return ll, list(w), list(seqweights[0])

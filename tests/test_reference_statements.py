@@ -125,3 +125,58 @@ def test_reexecuting_the_reference_statements_reproduces_the_committed_vectors()
             for j in range(0, c["score"].shape[1], 2):
                 v, k = ref.score(c["codes"][j:j + W], bool(strand))
                 assert k == c["sweeps"][strand, j] and v == c["score"][strand, j]
+
+
+# ---- the ZOOPS E-step -------------------------------------------------------------------
+def estep_inputs():
+    W = int(G["estep_W"])
+    pwm = [G["estep_pwm"][4 * t:4 * t + 4].reshape(1, 4) for t in range(W)]
+    return str(G["estep_newick"]), W, pwm, float(G["estep_zoops"])
+
+
+def test_oracle_estep_reproduces_the_jstacs_statements():
+    """SingleHiddenMotifMixture.getNewWeights / modify and Normalisation.logSumNormalisation executed from libs/jstacs.jar on
+    scores that the mean-field statements produced: the oracle's E-step gives the same log-likelihood, component statistics
+    and posterior, and so do its window scores and background columns."""
+    from util import orc
+    newick, W, pwm, zoops = estep_inputs()
+    fg, bg = oracle_fg(newick, pwm), oracle_bg(newick, 0)
+    off, codes = G["estep_col_offsets"], G["estep_codes"]
+    scores = np.concatenate([fg.score_windows(codes[off[i]:off[i + 1]])[0] for i in range(off.size - 1)])
+    assert np.max(np.abs(scores - G["estep_scores"]) / np.abs(G["estep_scores"])) < 1e-13
+    assert np.max(np.abs(bg.bg_columns(codes) - G["estep_bg_columns"]) / np.abs(G["estep_bg_columns"])) < 1e-13
+    res = orc.estep(fg, bg, off, codes, np.log([zoops, 1 - zoops]), None, G["estep_weights"])
+    assert abs(res["ll"] - float(G["estep_ll"])) <= 1e-13 * abs(float(G["estep_ll"]))
+    assert np.max(np.abs(res["w"] - G["estep_w"])) <= 1e-13 * np.max(G["estep_w"])
+    assert np.max(np.abs(res["gamma"] - G["estep_gamma"])) < 1e-13
+    # arg-max site call = first maximum of the posterior (util/Util.java:528-538)
+    lens = np.diff(off) - W + 1
+    woff = np.concatenate([[0], np.cumsum(lens)])
+    assert [int(np.argmax(G["estep_gamma"][woff[i]:woff[i + 1]])) for i in range(lens.size)] == res["argmax_off"].tolist()
+    # sum of an alignment's posterior = its probability of holding a site, times its weight
+    assert abs(G["estep_gamma"].sum() - G["estep_w"][0]) < 1e-12 and abs(G["estep_w"].sum() - G["estep_weights"].sum()) < 1e-12
+
+
+@needs_reference
+def test_jstacs_estep_statements_translate_and_reproduce_the_committed_vectors():
+    src = refexec.translate_estep()
+    gw = src["getNewWeights"]
+    # landmarks of jstacs SingleHiddenMotifMixture.java:533-564 and Normalisation.java:352-376
+    assert "b1 = - self.bgMaxMarkovOrder" in gw and "b2 = motifLength + self.bgMaxMarkovOrder - 1" in gw
+    assert gw.count("getLogProbFor") == 5 and "getLogPriorForPositions ( l , j )" in gw
+    assert "ll += currentWeight * ( logPSeq + self.modify ( help , seqweights [ 0 ] , start , w0Index ) )" in gw
+    assert "if sum != 1:" in src["lsn7"] and "return offset + _jlog ( sum )" in src["lsn7"]
+    assert "return - _jlog ( seqLength - self.motifLength + 1 )" in src["getLogPriorForPositions"]
+    newick, W, pwm, zoops = estep_inputs()
+    off = G["estep_col_offsets"]
+    col = G["estep_bg_columns"]
+
+    def background(i, s, e):
+        log_sum = 0.0
+        for c in range(s, e + 1):
+            log_sum += -col[off[i] + c]
+        return -log_sum if e >= s else 0.0
+
+    es = refexec.ReferenceEStep(np.diff(off), W, lambda w: G["estep_scores"][w], background, zoops, 0)
+    ll, w, gamma = es.getNewWeights(G["estep_weights"])
+    assert ll == float(G["estep_ll"]) and np.array_equal(w, G["estep_w"]) and np.array_equal(gamma, G["estep_gamma"])

@@ -51,3 +51,22 @@ def test_background_ranges_equal_the_reference_statements(ctx):
             assert abs(got - ref) <= TOL * abs(ref), (str(c["tree"]), order, j)
             n += 1
     assert n == 60
+
+
+def test_zoops_estep_equals_the_jstacs_statements(ctx):
+    """SingleHiddenMotifMixture.getNewWeights on the device against the posterior the Jstacs statements produced."""
+    from test_reference_statements import G, estep_inputs
+    from phyfoo_b200.data import PhyloSample
+    from phyfoo_b200.models import PhyloBackground, PhyloBayesModel, SingleHiddenMotifMixture
+    newick, W, pwm, zoops = estep_inputs()
+    fg = PhyloBayesModel(W, 0, newick, ctx)
+    fg.setCondProbs(pwm)
+    shm = SingleHiddenMotifMixture(fg, PhyloBackground(0, newick, ctx), zoops=zoops)
+    smp = PhyloSample(np.ascontiguousarray(G["estep_codes"], np.uint8), G["estep_col_offsets"])
+    res = shm.getNewWeights(smp, seqWeights=G["estep_weights"])
+    assert abs(res["ll"] - float(G["estep_ll"])) <= TOL * abs(float(G["estep_ll"]))
+    assert np.max(np.abs(res["w"] - G["estep_w"])) <= TOL * np.max(G["estep_w"])
+    assert np.max(np.abs(res["gamma"] - G["estep_gamma"])) < TOL
+    lens = np.diff(G["estep_col_offsets"]) - W + 1
+    woff = np.concatenate([[0], np.cumsum(lens)])
+    assert [int(np.argmax(G["estep_gamma"][woff[i]:woff[i + 1]])) for i in range(lens.size)] == res["argmax_off"].tolist()
