@@ -5,6 +5,8 @@ non-root node k at 4 + 16 (k - 1), row-major [parent symbol a][own symbol b].
 Used by the sufficient-statistics form of the M-step objective (SuffStatObjective): with the expected counts C from ONE
 device pass, f(theta) = sum_t sum_e C[t][e] log table_theta,t[e] - ENT is a host-side dot product for any pi or branch
 lengths."""
+import math
+
 import numpy as np
 
 from . import _abi
@@ -28,8 +30,8 @@ def transition(pi, length, evol=_abi.EVOL_F81ALPHA, hky_ratio=0.0):
         keep = 1.0 - length
         mix = length
     elif evol == _abi.EVOL_F81BETA:
-        beta = 1.0 / (1.0 - np.sum(pi * pi))
-        ta = float(np.exp(-length * beta))
+        beta = 1.0 / (1.0 - pi[0] * pi[0] - pi[1] * pi[1] - pi[2] * pi[2] - pi[3] * pi[3])       # the reference's order (FS81beta.java:86)
+        ta = math.exp(-length * beta)
         if ta < 1e-4:
             ta = 0.0
         elif ta > 1 - 1e-4:
@@ -54,8 +56,8 @@ def tables(pi, branch, evol=_abi.EVOL_F81ALPHA, hky_ratio=0.0):
     if evol == _abi.EVOL_F81ALPHA:
         keep, mix = 1.0 - b, b
     elif evol == _abi.EVOL_F81BETA:
-        beta = 1.0 / (1.0 - np.sum(pi * pi))
-        ta = np.exp(-b * beta)
+        beta = 1.0 / (1.0 - pi[0] * pi[0] - pi[1] * pi[1] - pi[2] * pi[2] - pi[3] * pi[3])       # the reference's order (FS81beta.java:86)
+        ta = np.array([math.exp(-x * beta) for x in b])                # libm's exp like csrc/model_host.hpp (numpy's differs by an ulp)
         ta = np.where(ta < 1e-4, 0.0, np.where(ta > 1 - 1e-4, 1.0, ta))
         keep, mix = ta, 1.0 - ta
     else:

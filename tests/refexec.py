@@ -630,3 +630,38 @@ class ReferenceEStep:
         dw = None if data_weights is None else _JArray([float(x) for x in data_weights])
         ll = self._ns["getNewWeights"](self, dw, w, seqweights)
         return ll, list(w), list(seqweights[0])
+
+
+# ---- the substitution tables: evolution/FS81alpha.java, FS81beta.java, HKY.java (reinit) -------------------------------------
+EVOL_DIR = "/root/reference/main/java/src/evolution/"
+
+
+class ReferenceEvolModel:
+    """reinit(evolDist) of one of the reference's evolution models with its own statements; the transition matrix has the
+    reference's layout [a1 + 4 * context][a2] (evolution/FS81alpha.java:76-92, FS81beta.java:81-103, HKY.java:77-106)."""
+    _cache = {}
+
+    def __init__(self, name, pi_rows, hky_field=0.0):
+        if name not in self._cache:
+            path = EVOL_DIR + name + ".java"
+            if not os.path.exists(path):
+                raise FileNotFoundError(path)
+            with open(path, encoding="latin-1") as f:
+                toks = tokenize(f.read())
+            fields = ["_dimension", "_alphabetSize", "_transitionMatrix", "_pi", "dimension", "transitionMatrix", "pi", "alpha_beta_ratio"]
+            src = _translate_method(toks, "reinit", "reinit", 1, fields, [])
+            ns = {"_jlog": _jlog, "_jexp": _jexp, "_NEG_INF": -math.inf, "_JArray": _JArray}
+            exec(compile(src, path + " (translated)", "exec"), ns)
+            self._cache[name] = (ns["reinit"], src)
+        self._reinit, self.source = self._cache[name]
+        rows = [[float(x) for x in r] for r in pi_rows]
+        self._pi = self.pi = _JArray(_JArray(r) for r in rows)
+        self._dimension = self.dimension = len(rows)
+        self._alphabetSize = 4
+        # HKY.java:32 assigns the constructor argument to itself, so the field keeps its default 0; hky_field is what the field holds
+        self.alpha_beta_ratio = hky_field
+        self._transitionMatrix = self.transitionMatrix = _JArray(_JArray([0.0] * 4) for _ in range(4 * len(rows)))
+
+    def reinit(self, dist):
+        self._reinit(self, _JArray([float(dist)]))
+        return [list(r) for r in self._transitionMatrix]

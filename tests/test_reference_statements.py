@@ -180,3 +180,31 @@ def test_jstacs_estep_statements_translate_and_reproduce_the_committed_vectors()
     es = refexec.ReferenceEStep(np.diff(off), W, lambda w: G["estep_scores"][w], background, zoops, 0)
     ll, w, gamma = es.getNewWeights(G["estep_weights"])
     assert ll == float(G["estep_ll"]) and np.array_equal(w, G["estep_w"]) and np.array_equal(gamma, G["estep_gamma"])
+
+
+# ---- substitution tables (row a3) -------------------------------------------------------------------------------------------
+@needs_reference
+def test_substitution_tables_equal_the_reference_reinit_statements():
+    """reinit() of FS81alpha / FS81beta / HKY executed from the reference's files against the tables the restatements build:
+    oracle/np_restatement.f81alpha (what the golden vectors above ran on) and phyfoo_b200.evolution.transition (the numpy mirror
+    of csrc/model_host.hpp::transition) -- bit for bit (FS81beta: to an ulp of its one exponential), including FS81beta's clamps and HKY with the field at 0 (as shipped)
+    and at the intended ratio."""
+    from phyfoo_b200 import _abi, evolution
+    rng = np.random.default_rng(12)
+    for _ in range(5):
+        pi = rng.dirichlet(np.ones(4), size=4)
+        for dist in (0.0005, 0.05, 0.2, 0.37, 0.9, 1.0):
+            ref = np.array(refexec.ReferenceEvolModel("FS81alpha", pi).reinit(dist))
+            assert np.array_equal(ref, npr.f81alpha(pi, dist))
+            for c in range(4):
+                assert np.array_equal(ref[4 * c:4 * c + 4], evolution.transition(pi[c], dist, _abi.EVOL_F81ALPHA))
+        for dist in (1e-6, 0.01, 0.2, 1.5, 40.0):                 # 1e-6 and 40 hit the two clamps (FS81beta.java:88-92)
+            ref = np.array(refexec.ReferenceEvolModel("FS81beta", pi).reinit(dist))
+            for c in range(4):
+                mine = evolution.transition(pi[c], dist, _abi.EVOL_F81BETA)
+                assert np.max(np.abs(ref[4 * c:4 * c + 4] - mine)) <= 4e-16      # one exp: Math.exp / libm / numpy agree to an ulp
+        for dist, field in ((0.2, 0.0), (0.2, 2.0), (0.4, 0.5)):
+            ref = np.array(refexec.ReferenceEvolModel("HKY", pi[:1], hky_field=field).reinit(dist))
+            assert np.array_equal(ref, evolution.hky_transition(pi[0], dist, dist * field))
+            if field == 0.0:
+                assert (ref == 0).sum() == 8                      # every transversion: probability zero as shipped
