@@ -5,10 +5,15 @@
 // --impl reference legs.  The product path is CUDA (phyfoo_b200/csrc) and fails loudly
 // when the extension is missing.
 //
-// PARITY UNPINNED BY THE REFERENCE: the reference (single-threaded Java on a patched
-// Jstacs 1.5) ships no tests, golden vectors or fixtures for this path and no JVM exists
-// in this image, so this restatement cannot be checked against reference outputs.  It is
-// pinned instead by (tests/test_oracle_*.py): closed forms (star tree under F81alpha),
+// PARITY: no JVM exists in this image and the reference (single-threaded Java on a patched
+// Jstacs 1.5) ships no tests, golden vectors or fixtures for this path, so there is no JVM run to
+// compare with.  The arithmetic is pinned by the reference's OWN STATEMENTS instead: tests/refexec.py
+// translates MeanFieldForBayesNet.init / optimizeByNormalisation / calcFreeEnergy, the evolution
+// models' reinit and the Jstacs E-step (getNewWeights / modify / logSumNormalisation) from the
+// reference's files at test time and executes them; this oracle reproduces their outputs to the
+// last bit (tests/test_reference_statements.py, golden vectors in tests/golden/refexec_meanfield.npz).
+// What those methods do not cover (selector, objective drivers, strand model, optimiser) is
+// restated only.  Further pins (tests/test_oracle_*.py): closed forms (star tree under F81alpha),
 // brute-force enumeration of the joint for exact mode, the invariant -F <= log P, and an
 // independently written numpy restatement (oracle/np_restatement.py) agreeing to 1e-12.
 // The only outputs of reference code in the image -- its bundled synthetic data, written by its own
