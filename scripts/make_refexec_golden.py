@@ -125,6 +125,29 @@ def estep_case(rng):
                 estep_bg_columns=np.array(minus_fe), estep_ll=ll, estep_w=np.array(w), estep_gamma=np.array(gamma))
 
 
+def objective_cases(rng):
+    """The M-step objective f(lambda) = -sum_u w_u F(q_u fixed; theta(lambda)) and its forward-difference gradient (eps = 1e-4)
+    for one motif position: MatrixLinearisation.lambda2pi, Normalisation.logSumNormalisation, MeanFieldForBayesNet.calcFreeEnergy
+    and NumericalDifferentiableFunction.evaluateGradientOfFunction executed from the reference (refexec.ReferenceObjective)."""
+    for i, (tree, order, W, pos) in enumerate((("cat5", 0, 4, 1), ("mixed6", 0, 4, 3), ("cat5", 1, 4, 0), ("cat5", 1, 4, 2), ("mixed6", 1, 4, 3))):
+        newick = TREES[tree]
+        S = len(npr.parse_newick(newick)[3])
+        pwm = synth.random_pwm(W, order, 500 + i)
+        net = npr.Net.motif(newick, W, order)
+        for t, p in enumerate(pwm):
+            net.set_pi(t, p)
+        net.build_tables()
+        windows = np.stack([codes(rng, W, S, 0.1 if i % 2 else 0.0) for _ in range(6)])
+        weights = rng.random(6) + 0.1
+        obj = refexec.ReferenceObjective(net, list(windows), weights, pos)
+        lam = np.log(np.ravel(pwm[pos])) + 0.3 * rng.normal(size=np.ravel(pwm[pos]).size)
+        f = obj.evaluateFunction(list(lam))
+        g = obj.evaluateGradientOfFunction(list(lam))
+        yield {f"obj{i}_newick": newick, f"obj{i}_order": order, f"obj{i}_W": W, f"obj{i}_pos": pos,
+               f"obj{i}_pwm": np.concatenate([np.ravel(p) for p in pwm]), f"obj{i}_windows": windows, f"obj{i}_weights": weights,
+               f"obj{i}_lambda": lam, f"obj{i}_f": f, f"obj{i}_grad": np.array(g)}
+
+
 def main():
     rng = np.random.default_rng(20261020)
     out, n = {}, 0
@@ -134,6 +157,11 @@ def main():
         n += 1
     out["n_cases"] = np.array(n)
     out.update({k: np.array(v) for k, v in estep_case(rng).items()})
+    n_obj = 0
+    for case in objective_cases(rng):
+        out.update({k: np.array(v) for k, v in case.items()})
+        n_obj += 1
+    out["n_objectives"] = np.array(n_obj)
     path = os.path.join(ROOT, "tests", "golden", "refexec_meanfield.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {os.path.getsize(path)} bytes, {n} cases, "

@@ -30,6 +30,12 @@ _TOKEN = re.compile(r"""
 TYPES = {"int", "double", "boolean", "long", "float"}
 
 
+def _py(name):
+    """a Java identifier that is a Python keyword gets a trailing underscore"""
+    import keyword
+    return name + "_" if keyword.iskeyword(name) else name
+
+
 def tokenize(src):
     out, pos = [], 0
     while pos < len(src):
@@ -117,7 +123,7 @@ class Translator:
                 elif t == "this":
                     out.append("self")
                 elif t in self.locals:
-                    out.append(t)
+                    out.append(_py(t))
                 elif t in self.methods and nxt == "(":
                     out.append("self." + t)
                 elif t in self.fields:
@@ -207,9 +213,9 @@ class Translator:
                     self.locals.add(name)
                     if len(d) > 1:
                         assert d[1][1] == "=", d
-                        self.emit(ind, f"{name} = {self.expr(d[2:])}")
+                        self.emit(ind, f"{_py(name)} = {self.expr(d[2:])}")
                     else:
-                        self.emit(ind, f"{name} = None")
+                        self.emit(ind, f"{_py(name)} = None")
                 return
         if v[-1] in ("++", "--"):
             self.emit(ind, f"{self.expr(toks[:-1])} {'+' if v[-1] == '++' else '-'}= 1")
@@ -331,7 +337,7 @@ def translate(path=REFERENCE_FILE):
                                   ("calcFreeEnergy2", "calcFreeEnergy", 2), ("calcFreeEnergy0", "calcFreeEnergy", 0)):
         params, body = find_method(toks, java_name, n)
         tr = Translator(FIELDS, METHODS, params)
-        tr.emit(0, f"def {py_name}(self{''.join(', ' + p for p in params)}):")
+        tr.emit(0, f"def {py_name}(self{''.join(', ' + _py(p) for p in params)}):")
         k = 0
         while k < len(body):
             k = tr.stmt(body, k, 1, [])
@@ -501,7 +507,7 @@ def _translate_method(tokens, py_name, java_name, n, fields, methods, signature=
         b = next(i for i in range(a, len(v)) if v[i] in ("case", "default"))
         body = body[a:b]
     tr = Translator(fields, methods, params)
-    tr.emit(0, f"def {py_name}(self{''.join(', ' + p for p in params)}):")
+    tr.emit(0, f"def {py_name}(self{''.join(', ' + _py(p) for p in params)}):")
     k = 0
     while k < len(body):
         k = tr.stmt(body, k, 1, [])
@@ -665,3 +671,55 @@ class ReferenceEvolModel:
     def reinit(self, dist):
         self._reinit(self, _JArray([float(dist)]))
         return [list(r) for r in self._transitionMatrix]
+
+
+# ---- the M-step objective and its forward-difference gradient (rows a14, a15) --------------------------------------------------
+MATRIX_LINEARISATION_JAVA = "/root/reference/main/java/src/util/MatrixLinearisation.java"
+NUMDIFF_JAVA = "de/jstacs/algorithms/optimization/NumericalDifferentiableFunction.java"
+
+
+class ReferenceObjective:
+    """FE_byParameter_ForBayesNodeJstacs.evaluateFunction (optimizing/FE_byParameter_ForBayesNodeJstacs.java:43-53) over windows
+    whose mean fields stay fixed (AbstractFreeEnergyOptimizer.OPTIMIZE_MEANFIELDS = false, :36): the statements executed from
+    the reference are MatrixLinearisation.lambda2pi (util/MatrixLinearisation.java:15-19) with Normalisation.logSumNormalisation,
+    MeanFieldForBayesNet.calcFreeEnergy for every window, and NumericalDifferentiableFunction.evaluateGradientOfFunction
+    (jstacs :64-84); the loop `sum -= calcFreeEnergy() * weights[u]` of getWeightedLogLikelihoodSum (:95-114; it sits in a
+    try / catch, outside the translated subset) is restated in evaluateFunction below."""
+    _ns = None
+
+    def __init__(self, net, windows, weights, position, eps=1e-4):
+        if ReferenceObjective._ns is None:
+            ReferenceEStep([1], 1, None, None, 0.5)              # (translates the Normalisation methods)
+            ns = dict(ReferenceEStep._ns)
+            with open(MATRIX_LINEARISATION_JAVA, encoding="latin-1") as f:
+                ml = tokenize(f.read())
+            exec(compile(_translate_method(ml, "lambda2pi", "lambda2pi", 3, [], []), MATRIX_LINEARISATION_JAVA, "exec"), ns)
+            src = _translate_method(_jar_tokens(NUMDIFF_JAVA), "evaluateGradientOfFunction", "evaluateGradientOfFunction", 1,
+                                    ["eps"], ["getDimensionOfScope", "evaluateFunction"])
+            exec(compile(src, NUMDIFF_JAVA, "exec"), ns)
+            ReferenceObjective._ns, ReferenceObjective.gradient_source = ns, src
+        self.net, self.pos, self.eps = net, position, eps
+        self.mf = ReferenceMeanField(net)
+        self.windows, self.weights, self.fixed = windows, [float(w) for w in weights], []
+        for cols in windows:                                    # the mean fields the E-step left in the cached objects
+            self.mf.score(cols)
+            self.fixed.append((list(self.mf.q), list(self.mf.node2hiddenNodeMap)))
+
+    def getDimensionOfScope(self):
+        return self.net.pi[self.pos].size
+
+    def evaluateFunction(self, lam):
+        pi = _JArray([0.0] * len(lam))
+        self._ns["lambda2pi"](None, _JArray(lam), pi, 4)        # initParameters :49-53
+        self.net.set_pi(self.pos, pi)
+        self.net.build_tables()
+        self.mf = ReferenceMeanField(self.net)
+        total = 0
+        for cols, w, (q, hidden) in zip(self.windows, self.weights, self.fixed):
+            self.mf.initObservation(cols)
+            self.mf.q, self.mf.node2hiddenNodeMap = _JArray(q), _JArray(hidden)
+            total -= self.mf.calcFreeEnergy() * w               # getWeightedLogLikelihoodSum :107-108
+        return total
+
+    def evaluateGradientOfFunction(self, lam):
+        return list(self._ns["evaluateGradientOfFunction"](self, _JArray([float(x) for x in lam])))

@@ -208,3 +208,41 @@ def test_substitution_tables_equal_the_reference_reinit_statements():
             assert np.array_equal(ref, evolution.hky_transition(pi[0], dist, dist * field))
             if field == 0.0:
                 assert (ref == 0).sum() == 8                      # every transversion: probability zero as shipped
+
+
+# ---- the M-step objective and its forward-difference gradient (rows a14, a15) -------------------------------------------------
+def objectives():
+    for i in range(int(G["n_objectives"])):
+        c = {k: G[f"obj{i}_{k}"] for k in ("newick", "order", "W", "pos", "pwm", "windows", "weights", "lambda", "f", "grad")}
+        yield c, motif_pwm(c)
+
+
+def test_oracle_objective_and_gradient_reproduce_the_reference_statements():
+    from util import orc
+    n = 0
+    for c, pwm in objectives():
+        m = oracle_fg(str(c["newick"]), pwm, order=int(c["order"]))
+        fs = orc.FESet(m, np.ascontiguousarray(c["windows"], np.uint8), c["weights"])
+        f = fs.eval(int(c["pos"]), c["lambda"])
+        assert abs(f - float(c["f"])) <= 1e-13 * abs(float(c["f"]))
+        f0, g = fs.grad(int(c["pos"]), c["lambda"], 1e-4)
+        assert abs(f0 - float(c["f"])) <= 1e-13 * abs(float(c["f"]))
+        # forward differences of two sums of magnitude |f|: a last-bit difference in f shows as ulp(f) / eps in g
+        assert np.all(np.abs(g - c["grad"]) <= 4 * np.finfo(float).eps * abs(f0) / 1e-4)
+        assert c["grad"].size == (16 if int(c["order"]) == 1 and int(c["pos"]) > 0 else 4)
+        n += 1
+    assert n == 5
+
+
+@needs_reference
+def test_reexecuting_the_objective_statements_reproduces_the_committed_vectors():
+    for c, pwm in objectives():
+        net = npr.Net.motif(str(c["newick"]), int(c["W"]), int(c["order"]))
+        for t, p in enumerate(pwm):
+            net.set_pi(t, p)
+        net.build_tables()
+        obj = refexec.ReferenceObjective(net, list(c["windows"]), c["weights"], int(c["pos"]))
+        assert obj.evaluateFunction(list(c["lambda"])) == float(c["f"])
+        assert np.array_equal(obj.evaluateGradientOfFunction(list(c["lambda"])), c["grad"])
+    src = refexec.ReferenceObjective.gradient_source
+    assert "gradient [ i ] = ( self.evaluateFunction ( x ) - current ) / self.eps" in src and "x [ i ] += self.eps" in src

@@ -70,3 +70,26 @@ def test_zoops_estep_equals_the_jstacs_statements(ctx):
     lens = np.diff(G["estep_col_offsets"]) - W + 1
     woff = np.concatenate([[0], np.cumsum(lens)])
     assert [int(np.argmax(G["estep_gamma"][woff[i]:woff[i + 1]])) for i in range(lens.size)] == res["argmax_off"].tolist()
+
+
+def test_objective_and_gradient_equal_the_reference_statements(ctx):
+    """phyfoo_fe_eval / phyfoo_fe_grad over windows with fixed mean fields against lambda2pi + calcFreeEnergy +
+    evaluateGradientOfFunction executed from the reference (every window its own alignment of exactly W columns)."""
+    from test_reference_statements import objectives
+    from phyfoo_b200 import core
+    from phyfoo_b200.data import PhyloSample
+    from phyfoo_b200.models import PhyloBayesModel
+    for c, pwm in objectives():
+        W, order, pos = int(c["W"]), int(c["order"]), int(c["pos"])
+        n = c["windows"].shape[0]
+        fg = PhyloBayesModel(W, order, str(c["newick"]), ctx)
+        fg.setCondProbs(pwm)
+        smp = PhyloSample(np.ascontiguousarray(c["windows"].reshape(n * W, -1), np.uint8), np.arange(n + 1) * W)
+        fe = core.FESet(ctx, smp.device(ctx), fg.device_model(), np.arange(n), np.zeros(n, np.int32), c["weights"])
+        assert len(fe) == n
+        f = fe.eval(pos, c["lambda"])
+        assert abs(f - float(c["f"])) <= TOL * abs(float(c["f"]))
+        f0, g = fe.grad(pos, c["lambda"], 1e-4)
+        assert abs(f0 - float(c["f"])) <= TOL * abs(float(c["f"]))
+        assert np.all(np.abs(g - c["grad"]) <= TOL * np.abs(c["grad"]) + 64 * np.finfo(float).eps * abs(f0) / 1e-4)
+        fe.free()
