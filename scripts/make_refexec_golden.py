@@ -148,6 +148,14 @@ def objective_cases(rng):
                f"obj{i}_lambda": lam, f"obj{i}_f": f, f"obj{i}_grad": np.array(g)}
 
 
+def selector_cases(rng):
+    """SequenceSpecificDataSelector.prepareForTraining on the posterior of one alignment's windows (refexec.ReferenceSelector)."""
+    for i, (n, t, q) in enumerate(((40, 0.8, 0.0), (40, 0.8, 0.01), (7, 0.5, 0.0), (1, 0.8, 0.0), (100, 0.95, 0.002), (25, 0.8, 0.0))):
+        w = rng.dirichlet(np.ones(n) * 0.3) * (0.4 + 0.6 * rng.random())
+        idx, ww = refexec.ReferenceSelector(list(w)).prepareForTraining(t, q)
+        yield {f"sel{i}_weights": w, f"sel{i}_t": t, f"sel{i}_q": q, f"sel{i}_index": np.array(idx, np.int32), f"sel{i}_picked": np.array(ww)}
+
+
 def main():
     rng = np.random.default_rng(20261020)
     out, n = {}, 0
@@ -162,6 +170,11 @@ def main():
         out.update({k: np.array(v) for k, v in case.items()})
         n_obj += 1
     out["n_objectives"] = np.array(n_obj)
+    n_sel = 0
+    for case in selector_cases(rng):
+        out.update({k: np.array(v) for k, v in case.items()})
+        n_sel += 1
+    out["n_selectors"] = np.array(n_sel)
     path = os.path.join(ROOT, "tests", "golden", "refexec_meanfield.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {os.path.getsize(path)} bytes, {n} cases, "

@@ -723,3 +723,60 @@ class ReferenceObjective:
 
     def evaluateGradientOfFunction(self, lam):
         return list(self._ns["evaluateGradientOfFunction"](self, _JArray([float(x) for x in lam])))
+
+
+# ---- the selector of the M-step (row a13) ---------------------------------------------------------------------------------------
+SELECTOR_JAVA = "/root/reference/main/java/src/io/SequenceSpecificDataSelector.java"
+
+
+class _JList(list):
+    """java.util.ArrayList / DoubleList as far as prepareForTraining uses them"""
+
+    def add(self, x):
+        self.append(x)
+
+
+class ReferenceSelector:
+    """SequenceSpecificDataSelector for the windows of ONE alignment (io/SequenceSpecificDataSelector.java:37-99).  Executed
+    from the reference: the walk of prepareForTraining (:82-96, its `for` statement) and Normalisation.sumNormalisation /
+    normalisation (jstacs!/de/jstacs/utils/Normalisation.java:390-392,410-418,450-454).  Restated: the grouping by parent
+    sequence and the ascending sort of transform() (AssociativeSort.quickSort; the order of equal weights is unspecified
+    there -- a stable sort is used here and the tests avoid ties)."""
+    _ns = None
+
+    def __init__(self, weights):
+        if ReferenceSelector._ns is None:
+            ns = {"_jlog": _jlog, "_jexp": _jexp, "_NEG_INF": -math.inf, "_JArray": _JArray}
+            nrm = _jar_tokens(NORMALISATION_JAVA)
+            methods = ["sumNormalisation", "normalisation"]
+            for py, java, n, sig in (("sum1", "sumNormalisation", 1, None), ("sum3", "sumNormalisation", 3, None),
+                                     ("normd", "normalisation", 4, "double[] d, double v, double[] dest, int start")):
+                exec(compile(_translate_method(nrm, py, java, n, [], methods, sig), NORMALISATION_JAVA, "exec"), ns)
+            with open(SELECTOR_JAVA, encoding="latin-1") as f:
+                toks = tokenize(f.read())
+            params, body = find_method(toks, "prepareForTraining", 2)
+            start = next(i for i, t in enumerate(body) if t[1] == "for")            # behind the two collection declarations
+            tr = Translator(["normWeightProfile", "weightProfile", "seqsPerParent"], [], params + ["seqs", "weights"])
+            tr.emit(0, "def walk(self, t, q, seqs, weights):")
+            tr.stmt(body, start, 1, [])
+            src = "\n".join(tr.lines) + "\n"
+            exec(compile(src, SELECTOR_JAVA, "exec"), ns)
+            ReferenceSelector._ns, ReferenceSelector.source = ns, src
+        order = sorted(range(len(weights)), key=lambda i: weights[i])                # transform(): ascending by weight
+        self.seqsPerParent = _JArray([_JArray(order)])
+        self.weightProfile = _JArray([_JArray(float(weights[i]) for i in order)])
+        self.normWeightProfile = _JArray([_JArray(self.weightProfile[0])])
+        self._ns["sum1"](self, self.normWeightProfile[0])                           # Normalisation.sumNormalisation(normWeightProfile[i])
+
+    # static methods of Normalisation as the translated bodies call them
+    def sumNormalisation(self, d, dest, start):
+        return self._ns["sum3"](self, d, dest, start)
+
+    def normalisation(self, d, v, dest, start):
+        return self._ns["normd"](self, d, v, dest, start)
+
+    def prepareForTraining(self, t, q):
+        """-> (window indices, weights) in the order the reference adds them"""
+        seqs, weights = _JList(), _JList()
+        self._ns["walk"](self, t, q, seqs, weights)
+        return list(seqs), list(weights)

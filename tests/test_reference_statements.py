@@ -246,3 +246,25 @@ def test_reexecuting_the_objective_statements_reproduces_the_committed_vectors()
         assert np.array_equal(obj.evaluateGradientOfFunction(list(c["lambda"])), c["grad"])
     src = refexec.ReferenceObjective.gradient_source
     assert "gradient [ i ] = ( self.evaluateFunction ( x ) - current ) / self.eps" in src and "x [ i ] += self.eps" in src
+
+
+# ---- the selector of the M-step (row a13) ---------------------------------------------------------------------------------------
+def selectors():
+    for i in range(int(G["n_selectors"])):
+        yield {k: G[f"sel{i}_{k}"] for k in ("weights", "t", "q", "index", "picked")}
+
+
+def test_oracle_selector_reproduces_the_reference_statements():
+    from util import orc
+    for c in selectors():
+        idx, w = orc.select_group(c["weights"], float(c["t"]), float(c["q"]))
+        assert np.array_equal(idx, c["index"]) and np.array_equal(w, c["picked"])
+        assert 1 <= idx.size <= c["weights"].size and np.all(np.diff(w) <= 0)           # from the largest posterior down
+
+
+@needs_reference
+def test_reexecuting_the_selector_statements_reproduces_the_committed_vectors():
+    for c in selectors():
+        idx, w = refexec.ReferenceSelector(list(c["weights"])).prepareForTraining(float(c["t"]), float(c["q"]))
+        assert np.array_equal(idx, c["index"]) and np.array_equal(w, c["picked"])
+    assert "if sum > t:" in refexec.ReferenceSelector.source and "if self.weightProfile [ i ] [ k ] >= q:" in refexec.ReferenceSelector.source

@@ -93,3 +93,17 @@ def test_objective_and_gradient_equal_the_reference_statements(ctx):
         assert abs(f0 - float(c["f"])) <= TOL * abs(float(c["f"]))
         assert np.all(np.abs(g - c["grad"]) <= TOL * np.abs(c["grad"]) + 64 * np.finfo(float).eps * abs(f0) / 1e-4)
         fe.free()
+
+
+def test_selector_equals_the_reference_statements(ctx):
+    """phyfoo_select on the windows of one alignment against SequenceSpecificDataSelector.prepareForTraining's walk."""
+    from test_reference_statements import selectors
+    from phyfoo_b200 import core
+    from phyfoo_b200.data import PhyloSample
+    W = 4
+    for c in selectors():
+        n = c["weights"].size
+        codes = np.random.default_rng(n).integers(0, 4, size=(n + W - 1, 5)).astype(np.uint8)
+        smp = PhyloSample(codes, [0, n + W - 1])
+        sa, so, sw = core.select(ctx, smp.device(ctx), W, c["weights"], float(c["t"]), float(c["q"]))
+        assert np.array_equal(so, c["index"]) and np.array_equal(sw, c["picked"]) and not sa.any()
