@@ -120,7 +120,14 @@ def estep_case(rng):
     weights = rng.random(len(lengths)) + 0.5
     es = refexec.ReferenceEStep(lengths, W, lambda w: scores[w], background, zoops, 0)
     ll, w, gamma = es.getNewWeights(weights)
-    return dict(estep_newick=newick, estep_W=W, estep_zoops=zoops, estep_pwm=np.concatenate([np.ravel(p) for p in pwm]),
+    # the same E-step with a StrandModel as motif component (forward weight 0.6): a window's score is
+    # Normalisation.getLogSum(logW0 + forward, logW1 + reverse complement) (jstacs AbstractMixtureModel.java:1158-1167)
+    rev = [fg.score(aln[off[i] + j:off[i] + j + W], True)[0] for i in range(len(lengths)) for j in range(lengths[i] - W + 1)]
+    slw = np.log([0.6, 0.4])
+    both = [refexec.reference_log_sum([slw[0] + a, slw[1] + b]) for a, b in zip(scores, rev)]
+    s_ll, s_w, s_gamma = refexec.ReferenceEStep(lengths, W, lambda w: both[w], background, zoops, 0).getNewWeights(weights)
+    strand = dict(strand_forward_weight=0.6, strand_rev_scores=np.array(rev), strand_ll=s_ll, strand_w=np.array(s_w), strand_gamma=np.array(s_gamma))
+    return dict(**strand, estep_newick=newick, estep_W=W, estep_zoops=zoops, estep_pwm=np.concatenate([np.ravel(p) for p in pwm]),
                 estep_codes=aln, estep_col_offsets=off, estep_weights=weights, estep_scores=np.array(scores),
                 estep_bg_columns=np.array(minus_fe), estep_ll=ll, estep_w=np.array(w), estep_gamma=np.array(gamma))
 

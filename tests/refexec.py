@@ -780,3 +780,19 @@ class ReferenceSelector:
         seqs, weights = _JList(), _JList()
         self._ns["walk"](self, t, q, seqs, weights)
         return list(seqs), list(weights)
+
+
+def reference_log_sum(values):
+    """Normalisation.getLogSum(double...) (jstacs!/de/jstacs/utils/Normalisation.java:43-45,63-93) -- what
+    AbstractMixtureModel.getLogProbFor (jstacs :1158-1167) applies to the two strand terms of a StrandModel."""
+    ns = reference_log_sum.__dict__.setdefault("ns", {})
+    if not ns:
+        ns.update({"_jlog": _jlog, "_jexp": _jexp, "_NEG_INF": -math.inf, "_JArray": _JArray, "_isinf": math.isinf})
+        nrm = _jar_tokens(NORMALISATION_JAVA)
+        exec(compile(_translate_method(nrm, "ls1", "getLogSum", 1, [], ["getLogSum"]), NORMALISATION_JAVA, "exec"), ns)
+        exec(compile(_translate_method(nrm, "ls3", "getLogSum", 3, [], ["getLogSum"]), NORMALISATION_JAVA, "exec"), ns)
+
+    class _Static:
+        def getLogSum(self, *a):
+            return ns["ls3"](self, *a) if len(a) == 3 else ns["ls1"](self, *a)
+    return ns["ls1"](_Static(), _JArray(float(v) for v in values))

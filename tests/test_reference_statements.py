@@ -268,3 +268,21 @@ def test_reexecuting_the_selector_statements_reproduces_the_committed_vectors():
         idx, w = refexec.ReferenceSelector(list(c["weights"])).prepareForTraining(float(c["t"]), float(c["q"]))
         assert np.array_equal(idx, c["index"]) and np.array_equal(w, c["picked"])
     assert "if sum > t:" in refexec.ReferenceSelector.source and "if self.weightProfile [ i ] [ k ] >= q:" in refexec.ReferenceSelector.source
+
+
+# ---- strand mixture inside the E-step (row a11) ---------------------------------------------------------------------------------
+def test_oracle_strand_estep_reproduces_the_jstacs_statements():
+    """A StrandModel as motif component: per window Normalisation.getLogSum(logW0 + forward, logW1 + reverse complement), then
+    the same getNewWeights -- all from the reference's statements; the oracle's strand E-step gives the same numbers."""
+    from util import orc
+    newick, W, pwm, zoops = estep_inputs()
+    fg, bg = oracle_fg(newick, pwm), oracle_bg(newick, 0)
+    off, codes = G["estep_col_offsets"], G["estep_codes"]
+    rev = np.concatenate([fg.score_windows(codes[off[i]:off[i + 1]], True)[0] for i in range(off.size - 1)])
+    assert np.max(np.abs(rev - G["strand_rev_scores"]) / np.abs(rev)) < 1e-13
+    fw = float(G["strand_forward_weight"])
+    res = orc.estep(fg, bg, off, codes, np.log([zoops, 1 - zoops]), np.log([fw, 1 - fw]), G["estep_weights"])
+    assert abs(res["ll"] - float(G["strand_ll"])) <= 1e-13 * abs(float(G["strand_ll"]))
+    assert np.max(np.abs(res["w"] - G["strand_w"])) <= 1e-13 * np.max(G["strand_w"])
+    assert np.max(np.abs(res["gamma"] - G["strand_gamma"])) < 1e-13
+    assert abs(float(G["strand_ll"]) - float(G["estep_ll"])) > 1e-3          # (not the single-strand E-step)

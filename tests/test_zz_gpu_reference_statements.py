@@ -107,3 +107,18 @@ def test_selector_equals_the_reference_statements(ctx):
         smp = PhyloSample(codes, [0, n + W - 1])
         sa, so, sw = core.select(ctx, smp.device(ctx), W, c["weights"], float(c["t"]), float(c["q"]))
         assert np.array_equal(so, c["index"]) and np.array_equal(sw, c["picked"]) and not sa.any()
+
+
+def test_strand_estep_equals_the_jstacs_statements(ctx):
+    from test_reference_statements import G, estep_inputs
+    from phyfoo_b200.data import PhyloSample
+    from phyfoo_b200.models import PhyloBackground, PhyloBayesModel, SingleHiddenMotifMixture, StrandModel
+    newick, W, pwm, zoops = estep_inputs()
+    fg = PhyloBayesModel(W, 0, newick, ctx)
+    fg.setCondProbs(pwm)
+    shm = SingleHiddenMotifMixture(StrandModel(fg, float(G["strand_forward_weight"])), PhyloBackground(0, newick, ctx), zoops=zoops)
+    smp = PhyloSample(np.ascontiguousarray(G["estep_codes"], np.uint8), G["estep_col_offsets"])
+    res = shm.getNewWeights(smp, seqWeights=G["estep_weights"])
+    assert abs(res["ll"] - float(G["strand_ll"])) <= TOL * abs(float(G["strand_ll"]))
+    assert np.max(np.abs(res["w"] - G["strand_w"])) <= TOL * np.max(G["strand_w"])
+    assert np.max(np.abs(res["gamma"] - G["strand_gamma"])) < TOL
