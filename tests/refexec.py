@@ -92,10 +92,11 @@ def find_method(tokens, name, n_params, signature=None):
 class Translator:
     """Java-subset statements -> Python source.  Every construct outside the subset raises."""
 
-    def __init__(self, fields, methods, params):
+    def __init__(self, fields, methods, params, int_division=False):
         self.fields, self.methods = set(fields), set(methods)
         self.locals = set(params)
         self.lines = []
+        self.int_division = int_division          # a method whose `/` operands are all ints (Java truncates; operands >= 0 here)
 
     # ---- expressions ---------------------------------------------------------------------------------------------------
     def expr(self, toks):
@@ -104,6 +105,13 @@ class Translator:
             kind, t = toks[i]
             prev = toks[i - 1][1] if i else None
             nxt = toks[i + 1][1] if i + 1 < len(toks) else None
+            if t == "(" and i + 2 < len(toks) and toks[i + 1][1] in TYPES and toks[i + 2][1] == ")":
+                i += 3                                          # a primitive cast in front of a value of that type already
+                continue
+            if t == "/" and self.int_division:
+                out.append("//")
+                i += 1
+                continue
             if t == "new":                                      # new double[expr] / new int[expr]
                 ty = toks[i + 1][1]
                 j = _match(toks, i + 2, "[", "]")
@@ -499,19 +507,38 @@ def _jar_tokens(member):
         return tokenize(z.read(member).decode("latin-1"))
 
 
-def _translate_method(tokens, py_name, java_name, n, fields, methods, signature=None, case=None):
+def _translate_method(tokens, py_name, java_name, n, fields, methods, signature=None, case=None, int_division=False):
     params, body = find_method(tokens, java_name, n, signature)
     if case is not None:                                        # the body of one `case X:` of the method's switch
         v = [t[1] for t in body]
         a = next(i for i in range(len(v) - 2) if v[i] == "case" and v[i + 1] == case and v[i + 2] == ":") + 3
         b = next(i for i in range(a, len(v)) if v[i] in ("case", "default"))
         body = body[a:b]
-    tr = Translator(fields, methods, params)
+    tr = Translator(fields, methods, params, int_division)
     tr.emit(0, f"def {py_name}(self{''.join(', ' + _py(p) for p in params)}):")
     k = 0
     while k < len(body):
         k = tr.stmt(body, k, 1, [])
     return "\n".join(tr.lines) + "\n"
+
+
+def reference_lookup_table(n_parents):
+    """CPF._lookup as CPF.generateLookUpTable builds it (bayesNet/CPF.java:280-289): row l = getQueryByIndex(l, false)
+    (:238-256, executed from the reference; its `/` is Java's int division), with _SizeBuffer[i] = 4^i (:52-59)."""
+    path = "/root/reference/main/java/src/bayesNet/CPF.java"
+    with open(path, encoding="latin-1") as f:
+        toks = tokenize(f.read())
+    src = _translate_method(toks, "getQueryByIndex", "getQueryByIndex", 2, ["_lookup", "_myNode", "_SizeBuffer"], [], int_division=True)
+    ns = {"_JArray": _JArray}
+    exec(compile(src, path, "exec"), ns)
+
+    class _Owner:
+        numberOfParents = n_parents
+
+    class _Cpf:
+        _myNode, _lookup = _Owner(), None
+        _SizeBuffer = _JArray(4 ** i for i in range(n_parents))
+    return [list(ns["getQueryByIndex"](_Cpf(), l, False)) for l in range(4 ** n_parents)], src
 
 
 def translate_estep():

@@ -286,3 +286,12 @@ def test_oracle_strand_estep_reproduces_the_jstacs_statements():
     assert np.max(np.abs(res["w"] - G["strand_w"])) <= 1e-13 * np.max(G["strand_w"])
     assert np.max(np.abs(res["gamma"] - G["strand_gamma"])) < 1e-13
     assert abs(float(G["strand_ll"]) - float(G["estep_ll"])) > 1e-3          # (not the single-strand E-step)
+
+
+@needs_reference
+def test_cpf_lookup_rows_equal_the_reference_statements():
+    """Row l of a CPF table stands for parent values query[p] = (l / 4^p) % 4 (bayesNet/CPF.java:238-256 executed): parent 0 --
+    the tree parent -- is the least significant digit, which is the row layout of the restatements and of the kernels' tables."""
+    for parents in range(4):
+        table, _ = refexec.reference_lookup_table(parents)
+        assert table == [[(l // 4 ** p) % 4 for p in range(parents)] for l in range(4 ** parents)]
