@@ -17,7 +17,8 @@ import math
 import os
 import re
 
-REFERENCE_FILE = "/root/reference/main/java/src/algorithm/MeanFieldForBayesNet.java"
+REFERENCE_ROOT = os.environ.get("PHYFOO_REFERENCE_ROOT", "/root/reference")      # (the tests set it to a missing path to rehearse the GPU box)
+REFERENCE_FILE = REFERENCE_ROOT + "/main/java/src/algorithm/MeanFieldForBayesNet.java"
 
 _TOKEN = re.compile(r"""
     (?P<bc>/\*.*?\*/) | (?P<lc>//[^\n]*) | (?P<str>"(?:\\.|[^"\\])*"|'(?:\\.|[^'\\])+') |
@@ -495,7 +496,7 @@ class ReferenceMeanField:
 
 
 # ---- the ZOOPS E-step: Jstacs statements from libs/jstacs.jar ----------------------------------------------------------------
-JSTACS_JAR = "/root/reference/libs/jstacs.jar"
+JSTACS_JAR = REFERENCE_ROOT + "/libs/jstacs.jar"
 SHM_JAVA = "de/jstacs/models/mixture/motif/SingleHiddenMotifMixture.java"
 NORMALISATION_JAVA = "de/jstacs/utils/Normalisation.java"
 PRIOR_JAVA = "de/jstacs/models/mixture/motif/positionprior/UniformPositionPrior.java"
@@ -525,7 +526,7 @@ def _translate_method(tokens, py_name, java_name, n, fields, methods, signature=
 def reference_lookup_table(n_parents):
     """CPF._lookup as CPF.generateLookUpTable builds it (bayesNet/CPF.java:280-289): row l = getQueryByIndex(l, false)
     (:238-256, executed from the reference; its `/` is Java's int division), with _SizeBuffer[i] = 4^i (:52-59)."""
-    path = "/root/reference/main/java/src/bayesNet/CPF.java"
+    path = REFERENCE_ROOT + "/main/java/src/bayesNet/CPF.java"
     with open(path, encoding="latin-1") as f:
         toks = tokenize(f.read())
     src = _translate_method(toks, "getQueryByIndex", "getQueryByIndex", 2, ["_lookup", "_myNode", "_SizeBuffer"], [], int_division=True)
@@ -666,7 +667,7 @@ class ReferenceEStep:
 
 
 # ---- the substitution tables: evolution/FS81alpha.java, FS81beta.java, HKY.java (reinit) -------------------------------------
-EVOL_DIR = "/root/reference/main/java/src/evolution/"
+EVOL_DIR = REFERENCE_ROOT + "/main/java/src/evolution/"
 
 
 class ReferenceEvolModel:
@@ -701,7 +702,7 @@ class ReferenceEvolModel:
 
 
 # ---- the M-step objective and its forward-difference gradient (rows a14, a15) --------------------------------------------------
-MATRIX_LINEARISATION_JAVA = "/root/reference/main/java/src/util/MatrixLinearisation.java"
+MATRIX_LINEARISATION_JAVA = REFERENCE_ROOT + "/main/java/src/util/MatrixLinearisation.java"
 NUMDIFF_JAVA = "de/jstacs/algorithms/optimization/NumericalDifferentiableFunction.java"
 
 
@@ -753,7 +754,7 @@ class ReferenceObjective:
 
 
 # ---- the selector of the M-step (row a13) ---------------------------------------------------------------------------------------
-SELECTOR_JAVA = "/root/reference/main/java/src/io/SequenceSpecificDataSelector.java"
+SELECTOR_JAVA = REFERENCE_ROOT + "/main/java/src/io/SequenceSpecificDataSelector.java"
 
 
 class _JList(list):
