@@ -824,3 +824,15 @@ def reference_log_sum(values):
         def getLogSum(self, *a):
             return ns["ls3"](self, *a) if len(a) == 3 else ns["ls1"](self, *a)
     return ns["ls1"](_Static(), _JArray(float(v) for v in values))
+
+
+def reference_which_max(values):
+    """Util.whichMax (util/Util.java:528-538): the arg-max rule of the site calls."""
+    ns = reference_which_max.__dict__.setdefault("ns", {})
+    if not ns:
+        path = REFERENCE_ROOT + "/main/java/src/util/Util.java"
+        with open(path, encoding="latin-1") as f:
+            toks = tokenize(f.read())
+        ns["_JArray"] = _JArray
+        exec(compile(_translate_method(toks, "whichMax", "whichMax", 1, [], []), path, "exec"), ns)
+    return ns["whichMax"](None, _JArray(float(v) for v in values))

@@ -295,3 +295,14 @@ def test_cpf_lookup_rows_equal_the_reference_statements():
     for parents in range(4):
         table, _ = refexec.reference_lookup_table(parents)
         assert table == [[(l // 4 ** p) % 4 for p in range(parents)] for l in range(4 ** parents)]
+
+
+@needs_reference
+def test_site_call_is_the_first_maximum():
+    """Util.whichMax executed (row a17): strict `>`, so of equal maxima the first wins -- numpy's argmax rule, which the
+    oracle and the posterior kernel follow (arg-max calls are compared bit for bit everywhere)."""
+    rng = np.random.default_rng(17)
+    for _ in range(50):
+        v = rng.integers(0, 4, size=rng.integers(1, 12)).astype(float)          # many ties
+        assert refexec.reference_which_max(v) == int(np.argmax(v))
+    assert refexec.reference_which_max(G["estep_gamma"][1:11]) == int(np.argmax(G["estep_gamma"][1:11]))
