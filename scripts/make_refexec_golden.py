@@ -163,6 +163,46 @@ def selector_cases(rng):
         yield {f"sel{i}_weights": w, f"sel{i}_t": t, f"sel{i}_q": q, f"sel{i}_index": np.array(idx, np.int32), f"sel{i}_picked": np.array(ww)}
 
 
+def background_driver_cases(rng):
+    """PhyloBackground.getLogProbFor executed whole (refexec.ReferenceBackground: the reference's driver, initObservation, init,
+    optimizeByNormalisation, calcFreeEnergy over ONE shared net): an ordered list of range calls on one alignment -- ranges
+    shorter than order + 1 columns depend on what the calls before them left in the trailing trees -- and a ZOOPS E-step with
+    such a background, in which getNewWeights issues the calls in the reference's order."""
+    newick, W = TREES["cat5"], 5
+    for order in (1, 2):
+        net = npr.Net.background(newick, order)
+        pis = [rng.dirichlet(np.ones(4), size=4 ** t) for t in range(order + 1)]
+        for t, p in enumerate(pis):
+            net.set_pi(t, p)
+        net.build_tables()
+        rb = refexec.ReferenceBackground(net)
+        aln = codes(rng, 12, 5, 0.1)
+        seq = refexec._MDSeq(aln)
+        calls = [(0, 11), (3, 7), (2, 2), (5, 5 + order), (4, 4 + order - 1), (0, 0), (9, 11), (6, 5), (1, 1 + order), (11, 11)]
+        values = [rb.getLogProbFor(seq, s, e) for s, e in calls]
+        # the E-step
+        lengths = [W, 11, 8]
+        ealn = codes(rng, sum(lengths), 5, 0.06)
+        off = np.concatenate([[0], np.cumsum(lengths)])
+        pwm = synth.random_pwm(W, 0, 700 + order)
+        mnet = npr.Net.motif(newick, W, 0)
+        for t, p in enumerate(pwm):
+            mnet.set_pi(t, p)
+        mnet.build_tables()
+        fg = refexec.ReferenceMeanField(mnet)
+        scores = [fg.score(ealn[off[i] + j:off[i] + j + W])[0] for i in range(len(lengths)) for j in range(lengths[i] - W + 1)]
+        rb = refexec.ReferenceBackground(net)
+        seqs = [refexec._MDSeq(ealn[off[i]:off[i + 1]]) for i in range(len(lengths))]
+        weights = rng.random(len(lengths)) + 0.5
+        es = refexec.ReferenceEStep(lengths, W, lambda w: scores[w], lambda i, s, e: rb.getLogProbFor(seqs[i], s, e), 0.8, order)
+        ll, w, gamma = es.getNewWeights(weights)
+        k = f"bgd{order}_"
+        yield {k + "newick": newick, k + "pi": np.concatenate([np.ravel(p) for p in pis]), k + "codes": aln, k + "calls": np.array(calls),
+               k + "values": np.array(values, dtype=np.float64), k + "W": W, k + "pwm": np.concatenate([np.ravel(p) for p in pwm]),
+               k + "estep_codes": ealn, k + "estep_col_offsets": off, k + "estep_weights": weights, k + "estep_ll": ll,
+               k + "estep_w": np.array(w), k + "estep_gamma": np.array(gamma)}
+
+
 def main():
     rng = np.random.default_rng(20261020)
     out, n = {}, 0
@@ -182,6 +222,8 @@ def main():
         out.update({k: np.array(v) for k, v in case.items()})
         n_sel += 1
     out["n_selectors"] = np.array(n_sel)
+    for case in background_driver_cases(rng):
+        out.update({k: np.array(v) for k, v in case.items()})
     path = os.path.join(ROOT, "tests", "golden", "refexec_meanfield.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {os.path.getsize(path)} bytes, {n} cases, "

@@ -106,6 +106,23 @@ class Translator:
             kind, t = toks[i]
             prev = toks[i - 1][1] if i else None
             nxt = toks[i + 1][1] if i + 1 < len(toks) else None
+            if t == "(" and i + 1 < len(toks) and toks[i + 1][0] == "id" and toks[i + 1][1][0].isupper():
+                j = i + 2                                       # ( Type ) x  or  ( Type < ... > ) x : a class cast -- dropped
+                if j < len(toks) and toks[j][1] == "<":
+                    j = _match(toks, j, "<", ">") + 1
+                if j + 1 < len(toks) and toks[j][1] == ")" and (toks[j + 1][0] == "id" or toks[j + 1][1] == "("):
+                    i = j + 1
+                    continue
+            if t == "instanceof":                               # x instanceof T  (x a single name)
+                out[-1] = f'_instanceof({out[-1]}, "{toks[i + 1][1]}")'
+                i += 2
+                continue
+            if t == "new" and toks[i + 1][1] == "ArrayList":    # new ArrayList<T>()
+                j = _match(toks, i + 2, "<", ">") if toks[i + 2][1] == "<" else i + 1
+                assert toks[j + 1][1] == "(" and toks[j + 2][1] == ")"
+                out.append("_JList()")
+                i = j + 3
+                continue
             if t == "(" and i + 2 < len(toks) and toks[i + 1][1] in TYPES and toks[i + 2][1] == ")":
                 i += 3                                          # a primitive cast in front of a value of that type already
                 continue
@@ -137,7 +154,7 @@ class Translator:
                     out.append("self." + t)
                 elif t in self.fields:
                     out.append("self." + t)
-                elif t in ("Math", "Double", "Alphabet", "MeanFieldForBayesNet", "Arrays", "System", "Normalisation"):
+                elif t in ("Math", "Double", "Alphabet", "MeanFieldForBayesNet", "Arrays", "System", "Normalisation", "SimpleNodeElimination"):
                     out.append(t)
                 else:
                     raise NameError(f"unknown identifier {t!r} in the reference statement")
@@ -149,7 +166,7 @@ class Translator:
                 out.append("or")
             elif t == "!":
                 out.append("not")
-            elif t in ("++", "--", "?", "instanceof"):
+            elif t in ("++", "--", "?"):
                 raise NotImplementedError(t + " inside an expression")
             elif kind == "str":
                 out.append(t)
@@ -211,9 +228,11 @@ class Translator:
             self.emit(ind, f"_fill({self.expr(a)}, {self.expr(b)})")
             return
         # declaration:  type [ [] ]* name [= expr] {, name [= expr]}
-        if toks[0][0] == "id" and (v[0] in TYPES or (v[0][0].isupper() and len(toks) > 1 and (toks[1][0] == "id" or v[1] == "["))) \
+        if toks[0][0] == "id" and (v[0] in TYPES or (v[0][0].isupper() and len(toks) > 1 and (toks[1][0] == "id" or v[1] in ("[", "<")))) \
                 and v[0] not in ("Math", "System", "Arrays"):
             j = 1
+            if j < len(toks) and v[j] == "<" and v[0][0].isupper():          # Type<...> name
+                j = _match(toks, j, "<", ">") + 1
             while j + 1 < len(toks) and v[j] == "[" and v[j + 1] == "]":
                 j += 2
             if j < len(toks) and toks[j][0] == "id":
@@ -836,3 +855,139 @@ def reference_which_max(values):
         ns["_JArray"] = _JArray
         exec(compile(_translate_method(toks, "whichMax", "whichMax", 1, [], []), path, "exec"), ns)
     return ns["whichMax"](None, _JArray(float(v) for v in values))
+
+
+# ---- PhyloBackground.getLogProbFor with the shared net (row a10, including ranges shorter than order + 1 columns) -------------
+BACKGROUND_JAVA = REFERENCE_ROOT + "/main/java/src/models/PhyloBackground.java"
+
+
+class _MDSeq:
+    """MultiDimensionalDiscreteSequence as the path uses it: containerForPhyloBayes[column][leaf] (io/PhyloSample.java:106-136)"""
+
+    def __init__(self, codes):
+        self.containerForPhyloBayes = _JArray(_JArray(int(x) for x in col) for col in codes)
+        self.learnedTopology = None
+
+    def getLength(self):
+        return len(self.containerForPhyloBayes)
+
+    def getSubSequence(self, start, length):
+        return _SubSeq(self, start, length)
+
+
+class _SubSeq:
+    def __init__(self, parent, start, length):
+        self._parent, self.start, self._length = parent, start, length
+
+    def getLength(self):
+        return self._length
+
+    def getParent(self):
+        return self._parent
+
+
+def _instanceof(x, name):
+    return {"MultiDimensionalDiscreteSequence": _MDSeq, "SubSequence": _SubSeq}[name] is type(x)
+
+
+class _SharedMeanField(ReferenceMeanField):
+    """A MeanFieldForBayesNet of one (sub)sequence over the model's ONE net: the observation lives in the shared nodes
+    (bayesNet/BayesNetNodeProperties.java:88-99), q and the hidden-node map are per object.  initObservation() is the
+    reference's (:78-89), translated."""
+    _init_obs = None
+
+    def __init__(self, base, seq):
+        if _SharedMeanField._init_obs is None:
+            with open(REFERENCE_FILE, encoding="latin-1") as f:
+                toks = tokenize(f.read())
+            src = _translate_method(toks, "initObservation", "initObservation", 0, FIELDS, METHODS)
+            ns = {"_instanceof": _instanceof, "_JArray": _JArray}
+            exec(compile(src, REFERENCE_FILE, "exec"), ns)
+            _SharedMeanField._init_obs, _SharedMeanField.init_observation_source = staticmethod(ns["initObservation"]), src
+        self.net, self.nodes, self.bnh, self.leaf_nodes = base.net, base.nodes, base.bnh, base.leaf_nodes
+        self.seq = seq
+        self.parent = seq if _instanceof(seq, "MultiDimensionalDiscreteSequence") else seq.getParent()     # constructor :40-49
+        self.q = self.node2hiddenNodeMap = self.ns = None
+        self.hiddenNodes = self.free_energy_calls = 0
+
+    def initObservation(self):
+        return self._init_obs(self)
+
+
+class _ObservedTree(_NodeList):
+    def __init__(self, nodes, leaves):
+        super().__init__(nodes)
+        self.leaves = leaves
+
+    def setObservation(self, obs):                              # bayesNet/VirtualTree.java:183-198, the leaves-only case
+        assert len(obs) == len(self.leaves)
+        for leaf, o in zip(self.leaves, obs):
+            leaf.props.setObservation(o)
+
+    def getNewickString(self):
+        return ""
+
+
+class ReferenceBackground:
+    """PhyloBackground.getLogProbFor(MultiDimensionalDiscreteSequence, int, int) (models/PhyloBackground.java:241-305) executed
+    from the reference over a net of order + 1 trees whose nodes every call shares -- so a range shorter than order + 1 columns
+    leaves the trailing trees with whatever an earlier call observed there, exactly as the Java's call order produces it.
+    Restated: getMFfromCache (models/AbstractPhyloModel.java:100-119: a new object per subsequence, initObservation, init), the
+    empty score cache, check()."""
+    _fn = None
+
+    def __init__(self, net):
+        if ReferenceBackground._fn is None:
+            with open(BACKGROUND_JAVA, encoding="latin-1") as f:
+                toks = tokenize(f.read())
+            fields = ["order", "bnh", "CALC_LOGLIKELIHOOD", "count", "_cachedScores"]
+            methods = ["check", "isScoreCached", "getBNH", "reinitEdgelengths", "getMFfromCache", "prepareCache"]
+            src = _translate_method(toks, "getLogProbFor", "getLogProbFor", 3, fields, methods,
+                                    "MultiDimensionalDiscreteSequence sequence, int startpos, int endpos")
+            ns = {"_JList": _JListGet, "_JArray": _JArray}
+            exec(compile(src, BACKGROUND_JAVA, "exec"), ns)
+            ReferenceBackground._fn, ReferenceBackground.source = staticmethod(ns["getLogProbFor"]), src
+        self.base = ReferenceMeanField(net)
+        self.base.bnh._myTreesArray = [_ObservedTree(t.nodes, self.base.leaf_nodes[i]) for i, t in enumerate(self.base.bnh._myTreesArray)]
+        self.bnh, self.order = self.base.bnh, net.W - 1
+        self.CALC_LOGLIKELIHOOD, self.count, self._cachedScores = False, 0, None
+        self.sweeps = 0
+
+    def check(self, *a):
+        pass
+
+    def isScoreCached(self, *a):
+        return False
+
+    def prepareCache(self, *a):
+        pass
+
+    def getBNH(self):
+        bnh = self.bnh
+
+        class _B:
+            def getVirtualTree(self, i):
+                return bnh._myTreesArray[i]
+        return _B()
+
+    def getMFfromCache(self, sequence):
+        mf = _SharedMeanField(self.base, sequence)
+        mf.initObservation()
+        mf.init()
+        return mf
+
+    def getLogProbFor(self, sequence, startpos, endpos):
+        return self._fn(self, sequence, startpos, endpos)
+
+
+class _JListGet(list):
+    """java.util.ArrayList: add / get / size"""
+
+    def add(self, x):
+        self.append(x)
+
+    def get(self, i):
+        return self[i]
+
+    def size(self):
+        return len(self)

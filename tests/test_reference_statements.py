@@ -306,3 +306,51 @@ def test_site_call_is_the_first_maximum():
         v = rng.integers(0, 4, size=rng.integers(1, 12)).astype(float)          # many ties
         assert refexec.reference_which_max(v) == int(np.argmax(v))
     assert refexec.reference_which_max(G["estep_gamma"][1:11]) == int(np.argmax(G["estep_gamma"][1:11]))
+
+
+# ---- PhyloBackground.getLogProbFor executed whole, over the shared net (row a10) ------------------------------------------------
+def background_driver(order):
+    k = f"bgd{order}_"
+    flat = G[k + "pi"]
+    rows = [4 ** t for t in range(order + 1)]
+    o = np.concatenate([[0], np.cumsum(rows)]) * 4
+    pis = [flat[o[t]:o[t + 1]].reshape(rows[t], 4) for t in range(order + 1)]
+    W = int(G[k + "W"])
+    pwm = [G[k + "pwm"][4 * t:4 * t + 4].reshape(1, 4) for t in range(W)]
+    return k, str(G[k + "newick"]), pis, W, pwm
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_oracle_background_reproduces_the_reference_driver(order):
+    """Range values in the reference's call order on one model object -- including ranges shorter than order + 1 columns, whose
+    trailing trees keep the observation an earlier call left (MeanFieldForBayesNet.java:84) -- and the ZOOPS E-step with that
+    background, against PhyloBackground.getLogProbFor + getNewWeights executed from the reference."""
+    from util import orc
+    k, newick, pis, W, pwm = background_driver(order)
+    ob = oracle_bg(newick, order, pis)
+    for (s, e), ref in zip(G[k + "calls"], G[k + "values"]):
+        got = ob.bg_range(G[k + "codes"], int(s), int(e))
+        assert abs(got - ref) <= 1e-13 * abs(ref) if ref else got == 0
+    short = [(int(s), int(e)) for s, e in G[k + "calls"] if 0 <= e - s < order]
+    assert len(short) >= 3
+    res = orc.estep(oracle_fg(newick, pwm), oracle_bg(newick, order, pis), G[k + "estep_col_offsets"], G[k + "estep_codes"],
+                    np.log([0.8, 0.2]), None, G[k + "estep_weights"])
+    assert abs(res["ll"] - float(G[k + "estep_ll"])) <= 1e-13 * abs(float(G[k + "estep_ll"]))
+    assert np.max(np.abs(res["w"] - G[k + "estep_w"])) <= 1e-13 * np.max(G[k + "estep_w"])
+    assert np.max(np.abs(res["gamma"] - G[k + "estep_gamma"])) < 1e-13
+
+
+@needs_reference
+@pytest.mark.parametrize("order", [1, 2])
+def test_reexecuting_the_background_driver_reproduces_the_committed_vectors(order):
+    k, newick, pis, W, pwm = background_driver(order)
+    net = npr.Net.background(newick, order)
+    for t, p in enumerate(pis):
+        net.set_pi(t, p)
+    net.build_tables()
+    rb = refexec.ReferenceBackground(net)
+    seq = refexec._MDSeq(G[k + "codes"])
+    assert [rb.getLogProbFor(seq, int(s), int(e)) for s, e in G[k + "calls"]] == G[k + "values"].tolist()
+    src = refexec.ReferenceBackground.source
+    assert "while i < self.order and startpos <= endpos:" in src and "logSum += tmpPointer . get ( i ) . calcFreeEnergy ( self.order , self.order )" in src
+    assert "min ( self.bnh . motifLength , self.seq . getLength ( ) )" in refexec._SharedMeanField.init_observation_source

@@ -122,3 +122,27 @@ def test_strand_estep_equals_the_jstacs_statements(ctx):
     assert abs(res["ll"] - float(G["strand_ll"])) <= TOL * abs(float(G["strand_ll"]))
     assert np.max(np.abs(res["w"] - G["strand_w"])) <= TOL * np.max(G["strand_w"])
     assert np.max(np.abs(res["gamma"] - G["strand_gamma"])) < TOL
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_estep_with_a_background_of_higher_order_equals_the_reference_driver(ctx, order):
+    """The E-step whose background ranges (flanks shorter than order + 1 columns included) come from PhyloBackground.getLogProbFor
+    executed from the reference in getNewWeights' call order."""
+    from test_reference_statements import G, background_driver
+    from phyfoo_b200.data import PhyloSample
+    from phyfoo_b200.models import PhyloBackground, PhyloBayesModel, SingleHiddenMotifMixture
+    k, newick, pis, W, pwm = background_driver(order)
+    fg = PhyloBayesModel(W, 0, newick, ctx)
+    fg.setCondProbs(pwm)
+    bg = PhyloBackground(order, newick, ctx)
+    bg.setCondProbs(pis)
+    smp = PhyloSample(np.ascontiguousarray(G[k + "estep_codes"], np.uint8), G[k + "estep_col_offsets"])
+    res = SingleHiddenMotifMixture(fg, bg, zoops=0.8).getNewWeights(smp, seqWeights=G[k + "estep_weights"])
+    assert abs(res["ll"] - float(G[k + "estep_ll"])) <= TOL * abs(float(G[k + "estep_ll"]))
+    assert np.max(np.abs(res["w"] - G[k + "estep_w"])) <= TOL * np.max(G[k + "estep_w"])
+    assert np.max(np.abs(res["gamma"] - G[k + "estep_gamma"])) < TOL
+    # full-length ranges through the range-terms call
+    for (s, e), ref in zip(G[k + "calls"], G[k + "values"]):
+        if e - s >= order:
+            one = PhyloSample(np.ascontiguousarray(G[k + "codes"], np.uint8), [0, G[k + "codes"].shape[0]])
+            assert abs(bg.getLogProbForRange(one, 0, int(s), int(e)) - ref) <= TOL * abs(ref)
