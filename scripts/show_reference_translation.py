@@ -38,6 +38,13 @@ def main():
     refexec.ReferenceSelector([0.2, 0.5, 0.3])
     parts.append(("io/SequenceSpecificDataSelector.java:82-96  prepareForTraining (its for statement)", refexec.ReferenceSelector.source))
     parts.append(("bayesNet/CPF.java:238-256  getQueryByIndex(int, boolean)", refexec.reference_lookup_table(2)[1]))
+    bnet = npr.Net.background("(A:0.1,B:0.2)", 1)
+    bnet.build_tables()
+    refexec.ReferenceBackground(bnet).getMFfromCache(refexec._MDSeq(np.zeros((2, 2), np.uint8)))
+    refexec.ReferenceMotif(net)
+    parts.append(("algorithm/MeanFieldForBayesNet.java:78-89  initObservation()", refexec._SharedMeanField.init_observation_source))
+    parts.append(("models/PhyloBackground.java:241-305  getLogProbFor(MultiDimensionalDiscreteSequence, int, int)", refexec.ReferenceBackground.source))
+    parts.append(("models/PhyloBayesModel.java:222-267  getLogProbFor(Sequence, int, int)", refexec.ReferenceMotif.motif_source))
     for title, text in parts:
         if want.lower() in title.lower():
             print("=" * 100 + "\n" + title + "\n" + "=" * 100 + "\n" + text)

@@ -135,7 +135,7 @@ class Translator:
                 j = _match(toks, i + 2, "[", "]")
                 if j + 1 < len(toks) and toks[j + 1][1] == "[":
                     raise NotImplementedError("multi-dimensional new")
-                zero = {"double": "0.0", "int": "0", "boolean": "False"}[ty]
+                zero = {"double": "0.0", "int": "0", "boolean": "False", "String": "None"}[ty]
                 out.append(f"_JArray([{zero}] * ({self.expr(toks[i + 3:j])}))")
                 i = j + 1
                 continue
@@ -154,7 +154,7 @@ class Translator:
                     out.append("self." + t)
                 elif t in self.fields:
                     out.append("self." + t)
-                elif t in ("Math", "Double", "Alphabet", "MeanFieldForBayesNet", "Arrays", "System", "Normalisation", "SimpleNodeElimination"):
+                elif t in ("Math", "Double", "Alphabet", "MeanFieldForBayesNet", "Arrays", "System", "Normalisation", "SimpleNodeElimination", "PhyloSample"):
                     out.append(t)
                 else:
                     raise NameError(f"unknown identifier {t!r} in the reference statement")
@@ -991,3 +991,39 @@ class _JListGet(list):
 
     def size(self):
         return len(self)
+
+
+MOTIF_JAVA = REFERENCE_ROOT + "/main/java/src/models/PhyloBayesModel.java"
+
+
+class ReferenceMotif(ReferenceBackground):
+    """PhyloBayesModel.getLogProbFor(Sequence, int, int) (models/PhyloBayesModel.java:222-267) executed from the reference: the
+    sub-sequence, the mean field from the (always missing) cache, initObservation, optimizeByNormalisation, -calcFreeEnergy()."""
+    _motif_fn = None
+
+    def __init__(self, net):
+        if ReferenceMotif._motif_fn is None:
+            with open(MOTIF_JAVA, encoding="latin-1") as f:
+                toks = tokenize(f.read())
+            fields = ["bnh", "CALC_LOGLIKELIHOOD", "length"]
+            methods = ["check", "getBNH", "reinitEdgelengths", "getMFfromCache", "getLength"]
+            src = _translate_method(toks, "getLogProbFor", "getLogProbFor", 3, fields, methods, "Sequence sequence, int startpos, int endpos")
+            ns = {"_instanceof": _instanceof, "_JArray": _JArray}
+            exec(compile(src, MOTIF_JAVA, "exec"), ns)
+            ReferenceMotif._motif_fn, ReferenceMotif.motif_source = staticmethod(ns["getLogProbFor"]), src
+        self.base = ReferenceMeanField(net)
+        self.base.bnh._myTreesArray = [_ObservedTree(t.nodes, self.base.leaf_nodes[i]) for i, t in enumerate(self.base.bnh._myTreesArray)]
+        self.bnh, self.length, self.CALC_LOGLIKELIHOOD = self.base.bnh, net.W, False
+        self.last = None
+
+    def getLength(self):
+        return self.length
+
+    def getMFfromCache(self, sequence):
+        self.last = super().getMFfromCache(sequence)
+        return self.last
+
+    def getLogProbFor(self, sequence, startpos, endpos):
+        """-> (log-score, sweeps)"""
+        v = self._motif_fn(self, sequence, startpos, endpos)
+        return v, self.last.free_energy_calls - 2              # no-argument calcFreeEnergy: before the loop, per sweep, and the score

@@ -354,3 +354,25 @@ def test_reexecuting_the_background_driver_reproduces_the_committed_vectors(orde
     src = refexec.ReferenceBackground.source
     assert "while i < self.order and startpos <= endpos:" in src and "logSum += tmpPointer . get ( i ) . calcFreeEnergy ( self.order , self.order )" in src
     assert "min ( self.bnh . motifLength , self.seq . getLength ( ) )" in refexec._SharedMeanField.init_observation_source
+
+
+@needs_reference
+def test_motif_get_log_prob_for_executed_whole_reproduces_the_committed_vectors():
+    """PhyloBayesModel.getLogProbFor (row a9) executed from the reference -- sub-sequence, mean field from the cache that never
+    hits, initObservation, optimizeByNormalisation, -calcFreeEnergy() -- gives the committed scores and sweep counts."""
+    n = 0
+    for c in cases("motif"):
+        if str(c["tree"]) == "rand12":
+            continue
+        W, order = int(c["W"]), int(c["order"])
+        net = npr.Net.motif(str(c["newick"]), W, order)
+        for t, p in enumerate(motif_pwm(c)):
+            net.set_pi(t, p)
+        net.build_tables()
+        model, seq = refexec.ReferenceMotif(net), refexec._MDSeq(c["codes"])
+        for j in range(0, c["score"].shape[1], 2):
+            v, k = model.getLogProbFor(seq, j, j + W - 1)
+            assert v == c["score"][0, j] and k == c["sweeps"][0, j]
+            n += 1
+    assert n == 36
+    assert "logLikelihood = - tmpPointer . calcFreeEnergy ( )" in refexec.ReferenceMotif.motif_source
