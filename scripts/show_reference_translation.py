@@ -35,6 +35,7 @@ def main():
     net.build_tables()
     refexec.ReferenceObjective(net, [np.zeros((1, 2), np.uint8)], [1.0], 0)
     parts.append(("jstacs.jar NumericalDifferentiableFunction.java:64-84  evaluateGradientOfFunction", refexec.ReferenceObjective.gradient_source))
+    parts.append(("optimizing/AbstractFreeEnergyOptimizer.java:95-114  getWeightedLogLikelihoodSum()", refexec.ReferenceObjective.sum_source))
     refexec.ReferenceSelector([0.2, 0.5, 0.3])
     parts.append(("io/SequenceSpecificDataSelector.java:82-96  prepareForTraining (its for statement)", refexec.ReferenceSelector.source))
     parts.append(("bayesNet/CPF.java:238-256  getQueryByIndex(int, boolean)", refexec.reference_lookup_table(2)[1]))

@@ -266,6 +266,15 @@ class Translator:
             return self._labelled(toks, i, ind, loop_labels)
         if t in ("for", "while"):
             return self._loop(toks, i, ind, loop_labels, None)
+        if t == "try":                                          # try { A } catch (E e) { B }: A runs; B only on an exception
+            k = self.stmt(toks, i + 1, ind, loop_labels)
+            while k < len(toks) and toks[k][1] in ("catch", "finally"):
+                if toks[k][1] == "catch":
+                    k = _match(toks, k + 1, "(", ")") + 1
+                else:
+                    raise NotImplementedError("finally")
+                k = _match(toks, k, "{", "}") + 1
+            return k
         if t == "if":
             j = _match(toks, i + 1, "(", ")")
             self.emit(ind, f"if {self.expr(toks[i + 2:j])}:")
@@ -730,8 +739,8 @@ class ReferenceObjective:
     whose mean fields stay fixed (AbstractFreeEnergyOptimizer.OPTIMIZE_MEANFIELDS = false, :36): the statements executed from
     the reference are MatrixLinearisation.lambda2pi (util/MatrixLinearisation.java:15-19) with Normalisation.logSumNormalisation,
     MeanFieldForBayesNet.calcFreeEnergy for every window, and NumericalDifferentiableFunction.evaluateGradientOfFunction
-    (jstacs :64-84); the loop `sum -= calcFreeEnergy() * weights[u]` of getWeightedLogLikelihoodSum (:95-114; it sits in a
-    try / catch, outside the translated subset) is restated in evaluateFunction below."""
+    (jstacs :64-84) and AbstractFreeEnergyOptimizer.getWeightedLogLikelihoodSum (:95-114) over mean-field objects that share the
+    model's net.  Restated: initParameters' hand-over of the new distribution to the tables (:49-53)."""
     _ns = None
 
     def __init__(self, net, windows, weights, position, eps=1e-4):
@@ -744,13 +753,27 @@ class ReferenceObjective:
             src = _translate_method(_jar_tokens(NUMDIFF_JAVA), "evaluateGradientOfFunction", "evaluateGradientOfFunction", 1,
                                     ["eps"], ["getDimensionOfScope", "evaluateFunction"])
             exec(compile(src, NUMDIFF_JAVA, "exec"), ns)
-            ReferenceObjective._ns, ReferenceObjective.gradient_source = ns, src
+            path = REFERENCE_ROOT + "/main/java/src/optimizing/AbstractFreeEnergyOptimizer.java"
+            with open(path, encoding="latin-1") as f:
+                afe = tokenize(f.read())
+            ssrc = _translate_method(afe, "getWeightedLogLikelihoodSum", "getWeightedLogLikelihoodSum", 0,
+                                     ["vlfbn", "OPTIMIZE_MEANFIELDS", "weights"], [])
+            exec(compile(ssrc, path, "exec"), ns)
+            ReferenceObjective._ns, ReferenceObjective.gradient_source, ReferenceObjective.sum_source = ns, src, ssrc
         self.net, self.pos, self.eps = net, position, eps
-        self.mf = ReferenceMeanField(net)
-        self.windows, self.weights, self.fixed = windows, [float(w) for w in weights], []
-        for cols in windows:                                    # the mean fields the E-step left in the cached objects
-            self.mf.score(cols)
-            self.fixed.append((list(self.mf.q), list(self.mf.node2hiddenNodeMap)))
+        self.OPTIMIZE_MEANFIELDS = False                        # optimizing/AbstractFreeEnergyOptimizer.java:36
+        self.weights = _JArray(float(w) for w in weights)
+        # vlfbn: one MeanFieldForBayesNet per selected window over the model's one net, holding the mean fields the E-step's
+        # scoring of that window left (models/PhyloBayesModel.java:139-147 collects them from the cache)
+        self.base = ReferenceMeanField(net)
+        self.base.bnh._myTreesArray = [_ObservedTree(t.nodes, self.base.leaf_nodes[i]) for i, t in enumerate(self.base.bnh._myTreesArray)]
+        self.vlfbn = _JArray()
+        for cols in windows:
+            mf = _SharedMeanField(self.base, _MDSeq(cols))
+            mf.initObservation()
+            mf.init()
+            mf.optimizeByNormalisation()
+            self.vlfbn.append(mf)
 
     def getDimensionOfScope(self):
         return self.net.pi[self.pos].size
@@ -759,14 +782,12 @@ class ReferenceObjective:
         pi = _JArray([0.0] * len(lam))
         self._ns["lambda2pi"](None, _JArray(lam), pi, 4)        # initParameters :49-53
         self.net.set_pi(self.pos, pi)
-        self.net.build_tables()
-        self.mf = ReferenceMeanField(self.net)
-        total = 0
-        for cols, w, (q, hidden) in zip(self.windows, self.weights, self.fixed):
-            self.mf.initObservation(cols)
-            self.mf.q, self.mf.node2hiddenNodeMap = _JArray(q), _JArray(hidden)
-            total -= self.mf.calcFreeEnergy() * w               # getWeightedLogLikelihoodSum :107-108
-        return total
+        self.net.build_tables()                                 # VirtualTree.initParametersFromGF: the tables of the changed position
+        index = {n: i for i, n in enumerate(self.net.order_nodes)}
+        for n, i in index.items():
+            node = self.base.nodes[i]
+            node.CPF = _CPF(node, self.net.tab[n].reshape(-1, 4), self.net.ind[n].reshape(-1, 4))
+        return self._ns["getWeightedLogLikelihoodSum"](self)    # :95-114, executed
 
     def evaluateGradientOfFunction(self, lam):
         return list(self._ns["evaluateGradientOfFunction"](self, _JArray([float(x) for x in lam])))
