@@ -1,8 +1,9 @@
 """libphyfoo.so against outputs of the reference's own statements (tests/golden/refexec_meanfield.npz: produced by executing
-MeanFieldForBayesNet.init / optimizeByNormalisation / calcFreeEnergy of the reference, translated token by token by
-tests/refexec.py -- see tests/test_reference_statements.py and scripts/make_refexec_golden.py).  Bars of north_star: window
-scores within 1e-9 relative, mean-field sweep counts exact; motif windows of orders 0 and 1 on four trees, both strands, with
-and without gaps, and background ranges of order + 1 columns for orders 0..2."""
+the reference's methods -- MeanFieldForBayesNet, PhyloBayesModel / PhyloBackground.getLogProbFor, the Jstacs E-step and
+normalisations, the M-step objective with its forward-difference gradient, the selector -- translated token by token by
+tests/refexec.py; see tests/test_reference_statements.py and scripts/make_refexec_golden.py).  Bars of north_star: scores,
+posteriors, objective values within 1e-9 relative, mean-field sweep counts, selected windows and arg-max calls exact.
+(Named to run after every other GPU test.)"""
 import numpy as np
 import pytest
 
