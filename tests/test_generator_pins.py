@@ -8,7 +8,8 @@ from (Pearson's chi-square over the 4^5 patterns, 1023 degrees of freedom, ~260 
 This pins, against reference-generated data and to that statistical resolution: the Newick parser and species order, the
 meaning of a branch length under F81alpha (a substitution PROBABILITY, evolution/FS81alpha.java:76-92: +-2.5 % is resolved),
 the CPF look-up order and the exact likelihood -- not the mean-field numbers bit for bit (nothing can: no JVM), but the model
-they approximate.  It is a statistical pin, so DESIGN.md keeps saying "parity unpinned" for the bit-level claim.
+they approximate.  It is a statistical pin of the model and of the object graph (tree, species order, tables); the bit-level pin of the
+arithmetic is tests/test_reference_statements.py, which executes the reference's own statements.
 """
 import os
 

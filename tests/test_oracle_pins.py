@@ -1,5 +1,5 @@
-"""Pins for the CPU oracle (the reference ships no tests, golden vectors or fixtures and no JVM exists here:
-"parity unpinned by the reference").  What pins it instead:
+"""Pins for the CPU oracle beside the executed reference statements of tests/test_reference_statements.py (the reference ships
+no tests, golden vectors or fixtures and no JVM exists here):
   * an independently written numpy restatement (oracle/np_restatement.py) agreeing to 1e-12;
   * the closed form for star trees under F81alpha;
   * brute-force enumeration of the joint for exact mode, and the literal frontier elimination;
