@@ -798,10 +798,16 @@ SELECTOR_JAVA = REFERENCE_ROOT + "/main/java/src/io/SequenceSpecificDataSelector
 
 
 class _JList(list):
-    """java.util.ArrayList / DoubleList as far as prepareForTraining uses them"""
+    """java.util.ArrayList / DoubleList as far as the translated methods use them: add / get / size"""
 
     def add(self, x):
         self.append(x)
+
+    def get(self, i):
+        return self[i]
+
+    def size(self):
+        return len(self)
 
 
 class ReferenceSelector:
@@ -965,7 +971,7 @@ class ReferenceBackground:
             methods = ["check", "isScoreCached", "getBNH", "reinitEdgelengths", "getMFfromCache", "prepareCache"]
             src = _translate_method(toks, "getLogProbFor", "getLogProbFor", 3, fields, methods,
                                     "MultiDimensionalDiscreteSequence sequence, int startpos, int endpos")
-            ns = {"_JList": _JListGet, "_JArray": _JArray}
+            ns = {"_JList": _JList, "_JArray": _JArray}
             exec(compile(src, BACKGROUND_JAVA, "exec"), ns)
             ReferenceBackground._fn, ReferenceBackground.source = staticmethod(ns["getLogProbFor"]), src
         self.base = ReferenceMeanField(net)
@@ -999,19 +1005,6 @@ class ReferenceBackground:
 
     def getLogProbFor(self, sequence, startpos, endpos):
         return self._fn(self, sequence, startpos, endpos)
-
-
-class _JListGet(list):
-    """java.util.ArrayList: add / get / size"""
-
-    def add(self, x):
-        self.append(x)
-
-    def get(self, i):
-        return self[i]
-
-    def size(self):
-        return len(self)
 
 
 MOTIF_JAVA = REFERENCE_ROOT + "/main/java/src/models/PhyloBayesModel.java"
