@@ -203,6 +203,25 @@ def background_driver_cases(rng):
                k + "estep_w": np.array(w), k + "estep_gamma": np.array(gamma)}
 
 
+def alignment_based_cases(rng):
+    """The non-phylogenetic motif model (models/AlignmentBasedModel.java): window score = sum over species rows and motif
+    positions of getLnCondProb (:176-228, :232-248), executed from the reference (refexec.ReferenceAlignmentBasedModel)."""
+    for order in (0, 1, 2):
+        W, S = 5, 4
+        cond = [rng.dirichlet(np.ones(4), size=4 ** min(p, order)).ravel() for p in range(W)]
+        aln = codes(rng, 14, S, 0.2)
+        model = refexec.ReferenceAlignmentBasedModel(cond, order)
+        score = np.zeros(aln.shape[0] - W + 1)
+        for j in range(score.size):
+            for o in range(S):                            # getLogProbFor :243-245, getLnCondProb(sequence, posSeq) :176-182
+                total = 0
+                for i in range(W):
+                    total += model.getLnCondProb(aln[:, o], j + i, i)
+                score[j] += total
+        k = f"ab{order}_"
+        yield {k + "cond": np.concatenate(cond), k + "W": W, k + "codes": aln, k + "score": score}
+
+
 def main():
     rng = np.random.default_rng(20261020)
     out, n = {}, 0
@@ -223,6 +242,8 @@ def main():
         n_sel += 1
     out["n_selectors"] = np.array(n_sel)
     for case in background_driver_cases(rng):
+        out.update({k: np.array(v) for k, v in case.items()})
+    for case in alignment_based_cases(rng):
         out.update({k: np.array(v) for k, v in case.items()})
     path = os.path.join(ROOT, "tests", "golden", "refexec_meanfield.npz")
     np.savez_compressed(path, **out)

@@ -101,6 +101,20 @@ class Translator:
 
     # ---- expressions ---------------------------------------------------------------------------------------------------
     def expr(self, toks):
+        depth = 0
+        for q, (_, tv) in enumerate(toks):                      # cond ? a : b at the top level of this expression
+            depth += tv in ("(", "[") 
+            depth -= tv in (")", "]")
+            if tv == "?" and depth == 0:
+                d2 = 0
+                for c in range(q + 1, len(toks)):
+                    d2 += toks[c][1] in ("(", "[", "?")
+                    d2 -= toks[c][1] in (")", "]")
+                    if toks[c][1] == ":" :
+                        if d2 == 0:
+                            return f"(({self.expr(toks[q + 1:c])}) if ({self.expr(toks[:q])}) else ({self.expr(toks[c + 1:])}))"
+                        d2 -= 1
+                raise SyntaxError("? without :")
         out, i = [], 0
         while i < len(toks):
             kind, t = toks[i]
@@ -154,7 +168,7 @@ class Translator:
                     out.append("self." + t)
                 elif t in self.fields:
                     out.append("self." + t)
-                elif t in ("Math", "Double", "Alphabet", "MeanFieldForBayesNet", "Arrays", "System", "Normalisation", "SimpleNodeElimination", "PhyloSample"):
+                elif t in ("Math", "Double", "Alphabet", "MeanFieldForBayesNet", "Arrays", "System", "Normalisation", "SimpleNodeElimination", "PhyloSample", "AlignmentBasedModel"):
                     out.append(t)
                 else:
                     raise NameError(f"unknown identifier {t!r} in the reference statement")
@@ -166,7 +180,7 @@ class Translator:
                 out.append("or")
             elif t == "!":
                 out.append("not")
-            elif t in ("++", "--", "?"):
+            elif t in ("++", "--"):
                 raise NotImplementedError(t + " inside an expression")
             elif kind == "str":
                 out.append(t)
@@ -219,6 +233,16 @@ class Translator:
             return
         if v[0] == "throw":
             self.emit(ind, "raise RuntimeError('the reference throws here')")
+            return
+        eq = next((k for k, x in enumerate(v) if x in ("=", "+=", "-=", "*=", "/=")), None)
+        if eq is not None and "?" in v[eq + 1:] and not any(x in ("++", "--") for x in v):
+            self.emit(ind, f"{self.expr(toks[:eq])} {v[eq]} {self.expr(toks[eq + 1:])}")
+            return
+        # NAME [ VAR ++ ] = rhs   with rhs free of VAR:   NAME[VAR] = rhs; VAR += 1   (Java takes the index before the increment)
+        if eq is not None and eq >= 5 and v[1] == "[" and v[3] == "++" and v[4] == "]" and eq == 5 and v[eq] == "=" \
+                and toks[2][0] == "id" and v[2] not in v[eq + 1:] and not any(x in ("++", "--") for x in v[eq + 1:]):
+            self.emit(ind, f"{self.expr(toks[:1])} [ {self.expr(toks[2:3])} ] = {self.expr(toks[eq + 1:])}")
+            self.emit(ind, f"{self.expr(toks[2:3])} += 1")
             return
         if any(x in ("++", "--") for x in v[:-1]):              # e.g. a[i++] = ...: outside the subset; fails only if reached
             self.emit(ind, "raise NotImplementedError('statement outside the translated subset of Java')")
@@ -316,7 +340,8 @@ class Translator:
         cv = [t[1] for t in cond]
         uv = [t[1] for t in upd]
         # for (int v = A; v < B; v++)  /  v <= B   -- the only shape the three methods use
-        if len(iv) >= 4 and iv[0] == "int" and iv[2] == "=" and cv[0] == iv[1] and cv[1] in ("<", "<=") and uv == [iv[1], "++"]:
+        if len(iv) >= 4 and iv[0] == "int" and iv[2] == "=" and cv[0] == iv[1] and cv[1] in ("<", "<=") and uv == [iv[1], "++"] \
+                and not any(x in ("&&", "||", "?") for x in cv) and iv[1] not in cv[2:]:
             var = iv[1]
             self.locals.add(var)
             lo, hi = self.expr(init[3:]), self.expr(cond[2:])
@@ -1041,3 +1066,50 @@ class ReferenceMotif(ReferenceBackground):
         """-> (log-score, sweeps)"""
         v = self._motif_fn(self, sequence, startpos, endpos)
         return v, self.last.free_energy_calls - 2              # no-argument calcFreeEnergy: before the loop, per sweep, and the score
+
+
+# ---- the non-phylogenetic motif model (row f-3): models/AlignmentBasedModel.java ------------------------------------------------
+AB_JAVA = REFERENCE_ROOT + "/main/java/src/models/AlignmentBasedModel.java"
+
+
+class _Row:
+    """one species row of an alignment as Sequence.discreteVal sees it"""
+
+    def __init__(self, codes):
+        self.codes = [int(c) for c in codes]
+
+    def discreteVal(self, i):
+        return self.codes[i]
+
+
+class ReferenceAlignmentBasedModel:
+    """AlignmentBasedModel.getLnCondProb(sequence, posSeq, posMot) and isCompletylUnObserved (models/AlignmentBasedModel.java:
+    187-228, 333-340) executed from the reference; cond[posMot] is the table of a motif position in the reference's index
+    order, ACCESS_TABLE and pows as its constructor sizes them (:33,65-69)."""
+    _ns = None
+
+    def __init__(self, cond, order):
+        if ReferenceAlignmentBasedModel._ns is None:
+            with open(AB_JAVA, encoding="latin-1") as f:
+                toks = tokenize(f.read())
+            fields = ["ACCESS_TABLE", "pows", "order", "length", "condProb", "IGNORE_GAPS_IN_LIKELIHOOD_CALC"]
+            ns = {"_jlog": _jlog, "_JArray": _JArray, "_fill": _fill}
+            src = _translate_method(toks, "getLnCondProb", "getLnCondProb", 3, fields, ["getLnCondProb"])
+            usrc = _translate_method(toks, "isCompletylUnObserved", "isCompletylUnObserved", 3, [], [])
+            exec(compile(src, AB_JAVA, "exec"), ns)
+            exec(compile(usrc, AB_JAVA, "exec"), ns)
+
+            class _Static:
+                @staticmethod
+                def isCompletylUnObserved(sequence, start, end):
+                    return ns["isCompletylUnObserved"](None, sequence, start, end)
+            ns["AlignmentBasedModel"] = _Static
+            ReferenceAlignmentBasedModel._ns, ReferenceAlignmentBasedModel.source = ns, src
+        self.order, self.length = order, len(cond)
+        self.condProb = _JArray(_JArray(float(x) for x in row) for row in cond)
+        self.pows = _JArray(4 ** i for i in range(order + 2))
+        self.ACCESS_TABLE = _JArray([0] * sum(4 ** (i + 1) for i in range(order + 1)))
+        self.IGNORE_GAPS_IN_LIKELIHOOD_CALC = False
+
+    def getLnCondProb(self, row, pos_seq, pos_mot):
+        return self._ns["getLnCondProb"](self, _Row(row), pos_seq, pos_mot)

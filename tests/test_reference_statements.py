@@ -376,3 +376,38 @@ def test_motif_get_log_prob_for_executed_whole_reproduces_the_committed_vectors(
             n += 1
     assert n == 36
     assert "logLikelihood = - tmpPointer . calcFreeEnergy ( )" in refexec.ReferenceMotif.motif_source
+
+
+# ---- the non-phylogenetic motif model (row f-3) ---------------------------------------------------------------------------------
+def alignment_based(order):
+    k = f"ab{order}_"
+    W, flat = int(G[k + "W"]), G[k + "cond"]
+    sizes = [4 * 4 ** min(p, order) for p in range(W)]
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    return [flat[off[p]:off[p + 1]] for p in range(W)], G[k + "codes"], G[k + "score"]
+
+
+@pytest.mark.parametrize("order", [0, 1, 2])
+def test_oracle_alignment_based_model_reproduces_the_reference_statements(order):
+    from util import orc
+    cond, codes, score = alignment_based(order)
+    got = orc.ab_score_windows_order(cond, order, codes)
+    assert got.shape == score.shape and np.max(np.abs(got - score) / np.abs(score)) < 1e-13
+    assert (codes == 4).any()
+
+
+@needs_reference
+def test_alignment_based_statements_against_every_gap_pattern():
+    """AlignmentBasedModel.getLnCondProb executed from the reference against the oracle's restatement for every pattern of
+    symbols and gaps in the context (orders 0 to 2): the same doubles."""
+    import itertools
+    from util import orc
+    rng = np.random.default_rng(2)
+    for order in (0, 1, 2):
+        W = order + 2
+        cond = [rng.dirichlet(np.ones(4), size=4 ** min(p, order)).ravel() for p in range(W)]
+        model = refexec.ReferenceAlignmentBasedModel(cond, order)
+        for row in itertools.product(range(5), repeat=W):
+            for pos in range(W):
+                assert model.getLnCondProb(list(row), pos, pos) == orc.ab_motif_ln_cond_prob(cond, order, list(row), pos, pos)
+    assert "self.ACCESS_TABLE [ accessHead ] = self.ACCESS_TABLE [ i ] + a * self.pows [ k ]" in refexec.ReferenceAlignmentBasedModel.source

@@ -147,3 +147,15 @@ def test_estep_with_a_background_of_higher_order_equals_the_reference_driver(ctx
         if e - s >= order:
             one = PhyloSample(np.ascontiguousarray(G[k + "codes"], np.uint8), [0, G[k + "codes"].shape[0]])
             assert abs(bg.getLogProbForRange(one, 0, int(s), int(e)) - ref) <= TOL * abs(ref)
+
+
+@pytest.mark.parametrize("order", [0, 1, 2])
+def test_alignment_based_model_equals_the_reference_statements(ctx, order):
+    from test_reference_statements import alignment_based
+    from phyfoo_b200.data import PhyloSample
+    from phyfoo_b200.models import AlignmentBasedModel
+    cond, codes, score = alignment_based(order)
+    m = AlignmentBasedModel(len(cond), order, ctx)
+    m.setCondProbs(cond)
+    got = m.getLogProbFor(PhyloSample(np.ascontiguousarray(codes, np.uint8), [0, codes.shape[0]]), strand=0)
+    assert got.shape == score.shape and np.max(np.abs(got - score) / np.abs(score)) < 1e-12
