@@ -218,8 +218,17 @@ def alignment_based_cases(rng):
                 for i in range(W):
                     total += model.getLnCondProb(aln[:, o], j + i, i)
                 score[j] += total
+        # the background model of the same family: per column the sum over species rows of AlignmentBasedBGModel.getLnCondProb
+        # (models/AlignmentBasedBGModel.java:173-222, :239-243)
+        bcond = [rng.dirichlet(np.ones(4), size=4 ** p).ravel() for p in range(order + 1)]
+        bmodel = refexec.ReferenceAlignmentBasedBackground(bcond, order)
+        columns = np.zeros(aln.shape[0])
+        for l in range(aln.shape[0]):
+            for o in range(S):
+                columns[l] += bmodel.getLnCondProb(aln[:, o], l)
         k = f"ab{order}_"
-        yield {k + "cond": np.concatenate(cond), k + "W": W, k + "codes": aln, k + "score": score}
+        yield {k + "cond": np.concatenate(cond), k + "W": W, k + "codes": aln, k + "score": score,
+               k + "bg_cond": np.concatenate(bcond), k + "bg_columns": columns}
 
 
 def main():

@@ -189,7 +189,7 @@ class Translator:
             i += 1
         s = " ".join(out)
         for a, b in (("Math . log", "_jlog"), ("Math . exp", "_jexp"), ("Math . abs", "abs"), ("Math . min", "min"),
-                     ("Math . max", "max"), ("Double . isInfinite", "_isinf"), ("Normalisation .", "_Normalisation ."),
+                     ("Math . max", "max"), ("Arrays . copyOf", "_copyOf"), ("Double . isInfinite", "_isinf"), ("Normalisation .", "_Normalisation ."),
                      ("Double . NEGATIVE_INFINITY", "_NEG_INF"), ("Alphabet . size", "4"),
                      ("MeanFieldForBayesNet . CALC_LIKELIHOOD", "self.CALC_LIKELIHOOD")):
             s = s.replace(a, b)
@@ -335,6 +335,12 @@ class Translator:
         if toks[i][1] == "while":
             self.emit(ind, f"while {self.expr(head)}:")
             return self.stmt(toks, j + 1, ind + 1, labels)
+        colon = [q for q, tk in enumerate(head) if tk[1] == ":"]
+        if colon and not any(tk[1] == ";" for tk in head):      # for (Type name : collection)
+            var = head[colon[0] - 1][1]
+            self.locals.add(var)
+            self.emit(ind, f"for {_py(var)} in {self.expr(head[colon[0] + 1:])}:")
+            return self.stmt(toks, j + 1, ind + 1, labels)
         init, cond, upd = self.split_top(head, ";")
         iv = [t[1] for t in init]
         cv = [t[1] for t in cond]
@@ -377,6 +383,11 @@ def _jexp(x):
 class _JArray(list):
     """a Java array: a list with a .length"""
     length = property(len)
+
+
+def _copyOf(a, n):
+    """java.util.Arrays.copyOf for numeric arrays"""
+    return _JArray((list(a) + [0] * n)[:n])
 
 
 def _fill(a, v):
@@ -1113,3 +1124,32 @@ class ReferenceAlignmentBasedModel:
 
     def getLnCondProb(self, row, pos_seq, pos_mot):
         return self._ns["getLnCondProb"](self, _Row(row), pos_seq, pos_mot)
+
+
+AB_BG_JAVA = REFERENCE_ROOT + "/main/java/src/models/AlignmentBasedBGModel.java"
+
+
+class ReferenceAlignmentBasedBackground:
+    """AlignmentBasedBGModel.getLnCondProb(sequence, posSeq) (models/AlignmentBasedBGModel.java:173-222) executed from the
+    reference -- including the list entries it keeps from before the last gap expansion; cond[min(posSeq, order)] is the table of
+    that context length."""
+    _ns = None
+
+    def __init__(self, cond, order):
+        if ReferenceAlignmentBasedBackground._ns is None:
+            ReferenceAlignmentBasedModel([[0.25] * 4], 0)        # (translates isCompletylUnObserved)
+            ns = dict(ReferenceAlignmentBasedModel._ns)
+            ns.update({"_JList": _JList, "_copyOf": _copyOf})
+            with open(AB_BG_JAVA, encoding="latin-1") as f:
+                toks = tokenize(f.read())
+            fields = ["pows", "order", "condProb", "IGNORE_GAPS_IN_LIKELIHOOD_CALC"]
+            src = _translate_method(toks, "getLnCondProbBG", "getLnCondProb", 2, fields, [], "Sequence<?> sequence, final int posSeq")
+            exec(compile(src, AB_BG_JAVA, "exec"), ns)
+            ReferenceAlignmentBasedBackground._ns, ReferenceAlignmentBasedBackground.source = ns, src
+        self.order = order
+        self.condProb = _JArray(_JArray(float(x) for x in row) for row in cond)
+        self.pows = _JArray(4 ** i for i in range(order + 2))
+        self.IGNORE_GAPS_IN_LIKELIHOOD_CALC = False
+
+    def getLnCondProb(self, row, pos_seq):
+        return self._ns["getLnCondProbBG"](self, _Row(row), pos_seq)

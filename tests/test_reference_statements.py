@@ -411,3 +411,36 @@ def test_alignment_based_statements_against_every_gap_pattern():
             for pos in range(W):
                 assert model.getLnCondProb(list(row), pos, pos) == orc.ab_motif_ln_cond_prob(cond, order, list(row), pos, pos)
     assert "self.ACCESS_TABLE [ accessHead ] = self.ACCESS_TABLE [ i ] + a * self.pows [ k ]" in refexec.ReferenceAlignmentBasedModel.source
+
+
+def alignment_based_background(order):
+    k = f"ab{order}_"
+    flat = G[k + "bg_cond"]
+    sizes = [4 * 4 ** p for p in range(order + 1)]
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    return [flat[off[p]:off[p + 1]] for p in range(order + 1)], G[k + "codes"], G[k + "bg_columns"]
+
+
+@pytest.mark.parametrize("order", [0, 1, 2])
+def test_oracle_alignment_based_background_reproduces_the_reference_statements(order):
+    from util import orc
+    cond, codes, columns = alignment_based_background(order)
+    for s, e in ((0, codes.shape[0] - 1), (3, 9), (5, 5)):
+        got = orc.ab_bg_range_order(cond, order, codes, s, e)
+        ref = columns[s:e + 1].sum()
+        assert abs(got - ref) <= 1e-12 * abs(ref)
+
+
+@needs_reference
+def test_alignment_based_background_statements_against_every_gap_pattern():
+    """AlignmentBasedBGModel.getLnCondProb executed from the reference (with the list entries it keeps from before the last gap
+    expansion, :185-191) against the oracle's restatement: the same doubles for every pattern (orders 0 to 2)."""
+    import itertools
+    from util import orc
+    rng = np.random.default_rng(3)
+    for order in (0, 1, 2):
+        cond = [rng.dirichlet(np.ones(4), size=4 ** p).ravel() for p in range(order + 1)]
+        model = refexec.ReferenceAlignmentBasedBackground(cond, order)
+        for row in itertools.product(range(5), repeat=order + 2):
+            for pos in range(order + 2):
+                assert model.getLnCondProb(list(row), pos) == orc.ab_bg_ln_cond_prob(cond, order, list(row), pos)

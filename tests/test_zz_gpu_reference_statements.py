@@ -159,3 +159,15 @@ def test_alignment_based_model_equals_the_reference_statements(ctx, order):
     m.setCondProbs(cond)
     got = m.getLogProbFor(PhyloSample(np.ascontiguousarray(codes, np.uint8), [0, codes.shape[0]]), strand=0)
     assert got.shape == score.shape and np.max(np.abs(got - score) / np.abs(score)) < 1e-12
+
+
+@pytest.mark.parametrize("order", [0, 1, 2])
+def test_alignment_based_background_equals_the_reference_statements(ctx, order):
+    from test_reference_statements import alignment_based_background
+    from phyfoo_b200.data import PhyloSample
+    from phyfoo_b200.models import AlignmentBasedBGModel
+    cond, codes, columns = alignment_based_background(order)
+    bg = AlignmentBasedBGModel(order, ctx)
+    bg.setCondProbs(cond[0] if order == 0 else cond)
+    got = bg.getColumnLogProbs(PhyloSample(np.ascontiguousarray(codes, np.uint8), [0, codes.shape[0]]))
+    assert got.shape == columns.shape and np.max(np.abs(got - columns) / np.abs(columns)) < 1e-12
