@@ -231,6 +231,23 @@ def alignment_based_cases(rng):
                k + "bg_cond": np.concatenate(bcond), k + "bg_columns": columns}
 
 
+def edge_case(rng):
+    """EdgeOptimizer.evaluateFunction (optimizing/branchlengths/EdgeOptimizer.java:44-74) executed from the reference: the
+    objective over fixed mean fields as a function of the branch-length parameters of one motif position."""
+    newick, W, pos = TREES["mixed6"], 3, 1
+    pwm = synth.random_pwm(W, 0, 901)
+    net = npr.Net.motif(newick, W, 0)
+    for t, p in enumerate(pwm):
+        net.set_pi(t, p)
+    net.build_tables()
+    windows = np.stack([codes(rng, W, 6, 0.1) for _ in range(5)])
+    weights = rng.random(5) + 0.1
+    obj = refexec.ReferenceEdgeObjective(net, list(windows), weights, pos)
+    xs = np.stack([rng.normal(size=net.N - 1) - 1.0 for _ in range(3)] + [np.array([-30.0] * (net.N - 1)), np.array([30.0] + [0.0] * (net.N - 2))])
+    return dict(edge_newick=newick, edge_W=W, edge_pos=pos, edge_pwm=np.concatenate([np.ravel(p) for p in pwm]), edge_windows=windows,
+                edge_weights=weights, edge_x=xs, edge_f=np.array([obj.evaluateEdges(x) for x in xs]))
+
+
 def main():
     rng = np.random.default_rng(20261020)
     out, n = {}, 0
@@ -254,6 +271,7 @@ def main():
         out.update({k: np.array(v) for k, v in case.items()})
     for case in alignment_based_cases(rng):
         out.update({k: np.array(v) for k, v in case.items()})
+    out.update({k: np.array(v) for k, v in edge_case(rng).items()})
     path = os.path.join(ROOT, "tests", "golden", "refexec_meanfield.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {os.path.getsize(path)} bytes, {n} cases, "

@@ -189,7 +189,7 @@ class Translator:
             i += 1
         s = " ".join(out)
         for a, b in (("Math . log", "_jlog"), ("Math . exp", "_jexp"), ("Math . abs", "abs"), ("Math . min", "min"),
-                     ("Math . max", "max"), ("Arrays . copyOf", "_copyOf"), ("Double . isInfinite", "_isinf"), ("Normalisation .", "_Normalisation ."),
+                     ("Math . max", "max"), ("Arrays . copyOf", "_copyOf"), ("Double . isNaN", "_isnan"), ("Double . isInfinite", "_isinf"), ("Normalisation .", "_Normalisation ."),
                      ("Double . NEGATIVE_INFINITY", "_NEG_INF"), ("Alphabet . size", "4"),
                      ("MeanFieldForBayesNet . CALC_LIKELIHOOD", "self.CALC_LIKELIHOOD")):
             s = s.replace(a, b)
@@ -1153,3 +1153,64 @@ class ReferenceAlignmentBasedBackground:
 
     def getLnCondProb(self, row, pos_seq):
         return self._ns["getLnCondProbBG"](self, _Row(row), pos_seq)
+
+
+# ---- branch-length learning (row f-2): optimizing/branchlengths/EdgeOptimizer.java ----------------------------------------------
+EDGE_JAVA = REFERENCE_ROOT + "/main/java/src/optimizing/branchlengths/EdgeOptimizer.java"
+
+
+class _PhyloProps(_Props):
+    def __init__(self, leaf, root):
+        super().__init__(leaf)
+        self._root = root
+
+    def isPhyloRoot(self):
+        return self._root
+
+
+class ReferenceEdgeObjective(ReferenceObjective):
+    """EdgeOptimizer.evaluateFunction (optimizing/branchlengths/EdgeOptimizer.java:44-74) executed from the reference: the
+    logit-like map of the parameters to branch lengths, the hand-over to the nodes of the tree at `pos`, and
+    getWeightedLogLikelihoodSum over fixed mean fields.  Restated: VirtualTree.initParametersFromGF (bayesNet/VirtualTree.java:
+    82-96: the tables of a tree from its nodes' distances, values as the reinit statements give them)."""
+    _edge = None
+
+    def __init__(self, net, windows, weights, position, equal=False):
+        super().__init__(net, windows, weights, position)
+        if ReferenceEdgeObjective._edge is None:
+            with open(EDGE_JAVA, encoding="latin-1") as f:
+                toks = tokenize(f.read())
+            fields = ["MINIMUM_BRANCH_LENGTH", "bnh", "optimzeGlobally", "pos", "optimizeBranchlengthsEqual"]
+            src = _translate_method(toks, "evaluateFunction", "evaluateFunction", 1, fields, ["getWeightedLogLikelihoodSum"])
+            ns = dict(self._ns)
+            ns["_isnan"] = math.isnan
+            exec(compile(src, EDGE_JAVA, "exec"), ns)
+            ReferenceEdgeObjective._edge, ReferenceEdgeObjective.edge_source = staticmethod(ns["evaluateFunction"]), src
+        self.MINIMUM_BRANCH_LENGTH, self.optimzeGlobally, self.optimizeBranchlengthsEqual = 0.0005, False, equal
+        self.bnh = self.base.bnh
+        index = {n: i for i, n in enumerate(net.order_nodes)}
+        owner = self
+
+        for t, tree in enumerate(self.bnh._myTreesArray):
+            for k, node in enumerate(tree.nodes):
+                node.props.__class__ = _PhyloProps
+                node.props._root = (k == 0)
+                node.distance = net.dist[k]
+                node.setDistanceToParent = (lambda v, node=node: setattr(node, "distance", float(v)))
+
+            def rebuild(t=t, tree=tree):
+                import numpy as np
+                from oracle import np_restatement as npr
+                for k, node in enumerate(tree.nodes):
+                    if k == 0:
+                        continue
+                    tab = npr.f81alpha(owner.net.pi[t], node.distance)
+                    node.CPF = _CPF(node, tab, np.array([owner.net.pi[t][l // 4] for l in range(tab.shape[0])]))
+            tree.initParametersFromGF = rebuild
+        self.bnh.getVirtualTree = lambda i: self.bnh._myTreesArray[i]
+
+    def getWeightedLogLikelihoodSum(self):
+        return self._ns["getWeightedLogLikelihoodSum"](self)
+
+    def evaluateEdges(self, x):
+        return self._edge(self, _JArray(float(v) for v in x))

@@ -444,3 +444,34 @@ def test_alignment_based_background_statements_against_every_gap_pattern():
         for row in itertools.product(range(5), repeat=order + 2):
             for pos in range(order + 2):
                 assert model.getLnCondProb(list(row), pos) == orc.ab_bg_ln_cond_prob(cond, order, list(row), pos)
+
+
+# ---- branch-length learning (row f-2) -------------------------------------------------------------------------------------------
+def test_oracle_branch_length_objective_reproduces_the_reference_statements():
+    """EdgeOptimizer.evaluateFunction executed from the reference (parameters -> branch lengths (e^x + 0.0005) / (1 + e^x), the
+    tables of the position, the weighted free-energy sum over fixed mean fields) against the oracle under the branch lengths
+    the host mirror's map gives (phyfoo_b200.evolution.branch_from_logit, what trainEdges optimises over)."""
+    from util import orc
+    from phyfoo_b200 import evolution
+    W, pos = int(G["edge_W"]), int(G["edge_pos"])
+    pwm = [G["edge_pwm"][4 * t:4 * t + 4].reshape(1, 4) for t in range(W)]
+    m = oracle_fg(str(G["edge_newick"]), pwm)
+    fs = orc.FESet(m, np.ascontiguousarray(G["edge_windows"], np.uint8), G["edge_weights"])
+    for x, f in zip(G["edge_x"], G["edge_f"]):
+        alpha = evolution.branch_from_logit(x)
+        assert alpha.min() >= 0.0005 * (1 - 1e-12) and alpha.max() <= 1
+        for k in range(1, x.size + 1):
+            m.set_branch(pos, k, float(alpha[k - 1]))
+        assert abs(fs.sum() - f) <= 1e-13 * abs(f)
+
+
+@needs_reference
+def test_reexecuting_the_branch_length_objective_reproduces_the_committed_vectors():
+    W, pos = int(G["edge_W"]), int(G["edge_pos"])
+    net = npr.Net.motif(str(G["edge_newick"]), W, 0)
+    for t in range(W):
+        net.set_pi(t, G["edge_pwm"][4 * t:4 * t + 4].reshape(1, 4))
+    net.build_tables()
+    obj = refexec.ReferenceEdgeObjective(net, list(G["edge_windows"]), G["edge_weights"], pos)
+    assert [obj.evaluateEdges(x) for x in G["edge_x"]] == G["edge_f"].tolist()
+    assert "( _jexp ( edgesExp [ i ] ) + self.MINIMUM_BRANCH_LENGTH ) / ( 1 + _jexp ( edgesExp [ i ] ) )" in refexec.ReferenceEdgeObjective.edge_source
