@@ -46,6 +46,11 @@ def main():
     parts.append(("algorithm/MeanFieldForBayesNet.java:78-89  initObservation()", refexec._SharedMeanField.init_observation_source))
     parts.append(("models/PhyloBackground.java:241-305  getLogProbFor(MultiDimensionalDiscreteSequence, int, int)", refexec.ReferenceBackground.source))
     parts.append(("models/PhyloBayesModel.java:222-267  getLogProbFor(Sequence, int, int)", refexec.ReferenceMotif.motif_source))
+    refexec.ReferenceAlignmentBasedBackground([[0.25] * 4], 0)
+    parts.append(("models/AlignmentBasedModel.java:187-228  getLnCondProb(sequence, posSeq, posMot)", refexec.ReferenceAlignmentBasedModel.source))
+    parts.append(("models/AlignmentBasedBGModel.java:173-222  getLnCondProb(sequence, posSeq)", refexec.ReferenceAlignmentBasedBackground.source))
+    refexec.ReferenceEdgeObjective(net, [np.zeros((1, 2), np.uint8)], [1.0], 0)
+    parts.append(("optimizing/branchlengths/EdgeOptimizer.java:44-74  evaluateFunction", refexec.ReferenceEdgeObjective.edge_source))
     for title, text in parts:
         if want.lower() in title.lower():
             print("=" * 100 + "\n" + title + "\n" + "=" * 100 + "\n" + text)
