@@ -51,6 +51,10 @@ def main():
     parts.append(("models/AlignmentBasedBGModel.java:173-222  getLnCondProb(sequence, posSeq)", refexec.ReferenceAlignmentBasedBackground.source))
     refexec.ReferenceEdgeObjective(net, [np.zeros((1, 2), np.uint8)], [1.0], 0)
     parts.append(("optimizing/branchlengths/EdgeOptimizer.java:44-74  evaluateFunction", refexec.ReferenceEdgeObjective.edge_source))
+    opt = refexec.ReferenceOptimizer(lambda x: 0.0, lambda x: [0.0]).source
+    parts += [("jstacs.jar Optimizer.java:122-146  findBracket", opt["findBracket"]), ("jstacs.jar Optimizer.java:202-303  brentsMethod", opt["brentsMethod"]),
+              ("jstacs.jar Optimizer.java:1000-1080  quasiNewtonBFGS", opt["quasiNewtonBFGS"]),
+              ("jstacs.jar OneDimensionalSubFunction.java:62-74  evaluateFunction", opt["along"])]
     for title, text in parts:
         if want.lower() in title.lower():
             print("=" * 100 + "\n" + title + "\n" + "=" * 100 + "\n" + text)

@@ -147,9 +147,12 @@ class Translator:
             if t == "new":                                      # new double[expr] / new int[expr]
                 ty = toks[i + 1][1]
                 j = _match(toks, i + 2, "[", "]")
-                if j + 1 < len(toks) and toks[j + 1][1] == "[":
-                    raise NotImplementedError("multi-dimensional new")
                 zero = {"double": "0.0", "int": "0", "boolean": "False", "String": "None"}[ty]
+                if j + 1 < len(toks) and toks[j + 1][1] == "[":
+                    j2 = _match(toks, j + 1, "[", "]")
+                    out.append(f"_JArray(_JArray([{zero}] * ({self.expr(toks[j + 2:j2])})) for _ in range({self.expr(toks[i + 3:j])}))")
+                    i = j2 + 1
+                    continue
                 out.append(f"_JArray([{zero}] * ({self.expr(toks[i + 3:j])}))")
                 i = j + 1
                 continue
@@ -189,7 +192,7 @@ class Translator:
             i += 1
         s = " ".join(out)
         for a, b in (("Math . log", "_jlog"), ("Math . exp", "_jexp"), ("Math . abs", "abs"), ("Math . min", "min"),
-                     ("Math . max", "max"), ("Arrays . copyOf", "_copyOf"), ("Double . isNaN", "_isnan"), ("Double . isInfinite", "_isinf"), ("Normalisation .", "_Normalisation ."),
+                     ("Math . max", "max"), ("Arrays . copyOf", "_copyOf"), ("Double . isNaN", "_isnan"), ("Math . sqrt", "_sqrt"), ("Double . POSITIVE_INFINITY", "_POS_INF"), ("Double . isInfinite", "_isinf"), ("Normalisation .", "_Normalisation ."),
                      ("Double . NEGATIVE_INFINITY", "_NEG_INF"), ("Alphabet . size", "4"),
                      ("MeanFieldForBayesNet . CALC_LIKELIHOOD", "self.CALC_LIKELIHOOD")):
             s = s.replace(a, b)
@@ -231,6 +234,13 @@ class Translator:
         if v[:3] == ["System", ".", "out"]:
             self.emit(ind, "pass")
             return
+        if v[0] == "myOut":                                     # progress output: only the side effects ( ++i ) are kept
+            bumped = [v[q + 1] for q in range(len(v) - 1) if v[q] == "++" and toks[q + 1][0] == "id"]
+            for name in bumped:
+                self.emit(ind, f"{name} += 1")
+            if not bumped:
+                self.emit(ind, "pass")
+            return
         if v[0] == "throw":
             self.emit(ind, "raise RuntimeError('the reference throws here')")
             return
@@ -263,7 +273,13 @@ class Translator:
                 for d in self.split_top(toks[j:], ","):
                     name = d[0][1]
                     self.locals.add(name)
-                    if len(d) > 1:
+                    if len(d) > 1 and v[0] == "SafeOutputStream":
+                        self.emit(ind, f"{_py(name)} = None")
+                    elif len(d) > 1 and d[2][1] == "{":          # array initialiser { a, b, ... }
+                        assert d[1][1] == "=" and d[-1][1] == "}", d
+                        items = ", ".join(self.expr(part) for part in self.split_top(d[3:-1], ","))
+                        self.emit(ind, f"{_py(name)} = _JArray([{items}])")
+                    elif len(d) > 1:
                         assert d[1][1] == "=", d
                         self.emit(ind, f"{_py(name)} = {self.expr(d[2:])}")
                     else:
@@ -288,6 +304,15 @@ class Translator:
             return j + 1
         if toks[i][0] == "id" and i + 1 < len(toks) and toks[i + 1][1] == ":" and t not in ("default", "case"):
             return self._labelled(toks, i, ind, loop_labels)
+        if t == "do":
+            end = _match(toks, i + 1, "{", "}")
+            assert toks[end + 1][1] == "while"
+            c_end = _match(toks, end + 2, "(", ")")
+            self.emit(ind, "while True:")
+            self.stmt(toks, i + 1, ind + 1, loop_labels + [None])
+            self.emit(ind + 1, f"if not ({self.expr(toks[end + 3:c_end])}):")
+            self.emit(ind + 2, "break")
+            return c_end + 2                                    # behind the semicolon
         if t in ("for", "while"):
             return self._loop(toks, i, ind, loop_labels, None)
         if t == "try":                                          # try { A } catch (E e) { B }: A runs; B only on an exception
@@ -1214,3 +1239,92 @@ class ReferenceEdgeObjective(ReferenceObjective):
 
     def evaluateEdges(self, x):
         return self._edge(self, _JArray(float(v) for v in x))
+
+
+# ---- the optimiser (row a16): jstacs Optimizer.quasiNewtonBFGS with its line search ---------------------------------------------
+OPTIMIZER_JAVA = "de/jstacs/algorithms/optimization/Optimizer.java"
+
+
+class ReferenceOptimizer:
+    """Optimizer.quasiNewtonBFGS (jstacs!/de/jstacs/algorithms/optimization/Optimizer.java:1000-1080), findBracket (:122-146),
+    brentsMethod (:202-303) and OneDimensionalSubFunction.evaluateFunction (:62-74) executed from the jar; the golden-section
+    constants from their initialisers (:66-70).  Restated (handed in as objects): the termination condition and the start
+    distance forecaster (phyfoo_b200.optimize.CombinedCondition / LimitedMedianStartDistance), DifferentiableFunction.
+    findOneDimensionalMin -> OneDimensionalFunction.findMin (two lines: bracket, then Brent)."""
+    _ns = None
+
+    def __init__(self, fun, grad):
+        if ReferenceOptimizer._ns is None:
+            toks = _jar_tokens(OPTIMIZER_JAVA)
+            ns = {"_JArray": _JArray, "_sqrt": math.sqrt, "_POS_INF": math.inf, "_NEG_INF": -math.inf}
+            tr = Translator([], [], [])
+            for name in ("limFib", "limFibPlus1", "limFibPlus2"):          # private static final double NAME = expr;
+                at = next(q for q in range(len(toks) - 1) if toks[q] == ("id", name) and toks[q + 1][1] == "=")
+                end = next(q for q in range(at, len(toks)) if toks[q][1] == ";")
+                tr.locals.add(name)
+                ns[name] = eval(tr.expr(toks[at + 2:end]), dict(ns))
+            fields = ["limFib", "limFibPlus1", "limFibPlus2"]
+            sigs = {"findBracket": (4, "OneDimensionalFunction f, double lower, double fLower, double startDistance"),
+                    "brentsMethod": (6, "OneDimensionalFunction f, double a, double x, double fx, double b, double tol"),
+                    "quasiNewtonBFGS": (7, None)}
+            src = {}
+            for name, (n, sig) in sigs.items():
+                src[name] = _translate_method(toks, name, name, n, fields, ["checkStartDistance"], sig)
+                exec(compile(src[name], OPTIMIZER_JAVA, "exec"), ns)
+            sub = _jar_tokens("de/jstacs/algorithms/optimization/OneDimensionalSubFunction.java")
+            src["along"] = _translate_method(sub, "along", "evaluateFunction", 1, ["f", "d", "current"], [])
+            exec(compile(src["along"], OPTIMIZER_JAVA, "exec"), ns)
+            ReferenceOptimizer._ns, ReferenceOptimizer.source = ns, src
+        self.fun, self.grad, self.evaluations = fun, grad, 0
+        self.limFib, self.limFibPlus1, self.limFibPlus2 = (self._ns[k] for k in ("limFib", "limFibPlus1", "limFibPlus2"))
+
+    # DifferentiableFunction as the optimiser sees it
+    def getDimensionOfScope(self):
+        return self.n
+
+    def evaluateFunction(self, x):
+        self.evaluations += 1
+        return float(self.fun(list(x)))
+
+    def evaluateGradientOfFunction(self, x):
+        self.evaluations += self.n + 1                           # NumericalDifferentiableFunction: f(x) and n perturbed points
+        return _JArray(float(g) for g in self.grad(list(x)))
+
+    def checkStartDistance(self, sd):
+        if not sd > 0:
+            raise ValueError("The start distance has to be positive.")
+
+    def findOneDimensionalMin(self, x, d, alpha_0, f_alpha_0, lin_eps, start_distance):
+        owner = self
+
+        class _Sub:                                              # OneDimensionalSubFunction( this, x, d )
+            f, current = owner, x
+
+            def evaluateFunction(self, alpha):
+                return owner._ns["along"](self, alpha)
+        sub = _Sub()
+        sub.d = d
+        bracket = self._ns["findBracket"](self, sub, alpha_0, f_alpha_0, start_distance)        # OneDimensionalFunction.findMin :78-81
+        return self._ns["brentsMethod"](self, sub, bracket[0], bracket[2], bracket[3], bracket[4], lin_eps)
+
+    def minimise(self, x0, condition, forecaster, lin_eps=1e-3):
+        """-> (x, iterations, function evaluations)"""
+        self.n = len(x0)
+        x = _JArray(float(v) for v in x0)
+
+        class _Termination:
+            def doNextIteration(self, i, f_last, f_cur, gradient, direction, alpha, t):
+                return condition.do_next_iteration(i, f_last, f_cur, list(gradient), list(direction), alpha)
+
+        class _Forecaster:
+            def getNewStartDistance(self):
+                return forecaster.get_new_start_distance()
+
+            def setLastDistance(self, v):
+                forecaster.set_last_distance(v)
+
+        class _Time:
+            def getElapsedTime(self):
+                return 0.0
+        it = self._ns["quasiNewtonBFGS"](self, self, x, _Termination(), lin_eps, _Forecaster(), None, _Time())
+        return list(x), it, self.evaluations

@@ -475,3 +475,44 @@ def test_reexecuting_the_branch_length_objective_reproduces_the_committed_vector
     obj = refexec.ReferenceEdgeObjective(net, list(G["edge_windows"]), G["edge_weights"], pos)
     assert [obj.evaluateEdges(x) for x in G["edge_x"]] == G["edge_f"].tolist()
     assert "( _jexp ( edgesExp [ i ] ) + self.MINIMUM_BRANCH_LENGTH ) / ( 1 + _jexp ( edgesExp [ i ] ) )" in refexec.ReferenceEdgeObjective.edge_source
+
+
+# ---- the optimiser (row a16) ------------------------------------------------------------------------------------------------------
+@needs_reference
+def test_bfgs_and_line_search_executed_from_the_jar_take_the_restatements_path():
+    """Optimizer.quasiNewtonBFGS with findBracket and brentsMethod, executed from libs/jstacs.jar on the M-step objective of a
+    motif position (the library's sufficient-statistics form, forward-difference gradient): the same number of iterations and
+    of function evaluations as phyfoo_b200.optimize.quasi_newton_bfgs and the same final point to the last bit -- and that
+    restatement is the one tests/test_optimize_host.py holds evaluation for evaluation against the C++ in libphyfoo.so."""
+    from phyfoo_b200 import _abi, core, optimize, synth
+    from phyfoo_b200.newick import parse_newick
+    tree = parse_newick("((A:0.1,B:0.3):0.15,(C:0.2,(D:0.05,E:0.2):0.25):0.1)")
+    W = 3
+    rng = np.random.default_rng(21)
+    pwm = synth.random_pwm(W, 0, 9)
+    counts = rng.uniform(0.0, 2.0, (W, 4 + 16 * (tree.n_nodes - 1)))
+    desc, keep = _abi.make_desc(_abi.MODEL_FG, W, 0, tree, np.tile(tree.branch, (W, 1)), pwm, _abi.EVOL_F81ALPHA, _abi.MODE_MEANFIELD)
+    ss = core.SSObjective(desc=desc, counts=counts, entropy=0.75)
+    iterations = []
+    for pos in range(W):
+        fun = lambda lam: -ss.eval(pos, np.asarray(lam, float))                                    # noqa: E731
+
+        def grad(lam, eps=1e-4):
+            lam = np.array(lam, float)
+            f0, g = fun(lam), np.zeros(lam.size)
+            for i in range(lam.size):
+                h = lam[i]
+                lam[i] += eps
+                g[i] = (fun(lam) - f0) / eps
+                lam[i] = h
+            return f0, g
+        x0 = np.log(np.ravel(pwm[pos]))
+        x, f, it, evals = optimize.quasi_newton_bfgs(fun, grad, x0.copy(), optimize.TC_MOTIF_SEPARATED_POSITIONS(), 1e-3, 0.1)
+        ref = refexec.ReferenceOptimizer(fun, lambda lam: grad(lam)[1])
+        xr, itr, evr = ref.minimise(list(x0), optimize.TC_MOTIF_SEPARATED_POSITIONS(), optimize.LimitedMedianStartDistance(10, 0.1), 1e-3)
+        assert (it, evals) == (itr, evr) and np.array_equal(x, xr)
+        iterations.append(it)
+    assert max(iterations) >= 3
+    src = refexec.ReferenceOptimizer.source
+    assert "erg [ 4 ] = self.limFibPlus2 * erg [ 2 ] - self.limFibPlus1 * erg [ 0 ]" in src["findBracket"]
+    assert "u [ counter1 ] = s [ counter1 ] / sv - matrixv [ counter1 ] / vmatrixv" in src["quasiNewtonBFGS"]
