@@ -24,7 +24,7 @@ _TOKEN = re.compile(r"""
     (?P<bc>/\*.*?\*/) | (?P<lc>//[^\n]*) | (?P<str>"(?:\\.|[^"\\])*"|'(?:\\.|[^'\\])+') |
     (?P<num>(?:\d+\.\d*|\.\d+|\d+)(?:[eE][+-]?\d+)?[dDfFlL]?) |
     (?P<id>[A-Za-z_$][A-Za-z_0-9$]*) |
-    (?P<op>\+\+|--|\+=|-=|\*=|/=|==|!=|<=|>=|&&|\|\||[{}()\[\];,.<>=+\-*/%!?:@&|^~]) |
+    (?P<op>\+\+|--|\+=|-=|\*=|/=|%=|==|!=|<=|>=|&&|\|\||[{}()\[\];,.<>=+\-*/%!?:@&|^~]) |
     (?P<ws>\s+)
 """, re.S | re.X)
 
@@ -244,7 +244,7 @@ class Translator:
         if v[0] == "throw":
             self.emit(ind, "raise RuntimeError('the reference throws here')")
             return
-        eq = next((k for k, x in enumerate(v) if x in ("=", "+=", "-=", "*=", "/=")), None)
+        eq = next((k for k, x in enumerate(v) if x in ("=", "+=", "-=", "*=", "/=", "%=")), None)
         if eq is not None and "?" in v[eq + 1:] and not any(x in ("++", "--") for x in v):
             self.emit(ind, f"{self.expr(toks[:eq])} {v[eq]} {self.expr(toks[eq + 1:])}")
             return
@@ -1328,3 +1328,69 @@ class ReferenceOptimizer:
                 return 0.0
         it = self._ns["quasiNewtonBFGS"](self, self, x, _Termination(), lin_eps, _Forecaster(), None, _Time())
         return list(x), it, self.evaluations
+
+
+TERMINATION_DIR = "de/jstacs/algorithms/optimization/termination/"
+PREPARED_CONDITIONS_JAVA = REFERENCE_ROOT + "/main/java/src/optimizing/PreparedConditions.java"
+
+
+def _sorted_inplace(a):
+    a.sort()
+
+
+def reference_condition(name="TC_MOTIF_SEPARATED_POSITIONS"):
+    """The termination condition PhyFoo hands to the optimiser (optimizing/PreparedConditions.java:22-31), as an object with the
+    do_next_iteration of phyfoo_b200.optimize.CombinedCondition: every doNextIteration (CombinedCondition,
+    SmallDifferenceOfFunctionEvaluationsCondition, IterationCondition, SmallGradientConditon, SmallStepCondition) is executed
+    from the jar; threshold and epsilons are read out of the constructor call in PreparedConditions.java."""
+    with open(PREPARED_CONDITIONS_JAVA, encoding="latin-1") as f:
+        text = re.sub(r"\s+", " ", f.read())
+    call = re.search(name + r" = new CombinedCondition\((\d+),(.*?)\);", text)
+    threshold = int(call.group(1))
+    parts = re.findall(r"new (\w+)\(([-+.\deE]+)\)", call.group(2))
+    field = {"SmallDifferenceOfFunctionEvaluationsCondition": "eps", "IterationCondition": "maxIter", "SmallGradientConditon": "eps",
+             "SmallStepCondition": "epsilon"}
+
+    class _Cond:
+        pass
+    conditions = _JArray()
+    for cls, value in parts:
+        toks = _jar_tokens(TERMINATION_DIR + cls + ".java")
+        ns = {"_JArray": _JArray}
+        exec(compile(_translate_method(toks, "doNextIteration", "doNextIteration", 7, [field[cls]], []), cls, "exec"), ns)
+        c = _Cond()
+        setattr(c, field[cls], int(value) if cls == "IterationCondition" else float(value))
+        c.doNextIteration = (lambda *a, c=c, fn=ns["doNextIteration"]: fn(c, *a))
+        conditions.append(c)
+    toks = _jar_tokens(TERMINATION_DIR + "CombinedCondition.java")
+    ns = {"_JArray": _JArray}
+    src = _translate_method(toks, "doNextIteration", "doNextIteration", 7, ["condition", "threshold"], [])
+    exec(compile(src, "CombinedCondition", "exec"), ns)
+    combined = _Cond()
+    combined.condition, combined.threshold, combined.source = conditions, threshold, src
+    combined.do_next_iteration = lambda it, f_last, f_cur, grad, direction, alpha: ns["doNextIteration"](
+        combined, it, f_last, f_cur, _JArray(grad), _JArray(direction), alpha, None)
+    return combined
+
+
+def reference_forecaster(slots=10, value=0.1):
+    """LimitedMedianStartDistance (jstacs!/de/jstacs/algorithms/optimization/LimitedMedianStartDistance.java:64-84) executed from
+    the jar: 0.667 times the median of the last `slots` step lengths, the memory initialised with `value` (:89-92)."""
+    toks = _jar_tokens("de/jstacs/algorithms/optimization/LimitedMedianStartDistance.java")
+    ns = {"_JArray": _JArray, "_arraycopy": lambda a, i, b, j, n: b.__setitem__(slice(j, j + n), a[i:i + n]), "_sort": _sorted_inplace}
+    fields = ["initial", "memory", "sorted", "index"]
+    get = _translate_method(toks, "getNewStartDistance", "getNewStartDistance", 0, fields, [], int_division=True)
+    put = _translate_method(toks, "setLastDistance", "setLastDistance", 1, fields, [])
+    for a, b in (("System . arraycopy", "_arraycopy"), ("Arrays . sort", "_sort")):
+        get = get.replace(a, b)
+    exec(compile(get, "LimitedMedianStartDistance", "exec"), ns)
+    exec(compile(put, "LimitedMedianStartDistance", "exec"), ns)
+
+    class _F:
+        pass
+    f = _F()
+    f.initial, f.memory, f.sorted, f.index = value, _JArray([value] * slots), _JArray([0.0] * slots), 0      # constructor + reset()
+    f.get_new_start_distance = lambda: ns["getNewStartDistance"](f)
+    f.set_last_distance = lambda last: ns["setLastDistance"](f, last)
+    f.source = get + put
+    return f

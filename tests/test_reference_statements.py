@@ -509,10 +509,36 @@ def test_bfgs_and_line_search_executed_from_the_jar_take_the_restatements_path()
         x0 = np.log(np.ravel(pwm[pos]))
         x, f, it, evals = optimize.quasi_newton_bfgs(fun, grad, x0.copy(), optimize.TC_MOTIF_SEPARATED_POSITIONS(), 1e-3, 0.1)
         ref = refexec.ReferenceOptimizer(fun, lambda lam: grad(lam)[1])
-        xr, itr, evr = ref.minimise(list(x0), optimize.TC_MOTIF_SEPARATED_POSITIONS(), optimize.LimitedMedianStartDistance(10, 0.1), 1e-3)
+        # termination condition and start-distance forecaster: PhyFoo's (PreparedConditions.java:22-26, FE_byParameter...:74-80),
+        # their doNextIteration / getNewStartDistance / setLastDistance executed from the jar as well
+        xr, itr, evr = ref.minimise(list(x0), refexec.reference_condition("TC_MOTIF_SEPARATED_POSITIONS"), refexec.reference_forecaster(10, 0.1), 1e-3)
         assert (it, evals) == (itr, evr) and np.array_equal(x, xr)
         iterations.append(it)
     assert max(iterations) >= 3
     src = refexec.ReferenceOptimizer.source
     assert "erg [ 4 ] = self.limFibPlus2 * erg [ 2 ] - self.limFibPlus1 * erg [ 0 ]" in src["findBracket"]
     assert "u [ counter1 ] = s [ counter1 ] / sv - matrixv [ counter1 ] / vmatrixv" in src["quasiNewtonBFGS"]
+
+
+@needs_reference
+def test_termination_conditions_and_forecaster_executed_from_the_jar_equal_the_restatements():
+    from phyfoo_b200 import optimize
+    rng = np.random.default_rng(1)
+    for name, mine in (("TC_MOTIF_SEPARATED_POSITIONS", optimize.TC_MOTIF_SEPARATED_POSITIONS()), ("TC_MOTIF_ALL_POSITIONS", optimize.TC_MOTIF_ALL_POSITIONS())):
+        ref, seen = refexec.reference_condition(name), set()
+        for _ in range(400):
+            it = int(rng.integers(0, 7))
+            f_last, f_cur = rng.normal(size=2) * 10.0 ** rng.integers(-6, 1)
+            g = rng.normal(size=4) * 10.0 ** rng.integers(-6, 0)
+            d = rng.normal(size=4) * 10.0 ** rng.integers(-4, 1)
+            alpha = float(rng.random() * 10.0 ** rng.integers(-3, 1))
+            r = ref.do_next_iteration(it, f_last, f_cur, list(g), list(d), alpha)
+            assert r == mine.do_next_iteration(it, f_last, f_cur, g, d, alpha)
+            seen.add(bool(r))
+        assert seen == {True, False}
+    ref, mine = refexec.reference_forecaster(10, 0.1), optimize.LimitedMedianStartDistance(10, 0.1)
+    for _ in range(25):
+        assert ref.get_new_start_distance() == mine.get_new_start_distance()
+        v = float(rng.random())
+        ref.set_last_distance(v)
+        mine.set_last_distance(v)
