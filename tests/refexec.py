@@ -254,6 +254,16 @@ class Translator:
             self.emit(ind, f"{self.expr(toks[:1])} [ {self.expr(toks[2:3])} ] = {self.expr(toks[eq + 1:])}")
             self.emit(ind, f"{self.expr(toks[2:3])} += 1")
             return
+        # post-increments used as values inside the statement (a[i++], w[k++] on either side), each variable occurring once:
+        # the statement with the plain variable, then the increments (Java reads the value before incrementing)
+        posts = [q for q in range(1, len(v) - 1) if v[q] == "++" and toks[q - 1][0] == "id" and v[q - 1] not in ("]", ")")]
+        if posts and all(v.count(v[q - 1]) == 1 for q in posts) and not any(x == "--" for x in v) \
+                and not any(v[q] == "++" and q not in posts for q in range(len(v) - 1)):
+            rest = [tk for q, tk in enumerate(toks) if q not in posts]
+            self.simple(rest, ind)
+            for q in posts:
+                self.emit(ind, f"{self.expr(toks[q - 1:q])} += 1")
+            return
         if any(x in ("++", "--") for x in v[:-1]):              # e.g. a[i++] = ...: outside the subset; fails only if reached
             self.emit(ind, "raise NotImplementedError('statement outside the translated subset of Java')")
             return
@@ -1394,3 +1404,47 @@ def reference_forecaster(slots=10, value=0.1):
     f.set_last_distance = lambda last: ns["setLastDistance"](f, last)
     f.source = get + put
     return f
+
+
+STRAND_JAVA = "de/jstacs/models/mixture/StrandModel.java"
+MIXTURE_JAVA = "de/jstacs/models/mixture/AbstractMixtureModel.java"
+
+
+class ReferenceStrandEStep:
+    """StrandModel.getNewWeights (jstacs!/de/jstacs/models/mixture/StrandModel.java:561-583) with AbstractMixtureModel.
+    modifyWeights (EM branch, :1074-1078) and Normalisation.logSumNormalisation, executed from the jar: per window the strand
+    posterior times the window's weight, the strand statistics w[2] and the log-likelihood L -- what the M-step of a mixture
+    with a StrandModel component runs (row a11).  sample[0] holds the windows in pairs (forward, reverse complement)."""
+    _ns = None
+
+    def __init__(self, forward, reverse, forward_weight, hyper=(0.0, 0.0)):
+        if ReferenceStrandEStep._ns is None:
+            ReferenceEStep([1], 1, None, None, 0.5)
+            ns = dict(ReferenceEStep._ns)
+            fields, methods = ["model", "sample", "logWeights", "algorithm"], ["initWithPrior", "modifyWeights"]
+            src = _translate_method(_jar_tokens(STRAND_JAVA), "strandNewWeights", "getNewWeights", 3, fields, methods)
+            msrc = _translate_method(_jar_tokens(MIXTURE_JAVA), "modifyWeights", "modifyWeights", 1, fields, methods, case="EM")
+            exec(compile(src, STRAND_JAVA, "exec"), ns)
+            exec(compile(msrc, MIXTURE_JAVA, "exec"), ns)
+            ReferenceStrandEStep._ns, ReferenceStrandEStep.source = ns, src + msrc
+        scores = [x for pair in zip(forward, reverse) for x in pair]
+
+        class _Model:
+            def getLogProbFor(self, window):
+                return float(scores[window])
+        self.model, self.sample, self.hyper = [_Model()], [_Windows(len(scores))], hyper
+        self.logWeights = _JArray([math.log(forward_weight), math.log(1.0 - forward_weight)])
+        self.n = len(scores)
+
+    def initWithPrior(self, w):
+        w[0], w[1] = self.hyper
+
+    def modifyWeights(self, w):
+        return self._ns["modifyWeights"](self, w)
+
+    def getNewWeights(self, data_weights=None):
+        """-> (L, w[2], seqweights[0] in (forward, reverse) pairs)"""
+        w, seqweights = _JArray([0.0, 0.0]), _JArray([_JArray([0.0] * self.n)])
+        dw = None if data_weights is None else _JArray(float(x) for x in data_weights)
+        L = self._ns["strandNewWeights"](self, dw, w, seqweights)
+        return L, list(w), list(seqweights[0])

@@ -542,3 +542,24 @@ def test_termination_conditions_and_forecaster_executed_from_the_jar_equal_the_r
         v = float(rng.random())
         ref.set_last_distance(v)
         mine.set_last_distance(v)
+
+
+@needs_reference
+def test_strand_model_m_step_weights_executed_from_the_jar_equal_the_host_mirror():
+    """StrandModel.getNewWeights (jstacs StrandModel.java:561-583, with modifyWeights and logSumNormalisation) executed from the
+    jar against phyfoo_b200.models.StrandModel.getNewWeights fed with the same window scores: per-window strand weights, the
+    strand statistics (without the prior) and the log-likelihood."""
+    from phyfoo_b200.models import StrandModel
+    rng = np.random.default_rng(5)
+    forward, reverse, weights = rng.normal(size=40) * 3 - 20, rng.normal(size=40) * 3 - 20, rng.random(40)
+
+    class Scores:                                             # the motif model: forward and reverse-complement window scores
+        def getLogProbFor(self, sample, strand):
+            return reverse if strand else forward
+    for dw in (weights, None):
+        L, w, sw = refexec.ReferenceStrandEStep(forward, reverse, 0.6).getNewWeights(dw)
+        f, r, w_mine, L_mine = StrandModel(Scores(), 0.6).getNewWeights(None, dw)
+        assert abs(L - L_mine) <= 1e-13 * abs(L)
+        assert np.max(np.abs(np.array(sw[0::2]) - f)) < 1e-14 and np.max(np.abs(np.array(sw[1::2]) - r)) < 1e-14
+        assert np.max(np.abs(np.array(w) - w_mine)) <= 1e-13 * max(w)
+    assert "w [ 1 ] += seqweights [ 0 ] [ counter1 ]" in refexec.ReferenceStrandEStep.source
