@@ -274,7 +274,9 @@ def parity_check(cfg, newick, pwm, sample, shm, k):
                          f"{np.array_equal(res['argmax_off'], ref['argmax_off'])}")
     sub.device(shm.motif.ctx).free()
     return {"alignments": int(k), "windows": int(res["gamma"].size), "ll_rel_err": err_ll, "gamma_abs_err": err_g,
-            "sweep_counts": "identical", "argmax_calls": "identical"}
+            "sweep_counts": "identical", "argmax_calls": "identical",
+            "against": "the CPU oracle, which reproduces to the last bit the reference's own statements executed from its source "
+                       "files (tests/test_reference_statements.py; no JVM exists in the image)"}
 
 
 class EStepRunner:
