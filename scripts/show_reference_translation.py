@@ -55,6 +55,10 @@ def main():
     parts += [("jstacs.jar Optimizer.java:122-146  findBracket", opt["findBracket"]), ("jstacs.jar Optimizer.java:202-303  brentsMethod", opt["brentsMethod"]),
               ("jstacs.jar Optimizer.java:1000-1080  quasiNewtonBFGS", opt["quasiNewtonBFGS"]),
               ("jstacs.jar OneDimensionalSubFunction.java:62-74  evaluateFunction", opt["along"])]
+    parts.append(("jstacs.jar StrandModel.java:561-583  getNewWeights + AbstractMixtureModel.java:1074-1078  modifyWeights (case EM)",
+                  (refexec.ReferenceStrandEStep([0.0], [0.0], 0.5), refexec.ReferenceStrandEStep.source)[1]))
+    parts.append(("jstacs.jar termination/CombinedCondition.java:108-117  doNextIteration", refexec.reference_condition().source))
+    parts.append(("jstacs.jar LimitedMedianStartDistance.java:64-84  getNewStartDistance / setLastDistance", refexec.reference_forecaster().source))
     for title, text in parts:
         if want.lower() in title.lower():
             print("=" * 100 + "\n" + title + "\n" + "=" * 100 + "\n" + text)
