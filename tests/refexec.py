@@ -138,6 +138,11 @@ class Translator:
                 i = j + 3
                 continue
             if t == "(" and i + 2 < len(toks) and toks[i + 1][1] in TYPES and toks[i + 2][1] == ")":
+                if toks[i + 1][1] in ("int", "long") and i + 3 < len(toks) and toks[i + 3][1] == "(":
+                    j = _match(toks, i + 3, "(", ")")            # (int) ( expr ): Java truncates towards zero, like int()
+                    out.append(f"int({self.expr(toks[i + 4:j])})")
+                    i = j + 1
+                    continue
                 i += 3                                          # a primitive cast in front of a value of that type already
                 continue
             if t == "/" and self.int_division:
@@ -192,7 +197,7 @@ class Translator:
             i += 1
         s = " ".join(out)
         for a, b in (("Math . log", "_jlog"), ("Math . exp", "_jexp"), ("Math . abs", "abs"), ("Math . min", "min"),
-                     ("Math . max", "max"), ("Arrays . copyOf", "_copyOf"), ("Double . isNaN", "_isnan"), ("Math . sqrt", "_sqrt"), ("Double . POSITIVE_INFINITY", "_POS_INF"), ("Double . isInfinite", "_isinf"), ("Normalisation .", "_Normalisation ."),
+                     ("Math . max", "max"), ("Arrays . copyOf", "_copyOf"), ("Double . isNaN", "_isnan"), ("Arrays . sort", "_sort"), ("Math . sqrt", "_sqrt"), ("Double . POSITIVE_INFINITY", "_POS_INF"), ("Double . isInfinite", "_isinf"), ("Normalisation .", "_Normalisation ."),
                      ("Double . NEGATIVE_INFINITY", "_NEG_INF"), ("Alphabet . size", "4"),
                      ("MeanFieldForBayesNet . CALC_LIKELIHOOD", "self.CALC_LIKELIHOOD")):
             s = s.replace(a, b)
@@ -382,7 +387,7 @@ class Translator:
         uv = [t[1] for t in upd]
         # for (int v = A; v < B; v++)  /  v <= B   -- the only shape the three methods use
         if len(iv) >= 4 and iv[0] == "int" and iv[2] == "=" and cv[0] == iv[1] and cv[1] in ("<", "<=") and uv == [iv[1], "++"] \
-                and not any(x in ("&&", "||", "?") for x in cv) and iv[1] not in cv[2:]:
+                and not any(x in ("&&", "||", "?") for x in cv) and iv[1] not in cv[2:] and "," not in iv:
             var = iv[1]
             self.locals.add(var)
             lo, hi = self.expr(init[3:]), self.expr(cond[2:])
@@ -392,8 +397,11 @@ class Translator:
         end = _match(toks, j + 1, "{", "}") if toks[j + 1][1] == "{" else None
         if end is None or any(t[1] == "continue" for t in toks[j + 1:end]):
             raise NotImplementedError("for-loop shape " + " ".join(iv + [";"] + cv + [";"] + uv))
-        for part in self.split_top(init, ","):
-            self.simple(part, ind)
+        if init and init[0][1] in TYPES:
+            self.simple(init, ind)                              # int i = 0, k = 0
+        else:
+            for part in self.split_top(init, ","):
+                self.simple(part, ind)
         self.emit(ind, f"while {self.expr(cond) if cond else 'True'}:")
         k = self.stmt(toks, j + 1, ind + 1, labels)
         for part in self.split_top(upd, ","):
@@ -1448,3 +1456,19 @@ class ReferenceStrandEStep:
         dw = None if data_weights is None else _JArray(float(x) for x in data_weights)
         L = self._ns["strandNewWeights"](self, dw, w, seqweights)
         return L, list(w), list(seqweights[0])
+
+
+CLASSIFICATION_JAVA = REFERENCE_ROOT + "/main/java/src/classification/ClassificationUtil.java"
+
+
+def reference_classification():
+    """{name: callable}: determineThresholdsForSpecifitiesPerPos and determineSensitivityPerSeq of
+    classification/ClassificationUtil.java (:244-278) executed from the reference (row f-1)."""
+    with open(CLASSIFICATION_JAVA, encoding="latin-1") as f:
+        toks = tokenize(f.read())
+    ns = {"_JArray": _JArray, "_sort": _sorted_inplace}
+    for name, n in (("determineThresholdsForSpecifitiesPerPos", 2), ("determineSensitivityPerSeq", 2)):
+        exec(compile(_translate_method(toks, name, name, n, [], []), CLASSIFICATION_JAVA, "exec"), ns)
+    wrap = lambda m: _JArray(_JArray(float(x) for x in row) for row in m)                       # noqa: E731
+    return {"thresholds": lambda neg, spec: list(ns["determineThresholdsForSpecifitiesPerPos"](None, wrap(neg), _JArray(float(x) for x in spec))),
+            "sensitivity": lambda thr, pos: ns["determineSensitivityPerSeq"](None, float(thr), wrap(pos))}

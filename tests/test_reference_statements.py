@@ -563,3 +563,22 @@ def test_strand_model_m_step_weights_executed_from_the_jar_equal_the_host_mirror
         assert np.max(np.abs(np.array(sw[0::2]) - f)) < 1e-14 and np.max(np.abs(np.array(sw[1::2]) - r)) < 1e-14
         assert np.max(np.abs(np.array(w) - w_mine)) <= 1e-13 * max(w)
     assert "w [ 1 ] += seqweights [ 0 ] [ counter1 ]" in refexec.ReferenceStrandEStep.source
+
+
+# ---- classification front-end (row f-1) -----------------------------------------------------------------------------------------
+@needs_reference
+def test_classification_thresholds_and_sensitivity_executed_from_the_reference_equal_the_host_mirror():
+    """ClassificationUtil.determineThresholdsForSpecifitiesPerPos / determineSensitivityPerSeq (:244-278) executed from the
+    reference against phyfoo_b200.classification on ragged score matrices (the device variants are held against these host
+    functions in tests/test_gpu_scan.py)."""
+    from phyfoo_b200 import classification as cl
+    ref = refexec.reference_classification()
+    rng = np.random.default_rng(4)
+    for _ in range(5):
+        neg = [rng.normal(size=rng.integers(1, 30)) for _ in range(20)]
+        pos = [rng.normal(size=rng.integers(1, 30)) + 1 for _ in range(20)]
+        spec = [0.0, 0.5, 0.9, 0.99, 0.999, 1.0]
+        thresholds = ref["thresholds"](neg, spec)
+        assert np.array_equal(thresholds, cl.determineThresholdsForSpecifitiesPerPos(neg, spec))
+        for t in thresholds:
+            assert ref["sensitivity"](t, pos) == cl.determineSensitivityPerSeq(t, pos)
