@@ -176,7 +176,7 @@ class Translator:
                     out.append("self." + t)
                 elif t in self.fields:
                     out.append("self." + t)
-                elif t in ("Math", "Double", "Alphabet", "MeanFieldForBayesNet", "Arrays", "System", "Normalisation", "SimpleNodeElimination", "PhyloSample", "AlignmentBasedModel"):
+                elif t in ("Math", "Double", "Alphabet", "MeanFieldForBayesNet", "Arrays", "System", "Normalisation", "SimpleNodeElimination", "PhyloSample", "AlignmentBasedModel", "EdgeOptimizer"):
                     out.append(t)
                 else:
                     raise NameError(f"unknown identifier {t!r} in the reference statement")
@@ -1472,3 +1472,30 @@ def reference_classification():
     wrap = lambda m: _JArray(_JArray(float(x) for x in row) for row in m)                       # noqa: E731
     return {"thresholds": lambda neg, spec: list(ns["determineThresholdsForSpecifitiesPerPos"](None, wrap(neg), _JArray(float(x) for x in spec))),
             "sensitivity": lambda thr, pos: ns["determineSensitivityPerSeq"](None, float(thr), wrap(pos))}
+
+
+GLOBAL_EDGE_JAVA = REFERENCE_ROOT + "/main/java/src/optimizing/branchlengths/GlobalEdgeOptimizer.java"
+
+
+class ReferenceGlobalEdgeObjective(ReferenceEdgeObjective):
+    """GlobalEdgeOptimizer.evaluateFunction (optimizing/branchlengths/GlobalEdgeOptimizer.java:33-58) executed from the reference:
+    one set of branch lengths for the trees of every motif position."""
+    _global = None
+
+    def __init__(self, net, windows, weights):
+        super().__init__(net, windows, weights, 0)
+        if ReferenceGlobalEdgeObjective._global is None:
+            with open(GLOBAL_EDGE_JAVA, encoding="latin-1") as f:
+                toks = tokenize(f.read())
+            src = _translate_method(toks, "evaluateFunctionGlobal", "evaluateFunction", 1, ["bnh"], ["getWeightedLogLikelihoodSum"])
+            ns = dict(self._ns)
+            ns["_isnan"] = math.isnan
+
+            class _EdgeOptimizer:
+                MINIMUM_BRANCH_LENGTH = 0.0005                   # optimizing/branchlengths/EdgeOptimizer.java:23
+            ns["EdgeOptimizer"] = _EdgeOptimizer
+            exec(compile(src, GLOBAL_EDGE_JAVA, "exec"), ns)
+            ReferenceGlobalEdgeObjective._global, ReferenceGlobalEdgeObjective.global_source = staticmethod(ns["evaluateFunctionGlobal"]), src
+
+    def evaluateEdges(self, x):
+        return self._global(self, _JArray(float(v) for v in x))

@@ -582,3 +582,32 @@ def test_classification_thresholds_and_sensitivity_executed_from_the_reference_e
         assert np.array_equal(thresholds, cl.determineThresholdsForSpecifitiesPerPos(neg, spec))
         for t in thresholds:
             assert ref["sensitivity"](t, pos) == cl.determineSensitivityPerSeq(t, pos)
+
+
+@needs_reference
+def test_global_branch_length_objective_executed_from_the_reference_equals_the_oracle():
+    """GlobalEdgeOptimizer.evaluateFunction (one set of branch lengths for the trees of every position; what EDGE_LEARNING = 2
+    optimises, models/PhyloBayesModel.java:204) executed from the reference against the oracle under those branch lengths."""
+    from util import orc, random_codes
+    from phyfoo_b200 import evolution, synth
+    rng = np.random.default_rng(12)
+    newick, W = "((A:0.1,B:0.3):0.15,(C:0.2,(D:0.05,E:0.4):0.25):0.1,F:0.3)", 3
+    pwm = synth.random_pwm(W, 0, 33)
+    net = npr.Net.motif(newick, W, 0)
+    for t, p in enumerate(pwm):
+        net.set_pi(t, p)
+    net.build_tables()
+    cols = [random_codes(rng, W, 6, 0.1) for _ in range(5)]
+    weights = rng.random(5) + 0.1
+    ref = refexec.ReferenceGlobalEdgeObjective(net, cols, weights)
+    m = oracle_fg(newick, pwm)
+    fs = orc.FESet(m, np.stack(cols), weights)
+    for _ in range(3):
+        x = rng.normal(size=net.N - 1) - 1.0
+        alpha = evolution.branch_from_logit(x)
+        for t in range(W):
+            for k in range(1, net.N):
+                m.set_branch(t, k, float(alpha[k - 1]))
+        f = ref.evaluateEdges(x)
+        assert abs(fs.sum() - f) <= 1e-13 * abs(f)
+    assert "bn . setDistanceToParent ( edgesPi [ k ] )" in refexec.ReferenceGlobalEdgeObjective.global_source
