@@ -57,6 +57,8 @@ def main():
               ("jstacs.jar OneDimensionalSubFunction.java:62-74  evaluateFunction", opt["along"])]
     parts.append(("jstacs.jar StrandModel.java:561-583  getNewWeights + AbstractMixtureModel.java:1074-1078  modifyWeights (case EM)",
                   (refexec.ReferenceStrandEStep([0.0], [0.0], 0.5), refexec.ReferenceStrandEStep.source)[1]))
+    refexec.ReferenceGlobalEdgeObjective(net, [np.zeros((1, 2), np.uint8)], [1.0])
+    parts.append(("optimizing/branchlengths/GlobalEdgeOptimizer.java:33-58  evaluateFunction", refexec.ReferenceGlobalEdgeObjective.global_source))
     parts.append(("jstacs.jar termination/CombinedCondition.java:108-117  doNextIteration", refexec.reference_condition().source))
     parts.append(("jstacs.jar LimitedMedianStartDistance.java:64-84  getNewStartDistance / setLastDistance", refexec.reference_forecaster().source))
     for title, text in parts:
