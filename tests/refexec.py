@@ -1,17 +1,22 @@
-"""Executes the reference's OWN statements for the mean-field sweep and the free energy.
+"""Executes the reference's OWN statements.
 
-TEST INFRASTRUCTURE ONLY.  No JVM exists in this image, so the Java cannot run as Java.  But the two methods that carry the
-path's arithmetic -- MeanFieldForBayesNet.optimizeByNormalisation (algorithm/MeanFieldForBayesNet.java:92-211) and
-calcFreeEnergy(int, int) (:232-365), plus init() (:52-69) -- are written in a C-like subset of Java (declarations, for / while /
-if, array indexing, field access, Math.log / exp / abs).  This module reads that file from /root/reference AT TEST TIME,
-translates those method bodies token by token into Python (same statements, same order, same operands; nothing is re-derived)
-and runs them against a small object graph with the field and method names the Java uses (nodes, parents, children, CPF tables
-with their look-up rows).  No reference source is copied into the repository: without /root/reference the functions here
-raise, and the tests that need them are skipped (the golden vectors they produced are committed and are what travels).
+TEST INFRASTRUCTURE ONLY.  No JVM exists in this image, so the Java cannot run as Java.  But the methods that carry the path's
+arithmetic are written in a C-like subset of Java (declarations, for / while / do / if, array indexing, field access, calls,
+Math.*): the mean-field sweep and the free energy (algorithm/MeanFieldForBayesNet.java), both getLogProbFor drivers
+(models/PhyloBayesModel.java, PhyloBackground.java), the substitution tables (evolution/*.java), the Jstacs E-step, strand
+mixture, normalisations, numerical gradient, optimiser, termination conditions and start-distance forecaster (libs/jstacs.jar),
+the M-step objective and the branch-length objectives (optimizing/*.java), the selector, the alignment-based models and the
+classification thresholds.  This module reads those files from /root/reference AT TEST TIME, translates the method bodies token
+by token into Python (same statements, same order, same operands; a construct outside the subset raises) and runs them over
+small objects that carry the field and method names the Java uses.  scripts/show_reference_translation.py prints what is
+generated.  No reference source is copied into the repository: without /root/reference the functions here raise and the tests
+that need them are skipped; the golden vectors they produced (tests/golden/refexec_meanfield.npz, scripts/make_refexec_golden.py)
+are committed and are what travels to the GPU box.
 
-What is mechanical: every statement of the three methods.  What is NOT: the object graph the statements walk (tree structure,
-parent / child order, table rows), which is built from oracle/np_restatement.py; that substrate is pinned separately against
-the reference's own sampler output (tests/test_generator_pins.py).
+What is mechanical: every statement of the translated methods.  What is NOT: the object graph the statements walk (tree
+structure from the Newick string, parent / child order: oracle/np_restatement.py; pinned separately against the reference's own
+sampler output, tests/test_generator_pins.py) and the few shims named in the class docstrings below (the mean-field cache, the
+hand-over of new parameters to the tables, java.util collections).
 """
 import math
 import os
